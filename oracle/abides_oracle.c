@@ -1,0 +1,751 @@
+/*
+ * abides_oracle.c -- CPU restatement (plain C) of the reference's hot path.  TEST INFRASTRUCTURE ONLY.
+ * See abides_oracle.h for the rules about who may call this and the parity status (PINNED).
+ *
+ * Compile WITHOUT floating-point contraction (-ffp-contract=off): the reference is CPython + libm, every
+ * fp64 operation is individually rounded.  All file:line citations are relative to /root/reference.
+ */
+#include "abides_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ====================================================================================================
+ * growable int64 row buffers
+ * ==================================================================================================== */
+typedef struct { int64_t *v; int64_t n, cap; } i64buf;
+static void ib_push(i64buf *b, const int64_t *row, int w) {
+  if (b->n + w > b->cap) { b->cap = b->cap ? b->cap * 2 : 4096; while (b->cap < b->n + w) b->cap *= 2; b->v = (int64_t *)realloc(b->v, sizeof(int64_t) * b->cap); }
+  memcpy(b->v + b->n, row, sizeof(int64_t) * w); b->n += w;
+}
+static const uint64_t FNV_OFF = 0xCBF29CE484222325ULL, FNV_PRIME = 0x100000001B3ULL;
+static inline uint64_t fnv_mix(uint64_t h, int64_t sv) { uint64_t v = (uint64_t)sv; for (int i = 0; i < 8; i++) { h = (h ^ (v & 0xFF)) * FNV_PRIME; v >>= 8; } return h; }
+
+/* ====================================================================================================
+ * numpy legacy RandomState: MT19937 + legacy distributions (numpy/random/src/legacy, mtrand.pyx).
+ * The reference draws everything through np.random.RandomState.
+ * ==================================================================================================== */
+struct abo_rng {
+  uint32_t mt[624]; int pos; int has_gauss; double gauss; uint32_t seed;
+  int record; uint8_t *tk; uint64_t *tv; int64_t tn, tcap;
+};
+static void rng_seed(abo_rng *r, uint32_t seed) { /* mt19937_seed */
+  r->seed = seed;
+  for (int i = 0; i < 624; i++) { r->mt[i] = seed; seed = 1812433253U * (seed ^ (seed >> 30)) + (uint32_t)i + 1U; }
+  r->pos = 624; r->has_gauss = 0; r->gauss = 0.0;
+}
+abo_rng *abo_rng_new(uint32_t seed) { abo_rng *r = (abo_rng *)calloc(1, sizeof(abo_rng)); rng_seed(r, seed); return r; }
+void abo_rng_free(abo_rng *r) { if (r) { free(r->tk); free(r->tv); free(r); } }
+static void rng_rec(abo_rng *r, uint8_t k, uint64_t bits) {
+  if (!r->record) return;
+  if (r->tn == r->tcap) { r->tcap = r->tcap ? r->tcap * 2 : 64; r->tk = (uint8_t *)realloc(r->tk, r->tcap); r->tv = (uint64_t *)realloc(r->tv, 8 * r->tcap); }
+  r->tk[r->tn] = k; r->tv[r->tn] = bits; r->tn++;
+}
+static inline uint64_t dbits(double d) { uint64_t u; memcpy(&u, &d, 8); return u; }
+static void mt_gen(abo_rng *r) {
+  uint32_t *mt = r->mt; int i; uint32_t y;
+  for (i = 0; i < 624 - 397; i++) { y = (mt[i] & 0x80000000U) | (mt[i + 1] & 0x7fffffffU); mt[i] = mt[i + 397] ^ (y >> 1) ^ (-(int32_t)(y & 1) & 0x9908b0dfU); }
+  for (; i < 623; i++) { y = (mt[i] & 0x80000000U) | (mt[i + 1] & 0x7fffffffU); mt[i] = mt[i + (397 - 624)] ^ (y >> 1) ^ (-(int32_t)(y & 1) & 0x9908b0dfU); }
+  y = (mt[623] & 0x80000000U) | (mt[0] & 0x7fffffffU); mt[623] = mt[396] ^ (y >> 1) ^ (-(int32_t)(y & 1) & 0x9908b0dfU);
+  r->pos = 0;
+}
+static inline uint32_t rng_u32_raw(abo_rng *r) {
+  if (r->pos == 624) mt_gen(r);
+  uint32_t y = r->mt[r->pos++];
+  y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680U; y ^= (y << 15) & 0xefc60000U; y ^= (y >> 18);
+  return y;
+}
+static inline double rng_double_raw(abo_rng *r) { /* mt19937_next_double */
+  int32_t a = (int32_t)(rng_u32_raw(r) >> 5), b = (int32_t)(rng_u32_raw(r) >> 6);
+  return (a * 67108864.0 + b) / 9007199254740992.0;
+}
+static double rng_gauss_raw(abo_rng *r) { /* legacy_gauss */
+  if (r->has_gauss) { double t = r->gauss; r->has_gauss = 0; r->gauss = 0.0; return t; }
+  double f, x1, x2, r2;
+  do { x1 = 2.0 * rng_double_raw(r) - 1.0; x2 = 2.0 * rng_double_raw(r) - 1.0; r2 = x1 * x1 + x2 * x2; } while (r2 >= 1.0 || r2 == 0.0);
+  f = sqrt(-2.0 * log(r2) / r2);
+  r->gauss = f * x1; r->has_gauss = 1;
+  return f * x2;
+}
+uint32_t abo_rng_u32(abo_rng *r) { return rng_u32_raw(r); }
+double abo_rng_double(abo_rng *r) { double u = rng_double_raw(r); rng_rec(r, 'u', dbits(u)); return u; }
+double abo_rng_gauss(abo_rng *r) { double z = rng_gauss_raw(r); rng_rec(r, 'n', dbits(z)); return z; }
+double abo_rng_std_exponential(abo_rng *r) { double e = -log(1.0 - rng_double_raw(r)); rng_rec(r, 'e', dbits(e)); return e; }
+int64_t abo_rng_randint(abo_rng *r, int64_t low, int64_t high) { /* _rand_int64 + random_bounded_uint64_fill, use_masked */
+  uint64_t rng = (uint64_t)(high - 1 - low), v;
+  if (rng == 0) v = 0;
+  else if (rng <= 0xFFFFFFFFULL) {
+    if (rng == 0xFFFFFFFFULL) v = rng_u32_raw(r);
+    else { uint64_t mask = rng; mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+           do { v = rng_u32_raw(r) & mask; } while (v > rng); }
+  } else { uint64_t mask = rng; mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16; mask |= mask >> 32;
+           do { uint64_t hi = rng_u32_raw(r); uint64_t lo = rng_u32_raw(r); v = ((hi << 32) | lo) & mask; } while (v > rng); }
+  rng_rec(r, 'i', v);
+  return low + (int64_t)v;
+}
+/* scaled forms, written as the identities of SURVEY App. C */
+static inline double rng_normal(abo_rng *r, double loc, double scale) { return loc + scale * abo_rng_gauss(r); }
+static inline double rng_exponential(abo_rng *r, double scale) { return abo_rng_std_exponential(r) * scale; }
+static inline double rng_uniform(abo_rng *r, double low, double high) { return low + (high - low) * abo_rng_double(r); }
+
+/* Python int(round(x)) for a float x: round-half-even (nearbyint under the default rounding mode). */
+static inline int64_t py_round(double x) { return (int64_t)nearbyint(x); }
+
+/* ====================================================================================================
+ * Order book -- util/OrderBook.py
+ * ==================================================================================================== */
+typedef struct { int64_t agent_id, order_id, quantity, limit_price, fill_price; int is_buy; } order_t; /* util/order/LimitOrder.py:14-20 */
+typedef struct { order_t *o; int n, cap; } level_t;          /* one price level: FIFO list, oldest at 0 */
+typedef struct { level_t *lv; int n, cap; } side_t;          /* OrderBook.bids / .asks, best at 0 (OrderBook.py:24-25) */
+typedef struct { int64_t t, q; } tx_t;
+typedef struct { int64_t order_id; tx_t *tx; int ntx, captx; } hrec_t; /* history record (OrderBook.py:52-60), only what is read back */
+typedef struct { hrec_t *r; int n, cap; } hbucket_t;
+
+typedef void (*send_fn)(void *owner, int64_t recipient, int kind, const order_t *o);
+
+struct abo_book {
+  side_t bids, asks; int64_t last_trade; int has_last_trade;
+  hbucket_t *hist; int nhist; int stream_history;
+  int64_t now; void *owner; send_fn send;
+  i64buf notes; /* standalone use */
+  int64_t n_fills;
+};
+
+static void level_push(level_t *l, const order_t *o) { if (l->n == l->cap) { l->cap = l->cap ? l->cap * 2 : 4; l->o = (order_t *)realloc(l->o, sizeof(order_t) * l->cap); } l->o[l->n++] = *o; }
+static void level_pop_at(level_t *l, int i) { memmove(l->o + i, l->o + i + 1, sizeof(order_t) * (l->n - i - 1)); l->n--; }
+static void side_insert(side_t *s, int i, const order_t *o) {
+  if (s->n == s->cap) { s->cap = s->cap ? s->cap * 2 : 64; s->lv = (level_t *)realloc(s->lv, sizeof(level_t) * s->cap); }
+  memmove(s->lv + i + 1, s->lv + i, sizeof(level_t) * (s->n - i)); s->n++;
+  s->lv[i].o = NULL; s->lv[i].n = s->lv[i].cap = 0; level_push(&s->lv[i], o);
+}
+static void side_delete(side_t *s, int i) { free(s->lv[i].o); memmove(s->lv + i, s->lv + i + 1, sizeof(level_t) * (s->n - i - 1)); s->n--; }
+
+static hrec_t *hist_find(hbucket_t *b, int64_t id) { for (int i = 0; i < b->n; i++) if (b->r[i].order_id == id) return &b->r[i]; return NULL; }
+static void hist_add_tx(hrec_t *r, int64_t t, int64_t q) { if (r->ntx == r->captx) { r->captx = r->captx ? r->captx * 2 : 2; r->tx = (tx_t *)realloc(r->tx, sizeof(tx_t) * r->captx); } r->tx[r->ntx].t = t; r->tx[r->ntx].q = q; r->ntx++; }
+static void hist_bucket_free(hbucket_t *b) { for (int i = 0; i < b->n; i++) free(b->r[i].tx); free(b->r); b->r = NULL; b->n = b->cap = 0; }
+
+static void book_note_send(void *owner, int64_t recipient, int kind, const order_t *o) { /* standalone book: record rows */
+  abo_book *b = (abo_book *)owner;
+  int64_t row[13] = { b->now, recipient, kind, o->order_id, o->is_buy, o->quantity, o->limit_price, o->fill_price, 0, 0, 0, 0, 0 };
+  ib_push(&b->notes, row, 13);
+}
+static void book_init(abo_book *b, int stream_history, void *owner, send_fn send) { /* OrderBook.__init__ :21-36 */
+  memset(b, 0, sizeof(*b)); b->stream_history = stream_history; b->owner = owner; b->send = send;
+  b->hist = (hbucket_t *)calloc(stream_history + 2, sizeof(hbucket_t)); b->nhist = 1;
+}
+static void book_destroy(abo_book *b) {
+  for (int i = 0; i < b->bids.n; i++) free(b->bids.lv[i].o);
+  for (int i = 0; i < b->asks.n; i++) free(b->asks.lv[i].o);
+  free(b->bids.lv); free(b->asks.lv);
+  for (int i = 0; i < b->nhist; i++) hist_bucket_free(&b->hist[i]);
+  free(b->hist); free(b->notes.v);
+}
+/* isMatch :242-254 (same-side case cannot occur: caller picks the opposite side) */
+static inline int is_match(const order_t *order, const order_t *o) { return order->is_buy ? order->limit_price >= o->limit_price : order->limit_price <= o->limit_price; }
+/* isBetterPrice :440-453 */
+static inline int is_better(const order_t *order, const order_t *o) { return order->is_buy ? order->limit_price > o->limit_price : order->limit_price < o->limit_price; }
+
+/* executeOrder :172-240.  Returns 1 and fills *matched when the head of the best opposite level matches. */
+static int book_execute(abo_book *b, order_t *order, order_t *matched) {
+  side_t *book = order->is_buy ? &b->asks : &b->bids;
+  if (book->n == 0) return 0;
+  if (!is_match(order, &book->lv[0].o[0])) return 0;
+  if (order->quantity >= book->lv[0].o[0].quantity) {       /* :204-210 consumed the whole resting order */
+    *matched = book->lv[0].o[0]; level_pop_at(&book->lv[0], 0);
+    if (book->lv[0].n == 0) side_delete(book, 0);
+  } else {                                                  /* :212-217 partial */
+    *matched = book->lv[0].o[0]; matched->quantity = order->quantity;
+    book->lv[0].o[0].quantity -= matched->quantity;
+  }
+  matched->fill_price = matched->limit_price;               /* :221 */
+  hrec_t *r = hist_find(&b->hist[0], order->order_id);      /* :227 incoming order's PRE-fill remaining qty */
+  if (r) hist_add_tx(r, b->now, order->quantity);
+  for (int i = 0; i < b->nhist; i++) { hrec_t *m = hist_find(&b->hist[i], matched->order_id); if (m) hist_add_tx(m, b->now, matched->quantity); } /* :230-237 */
+  return 1;
+}
+/* enterOrder :256-282 */
+static void book_enter(abo_book *b, const order_t *order) {
+  side_t *book = order->is_buy ? &b->bids : &b->asks;
+  if (book->n == 0) { side_insert(book, 0, order); return; }
+  const order_t *last = &book->lv[book->n - 1].o[0];
+  if (!is_better(order, last) && order->limit_price != last->limit_price) { side_insert(book, book->n, order); return; }
+  for (int i = 0; i < book->n; i++) {
+    if (is_better(order, &book->lv[i].o[0])) { side_insert(book, i, order); return; }
+    else if (order->limit_price == book->lv[i].o[0].limit_price) { level_push(&book->lv[i], order); return; }
+  }
+}
+/* handleLimitOrder :38-170 (symbol check is the caller's; book_log/prettyPrint have no state effect) */
+static void book_handle_limit(abo_book *b, order_t order) {
+  if (order.quantity <= 0) return;                                                   /* :47-49 */
+  hbucket_t *h0 = &b->hist[0]; hrec_t *r = hist_find(h0, order.order_id);            /* :52-60 */
+  if (r) { r->ntx = 0; }
+  else { if (h0->n == h0->cap) { h0->cap = h0->cap ? h0->cap * 2 : 16; h0->r = (hrec_t *)realloc(h0->r, sizeof(hrec_t) * h0->cap); }
+         h0->r[h0->n].order_id = order.order_id; h0->r[h0->n].tx = NULL; h0->r[h0->n].ntx = h0->r[h0->n].captx = 0; h0->n++; }
+  int matching = 1; int64_t trade_qty = 0, trade_price = 0; int executed = 0;
+  while (matching) {                                                                 /* :68-110 */
+    order_t matched;
+    if (book_execute(b, &order, &matched)) {
+      order_t filled = order; filled.quantity = matched.quantity; filled.fill_price = matched.fill_price; /* :73-75 */
+      order.quantity -= filled.quantity;                                             /* :77 */
+      b->send(b->owner, order.agent_id, ABO_ORDER_EXECUTED, &filled);                /* :88 */
+      b->send(b->owner, matched.agent_id, ABO_ORDER_EXECUTED, &matched);             /* :89-91 */
+      trade_qty += filled.quantity; trade_price += filled.fill_price * filled.quantity; executed = 1; b->n_fills++; /* :94,131-137 */
+      if (order.quantity <= 0) matching = 0;
+    } else {
+      book_enter(b, &order);                                                         /* :101 */
+      b->send(b->owner, order.agent_id, ABO_ORDER_ACCEPTED, &order);                 /* :108 */
+      matching = 0;
+    }
+  }
+  if (executed) {                                                                    /* :131-149 */
+    b->last_trade = py_round((double)trade_price / (double)trade_qty); b->has_last_trade = 1; /* int(round(a / b)): true division */
+    /* history.insert(0, {}) then truncate to stream_history+1 */
+    if (b->nhist == b->stream_history + 1) { hist_bucket_free(&b->hist[b->nhist - 1]); b->nhist--; }
+    memmove(b->hist + 1, b->hist, sizeof(hbucket_t) * b->nhist); memset(&b->hist[0], 0, sizeof(hbucket_t)); b->nhist++;
+  }
+}
+/* cancelOrder :284-339 */
+static void book_cancel(abo_book *b, const order_t *order) {
+  side_t *book = order->is_buy ? &b->bids : &b->asks;
+  if (book->n == 0) return;
+  for (int i = 0; i < book->n; i++) {
+    if (order->limit_price == book->lv[i].o[0].limit_price) {                        /* :306 level price is slot 0's */
+      for (int ci = 0; ci < book->lv[i].n; ci++) {
+        if (order->order_id == book->lv[i].o[ci].order_id) {
+          order_t cancelled = book->lv[i].o[ci]; level_pop_at(&book->lv[i], ci);     /* :311 */
+          /* :314-321 history cancellations: never read back on this path */
+          if (book->lv[i].n == 0) side_delete(book, i);                              /* :324-325 */
+          b->send(b->owner, order->agent_id, ABO_ORDER_CANCELLED, &cancelled);       /* :334-336 recipient = REQUEST's agent_id */
+          return;
+        }
+      }
+    }
+  }
+}
+/* modifyOrder :341-372 -- including the slot-0 overwrite and the live iteration */
+static void book_modify(abo_book *b, const order_t *order, const order_t *new_order) {
+  if (order->order_id != new_order->order_id) return;                                /* :343 */
+  side_t *book = order->is_buy ? &b->bids : &b->asks;
+  if (book->n == 0) return;
+  for (int i = 0; i < book->n; i++) {
+    if (order->limit_price == book->lv[i].o[0].limit_price) {                        /* :349 evaluated once per level */
+      for (int mi = 0; mi < book->lv[i].n; mi++) {
+        if (order->order_id == book->lv[i].o[mi].order_id) {                         /* :351 sees the overwritten slot 0 on later mi */
+          book->lv[i].o[0] = *new_order;                                             /* :352 */
+          for (int idx = 0; idx < b->nhist; idx++) {                                 /* :353-367 one ORDER_MODIFIED per bucket holding the id */
+            if (!hist_find(&b->hist[idx], new_order->order_id)) continue;
+            b->send(b->owner, order->agent_id, ABO_ORDER_MODIFIED, new_order);
+          }
+        }
+      }
+    }
+  }
+}
+/* getInsideBids / getInsideAsks :377-398 */
+static int book_inside(const abo_book *b, int is_bid, int depth, int64_t *out) {
+  const side_t *s = is_bid ? &b->bids : &b->asks; int n = depth < s->n ? depth : s->n;
+  for (int i = 0; i < n; i++) { int64_t q = 0; for (int k = 0; k < s->lv[i].n; k++) q += s->lv[i].o[k].quantity; out[2 * i] = s->lv[i].o[0].limit_price; out[2 * i + 1] = q; }
+  return n;
+}
+/* get_transacted_volume :400-436: distinct (time, qty) tuples over the surviving history buckets, time >= now - lookback */
+static int64_t book_transacted_volume(const abo_book *b, int64_t lookback) {
+  tx_t *all = NULL; int n = 0, cap = 0;
+  for (int i = 0; i < b->nhist; i++) for (int k = 0; k < b->hist[i].n; k++) for (int j = 0; j < b->hist[i].r[k].ntx; j++) {
+    tx_t t = b->hist[i].r[k].tx[j]; int dup = 0;
+    for (int m = 0; m < n; m++) if (all[m].t == t.t && all[m].q == t.q) { dup = 1; break; }
+    if (dup) continue;
+    if (n == cap) { cap = cap ? cap * 2 : 64; all = (tx_t *)realloc(all, sizeof(tx_t) * cap); }
+    all[n++] = t;
+  }
+  int64_t start = b->now - lookback, sum = 0;
+  for (int m = 0; m < n; m++) if (all[m].t >= start) sum += all[m].q;
+  free(all); return sum;
+}
+
+/* ---- standalone book API ---- */
+abo_book *abo_book_new(int stream_history) { abo_book *b = (abo_book *)malloc(sizeof(abo_book)); book_init(b, stream_history, b, book_note_send); return b; }
+void abo_book_free(abo_book *b) { if (b) { book_destroy(b); free(b); } }
+void abo_book_set_time(abo_book *b, int64_t t) { b->now = t; }
+void abo_book_limit(abo_book *b, int64_t agent, int64_t id, int is_buy, int64_t price, int64_t qty) { order_t o = { agent, id, qty, price, 0, is_buy }; book_handle_limit(b, o); }
+void abo_book_cancel(abo_book *b, int64_t agent, int64_t id, int is_buy, int64_t price) { order_t o = { agent, id, 0, price, 0, is_buy }; book_cancel(b, &o); }
+void abo_book_modify(abo_book *b, int64_t agent, int64_t id, int is_buy, int64_t price, int64_t nid, int64_t nprice, int64_t nqty) {
+  order_t o = { agent, id, 0, price, 0, is_buy }, n = { agent, nid, nqty, nprice, 0, is_buy }; book_modify(b, &o, &n);
+}
+int abo_book_inside(abo_book *b, int is_bid, int depth, int64_t *out) { return book_inside(b, is_bid, depth, out); }
+int64_t abo_book_last_trade(abo_book *b) { return b->has_last_trade ? b->last_trade : -1; }
+int64_t abo_book_transacted_volume(abo_book *b, int64_t lookback) { return book_transacted_volume(b, lookback); }
+int abo_book_n_levels(abo_book *b, int is_bid) { return is_bid ? b->bids.n : b->asks.n; }
+int abo_book_n_resting(abo_book *b) { int n = 0; for (int i = 0; i < b->bids.n; i++) n += b->bids.lv[i].n; for (int i = 0; i < b->asks.n; i++) n += b->asks.lv[i].n; return n; }
+int64_t abo_book_n_notes(abo_book *b) { return b->notes.n / 13; }
+const int64_t *abo_book_notes(abo_book *b) { return b->notes.v; }
+void abo_book_clear_notes(abo_book *b) { b->notes.n = 0; }
+int abo_book_level_orders(abo_book *b, int is_bid, int level, int64_t *out, int max_orders) {
+  side_t *s = is_bid ? &b->bids : &b->asks; if (level >= s->n) return 0;
+  int n = s->lv[level].n < max_orders ? s->lv[level].n : max_orders;
+  for (int k = 0; k < n; k++) { out[3 * k] = s->lv[level].o[k].order_id; out[3 * k + 1] = s->lv[level].o[k].quantity; out[3 * k + 2] = s->lv[level].o[k].limit_price; }
+  return n;
+}
+
+/* ====================================================================================================
+ * Simulation: Kernel + ExchangeAgent + TradingAgent/ZeroIntelligenceAgent + SparseMeanRevertingOracle
+ * ==================================================================================================== */
+typedef struct {            /* one PriorityQueue entry: (deliverAt, (recipient, type, Message)) Kernel.py:425,462 */
+  int64_t t; int32_t recipient; int32_t type; int64_t uniq;  /* Message.uniq (message/Message.py:33-34); -1 for msg=None */
+  int32_t kind; int32_t sender;
+  order_t order;                                             /* body["order"] */
+  int64_t bid, bid_q, ask, ask_q, data; int mkt_closed;      /* QUERY_SPREAD reply (depth-1 lists; has_* by qty>0), body["data"] */
+  int has_bid, has_ask;
+} event_t;
+
+static inline int ev_less(const event_t *a, const event_t *b) { /* tuple order (t, recipient, type.value, msg.uniq) */
+  if (a->t != b->t) return a->t < b->t;
+  if (a->recipient != b->recipient) return a->recipient < b->recipient;
+  if (a->type != b->type) return a->type < b->type;
+  return a->uniq < b->uniq;
+}
+typedef struct { event_t *e; int n, cap; } heap_t;
+static void heap_push(heap_t *h, const event_t *ev) { /* heapq.heappush */
+  if (h->n == h->cap) { h->cap = h->cap ? h->cap * 2 : 4096; h->e = (event_t *)realloc(h->e, sizeof(event_t) * h->cap); }
+  int i = h->n++; h->e[i] = *ev;
+  while (i > 0) { int p = (i - 1) >> 1; if (!ev_less(&h->e[i], &h->e[p])) break; event_t t = h->e[i]; h->e[i] = h->e[p]; h->e[p] = t; i = p; }
+}
+static void heap_pop(heap_t *h, event_t *out) { /* heapq.heappop */
+  *out = h->e[0]; h->n--; if (h->n == 0) return; h->e[0] = h->e[h->n];
+  int i = 0; for (;;) { int l = 2 * i + 1, r = l + 1, m = i; if (l < h->n && ev_less(&h->e[l], &h->e[m])) m = l; if (r < h->n && ev_less(&h->e[r], &h->e[m])) m = r; if (m == i) break; event_t t = h->e[i]; h->e[i] = h->e[m]; h->e[m] = t; i = m; }
+}
+
+typedef struct { int64_t order_id, quantity, limit_price; int is_buy; } open_order_t;
+enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE, ST_AWAITING_SPREAD };
+
+typedef struct {            /* TradingAgent (agent/TradingAgent.py:19-98) + ZeroIntelligenceAgent (:65-70) state */
+  abo_rng *rs; int group;
+  int64_t R_min, R_max; double eta;
+  int64_t shares, cash, starting_cash;                  /* holdings[symbol], holdings["CASH"] */
+  int has_open, has_close; int64_t mkt_open, mkt_close; /* mkt_open/mkt_close None until the replies arrive */
+  int mkt_closed, first_wake, trading, state;
+  int has_last_trade, has_daily_close; int64_t last_trade, daily_close;
+  int has_known; int64_t bid, bid_q, ask, ask_q; int has_bid, has_ask;
+  open_order_t *orders; int n_orders, cap_orders;       /* self.orders dict, insertion ordered */
+  double r_t, sigma_t; int has_prev; int64_t prev_wake;
+  int32_t theta[64]; int q_max;
+  int64_t current_time;                                 /* Agent.currentTime */
+  int64_t surplus;
+} zi_t;
+
+struct abo_sim {
+  int variant; uint32_t seed; int trace; int n_agents;
+  /* kernel */
+  heap_t q; int64_t now, start_time, stop_time; int64_t *agent_time; int64_t *comp_delay; int64_t addl_delay;
+  int64_t ttl; int64_t uniq; int64_t next_order_id; int started, loop_done;
+  abo_rng *g, *kernel_rs, *lat_rs, *sym_rs, *exch_rs;
+  int use_latency_model; double *latency; int n_noise; double jitter, jitter_clip, jitter_unit;
+  /* exchange */
+  abo_book book; int64_t mkt_open, mkt_close, pipeline_delay, exch_comp_delay;
+  /* oracle (SparseMeanRevertingOracle) */
+  double r_bar, kappa, fund_vol, megashock_lambda, megashock_mean, megashock_var;
+  int64_t or_t, or_v; int64_t ms_t; double ms_v; double *gexp; int64_t n_gexp, cap_gexp;
+  /* agents */
+  zi_t *zi; double sigma_n, agent_kappa, sigma_s, lambda_a;
+  /* traces */
+  i64buf pops, ops, notes, snaps; uint64_t pop_hash, note_hash, snap_hash; uint64_t *ckpt; int64_t n_ckpt, cap_ckpt;
+  int64_t c_limit, c_cancel, c_query, max_queue, max_bid_lv, max_ask_lv, max_resting;
+};
+
+/* ---------------- kernel services ---------------- */
+static void k_put(abo_sim *s, const event_t *e) { heap_push(&s->q, e); if (s->q.n > s->max_queue) s->max_queue = s->q.n; }
+
+/* Kernel.setWakeup :435-462 */
+static void k_set_wakeup(abo_sim *s, int sender, int64_t t) {
+  event_t e; memset(&e, 0, sizeof(e)); e.t = t; e.recipient = sender; e.type = ABO_T_WAKEUP; e.uniq = -1; k_put(s, &e);
+}
+/* Message() construction: message/Message.py:28-34 */
+static inline int64_t new_uniq(abo_sim *s) { return s->uniq++; }
+
+/* Kernel.sendMessage :347-433.  `e` carries the body and e->uniq from Message construction. */
+static void k_send(abo_sim *s, int sender, int recipient, event_t *e, int64_t delay) {
+  int64_t sent = s->now + (s->comp_delay[sender] + s->addl_delay + delay);                 /* :391-393 */
+  int64_t deliver;
+  if (s->use_latency_model) {                                                              /* :397-399, model/LatencyModel.py:109-140 */
+    double min_latency = s->latency[(size_t)sender * s->n_agents + recipient];
+    double x = rng_uniform(s->lat_rs, s->jitter_clip, 1.0);
+    double latency = min_latency + ((s->jitter / pow(x, 3.0)) * (min_latency / s->jitter_unit));
+    deliver = sent + (int64_t)latency;                                                     /* pd.Timedelta(float) truncates */
+  } else {                                                                                 /* :410-412 */
+    double latency = s->latency[(size_t)sender * s->n_agents + recipient];
+    int64_t noise = abo_rng_randint(s->kernel_rs, 0, s->n_noise);                          /* choice(len, 1, <list as replace>) == randint(0,len) */
+    deliver = sent + (int64_t)(latency + (double)noise);
+  }
+  e->t = deliver; e->recipient = recipient; e->type = ABO_T_MESSAGE; e->sender = sender;
+  k_put(s, e);                                                                             /* :425 */
+}
+
+/* ---------------- SparseMeanRevertingOracle ---------------- */
+static inline int64_t ns_from_float_string(double x) { return (int64_t)x; } /* pd.Timedelta("{}ns".format(float)) truncates */
+static double g_exponential(abo_sim *s, double scale) { /* np.random.exponential on the GLOBAL stream :69,168 */
+  double e = -log(1.0 - rng_double_raw(s->g));
+  if (s->n_gexp == s->cap_gexp) { s->cap_gexp = s->cap_gexp ? s->cap_gexp * 2 : 32; s->gexp = (double *)realloc(s->gexp, 8 * s->cap_gexp); }
+  s->gexp[s->n_gexp++] = e;
+  return e * scale;
+}
+static void oracle_new_megashock(abo_sim *s, int64_t from) { /* :67-73, :168-171 */
+  s->ms_t = from + ns_from_float_string(g_exponential(s, 1.0 / s->megashock_lambda));
+  double msv = rng_normal(s->sym_rs, s->megashock_mean, sqrt(s->megashock_var));
+  s->ms_v = abo_rng_randint(s->sym_rs, 0, 2) == 0 ? msv : -msv;
+}
+/* compute_fundamental_at_timestamp :88-125 */
+static int64_t oracle_compute(abo_sim *s, int64_t ts, double v_adj, int64_t pt, int64_t pv) {
+  int64_t d = ts - pt; double mu = s->r_bar, gamma = s->kappa, theta = s->fund_vol;
+  double v = rng_normal(s->sym_rs, mu + ((double)pv - mu) * exp(-gamma * (double)d),
+                        ((theta * theta) / (2 * gamma)) * (1 - exp(-2 * gamma * (double)d)));   /* variance formula passed as scale */
+  v += v_adj; if (!(v > 0)) v = 0;                                                         /* max(0, v) */
+  int64_t iv = py_round(v); s->or_t = ts; s->or_v = iv; return iv;
+}
+/* advance_fundamental_value_series :131-181 */
+static int64_t oracle_advance(abo_sim *s, int64_t t) {
+  int64_t pt = s->or_t, pv = s->or_v;
+  if (t <= pt) return pv;
+  while (s->ms_t < t) { int64_t v = oracle_compute(s, s->ms_t, s->ms_v, pt, pv); pt = s->ms_t; pv = v; oracle_new_megashock(s, pt); }
+  return oracle_compute(s, t, 0.0, pt, pv);
+}
+/* observePrice :210-227 */
+static int64_t oracle_observe(abo_sim *s, int64_t t, double sigma_n, abo_rng *rs) {
+  int64_t r_t = (t >= s->mkt_close) ? oracle_advance(s, s->mkt_close - 1) : oracle_advance(s, t);
+  if (sigma_n == 0) return r_t;
+  return py_round(rng_normal(rs, (double)r_t, sqrt(sigma_n)));
+}
+
+/* ---------------- exchange ---------------- */
+static void trace_note(abo_sim *s, int recipient, const event_t *e) {
+  int64_t row[13] = { s->now, recipient, e->kind, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+  if (e->kind == ABO_ORDER_ACCEPTED || e->kind == ABO_ORDER_EXECUTED || e->kind == ABO_ORDER_CANCELLED || e->kind == ABO_ORDER_MODIFIED) {
+    row[3] = e->order.order_id; row[4] = e->order.is_buy; row[5] = e->order.quantity; row[6] = e->order.limit_price; row[7] = e->order.fill_price;
+  }
+  if (e->kind == ABO_QUERY_SPREAD) { row[7] = e->data; if (e->has_bid) { row[8] = e->bid; row[9] = e->bid_q; } if (e->has_ask) { row[10] = e->ask; row[11] = e->ask_q; } row[12] = e->mkt_closed; }
+  for (int i = 0; i < 13; i++) s->note_hash = fnv_mix(s->note_hash, row[i]);
+  if (s->trace & ABO_TRACE_NOTES) ib_push(&s->notes, row, 13);
+}
+/* ExchangeAgent.sendMessage :471-485 */
+static void exch_send(abo_sim *s, int recipient, event_t *e) {
+  e->uniq = new_uniq(s);
+  trace_note(s, recipient, e);
+  int64_t delay = (e->kind == ABO_ORDER_ACCEPTED || e->kind == ABO_ORDER_CANCELLED || e->kind == ABO_ORDER_EXECUTED) ? s->pipeline_delay : 0;
+  k_send(s, 0, recipient, e, delay);
+}
+static void exch_book_send(void *owner, int64_t recipient, int kind, const order_t *o) { /* book -> owner.sendMessage */
+  abo_sim *s = (abo_sim *)owner; event_t e; memset(&e, 0, sizeof(e)); e.kind = kind; e.order = *o; exch_send(s, (int)recipient, &e);
+}
+static void trace_snap(abo_sim *s) {
+  int64_t row[16]; memset(row, 0, sizeof(row));
+  int nb = s->book.bids.n, na = s->book.asks.n; int64_t rest = abo_book_n_resting(&s->book);
+  row[0] = nb; row[1] = na; row[2] = rest;
+  book_inside(&s->book, 1, 3, row + 3); book_inside(&s->book, 0, 3, row + 9);
+  row[15] = s->book.has_last_trade ? s->book.last_trade : -1;
+  if (nb > s->max_bid_lv) s->max_bid_lv = nb;
+  if (na > s->max_ask_lv) s->max_ask_lv = na;
+  if (rest > s->max_resting) s->max_resting = rest;
+  for (int i = 0; i < 16; i++) s->snap_hash = fnv_mix(s->snap_hash, row[i]);
+  if (s->trace & ABO_TRACE_SNAPS) ib_push(&s->snaps, row, 16);
+}
+static void trace_op(abo_sim *s, int op, const order_t *o, int64_t np, int64_t nq) {
+  if (!(s->trace & ABO_TRACE_OPS)) return;
+  int64_t row[9] = { s->now, op, o->agent_id, o->order_id, o->is_buy, o->limit_price, o->quantity, np, nq }; ib_push(&s->ops, row, 9);
+}
+/* ExchangeAgent.receiveMessage :129-340 */
+static void exch_receive(abo_sim *s, const event_t *m) {
+  s->comp_delay[0] = s->exch_comp_delay;                                                    /* :139 */
+  int t_closed = s->now > s->mkt_close;
+  if (t_closed) {                                                                           /* :142-160 */
+    int is_order = m->kind == ABO_LIMIT_ORDER || m->kind == ABO_CANCEL_ORDER || m->kind == ABO_MODIFY_ORDER;
+    int is_query = m->kind == ABO_QUERY_SPREAD || m->kind == ABO_QUERY_LAST_TRADE || m->kind == ABO_QUERY_TRANSACTED_VOLUME || m->kind == ABO_QUERY_ORDER_STREAM;
+    if (is_order || !is_query) { event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_MKT_CLOSED; exch_send(s, m->sender, &e); return; }
+  }
+  event_t e; memset(&e, 0, sizeof(e));
+  switch (m->kind) {
+    case ABO_WHEN_MKT_OPEN: s->comp_delay[0] = 0; e.kind = ABO_WHEN_MKT_OPEN; e.data = s->mkt_open; exch_send(s, m->sender, &e); break;     /* :175-183 */
+    case ABO_WHEN_MKT_CLOSE: s->comp_delay[0] = 0; e.kind = ABO_WHEN_MKT_CLOSE; e.data = s->mkt_close; exch_send(s, m->sender, &e); break;  /* :184-192 */
+    case ABO_QUERY_SPREAD: {                                                                /* :215-245, depth 1 on this path */
+      int64_t pq[2]; s->c_query++;
+      e.kind = ABO_QUERY_SPREAD;
+      if (book_inside(&s->book, 1, 1, pq)) { e.has_bid = 1; e.bid = pq[0]; e.bid_q = pq[1]; }
+      if (book_inside(&s->book, 0, 1, pq)) { e.has_ask = 1; e.ask = pq[0]; e.ask_q = pq[1]; }
+      e.data = s->book.last_trade; e.mkt_closed = t_closed; exch_send(s, m->sender, &e); break; }
+    case ABO_LIMIT_ORDER: s->c_limit++; trace_op(s, 0, &m->order, 0, 0); s->book.now = s->now; book_handle_limit(&s->book, m->order); trace_snap(s); break; /* :304-312 */
+    case ABO_CANCEL_ORDER: s->c_cancel++; trace_op(s, 1, &m->order, 0, 0); s->book.now = s->now; book_cancel(&s->book, &m->order); trace_snap(s); break;   /* :313-325 */
+    default: break;
+  }
+}
+
+/* ---------------- trading agent / ZI ---------------- */
+static void ta_send(abo_sim *s, int id, event_t *e) { e->uniq = new_uniq(s); k_send(s, id, 0, e, 0); } /* Agent.sendMessage :148-149 */
+
+/* TradingAgent.getCurrentSpread :277-282 -- builds a second, never-sent Message (uniq += 2) */
+static void ta_get_spread(abo_sim *s, int id) { event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_QUERY_SPREAD; ta_send(s, id, &e); (void)new_uniq(s); }
+
+/* ZeroIntelligenceAgent.wakeup :125-187 (+ TradingAgent.wakeup :142-158) */
+static void zi_wakeup(abo_sim *s, int id) {
+  zi_t *a = &s->zi[id]; a->current_time = s->now; a->first_wake = 0;
+  if (!a->has_open) {                                                                       /* TradingAgent.py:149-153 */
+    event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_WHEN_MKT_OPEN; ta_send(s, id, &e);
+    memset(&e, 0, sizeof(e)); e.kind = ABO_WHEN_MKT_CLOSE; ta_send(s, id, &e);
+  }
+  a->state = ST_INACTIVE;
+  if (!a->has_open || !a->has_close) return;                                                /* :130-131 */
+  a->trading = 1;
+  if (a->mkt_closed && a->has_daily_close) return;                                          /* :145-147 */
+  double delta_time = rng_exponential(a->rs, 1.0 / s->lambda_a);                            /* :157 */
+  k_set_wakeup(s, id, s->now + py_round(delta_time));                                       /* :158 */
+  if (a->mkt_closed && !a->has_daily_close) { ta_get_spread(s, id); a->state = ST_AWAITING_SPREAD; return; } /* :162-166 */
+  for (int i = 0; i < a->n_orders; i++) {                                                   /* cancelOrders :336-344 -> TradingAgent.cancelOrder :399-406 */
+    event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_CANCEL_ORDER;
+    e.order.agent_id = id; e.order.order_id = a->orders[i].order_id; e.order.quantity = a->orders[i].quantity; e.order.limit_price = a->orders[i].limit_price; e.order.is_buy = a->orders[i].is_buy;
+    ta_send(s, id, &e);
+  }
+  ta_get_spread(s, id); a->state = ST_AWAITING_SPREAD;                                      /* :183-185 */
+}
+/* ZeroIntelligenceAgent.updateEstimates :189-275 */
+static int zi_update_estimates(abo_sim *s, int id, int64_t *v_out, int *buy_out) {
+  zi_t *a = &s->zi[id];
+  int64_t obs_t = oracle_observe(s, a->current_time, s->sigma_n, a->rs);                    /* :190-192 */
+  int64_t q = (int64_t)((double)a->shares / 100);                                           /* :203 int(x / 100) */
+  int buy;
+  if (q >= a->q_max) buy = 0; else if (q <= -a->q_max) buy = 1; else buy = (int)abo_rng_randint(a->rs, 0, 2); /* :205-213 */
+  if (!a->has_prev) { a->prev_wake = a->mkt_open; a->has_prev = 1; }                         /* :217-218 */
+  double kappa = s->agent_kappa, r_bar = s->r_bar, sigma_n = s->sigma_n;
+  double delta = (double)(a->current_time - a->prev_wake);                                  /* :221 */
+  double pw = pow(1 - kappa, delta);
+  double r_tprime = (1 - pw) * r_bar;                                                       /* :229 */
+  r_tprime += pw * a->r_t;                                                                  /* :230 */
+  double pw2 = pow(1 - kappa, 2 * delta);
+  double sigma_tprime = pw2 * a->sigma_t;                                                   /* :233 */
+  sigma_tprime += ((1 - pw2) / (1 - pow(1 - kappa, 2.0))) * s->sigma_s;                     /* :234 */
+  a->r_t = (sigma_n / (sigma_n + sigma_tprime)) * r_tprime;                                 /* :239 */
+  a->r_t += (sigma_tprime / (sigma_n + sigma_tprime)) * (double)obs_t;                      /* :240 */
+  a->sigma_t = (sigma_n * a->sigma_t) / (sigma_n + a->sigma_t);                             /* :242 */
+  double d2 = (double)(a->mkt_close - a->current_time); if (!(d2 > 0)) d2 = 0;              /* :251 max(0, .) */
+  double pw3 = pow(1 - kappa, d2);
+  double r_T = (1 - pw3) * r_bar;                                                           /* :255 */
+  r_T += pw3 * a->r_t;                                                                      /* :256 */
+  int64_t r_Ti = py_round(r_T);                                                             /* :259 */
+  a->prev_wake = a->current_time;                                                           /* :262 */
+  q += a->q_max - 1;                                                                        /* :267 */
+  int64_t idx = buy ? q + 1 : q; int n = 2 * a->q_max;                                      /* :268 Python list indexing */
+  if (idx < 0) idx += n;
+  if (idx < 0 || idx >= n) { fprintf(stderr, "abides_oracle: theta index out of range (reference would raise IndexError)\n"); return -1; }
+  *v_out = r_Ti + a->theta[idx]; *buy_out = buy;                                            /* :270 */
+  return 0;
+}
+/* TradingAgent.placeLimitOrder :309-349 */
+static void ta_place_limit(abo_sim *s, int id, int64_t qty, int is_buy, int64_t price) {
+  zi_t *a = &s->zi[id];
+  int64_t oid = s->next_order_id++;                                                         /* util/order/Order.py:27,35-42 dense global ids */
+  if (qty <= 0) return;
+  if (a->n_orders == a->cap_orders) { a->cap_orders = a->cap_orders ? a->cap_orders * 2 : 4; a->orders = (open_order_t *)realloc(a->orders, sizeof(open_order_t) * a->cap_orders); }
+  open_order_t *oo = &a->orders[a->n_orders++]; oo->order_id = oid; oo->quantity = qty; oo->limit_price = price; oo->is_buy = is_buy; /* :342 */
+  event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_LIMIT_ORDER;
+  e.order.agent_id = id; e.order.order_id = oid; e.order.quantity = qty; e.order.limit_price = price; e.order.is_buy = is_buy;
+  ta_send(s, id, &e);                                                                       /* :343 */
+}
+/* ZeroIntelligenceAgent.placeOrder :277-309 */
+static void zi_place_order(abo_sim *s, int id) {
+  zi_t *a = &s->zi[id]; int64_t v; int buy;
+  if (zi_update_estimates(s, id, &v, &buy)) return;
+  int64_t R = abo_rng_randint(a->rs, a->R_min, a->R_max + 1);                               /* :284 */
+  int64_t p = buy ? v - R : v + R;                                                          /* :287 */
+  int64_t ask_vol = a->has_ask ? a->ask_q : 0, bid_vol = a->has_bid ? a->bid_q : 0;         /* getKnownBidAsk :564-574 */
+  if (buy && ask_vol > 0) { int64_t R_ask = v - a->ask; if ((double)R_ask >= a->eta * (double)R) p = a->ask; }   /* :291-297 */
+  else if (!buy && bid_vol > 0) { int64_t R_bid = a->bid - v; if ((double)R_bid >= a->eta * (double)R) p = a->bid; } /* :298-305 */
+  ta_place_limit(s, id, 100, buy, p);                                                       /* :308-309 */
+}
+static void orders_remove(zi_t *a, int i) { memmove(a->orders + i, a->orders + i + 1, sizeof(open_order_t) * (a->n_orders - i - 1)); a->n_orders--; }
+/* TradingAgent.receiveMessage :181-268 + ZeroIntelligenceAgent.receiveMessage :311-334 */
+static void zi_receive(abo_sim *s, int id, const event_t *m) {
+  zi_t *a = &s->zi[id]; a->current_time = s->now;
+  int had = a->has_open && a->has_close;
+  switch (m->kind) {
+    case ABO_WHEN_MKT_OPEN: a->mkt_open = m->data; a->has_open = 1; break;
+    case ABO_WHEN_MKT_CLOSE: a->mkt_close = m->data; a->has_close = 1; break;
+    case ABO_ORDER_EXECUTED: {                                                              /* orderExecuted :422-462 */
+      int64_t qty = m->order.is_buy ? m->order.quantity : -m->order.quantity;
+      a->shares += qty; a->cash -= qty * m->order.fill_price;
+      for (int i = 0; i < a->n_orders; i++) if (a->orders[i].order_id == m->order.order_id) {
+        if (m->order.quantity >= a->orders[i].quantity) orders_remove(a, i); else a->orders[i].quantity -= m->order.quantity; break; }
+      break; }
+    case ABO_ORDER_ACCEPTED: break;
+    case ABO_ORDER_CANCELLED:                                                               /* orderCancelled :476-489 */
+      for (int i = 0; i < a->n_orders; i++) if (a->orders[i].order_id == m->order.order_id) { orders_remove(a, i); break; }
+      break;
+    case ABO_MKT_CLOSED: a->mkt_closed = 1; break;                                          /* marketClosed :492-499 */
+    case ABO_QUERY_SPREAD:                                                                  /* :232-238, querySpread :514-537, queryLastTrade :502-511 */
+      if (m->mkt_closed) a->mkt_closed = 1;
+      a->last_trade = m->data; a->has_last_trade = 1;
+      if (a->mkt_closed) { a->daily_close = a->last_trade; a->has_daily_close = 1; }
+      a->has_known = 1; a->has_bid = m->has_bid; a->bid = m->bid; a->bid_q = m->bid_q; a->has_ask = m->has_ask; a->ask = m->ask; a->ask_q = m->ask_q;
+      break;
+    default: break;
+  }
+  if (a->has_open && a->has_close && !had) {                                                /* :258-268 */
+    int64_t off = abo_rng_randint(a->rs, 0, 100);                                           /* ZI.getWakeFrequency :349-350 */
+    k_set_wakeup(s, id, a->mkt_open + off);
+  }
+  if (a->state == ST_AWAITING_SPREAD && m->kind == ABO_QUERY_SPREAD) {                      /* ZI :319-334 */
+    if (a->mkt_closed) return;
+    zi_place_order(s, id);
+    a->state = ST_AWAITING_WAKEUP;
+  }
+}
+
+/* ---------------- config: config/sparse_zi_100.py / config/sparse_zi_1000.py ---------------- */
+static abo_rng *new_stream(abo_sim *s) { /* RandomState(seed=np.random.randint(0, 2**32, dtype=uint64)) */
+  abo_rng *r = abo_rng_new(rng_u32_raw(s->g)); r->record = (s->trace & ABO_TRACE_TAPES) != 0; return r;
+}
+static const int ZI_1000[7][3] = { {143, 0, 250}, {143, 0, 500}, {143, 0, 1000}, {143, 0, 1000}, {143, 0, 2000}, {143, 250, 500}, {142, 250, 500} };
+static const int ZI_100[7][3] = { {15, 0, 250}, {15, 0, 500}, {14, 0, 1000}, {14, 0, 1000}, {14, 0, 2000}, {14, 250, 500}, {14, 250, 500} };
+static const double ZI_ETA[7] = { 1, 1, 0.8, 1, 0.8, 0.8, 1 };
+#define NS_PER_S 1000000000LL
+
+abo_sim *abo_sim_new_sparse_zi(int variant, uint32_t seed, int trace) {
+  if (variant != 100 && variant != 1000) return NULL;
+  abo_sim *s = (abo_sim *)calloc(1, sizeof(abo_sim));
+  s->variant = variant; s->seed = seed; s->trace = trace;
+  s->pop_hash = s->note_hash = s->snap_hash = FNV_OFF;
+  const int (*zi)[3] = variant == 1000 ? ZI_1000 : ZI_100;
+  int n = 1; for (int i = 0; i < 7; i++) n += zi[i][0];
+  s->n_agents = n;
+  s->g = abo_rng_new(seed);                                              /* np.random.seed(seed)  sparse_zi_1000.py:72 */
+  s->start_time = 0; s->stop_time = 17 * 3600 * NS_PER_S;                /* :86-88 midnight .. 17:00 */
+  /* symbols["JPM"] :130-142 */
+  s->r_bar = 1e5; s->kappa = 1.67e-12; s->agent_kappa = 1.67e-15; s->sigma_s = 1e-4; s->fund_vol = 1e-4;
+  s->megashock_lambda = 2.77778e-13; s->megashock_mean = 1e3; s->megashock_var = 5e4;
+  s->sym_rs = new_stream(s);                                             /* :140 */
+  s->kernel_rs = new_stream(s);                                          /* :146-148 */
+  if (variant == 100) s->lat_rs = new_stream(s);                         /* sparse_zi_100.py:152 */
+  s->mkt_open = (9 * 3600 + 30 * 60) * NS_PER_S; s->mkt_close = 16 * 3600 * NS_PER_S;
+  /* SparseMeanRevertingOracle.__init__ :36-79 */
+  s->or_t = s->mkt_open; s->or_v = (int64_t)s->r_bar;
+  oracle_new_megashock(s, s->mkt_open);
+  /* ExchangeAgent :174-194 */
+  s->exch_rs = new_stream(s); s->pipeline_delay = 0; s->exch_comp_delay = 0;
+  book_init(&s->book, 10, s, exch_book_send);
+  /* ZI agents :211-251 */
+  s->sigma_n = 1000000.0; s->lambda_a = 1e-12;
+  s->zi = (zi_t *)calloc(n, sizeof(zi_t));
+  int id = 1;
+  for (int g = 0; g < 7; g++) for (int k = 0; k < zi[g][0]; k++, id++) {
+    zi_t *a = &s->zi[id]; a->rs = new_stream(s); a->group = g; a->R_min = zi[g][1]; a->R_max = zi[g][2]; a->eta = ZI_ETA[g];
+    a->starting_cash = a->cash = 10000000; a->first_wake = 1; a->state = ST_AWAITING_WAKEUP; a->r_t = s->r_bar; a->sigma_t = 0; a->q_max = 10;
+    /* theta: sorted(np.round(normal(0, sqrt(sigma_pv), size=2*q_max)), reverse=True) -> int   ZeroIntelligenceAgent.py:65-70 */
+    double th[64]; int m = 2 * a->q_max;
+    for (int i = 0; i < m; i++) th[i] = nearbyint(rng_normal(a->rs, 0.0, sqrt(5e6)));
+    for (int i = 1; i < m; i++) { double x = th[i]; int j = i - 1; while (j >= 0 && th[j] < x) { th[j + 1] = th[j]; j--; } th[j + 1] = x; }
+    for (int i = 0; i < m; i++) a->theta[i] = (int32_t)th[i];
+  }
+  /* latency :264-286 / sparse_zi_100.py:305-318 : N x N uniform draws from the global stream, row-major */
+  s->latency = (double *)malloc(sizeof(double) * (size_t)n * n);
+  if (variant == 1000) {
+    for (size_t i = 0; i < (size_t)n * n; i++) s->latency[i] = 21000.0 + (13000000.0 - 21000.0) * rng_double_raw(s->g);
+    /* mirror the upper triangle, diagonal 20000; the ZI<->ZI 24h override never fires */
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) { if (i > j) s->latency[(size_t)i * n + j] = s->latency[(size_t)j * n + i]; else if (i == j) s->latency[(size_t)i * n + j] = 20000; }
+    s->n_noise = 6; s->use_latency_model = 0;
+  } else {
+    for (size_t i = 0; i < (size_t)n * n; i++) s->latency[i] = 21000.0 + (100000.0 - 21000.0) * rng_double_raw(s->g);
+    s->use_latency_model = 1; s->jitter = 0.3; s->jitter_clip = 0.05; s->jitter_unit = 5.0;
+  }
+  /* Kernel.runner :97,105 */
+  s->agent_time = (int64_t *)calloc(n, sizeof(int64_t)); s->comp_delay = (int64_t *)malloc(sizeof(int64_t) * n);
+  for (int i = 0; i < n; i++) { s->agent_time[i] = s->start_time; s->comp_delay[i] = NS_PER_S; }      /* defaultComputationDelay 1e9 */
+  return s;
+}
+void abo_sim_free(abo_sim *s) {
+  if (!s) return;
+  for (int i = 1; i < s->n_agents; i++) { abo_rng_free(s->zi[i].rs); free(s->zi[i].orders); }
+  free(s->zi); abo_rng_free(s->g); abo_rng_free(s->kernel_rs); abo_rng_free(s->lat_rs); abo_rng_free(s->sym_rs); abo_rng_free(s->exch_rs);
+  book_destroy(&s->book); free(s->latency); free(s->agent_time); free(s->comp_delay); free(s->q.e); free(s->gexp);
+  free(s->pops.v); free(s->ops.v); free(s->notes.v); free(s->snaps.v); free(s->ckpt); free(s);
+}
+
+/* Kernel.runner :154-175 */
+void abo_sim_start(abo_sim *s) {
+  if (s->started) return; s->started = 1;
+  s->book.last_trade = (int64_t)s->r_bar; s->book.has_last_trade = 1;   /* ExchangeAgent.kernelInitializing :91-102, getDailyOpenPrice */
+  s->now = s->start_time;
+  for (int i = 0; i < s->n_agents; i++) k_set_wakeup(s, i, s->start_time);   /* Agent.kernelStarting :78 */
+}
+static void ckpt_push(abo_sim *s) { if (s->n_ckpt == s->cap_ckpt) { s->cap_ckpt = s->cap_ckpt ? s->cap_ckpt * 2 : 256; s->ckpt = (uint64_t *)realloc(s->ckpt, 8 * s->cap_ckpt); } s->ckpt[s->n_ckpt++] = s->pop_hash; }
+
+/* Kernel.runner hot loop :190-292 */
+int64_t abo_sim_run_until(abo_sim *s, int64_t until, int *done) {
+  int64_t n0 = s->ttl;
+  abo_sim_start(s);
+  while (!s->loop_done) {
+    if (s->q.n == 0 || !(s->now <= s->stop_time)) { s->loop_done = 1; break; }              /* :190 condition tested BEFORE the pop */
+    if (s->q.e[0].t > until) break;
+    event_t ev; heap_pop(&s->q, &ev); s->now = ev.t;                                         /* :192 */
+    s->ttl++;                                                                                /* :211 */
+    s->pop_hash = fnv_mix(fnv_mix(fnv_mix(fnv_mix(s->pop_hash, ev.t), ev.recipient), ev.type), ev.uniq);
+    if (s->ttl % 1000 == 0) ckpt_push(s);
+    if (s->trace & ABO_TRACE_POPS) { int64_t row[5] = { ev.t, ev.recipient, ev.type, ev.uniq, ev.kind }; ib_push(&s->pops, row, 5); }
+    s->addl_delay = 0;                                                                       /* :214 */
+    int a = ev.recipient;
+    if (s->agent_time[a] > s->now) { ev.t = s->agent_time[a]; k_put(s, &ev); continue; }     /* :224-230 / :258-264 requeue, same uniq */
+    s->agent_time[a] = s->now;                                                               /* :234 / :268 */
+    if (ev.type == ABO_T_WAKEUP) { if (a != 0) zi_wakeup(s, a); /* exchange: Agent.wakeup no-op */ }
+    else { if (a == 0) exch_receive(s, &ev); else zi_receive(s, a, &ev); }
+    s->agent_time[a] += s->comp_delay[a] + s->addl_delay;                                    /* :240-242 / :274-276 */
+  }
+  if (done) *done = s->loop_done;
+  return s->ttl - n0;
+}
+/* Kernel.runner :310-311 -> TradingAgent.kernelStopping :110-140, ZeroIntelligenceAgent.kernelStopping :80-123 */
+void abo_sim_stop(abo_sim *s) {
+  for (int id = 1; id < s->n_agents; id++) {
+    zi_t *a = &s->zi[id];
+    double hr = nearbyint((double)a->shares / 100.0) * 100.0; /* round(int, -2): half-even on hundreds */
+    int64_t H = (int64_t)(hr / 100);
+    int64_t rT = oracle_observe(s, a->current_time, 0, a->rs);
+    int64_t surplus = 0;
+    if (H > 0) for (int64_t x = 1; x <= H; x++) surplus += a->theta[x + a->q_max - 1];
+    else if (H < 0) { for (int64_t x = H + 1; x <= 0; x++) surplus += a->theta[x + a->q_max - 1]; surplus = -surplus; }
+    surplus += rT * H; surplus += a->cash - a->starting_cash; a->surplus = surplus;
+  }
+}
+int64_t abo_sim_run(abo_sim *s) {
+  int done = 0; abo_sim_run_until(s, INT64_MAX, &done); ckpt_push(s); abo_sim_stop(s); return s->ttl;
+}
+
+/* ---------------- accessors ---------------- */
+int abo_sim_n_agents(abo_sim *s) { return s->n_agents; }
+int64_t abo_sim_n_pops(abo_sim *s) { return s->ttl; }
+void abo_sim_holdings(abo_sim *s, int64_t *out) {
+  for (int id = 1; id < s->n_agents; id++) { zi_t *a = &s->zi[id]; int64_t *r = out + 5 * (id - 1);
+    r[0] = id; r[1] = a->shares; r[2] = a->cash; r[3] = a->cash + a->shares * (a->has_last_trade ? a->last_trade : 0); r[4] = a->surplus; } /* markToMarket :609-633 */
+}
+uint64_t abo_sim_pop_hash(abo_sim *s) { return s->pop_hash; }
+int64_t abo_sim_n_hash_ckpt(abo_sim *s) { return s->n_ckpt; }
+const uint64_t *abo_sim_hash_ckpt(abo_sim *s) { return s->ckpt; }
+uint64_t abo_sim_note_hash(abo_sim *s) { return s->note_hash; }
+uint64_t abo_sim_snap_hash(abo_sim *s) { return s->snap_hash; }
+int64_t abo_sim_trace(abo_sim *s, int which, const int64_t **rows) {
+  i64buf *b = which == 0 ? &s->pops : which == 1 ? &s->ops : which == 2 ? &s->notes : &s->snaps; int w = which == 0 ? 5 : which == 1 ? 9 : which == 2 ? 13 : 16;
+  *rows = b->v; return b->n / w;
+}
+static abo_rng *stream_at(abo_sim *s, int i) {
+  int base = s->variant == 100 ? 4 : 3;
+  if (i == 0) return s->sym_rs; if (i == 1) return s->kernel_rs;
+  if (s->variant == 100) { if (i == 2) return s->lat_rs; if (i == 3) return s->exch_rs; } else if (i == 2) return s->exch_rs;
+  return s->zi[i - base + 1].rs;
+}
+int abo_sim_n_streams(abo_sim *s) { return s->n_agents - 1 + (s->variant == 100 ? 4 : 3); }
+int64_t abo_sim_tape(abo_sim *s, int i, const uint8_t **k, const uint64_t **b) { abo_rng *r = stream_at(s, i); *k = r->tk; *b = r->tv; return r->tn; }
+uint32_t abo_sim_stream_seed(abo_sim *s, int i) { return stream_at(s, i)->seed; }
+int64_t abo_sim_global_exp_tape(abo_sim *s, const double **v) { *v = s->gexp; return s->n_gexp; }
+void abo_sim_theta(abo_sim *s, int agent, int32_t *out) { memcpy(out, s->zi[agent].theta, sizeof(int32_t) * 2 * s->zi[agent].q_max); }
+void abo_sim_latency_vectors(abo_sim *s, double *to_x, double *from_x) { int n = s->n_agents; for (int j = 0; j < n; j++) { to_x[j] = s->latency[(size_t)j * n]; from_x[j] = s->latency[j]; } }
+void abo_sim_zi_params(abo_sim *s, int agent, double *out) { zi_t *a = &s->zi[agent]; out[0] = (double)a->R_min; out[1] = (double)a->R_max; out[2] = a->eta; out[3] = a->group; }
+int64_t abo_sim_counter(abo_sim *s, int w) {
+  switch (w) { case 0: return s->c_limit; case 1: return s->c_cancel; case 2: return s->book.n_fills; case 3: return s->c_query; case 4: return s->max_queue;
+    case 5: return s->max_bid_lv; case 6: return s->max_ask_lv; case 7: return s->max_resting; case 8: return s->next_order_id; case 9: return s->uniq; default: return -1; }
+}
+void abo_sim_book_l1(abo_sim *s, int64_t *o) { int64_t pq[2]; o[0] = o[1] = o[2] = o[3] = 0; if (book_inside(&s->book, 1, 1, pq)) { o[0] = pq[0]; o[1] = pq[1]; } if (book_inside(&s->book, 0, 1, pq)) { o[2] = pq[0]; o[3] = pq[1]; } o[4] = s->book.has_last_trade ? s->book.last_trade : -1; }
+int64_t abo_sim_fundamental(abo_sim *s) { return s->or_v; }

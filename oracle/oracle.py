@@ -1,0 +1,293 @@
+"""ctypes wrapper around oracle/libabides_oracle.so -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module (see oracle/abides_oracle.h).  The product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libabides_oracle.so")
+
+TRACE_POPS, TRACE_OPS, TRACE_NOTES, TRACE_SNAPS, TRACE_TAPES = 1, 2, 4, 8, 16
+TRACE_ALL = 31
+
+
+def build(force=False):
+    """Compile the C restatement (gcc, -ffp-contract=off)."""
+    src = [os.path.join(_HERE, f) for f in ("abides_oracle.c", "abides_oracle.h")]
+    if (not force and os.path.exists(_LIB_PATH)
+            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-C", _HERE, "-B", "libabides_oracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(_LIB_PATH)
+    vp, i64, i32, u32, u64, dbl = C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_uint64, C.c_double
+    P = C.POINTER
+
+    def sig(name, res, *args):
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = list(args)
+
+    sig("abo_rng_new", vp, u32)
+    sig("abo_rng_free", None, vp)
+    sig("abo_rng_u32", u32, vp)
+    sig("abo_rng_double", dbl, vp)
+    sig("abo_rng_gauss", dbl, vp)
+    sig("abo_rng_std_exponential", dbl, vp)
+    sig("abo_rng_randint", i64, vp, i64, i64)
+    sig("abo_book_new", vp, i32)
+    sig("abo_book_free", None, vp)
+    sig("abo_book_set_time", None, vp, i64)
+    sig("abo_book_limit", None, vp, i64, i64, i32, i64, i64)
+    sig("abo_book_cancel", None, vp, i64, i64, i32, i64)
+    sig("abo_book_modify", None, vp, i64, i64, i32, i64, i64, i64, i64)
+    sig("abo_book_inside", i32, vp, i32, i32, P(i64))
+    sig("abo_book_last_trade", i64, vp)
+    sig("abo_book_transacted_volume", i64, vp, i64)
+    sig("abo_book_n_levels", i32, vp, i32)
+    sig("abo_book_n_resting", i32, vp)
+    sig("abo_book_n_notes", i64, vp)
+    sig("abo_book_notes", P(i64), vp)
+    sig("abo_book_clear_notes", None, vp)
+    sig("abo_book_level_orders", i32, vp, i32, i32, P(i64), i32)
+    sig("abo_sim_new_sparse_zi", vp, i32, u32, i32)
+    sig("abo_sim_free", None, vp)
+    sig("abo_sim_run", i64, vp)
+    sig("abo_sim_run_until", i64, vp, i64, P(i32))
+    sig("abo_sim_start", None, vp)
+    sig("abo_sim_stop", None, vp)
+    sig("abo_sim_n_agents", i32, vp)
+    sig("abo_sim_n_pops", i64, vp)
+    sig("abo_sim_holdings", None, vp, P(i64))
+    sig("abo_sim_pop_hash", u64, vp)
+    sig("abo_sim_n_hash_ckpt", i64, vp)
+    sig("abo_sim_hash_ckpt", P(u64), vp)
+    sig("abo_sim_note_hash", u64, vp)
+    sig("abo_sim_snap_hash", u64, vp)
+    sig("abo_sim_trace", i64, vp, i32, P(P(i64)))
+    sig("abo_sim_n_streams", i32, vp)
+    sig("abo_sim_tape", i64, vp, i32, P(P(C.c_uint8)), P(P(u64)))
+    sig("abo_sim_stream_seed", u32, vp, i32)
+    sig("abo_sim_global_exp_tape", i64, vp, P(P(dbl)))
+    sig("abo_sim_theta", None, vp, i32, P(C.c_int32))
+    sig("abo_sim_latency_vectors", None, vp, P(dbl), P(dbl))
+    sig("abo_sim_zi_params", None, vp, i32, P(dbl))
+    sig("abo_sim_counter", i64, vp, i32)
+    sig("abo_sim_book_l1", None, vp, P(i64))
+    sig("abo_sim_fundamental", i64, vp)
+    _lib = L
+    return L
+
+
+class NumpyLegacyRng:
+    """MT19937 + legacy numpy distributions (restated in C); checked against numpy itself in tests."""
+
+    def __init__(self, seed):
+        self._h = lib().abo_rng_new(seed)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().abo_rng_free(self._h)
+            self._h = None
+
+    def u32(self):
+        return lib().abo_rng_u32(self._h)
+
+    def random_sample(self):
+        return lib().abo_rng_double(self._h)
+
+    def standard_normal(self):
+        return lib().abo_rng_gauss(self._h)
+
+    def standard_exponential(self):
+        return lib().abo_rng_std_exponential(self._h)
+
+    def randint(self, low, high):
+        return lib().abo_rng_randint(self._h, low, high)
+
+
+class OracleBook:
+    """util/OrderBook.py restated (oracle/abides_oracle.c); notifications come back as int64 rows
+    (t, recipient, kind, order_id, is_buy, qty, limit_price, fill_price, 0...)."""
+
+    def __init__(self, stream_history=10):
+        self._h = lib().abo_book_new(stream_history)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().abo_book_free(self._h)
+            self._h = None
+
+    def set_time(self, t):
+        lib().abo_book_set_time(self._h, int(t))
+
+    def limit(self, agent, order_id, is_buy, price, qty):
+        lib().abo_book_limit(self._h, agent, order_id, int(is_buy), price, qty)
+
+    def cancel(self, agent, order_id, is_buy, price):
+        lib().abo_book_cancel(self._h, agent, order_id, int(is_buy), price)
+
+    def modify(self, agent, order_id, is_buy, price, new_price, new_qty, new_order_id=None):
+        lib().abo_book_modify(self._h, agent, order_id, int(is_buy), price,
+                              order_id if new_order_id is None else new_order_id, new_price, new_qty)
+
+    def inside(self, is_bid, depth):
+        depth = min(depth, max(1, lib().abo_book_n_levels(self._h, int(is_bid))))
+        buf = (C.c_int64 * (2 * depth))()
+        n = lib().abo_book_inside(self._h, int(is_bid), depth, buf)
+        return [(buf[2 * i], buf[2 * i + 1]) for i in range(n)]
+
+    def level_orders(self, is_bid, level, max_orders=4096):
+        buf = (C.c_int64 * (3 * max_orders))()
+        n = lib().abo_book_level_orders(self._h, int(is_bid), level, buf, max_orders)
+        return [(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]) for i in range(n)]
+
+    @property
+    def last_trade(self):
+        v = lib().abo_book_last_trade(self._h)
+        return None if v < 0 else v
+
+    def transacted_volume(self, lookback_ns):
+        return lib().abo_book_transacted_volume(self._h, lookback_ns)
+
+    def n_levels(self, is_bid):
+        return lib().abo_book_n_levels(self._h, int(is_bid))
+
+    def n_resting(self):
+        return lib().abo_book_n_resting(self._h)
+
+    def take_notes(self):
+        n = lib().abo_book_n_notes(self._h)
+        arr = np.ctypeslib.as_array(lib().abo_book_notes(self._h), shape=(n * 13,)).reshape(n, 13).copy() if n else \
+            np.zeros((0, 13), np.int64)
+        lib().abo_book_clear_notes(self._h)
+        return arr
+
+
+class OracleSim:
+    """config/sparse_zi_100.py / sparse_zi_1000.py + Kernel.runner restated (oracle/abides_oracle.c)."""
+
+    def __init__(self, variant, seed, trace=0):
+        self._h = lib().abo_sim_new_sparse_zi(variant, seed, trace)
+        if not self._h:
+            raise ValueError("unknown sparse_zi variant %r" % (variant,))
+        self.variant, self.seed = variant, seed
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().abo_sim_free(self._h)
+            self._h = None
+
+    def run(self):
+        return lib().abo_sim_run(self._h)
+
+    def start(self):
+        lib().abo_sim_start(self._h)
+
+    def stop(self):
+        lib().abo_sim_stop(self._h)
+
+    def run_until(self, until_ns):
+        done = C.c_int(0)
+        n = lib().abo_sim_run_until(self._h, int(until_ns), C.byref(done))
+        return n, bool(done.value)
+
+    @property
+    def n_agents(self):
+        return lib().abo_sim_n_agents(self._h)
+
+    @property
+    def n_pops(self):
+        return lib().abo_sim_n_pops(self._h)
+
+    def holdings(self):
+        n = self.n_agents - 1
+        out = np.zeros((n, 5), np.int64)
+        lib().abo_sim_holdings(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)))
+        return out
+
+    def pop_hash(self):
+        return lib().abo_sim_pop_hash(self._h)
+
+    def hash_ckpt(self):
+        n = lib().abo_sim_n_hash_ckpt(self._h)
+        return np.ctypeslib.as_array(lib().abo_sim_hash_ckpt(self._h), shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+
+    def note_hash(self):
+        return lib().abo_sim_note_hash(self._h)
+
+    def snap_hash(self):
+        return lib().abo_sim_snap_hash(self._h)
+
+    def trace(self, which):
+        w = {"pops": (0, 5), "ops": (1, 9), "notes": (2, 13), "snaps": (3, 16)}[which]
+        p = C.POINTER(C.c_int64)()
+        n = lib().abo_sim_trace(self._h, w[0], C.byref(p))
+        if n == 0:
+            return np.zeros((0, w[1]), np.int64)
+        return np.ctypeslib.as_array(p, shape=(n * w[1],)).reshape(n, w[1]).copy()
+
+    @property
+    def n_streams(self):
+        return lib().abo_sim_n_streams(self._h)
+
+    def tape(self, stream):
+        k = C.POINTER(C.c_uint8)()
+        b = C.POINTER(C.c_uint64)()
+        n = lib().abo_sim_tape(self._h, stream, C.byref(k), C.byref(b))
+        if n == 0:
+            return np.zeros(0, np.uint8), np.zeros(0, np.uint64)
+        return (np.ctypeslib.as_array(k, shape=(n,)).copy(), np.ctypeslib.as_array(b, shape=(n,)).copy())
+
+    def stream_seed(self, stream):
+        return lib().abo_sim_stream_seed(self._h, stream)
+
+    def global_exp_tape(self):
+        p = C.POINTER(C.c_double)()
+        n = lib().abo_sim_global_exp_tape(self._h, C.byref(p))
+        return np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.zeros(0)
+
+    def theta(self, agent):
+        out = np.zeros(20, np.int32)
+        lib().abo_sim_theta(self._h, agent, out.ctypes.data_as(C.POINTER(C.c_int32)))
+        return out
+
+    def latency_vectors(self):
+        n = self.n_agents
+        a, b = np.zeros(n), np.zeros(n)
+        lib().abo_sim_latency_vectors(self._h, a.ctypes.data_as(C.POINTER(C.c_double)),
+                                      b.ctypes.data_as(C.POINTER(C.c_double)))
+        return a, b
+
+    def zi_params(self, agent):
+        out = np.zeros(4)
+        lib().abo_sim_zi_params(self._h, agent, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    def counter(self, which):
+        names = ["limit", "cancel", "fills", "spread_queries", "max_queue", "max_bid_levels", "max_ask_levels",
+                 "max_resting", "orders_allocated", "uniq"]
+        return lib().abo_sim_counter(self._h, names.index(which))
+
+    def book_l1(self):
+        out = np.zeros(5, np.int64)
+        lib().abo_sim_book_l1(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)))
+        return out
+
+    def fundamental(self):
+        return lib().abo_sim_fundamental(self._h)

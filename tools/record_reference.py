@@ -1,0 +1,310 @@
+#!/usr/bin/env python3
+"""Record golden traces from the UNMODIFIED reference (/root/reference) for tests/golden/.
+
+Runs in the build container only (the reference is a Python program and cannot travel to the
+GPU box).  Nothing from /root/reference is copied: this script imports it with the App. D shims
+(tools/shims) and hooks four observation points at run time:
+
+  * kernel event-queue pops      Kernel.py:192       -> (t_ns, recipient, type, uniq, msg kind)
+  * book operations (inputs)     util/OrderBook.py:38,284,341 (called from agent/ExchangeAgent.py:311,324,339)
+  * exchange outbound messages   agent/ExchangeAgent.py:471-485 -> fills, accepts, cancels, L1 replies
+  * every RandomState draw       as the *standard* variate (SURVEY App. C identities) per stream
+
+Usage:  python tools/record_reference.py sparse_zi_100 123456789 tests/golden/z100_s123456789.npz [--full]
+        --full  also stores the pop / op / notification traces and RNG tapes (default stores
+                checkpointed hashes, counts and final holdings only).
+"""
+import importlib
+import os
+import queue
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("ABIDES_REFERENCE", "/root/reference")
+
+# Message kinds (the reference's msg.body["msg"] strings), in the numbering the
+# C-ABI uses (include/abides_b200.h, enum abx_msg_kind).
+MSG_KINDS = [
+    "NONE", "WHEN_MKT_OPEN", "WHEN_MKT_CLOSE", "QUERY_SPREAD", "LIMIT_ORDER", "CANCEL_ORDER",
+    "MODIFY_ORDER", "ORDER_ACCEPTED", "ORDER_EXECUTED", "ORDER_CANCELLED", "MKT_CLOSED",
+    "QUERY_LAST_TRADE", "QUERY_TRANSACTED_VOLUME", "ORDER_MODIFIED", "QUERY_ORDER_STREAM", "MARKET_DATA",
+]
+KIND = {k: i for i, k in enumerate(MSG_KINDS)}
+
+FNV_OFF = 0xCBF29CE484222325
+FNV_PRIME = 0x100000001B3
+M64 = (1 << 64) - 1
+
+
+def fnv_mix(h, v):
+    """FNV-1a over the 8 little-endian bytes of v (two's complement)."""
+    v &= M64
+    for _ in range(8):
+        h = ((h ^ (v & 0xFF)) * FNV_PRIME) & M64
+        v >>= 8
+    return h
+
+
+class Recorder:
+    def __init__(self):
+        self.midnight = None
+        self.pops = []       # (t, recipient, type, uniq, kind)
+        self.ops = []        # (t, op, agent, order_id, is_buy, price, qty, new_price, new_qty)
+        self.notes = []      # (t, recipient, kind, order_id, is_buy, qty, price, fill_price|last_trade, bid, bid_q, ask, ask_q, mkt_closed)
+        self.snaps = []      # after every book op: (n_bid_lv, n_ask_lv, n_resting, b0,bq0,b1,bq1,b2,bq2, a0,aq0,a1,aq1,a2,aq2, last_trade)
+        self.streams = []    # RecRS objects in creation order
+        self.global_tape = []
+
+    def ns(self, ts):
+        return int((ts - self.midnight).value)
+
+
+REC = Recorder()
+
+
+class RecRS(np.random.RandomState):
+    """RandomState that logs each draw as its standard variate (bit-equal identities)."""
+
+    def __init__(self, seed=None):
+        super().__init__(seed)
+        self.tape_kind = []
+        self.tape_val = []
+        self.seed_value = None if seed is None else int(seed)
+        REC.streams.append(self)
+
+    def _rec(self, k, v):
+        self.tape_kind.append(k)
+        self.tape_val.append(v)
+
+    def normal(self, loc=0.0, scale=1.0, size=None):
+        if size is None:
+            z = super().standard_normal()
+            self._rec(b"n", z)
+            return loc + scale * z
+        n = int(np.prod(size))
+        out = np.empty(n)
+        for i in range(n):
+            z = super().standard_normal()
+            self._rec(b"n", z)
+            out[i] = loc + scale * z
+        return out.reshape(size)
+
+    def exponential(self, scale=1.0, size=None):
+        assert size is None
+        e = super().standard_exponential()
+        self._rec(b"e", e)
+        return e * scale
+
+    def uniform(self, low=0.0, high=1.0, size=None):
+        assert size is None
+        u = super().random_sample()
+        self._rec(b"u", u)
+        return low + (high - low) * u
+
+    def randint(self, low, high=None, size=None, dtype=int):
+        v = super().randint(low, high, size=size, dtype=dtype)
+        lo = 0 if high is None else low
+        if size is None:
+            self._rec(b"i", int(v) - int(lo))
+        else:
+            for x in np.asarray(v).ravel():
+                self._rec(b"i", int(x) - int(lo))
+        return v
+
+    def choice(self, a, size=None, replace=True, p=None):
+        # Kernel.py:411 passes the noise list as `replace`; numpy then draws randint(0, a, size).
+        assert isinstance(a, int) and p is None
+        v = super().randint(0, a, size=size)
+        for x in np.asarray(v).ravel():
+            self._rec(b"i", int(x))
+        return v
+
+
+class RecPQ(queue.PriorityQueue):
+    def get(self, *a, **k):
+        item = super().get(*a, **k)
+        t, (recipient, mtype, msg) = item
+        if REC.midnight is not None:
+            if msg is None:
+                uniq, kind = -1, 0
+            else:
+                uniq, kind = msg.uniq, KIND[msg.body["msg"]]
+            REC.pops.append((REC.ns(t), int(recipient), int(mtype.value), uniq, kind))
+        return item
+
+
+def install_hooks():
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(HERE, "shims"))
+    import pandas
+    import pandas.io.json
+
+    if not hasattr(pandas.io.json, "json_normalize"):  # same alias tools/shims/sitecustomize.py installs
+        pandas.io.json.json_normalize = pandas.json_normalize
+
+    queue.PriorityQueue = RecPQ
+    np.random.RandomState = RecRS
+
+    # Global-stream draws that happen at run time (megashock gaps, SparseMeanRevertingOracle.py:69,168).
+    g_exponential = np.random.exponential
+
+    def rec_exponential(scale=1.0, size=None):
+        v = g_exponential(scale, size)
+        REC.global_tape.append(float(v) / scale)
+        return v
+
+    np.random.exponential = rec_exponential
+
+    import util.OrderBook as OB
+    import agent.ExchangeAgent as EA
+
+    def snap(book):
+        b = book.getInsideBids(3)
+        a = book.getInsideAsks(3)
+        row = [len(book.bids), len(book.asks), sum(len(l) for l in book.bids) + sum(len(l) for l in book.asks)]
+        for side in (b, a):
+            for i in range(3):
+                row += list(side[i]) if i < len(side) else [0, 0]
+        row.append(-1 if book.last_trade is None else int(book.last_trade))
+        REC.snaps.append(tuple(int(x) for x in row))
+
+    h0, c0, m0 = OB.OrderBook.handleLimitOrder, OB.OrderBook.cancelOrder, OB.OrderBook.modifyOrder
+
+    def handleLimitOrder(self, order):
+        REC.ops.append((REC.ns(self.owner.currentTime), 0, order.agent_id, order.order_id, int(order.is_buy_order),
+                        int(order.limit_price), int(order.quantity), 0, 0))
+        h0(self, order)
+        snap(self)
+
+    def cancelOrder(self, order):
+        REC.ops.append((REC.ns(self.owner.currentTime), 1, order.agent_id, order.order_id, int(order.is_buy_order),
+                        int(order.limit_price), int(order.quantity), 0, 0))
+        c0(self, order)
+        snap(self)
+
+    def modifyOrder(self, order, new_order):
+        REC.ops.append((REC.ns(self.owner.currentTime), 2, order.agent_id, order.order_id, int(order.is_buy_order),
+                        int(order.limit_price), int(order.quantity), int(new_order.limit_price),
+                        int(new_order.quantity)))
+        m0(self, order, new_order)
+        snap(self)
+
+    OB.OrderBook.handleLimitOrder = handleLimitOrder
+    OB.OrderBook.cancelOrder = cancelOrder
+    OB.OrderBook.modifyOrder = modifyOrder
+
+    s0 = EA.ExchangeAgent.sendMessage
+
+    def sendMessage(self, recipientID, msg):
+        b = msg.body
+        kind = KIND[b["msg"]]
+        row = [REC.ns(self.currentTime), int(recipientID), kind, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0]
+        o = b.get("order", b.get("new_order"))
+        if o is not None:
+            row[3:8] = [o.order_id, int(o.is_buy_order), int(o.quantity), int(o.limit_price),
+                        0 if o.fill_price is None else int(o.fill_price)]
+        if b["msg"] == "QUERY_SPREAD":
+            row[7] = int(b["data"])
+            if b["bids"]:
+                row[8], row[9] = b["bids"][0]
+            if b["asks"]:
+                row[10], row[11] = b["asks"][0]
+            row[12] = int(bool(b["mkt_closed"]))
+        REC.notes.append(tuple(int(x) for x in row))
+        s0(self, recipientID, msg)
+
+    EA.ExchangeAgent.sendMessage = sendMessage
+
+
+def run(config, seed, extra_args=()):
+    import pandas as pd
+
+    REC.midnight = pd.to_datetime("2019-06-28")
+    sys.argv = ["abides.py", "-c", config, "-l", "rec", "-s", str(seed), *extra_args]
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="abides_rec_")
+    os.chdir(tmp)
+    try:
+        mod = importlib.import_module("config." + config)
+    finally:
+        os.chdir(cwd)
+    return mod
+
+
+def main():
+    config, seed, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+    full = "--full" in sys.argv[4:]
+    install_hooks()
+    mod = run(config, seed)
+
+    pops = np.array(REC.pops, dtype=np.int64).reshape(-1, 5)
+    ops = np.array(REC.ops, dtype=np.int64).reshape(-1, 9)
+    notes = np.array(REC.notes, dtype=np.int64).reshape(-1, 13)
+    snaps = np.array(REC.snaps, dtype=np.int64).reshape(-1, 16)
+
+    # Checkpointed FNV-1a hash of the pop sequence (every 1000 pops + final).
+    h = FNV_OFF
+    ck = []
+    for i, row in enumerate(REC.pops):
+        for v in row[:4]:
+            h = fnv_mix(h, v)
+        if (i + 1) % 1000 == 0:
+            ck.append(h)
+    ck.append(h)
+    hn = FNV_OFF
+    for row in REC.notes:
+        for v in row:
+            hn = fnv_mix(hn, v)
+    hs = FNV_OFF
+    for row in REC.snaps:
+        for v in row:
+            hs = fnv_mix(hs, v)
+
+    agents = mod.agents
+    sym = getattr(mod, "symbol", "JPM")
+    hold = []
+    for a in agents[1:]:
+        shares = int(a.holdings.get(sym, 0))
+        cash = int(a.holdings["CASH"])
+        lt = int(a.last_trade[sym]) if sym in a.last_trade else 0
+        surplus = [e["Event"] for e in a.log if e["EventType"] == "FINAL_VALUATION"]
+        hold.append((a.id, shares, cash, cash + shares * lt, int(surplus[-1]) if surplus else 0))
+    hold = np.array(hold, dtype=np.int64)
+
+    data = dict(
+        config=np.array(config), seed=np.array(seed), n_pops=np.array(len(pops)),
+        pop_hash_ckpt=np.array(ck, dtype=np.uint64), note_hash=np.array(hn, dtype=np.uint64),
+        snap_hash=np.array(hs, dtype=np.uint64), n_ops=np.array(len(ops)), n_notes=np.array(len(notes)),
+        holdings=hold, kind_counts=np.bincount(pops[:, 4], minlength=len(MSG_KINDS)),
+        type_counts=np.bincount(pops[:, 2], minlength=4),
+        stream_seeds=np.array([-1 if s.seed_value is None else s.seed_value for s in REC.streams], dtype=np.int64),
+        stream_draws=np.array([len(s.tape_val) for s in REC.streams], dtype=np.int64),
+        global_exp_tape=np.array(REC.global_tape, dtype=np.float64),
+        max_levels=np.array([snaps[:, 0].max() if len(snaps) else 0, snaps[:, 1].max() if len(snaps) else 0]),
+        max_resting=np.array(snaps[:, 2].max() if len(snaps) else 0),
+    )
+    if full:
+        kinds = np.frombuffer(b"".join(b"".join(s.tape_kind) for s in REC.streams), dtype="S1")
+        vals = []
+        for s in REC.streams:
+            for k, v in zip(s.tape_kind, s.tape_val):
+                if k == b"i":
+                    vals.append(np.int64(v).view(np.uint64))
+                else:
+                    vals.append(np.float64(v).view(np.uint64))
+        data.update(
+            pops=pops, ops=ops, notes=notes, snaps=snaps,
+            tape_kind=kinds, tape_bits=np.array(vals, dtype=np.uint64),
+            tape_offsets=np.concatenate([[0], np.cumsum([len(s.tape_val) for s in REC.streams])]).astype(np.int64),
+        )
+    os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
+    np.savez_compressed(out, **data)
+    print("recorded", config, "seed", seed, "pops", len(pops), "ops", len(ops), "notes", len(notes),
+          "streams", len(REC.streams), "->", out)
+
+
+if __name__ == "__main__":
+    main()
