@@ -1,0 +1,195 @@
+/*
+ * abides_b200.h -- C ABI of the B200-native batched ABIDES market simulator (libabides_b200.so).
+ *
+ * The reference (yutiansut/marl-optimal-execution, an ABIDES fork) is 100 % Python and has no FFI; its
+ * hot path is entered through three plain call surfaces.  Each entry point below
+ * names the reference interface it replaces (paths relative to the reference root).  All functions are
+ * extern "C", take plain pointers and sizes (no torch / C++ types), return an int32 status
+ * (ABX_OK == 0, negative == error, see abx_strerror) and never throw.  A handle is owned by one host
+ * thread at a time (the reference's callers are single threaded: Kernel.py:190, ABIDESEnv.py:30).
+ * `stream` arguments are a cudaStream_t passed as void* (NULL == default stream).
+ *
+ * There is no CPU fallback: every entry point that computes runs hand-written sm_100a kernels and
+ * returns ABX_ERR_CUDA when no usable device is present.
+ */
+#ifndef ABIDES_B200_H
+#define ABIDES_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABX_VERSION 1
+
+enum abx_status {
+  ABX_OK = 0,
+  ABX_ERR_ARG = -1,       /* bad argument / config */
+  ABX_ERR_CUDA = -2,      /* CUDA runtime error (abx_last_cuda_error has the text) */
+  ABX_ERR_STATE = -3,     /* call sequence error (e.g. run before reset) */
+  ABX_ERR_CAPACITY = -4   /* a fixed-capacity structure overflowed in some environment (see abx_env_stats.flags) */
+};
+
+/* msg.body["msg"] strings of the reference protocol (agent/ExchangeAgent.py:129-340,
+ * agent/TradingAgent.py:181-268). */
+enum abx_msg_kind {
+  ABX_NONE = 0, ABX_WHEN_MKT_OPEN, ABX_WHEN_MKT_CLOSE, ABX_QUERY_SPREAD, ABX_LIMIT_ORDER, ABX_CANCEL_ORDER,
+  ABX_MODIFY_ORDER, ABX_ORDER_ACCEPTED, ABX_ORDER_EXECUTED, ABX_ORDER_CANCELLED, ABX_MKT_CLOSED,
+  ABX_QUERY_LAST_TRADE, ABX_QUERY_TRANSACTED_VOLUME, ABX_ORDER_MODIFIED, ABX_QUERY_ORDER_STREAM, ABX_MARKET_DATA
+};
+/* queue entry types, message/Message.py:5-10 (tie-break order MESSAGE < WAKEUP < CANCEL_ORDER) */
+enum abx_event_type { ABX_T_MESSAGE = 1, ABX_T_WAKEUP = 2, ABX_T_CANCEL_ORDER = 3 };
+
+enum abx_rng_mode {
+  ABX_RNG_PHILOX = 0, /* counter-based Philox4x32-10 streams keyed by (env seed, stream id) */
+  ABX_RNG_TAPE = 1    /* replay of recorded standard variates, one tape per RandomState of the reference */
+};
+enum abx_latency_model {
+  ABX_LAT_MATRIX_NOISE = 0, /* Kernel.py:410-412: pairwise latency + uniform integer noise in [0, n_noise) */
+  ABX_LAT_CUBIC = 1         /* model/LatencyModel.py:109-140 */
+};
+
+/* per-environment flag bits in abx_env_stats.flags */
+#define ABX_F_DONE            0x001u /* event loop ended (queue empty or past stop time, Kernel.py:190) */
+#define ABX_F_QUEUE_OVERFLOW  0x002u
+#define ABX_F_LEVEL_OVERFLOW  0x004u
+#define ABX_F_ORDER_OVERFLOW  0x008u
+#define ABX_F_AGENT_ORDERS_OVERFLOW 0x010u
+#define ABX_F_THETA_INDEX     0x020u /* the reference would have raised IndexError (ZeroIntelligenceAgent.py:268) */
+#define ABX_F_TAPE_UNDERRUN   0x040u
+#define ABX_F_TAPE_KIND       0x080u /* tape entry kind differs from the draw the simulator asked for */
+#define ABX_F_TRACE_OVERFLOW  0x100u
+#define ABX_F_TIME_RANGE      0x200u
+
+/* One ZeroIntelligenceAgent strategy group: config/sparse_zi_1000.py:196-204 tuples (n, R_min, R_max, eta). */
+typedef struct abx_zi_group {
+  int32_t count, r_min, r_max, _pad;
+  double eta;
+} abx_zi_group;
+
+/* Replaces the config-as-script surface (config/sparse_zi_100.py, config/sparse_zi_1000.py) plus the
+ * Kernel.runner arguments (Kernel.py:50-64).  Times are int64 ns since midnight of the simulated date. */
+typedef struct abx_sim_config {
+  int32_t version;                 /* ABX_VERSION */
+  int32_t n_agents;                /* exchange (id 0) + traders */
+  int32_t n_groups;                /* <= 8 */
+  int32_t q_max;                   /* ZeroIntelligenceAgent q_max (theta has 2*q_max entries, <= 20) */
+  abx_zi_group groups[8];
+  int64_t start_ns, stop_ns;       /* Kernel.runner startTime / stopTime */
+  int64_t mkt_open_ns, mkt_close_ns;
+  int64_t default_computation_delay_ns; /* Kernel.runner defaultComputationDelay */
+  int64_t exchange_computation_delay_ns, exchange_pipeline_delay_ns; /* ExchangeAgent.py:56-59 */
+  int64_t starting_cash;           /* cents */
+  int32_t order_size;              /* ZeroIntelligenceAgent.py:308 (100) */
+  int32_t stream_history;          /* ExchangeAgent stream_history (not read on this path) */
+  /* util/oracle/SparseMeanRevertingOracle.py symbol parameters */
+  double r_bar, kappa, fund_vol, megashock_lambda_a, megashock_mean, megashock_var;
+  /* ZeroIntelligenceAgent parameters */
+  double sigma_n, agent_kappa, sigma_s, sigma_pv, lambda_a;
+  /* latency */
+  int32_t latency_model;           /* abx_latency_model */
+  int32_t n_noise;                 /* len(latencyNoise) for ABX_LAT_MATRIX_NOISE */
+  int32_t latency_mirrored;        /* 1: latency[i][0] == latency[0][i] (config/sparse_zi_1000.py:264-277) */
+  int32_t _pad0;
+  double latency_lo, latency_hi;   /* U(lo, hi) pairwise (min) latency, ns (Philox mode draws it on device) */
+  double jitter, jitter_clip, jitter_unit;
+  /* capacities (per environment) */
+  int32_t queue_cap;               /* event slots, multiple of 32, <= 4096 */
+  int32_t level_cap;               /* price levels per side, <= 2048 */
+  int32_t order_cap;               /* resting orders, <= 65535 */
+  int32_t rng_mode;                /* abx_rng_mode */
+  int32_t trace_cap;               /* trace records per environment (0 = tracing off) */
+  int32_t hash_pops;               /* 1: maintain the FNV-1a hash of the pop sequence (parity runs) */
+} abx_sim_config;
+
+/* Per-environment counters; replaces the "Event Queue elapsed ..., messages: N" line (Kernel.py:321-327). */
+typedef struct abx_env_stats {
+  int64_t messages;      /* ttl_messages, Kernel.py:211 (requeued pops included) */
+  int64_t now_ns;        /* Kernel.currentTime */
+  uint64_t pop_hash;     /* FNV-1a over (t, recipient, type, uniq) of every pop when hash_pops */
+  uint32_t limit_orders, cancels, fills, spread_queries;
+  uint32_t max_queue, n_bid_levels, n_ask_levels, n_resting;
+  int32_t best_bid, best_bid_qty, best_ask, best_ask_qty; /* getInsideBids(1)/getInsideAsks(1); qty 0 == empty */
+  int32_t last_trade, fundamental;
+  uint32_t flags, trace_len;
+  uint32_t uniq, orders_allocated;
+  int64_t sum_shares, sum_cash; /* filled by abx_sim_finalize: conservation checksums over traders */
+} abx_env_stats;
+
+/* One trace record (80 bytes), written when trace_cap > 0; layouts mirror tools/record_reference.py rows.
+ *   tag 0  queue pop (Kernel.py:192):        a = recipient, t, v = {type, uniq (-1 for msg None), kind}
+ *   tag 1  exchange outbound message          a = recipient, t, v = {kind, order_id, is_buy, qty, limit_price,
+ *          (agent/ExchangeAgent.py:471-485):      fill_price | last_trade, bid, bid_qty, ask, ask_qty, mkt_closed}
+ *   tag 2  book state after a book op:        t, v = {n_bid_levels, n_ask_levels, n_resting,
+ *          (util/OrderBook.py:38,284)             bid p,q x3, ask p,q x3, last_trade}                         */
+typedef struct abx_trace_rec {
+  int32_t tag;
+  int32_t a;
+  int64_t t;
+  int32_t v[16];
+} abx_trace_rec;
+
+typedef struct abx_sim abx_sim; /* opaque */
+
+const char *abx_strerror(int32_t status);
+const char *abx_last_cuda_error(void);
+int32_t abx_device_count(void);
+
+/* Fill `cfg` with the population/parameters of config/sparse_zi_100.py (variant 100) or
+ * config/sparse_zi_1000.py (variant 1000), capacities sized from the measured maxima. */
+int32_t abx_config_sparse_zi(int32_t variant, abx_sim_config *cfg);
+
+/* Replaces: Kernel(...) construction + agent list construction (config/sparse_zi_1000.py:146-251).
+ * Allocates all per-environment state for n_envs independent simulations on CUDA device `device`. */
+int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device, abx_sim **out);
+int32_t abx_sim_destroy(abx_sim *h);
+int64_t abx_sim_device_bytes(const abx_sim *h);
+
+/* Replaces: np.random.seed(seed) and the per-object RandomState cascade, agent __init__
+ * (ZeroIntelligenceAgent.py:65-70 theta draw), latency matrix draw, oracle __init__, Kernel.runner :154-175
+ * (kernelInitializing / kernelStarting: one WAKEUP per agent at start_ns).  seeds: host array [n_envs]. */
+int32_t abx_sim_reset_philox(abx_sim *h, const uint64_t *seeds, void *stream);
+
+/* Tape-mode reset of ALL environments.  Host arrays:
+ *   tape_bits  [total]            standard variates: fp64 bits for kinds 'n','e','u', integer offset for 'i'
+ *   tape_kinds [total]            'n' normal, 'e' exponential, 'u' uniform, 'i' randint (value - low)
+ *   tape_offsets [n_envs*(n_agents+3)+1]  per env, streams in order: 0 symbol, 1 kernel, 2 latency model,
+ *                                 3 global (megashock gaps, kind 'e'), 3+a agent a (a = 1..n_agents-1)
+ *   lat_to_exchange / lat_from_exchange [n_envs*n_agents]  fp64 ns: latency[a][0] / latency[0][a]
+ * Replays what Kernel/agents/oracle drew in a recorded reference run (rng_mode must be ABX_RNG_TAPE). */
+int32_t abx_sim_reset_tape(abx_sim *h, const uint64_t *tape_bits, const uint8_t *tape_kinds,
+                           const int64_t *tape_offsets, const double *lat_to_exchange,
+                           const double *lat_from_exchange, void *stream);
+
+/* Replaces: the hot loop of Kernel.runner (Kernel.py:190-292) for every environment at once.  Pops events
+ * while the next event time <= until_ns (and the reference loop condition holds).  Asynchronous on `stream`. */
+int32_t abx_sim_run(abx_sim *h, int64_t until_ns, void *stream);
+
+/* Replaces: Kernel.runner :310-311 (kernelStopping of every agent: mark to market, ZI surplus valuation,
+ * which advances the shared fundamental, ZeroIntelligenceAgent.py:80-123). */
+int32_t abx_sim_finalize(abx_sim *h, void *stream);
+
+/* Device -> host copy of per-environment counters (synchronises `stream`).  out: host [n_envs]. */
+int32_t abx_sim_stats(abx_sim *h, abx_env_stats *out, void *stream);
+/* Same counters left on the device: out_dev is a DEVICE pointer [n_envs] (e.g. a torch tensor's data_ptr). */
+int32_t abx_sim_stats_device(abx_sim *h, abx_env_stats *out_dev, void *stream);
+
+/* Replaces: the "Final holdings for ..." lines (agent/TradingAgent.py:124-126) for one environment.
+ * out: host int64 [(n_agents-1) * 5] rows (agent id, shares, cash, marked_to_market, surplus). */
+int32_t abx_sim_holdings(abx_sim *h, int32_t env, int64_t *out, void *stream);
+
+/* Replaces: OrderBook.getInsideBids(depth) / getInsideAsks(depth) (util/OrderBook.py:377-398) for one env.
+ * out: host int32 [2*depth] (price, qty) pairs best first; returns the number of levels in *n_levels. */
+int32_t abx_sim_book_snapshot(abx_sim *h, int32_t env, int32_t is_bid, int32_t depth, int32_t *out,
+                              int32_t *n_levels, void *stream);
+
+/* Copy the trace of one environment to the host.  out: host [max_recs]; *n_recs = records written. */
+int32_t abx_sim_trace(abx_sim *h, int32_t env, abx_trace_rec *out, int32_t max_recs, int32_t *n_recs, void *stream);
+
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+int64_t abx_sim_launch_count(const abx_sim *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABIDES_B200_H */

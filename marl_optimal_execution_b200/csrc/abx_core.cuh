@@ -1,0 +1,714 @@
+// abx_core.cuh -- warp-uniform simulation logic of the batched ABIDES simulator (one warp == one environment).
+//
+// Everything in this header is *uniform* code: on the GPU all 32 lanes of the environment's warp execute it
+// redundantly with identical register values (so ballots/shuffles inside the cooperative primitives of the
+// context type never diverge), and only the context's primitives (abx_warp.cuh: event queue, price ladders,
+// agent-record staging) split work across lanes.  The same header compiles as plain C++ for the host
+// emulation harness under tests/emu (CPU CI of this logic; it is not part of libabides_b200.so).
+//
+// Reference semantics restated here (paths relative to the reference root):
+//   Kernel.py:190-292,347-462            event loop, requeue rule, send/wakeup
+//   agent/ExchangeAgent.py:129-340,471   exchange protocol
+//   util/OrderBook.py:38-398             matching engine
+//   agent/TradingAgent.py, agent/ZeroIntelligenceAgent.py   trader state machine, belief update, pricing
+//   util/oracle/SparseMeanRevertingOracle.py:88-227        sparse OU fundamental with megashocks
+//   model/LatencyModel.py:109-140        cubic latency
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include "../../include/abides_b200.h"
+
+#if defined(__CUDACC__)
+#define ABX_HD __host__ __device__ __forceinline__
+#define ABX_D __device__ __forceinline__
+#else
+#define ABX_HD inline
+#endif
+
+#if !defined(__CUDACC__)
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
+inline double cospi(double x) { return cos(3.14159265358979323846 * x); }
+#endif
+
+namespace abx {
+
+// ---------------------------------------------------------------------------------------------------
+// state structs (HBM layout; all 16-byte aligned so a warp moves them with 128-bit loads/stores)
+// ---------------------------------------------------------------------------------------------------
+struct alignas(16) EnvState {           // 192 B per environment
+  int64_t now, ttl;                     // Kernel.currentTime, ttl_messages
+  int64_t exch_time, exch_comp_delay;   // agentCurrentTimes[0], agentComputationDelays[0]
+  int64_t or_t, ms_t;                   // oracle r[symbol][0], next megashock time
+  double ms_v; uint64_t pop_hash;       // next megashock value; FNV-1a of the pop sequence
+  uint64_t seed; int32_t or_v, last_trade; // oracle r[symbol][1]; OrderBook.last_trade
+  uint32_t uniq, next_order_id, q_count, max_q; // Message.uniq, Order.order_id counters; queue fill
+  int32_t n_lv[2]; int32_t n_resting; uint32_t free_head; // ladder sizes (0 bids, 1 asks); order-node free list
+  uint32_t pool_top, flags, trace_n, c_limit;
+  uint32_t c_cancel, c_fills, c_query, ctr_symbol;
+  uint32_t ctr_kernel, ctr_latency, ctr_global, started;
+  int64_t sum_shares, sum_cash;
+  uint32_t pad[4];
+};
+static_assert(sizeof(EnvState) == 192, "EnvState layout");
+
+enum : uint32_t {
+  AF_HAS_OPEN = 1u, AF_HAS_CLOSE = 2u, AF_MKT_CLOSED = 4u, AF_HAS_LAST = 8u, AF_HAS_DAILY = 16u, AF_HAS_PREV = 32u,
+  AF_HAS_BID = 64u, AF_HAS_ASK = 128u, AF_STATE_SHIFT = 8, AF_STATE_MASK = 3u << 8, AF_GROUP_SHIFT = 12, AF_GROUP_MASK = 7u << 12
+};
+enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE = 1, ST_AWAITING_SPREAD = 2 }; // ZeroIntelligenceAgent.state
+constexpr int AGENT_ORDER_CAP = 4;      // open orders tracked per trader (ZI holds <= 2)
+
+struct alignas(16) ZiAgent {            // 192 B per trader: TradingAgent + ZeroIntelligenceAgent state
+  int64_t agent_time;                   // Kernel.agentCurrentTimes[id]
+  int64_t prev_wake;                    // ZI.prev_wake_time (valid with AF_HAS_PREV)
+  double r_t, sigma_t;                  // ZI belief
+  int64_t cash; int32_t shares, last_trade;     // holdings["CASH"], holdings[symbol], last_trade[symbol]
+  int32_t daily_close, bid, bid_q, ask;         // daily_close_price, known_bids[0], known_asks[0]
+  int32_t ask_q; uint32_t flags, rng_ctr; int32_t n_orders;
+  uint32_t oid[AGENT_ORDER_CAP]; int32_t oprice[AGENT_ORDER_CAP]; int32_t oqty[AGENT_ORDER_CAP]; // self.orders (qty > 0 buy, < 0 sell)
+  int16_t theta[20];                    // private values, sorted descending
+  double lat_to, lat_from;              // latency[id][0], latency[0][id]  (min_latency for the cubic model)
+  int64_t surplus;                      // FINAL_VALUATION (kernelStopping)
+};
+static_assert(sizeof(ZiAgent) == 192, "ZiAgent layout");
+
+struct Event {                          // one PriorityQueue entry, unpacked
+  int64_t t; int32_t recipient, type; uint32_t uniq; int32_t kind, sender;
+  int32_t p[6];                         // order: {order_id, limit_price, qty, fill_price, is_buy, -}
+                                        // spread reply: {bid, bid_qty, ask, ask_qty, last_trade, has_bid|has_ask<<1|mkt_closed<<2}
+  double lat_back;                      // trader -> exchange messages carry latency[0][sender] for the reply
+};
+
+// 64-bit sort key: [ time : 47 | recipient : 15 | type : 2 ], ties broken by uniq (message/Message.py:39-45)
+constexpr int KEY_T_SHIFT = 17;
+constexpr int64_t KEY_T_MAX = (int64_t(1) << 46);   // times are saturated below 2^46 ns (19.5 h) -- far past any stop time
+ABX_HD uint64_t key_pack(int64_t t, int recipient, int type) { return (uint64_t(t) << KEY_T_SHIFT) | (uint64_t(recipient) << 2) | uint64_t(type); }
+ABX_HD int64_t key_time(uint64_t k) { return int64_t(k >> KEY_T_SHIFT); }
+ABX_HD int key_recipient(uint64_t k) { return int((k >> 2) & 0x7fff); }
+ABX_HD int key_type(uint64_t k) { return int(k & 3); }
+constexpr uint64_t KEY_EMPTY = ~uint64_t(0);
+
+struct NodeRec { uint32_t id; int32_t qty; uint32_t agent; uint32_t next; };   // one resting order (16 B)
+constexpr uint32_t NIL = 0xffffffffu;
+
+// Device-side parameter block (config + derived constants + HBM base pointers).
+struct SimParams {
+  abx_sim_config c;
+  int32_t n_envs, n_qgroups, n_streams, pad0;
+  double one_minus_kappa_a;     // 1 - agent_kappa
+  double sigma_denom;           // 1 - (1 - agent_kappa) ** 2      (host libm pow, ZeroIntelligenceAgent.py:234)
+  double sqrt_sigma_n, sqrt_sigma_pv, sqrt_megashock_var;
+  double inv_lambda_a, inv_megashock_lambda;
+  double ou_scale;              // (fund_vol ** 2) / (2 * kappa)     SparseMeanRevertingOracle.py:106
+  // HBM arrays, environment-major
+  uint4 *qkey, *qpay0, *qpay1;  // [n_envs][queue_cap]
+  uint4 *qcache;                // [n_envs][n_qgroups]   {min key lo, hi, min uniq, occupancy mask}
+  ZiAgent *agents;              // [n_envs][n_agents]    (index 0 unused: the exchange lives in EnvState)
+  int32_t *lv_price, *lv_qty; uint32_t *lv_ht;  // [n_envs][2][level_cap]
+  uint4 *nodes;                 // [n_envs][order_cap]
+  EnvState *env;                // [n_envs]
+  abx_trace_rec *trace;         // [n_envs][trace_cap]
+  const uint64_t *tape_bits; const uint8_t *tape_kinds; const int64_t *tape_off; // tape mode
+};
+
+// ---------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------
+ABX_HD int64_t py_round_i64(double x) { return (int64_t)rint(x); }   // Python int(round(x)): half-to-even
+ABX_HD uint64_t fnv_mix(uint64_t h, int64_t sv) {
+  uint64_t v = (uint64_t)sv;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { h = (h ^ (v & 0xFF)) * 0x100000001B3ULL; v >>= 8; }
+  return h;
+}
+ABX_HD uint64_t dbl_bits(double d) { union { double d; uint64_t u; } x; x.d = d; return x.u; }
+ABX_HD double bits_dbl(uint64_t u) { union { double d; uint64_t u; } x; x.u = u; return x.d; }
+// fp64 arithmetic that must not be contracted into FMAs (the reference is CPython: every op rounds)
+#if defined(__CUDA_ARCH__)
+ABX_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+ABX_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+ABX_HD double dsub(double a, double b) { return __dsub_rn(a, b); }
+#else
+ABX_HD double dmul(double a, double b) { volatile double r = a * b; return r; }
+ABX_HD double dadd(double a, double b) { volatile double r = a + b; return r; }
+ABX_HD double dsub(double a, double b) { volatile double r = a - b; return r; }
+#endif
+
+// queue slot encoding: key {hi.lo, hi.hi, uniq, kind | sender << 8}, pay0 {p0..p3}, pay1 {p4, p5, lat_back bits}
+ABX_HD void event_pack(const Event &e, uint4 &k, uint4 &a, uint4 &b) {
+  uint64_t hi = key_pack(e.t, e.recipient, e.type); uint64_t lb = dbl_bits(e.lat_back);
+  k.x = (uint32_t)hi; k.y = (uint32_t)(hi >> 32); k.z = e.uniq; k.w = (uint32_t)e.kind | ((uint32_t)e.sender << 8);
+  a.x = (uint32_t)e.p[0]; a.y = (uint32_t)e.p[1]; a.z = (uint32_t)e.p[2]; a.w = (uint32_t)e.p[3];
+  b.x = (uint32_t)e.p[4]; b.y = (uint32_t)e.p[5]; b.z = (uint32_t)lb; b.w = (uint32_t)(lb >> 32);
+}
+ABX_HD void event_unpack(const uint4 &k, const uint4 &a, const uint4 &b, Event &e) {
+  uint64_t hi = (uint64_t)k.x | ((uint64_t)k.y << 32);
+  e.t = key_time(hi); e.recipient = key_recipient(hi); e.type = key_type(hi); e.uniq = k.z; e.kind = (int)(k.w & 0xffu); e.sender = (int)(k.w >> 8);
+  e.p[0] = (int32_t)a.x; e.p[1] = (int32_t)a.y; e.p[2] = (int32_t)a.z; e.p[3] = (int32_t)a.w; e.p[4] = (int32_t)b.x; e.p[5] = (int32_t)b.y;
+  e.lat_back = bits_dbl((uint64_t)b.z | ((uint64_t)b.w << 32));
+}
+ABX_HD bool key_less(uint64_t ah, uint32_t au, uint64_t bh, uint32_t bu) { return ah < bh || (ah == bh && au < bu); }
+
+// ---------------------------------------------------------------------------------------------------
+// RNG: Philox4x32-10 counter streams, or replay of recorded standard variates (tape)
+// ---------------------------------------------------------------------------------------------------
+ABX_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = uint64_t(0xD2511F53u) * c0, p1 = uint64_t(0xCD9E8D57u) * c2;
+    uint32_t n0 = uint32_t(p1 >> 32) ^ c1 ^ k0, n1 = uint32_t(p1), n2 = uint32_t(p0 >> 32) ^ c3 ^ k1, n3 = uint32_t(p0);
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+enum { S_SYMBOL = 0, S_KERNEL = 1, S_LATENCY = 2, S_GLOBAL = 3, S_AGENT0 = 3 };  // agent a uses stream S_AGENT0 + a
+
+struct Rng {
+  const SimParams *P; int env; uint64_t seed; uint32_t err;
+  ABX_HD uint64_t tape_next(int stream, uint32_t &ctr, uint8_t kind) {
+    const int64_t *off = P->tape_off + (int64_t)env * P->n_streams + stream;
+    int64_t i = off[0] + ctr;
+    if (i >= off[1]) { err |= ABX_F_TAPE_UNDERRUN; return 0; }
+    ctr++;
+    if (P->tape_kinds[i] != kind) err |= ABX_F_TAPE_KIND;
+    return P->tape_bits[i];
+  }
+  ABX_HD void philox(int stream, uint32_t &ctr, uint32_t o[4]) { philox4x32_10(ctr, (uint32_t)stream, 0x41424958u, 0, (uint32_t)seed, (uint32_t)(seed >> 32), o); ctr++; }
+  static ABX_HD double u53(uint32_t a, uint32_t b) { return ((a >> 5) * 67108864.0 + (b >> 6)) / 9007199254740992.0; }
+  ABX_HD double std_normal(int stream, uint32_t &ctr) {
+    if (P->c.rng_mode == ABX_RNG_TAPE) return bits_dbl(tape_next(stream, ctr, 'n'));
+    uint32_t o[4]; philox(stream, ctr, o);
+    double u1 = 1.0 - u53(o[0], o[1]), u2 = u53(o[2], o[3]);                 // u1 in (0,1]
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+  }
+  ABX_HD double std_exponential(int stream, uint32_t &ctr) {
+    if (P->c.rng_mode == ABX_RNG_TAPE) return bits_dbl(tape_next(stream, ctr, 'e'));
+    uint32_t o[4]; philox(stream, ctr, o); return -log(1.0 - u53(o[0], o[1]));
+  }
+  ABX_HD double u01(int stream, uint32_t &ctr) {
+    if (P->c.rng_mode == ABX_RNG_TAPE) return bits_dbl(tape_next(stream, ctr, 'u'));
+    uint32_t o[4]; philox(stream, ctr, o); return u53(o[0], o[1]);
+  }
+  // integer in [0, range] (numpy randint(low, high) with range = high - 1 - low; no draw when range == 0)
+  ABX_HD int64_t randint(int stream, uint32_t &ctr, uint32_t range) {
+    if (range == 0) { if (P->c.rng_mode == ABX_RNG_TAPE) return (int64_t)tape_next(stream, ctr, 'i'); return 0; }
+    if (P->c.rng_mode == ABX_RNG_TAPE) return (int64_t)tape_next(stream, ctr, 'i');
+    uint32_t o[4]; philox(stream, ctr, o); return (int64_t)((uint64_t(o[0]) * (uint64_t(range) + 1)) >> 32);
+  }
+  ABX_HD double normal(int stream, uint32_t &ctr, double loc, double scale) { return dadd(loc, dmul(scale, std_normal(stream, ctr))); }
+};
+
+
+// ---------------------------------------------------------------------------------------------------
+// reset: agent construction (config/sparse_zi_1000.py:211-251, ZeroIntelligenceAgent.__init__ :65-70) -- one
+// thread per (environment, trader) on the GPU.  In tape mode lat_to / lat_from were preloaded by the host.
+// ---------------------------------------------------------------------------------------------------
+ABX_HD void init_agent_record(const SimParams &P, int env, int id, uint64_t seed, ZiAgent *z, uint32_t *err) {
+  Rng rng; rng.P = &P; rng.env = env; rng.seed = seed; rng.err = 0;
+  int grp = 0, acc = 1;
+  for (int g = 0; g < P.c.n_groups; g++) { if (id >= acc && id < acc + P.c.groups[g].count) grp = g; acc += P.c.groups[g].count; }
+  uint32_t ctr = 0; int stream = S_AGENT0 + id; int m = 2 * P.c.q_max;
+  double th[20];
+  for (int i = 0; i < 20; i++) th[i] = 0;
+  for (int i = 0; i < m; i++) th[i] = rint(rng.normal(stream, ctr, 0.0, P.sqrt_sigma_pv));   // np.round(normal(0, sqrt(sigma_pv)))
+  for (int i = 1; i < m; i++) { double x = th[i]; int j = i - 1; while (j >= 0 && th[j] < x) { th[j + 1] = th[j]; j--; } th[j + 1] = x; }  // sorted(reverse=True)
+  double lat_to = z->lat_to, lat_from = z->lat_from;
+  if (P.c.rng_mode == ABX_RNG_PHILOX) {           // the config's pairwise latency matrix row/column 0, drawn per environment
+    uint32_t c2 = 0; int cs = P.n_streams + id;
+    lat_to = dadd(P.c.latency_lo, dmul(dsub(P.c.latency_hi, P.c.latency_lo), rng.u01(cs, c2)));
+    lat_from = P.c.latency_mirrored ? lat_to : dadd(P.c.latency_lo, dmul(dsub(P.c.latency_hi, P.c.latency_lo), rng.u01(cs, c2)));
+  }
+  z->agent_time = P.c.start_ns; z->prev_wake = 0; z->r_t = P.c.r_bar; z->sigma_t = 0.0; z->cash = P.c.starting_cash; z->shares = 0; z->last_trade = 0;
+  z->daily_close = 0; z->bid = 0; z->bid_q = 0; z->ask = 0; z->ask_q = 0; z->flags = ((uint32_t)grp << AF_GROUP_SHIFT) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT);
+  z->rng_ctr = ctr; z->n_orders = 0;
+  for (int i = 0; i < AGENT_ORDER_CAP; i++) { z->oid[i] = 0; z->oprice[i] = 0; z->oqty[i] = 0; }
+  for (int i = 0; i < 20; i++) { double v = th[i]; if (v > 32767.0) { v = 32767.0; rng.err |= ABX_F_THETA_INDEX; } if (v < -32768.0) { v = -32768.0; rng.err |= ABX_F_THETA_INDEX; } z->theta[i] = (int16_t)v; }
+  z->lat_to = lat_to; z->lat_from = lat_from; z->surplus = 0;
+  if (rng.err) *err |= rng.err;
+}
+ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
+  s.now = P.c.start_ns; s.ttl = 0; s.exch_time = P.c.start_ns; s.exch_comp_delay = P.c.default_computation_delay_ns;   // Kernel.py:97,105
+  s.or_t = P.c.mkt_open_ns; s.ms_t = 0; s.ms_v = 0.0; s.pop_hash = 0xCBF29CE484222325ULL; s.seed = seed;
+  s.or_v = (int32_t)P.c.r_bar; s.last_trade = (int32_t)P.c.r_bar;     // SparseMeanRevertingOracle.py:58; ExchangeAgent.kernelInitializing :91-102
+  s.uniq = 0; s.next_order_id = 0; s.q_count = 0; s.max_q = 0; s.n_lv[0] = s.n_lv[1] = 0; s.n_resting = 0; s.free_head = NIL;
+  s.pool_top = 0; s.flags = 0; s.trace_n = 0; s.c_limit = s.c_cancel = s.c_fills = s.c_query = 0;
+  s.ctr_symbol = s.ctr_kernel = s.ctr_latency = s.ctr_global = 0; s.started = 1; s.sum_shares = 0; s.sum_cash = 0;
+  for (int i = 0; i < 4; i++) s.pad[i] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The simulation, templated on the context type that supplies the cooperative primitives:
+//   queue:   bool q_min(uint64_t&hi, uint32_t&uniq, int&group); void q_fetch(group, Event&); void q_remove(); void q_requeue(int64_t t);
+//            bool q_push(const Event&)            (false == overflow)
+//   ladders: void lv_find(side, price, int n, int&pos, bool&found); lv_insert/lv_remove; lv_price/lv_qty/lv_head/lv_tail get/set
+//   nodes:   NodeRec node_load(i); void node_store(i, rec)
+//   agents:  ZiAgent* agent_stage(id)  -- 128-bit cooperative copy HBM -> on-chip staging record, returned pointer is
+//            readable by every lane; void agent_commit(id) -- staging record -> HBM; double agent_lat_from(id)
+//   outbox:  uint32_t* outbox()  -- on-chip array of OUT_CAP * OUT_WORDS words
+//   misc:    bool leader(); void trace(const abx_trace_rec&, uint32_t idx); void sync();
+// Rule for on-chip memory shared by the lanes: only the leader lane writes, and c.sync() separates a write
+// from later reads by other lanes.
+// ---------------------------------------------------------------------------------------------------
+constexpr int OUT_CAP = 32, OUT_WORDS = 12;
+enum : uint32_t { OF_WAKEUP = 1u << 24, OF_BUMP_UNIQ = 1u << 25, OF_FROM_EXCH = 1u << 26 };
+
+struct AgentRegs {                      // scalar part of ZiAgent held in registers while an event is handled
+  int64_t agent_time, prev_wake, cash; double r_t, sigma_t, lat_to, lat_from;
+  int32_t shares, last_trade, daily_close, bid, bid_q, ask, ask_q, n_orders; uint32_t flags, rng_ctr;
+};
+ABX_HD void regs_load(AgentRegs &a, const ZiAgent *z) {
+  a.agent_time = z->agent_time; a.prev_wake = z->prev_wake; a.cash = z->cash; a.r_t = z->r_t; a.sigma_t = z->sigma_t;
+  a.lat_to = z->lat_to; a.lat_from = z->lat_from; a.shares = z->shares; a.last_trade = z->last_trade; a.daily_close = z->daily_close;
+  a.bid = z->bid; a.bid_q = z->bid_q; a.ask = z->ask; a.ask_q = z->ask_q; a.n_orders = z->n_orders; a.flags = z->flags; a.rng_ctr = z->rng_ctr;
+}
+ABX_HD void regs_store(ZiAgent *z, const AgentRegs &a) {
+  z->agent_time = a.agent_time; z->prev_wake = a.prev_wake; z->cash = a.cash; z->r_t = a.r_t; z->sigma_t = a.sigma_t;
+  z->shares = a.shares; z->last_trade = a.last_trade; z->daily_close = a.daily_close;
+  z->bid = a.bid; z->bid_q = a.bid_q; z->ask = a.ask; z->ask_q = a.ask_q; z->n_orders = a.n_orders; z->flags = a.flags; z->rng_ctr = a.rng_ctr;
+}
+
+template <class Ctx>
+struct Sim {
+  Ctx &c; const SimParams &P; EnvState s; Rng rng; int64_t addl_delay; int n_out; int self_id;
+  AgentRegs a; ZiAgent *z;                // the trader whose event is being handled (registers + staged record)
+
+  ABX_HD Sim(Ctx &c_, const SimParams &P_, const EnvState &s_, int env) : c(c_), P(P_), s(s_), addl_delay(0), n_out(0), self_id(0), z(nullptr) {
+    rng.P = &P; rng.env = env; rng.seed = s.seed; rng.err = 0;
+  }
+
+  // ---- tracing (parity runs only) ----
+  ABX_HD void trace_rec(const abx_trace_rec &r) {
+    if (s.trace_n >= (uint32_t)P.c.trace_cap) { s.flags |= ABX_F_TRACE_OVERFLOW; return; }
+    c.trace(r, s.trace_n); s.trace_n++;
+  }
+  ABX_HD void trace_note(int recipient, int kind, const int32_t p[6]) {
+    abx_trace_rec r; r.tag = 1; r.a = recipient; r.t = s.now;
+    for (int i = 0; i < 16; i++) r.v[i] = 0;
+    r.v[0] = kind;
+    if (kind == ABX_ORDER_ACCEPTED || kind == ABX_ORDER_EXECUTED || kind == ABX_ORDER_CANCELLED || kind == ABX_ORDER_MODIFIED) {
+      r.v[1] = p[0]; r.v[2] = p[4]; r.v[3] = p[2]; r.v[4] = p[1]; r.v[5] = p[3];
+    } else if (kind == ABX_QUERY_SPREAD) {
+      r.v[5] = p[4];
+      if (p[5] & 1) { r.v[6] = p[0]; r.v[7] = p[1]; }
+      if (p[5] & 2) { r.v[8] = p[2]; r.v[9] = p[3]; }
+      r.v[10] = (p[5] >> 2) & 1;
+    }
+    trace_rec(r);
+  }
+  ABX_HD void trace_snap() {
+    if (P.c.trace_cap <= 0) return;
+    abx_trace_rec r; r.tag = 2; r.a = 0; r.t = s.now;
+    for (int i = 0; i < 16; i++) r.v[i] = 0;
+    r.v[0] = s.n_lv[0]; r.v[1] = s.n_lv[1]; r.v[2] = s.n_resting;
+    for (int side = 0; side < 2; side++) for (int k = 0; k < 3; k++) {
+      int n = s.n_lv[side]; if (k < n) { r.v[3 + side * 6 + 2 * k] = c.lv_price(side, n - 1 - k); r.v[4 + side * 6 + 2 * k] = c.lv_qty(side, n - 1 - k); }
+    }
+    r.v[15] = s.last_trade;
+    trace_rec(r);
+  }
+
+  // ---- outbox: messages and wakeups produced while handling one event, delivered in order by flush() ----
+  // entry words: [0] recipient | kind<<16 | flags, [1..6] payload, [7,8] pair latency (fp64 bits), [9,10] int64:
+  // send offset (computation delay + additional + pipeline delay) for messages, absolute time for wakeups.
+  ABX_HD void emit(uint32_t w0, const int32_t p[6], double lat, int64_t off) {
+    if (n_out >= OUT_CAP) { s.flags |= ABX_F_QUEUE_OVERFLOW; return; }
+    if (c.leader()) {
+      uint32_t *o = c.outbox() + n_out * OUT_WORDS;
+      o[0] = w0; for (int i = 0; i < 6; i++) o[1 + i] = (uint32_t)p[i];
+      uint64_t lb = dbl_bits(lat); o[7] = (uint32_t)lb; o[8] = (uint32_t)(lb >> 32);
+      o[9] = (uint32_t)(uint64_t)off; o[10] = (uint32_t)((uint64_t)off >> 32);
+    }
+    n_out++;
+  }
+  // Kernel.setWakeup (Kernel.py:435-462)
+  ABX_HD void set_wakeup(int sender, int64_t t) { int32_t p[6] = {0, 0, 0, 0, 0, 0}; emit((uint32_t)sender | OF_WAKEUP, p, 0.0, t); }
+  // ExchangeAgent.sendMessage (agent/ExchangeAgent.py:471-485) -> Kernel.sendMessage
+  ABX_HD void exch_send(int recipient, int kind, const int32_t p[6], double lat_to_recipient) {
+    int64_t delay = (kind == ABX_ORDER_ACCEPTED || kind == ABX_ORDER_CANCELLED || kind == ABX_ORDER_EXECUTED) ? P.c.exchange_pipeline_delay_ns : 0;
+    emit((uint32_t)recipient | ((uint32_t)kind << 16) | OF_FROM_EXCH, p, lat_to_recipient, s.exch_comp_delay + addl_delay + delay);
+  }
+  ABX_HD void exch_send_order(int recipient, int kind, uint32_t oid, int32_t price, int32_t qty, int32_t fill, int is_buy, double lat) {
+    int32_t p[6] = {(int32_t)oid, price, qty, fill, is_buy, 0}; exch_send(recipient, kind, p, lat);
+  }
+  // Agent.sendMessage (agent/Agent.py:148-149) from the trader being handled, always to the exchange
+  ABX_HD void ta_send(int kind, const int32_t p[6], bool bump_uniq) {
+    emit(0u | ((uint32_t)kind << 16) | (bump_uniq ? OF_BUMP_UNIQ : 0u), p, a.lat_to, P.c.default_computation_delay_ns + addl_delay);
+  }
+  // Kernel.sendMessage (Kernel.py:347-433) for every queued entry, in emission order
+  ABX_HD void flush() {
+    c.sync();
+#pragma unroll 1
+    for (int i = 0; i < n_out; i++) {
+      const uint32_t *o = c.outbox() + i * OUT_WORDS;
+      uint32_t w0 = o[0]; Event e;
+      for (int k = 0; k < 6; k++) e.p[k] = (int32_t)o[1 + k];
+      double lat = bits_dbl((uint64_t)o[7] | ((uint64_t)o[8] << 32));
+      int64_t off = (int64_t)((uint64_t)o[9] | ((uint64_t)o[10] << 32));
+      e.recipient = (int)(w0 & 0xffffu); e.kind = (int)((w0 >> 16) & 0xffu);
+      if (w0 & OF_WAKEUP) {
+        e.t = off < KEY_T_MAX ? off : KEY_T_MAX; e.type = ABX_T_WAKEUP; e.uniq = 0; e.sender = e.recipient; e.lat_back = 0.0;
+      } else {
+        e.uniq = s.uniq++;                                                            // Message() construction order (message/Message.py:33-34)
+        if (w0 & OF_BUMP_UNIQ) s.uniq++;                                              // TradingAgent.getCurrentSpread's never-sent msg_copy (:281)
+        bool from_exch = (w0 & OF_FROM_EXCH) != 0;
+        if (from_exch && P.c.trace_cap > 0) trace_note(e.recipient, e.kind, e.p);
+        int64_t sent = s.now + off;                                                   // Kernel.py:391-393
+        int64_t deliver;
+        if (P.c.latency_model == ABX_LAT_CUBIC) {                                     // model/LatencyModel.py:133-138
+          double u = rng.u01(S_LATENCY, s.ctr_latency);
+          double x = dadd(P.c.jitter_clip, dmul(dsub(1.0, P.c.jitter_clip), u));      // uniform(low=clip, high=1.0)
+          double latency = dadd(lat, dmul(P.c.jitter / pow(x, 3.0), lat / P.c.jitter_unit));
+          deliver = sent + (int64_t)latency;                                          // pd.Timedelta(float) truncates
+        } else {                                                                      // Kernel.py:410-412
+          int64_t noise = rng.randint(S_KERNEL, s.ctr_kernel, (uint32_t)(P.c.n_noise - 1));
+          deliver = sent + (int64_t)dadd(lat, (double)noise);
+        }
+        e.t = deliver < KEY_T_MAX ? deliver : KEY_T_MAX; e.type = ABX_T_MESSAGE;
+        e.sender = from_exch ? 0 : self_id; e.lat_back = from_exch ? 0.0 : a.lat_from;
+      }
+      if (!c.q_push(e)) s.flags |= ABX_F_QUEUE_OVERFLOW;                              // Kernel.py:425 / :462
+      else { s.q_count++; if (s.q_count > s.max_q) s.max_q = s.q_count; }
+    }
+    n_out = 0;
+    c.sync();
+  }
+
+  // ---- SparseMeanRevertingOracle ----
+  ABX_HD void oracle_new_megashock(int64_t from) {                                      // :67-73, :168-171
+    double gap = dmul(rng.std_exponential(S_GLOBAL, s.ctr_global), P.inv_megashock_lambda);
+    s.ms_t = from + (int64_t)gap;                                                       // Timedelta("{}ns".format(float)) truncates
+    double msv = rng.normal(S_SYMBOL, s.ctr_symbol, P.c.megashock_mean, P.sqrt_megashock_var);
+    s.ms_v = rng.randint(S_SYMBOL, s.ctr_symbol, 1) == 0 ? msv : -msv;
+  }
+  ABX_HD int32_t oracle_compute(int64_t ts, double v_adj, int64_t pt, int32_t pv) {     // :88-125
+    double d = (double)(ts - pt); double mu = P.c.r_bar;
+    double loc = dadd(mu, dmul(dsub((double)pv, mu), exp(dmul(-P.c.kappa, d))));
+    double scale = dmul(P.ou_scale, dsub(1.0, exp(dmul(dmul(-2.0, P.c.kappa), d))));    // variance formula passed as scale
+    double v = rng.normal(S_SYMBOL, s.ctr_symbol, loc, scale);
+    v = dadd(v, v_adj); if (!(v > 0)) v = 0;
+    int32_t iv = (int32_t)py_round_i64(v); s.or_t = ts; s.or_v = iv; return iv;
+  }
+  ABX_HD int32_t oracle_advance(int64_t t) {                                            // :131-181
+    int64_t pt = s.or_t; int32_t pv = s.or_v;
+    if (t <= pt) return pv;
+#pragma unroll 1
+    while (s.ms_t < t) { int32_t v = oracle_compute(s.ms_t, s.ms_v, pt, pv); pt = s.ms_t; pv = v; oracle_new_megashock(pt); }
+    return oracle_compute(t, 0.0, pt, pv);
+  }
+
+  // ---- order book (util/OrderBook.py).  Ladders are sorted so that the BEST level is the LAST element. ----
+  ABX_HD uint32_t node_alloc() {
+    uint32_t n;
+    if (s.free_head != NIL) { n = s.free_head; s.free_head = c.node_load(n).next; }
+    else if (s.pool_top < (uint32_t)P.c.order_cap) { n = s.pool_top++; }
+    else { s.flags |= ABX_F_ORDER_OVERFLOW; return NIL; }
+    return n;
+  }
+  ABX_HD void node_free(uint32_t n) { NodeRec r; r.id = 0; r.qty = 0; r.agent = 0; r.next = s.free_head; c.node_store(n, r); s.free_head = n; }
+
+  // enterOrder :256-282
+  ABX_HD void book_enter(int side, uint32_t oid, int agent, int32_t price, int32_t qty) {
+    int n = s.n_lv[side]; int pos; bool found;
+    c.lv_find(side, price, n, pos, found);
+    uint32_t node = node_alloc(); if (node == NIL) return;
+    NodeRec r; r.id = oid; r.qty = qty; r.agent = (uint32_t)agent; r.next = NIL; c.node_store(node, r);
+    if (found) {
+      uint32_t tail = c.lv_tail(side, pos);
+      NodeRec tr = c.node_load(tail); tr.next = node; c.node_store(tail, tr);
+      c.lv_set(side, pos, c.lv_qty(side, pos) + qty, c.lv_head(side, pos), node);
+    } else {
+      if (n >= P.c.level_cap) { s.flags |= ABX_F_LEVEL_OVERFLOW; node_free(node); return; }
+      c.lv_insert(side, pos, n, price, qty, node, node); s.n_lv[side] = n + 1;
+    }
+    s.n_resting++;
+  }
+  // handleLimitOrder :38-170 (+ executeOrder :172-240).  lat_in = latency[0][incoming agent]
+  ABX_HD void book_handle_limit(uint32_t oid, int agent, int is_buy, int32_t price, int32_t qty, double lat_in) {
+    if (qty <= 0) return;                                                               // :47-49
+    int opp = is_buy ? 1 : 0;                                                           // a buy matches asks (side 1)
+    int64_t trade_qty = 0, trade_px = 0;
+    bool matching = true;
+#pragma unroll 1
+    while (matching) {                                                                  // :68-110
+      int n = s.n_lv[opp]; bool matched = false;
+      if (n > 0) {
+        int32_t bp = c.lv_price(opp, n - 1);
+        if (is_buy ? price >= bp : price <= bp) {                                       // isMatch :242-254, head of best level only
+          uint32_t h = c.lv_head(opp, n - 1); NodeRec hr = c.node_load(h);
+          int32_t fq;
+          if (qty >= hr.qty) {                                                          // :204-210 whole resting order consumed
+            fq = hr.qty;
+            if (hr.next == NIL) s.n_lv[opp] = n - 1;                                    // level emptied: it is the last element
+            else c.lv_set(opp, n - 1, c.lv_qty(opp, n - 1) - fq, hr.next, c.lv_tail(opp, n - 1));
+            node_free(h); s.n_resting--;
+          } else {                                                                      // :212-217 partial
+            fq = qty; hr.qty -= fq; c.node_store(h, hr); c.lv_set(opp, n - 1, c.lv_qty(opp, n - 1) - fq, h, c.lv_tail(opp, n - 1));
+          }
+          qty -= fq;                                                                    // :77
+          exch_send_order(agent, ABX_ORDER_EXECUTED, oid, price, fq, bp, is_buy, lat_in);             // :88 (incoming copy)
+          exch_send_order((int)hr.agent, ABX_ORDER_EXECUTED, hr.id, bp, fq, bp, !is_buy, c.agent_lat_from((int)hr.agent)); // :89-91
+          trade_qty += fq; trade_px += (int64_t)bp * fq; s.c_fills++; matched = true;
+          if (qty <= 0) matching = false;
+          if (n_out >= OUT_CAP - 3) flush(); else c.sync();
+        }
+      }
+      if (!matched) {
+        book_enter(is_buy ? 0 : 1, oid, agent, price, qty);                             // :101
+        exch_send_order(agent, ABX_ORDER_ACCEPTED, oid, price, qty, 0, is_buy, lat_in); // :108
+        matching = false;
+      }
+    }
+    if (trade_qty > 0) s.last_trade = (int32_t)py_round_i64((double)trade_px / (double)trade_qty); // :131-143
+  }
+  // cancelOrder :284-339
+  ABX_HD void book_cancel(uint32_t oid, int agent, int is_buy, int32_t price, double lat_in) {
+    int side = is_buy ? 0 : 1; int n = s.n_lv[side]; if (n == 0) return;
+    int pos; bool found; c.lv_find(side, price, n, pos, found);
+    if (!found) return;
+    uint32_t prev = NIL, cur = c.lv_head(side, pos);
+#pragma unroll 1
+    while (cur != NIL) {
+      NodeRec r = c.node_load(cur);
+      if (r.id == oid) {
+        if (prev == NIL) {
+          if (r.next == NIL) { c.lv_remove(side, pos, n); s.n_lv[side] = n - 1; }
+          else c.lv_set(side, pos, c.lv_qty(side, pos) - r.qty, r.next, c.lv_tail(side, pos));
+        } else {
+          NodeRec pr = c.node_load(prev); pr.next = r.next; c.node_store(prev, pr);
+          c.lv_set(side, pos, c.lv_qty(side, pos) - r.qty, c.lv_head(side, pos), r.next == NIL ? prev : c.lv_tail(side, pos));
+        }
+        node_free(cur); s.n_resting--;
+        exch_send_order(agent, ABX_ORDER_CANCELLED, r.id, price, r.qty, 0, is_buy, lat_in);           // :334-336 to the REQUEST's agent
+        return;
+      }
+      prev = cur; cur = r.next;
+    }
+  }
+
+  // ---- ExchangeAgent.receiveMessage :129-340 ----
+  ABX_HD void exch_receive(const Event &m) {
+    s.exch_comp_delay = P.c.exchange_computation_delay_ns;                              // :139
+    bool t_closed = s.now > P.c.mkt_close_ns;
+    double lat = m.lat_back;                                                            // latency[0][sender]
+    int32_t p[6] = {0, 0, 0, 0, 0, 0};
+    if (t_closed) {                                                                     // :142-160
+      bool is_order = m.kind == ABX_LIMIT_ORDER || m.kind == ABX_CANCEL_ORDER || m.kind == ABX_MODIFY_ORDER;
+      bool is_query = m.kind == ABX_QUERY_SPREAD || m.kind == ABX_QUERY_LAST_TRADE || m.kind == ABX_QUERY_TRANSACTED_VOLUME || m.kind == ABX_QUERY_ORDER_STREAM;
+      if (is_order || !is_query) { exch_send(m.sender, ABX_MKT_CLOSED, p, lat); return; }
+    }
+    if (m.kind == ABX_WHEN_MKT_OPEN) { s.exch_comp_delay = 0; exch_send(m.sender, ABX_WHEN_MKT_OPEN, p, lat); }           // :175-183
+    else if (m.kind == ABX_WHEN_MKT_CLOSE) { s.exch_comp_delay = 0; exch_send(m.sender, ABX_WHEN_MKT_CLOSE, p, lat); }    // :184-192
+    else if (m.kind == ABX_QUERY_SPREAD) {                                              // :215-245 (depth 1)
+      s.c_query++; int f = 0;
+      int nb = s.n_lv[0], na = s.n_lv[1];
+      if (nb > 0) { p[0] = c.lv_price(0, nb - 1); p[1] = c.lv_qty(0, nb - 1); f |= 1; }
+      if (na > 0) { p[2] = c.lv_price(1, na - 1); p[3] = c.lv_qty(1, na - 1); f |= 2; }
+      if (t_closed) f |= 4;
+      p[4] = s.last_trade; p[5] = f; exch_send(m.sender, ABX_QUERY_SPREAD, p, lat);
+    } else if (m.kind == ABX_LIMIT_ORDER) {                                             // :304-312
+      s.c_limit++; book_handle_limit((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[2], lat); c.sync(); trace_snap();
+    } else if (m.kind == ABX_CANCEL_ORDER) {                                            // :313-325
+      s.c_cancel++; book_cancel((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], lat); c.sync(); trace_snap();
+    }
+  }
+
+  // ---- TradingAgent / ZeroIntelligenceAgent (the trader is in `a` / `z`) ----
+  ABX_HD void ta_get_spread() { int32_t p[6] = {0, 0, 0, 0, 0, 0}; ta_send(ABX_QUERY_SPREAD, p, true); }   // TradingAgent.getCurrentSpread :277-282
+  // ZeroIntelligenceAgent.wakeup :125-187 (+ TradingAgent.wakeup :142-158)
+  ABX_HD void zi_wakeup(int id) {
+    if (!(a.flags & AF_HAS_OPEN)) {                                                     // TradingAgent.py:149-153
+      int32_t p[6] = {0, 0, 0, 0, 0, 0};
+      ta_send(ABX_WHEN_MKT_OPEN, p, false); ta_send(ABX_WHEN_MKT_CLOSE, p, false);
+    }
+    uint32_t st = ST_INACTIVE;
+    if ((a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE) && !((a.flags & AF_MKT_CLOSED) && (a.flags & AF_HAS_DAILY))) {   // :130-147
+      double delta_time = dmul(rng.std_exponential(S_AGENT0 + id, a.rng_ctr), P.inv_lambda_a);       // :157
+      set_wakeup(id, s.now + py_round_i64(delta_time));                                              // :158
+      if (!((a.flags & AF_MKT_CLOSED) && !(a.flags & AF_HAS_DAILY))) {                  // :162-166 skip cancels when waiting for the close price
+#pragma unroll 1
+        for (int i = 0; i < a.n_orders; i++) {                                          // cancelOrders :336-344
+          int32_t q = z->oqty[i];
+          int32_t p[6] = {(int32_t)z->oid[i], z->oprice[i], q < 0 ? -q : q, 0, q > 0, 0};
+          ta_send(ABX_CANCEL_ORDER, p, false);
+        }
+      }
+      ta_get_spread(); st = ST_AWAITING_SPREAD;                                         // :164 / :183-185
+    }
+    a.flags = (a.flags & ~AF_STATE_MASK) | (st << AF_STATE_SHIFT);
+  }
+  // ZeroIntelligenceAgent.placeOrder :277-309 (+ updateEstimates :189-275, TradingAgent.placeLimitOrder :309-349)
+  ABX_HD void zi_place_order(int id) {
+    int stream = S_AGENT0 + id;
+    int32_t r_now = (s.now >= P.c.mkt_close_ns) ? oracle_advance(P.c.mkt_close_ns - 1) : oracle_advance(s.now);   // observePrice :210-227
+    int32_t obs_t = (int32_t)py_round_i64(rng.normal(stream, a.rng_ctr, (double)r_now, P.sqrt_sigma_n));
+    int q = (int)((double)a.shares / 100.0);                                            // :203 int(x / 100)
+    int q_max = P.c.q_max; bool buy;
+    if (q >= q_max) buy = false; else if (q <= -q_max) buy = true; else buy = rng.randint(stream, a.rng_ctr, 1) != 0; // :205-213
+    if (!(a.flags & AF_HAS_PREV)) { a.prev_wake = P.c.mkt_open_ns; a.flags |= AF_HAS_PREV; }         // :217-218
+    double base = P.one_minus_kappa_a, r_bar = P.c.r_bar, sigma_n = P.c.sigma_n;
+    double delta = (double)(s.now - a.prev_wake);                                       // :221
+    double d2 = (double)(P.c.mkt_close_ns - s.now); if (!(d2 > 0)) d2 = 0;              // :251
+    double pw0 = 0, pw1 = 0, pw2 = 0;                                                   // (1 - kappa) ** {delta, 2*delta, d2}: one pow() site
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) { double ex = k == 0 ? delta : (k == 1 ? dmul(2.0, delta) : d2); double r = pow(base, ex); if (k == 0) pw0 = r; else if (k == 1) pw1 = r; else pw2 = r; }
+    double r_tprime = dmul(dsub(1.0, pw0), r_bar);                                    // :229
+    r_tprime = dadd(r_tprime, dmul(pw0, a.r_t));                                      // :230
+    double sigma_tprime = dmul(pw1, a.sigma_t);                                       // :233
+    sigma_tprime = dadd(sigma_tprime, dmul(dsub(1.0, pw1) / P.sigma_denom, P.c.sigma_s)); // :234
+    double den = dadd(sigma_n, sigma_tprime);
+    double r_t = dmul(sigma_n / den, r_tprime);                                         // :239
+    r_t = dadd(r_t, dmul(sigma_tprime / den, (double)obs_t));                           // :240
+    a.r_t = r_t;
+    a.sigma_t = dmul(sigma_n, a.sigma_t) / dadd(sigma_n, a.sigma_t);                    // :242
+    double r_T = dmul(dsub(1.0, pw2), r_bar);                                         // :255
+    r_T = dadd(r_T, dmul(pw2, a.r_t));                                                // :256
+    int32_t r_Ti = (int32_t)py_round_i64(r_T);                                          // :259
+    a.prev_wake = s.now;                                                                // :262
+    q += q_max - 1;                                                                     // :267
+    int idx = buy ? q + 1 : q, n = 2 * q_max;                                           // :268 (Python list indexing)
+    if (idx < 0) idx += n;
+    if (idx < 0 || idx >= n) { s.flags |= ABX_F_THETA_INDEX; idx = idx < 0 ? 0 : n - 1; }
+    int32_t v = r_Ti + (int32_t)z->theta[idx];                                          // :270
+    // placeOrder
+    int grp = (a.flags & AF_GROUP_MASK) >> AF_GROUP_SHIFT;
+    int32_t r_min = P.c.groups[grp].r_min, r_max = P.c.groups[grp].r_max; double eta = P.c.groups[grp].eta;
+    int32_t R = r_min + (int32_t)rng.randint(stream, a.rng_ctr, (uint32_t)(r_max - r_min));          // :284
+    int32_t p = buy ? v - R : v + R;                                                    // :287
+    int32_t ask_vol = (a.flags & AF_HAS_ASK) ? a.ask_q : 0, bid_vol = (a.flags & AF_HAS_BID) ? a.bid_q : 0;
+    if (buy && ask_vol > 0) { int32_t R_ask = v - a.ask; if ((double)R_ask >= dmul(eta, (double)R)) p = a.ask; }             // :291-297
+    else if (!buy && bid_vol > 0) { int32_t R_bid = a.bid - v; if ((double)R_bid >= dmul(eta, (double)R)) p = a.bid; }       // :298-305
+    // TradingAgent.placeLimitOrder :309-349
+    uint32_t oid = s.next_order_id++;                                                   // util/order/Order.py:27,35-42
+    int32_t size = P.c.order_size;
+    if (size > 0) {
+      if (a.n_orders < AGENT_ORDER_CAP) {
+        if (c.leader()) { int k = a.n_orders; z->oid[k] = oid; z->oprice[k] = p; z->oqty[k] = buy ? size : -size; }
+        a.n_orders++;
+      } else s.flags |= ABX_F_AGENT_ORDERS_OVERFLOW;
+      int32_t pl[6] = {(int32_t)oid, p, size, 0, buy, 0};
+      ta_send(ABX_LIMIT_ORDER, pl, false);                                              // :343
+    }
+  }
+  // index of order_id in self.orders, or -1
+  ABX_HD int orders_find(uint32_t oid) { int f = -1; for (int i = 0; i < AGENT_ORDER_CAP; i++) if (i < a.n_orders && f < 0 && z->oid[i] == oid) f = i; return f; }
+  ABX_HD void orders_remove(int i) {
+    c.sync();
+    if (c.leader()) for (int k = i; k + 1 < AGENT_ORDER_CAP; k++) { z->oid[k] = z->oid[k + 1]; z->oprice[k] = z->oprice[k + 1]; z->oqty[k] = z->oqty[k + 1]; }
+    a.n_orders--;
+    c.sync();
+  }
+  // TradingAgent.receiveMessage :181-268 + ZeroIntelligenceAgent.receiveMessage :311-334
+  ABX_HD void zi_receive(int id, const Event &m) {
+    bool had = (a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE);
+    if (m.kind == ABX_WHEN_MKT_OPEN) a.flags |= AF_HAS_OPEN;
+    else if (m.kind == ABX_WHEN_MKT_CLOSE) a.flags |= AF_HAS_CLOSE;
+    else if (m.kind == ABX_ORDER_EXECUTED) {                                            // orderExecuted :422-462
+      int32_t q = m.p[2]; int32_t sq = m.p[4] ? q : -q;
+      a.shares += sq; a.cash -= (int64_t)sq * m.p[3];
+      int i = orders_find((uint32_t)m.p[0]);
+      if (i >= 0) {
+        int32_t oq0 = z->oqty[i]; int32_t oq = oq0 < 0 ? -oq0 : oq0;
+        if (q >= oq) orders_remove(i);
+        else { c.sync(); if (c.leader()) z->oqty[i] = oq0 < 0 ? -(oq - q) : (oq - q); c.sync(); }
+      }
+    } else if (m.kind == ABX_ORDER_CANCELLED) {                                         // orderCancelled :476-489
+      int i = orders_find((uint32_t)m.p[0]); if (i >= 0) orders_remove(i);
+    } else if (m.kind == ABX_MKT_CLOSED) a.flags |= AF_MKT_CLOSED;                      // marketClosed :492-499
+    else if (m.kind == ABX_QUERY_SPREAD) {                                              // :232-238, querySpread :514-537
+      if (m.p[5] & 4) a.flags |= AF_MKT_CLOSED;
+      a.last_trade = m.p[4]; a.flags |= AF_HAS_LAST;
+      if (a.flags & AF_MKT_CLOSED) { a.daily_close = a.last_trade; a.flags |= AF_HAS_DAILY; }
+      a.flags &= ~(AF_HAS_BID | AF_HAS_ASK);
+      if (m.p[5] & 1) { a.flags |= AF_HAS_BID; a.bid = m.p[0]; a.bid_q = m.p[1]; } else { a.bid = 0; a.bid_q = 0; }
+      if (m.p[5] & 2) { a.flags |= AF_HAS_ASK; a.ask = m.p[2]; a.ask_q = m.p[3]; } else { a.ask = 0; a.ask_q = 0; }
+    }
+    if ((a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE) && !had) {                  // :258-268
+      int64_t off = rng.randint(S_AGENT0 + id, a.rng_ctr, 99);                          // ZI.getWakeFrequency :349-350
+      set_wakeup(id, P.c.mkt_open_ns + off);
+    }
+    uint32_t st = (a.flags & AF_STATE_MASK) >> AF_STATE_SHIFT;
+    if (st == ST_AWAITING_SPREAD && m.kind == ABX_QUERY_SPREAD && !(a.flags & AF_MKT_CLOSED)) {      // ZI :319-334
+      zi_place_order(id);
+      a.flags = (a.flags & ~AF_STATE_MASK) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT);
+    }
+  }
+
+  // ---- reset of one environment: oracle __init__ (first megashock) and Kernel.runner :154-175 (one WAKEUP per agent) ----
+  ABX_HD void reset_env() {
+    oracle_new_megashock(P.c.mkt_open_ns);                                              // SparseMeanRevertingOracle.py:67-73
+#pragma unroll 1
+    for (int id = 0; id < P.c.n_agents; id++) {                                         // Agent.kernelStarting :78
+      set_wakeup(id, P.c.start_ns);
+      if (n_out >= OUT_CAP - 1) flush();
+    }
+    flush();
+    s.flags |= rng.err;
+  }
+
+  // ---- Kernel.runner hot loop :190-292 ----
+  ABX_HD void run(int64_t until) {
+#pragma unroll 1
+    while (!(s.flags & ABX_F_DONE)) {
+      uint64_t khi; uint32_t kuniq; int grp;
+      bool any = c.q_min(khi, kuniq, grp);
+      if (!any || !(s.now <= P.c.stop_ns)) { s.flags |= ABX_F_DONE; break; }            // :190 tested BEFORE the pop
+      if (key_time(khi) > until) break;
+      Event ev; c.q_fetch(grp, ev);                                                     // :192
+      s.now = ev.t; s.ttl++;                                                            // :211
+      if (P.c.hash_pops) s.pop_hash = fnv_mix(fnv_mix(fnv_mix(fnv_mix(s.pop_hash, ev.t), ev.recipient), ev.type), ev.type == ABX_T_MESSAGE ? (int64_t)ev.uniq : -1);
+      if (P.c.trace_cap > 0) {
+        abx_trace_rec r; r.tag = 0; r.a = ev.recipient; r.t = ev.t; for (int i = 0; i < 16; i++) r.v[i] = 0;
+        r.v[0] = ev.type; r.v[1] = ev.type == ABX_T_MESSAGE ? (int32_t)ev.uniq : -1; r.v[2] = ev.kind; trace_rec(r);
+      }
+      addl_delay = 0;                                                                   // :214
+      int id = ev.recipient;
+      if (id == 0) {
+        if (s.exch_time > s.now) { c.q_requeue(s.exch_time); continue; }                // :224-230 / :258-264 (same uniq)
+        c.q_remove(); s.q_count--;
+        s.exch_time = s.now;                                                            // :234 / :268
+        self_id = 0;
+        if (ev.type == ABX_T_MESSAGE) exch_receive(ev);                                 // exchange WAKEUP: Agent.wakeup is a no-op
+        s.exch_time += s.exch_comp_delay + addl_delay;                                  // :240-242 / :274-276
+      } else {
+        z = c.agent_stage(id); regs_load(a, z);
+        if (a.agent_time > s.now) { c.q_requeue(a.agent_time); continue; }
+        c.q_remove(); s.q_count--;
+        a.agent_time = s.now; self_id = id;
+        if (ev.type == ABX_T_WAKEUP) zi_wakeup(id); else zi_receive(id, ev);
+        a.agent_time += P.c.default_computation_delay_ns + addl_delay;
+        c.sync();
+        if (c.leader()) regs_store(z, a);
+        c.sync();
+        c.agent_commit(id);
+      }
+      flush();                                                                          // deliver what this event sent
+    }
+    s.flags |= rng.err;
+  }
+
+  // ---- Kernel.runner :310-311 kernelStopping for every trader, in id order (ZeroIntelligenceAgent.py:80-123) ----
+  ABX_HD void finalize() {
+    int64_t sum_sh = 0, sum_cash = 0; int q_max = P.c.q_max;
+#pragma unroll 1
+    for (int id = 1; id < P.c.n_agents; id++) {
+      z = c.agent_stage(id); regs_load(a, z);
+      double hr = dmul(rint((double)a.shares / 100.0), 100.0);                          // round(int, -2): half-even on hundreds
+      int H = (int)(hr / 100.0);
+      int64_t cur = a.agent_time - P.c.default_computation_delay_ns;                    // Agent.currentTime of the trader's last event
+      int32_t rT = (cur >= P.c.mkt_close_ns) ? oracle_advance(P.c.mkt_close_ns - 1) : oracle_advance(cur);   // observePrice(sigma_n=0)
+      int64_t surplus = 0;
+      if (H > 0) { for (int x = 1; x <= H; x++) { int k = x + q_max - 1; if (k < 2 * q_max) surplus += z->theta[k]; } }
+      else if (H < 0) { for (int x = H + 1; x <= 0; x++) { int k = x + q_max - 1; if (k >= 0) surplus += z->theta[k]; } surplus = -surplus; }
+      surplus += (int64_t)rT * H; surplus += a.cash - P.c.starting_cash;
+      sum_sh += a.shares; sum_cash += a.cash;
+      c.sync();
+      if (c.leader()) z->surplus = surplus;
+      c.sync();
+      c.agent_commit(id);
+    }
+    s.sum_shares = sum_sh; s.sum_cash = sum_cash;
+    s.flags |= rng.err;
+  }
+};
+
+}  // namespace abx

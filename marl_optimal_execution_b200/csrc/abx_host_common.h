@@ -1,0 +1,90 @@
+// abx_host_common.h -- host-side helpers shared by the CUDA C-ABI (abx_capi.cu) and the host emulation harness
+// (tests/emu): config presets mirroring config/sparse_zi_100.py / config/sparse_zi_1000.py, validation, and the
+// derived constants that the reference computes with libm on the host side of every call.
+#pragma once
+#include <math.h>
+#include <string.h>
+#include "abx_core.cuh"
+
+namespace abx {
+
+static const int64_t NS = 1000000000LL;
+
+// config/sparse_zi_1000.py:196-204 and config/sparse_zi_100.py:204-212: (n, R_min, R_max, eta)
+static inline int config_sparse_zi(int variant, abx_sim_config *c) {
+  if (!c || (variant != 100 && variant != 1000)) return ABX_ERR_ARG;
+  memset(c, 0, sizeof(*c));
+  static const int n1000[7] = {143, 143, 143, 143, 143, 143, 142}, n100[7] = {15, 15, 14, 14, 14, 14, 14};
+  static const int rmin[7] = {0, 0, 0, 0, 0, 250, 250}, rmax[7] = {250, 500, 1000, 1000, 2000, 500, 500};
+  static const double eta[7] = {1, 1, 0.8, 1, 0.8, 0.8, 1};
+  c->version = ABX_VERSION; c->n_groups = 7; c->q_max = 10; c->n_agents = 1;
+  for (int g = 0; g < 7; g++) {
+    c->groups[g].count = variant == 1000 ? n1000[g] : n100[g]; c->groups[g].r_min = rmin[g]; c->groups[g].r_max = rmax[g]; c->groups[g].eta = eta[g];
+    c->n_agents += c->groups[g].count;
+  }
+  c->start_ns = 0; c->stop_ns = 17 * 3600 * NS;                               // :86-88 midnight .. 17:00
+  c->mkt_open_ns = (9 * 3600 + 30 * 60) * NS; c->mkt_close_ns = 16 * 3600 * NS; // :163-164
+  c->default_computation_delay_ns = NS;                                        // :90 one second
+  c->exchange_computation_delay_ns = 0; c->exchange_pipeline_delay_ns = 0;    // :186-187
+  c->starting_cash = 10000000; c->order_size = 100; c->stream_history = 10;
+  c->r_bar = 1e5; c->kappa = 1.67e-12; c->fund_vol = 1e-4;                    // :130-142
+  c->megashock_lambda_a = 2.77778e-13; c->megashock_mean = 1e3; c->megashock_var = 5e4;
+  c->sigma_n = 1000000.0; c->agent_kappa = 1.67e-15; c->sigma_s = 1e-4; c->sigma_pv = 5e6; c->lambda_a = 1e-12; // :232-250
+  if (variant == 1000) {                                                      // :264-286 old latency model
+    c->latency_model = ABX_LAT_MATRIX_NOISE; c->n_noise = 6; c->latency_mirrored = 1; c->latency_lo = 21000; c->latency_hi = 13000000;
+    c->queue_cap = 2560; c->level_cap = 512; c->order_cap = 2048;
+  } else {                                                                    // sparse_zi_100.py:305-318 cubic model
+    c->latency_model = ABX_LAT_CUBIC; c->n_noise = 1; c->latency_mirrored = 0; c->latency_lo = 21000; c->latency_hi = 100000;
+    c->jitter = 0.3; c->jitter_clip = 0.05; c->jitter_unit = 5.0;
+    c->queue_cap = 384; c->level_cap = 128; c->order_cap = 512;
+  }
+  c->rng_mode = ABX_RNG_PHILOX; c->trace_cap = 0; c->hash_pops = 0;
+  return ABX_OK;
+}
+
+static inline int config_validate(const abx_sim_config *c) {
+  if (!c || c->version != ABX_VERSION) return ABX_ERR_ARG;
+  if (c->n_agents < 2 || c->n_agents > 32767 || c->n_groups < 1 || c->n_groups > 8 || c->q_max < 1 || c->q_max > 10) return ABX_ERR_ARG;
+  int n = 1; for (int g = 0; g < c->n_groups; g++) { if (c->groups[g].count < 0 || c->groups[g].r_max < c->groups[g].r_min) return ABX_ERR_ARG; n += c->groups[g].count; }
+  if (n != c->n_agents) return ABX_ERR_ARG;
+  if (c->queue_cap < 32 || c->queue_cap % 32 || c->queue_cap > 4096) return ABX_ERR_ARG;
+  if (c->level_cap < 8 || c->level_cap > 2048 || c->order_cap < 8 || c->order_cap > 65535) return ABX_ERR_ARG;
+  if (c->stop_ns >= KEY_T_MAX || c->start_ns < 0 || c->mkt_close_ns >= KEY_T_MAX) return ABX_ERR_ARG;
+  if (c->latency_model != ABX_LAT_MATRIX_NOISE && c->latency_model != ABX_LAT_CUBIC) return ABX_ERR_ARG;
+  if (c->latency_model == ABX_LAT_MATRIX_NOISE && c->n_noise < 1) return ABX_ERR_ARG;
+  if (c->rng_mode != ABX_RNG_PHILOX && c->rng_mode != ABX_RNG_TAPE) return ABX_ERR_ARG;
+  if (c->trace_cap < 0 || !(c->kappa > 0) || !(c->lambda_a > 0) || !(c->megashock_lambda_a > 0)) return ABX_ERR_ARG;
+  return ABX_OK;
+}
+
+// Constants the reference evaluates with CPython/libm on every call; evaluated once here with the same libm.
+static inline void derive_params(SimParams &P) {
+  const abx_sim_config &c = P.c;
+  P.n_qgroups = c.queue_cap / 32; P.n_streams = c.n_agents + 3;
+  P.one_minus_kappa_a = 1 - c.agent_kappa;
+  P.sigma_denom = 1 - pow(1 - c.agent_kappa, 2.0);                 // ZeroIntelligenceAgent.py:234
+  P.sqrt_sigma_n = sqrt(c.sigma_n); P.sqrt_sigma_pv = sqrt(c.sigma_pv); P.sqrt_megashock_var = sqrt(c.megashock_var);
+  P.inv_lambda_a = 1.0 / c.lambda_a; P.inv_megashock_lambda = 1.0 / c.megashock_lambda_a;
+  P.ou_scale = pow(c.fund_vol, 2.0) / (2 * c.kappa);               // SparseMeanRevertingOracle.py:106
+}
+
+static inline const char *status_string(int32_t st) {
+  switch (st) {
+    case ABX_OK: return "ok";
+    case ABX_ERR_ARG: return "invalid argument or configuration";
+    case ABX_ERR_CUDA: return "CUDA runtime error";
+    case ABX_ERR_STATE: return "call sequence error";
+    case ABX_ERR_CAPACITY: return "fixed-capacity structure overflowed";
+    default: return "unknown status";
+  }
+}
+
+// stats record from an EnvState plus the top of the two ladders
+ABX_HD void fill_stats(const EnvState &s, int32_t bb, int32_t bbq, int32_t ba, int32_t baq, abx_env_stats *o) {
+  o->messages = s.ttl; o->now_ns = s.now; o->pop_hash = s.pop_hash; o->limit_orders = s.c_limit; o->cancels = s.c_cancel; o->fills = s.c_fills;
+  o->spread_queries = s.c_query; o->max_queue = s.max_q; o->n_bid_levels = s.n_lv[0]; o->n_ask_levels = s.n_lv[1]; o->n_resting = s.n_resting;
+  o->best_bid = bb; o->best_bid_qty = bbq; o->best_ask = ba; o->best_ask_qty = baq; o->last_trade = s.last_trade; o->fundamental = s.or_v;
+  o->flags = s.flags; o->trace_len = s.trace_n; o->uniq = s.uniq; o->orders_allocated = s.next_order_id; o->sum_shares = s.sum_shares; o->sum_cash = s.sum_cash;
+}
+
+}  // namespace abx

@@ -1,0 +1,266 @@
+// abx_sim.cu -- kernels and C ABI of the batched ABIDES simulator (sm_100a).  See include/abides_b200.h.
+//
+// Launch geometry: one warp per environment, ABX_WARPS_PER_CTA warps per CTA, each warp owning a private slice of
+// dynamic shared memory (abx_warp.cuh).  A warp runs its environment's whole event loop (Kernel.py:190-292) up to
+// the requested simulated time in one launch; environments never communicate.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <new>
+#include "abx_warp.cuh"
+#include "abx_host_common.h"
+
+using namespace abx;
+
+#ifndef ABX_WARPS_PER_CTA
+#define ABX_WARPS_PER_CTA 1
+#endif
+
+// ---------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------
+__global__ void abx_init_agents_kernel(SimParams P, const uint64_t *__restrict__ seeds, uint32_t *__restrict__ init_err) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)P.n_envs * P.c.n_agents;
+  if (t >= total) return;
+  int env = (int)(t / P.c.n_agents), id = (int)(t % P.c.n_agents);
+  if (id == 0) return;
+  uint32_t err = 0;
+  init_agent_record(P, env, id, seeds ? seeds[env] : 0, P.agents + t, &err);
+  if (err) atomicOr(init_err + env, err);
+}
+
+__device__ __forceinline__ EnvState env_load(const EnvState *g) {
+  EnvState s; const uint4 *src = reinterpret_cast<const uint4 *>(g); uint4 *dst = reinterpret_cast<uint4 *>(&s);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(EnvState) / 16); i++) dst[i] = __ldcg(src + i);
+  return s;
+}
+__device__ __forceinline__ void env_store(EnvState *g, const EnvState &s, int lane) {
+  if (lane == 0) { const uint4 *src = reinterpret_cast<const uint4 *>(&s); uint4 *dst = reinterpret_cast<uint4 *>(g);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(EnvState) / 16); i++) __stcg(dst + i, src[i]); }
+}
+
+__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
+abx_reset_env_kernel(SimParams P, const uint64_t *__restrict__ seeds, const uint32_t *__restrict__ init_err, size_t smem_per_warp) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
+  if (env >= P.n_envs) return;
+  WarpCtx ctx(P, env, smem + warp * smem_per_warp);
+  EnvState s; init_env_state(P, seeds ? seeds[env] : 0, s); s.flags |= init_err[env];
+  ctx.q_clear();
+  Sim<WarpCtx> sim(ctx, P, s, env);
+  sim.reset_env();
+  ctx.store_onchip(sim.s);
+  env_store(P.env + env, sim.s, ctx.lane);
+}
+
+__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
+abx_run_kernel(SimParams P, int64_t until_ns, size_t smem_per_warp) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
+  if (env >= P.n_envs) return;
+  WarpCtx ctx(P, env, smem + warp * smem_per_warp);
+  EnvState s = env_load(P.env + env);
+  if (s.flags & ABX_F_DONE) return;
+  ctx.load_onchip(s);
+  Sim<WarpCtx> sim(ctx, P, s, env);
+  sim.run(until_ns);
+  ctx.store_onchip(sim.s);
+  env_store(P.env + env, sim.s, ctx.lane);
+}
+
+__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
+abx_finalize_kernel(SimParams P, size_t smem_per_warp) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
+  if (env >= P.n_envs) return;
+  WarpCtx ctx(P, env, smem + warp * smem_per_warp);
+  EnvState s = env_load(P.env + env);
+  Sim<WarpCtx> sim(ctx, P, s, env);
+  sim.finalize();
+  env_store(P.env + env, sim.s, ctx.lane);
+}
+
+__global__ void abx_stats_kernel(SimParams P, abx_env_stats *__restrict__ out) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= P.n_envs) return;
+  const EnvState &s = P.env[env];
+  size_t l = (size_t)env * 2 * P.c.level_cap; int nb = s.n_lv[0], na = s.n_lv[1];
+  abx_env_stats o;
+  fill_stats(s, nb ? P.lv_price[l + nb - 1] : 0, nb ? P.lv_qty[l + nb - 1] : 0,
+             na ? P.lv_price[l + P.c.level_cap + na - 1] : 0, na ? P.lv_qty[l + P.c.level_cap + na - 1] : 0, &o);
+  out[env] = o;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_cuda_err[512] = "";
+#define CU(call)                                                                                         \
+  do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_cuda_err, sizeof(g_cuda_err), "%s at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); return ABX_ERR_CUDA; } } while (0)
+
+struct abx_sim {
+  SimParams P; int n_envs, device; bool reset_done; size_t smem_per_warp; int64_t bytes, launches;
+  uint64_t *d_seeds; uint32_t *d_init_err; abx_env_stats *d_stats;
+  uint64_t *d_tbits; uint8_t *d_tkinds; int64_t *d_toff;
+};
+
+template <class T> static int dalloc(T **p, size_t n, int64_t *acc) {
+  size_t b = n * sizeof(T); if (b == 0) { *p = nullptr; return ABX_OK; }
+  CU(cudaMalloc((void **)p, b)); *acc += (int64_t)b; return ABX_OK;
+}
+static inline unsigned grid_for(int n_envs) { return (unsigned)((n_envs + ABX_WARPS_PER_CTA - 1) / ABX_WARPS_PER_CTA); }
+
+extern "C" {
+
+const char *abx_strerror(int32_t st) { return status_string(st); }
+const char *abx_last_cuda_error(void) { return g_cuda_err; }
+int32_t abx_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+int32_t abx_config_sparse_zi(int32_t variant, abx_sim_config *cfg) { return config_sparse_zi(variant, cfg); }
+
+int32_t abx_sim_destroy(abx_sim *h) {
+  if (!h) return ABX_OK;
+  cudaSetDevice(h->device);
+  void *ptrs[] = {h->P.qkey, h->P.qpay0, h->P.qpay1, h->P.qcache, h->P.agents, h->P.lv_price, h->P.lv_qty, h->P.lv_ht, h->P.nodes, h->P.env,
+                  h->P.trace, h->d_seeds, h->d_init_err, h->d_stats, h->d_tbits, h->d_tkinds, h->d_toff};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  delete h; return ABX_OK;
+}
+
+int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device, abx_sim **out) {
+  if (!out || n_envs < 1 || config_validate(cfg) != ABX_OK) return ABX_ERR_ARG;
+  int ndev = 0; CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d not present (%d visible)", device, ndev); return ABX_ERR_CUDA; }
+  CU(cudaSetDevice(device));
+  abx_sim *h = new (std::nothrow) abx_sim(); if (!h) return ABX_ERR_ARG;
+  memset(h, 0, sizeof(*h)); h->P.c = *cfg; h->P.n_envs = n_envs; h->n_envs = n_envs; h->device = device; derive_params(h->P);
+  h->smem_per_warp = (warp_smem_bytes(*cfg) + 15) & ~(size_t)15;
+  size_t smem_cta = h->smem_per_warp * ABX_WARPS_PER_CTA;
+  if (smem_cta > 227 * 1024) { delete h; return ABX_ERR_ARG; }
+  const abx_sim_config &c = *cfg; size_t E = (size_t)n_envs; int st;
+#define DA(ptr, n) if ((st = dalloc(&(ptr), (n), &h->bytes)) != ABX_OK) { abx_sim_destroy(h); return st; }
+  DA(h->P.qkey, E * c.queue_cap) DA(h->P.qpay0, E * c.queue_cap) DA(h->P.qpay1, E * c.queue_cap) DA(h->P.qcache, E * h->P.n_qgroups)
+  DA(h->P.agents, E * c.n_agents) DA(h->P.lv_price, E * 2 * c.level_cap) DA(h->P.lv_qty, E * 2 * c.level_cap) DA(h->P.lv_ht, E * 2 * c.level_cap)
+  DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap)
+  DA(h->d_seeds, E) DA(h->d_init_err, E) DA(h->d_stats, E)
+#undef DA
+  if (smem_cta > 48 * 1024) {
+    CU(cudaFuncSetAttribute(abx_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CU(cudaFuncSetAttribute(abx_reset_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CU(cudaFuncSetAttribute(abx_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+  }
+  CU(cudaMemset(h->P.agents, 0, E * c.n_agents * sizeof(ZiAgent)));
+  *out = h; return ABX_OK;
+}
+int64_t abx_sim_device_bytes(const abx_sim *h) { return h ? h->bytes : 0; }
+int64_t abx_sim_launch_count(const abx_sim *h) { return h ? h->launches : 0; }
+
+static int32_t do_reset(abx_sim *h, bool have_seeds, cudaStream_t st) {
+  const abx_sim_config &c = h->P.c;
+  CU(cudaMemsetAsync(h->d_init_err, 0, sizeof(uint32_t) * h->n_envs, st));
+  int64_t total = (int64_t)h->n_envs * c.n_agents;
+  abx_init_agents_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(h->P, have_seeds ? h->d_seeds : nullptr, h->d_init_err);
+  abx_reset_env_kernel<<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, st>>>(h->P, have_seeds ? h->d_seeds : nullptr, h->d_init_err, h->smem_per_warp);
+  h->launches += 2;
+  CU(cudaGetLastError());
+  h->reset_done = true; return ABX_OK;
+}
+
+int32_t abx_sim_reset_philox(abx_sim *h, const uint64_t *seeds, void *stream) {
+  if (!h || !seeds || h->P.c.rng_mode != ABX_RNG_PHILOX) return ABX_ERR_ARG;
+  CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaMemcpyAsync(h->d_seeds, seeds, sizeof(uint64_t) * h->n_envs, cudaMemcpyHostToDevice, st));
+  return do_reset(h, true, st);
+}
+
+int32_t abx_sim_reset_tape(abx_sim *h, const uint64_t *bits, const uint8_t *kinds, const int64_t *off, const double *lat_to,
+                           const double *lat_from, void *stream) {
+  if (!h || !bits || !kinds || !off || !lat_to || !lat_from || h->P.c.rng_mode != ABX_RNG_TAPE) return ABX_ERR_ARG;
+  CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
+  size_t nS = (size_t)h->n_envs * h->P.n_streams; int64_t total = off[nS]; if (total < 0) return ABX_ERR_ARG;
+  if (h->d_tbits) { cudaFree(h->d_tbits); h->d_tbits = nullptr; } if (h->d_tkinds) { cudaFree(h->d_tkinds); h->d_tkinds = nullptr; } if (h->d_toff) { cudaFree(h->d_toff); h->d_toff = nullptr; }
+  int64_t dummy = 0;
+  if (dalloc(&h->d_tbits, (size_t)total + 1, &dummy) || dalloc(&h->d_tkinds, (size_t)total + 1, &dummy) || dalloc(&h->d_toff, nS + 1, &dummy)) return ABX_ERR_CUDA;
+  CU(cudaMemcpyAsync(h->d_tbits, bits, sizeof(uint64_t) * total, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->d_tkinds, kinds, (size_t)total, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->d_toff, off, sizeof(int64_t) * (nS + 1), cudaMemcpyHostToDevice, st));
+  h->P.tape_bits = h->d_tbits; h->P.tape_kinds = h->d_tkinds; h->P.tape_off = h->d_toff;
+  // latency[a][0] / latency[0][a] into the trader records (strided 8-byte columns of the 192-byte records)
+  size_t n = (size_t)h->n_envs * h->P.c.n_agents;
+  CU(cudaMemcpy2DAsync((char *)h->P.agents + offsetof(ZiAgent, lat_to), sizeof(ZiAgent), lat_to, sizeof(double), sizeof(double), n, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpy2DAsync((char *)h->P.agents + offsetof(ZiAgent, lat_from), sizeof(ZiAgent), lat_from, sizeof(double), sizeof(double), n, cudaMemcpyHostToDevice, st));
+  return do_reset(h, false, st);
+}
+
+int32_t abx_sim_run(abx_sim *h, int64_t until_ns, void *stream) {
+  if (!h) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  CU(cudaSetDevice(h->device));
+  abx_run_kernel<<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, (cudaStream_t)stream>>>(h->P, until_ns, h->smem_per_warp);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return ABX_OK;
+}
+
+int32_t abx_sim_finalize(abx_sim *h, void *stream) {
+  if (!h) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  CU(cudaSetDevice(h->device));
+  abx_finalize_kernel<<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, (cudaStream_t)stream>>>(h->P, h->smem_per_warp);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return ABX_OK;
+}
+
+int32_t abx_sim_stats_device(abx_sim *h, abx_env_stats *out_dev, void *stream) {
+  if (!h || !out_dev) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  CU(cudaSetDevice(h->device));
+  abx_stats_kernel<<<(h->n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->P, out_dev);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return ABX_OK;
+}
+int32_t abx_sim_stats(abx_sim *h, abx_env_stats *out, void *stream) {
+  if (!h || !out) return ABX_ERR_ARG;
+  int32_t st = abx_sim_stats_device(h, h->d_stats, stream); if (st != ABX_OK) return st;
+  CU(cudaMemcpyAsync(out, h->d_stats, sizeof(abx_env_stats) * h->n_envs, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return ABX_OK;
+}
+
+int32_t abx_sim_holdings(abx_sim *h, int32_t env, int64_t *out, void *stream) {
+  if (!h || !out || env < 0 || env >= h->n_envs) return ABX_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  int n = h->P.c.n_agents; ZiAgent *tmp = (ZiAgent *)malloc(sizeof(ZiAgent) * n); if (!tmp) return ABX_ERR_ARG;
+  cudaError_t e = cudaMemcpyAsync(tmp, h->P.agents + (size_t)env * n, sizeof(ZiAgent) * n, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) { free(tmp); snprintf(g_cuda_err, sizeof(g_cuda_err), "holdings copy: %s", cudaGetErrorString(e)); return ABX_ERR_CUDA; }
+  for (int id = 1; id < n; id++) { const ZiAgent &z = tmp[id]; int64_t *r = out + 5 * (id - 1);      // agent/TradingAgent.py:124-126, markToMarket :609-633
+    r[0] = id; r[1] = z.shares; r[2] = z.cash; r[3] = z.cash + (int64_t)z.shares * ((z.flags & AF_HAS_LAST) ? z.last_trade : 0); r[4] = z.surplus; }
+  free(tmp); return ABX_OK;
+}
+
+int32_t abx_sim_book_snapshot(abx_sim *h, int32_t env, int32_t is_bid, int32_t depth, int32_t *out, int32_t *n_levels, void *stream) {
+  if (!h || !out || !n_levels || env < 0 || env >= h->n_envs || depth < 0) return ABX_ERR_ARG;
+  CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
+  EnvState s; CU(cudaMemcpyAsync(&s, h->P.env + env, sizeof(s), cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st));
+  int side = is_bid ? 0 : 1, n = s.n_lv[side], m = depth < n ? depth : n; *n_levels = m; if (m == 0) return ABX_OK;
+  int32_t *p = (int32_t *)malloc(sizeof(int32_t) * 2 * m); if (!p) return ABX_ERR_ARG;
+  size_t base = ((size_t)env * 2 + side) * h->P.c.level_cap + (n - m);
+  cudaError_t e = cudaMemcpyAsync(p, h->P.lv_price + base, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p + m, h->P.lv_qty + base, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { free(p); snprintf(g_cuda_err, sizeof(g_cuda_err), "snapshot copy: %s", cudaGetErrorString(e)); return ABX_ERR_CUDA; }
+  for (int k = 0; k < m; k++) { out[2 * k] = p[m - 1 - k]; out[2 * k + 1] = p[m + m - 1 - k]; }   // best level is stored last
+  free(p); return ABX_OK;
+}
+
+int32_t abx_sim_trace(abx_sim *h, int32_t env, abx_trace_rec *out, int32_t max_recs, int32_t *n_recs, void *stream) {
+  if (!h || !out || !n_recs || env < 0 || env >= h->n_envs) return ABX_ERR_ARG;
+  CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
+  EnvState s; CU(cudaMemcpyAsync(&s, h->P.env + env, sizeof(s), cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st));
+  int n = (int)s.trace_n; if (n > max_recs) n = max_recs; if (n > h->P.c.trace_cap) n = h->P.c.trace_cap;
+  if (n > 0) { CU(cudaMemcpyAsync(out, h->P.trace + (size_t)env * h->P.c.trace_cap, sizeof(abx_trace_rec) * n, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
+  *n_recs = n; return ABX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,217 @@
+// abx_warp.cuh -- warp-cooperative context for abx::Sim (one 32-lane warp == one environment), sm_100a.
+//
+// On-chip (shared memory, per warp):   staged trader record (192 B, moved with 128-bit loads/stores),
+//                                      outbox, event-queue group cache, both price ladders.
+// HBM (per environment):               event slots (SoA: 16 B key + 2 x 16 B payload), trader records, order nodes.
+//
+// Event queue = unordered slots in groups of 32 + a cached (min key, occupancy mask) per group:
+//   pop  : REDUX-min over the group cache (on chip) -> ONE coalesced 3 x 512 B load of the winning group -> REDUX-min
+//   push : ballot for a group with a free slot -> three 16 B stores -> cache update
+// so a pop costs one dependent HBM round trip instead of the ~11 of a binary heap with 2 000 entries, and the
+// (time, recipient, type, uniq) order of the reference's heapq (Kernel.py:192,425; message/Message.py:39-45)
+// is reproduced exactly because the minimum is recomputed from full keys.
+//
+// Price ladders = two sorted arrays (best level LAST) of {price, total qty, FIFO head|tail} searched with one
+// pass of 32 lanes + ballot/REDUX, shifted in 32-wide chunks on insert/remove; FIFO order within a level is a
+// linked list of 16 B order nodes in HBM (util/OrderBook.py:24-25 bids/asks[level][fifo]).
+#pragma once
+#include "abx_core.cuh"
+
+namespace abx {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ uint4 ldcg4(const uint4 *p) { return __ldcg(p); }
+
+// lane index of the smallest (hi, uniq) among lanes with valid == true, or -1
+__device__ __forceinline__ int warp_argmin(uint64_t hi, uint32_t uniq, bool valid) {
+  uint32_t h = valid ? (uint32_t)(hi >> 32) : 0xffffffffu;
+  uint32_t m = __reduce_min_sync(FULL, h);
+  bool c = valid && h == m;
+  uint32_t l = c ? (uint32_t)hi : 0xffffffffu;
+  uint32_t m2 = __reduce_min_sync(FULL, l);
+  c = c && l == m2;
+  uint32_t u = c ? uniq : 0xffffffffu;
+  uint32_t m3 = __reduce_min_sync(FULL, u);
+  c = c && u == m3;
+  uint32_t b = __ballot_sync(FULL, c);
+  return b ? __ffs(b) - 1 : -1;
+}
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+  uint32_t lo = __shfl_sync(FULL, (uint32_t)v, src), hi = __shfl_sync(FULL, (uint32_t)(v >> 32), src);
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+__device__ __forceinline__ uint4 shfl4(uint4 v, int src) {
+  uint4 r; r.x = __shfl_sync(FULL, v.x, src); r.y = __shfl_sync(FULL, v.y, src); r.z = __shfl_sync(FULL, v.z, src); r.w = __shfl_sync(FULL, v.w, src); return r;
+}
+
+// bytes of shared memory one environment needs
+__host__ __device__ inline size_t warp_smem_bytes(const abx_sim_config &c) {
+  return sizeof(ZiAgent) + OUT_CAP * OUT_WORDS * 4 + (size_t)(c.queue_cap / 32) * 16 + (size_t)c.level_cap * 2 * 12;
+}
+
+struct WarpCtx {
+  const SimParams &P; int env, lane;
+  // HBM bases of this environment
+  uint4 *qkey, *qpay0, *qpay1; ZiAgent *agents; uint4 *nodes; abx_trace_rec *tr;
+  // shared memory of this warp
+  ZiAgent *staged; uint32_t *obox; uint4 *qc; int32_t *lvp, *lvq; uint32_t *lvht;
+  // registers describing the group fetched by q_fetch
+  uint64_t my_hi; uint32_t my_uniq; uint32_t cur_mask; int cur_group, cur_lane;
+
+  __device__ WarpCtx(const SimParams &P_, int env_, unsigned char *smem) : P(P_), env(env_), lane(threadIdx.x & 31) {
+    size_t q = (size_t)env * P.c.queue_cap; qkey = P.qkey + q; qpay0 = P.qpay0 + q; qpay1 = P.qpay1 + q;
+    agents = P.agents + (size_t)env * P.c.n_agents; nodes = P.nodes + (size_t)env * P.c.order_cap;
+    tr = P.trace ? P.trace + (size_t)env * P.c.trace_cap : nullptr;
+    staged = reinterpret_cast<ZiAgent *>(smem); smem += sizeof(ZiAgent);
+    obox = reinterpret_cast<uint32_t *>(smem); smem += OUT_CAP * OUT_WORDS * 4;
+    qc = reinterpret_cast<uint4 *>(smem); smem += (size_t)P.n_qgroups * 16;
+    lvp = reinterpret_cast<int32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
+    lvq = reinterpret_cast<int32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
+    lvht = reinterpret_cast<uint32_t *>(smem);
+    cur_group = cur_lane = -1; cur_mask = 0; my_hi = KEY_EMPTY; my_uniq = 0xffffffffu;
+  }
+  __device__ __forceinline__ bool leader() const { return lane == 0; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ uint32_t *outbox() const { return obox; }
+  __device__ __forceinline__ void trace(const abx_trace_rec &r, uint32_t i) { if (lane == 0) tr[i] = r; }
+
+  // ---- staging of the on-chip structures between launches ----
+  __device__ void load_onchip(const EnvState &s) {
+    const uint4 *gc = P.qcache + (size_t)env * P.n_qgroups;
+    for (int g = lane; g < P.n_qgroups; g += 32) qc[g] = ldcg4(gc + g);
+    size_t l = (size_t)env * 2 * P.c.level_cap;
+    for (int side = 0; side < 2; side++) for (int i = lane; i < s.n_lv[side]; i += 32) {
+      int k = side * P.c.level_cap + i; lvp[k] = P.lv_price[l + k]; lvq[k] = P.lv_qty[l + k]; lvht[k] = P.lv_ht[l + k];
+    }
+    __syncwarp();
+  }
+  __device__ void store_onchip(const EnvState &s) {
+    __syncwarp();
+    uint4 *gc = P.qcache + (size_t)env * P.n_qgroups;
+    for (int g = lane; g < P.n_qgroups; g += 32) gc[g] = qc[g];
+    size_t l = (size_t)env * 2 * P.c.level_cap;
+    for (int side = 0; side < 2; side++) for (int i = lane; i < s.n_lv[side]; i += 32) {
+      int k = side * P.c.level_cap + i; P.lv_price[l + k] = lvp[k]; P.lv_qty[l + k] = lvq[k]; P.lv_ht[l + k] = lvht[k];
+    }
+  }
+  __device__ void q_clear() { for (int g = lane; g < P.n_qgroups; g += 32) qc[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); __syncwarp(); }
+
+  // ---- event queue ----
+  __device__ __forceinline__ bool q_min(uint64_t &hi, uint32_t &uniq, int &grp) {
+    uint64_t bh = KEY_EMPTY; uint32_t bu = 0xffffffffu; int bg = -1;
+    for (int g = lane; g < P.n_qgroups; g += 32) {
+      uint4 cc = qc[g];
+      if (cc.w) { uint64_t h = (uint64_t)cc.x | ((uint64_t)cc.y << 32); if (bg < 0 || key_less(h, cc.z, bh, bu)) { bh = h; bu = cc.z; bg = g; } }
+    }
+    int wl = warp_argmin(bh, bu, bg >= 0);
+    if (wl < 0) return false;
+    grp = __shfl_sync(FULL, bg, wl); hi = shfl64(bh, wl); uniq = __shfl_sync(FULL, bu, wl);
+    return true;
+  }
+  __device__ __forceinline__ void q_fetch(int g, Event &e) {
+    int slot = g * 32 + lane;
+    uint4 k = ldcg4(qkey + slot), a = ldcg4(qpay0 + slot), b = ldcg4(qpay1 + slot);     // 3 x 512 B coalesced
+    cur_mask = qc[g].w; cur_group = g;
+    bool occ = (cur_mask >> lane) & 1u;
+    my_hi = (uint64_t)k.x | ((uint64_t)k.y << 32); my_uniq = k.z;
+    int w = warp_argmin(my_hi, my_uniq, occ);
+    cur_lane = w;
+    event_unpack(shfl4(k, w), shfl4(a, w), shfl4(b, w), e);
+  }
+  __device__ __forceinline__ void group_writeback() {     // recompute the cached minimum of cur_group from the keys in registers
+    bool occ = (cur_mask >> lane) & 1u;
+    int w2 = warp_argmin(my_hi, my_uniq, occ);
+    uint64_t nh = KEY_EMPTY; uint32_t nu = 0xffffffffu;
+    if (w2 >= 0) { nh = shfl64(my_hi, w2); nu = __shfl_sync(FULL, my_uniq, w2); }
+    if (lane == 0) qc[cur_group] = make_uint4((uint32_t)nh, (uint32_t)(nh >> 32), nu, cur_mask);
+    __syncwarp();
+  }
+  __device__ __forceinline__ void q_remove() { cur_mask &= ~(1u << cur_lane); group_writeback(); }
+  __device__ __forceinline__ void q_requeue(int64_t t) {   // Kernel.py:226,260: same entry, new time, same uniq
+    if (lane == cur_lane) {
+      my_hi = key_pack(t < KEY_T_MAX ? t : KEY_T_MAX, key_recipient(my_hi), key_type(my_hi));
+      uint2 *kp = reinterpret_cast<uint2 *>(qkey + cur_group * 32 + lane); *kp = make_uint2((uint32_t)my_hi, (uint32_t)(my_hi >> 32));
+    }
+    group_writeback();
+  }
+  __device__ __forceinline__ bool q_push(const Event &e) {
+    int fg = -1;
+    for (int g = lane; g < P.n_qgroups; g += 32) if (qc[g].w != 0xffffffffu) { fg = g; break; }
+    uint32_t bal = __ballot_sync(FULL, fg >= 0);
+    if (!bal) return false;
+    int g = __shfl_sync(FULL, fg, __ffs(bal) - 1);
+    uint4 cc = qc[g]; int i = __ffs(~cc.w) - 1;
+    uint4 k, a, b; event_pack(e, k, a, b);
+    int slot = g * 32 + i;
+    if (lane < 3) { uint4 *dst = lane == 0 ? qkey : (lane == 1 ? qpay0 : qpay1); dst[slot] = lane == 0 ? k : (lane == 1 ? a : b); }
+    if (lane == 0) {
+      uint64_t h = (uint64_t)k.x | ((uint64_t)k.y << 32), ch = (uint64_t)cc.x | ((uint64_t)cc.y << 32);
+      if (cc.w == 0 || key_less(h, k.z, ch, cc.z)) { cc.x = k.x; cc.y = k.y; cc.z = k.z; }
+      cc.w |= 1u << i; qc[g] = cc;
+    }
+    __syncwarp();
+    return true;
+  }
+
+  // ---- ladders (side 0 bids ascending, side 1 asks descending: best level last) ----
+  __device__ __forceinline__ int32_t lv_price(int side, int i) const { return lvp[side * P.c.level_cap + i]; }
+  __device__ __forceinline__ int32_t lv_qty(int side, int i) const { return lvq[side * P.c.level_cap + i]; }
+  __device__ __forceinline__ uint32_t lv_head(int side, int i) const { return lvht[side * P.c.level_cap + i] & 0xffffu; }
+  __device__ __forceinline__ uint32_t lv_tail(int side, int i) const { return lvht[side * P.c.level_cap + i] >> 16; }
+  __device__ __forceinline__ void lv_set(int side, int i, int32_t qty, uint32_t head, uint32_t tail) {
+    __syncwarp();
+    if (lane == 0) { lvq[side * P.c.level_cap + i] = qty; lvht[side * P.c.level_cap + i] = head | (tail << 16); }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void lv_find(int side, int32_t price, int n, int &pos, bool &found) {
+    const int32_t *p = lvp + side * P.c.level_cap; int cnt = 0, fidx = -1;
+    for (int i = lane; i < n; i += 32) { int32_t v = p[i]; if (v == price) fidx = i; else if (side == 0 ? v < price : v > price) cnt++; }
+    cnt = __reduce_add_sync(FULL, cnt);
+    uint32_t fb = __ballot_sync(FULL, fidx >= 0);
+    if (fb) { found = true; pos = __shfl_sync(FULL, fidx, __ffs(fb) - 1); } else { found = false; pos = cnt; }
+  }
+  __device__ __forceinline__ void lv_insert(int side, int pos, int n, int32_t price, int32_t qty, uint32_t head, uint32_t tail) {
+    int b = side * P.c.level_cap;
+    __syncwarp();
+    for (int hi = n; hi > pos; hi -= 32) {                  // shift [pos, n) up by one, top chunk first
+      int i = hi - 1 - lane; bool act = i >= pos; int32_t x = 0, y = 0; uint32_t z = 0;
+      if (act) { x = lvp[b + i]; y = lvq[b + i]; z = lvht[b + i]; }
+      __syncwarp();
+      if (act) { lvp[b + i + 1] = x; lvq[b + i + 1] = y; lvht[b + i + 1] = z; }
+      __syncwarp();
+    }
+    if (lane == 0) { lvp[b + pos] = price; lvq[b + pos] = qty; lvht[b + pos] = head | (tail << 16); }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void lv_remove(int side, int pos, int n) {
+    int b = side * P.c.level_cap;
+    __syncwarp();
+    for (int lo = pos + 1; lo < n; lo += 32) {              // shift (pos, n) down by one, bottom chunk first
+      int i = lo + lane; bool act = i < n; int32_t x = 0, y = 0; uint32_t z = 0;
+      if (act) { x = lvp[b + i]; y = lvq[b + i]; z = lvht[b + i]; }
+      __syncwarp();
+      if (act) { lvp[b + i - 1] = x; lvq[b + i - 1] = y; lvht[b + i - 1] = z; }
+      __syncwarp();
+    }
+  }
+
+  // ---- order nodes (HBM, 16 B each) ----
+  __device__ __forceinline__ NodeRec node_load(uint32_t i) const { uint4 v = ldcg4(nodes + i); NodeRec r; r.id = v.x; r.qty = (int32_t)v.y; r.agent = v.z; r.next = v.w; return r; }
+  __device__ __forceinline__ void node_store(uint32_t i, const NodeRec &r) { if (lane == 0) __stcg(nodes + i, make_uint4(r.id, (uint32_t)r.qty, r.agent, r.next)); __syncwarp(); }
+
+  // ---- trader records: 12 lanes x 128-bit, HBM <-> shared ----
+  __device__ __forceinline__ ZiAgent *agent_stage(int id) {
+    __syncwarp();
+    if (lane < (int)(sizeof(ZiAgent) / 16)) reinterpret_cast<uint4 *>(staged)[lane] = ldcg4(reinterpret_cast<const uint4 *>(agents + id) + lane);
+    __syncwarp();
+    return staged;
+  }
+  __device__ __forceinline__ void agent_commit(int id) {
+    __syncwarp();
+    if (lane < (int)(sizeof(ZiAgent) / 16)) __stcg(reinterpret_cast<uint4 *>(agents + id) + lane, reinterpret_cast<const uint4 *>(staged)[lane]);
+  }
+  __device__ __forceinline__ double agent_lat_from(int id) const { return __ldcg(&agents[id].lat_from); }
+};
+
+}  // namespace abx

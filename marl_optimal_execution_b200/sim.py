@@ -1,0 +1,139 @@
+"""BatchedSim: thousands of independent ABIDES simulations stepped at once on one B200.
+
+Python mirror of the reference's config + Kernel surface for the background-population configs
+(config/sparse_zi_100.py, config/sparse_zi_1000.py -> Kernel.runner, Kernel.py:50-345), calling the
+hand-written sm_100a kernels through the C ABI (include/abides_b200.h).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import EnvStats, SimConfig, TraceRec
+
+
+def sparse_zi_config(variant, lib=None, **overrides):
+    """abx_sim_config for config/sparse_zi_100.py (variant=100) or config/sparse_zi_1000.py (variant=1000)."""
+    L = lib or _lib.load()
+    cfg = SimConfig()
+    _lib.check(L, L.abx_config_sparse_zi(int(variant), C.byref(cfg)), "abx_config_sparse_zi")
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError("abx_sim_config has no field %r" % k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+class BatchedSim:
+    """n_envs independent simulations of one population config on one GPU.
+
+    run(until_ns) advances every environment's event loop (Kernel.py:190-292) to `until_ns`;
+    stats() returns the per-environment counters (messages == the reference's ttl_messages).
+    """
+
+    def __init__(self, cfg, n_envs, device=0, lib_path=None):
+        self._L = _lib.load(lib_path)
+        self.cfg = cfg
+        self.n_envs = int(n_envs)
+        self.n_agents = int(cfg.n_agents)
+        self._h = C.c_void_p()
+        _lib.check(self._L, self._L.abx_sim_create(C.byref(cfg), self.n_envs, int(device), C.byref(self._h)),
+                   "abx_sim_create")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.abx_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- reset ----
+    def reset(self, seeds, stream=None):
+        """Philox mode: environment e draws every random variate from counter streams keyed by seeds[e]."""
+        seeds = np.ascontiguousarray(np.broadcast_to(np.asarray(seeds, dtype=np.uint64), (self.n_envs,)))
+        _lib.check(self._L, self._L.abx_sim_reset_philox(self._h, seeds.ctypes.data_as(C.POINTER(C.c_uint64)), stream),
+                   "abx_sim_reset_philox")
+
+    def reset_tape(self, tape_bits, tape_kinds, tape_offsets, lat_to_exchange, lat_from_exchange, stream=None):
+        """Tape mode: replay the RandomState draws of a recorded reference run (include/abides_b200.h)."""
+        n_streams = self.n_agents + 3
+        bits = np.ascontiguousarray(tape_bits, dtype=np.uint64)
+        kinds = np.ascontiguousarray(tape_kinds, dtype=np.uint8)
+        off = np.ascontiguousarray(tape_offsets, dtype=np.int64)
+        lt = np.ascontiguousarray(lat_to_exchange, dtype=np.float64)
+        lf = np.ascontiguousarray(lat_from_exchange, dtype=np.float64)
+        if off.shape != (self.n_envs * n_streams + 1,) or off[-1] != bits.size or kinds.size != bits.size:
+            raise ValueError("tape arrays have inconsistent shapes")
+        if lt.size != self.n_envs * self.n_agents or lf.size != lt.size:
+            raise ValueError("latency vectors must be [n_envs * n_agents]")
+        _lib.check(self._L, self._L.abx_sim_reset_tape(
+            self._h, bits.ctypes.data_as(C.POINTER(C.c_uint64)), kinds.ctypes.data_as(C.POINTER(C.c_uint8)),
+            off.ctypes.data_as(C.POINTER(C.c_int64)), lt.ctypes.data_as(C.POINTER(C.c_double)),
+            lf.ctypes.data_as(C.POINTER(C.c_double)), stream), "abx_sim_reset_tape")
+
+    # ---- stepping ----
+    def run(self, until_ns=None, stream=None):
+        until = int(self.cfg.stop_ns) + 10 ** 15 if until_ns is None else int(until_ns)
+        _lib.check(self._L, self._L.abx_sim_run(self._h, until, stream), "abx_sim_run")
+
+    def finalize(self, stream=None):
+        _lib.check(self._L, self._L.abx_sim_finalize(self._h, stream), "abx_sim_finalize")
+
+    # ---- results ----
+    def stats(self, stream=None):
+        out = np.zeros(self.n_envs, dtype=_lib.STATS_DTYPE)
+        _lib.check(self._L, self._L.abx_sim_stats(self._h, out.ctypes.data, stream), "abx_sim_stats")
+        return out
+
+    def stats_into(self, device_ptr, stream=None):
+        """Leave the abx_env_stats records on the device (device_ptr: e.g. torch tensor .data_ptr(), 112 B/env)."""
+        _lib.check(self._L, self._L.abx_sim_stats_device(self._h, C.c_void_p(device_ptr), stream), "abx_sim_stats_device")
+
+    def holdings(self, env, stream=None):
+        out = np.zeros((self.n_agents - 1, 5), dtype=np.int64)
+        _lib.check(self._L, self._L.abx_sim_holdings(self._h, int(env), out.ctypes.data_as(C.POINTER(C.c_int64)), stream),
+                   "abx_sim_holdings")
+        return out
+
+    def book_snapshot(self, env, is_bid, depth, stream=None):
+        out = np.zeros(2 * max(depth, 1), dtype=np.int32)
+        n = C.c_int32(0)
+        _lib.check(self._L, self._L.abx_sim_book_snapshot(self._h, int(env), int(bool(is_bid)), int(depth),
+                                                          out.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n), stream),
+                   "abx_sim_book_snapshot")
+        return [(int(out[2 * i]), int(out[2 * i + 1])) for i in range(n.value)]
+
+    def trace(self, env, stream=None):
+        cap = int(self.cfg.trace_cap)
+        out = np.zeros(max(cap, 1), dtype=_lib.TRACE_DTYPE)
+        n = C.c_int32(0)
+        _lib.check(self._L, self._L.abx_sim_trace(self._h, int(env), out.ctypes.data, cap, C.byref(n), stream),
+                   "abx_sim_trace")
+        return out[: n.value]
+
+    def split_trace(self, env):
+        """Trace -> (pops[n,5], notes[n,13], snaps[n,16]) int64 arrays in tools/record_reference.py row layout."""
+        tr = self.trace(env)
+        pops = tr[tr["tag"] == 0]
+        notes = tr[tr["tag"] == 1]
+        snaps = tr[tr["tag"] == 2]
+        p = np.zeros((len(pops), 5), np.int64)
+        p[:, 0], p[:, 1] = pops["t"], pops["a"]
+        p[:, 2:5] = pops["v"][:, 0:3]
+        nt = np.zeros((len(notes), 13), np.int64)
+        nt[:, 0], nt[:, 1] = notes["t"], notes["a"]
+        nt[:, 2:13] = notes["v"][:, 0:11]
+        sn = snaps["v"].astype(np.int64)
+        return p, nt, sn
+
+    @property
+    def launch_count(self):
+        return int(self._L.abx_sim_launch_count(self._h))
+
+    @property
+    def device_bytes(self):
+        return int(self._L.abx_sim_device_bytes(self._h))

@@ -1,0 +1,170 @@
+// abx_host_emu.cpp -- HOST EMULATION HARNESS (test tool, CPU CI only).
+//
+// Compiles the product's warp-uniform simulation logic (marl_optimal_execution_b200/csrc/abx_core.cuh) as plain
+// C++ with a serial context in place of the warp-cooperative one, so that the scalar logic (event rules,
+// exchange protocol, matching, ZI agent, sparse OU oracle, latency models, RNG tape plumbing, HBM record
+// layouts) is checked against the oracle on the CPU before any GPU minute is spent.  It is NOT part of
+// libabides_b200.so, is not importable from the package and is never a fallback: the product fails loudly
+// without the CUDA library.  It exposes the same C ABI names as include/abides_b200.h for the subset it
+// implements so tests can drive both through one Python wrapper class.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../marl_optimal_execution_b200/csrc/abx_host_common.h"
+
+using namespace abx;
+
+struct HostCtx {
+  const SimParams &P; int env;
+  uint4 *qkey, *qpay0, *qpay1, *qcache; ZiAgent *agents; int32_t *lvp, *lvq; uint32_t *lvht; uint4 *nodes; abx_trace_rec *tr;
+  uint32_t outbox_[OUT_CAP * OUT_WORDS]; ZiAgent staged; int cur_group, cur_slot;
+  HostCtx(const SimParams &P_, int e) : P(P_), env(e) {
+    size_t q = (size_t)e * P.c.queue_cap; qkey = P.qkey + q; qpay0 = P.qpay0 + q; qpay1 = P.qpay1 + q; qcache = P.qcache + (size_t)e * P.n_qgroups;
+    agents = P.agents + (size_t)e * P.c.n_agents; size_t l = (size_t)e * 2 * P.c.level_cap; lvp = P.lv_price + l; lvq = P.lv_qty + l; lvht = P.lv_ht + l;
+    nodes = P.nodes + (size_t)e * P.c.order_cap; tr = P.trace ? P.trace + (size_t)e * P.c.trace_cap : nullptr; cur_group = cur_slot = -1;
+  }
+  bool leader() { return true; }
+  void sync() {}
+  uint32_t *outbox() { return outbox_; }
+  void trace(const abx_trace_rec &r, uint32_t i) { tr[i] = r; }
+  // ---- queue ----
+  void q_clear() { for (int g = 0; g < P.n_qgroups; g++) { qcache[g].x = qcache[g].y = 0xffffffffu; qcache[g].z = 0xffffffffu; qcache[g].w = 0; } }
+  void group_recompute(int g) {
+    uint64_t bh = KEY_EMPTY; uint32_t bu = 0xffffffffu; uint32_t mask = qcache[g].w;
+    for (int i = 0; i < 32; i++) if (mask >> i & 1) { uint4 k = qkey[g * 32 + i]; uint64_t h = (uint64_t)k.x | ((uint64_t)k.y << 32); if (key_less(h, k.z, bh, bu)) { bh = h; bu = k.z; } }
+    qcache[g].x = (uint32_t)bh; qcache[g].y = (uint32_t)(bh >> 32); qcache[g].z = bu;
+  }
+  bool q_min(uint64_t &hi, uint32_t &uniq, int &grp) {
+    uint64_t bh = KEY_EMPTY; uint32_t bu = 0xffffffffu; grp = -1;
+    for (int g = 0; g < P.n_qgroups; g++) { if (!qcache[g].w) continue; uint64_t h = (uint64_t)qcache[g].x | ((uint64_t)qcache[g].y << 32); if (grp < 0 || key_less(h, qcache[g].z, bh, bu)) { bh = h; bu = qcache[g].z; grp = g; } }
+    hi = bh; uniq = bu; return grp >= 0;
+  }
+  void q_fetch(int g, Event &e) {
+    uint64_t bh = KEY_EMPTY; uint32_t bu = 0xffffffffu; int best = -1; uint32_t mask = qcache[g].w;
+    for (int i = 0; i < 32; i++) if (mask >> i & 1) { uint4 k = qkey[g * 32 + i]; uint64_t h = (uint64_t)k.x | ((uint64_t)k.y << 32); if (best < 0 || key_less(h, k.z, bh, bu)) { bh = h; bu = k.z; best = i; } }
+    cur_group = g; cur_slot = best; event_unpack(qkey[g * 32 + best], qpay0[g * 32 + best], qpay1[g * 32 + best], e);
+  }
+  void q_remove() { qcache[cur_group].w &= ~(1u << cur_slot); group_recompute(cur_group); }
+  void q_requeue(int64_t t) {
+    uint4 &k = qkey[cur_group * 32 + cur_slot]; uint64_t h = (uint64_t)k.x | ((uint64_t)k.y << 32);
+    h = key_pack(t < KEY_T_MAX ? t : KEY_T_MAX, key_recipient(h), key_type(h)); k.x = (uint32_t)h; k.y = (uint32_t)(h >> 32); group_recompute(cur_group);
+  }
+  bool q_push(const Event &e) {
+    for (int g = 0; g < P.n_qgroups; g++) if (qcache[g].w != 0xffffffffu) {
+      int i = __builtin_ctz(~qcache[g].w); event_pack(e, qkey[g * 32 + i], qpay0[g * 32 + i], qpay1[g * 32 + i]); qcache[g].w |= 1u << i; group_recompute(g); return true; }
+    return false;
+  }
+  // ---- ladders: ascending in "goodness", best level LAST.  side 0 bids (ascending price), side 1 asks (descending price) ----
+  int32_t lv_price(int side, int i) { return lvp[side * P.c.level_cap + i]; }
+  int32_t lv_qty(int side, int i) { return lvq[side * P.c.level_cap + i]; }
+  uint32_t lv_head(int side, int i) { return lvht[side * P.c.level_cap + i] & 0xffffu; }
+  uint32_t lv_tail(int side, int i) { return lvht[side * P.c.level_cap + i] >> 16; }
+  void lv_set(int side, int i, int32_t qty, uint32_t head, uint32_t tail) { lvq[side * P.c.level_cap + i] = qty; lvht[side * P.c.level_cap + i] = head | (tail << 16); }
+  void lv_find(int side, int32_t price, int n, int &pos, bool &found) {
+    pos = 0; found = false;
+    for (int i = 0; i < n; i++) { int32_t p = lv_price(side, i); if (p == price) { found = true; pos = i; return; } if (side == 0 ? p < price : p > price) pos = i + 1; }
+  }
+  void lv_insert(int side, int pos, int n, int32_t price, int32_t qty, uint32_t head, uint32_t tail) {
+    int b = side * P.c.level_cap;
+    for (int i = n; i > pos; i--) { lvp[b + i] = lvp[b + i - 1]; lvq[b + i] = lvq[b + i - 1]; lvht[b + i] = lvht[b + i - 1]; }
+    lvp[b + pos] = price; lvq[b + pos] = qty; lvht[b + pos] = head | (tail << 16);
+  }
+  void lv_remove(int side, int pos, int n) { int b = side * P.c.level_cap; for (int i = pos; i + 1 < n; i++) { lvp[b + i] = lvp[b + i + 1]; lvq[b + i] = lvq[b + i + 1]; lvht[b + i] = lvht[b + i + 1]; } }
+  // ---- order nodes ----
+  NodeRec node_load(uint32_t i) { uint4 v = nodes[i]; NodeRec r; r.id = v.x; r.qty = (int32_t)v.y; r.agent = v.z; r.next = v.w; return r; }
+  void node_store(uint32_t i, const NodeRec &r) { uint4 v; v.x = r.id; v.y = (uint32_t)r.qty; v.z = r.agent; v.w = r.next; nodes[i] = v; }
+  // ---- agents ----
+  ZiAgent *agent_stage(int id) { staged = agents[id]; return &staged; }
+  void agent_commit(int id) { agents[id] = staged; }
+  double agent_lat_from(int id) { return agents[id].lat_from; }
+};
+
+struct abx_sim {
+  SimParams P; int n_envs; bool reset_done;
+  std::vector<uint4> qkey, qpay0, qpay1, qcache, nodes; std::vector<ZiAgent> agents; std::vector<int32_t> lvp, lvq; std::vector<uint32_t> lvht;
+  std::vector<EnvState> env; std::vector<abx_trace_rec> trace; std::vector<uint64_t> tbits; std::vector<uint8_t> tkinds; std::vector<int64_t> toff;
+};
+
+extern "C" {
+const char *abx_strerror(int32_t st) { return status_string(st); }
+const char *abx_last_cuda_error(void) { return "host emulation harness: no CUDA"; }
+int32_t abx_device_count(void) { return 0; }
+int32_t abx_config_sparse_zi(int32_t variant, abx_sim_config *cfg) { return config_sparse_zi(variant, cfg); }
+
+int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device, abx_sim **out) {
+  (void)device;
+  if (!out || n_envs < 1 || config_validate(cfg) != ABX_OK) return ABX_ERR_ARG;
+  abx_sim *h = new abx_sim(); memset(&h->P, 0, sizeof(h->P)); h->P.c = *cfg; h->P.n_envs = n_envs; h->n_envs = n_envs; h->reset_done = false; derive_params(h->P);
+  size_t E = n_envs; const abx_sim_config &c = *cfg;
+  h->qkey.resize(E * c.queue_cap); h->qpay0.resize(E * c.queue_cap); h->qpay1.resize(E * c.queue_cap); h->qcache.resize(E * h->P.n_qgroups);
+  h->agents.resize(E * c.n_agents); h->lvp.resize(E * 2 * c.level_cap); h->lvq.resize(E * 2 * c.level_cap); h->lvht.resize(E * 2 * c.level_cap);
+  h->nodes.resize(E * c.order_cap); h->env.resize(E); h->trace.resize(E * (size_t)c.trace_cap);
+  h->P.qkey = h->qkey.data(); h->P.qpay0 = h->qpay0.data(); h->P.qpay1 = h->qpay1.data(); h->P.qcache = h->qcache.data(); h->P.agents = h->agents.data();
+  h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
+  h->P.trace = c.trace_cap ? h->trace.data() : nullptr;
+  *out = h; return ABX_OK;
+}
+int32_t abx_sim_destroy(abx_sim *h) { delete h; return ABX_OK; }
+int64_t abx_sim_device_bytes(const abx_sim *h) { (void)h; return 0; }
+
+static int32_t do_reset(abx_sim *h, const uint64_t *seeds) {
+  const abx_sim_config &c = h->P.c;
+  for (int e = 0; e < h->n_envs; e++) {
+    uint64_t seed = seeds ? seeds[e] : 0; uint32_t err = 0;
+    for (int id = 1; id < c.n_agents; id++) init_agent_record(h->P, e, id, seed, &h->agents[(size_t)e * c.n_agents + id], &err);
+    EnvState s; init_env_state(h->P, seed, s); s.flags |= err;
+    HostCtx ctx(h->P, e); ctx.q_clear();
+    Sim<HostCtx> sim(ctx, h->P, s, e); sim.reset_env(); h->env[e] = sim.s;
+  }
+  h->reset_done = true; return ABX_OK;
+}
+int32_t abx_sim_reset_philox(abx_sim *h, const uint64_t *seeds, void *stream) {
+  (void)stream; if (!h || !seeds || h->P.c.rng_mode != ABX_RNG_PHILOX) return ABX_ERR_ARG; return do_reset(h, seeds);
+}
+int32_t abx_sim_reset_tape(abx_sim *h, const uint64_t *bits, const uint8_t *kinds, const int64_t *off, const double *lat_to, const double *lat_from, void *stream) {
+  (void)stream; if (!h || !bits || !kinds || !off || !lat_to || !lat_from || h->P.c.rng_mode != ABX_RNG_TAPE) return ABX_ERR_ARG;
+  size_t nS = (size_t)h->n_envs * h->P.n_streams; int64_t total = off[nS];
+  h->tbits.assign(bits, bits + total); h->tkinds.assign(kinds, kinds + total); h->toff.assign(off, off + nS + 1);
+  h->P.tape_bits = h->tbits.data(); h->P.tape_kinds = h->tkinds.data(); h->P.tape_off = h->toff.data();
+  for (int e = 0; e < h->n_envs; e++) for (int id = 0; id < h->P.c.n_agents; id++) { ZiAgent &z = h->agents[(size_t)e * h->P.c.n_agents + id]; z.lat_to = lat_to[(size_t)e * h->P.c.n_agents + id]; z.lat_from = lat_from[(size_t)e * h->P.c.n_agents + id]; }
+  return do_reset(h, nullptr);
+}
+int32_t abx_sim_run(abx_sim *h, int64_t until_ns, void *stream) {
+  (void)stream; if (!h) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  for (int e = 0; e < h->n_envs; e++) { HostCtx ctx(h->P, e); Sim<HostCtx> sim(ctx, h->P, h->env[e], e); sim.run(until_ns); h->env[e] = sim.s; }
+  return ABX_OK;
+}
+int32_t abx_sim_finalize(abx_sim *h, void *stream) {
+  (void)stream; if (!h) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  for (int e = 0; e < h->n_envs; e++) { HostCtx ctx(h->P, e); Sim<HostCtx> sim(ctx, h->P, h->env[e], e); sim.finalize(); h->env[e] = sim.s; }
+  return ABX_OK;
+}
+int32_t abx_sim_stats(abx_sim *h, abx_env_stats *out, void *stream) {
+  (void)stream; if (!h || !out) return ABX_ERR_ARG;
+  for (int e = 0; e < h->n_envs; e++) {
+    const EnvState &s = h->env[e]; HostCtx ctx(h->P, e); int nb = s.n_lv[0], na = s.n_lv[1];
+    fill_stats(s, nb ? ctx.lv_price(0, nb - 1) : 0, nb ? ctx.lv_qty(0, nb - 1) : 0, na ? ctx.lv_price(1, na - 1) : 0, na ? ctx.lv_qty(1, na - 1) : 0, &out[e]);
+  }
+  return ABX_OK;
+}
+int32_t abx_sim_stats_device(abx_sim *h, abx_env_stats *out, void *stream) { return abx_sim_stats(h, out, stream); }
+int32_t abx_sim_holdings(abx_sim *h, int32_t env, int64_t *out, void *stream) {
+  (void)stream; if (!h || !out || env < 0 || env >= h->n_envs) return ABX_ERR_ARG;
+  for (int id = 1; id < h->P.c.n_agents; id++) { const ZiAgent &z = h->agents[(size_t)env * h->P.c.n_agents + id]; int64_t *r = out + 5 * (id - 1);
+    r[0] = id; r[1] = z.shares; r[2] = z.cash; r[3] = z.cash + (int64_t)z.shares * ((z.flags & AF_HAS_LAST) ? z.last_trade : 0); r[4] = z.surplus; }
+  return ABX_OK;
+}
+int32_t abx_sim_book_snapshot(abx_sim *h, int32_t env, int32_t is_bid, int32_t depth, int32_t *out, int32_t *n_levels, void *stream) {
+  (void)stream; if (!h || !out || !n_levels || env < 0 || env >= h->n_envs || depth < 0) return ABX_ERR_ARG;
+  HostCtx ctx(h->P, env); int side = is_bid ? 0 : 1, n = h->env[env].n_lv[side], m = depth < n ? depth : n;
+  for (int k = 0; k < m; k++) { out[2 * k] = ctx.lv_price(side, n - 1 - k); out[2 * k + 1] = ctx.lv_qty(side, n - 1 - k); }
+  *n_levels = m; return ABX_OK;
+}
+int32_t abx_sim_trace(abx_sim *h, int32_t env, abx_trace_rec *out, int32_t max_recs, int32_t *n_recs, void *stream) {
+  (void)stream; if (!h || !out || !n_recs || env < 0 || env >= h->n_envs) return ABX_ERR_ARG;
+  int n = (int)h->env[env].trace_n; if (n > max_recs) n = max_recs;
+  if (n) memcpy(out, h->P.trace + (size_t)env * h->P.c.trace_cap, sizeof(abx_trace_rec) * n);
+  *n_recs = n; return ABX_OK;
+}
+int64_t abx_sim_launch_count(const abx_sim *h) { (void)h; return 0; }
+}

@@ -1,0 +1,44 @@
+"""Shared test helpers: oracle -> device tape conversion, host-emulation harness loader."""
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_LIB = os.path.join(EMU_DIR, "libabx_host_emu.so")
+
+
+def build_emu():
+    """Compile tests/emu (the product's warp-uniform logic as plain C++; CPU CI only, never a fallback)."""
+    src = os.path.join(EMU_DIR, "abx_host_emu.cpp")
+    deps = [src] + [os.path.join(ROOT, "marl_optimal_execution_b200", "csrc", f)
+                    for f in ("abx_core.cuh", "abx_host_common.h")] + [os.path.join(ROOT, "include", "abides_b200.h")]
+    if os.path.exists(EMU_LIB) and all(os.path.getmtime(EMU_LIB) >= os.path.getmtime(d) for d in deps):
+        return EMU_LIB
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                           "-o", EMU_LIB, src])
+    return EMU_LIB
+
+
+def oracle_tapes(sims):
+    """Device tape arrays (include/abides_b200.h: abx_sim_reset_tape) from finished OracleSim runs (one per env)."""
+    bits, kinds, off, lat_to, lat_from = [], [], [0], [], []
+    for s in sims:
+        n = s.n_agents
+        base = 4 if s.variant == 100 else 3           # oracle stream order: symbol, kernel, [latency], exchange, agents
+        streams = [s.tape(0), s.tape(1)]
+        streams.append(s.tape(2) if s.variant == 100 else (np.zeros(0, np.uint8), np.zeros(0, np.uint64)))
+        g = s.global_exp_tape()
+        streams.append((np.full(len(g), ord("e"), np.uint8), g.view(np.uint64)))
+        for a in range(1, n):
+            streams.append(s.tape(base + a - 1))
+        for k, b in streams:
+            kinds.append(k)
+            bits.append(b)
+            off.append(off[-1] + len(b))
+        a, b = s.latency_vectors()
+        lat_to.append(a)
+        lat_from.append(b)
+    return (np.concatenate(bits), np.concatenate(kinds), np.array(off, np.int64), np.concatenate(lat_to),
+            np.concatenate(lat_from))

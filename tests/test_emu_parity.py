@@ -1,0 +1,71 @@
+"""CPU CI of the product's warp-uniform logic (marl_optimal_execution_b200/csrc/abx_core.cuh compiled as plain C++
+by tests/emu, a test tool -- never a fallback): replayed RNG tapes must reproduce the oracle bit for bit."""
+import numpy as np
+import pytest
+
+from helpers import build_emu, oracle_tapes
+from marl_optimal_execution_b200 import _lib
+from marl_optimal_execution_b200.sim import BatchedSim, sparse_zi_config
+from oracle.oracle import OracleSim, TRACE_ALL
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return build_emu()
+
+
+@pytest.mark.parametrize("variant,seed", [(100, 123456789), (100, 1001), (1000, 123456789)])
+def test_tape_replay_matches_oracle(emu, variant, seed):
+    o = OracleSim(variant, seed, TRACE_ALL)
+    n = o.run()
+    cfg = sparse_zi_config(variant, lib=_lib.load(emu), rng_mode=_lib.RNG_TAPE,
+                           trace_cap=600000 if variant == 1000 else 60000, hash_pops=1)
+    sim = BatchedSim(cfg, 1, lib_path=emu)
+    sim.reset_tape(*oracle_tapes([o]))
+    sim.run()
+    sim.finalize()
+    st = sim.stats()[0]
+    assert int(st["messages"]) == n and int(st["flags"]) == _lib.F_DONE
+    assert int(st["pop_hash"]) == o.pop_hash()
+    p, nt, sn = sim.split_trace(0)
+    assert np.array_equal(p, o.trace("pops")) and np.array_equal(nt, o.trace("notes")) and np.array_equal(sn, o.trace("snaps"))
+    assert np.array_equal(sim.holdings(0), o.holdings())
+    assert int(st["limit_orders"]) == o.counter("limit") and int(st["fills"]) == o.counter("fills")
+    assert int(st["max_queue"]) == o.counter("max_queue")
+
+
+def test_sliced_run_equals_single_run(emu):
+    o = OracleSim(100, 123456789, TRACE_ALL)
+    o.run()
+    cfg = sparse_zi_config(100, lib=_lib.load(emu), rng_mode=_lib.RNG_TAPE, hash_pops=1)
+    sim = BatchedSim(cfg, 1, lib_path=emu)
+    sim.reset_tape(*oracle_tapes([o]))
+    for h in range(0, 18):
+        sim.run(h * 3600 * 10 ** 9)
+    sim.run()
+    assert int(sim.stats()[0]["pop_hash"]) == o.pop_hash()
+
+
+def test_philox_conservation_and_determinism(emu):
+    cfg = sparse_zi_config(100, lib=_lib.load(emu))
+    res = []
+    for _ in range(2):
+        sim = BatchedSim(cfg, 4, lib_path=emu)
+        sim.reset([5, 6, 7, 5])
+        sim.run()
+        sim.finalize()
+        res.append(sim.stats())
+    a, b = res
+    assert (a["flags"] == _lib.F_DONE).all()
+    assert (a["sum_shares"] == 0).all() and (a["sum_cash"] == 100 * cfg.starting_cash).all()
+    assert a.tobytes() == b.tobytes()
+    assert a[0].tobytes() == a[3].tobytes() and a[0]["messages"] != a[1]["messages"]
+    assert 15000 < a["messages"].mean() < 22000
+
+
+def test_capacity_flags(emu):
+    cfg = sparse_zi_config(100, lib=_lib.load(emu), queue_cap=64)
+    sim = BatchedSim(cfg, 1, lib_path=emu)
+    sim.reset([1])
+    sim.run()
+    assert int(sim.stats()[0]["flags"]) & _lib.F_QUEUE_OVERFLOW

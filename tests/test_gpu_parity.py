@@ -1,0 +1,102 @@
+"""GPU parity tests (run on the B200 box, through the C ABI): RNG draws recorded by the oracle are replayed through
+the CUDA simulator; event order, every outbound exchange message (fills, L1 replies), the book state after every
+book op and the final holdings must equal the oracle's -- bit-exact (integer work).  The oracle itself is pinned to
+the reference's recorded runs by the CPU suite (test_oracle_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import oracle_tapes
+from marl_optimal_execution_b200 import _lib
+from marl_optimal_execution_b200.sim import BatchedSim, sparse_zi_config
+from oracle.oracle import OracleSim, TRACE_ALL
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_env(sim, e, o, n, st):
+    assert int(st["messages"][e]) == n
+    assert int(st["flags"][e]) == _lib.F_DONE, hex(int(st["flags"][e]))
+    assert int(st["pop_hash"][e]) == o.pop_hash()
+    p, nt, sn = sim.split_trace(e)
+    for name, a, b in (("pops", p, o.trace("pops")), ("notes", nt, o.trace("notes")), ("snaps", sn, o.trace("snaps"))):
+        assert a.shape == b.shape, (name, a.shape, b.shape)
+        d = np.nonzero((a != b).any(axis=1))[0]
+        assert len(d) == 0, (name, int(d[0]), a[d[0]], b[d[0]])
+    assert np.array_equal(sim.holdings(e), o.holdings())
+    assert int(st["limit_orders"][e]) == o.counter("limit") and int(st["cancels"][e]) == o.counter("cancel")
+    assert int(st["fills"][e]) == o.counter("fills") and int(st["spread_queries"][e]) == o.counter("spread_queries")
+    assert int(st["max_queue"][e]) == o.counter("max_queue") and int(st["uniq"][e]) == o.counter("uniq")
+    l1 = o.book_l1()
+    assert (int(st["best_bid"][e]), int(st["best_bid_qty"][e]), int(st["best_ask"][e]), int(st["best_ask_qty"][e]),
+            int(st["last_trade"][e])) == tuple(int(x) for x in l1)
+    assert int(st["fundamental"][e]) == o.fundamental()
+    assert int(st["sum_shares"][e]) == 0 and int(st["sum_cash"][e]) == (o.n_agents - 1) * 10 ** 7
+
+
+def test_z100_tape_replay_batch():
+    seeds = [123456789, 1001, 7, 424242]
+    oracles = [OracleSim(100, s, TRACE_ALL) for s in seeds]
+    counts = [o.run() for o in oracles]
+    cfg = sparse_zi_config(100, rng_mode=_lib.RNG_TAPE, trace_cap=60000, hash_pops=1)
+    sim = BatchedSim(cfg, len(seeds))
+    sim.reset_tape(*oracle_tapes(oracles))
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    for e, o in enumerate(oracles):
+        _check_env(sim, e, o, counts[e], st)
+    # depth-k snapshot accessor vs the trace's last snapshot row
+    _, _, sn = sim.split_trace(0)
+    bids = sim.book_snapshot(0, True, 3)
+    assert [x for pq in bids for x in pq] == [int(v) for v in sn[-1][3:3 + 2 * len(bids)]]
+
+
+def test_z1000_tape_replay_reproduces_reference_golden(golden_dir):
+    """config/sparse_zi_1000.py seed 123456789 == the reference's tests/sparse_zi_1000.txt run (185 200 messages)."""
+    o = OracleSim(1000, 123456789, TRACE_ALL)
+    n = o.run()
+    assert n == 185200
+    cfg = sparse_zi_config(1000, rng_mode=_lib.RNG_TAPE, trace_cap=300000, hash_pops=1)
+    sim = BatchedSim(cfg, 1)
+    sim.reset_tape(*oracle_tapes([o]))
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    _check_env(sim, 0, o, n, st)
+    g = np.load(os.path.join(golden_dir, "z1000_s123456789.npz"))        # recorded from the live reference
+    assert np.array_equal(sim.holdings(0), g["holdings"])
+    assert int(st["pop_hash"][0]) == int(g["pop_hash_ckpt"][-1])
+
+
+def test_sliced_runs_equal_single_run():
+    o = OracleSim(100, 1001, TRACE_ALL)
+    o.run()
+    cfg = sparse_zi_config(100, rng_mode=_lib.RNG_TAPE, hash_pops=1)
+    sim = BatchedSim(cfg, 1)
+    sim.reset_tape(*oracle_tapes([o]))
+    for q in range(0, 17 * 4):
+        sim.run(q * 900 * 10 ** 9)
+    sim.run()
+    st = sim.stats()
+    assert int(st["pop_hash"][0]) == o.pop_hash() and int(st["messages"][0]) == o.n_pops
+
+
+def test_intermediate_state_matches_oracle():
+    """Stop both at 11:00 and compare the live book + counters (not only end-of-day state)."""
+    o = OracleSim(100, 123456789, TRACE_ALL)
+    o.run()
+    o2 = OracleSim(100, 123456789, 0)
+    t = 11 * 3600 * 10 ** 9
+    n2, done = o2.run_until(t)
+    cfg = sparse_zi_config(100, rng_mode=_lib.RNG_TAPE, hash_pops=1)
+    sim = BatchedSim(cfg, 1)
+    sim.reset_tape(*oracle_tapes([o]))
+    sim.run(t)
+    st = sim.stats()
+    assert int(st["messages"][0]) == n2 and not done and int(st["flags"][0]) == 0
+    assert int(st["pop_hash"][0]) == o2.pop_hash()
+    l1 = o2.book_l1()
+    assert (int(st["best_bid"][0]), int(st["best_bid_qty"][0]), int(st["best_ask"][0]), int(st["best_ask_qty"][0]),
+            int(st["last_trade"][0])) == tuple(int(x) for x in l1)

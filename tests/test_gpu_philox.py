@@ -1,0 +1,78 @@
+"""GPU tests under the GPU-native Philox streams: size-independent properties at large batch (conservation of shares
+and cash == checksum of checksums, determinism, placement invariance, capacity flags) and order-flow statistics in
+distribution against the oracle's reference-RNG runs."""
+import numpy as np
+import pytest
+
+from marl_optimal_execution_b200 import _lib
+from marl_optimal_execution_b200.sim import BatchedSim, sparse_zi_config
+from oracle.oracle import OracleSim
+
+pytestmark = pytest.mark.gpu
+NS = 10 ** 9
+
+
+def test_z1000_batch_conservation_and_flags():
+    cfg = sparse_zi_config(1000)
+    n = 1024
+    sim = BatchedSim(cfg, n)
+    sim.reset(np.arange(n, dtype=np.uint64) + 123456789)
+    sim.run(int(cfg.mkt_open_ns) + 1800 * NS)
+    sim.finalize()
+    st = sim.stats()
+    assert (st["flags"] & _lib.F_ERROR_MASK == 0).all(), np.unique(st["flags"])
+    assert (st["sum_shares"] == 0).all()                                  # every fill moves shares between two traders
+    assert (st["sum_cash"] == 1000 * cfg.starting_cash).all()             # ... and cash
+    assert st["messages"].min() > 15000 and (st["fills"] > 0).all()
+    assert (st["best_bid"] < st["best_ask"]).all()                        # uncrossed books
+
+
+def test_determinism_and_placement_invariance():
+    cfg = sparse_zi_config(100)
+    seeds = np.array([11, 12, 13, 14, 15, 16, 17, 11], dtype=np.uint64)
+    out = []
+    for _ in range(2):
+        sim = BatchedSim(cfg, len(seeds))
+        sim.reset(seeds)
+        sim.run()
+        sim.finalize()
+        out.append((sim.stats(), sim.holdings(0), sim.holdings(7)))
+    assert out[0][0].tobytes() == out[1][0].tobytes()
+    assert np.array_equal(out[0][1], out[0][2]) and out[0][0][0].tobytes() == out[0][0][7].tobytes()
+    assert len(set(int(m) for m in out[0][0]["messages"][:7])) > 1
+
+
+def test_full_day_statistics_agree_with_reference_rng_runs():
+    """Philox runs are not bit-comparable with MT19937 runs; their per-day order-flow statistics must agree in
+    distribution with reference-RNG runs of the same config (oracle, 8 seeds): within 6 sigma of the oracle mean."""
+    ref = []
+    for s in range(1001, 1009):
+        o = OracleSim(100, s, 0)
+        n = o.run()
+        ref.append((n, o.counter("limit"), o.counter("fills"), o.counter("cancel"), o.counter("spread_queries")))
+    ref = np.array(ref, float)
+    cfg = sparse_zi_config(100)
+    n = 256
+    sim = BatchedSim(cfg, n)
+    sim.reset(np.arange(n, dtype=np.uint64) + 99)
+    sim.run()
+    st = sim.stats()
+    assert (st["flags"] == _lib.F_DONE).all()
+    got = np.stack([st["messages"], st["limit_orders"], st["fills"], st["cancels"], st["spread_queries"]], 1).astype(float)
+    for k in range(5):
+        mu, sd = ref[:, k].mean(), max(ref[:, k].std(ddof=1), 1.0)
+        se = np.sqrt(sd ** 2 / len(ref) + got[:, k].var(ddof=1) / n)
+        assert abs(got[:, k].mean() - mu) < 6 * se + 0.02 * mu, (k, got[:, k].mean(), mu, se)
+
+
+def test_overflow_is_flagged_not_silent():
+    cfg = sparse_zi_config(100, queue_cap=64)
+    sim = BatchedSim(cfg, 2)
+    sim.reset([1, 2])
+    sim.run()
+    assert (sim.stats()["flags"] & _lib.F_QUEUE_OVERFLOW).all()
+    cfg = sparse_zi_config(100, level_cap=8)
+    sim = BatchedSim(cfg, 2)
+    sim.reset([1, 2])
+    sim.run()
+    assert (sim.stats()["flags"] & _lib.F_LEVEL_OVERFLOW).all()

@@ -1,0 +1,63 @@
+"""Pin the oracle (oracle/abides_oracle.c) against traces recorded from the live reference
+(tools/record_reference.py -> tests/golden/*.npz) and against the reference's own recorded run
+tests/sparse_zi_1000.txt."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle.oracle import OracleSim, TRACE_ALL
+
+
+def test_z100_full_trace_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "z100_s123456789_full.npz"))
+    s = OracleSim(100, 123456789, TRACE_ALL)
+    assert s.run() == int(g["n_pops"]) == 18871
+    for k in ("pops", "ops", "notes", "snaps"):
+        assert np.array_equal(s.trace(k), g[k]), k
+    assert np.array_equal(s.holdings(), g["holdings"])
+    off = g["tape_offsets"]
+    assert s.n_streams == len(off) - 1
+    for i in range(s.n_streams):
+        kinds, bits = s.tape(i)
+        assert s.stream_seed(i) == g["stream_seeds"][i]
+        assert np.array_equal(kinds, g["tape_kind"][off[i]:off[i + 1]].view(np.uint8)), i
+        assert np.array_equal(bits, g["tape_bits"][off[i]:off[i + 1]]), i
+    assert np.array_equal(s.global_exp_tape(), g["global_exp_tape"])
+
+
+@pytest.mark.parametrize("variant,seed,name", [(1000, 123456789, "z1000_s123456789"), (1000, 1001, "z1000_s1001"),
+                                               (100, 1001, "z100_s1001")])
+def test_digest_bit_exact(golden_dir, variant, seed, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    s = OracleSim(variant, seed, 0)
+    assert s.run() == int(g["n_pops"])
+    assert np.array_equal(s.hash_ckpt(), g["pop_hash_ckpt"])           # event order, every 1000 pops
+    assert s.note_hash() == int(g["note_hash"])                        # every outbound exchange message (fills, L1 replies)
+    assert s.snap_hash() == int(g["snap_hash"])                        # book state after every book op
+    assert np.array_equal(s.holdings(), g["holdings"])
+    assert s.counter("max_bid_levels") == g["max_levels"][0] and s.counter("max_ask_levels") == g["max_levels"][1]
+    assert s.counter("max_resting") == int(g["max_resting"])
+
+
+def test_z1000_known_answers():
+    s = OracleSim(1000, 123456789, 0)
+    assert s.run() == 185200                                           # tests/sparse_zi_1000.txt:22
+    # SURVEY App. B.3 shape facts
+    assert s.counter("limit") == 24416 and s.counter("fills") == 5459 and s.counter("cancel") == 12975
+    assert s.counter("spread_queries") == 25424 and s.counter("max_queue") == 2004
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/tests/sparse_zi_1000.txt"), reason="reference tree not present")
+def test_z1000_matches_reference_recorded_stdout():
+    """The reference's own golden file: 1000 'Final holdings' lines + message count."""
+    txt = open("/root/reference/tests/sparse_zi_1000.txt").read()
+    assert re.search(r"messages: (\d+)", txt).group(1) == "185200"
+    rows = re.findall(r"Final holdings for ZI Agent (\d+) .*?\{ (?:JPM: (-?\d+), )?CASH: (-?\d+) \}\.  Marked to market: (-?\d+)", txt)
+    assert len(rows) == 1000
+    ref = {int(a): (int(sh or 0), int(c), int(m)) for a, sh, c, m in rows}
+    s = OracleSim(1000, 123456789, 0)
+    s.run()
+    for aid, sh, cash, mtm, _ in s.holdings():
+        assert ref[int(aid)] == (sh, cash, mtm), aid
