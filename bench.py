@@ -1,0 +1,280 @@
+#!/usr/bin/env python3
+"""bench.py -- LOB messages/s of the batched ABIDES simulator on the sparse_zi_1000 shape.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (hand-written sm_100a kernels through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  reference arm: the reference's CPU algorithm (oracle port,
+                                                            the Python reference cannot travel to the GPU box) on all host cores
+
+Workload (BASELINE.json configs[1]): config/sparse_zi_1000.py -- 1000 ZeroIntelligenceAgents + exchange, sparse OU
+oracle -- 16 384 independent environments per GPU, environment e seeded base+e, GPU-native Philox streams.
+A "step" advances every environment's event loop (Kernel.py:190-292) by `--slice-s` simulated seconds with ONE launch
+of abx_run_kernel.  A "message" is one event-queue pop counted exactly like the reference's ttl_messages
+(Kernel.py:211).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NS = 10 ** 9
+B_MSG = 320                 # algorithmic bytes per LOB message (DESIGN.md "Roofline")
+PUBLISHED_MSGS_PER_S = 3100.4   # reference's own sparse_zi_1000 run (tests/sparse_zi_1000.txt:22)
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic():
+    """dram bytes per launch of abx_run_kernel from the committed ncu --set full capture, if one exists."""
+    p = os.path.join(ROOT, "profiles", "run_kernel_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_msgs_per_s(n_env_days, threads, variant=1000, seed0=5000):
+    """Reference CPU algorithm (oracle/abides_oracle.c, scalar C port) on `threads` host threads: full env-days."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.oracle import OracleSim, lib
+    lib()
+
+    def one(i):
+        s = OracleSim(variant, seed0 + i, 0)
+        s.start()
+        t0 = time.perf_counter()
+        n, _ = s.run_until(2 ** 62)          # event loop only, like Kernel.py:184,301 (construction excluded)
+        return n, time.perf_counter() - t0
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:       # ctypes releases the GIL during the C call
+        res = list(ex.map(one, range(n_env_days)))
+    wall = time.perf_counter() - t0
+    msgs = sum(r[0] for r in res)
+    return msgs, wall, sum(r[1] for r in res)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = max(2 * cores, 8)
+    oracle_msgs_per_s(min(cores, 8), cores, args.variant)                       # warm-up (library load, page-in)
+    for _ in range(max(args.warmup - 1, 0)):
+        oracle_msgs_per_s(per_step, cores, args.variant)
+    tot_m, tot_w = 0, 0.0
+    for k in range(args.steps):
+        m, w, _ = oracle_msgs_per_s(per_step, cores, args.variant, seed0=9000 + k * per_step)
+        tot_m += m; tot_w += w
+    v = tot_m / tot_w
+    sample = "%d steps x %d full env-days of sparse_zi_%d (event loop only), %d threads" % (args.steps, per_step, args.variant, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "LOB msgs/sec", "value": v, "unit": "msgs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_w / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": v / PUBLISHED_MSGS_PER_S, "dtype": "int64+f64", "data": "synthetic",
+        "config": {"workload": "config/sparse_zi_%d.py: %d ZI agents + exchange, sparse OU oracle; reference CPU algorithm "
+                               "(oracle/abides_oracle.c port of the Python reference) on host cores" % (args.variant, args.variant)},
+        "cpu_baseline": {"value": v, "unit": "msgs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "msgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    from marl_optimal_execution_b200 import _lib, distributed as D
+    from marl_optimal_execution_b200.sim import BatchedSim, sparse_zi_config
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    cfg = sparse_zi_config(args.variant)
+    n_envs = args.envs_per_gpu
+    sim = BatchedSim(cfg, n_envs, device=local_rank)
+    lo = rank * n_envs
+    seeds = D.env_seeds(args.seed, lo, lo + n_envs)
+    stream = torch.cuda.current_stream(dev)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+
+    # simulated-time budget: prefix + (W + 2K) slices must stay inside market hours
+    t_open, t_close = int(cfg.mkt_open_ns), int(cfg.mkt_close_ns)
+    prefix = 120 * NS
+    n_slices = args.warmup + 2 * args.steps
+    slice_ns = min(int(args.slice_s * NS), (t_close - t_open - prefix - 60 * NS) // max(n_slices, 1))
+    sim.reset(seeds, stream=sp)
+    t = t_open + prefix
+    sim.run(t, stream=sp)                               # 00:00 -> 09:32 start-up transient, untimed
+    for _ in range(args.warmup):
+        t += slice_ns
+        sim.run(t, stream=sp)
+    torch.cuda.synchronize(dev)
+    st0 = sim.stats(stream=sp)
+    launches0 = sim.launch_count
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    D.barrier(); torch.cuda.synchronize(dev)
+    ev[0].record(stream)
+    for k in range(args.steps):                         # ---- timed region: K launches of abx_run_kernel, state resident in HBM
+        t += slice_ns
+        sim.run(t, stream=sp)
+        ev[k + 1].record(stream)
+    torch.cuda.synchronize(dev); D.barrier()
+    launches = sim.launch_count - launches0
+    elapsed_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    clocks = sampler.stop() if sampler else None
+    st1 = sim.stats(stream=sp)
+    msgs_local = int(st1["messages"].sum() - st0["messages"].sum())
+    err_envs = int(((st1["flags"] & _lib.F_ERROR_MASK) != 0).sum())
+
+    # ---- e2e: same metric through the C ABI with HOST buffers (pinned): per step H2D of the per-env horizons,
+    #      launch, D2H of every environment's abx_env_stats record; wall clock around sync points.
+    until_pin = torch.empty(n_envs, dtype=torch.int64).pin_memory()
+    stats_pin = torch.empty(n_envs * ctypes.sizeof(_lib.EnvStats), dtype=torch.uint8).pin_memory()
+    stats_np = stats_pin.numpy().view(_lib.STATS_DTYPE)
+    D.barrier(); torch.cuda.synchronize(dev)
+    w0 = time.perf_counter()
+    for k in range(args.steps):
+        t += slice_ns
+        until_pin.fill_(t)
+        sim.run_each(until_pin.data_ptr(), stream=sp)
+        sim.stats(stream=sp, out=stats_np)              # synchronises the stream
+    torch.cuda.synchronize(dev)
+    e2e_s_local = time.perf_counter() - w0
+    D.barrier()
+    e2e_msgs_local = int(stats_np["messages"].sum() - st1["messages"].sum())
+
+    # ---- aggregate over ranks: sums by all-gather of the summary vectors (NCCL), times by max
+    g = D.gather_summaries(torch.tensor([msgs_local, e2e_msgs_local, err_envs], dtype=torch.int64), device=dev)
+    elapsed_ms = D.max_over_ranks(elapsed_ms, device=dev)
+    e2e_s = D.max_over_ranks(e2e_s_local, device=dev)
+    if rank != 0:
+        return
+    msgs, e2e_msgs, errs = int(g[:, 0].sum()), int(g[:, 1].sum()), int(g[:, 2].sum())
+    value = msgs / (elapsed_ms / 1e3)
+    peak, peak_src = measured_peak_hbm()
+    # roofline of the dominant (only) kernel in the timed region, per launch, on rank 0's launches
+    kern_ms = statistics.mean(step_ms)
+    alg_bytes_per_launch = (msgs_local / args.steps) * B_MSG
+    achieved = alg_bytes_per_launch / (kern_ms / 1e3) / 1e9
+    traffic = profiled_traffic()
+    out = {
+        "metric": "LOB msgs/sec", "value": value, "unit": "msgs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": value / PUBLISHED_MSGS_PER_S, "dtype": "int64+f64", "data": "synthetic",
+        "config": {
+            "workload": "config/sparse_zi_%d.py shape: %d ZI agents + exchange, sparse OU oracle, %d envs/GPU, env e seeded %d+e "
+                        "(Philox streams)" % (args.variant, args.variant, n_envs, args.seed),
+            "envs_per_gpu": n_envs, "step": "%.1f simulated seconds per environment per launch" % (slice_ns / NS),
+            "messages_per_step": msgs // args.steps, "state_bytes_per_gpu": sim.device_bytes,
+            "l2_policy": "inputs larger than L2: %.1f GB of per-environment state streamed per step, no flush needed" % (sim.device_bytes / 1e9),
+            "vs_baseline_ref": "BASELINE.md section 1: 3100.4 msgs/s, reference single process, i7 2.6 GHz", "error_envs": errs,
+        },
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "peak_source": peak_src,
+                     "kernel": "abx_run_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_msg": B_MSG,
+                     "note": "latency-bound by design (one dependent event chain per environment); see DESIGN.md"},
+        "e2e": {"value": e2e_msgs / e2e_s, "unit": "msgs/s", "h2d_bytes_per_step": 8 * n_envs * 1,
+                "d2h_bytes_per_step": ctypes.sizeof(_lib.EnvStats) * n_envs},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_days = max(2 * cores, 16)
+        oracle_msgs_per_s(min(cores, 4), cores, args.variant)
+        m, w, cpu_s = oracle_msgs_per_s(n_days, cores, args.variant)
+        out["cpu_baseline"] = {"value": m / w, "unit": "msgs/s", "cores": cores, "kind": "port",
+                               "sample": "%d full env-days of sparse_zi_%d, event loop only, %d threads, %.1f CPU-s" % (n_days, args.variant, cores, cpu_s),
+                               "single_thread_value": m / cpu_s}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=16384)
+    ap.add_argument("--slice-s", type=float, default=300.0)
+    ap.add_argument("--variant", type=int, default=1000, choices=[100, 1000])
+    ap.add_argument("--seed", type=int, default=123456789)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        print("bench.py: note: W >= 3 is required for a valid number", file=sys.stderr)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    from marl_optimal_execution_b200 import distributed as D
+    rank, local_rank, world = D.init()
+    try:
+        run_ours(args, rank, local_rank, world)
+    finally:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -165,6 +165,12 @@ int32_t abx_sim_reset_tape(abx_sim *h, const uint64_t *tape_bits, const uint8_t 
  * while the next event time <= until_ns (and the reference loop condition holds).  Asynchronous on `stream`. */
 int32_t abx_sim_run(abx_sim *h, int64_t until_ns, void *stream);
 
+/* Same, with a per-environment horizon: until_ns_host is a HOST array [n_envs] (pinned memory makes the copy
+ * asynchronous); it is copied to the device on `stream` before the launch.  This is the vectorised form of the
+ * gym-style stepping surface (GymKernel.stepRunner, GymKernel.py:158-306), where every environment stops at its
+ * own next decision time. */
+int32_t abx_sim_run_each(abx_sim *h, const int64_t *until_ns_host, void *stream);
+
 /* Replaces: Kernel.runner :310-311 (kernelStopping of every agent: mark to market, ZI surplus valuation,
  * which advances the shared fundamental, ZeroIntelligenceAgent.py:80-123). */
 int32_t abx_sim_finalize(abx_sim *h, void *stream);

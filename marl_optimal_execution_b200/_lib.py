@@ -102,6 +102,7 @@ def _bind(L):
     sig("abx_sim_reset_philox", i32, vp, P(C.c_uint64), vp)
     sig("abx_sim_reset_tape", i32, vp, P(C.c_uint64), P(C.c_uint8), P(i64), P(C.c_double), P(C.c_double), vp)
     sig("abx_sim_run", i32, vp, i64, vp)
+    sig("abx_sim_run_each", i32, vp, vp, vp)
     sig("abx_sim_finalize", i32, vp, vp)
     sig("abx_sim_stats", i32, vp, vp, vp)
     sig("abx_sim_stats_device", i32, vp, vp, vp)

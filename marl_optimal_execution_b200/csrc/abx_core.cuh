@@ -42,7 +42,7 @@ struct alignas(16) EnvState {           // 192 B per environment
   double ms_v; uint64_t pop_hash;       // next megashock value; FNV-1a of the pop sequence
   uint64_t seed; int32_t or_v, last_trade; // oracle r[symbol][1]; OrderBook.last_trade
   uint32_t uniq, next_order_id, q_count, max_q; // Message.uniq, Order.order_id counters; queue fill
-  int32_t n_lv[2]; int32_t n_resting; uint32_t free_head; // ladder sizes (0 bids, 1 asks); order-node free list
+  int32_t n_bid_lv, n_ask_lv; int32_t n_resting; uint32_t free_head; // ladder sizes (0 bids, 1 asks); order-node free list
   uint32_t pool_top, flags, trace_n, c_limit;
   uint32_t c_cancel, c_fills, c_query, ctr_symbol;
   uint32_t ctr_kernel, ctr_latency, ctr_global, started;
@@ -163,8 +163,11 @@ ABX_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 }
 enum { S_SYMBOL = 0, S_KERNEL = 1, S_LATENCY = 2, S_GLOBAL = 3, S_AGENT0 = 3 };  // agent a uses stream S_AGENT0 + a
 
-struct Rng {
+// MODE: ABX_RNG_PHILOX / ABX_RNG_TAPE fixed at compile time (one kernel instantiation per mode), or -1 = read P->c.rng_mode
+template <int MODE>
+struct RngT {
   const SimParams *P; int env; uint64_t seed; uint32_t err;
+  ABX_HD bool tape() const { return MODE < 0 ? P->c.rng_mode == ABX_RNG_TAPE : MODE == ABX_RNG_TAPE; }
   ABX_HD uint64_t tape_next(int stream, uint32_t &ctr, uint8_t kind) {
     const int64_t *off = P->tape_off + (int64_t)env * P->n_streams + stream;
     int64_t i = off[0] + ctr;
@@ -176,27 +179,28 @@ struct Rng {
   ABX_HD void philox(int stream, uint32_t &ctr, uint32_t o[4]) { philox4x32_10(ctr, (uint32_t)stream, 0x41424958u, 0, (uint32_t)seed, (uint32_t)(seed >> 32), o); ctr++; }
   static ABX_HD double u53(uint32_t a, uint32_t b) { return ((a >> 5) * 67108864.0 + (b >> 6)) / 9007199254740992.0; }
   ABX_HD double std_normal(int stream, uint32_t &ctr) {
-    if (P->c.rng_mode == ABX_RNG_TAPE) return bits_dbl(tape_next(stream, ctr, 'n'));
+    if (tape()) return bits_dbl(tape_next(stream, ctr, 'n'));
     uint32_t o[4]; philox(stream, ctr, o);
     double u1 = 1.0 - u53(o[0], o[1]), u2 = u53(o[2], o[3]);                 // u1 in (0,1]
     return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
   }
   ABX_HD double std_exponential(int stream, uint32_t &ctr) {
-    if (P->c.rng_mode == ABX_RNG_TAPE) return bits_dbl(tape_next(stream, ctr, 'e'));
+    if (tape()) return bits_dbl(tape_next(stream, ctr, 'e'));
     uint32_t o[4]; philox(stream, ctr, o); return -log(1.0 - u53(o[0], o[1]));
   }
   ABX_HD double u01(int stream, uint32_t &ctr) {
-    if (P->c.rng_mode == ABX_RNG_TAPE) return bits_dbl(tape_next(stream, ctr, 'u'));
+    if (tape()) return bits_dbl(tape_next(stream, ctr, 'u'));
     uint32_t o[4]; philox(stream, ctr, o); return u53(o[0], o[1]);
   }
   // integer in [0, range] (numpy randint(low, high) with range = high - 1 - low; no draw when range == 0)
   ABX_HD int64_t randint(int stream, uint32_t &ctr, uint32_t range) {
-    if (range == 0) { if (P->c.rng_mode == ABX_RNG_TAPE) return (int64_t)tape_next(stream, ctr, 'i'); return 0; }
-    if (P->c.rng_mode == ABX_RNG_TAPE) return (int64_t)tape_next(stream, ctr, 'i');
+    if (range == 0) { if (tape()) return (int64_t)tape_next(stream, ctr, 'i'); return 0; }
+    if (tape()) return (int64_t)tape_next(stream, ctr, 'i');
     uint32_t o[4]; philox(stream, ctr, o); return (int64_t)((uint64_t(o[0]) * (uint64_t(range) + 1)) >> 32);
   }
   ABX_HD double normal(int stream, uint32_t &ctr, double loc, double scale) { return dadd(loc, dmul(scale, std_normal(stream, ctr))); }
 };
+typedef RngT<-1> Rng;
 
 
 // ---------------------------------------------------------------------------------------------------
@@ -230,7 +234,7 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
   s.now = P.c.start_ns; s.ttl = 0; s.exch_time = P.c.start_ns; s.exch_comp_delay = P.c.default_computation_delay_ns;   // Kernel.py:97,105
   s.or_t = P.c.mkt_open_ns; s.ms_t = 0; s.ms_v = 0.0; s.pop_hash = 0xCBF29CE484222325ULL; s.seed = seed;
   s.or_v = (int32_t)P.c.r_bar; s.last_trade = (int32_t)P.c.r_bar;     // SparseMeanRevertingOracle.py:58; ExchangeAgent.kernelInitializing :91-102
-  s.uniq = 0; s.next_order_id = 0; s.q_count = 0; s.max_q = 0; s.n_lv[0] = s.n_lv[1] = 0; s.n_resting = 0; s.free_head = NIL;
+  s.uniq = 0; s.next_order_id = 0; s.q_count = 0; s.max_q = 0; s.n_bid_lv = s.n_ask_lv = 0; s.n_resting = 0; s.free_head = NIL;
   s.pool_top = 0; s.flags = 0; s.trace_n = 0; s.c_limit = s.c_cancel = s.c_fills = s.c_query = 0;
   s.ctr_symbol = s.ctr_kernel = s.ctr_latency = s.ctr_global = 0; s.started = 1; s.sum_shares = 0; s.sum_cash = 0;
   for (int i = 0; i < 4; i++) s.pad[i] = 0;
@@ -267,17 +271,23 @@ ABX_HD void regs_store(ZiAgent *z, const AgentRegs &a) {
   z->bid = a.bid; z->bid_q = a.bid_q; z->ask = a.ask; z->ask_q = a.ask_q; z->n_orders = a.n_orders; z->flags = a.flags; z->rng_ctr = a.rng_ctr;
 }
 
-template <class Ctx>
+// RNG_MODE / LAT_MODEL: compile-time copies of cfg.rng_mode / cfg.latency_model (-1 = decide at run time);
+// INSTR: parity instrumentation (pop hash + trace records) compiled in or out.
+template <class Ctx, int RNG_MODE = -1, int LAT_MODEL = -1, bool INSTR = true>
 struct Sim {
-  Ctx &c; const SimParams &P; EnvState s; Rng rng; int64_t addl_delay; int n_out; int self_id;
+  Ctx &c; const SimParams &P; EnvState s; RngT<RNG_MODE> rng; int64_t addl_delay; int n_out; int self_id;
   AgentRegs a; ZiAgent *z;                // the trader whose event is being handled (registers + staged record)
 
   ABX_HD Sim(Ctx &c_, const SimParams &P_, const EnvState &s_, int env) : c(c_), P(P_), s(s_), addl_delay(0), n_out(0), self_id(0), z(nullptr) {
     rng.P = &P; rng.env = env; rng.seed = s.seed; rng.err = 0;
   }
 
+  ABX_HD int n_lv(int side) const { return side ? s.n_ask_lv : s.n_bid_lv; }
+  ABX_HD void set_n_lv(int side, int n) { if (side) s.n_ask_lv = n; else s.n_bid_lv = n; }
+
   // ---- tracing (parity runs only) ----
   ABX_HD void trace_rec(const abx_trace_rec &r) {
+    if (!INSTR) return;
     if (s.trace_n >= (uint32_t)P.c.trace_cap) { s.flags |= ABX_F_TRACE_OVERFLOW; return; }
     c.trace(r, s.trace_n); s.trace_n++;
   }
@@ -296,12 +306,12 @@ struct Sim {
     trace_rec(r);
   }
   ABX_HD void trace_snap() {
-    if (P.c.trace_cap <= 0) return;
+    if (!INSTR || P.c.trace_cap <= 0) return;
     abx_trace_rec r; r.tag = 2; r.a = 0; r.t = s.now;
     for (int i = 0; i < 16; i++) r.v[i] = 0;
-    r.v[0] = s.n_lv[0]; r.v[1] = s.n_lv[1]; r.v[2] = s.n_resting;
+    r.v[0] = s.n_bid_lv; r.v[1] = s.n_ask_lv; r.v[2] = s.n_resting;
     for (int side = 0; side < 2; side++) for (int k = 0; k < 3; k++) {
-      int n = s.n_lv[side]; if (k < n) { r.v[3 + side * 6 + 2 * k] = c.lv_price(side, n - 1 - k); r.v[4 + side * 6 + 2 * k] = c.lv_qty(side, n - 1 - k); }
+      int n = n_lv(side); if (k < n) { r.v[3 + side * 6 + 2 * k] = c.lv_price(side, n - 1 - k); r.v[4 + side * 6 + 2 * k] = c.lv_qty(side, n - 1 - k); }
     }
     r.v[15] = s.last_trade;
     trace_rec(r);
@@ -351,10 +361,10 @@ struct Sim {
         e.uniq = s.uniq++;                                                            // Message() construction order (message/Message.py:33-34)
         if (w0 & OF_BUMP_UNIQ) s.uniq++;                                              // TradingAgent.getCurrentSpread's never-sent msg_copy (:281)
         bool from_exch = (w0 & OF_FROM_EXCH) != 0;
-        if (from_exch && P.c.trace_cap > 0) trace_note(e.recipient, e.kind, e.p);
+        if (INSTR && from_exch && P.c.trace_cap > 0) trace_note(e.recipient, e.kind, e.p);
         int64_t sent = s.now + off;                                                   // Kernel.py:391-393
         int64_t deliver;
-        if (P.c.latency_model == ABX_LAT_CUBIC) {                                     // model/LatencyModel.py:133-138
+        if (LAT_MODEL < 0 ? P.c.latency_model == ABX_LAT_CUBIC : LAT_MODEL == ABX_LAT_CUBIC) {   // model/LatencyModel.py:133-138
           double u = rng.u01(S_LATENCY, s.ctr_latency);
           double x = dadd(P.c.jitter_clip, dmul(dsub(1.0, P.c.jitter_clip), u));      // uniform(low=clip, high=1.0)
           double latency = dadd(lat, dmul(P.c.jitter / pow(x, 3.0), lat / P.c.jitter_unit));
@@ -408,7 +418,7 @@ struct Sim {
 
   // enterOrder :256-282
   ABX_HD void book_enter(int side, uint32_t oid, int agent, int32_t price, int32_t qty) {
-    int n = s.n_lv[side]; int pos; bool found;
+    int n = n_lv(side); int pos; bool found;
     c.lv_find(side, price, n, pos, found);
     uint32_t node = node_alloc(); if (node == NIL) return;
     NodeRec r; r.id = oid; r.qty = qty; r.agent = (uint32_t)agent; r.next = NIL; c.node_store(node, r);
@@ -418,7 +428,7 @@ struct Sim {
       c.lv_set(side, pos, c.lv_qty(side, pos) + qty, c.lv_head(side, pos), node);
     } else {
       if (n >= P.c.level_cap) { s.flags |= ABX_F_LEVEL_OVERFLOW; node_free(node); return; }
-      c.lv_insert(side, pos, n, price, qty, node, node); s.n_lv[side] = n + 1;
+      c.lv_insert(side, pos, n, price, qty, node, node); set_n_lv(side, n + 1);
     }
     s.n_resting++;
   }
@@ -430,7 +440,7 @@ struct Sim {
     bool matching = true;
 #pragma unroll 1
     while (matching) {                                                                  // :68-110
-      int n = s.n_lv[opp]; bool matched = false;
+      int n = n_lv(opp); bool matched = false;
       if (n > 0) {
         int32_t bp = c.lv_price(opp, n - 1);
         if (is_buy ? price >= bp : price <= bp) {                                       // isMatch :242-254, head of best level only
@@ -438,7 +448,7 @@ struct Sim {
           int32_t fq;
           if (qty >= hr.qty) {                                                          // :204-210 whole resting order consumed
             fq = hr.qty;
-            if (hr.next == NIL) s.n_lv[opp] = n - 1;                                    // level emptied: it is the last element
+            if (hr.next == NIL) set_n_lv(opp, n - 1);                                    // level emptied: it is the last element
             else c.lv_set(opp, n - 1, c.lv_qty(opp, n - 1) - fq, hr.next, c.lv_tail(opp, n - 1));
             node_free(h); s.n_resting--;
           } else {                                                                      // :212-217 partial
@@ -462,7 +472,7 @@ struct Sim {
   }
   // cancelOrder :284-339
   ABX_HD void book_cancel(uint32_t oid, int agent, int is_buy, int32_t price, double lat_in) {
-    int side = is_buy ? 0 : 1; int n = s.n_lv[side]; if (n == 0) return;
+    int side = is_buy ? 0 : 1; int n = n_lv(side); if (n == 0) return;
     int pos; bool found; c.lv_find(side, price, n, pos, found);
     if (!found) return;
     uint32_t prev = NIL, cur = c.lv_head(side, pos);
@@ -471,7 +481,7 @@ struct Sim {
       NodeRec r = c.node_load(cur);
       if (r.id == oid) {
         if (prev == NIL) {
-          if (r.next == NIL) { c.lv_remove(side, pos, n); s.n_lv[side] = n - 1; }
+          if (r.next == NIL) { c.lv_remove(side, pos, n); set_n_lv(side, n - 1); }
           else c.lv_set(side, pos, c.lv_qty(side, pos) - r.qty, r.next, c.lv_tail(side, pos));
         } else {
           NodeRec pr = c.node_load(prev); pr.next = r.next; c.node_store(prev, pr);
@@ -500,7 +510,7 @@ struct Sim {
     else if (m.kind == ABX_WHEN_MKT_CLOSE) { s.exch_comp_delay = 0; exch_send(m.sender, ABX_WHEN_MKT_CLOSE, p, lat); }    // :184-192
     else if (m.kind == ABX_QUERY_SPREAD) {                                              // :215-245 (depth 1)
       s.c_query++; int f = 0;
-      int nb = s.n_lv[0], na = s.n_lv[1];
+      int nb = s.n_bid_lv, na = s.n_ask_lv;
       if (nb > 0) { p[0] = c.lv_price(0, nb - 1); p[1] = c.lv_qty(0, nb - 1); f |= 1; }
       if (na > 0) { p[2] = c.lv_price(1, na - 1); p[3] = c.lv_qty(1, na - 1); f |= 2; }
       if (t_closed) f |= 4;
@@ -655,8 +665,8 @@ struct Sim {
       if (key_time(khi) > until) break;
       Event ev; c.q_fetch(grp, ev);                                                     // :192
       s.now = ev.t; s.ttl++;                                                            // :211
-      if (P.c.hash_pops) s.pop_hash = fnv_mix(fnv_mix(fnv_mix(fnv_mix(s.pop_hash, ev.t), ev.recipient), ev.type), ev.type == ABX_T_MESSAGE ? (int64_t)ev.uniq : -1);
-      if (P.c.trace_cap > 0) {
+      if (INSTR && P.c.hash_pops) s.pop_hash = fnv_mix(fnv_mix(fnv_mix(fnv_mix(s.pop_hash, ev.t), ev.recipient), ev.type), ev.type == ABX_T_MESSAGE ? (int64_t)ev.uniq : -1);
+      if (INSTR && P.c.trace_cap > 0) {
         abx_trace_rec r; r.tag = 0; r.a = ev.recipient; r.t = ev.t; for (int i = 0; i < 16; i++) r.v[i] = 0;
         r.v[0] = ev.type; r.v[1] = ev.type == ABX_T_MESSAGE ? (int32_t)ev.uniq : -1; r.v[2] = ev.kind; trace_rec(r);
       }

@@ -82,7 +82,7 @@ static inline const char *status_string(int32_t st) {
 // stats record from an EnvState plus the top of the two ladders
 ABX_HD void fill_stats(const EnvState &s, int32_t bb, int32_t bbq, int32_t ba, int32_t baq, abx_env_stats *o) {
   o->messages = s.ttl; o->now_ns = s.now; o->pop_hash = s.pop_hash; o->limit_orders = s.c_limit; o->cancels = s.c_cancel; o->fills = s.c_fills;
-  o->spread_queries = s.c_query; o->max_queue = s.max_q; o->n_bid_levels = s.n_lv[0]; o->n_ask_levels = s.n_lv[1]; o->n_resting = s.n_resting;
+  o->spread_queries = s.c_query; o->max_queue = s.max_q; o->n_bid_levels = s.n_bid_lv; o->n_ask_levels = s.n_ask_lv; o->n_resting = s.n_resting;
   o->best_bid = bb; o->best_bid_qty = bbq; o->best_ask = ba; o->best_ask_qty = baq; o->last_trade = s.last_trade; o->fundamental = s.or_v;
   o->flags = s.flags; o->trace_len = s.trace_n; o->uniq = s.uniq; o->orders_allocated = s.next_order_id; o->sum_shares = s.sum_shares; o->sum_cash = s.sum_cash;
 }

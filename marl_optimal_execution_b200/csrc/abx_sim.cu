@@ -55,8 +55,11 @@ abx_reset_env_kernel(SimParams P, const uint64_t *__restrict__ seeds, const uint
   env_store(P.env + env, sim.s, ctx.lane);
 }
 
+// One instantiation per (RNG mode, latency model, instrumentation): the production path (Philox, no instrumentation)
+// carries neither the tape-replay branches nor the parity hash/trace code.
+template <int RNG, int LAT, bool INSTR>
 __global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
-abx_run_kernel(SimParams P, int64_t until_ns, size_t smem_per_warp) {
+abx_run_kernel(SimParams P, int64_t until_ns, const int64_t *__restrict__ until_each, size_t smem_per_warp) {
   extern __shared__ __align__(16) unsigned char smem[];
   int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
   if (env >= P.n_envs) return;
@@ -64,10 +67,18 @@ abx_run_kernel(SimParams P, int64_t until_ns, size_t smem_per_warp) {
   EnvState s = env_load(P.env + env);
   if (s.flags & ABX_F_DONE) return;
   ctx.load_onchip(s);
-  Sim<WarpCtx> sim(ctx, P, s, env);
-  sim.run(until_ns);
+  Sim<WarpCtx, RNG, LAT, INSTR> sim(ctx, P, s, env);
+  sim.run(until_each ? until_each[env] : until_ns);
   ctx.store_onchip(sim.s);
   env_store(P.env + env, sim.s, ctx.lane);
+}
+typedef void (*run_kernel_fn)(SimParams, int64_t, const int64_t *, size_t);
+static run_kernel_fn run_kernel_for(const abx_sim_config &c) {
+  bool instr = c.trace_cap > 0 || c.hash_pops != 0; int r = c.rng_mode, l = c.latency_model;
+#define PICK(R, L) (instr ? (run_kernel_fn)abx_run_kernel<R, L, true> : (run_kernel_fn)abx_run_kernel<R, L, false>)
+  if (r == ABX_RNG_PHILOX) return l == ABX_LAT_CUBIC ? PICK(ABX_RNG_PHILOX, ABX_LAT_CUBIC) : PICK(ABX_RNG_PHILOX, ABX_LAT_MATRIX_NOISE);
+  return l == ABX_LAT_CUBIC ? PICK(ABX_RNG_TAPE, ABX_LAT_CUBIC) : PICK(ABX_RNG_TAPE, ABX_LAT_MATRIX_NOISE);
+#undef PICK
 }
 
 __global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
@@ -86,7 +97,7 @@ __global__ void abx_stats_kernel(SimParams P, abx_env_stats *__restrict__ out) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= P.n_envs) return;
   const EnvState &s = P.env[env];
-  size_t l = (size_t)env * 2 * P.c.level_cap; int nb = s.n_lv[0], na = s.n_lv[1];
+  size_t l = (size_t)env * 2 * P.c.level_cap; int nb = s.n_bid_lv, na = s.n_ask_lv;
   abx_env_stats o;
   fill_stats(s, nb ? P.lv_price[l + nb - 1] : 0, nb ? P.lv_qty[l + nb - 1] : 0,
              na ? P.lv_price[l + P.c.level_cap + na - 1] : 0, na ? P.lv_qty[l + P.c.level_cap + na - 1] : 0, &o);
@@ -102,7 +113,7 @@ static thread_local char g_cuda_err[512] = "";
 
 struct abx_sim {
   SimParams P; int n_envs, device; bool reset_done; size_t smem_per_warp; int64_t bytes, launches;
-  uint64_t *d_seeds; uint32_t *d_init_err; abx_env_stats *d_stats;
+  uint64_t *d_seeds; uint32_t *d_init_err; abx_env_stats *d_stats; int64_t *d_until;
   uint64_t *d_tbits; uint8_t *d_tkinds; int64_t *d_toff;
 };
 
@@ -123,7 +134,7 @@ int32_t abx_sim_destroy(abx_sim *h) {
   if (!h) return ABX_OK;
   cudaSetDevice(h->device);
   void *ptrs[] = {h->P.qkey, h->P.qpay0, h->P.qpay1, h->P.qcache, h->P.agents, h->P.lv_price, h->P.lv_qty, h->P.lv_ht, h->P.nodes, h->P.env,
-                  h->P.trace, h->d_seeds, h->d_init_err, h->d_stats, h->d_tbits, h->d_tkinds, h->d_toff};
+                  h->P.trace, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff};
   for (void *p : ptrs) if (p) cudaFree(p);
   delete h; return ABX_OK;
 }
@@ -143,10 +154,10 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   DA(h->P.qkey, E * c.queue_cap) DA(h->P.qpay0, E * c.queue_cap) DA(h->P.qpay1, E * c.queue_cap) DA(h->P.qcache, E * h->P.n_qgroups)
   DA(h->P.agents, E * c.n_agents) DA(h->P.lv_price, E * 2 * c.level_cap) DA(h->P.lv_qty, E * 2 * c.level_cap) DA(h->P.lv_ht, E * 2 * c.level_cap)
   DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap)
-  DA(h->d_seeds, E) DA(h->d_init_err, E) DA(h->d_stats, E)
+  DA(h->d_seeds, E) DA(h->d_init_err, E) DA(h->d_stats, E) DA(h->d_until, E)
 #undef DA
   if (smem_cta > 48 * 1024) {
-    CU(cudaFuncSetAttribute(abx_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CU(cudaFuncSetAttribute((const void *)run_kernel_for(*cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
     CU(cudaFuncSetAttribute(abx_reset_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
     CU(cudaFuncSetAttribute(abx_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
   }
@@ -196,7 +207,17 @@ int32_t abx_sim_reset_tape(abx_sim *h, const uint64_t *bits, const uint8_t *kind
 int32_t abx_sim_run(abx_sim *h, int64_t until_ns, void *stream) {
   if (!h) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
   CU(cudaSetDevice(h->device));
-  abx_run_kernel<<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, (cudaStream_t)stream>>>(h->P, until_ns, h->smem_per_warp);
+  run_kernel_for(h->P.c)<<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, (cudaStream_t)stream>>>(h->P, until_ns, nullptr, h->smem_per_warp);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return ABX_OK;
+}
+
+int32_t abx_sim_run_each(abx_sim *h, const int64_t *until_ns_host, void *stream) {
+  if (!h || !until_ns_host) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->d_until, until_ns_host, sizeof(int64_t) * h->n_envs, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  run_kernel_for(h->P.c)<<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, (cudaStream_t)stream>>>(h->P, 0, h->d_until, h->smem_per_warp);
   h->launches += 1;
   CU(cudaGetLastError());
   return ABX_OK;
@@ -243,7 +264,7 @@ int32_t abx_sim_book_snapshot(abx_sim *h, int32_t env, int32_t is_bid, int32_t d
   if (!h || !out || !n_levels || env < 0 || env >= h->n_envs || depth < 0) return ABX_ERR_ARG;
   CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
   EnvState s; CU(cudaMemcpyAsync(&s, h->P.env + env, sizeof(s), cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st));
-  int side = is_bid ? 0 : 1, n = s.n_lv[side], m = depth < n ? depth : n; *n_levels = m; if (m == 0) return ABX_OK;
+  int side = is_bid ? 0 : 1, n = side ? s.n_ask_lv : s.n_bid_lv, m = depth < n ? depth : n; *n_levels = m; if (m == 0) return ABX_OK;
   int32_t *p = (int32_t *)malloc(sizeof(int32_t) * 2 * m); if (!p) return ABX_ERR_ARG;
   size_t base = ((size_t)env * 2 + side) * h->P.c.level_cap + (n - m);
   cudaError_t e = cudaMemcpyAsync(p, h->P.lv_price + base, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, st);

@@ -81,7 +81,7 @@ struct WarpCtx {
     const uint4 *gc = P.qcache + (size_t)env * P.n_qgroups;
     for (int g = lane; g < P.n_qgroups; g += 32) qc[g] = ldcg4(gc + g);
     size_t l = (size_t)env * 2 * P.c.level_cap;
-    for (int side = 0; side < 2; side++) for (int i = lane; i < s.n_lv[side]; i += 32) {
+    for (int side = 0; side < 2; side++) for (int i = lane; i < (side ? s.n_ask_lv : s.n_bid_lv); i += 32) {
       int k = side * P.c.level_cap + i; lvp[k] = P.lv_price[l + k]; lvq[k] = P.lv_qty[l + k]; lvht[k] = P.lv_ht[l + k];
     }
     __syncwarp();
@@ -91,7 +91,7 @@ struct WarpCtx {
     uint4 *gc = P.qcache + (size_t)env * P.n_qgroups;
     for (int g = lane; g < P.n_qgroups; g += 32) gc[g] = qc[g];
     size_t l = (size_t)env * 2 * P.c.level_cap;
-    for (int side = 0; side < 2; side++) for (int i = lane; i < s.n_lv[side]; i += 32) {
+    for (int side = 0; side < 2; side++) for (int i = lane; i < (side ? s.n_ask_lv : s.n_bid_lv); i += 32) {
       int k = side * P.c.level_cap + i; P.lv_price[l + k] = lvp[k]; P.lv_qty[l + k] = lvq[k]; P.lv_ht[l + k] = lvht[k];
     }
   }

@@ -80,12 +80,20 @@ class BatchedSim:
         until = int(self.cfg.stop_ns) + 10 ** 15 if until_ns is None else int(until_ns)
         _lib.check(self._L, self._L.abx_sim_run(self._h, until, stream), "abx_sim_run")
 
+    def run_each(self, until_ns_host_ptr, stream=None):
+        """Per-environment horizons: `until_ns_host_ptr` is the address of a HOST int64[n_envs] array (pinned
+        memory, e.g. a torch pinned tensor's data_ptr(), keeps the copy asynchronous)."""
+        _lib.check(self._L, self._L.abx_sim_run_each(self._h, C.c_void_p(until_ns_host_ptr), stream), "abx_sim_run_each")
+
     def finalize(self, stream=None):
         _lib.check(self._L, self._L.abx_sim_finalize(self._h, stream), "abx_sim_finalize")
 
     # ---- results ----
-    def stats(self, stream=None):
-        out = np.zeros(self.n_envs, dtype=_lib.STATS_DTYPE)
+    def stats(self, stream=None, out=None):
+        """Per-environment abx_env_stats as a numpy structured array (device -> host copy, synchronises `stream`).
+        `out` may be a preallocated (e.g. pinned) buffer exposing the array interface with 112 bytes per env."""
+        if out is None:
+            out = np.zeros(self.n_envs, dtype=_lib.STATS_DTYPE)
         _lib.check(self._L, self._L.abx_sim_stats(self._h, out.ctypes.data, stream), "abx_sim_stats")
         return out
 

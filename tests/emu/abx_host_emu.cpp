@@ -134,6 +134,11 @@ int32_t abx_sim_run(abx_sim *h, int64_t until_ns, void *stream) {
   for (int e = 0; e < h->n_envs; e++) { HostCtx ctx(h->P, e); Sim<HostCtx> sim(ctx, h->P, h->env[e], e); sim.run(until_ns); h->env[e] = sim.s; }
   return ABX_OK;
 }
+int32_t abx_sim_run_each(abx_sim *h, const int64_t *until, void *stream) {
+  (void)stream; if (!h || !until) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  for (int e = 0; e < h->n_envs; e++) { HostCtx ctx(h->P, e); Sim<HostCtx> sim(ctx, h->P, h->env[e], e); sim.run(until[e]); h->env[e] = sim.s; }
+  return ABX_OK;
+}
 int32_t abx_sim_finalize(abx_sim *h, void *stream) {
   (void)stream; if (!h) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
   for (int e = 0; e < h->n_envs; e++) { HostCtx ctx(h->P, e); Sim<HostCtx> sim(ctx, h->P, h->env[e], e); sim.finalize(); h->env[e] = sim.s; }
@@ -142,7 +147,7 @@ int32_t abx_sim_finalize(abx_sim *h, void *stream) {
 int32_t abx_sim_stats(abx_sim *h, abx_env_stats *out, void *stream) {
   (void)stream; if (!h || !out) return ABX_ERR_ARG;
   for (int e = 0; e < h->n_envs; e++) {
-    const EnvState &s = h->env[e]; HostCtx ctx(h->P, e); int nb = s.n_lv[0], na = s.n_lv[1];
+    const EnvState &s = h->env[e]; HostCtx ctx(h->P, e); int nb = s.n_bid_lv, na = s.n_ask_lv;
     fill_stats(s, nb ? ctx.lv_price(0, nb - 1) : 0, nb ? ctx.lv_qty(0, nb - 1) : 0, na ? ctx.lv_price(1, na - 1) : 0, na ? ctx.lv_qty(1, na - 1) : 0, &out[e]);
   }
   return ABX_OK;
@@ -156,7 +161,7 @@ int32_t abx_sim_holdings(abx_sim *h, int32_t env, int64_t *out, void *stream) {
 }
 int32_t abx_sim_book_snapshot(abx_sim *h, int32_t env, int32_t is_bid, int32_t depth, int32_t *out, int32_t *n_levels, void *stream) {
   (void)stream; if (!h || !out || !n_levels || env < 0 || env >= h->n_envs || depth < 0) return ABX_ERR_ARG;
-  HostCtx ctx(h->P, env); int side = is_bid ? 0 : 1, n = h->env[env].n_lv[side], m = depth < n ? depth : n;
+  HostCtx ctx(h->P, env); int side = is_bid ? 0 : 1, n = side ? h->env[env].n_ask_lv : h->env[env].n_bid_lv, m = depth < n ? depth : n;
   for (int k = 0; k < m; k++) { out[2 * k] = ctx.lv_price(side, n - 1 - k); out[2 * k + 1] = ctx.lv_qty(side, n - 1 - k); }
   *n_levels = m; return ABX_OK;
 }
