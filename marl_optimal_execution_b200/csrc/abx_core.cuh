@@ -21,8 +21,10 @@
 #if defined(__CUDACC__)
 #define ABX_HD __host__ __device__ __forceinline__
 #define ABX_D __device__ __forceinline__
+#define ABX_NI __host__ __device__ __noinline__     // one copy of the long libm / Philox bodies instead of one per call site
 #else
 #define ABX_HD inline
+#define ABX_NI static inline
 #endif
 
 #if !defined(__CUDACC__)
@@ -47,7 +49,7 @@ struct alignas(16) EnvState {           // 192 B per environment
   uint32_t c_cancel, c_fills, c_query, ctr_symbol;
   uint32_t ctr_kernel, ctr_latency, ctr_global, started;
   int64_t sum_shares, sum_cash;
-  uint32_t pad[4];
+  uint32_t kblk[4];                     // cached Philox block of the kernel (latency-noise) stream
 };
 static_assert(sizeof(EnvState) == 192, "EnvState layout");
 
@@ -152,15 +154,20 @@ ABX_HD bool key_less(uint64_t ah, uint32_t au, uint64_t bh, uint32_t bu) { retur
 // ---------------------------------------------------------------------------------------------------
 // RNG: Philox4x32-10 counter streams, or replay of recorded standard variates (tape)
 // ---------------------------------------------------------------------------------------------------
-ABX_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
-#pragma unroll
+struct U4 { uint32_t x, y, z, w; };
+ABX_NI U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll 1
   for (int r = 0; r < 10; r++) {
     uint64_t p0 = uint64_t(0xD2511F53u) * c0, p1 = uint64_t(0xCD9E8D57u) * c2;
     uint32_t n0 = uint32_t(p1 >> 32) ^ c1 ^ k0, n1 = uint32_t(p1), n2 = uint32_t(p0 >> 32) ^ c3 ^ k1, n3 = uint32_t(p0);
     c0 = n0; c1 = n1; c2 = n2; c3 = n3; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3; return o;
 }
+ABX_NI double exp_ni(double x) { return exp(x); }
+ABX_NI double log_ni(double x) { return log(x); }
+ABX_NI double pow_ni(double x, double y) { return pow(x, y); }
+ABX_NI double cospi_ni(double x) { return cospi(x); }
 enum { S_SYMBOL = 0, S_KERNEL = 1, S_LATENCY = 2, S_GLOBAL = 3, S_AGENT0 = 3 };  // agent a uses stream S_AGENT0 + a
 
 // MODE: ABX_RNG_PHILOX / ABX_RNG_TAPE fixed at compile time (one kernel instantiation per mode), or -1 = read P->c.rng_mode
@@ -176,27 +183,36 @@ struct RngT {
     if (P->tape_kinds[i] != kind) err |= ABX_F_TAPE_KIND;
     return P->tape_bits[i];
   }
-  ABX_HD void philox(int stream, uint32_t &ctr, uint32_t o[4]) { philox4x32_10(ctr, (uint32_t)stream, 0x41424958u, 0, (uint32_t)seed, (uint32_t)(seed >> 32), o); ctr++; }
+  ABX_HD U4 philox(int stream, uint32_t &ctr) { U4 o = philox4x32_10(ctr, (uint32_t)stream, 0x41424958u, 0, (uint32_t)seed, (uint32_t)(seed >> 32)); ctr++; return o; }
   static ABX_HD double u53(uint32_t a, uint32_t b) { return ((a >> 5) * 67108864.0 + (b >> 6)) / 9007199254740992.0; }
   ABX_HD double std_normal(int stream, uint32_t &ctr) {
     if (tape()) return bits_dbl(tape_next(stream, ctr, 'n'));
-    uint32_t o[4]; philox(stream, ctr, o);
-    double u1 = 1.0 - u53(o[0], o[1]), u2 = u53(o[2], o[3]);                 // u1 in (0,1]
-    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    U4 o = philox(stream, ctr);
+    double u1 = 1.0 - u53(o.x, o.y), u2 = u53(o.z, o.w);                     // u1 in (0,1]
+    return sqrt(-2.0 * log_ni(u1)) * cospi_ni(2.0 * u2);
   }
   ABX_HD double std_exponential(int stream, uint32_t &ctr) {
     if (tape()) return bits_dbl(tape_next(stream, ctr, 'e'));
-    uint32_t o[4]; philox(stream, ctr, o); return -log(1.0 - u53(o[0], o[1]));
+    U4 o = philox(stream, ctr); return -log_ni(1.0 - u53(o.x, o.y));
   }
   ABX_HD double u01(int stream, uint32_t &ctr) {
     if (tape()) return bits_dbl(tape_next(stream, ctr, 'u'));
-    uint32_t o[4]; philox(stream, ctr, o); return u53(o[0], o[1]);
+    U4 o = philox(stream, ctr); return u53(o.x, o.y);
   }
   // integer in [0, range] (numpy randint(low, high) with range = high - 1 - low; no draw when range == 0)
   ABX_HD int64_t randint(int stream, uint32_t &ctr, uint32_t range) {
     if (range == 0) { if (tape()) return (int64_t)tape_next(stream, ctr, 'i'); return 0; }
     if (tape()) return (int64_t)tape_next(stream, ctr, 'i');
-    uint32_t o[4]; philox(stream, ctr, o); return (int64_t)((uint64_t(o[0]) * (uint64_t(range) + 1)) >> 32);
+    U4 o = philox(stream, ctr); return (int64_t)((uint64_t(o.x) * (uint64_t(range) + 1)) >> 32);
+  }
+  // Latency-noise draws (one per sendMessage, Kernel.py:411) take successive 32-bit words of the kernel stream's Philox
+  // blocks; the current block is cached in EnvState so only every 4th send runs the 10 rounds.
+  ABX_HD int64_t randint_cached(int stream, uint32_t &ctr, uint32_t range, uint32_t blk[4]) {
+    if (tape()) return (int64_t)tape_next(stream, ctr, 'i');
+    uint32_t i = ctr++;
+    if ((i & 3u) == 0u) { U4 o = philox4x32_10(i >> 2, (uint32_t)stream, 0x4b424958u, 0, (uint32_t)seed, (uint32_t)(seed >> 32)); blk[0] = o.x; blk[1] = o.y; blk[2] = o.z; blk[3] = o.w; }
+    uint32_t w = (i & 3u) == 0u ? blk[0] : ((i & 3u) == 1u ? blk[1] : ((i & 3u) == 2u ? blk[2] : blk[3]));
+    return (int64_t)((uint64_t(w) * (uint64_t(range) + 1)) >> 32);
   }
   ABX_HD double normal(int stream, uint32_t &ctr, double loc, double scale) { return dadd(loc, dmul(scale, std_normal(stream, ctr))); }
 };
@@ -237,7 +253,7 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
   s.uniq = 0; s.next_order_id = 0; s.q_count = 0; s.max_q = 0; s.n_bid_lv = s.n_ask_lv = 0; s.n_resting = 0; s.free_head = NIL;
   s.pool_top = 0; s.flags = 0; s.trace_n = 0; s.c_limit = s.c_cancel = s.c_fills = s.c_query = 0;
   s.ctr_symbol = s.ctr_kernel = s.ctr_latency = s.ctr_global = 0; s.started = 1; s.sum_shares = 0; s.sum_cash = 0;
-  for (int i = 0; i < 4; i++) s.pad[i] = 0;
+  s.kblk[0] = s.kblk[1] = s.kblk[2] = s.kblk[3] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -367,10 +383,10 @@ struct Sim {
         if (LAT_MODEL < 0 ? P.c.latency_model == ABX_LAT_CUBIC : LAT_MODEL == ABX_LAT_CUBIC) {   // model/LatencyModel.py:133-138
           double u = rng.u01(S_LATENCY, s.ctr_latency);
           double x = dadd(P.c.jitter_clip, dmul(dsub(1.0, P.c.jitter_clip), u));      // uniform(low=clip, high=1.0)
-          double latency = dadd(lat, dmul(P.c.jitter / pow(x, 3.0), lat / P.c.jitter_unit));
+          double latency = dadd(lat, dmul(P.c.jitter / pow_ni(x, 3.0), lat / P.c.jitter_unit));
           deliver = sent + (int64_t)latency;                                          // pd.Timedelta(float) truncates
         } else {                                                                      // Kernel.py:410-412
-          int64_t noise = rng.randint(S_KERNEL, s.ctr_kernel, (uint32_t)(P.c.n_noise - 1));
+          int64_t noise = rng.randint_cached(S_KERNEL, s.ctr_kernel, (uint32_t)(P.c.n_noise - 1), s.kblk);
           deliver = sent + (int64_t)dadd(lat, (double)noise);
         }
         e.t = deliver < KEY_T_MAX ? deliver : KEY_T_MAX; e.type = ABX_T_MESSAGE;
@@ -392,8 +408,8 @@ struct Sim {
   }
   ABX_HD int32_t oracle_compute(int64_t ts, double v_adj, int64_t pt, int32_t pv) {     // :88-125
     double d = (double)(ts - pt); double mu = P.c.r_bar;
-    double loc = dadd(mu, dmul(dsub((double)pv, mu), exp(dmul(-P.c.kappa, d))));
-    double scale = dmul(P.ou_scale, dsub(1.0, exp(dmul(dmul(-2.0, P.c.kappa), d))));    // variance formula passed as scale
+    double loc = dadd(mu, dmul(dsub((double)pv, mu), exp_ni(dmul(-P.c.kappa, d))));
+    double scale = dmul(P.ou_scale, dsub(1.0, exp_ni(dmul(dmul(-2.0, P.c.kappa), d))));    // variance formula passed as scale
     double v = rng.normal(S_SYMBOL, s.ctr_symbol, loc, scale);
     v = dadd(v, v_adj); if (!(v > 0)) v = 0;
     int32_t iv = (int32_t)py_round_i64(v); s.or_t = ts; s.or_v = iv; return iv;
@@ -402,8 +418,14 @@ struct Sim {
     int64_t pt = s.or_t; int32_t pv = s.or_v;
     if (t <= pt) return pv;
 #pragma unroll 1
-    while (s.ms_t < t) { int32_t v = oracle_compute(s.ms_t, s.ms_v, pt, pv); pt = s.ms_t; pv = v; oracle_new_megashock(pt); }
-    return oracle_compute(t, 0.0, pt, pv);
+    for (;;) {                                                                          // megashocks strictly before t, then t itself
+      bool shock = s.ms_t < t;
+      int64_t ts = shock ? s.ms_t : t;
+      pv = oracle_compute(ts, shock ? s.ms_v : 0.0, pt, pv); pt = ts;
+      if (!shock) break;
+      oracle_new_megashock(pt);
+    }
+    return pv;
   }
 
   // ---- order book (util/OrderBook.py).  Ladders are sorted so that the BEST level is the LAST element. ----
@@ -549,7 +571,7 @@ struct Sim {
   // ZeroIntelligenceAgent.placeOrder :277-309 (+ updateEstimates :189-275, TradingAgent.placeLimitOrder :309-349)
   ABX_HD void zi_place_order(int id) {
     int stream = S_AGENT0 + id;
-    int32_t r_now = (s.now >= P.c.mkt_close_ns) ? oracle_advance(P.c.mkt_close_ns - 1) : oracle_advance(s.now);   // observePrice :210-227
+    int32_t r_now = oracle_advance(s.now >= P.c.mkt_close_ns ? P.c.mkt_close_ns - 1 : s.now);             // observePrice :210-227
     int32_t obs_t = (int32_t)py_round_i64(rng.normal(stream, a.rng_ctr, (double)r_now, P.sqrt_sigma_n));
     int q = (int)((double)a.shares / 100.0);                                            // :203 int(x / 100)
     int q_max = P.c.q_max; bool buy;
@@ -558,9 +580,7 @@ struct Sim {
     double base = P.one_minus_kappa_a, r_bar = P.c.r_bar, sigma_n = P.c.sigma_n;
     double delta = (double)(s.now - a.prev_wake);                                       // :221
     double d2 = (double)(P.c.mkt_close_ns - s.now); if (!(d2 > 0)) d2 = 0;              // :251
-    double pw0 = 0, pw1 = 0, pw2 = 0;                                                   // (1 - kappa) ** {delta, 2*delta, d2}: one pow() site
-#pragma unroll 1
-    for (int k = 0; k < 3; k++) { double ex = k == 0 ? delta : (k == 1 ? dmul(2.0, delta) : d2); double r = pow(base, ex); if (k == 0) pw0 = r; else if (k == 1) pw1 = r; else pw2 = r; }
+    double pw0 = pow_ni(base, delta), pw1 = pow_ni(base, dmul(2.0, delta)), pw2 = pow_ni(base, d2);   // (1 - kappa) ** x
     double r_tprime = dmul(dsub(1.0, pw0), r_bar);                                    // :229
     r_tprime = dadd(r_tprime, dmul(pw0, a.r_t));                                      // :230
     double sigma_tprime = dmul(pw1, a.sigma_t);                                       // :233
@@ -705,7 +725,7 @@ struct Sim {
       double hr = dmul(rint((double)a.shares / 100.0), 100.0);                          // round(int, -2): half-even on hundreds
       int H = (int)(hr / 100.0);
       int64_t cur = a.agent_time - P.c.default_computation_delay_ns;                    // Agent.currentTime of the trader's last event
-      int32_t rT = (cur >= P.c.mkt_close_ns) ? oracle_advance(P.c.mkt_close_ns - 1) : oracle_advance(cur);   // observePrice(sigma_n=0)
+      int32_t rT = oracle_advance(cur >= P.c.mkt_close_ns ? P.c.mkt_close_ns - 1 : cur);                    // observePrice(sigma_n=0)
       int64_t surplus = 0;
       if (H > 0) { for (int x = 1; x <= H; x++) { int k = x + q_max - 1; if (k < 2 * q_max) surplus += z->theta[k]; } }
       else if (H < 0) { for (int x = H + 1; x <= 0; x++) { int k = x + q_max - 1; if (k >= 0) surplus += z->theta[k]; } surplus = -surplus; }

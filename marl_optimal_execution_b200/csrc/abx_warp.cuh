@@ -79,9 +79,13 @@ struct WarpCtx {
   // ---- staging of the on-chip structures between launches ----
   __device__ void load_onchip(const EnvState &s) {
     const uint4 *gc = P.qcache + (size_t)env * P.n_qgroups;
+#pragma unroll 1
     for (int g = lane; g < P.n_qgroups; g += 32) qc[g] = ldcg4(gc + g);
     size_t l = (size_t)env * 2 * P.c.level_cap;
-    for (int side = 0; side < 2; side++) for (int i = lane; i < (side ? s.n_ask_lv : s.n_bid_lv); i += 32) {
+#pragma unroll 1
+    for (int side = 0; side < 2; side++)
+#pragma unroll 1
+      for (int i = lane; i < (side ? s.n_ask_lv : s.n_bid_lv); i += 32) {
       int k = side * P.c.level_cap + i; lvp[k] = P.lv_price[l + k]; lvq[k] = P.lv_qty[l + k]; lvht[k] = P.lv_ht[l + k];
     }
     __syncwarp();
@@ -89,9 +93,13 @@ struct WarpCtx {
   __device__ void store_onchip(const EnvState &s) {
     __syncwarp();
     uint4 *gc = P.qcache + (size_t)env * P.n_qgroups;
+#pragma unroll 1
     for (int g = lane; g < P.n_qgroups; g += 32) gc[g] = qc[g];
     size_t l = (size_t)env * 2 * P.c.level_cap;
-    for (int side = 0; side < 2; side++) for (int i = lane; i < (side ? s.n_ask_lv : s.n_bid_lv); i += 32) {
+#pragma unroll 1
+    for (int side = 0; side < 2; side++)
+#pragma unroll 1
+      for (int i = lane; i < (side ? s.n_ask_lv : s.n_bid_lv); i += 32) {
       int k = side * P.c.level_cap + i; P.lv_price[l + k] = lvp[k]; P.lv_qty[l + k] = lvq[k]; P.lv_ht[l + k] = lvht[k];
     }
   }
@@ -166,6 +174,7 @@ struct WarpCtx {
   }
   __device__ __forceinline__ void lv_find(int side, int32_t price, int n, int &pos, bool &found) {
     const int32_t *p = lvp + side * P.c.level_cap; int cnt = 0, fidx = -1;
+#pragma unroll 1
     for (int i = lane; i < n; i += 32) { int32_t v = p[i]; if (v == price) fidx = i; else if (side == 0 ? v < price : v > price) cnt++; }
     cnt = __reduce_add_sync(FULL, cnt);
     uint32_t fb = __ballot_sync(FULL, fidx >= 0);
