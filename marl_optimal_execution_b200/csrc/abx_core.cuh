@@ -29,7 +29,7 @@
 
 #if !defined(__CUDACC__)
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
-inline double cospi(double x) { return cos(3.14159265358979323846 * x); }
+inline float cospif(float x) { return (float)cos(3.14159265358979323846 * (double)x); }
 #endif
 
 namespace abx {
@@ -156,7 +156,7 @@ ABX_HD bool key_less(uint64_t ah, uint32_t au, uint64_t bh, uint32_t bu) { retur
 // ---------------------------------------------------------------------------------------------------
 struct U4 { uint32_t x, y, z, w; };
 ABX_NI U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-#pragma unroll 1
+#pragma unroll
   for (int r = 0; r < 10; r++) {
     uint64_t p0 = uint64_t(0xD2511F53u) * c0, p1 = uint64_t(0xCD9E8D57u) * c2;
     uint32_t n0 = uint32_t(p1 >> 32) ^ c1 ^ k0, n1 = uint32_t(p1), n2 = uint32_t(p0 >> 32) ^ c3 ^ k1, n3 = uint32_t(p0);
@@ -167,7 +167,6 @@ ABX_NI U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
 ABX_NI double exp_ni(double x) { return exp(x); }
 ABX_NI double log_ni(double x) { return log(x); }
 ABX_NI double pow_ni(double x, double y) { return pow(x, y); }
-ABX_NI double cospi_ni(double x) { return cospi(x); }
 enum { S_SYMBOL = 0, S_KERNEL = 1, S_LATENCY = 2, S_GLOBAL = 3, S_AGENT0 = 3 };  // agent a uses stream S_AGENT0 + a
 
 // MODE: ABX_RNG_PHILOX / ABX_RNG_TAPE fixed at compile time (one kernel instantiation per mode), or -1 = read P->c.rng_mode
@@ -188,8 +187,9 @@ struct RngT {
   ABX_HD double std_normal(int stream, uint32_t &ctr) {
     if (tape()) return bits_dbl(tape_next(stream, ctr, 'n'));
     U4 o = philox(stream, ctr);
-    double u1 = 1.0 - u53(o.x, o.y), u2 = u53(o.z, o.w);                     // u1 in (0,1]
-    return sqrt(-2.0 * log_ni(u1)) * cospi_ni(2.0 * u2);
+    double u1 = 1.0 - u53(o.x, o.y);                                         // u1 in (0,1]
+    float ang = (float)(o.z >> 8) * (2.0f / 16777216.0f);                    // angle / pi in [0, 2): 24 random bits, fp32 cos
+    return sqrt(-2.0 * log_ni(u1)) * (double)cospif(ang);
   }
   ABX_HD double std_exponential(int stream, uint32_t &ctr) {
     if (tape()) return bits_dbl(tape_next(stream, ctr, 'e'));
@@ -265,9 +265,10 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
 //   agents:  ZiAgent* agent_stage(id)  -- 128-bit cooperative copy HBM -> on-chip staging record, returned pointer is
 //            readable by every lane; void agent_commit(id) -- staging record -> HBM; double agent_lat_from(id)
 //   outbox:  uint32_t* outbox()  -- on-chip array of OUT_CAP * OUT_WORDS words
-//   misc:    bool leader(); void trace(const abx_trace_rec&, uint32_t idx); void sync();
-// Rule for on-chip memory shared by the lanes: only the leader lane writes, and c.sync() separates a write
-// from later reads by other lanes.
+//   misc:    bool onchip_writer(); void trace(const abx_trace_rec&, uint32_t idx); void sync();
+// Rule for on-chip memory shared by the lanes: uniform code lets EVERY lane store the same value (one STS, no
+// divergent branch), and c.sync() -- a compiler fence on the GPU, where a converged warp issues its memory
+// instructions in program order -- separates a write from later reads.
 // ---------------------------------------------------------------------------------------------------
 constexpr int OUT_CAP = 32, OUT_WORDS = 12;
 enum : uint32_t { OF_WAKEUP = 1u << 24, OF_BUMP_UNIQ = 1u << 25, OF_FROM_EXCH = 1u << 26 };
@@ -338,7 +339,7 @@ struct Sim {
   // send offset (computation delay + additional + pipeline delay) for messages, absolute time for wakeups.
   ABX_HD void emit(uint32_t w0, const int32_t p[6], double lat, int64_t off) {
     if (n_out >= OUT_CAP) { s.flags |= ABX_F_QUEUE_OVERFLOW; return; }
-    if (c.leader()) {
+    if (c.onchip_writer()) {
       uint32_t *o = c.outbox() + n_out * OUT_WORDS;
       o[0] = w0; for (int i = 0; i < 6; i++) o[1 + i] = (uint32_t)p[i];
       uint64_t lb = dbl_bits(lat); o[7] = (uint32_t)lb; o[8] = (uint32_t)(lb >> 32);
@@ -612,7 +613,7 @@ struct Sim {
     int32_t size = P.c.order_size;
     if (size > 0) {
       if (a.n_orders < AGENT_ORDER_CAP) {
-        if (c.leader()) { int k = a.n_orders; z->oid[k] = oid; z->oprice[k] = p; z->oqty[k] = buy ? size : -size; }
+        if (c.onchip_writer()) { int k = a.n_orders; z->oid[k] = oid; z->oprice[k] = p; z->oqty[k] = buy ? size : -size; }
         a.n_orders++;
       } else s.flags |= ABX_F_AGENT_ORDERS_OVERFLOW;
       int32_t pl[6] = {(int32_t)oid, p, size, 0, buy, 0};
@@ -623,7 +624,7 @@ struct Sim {
   ABX_HD int orders_find(uint32_t oid) { int f = -1; for (int i = 0; i < AGENT_ORDER_CAP; i++) if (i < a.n_orders && f < 0 && z->oid[i] == oid) f = i; return f; }
   ABX_HD void orders_remove(int i) {
     c.sync();
-    if (c.leader()) for (int k = i; k + 1 < AGENT_ORDER_CAP; k++) { z->oid[k] = z->oid[k + 1]; z->oprice[k] = z->oprice[k + 1]; z->oqty[k] = z->oqty[k + 1]; }
+    if (c.onchip_writer()) for (int k = i; k + 1 < AGENT_ORDER_CAP; k++) { z->oid[k] = z->oid[k + 1]; z->oprice[k] = z->oprice[k + 1]; z->oqty[k] = z->oqty[k + 1]; }
     a.n_orders--;
     c.sync();
   }
@@ -639,7 +640,7 @@ struct Sim {
       if (i >= 0) {
         int32_t oq0 = z->oqty[i]; int32_t oq = oq0 < 0 ? -oq0 : oq0;
         if (q >= oq) orders_remove(i);
-        else { c.sync(); if (c.leader()) z->oqty[i] = oq0 < 0 ? -(oq - q) : (oq - q); c.sync(); }
+        else { c.sync(); if (c.onchip_writer()) z->oqty[i] = oq0 < 0 ? -(oq - q) : (oq - q); c.sync(); }
       }
     } else if (m.kind == ABX_ORDER_CANCELLED) {                                         // orderCancelled :476-489
       int i = orders_find((uint32_t)m.p[0]); if (i >= 0) orders_remove(i);
@@ -707,7 +708,7 @@ struct Sim {
         if (ev.type == ABX_T_WAKEUP) zi_wakeup(id); else zi_receive(id, ev);
         a.agent_time += P.c.default_computation_delay_ns + addl_delay;
         c.sync();
-        if (c.leader()) regs_store(z, a);
+        if (c.onchip_writer()) regs_store(z, a);
         c.sync();
         c.agent_commit(id);
       }
@@ -732,7 +733,7 @@ struct Sim {
       surplus += (int64_t)rT * H; surplus += a.cash - P.c.starting_cash;
       sum_sh += a.shares; sum_cash += a.cash;
       c.sync();
-      if (c.leader()) z->surplus = surplus;
+      if (c.onchip_writer()) z->surplus = surplus;
       c.sync();
       c.agent_commit(id);
     }

@@ -71,8 +71,17 @@ struct WarpCtx {
     lvht = reinterpret_cast<uint32_t *>(smem);
     cur_group = cur_lane = -1; cur_mask = 0; my_hi = KEY_EMPTY; my_uniq = 0xffffffffu;
   }
-  __device__ __forceinline__ bool leader() const { return lane == 0; }
+  // Uniform code stores on-chip state from every lane (same value, same address: one STS, no branch).
+  __device__ __forceinline__ bool onchip_writer() const { return true; }
+  // A converged warp issues its memory instructions in program order and the LSU serves one warp's shared-memory
+  // accesses in order, so between uniform code and the cooperative primitives a COMPILER fence is enough.  Real
+  // __syncwarp() (7 SASS instructions each: BSSY/WARPSYNC/ENDCOLLECTIVE/...) is kept only where lanes hand data to
+  // each other through HBM (q_push, node_store, agent_commit).  -DABX_STRICT_SYNC restores __syncwarp() everywhere.
+#ifdef ABX_STRICT_SYNC
   __device__ __forceinline__ void sync() const { __syncwarp(); }
+#else
+  __device__ __forceinline__ void sync() const { asm volatile("" ::: "memory"); }
+#endif
   __device__ __forceinline__ uint32_t *outbox() const { return obox; }
   __device__ __forceinline__ void trace(const abx_trace_rec &r, uint32_t i) { if (lane == 0) tr[i] = r; }
 
@@ -88,10 +97,10 @@ struct WarpCtx {
       for (int i = lane; i < (side ? s.n_ask_lv : s.n_bid_lv); i += 32) {
       int k = side * P.c.level_cap + i; lvp[k] = P.lv_price[l + k]; lvq[k] = P.lv_qty[l + k]; lvht[k] = P.lv_ht[l + k];
     }
-    __syncwarp();
+    sync();
   }
   __device__ void store_onchip(const EnvState &s) {
-    __syncwarp();
+    sync();
     uint4 *gc = P.qcache + (size_t)env * P.n_qgroups;
 #pragma unroll 1
     for (int g = lane; g < P.n_qgroups; g += 32) gc[g] = qc[g];
@@ -103,7 +112,7 @@ struct WarpCtx {
       int k = side * P.c.level_cap + i; P.lv_price[l + k] = lvp[k]; P.lv_qty[l + k] = lvq[k]; P.lv_ht[l + k] = lvht[k];
     }
   }
-  __device__ void q_clear() { for (int g = lane; g < P.n_qgroups; g += 32) qc[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); __syncwarp(); }
+  __device__ void q_clear() { for (int g = lane; g < P.n_qgroups; g += 32) qc[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); sync(); }
 
   // ---- event queue ----
   __device__ __forceinline__ bool q_min(uint64_t &hi, uint32_t &uniq, int &grp) {
@@ -132,8 +141,8 @@ struct WarpCtx {
     int w2 = warp_argmin(my_hi, my_uniq, occ);
     uint64_t nh = KEY_EMPTY; uint32_t nu = 0xffffffffu;
     if (w2 >= 0) { nh = shfl64(my_hi, w2); nu = __shfl_sync(FULL, my_uniq, w2); }
-    if (lane == 0) qc[cur_group] = make_uint4((uint32_t)nh, (uint32_t)(nh >> 32), nu, cur_mask);
-    __syncwarp();
+    qc[cur_group] = make_uint4((uint32_t)nh, (uint32_t)(nh >> 32), nu, cur_mask);
+    sync();
   }
   __device__ __forceinline__ void q_remove() { cur_mask &= ~(1u << cur_lane); group_writeback(); }
   __device__ __forceinline__ void q_requeue(int64_t t) {   // Kernel.py:226,260: same entry, new time, same uniq
@@ -153,7 +162,7 @@ struct WarpCtx {
     uint4 k, a, b; event_pack(e, k, a, b);
     int slot = g * 32 + i;
     if (lane < 3) { uint4 *dst = lane == 0 ? qkey : (lane == 1 ? qpay0 : qpay1); dst[slot] = lane == 0 ? k : (lane == 1 ? a : b); }
-    if (lane == 0) {
+    {
       uint64_t h = (uint64_t)k.x | ((uint64_t)k.y << 32), ch = (uint64_t)cc.x | ((uint64_t)cc.y << 32);
       if (cc.w == 0 || key_less(h, k.z, ch, cc.z)) { cc.x = k.x; cc.y = k.y; cc.z = k.z; }
       cc.w |= 1u << i; qc[g] = cc;
@@ -168,9 +177,9 @@ struct WarpCtx {
   __device__ __forceinline__ uint32_t lv_head(int side, int i) const { return lvht[side * P.c.level_cap + i] & 0xffffu; }
   __device__ __forceinline__ uint32_t lv_tail(int side, int i) const { return lvht[side * P.c.level_cap + i] >> 16; }
   __device__ __forceinline__ void lv_set(int side, int i, int32_t qty, uint32_t head, uint32_t tail) {
-    __syncwarp();
-    if (lane == 0) { lvq[side * P.c.level_cap + i] = qty; lvht[side * P.c.level_cap + i] = head | (tail << 16); }
-    __syncwarp();
+    sync();
+    lvq[side * P.c.level_cap + i] = qty; lvht[side * P.c.level_cap + i] = head | (tail << 16);
+    sync();
   }
   __device__ __forceinline__ void lv_find(int side, int32_t price, int n, int &pos, bool &found) {
     const int32_t *p = lvp + side * P.c.level_cap; int cnt = 0, fidx = -1;
@@ -182,26 +191,26 @@ struct WarpCtx {
   }
   __device__ __forceinline__ void lv_insert(int side, int pos, int n, int32_t price, int32_t qty, uint32_t head, uint32_t tail) {
     int b = side * P.c.level_cap;
-    __syncwarp();
+    sync();
     for (int hi = n; hi > pos; hi -= 32) {                  // shift [pos, n) up by one, top chunk first
       int i = hi - 1 - lane; bool act = i >= pos; int32_t x = 0, y = 0; uint32_t z = 0;
       if (act) { x = lvp[b + i]; y = lvq[b + i]; z = lvht[b + i]; }
-      __syncwarp();
+      sync();
       if (act) { lvp[b + i + 1] = x; lvq[b + i + 1] = y; lvht[b + i + 1] = z; }
-      __syncwarp();
+      sync();
     }
-    if (lane == 0) { lvp[b + pos] = price; lvq[b + pos] = qty; lvht[b + pos] = head | (tail << 16); }
-    __syncwarp();
+    lvp[b + pos] = price; lvq[b + pos] = qty; lvht[b + pos] = head | (tail << 16);
+    sync();
   }
   __device__ __forceinline__ void lv_remove(int side, int pos, int n) {
     int b = side * P.c.level_cap;
-    __syncwarp();
+    sync();
     for (int lo = pos + 1; lo < n; lo += 32) {              // shift (pos, n) down by one, bottom chunk first
       int i = lo + lane; bool act = i < n; int32_t x = 0, y = 0; uint32_t z = 0;
       if (act) { x = lvp[b + i]; y = lvq[b + i]; z = lvht[b + i]; }
-      __syncwarp();
+      sync();
       if (act) { lvp[b + i - 1] = x; lvq[b + i - 1] = y; lvht[b + i - 1] = z; }
-      __syncwarp();
+      sync();
     }
   }
 
@@ -211,9 +220,9 @@ struct WarpCtx {
 
   // ---- trader records: 12 lanes x 128-bit, HBM <-> shared ----
   __device__ __forceinline__ ZiAgent *agent_stage(int id) {
-    __syncwarp();
+    sync();
     if (lane < (int)(sizeof(ZiAgent) / 16)) reinterpret_cast<uint4 *>(staged)[lane] = ldcg4(reinterpret_cast<const uint4 *>(agents + id) + lane);
-    __syncwarp();
+    sync();
     return staged;
   }
   __device__ __forceinline__ void agent_commit(int id) {

@@ -23,7 +23,7 @@ struct HostCtx {
     agents = P.agents + (size_t)e * P.c.n_agents; size_t l = (size_t)e * 2 * P.c.level_cap; lvp = P.lv_price + l; lvq = P.lv_qty + l; lvht = P.lv_ht + l;
     nodes = P.nodes + (size_t)e * P.c.order_cap; tr = P.trace ? P.trace + (size_t)e * P.c.trace_cap : nullptr; cur_group = cur_slot = -1;
   }
-  bool leader() { return true; }
+  bool onchip_writer() { return true; }
   void sync() {}
   uint32_t *outbox() { return outbox_; }
   void trace(const abx_trace_rec &r, uint32_t i) { tr[i] = r; }
