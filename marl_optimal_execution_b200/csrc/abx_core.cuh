@@ -98,6 +98,7 @@ struct SimParams {
   abx_sim_config c;
   int32_t n_envs, n_qgroups, n_streams, pad0;
   double one_minus_kappa_a;     // 1 - agent_kappa
+  double log_base_a;            // log(1 - agent_kappa)
   double sigma_denom;           // 1 - (1 - agent_kappa) ** 2      (host libm pow, ZeroIntelligenceAgent.py:234)
   double sqrt_sigma_n, sqrt_sigma_pv, sqrt_megashock_var;
   double inv_lambda_a, inv_megashock_lambda;
@@ -578,10 +579,12 @@ struct Sim {
     int q_max = P.c.q_max; bool buy;
     if (q >= q_max) buy = false; else if (q <= -q_max) buy = true; else buy = rng.randint(stream, a.rng_ctr, 1) != 0; // :205-213
     if (!(a.flags & AF_HAS_PREV)) { a.prev_wake = P.c.mkt_open_ns; a.flags |= AF_HAS_PREV; }         // :217-218
-    double base = P.one_minus_kappa_a, r_bar = P.c.r_bar, sigma_n = P.c.sigma_n;
+    double r_bar = P.c.r_bar, sigma_n = P.c.sigma_n;
     double delta = (double)(s.now - a.prev_wake);                                       // :221
     double d2 = (double)(P.c.mkt_close_ns - s.now); if (!(d2 > 0)) d2 = 0;              // :251
-    double pw0 = pow_ni(base, delta), pw1 = pow_ni(base, dmul(2.0, delta)), pw2 = pow_ni(base, d2);   // (1 - kappa) ** x
+    // (1 - kappa) ** x evaluated as exp(x * log(1 - kappa)) with the logarithm precomputed on the host (log1p): both are
+    // within an ulp of the true power; the result only feeds int(round(.)) of values ~1e5.
+    double pw0 = exp_ni(dmul(delta, P.log_base_a)), pw1 = exp_ni(dmul(dmul(2.0, delta), P.log_base_a)), pw2 = exp_ni(dmul(d2, P.log_base_a));
     double r_tprime = dmul(dsub(1.0, pw0), r_bar);                                    // :229
     r_tprime = dadd(r_tprime, dmul(pw0, a.r_t));                                      // :230
     double sigma_tprime = dmul(pw1, a.sigma_t);                                       // :233

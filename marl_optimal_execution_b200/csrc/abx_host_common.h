@@ -62,6 +62,7 @@ static inline void derive_params(SimParams &P) {
   const abx_sim_config &c = P.c;
   P.n_qgroups = c.queue_cap / 32; P.n_streams = c.n_agents + 3;
   P.one_minus_kappa_a = 1 - c.agent_kappa;
+  P.log_base_a = log(P.one_minus_kappa_a);                         // exact argument: 1 - kappa as CPython rounds it
   P.sigma_denom = 1 - pow(1 - c.agent_kappa, 2.0);                 // ZeroIntelligenceAgent.py:234
   P.sqrt_sigma_n = sqrt(c.sigma_n); P.sqrt_sigma_pv = sqrt(c.sigma_pv); P.sqrt_megashock_var = sqrt(c.megashock_var);
   P.inv_lambda_a = 1.0 / c.lambda_a; P.inv_megashock_lambda = 1.0 / c.megashock_lambda_a;
