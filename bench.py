@@ -228,7 +228,8 @@ def run_ours(args, rank, local_rank, world):
             "vs_baseline_ref": "BASELINE.md section 1: 3100.4 msgs/s, reference single process, i7 2.6 GHz", "error_envs": errs,
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "peak_source": peak_src,
+                     "traffic": traffic["dram_bytes_per_message"] * (msgs_local / args.steps) if traffic else None,
+                     "traffic_source": traffic["source"] if traffic else None, "peak_source": peak_src,
                      "kernel": "abx_run_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_msg": B_MSG,
                      "note": "latency-bound by design (one dependent event chain per environment); see DESIGN.md"},
         "e2e": {"value": e2e_msgs / e2e_s, "unit": "msgs/s", "h2d_bytes_per_step": 8 * n_envs * 1,
