@@ -297,6 +297,8 @@ typedef struct {            /* one PriorityQueue entry: (deliverAt, (recipient, 
   order_t order;                                             /* body["order"] */
   int64_t bid, bid_q, ask, ask_q, data; int mkt_closed;      /* QUERY_SPREAD reply (depth-1 lists; has_* by qty>0), body["data"] */
   int has_bid, has_ask;
+  int64_t bid2, ask2; int n_bids, n_asks;                    /* depth > 1 replies: second level price, level counts (capped at 2) */
+  order_t new_order;                                         /* MODIFY_ORDER body["new_order"] */
 } event_t;
 
 static inline int ev_less(const event_t *a, const event_t *b) { /* tuple order (t, recipient, type.value, msg.uniq) */
@@ -749,3 +751,318 @@ int64_t abo_sim_counter(abo_sim *s, int w) {
 }
 void abo_sim_book_l1(abo_sim *s, int64_t *o) { int64_t pq[2]; o[0] = o[1] = o[2] = o[3] = 0; if (book_inside(&s->book, 1, 1, pq)) { o[0] = pq[0]; o[1] = pq[1]; } if (book_inside(&s->book, 0, 1, pq)) { o[2] = pq[0]; o[3] = pq[1]; } o[4] = s->book.has_last_trade ? s->book.last_trade : -1; }
 int64_t abo_sim_fundamental(abo_sim *s) { return s->or_v; }
+
+/* ====================================================================================================
+ * ABIDESEnv: Exchange + MarketReplayAgent + DummyRLExecutionAgent under GymKernel
+ *   ABIDESEnv.py:8-103, agent_config.py:42-154, GymKernel.py:25-306,364-389,
+ *   agent/examples/MarketReplayAgent.py:14-100, agent/execution/rl/dummy_rl_execution_agent.py,
+ *   agent/execution/baselines/execution_agent.py:9-130, ABIDESEnvMetrics.py:9-258
+ * Zero latency, zero computation delay, noise [1.0] (no MT draw: randint(0,1)); no oracle (last_trade None until
+ * the first trade).  Fully deterministic given the order stream and the actions.
+ * ==================================================================================================== */
+typedef struct { int64_t t, id, price, size; int is_buy; } srow_t;
+typedef struct { int64_t key; int64_t qty, price; int is_buy; int used; } omap_ent;   /* TradingAgent.orders of the replay agent */
+typedef struct { omap_ent *e; int cap, n; } omap_t;
+static void omap_init(omap_t *m, int cap) { m->cap = 1; while (m->cap < cap * 2) m->cap <<= 1; m->e = (omap_ent *)calloc(m->cap, sizeof(omap_ent)); m->n = 0; }
+static omap_ent *omap_find(omap_t *m, int64_t k) { uint64_t h = (uint64_t)k * 0x9E3779B97F4A7C15ULL; int i = (int)(h >> 40) & (m->cap - 1); while (m->e[i].used) { if (m->e[i].used == 1 && m->e[i].key == k) return &m->e[i]; i = (i + 1) & (m->cap - 1); } return NULL; }
+static void omap_put(omap_t *m, int64_t k, int64_t qty, int64_t price, int is_buy) { uint64_t h = (uint64_t)k * 0x9E3779B97F4A7C15ULL; int i = (int)(h >> 40) & (m->cap - 1); while (m->e[i].used == 1) i = (i + 1) & (m->cap - 1); m->e[i].key = k; m->e[i].qty = qty; m->e[i].price = price; m->e[i].is_buy = is_buy; m->e[i].used = 1; m->n++; }
+static void omap_del(omap_t *m, omap_ent *e) { e->used = 2; m->n--; (void)m; }   /* tombstone */
+
+typedef struct { int64_t bid1, bidq1, bid2, ask1, askq1, ask2, data; int n_bids, n_asks; } lob_t;   /* what the agent reads of a stored QUERY_SPREAD body */
+
+typedef struct {
+  /* TradingAgent common */
+  int has_open, has_close, mkt_closed; int64_t mkt_open, mkt_close; int64_t shares, cash; int has_last_trade; int64_t last_trade;
+} tagent_t;
+
+struct abo_env {
+  heap_t q; int64_t now, stop_time; int64_t agent_time[3]; int64_t comp_delay[3]; int64_t ttl, uniq; int done;
+  int64_t next_order_id; omap_t used_ids;   /* util/order/Order.py:8-9,35-42 global id allocator (ids seen so far) */
+  abo_book book; int64_t mkt_open, mkt_close;
+  /* replay agent (id 1) */
+  tagent_t ra; srow_t *rows; int64_t n_rows; int64_t *ts; int64_t *ts_first; int64_t n_ts; int64_t wt_cursor; omap_t ra_orders;
+  /* RL agent (id 2) */
+  tagent_t rl; int rl_state; int rl_trade; double quantity, rem_quantity, executed_sum; int64_t n_executed;
+  open_order_t *rl_orders; double *rl_oqty; int rl_n_orders, rl_cap_orders;
+  int64_t *horizon; int n_h; int order_level; double steep;
+  lob_t lobs[100]; int n_lobs, lob_head; int64_t p0; int metrics_init; int rem_time;
+  /* step outputs */
+  double obs[9]; int obs_len; int end_step;
+  /* traces */
+  int trace; i64buf pops, ops, notes, snaps; uint64_t pop_hash, note_hash, snap_hash; uint64_t *ckpt; int64_t n_ckpt, cap_ckpt;
+  int64_t max_bid_lv, max_ask_lv, max_resting, max_queue;
+};
+typedef struct abo_env abo_env;
+
+static void env_put(abo_env *s, const event_t *e) { heap_push(&s->q, e); if (s->q.n > s->max_queue) s->max_queue = s->q.n; }
+static void env_set_wakeup(abo_env *s, int sender, int64_t t) { event_t e; memset(&e, 0, sizeof(e)); e.t = t; e.recipient = sender; e.type = ABO_T_WAKEUP; e.uniq = -1; env_put(s, &e); }
+static void env_set_cancel(abo_env *s, int sender, int64_t t) { event_t e; memset(&e, 0, sizeof(e)); e.t = t; e.recipient = sender; e.type = ABO_T_CANCEL_ORDER; e.uniq = -1; env_put(s, &e); } /* GymKernel.setCancelOrder :364-389 */
+/* Kernel.sendMessage :347-433 with zero latency; noise = choice(1, 1, [1.0])[0] == 0 without an MT draw */
+static void env_send(abo_env *s, int sender, int recipient, event_t *e, int64_t delay) {
+  e->uniq = s->uniq++; e->t = s->now + s->comp_delay[sender] + delay; e->recipient = recipient; e->type = ABO_T_MESSAGE; e->sender = sender; env_put(s, e);
+}
+static void env_trace_note(abo_env *s, int recipient, const event_t *e) {
+  int64_t row[13] = { s->now, recipient, e->kind, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+  if (e->kind == ABO_ORDER_ACCEPTED || e->kind == ABO_ORDER_EXECUTED || e->kind == ABO_ORDER_CANCELLED || e->kind == ABO_ORDER_MODIFIED) {
+    row[3] = e->order.order_id; row[4] = e->order.is_buy; row[5] = e->order.quantity; row[6] = e->order.limit_price; row[7] = e->order.fill_price; }
+  if (e->kind == ABO_QUERY_SPREAD) { row[7] = e->data; if (e->has_bid) { row[8] = e->bid; row[9] = e->bid_q; } if (e->has_ask) { row[10] = e->ask; row[11] = e->ask_q; } row[12] = e->mkt_closed; }
+  for (int i = 0; i < 13; i++) s->note_hash = fnv_mix(s->note_hash, row[i]);
+  if (s->trace & ABO_TRACE_NOTES) ib_push(&s->notes, row, 13);
+}
+static void env_exch_send(abo_env *s, int recipient, event_t *e) { /* ExchangeAgent.sendMessage :471-485 (pipeline delay 0) */
+  /* uniq is taken at Message construction, which precedes the trace hook in the recorder as well */
+  int64_t u = s->uniq; env_trace_note(s, recipient, e); (void)u; env_send(s, 0, recipient, e, 0);
+}
+static void env_book_send(void *owner, int64_t recipient, int kind, const order_t *o) { abo_env *s = (abo_env *)owner; event_t e; memset(&e, 0, sizeof(e)); e.kind = kind; e.order = *o; env_exch_send(s, (int)recipient, &e); }
+static void env_trace_snap(abo_env *s) {
+  int64_t row[16]; memset(row, 0, sizeof(row));
+  int nb = s->book.bids.n, na = s->book.asks.n; int64_t rest = abo_book_n_resting(&s->book);
+  row[0] = nb; row[1] = na; row[2] = rest; book_inside(&s->book, 1, 3, row + 3); book_inside(&s->book, 0, 3, row + 9);
+  row[15] = s->book.has_last_trade ? s->book.last_trade : -1;
+  if (nb > s->max_bid_lv) s->max_bid_lv = nb; if (na > s->max_ask_lv) s->max_ask_lv = na; if (rest > s->max_resting) s->max_resting = rest;
+  for (int i = 0; i < 16; i++) s->snap_hash = fnv_mix(s->snap_hash, row[i]);
+  if (s->trace & ABO_TRACE_SNAPS) ib_push(&s->snaps, row, 16);
+}
+static void env_trace_op(abo_env *s, int op, const order_t *o, int64_t np, int64_t nq) {
+  if (!(s->trace & ABO_TRACE_OPS)) return;
+  int64_t row[9] = { s->now, op, o->agent_id, o->order_id, o->is_buy, o->limit_price, o->quantity, np, nq }; ib_push(&s->ops, row, 9);
+}
+/* ExchangeAgent.receiveMessage :129-340 (oracle None, depth-k QUERY_SPREAD, MODIFY_ORDER) */
+static void env_exch_receive(abo_env *s, const event_t *m) {
+  s->comp_delay[0] = 0;
+  int t_closed = s->now > s->mkt_close;
+  if (t_closed) {
+    int is_order = m->kind == ABO_LIMIT_ORDER || m->kind == ABO_CANCEL_ORDER || m->kind == ABO_MODIFY_ORDER;
+    int is_query = m->kind == ABO_QUERY_SPREAD;
+    if (is_order || !is_query) { event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_MKT_CLOSED; env_exch_send(s, m->sender, &e); return; }
+  }
+  event_t e; memset(&e, 0, sizeof(e)); s->book.now = s->now;
+  switch (m->kind) {
+    case ABO_WHEN_MKT_OPEN: e.kind = ABO_WHEN_MKT_OPEN; e.data = s->mkt_open; env_exch_send(s, m->sender, &e); break;
+    case ABO_WHEN_MKT_CLOSE: e.kind = ABO_WHEN_MKT_CLOSE; e.data = s->mkt_close; env_exch_send(s, m->sender, &e); break;
+    case ABO_QUERY_SPREAD: {                                                                  /* :215-245 */
+      int64_t pq[4]; e.kind = ABO_QUERY_SPREAD;
+      e.n_bids = book_inside(&s->book, 1, 2, pq); if (e.n_bids > 0) { e.has_bid = 1; e.bid = pq[0]; e.bid_q = pq[1]; } if (e.n_bids > 1) e.bid2 = pq[2];
+      e.n_asks = book_inside(&s->book, 0, 2, pq); if (e.n_asks > 0) { e.has_ask = 1; e.ask = pq[0]; e.ask_q = pq[1]; } if (e.n_asks > 1) e.ask2 = pq[2];
+      e.data = s->book.has_last_trade ? s->book.last_trade : -1; e.mkt_closed = t_closed; env_exch_send(s, m->sender, &e); break; }
+    case ABO_LIMIT_ORDER: env_trace_op(s, 0, &m->order, 0, 0); book_handle_limit(&s->book, m->order); env_trace_snap(s); break;
+    case ABO_CANCEL_ORDER: env_trace_op(s, 1, &m->order, 0, 0); book_cancel(&s->book, &m->order); env_trace_snap(s); break;
+    case ABO_MODIFY_ORDER: env_trace_op(s, 2, &m->order, m->new_order.limit_price, m->new_order.quantity); book_modify(&s->book, &m->order, &m->new_order); env_trace_snap(s); break; /* :326-340 */
+    default: break;
+  }
+}
+/* Order.__init__ / generateOrderId (util/order/Order.py:27,35-42) */
+static int64_t env_new_order_id(abo_env *s, int64_t given) {
+  int64_t id;
+  if (given) id = given;
+  else { while (omap_find(&s->used_ids, s->next_order_id)) s->next_order_id++; id = s->next_order_id; }
+  if (!omap_find(&s->used_ids, id)) { if (s->used_ids.n * 2 >= s->used_ids.cap) { omap_t old = s->used_ids; omap_init(&s->used_ids, old.cap); for (int i = 0; i < old.cap; i++) if (old.e[i].used == 1) omap_put(&s->used_ids, old.e[i].key, 0, 0, 0); free(old.e); } omap_put(&s->used_ids, id, 0, 0, 0); }
+  return id;
+}
+/* TradingAgent.wakeup :142-158: returns can_trade */
+static int env_ta_wakeup(abo_env *s, int id, tagent_t *a) {
+  if (!a->has_open) { event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_WHEN_MKT_OPEN; env_send(s, id, 0, &e, 0); memset(&e, 0, sizeof(e)); e.kind = ABO_WHEN_MKT_CLOSE; env_send(s, id, 0, &e, 0); }
+  return a->has_open && a->has_close && !a->mkt_closed;
+}
+/* TradingAgent.receiveMessage :181-268 common part; returns 1 when the market hours just became known */
+static int env_ta_receive(abo_env *s, tagent_t *a, const event_t *m) {
+  (void)s; int had = a->has_open && a->has_close;
+  switch (m->kind) {
+    case ABO_WHEN_MKT_OPEN: a->mkt_open = m->data; a->has_open = 1; break;
+    case ABO_WHEN_MKT_CLOSE: a->mkt_close = m->data; a->has_close = 1; break;
+    case ABO_ORDER_EXECUTED: { int64_t qty = m->order.is_buy ? m->order.quantity : -m->order.quantity; a->shares += qty; a->cash -= qty * m->order.fill_price; break; }
+    case ABO_MKT_CLOSED: a->mkt_closed = 1; break;
+    case ABO_QUERY_SPREAD: if (m->mkt_closed) a->mkt_closed = 1; a->last_trade = m->data; a->has_last_trade = 1; break;
+    default: break;
+  }
+  return a->has_open && a->has_close && !had;
+}
+/* MarketReplayAgent.placeOrder :69-96 for one row */
+static void replay_place(abo_env *s, const srow_t *r) {
+  omap_ent *ex = omap_find(&s->ra_orders, r->id);
+  if (!ex && r->size > 0) {                                                          /* placeLimitOrder(order_id=ORDER_ID) TradingAgent.py:309-349 */
+    int64_t oid = env_new_order_id(s, r->id);
+    omap_put(&s->ra_orders, oid, r->size, r->price, r->is_buy);
+    event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_LIMIT_ORDER; e.order.agent_id = 1; e.order.order_id = oid; e.order.quantity = r->size; e.order.limit_price = r->price; e.order.is_buy = r->is_buy;
+    env_send(s, 1, 0, &e, 0);
+  } else if (ex && r->size == 0) {                                                   /* cancelOrder :399-406 */
+    event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_CANCEL_ORDER; e.order.agent_id = 1; e.order.order_id = ex->key; e.order.quantity = ex->qty; e.order.limit_price = ex->price; e.order.is_buy = ex->is_buy;
+    env_send(s, 1, 0, &e, 0);
+  } else if (ex) {                                                                   /* modifyOrder :408-418 */
+    env_new_order_id(s, r->id);                                                      /* LimitOrder(..., order_id=order_id) constructed for new_order */
+    event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_MODIFY_ORDER;
+    e.order.agent_id = 1; e.order.order_id = ex->key; e.order.quantity = ex->qty; e.order.limit_price = ex->price; e.order.is_buy = ex->is_buy;
+    e.new_order.agent_id = 1; e.new_order.order_id = r->id; e.new_order.quantity = r->size; e.new_order.limit_price = r->price; e.new_order.is_buy = r->is_buy;
+    env_send(s, 1, 0, &e, 0);
+  }
+}
+/* MarketReplayAgent.wakeup :50-60 */
+static void replay_wakeup(abo_env *s) {
+  tagent_t *a = &s->ra; env_ta_wakeup(s, 1, a);
+  if (!a->has_open || !a->has_close) return;
+  if (s->wt_cursor >= s->n_ts) return;                                               /* wakeup_times[0] -> IndexError: nothing placed */
+  env_set_wakeup(s, 1, s->ts[s->wt_cursor]); s->wt_cursor++;                         /* setWakeup(wakeup_times[0]); pop(0) */
+  /* orders_dict[currentTime]: rows of the timestamp equal to now */
+  int64_t lo = 0, hi = s->n_ts - 1, k = -1;
+  while (lo <= hi) { int64_t mid = (lo + hi) / 2; if (s->ts[mid] == s->now) { k = mid; break; } if (s->ts[mid] < s->now) lo = mid + 1; else hi = mid - 1; }
+  if (k < 0) return;                                                                 /* KeyError would propagate in the reference; cannot happen */
+  int64_t r0 = s->ts_first[k], r1 = (k + 1 < s->n_ts) ? s->ts_first[k + 1] : s->n_rows;
+  for (int64_t r = r0; r < r1; r++) replay_place(s, &s->rows[r]);
+}
+static void replay_receive(abo_env *s, const event_t *m) {
+  tagent_t *a = &s->ra;
+  int newly = env_ta_receive(s, a, m);
+  if (m->kind == ABO_ORDER_EXECUTED) {                                               /* orderExecuted :422-462 */
+    omap_ent *o = omap_find(&s->ra_orders, m->order.order_id);
+    if (o) { if (m->order.quantity >= o->qty) omap_del(&s->ra_orders, o); else o->qty -= m->order.quantity; }
+    a->last_trade = m->order.fill_price; a->has_last_trade = 1;                      /* MarketReplayAgent.receiveMessage :62-67 */
+  } else if (m->kind == ABO_ORDER_CANCELLED) { omap_ent *o = omap_find(&s->ra_orders, m->order.order_id); if (o) omap_del(&s->ra_orders, o); }
+  if (newly) env_set_wakeup(s, 1, a->mkt_open + (s->ts[0] - a->mkt_open));           /* getWakeFrequency :98-100 */
+}
+/* ---- DummyRLExecutionAgent ---- */
+static void rl_orders_remove(abo_env *s, int i) { memmove(s->rl_orders + i, s->rl_orders + i + 1, sizeof(open_order_t) * (s->rl_n_orders - i - 1)); memmove(s->rl_oqty + i, s->rl_oqty + i + 1, sizeof(double) * (s->rl_n_orders - i - 1)); s->rl_n_orders--; }
+static void rl_get_spread(abo_env *s) { event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_QUERY_SPREAD; env_send(s, 2, 0, &e, 0); s->uniq++; }  /* getCurrentSpread(depth=500) + msg_copy */
+/* wakeup :184-218 */
+static void rl_wakeup(abo_env *s) {
+  if (!env_ta_wakeup(s, 2, &s->rl)) return;
+  if (s->rl_trade) { int k = -1; for (int i = 0; i < s->n_h; i++) if (s->horizon[i] > s->now) { k = i; break; }
+    if (k >= 0) env_set_cancel(s, 2, s->horizon[k]); else s->rl_trade = 0; }                         /* requestedTime - Timedelta(0.5) == requestedTime */
+  if (s->rl_trade) { int k = -1; for (int i = 0; i < s->n_h - 1; i++) if (s->horizon[i] > s->now) { k = i; break; }
+    if (k >= 0) env_set_wakeup(s, 2, s->horizon[k]); else s->rl_trade = 0; }
+  rl_get_spread(s); s->rl_state = ST_AWAITING_SPREAD;
+}
+/* receiveMessage :230-245 (+ ExecutionAgent.handleOrderExecution :88-99, ABIDESEnvMetrics.addLOB :62-84) */
+static void rl_receive(abo_env *s, const event_t *m) {
+  tagent_t *a = &s->rl;
+  int newly = env_ta_receive(s, a, m);
+  if (m->kind == ABO_ORDER_EXECUTED) {
+    for (int i = 0; i < s->rl_n_orders; i++) if (s->rl_orders[i].order_id == m->order.order_id) {
+      if ((double)m->order.quantity >= s->rl_oqty[i]) rl_orders_remove(s, i); else s->rl_oqty[i] -= (double)m->order.quantity; break; }
+    s->executed_sum += (double)m->order.quantity; s->n_executed++; s->rem_quantity = s->quantity - s->executed_sum;
+  } else if (m->kind == ABO_ORDER_CANCELLED) {
+    for (int i = 0; i < s->rl_n_orders; i++) if (s->rl_orders[i].order_id == m->order.order_id) { rl_orders_remove(s, i); break; }
+  }
+  if (newly) env_set_wakeup(s, 2, a->mkt_open + (s->horizon[0] - a->mkt_open));               /* ExecutionAgent.getWakeFrequency :129-130 */
+  if (s->rem_quantity > 0 && s->rl_state == ST_AWAITING_SPREAD && m->kind == ABO_QUERY_SPREAD) {
+    s->rl_state = ST_AWAITING_WAKEUP;
+    if (!s->metrics_init) { s->p0 = m->data; s->metrics_init = 1; }
+    s->lob_head = (s->lob_head + 99) % 100;                                                   /* deque.appendleft, maxlen 100 */
+    lob_t *l = &s->lobs[s->lob_head]; l->bid1 = m->bid; l->bidq1 = m->bid_q; l->bid2 = m->bid2; l->ask1 = m->ask; l->askq1 = m->ask_q; l->ask2 = m->ask2; l->data = m->data; l->n_bids = m->n_bids; l->n_asks = m->n_asks;
+    if (s->n_lobs < 100) s->n_lobs++;
+  }
+}
+static const lob_t *rl_lob(const abo_env *s, int idx) { if (idx < 0) idx += s->n_lobs; return &s->lobs[(s->lob_head + idx) % 100]; }   /* deque[idx], negative from the right */
+/* get_observation :294-315; returns 0 on the ValueError paths of ABIDESEnvMetrics (empty side / no LOB) */
+static int rl_observe(abo_env *s) {
+  /* get_remaining_time :282-292 */
+  int64_t curr = s->now - (s->now % (30 * NS_PER_S)); int rem = s->n_h;
+  for (int i = 0; i < s->n_h; i++) if (s->horizon[i] == curr) { rem = s->n_h - 1 - i; break; }
+  s->rem_time = rem; s->obs_len = 0;
+  if (s->n_lobs == 0) return 0;
+  const lob_t *l = rl_lob(s, 0);
+  if (l->n_bids == 0 || l->n_asks == 0) return 0;
+  double p0 = (double)s->p0, pt = (double)l->data;
+  double mid = ((double)l->bid1 + (double)l->ask1) / 2;
+  double *o = s->obs;
+  o[0] = rem; o[1] = s->rem_quantity;
+  o[2] = log(pt / p0);                                                                        /* getLogReturn */
+  o[3] = (double)(l->ask1 - l->bid1);                                                         /* getBidAskSpread */
+  o[4] = ((double)l->bidq1 - (double)l->askq1) / ((double)l->bidq1 + (double)l->askq1);       /* getVolImbalance level 1 */
+  o[5] = tanh((double)l->ask1 / (double)l->askq1 - (double)l->bid1 / (double)l->bidq1);       /* getSmartPrice */
+  { double v[100], mean = 0, var = 0; int n = s->n_lobs;                                      /* getMidPriceVolatility: np.std(ddof=0) */
+    for (int i = 0; i < n; i++) { const lob_t *li = rl_lob(s, i); if (li->n_bids == 0 || li->n_asks == 0) return 0; v[i] = log((((double)li->bid1 + (double)li->ask1) / 2) / p0); mean += v[i]; }
+    mean /= n; for (int i = 0; i < n; i++) var += (v[i] - mean) * (v[i] - mean); o[6] = sqrt(var / n); }
+  int d;                                                                                      /* getTradeDirection :197-216 */
+  if (pt > mid) d = 1; else if (pt < mid) d = -1;
+  else { const lob_t *ll = rl_lob(s, -1); if (ll->n_bids == 0 || ll->n_asks == 0) return 0; double lm = ((double)ll->bid1 + (double)ll->ask1) / 2; d = mid > lm ? 1 : -1; }
+  o[7] = d; o[8] = 2 * d * (pt - mid) / mid;                                                  /* getEffectiveSpread */
+  s->obs_len = 9; return 1;
+}
+/* place_orders :159-181 + process_action :138-157 */
+static void rl_place_orders(abo_env *s, const double *action) {
+  int n = s->order_level; double q0 = s->quantity, q = s->quantity /* metrics.rem_quantity is never updated (typo, App. A-10) */;
+  double sum = 0; for (int i = 0; i < n; i++) sum = sum + action[1 + i];
+  double o_hat[8], o[8];
+  for (int i = 0; i < n; i++) o_hat[i] = sum == 0.0 ? 1.0 / n : action[1 + i] / sum;
+  double q_hat = q / q0;
+  double o_total = nearbyint(q0 * q_hat * pow(action[0], pow(q_hat, s->steep)));
+  double part = 0; for (int i = 0; i < n; i++) o[i] = nearbyint(o_total * o_hat[i]);
+  for (int i = 0; i < n - 1; i++) part = part + o[i];
+  o[n - 1] = o_total - part;
+  for (int l = 0; l < n; l++) {
+    if (s->n_lobs == 0) continue;                                                             /* exception swallowed */
+    const lob_t *lb = rl_lob(s, 0);
+    if (lb->n_bids == 0 || lb->n_asks == 0) continue;                                         /* ValueError swallowed */
+    if (l >= lb->n_bids || l >= lb->n_asks) continue;                                         /* IndexError swallowed (needs both sides at this level) */
+    int64_t price = l == 0 ? lb->bid1 : lb->bid2;                                             /* BUY: bid price of level l+1 */
+    int64_t oid = env_new_order_id(s, 0);                                                     /* LimitOrder() is constructed before the qty test */
+    if (!(o[l] > 0)) continue;
+    if (s->rl_n_orders == s->rl_cap_orders) { s->rl_cap_orders = s->rl_cap_orders ? 2 * s->rl_cap_orders : 8; s->rl_orders = (open_order_t *)realloc(s->rl_orders, sizeof(open_order_t) * s->rl_cap_orders); s->rl_oqty = (double *)realloc(s->rl_oqty, sizeof(double) * s->rl_cap_orders); }
+    open_order_t *oo = &s->rl_orders[s->rl_n_orders]; oo->order_id = oid; oo->limit_price = price; oo->is_buy = 1; oo->quantity = (int64_t)o[l]; s->rl_oqty[s->rl_n_orders] = o[l]; s->rl_n_orders++;
+    event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_LIMIT_ORDER; e.order.agent_id = 2; e.order.order_id = oid; e.order.quantity = (int64_t)o[l]; e.order.limit_price = price; e.order.is_buy = 1;
+    env_send(s, 2, 0, &e, 0);
+  }
+}
+/* cancelAllOrders :247-255 */
+static void rl_cancel_all(abo_env *s) {
+  for (int i = 0; i < s->rl_n_orders; i++) {
+    event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_CANCEL_ORDER; e.order.agent_id = 2; e.order.order_id = s->rl_orders[i].order_id; e.order.quantity = (int64_t)s->rl_oqty[i]; e.order.limit_price = s->rl_orders[i].limit_price; e.order.is_buy = 1;
+    env_send(s, 2, 0, &e, 0);
+  }
+}
+
+abo_env *abo_env_new(const int64_t *stream5, int64_t n_rows, double quantity, int order_level, int trace) {
+  abo_env *s = (abo_env *)calloc(1, sizeof(abo_env));
+  s->trace = trace; s->pop_hash = s->note_hash = s->snap_hash = FNV_OFF;
+  s->mkt_open = (9 * 3600 + 30 * 60) * NS_PER_S; s->mkt_close = 16 * 3600 * NS_PER_S; s->stop_time = (16 * 3600 + 600) * NS_PER_S;   /* ABIDESEnv.py:87-88 16:10 */
+  book_init(&s->book, 10, s, env_book_send);
+  s->rows = (srow_t *)malloc(sizeof(srow_t) * (n_rows > 0 ? n_rows : 1)); s->n_rows = n_rows;
+  s->ts = (int64_t *)malloc(8 * (n_rows + 1)); s->ts_first = (int64_t *)malloc(8 * (n_rows + 1));
+  for (int64_t i = 0; i < n_rows; i++) { srow_t *r = &s->rows[i]; r->t = stream5[5 * i]; r->id = stream5[5 * i + 1]; r->price = stream5[5 * i + 2]; r->size = stream5[5 * i + 3]; r->is_buy = (int)stream5[5 * i + 4];
+    if (i == 0 || r->t != s->rows[i - 1].t) { s->ts[s->n_ts] = r->t; s->ts_first[s->n_ts] = i; s->n_ts++; } }
+  omap_init(&s->ra_orders, (int)n_rows + 16); omap_init(&s->used_ids, 1 << 12);
+  s->quantity = s->rem_quantity = quantity; s->order_level = order_level; s->steep = 0.5; s->rl_trade = 1; s->rl_state = ST_AWAITING_WAKEUP;
+  s->n_h = 761; s->horizon = (int64_t *)malloc(8 * s->n_h);                                   /* date_range(09:40, 16:00, freq 30s)  agent_config.py:134-136 */
+  for (int i = 0; i < s->n_h; i++) s->horizon[i] = (9 * 3600 + 40 * 60) * NS_PER_S + (int64_t)i * 30 * NS_PER_S;
+  s->wt_cursor = 1;                                                                           /* wakeup_times = [*orders_dict]; first_wakeup stays in the list */
+  s->wt_cursor = 0;
+  for (int i = 0; i < 3; i++) env_set_wakeup(s, i, 0);                                        /* GymKernel.initRunner :139-146 kernelStarting */
+  return s;
+}
+void abo_env_free(abo_env *s) {
+  if (!s) return; book_destroy(&s->book); free(s->rows); free(s->ts); free(s->ts_first); free(s->ra_orders.e); free(s->used_ids.e); free(s->rl_orders); free(s->rl_oqty);
+  free(s->horizon); free(s->q.e); free(s->pops.v); free(s->ops.v); free(s->notes.v); free(s->snaps.v); free(s->ckpt); free(s);
+}
+/* GymKernel.stepRunner :158-306.  Returns obs length (0 or 9); *done as ABIDESEnv.step computes it (ABIDESEnv.py:42-46). */
+int abo_env_step(abo_env *s, const double *action, double *obs_out, int *done) {
+  rl_place_orders(s, action);
+  s->end_step = 0;
+  while (!s->end_step && s->q.n > 0 && s->now <= s->stop_time) {
+    event_t ev; heap_pop(&s->q, &ev); s->now = ev.t; s->ttl++;
+    s->pop_hash = fnv_mix(fnv_mix(fnv_mix(fnv_mix(s->pop_hash, ev.t), ev.recipient), ev.type), ev.uniq);
+    if (s->ttl % 1000 == 0) { if (s->n_ckpt == s->cap_ckpt) { s->cap_ckpt = s->cap_ckpt ? s->cap_ckpt * 2 : 256; s->ckpt = (uint64_t *)realloc(s->ckpt, 8 * s->cap_ckpt); } s->ckpt[s->n_ckpt++] = s->pop_hash; }
+    if (s->trace & ABO_TRACE_POPS) { int64_t row[5] = { ev.t, ev.recipient, ev.type, ev.uniq, ev.kind }; ib_push(&s->pops, row, 5); }
+    int a = ev.recipient;
+    if (ev.type == ABO_T_CANCEL_ORDER) { rl_cancel_all(s); continue; }                        /* :241-245 (get_reward returns None) */
+    if (s->agent_time[a] > s->now) { ev.t = s->agent_time[a]; env_put(s, &ev); continue; }
+    s->agent_time[a] = s->now;
+    if (ev.type == ABO_T_WAKEUP) { if (a == 1) replay_wakeup(s); else if (a == 2) rl_wakeup(s); }
+    else {
+      if (a == 0) env_exch_receive(s, &ev); else if (a == 1) replay_receive(s, &ev); else rl_receive(s, &ev);
+      if (a == 2 && ev.kind == ABO_QUERY_SPREAD) { rl_observe(s); s->end_step = 1; }          /* :286-289 */
+    }
+    s->agent_time[a] += s->comp_delay[a];
+  }
+  *done = !(s->q.n > 0 && s->now <= s->stop_time);
+  for (int i = 0; i < s->obs_len; i++) obs_out[i] = s->obs[i];
+  return s->obs_len;
+}
+int64_t abo_env_n_pops(abo_env *s) { return s->ttl; }
+uint64_t abo_env_pop_hash(abo_env *s) { return s->pop_hash; }
+uint64_t abo_env_note_hash(abo_env *s) { return s->note_hash; }
+uint64_t abo_env_snap_hash(abo_env *s) { return s->snap_hash; }
+int64_t abo_env_n_hash_ckpt(abo_env *s) { return s->n_ckpt; }
+const uint64_t *abo_env_hash_ckpt(abo_env *s) { return s->ckpt; }
+int64_t abo_env_trace(abo_env *s, int which, const int64_t **rows) { i64buf *b = which == 0 ? &s->pops : which == 1 ? &s->ops : which == 2 ? &s->notes : &s->snaps; int w = which == 0 ? 5 : which == 1 ? 9 : which == 2 ? 13 : 16; *rows = b->v; return b->n / w; }
+void abo_env_final(abo_env *s, double *out8) { out8[0] = s->rem_quantity; out8[1] = (double)s->rl.shares; out8[2] = (double)s->rl.cash; out8[3] = (double)s->n_executed; out8[4] = (double)s->ra.shares; out8[5] = (double)s->ra.cash; out8[6] = (double)s->ra_orders.n; out8[7] = (double)s->now; }
+int64_t abo_env_counter(abo_env *s, int w) { switch (w) { case 0: return s->max_queue; case 1: return s->max_bid_lv; case 2: return s->max_ask_lv; case 3: return s->max_resting; case 4: return s->uniq; case 5: return s->next_order_id; default: return -1; } }

@@ -99,6 +99,24 @@ int64_t abo_sim_counter(abo_sim *, int which); /* 0 limit, 1 cancel, 2 fills, 3 
 void abo_sim_book_l1(abo_sim *, int64_t *out5); /* bid, bid_qty, ask, ask_qty, last_trade */
 int64_t abo_sim_fundamental(abo_sim *);          /* last oracle value r[symbol][1] */
 
+/* ---------------- ABIDESEnv: Exchange + MarketReplayAgent + DummyRLExecutionAgent under GymKernel ---------------- */
+typedef struct abo_env abo_env;
+/* stream5: rows (t_ns since midnight, ORDER_ID, PRICE cents, SIZE, is_buy) as LOBSTEROrdersProcessor yields them
+ * (agent/examples/MarketReplayAgent.py:162-220), sorted by time.  quantity / order_level: agent_config.py:132-154. */
+abo_env *abo_env_new(const int64_t *stream5, int64_t n_rows, double quantity, int order_level, int trace_flags);
+void abo_env_free(abo_env *);
+/* ABIDESEnv.step (ABIDESEnv.py:30-49): returns len(obs) (0 or 9), fills obs_out[9] and *done */
+int abo_env_step(abo_env *, const double *action, double *obs_out, int *done);
+int64_t abo_env_n_pops(abo_env *);
+uint64_t abo_env_pop_hash(abo_env *);
+uint64_t abo_env_note_hash(abo_env *);
+uint64_t abo_env_snap_hash(abo_env *);
+int64_t abo_env_n_hash_ckpt(abo_env *);
+const uint64_t *abo_env_hash_ckpt(abo_env *);
+int64_t abo_env_trace(abo_env *, int which, const int64_t **rows);
+void abo_env_final(abo_env *, double *out8); /* rl rem_quantity, shares, cash, n_executed, replay shares, cash, open orders, now */
+int64_t abo_env_counter(abo_env *, int which); /* 0 max queue, 1 max bid levels, 2 max ask levels, 3 max resting, 4 uniq, 5 next order id */
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,18 @@ def lib():
     sig("abo_sim_counter", i64, vp, i32)
     sig("abo_sim_book_l1", None, vp, P(i64))
     sig("abo_sim_fundamental", i64, vp)
+    sig("abo_env_new", vp, P(i64), i64, dbl, i32, i32)
+    sig("abo_env_free", None, vp)
+    sig("abo_env_step", i32, vp, P(dbl), P(dbl), P(i32))
+    sig("abo_env_n_pops", i64, vp)
+    sig("abo_env_pop_hash", u64, vp)
+    sig("abo_env_note_hash", u64, vp)
+    sig("abo_env_snap_hash", u64, vp)
+    sig("abo_env_n_hash_ckpt", i64, vp)
+    sig("abo_env_hash_ckpt", P(u64), vp)
+    sig("abo_env_trace", i64, vp, i32, P(P(i64)))
+    sig("abo_env_final", None, vp, P(dbl))
+    sig("abo_env_counter", i64, vp, i32)
     _lib = L
     return L
 
@@ -291,3 +303,60 @@ class OracleSim:
 
     def fundamental(self):
         return lib().abo_sim_fundamental(self._h)
+
+
+class OracleEnv:
+    """ABIDESEnv (ABIDESEnv.py) restated: Exchange + MarketReplayAgent + DummyRLExecutionAgent under GymKernel.
+    `stream` is an int64 [n,5] array of (t_ns, ORDER_ID, PRICE, SIZE, is_buy) rows."""
+
+    def __init__(self, stream, quantity=1e5, order_level=2, trace=0):
+        self._stream = np.ascontiguousarray(stream, dtype=np.int64)
+        self._h = lib().abo_env_new(self._stream.ctypes.data_as(C.POINTER(C.c_int64)), len(self._stream), float(quantity),
+                                    int(order_level), int(trace))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().abo_env_free(self._h)
+            self._h = None
+
+    def step(self, action):
+        a = np.ascontiguousarray(action, dtype=np.float64)
+        obs = np.zeros(9)
+        done = C.c_int(0)
+        n = lib().abo_env_step(self._h, a.ctypes.data_as(C.POINTER(C.c_double)), obs.ctypes.data_as(C.POINTER(C.c_double)),
+                               C.byref(done))
+        return obs[:n], None, int(done.value), None
+
+    @property
+    def n_pops(self):
+        return lib().abo_env_n_pops(self._h)
+
+    def pop_hash(self):
+        return lib().abo_env_pop_hash(self._h)
+
+    def note_hash(self):
+        return lib().abo_env_note_hash(self._h)
+
+    def snap_hash(self):
+        return lib().abo_env_snap_hash(self._h)
+
+    def hash_ckpt(self):
+        n = lib().abo_env_n_hash_ckpt(self._h)
+        return np.ctypeslib.as_array(lib().abo_env_hash_ckpt(self._h), shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+
+    def trace(self, which):
+        w = {"pops": (0, 5), "ops": (1, 9), "notes": (2, 13), "snaps": (3, 16)}[which]
+        p = C.POINTER(C.c_int64)()
+        n = lib().abo_env_trace(self._h, w[0], C.byref(p))
+        if n == 0:
+            return np.zeros((0, w[1]), np.int64)
+        return np.ctypeslib.as_array(p, shape=(n * w[1],)).reshape(n, w[1]).copy()
+
+    def final(self):
+        out = np.zeros(8)
+        lib().abo_env_final(self._h, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    def counter(self, which):
+        names = ["max_queue", "max_bid_levels", "max_ask_levels", "max_resting", "uniq", "next_order_id"]
+        return lib().abo_env_counter(self._h, names.index(which))

@@ -1,0 +1,36 @@
+"""Pin the oracle's ABIDESEnv restatement (GymKernel + MarketReplayAgent + DummyRLExecutionAgent + ABIDESEnvMetrics +
+modifyOrder/history) against an episode recorded from the live reference (tools/record_reference_env.py)."""
+import os
+
+import numpy as np
+
+from oracle.oracle import OracleEnv, TRACE_ALL
+
+
+def test_env_episode_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "env_IBM_2003-01-14_s789.npz"))
+    env = OracleEnv(g["stream"], quantity=1e5, order_level=2, trace=TRACE_ALL)
+    obs, dones = [], []
+    for a in g["actions"]:
+        o, reward, done, info = env.step(a)
+        assert reward is None and info is None                       # dummy_rl_execution_agent.py:325-352 returns None
+        oo = np.full(9, np.nan)
+        oo[: len(o)] = o
+        obs.append(oo)
+        dones.append(done)
+        if done:
+            break
+    obs = np.array(obs)
+    assert len(obs) == len(g["obs"]) == 761 and dones == list(g["done"])
+    assert env.n_pops == int(g["n_pops"]) == 144099
+    assert np.array_equal(env.hash_ckpt(), g["pop_hash_ckpt"][:-1]) and env.pop_hash() == int(g["pop_hash_ckpt"][-1])
+    assert env.note_hash() == int(g["note_hash"]) and env.snap_hash() == int(g["snap_hash"])
+    for name in ("pops", "ops", "notes", "snaps"):
+        a, b = env.trace(name), g[name + "_head"]
+        assert np.array_equal(a[: len(b)], b), name
+    # observations: fp64, 1e-6 relative (north star); measured 2e-15
+    assert np.array_equal(np.isnan(obs), np.isnan(g["obs"]))
+    err = np.nanmax(np.abs(obs - g["obs"]) / np.maximum(np.abs(g["obs"]), 1e-300))
+    assert err < 1e-6, err
+    f = env.final()
+    assert np.array_equal(f[:4], g["rl_final"]) and np.array_equal(f[4:7], g["replay_final"])
