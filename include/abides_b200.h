@@ -46,7 +46,8 @@ enum abx_rng_mode {
 };
 enum abx_latency_model {
   ABX_LAT_MATRIX_NOISE = 0, /* Kernel.py:410-412: pairwise latency + uniform integer noise in [0, n_noise) */
-  ABX_LAT_CUBIC = 1         /* model/LatencyModel.py:109-140 */
+  ABX_LAT_CUBIC = 1,        /* model/LatencyModel.py:109-140 */
+  ABX_LAT_ZERO = 2          /* zero latency matrix with noise [1.0] (ABIDESEnv.py:91-92): delivery == send time, no draw */
 };
 
 /* per-environment flag bits in abx_env_stats.flags */
@@ -60,6 +61,8 @@ enum abx_latency_model {
 #define ABX_F_TAPE_KIND       0x080u /* tape entry kind differs from the draw the simulator asked for */
 #define ABX_F_TRACE_OVERFLOW  0x100u
 #define ABX_F_TIME_RANGE      0x200u
+#define ABX_F_UNSUPPORTED     0x400u /* a reference behaviour this build does not model was hit (e.g. re-pricing MODIFY) */
+#define ABX_F_OBS_INVALID     0x800u /* get_observation would have raised in the reference (empty side / no stored LOB) */
 
 /* One ZeroIntelligenceAgent strategy group: config/sparse_zi_1000.py:196-204 tuples (n, R_min, R_max, eta). */
 typedef struct abx_zi_group {
@@ -191,6 +194,42 @@ int32_t abx_sim_book_snapshot(abx_sim *h, int32_t env, int32_t is_bid, int32_t d
 
 /* Copy the trace of one environment to the host.  out: host [max_recs]; *n_recs = records written. */
 int32_t abx_sim_trace(abx_sim *h, int32_t env, abx_trace_rec *out, int32_t max_recs, int32_t *n_recs, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ABIDESEnv shape: Exchange (id 0) + MarketReplayAgent (id 1) + DummyRLExecutionAgent (id 2) under GymKernel.
+ * Replaces the gym surface ABIDESEnv.py:7-57 (reset / step) for n_envs environments at once.  Handles are abx_sim*;
+ * abx_sim_stats / abx_sim_trace / abx_sim_book_snapshot / abx_sim_destroy / abx_sim_launch_count work on them too
+ * (traces report the stream's original ORDER_IDs).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct abx_env_config {
+  int32_t version;                 /* ABX_VERSION */
+  int32_t order_level;             /* DummyRLExecutionAgent order_level (1 or 2): action has order_level + 1 entries */
+  int32_t is_buy;                  /* direction == "BUY" */
+  int32_t n_horizon;               /* len(execution_time_horizon) (agent_config.py:134-136: 761) */
+  int64_t start_ns, stop_ns;       /* ABIDESEnv.py:86-88: midnight .. 16:10 */
+  int64_t mkt_open_ns, mkt_close_ns;
+  int64_t horizon_start_ns, horizon_step_ns; /* 09:40:00, 30 s */
+  double quantity, steep;          /* parent order size, a_q_map_steep_factor */
+  int32_t stream_history;          /* ExchangeAgent stream_history (10): bounds the ORDER_MODIFIED fan-out */
+  int32_t queue_cap, level_cap, order_cap;   /* per-environment capacities */
+  int32_t trace_cap, hash_pops;
+} abx_env_config;
+
+/* Defaults of ABIDESEnv.initAgents / agent_config.py (BUY 1e5 shares, "30S", 09:40 -> 16:00, order_level 2, steep 0.5). */
+int32_t abx_env_config_default(abx_env_config *cfg);
+
+/* Replaces: ABIDESEnv.__init__ (ABIDESEnv.py:8-26) + LOBSTEROrdersProcessor (agent/examples/MarketReplayAgent.py:162-220
+ * output: the parsed stream).  stream5: HOST int64 [n_rows][5] rows (t_ns since midnight, ORDER_ID, PRICE cents, SIZE,
+ * is_buy) sorted by time; every environment replays this stream. */
+int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out);
+/* Replaces: ABIDESEnv.reset() (ABIDESEnv.py:51-57): initAgents + GymKernel.initRunner. */
+int32_t abx_env_reset(abx_sim *h, void *stream);
+/* Replaces: ABIDESEnv.step(action) (ABIDESEnv.py:30-49) -> GymKernel.stepRunner (GymKernel.py:158-306) for every environment.
+ * DEVICE pointers: actions fp64 [n_envs][3] (x_hat, o_hat_1, o_hat_2), obs fp64 [n_envs][9] (zeros when the reference
+ * would return []), reward fp64 [n_envs] (0: the reference's get_reward returns None), done uint8 [n_envs]. */
+int32_t abx_env_step(abx_sim *h, const double *actions_dev, double *obs_dev, double *reward_dev, uint8_t *done_dev, void *stream);
+/* Same call with HOST buffers (pinned memory keeps the copies asynchronous); synchronises `stream`. */
+int32_t abx_env_step_host(abx_sim *h, const double *actions, double *obs, double *reward, uint8_t *done, void *stream);
 
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t abx_sim_launch_count(const abx_sim *h);

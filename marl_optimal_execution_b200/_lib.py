@@ -16,7 +16,8 @@ LAT_MATRIX_NOISE, LAT_CUBIC = 0, 1
 
 F_DONE, F_QUEUE_OVERFLOW, F_LEVEL_OVERFLOW, F_ORDER_OVERFLOW, F_AGENT_ORDERS_OVERFLOW = 0x1, 0x2, 0x4, 0x8, 0x10
 F_THETA_INDEX, F_TAPE_UNDERRUN, F_TAPE_KIND, F_TRACE_OVERFLOW, F_TIME_RANGE = 0x20, 0x40, 0x80, 0x100, 0x200
-F_ERROR_MASK = 0x3FE
+F_UNSUPPORTED, F_OBS_INVALID = 0x400, 0x800
+F_ERROR_MASK = 0xFFE
 
 MSG_KINDS = [
     "NONE", "WHEN_MKT_OPEN", "WHEN_MKT_CLOSE", "QUERY_SPREAD", "LIMIT_ORDER", "CANCEL_ORDER", "MODIFY_ORDER",
@@ -47,6 +48,17 @@ class SimConfig(C.Structure):
         ("latency_lo", C.c_double), ("latency_hi", C.c_double),
         ("jitter", C.c_double), ("jitter_clip", C.c_double), ("jitter_unit", C.c_double),
         ("queue_cap", C.c_int32), ("level_cap", C.c_int32), ("order_cap", C.c_int32), ("rng_mode", C.c_int32),
+        ("trace_cap", C.c_int32), ("hash_pops", C.c_int32),
+    ]
+
+
+class EnvConfig(C.Structure):
+    """abx_env_config (include/abides_b200.h)."""
+    _fields_ = [
+        ("version", C.c_int32), ("order_level", C.c_int32), ("is_buy", C.c_int32), ("n_horizon", C.c_int32),
+        ("start_ns", C.c_int64), ("stop_ns", C.c_int64), ("mkt_open_ns", C.c_int64), ("mkt_close_ns", C.c_int64),
+        ("horizon_start_ns", C.c_int64), ("horizon_step_ns", C.c_int64), ("quantity", C.c_double), ("steep", C.c_double),
+        ("stream_history", C.c_int32), ("queue_cap", C.c_int32), ("level_cap", C.c_int32), ("order_cap", C.c_int32),
         ("trace_cap", C.c_int32), ("hash_pops", C.c_int32),
     ]
 
@@ -110,6 +122,11 @@ def _bind(L):
     sig("abx_sim_book_snapshot", i32, vp, i32, i32, i32, P(i32), P(i32), vp)
     sig("abx_sim_trace", i32, vp, i32, vp, i32, P(i32), vp)
     sig("abx_sim_launch_count", i64, vp)
+    sig("abx_env_config_default", i32, P(EnvConfig))
+    sig("abx_env_create", i32, P(EnvConfig), P(i64), i64, i32, i32, P(vp))
+    sig("abx_env_reset", i32, vp, vp)
+    sig("abx_env_step", i32, vp, vp, vp, vp, vp, vp)
+    sig("abx_env_step_host", i32, vp, vp, vp, vp, vp, vp)
     return L
 
 

@@ -29,6 +29,7 @@
 
 #if !defined(__CUDACC__)
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
+struct alignas(16) int4 { int32_t x, y, z, w; };
 inline float cospif(float x) { return (float)cos(3.14159265358979323846 * (double)x); }
 #endif
 
@@ -47,7 +48,7 @@ struct alignas(16) EnvState {           // 192 B per environment
   int32_t n_bid_lv, n_ask_lv; int32_t n_resting; uint32_t free_head; // ladder sizes (0 bids, 1 asks); order-node free list
   uint32_t pool_top, flags, trace_n, c_limit;
   uint32_t c_cancel, c_fills, c_query, ctr_symbol;
-  uint32_t ctr_kernel, ctr_latency, ctr_global, started;
+  uint32_t ctr_kernel, ctr_latency, ctr_global, trade_epoch;   // trade_epoch: OrderBook.history rotations (util/OrderBook.py:146)
   int64_t sum_shares, sum_cash;
   uint32_t kblk[4];                     // cached Philox block of the kernel (latency-noise) stream
 };
@@ -79,6 +80,7 @@ struct Event {                          // one PriorityQueue entry, unpacked
   int32_t p[6];                         // order: {order_id, limit_price, qty, fill_price, is_buy, -}
                                         // spread reply: {bid, bid_qty, ask, ask_qty, last_trade, has_bid|has_ask<<1|mkt_closed<<2}
   double lat_back;                      // trader -> exchange messages carry latency[0][sender] for the reply
+  int32_t x0, x1;                       // exchange -> agent QUERY_SPREAD replies with depth > 1: level-2 bid / ask price (shares the lat_back words)
 };
 
 // 64-bit sort key: [ time : 47 | recipient : 15 | type : 2 ], ties broken by uniq (message/Message.py:39-45)
@@ -90,6 +92,7 @@ ABX_HD int key_recipient(uint64_t k) { return int((k >> 2) & 0x7fff); }
 ABX_HD int key_type(uint64_t k) { return int(k & 3); }
 constexpr uint64_t KEY_EMPTY = ~uint64_t(0);
 
+struct EnvX;
 struct NodeRec { uint32_t id; int32_t qty; uint32_t agent; uint32_t next; };   // one resting order (16 B)
 constexpr uint32_t NIL = 0xffffffffu;
 
@@ -112,7 +115,35 @@ struct SimParams {
   EnvState *env;                // [n_envs]
   abx_trace_rec *trace;         // [n_envs][trace_cap]
   const uint64_t *tape_bits; const uint8_t *tape_kinds; const int64_t *tape_off; // tape mode
+  // ---- ABIDESEnv shape (exchange + MarketReplayAgent + RL execution agent); zero for the sparse_zi shape ----
+  int32_t n_ts, n_rows, n_ids, n_h;                 // replayed stream: timestamps, rows, distinct order ids; horizon length
+  int64_t h0_ns, h_step_ns;                         // execution_time_horizon = h0 + k * step, k < n_h (agent_config.py:134-136)
+  double rl_quantity, rl_steep; int32_t order_level, rl_is_buy;
+  const int64_t *st_ts;                             // [n_ts]      distinct timestamps (ns), ascending
+  const int32_t *st_first;                          // [n_ts + 1]  first row of each timestamp
+  const int4 *st_rows;                              // [n_rows]    {dense id, PRICE cents, SIZE, is_buy}
+  struct EnvX *envx;                                // [n_envs]
+  uint4 *idtab;                                     // [n_envs][n_ids] {agent-view qty, price<<1|is_buy, last registration epoch, epoch mask}
+  int4 *lobs;                                       // [n_envs][LOB_CAP][3] stored QUERY_SPREAD replies (ABIDESEnvMetrics.data)
 };
+constexpr int LOB_CAP = 100;                        // ABIDESEnvMetrics(maxlen = 100) dummy_rl_execution_agent.py:125
+constexpr int RL_ORDER_CAP = 8;
+constexpr uint32_t REPLAY_ID_BASE = 0x40000000u;    // device order id of replayed order k = REPLAY_ID_BASE + dense id k
+enum : uint32_t { RLF_TRADE = 1u << 16, RLF_METRICS_INIT = 1u << 17 };
+
+struct alignas(16) EnvX {                           // per-environment state of the two ABIDESEnv traders (shared memory while stepping)
+  int64_t ra_time, rl_time;                         // Kernel.agentCurrentTimes[1], [2]
+  int64_t ra_cash, rl_cash;
+  double rem_quantity, executed_sum;                // ExecutionAgent.rem_quantity, sum of executed quantities
+  int32_t ra_shares, rl_shares, ra_last_trade, rl_last_trade;
+  uint32_t ra_flags, rl_flags; int32_t wt_cursor, n_executed;
+  int32_t rl_n_orders, n_lobs, lob_head, p0;
+  int32_t rem_time, obs_len, ra_open, steps;
+  uint32_t rl_oid[RL_ORDER_CAP]; int32_t rl_oprice[RL_ORDER_CAP]; int32_t rl_oqty[RL_ORDER_CAP];
+  double obs[9]; double pad0;
+};
+static_assert(sizeof(EnvX) % 16 == 0, "EnvX layout");
+
 
 // ---------------------------------------------------------------------------------------------------
 // small helpers
@@ -123,6 +154,13 @@ ABX_HD uint64_t fnv_mix(uint64_t h, int64_t sv) {
 #pragma unroll
   for (int i = 0; i < 8; i++) { h = (h ^ (v & 0xFF)) * 0x100000001B3ULL; v >>= 8; }
   return h;
+}
+ABX_HD int __popc_compat(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __popc(v);
+#else
+  return __builtin_popcount(v);
+#endif
 }
 ABX_HD uint64_t dbl_bits(double d) { union { double d; uint64_t u; } x; x.d = d; return x.u; }
 ABX_HD double bits_dbl(uint64_t u) { union { double d; uint64_t u; } x; x.u = u; return x.d; }
@@ -139,7 +177,8 @@ ABX_HD double dsub(double a, double b) { volatile double r = a - b; return r; }
 
 // queue slot encoding: key {hi.lo, hi.hi, uniq, kind | sender << 8}, pay0 {p0..p3}, pay1 {p4, p5, lat_back bits}
 ABX_HD void event_pack(const Event &e, uint4 &k, uint4 &a, uint4 &b) {
-  uint64_t hi = key_pack(e.t, e.recipient, e.type); uint64_t lb = dbl_bits(e.lat_back);
+  uint64_t hi = key_pack(e.t, e.recipient, e.type);
+  uint64_t lb = e.sender == 0 ? ((uint64_t)(uint32_t)e.x0 | ((uint64_t)(uint32_t)e.x1 << 32)) : dbl_bits(e.lat_back);
   k.x = (uint32_t)hi; k.y = (uint32_t)(hi >> 32); k.z = e.uniq; k.w = (uint32_t)e.kind | ((uint32_t)e.sender << 8);
   a.x = (uint32_t)e.p[0]; a.y = (uint32_t)e.p[1]; a.z = (uint32_t)e.p[2]; a.w = (uint32_t)e.p[3];
   b.x = (uint32_t)e.p[4]; b.y = (uint32_t)e.p[5]; b.z = (uint32_t)lb; b.w = (uint32_t)(lb >> 32);
@@ -148,7 +187,7 @@ ABX_HD void event_unpack(const uint4 &k, const uint4 &a, const uint4 &b, Event &
   uint64_t hi = (uint64_t)k.x | ((uint64_t)k.y << 32);
   e.t = key_time(hi); e.recipient = key_recipient(hi); e.type = key_type(hi); e.uniq = k.z; e.kind = (int)(k.w & 0xffu); e.sender = (int)(k.w >> 8);
   e.p[0] = (int32_t)a.x; e.p[1] = (int32_t)a.y; e.p[2] = (int32_t)a.z; e.p[3] = (int32_t)a.w; e.p[4] = (int32_t)b.x; e.p[5] = (int32_t)b.y;
-  e.lat_back = bits_dbl((uint64_t)b.z | ((uint64_t)b.w << 32));
+  e.lat_back = bits_dbl((uint64_t)b.z | ((uint64_t)b.w << 32)); e.x0 = (int32_t)b.z; e.x1 = (int32_t)b.w;
 }
 ABX_HD bool key_less(uint64_t ah, uint32_t au, uint64_t bh, uint32_t bu) { return ah < bh || (ah == bh && au < bu); }
 
@@ -253,7 +292,7 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
   s.or_v = (int32_t)P.c.r_bar; s.last_trade = (int32_t)P.c.r_bar;     // SparseMeanRevertingOracle.py:58; ExchangeAgent.kernelInitializing :91-102
   s.uniq = 0; s.next_order_id = 0; s.q_count = 0; s.max_q = 0; s.n_bid_lv = s.n_ask_lv = 0; s.n_resting = 0; s.free_head = NIL;
   s.pool_top = 0; s.flags = 0; s.trace_n = 0; s.c_limit = s.c_cancel = s.c_fills = s.c_query = 0;
-  s.ctr_symbol = s.ctr_kernel = s.ctr_latency = s.ctr_global = 0; s.started = 1; s.sum_shares = 0; s.sum_cash = 0;
+  s.ctr_symbol = s.ctr_kernel = s.ctr_latency = s.ctr_global = 0; s.trade_epoch = 16; s.sum_shares = 0; s.sum_cash = 0;
   s.kblk[0] = s.kblk[1] = s.kblk[2] = s.kblk[3] = 0;
 }
 
@@ -272,7 +311,7 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
 // instructions in program order -- separates a write from later reads.
 // ---------------------------------------------------------------------------------------------------
 constexpr int OUT_CAP = 32, OUT_WORDS = 12;
-enum : uint32_t { OF_WAKEUP = 1u << 24, OF_BUMP_UNIQ = 1u << 25, OF_FROM_EXCH = 1u << 26 };
+enum : uint32_t { OF_WAKEUP = 1u << 24, OF_BUMP_UNIQ = 1u << 25, OF_FROM_EXCH = 1u << 26, OF_CANCEL_EVT = 1u << 27 };
 
 struct AgentRegs {                      // scalar part of ZiAgent held in registers while an event is handled
   int64_t agent_time, prev_wake, cash; double r_t, sigma_t, lat_to, lat_from;
@@ -291,13 +330,13 @@ ABX_HD void regs_store(ZiAgent *z, const AgentRegs &a) {
 
 // RNG_MODE / LAT_MODEL: compile-time copies of cfg.rng_mode / cfg.latency_model (-1 = decide at run time);
 // INSTR: parity instrumentation (pop hash + trace records) compiled in or out.
-template <class Ctx, int RNG_MODE = -1, int LAT_MODEL = -1, bool INSTR = true>
+template <class Ctx, int RNG_MODE = -1, int LAT_MODEL = -1, bool INSTR = true, bool ENV = false>
 struct Sim {
   Ctx &c; const SimParams &P; EnvState s; RngT<RNG_MODE> rng; int64_t addl_delay; int n_out; int self_id;
   AgentRegs a; ZiAgent *z;                // the trader whose event is being handled (registers + staged record)
 
   ABX_HD Sim(Ctx &c_, const SimParams &P_, const EnvState &s_, int env) : c(c_), P(P_), s(s_), addl_delay(0), n_out(0), self_id(0), z(nullptr) {
-    rng.P = &P; rng.env = env; rng.seed = s.seed; rng.err = 0;
+    rng.P = &P; rng.env = env; rng.seed = s.seed; rng.err = 0; a.lat_from = 0.0; a.lat_to = 0.0;
   }
 
   ABX_HD int n_lv(int side) const { return side ? s.n_ask_lv : s.n_bid_lv; }
@@ -374,7 +413,7 @@ struct Sim {
       int64_t off = (int64_t)((uint64_t)o[9] | ((uint64_t)o[10] << 32));
       e.recipient = (int)(w0 & 0xffffu); e.kind = (int)((w0 >> 16) & 0xffu);
       if (w0 & OF_WAKEUP) {
-        e.t = off < KEY_T_MAX ? off : KEY_T_MAX; e.type = ABX_T_WAKEUP; e.uniq = 0; e.sender = e.recipient; e.lat_back = 0.0;
+        e.t = off < KEY_T_MAX ? off : KEY_T_MAX; e.type = (w0 & OF_CANCEL_EVT) ? ABX_T_CANCEL_ORDER : ABX_T_WAKEUP; e.uniq = 0; e.sender = e.recipient; e.lat_back = 0.0; e.x0 = e.x1 = 0;
       } else {
         e.uniq = s.uniq++;                                                            // Message() construction order (message/Message.py:33-34)
         if (w0 & OF_BUMP_UNIQ) s.uniq++;                                              // TradingAgent.getCurrentSpread's never-sent msg_copy (:281)
@@ -382,7 +421,8 @@ struct Sim {
         if (INSTR && from_exch && P.c.trace_cap > 0) trace_note(e.recipient, e.kind, e.p);
         int64_t sent = s.now + off;                                                   // Kernel.py:391-393
         int64_t deliver;
-        if (LAT_MODEL < 0 ? P.c.latency_model == ABX_LAT_CUBIC : LAT_MODEL == ABX_LAT_CUBIC) {   // model/LatencyModel.py:133-138
+        if (LAT_MODEL == ABX_LAT_ZERO) { deliver = sent; }                                // zero latency matrix, noise [1.0]: no draw (ABIDESEnv.py:91-92)
+        else if (LAT_MODEL < 0 ? P.c.latency_model == ABX_LAT_CUBIC : LAT_MODEL == ABX_LAT_CUBIC) {   // model/LatencyModel.py:133-138
           double u = rng.u01(S_LATENCY, s.ctr_latency);
           double x = dadd(P.c.jitter_clip, dmul(dsub(1.0, P.c.jitter_clip), u));      // uniform(low=clip, high=1.0)
           double latency = dadd(lat, dmul(P.c.jitter / pow_ni(x, 3.0), lat / P.c.jitter_unit));
@@ -393,6 +433,7 @@ struct Sim {
         }
         e.t = deliver < KEY_T_MAX ? deliver : KEY_T_MAX; e.type = ABX_T_MESSAGE;
         e.sender = from_exch ? 0 : self_id; e.lat_back = from_exch ? 0.0 : a.lat_from;
+        e.x0 = (int32_t)o[7]; e.x1 = (int32_t)o[8];                                   // exchange replies: level-2 prices ride in the latency words
       }
       if (!c.q_push(e)) s.flags |= ABX_F_QUEUE_OVERFLOW;                              // Kernel.py:425 / :462
       else { s.q_count++; if (s.q_count > s.max_q) s.max_q = s.q_count; }
@@ -459,6 +500,10 @@ struct Sim {
   // handleLimitOrder :38-170 (+ executeOrder :172-240).  lat_in = latency[0][incoming agent]
   ABX_HD void book_handle_limit(uint32_t oid, int agent, int is_buy, int32_t price, int32_t qty, double lat_in) {
     if (qty <= 0) return;                                                               // :47-49
+    if (ENV && oid >= REPLAY_ID_BASE) {                                                 // :52-60 history[0][order_id] = {...}
+      uint4 t = c.id_load((int)(oid - REPLAY_ID_BASE)); uint32_t d = s.trade_epoch - t.z;
+      t.w = (t.w == 0 || d >= 16) ? 1u : (((t.w << d) | 1u) & 0xffffu); t.z = s.trade_epoch; c.id_store((int)(oid - REPLAY_ID_BASE), t);
+    }
     int opp = is_buy ? 1 : 0;                                                           // a buy matches asks (side 1)
     int64_t trade_qty = 0, trade_px = 0;
     bool matching = true;
@@ -480,7 +525,7 @@ struct Sim {
           }
           qty -= fq;                                                                    // :77
           exch_send_order(agent, ABX_ORDER_EXECUTED, oid, price, fq, bp, is_buy, lat_in);             // :88 (incoming copy)
-          exch_send_order((int)hr.agent, ABX_ORDER_EXECUTED, hr.id, bp, fq, bp, !is_buy, c.agent_lat_from((int)hr.agent)); // :89-91
+          exch_send_order((int)hr.agent, ABX_ORDER_EXECUTED, hr.id, bp, fq, bp, !is_buy, ENV ? 0.0 : c.agent_lat_from((int)hr.agent)); // :89-91
           trade_qty += fq; trade_px += (int64_t)bp * fq; s.c_fills++; matched = true;
           if (qty <= 0) matching = false;
           if (n_out >= OUT_CAP - 3) flush(); else c.sync();
@@ -492,7 +537,7 @@ struct Sim {
         matching = false;
       }
     }
-    if (trade_qty > 0) s.last_trade = (int32_t)py_round_i64((double)trade_px / (double)trade_qty); // :131-143
+    if (trade_qty > 0) { s.last_trade = (int32_t)py_round_i64((double)trade_px / (double)trade_qty); s.trade_epoch++; } // :131-149 (history.insert(0, {}))
   }
   // cancelOrder :284-339
   ABX_HD void book_cancel(uint32_t oid, int agent, int is_buy, int32_t price, double lat_in) {
@@ -718,6 +763,250 @@ struct Sim {
       flush();                                                                          // deliver what this event sent
     }
     s.flags |= rng.err;
+  }
+
+
+  // =================================================================================================
+  // ABIDESEnv shape: GymKernel.stepRunner (GymKernel.py:158-306) over Exchange (id 0), MarketReplayAgent (id 1,
+  // agent/examples/MarketReplayAgent.py) and DummyRLExecutionAgent (id 2, agent/execution/rl/dummy_rl_execution_agent.py,
+  // agent/execution/baselines/execution_agent.py, ABIDESEnvMetrics.py).  Latency 0, computation delay 0, no oracle.
+  // =================================================================================================
+  ABX_HD void env_send(int kind, const int32_t p[6], bool bump) {                       // Agent.sendMessage from trader self_id to the exchange
+    emit(0u | ((uint32_t)kind << 16) | (bump ? OF_BUMP_UNIQ : 0u), p, 0.0, P.c.default_computation_delay_ns + addl_delay);
+  }
+  ABX_HD void env_set_cancel(int sender, int64_t t) { int32_t p[6] = {0, 0, 0, 0, 0, 0}; emit((uint32_t)sender | OF_WAKEUP | OF_CANCEL_EVT, p, 0.0, t); }   // GymKernel.setCancelOrder :364-389
+  ABX_HD bool ta_wakeup(uint32_t flags) {                                               // TradingAgent.wakeup :142-158 -> can_trade
+    if (!(flags & AF_HAS_OPEN)) { int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_WHEN_MKT_OPEN, p, false); env_send(ABX_WHEN_MKT_CLOSE, p, false); }
+    return (flags & AF_HAS_OPEN) && (flags & AF_HAS_CLOSE) && !(flags & AF_MKT_CLOSED);
+  }
+  // TradingAgent.receiveMessage :181-268 common part; true when the market hours just became known
+  ABX_HD bool ta_receive(const Event &m, uint32_t &flags, int32_t &shares, int64_t &cash, int32_t &last_trade) {
+    bool had = (flags & AF_HAS_OPEN) && (flags & AF_HAS_CLOSE);
+    if (m.kind == ABX_WHEN_MKT_OPEN) flags |= AF_HAS_OPEN;
+    else if (m.kind == ABX_WHEN_MKT_CLOSE) flags |= AF_HAS_CLOSE;
+    else if (m.kind == ABX_ORDER_EXECUTED) { int32_t sq = m.p[4] ? m.p[2] : -m.p[2]; shares += sq; cash -= (int64_t)sq * m.p[3]; }
+    else if (m.kind == ABX_MKT_CLOSED) flags |= AF_MKT_CLOSED;
+    else if (m.kind == ABX_QUERY_SPREAD) { if (m.p[5] & 4) flags |= AF_MKT_CLOSED; last_trade = m.p[4]; flags |= AF_HAS_LAST; }
+    return (flags & AF_HAS_OPEN) && (flags & AF_HAS_CLOSE) && !had;
+  }
+  // ---- exchange additions: MODIFY_ORDER (util/OrderBook.py:341-372) ----
+  ABX_HD void book_modify(uint32_t oid, int agent, int is_buy, int32_t price, int32_t new_price, int32_t new_qty) {
+    int side = is_buy ? 0 : 1; int n = n_lv(side); if (n == 0) return;                  // :345-347
+    int pos; bool found; c.lv_find(side, price, n, pos, found);                         // :349 level whose head price equals the OLD order's price
+    if (!found) return;
+    uint32_t head = c.lv_head(side, pos); int matches = 0; uint32_t cur = head;
+#pragma unroll 1
+    while (cur != NIL) { NodeRec r = c.node_load(cur); if (r.id == oid) matches++; cur = r.next; }   // :350-351 live scan: every node carrying the id
+    if (matches == 0) return;
+    NodeRec hr = c.node_load(head);
+    c.lv_set(side, pos, c.lv_qty(side, pos) - hr.qty + new_qty, head, c.lv_tail(side, pos));
+    hr.id = oid; hr.qty = new_qty; hr.agent = (uint32_t)agent; c.node_store(head, hr);  // :352 book[i][0] = new_order  (slot 0, App. A-13)
+    if (new_price != price) s.flags |= ABX_F_UNSUPPORTED;                               // a re-priced head would unsort the ladder; never in LOBSTER replays
+    int buckets = 0;                                                                    // :353-367 one ORDER_MODIFIED per history bucket holding the id
+    if (oid >= REPLAY_ID_BASE) { uint4 t = c.id_load((int)(oid - REPLAY_ID_BASE)); uint32_t d = s.trade_epoch - t.z; if (t.w != 0 && d <= (uint32_t)P.c.stream_history) buckets = __popc_compat(t.w & ((1u << (P.c.stream_history + 1 - d)) - 1u)); }
+#pragma unroll 1
+    for (int k = 0; k < matches * buckets; k++) {
+      exch_send_order(agent, ABX_ORDER_MODIFIED, oid, new_price, new_qty, 0, is_buy, 0.0);
+      if (n_out >= OUT_CAP - 3) flush();
+    }
+  }
+  ABX_HD void env_exch_receive(const Event &m) {                                        // ExchangeAgent.receiveMessage :129-340
+    s.exch_comp_delay = P.c.exchange_computation_delay_ns;
+    bool t_closed = s.now > P.c.mkt_close_ns;
+    int32_t p[6] = {0, 0, 0, 0, 0, 0};
+    if (t_closed && m.kind != ABX_QUERY_SPREAD) { exch_send(m.sender, ABX_MKT_CLOSED, p, 0.0); return; }       // :142-160
+    if (m.kind == ABX_WHEN_MKT_OPEN) { s.exch_comp_delay = 0; exch_send(m.sender, ABX_WHEN_MKT_OPEN, p, 0.0); }
+    else if (m.kind == ABX_WHEN_MKT_CLOSE) { s.exch_comp_delay = 0; exch_send(m.sender, ABX_WHEN_MKT_CLOSE, p, 0.0); }
+    else if (m.kind == ABX_QUERY_SPREAD) {                                              // :215-245, depth 500: the agent reads 2 levels
+      s.c_query++; int nb = s.n_bid_lv, na = s.n_ask_lv; int f = 0; int32_t b2 = 0, a2 = 0;
+      if (nb > 0) { p[0] = c.lv_price(0, nb - 1); p[1] = c.lv_qty(0, nb - 1); f |= 1; } if (nb > 1) b2 = c.lv_price(0, nb - 2);
+      if (na > 0) { p[2] = c.lv_price(1, na - 1); p[3] = c.lv_qty(1, na - 1); f |= 2; } if (na > 1) a2 = c.lv_price(1, na - 2);
+      if (t_closed) f |= 4;
+      f |= (nb > 2 ? 2 : nb) << 3; f |= (na > 2 ? 2 : na) << 5;
+      p[4] = s.last_trade; p[5] = f;
+      exch_send(m.sender, ABX_QUERY_SPREAD, p, bits_dbl((uint64_t)(uint32_t)b2 | ((uint64_t)(uint32_t)a2 << 32)));
+    } else if (m.kind == ABX_LIMIT_ORDER) { s.c_limit++; book_handle_limit((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[2], 0.0); c.sync(); trace_snap(); }
+    else if (m.kind == ABX_CANCEL_ORDER) { s.c_cancel++; book_cancel((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], 0.0); c.sync(); trace_snap(); }
+    else if (m.kind == ABX_MODIFY_ORDER) { book_modify((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[3], m.p[5]); c.sync(); trace_snap(); }   // :326-340
+  }
+  // ---- MarketReplayAgent ----
+  ABX_HD void replay_place(int r) {                                                     // placeOrder :69-96 for one row
+    int4 row = c.row_load(r); uint32_t oid = REPLAY_ID_BASE + (uint32_t)row.x;
+    uint4 t = c.id_load(row.x); bool existing = t.x != 0;
+    if (!existing && row.z > 0) {                                                       // placeLimitOrder(order_id=ORDER_ID)
+      t.x = (uint32_t)row.z; t.y = ((uint32_t)row.y << 1) | (uint32_t)(row.w & 1); c.id_store(row.x, t);
+      int32_t p[6] = {(int32_t)oid, row.y, row.z, 0, row.w, 0}; env_send(ABX_LIMIT_ORDER, p, false);
+    } else if (existing && row.z == 0) {                                                // cancelOrder(existing_order)
+      int32_t p[6] = {(int32_t)oid, (int32_t)(t.y >> 1), (int32_t)t.x, 0, (int32_t)(t.y & 1u), 0}; env_send(ABX_CANCEL_ORDER, p, false);
+    } else if (existing) {                                                              // modifyOrder(existing_order, LimitOrder(new SIZE, PRICE))
+      int32_t p[6] = {(int32_t)oid, (int32_t)(t.y >> 1), (int32_t)t.x, row.y, (int32_t)(t.y & 1u), row.z}; env_send(ABX_MODIFY_ORDER, p, false);
+    }
+    if (n_out >= OUT_CAP - 3) flush();
+  }
+  ABX_HD void replay_wakeup(EnvX *x) {                                                  // wakeup :50-60
+    ta_wakeup(x->ra_flags);
+    if (!(x->ra_flags & AF_HAS_OPEN) || !(x->ra_flags & AF_HAS_CLOSE)) return;
+    int cur = x->wt_cursor;
+    if (cur >= P.n_ts) return;                                                          // wakeup_times[0] -> IndexError: nothing placed
+    set_wakeup(1, c.ts_load(cur)); if (c.onchip_writer()) x->wt_cursor = cur + 1;       // setWakeup(wakeup_times[0]); pop(0)
+    int k = cur == 0 ? 0 : cur - 1;                                                     // orders_dict[currentTime]: the list's first entry is woken twice
+    if (c.ts_load(k) != s.now) { s.flags |= ABX_F_UNSUPPORTED; return; }
+    int r0 = c.first_load(k), r1 = c.first_load(k + 1);
+#pragma unroll 1
+    for (int r = r0; r < r1; r++) replay_place(r);
+  }
+  ABX_HD void replay_receive(EnvX *x, const Event &m) {
+    uint32_t fl = x->ra_flags; int32_t sh = x->ra_shares, lt = x->ra_last_trade; int64_t cash = x->ra_cash;
+    bool newly = ta_receive(m, fl, sh, cash, lt);
+    if (m.kind == ABX_ORDER_EXECUTED || m.kind == ABX_ORDER_CANCELLED) {                // orderExecuted :422-462 / orderCancelled :476-489
+      uint32_t oid = (uint32_t)m.p[0];
+      if (oid >= REPLAY_ID_BASE) { uint4 t = c.id_load((int)(oid - REPLAY_ID_BASE));
+        if (t.x != 0) { if (m.kind == ABX_ORDER_CANCELLED || (uint32_t)m.p[2] >= t.x) t.x = 0; else t.x -= (uint32_t)m.p[2]; c.id_store((int)(oid - REPLAY_ID_BASE), t); } }
+      if (m.kind == ABX_ORDER_EXECUTED) { lt = m.p[3]; fl |= AF_HAS_LAST; }             // MarketReplayAgent.receiveMessage :62-67
+    }
+    if (newly) set_wakeup(1, c.ts_load(0));                                             // mkt_open + getWakeFrequency() == first_wakeup
+    if (c.onchip_writer()) { x->ra_flags = fl; x->ra_shares = sh; x->ra_last_trade = lt; x->ra_cash = cash; }
+  }
+  // ---- DummyRLExecutionAgent ----
+  ABX_HD void rl_wakeup(EnvX *x) {                                                      // wakeup :184-218
+    uint32_t fl = x->rl_flags;
+    if (!ta_wakeup(fl)) return;
+    if (fl & RLF_TRADE) {                                                               // first horizon time > now -> CANCEL_ORDER event (Timedelta(0.5) == 0)
+      int64_t k = s.now < P.h0_ns ? 0 : (s.now - P.h0_ns) / P.h_step_ns + 1;
+      if (k < P.n_h) env_set_cancel(2, P.h0_ns + k * P.h_step_ns); else fl &= ~RLF_TRADE;
+    }
+    if (fl & RLF_TRADE) {                                                               // effective horizon = horizon[:-1]
+      int64_t k = s.now < P.h0_ns ? 0 : (s.now - P.h0_ns) / P.h_step_ns + 1;
+      if (k < P.n_h - 1) set_wakeup(2, P.h0_ns + k * P.h_step_ns); else fl &= ~RLF_TRADE;
+    }
+    { int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); }         // getCurrentSpread(depth=500)
+    fl = (fl & ~AF_STATE_MASK) | (ST_AWAITING_SPREAD << AF_STATE_SHIFT);
+    if (c.onchip_writer()) x->rl_flags = fl;
+  }
+  ABX_HD void rl_orders_remove(EnvX *x, int i) {
+    c.sync();
+    if (c.onchip_writer()) { for (int k = i; k + 1 < RL_ORDER_CAP; k++) { x->rl_oid[k] = x->rl_oid[k + 1]; x->rl_oprice[k] = x->rl_oprice[k + 1]; x->rl_oqty[k] = x->rl_oqty[k + 1]; } x->rl_n_orders = x->rl_n_orders - 1; }
+    c.sync();
+  }
+  ABX_HD int rl_orders_find(EnvX *x, uint32_t oid) { int f = -1; int n = x->rl_n_orders; for (int i = 0; i < RL_ORDER_CAP; i++) if (i < n && f < 0 && x->rl_oid[i] == oid) f = i; return f; }
+  ABX_HD void rl_receive(EnvX *x, const Event &m) {                                     // receiveMessage :230-245
+    uint32_t fl = x->rl_flags; int32_t sh = x->rl_shares, lt = x->rl_last_trade; int64_t cash = x->rl_cash;
+    bool newly = ta_receive(m, fl, sh, cash, lt);
+    double rem = x->rem_quantity;
+    if (m.kind == ABX_ORDER_EXECUTED) {                                                 // orderExecuted + ExecutionAgent.handleOrderExecution :88-99
+      int i = rl_orders_find(x, (uint32_t)m.p[0]);
+      if (i >= 0) { int32_t oq = x->rl_oqty[i]; if (m.p[2] >= oq) rl_orders_remove(x, i); else { c.sync(); if (c.onchip_writer()) x->rl_oqty[i] = oq - m.p[2]; c.sync(); } }
+      double ex = x->executed_sum + (double)m.p[2]; rem = P.rl_quantity - ex;
+      if (c.onchip_writer()) { x->executed_sum = ex; x->n_executed = x->n_executed + 1; x->rem_quantity = rem; }
+    } else if (m.kind == ABX_ORDER_CANCELLED) { int i = rl_orders_find(x, (uint32_t)m.p[0]); if (i >= 0) rl_orders_remove(x, i); }
+    if (newly) set_wakeup(2, P.h0_ns);                                                  // mkt_open + (horizon[0] - mkt_open)
+    uint32_t st = (fl & AF_STATE_MASK) >> AF_STATE_SHIFT;
+    if (rem > 0 && st == ST_AWAITING_SPREAD && m.kind == ABX_QUERY_SPREAD) {            // metrics.addLOB :62-84
+      fl = (fl & ~AF_STATE_MASK) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT);
+      int head = (x->lob_head + LOB_CAP - 1) % LOB_CAP; int n = x->n_lobs;
+      int32_t w[12] = {m.p[0], m.p[1], m.x0, m.p[2], m.p[3], m.x1, m.p[4], (m.p[5] >> 3) & 3, (m.p[5] >> 5) & 3, 0, 0, 0};
+      c.lob_store(head, w);
+      if (c.onchip_writer()) { if (!(fl & RLF_METRICS_INIT)) x->p0 = m.p[4]; x->lob_head = head; x->n_lobs = n < LOB_CAP ? n + 1 : n; }
+      fl |= RLF_METRICS_INIT;
+    }
+    if (c.onchip_writer()) { x->rl_flags = fl; x->rl_shares = sh; x->rl_last_trade = lt; x->rl_cash = cash; }
+    c.sync();
+  }
+  ABX_HD void rl_observe(EnvX *x) {                                                     // get_observation :294-315
+    int64_t curr = s.now - (s.now % P.h_step_ns); int rem = P.n_h;                      // get_remaining_time :282-292 (Timestamp.floor(freq))
+    if (curr >= P.h0_ns && (curr - P.h0_ns) / P.h_step_ns < P.n_h) rem = P.n_h - 1 - (int)((curr - P.h0_ns) / P.h_step_ns);
+    int n = x->n_lobs, head = x->lob_head; int obs_len = 0; double o[9];
+    for (int i = 0; i < 9; i++) o[i] = 0.0;
+    if (n > 0) {
+      int32_t l[12]; c.lob_load(head, l);
+      if (l[7] > 0 && l[8] > 0) {
+        double p0 = (double)x->p0, pt = (double)l[6];
+        double mid = ((double)l[0] + (double)l[3]) / 2;
+        bool bad = false; double vol = c.lob_midvol(n, head, p0, bad);                  // getMidPriceVolatility: np.std over the stored LOBs
+        int d;                                                                          // getTradeDirection :197-216
+        if (pt > mid) d = 1; else if (pt < mid) d = -1;
+        else { int32_t lo[12]; c.lob_load((head + n - 1) % LOB_CAP, lo); if (lo[7] == 0 || lo[8] == 0) bad = true; double lm = ((double)lo[0] + (double)lo[3]) / 2; d = mid > lm ? 1 : -1; }
+        if (!bad) {
+          o[0] = rem; o[1] = x->rem_quantity; o[2] = log_ni(pt / p0); o[3] = (double)(l[3] - l[0]);
+          o[4] = ((double)l[1] - (double)l[4]) / ((double)l[1] + (double)l[4]);
+          o[5] = tanh((double)l[3] / (double)l[4] - (double)l[0] / (double)l[1]);
+          o[6] = vol; o[7] = d; o[8] = 2 * d * (pt - mid) / mid; obs_len = 9;
+        }
+      }
+    }
+    if (obs_len == 0) s.flags |= ABX_F_OBS_INVALID;                                     // the reference raises ValueError here
+    if (c.onchip_writer()) { x->rem_time = rem; x->obs_len = obs_len; for (int i = 0; i < 9; i++) x->obs[i] = o[i]; }
+    c.sync();
+  }
+  ABX_HD void rl_place_orders(EnvX *x, double a0, double a1, double a2) {               // place_orders :159-181 + process_action :138-157
+    int n = P.order_level; double q0 = P.rl_quantity, q = P.rl_quantity;                // metrics.rem_quantity is never updated (App. A-10)
+    double act[2] = {a1, a2}; double sum = 0; for (int i = 0; i < 2; i++) if (i < n) sum = dadd(sum, act[i]);
+    double q_hat = q / q0;
+    double o_total = rint(dmul(dmul(q0, q_hat), pow_ni(a0, pow_ni(q_hat, P.rl_steep))));
+    double o[2]; double part = 0;
+    for (int i = 0; i < 2; i++) { double oh = sum == 0.0 ? 1.0 / n : act[i] / sum; o[i] = i < n ? rint(dmul(o_total, oh)) : 0.0; }
+    for (int i = 0; i < 2; i++) if (i < n - 1) part = dadd(part, o[i]);
+    if (n == 1) o[0] = dsub(o_total, part); else o[1] = dsub(o_total, part);
+    int nl = x->n_lobs; if (nl == 0) return;                                            // exceptions are swallowed (bare except)
+    int32_t l[12]; c.lob_load(x->lob_head, l);
+    if (l[7] == 0 || l[8] == 0) return;
+    self_id = 2;
+    for (int lv = 0; lv < 2; lv++) if (lv < n) {
+      if (lv >= l[7] || lv >= l[8]) continue;                                           // IndexError swallowed
+      int32_t price = P.rl_is_buy ? (lv == 0 ? l[0] : l[2]) : (lv == 0 ? l[3] : l[5]);
+      uint32_t oid = s.next_order_id++;                                                 // LimitOrder() built before the quantity test
+      if (!(o[lv] > 0)) continue;
+      int k = x->rl_n_orders;
+      if (k < RL_ORDER_CAP) { c.sync(); if (c.onchip_writer()) { x->rl_oid[k] = oid; x->rl_oprice[k] = price; x->rl_oqty[k] = (int32_t)o[lv]; x->rl_n_orders = k + 1; } c.sync(); }
+      else s.flags |= ABX_F_AGENT_ORDERS_OVERFLOW;
+      int32_t p[6] = {(int32_t)oid, price, (int32_t)o[lv], 0, P.rl_is_buy, 0}; env_send(ABX_LIMIT_ORDER, p, false);
+    }
+  }
+  ABX_HD void rl_cancel_all(EnvX *x) {                                                  // cancelAllOrders :247-255
+    self_id = 2; int n = x->rl_n_orders;
+#pragma unroll 1
+    for (int i = 0; i < n; i++) { int32_t p[6] = {(int32_t)x->rl_oid[i], x->rl_oprice[i], x->rl_oqty[i], 0, P.rl_is_buy, 0}; env_send(ABX_CANCEL_ORDER, p, false); }
+  }
+  // reset: Kernel/GymKernel.initRunner :139-146 -- one WAKEUP per agent at start
+  ABX_HD void env_reset() { for (int id = 0; id < 3; id++) set_wakeup(id, P.c.start_ns); flush(); }
+  // GymKernel.stepRunner :158-306.  Returns done as ABIDESEnv.step computes it (ABIDESEnv.py:42-46).
+  ABX_HD bool env_step(double a0, double a1, double a2) {
+    EnvX *x = c.envx();
+    rl_place_orders(x, a0, a1, a2); flush();
+    bool end_step = false, more = true;
+#pragma unroll 1
+    while (!end_step) {
+      uint64_t khi; uint32_t kuniq; int grp;
+      bool any = c.q_min(khi, kuniq, grp);
+      if (!any || !(s.now <= P.c.stop_ns)) { more = false; break; }
+      Event ev; c.q_fetch(grp, ev);
+      s.now = ev.t; s.ttl++;
+      if (INSTR && P.c.hash_pops) s.pop_hash = fnv_mix(fnv_mix(fnv_mix(fnv_mix(s.pop_hash, ev.t), ev.recipient), ev.type), ev.type == ABX_T_MESSAGE ? (int64_t)ev.uniq : -1);
+      if (INSTR && P.c.trace_cap > 0) {
+        abx_trace_rec r; r.tag = 0; r.a = ev.recipient; r.t = ev.t; for (int i = 0; i < 16; i++) r.v[i] = 0;
+        r.v[0] = ev.type; r.v[1] = ev.type == ABX_T_MESSAGE ? (int32_t)ev.uniq : -1; r.v[2] = ev.kind; trace_rec(r);
+      }
+      addl_delay = 0;
+      int id = ev.recipient;
+      if (ev.type == ABX_T_CANCEL_ORDER) { c.q_remove(); s.q_count--; rl_cancel_all(x); flush(); continue; }   // :241-245 (get_reward is None)
+      int64_t at = id == 0 ? s.exch_time : (id == 1 ? x->ra_time : x->rl_time);
+      if (at > s.now) { c.q_requeue(at); continue; }
+      c.q_remove(); s.q_count--;
+      self_id = id; int64_t delay = P.c.default_computation_delay_ns;
+      if (id == 0) { if (ev.type == ABX_T_MESSAGE) env_exch_receive(ev); delay = s.exch_comp_delay; s.exch_time = s.now + delay + addl_delay; }
+      else if (id == 1) { if (ev.type == ABX_T_WAKEUP) replay_wakeup(x); else replay_receive(x, ev); if (c.onchip_writer()) x->ra_time = s.now + delay + addl_delay; }
+      else {
+        if (ev.type == ABX_T_WAKEUP) rl_wakeup(x); else rl_receive(x, ev);
+        if (c.onchip_writer()) x->rl_time = s.now + delay + addl_delay;
+        if (ev.type == ABX_T_MESSAGE && ev.kind == ABX_QUERY_SPREAD) { rl_observe(x); end_step = true; }       // :286-289
+      }
+      flush();
+    }
+    if (more) { uint64_t khi; uint32_t kuniq; int grp; more = c.q_min(khi, kuniq, grp) && (s.now <= P.c.stop_ns); }
+    if (!more) s.flags |= ABX_F_DONE;
+    if (c.onchip_writer()) x->steps = x->steps + 1;
+    c.sync();
+    return !more;
   }
 
   // ---- Kernel.runner :310-311 kernelStopping for every trader, in id order (ZeroIntelligenceAgent.py:80-123) ----

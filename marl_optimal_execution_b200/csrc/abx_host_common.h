@@ -4,6 +4,8 @@
 #pragma once
 #include <math.h>
 #include <string.h>
+#include <vector>
+#include <unordered_map>
 #include "abx_core.cuh"
 
 namespace abx {
@@ -67,6 +69,62 @@ static inline void derive_params(SimParams &P) {
   P.sqrt_sigma_n = sqrt(c.sigma_n); P.sqrt_sigma_pv = sqrt(c.sigma_pv); P.sqrt_megashock_var = sqrt(c.megashock_var);
   P.inv_lambda_a = 1.0 / c.lambda_a; P.inv_megashock_lambda = 1.0 / c.megashock_lambda_a;
   P.ou_scale = pow(c.fund_vol, 2.0) / (2 * c.kappa);               // SparseMeanRevertingOracle.py:106
+}
+
+// ---- ABIDESEnv shape ----
+static inline int env_config_default(abx_env_config *c) {                       // ABIDESEnv.py:59-103, agent_config.py:42-154
+  if (!c) return ABX_ERR_ARG;
+  memset(c, 0, sizeof(*c));
+  c->version = ABX_VERSION; c->order_level = 2; c->is_buy = 1; c->n_horizon = 761;
+  c->start_ns = 0; c->stop_ns = (16 * 3600 + 600) * NS; c->mkt_open_ns = (9 * 3600 + 1800) * NS; c->mkt_close_ns = 16 * 3600 * NS;
+  c->horizon_start_ns = (9 * 3600 + 2400) * NS; c->horizon_step_ns = 30 * NS; c->quantity = 1e5; c->steep = 0.5;
+  c->stream_history = 10; c->queue_cap = 64; c->level_cap = 256; c->order_cap = 16384; c->trace_cap = 0; c->hash_pops = 0;
+  return ABX_OK;
+}
+static inline int env_config_validate(const abx_env_config *c) {
+  if (!c || c->version != ABX_VERSION || c->order_level < 1 || c->order_level > 2 || c->n_horizon < 2) return ABX_ERR_ARG;
+  if (c->queue_cap < 32 || c->queue_cap % 32 || c->queue_cap > 4096 || c->level_cap < 8 || c->level_cap > 2048) return ABX_ERR_ARG;
+  if (c->order_cap < 8 || c->order_cap > 65535 || c->stop_ns >= KEY_T_MAX || c->start_ns < 0 || c->horizon_step_ns <= 0) return ABX_ERR_ARG;
+  if (c->stream_history < 0 || c->stream_history > 14 || !(c->quantity > 0) || c->trace_cap < 0) return ABX_ERR_ARG;
+  return ABX_OK;
+}
+// the generic (abx_sim_config) part of the parameter block for the ABIDESEnv shape: 3 agents, zero delays, no oracle
+static inline void env_fill_params(const abx_env_config &e, SimParams &P) {
+  abx_sim_config &c = P.c; memset(&c, 0, sizeof(c));
+  c.version = ABX_VERSION; c.n_agents = 3; c.n_groups = 1; c.q_max = 1; c.groups[0].count = 2;
+  c.start_ns = e.start_ns; c.stop_ns = e.stop_ns; c.mkt_open_ns = e.mkt_open_ns; c.mkt_close_ns = e.mkt_close_ns;
+  c.default_computation_delay_ns = 0; c.exchange_computation_delay_ns = 0; c.exchange_pipeline_delay_ns = 0;   // ABIDESEnv.py:89, agent_config.py:49-50
+  c.stream_history = e.stream_history; c.latency_model = ABX_LAT_ZERO; c.n_noise = 1;
+  c.queue_cap = e.queue_cap; c.level_cap = e.level_cap; c.order_cap = e.order_cap; c.rng_mode = ABX_RNG_PHILOX; c.trace_cap = e.trace_cap; c.hash_pops = e.hash_pops;
+  P.n_qgroups = c.queue_cap / 32; P.n_streams = 0;
+  P.n_h = e.n_horizon; P.h0_ns = e.horizon_start_ns; P.h_step_ns = e.horizon_step_ns; P.rl_quantity = e.quantity; P.rl_steep = e.steep;
+  P.order_level = e.order_level; P.rl_is_buy = e.is_buy;
+}
+struct EnvStreamHost { std::vector<int64_t> ts, id_orig; std::vector<int32_t> first; std::vector<int4> rows; };
+// LOBSTER ORDER_IDs -> dense indices; rows grouped by identical timestamp (orders_dict of MarketReplayAgent.py:214)
+static inline int env_build_stream(const int64_t *s5, int64_t n, int64_t max_rl_ids, EnvStreamHost &o) {
+  if (!s5 || n < 1 || n > 0x3fffffff) return ABX_ERR_ARG;
+  std::unordered_map<int64_t, int32_t> dense;
+  o.rows.resize(n);
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t *r = s5 + 5 * i;
+    if (i > 0 && r[0] < s5[5 * (i - 1)]) return ABX_ERR_ARG;                                     // must be time sorted
+    if (r[1] <= max_rl_ids || r[1] > 0x7fffffffLL || r[2] <= 0 || r[2] > 0x3fffffffLL || r[3] < 0 || r[3] > 0x7fffffffLL) return ABX_ERR_ARG;  // ids must not collide with generated ids (util/order/Order.py:35-42)
+    auto it = dense.find(r[1]); int32_t d;
+    if (it == dense.end()) { d = (int32_t)o.id_orig.size(); dense.emplace(r[1], d); o.id_orig.push_back(r[1]); } else d = it->second;
+    if (i == 0 || r[0] != s5[5 * (i - 1)]) { o.ts.push_back(r[0]); o.first.push_back((int32_t)i); }
+    int4 row; row.x = d; row.y = (int32_t)r[2]; row.z = (int32_t)r[3]; row.w = r[4] ? 1 : 0; o.rows[i] = row;
+  }
+  o.first.push_back((int32_t)n);
+  return ABX_OK;
+}
+ABX_HD void init_envx(const SimParams &P, EnvX &x) {
+  x.ra_time = x.rl_time = P.c.start_ns; x.ra_cash = x.rl_cash = 0; x.rem_quantity = P.rl_quantity; x.executed_sum = 0.0;   // starting_cash 0 (agent_config.py:73,133)
+  x.ra_shares = x.rl_shares = 0; x.ra_last_trade = x.rl_last_trade = 0; x.ra_flags = 0;
+  x.rl_flags = RLF_TRADE | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT); x.wt_cursor = 0; x.n_executed = 0; x.rl_n_orders = 0; x.n_lobs = 0; x.lob_head = 0; x.p0 = 0;
+  x.rem_time = P.n_h - 1; x.obs_len = 0; x.ra_open = 0; x.steps = 0;
+  for (int i = 0; i < RL_ORDER_CAP; i++) { x.rl_oid[i] = 0; x.rl_oprice[i] = 0; x.rl_oqty[i] = 0; }
+  for (int i = 0; i < 9; i++) x.obs[i] = 0.0; x.pad0 = 0.0;
 }
 
 static inline const char *status_string(int32_t st) {

@@ -93,6 +93,49 @@ abx_finalize_kernel(SimParams P, size_t smem_per_warp) {
   env_store(P.env + env, sim.s, ctx.lane);
 }
 
+// ---- ABIDESEnv shape: reset and step (GymKernel.initRunner / stepRunner) ----
+typedef Sim<WarpCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, false, true> EnvSimFast;
+typedef Sim<WarpCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, true> EnvSimInstr;
+
+__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
+abx_env_reset_kernel(SimParams P, size_t smem_per_warp) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
+  if (env >= P.n_envs) return;
+  WarpCtx ctx(P, env, smem + warp * smem_per_warp);
+  EnvState s; init_env_state(P, 0, s); s.last_trade = -1;               // no oracle: OrderBook.last_trade stays None (ExchangeAgent.py:97-102)
+  init_envx(P, *ctx.envx()); ctx.sync();
+  ctx.q_clear();
+  EnvSimInstr sim(ctx, P, s, env);
+  sim.env_reset();
+  ctx.store_onchip(sim.s); ctx.envx_store();
+  env_store(P.env + env, sim.s, ctx.lane);
+}
+
+template <bool INSTR>
+__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
+abx_env_step_kernel(SimParams P, const double *__restrict__ actions, double *__restrict__ obs, double *__restrict__ reward,
+                    uint8_t *__restrict__ done, size_t smem_per_warp) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
+  if (env >= P.n_envs) return;
+  WarpCtx ctx(P, env, smem + warp * smem_per_warp);
+  EnvState s = env_load(P.env + env);
+  bool was_done = (s.flags & ABX_F_DONE) != 0;
+  if (!was_done) {
+    ctx.envx_load(); ctx.load_onchip(s);
+    Sim<WarpCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, INSTR, true> sim(ctx, P, s, env);
+    sim.env_step(actions[3 * env], actions[3 * env + 1], actions[3 * env + 2]);
+    ctx.store_onchip(sim.s); ctx.envx_store();
+    env_store(P.env + env, sim.s, ctx.lane);
+    s.flags = sim.s.flags;
+  }
+  // obs (9 x fp64), reward, done: lanes 0..8 write one observation value each (72 contiguous bytes per environment)
+  const EnvX *x = ctx.envx();
+  if (ctx.lane < 9) obs[9 * env + ctx.lane] = (!was_done && x->obs_len) ? x->obs[ctx.lane] : 0.0;
+  if (ctx.lane == 0) { if (reward) reward[env] = 0.0; done[env] = (s.flags & ABX_F_DONE) ? 1 : 0; }
+}
+
 __global__ void abx_stats_kernel(SimParams P, abx_env_stats *__restrict__ out) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= P.n_envs) return;
@@ -115,6 +158,7 @@ struct abx_sim {
   SimParams P; int n_envs, device; bool reset_done; size_t smem_per_warp; int64_t bytes, launches;
   uint64_t *d_seeds; uint32_t *d_init_err; abx_env_stats *d_stats; int64_t *d_until;
   uint64_t *d_tbits; uint8_t *d_tkinds; int64_t *d_toff;
+  bool is_env; EnvStreamHost *st; int64_t *d_ts; int32_t *d_first; int4 *d_rows; double *d_act, *d_obs, *d_rew; uint8_t *d_done;
 };
 
 template <class T> static int dalloc(T **p, size_t n, int64_t *acc) {
@@ -134,9 +178,10 @@ int32_t abx_sim_destroy(abx_sim *h) {
   if (!h) return ABX_OK;
   cudaSetDevice(h->device);
   void *ptrs[] = {h->P.qkey, h->P.qpay0, h->P.qpay1, h->P.qcache, h->P.agents, h->P.lv_price, h->P.lv_qty, h->P.lv_ht, h->P.nodes, h->P.env,
-                  h->P.trace, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff};
+                  h->P.trace, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff,
+                  h->P.envx, h->P.idtab, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done};
   for (void *p : ptrs) if (p) cudaFree(p);
-  delete h; return ABX_OK;
+  delete h->st; delete h; return ABX_OK;
 }
 
 int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device, abx_sim **out) {
@@ -249,7 +294,7 @@ int32_t abx_sim_stats(abx_sim *h, abx_env_stats *out, void *stream) {
 }
 
 int32_t abx_sim_holdings(abx_sim *h, int32_t env, int64_t *out, void *stream) {
-  if (!h || !out || env < 0 || env >= h->n_envs) return ABX_ERR_ARG;
+  if (!h || h->is_env || !out || env < 0 || env >= h->n_envs) return ABX_ERR_ARG;
   CU(cudaSetDevice(h->device));
   int n = h->P.c.n_agents; ZiAgent *tmp = (ZiAgent *)malloc(sizeof(ZiAgent) * n); if (!tmp) return ABX_ERR_ARG;
   cudaError_t e = cudaMemcpyAsync(tmp, h->P.agents + (size_t)env * n, sizeof(ZiAgent) * n, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
@@ -281,7 +326,80 @@ int32_t abx_sim_trace(abx_sim *h, int32_t env, abx_trace_rec *out, int32_t max_r
   EnvState s; CU(cudaMemcpyAsync(&s, h->P.env + env, sizeof(s), cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st));
   int n = (int)s.trace_n; if (n > max_recs) n = max_recs; if (n > h->P.c.trace_cap) n = h->P.c.trace_cap;
   if (n > 0) { CU(cudaMemcpyAsync(out, h->P.trace + (size_t)env * h->P.c.trace_cap, sizeof(abx_trace_rec) * n, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
+  if (h->is_env) for (int i = 0; i < n; i++) if (out[i].tag == 1 && (uint32_t)out[i].v[1] >= REPLAY_ID_BASE) out[i].v[1] = (int32_t)h->st->id_orig[(uint32_t)out[i].v[1] - REPLAY_ID_BASE];
   *n_recs = n; return ABX_OK;
+}
+
+// ---------------- ABIDESEnv shape ----------------
+int32_t abx_env_config_default(abx_env_config *cfg) { return env_config_default(cfg); }
+
+int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
+  if (!out || n_envs < 1 || env_config_validate(cfg) != ABX_OK) return ABX_ERR_ARG;
+  EnvStreamHost *st = new (std::nothrow) EnvStreamHost(); if (!st) return ABX_ERR_ARG;
+  if (env_build_stream(stream5, n_rows, 4LL * cfg->n_horizon + 16, *st) != ABX_OK) { delete st; return ABX_ERR_ARG; }
+  int ndev = 0; cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || device < 0 || device >= ndev) { delete st; snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d not present (%d visible): %s", device, ndev, cudaGetErrorString(ce)); return ABX_ERR_CUDA; }
+  if (cudaSetDevice(device) != cudaSuccess) { delete st; return ABX_ERR_CUDA; }
+  abx_sim *h = new (std::nothrow) abx_sim(); if (!h) { delete st; return ABX_ERR_ARG; }
+  memset(h, 0, sizeof(*h)); h->is_env = true; h->st = st; h->n_envs = n_envs; h->device = device;
+  env_fill_params(*cfg, h->P); h->P.n_envs = n_envs;
+  h->P.n_ts = (int)st->ts.size(); h->P.n_rows = (int)n_rows; h->P.n_ids = (int)st->id_orig.size();
+  h->smem_per_warp = (warp_smem_bytes(h->P.c, true) + 15) & ~(size_t)15;
+  size_t smem_cta = h->smem_per_warp * ABX_WARPS_PER_CTA;
+  if (smem_cta > 227 * 1024) { abx_sim_destroy(h); return ABX_ERR_ARG; }
+  const abx_sim_config &c = h->P.c; size_t E = (size_t)n_envs; int stt;
+#define DA(ptr, n) if ((stt = dalloc(&(ptr), (n), &h->bytes)) != ABX_OK) { abx_sim_destroy(h); return stt; }
+  DA(h->P.qkey, E * c.queue_cap) DA(h->P.qpay0, E * c.queue_cap) DA(h->P.qpay1, E * c.queue_cap) DA(h->P.qcache, E * h->P.n_qgroups)
+  DA(h->P.lv_price, E * 2 * c.level_cap) DA(h->P.lv_qty, E * 2 * c.level_cap) DA(h->P.lv_ht, E * 2 * c.level_cap)
+  DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap) DA(h->d_stats, E)
+  DA(h->P.envx, E) DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
+  DA(h->d_ts, st->ts.size()) DA(h->d_first, st->first.size()) DA(h->d_rows, st->rows.size())
+  DA(h->d_act, E * 3) DA(h->d_obs, E * 9) DA(h->d_rew, E) DA(h->d_done, E)
+#undef DA
+  CU(cudaMemcpy(h->d_ts, st->ts.data(), sizeof(int64_t) * st->ts.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_first, st->first.data(), sizeof(int32_t) * st->first.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_rows, st->rows.data(), sizeof(int4) * st->rows.size(), cudaMemcpyHostToDevice));
+  h->P.st_ts = h->d_ts; h->P.st_first = h->d_first; h->P.st_rows = h->d_rows;
+  if (smem_cta > 48 * 1024) {
+    CU(cudaFuncSetAttribute(abx_env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CU(cudaFuncSetAttribute(abx_env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CU(cudaFuncSetAttribute(abx_env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+  }
+  *out = h; return ABX_OK;
+}
+
+int32_t abx_env_reset(abx_sim *h, void *stream) {
+  if (!h || !h->is_env) return ABX_ERR_ARG;
+  CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaMemsetAsync(h->P.idtab, 0, sizeof(uint4) * (size_t)h->n_envs * h->P.n_ids, st));
+  abx_env_reset_kernel<<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, st>>>(h->P, h->smem_per_warp);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  h->reset_done = true; return ABX_OK;
+}
+
+int32_t abx_env_step(abx_sim *h, const double *actions_dev, double *obs_dev, double *reward_dev, uint8_t *done_dev, void *stream) {
+  if (!h || !h->is_env || !actions_dev || !obs_dev || !done_dev) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  CU(cudaSetDevice(h->device));
+  bool instr = h->P.c.trace_cap > 0 || h->P.c.hash_pops != 0;
+  if (instr) abx_env_step_kernel<true><<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, (cudaStream_t)stream>>>(h->P, actions_dev, obs_dev, reward_dev, done_dev, h->smem_per_warp);
+  else abx_env_step_kernel<false><<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, (cudaStream_t)stream>>>(h->P, actions_dev, obs_dev, reward_dev, done_dev, h->smem_per_warp);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return ABX_OK;
+}
+
+int32_t abx_env_step_host(abx_sim *h, const double *actions, double *obs, double *reward, uint8_t *done, void *stream) {
+  if (!h || !h->is_env || !actions || !obs || !done) return ABX_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream; size_t E = (size_t)h->n_envs;
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->d_act, actions, sizeof(double) * 3 * E, cudaMemcpyHostToDevice, st));
+  int32_t rc = abx_env_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, stream); if (rc != ABX_OK) return rc;
+  CU(cudaMemcpyAsync(obs, h->d_obs, sizeof(double) * 9 * E, cudaMemcpyDeviceToHost, st));
+  if (reward) CU(cudaMemcpyAsync(reward, h->d_rew, sizeof(double) * E, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(done, h->d_done, E, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return ABX_OK;
 }
 
 }  // extern "C"

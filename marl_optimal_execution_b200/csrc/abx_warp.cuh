@@ -46,8 +46,13 @@ __device__ __forceinline__ uint4 shfl4(uint4 v, int src) {
 }
 
 // bytes of shared memory one environment needs
-__host__ __device__ inline size_t warp_smem_bytes(const abx_sim_config &c) {
-  return sizeof(ZiAgent) + OUT_CAP * OUT_WORDS * 4 + (size_t)(c.queue_cap / 32) * 16 + (size_t)c.level_cap * 2 * 12;
+__host__ __device__ inline size_t warp_smem_bytes(const abx_sim_config &c, bool env_shape = false) {
+  return sizeof(ZiAgent) + OUT_CAP * OUT_WORDS * 4 + (size_t)(c.queue_cap / 32) * 16 + (size_t)c.level_cap * 2 * 12 + (env_shape ? sizeof(EnvX) : 0);
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { uint64_t b = dbl_bits(v); uint32_t lo = __shfl_xor_sync(FULL, (uint32_t)b, o), hi = __shfl_xor_sync(FULL, (uint32_t)(b >> 32), o); v += bits_dbl((uint64_t)lo | ((uint64_t)hi << 32)); }
+  return v;
 }
 
 struct WarpCtx {
@@ -55,7 +60,8 @@ struct WarpCtx {
   // HBM bases of this environment
   uint4 *qkey, *qpay0, *qpay1; ZiAgent *agents; uint4 *nodes; abx_trace_rec *tr;
   // shared memory of this warp
-  ZiAgent *staged; uint32_t *obox; uint4 *qc; int32_t *lvp, *lvq; uint32_t *lvht;
+  ZiAgent *staged; uint32_t *obox; uint4 *qc; int32_t *lvp, *lvq; uint32_t *lvht; EnvX *ex;
+  uint4 *idt; int4 *lob;          // ABIDESEnv shape: replay agent's per-order table, stored LOBs (HBM)
   // registers describing the group fetched by q_fetch
   uint64_t my_hi; uint32_t my_uniq; uint32_t cur_mask; int cur_group, cur_lane;
 
@@ -68,7 +74,9 @@ struct WarpCtx {
     qc = reinterpret_cast<uint4 *>(smem); smem += (size_t)P.n_qgroups * 16;
     lvp = reinterpret_cast<int32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
     lvq = reinterpret_cast<int32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
-    lvht = reinterpret_cast<uint32_t *>(smem);
+    lvht = reinterpret_cast<uint32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
+    ex = reinterpret_cast<EnvX *>(smem);
+    idt = P.idtab ? P.idtab + (size_t)env * P.n_ids : nullptr; lob = P.lobs ? P.lobs + (size_t)env * LOB_CAP * 3 : nullptr;
     cur_group = cur_lane = -1; cur_mask = 0; my_hi = KEY_EMPTY; my_uniq = 0xffffffffu;
   }
   // Uniform code stores on-chip state from every lane (same value, same address: one STS, no branch).
@@ -217,6 +225,36 @@ struct WarpCtx {
   // ---- order nodes (HBM, 16 B each) ----
   __device__ __forceinline__ NodeRec node_load(uint32_t i) const { uint4 v = ldcg4(nodes + i); NodeRec r; r.id = v.x; r.qty = (int32_t)v.y; r.agent = v.z; r.next = v.w; return r; }
   __device__ __forceinline__ void node_store(uint32_t i, const NodeRec &r) { if (lane == 0) __stcg(nodes + i, make_uint4(r.id, (uint32_t)r.qty, r.agent, r.next)); __syncwarp(); }
+
+  // ---- ABIDESEnv shape ----
+  __device__ __forceinline__ EnvX *envx() const { return ex; }
+  __device__ void envx_load() { const uint4 *src = reinterpret_cast<const uint4 *>(P.envx + env); for (int i = lane; i < (int)(sizeof(EnvX) / 16); i += 32) reinterpret_cast<uint4 *>(ex)[i] = ldcg4(src + i); sync(); }
+  __device__ void envx_store() { sync(); uint4 *dst = reinterpret_cast<uint4 *>(P.envx + env); for (int i = lane; i < (int)(sizeof(EnvX) / 16); i += 32) __stcg(dst + i, reinterpret_cast<const uint4 *>(ex)[i]); }
+  __device__ __forceinline__ uint4 id_load(int i) const { return ldcg4(idt + i); }
+  __device__ __forceinline__ void id_store(int i, uint4 v) { if (lane == 0) __stcg(idt + i, v); __syncwarp(); }
+  __device__ __forceinline__ int4 row_load(int r) const { return __ldg(P.st_rows + r); }
+  __device__ __forceinline__ int64_t ts_load(int k) const { return __ldg(P.st_ts + k); }
+  __device__ __forceinline__ int first_load(int k) const { return __ldg(P.st_first + k); }
+  __device__ __forceinline__ void lob_store(int slot, const int32_t w[12]) {
+    if (lane < 3) __stcg(lob + slot * 3 + lane, make_int4(w[lane * 4], w[lane * 4 + 1], w[lane * 4 + 2], w[lane * 4 + 3]));
+    __syncwarp();
+  }
+  __device__ __forceinline__ void lob_load(int slot, int32_t w[12]) const {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { int4 v = __ldcg(lob + slot * 3 + k); w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+  }
+  // np.std (ddof 0) of log(mid_i / p0) over the n stored LOBs: lanes take LOBs lane, lane+32, ... (ABIDESEnvMetrics.py:183-192)
+  __device__ double lob_midvol(int n, int head, double p0, bool &bad) const {
+    double v[4]; double sum = 0.0; bool b = false;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { int i = lane + 32 * k; v[k] = 0.0;
+      if (i < n) { int4 a = __ldcg(lob + ((head + i) % LOB_CAP) * 3); if (a.x <= 0 || a.w <= 0) b = true; v[k] = log_ni((((double)a.x + (double)a.w) / 2) / p0); sum += v[k]; } }
+    bad = bad || __any_sync(FULL, b);
+    double mean = warp_sum(sum) / n, var = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (lane + 32 * k < n) var += (v[k] - mean) * (v[k] - mean);
+    return sqrt(warp_sum(var) / n);
+  }
 
   // ---- trader records: 12 lanes x 128-bit, HBM <-> shared ----
   __device__ __forceinline__ ZiAgent *agent_stage(int id) {

@@ -1,0 +1,122 @@
+"""ABIDESEnv: batched, GPU-resident mirror of the reference's gym surface (ABIDESEnv.py:7-57).
+
+    env = ABIDESEnv(stream, n_envs=8192)      # stream: int64 [n,5] rows (t_ns, ORDER_ID, PRICE cents, SIZE, is_buy)
+    env.reset()
+    obs, reward, done, info = env.step(actions)   # actions [n_envs, 3] in [0,1]: (x_hat, o_hat_1, o_hat_2)
+
+Same names and tuple order as the reference; everything is batched over independent environments that all replay the
+same LOBSTER order stream (Exchange + MarketReplayAgent + DummyRLExecutionAgent under GymKernel).  `actions` may be a
+CUDA torch tensor (fp64; obs/reward/done come back as CUDA tensors, nothing touches the host) or a numpy array (host
+buffers through abx_env_step_host).  reward is 0 where the reference returns None (its get_reward ends in `return None`,
+agent/execution/rl/dummy_rl_execution_agent.py:325-352); obs rows are 0 where the reference returns [].
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import EnvConfig
+
+
+def env_config(lib=None, **overrides):
+    L = lib or _lib.load()
+    cfg = EnvConfig()
+    _lib.check(L, L.abx_env_config_default(C.byref(cfg)), "abx_env_config_default")
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError("abx_env_config has no field %r" % k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def load_lobster_fixture(path):
+    """tests/golden/*.npz written by tools/record_reference_env.py: the stream as the reference parsed it."""
+    return np.ascontiguousarray(np.load(path)["stream"], dtype=np.int64)
+
+
+class ABIDESEnv:
+    OBS_SIZE = 9          # get_observation returns 9 values (get_observation_space_size says 10)
+
+    def __init__(self, stream, n_envs=1, device=0, cfg=None, lib_path=None):
+        self._L = _lib.load(lib_path)
+        self.cfg = cfg or env_config(self._L)
+        self.n_envs = int(n_envs)
+        self.device = int(device)
+        self.action_size = int(self.cfg.order_level) + 1                  # get_action_space_size :128-134
+        st = np.ascontiguousarray(stream, dtype=np.int64)
+        if st.ndim != 2 or st.shape[1] != 5:
+            raise ValueError("stream must be int64 [n, 5]: (t_ns, ORDER_ID, PRICE, SIZE, is_buy)")
+        self._h = C.c_void_p()
+        _lib.check(self._L, self._L.abx_env_create(C.byref(self.cfg), st.ctypes.data_as(C.POINTER(C.c_int64)), len(st), self.n_envs,
+                                                   self.device, C.byref(self._h)), "abx_env_create")
+        self._torch_out = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.abx_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self, stream=None):
+        """ABIDESEnv.reset() (ABIDESEnv.py:51-57).  Like the reference it returns None: the first observation comes
+        from the first step()."""
+        _lib.check(self._L, self._L.abx_env_reset(self._h, stream), "abx_env_reset")
+        return None
+
+    def step(self, actions, stream=None):
+        """(obs [n_envs, 9], reward [n_envs], done [n_envs], None), as ABIDESEnv.step (ABIDESEnv.py:30-49)."""
+        try:
+            import torch
+            is_torch = isinstance(actions, torch.Tensor)
+        except ImportError:      # pragma: no cover
+            is_torch = False
+        if is_torch and actions.is_cuda:
+            import torch
+            a = actions.to(torch.float64).contiguous().view(self.n_envs, 3)
+            if self._torch_out is None:
+                self._torch_out = (torch.zeros(self.n_envs, 9, dtype=torch.float64, device=a.device),
+                                   torch.zeros(self.n_envs, dtype=torch.float64, device=a.device),
+                                   torch.zeros(self.n_envs, dtype=torch.uint8, device=a.device))
+            obs, rew, done = self._torch_out
+            sp = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream) if stream is None else stream
+            _lib.check(self._L, self._L.abx_env_step(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(obs.data_ptr()),
+                                                     C.c_void_p(rew.data_ptr()), C.c_void_p(done.data_ptr()), sp), "abx_env_step")
+            return obs, rew, done, None
+        a = np.ascontiguousarray(np.asarray(actions, dtype=np.float64).reshape(self.n_envs, 3))
+        obs = np.zeros((self.n_envs, 9))
+        rew = np.zeros(self.n_envs)
+        done = np.zeros(self.n_envs, dtype=np.uint8)
+        _lib.check(self._L, self._L.abx_env_step_host(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data,
+                                                      stream), "abx_env_step_host")
+        return obs, rew, done, None
+
+    def step_host_buffers(self, actions_ptr, obs_ptr, reward_ptr, done_ptr, stream=None):
+        """Raw-pointer form of the host-buffer step (pinned buffers make the copies asynchronous)."""
+        _lib.check(self._L, self._L.abx_env_step_host(self._h, C.c_void_p(actions_ptr), C.c_void_p(obs_ptr), C.c_void_p(reward_ptr),
+                                                      C.c_void_p(done_ptr), stream), "abx_env_step_host")
+
+    # shared with BatchedSim: per-environment counters and traces
+    def stats(self, stream=None):
+        out = np.zeros(self.n_envs, dtype=_lib.STATS_DTYPE)
+        _lib.check(self._L, self._L.abx_sim_stats(self._h, out.ctypes.data, stream), "abx_sim_stats")
+        return out
+
+    def trace(self, env, stream=None):
+        cap = int(self.cfg.trace_cap)
+        out = np.zeros(max(cap, 1), dtype=_lib.TRACE_DTYPE)
+        n = C.c_int32(0)
+        _lib.check(self._L, self._L.abx_sim_trace(self._h, int(env), out.ctypes.data, cap, C.byref(n), stream), "abx_sim_trace")
+        return out[: n.value]
+
+    def split_trace(self, env):
+        from .sim import BatchedSim
+        return BatchedSim.split_trace(self, env)
+
+    @property
+    def launch_count(self):
+        return int(self._L.abx_sim_launch_count(self._h))

@@ -17,11 +17,12 @@ using namespace abx;
 struct HostCtx {
   const SimParams &P; int env;
   uint4 *qkey, *qpay0, *qpay1, *qcache; ZiAgent *agents; int32_t *lvp, *lvq; uint32_t *lvht; uint4 *nodes; abx_trace_rec *tr;
-  uint32_t outbox_[OUT_CAP * OUT_WORDS]; ZiAgent staged; int cur_group, cur_slot;
+  uint32_t outbox_[OUT_CAP * OUT_WORDS]; ZiAgent staged; int cur_group, cur_slot; uint4 *idt; int4 *lob;
   HostCtx(const SimParams &P_, int e) : P(P_), env(e) {
     size_t q = (size_t)e * P.c.queue_cap; qkey = P.qkey + q; qpay0 = P.qpay0 + q; qpay1 = P.qpay1 + q; qcache = P.qcache + (size_t)e * P.n_qgroups;
     agents = P.agents + (size_t)e * P.c.n_agents; size_t l = (size_t)e * 2 * P.c.level_cap; lvp = P.lv_price + l; lvq = P.lv_qty + l; lvht = P.lv_ht + l;
     nodes = P.nodes + (size_t)e * P.c.order_cap; tr = P.trace ? P.trace + (size_t)e * P.c.trace_cap : nullptr; cur_group = cur_slot = -1;
+    idt = P.idtab ? P.idtab + (size_t)e * P.n_ids : nullptr; lob = P.lobs ? P.lobs + (size_t)e * LOB_CAP * 3 : nullptr;
   }
   bool onchip_writer() { return true; }
   void sync() {}
@@ -73,6 +74,21 @@ struct HostCtx {
   // ---- order nodes ----
   NodeRec node_load(uint32_t i) { uint4 v = nodes[i]; NodeRec r; r.id = v.x; r.qty = (int32_t)v.y; r.agent = v.z; r.next = v.w; return r; }
   void node_store(uint32_t i, const NodeRec &r) { uint4 v; v.x = r.id; v.y = (uint32_t)r.qty; v.z = r.agent; v.w = r.next; nodes[i] = v; }
+  // ---- ABIDESEnv shape ----
+  EnvX *envx() { return P.envx + env; }
+  uint4 id_load(int i) { return idt[i]; }
+  void id_store(int i, uint4 v) { idt[i] = v; }
+  int4 row_load(int r) { return P.st_rows[r]; }
+  int64_t ts_load(int k) { return P.st_ts[k]; }
+  int first_load(int k) { return P.st_first[k]; }
+  void lob_store(int slot, const int32_t w[12]) { for (int k = 0; k < 3; k++) { int4 v; v.x = w[4 * k]; v.y = w[4 * k + 1]; v.z = w[4 * k + 2]; v.w = w[4 * k + 3]; lob[slot * 3 + k] = v; } }
+  void lob_load(int slot, int32_t w[12]) { for (int k = 0; k < 3; k++) { int4 v = lob[slot * 3 + k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; } }
+  double lob_midvol(int n, int head, double p0, bool &bad) {
+    double v[LOB_CAP], mean = 0, var = 0;
+    for (int i = 0; i < n; i++) { int4 a = lob[((head + i) % LOB_CAP) * 3]; if (a.x <= 0 || a.w <= 0) bad = true; v[i] = log((((double)a.x + (double)a.w) / 2) / p0); mean += v[i]; }
+    mean /= n; for (int i = 0; i < n; i++) var += (v[i] - mean) * (v[i] - mean);
+    return sqrt(var / n);
+  }
   // ---- agents ----
   ZiAgent *agent_stage(int id) { staged = agents[id]; return &staged; }
   void agent_commit(int id) { agents[id] = staged; }
@@ -83,6 +99,7 @@ struct abx_sim {
   SimParams P; int n_envs; bool reset_done;
   std::vector<uint4> qkey, qpay0, qpay1, qcache, nodes; std::vector<ZiAgent> agents; std::vector<int32_t> lvp, lvq; std::vector<uint32_t> lvht;
   std::vector<EnvState> env; std::vector<abx_trace_rec> trace; std::vector<uint64_t> tbits; std::vector<uint8_t> tkinds; std::vector<int64_t> toff;
+  bool is_env; EnvStreamHost st; std::vector<EnvX> envx; std::vector<uint4> idtab; std::vector<int4> lobs;
 };
 
 extern "C" {
@@ -94,7 +111,7 @@ int32_t abx_config_sparse_zi(int32_t variant, abx_sim_config *cfg) { return conf
 int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device, abx_sim **out) {
   (void)device;
   if (!out || n_envs < 1 || config_validate(cfg) != ABX_OK) return ABX_ERR_ARG;
-  abx_sim *h = new abx_sim(); memset(&h->P, 0, sizeof(h->P)); h->P.c = *cfg; h->P.n_envs = n_envs; h->n_envs = n_envs; h->reset_done = false; derive_params(h->P);
+  abx_sim *h = new abx_sim(); memset(&h->P, 0, sizeof(h->P)); h->is_env = false; h->P.c = *cfg; h->P.n_envs = n_envs; h->n_envs = n_envs; h->reset_done = false; derive_params(h->P);
   size_t E = n_envs; const abx_sim_config &c = *cfg;
   h->qkey.resize(E * c.queue_cap); h->qpay0.resize(E * c.queue_cap); h->qpay1.resize(E * c.queue_cap); h->qcache.resize(E * h->P.n_qgroups);
   h->agents.resize(E * c.n_agents); h->lvp.resize(E * 2 * c.level_cap); h->lvq.resize(E * 2 * c.level_cap); h->lvht.resize(E * 2 * c.level_cap);
@@ -169,7 +186,48 @@ int32_t abx_sim_trace(abx_sim *h, int32_t env, abx_trace_rec *out, int32_t max_r
   (void)stream; if (!h || !out || !n_recs || env < 0 || env >= h->n_envs) return ABX_ERR_ARG;
   int n = (int)h->env[env].trace_n; if (n > max_recs) n = max_recs;
   if (n) memcpy(out, h->P.trace + (size_t)env * h->P.c.trace_cap, sizeof(abx_trace_rec) * n);
+  if (h->is_env) for (int i = 0; i < n; i++) if (out[i].tag == 1 && (uint32_t)out[i].v[1] >= REPLAY_ID_BASE) out[i].v[1] = (int32_t)h->st.id_orig[(uint32_t)out[i].v[1] - REPLAY_ID_BASE];
   *n_recs = n; return ABX_OK;
 }
 int64_t abx_sim_launch_count(const abx_sim *h) { (void)h; return 0; }
+
+typedef Sim<HostCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, true> EnvSimHost;
+int32_t abx_env_config_default(abx_env_config *cfg) { return env_config_default(cfg); }
+int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
+  (void)device; if (!out || n_envs < 1 || env_config_validate(cfg) != ABX_OK) return ABX_ERR_ARG;
+  abx_sim *h = new abx_sim(); memset(&h->P, 0, sizeof(h->P)); h->is_env = true; h->n_envs = n_envs; h->reset_done = false;
+  if (env_build_stream(stream5, n_rows, 4LL * cfg->n_horizon + 16, h->st) != ABX_OK) { delete h; return ABX_ERR_ARG; }
+  env_fill_params(*cfg, h->P); h->P.n_envs = n_envs; const abx_sim_config &c = h->P.c; size_t E = n_envs;
+  h->P.n_ts = (int)h->st.ts.size(); h->P.n_rows = (int)n_rows; h->P.n_ids = (int)h->st.id_orig.size();
+  h->qkey.resize(E * c.queue_cap); h->qpay0.resize(E * c.queue_cap); h->qpay1.resize(E * c.queue_cap); h->qcache.resize(E * h->P.n_qgroups);
+  h->agents.resize(4); h->lvp.resize(E * 2 * c.level_cap); h->lvq.resize(E * 2 * c.level_cap); h->lvht.resize(E * 2 * c.level_cap);
+  h->nodes.resize(E * c.order_cap); h->env.resize(E); h->trace.resize(E * (size_t)c.trace_cap);
+  h->envx.resize(E); h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3);
+  h->P.qkey = h->qkey.data(); h->P.qpay0 = h->qpay0.data(); h->P.qpay1 = h->qpay1.data(); h->P.qcache = h->qcache.data(); h->P.agents = h->agents.data();
+  h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
+  h->P.trace = c.trace_cap ? h->trace.data() : nullptr; h->P.envx = h->envx.data(); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data();
+  h->P.st_ts = h->st.ts.data(); h->P.st_first = h->st.first.data(); h->P.st_rows = h->st.rows.data();
+  *out = h; return ABX_OK;
+}
+int32_t abx_env_reset(abx_sim *h, void *stream) {
+  (void)stream; if (!h || !h->is_env) return ABX_ERR_ARG;
+  memset(h->idtab.data(), 0, h->idtab.size() * sizeof(uint4));
+  for (int e = 0; e < h->n_envs; e++) {
+    EnvState s; init_env_state(h->P, 0, s); s.last_trade = -1; init_envx(h->P, h->envx[e]);     // no oracle: last_trade None (ExchangeAgent.py:97-102)
+    HostCtx ctx(h->P, e); ctx.q_clear(); EnvSimHost sim(ctx, h->P, s, e); sim.env_reset(); h->env[e] = sim.s;
+  }
+  h->reset_done = true; return ABX_OK;
+}
+int32_t abx_env_step_host(abx_sim *h, const double *actions, double *obs, double *reward, uint8_t *done, void *stream) {
+  (void)stream; if (!h || !h->is_env || !actions || !obs || !done) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  for (int e = 0; e < h->n_envs; e++) {
+    EnvX &x = h->envx[e];
+    if (!(h->env[e].flags & ABX_F_DONE)) { HostCtx ctx(h->P, e); EnvSimHost sim(ctx, h->P, h->env[e], e); sim.env_step(actions[3 * e], actions[3 * e + 1], actions[3 * e + 2]); h->env[e] = sim.s; }
+    else x.obs_len = 0;
+    for (int i = 0; i < 9; i++) obs[9 * e + i] = x.obs_len ? x.obs[i] : 0.0;
+    if (reward) reward[e] = 0.0; done[e] = (h->env[e].flags & ABX_F_DONE) ? 1 : 0;
+  }
+  return ABX_OK;
+}
+int32_t abx_env_step(abx_sim *h, const double *a, double *o, double *r, uint8_t *d, void *s) { return abx_env_step_host(h, a, o, r, d, s); }
 }

@@ -1,0 +1,47 @@
+"""CPU CI of the product's ABIDESEnv logic (abx_core.cuh compiled as plain C++ by tests/emu; a test tool, never a
+fallback): a full recorded episode must reproduce the oracle -- and therefore the reference -- step by step."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import build_emu
+from marl_optimal_execution_b200 import _lib
+from marl_optimal_execution_b200.env import ABIDESEnv, env_config
+from oracle.oracle import OracleEnv, TRACE_ALL
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return build_emu()
+
+
+def test_episode_matches_oracle_and_reference(emu, golden_dir):
+    g = np.load(os.path.join(golden_dir, "env_IBM_2003-01-14_s789.npz"))
+    L = _lib.load(emu)
+    env = ABIDESEnv(g["stream"], n_envs=2, cfg=env_config(L, trace_cap=300000, hash_pops=1), lib_path=emu)
+    assert env.reset() is None and env.action_size == 3
+    o = OracleEnv(g["stream"], trace=TRACE_ALL)
+    for k, a in enumerate(g["actions"]):
+        acts = np.stack([a, a * np.array([0.5, 1.0, 1.0])])            # env 1 takes half the size: diverges from env 0
+        obs, rew, done, info = env.step(acts)
+        oo, _, od, _ = o.step(a)
+        ref = np.nan_to_num(g["obs"][k], nan=0.0)
+        assert info is None and rew[0] == 0.0 and int(done[0]) == od == int(g["done"][k]), k
+        assert np.allclose(obs[0], ref, rtol=1e-6, atol=0), (k, obs[0], ref)   # vs the reference recording: 1e-6 relative, fp64
+        oo9 = np.zeros(9)
+        oo9[: len(oo)] = oo
+        assert np.allclose(obs[0], oo9, rtol=1e-12, atol=0), k
+    st = env.stats()
+    assert int(st["messages"][0]) == o.n_pops == int(g["n_pops"]) and int(st["flags"][0]) == _lib.F_DONE
+    assert int(st["pop_hash"][0]) == o.pop_hash() == int(g["pop_hash_ckpt"][-1])
+    p, nt, sn = env.split_trace(0)
+    assert np.array_equal(p, o.trace("pops")) and np.array_equal(nt, o.trace("notes")) and np.array_equal(sn, o.trace("snaps"))
+    assert int(st["flags"][1]) == _lib.F_DONE and int(st["pop_hash"][1]) != int(st["pop_hash"][0])
+
+
+def test_rejects_streams_whose_ids_collide_with_generated_ids(emu):
+    L = _lib.load(emu)
+    bad = np.array([[34200 * 10 ** 9, 5, 1000, 100, 1]], dtype=np.int64)      # ORDER_ID 5 could equal an RL-agent order id
+    with pytest.raises(_lib.AbxError):
+        ABIDESEnv(bad, n_envs=1, cfg=env_config(L), lib_path=emu)
