@@ -25,8 +25,27 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NS = 10 ** 9
+FIXTURE = os.path.join(ROOT, "tests", "golden", "env_IBM_2003-01-14_s789.npz")   # LOBSTER sample day as the reference parsed it
 B_MSG = 320                 # algorithmic bytes per LOB message (DESIGN.md "Roofline")
 PUBLISHED_MSGS_PER_S = 3100.4   # reference's own sparse_zi_1000 run (tests/sparse_zi_1000.txt:22)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner) write to fd 1; the contract is ONE JSON line on stdout, so everything else goes to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_json(obj):
+    f = _REAL_STDOUT or sys.stdout
+    f.write(json.dumps(obj) + "\n")
+    f.flush()
 
 
 def measured_peak_hbm():
@@ -108,6 +127,32 @@ def oracle_msgs_per_s(n_env_days, threads, variant=1000, seed0=5000):
     return msgs, wall, sum(r[1] for r in res)
 
 
+def oracle_env_steps_per_s(n_episodes, steps, threads):
+    """Reference CPU algorithm of ABIDESEnv.step (oracle port) on `threads` host threads: `steps` steps after the first."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.oracle import OracleEnv, lib
+    lib()
+    stream = np.load(FIXTURE)["stream"]
+
+    def one(i):
+        rng = np.random.RandomState(100 + i)
+        env = OracleEnv(stream)
+        env.step(np.array([0.02, 0.5, 0.5]))              # 00:00 -> 09:40 start-up, untimed like the GPU arm
+        n0 = env.n_pops
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            env.step(np.array([rng.uniform(0, 0.04), rng.uniform(), rng.uniform()]))
+        return steps, env.n_pops - n0, time.perf_counter() - t0
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        res = list(ex.map(one, range(n_episodes)))
+    wall = time.perf_counter() - t0 - 0.0
+    busy = max(r[2] for r in res)
+    return sum(r[0] for r in res), sum(r[1] for r in res), sum(r[2] for r in res) / threads if n_episodes >= threads else busy, wall
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -122,7 +167,7 @@ def run_reference(args, rank, world):
         tot_m += m; tot_w += w
     v = tot_m / tot_w
     sample = "%d steps x %d full env-days of sparse_zi_%d (event loop only), %d threads" % (args.steps, per_step, args.variant, cores)
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": "LOB msgs/sec", "value": v, "unit": "msgs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_w / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": v / PUBLISHED_MSGS_PER_S, "dtype": "int64+f64", "data": "synthetic",
@@ -130,8 +175,14 @@ def run_reference(args, rank, world):
                                "(oracle/abides_oracle.c port of the Python reference) on host cores" % (args.variant, args.variant)},
         "cpu_baseline": {"value": v, "unit": "msgs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "msgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }))
+        "gpu_launches": 0, "env": reference_env_block(cores),
+    })
+
+
+def reference_env_block(cores):
+    st, msgs, busy, wall = oracle_env_steps_per_s(max(cores, 2), 120, cores)
+    return {"metric": "ABIDESEnv steps/sec", "value": st / busy, "unit": "steps/s", "msgs_per_s": msgs / busy, "cores": cores, "kind": "port",
+            "sample": "%d episodes x 120 steps after the 09:40 start-up (IBM 2003-01-14 LOBSTER fixture), %d threads" % (max(cores, 2), cores)}
 
 
 def run_ours(args, rank, local_rank, world):
@@ -201,10 +252,29 @@ def run_ours(args, rank, local_rank, world):
     D.barrier()
     e2e_msgs_local = int(stats_np["messages"].sum() - st1["messages"].sum())
 
+    # ---- second headline metric: ABIDESEnv steps/s (Exchange + MarketReplayAgent + RL execution agent under GymKernel)
+    env_local = None
+    state_bytes = sim.device_bytes
+    if not args.no_env:
+        sim.close()
+        env_local = bench_env(args, rank, local_rank, dev, stream, sp)
+
     # ---- aggregate over ranks: sums by all-gather of the summary vectors (NCCL), times by max
     g = D.gather_summaries(torch.tensor([msgs_local, e2e_msgs_local, err_envs], dtype=torch.int64), device=dev)
     elapsed_ms = D.max_over_ranks(elapsed_ms, device=dev)
     e2e_s = D.max_over_ranks(e2e_s_local, device=dev)
+    env_block = None
+    if env_local is not None:
+        ge = D.gather_summaries(torch.tensor([env_local["steps"], env_local["msgs"], env_local["e2e_steps"], env_local["errs"]], dtype=torch.int64), device=dev)
+        t_env = D.max_over_ranks(env_local["ms"], device=dev) / 1e3
+        t_e2e = D.max_over_ranks(env_local["e2e_s"], device=dev)
+        env_block = {"metric": "ABIDESEnv steps/sec", "value": int(ge[:, 0].sum()) / t_env, "unit": "steps/s", "msgs_per_s": int(ge[:, 1].sum()) / t_env,
+                     "envs_per_gpu": args.env_envs_per_gpu, "steps": args.env_steps, "ms_per_step": 1e3 * t_env / args.env_steps,
+                     "messages_per_env_step": int(ge[:, 1].sum()) / max(int(ge[:, 0].sum()), 1), "error_envs": int(ge[:, 3].sum()),
+                     "e2e": {"value": int(ge[:, 2].sum()) / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": 24 * args.env_envs_per_gpu,
+                             "d2h_bytes_per_step": 81 * args.env_envs_per_gpu},
+                     "gpu_launches": env_local["launches"], "workload": "ABIDESEnv.py shape: exchange + MarketReplayAgent (IBM 2003-01-14 LOBSTER sample day fixture) + "
+                     "DummyRLExecutionAgent (BUY 1e5, 30 s, order_level 2), random actions; one abx_env_step_kernel launch per step"}
     if rank != 0:
         return
     msgs, e2e_msgs, errs = int(g[:, 0].sum()), int(g[:, 1].sum()), int(g[:, 2].sum())
@@ -223,8 +293,8 @@ def run_ours(args, rank, local_rank, world):
             "workload": "config/sparse_zi_%d.py shape: %d ZI agents + exchange, sparse OU oracle, %d envs/GPU, env e seeded %d+e "
                         "(Philox streams)" % (args.variant, args.variant, n_envs, args.seed),
             "envs_per_gpu": n_envs, "step": "%.1f simulated seconds per environment per launch" % (slice_ns / NS),
-            "messages_per_step": msgs // args.steps, "state_bytes_per_gpu": sim.device_bytes,
-            "l2_policy": "inputs larger than L2: %.1f GB of per-environment state streamed per step, no flush needed" % (sim.device_bytes / 1e9),
+            "messages_per_step": msgs // args.steps, "state_bytes_per_gpu": state_bytes,
+            "l2_policy": "inputs larger than L2: %.1f GB of per-environment state streamed per step, no flush needed" % (state_bytes / 1e9),
             "vs_baseline_ref": "BASELINE.md section 1: 3100.4 msgs/s, reference single process, i7 2.6 GHz", "error_envs": errs,
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -236,6 +306,8 @@ def run_ours(args, rank, local_rank, world):
                 "d2h_bytes_per_step": ctypes.sizeof(_lib.EnvStats) * n_envs},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if not args.no_env:
+        out["env"] = env_block
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_days = max(2 * cores, 16)
@@ -244,7 +316,50 @@ def run_ours(args, rank, local_rank, world):
         out["cpu_baseline"] = {"value": m / w, "unit": "msgs/s", "cores": cores, "kind": "port",
                                "sample": "%d full env-days of sparse_zi_%d, event loop only, %d threads, %.1f CPU-s" % (n_days, args.variant, cores, cpu_s),
                                "single_thread_value": m / cpu_s}
-    print(json.dumps(out))
+        if not args.no_env:
+            out["cpu_baseline"]["env"] = reference_env_block(cores)
+    emit_json(out)
+
+
+def bench_env(args, rank, local_rank, dev, stream, sp):
+    import numpy as np
+    import torch
+    from marl_optimal_execution_b200 import _lib, distributed as D
+    from marl_optimal_execution_b200.env import ABIDESEnv
+
+    n, K, W = args.env_envs_per_gpu, args.env_steps, max(args.warmup, 3)
+    env = ABIDESEnv(np.load(FIXTURE)["stream"], n_envs=n, device=local_rank)
+    env.reset(stream=sp)
+    gen = torch.Generator(device=dev); gen.manual_seed(args.seed + rank)
+    acts = torch.rand(W + K + 1, n, 3, dtype=torch.float64, device=dev, generator=gen)
+    acts[:, :, 0] *= 0.04
+    for k in range(W + 1):                                # first step replays 00:00 -> 09:40 (13.5 k messages/env), untimed
+        env.step(acts[k], stream=sp)
+    torch.cuda.synchronize(dev)
+    m0 = int(env.stats(stream=sp)["messages"].sum()); l0 = env.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    D.barrier(); torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for k in range(K):
+        env.step(acts[W + 1 + k], stream=sp)
+    e1.record(stream)
+    torch.cuda.synchronize(dev); D.barrier()
+    launches = env.launch_count - l0
+    st = env.stats(stream=sp)
+    m1 = int(st["messages"].sum())
+    # e2e: host (pinned) buffers through abx_env_step_host: actions H2D, obs/reward/done D2H every step
+    a_pin = torch.rand(n, 3, dtype=torch.float64).pin_memory(); a_pin[:, 0] *= 0.04
+    o_pin = torch.empty(n, 9, dtype=torch.float64).pin_memory(); r_pin = torch.empty(n, dtype=torch.float64).pin_memory()
+    d_pin = torch.empty(n, dtype=torch.uint8).pin_memory()
+    D.barrier(); torch.cuda.synchronize(dev)
+    w0 = time.perf_counter()
+    for k in range(K):
+        env.step_host_buffers(a_pin.data_ptr(), o_pin.data_ptr(), r_pin.data_ptr(), d_pin.data_ptr(), stream=sp)
+    e2e_s = time.perf_counter() - w0
+    D.barrier()
+    errs = int(((env.stats(stream=sp)["flags"] & _lib.F_ERROR_MASK) != 0).sum())
+    env.close()
+    return {"steps": n * K, "msgs": m1 - m0, "ms": e0.elapsed_time(e1), "e2e_steps": n * K, "e2e_s": e2e_s, "errs": errs, "launches": int(launches)}
 
 
 def main():
@@ -258,7 +373,11 @@ def main():
     ap.add_argument("--variant", type=int, default=1000, choices=[100, 1000])
     ap.add_argument("--seed", type=int, default=123456789)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-env", action="store_true", help="skip the ABIDESEnv steps/s measurement")
+    ap.add_argument("--env-envs-per-gpu", type=int, default=8192)
+    ap.add_argument("--env-steps", type=int, default=40)
     args = ap.parse_args()
+    quiet_stdout()
     if args.warmup < 3 and args.impl == "ours":
         print("bench.py: note: W >= 3 is required for a valid number", file=sys.stderr)
 
