@@ -138,9 +138,9 @@ struct alignas(16) EnvX {                           // per-environment state of 
   int32_t ra_shares, rl_shares, ra_last_trade, rl_last_trade;
   uint32_t ra_flags, rl_flags; int32_t wt_cursor, n_executed;
   int32_t rl_n_orders, n_lobs, lob_head, p0;
-  int32_t rem_time, obs_len, ra_open, steps;
+  int32_t rem_time, obs_len, g0_qty, steps;          // g0_*: the replay agent's order under GENERATED id 0 (rows with ORDER_ID 0)
   uint32_t rl_oid[RL_ORDER_CAP]; int32_t rl_oprice[RL_ORDER_CAP]; int32_t rl_oqty[RL_ORDER_CAP];
-  double obs[9]; double pad0;
+  double obs[9]; int32_t g0_pq, pad1;
 };
 static_assert(sizeof(EnvX) % 16 == 0, "EnvX layout");
 
@@ -827,11 +827,27 @@ struct Sim {
       exch_send(m.sender, ABX_QUERY_SPREAD, p, bits_dbl((uint64_t)(uint32_t)b2 | ((uint64_t)(uint32_t)a2 << 32)));
     } else if (m.kind == ABX_LIMIT_ORDER) { s.c_limit++; book_handle_limit((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[2], 0.0); c.sync(); trace_snap(); }
     else if (m.kind == ABX_CANCEL_ORDER) { s.c_cancel++; book_cancel((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], 0.0); c.sync(); trace_snap(); }
-    else if (m.kind == ABX_MODIFY_ORDER) { book_modify((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[3], m.p[5]); c.sync(); trace_snap(); }   // :326-340
+    else if (m.kind == ABX_MODIFY_ORDER) { if (!(m.p[4] & 2)) book_modify((uint32_t)m.p[0], m.sender, m.p[4] & 1, m.p[1], m.p[3], m.p[5]); c.sync(); trace_snap(); }   // :326-340 (bit 1: ids differ, :343)
   }
   // ---- MarketReplayAgent ----
-  ABX_HD void replay_place(int r) {                                                     // placeOrder :69-96 for one row
-    int4 row = c.row_load(r); uint32_t oid = REPLAY_ID_BASE + (uint32_t)row.x;
+  ABX_HD void replay_place(EnvX *x, int r) {                                            // placeOrder :69-96 for one row
+    int4 row = c.row_load(r);
+    if (row.x < 0) {                                                                    // ORDER_ID 0 == "unset" (util/order/Order.py:27): orders.get(0) finds
+      int32_t gq = x->g0_qty, gp = x->g0_pq;                                            // only the order that received GENERATED id 0
+      if (gq == 0 && row.z > 0) {
+        uint32_t oid = s.next_order_id++;
+        if (oid == 0) { c.sync(); if (c.onchip_writer()) { x->g0_qty = row.z; x->g0_pq = (row.y << 1) | (row.w & 1); } c.sync(); }
+        int32_t p[6] = {(int32_t)oid, row.y, row.z, 0, row.w, 0}; env_send(ABX_LIMIT_ORDER, p, false);
+      } else if (gq != 0 && row.z == 0) {
+        int32_t p[6] = {0, gp >> 1, gq, 0, gp & 1, 0}; env_send(ABX_CANCEL_ORDER, p, false);
+      } else if (gq != 0) {                                                             // new_order gets a fresh id != 0: isSameOrder fails at the exchange
+        s.next_order_id++;
+        int32_t p[6] = {0, gp >> 1, gq, row.y, (gp & 1) | 2, row.z}; env_send(ABX_MODIFY_ORDER, p, false);
+      }
+      if (n_out >= OUT_CAP - 3) flush();
+      return;
+    }
+    uint32_t oid = REPLAY_ID_BASE + (uint32_t)row.x;
     uint4 t = c.id_load(row.x); bool existing = t.x != 0;
     if (!existing && row.z > 0) {                                                       // placeLimitOrder(order_id=ORDER_ID)
       t.x = (uint32_t)row.z; t.y = ((uint32_t)row.y << 1) | (uint32_t)(row.w & 1); c.id_store(row.x, t);
@@ -853,7 +869,7 @@ struct Sim {
     if (c.ts_load(k) != s.now) { s.flags |= ABX_F_UNSUPPORTED; return; }
     int r0 = c.first_load(k), r1 = c.first_load(k + 1);
 #pragma unroll 1
-    for (int r = r0; r < r1; r++) replay_place(r);
+    for (int r = r0; r < r1; r++) replay_place(x, r);
   }
   ABX_HD void replay_receive(EnvX *x, const Event &m) {
     uint32_t fl = x->ra_flags; int32_t sh = x->ra_shares, lt = x->ra_last_trade; int64_t cash = x->ra_cash;
@@ -862,6 +878,7 @@ struct Sim {
       uint32_t oid = (uint32_t)m.p[0];
       if (oid >= REPLAY_ID_BASE) { uint4 t = c.id_load((int)(oid - REPLAY_ID_BASE));
         if (t.x != 0) { if (m.kind == ABX_ORDER_CANCELLED || (uint32_t)m.p[2] >= t.x) t.x = 0; else t.x -= (uint32_t)m.p[2]; c.id_store((int)(oid - REPLAY_ID_BASE), t); } }
+      else if (oid == 0 && x->g0_qty != 0) { int32_t gq = x->g0_qty; gq = (m.kind == ABX_ORDER_CANCELLED || m.p[2] >= gq) ? 0 : gq - m.p[2]; c.sync(); if (c.onchip_writer()) x->g0_qty = gq; c.sync(); }
       if (m.kind == ABX_ORDER_EXECUTED) { lt = m.p[3]; fl |= AF_HAS_LAST; }             // MarketReplayAgent.receiveMessage :62-67
     }
     if (newly) set_wakeup(1, c.ts_load(0));                                             // mkt_open + getWakeFrequency() == first_wakeup
@@ -968,11 +985,11 @@ struct Sim {
     for (int i = 0; i < n; i++) { int32_t p[6] = {(int32_t)x->rl_oid[i], x->rl_oprice[i], x->rl_oqty[i], 0, P.rl_is_buy, 0}; env_send(ABX_CANCEL_ORDER, p, false); }
   }
   // reset: Kernel/GymKernel.initRunner :139-146 -- one WAKEUP per agent at start
-  ABX_HD void env_reset() { for (int id = 0; id < 3; id++) set_wakeup(id, P.c.start_ns); flush(); }
+  ABX_HD void env_reset() { for (int id = 0; id < P.c.n_agents; id++) set_wakeup(id, P.c.start_ns); flush(); }
   // GymKernel.stepRunner :158-306.  Returns done as ABIDESEnv.step computes it (ABIDESEnv.py:42-46).
   ABX_HD bool env_step(double a0, double a1, double a2) {
     EnvX *x = c.envx();
-    rl_place_orders(x, a0, a1, a2); flush();
+    if (P.order_level > 0) { rl_place_orders(x, a0, a1, a2); flush(); }                 // order_level 0: no RL agent (config/marketreplay.py)
     bool end_step = false, more = true;
 #pragma unroll 1
     while (!end_step) {

@@ -82,7 +82,7 @@ static inline int env_config_default(abx_env_config *c) {                       
   return ABX_OK;
 }
 static inline int env_config_validate(const abx_env_config *c) {
-  if (!c || c->version != ABX_VERSION || c->order_level < 1 || c->order_level > 2 || c->n_horizon < 2) return ABX_ERR_ARG;
+  if (!c || c->version != ABX_VERSION || c->order_level < 0 || c->order_level > 2 || c->n_horizon < 2) return ABX_ERR_ARG;
   if (c->queue_cap < 32 || c->queue_cap % 32 || c->queue_cap > 4096 || c->level_cap < 8 || c->level_cap > 2048) return ABX_ERR_ARG;
   if (c->order_cap < 8 || c->order_cap > 65535 || c->stop_ns >= KEY_T_MAX || c->start_ns < 0 || c->horizon_step_ns <= 0) return ABX_ERR_ARG;
   if (c->stream_history < 0 || c->stream_history > 14 || !(c->quantity > 0) || c->trace_cap < 0) return ABX_ERR_ARG;
@@ -91,7 +91,7 @@ static inline int env_config_validate(const abx_env_config *c) {
 // the generic (abx_sim_config) part of the parameter block for the ABIDESEnv shape: 3 agents, zero delays, no oracle
 static inline void env_fill_params(const abx_env_config &e, SimParams &P) {
   abx_sim_config &c = P.c; memset(&c, 0, sizeof(c));
-  c.version = ABX_VERSION; c.n_agents = 3; c.n_groups = 1; c.q_max = 1; c.groups[0].count = 2;
+  c.version = ABX_VERSION; c.n_agents = e.order_level > 0 ? 3 : 2; c.n_groups = 1; c.q_max = 1; c.groups[0].count = c.n_agents - 1;
   c.start_ns = e.start_ns; c.stop_ns = e.stop_ns; c.mkt_open_ns = e.mkt_open_ns; c.mkt_close_ns = e.mkt_close_ns;
   c.default_computation_delay_ns = 0; c.exchange_computation_delay_ns = 0; c.exchange_pipeline_delay_ns = 0;   // ABIDESEnv.py:89, agent_config.py:49-50
   c.stream_history = e.stream_history; c.latency_model = ABX_LAT_ZERO; c.n_noise = 1;
@@ -104,27 +104,32 @@ struct EnvStreamHost { std::vector<int64_t> ts, id_orig; std::vector<int32_t> fi
 // LOBSTER ORDER_IDs -> dense indices; rows grouped by identical timestamp (orders_dict of MarketReplayAgent.py:214)
 static inline int env_build_stream(const int64_t *s5, int64_t n, int64_t max_rl_ids, EnvStreamHost &o) {
   if (!s5 || n < 1 || n > 0x3fffffff) return ABX_ERR_ARG;
-  std::unordered_map<int64_t, int32_t> dense;
+  std::unordered_map<int64_t, int32_t> dense; int64_t n_zero = 0, min_id = 0x7fffffffffffLL;
   o.rows.resize(n);
   for (int64_t i = 0; i < n; i++) {
     const int64_t *r = s5 + 5 * i;
     if (i > 0 && r[0] < s5[5 * (i - 1)]) return ABX_ERR_ARG;                                     // must be time sorted
-    if (r[1] <= max_rl_ids || r[1] > 0x7fffffffLL || r[2] <= 0 || r[2] > 0x3fffffffLL || r[3] < 0 || r[3] > 0x7fffffffLL) return ABX_ERR_ARG;  // ids must not collide with generated ids (util/order/Order.py:35-42)
-    auto it = dense.find(r[1]); int32_t d;
-    if (it == dense.end()) { d = (int32_t)o.id_orig.size(); dense.emplace(r[1], d); o.id_orig.push_back(r[1]); } else d = it->second;
+    if (r[1] < 0 || r[1] > 0x3fffffffLL || r[2] <= 0 || r[2] > 0x3fffffffLL || r[3] < 0 || r[3] > 0x7fffffffLL) return ABX_ERR_ARG;
+    int32_t d;
+    if (r[1] == 0) { d = -1; n_zero++; }                                                          // ORDER_ID 0: "unset", the agent gets generated ids
+    else { if (r[1] < min_id) min_id = r[1];
+      auto it = dense.find(r[1]);
+      if (it == dense.end()) { d = (int32_t)o.id_orig.size(); dense.emplace(r[1], d); o.id_orig.push_back(r[1]); } else d = it->second; }
     if (i == 0 || r[0] != s5[5 * (i - 1)]) { o.ts.push_back(r[0]); o.first.push_back((int32_t)i); }
     int4 row; row.x = d; row.y = (int32_t)r[2]; row.z = (int32_t)r[3]; row.w = r[4] ? 1 : 0; o.rows[i] = row;
   }
   o.first.push_back((int32_t)n);
+  if (min_id <= max_rl_ids + 2 * n_zero) return ABX_ERR_ARG;          // explicit ids must stay clear of every id the generator can hand out (util/order/Order.py:35-42)
+  if (o.id_orig.empty()) o.id_orig.push_back(0);
   return ABX_OK;
 }
 ABX_HD void init_envx(const SimParams &P, EnvX &x) {
   x.ra_time = x.rl_time = P.c.start_ns; x.ra_cash = x.rl_cash = 0; x.rem_quantity = P.rl_quantity; x.executed_sum = 0.0;   // starting_cash 0 (agent_config.py:73,133)
   x.ra_shares = x.rl_shares = 0; x.ra_last_trade = x.rl_last_trade = 0; x.ra_flags = 0;
   x.rl_flags = RLF_TRADE | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT); x.wt_cursor = 0; x.n_executed = 0; x.rl_n_orders = 0; x.n_lobs = 0; x.lob_head = 0; x.p0 = 0;
-  x.rem_time = P.n_h - 1; x.obs_len = 0; x.ra_open = 0; x.steps = 0;
+  x.rem_time = P.n_h - 1; x.obs_len = 0; x.g0_qty = 0; x.steps = 0;
   for (int i = 0; i < RL_ORDER_CAP; i++) { x.rl_oid[i] = 0; x.rl_oprice[i] = 0; x.rl_oqty[i] = 0; }
-  for (int i = 0; i < 9; i++) x.obs[i] = 0.0; x.pad0 = 0.0;
+  for (int i = 0; i < 9; i++) x.obs[i] = 0.0; x.g0_pq = 0; x.pad1 = 0;
 }
 
 static inline const char *status_string(int32_t st) {

@@ -889,10 +889,10 @@ static void replay_place(abo_env *s, const srow_t *r) {
     event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_CANCEL_ORDER; e.order.agent_id = 1; e.order.order_id = ex->key; e.order.quantity = ex->qty; e.order.limit_price = ex->price; e.order.is_buy = ex->is_buy;
     env_send(s, 1, 0, &e, 0);
   } else if (ex) {                                                                   /* modifyOrder :408-418 */
-    env_new_order_id(s, r->id);                                                      /* LimitOrder(..., order_id=order_id) constructed for new_order */
+    int64_t nid = env_new_order_id(s, r->id);                                        /* LimitOrder(..., order_id=order_id): id 0 is "unset" -> a fresh generated id (Order.py:27) */
     event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_MODIFY_ORDER;
     e.order.agent_id = 1; e.order.order_id = ex->key; e.order.quantity = ex->qty; e.order.limit_price = ex->price; e.order.is_buy = ex->is_buy;
-    e.new_order.agent_id = 1; e.new_order.order_id = r->id; e.new_order.quantity = r->size; e.new_order.limit_price = r->price; e.new_order.is_buy = r->is_buy;
+    e.new_order.agent_id = 1; e.new_order.order_id = nid; e.new_order.quantity = r->size; e.new_order.limit_price = r->price; e.new_order.is_buy = r->is_buy;
     env_send(s, 1, 0, &e, 0);
   }
 }
@@ -1011,10 +1011,10 @@ static void rl_cancel_all(abo_env *s) {
   }
 }
 
-abo_env *abo_env_new(const int64_t *stream5, int64_t n_rows, double quantity, int order_level, int trace) {
+abo_env *abo_env_new2(const int64_t *stream5, int64_t n_rows, double quantity, int order_level, int trace, int64_t stop_ns) {
   abo_env *s = (abo_env *)calloc(1, sizeof(abo_env));
   s->trace = trace; s->pop_hash = s->note_hash = s->snap_hash = FNV_OFF;
-  s->mkt_open = (9 * 3600 + 30 * 60) * NS_PER_S; s->mkt_close = 16 * 3600 * NS_PER_S; s->stop_time = (16 * 3600 + 600) * NS_PER_S;   /* ABIDESEnv.py:87-88 16:10 */
+  s->mkt_open = (9 * 3600 + 30 * 60) * NS_PER_S; s->mkt_close = 16 * 3600 * NS_PER_S; s->stop_time = stop_ns;   /* ABIDESEnv.py:87-88 16:10; config/marketreplay.py:135 16:01 */
   book_init(&s->book, 10, s, env_book_send);
   s->rows = (srow_t *)malloc(sizeof(srow_t) * (n_rows > 0 ? n_rows : 1)); s->n_rows = n_rows;
   s->ts = (int64_t *)malloc(8 * (n_rows + 1)); s->ts_first = (int64_t *)malloc(8 * (n_rows + 1));
@@ -1026,16 +1026,17 @@ abo_env *abo_env_new(const int64_t *stream5, int64_t n_rows, double quantity, in
   for (int i = 0; i < s->n_h; i++) s->horizon[i] = (9 * 3600 + 40 * 60) * NS_PER_S + (int64_t)i * 30 * NS_PER_S;
   s->wt_cursor = 1;                                                                           /* wakeup_times = [*orders_dict]; first_wakeup stays in the list */
   s->wt_cursor = 0;
-  for (int i = 0; i < 3; i++) env_set_wakeup(s, i, 0);                                        /* GymKernel.initRunner :139-146 kernelStarting */
+  for (int i = 0; i < (order_level > 0 ? 3 : 2); i++) env_set_wakeup(s, i, 0);               /* initRunner :139-146 kernelStarting; order_level 0: no RL agent (config/marketreplay.py) */
   return s;
 }
+abo_env *abo_env_new(const int64_t *stream5, int64_t n_rows, double quantity, int order_level, int trace) { return abo_env_new2(stream5, n_rows, quantity, order_level, trace, (16 * 3600 + 600) * NS_PER_S); }
 void abo_env_free(abo_env *s) {
   if (!s) return; book_destroy(&s->book); free(s->rows); free(s->ts); free(s->ts_first); free(s->ra_orders.e); free(s->used_ids.e); free(s->rl_orders); free(s->rl_oqty);
   free(s->horizon); free(s->q.e); free(s->pops.v); free(s->ops.v); free(s->notes.v); free(s->snaps.v); free(s->ckpt); free(s);
 }
 /* GymKernel.stepRunner :158-306.  Returns obs length (0 or 9); *done as ABIDESEnv.step computes it (ABIDESEnv.py:42-46). */
 int abo_env_step(abo_env *s, const double *action, double *obs_out, int *done) {
-  rl_place_orders(s, action);
+  if (s->order_level > 0) rl_place_orders(s, action);
   s->end_step = 0;
   while (!s->end_step && s->q.n > 0 && s->now <= s->stop_time) {
     event_t ev; heap_pop(&s->q, &ev); s->now = ev.t; s->ttl++;

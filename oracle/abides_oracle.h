@@ -104,6 +104,8 @@ typedef struct abo_env abo_env;
 /* stream5: rows (t_ns since midnight, ORDER_ID, PRICE cents, SIZE, is_buy) as LOBSTEROrdersProcessor yields them
  * (agent/examples/MarketReplayAgent.py:162-220), sorted by time.  quantity / order_level: agent_config.py:132-154. */
 abo_env *abo_env_new(const int64_t *stream5, int64_t n_rows, double quantity, int order_level, int trace_flags);
+/* order_level 0: no RL agent == config/marketreplay.py (Exchange + MarketReplayAgent under Kernel.runner); one step() runs to the end */
+abo_env *abo_env_new2(const int64_t *stream5, int64_t n_rows, double quantity, int order_level, int trace_flags, int64_t stop_ns);
 void abo_env_free(abo_env *);
 /* ABIDESEnv.step (ABIDESEnv.py:30-49): returns len(obs) (0 or 9), fills obs_out[9] and *done */
 int abo_env_step(abo_env *, const double *action, double *obs_out, int *done);

@@ -91,6 +91,7 @@ def lib():
     sig("abo_sim_book_l1", None, vp, P(i64))
     sig("abo_sim_fundamental", i64, vp)
     sig("abo_env_new", vp, P(i64), i64, dbl, i32, i32)
+    sig("abo_env_new2", vp, P(i64), i64, dbl, i32, i32, i64)
     sig("abo_env_free", None, vp)
     sig("abo_env_step", i32, vp, P(dbl), P(dbl), P(i32))
     sig("abo_env_n_pops", i64, vp)
@@ -309,10 +310,11 @@ class OracleEnv:
     """ABIDESEnv (ABIDESEnv.py) restated: Exchange + MarketReplayAgent + DummyRLExecutionAgent under GymKernel.
     `stream` is an int64 [n,5] array of (t_ns, ORDER_ID, PRICE, SIZE, is_buy) rows."""
 
-    def __init__(self, stream, quantity=1e5, order_level=2, trace=0):
+    def __init__(self, stream, quantity=1e5, order_level=2, trace=0, stop_ns=(16 * 3600 + 600) * 10 ** 9):
+        """order_level 0 = no RL agent: config/marketreplay.py (stop_ns 16:01); one step() then runs the whole day."""
         self._stream = np.ascontiguousarray(stream, dtype=np.int64)
-        self._h = lib().abo_env_new(self._stream.ctypes.data_as(C.POINTER(C.c_int64)), len(self._stream), float(quantity),
-                                    int(order_level), int(trace))
+        self._h = lib().abo_env_new2(self._stream.ctypes.data_as(C.POINTER(C.c_int64)), len(self._stream), float(quantity),
+                                     int(order_level), int(trace), int(stop_ns))
 
     def __del__(self):
         if getattr(self, "_h", None):

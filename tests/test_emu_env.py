@@ -45,3 +45,20 @@ def test_rejects_streams_whose_ids_collide_with_generated_ids(emu):
     bad = np.array([[34200 * 10 ** 9, 5, 1000, 100, 1]], dtype=np.int64)      # ORDER_ID 5 could equal an RL-agent order id
     with pytest.raises(_lib.AbxError):
         ABIDESEnv(bad, n_envs=1, cfg=env_config(L), lib_path=emu)
+
+
+def test_marketreplay_config_matches_oracle(emu, golden_dir):
+    g = np.load(os.path.join(golden_dir, "mr_GOOG_2012-06-21.npz"))
+    L = _lib.load(emu)
+    stop = (16 * 3600 + 60) * 10 ** 9
+    cfg = env_config(L, order_level=0, stop_ns=stop, queue_cap=256, level_cap=1024, trace_cap=400000, hash_pops=1)
+    env = ABIDESEnv(g["stream"], n_envs=1, cfg=cfg, lib_path=emu)
+    env.reset()
+    o = OracleEnv(g["stream"], order_level=0, trace=TRACE_ALL, stop_ns=stop)
+    _, _, done, _ = env.step(np.zeros((1, 3)))
+    o.step([0, 0, 0])
+    st = env.stats()[0]
+    assert int(done[0]) == 1 and int(st["messages"]) == o.n_pops == 193264 and int(st["flags"]) == _lib.F_DONE
+    assert int(st["pop_hash"]) == o.pop_hash() == int(g["pop_hash_ckpt"][-1])
+    p, nt, sn = env.split_trace(0)
+    assert np.array_equal(p, o.trace("pops")) and np.array_equal(nt, o.trace("notes")) and np.array_equal(sn, o.trace("snaps"))

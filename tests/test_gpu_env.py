@@ -55,3 +55,23 @@ def test_batch_of_identical_envs_is_deterministic(golden_dir):
     st = env.stats()
     assert len(set(int(h) for h in st["pop_hash"])) == 1 and (st["flags"] == 0).all()
     assert torch.equal(obs[0], obs[-1]) and int(done.sum()) == 0
+
+
+def test_marketreplay_config_on_gpu(golden_dir):
+    """BASELINE.json configs[4]: config/marketreplay.py replaying a LOBSTER order stream through the GPU books --
+    fills, snapshots and event order bit-exact against the reference recording (via the pinned oracle)."""
+    g = np.load(os.path.join(golden_dir, "mr_GOOG_2012-06-21.npz"))
+    stop = (16 * 3600 + 60) * 10 ** 9
+    cfg = env_config(order_level=0, stop_ns=stop, queue_cap=256, level_cap=1024, trace_cap=400000, hash_pops=1)
+    env = ABIDESEnv(g["stream"], n_envs=2, cfg=cfg)
+    env.reset()
+    o = OracleEnv(g["stream"], order_level=0, trace=TRACE_ALL, stop_ns=stop)
+    _, _, done, _ = env.step(np.zeros((2, 3)))
+    o.step([0, 0, 0])
+    st = env.stats()
+    assert done.tolist() == [1, 1] and (st["messages"] == 193264).all() and (st["flags"] == _lib.F_DONE).all()
+    assert (st["pop_hash"] == np.uint64(int(g["pop_hash_ckpt"][-1]))).all()
+    p, nt, sn = env.split_trace(1)
+    assert np.array_equal(p, o.trace("pops")) and np.array_equal(nt, o.trace("notes")) and np.array_equal(sn, o.trace("snaps"))
+    assert np.array_equal(nt[: len(g["notes_head"])], g["notes_head"]) and np.array_equal(sn[: len(g["snaps_head"])], g["snaps_head"])
+    assert int(st["max_queue"][0]) == o.counter("max_queue")

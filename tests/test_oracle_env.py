@@ -34,3 +34,19 @@ def test_env_episode_matches_reference(golden_dir):
     assert err < 1e-6, err
     f = env.final()
     assert np.array_equal(f[:4], g["rl_final"]) and np.array_equal(f[4:7], g["replay_final"])
+
+
+def test_marketreplay_config_matches_reference(golden_dir):
+    """config/marketreplay.py on GOOG 2012-06-21 (Exchange + MarketReplayAgent under Kernel.runner, stop 16:01): 193 264
+    kernel messages, 49 482 book ops incl. 3 913 rows with ORDER_ID 0 (generated ids, util/order/Order.py:27)."""
+    g = np.load(os.path.join(golden_dir, "mr_GOOG_2012-06-21.npz"))
+    env = OracleEnv(g["stream"], order_level=0, trace=TRACE_ALL, stop_ns=(16 * 3600 + 60) * 10 ** 9)
+    _, _, done, _ = env.step([0, 0, 0])
+    assert done == 1 and env.n_pops == int(g["n_pops"]) == 193264
+    assert np.array_equal(env.hash_ckpt(), g["pop_hash_ckpt"][:-1]) and env.pop_hash() == int(g["pop_hash_ckpt"][-1])
+    assert env.note_hash() == int(g["note_hash"]) and env.snap_hash() == int(g["snap_hash"])
+    for name in ("pops", "notes", "snaps"):
+        b = g[name + "_head"]
+        assert np.array_equal(env.trace(name)[: len(b)], b), name
+    assert env.counter("max_bid_levels") == g["max_levels"][0] and env.counter("max_ask_levels") == g["max_levels"][1]
+    assert env.counter("max_resting") == int(g["max_resting"])

@@ -219,13 +219,15 @@ def install_hooks():
     EA.ExchangeAgent.sendMessage = sendMessage
 
 
-def run(config, seed, extra_args=()):
+def run(config, seed, extra_args=(), date="2019-06-28"):
     import pandas as pd
 
-    REC.midnight = pd.to_datetime("2019-06-28")
+    REC.midnight = pd.to_datetime(date)
     sys.argv = ["abides.py", "-c", config, "-l", "rec", "-s", str(seed), *extra_args]
     cwd = os.getcwd()
     tmp = tempfile.mkdtemp(prefix="abides_rec_")
+    os.makedirs(os.path.join(tmp, "data", "marketreplay", "level_1"))          # fresh cache: the CURRENT loader builds int-cent prices
+    os.symlink(os.path.join(REF, "data", "lobster"), os.path.join(tmp, "data", "lobster"))
     os.chdir(tmp)
     try:
         mod = importlib.import_module("config." + config)
@@ -236,9 +238,17 @@ def run(config, seed, extra_args=()):
 
 def main():
     config, seed, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
-    full = "--full" in sys.argv[4:]
+    rest = sys.argv[4:]
+    full = "--full" in rest
+    date = rest[rest.index("--date") + 1] if "--date" in rest else "2019-06-28"
+    extra = rest[rest.index("--extra") + 1:] if "--extra" in rest else []
     install_hooks()
-    mod = run(config, seed)
+    if config == "marketreplay":
+        # order-book archival (agent/ExchangeAgent.py:389-469) uses pd.SparseDataFrame, removed from pandas; it runs after the
+        # simulation ended and is out of scope, so the recorder skips it.
+        import agent.ExchangeAgent as EA
+        EA.ExchangeAgent.logOrderBookSnapshots = lambda self, symbol: None
+    mod = run(config, seed, extra, date)
 
     pops = np.array(REC.pops, dtype=np.int64).reshape(-1, 5)
     ops = np.array(REC.ops, dtype=np.int64).reshape(-1, 9)
@@ -286,6 +296,12 @@ def main():
         max_levels=np.array([snaps[:, 0].max() if len(snaps) else 0, snaps[:, 1].max() if len(snaps) else 0]),
         max_resting=np.array(snaps[:, 2].max() if len(snaps) else 0),
     )
+    replay = [a for a in agents if type(a).__name__ == "MarketReplayAgent"]
+    if replay:                                   # the replayed stream exactly as LOBSTEROrdersProcessor parsed it
+        od = replay[0].historical_orders.orders_dict
+        data["stream"] = np.array([(REC.ns(ts), int(r["ORDER_ID"]), int(r["PRICE"]), int(r["SIZE"]), 1 if r["BUY_SELL_FLAG"] == "BUY" else 0)
+                                   for ts in od for r in od[ts]], dtype=np.int64)
+        data["pops_head"], data["notes_head"], data["snaps_head"] = pops[:20000], notes[:20000], snaps[:10000]
     if full:
         kinds = np.frombuffer(b"".join(b"".join(s.tape_kind) for s in REC.streams), dtype="S1")
         vals = []
