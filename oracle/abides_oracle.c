@@ -952,6 +952,15 @@ static void rl_receive(abo_env *s, const event_t *m) {
   }
 }
 static const lob_t *rl_lob(const abo_env *s, int idx) { if (idx < 0) idx += s->n_lobs; return &s->lobs[(s->lob_head + idx) % 100]; }   /* deque[idx], negative from the right */
+/* numpy's pairwise summation for n <= 128 (numpy/core/src/umath/loops_utils.h.src pairwise_sum): np.mean / np.std use it */
+static double np_pairwise_sum(const double *a, int n) {
+  if (n < 8) { double r = 0.0; for (int i = 0; i < n; i++) r += a[i]; return r; }
+  double r[8]; for (int k = 0; k < 8; k++) r[k] = a[k];
+  int i; for (i = 8; i < n - (n % 8); i += 8) for (int k = 0; k < 8; k++) r[k] += a[i + k];
+  double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  for (; i < n; i++) res += a[i];
+  return res;
+}
 /* get_observation :294-315; returns 0 on the ValueError paths of ABIDESEnvMetrics (empty side / no LOB) */
 static int rl_observe(abo_env *s) {
   /* get_remaining_time :282-292 */
@@ -971,7 +980,7 @@ static int rl_observe(abo_env *s) {
   o[5] = tanh((double)l->ask1 / (double)l->askq1 - (double)l->bid1 / (double)l->bidq1);       /* getSmartPrice */
   { double v[100], mean = 0, var = 0; int n = s->n_lobs;                                      /* getMidPriceVolatility: np.std(ddof=0) */
     for (int i = 0; i < n; i++) { const lob_t *li = rl_lob(s, i); if (li->n_bids == 0 || li->n_asks == 0) return 0; v[i] = log((((double)li->bid1 + (double)li->ask1) / 2) / p0); mean += v[i]; }
-    mean /= n; for (int i = 0; i < n; i++) var += (v[i] - mean) * (v[i] - mean); o[6] = sqrt(var / n); }
+    mean = np_pairwise_sum(v, n) / n; for (int i = 0; i < n; i++) v[i] = (v[i] - mean) * (v[i] - mean); var = np_pairwise_sum(v, n); o[6] = sqrt(var / n); }
   int d;                                                                                      /* getTradeDirection :197-216 */
   if (pt > mid) d = 1; else if (pt < mid) d = -1;
   else { const lob_t *ll = rl_lob(s, -1); if (ll->n_bids == 0 || ll->n_asks == 0) return 0; double lm = ((double)ll->bid1 + (double)ll->ask1) / 2; d = mid > lm ? 1 : -1; }

@@ -14,8 +14,9 @@ from oracle.oracle import OracleEnv, TRACE_ALL
 pytestmark = pytest.mark.gpu
 
 
-def test_episode_matches_reference_recording_and_oracle(golden_dir):
-    g = np.load(os.path.join(golden_dir, "env_IBM_2003-01-14_s789.npz"))
+@pytest.mark.parametrize("fixture", ["env_IBM_2003-01-14_s789.npz", "env_IBM_2003-01-15_s4242.npz"])
+def test_episode_matches_reference_recording_and_oracle(golden_dir, fixture):
+    g = np.load(os.path.join(golden_dir, fixture))
     env = ABIDESEnv(g["stream"], n_envs=3, cfg=env_config(trace_cap=300000, hash_pops=1))
     env.reset()
     o = OracleEnv(g["stream"], trace=TRACE_ALL)
@@ -29,10 +30,10 @@ def test_episode_matches_reference_recording_and_oracle(golden_dir):
         oo, _, od, _ = o.step(a)
         ref = np.nan_to_num(g["obs"][k], nan=0.0)
         assert int(done[0]) == od == int(g["done"][k]) and rew[0] == 0.0, k
-        assert np.allclose(obs[0], ref, rtol=1e-6, atol=0), (k, obs[0], ref)
+        assert np.allclose(obs[0], ref, rtol=1e-6, atol=1e-12), (k, obs[0], ref)
         assert np.array_equal(obs[0], obs[1]) and done[0] == done[1]
     st = env.stats()
-    assert int(st["messages"][0]) == o.n_pops == int(g["n_pops"]) == 144099
+    assert int(st["messages"][0]) == o.n_pops == int(g["n_pops"])
     assert (st["flags"] == _lib.F_DONE).all(), st["flags"]
     assert int(st["pop_hash"][0]) == int(st["pop_hash"][1]) == o.pop_hash() == int(g["pop_hash_ckpt"][-1])
     assert int(st["pop_hash"][2]) != int(st["pop_hash"][0])

@@ -7,8 +7,14 @@ import numpy as np
 from oracle.oracle import OracleEnv, TRACE_ALL
 
 
-def test_env_episode_matches_reference(golden_dir):
-    g = np.load(os.path.join(golden_dir, "env_IBM_2003-01-14_s789.npz"))
+import pytest
+
+EPISODES = [("env_IBM_2003-01-14_s789.npz", 144099), ("env_IBM_2003-01-15_s4242.npz", 165100)]
+
+
+@pytest.mark.parametrize("fixture,n_pops", EPISODES)
+def test_env_episode_matches_reference(golden_dir, fixture, n_pops):
+    g = np.load(os.path.join(golden_dir, fixture))
     env = OracleEnv(g["stream"], quantity=1e5, order_level=2, trace=TRACE_ALL)
     obs, dones = [], []
     for a in g["actions"]:
@@ -22,7 +28,7 @@ def test_env_episode_matches_reference(golden_dir):
             break
     obs = np.array(obs)
     assert len(obs) == len(g["obs"]) == 761 and dones == list(g["done"])
-    assert env.n_pops == int(g["n_pops"]) == 144099
+    assert env.n_pops == int(g["n_pops"]) == n_pops
     assert np.array_equal(env.hash_ckpt(), g["pop_hash_ckpt"][:-1]) and env.pop_hash() == int(g["pop_hash_ckpt"][-1])
     assert env.note_hash() == int(g["note_hash"]) and env.snap_hash() == int(g["snap_hash"])
     for name in ("pops", "ops", "notes", "snaps"):
@@ -30,8 +36,8 @@ def test_env_episode_matches_reference(golden_dir):
         assert np.array_equal(a[: len(b)], b), name
     # observations: fp64, 1e-6 relative (north star); measured 2e-15
     assert np.array_equal(np.isnan(obs), np.isnan(g["obs"]))
-    err = np.nanmax(np.abs(obs - g["obs"]) / np.maximum(np.abs(g["obs"]), 1e-300))
-    assert err < 1e-6, err
+    err = np.nanmax(np.abs(obs - g["obs"]) / np.maximum(np.abs(g["obs"]), 1e-12))
+    assert err < 1e-12, err                                           # north star: 1e-6 relative; measured < 1e-15
     f = env.final()
     assert np.array_equal(f[:4], g["rl_final"]) and np.array_equal(f[4:7], g["replay_final"])
 
