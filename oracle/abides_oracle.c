@@ -299,6 +299,7 @@ typedef struct {            /* one PriorityQueue entry: (deliverAt, (recipient, 
   int has_bid, has_ask;
   int64_t bid2, ask2; int n_bids, n_asks;                    /* depth > 1 replies: second level price, level counts (capped at 2) */
   order_t new_order;                                         /* MODIFY_ORDER body["new_order"] */
+  int64_t tv, lookback;                                      /* QUERY_TRANSACTED_VOLUME: transacted_volume / lookback_period (ns) */
 } event_t;
 
 static inline int ev_less(const event_t *a, const event_t *b) { /* tuple order (t, recipient, type.value, msg.uniq) */
@@ -334,7 +335,13 @@ typedef struct {            /* TradingAgent (agent/TradingAgent.py:19-98) + Zero
   int32_t theta[64]; int q_max;
   int64_t current_time;                                 /* Agent.currentTime */
   int64_t surplus;
+  /* rmsc03 population (config/rmsc03.py): agent class and its extra state */
+  int type;                                             /* AT_ZI, AT_NOISE, AT_VALUE, AT_MOMENTUM, AT_POVMM */
+  int64_t wakeup_time, size;                            /* NoiseAgent.wakeup_time[0]; NoiseAgent/ValueAgent/MomentumAgent.size */
+  double *mids; int n_mids, cap_mids; double avg20, avg50; int has20, has50;   /* MomentumAgent.mid_list, avg_20_list[-1], avg_50_list[-1] */
+  int64_t order_size, last_mid, transacted_volume; int has_last_mid, aw_spread, aw_vol;   /* POVMarketMakerAgent */
 } zi_t;
+enum { AT_ZI = 0, AT_NOISE, AT_VALUE, AT_MOMENTUM, AT_POVMM };
 
 struct abo_sim {
   int variant; uint32_t seed; int trace; int n_agents;
@@ -350,6 +357,7 @@ struct abo_sim {
   int64_t or_t, or_v; int64_t ms_t; double ms_v; double *gexp; int64_t n_gexp, cap_gexp;
   /* agents */
   zi_t *zi; double sigma_n, agent_kappa, sigma_s, lambda_a;
+  double mm_pov; int64_t mm_min_size, mm_window, mm_ticks, mm_wake_ns, mom_wake_ns;   /* config/rmsc03.py:41-45,176-200 */
   /* traces */
   i64buf pops, ops, notes, snaps; uint64_t pop_hash, note_hash, snap_hash; uint64_t *ckpt; int64_t n_ckpt, cap_ckpt;
   int64_t c_limit, c_cancel, c_query, max_queue, max_bid_lv, max_ask_lv, max_resting;
@@ -386,7 +394,7 @@ static void k_send(abo_sim *s, int sender, int recipient, event_t *e, int64_t de
 /* ---------------- SparseMeanRevertingOracle ---------------- */
 static inline int64_t ns_from_float_string(double x) { return (int64_t)x; } /* pd.Timedelta("{}ns".format(float)) truncates */
 static double g_exponential(abo_sim *s, double scale) { /* np.random.exponential on the GLOBAL stream :69,168 */
-  double e = -log(1.0 - rng_double_raw(s->g));
+  double e = -log(1.0 - rng_double_raw(s->g)); rng_rec(s->g, 'e', dbits(e));
   if (s->n_gexp == s->cap_gexp) { s->cap_gexp = s->cap_gexp ? s->cap_gexp * 2 : 32; s->gexp = (double *)realloc(s->gexp, 8 * s->cap_gexp); }
   s->gexp[s->n_gexp++] = e;
   return e * scale;
@@ -465,6 +473,7 @@ static void exch_receive(abo_sim *s, const event_t *m) {
   }
   event_t e; memset(&e, 0, sizeof(e));
   switch (m->kind) {
+    case ABO_QUERY_TRANSACTED_VOLUME: s->book.now = s->now; e.kind = ABO_QUERY_TRANSACTED_VOLUME; e.tv = book_transacted_volume(&s->book, m->lookback); e.mkt_closed = t_closed; exch_send(s, m->sender, &e); break; /* :280-303 */
     case ABO_WHEN_MKT_OPEN: s->comp_delay[0] = 0; e.kind = ABO_WHEN_MKT_OPEN; e.data = s->mkt_open; exch_send(s, m->sender, &e); break;     /* :175-183 */
     case ABO_WHEN_MKT_CLOSE: s->comp_delay[0] = 0; e.kind = ABO_WHEN_MKT_CLOSE; e.data = s->mkt_close; exch_send(s, m->sender, &e); break;  /* :184-192 */
     case ABO_QUERY_SPREAD: {                                                                /* :215-245, depth 1 on this path */
@@ -561,6 +570,8 @@ static void zi_place_order(abo_sim *s, int id) {
   ta_place_limit(s, id, 100, buy, p);                                                       /* :308-309 */
 }
 static void orders_remove(zi_t *a, int i) { memmove(a->orders + i, a->orders + i + 1, sizeof(open_order_t) * (a->n_orders - i - 1)); a->n_orders--; }
+static void povmm_receive_tail(abo_sim *s, int id, const event_t *m); static void momentum_place_orders(abo_sim *s, int id);
+static void noise_place_order(abo_sim *s, int id); static void value_place_order(abo_sim *s, int id);
 /* TradingAgent.receiveMessage :181-268 + ZeroIntelligenceAgent.receiveMessage :311-334 */
 static void zi_receive(abo_sim *s, int id, const event_t *m) {
   zi_t *a = &s->zi[id]; a->current_time = s->now;
@@ -579,6 +590,7 @@ static void zi_receive(abo_sim *s, int id, const event_t *m) {
       for (int i = 0; i < a->n_orders; i++) if (a->orders[i].order_id == m->order.order_id) { orders_remove(a, i); break; }
       break;
     case ABO_MKT_CLOSED: a->mkt_closed = 1; break;                                          /* marketClosed :492-499 */
+    case ABO_QUERY_TRANSACTED_VOLUME: if (m->mkt_closed) a->mkt_closed = 1; a->transacted_volume = m->tv; break;   /* :248-251,556-558 */
     case ABO_QUERY_SPREAD:                                                                  /* :232-238, querySpread :514-537, queryLastTrade :502-511 */
       if (m->mkt_closed) a->mkt_closed = 1;
       a->last_trade = m->data; a->has_last_trade = 1;
@@ -588,14 +600,135 @@ static void zi_receive(abo_sim *s, int id, const event_t *m) {
     default: break;
   }
   if (a->has_open && a->has_close && !had) {                                                /* :258-268 */
-    int64_t off = abo_rng_randint(a->rs, 0, 100);                                           /* ZI.getWakeFrequency :349-350 */
+    int64_t off = a->type == AT_MOMENTUM ? s->mom_wake_ns : a->type == AT_POVMM ? s->mm_wake_ns
+                : abo_rng_randint(a->rs, 0, 100);                                           /* ZI/Noise/Value.getWakeFrequency: randint(0, 100) ns */
     k_set_wakeup(s, id, a->mkt_open + off);
   }
-  if (a->state == ST_AWAITING_SPREAD && m->kind == ABO_QUERY_SPREAD) {                      /* ZI :319-334 */
+  if (a->type == AT_POVMM) { povmm_receive_tail(s, id, m); return; }
+  if (a->type == AT_MOMENTUM) {                                                             /* MomentumAgent.receiveMessage :65-76 */
+    if (a->state == ST_AWAITING_SPREAD && m->kind == ABO_QUERY_SPREAD) { momentum_place_orders(s, id); k_set_wakeup(s, id, s->now + s->mom_wake_ns); a->state = ST_AWAITING_WAKEUP; }
+    return;
+  }
+  if (a->state == ST_AWAITING_SPREAD && m->kind == ABO_QUERY_SPREAD) {                      /* ZI :319-334, NoiseAgent :123-129, ValueAgent :245-251 */
     if (a->mkt_closed) return;
-    zi_place_order(s, id);
+    if (a->type == AT_NOISE) noise_place_order(s, id); else if (a->type == AT_VALUE) value_place_order(s, id); else zi_place_order(s, id);
     a->state = ST_AWAITING_WAKEUP;
   }
+}
+
+
+/* ====================================================================================================
+ * rmsc03 population: NoiseAgent, ValueAgent, MomentumAgent, POVMarketMakerAgent (config/rmsc03.py)
+ * ==================================================================================================== */
+static void ta_cancel_all(abo_sim *s, int id) {                       /* cancelOrders / cancelAllOrders: one CANCEL_ORDER per open order */
+  zi_t *a = &s->zi[id];
+  for (int i = 0; i < a->n_orders; i++) {
+    event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_CANCEL_ORDER;
+    e.order.agent_id = id; e.order.order_id = a->orders[i].order_id; e.order.quantity = a->orders[i].quantity; e.order.limit_price = a->orders[i].limit_price; e.order.is_buy = a->orders[i].is_buy;
+    ta_send(s, id, &e);
+  }
+}
+/* TradingAgent.wakeup :142-158 -> can_trade */
+static int ta_wakeup_common(abo_sim *s, int id) {
+  zi_t *a = &s->zi[id]; a->current_time = s->now; a->first_wake = 0;
+  if (!a->has_open) { event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_WHEN_MKT_OPEN; ta_send(s, id, &e); memset(&e, 0, sizeof(e)); e.kind = ABO_WHEN_MKT_CLOSE; ta_send(s, id, &e); }
+  return a->has_open && a->has_close && !a->mkt_closed;
+}
+/* NoiseAgent.wakeup (agent/NoiseAgent.py:82-112) */
+static void noise_wakeup(abo_sim *s, int id) {
+  zi_t *a = &s->zi[id]; ta_wakeup_common(s, id); a->state = ST_INACTIVE;
+  if (!a->has_open || !a->has_close) return;
+  a->trading = 1;
+  if (a->mkt_closed && a->has_daily_close) return;
+  if (a->wakeup_time > s->now) k_set_wakeup(s, id, a->wakeup_time);                       /* :98-99 */
+  ta_get_spread(s, id); a->state = ST_AWAITING_SPREAD;                                      /* :101-108 (both branches query the spread) */
+}
+static void noise_place_order(abo_sim *s, int id) {                                         /* :114-121 */
+  zi_t *a = &s->zi[id];
+  int buy = (int)abo_rng_randint(s->g, 0, 2);                                               /* np.random.randint(0, 1 + 1): GLOBAL stream */
+  if (buy && a->has_ask && a->ask != 0) ta_place_limit(s, id, a->size, 1, a->ask);
+  else if (!buy && a->has_bid && a->bid != 0) ta_place_limit(s, id, a->size, 0, a->bid);
+}
+/* ValueAgent.wakeup (agent/ValueAgent.py:100-138): same shape as the ZI wakeup */
+static void value_wakeup(abo_sim *s, int id) {
+  zi_t *a = &s->zi[id]; ta_wakeup_common(s, id); a->state = ST_INACTIVE;
+  if (!a->has_open || !a->has_close) return;
+  a->trading = 1;
+  if (a->mkt_closed && a->has_daily_close) return;
+  double delta_time = rng_exponential(a->rs, 1.0 / s->lambda_a);
+  k_set_wakeup(s, id, s->now + py_round(delta_time));
+  if (a->mkt_closed && !a->has_daily_close) { ta_get_spread(s, id); a->state = ST_AWAITING_SPREAD; return; }
+  ta_cancel_all(s, id);
+  ta_get_spread(s, id); a->state = ST_AWAITING_SPREAD;
+}
+/* ValueAgent.updateEstimates :140-205 + placeOrder :207-243 */
+static void value_place_order(abo_sim *s, int id) {
+  zi_t *a = &s->zi[id];
+  int64_t obs_t = oracle_observe(s, a->current_time, s->sigma_n, a->rs);
+  if (!a->has_prev) { a->prev_wake = a->mkt_open; a->has_prev = 1; }
+  double kappa = s->agent_kappa, r_bar = s->r_bar, sigma_n = s->sigma_n;
+  double delta = (double)(a->current_time - a->prev_wake);
+  double pw = pow(1 - kappa, delta);
+  double r_tprime = (1 - pw) * r_bar; r_tprime += pw * a->r_t;
+  double pw2 = pow(1 - kappa, 2 * delta);
+  double sigma_tprime = pw2 * a->sigma_t; sigma_tprime += ((1 - pw2) / (1 - pow(1 - kappa, 2.0))) * s->sigma_s;
+  a->r_t = (sigma_n / (sigma_n + sigma_tprime)) * r_tprime; a->r_t += (sigma_tprime / (sigma_n + sigma_tprime)) * (double)obs_t;
+  a->sigma_t = (sigma_n * a->sigma_t) / (sigma_n + a->sigma_t);
+  double d2 = (double)(a->mkt_close - a->current_time); if (!(d2 > 0)) d2 = 0;
+  double pw3 = pow(1 - kappa, d2);
+  double r_T = (1 - pw3) * r_bar; r_T += pw3 * a->r_t;
+  int64_t r_Ti = py_round(r_T); a->prev_wake = a->current_time;
+  int buy; int64_t p;
+  if (a->has_bid && a->bid != 0 && a->has_ask && a->ask != 0) {                              /* if bid and ask */
+    int64_t mid = (int64_t)((double)(a->ask + a->bid) / 2); int64_t spread = llabs(a->ask - a->bid); int64_t adjust;
+    if (abo_rng_double(s->g) < 0.1) adjust = 0;                                              /* np.random.rand() < percent_aggr */
+    else adjust = abo_rng_randint(s->g, 0, 2 * spread);                                      /* np.random.randint(0, depth_spread * spread) */
+    if (r_Ti < mid) { buy = 0; p = a->bid + adjust; } else { buy = 1; p = a->ask - adjust; }
+  } else { buy = (int)abo_rng_randint(s->g, 0, 2); p = r_Ti; }
+  ta_place_limit(s, id, a->size, buy, p);
+}
+/* MomentumAgent.wakeup (agent/examples/MomentumAgent.py:53-63) */
+static void momentum_wakeup(abo_sim *s, int id) {
+  zi_t *a = &s->zi[id];
+  if (ta_wakeup_common(s, id)) { ta_get_spread(s, id); a->state = ST_AWAITING_SPREAD; }
+}
+static double np_round2(double x) { return nearbyint(x * 100.0) / 100.0; }                   /* numpy float64.round(2) */
+static void momentum_place_orders(abo_sim *s, int id) {                                     /* placeOrders :78-93, ma :95-99 */
+  zi_t *a = &s->zi[id];
+  if (!(a->has_bid && a->bid != 0 && a->has_ask && a->ask != 0)) return;
+  if (a->n_mids == a->cap_mids) { a->cap_mids = a->cap_mids ? 2 * a->cap_mids : 64; a->mids = (double *)realloc(a->mids, 8 * a->cap_mids); }
+  a->mids[a->n_mids++] = (double)(a->bid + a->ask) / 2;
+  int L = a->n_mids;
+  for (int w = 0; w < 2; w++) { int n = w ? 50 : 20;
+    if (L > n) { double c1 = 0, c0 = 0; for (int i = 0; i < L; i++) { c1 += a->mids[i]; if (i == L - 1 - n) c0 = c1; }      /* np.cumsum; ret[n:] - ret[:-n] */
+      double v = np_round2((c1 - c0) / n); if (w) { a->avg50 = v; a->has50 = 1; } else { a->avg20 = v; a->has20 = 1; } } }
+  if (a->has20 && a->has50) { if (a->avg20 >= a->avg50) ta_place_limit(s, id, a->size, 1, a->ask); else ta_place_limit(s, id, a->size, 0, a->bid); }
+}
+/* POVMarketMakerAgent.wakeup (agent/market_makers/POVMarketMakerAgent.py:83-100), with the getTransactedVolume alias */
+static void povmm_wakeup(abo_sim *s, int id) {
+  if (!ta_wakeup_common(s, id)) return;
+  ta_get_spread(s, id);                                                                      /* depth = subscribe_num_levels = 1 */
+  event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_QUERY_TRANSACTED_VOLUME; e.lookback = s->mm_wake_ns; ta_send(s, id, &e);
+}
+static void povmm_receive_tail(abo_sim *s, int id, const event_t *m) {                      /* receiveMessage :102-150 */
+  zi_t *a = &s->zi[id];
+  if (m->kind == ABO_QUERY_TRANSACTED_VOLUME && a->aw_vol) {                                 /* updateOrderSize :152-156 */
+    int64_t qty = py_round(s->mm_pov * (double)a->transacted_volume); a->order_size = qty >= s->mm_min_size ? qty : s->mm_min_size; a->aw_vol = 0; }
+  if (m->kind == ABO_QUERY_SPREAD && a->aw_spread) {
+    if (a->has_bid && a->bid != 0 && a->has_ask && a->ask != 0) { a->last_mid = (int64_t)((double)(a->ask + a->bid) / 2); a->has_last_mid = 1; a->aw_spread = 0; } }
+  if (!a->aw_spread && !a->aw_vol) {
+    ta_cancel_all(s, id);
+    int64_t mid = a->last_mid, highest_bid = mid - 1, lowest_ask = mid + s->mm_window;      /* computeOrdersToPlace :158-177, anchor bottom */
+    int64_t lowest_bid = highest_bid - s->mm_ticks, highest_ask = lowest_ask + s->mm_ticks;
+    for (int64_t p = lowest_bid; p <= highest_bid; p++) ta_place_limit(s, id, a->order_size, 1, p);
+    for (int64_t p = lowest_ask; p <= highest_ask; p++) ta_place_limit(s, id, a->order_size, 0, p);
+    a->aw_spread = a->aw_vol = 1;
+    k_set_wakeup(s, id, s->now + s->mm_wake_ns);
+  }
+}
+static void agent_wakeup(abo_sim *s, int id) {
+  switch (s->zi[id].type) { case AT_NOISE: noise_wakeup(s, id); break; case AT_VALUE: value_wakeup(s, id); break; case AT_MOMENTUM: momentum_wakeup(s, id); break;
+    case AT_POVMM: povmm_wakeup(s, id); break; default: zi_wakeup(s, id); }
 }
 
 /* ---------------- config: config/sparse_zi_100.py / config/sparse_zi_1000.py ---------------- */
@@ -659,9 +792,51 @@ abo_sim *abo_sim_new_sparse_zi(int variant, uint32_t seed, int trace) {
   for (int i = 0; i < n; i++) { s->agent_time[i] = s->start_time; s->comp_delay[i] = NS_PER_S; }      /* defaultComputationDelay 1e9 */
   return s;
 }
+
+/* config/rmsc03.py:49-232 (ticker/date only name things): 1 exchange, 50 noise, 10 value, 1 POV market maker, 2 momentum */
+static double u_quadratic_inverse_cdf(double y) {                      /* util/util.py:35-58, a = 0, b = 1 */
+  double alpha = 12.0 / pow(1.0 - 0.0, 3.0), beta = (1.0 + 0.0) / 2;
+  double n = (3 / alpha) * y - pow(beta - 0.0, 3.0);
+  double c = n < 0 ? -pow(-n, 1.0 / 3.0) : pow(n, 1.0 / 3.0);
+  return c + beta;
+}
+abo_sim *abo_sim_new_rmsc03(uint32_t seed, int trace) {
+  abo_sim *s = (abo_sim *)calloc(1, sizeof(abo_sim));
+  s->variant = 3; s->seed = seed; s->trace = trace; s->pop_hash = s->note_hash = s->snap_hash = FNV_OFF;
+  int n = 1 + 50 + 10 + 1 + 2; s->n_agents = n;
+  s->g = abo_rng_new(seed);                                              /* np.random.seed(seed) :58 */
+  s->mkt_open = (9 * 3600 + 30 * 60) * NS_PER_S; s->mkt_close = (9 * 3600 + 45 * 60) * NS_PER_S;   /* :69-70 */
+  s->start_time = s->mkt_open; s->stop_time = s->mkt_close + 60 * NS_PER_S;                           /* :205-207 */
+  s->r_bar = 1e5; s->kappa = 1.67e-12; s->fund_vol = 1e-4; s->megashock_lambda = 2.77778e-13; s->megashock_mean = 1e3; s->megashock_var = 5e4;
+  s->sigma_n = 1e5 / 10; s->agent_kappa = 1.67e-15; s->sigma_s = 100000; s->lambda_a = 7e-11;       /* :77-80; sigma_s is ValueAgent's default */
+  s->mm_pov = 0.05; s->mm_min_size = 20; s->mm_window = 5; s->mm_ticks = 20; s->mm_wake_ns = NS_PER_S; s->mom_wake_ns = 20 * NS_PER_S;
+  s->sym_rs = new_stream(s);                                             /* :88 */
+  s->or_t = s->mkt_open; s->or_v = (int64_t)s->r_bar; oracle_new_megashock(s, s->mkt_open);          /* :91 oracle __init__ */
+  s->exch_rs = new_stream(s); s->pipeline_delay = 0; s->exch_comp_delay = 0;                          /* :108 */
+  book_init(&s->book, 10, s, exch_book_send);
+  s->zi = (zi_t *)calloc(n, sizeof(zi_t));
+  int64_t n_open = 9 * 3600 * NS_PER_S, n_close = 16 * 3600 * NS_PER_S;                               /* noise_mkt_open/close :115-116 */
+  for (int id = 1; id < n; id++) {
+    zi_t *a = &s->zi[id]; a->starting_cash = a->cash = 10000000; a->first_wake = 1; a->state = ST_AWAITING_WAKEUP; a->q_max = 10;
+    if (id <= 50) {                                                      /* NoiseAgent :117-131: wakeup_time (global rand), seed, then __init__ size (global randint) */
+      a->type = AT_NOISE; double mult = u_quadratic_inverse_cdf(rng_double_raw(s->g));
+      /* float * Timedelta truncates to the Timedelta's unit: microseconds for string-parsed times under pandas >= 3 (the
+         recording environment); the reference's pinned pandas 0.24 would truncate to nanoseconds (differs by < 1 us) */
+      a->wakeup_time = n_open + (int64_t)(mult * (double)((n_close - n_open) / 1000)) * 1000;
+      a->rs = new_stream(s); a->size = abo_rng_randint(s->g, 20, 50);
+    } else if (id <= 60) { a->type = AT_VALUE; a->rs = new_stream(s); a->size = abo_rng_randint(s->g, 20, 50); a->r_t = s->r_bar; a->sigma_t = 0; }   /* :137-155 */
+    else if (id == 61) { a->type = AT_POVMM; a->rs = new_stream(s); a->order_size = s->mm_min_size; a->aw_spread = a->aw_vol = 1; }                  /* :160-178 */
+    else { a->type = AT_MOMENTUM; a->rs = new_stream(s); a->size = abo_rng_randint(a->rs, 1, 10); }                                                   /* :183-200, MomentumAgent.py:42 */
+  }
+  s->kernel_rs = new_stream(s);                                          /* :201-204 */
+  s->latency = (double *)calloc((size_t)n * n, sizeof(double)); s->n_noise = 1; s->use_latency_model = 0;   /* np.zeros, noise [0.0] :209-210 */
+  s->agent_time = (int64_t *)calloc(n, sizeof(int64_t)); s->comp_delay = (int64_t *)calloc(n, sizeof(int64_t));
+  for (int i = 0; i < n; i++) { s->agent_time[i] = s->start_time; s->comp_delay[i] = 0; }           /* defaultComputationDelay 0 :208 */
+  return s;
+}
 void abo_sim_free(abo_sim *s) {
   if (!s) return;
-  for (int i = 1; i < s->n_agents; i++) { abo_rng_free(s->zi[i].rs); free(s->zi[i].orders); }
+  for (int i = 1; i < s->n_agents; i++) { abo_rng_free(s->zi[i].rs); free(s->zi[i].orders); free(s->zi[i].mids); }
   free(s->zi); abo_rng_free(s->g); abo_rng_free(s->kernel_rs); abo_rng_free(s->lat_rs); abo_rng_free(s->sym_rs); abo_rng_free(s->exch_rs);
   book_destroy(&s->book); free(s->latency); free(s->agent_time); free(s->comp_delay); free(s->q.e); free(s->gexp);
   free(s->pops.v); free(s->ops.v); free(s->notes.v); free(s->snaps.v); free(s->ckpt); free(s);
@@ -670,6 +845,7 @@ void abo_sim_free(abo_sim *s) {
 /* Kernel.runner :154-175 */
 void abo_sim_start(abo_sim *s) {
   if (s->started) return; s->started = 1;
+  s->g->record = (s->trace & ABO_TRACE_TAPES) != 0;                      /* runtime draws on the GLOBAL np.random stream */
   s->book.last_trade = (int64_t)s->r_bar; s->book.has_last_trade = 1;   /* ExchangeAgent.kernelInitializing :91-102, getDailyOpenPrice */
   s->now = s->start_time;
   for (int i = 0; i < s->n_agents; i++) k_set_wakeup(s, i, s->start_time);   /* Agent.kernelStarting :78 */
@@ -692,7 +868,7 @@ int64_t abo_sim_run_until(abo_sim *s, int64_t until, int *done) {
     int a = ev.recipient;
     if (s->agent_time[a] > s->now) { ev.t = s->agent_time[a]; k_put(s, &ev); continue; }     /* :224-230 / :258-264 requeue, same uniq */
     s->agent_time[a] = s->now;                                                               /* :234 / :268 */
-    if (ev.type == ABO_T_WAKEUP) { if (a != 0) zi_wakeup(s, a); /* exchange: Agent.wakeup no-op */ }
+    if (ev.type == ABO_T_WAKEUP) { if (a != 0) agent_wakeup(s, a); /* exchange: Agent.wakeup no-op */ }
     else { if (a == 0) exch_receive(s, &ev); else zi_receive(s, a, &ev); }
     s->agent_time[a] += s->comp_delay[a] + s->addl_delay;                                    /* :240-242 / :274-276 */
   }
@@ -703,6 +879,7 @@ int64_t abo_sim_run_until(abo_sim *s, int64_t until, int *done) {
 void abo_sim_stop(abo_sim *s) {
   for (int id = 1; id < s->n_agents; id++) {
     zi_t *a = &s->zi[id];
+    if (a->type != AT_ZI) { if (a->type == AT_VALUE) oracle_observe(s, a->current_time, 0, a->rs); a->surplus = 0; continue; }   /* ValueAgent.kernelStopping :57-61 advances the fundamental */
     double hr = nearbyint((double)a->shares / 100.0) * 100.0; /* round(int, -2): half-even on hundreds */
     int64_t H = (int64_t)(hr / 100);
     int64_t rT = oracle_observe(s, a->current_time, 0, a->rs);
@@ -733,12 +910,15 @@ int64_t abo_sim_trace(abo_sim *s, int which, const int64_t **rows) {
   *rows = b->v; return b->n / w;
 }
 static abo_rng *stream_at(abo_sim *s, int i) {
+  if (s->variant == 3) { if (i == 0) return s->sym_rs; if (i == 1) return s->exch_rs; if (i == s->n_agents + 1) return s->kernel_rs; return s->zi[i - 1].rs; }
   int base = s->variant == 100 ? 4 : 3;
   if (i == 0) return s->sym_rs; if (i == 1) return s->kernel_rs;
   if (s->variant == 100) { if (i == 2) return s->lat_rs; if (i == 3) return s->exch_rs; } else if (i == 2) return s->exch_rs;
   return s->zi[i - base + 1].rs;
 }
 int abo_sim_n_streams(abo_sim *s) { return s->n_agents - 1 + (s->variant == 100 ? 4 : 3); }
+int64_t abo_sim_global_tape(abo_sim *s, const uint8_t **k, const uint64_t **b) { *k = s->g->tk; *b = s->g->tv; return s->g->tn; }
+void abo_sim_agent_info(abo_sim *s, int id, int64_t *out4) { out4[0] = s->zi[id].type; out4[1] = s->zi[id].size; out4[2] = s->zi[id].wakeup_time; out4[3] = s->zi[id].order_size; }
 int64_t abo_sim_tape(abo_sim *s, int i, const uint8_t **k, const uint64_t **b) { abo_rng *r = stream_at(s, i); *k = r->tk; *b = r->tv; return r->tn; }
 uint32_t abo_sim_stream_seed(abo_sim *s, int i) { return stream_at(s, i)->seed; }
 int64_t abo_sim_global_exp_tape(abo_sim *s, const double **v) { *v = s->gexp; return s->n_gexp; }

@@ -66,7 +66,12 @@ int abo_book_level_orders(abo_book *, int is_bid, int level, int64_t *out, int m
 typedef struct abo_sim abo_sim;
 /* variant: 100 or 1000.  seed: the -s argument.  trace_flags: OR of abo_trace_flags. */
 abo_sim *abo_sim_new_sparse_zi(int variant, uint32_t seed, int trace_flags);
+/* config/rmsc03.py: 1 exchange + 50 NoiseAgents + 10 ValueAgents + 1 POVMarketMakerAgent + 2 MomentumAgents, 09:30-09:45 */
+abo_sim *abo_sim_new_rmsc03(uint32_t seed, int trace_flags);
 void abo_sim_free(abo_sim *);
+/* runtime draws on the GLOBAL np.random stream (kinds 'e','u','i') */
+int64_t abo_sim_global_tape(abo_sim *, const uint8_t **kinds, const uint64_t **bits);
+void abo_sim_agent_info(abo_sim *, int id, int64_t *out4); /* type, size, noise wakeup_time, MM order_size */
 /* Kernel.runner (Kernel.py:50-345): start, event loop, kernelStopping.  Returns ttl_messages. */
 int64_t abo_sim_run(abo_sim *);
 /* Event loop only, until the next pop would be later than `until_ns` or the loop ends (used to compare

@@ -66,6 +66,9 @@ def lib():
     sig("abo_book_clear_notes", None, vp)
     sig("abo_book_level_orders", i32, vp, i32, i32, P(i64), i32)
     sig("abo_sim_new_sparse_zi", vp, i32, u32, i32)
+    sig("abo_sim_new_rmsc03", vp, u32, i32)
+    sig("abo_sim_global_tape", i64, vp, P(P(C.c_uint8)), P(P(u64)))
+    sig("abo_sim_agent_info", None, vp, i32, P(i64))
     sig("abo_sim_free", None, vp)
     sig("abo_sim_run", i64, vp)
     sig("abo_sim_run_until", i64, vp, i64, P(i32))
@@ -196,7 +199,8 @@ class OracleSim:
     """config/sparse_zi_100.py / sparse_zi_1000.py + Kernel.runner restated (oracle/abides_oracle.c)."""
 
     def __init__(self, variant, seed, trace=0):
-        self._h = lib().abo_sim_new_sparse_zi(variant, seed, trace)
+        """variant 100 / 1000: config/sparse_zi_*.py; variant 3: config/rmsc03.py."""
+        self._h = lib().abo_sim_new_rmsc03(seed, trace) if variant == 3 else lib().abo_sim_new_sparse_zi(variant, seed, trace)
         if not self._h:
             raise ValueError("unknown sparse_zi variant %r" % (variant,))
         self.variant, self.seed = variant, seed
@@ -269,6 +273,19 @@ class OracleSim:
 
     def stream_seed(self, stream):
         return lib().abo_sim_stream_seed(self._h, stream)
+
+    def global_tape(self):
+        k = C.POINTER(C.c_uint8)()
+        b = C.POINTER(C.c_uint64)()
+        n = lib().abo_sim_global_tape(self._h, C.byref(k), C.byref(b))
+        if n == 0:
+            return np.zeros(0, np.uint8), np.zeros(0, np.uint64)
+        return (np.ctypeslib.as_array(k, shape=(n,)).copy(), np.ctypeslib.as_array(b, shape=(n,)).copy())
+
+    def agent_info(self, agent):
+        out = np.zeros(4, np.int64)
+        lib().abo_sim_agent_info(self._h, agent, out.ctypes.data_as(C.POINTER(C.c_int64)))
+        return out
 
     def global_exp_tape(self):
         p = C.POINTER(C.c_double)()

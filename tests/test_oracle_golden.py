@@ -61,3 +61,24 @@ def test_z1000_matches_reference_recorded_stdout():
     s.run()
     for aid, sh, cash, mtm, _ in s.holdings():
         assert ref[int(aid)] == (sh, cash, mtm), aid
+
+
+@pytest.mark.parametrize("seed", [123456789, 1001])
+def test_rmsc03_digest_bit_exact(golden_dir, seed):
+    """config/rmsc03.py (50 Noise + 10 Value + POV market maker + 2 Momentum, with the one-line getTransactedVolume alias the
+    shipped config needs): event order, exchange messages incl. transacted-volume driven ladder sizes, book snapshots,
+    every RNG draw incl. the GLOBAL np.random stream, final holdings."""
+    path = os.path.join(golden_dir, "rmsc03_s%d.npz" % seed)
+    if not os.path.exists(path):
+        pytest.skip("fixture not recorded")
+    g = np.load(path)
+    s = OracleSim(3, seed, 16)
+    assert s.run() == int(g["n_pops"])
+    assert np.array_equal(s.hash_ckpt(), g["pop_hash_ckpt"])
+    assert s.note_hash() == int(g["note_hash"]) and s.snap_hash() == int(g["snap_hash"])
+    assert np.array_equal(s.holdings()[:, :4], g["holdings"][:, :4])
+    assert [s.stream_seed(i) for i in range(s.n_streams)] == list(g["stream_seeds"])
+    assert [len(s.tape(i)[0]) for i in range(s.n_streams)] == list(g["stream_draws"])
+    gk, gb = s.global_tape()
+    assert np.array_equal(gk, g["global_kind"].view(np.uint8)) and np.array_equal(gb, g["global_bits"])
+    assert s.counter("max_bid_levels") == g["max_levels"][0] and s.counter("max_resting") == int(g["max_resting"])

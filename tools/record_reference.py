@@ -57,6 +57,8 @@ class Recorder:
         self.snaps = []      # after every book op: (n_bid_lv, n_ask_lv, n_resting, b0,bq0,b1,bq1,b2,bq2, a0,aq0,a1,aq1,a2,aq2, last_trade)
         self.streams = []    # RecRS objects in creation order
         self.global_tape = []
+        self.runtime = False       # set when Kernel.runner starts: global-stream draws after that point are runtime draws
+        self.gkind, self.gbits = [], []   # runtime draws on the GLOBAL np.random stream (kinds 'e','u','i'), in order
 
     def ns(self, ts):
         return int((ts - self.midnight).value)
@@ -151,12 +153,40 @@ def install_hooks():
     # Global-stream draws that happen at run time (megashock gaps, SparseMeanRevertingOracle.py:69,168).
     g_exponential = np.random.exponential
 
+    g_state = np.random.mtrand._rand
+
     def rec_exponential(scale=1.0, size=None):
-        v = g_exponential(scale, size)
-        REC.global_tape.append(float(v) / scale)
-        return v
+        e = g_state.standard_exponential()
+        REC.global_tape.append(float(e))
+        if REC.runtime:
+            REC.gkind.append(b"e"); REC.gbits.append(np.float64(e).view(np.uint64))
+        return e * scale
 
     np.random.exponential = rec_exponential
+    g_rand, g_randint = np.random.rand, np.random.randint
+
+    def rec_rand(*shape):
+        v = g_rand(*shape)
+        if REC.runtime and not shape:
+            REC.gkind.append(b"u"); REC.gbits.append(np.float64(v).view(np.uint64))
+        return v
+
+    def rec_randint(low, high=None, size=None, dtype=int):
+        v = g_randint(low, high, size=size, dtype=dtype)
+        if REC.runtime and size is None:
+            REC.gkind.append(b"i"); REC.gbits.append(np.uint64(int(v) - (0 if high is None else int(low))))
+        return v
+
+    np.random.rand = rec_rand
+    np.random.randint = rec_randint
+    import Kernel as K
+    r0 = K.Kernel.runner
+
+    def runner(self, *a, **k):
+        REC.runtime = True
+        return r0(self, *a, **k)
+
+    K.Kernel.runner = runner
 
     import util.OrderBook as OB
     import agent.ExchangeAgent as EA
@@ -243,6 +273,12 @@ def main():
     date = rest[rest.index("--date") + 1] if "--date" in rest else "2019-06-28"
     extra = rest[rest.index("--extra") + 1:] if "--extra" in rest else []
     install_hooks()
+    if config == "rmsc03":
+        # the shipped config calls a method that does not exist: one-line alias so that it runs
+        import agent.TradingAgent as TA
+        TA.TradingAgent.getTransactedVolume = TA.TradingAgent.get_transacted_volume
+        import agent.ExchangeAgent as EA
+        EA.ExchangeAgent.logOrderBookSnapshots = lambda self, symbol: None      # archival: pd.SparseDataFrame, out of scope
     if config == "marketreplay":
         # order-book archival (agent/ExchangeAgent.py:389-469) uses pd.SparseDataFrame, removed from pandas; it runs after the
         # simulation ended and is out of scope, so the recorder skips it.
@@ -293,6 +329,7 @@ def main():
         stream_seeds=np.array([-1 if s.seed_value is None else s.seed_value for s in REC.streams], dtype=np.int64),
         stream_draws=np.array([len(s.tape_val) for s in REC.streams], dtype=np.int64),
         global_exp_tape=np.array(REC.global_tape, dtype=np.float64),
+        global_kind=np.frombuffer(b"".join(REC.gkind), dtype="S1"), global_bits=np.array(REC.gbits, dtype=np.uint64),
         max_levels=np.array([snaps[:, 0].max() if len(snaps) else 0, snaps[:, 1].max() if len(snaps) else 0]),
         max_resting=np.array(snaps[:, 2].max() if len(snaps) else 0),
     )
@@ -301,7 +338,7 @@ def main():
         od = replay[0].historical_orders.orders_dict
         data["stream"] = np.array([(REC.ns(ts), int(r["ORDER_ID"]), int(r["PRICE"]), int(r["SIZE"]), 1 if r["BUY_SELL_FLAG"] == "BUY" else 0)
                                    for ts in od for r in od[ts]], dtype=np.int64)
-        data["pops_head"], data["notes_head"], data["snaps_head"] = pops[:20000], notes[:20000], snaps[:10000]
+    data["pops_head"], data["notes_head"], data["snaps_head"] = pops[:20000], notes[:20000], snaps[:10000]
     if full:
         kinds = np.frombuffer(b"".join(b"".join(s.tape_kind) for s in REC.streams), dtype="S1")
         vals = []
