@@ -103,6 +103,16 @@ typedef struct abx_sim_config {
   int32_t rng_mode;                /* abx_rng_mode */
   int32_t trace_cap;               /* trace records per environment (0 = tracing off) */
   int32_t hash_pops;               /* 1: maintain the FNV-1a hash of the pop sequence (parity runs) */
+  /* population layout.  0: ZeroIntelligence groups (above).  1: config/rmsc03.py -- ids 1..n_noise_agents NoiseAgents, then n_value_agents
+   * ValueAgents (they use sigma_n / agent_kappa / sigma_s / lambda_a above), n_mm_agents POVMarketMakerAgents (0 or 1), n_momentum_agents
+   * MomentumAgents; zero latency (latency_model ABX_LAT_ZERO). */
+  int32_t population, n_noise_agents, n_value_agents, n_mm_agents, n_momentum_agents;
+  int32_t size_lo, size_hi;        /* Noise/Value order size = np.random.randint(lo, hi) (agent/NoiseAgent.py:34, ValueAgent.py:55) */
+  int32_t value_depth_spread;      /* ValueAgent.depth_spread (2) */
+  double value_percent_aggr;       /* ValueAgent.percent_aggr (0.1) */
+  int64_t noise_wake_lo_ns, noise_wake_hi_ns;  /* util.get_wake_time(noise_mkt_open, noise_mkt_close) window (config/rmsc03.py:115-116) */
+  int32_t mom_min_size, mom_max_size; int64_t mom_wake_ns;            /* MomentumAgent min_size, max_size, wake_up_freq */
+  double mm_pov; int32_t mm_min_order_size, mm_window_size, mm_num_ticks, _pad1; int64_t mm_wake_ns;   /* POVMarketMakerAgent */
 } abx_sim_config;
 
 /* Per-environment counters; replaces the "Event Queue elapsed ..., messages: N" line (Kernel.py:321-327). */
@@ -141,6 +151,8 @@ int32_t abx_device_count(void);
 /* Fill `cfg` with the population/parameters of config/sparse_zi_100.py (variant 100) or
  * config/sparse_zi_1000.py (variant 1000), capacities sized from the measured maxima. */
 int32_t abx_config_sparse_zi(int32_t variant, abx_sim_config *cfg);
+/* config/rmsc03.py:49-232: 1 exchange + 50 Noise + 10 Value + 1 POV market maker + 2 Momentum agents, 09:30 -> 09:45 (+1 min). */
+int32_t abx_config_rmsc03(abx_sim_config *cfg);
 
 /* Replaces: Kernel(...) construction + agent list construction (config/sparse_zi_1000.py:146-251).
  * Allocates all per-environment state for n_envs independent simulations on CUDA device `device`. */
@@ -159,6 +171,8 @@ int32_t abx_sim_reset_philox(abx_sim *h, const uint64_t *seeds, void *stream);
  *   tape_offsets [n_envs*(n_agents+3)+1]  per env, streams in order: 0 symbol, 1 kernel, 2 latency model,
  *                                 3 global (megashock gaps, kind 'e'), 3+a agent a (a = 1..n_agents-1)
  *   lat_to_exchange / lat_from_exchange [n_envs*n_agents]  fp64 ns: latency[a][0] / latency[0][a]
+ *       (population 1 has zero latency: the two arrays instead carry what the config script drew from the global stream
+ *        before the kernel started -- lat_to = NoiseAgent/ValueAgent.size, lat_from = NoiseAgent.wakeup_time in ns)
  * Replays what Kernel/agents/oracle drew in a recorded reference run (rng_mode must be ABX_RNG_TAPE). */
 int32_t abx_sim_reset_tape(abx_sim *h, const uint64_t *tape_bits, const uint8_t *tape_kinds,
                            const int64_t *tape_offsets, const double *lat_to_exchange,

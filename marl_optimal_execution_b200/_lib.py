@@ -49,6 +49,13 @@ class SimConfig(C.Structure):
         ("jitter", C.c_double), ("jitter_clip", C.c_double), ("jitter_unit", C.c_double),
         ("queue_cap", C.c_int32), ("level_cap", C.c_int32), ("order_cap", C.c_int32), ("rng_mode", C.c_int32),
         ("trace_cap", C.c_int32), ("hash_pops", C.c_int32),
+        ("population", C.c_int32), ("n_noise_agents", C.c_int32), ("n_value_agents", C.c_int32), ("n_mm_agents", C.c_int32),
+        ("n_momentum_agents", C.c_int32),
+        ("size_lo", C.c_int32), ("size_hi", C.c_int32), ("value_depth_spread", C.c_int32), ("value_percent_aggr", C.c_double),
+        ("noise_wake_lo_ns", C.c_int64), ("noise_wake_hi_ns", C.c_int64),
+        ("mom_min_size", C.c_int32), ("mom_max_size", C.c_int32), ("mom_wake_ns", C.c_int64),
+        ("mm_pov", C.c_double), ("mm_min_order_size", C.c_int32), ("mm_window_size", C.c_int32), ("mm_num_ticks", C.c_int32),
+        ("_pad1", C.c_int32), ("mm_wake_ns", C.c_int64),
     ]
 
 
@@ -108,6 +115,7 @@ def _bind(L):
     sig("abx_last_cuda_error", C.c_char_p)
     sig("abx_device_count", i32)
     sig("abx_config_sparse_zi", i32, i32, P(SimConfig))
+    sig("abx_config_rmsc03", i32, P(SimConfig))
     sig("abx_sim_create", i32, P(SimConfig), i32, i32, P(vp))
     sig("abx_sim_destroy", i32, vp)
     sig("abx_sim_device_bytes", i64, vp)

@@ -59,6 +59,8 @@ enum : uint32_t {
   AF_HAS_BID = 64u, AF_HAS_ASK = 128u, AF_STATE_SHIFT = 8, AF_STATE_MASK = 3u << 8, AF_GROUP_SHIFT = 12, AF_GROUP_MASK = 7u << 12
 };
 enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE = 1, ST_AWAITING_SPREAD = 2 }; // ZeroIntelligenceAgent.state
+enum : uint32_t { AF_TYPE_SHIFT = 16, AF_TYPE_MASK = 7u << 16 };
+enum { AT_ZI = 0, AT_NOISE = 1, AT_VALUE = 2, AT_MOMENTUM = 3, AT_POVMM = 4 };   // agent class (config/rmsc03.py population)
 constexpr int AGENT_ORDER_CAP = 4;      // open orders tracked per trader (ZI holds <= 2)
 
 struct alignas(16) ZiAgent {            // 192 B per trader: TradingAgent + ZeroIntelligenceAgent state
@@ -74,6 +76,14 @@ struct alignas(16) ZiAgent {            // 192 B per trader: TradingAgent + Zero
   int64_t surplus;                      // FINAL_VALUATION (kernelStopping)
 };
 static_assert(sizeof(ZiAgent) == 192, "ZiAgent layout");
+
+// rmsc03 agents overlay these 40 bytes on ZiAgent.theta (only ZI agents have private values)
+struct AgentAux { int32_t size, order_size, last_mid, tv; uint32_t mmflags; int32_t n_mids; double avg20, avg50; };
+static_assert(sizeof(AgentAux) == 40, "AgentAux overlays ZiAgent.theta");
+enum : uint32_t { MMF_AW_SPREAD = 1u, MMF_AW_VOL = 2u, MMF_HAS_MID = 4u, MOF_HAS20 = 8u, MOF_HAS50 = 16u };
+constexpr int MM_ORDER_CAP = 128;       // POV market maker: 2 * (num_ticks + 1) = 42 orders placed per wake, cancelled at the next
+constexpr int TV_RING = 512;            // recent (time, qty) transaction tuples kept for get_transacted_volume
+constexpr int MOM_MIDS = 64;            // MomentumAgent: last 50 mid prices are all ma(20)/ma(50) need
 
 struct Event {                          // one PriorityQueue entry, unpacked
   int64_t t; int32_t recipient, type; uint32_t uniq; int32_t kind, sender;
@@ -263,7 +273,39 @@ typedef RngT<-1> Rng;
 // reset: agent construction (config/sparse_zi_1000.py:211-251, ZeroIntelligenceAgent.__init__ :65-70) -- one
 // thread per (environment, trader) on the GPU.  In tape mode lat_to / lat_from were preloaded by the host.
 // ---------------------------------------------------------------------------------------------------
+ABX_HD int agent_type_of(const abx_sim_config &c, int id) {
+  if (c.population == 0) return AT_ZI;
+  if (id <= c.n_noise_agents) return AT_NOISE;
+  if (id <= c.n_noise_agents + c.n_value_agents) return AT_VALUE;
+  if (id <= c.n_noise_agents + c.n_value_agents + c.n_mm_agents) return AT_POVMM;
+  return AT_MOMENTUM;
+}
+// util.get_wake_time (util/util.py:35-58): U-quadratic inverse CDF on [0, 1]
+ABX_HD double u_quadratic_inverse_cdf(double y) {
+  double n = dsub(dmul(3.0 / 12.0, y), 0.125);
+  double c = n < 0 ? -pow(-n, 1.0 / 3.0) : pow(n, 1.0 / 3.0);
+  return dadd(c, 0.5);
+}
+ABX_HD void init_agent_record_r3(const SimParams &P, int env, int id, uint64_t seed, ZiAgent *z, uint32_t *err) {
+  RngT<-1> rng; rng.P = &P; rng.env = env; rng.seed = seed; rng.err = 0;
+  int type = agent_type_of(P.c, id); uint32_t ctr = 0, c2 = 0; int cs = P.n_streams + id;
+  int32_t size = (int32_t)z->lat_to; int64_t wake = (int64_t)z->lat_from;        // tape mode: preloaded by the host (drawn by the config script)
+  if (P.c.rng_mode == ABX_RNG_PHILOX) {
+    if (type == AT_NOISE) { double m = u_quadratic_inverse_cdf(rng.u01(cs, c2)); wake = P.c.noise_wake_lo_ns + (int64_t)dmul(m, (double)(P.c.noise_wake_hi_ns - P.c.noise_wake_lo_ns)); }
+    if (type == AT_NOISE || type == AT_VALUE) size = P.c.size_lo + (int32_t)rng.randint(cs, c2, (uint32_t)(P.c.size_hi - P.c.size_lo - 1));
+  }
+  if (type == AT_MOMENTUM) size = P.c.mom_min_size + (int32_t)rng.randint(S_AGENT0 + id, ctr, (uint32_t)(P.c.mom_max_size - P.c.mom_min_size - 1));   // MomentumAgent.py:42 (own stream)
+  z->agent_time = P.c.start_ns; z->prev_wake = type == AT_NOISE ? wake : 0; z->r_t = P.c.r_bar; z->sigma_t = 0.0; z->cash = P.c.starting_cash; z->shares = 0; z->last_trade = 0;
+  z->daily_close = 0; z->bid = 0; z->bid_q = 0; z->ask = 0; z->ask_q = 0;
+  z->flags = ((uint32_t)type << AF_TYPE_SHIFT) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT); z->rng_ctr = ctr; z->n_orders = 0;
+  for (int i = 0; i < AGENT_ORDER_CAP; i++) { z->oid[i] = 0; z->oprice[i] = 0; z->oqty[i] = 0; }
+  AgentAux ax; ax.size = size; ax.order_size = P.c.mm_min_order_size; ax.last_mid = 0; ax.tv = 0; ax.mmflags = type == AT_POVMM ? (MMF_AW_SPREAD | MMF_AW_VOL) : 0u; ax.n_mids = 0; ax.avg20 = 0.0; ax.avg50 = 0.0;
+  *reinterpret_cast<AgentAux *>(z->theta) = ax;
+  z->lat_to = 0.0; z->lat_from = 0.0; z->surplus = 0;
+  if (rng.err) *err |= rng.err;
+}
 ABX_HD void init_agent_record(const SimParams &P, int env, int id, uint64_t seed, ZiAgent *z, uint32_t *err) {
+  if (P.c.population != 0) { init_agent_record_r3(P, env, id, seed, z, err); return; }
   Rng rng; rng.P = &P; rng.env = env; rng.seed = seed; rng.err = 0;
   int grp = 0, acc = 1;
   for (int g = 0; g < P.c.n_groups; g++) { if (id >= acc && id < acc + P.c.groups[g].count) grp = g; acc += P.c.groups[g].count; }
@@ -330,8 +372,10 @@ ABX_HD void regs_store(ZiAgent *z, const AgentRegs &a) {
 
 // RNG_MODE / LAT_MODEL: compile-time copies of cfg.rng_mode / cfg.latency_model (-1 = decide at run time);
 // INSTR: parity instrumentation (pop hash + trace records) compiled in or out.
-template <class Ctx, int RNG_MODE = -1, int LAT_MODEL = -1, bool INSTR = true, bool ENV = false>
+enum { SHAPE_ZI = 0, SHAPE_ENV = 1, SHAPE_R3 = 2 };   // sparse_zi population | ABIDESEnv / marketreplay | rmsc03 population
+template <class Ctx, int RNG_MODE = -1, int LAT_MODEL = -1, bool INSTR = true, int SHAPE = SHAPE_ZI>
 struct Sim {
+  static constexpr bool ENV = SHAPE == SHAPE_ENV, R3 = SHAPE == SHAPE_R3;
   Ctx &c; const SimParams &P; EnvState s; RngT<RNG_MODE> rng; int64_t addl_delay; int n_out; int self_id;
   AgentRegs a; ZiAgent *z;                // the trader whose event is being handled (registers + staged record)
 
@@ -421,7 +465,7 @@ struct Sim {
         if (INSTR && from_exch && P.c.trace_cap > 0) trace_note(e.recipient, e.kind, e.p);
         int64_t sent = s.now + off;                                                   // Kernel.py:391-393
         int64_t deliver;
-        if (LAT_MODEL == ABX_LAT_ZERO) { deliver = sent; }                                // zero latency matrix, noise [1.0]: no draw (ABIDESEnv.py:91-92)
+        if (LAT_MODEL < 0 ? P.c.latency_model == ABX_LAT_ZERO : LAT_MODEL == ABX_LAT_ZERO) { deliver = sent; }                                // zero latency matrix, noise [1.0]: no draw (ABIDESEnv.py:91-92)
         else if (LAT_MODEL < 0 ? P.c.latency_model == ABX_LAT_CUBIC : LAT_MODEL == ABX_LAT_CUBIC) {   // model/LatencyModel.py:133-138
           double u = rng.u01(S_LATENCY, s.ctr_latency);
           double x = dadd(P.c.jitter_clip, dmul(dsub(1.0, P.c.jitter_clip), u));      // uniform(low=clip, high=1.0)
@@ -486,7 +530,7 @@ struct Sim {
     int n = n_lv(side); int pos; bool found;
     c.lv_find(side, price, n, pos, found);
     uint32_t node = node_alloc(); if (node == NIL) return;
-    NodeRec r; r.id = oid; r.qty = qty; r.agent = (uint32_t)agent; r.next = NIL; c.node_store(node, r);
+    NodeRec r; r.id = oid; r.qty = qty; r.agent = (uint32_t)agent | (R3 ? (s.trade_epoch << 16) : 0u); r.next = NIL; c.node_store(node, r);   // R3: + registration epoch
     if (found) {
       uint32_t tail = c.lv_tail(side, pos);
       NodeRec tr = c.node_load(tail); tr.next = node; c.node_store(tail, tr);
@@ -505,6 +549,7 @@ struct Sim {
       t.w = (t.w == 0 || d >= 16) ? 1u : (((t.w << d) | 1u) & 0xffffu); t.z = s.trade_epoch; c.id_store((int)(oid - REPLAY_ID_BASE), t);
     }
     int opp = is_buy ? 1 : 0;                                                           // a buy matches asks (side 1)
+    uint32_t epoch0 = s.trade_epoch;                                                    // the incoming order's history bucket (:52-60)
     int64_t trade_qty = 0, trade_px = 0;
     bool matching = true;
 #pragma unroll 1
@@ -523,9 +568,13 @@ struct Sim {
           } else {                                                                      // :212-217 partial
             fq = qty; hr.qty -= fq; c.node_store(h, hr); c.lv_set(opp, n - 1, c.lv_qty(opp, n - 1) - fq, h, c.lv_tail(opp, n - 1));
           }
+          if (R3) {                                                                     // :227,230-237 history "transactions" tuples read back by get_transacted_volume
+            tv_record(qty, epoch0);                                                     //   incoming order: its PRE-fill remaining quantity
+            uint32_t re = hr.agent >> 16; if (((epoch0 - re) & 0xffffu) <= (uint32_t)P.c.stream_history) tv_record(fq, (epoch0 & 0xffff0000u) | re);   // resting order, if its bucket survives
+          }
           qty -= fq;                                                                    // :77
           exch_send_order(agent, ABX_ORDER_EXECUTED, oid, price, fq, bp, is_buy, lat_in);             // :88 (incoming copy)
-          exch_send_order((int)hr.agent, ABX_ORDER_EXECUTED, hr.id, bp, fq, bp, !is_buy, ENV ? 0.0 : c.agent_lat_from((int)hr.agent)); // :89-91
+          exch_send_order((int)(hr.agent & 0xffffu), ABX_ORDER_EXECUTED, hr.id, bp, fq, bp, !is_buy, (ENV || R3) ? 0.0 : c.agent_lat_from((int)hr.agent)); // :89-91
           trade_qty += fq; trade_px += (int64_t)bp * fq; s.c_fills++; matched = true;
           if (qty <= 0) matching = false;
           if (n_out >= OUT_CAP - 3) flush(); else c.sync();
@@ -1024,6 +1073,273 @@ struct Sim {
     if (c.onchip_writer()) x->steps = x->steps + 1;
     c.sync();
     return !more;
+  }
+
+
+  // =================================================================================================
+  // rmsc03 population (config/rmsc03.py): NoiseAgent, ValueAgent, MomentumAgent, POVMarketMakerAgent + the exchange's
+  // QUERY_TRANSACTED_VOLUME (util/OrderBook.py:400-436).  Zero latency, computation delay 0.
+  // Per-environment tables (HBM): idtab[0 .. MM_ORDER_CAP) = the market maker's open orders {id, price, signed qty, -},
+  // idtab[MM_ORDER_CAP .. +TV_RING) = ring of transaction tuples {time lo, time hi, qty, record epoch | add epoch << 16},
+  // lobs[k * MOM_MIDS/4 ...] = last MOM_MIDS doubled mid prices of momentum agent k.
+  // =================================================================================================
+  ABX_HD void tv_record(int32_t qty, uint32_t rec_epoch) {
+    uint32_t i = s.ctr_latency++;                                                       // ring cursor (the latency stream is unused with zero latency)
+    uint4 v; v.x = (uint32_t)(uint64_t)s.now; v.y = (uint32_t)((uint64_t)s.now >> 32); v.z = (uint32_t)qty; v.w = (rec_epoch & 0xffffu) | (s.trade_epoch << 16);
+    c.id_store(MM_ORDER_CAP + (int)(i % TV_RING), v);
+  }
+  // get_transacted_volume :400-436: distinct (time, qty) tuples on surviving history records with time >= now - lookback
+  ABX_HD int32_t transacted_volume(int64_t lookback) {
+    uint32_t n = s.ctr_latency < (uint32_t)TV_RING ? s.ctr_latency : (uint32_t)TV_RING; int64_t start = s.now - lookback; int64_t sum = 0;
+    uint32_t E = s.trade_epoch;
+    if (s.ctr_latency > (uint32_t)TV_RING) { uint4 o = c.id_load(MM_ORDER_CAP + (int)(s.ctr_latency % TV_RING)); if (((E - (o.w >> 16)) & 0xffffu) <= (uint32_t)P.c.stream_history) s.flags |= ABX_F_UNSUPPORTED; }  // ring too short
+#pragma unroll 1
+    for (uint32_t k = 0; k < n; k++) {                                                  // newest first
+      uint4 v = c.id_load(MM_ORDER_CAP + (int)((s.ctr_latency - 1 - k) % TV_RING));
+      int64_t t = (int64_t)((uint64_t)v.x | ((uint64_t)v.y << 32));
+      if (((E - (v.w >> 16)) & 0xffffu) > (uint32_t)P.c.stream_history + 1) break;      // added more than stream_history + 1 rotations ago: nothing older can survive
+      if (t < start || ((E - (v.w & 0xffffu)) & 0xffffu) > (uint32_t)P.c.stream_history) continue;
+      bool dup = false;
+#pragma unroll 1
+      for (uint32_t j = 0; j < k && !dup; j++) {
+        uint4 w = c.id_load(MM_ORDER_CAP + (int)((s.ctr_latency - 1 - j) % TV_RING));
+        if (w.x == v.x && w.y == v.y && w.z == v.z && ((E - (w.w & 0xffffu)) & 0xffffu) <= (uint32_t)P.c.stream_history) dup = true;
+      }
+      if (!dup) sum += (int32_t)v.z;
+    }
+    return (int32_t)sum;
+  }
+  ABX_HD void r3_exch_receive(const Event &m) {                                         // ExchangeAgent.receiveMessage :129-340
+    s.exch_comp_delay = P.c.exchange_computation_delay_ns;
+    bool t_closed = s.now > P.c.mkt_close_ns;
+    int32_t p[6] = {0, 0, 0, 0, 0, 0};
+    bool is_query = m.kind == ABX_QUERY_SPREAD || m.kind == ABX_QUERY_TRANSACTED_VOLUME;
+    if (t_closed && !is_query) { exch_send(m.sender, ABX_MKT_CLOSED, p, 0.0); return; }
+    if (m.kind == ABX_WHEN_MKT_OPEN) { s.exch_comp_delay = 0; exch_send(m.sender, ABX_WHEN_MKT_OPEN, p, 0.0); }
+    else if (m.kind == ABX_WHEN_MKT_CLOSE) { s.exch_comp_delay = 0; exch_send(m.sender, ABX_WHEN_MKT_CLOSE, p, 0.0); }
+    else if (m.kind == ABX_QUERY_TRANSACTED_VOLUME) {                                   // :280-303
+      int64_t lookback = (int64_t)((uint64_t)(uint32_t)m.p[0] | ((uint64_t)(uint32_t)m.p[1] << 32));
+      p[0] = transacted_volume(lookback); p[5] = t_closed ? 4 : 0; exch_send(m.sender, ABX_QUERY_TRANSACTED_VOLUME, p, 0.0);
+    } else if (m.kind == ABX_QUERY_SPREAD) {
+      s.c_query++; int f = 0; int nb = s.n_bid_lv, na = s.n_ask_lv;
+      if (nb > 0) { p[0] = c.lv_price(0, nb - 1); p[1] = c.lv_qty(0, nb - 1); f |= 1; }
+      if (na > 0) { p[2] = c.lv_price(1, na - 1); p[3] = c.lv_qty(1, na - 1); f |= 2; }
+      if (t_closed) f |= 4;
+      p[4] = s.last_trade; p[5] = f; exch_send(m.sender, ABX_QUERY_SPREAD, p, 0.0);
+    } else if (m.kind == ABX_LIMIT_ORDER) { s.c_limit++; book_handle_limit((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[2], 0.0); c.sync(); trace_snap(); }
+    else if (m.kind == ABX_CANCEL_ORDER) { s.c_cancel++; book_cancel((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], 0.0); c.sync(); trace_snap(); }
+  }
+  ABX_HD AgentAux *aux() { return reinterpret_cast<AgentAux *>(z->theta); }
+  // TradingAgent.placeLimitOrder :309-349 for the staged trader; `track`: the agent later iterates self.orders (Value, market maker)
+  ABX_HD void r3_place_limit(int id, int32_t size, bool buy, int32_t price, bool track) {
+    uint32_t oid = s.next_order_id++;
+    if (size <= 0) return;
+    if (track) {
+      int type = (int)((a.flags & AF_TYPE_MASK) >> AF_TYPE_SHIFT);
+      if (type == AT_POVMM) { if (a.n_orders < MM_ORDER_CAP) { uint4 v; v.x = oid; v.y = (uint32_t)price; v.z = (uint32_t)(buy ? size : -size); v.w = 0; c.id_store(a.n_orders, v); a.n_orders++; } else s.flags |= ABX_F_AGENT_ORDERS_OVERFLOW; }
+      else if (a.n_orders < AGENT_ORDER_CAP) { c.sync(); if (c.onchip_writer()) { int k = a.n_orders; z->oid[k] = oid; z->oprice[k] = price; z->oqty[k] = buy ? size : -size; } c.sync(); a.n_orders++; }
+      else s.flags |= ABX_F_AGENT_ORDERS_OVERFLOW;
+    }
+    int32_t pl[6] = {(int32_t)oid, price, size, 0, buy, 0}; env_send(ABX_LIMIT_ORDER, pl, false);
+    if (n_out >= OUT_CAP - 3) flush();
+    (void)id;
+  }
+  ABX_HD void r3_cancel_all(int type) {                                                 // cancelOrders / cancelAllOrders
+#pragma unroll 1
+    for (int i = 0; i < a.n_orders; i++) {
+      uint32_t oid; int32_t price, q;
+      if (type == AT_POVMM) { uint4 v = c.id_load(i); oid = v.x; price = (int32_t)v.y; q = (int32_t)v.z; } else { oid = z->oid[i]; price = z->oprice[i]; q = z->oqty[i]; }
+      int32_t p[6] = {(int32_t)oid, price, q < 0 ? -q : q, 0, q > 0, 0}; env_send(ABX_CANCEL_ORDER, p, false);
+      if (n_out >= OUT_CAP - 3) flush();
+    }
+  }
+  ABX_HD void r3_wakeup(int id) {
+    int type = (int)((a.flags & AF_TYPE_MASK) >> AF_TYPE_SHIFT);
+    bool can_trade = ta_wakeup(a.flags);                                                // TradingAgent.wakeup :142-158
+    uint32_t st = (a.flags & AF_STATE_MASK) >> AF_STATE_SHIFT;
+    bool hours = (a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE);
+    bool closed_done = (a.flags & AF_MKT_CLOSED) && (a.flags & AF_HAS_DAILY), closed_wait = (a.flags & AF_MKT_CLOSED) && !(a.flags & AF_HAS_DAILY);
+    if (type == AT_NOISE) {                                                             // agent/NoiseAgent.py:82-112
+      st = ST_INACTIVE;
+      if (hours && !closed_done) { if (a.prev_wake > s.now) set_wakeup(id, a.prev_wake); { int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); } st = ST_AWAITING_SPREAD; }
+    } else if (type == AT_VALUE) {                                                      // agent/ValueAgent.py:100-138
+      st = ST_INACTIVE;
+      if (hours && !closed_done) {
+        double delta_time = dmul(rng.std_exponential(S_AGENT0 + id, a.rng_ctr), P.inv_lambda_a);
+        set_wakeup(id, s.now + py_round_i64(delta_time));
+        if (!closed_wait) r3_cancel_all(type);
+        { int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); } st = ST_AWAITING_SPREAD;
+      }
+    } else if (type == AT_MOMENTUM) {                                                   // agent/examples/MomentumAgent.py:53-63
+      if (can_trade) { int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); st = ST_AWAITING_SPREAD; }
+    } else {                                                                            // POVMarketMakerAgent.py:83-100 (with the getTransactedVolume alias)
+      if (can_trade) {
+        int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true);
+        int32_t q[6] = {(int32_t)(uint32_t)(uint64_t)P.c.mm_wake_ns, (int32_t)(uint32_t)((uint64_t)P.c.mm_wake_ns >> 32), 0, 0, 0, 0}; env_send(ABX_QUERY_TRANSACTED_VOLUME, q, false);
+      }
+    }
+    a.flags = (a.flags & ~AF_STATE_MASK) | (st << AF_STATE_SHIFT);
+  }
+  ABX_HD void r3_value_place(int id) {                                                  // ValueAgent.updateEstimates :140-205 + placeOrder :207-243
+    int stream = S_AGENT0 + id; AgentAux ax = *aux();
+    int32_t r_now = oracle_advance(s.now >= P.c.mkt_close_ns ? P.c.mkt_close_ns - 1 : s.now);
+    int32_t obs_t = (int32_t)py_round_i64(rng.normal(stream, a.rng_ctr, (double)r_now, P.sqrt_sigma_n));
+    if (!(a.flags & AF_HAS_PREV)) { a.prev_wake = P.c.mkt_open_ns; a.flags |= AF_HAS_PREV; }
+    double r_bar = P.c.r_bar, sigma_n = P.c.sigma_n;
+    double delta = (double)(s.now - a.prev_wake);
+    double d2 = (double)(P.c.mkt_close_ns - s.now); if (!(d2 > 0)) d2 = 0;
+    double pw0 = exp_ni(dmul(delta, P.log_base_a)), pw1 = exp_ni(dmul(dmul(2.0, delta), P.log_base_a)), pw2 = exp_ni(dmul(d2, P.log_base_a));
+    double r_tprime = dmul(dsub(1.0, pw0), r_bar); r_tprime = dadd(r_tprime, dmul(pw0, a.r_t));
+    double sigma_tprime = dmul(pw1, a.sigma_t); sigma_tprime = dadd(sigma_tprime, dmul(dsub(1.0, pw1) / P.sigma_denom, P.c.sigma_s));
+    double den = dadd(sigma_n, sigma_tprime);
+    double r_t = dmul(sigma_n / den, r_tprime); r_t = dadd(r_t, dmul(sigma_tprime / den, (double)obs_t)); a.r_t = r_t;
+    a.sigma_t = dmul(sigma_n, a.sigma_t) / dadd(sigma_n, a.sigma_t);
+    double r_T = dmul(dsub(1.0, pw2), r_bar); r_T = dadd(r_T, dmul(pw2, a.r_t));
+    int32_t r_Ti = (int32_t)py_round_i64(r_T); a.prev_wake = s.now;
+    bool buy; int32_t p;
+    bool has_bid = (a.flags & AF_HAS_BID) && a.bid != 0, has_ask = (a.flags & AF_HAS_ASK) && a.ask != 0;
+    if (has_bid && has_ask) {
+      int32_t mid = (int32_t)((double)(a.ask + a.bid) / 2); int32_t spread = a.ask > a.bid ? a.ask - a.bid : a.bid - a.ask; int32_t adjust;
+      if (rng.u01(S_GLOBAL, s.ctr_global) < P.c.value_percent_aggr) adjust = 0;          // np.random.rand() < percent_aggr (GLOBAL stream)
+      else adjust = (int32_t)rng.randint(S_GLOBAL, s.ctr_global, (uint32_t)(P.c.value_depth_spread * spread - 1));
+      if (r_Ti < mid) { buy = false; p = a.bid + adjust; } else { buy = true; p = a.ask - adjust; }
+    } else { buy = rng.randint(S_GLOBAL, s.ctr_global, 1) != 0; p = r_Ti; }
+    r3_place_limit(id, ax.size, buy, p, true);
+  }
+  ABX_HD void r3_momentum_place(int id) {                                               // MomentumAgent.placeOrders :78-93, ma :95-99
+    bool has_bid = (a.flags & AF_HAS_BID) && a.bid != 0, has_ask = (a.flags & AF_HAS_ASK) && a.ask != 0;
+    if (!has_bid || !has_ask) return;
+    AgentAux ax = *aux();
+    int k = id - (1 + P.c.n_noise_agents + P.c.n_value_agents + P.c.n_mm_agents);                            // momentum agent index
+    c.mid_store(k, ax.n_mids % MOM_MIDS, a.bid + a.ask);                                // 2 * mid: exact integer
+    ax.n_mids++;
+    int L = ax.n_mids;
+    if (L > 20) { int64_t sum2 = 0; for (int i = 0; i < 20; i++) sum2 += c.mid_load(k, (L - 1 - i) % MOM_MIDS); ax.avg20 = rint(dmul(((double)sum2 / 2) / 20, 100.0)) / 100.0; ax.mmflags |= MOF_HAS20; }
+    if (L > 50) { int64_t sum2 = 0; for (int i = 0; i < 50; i++) sum2 += c.mid_load(k, (L - 1 - i) % MOM_MIDS); ax.avg50 = rint(dmul(((double)sum2 / 2) / 50, 100.0)) / 100.0; ax.mmflags |= MOF_HAS50; }
+    c.sync(); if (c.onchip_writer()) *aux() = ax; c.sync();
+    if ((ax.mmflags & MOF_HAS20) && (ax.mmflags & MOF_HAS50)) { if (ax.avg20 >= ax.avg50) r3_place_limit(id, ax.size, true, a.ask, false); else r3_place_limit(id, ax.size, false, a.bid, false); }
+  }
+  ABX_HD void r3_receive(int id, const Event &m) {
+    int type = (int)((a.flags & AF_TYPE_MASK) >> AF_TYPE_SHIFT);
+    bool had = (a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE);
+    if (m.kind == ABX_WHEN_MKT_OPEN) a.flags |= AF_HAS_OPEN;
+    else if (m.kind == ABX_WHEN_MKT_CLOSE) a.flags |= AF_HAS_CLOSE;
+    else if (m.kind == ABX_ORDER_EXECUTED) {                                            // orderExecuted :422-462
+      int32_t q = m.p[2]; int32_t sq = m.p[4] ? q : -q; a.shares += sq; a.cash -= (int64_t)sq * m.p[3];
+      if (type == AT_VALUE) { int i = orders_find((uint32_t)m.p[0]); if (i >= 0) { int32_t oq0 = z->oqty[i]; int32_t oq = oq0 < 0 ? -oq0 : oq0; if (q >= oq) orders_remove(i); else { c.sync(); if (c.onchip_writer()) z->oqty[i] = oq0 < 0 ? -(oq - q) : (oq - q); c.sync(); } } }
+      else if (type == AT_POVMM) r3_mm_order_update((uint32_t)m.p[0], q, false);
+    } else if (m.kind == ABX_ORDER_CANCELLED) {
+      if (type == AT_VALUE) { int i = orders_find((uint32_t)m.p[0]); if (i >= 0) orders_remove(i); }
+      else if (type == AT_POVMM) r3_mm_order_update((uint32_t)m.p[0], 0, true);
+    } else if (m.kind == ABX_MKT_CLOSED) a.flags |= AF_MKT_CLOSED;
+    else if (m.kind == ABX_QUERY_TRANSACTED_VOLUME) {                                   // :248-251,556-558
+      if (m.p[5] & 4) a.flags |= AF_MKT_CLOSED;
+      AgentAux ax = *aux(); ax.tv = m.p[0]; c.sync(); if (c.onchip_writer()) *aux() = ax; c.sync();
+    } else if (m.kind == ABX_QUERY_SPREAD) {
+      if (m.p[5] & 4) a.flags |= AF_MKT_CLOSED;
+      a.last_trade = m.p[4]; a.flags |= AF_HAS_LAST;
+      if (a.flags & AF_MKT_CLOSED) { a.daily_close = a.last_trade; a.flags |= AF_HAS_DAILY; }
+      a.flags &= ~(AF_HAS_BID | AF_HAS_ASK);
+      if (m.p[5] & 1) { a.flags |= AF_HAS_BID; a.bid = m.p[0]; a.bid_q = m.p[1]; } else { a.bid = 0; a.bid_q = 0; }
+      if (m.p[5] & 2) { a.flags |= AF_HAS_ASK; a.ask = m.p[2]; a.ask_q = m.p[3]; } else { a.ask = 0; a.ask_q = 0; }
+    }
+    if ((a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE) && !had) {                  // :258-268 getWakeFrequency per class
+      int64_t off = type == AT_MOMENTUM ? P.c.mom_wake_ns : (type == AT_POVMM ? P.c.mm_wake_ns : rng.randint(S_AGENT0 + id, a.rng_ctr, 99));
+      set_wakeup(id, P.c.mkt_open_ns + off);
+    }
+    uint32_t st = (a.flags & AF_STATE_MASK) >> AF_STATE_SHIFT;
+    if (type == AT_POVMM) {                                                             // POVMarketMakerAgent.receiveMessage :102-150
+      AgentAux ax = *aux();
+      if (m.kind == ABX_QUERY_TRANSACTED_VOLUME && (ax.mmflags & MMF_AW_VOL)) {         // updateOrderSize :152-156
+        int32_t qty = (int32_t)py_round_i64(dmul(P.c.mm_pov, (double)ax.tv)); ax.order_size = qty >= P.c.mm_min_order_size ? qty : P.c.mm_min_order_size; ax.mmflags &= ~MMF_AW_VOL; }
+      if (m.kind == ABX_QUERY_SPREAD && (ax.mmflags & MMF_AW_SPREAD)) {
+        bool has_bid = (a.flags & AF_HAS_BID) && a.bid != 0, has_ask = (a.flags & AF_HAS_ASK) && a.ask != 0;
+        if (has_bid && has_ask) { ax.last_mid = (int32_t)((double)(a.ask + a.bid) / 2); ax.mmflags |= MMF_HAS_MID; ax.mmflags &= ~MMF_AW_SPREAD; } }
+      bool go = !(ax.mmflags & MMF_AW_SPREAD) && !(ax.mmflags & MMF_AW_VOL);
+      if (go) ax.mmflags |= MMF_AW_SPREAD | MMF_AW_VOL;                                 // self.state = self.initialiseState()
+      c.sync(); if (c.onchip_writer()) *aux() = ax; c.sync();
+      if (go) {
+        r3_cancel_all(type);                                                            // the cancelled orders stay in self.orders until ORDER_CANCELLED arrives
+        int32_t mid = ax.last_mid, highest_bid = mid - 1, lowest_ask = mid + P.c.mm_window_size;   // computeOrdersToPlace :158-177 (anchor bottom)
+        int32_t lowest_bid = highest_bid - P.c.mm_num_ticks, highest_ask = lowest_ask + P.c.mm_num_ticks;
+#pragma unroll 1
+        for (int32_t px = lowest_bid; px <= highest_bid; px++) r3_place_limit(id, ax.order_size, true, px, true);
+#pragma unroll 1
+        for (int32_t px = lowest_ask; px <= highest_ask; px++) r3_place_limit(id, ax.order_size, false, px, true);
+        set_wakeup(id, s.now + P.c.mm_wake_ns);
+      }
+      return;
+    }
+    if (type == AT_MOMENTUM) {                                                          // MomentumAgent.receiveMessage :65-76
+      if (st == ST_AWAITING_SPREAD && m.kind == ABX_QUERY_SPREAD) { r3_momentum_place(id); set_wakeup(id, s.now + P.c.mom_wake_ns); a.flags = (a.flags & ~AF_STATE_MASK) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT); }
+      return;
+    }
+    if (st == ST_AWAITING_SPREAD && m.kind == ABX_QUERY_SPREAD && !(a.flags & AF_MKT_CLOSED)) {      // NoiseAgent :123-129 / ValueAgent :245-251
+      if (type == AT_NOISE) {                                                           // NoiseAgent.placeOrder :114-121
+        bool buy = rng.randint(S_GLOBAL, s.ctr_global, 1) != 0; int32_t size = aux()->size;
+        bool has_bid = (a.flags & AF_HAS_BID) && a.bid != 0, has_ask = (a.flags & AF_HAS_ASK) && a.ask != 0;
+        if (buy && has_ask) r3_place_limit(id, size, true, a.ask, false); else if (!buy && has_bid) r3_place_limit(id, size, false, a.bid, false);
+      } else r3_value_place(id);
+      a.flags = (a.flags & ~AF_STATE_MASK) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT);
+    }
+  }
+  // the market maker's self.orders: fill / cancel bookkeeping (TradingAgent.orderExecuted :445-452, orderCancelled :480-483)
+  ABX_HD void r3_mm_order_update(uint32_t oid, int32_t fill, bool cancel) {
+    int f = -1;
+#pragma unroll 1
+    for (int i = 0; i < a.n_orders && f < 0; i++) { uint4 v = c.id_load(i); if (v.x == oid) f = i; }
+    if (f < 0) return;
+    uint4 v = c.id_load(f); int32_t q = (int32_t)v.z, aq = q < 0 ? -q : q;
+    if (!cancel && fill < aq) { v.z = (uint32_t)(q < 0 ? -(aq - fill) : (aq - fill)); c.id_store(f, v); return; }
+#pragma unroll 1
+    for (int i = f; i + 1 < a.n_orders; i++) c.id_store(i, c.id_load(i + 1));           // dict deletion keeps the order of the others
+    a.n_orders--;
+  }
+  // Kernel.runner hot loop for the rmsc03 population
+  ABX_HD void r3_run(int64_t until) {
+#pragma unroll 1
+    while (!(s.flags & ABX_F_DONE)) {
+      uint64_t khi; uint32_t kuniq; int grp;
+      bool any = c.q_min(khi, kuniq, grp);
+      if (!any || !(s.now <= P.c.stop_ns)) { s.flags |= ABX_F_DONE; break; }
+      if (key_time(khi) > until) break;
+      Event ev; c.q_fetch(grp, ev);
+      s.now = ev.t; s.ttl++;
+      if (INSTR && P.c.hash_pops) s.pop_hash = fnv_mix(fnv_mix(fnv_mix(fnv_mix(s.pop_hash, ev.t), ev.recipient), ev.type), ev.type == ABX_T_MESSAGE ? (int64_t)ev.uniq : -1);
+      if (INSTR && P.c.trace_cap > 0) {
+        abx_trace_rec r; r.tag = 0; r.a = ev.recipient; r.t = ev.t; for (int i = 0; i < 16; i++) r.v[i] = 0;
+        r.v[0] = ev.type; r.v[1] = ev.type == ABX_T_MESSAGE ? (int32_t)ev.uniq : -1; r.v[2] = ev.kind; trace_rec(r);
+      }
+      addl_delay = 0;
+      int id = ev.recipient;
+      if (id == 0) {
+        if (s.exch_time > s.now) { c.q_requeue(s.exch_time); continue; }
+        c.q_remove(); s.q_count--; self_id = 0;
+        if (ev.type == ABX_T_MESSAGE) r3_exch_receive(ev);
+        s.exch_time = s.now + s.exch_comp_delay + addl_delay;
+      } else {
+        z = c.agent_stage(id); regs_load(a, z);
+        if (a.agent_time > s.now) { c.q_requeue(a.agent_time); continue; }
+        c.q_remove(); s.q_count--; self_id = id;
+        if (ev.type == ABX_T_WAKEUP) r3_wakeup(id); else r3_receive(id, ev);
+        a.agent_time = s.now + P.c.default_computation_delay_ns + addl_delay;
+        c.sync(); if (c.onchip_writer()) regs_store(z, a); c.sync();
+        c.agent_commit(id);
+      }
+      flush();
+    }
+    s.flags |= rng.err;
+  }
+  // kernelStopping: ValueAgent.kernelStopping :49-61 observes the fundamental (advances the oracle); holdings are read by the host
+  ABX_HD void r3_finalize() {
+    int64_t sum_sh = 0, sum_cash = 0;
+#pragma unroll 1
+    for (int id = 1; id < P.c.n_agents; id++) {
+      z = c.agent_stage(id); regs_load(a, z);
+      if (agent_type_of(P.c, id) == AT_VALUE) { int64_t cur = a.agent_time - P.c.default_computation_delay_ns; oracle_advance(cur >= P.c.mkt_close_ns ? P.c.mkt_close_ns - 1 : cur); }
+      sum_sh += a.shares; sum_cash += a.cash;
+    }
+    s.sum_shares = sum_sh; s.sum_cash = sum_cash; s.flags |= rng.err;
   }
 
   // ---- Kernel.runner :310-311 kernelStopping for every trader, in id order (ZeroIntelligenceAgent.py:80-123) ----

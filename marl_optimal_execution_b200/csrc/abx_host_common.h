@@ -44,15 +44,40 @@ static inline int config_sparse_zi(int variant, abx_sim_config *c) {
   return ABX_OK;
 }
 
+// config/rmsc03.py:49-232
+static inline int config_rmsc03(abx_sim_config *c) {
+  if (!c) return ABX_ERR_ARG;
+  memset(c, 0, sizeof(*c));
+  c->version = ABX_VERSION; c->population = 1; c->n_noise_agents = 50; c->n_value_agents = 10; c->n_mm_agents = 1; c->n_momentum_agents = 2; c->n_agents = 64; c->n_groups = 0; c->q_max = 10;
+  c->mkt_open_ns = (9 * 3600 + 1800) * NS; c->mkt_close_ns = (9 * 3600 + 2700) * NS;       // :69-70 09:30 .. 09:45
+  c->start_ns = c->mkt_open_ns; c->stop_ns = c->mkt_close_ns + 60 * NS;                      // :205-207
+  c->default_computation_delay_ns = 0; c->exchange_computation_delay_ns = 0; c->exchange_pipeline_delay_ns = 0;
+  c->starting_cash = 10000000; c->order_size = 0; c->stream_history = 10;
+  c->r_bar = 1e5; c->kappa = 1.67e-12; c->fund_vol = 1e-4; c->megashock_lambda_a = 2.77778e-13; c->megashock_mean = 1e3; c->megashock_var = 5e4;
+  c->sigma_n = 1e5 / 10; c->agent_kappa = 1.67e-15; c->sigma_s = 100000; c->sigma_pv = 0; c->lambda_a = 7e-11;   // :77-80; sigma_s: ValueAgent default
+  c->latency_model = ABX_LAT_ZERO; c->n_noise = 1;                                         // np.zeros latency, noise [0.0] :209-210
+  c->size_lo = 20; c->size_hi = 50; c->value_depth_spread = 2; c->value_percent_aggr = 0.1;   // NoiseAgent.py:34, ValueAgent.py:53-56
+  c->noise_wake_lo_ns = 9 * 3600 * NS; c->noise_wake_hi_ns = 16 * 3600 * NS;                // :115-116
+  c->mom_min_size = 1; c->mom_max_size = 10; c->mom_wake_ns = 20 * NS;                      // :190-192
+  c->mm_pov = 0.05; c->mm_min_order_size = 20; c->mm_window_size = 5; c->mm_num_ticks = 20; c->mm_wake_ns = NS;   // :41-45
+  c->queue_cap = 256; c->level_cap = 128; c->order_cap = 512; c->rng_mode = ABX_RNG_PHILOX; c->trace_cap = 0; c->hash_pops = 0;
+  return ABX_OK;
+}
 static inline int config_validate(const abx_sim_config *c) {
   if (!c || c->version != ABX_VERSION) return ABX_ERR_ARG;
-  if (c->n_agents < 2 || c->n_agents > 32767 || c->n_groups < 1 || c->n_groups > 8 || c->q_max < 1 || c->q_max > 10) return ABX_ERR_ARG;
-  int n = 1; for (int g = 0; g < c->n_groups; g++) { if (c->groups[g].count < 0 || c->groups[g].r_max < c->groups[g].r_min) return ABX_ERR_ARG; n += c->groups[g].count; }
+  if (c->n_agents < 2 || c->n_agents > 32767 || c->n_groups < 0 || c->n_groups > 8 || c->q_max < 1 || c->q_max > 10) return ABX_ERR_ARG;
+  int n = 1;
+  if (c->population == 0) { if (c->n_groups < 1) return ABX_ERR_ARG; for (int g = 0; g < c->n_groups; g++) { if (c->groups[g].count < 0 || c->groups[g].r_max < c->groups[g].r_min) return ABX_ERR_ARG; n += c->groups[g].count; } }
+  else if (c->population == 1) {
+    if (c->n_noise_agents < 0 || c->n_value_agents < 0 || c->n_mm_agents < 0 || c->n_mm_agents > 1 || c->n_momentum_agents < 0 || c->n_momentum_agents > 4) return ABX_ERR_ARG;
+    if (c->latency_model != ABX_LAT_ZERO || c->size_hi <= c->size_lo || c->mom_max_size <= c->mom_min_size || 2 * (c->mm_num_ticks + 1) > MM_ORDER_CAP / 2 || c->mm_wake_ns <= 0 || c->mom_wake_ns <= 0) return ABX_ERR_ARG;
+    n += c->n_noise_agents + c->n_value_agents + c->n_mm_agents + c->n_momentum_agents;
+  } else return ABX_ERR_ARG;
   if (n != c->n_agents) return ABX_ERR_ARG;
   if (c->queue_cap < 32 || c->queue_cap % 32 || c->queue_cap > 4096) return ABX_ERR_ARG;
   if (c->level_cap < 8 || c->level_cap > 2048 || c->order_cap < 8 || c->order_cap > 65535) return ABX_ERR_ARG;
   if (c->stop_ns >= KEY_T_MAX || c->start_ns < 0 || c->mkt_close_ns >= KEY_T_MAX) return ABX_ERR_ARG;
-  if (c->latency_model != ABX_LAT_MATRIX_NOISE && c->latency_model != ABX_LAT_CUBIC) return ABX_ERR_ARG;
+  if (c->latency_model != ABX_LAT_MATRIX_NOISE && c->latency_model != ABX_LAT_CUBIC && c->latency_model != ABX_LAT_ZERO) return ABX_ERR_ARG;
   if (c->latency_model == ABX_LAT_MATRIX_NOISE && c->n_noise < 1) return ABX_ERR_ARG;
   if (c->rng_mode != ABX_RNG_PHILOX && c->rng_mode != ABX_RNG_TAPE) return ABX_ERR_ARG;
   if (c->trace_cap < 0 || !(c->kappa > 0) || !(c->lambda_a > 0) || !(c->megashock_lambda_a > 0)) return ABX_ERR_ARG;

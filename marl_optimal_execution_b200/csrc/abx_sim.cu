@@ -57,7 +57,7 @@ abx_reset_env_kernel(SimParams P, const uint64_t *__restrict__ seeds, const uint
 
 // One instantiation per (RNG mode, latency model, instrumentation): the production path (Philox, no instrumentation)
 // carries neither the tape-replay branches nor the parity hash/trace code.
-template <int RNG, int LAT, bool INSTR>
+template <int RNG, int LAT, bool INSTR, int SHAPE = SHAPE_ZI>
 __global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
 abx_run_kernel(SimParams P, int64_t until_ns, const int64_t *__restrict__ until_each, size_t smem_per_warp) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -67,14 +67,18 @@ abx_run_kernel(SimParams P, int64_t until_ns, const int64_t *__restrict__ until_
   EnvState s = env_load(P.env + env);
   if (s.flags & ABX_F_DONE) return;
   ctx.load_onchip(s);
-  Sim<WarpCtx, RNG, LAT, INSTR> sim(ctx, P, s, env);
-  sim.run(until_each ? until_each[env] : until_ns);
+  Sim<WarpCtx, RNG, LAT, INSTR, SHAPE> sim(ctx, P, s, env);
+  if (SHAPE == SHAPE_R3) sim.r3_run(until_each ? until_each[env] : until_ns); else sim.run(until_each ? until_each[env] : until_ns);
   ctx.store_onchip(sim.s);
   env_store(P.env + env, sim.s, ctx.lane);
 }
 typedef void (*run_kernel_fn)(SimParams, int64_t, const int64_t *, size_t);
 static run_kernel_fn run_kernel_for(const abx_sim_config &c) {
   bool instr = c.trace_cap > 0 || c.hash_pops != 0; int r = c.rng_mode, l = c.latency_model;
+  if (c.population == 1) {                       // config/rmsc03.py population: zero latency
+    if (r == ABX_RNG_PHILOX) return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_R3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_ZERO, false, SHAPE_R3>;
+    return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_ZERO, true, SHAPE_R3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_ZERO, false, SHAPE_R3>;
+  }
 #define PICK(R, L) (instr ? (run_kernel_fn)abx_run_kernel<R, L, true> : (run_kernel_fn)abx_run_kernel<R, L, false>)
   if (r == ABX_RNG_PHILOX) return l == ABX_LAT_CUBIC ? PICK(ABX_RNG_PHILOX, ABX_LAT_CUBIC) : PICK(ABX_RNG_PHILOX, ABX_LAT_MATRIX_NOISE);
   return l == ABX_LAT_CUBIC ? PICK(ABX_RNG_TAPE, ABX_LAT_CUBIC) : PICK(ABX_RNG_TAPE, ABX_LAT_MATRIX_NOISE);
@@ -88,14 +92,14 @@ abx_finalize_kernel(SimParams P, size_t smem_per_warp) {
   if (env >= P.n_envs) return;
   WarpCtx ctx(P, env, smem + warp * smem_per_warp);
   EnvState s = env_load(P.env + env);
+  if (P.c.population == 1) { Sim<WarpCtx, -1, ABX_LAT_ZERO, false, SHAPE_R3> sim(ctx, P, s, env); sim.r3_finalize(); env_store(P.env + env, sim.s, ctx.lane); return; }
   Sim<WarpCtx> sim(ctx, P, s, env);
   sim.finalize();
   env_store(P.env + env, sim.s, ctx.lane);
 }
 
 // ---- ABIDESEnv shape: reset and step (GymKernel.initRunner / stepRunner) ----
-typedef Sim<WarpCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, false, true> EnvSimFast;
-typedef Sim<WarpCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, true> EnvSimInstr;
+typedef Sim<WarpCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_ENV> EnvSimInstr;
 
 __global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
 abx_env_reset_kernel(SimParams P, size_t smem_per_warp) {
@@ -124,7 +128,7 @@ abx_env_step_kernel(SimParams P, const double *__restrict__ actions, double *__r
   bool was_done = (s.flags & ABX_F_DONE) != 0;
   if (!was_done) {
     ctx.envx_load(); ctx.load_onchip(s);
-    Sim<WarpCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, INSTR, true> sim(ctx, P, s, env);
+    Sim<WarpCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, INSTR, SHAPE_ENV> sim(ctx, P, s, env);
     sim.env_step(actions[3 * env], actions[3 * env + 1], actions[3 * env + 2]);
     ctx.store_onchip(sim.s); ctx.envx_store();
     env_store(P.env + env, sim.s, ctx.lane);
@@ -173,6 +177,7 @@ const char *abx_strerror(int32_t st) { return status_string(st); }
 const char *abx_last_cuda_error(void) { return g_cuda_err; }
 int32_t abx_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 int32_t abx_config_sparse_zi(int32_t variant, abx_sim_config *cfg) { return config_sparse_zi(variant, cfg); }
+int32_t abx_config_rmsc03(abx_sim_config *cfg) { return config_rmsc03(cfg); }
 
 int32_t abx_sim_destroy(abx_sim *h) {
   if (!h) return ABX_OK;
@@ -200,6 +205,7 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   DA(h->P.agents, E * c.n_agents) DA(h->P.lv_price, E * 2 * c.level_cap) DA(h->P.lv_qty, E * 2 * c.level_cap) DA(h->P.lv_ht, E * 2 * c.level_cap)
   DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap)
   DA(h->d_seeds, E) DA(h->d_init_err, E) DA(h->d_stats, E) DA(h->d_until, E)
+  if (c.population == 1) { h->P.n_ids = MM_ORDER_CAP + TV_RING; DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3) }   // market maker orders + transaction ring; momentum mids
 #undef DA
   if (smem_cta > 48 * 1024) {
     CU(cudaFuncSetAttribute((const void *)run_kernel_for(*cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));

@@ -243,6 +243,9 @@ struct WarpCtx {
 #pragma unroll
     for (int k = 0; k < 3; k++) { int4 v = __ldcg(lob + slot * 3 + k); w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
   }
+  // rmsc03: momentum agent k's ring of doubled mid prices lives in the per-environment int4 table
+  __device__ __forceinline__ int32_t mid_load(int k, int slot) const { return __ldcg(reinterpret_cast<const int32_t *>(lob) + k * MOM_MIDS + slot); }
+  __device__ __forceinline__ void mid_store(int k, int slot, int32_t v) { if (lane == 0) __stcg(reinterpret_cast<int32_t *>(lob) + k * MOM_MIDS + slot, v); __syncwarp(); }
   // np.std (ddof 0) of log(mid_i / p0) over the n stored LOBs: lanes take LOBs lane, lane+32, ... (ABIDESEnvMetrics.py:183-192)
   __device__ double lob_midvol(int n, int head, double p0, bool &bad) const {
     double v[4]; double sum = 0.0; bool b = false;

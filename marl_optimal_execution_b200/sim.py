@@ -24,6 +24,18 @@ def sparse_zi_config(variant, lib=None, **overrides):
     return cfg
 
 
+def rmsc03_config(lib=None, **overrides):
+    """abx_sim_config for config/rmsc03.py (50 Noise + 10 Value + 1 POV market maker + 2 Momentum agents, 09:30-09:45)."""
+    L = lib or _lib.load()
+    cfg = SimConfig()
+    _lib.check(L, L.abx_config_rmsc03(C.byref(cfg)), "abx_config_rmsc03")
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError("abx_sim_config has no field %r" % k)
+        setattr(cfg, k, v)
+    return cfg
+
+
 class BatchedSim:
     """n_envs independent simulations of one population config on one GPU.
 

@@ -83,6 +83,8 @@ struct HostCtx {
   int first_load(int k) { return P.st_first[k]; }
   void lob_store(int slot, const int32_t w[12]) { for (int k = 0; k < 3; k++) { int4 v; v.x = w[4 * k]; v.y = w[4 * k + 1]; v.z = w[4 * k + 2]; v.w = w[4 * k + 3]; lob[slot * 3 + k] = v; } }
   void lob_load(int slot, int32_t w[12]) { for (int k = 0; k < 3; k++) { int4 v = lob[slot * 3 + k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; } }
+  int32_t mid_load(int k, int slot) { return reinterpret_cast<int32_t *>(lob)[k * MOM_MIDS + slot]; }
+  void mid_store(int k, int slot, int32_t v) { reinterpret_cast<int32_t *>(lob)[k * MOM_MIDS + slot] = v; }
   double lob_midvol(int n, int head, double p0, bool &bad) {
     double v[LOB_CAP], mean = 0, var = 0;
     for (int i = 0; i < n; i++) { int4 a = lob[((head + i) % LOB_CAP) * 3]; if (a.x <= 0 || a.w <= 0) bad = true; v[i] = log((((double)a.x + (double)a.w) / 2) / p0); mean += v[i]; }
@@ -107,6 +109,8 @@ const char *abx_strerror(int32_t st) { return status_string(st); }
 const char *abx_last_cuda_error(void) { return "host emulation harness: no CUDA"; }
 int32_t abx_device_count(void) { return 0; }
 int32_t abx_config_sparse_zi(int32_t variant, abx_sim_config *cfg) { return config_sparse_zi(variant, cfg); }
+int32_t abx_config_rmsc03(abx_sim_config *cfg) { return config_rmsc03(cfg); }
+typedef Sim<HostCtx, -1, ABX_LAT_ZERO, true, SHAPE_R3> R3SimHost;
 
 int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device, abx_sim **out) {
   (void)device;
@@ -119,6 +123,7 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   h->P.qkey = h->qkey.data(); h->P.qpay0 = h->qpay0.data(); h->P.qpay1 = h->qpay1.data(); h->P.qcache = h->qcache.data(); h->P.agents = h->agents.data();
   h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
   h->P.trace = c.trace_cap ? h->trace.data() : nullptr;
+  if (c.population == 1) { h->P.n_ids = MM_ORDER_CAP + TV_RING; h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); }
   *out = h; return ABX_OK;
 }
 int32_t abx_sim_destroy(abx_sim *h) { delete h; return ABX_OK; }
@@ -148,17 +153,23 @@ int32_t abx_sim_reset_tape(abx_sim *h, const uint64_t *bits, const uint8_t *kind
 }
 int32_t abx_sim_run(abx_sim *h, int64_t until_ns, void *stream) {
   (void)stream; if (!h) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
-  for (int e = 0; e < h->n_envs; e++) { HostCtx ctx(h->P, e); Sim<HostCtx> sim(ctx, h->P, h->env[e], e); sim.run(until_ns); h->env[e] = sim.s; }
+  for (int e = 0; e < h->n_envs; e++) { HostCtx ctx(h->P, e);
+    if (h->P.c.population == 1) { R3SimHost sim(ctx, h->P, h->env[e], e); sim.r3_run(until_ns); h->env[e] = sim.s; }
+    else { Sim<HostCtx> sim(ctx, h->P, h->env[e], e); sim.run(until_ns); h->env[e] = sim.s; } }
   return ABX_OK;
 }
 int32_t abx_sim_run_each(abx_sim *h, const int64_t *until, void *stream) {
   (void)stream; if (!h || !until) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
-  for (int e = 0; e < h->n_envs; e++) { HostCtx ctx(h->P, e); Sim<HostCtx> sim(ctx, h->P, h->env[e], e); sim.run(until[e]); h->env[e] = sim.s; }
+  for (int e = 0; e < h->n_envs; e++) { HostCtx ctx(h->P, e);
+    if (h->P.c.population == 1) { R3SimHost sim(ctx, h->P, h->env[e], e); sim.r3_run(until[e]); h->env[e] = sim.s; }
+    else { Sim<HostCtx> sim(ctx, h->P, h->env[e], e); sim.run(until[e]); h->env[e] = sim.s; } }
   return ABX_OK;
 }
 int32_t abx_sim_finalize(abx_sim *h, void *stream) {
   (void)stream; if (!h) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
-  for (int e = 0; e < h->n_envs; e++) { HostCtx ctx(h->P, e); Sim<HostCtx> sim(ctx, h->P, h->env[e], e); sim.finalize(); h->env[e] = sim.s; }
+  for (int e = 0; e < h->n_envs; e++) { HostCtx ctx(h->P, e);
+    if (h->P.c.population == 1) { R3SimHost sim(ctx, h->P, h->env[e], e); sim.r3_finalize(); h->env[e] = sim.s; }
+    else { Sim<HostCtx> sim(ctx, h->P, h->env[e], e); sim.finalize(); h->env[e] = sim.s; } }
   return ABX_OK;
 }
 int32_t abx_sim_stats(abx_sim *h, abx_env_stats *out, void *stream) {
@@ -191,7 +202,7 @@ int32_t abx_sim_trace(abx_sim *h, int32_t env, abx_trace_rec *out, int32_t max_r
 }
 int64_t abx_sim_launch_count(const abx_sim *h) { (void)h; return 0; }
 
-typedef Sim<HostCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, true> EnvSimHost;
+typedef Sim<HostCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_ENV> EnvSimHost;
 int32_t abx_env_config_default(abx_env_config *cfg) { return env_config_default(cfg); }
 int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
   (void)device; if (!out || n_envs < 1 || env_config_validate(cfg) != ABX_OK) return ABX_ERR_ARG;

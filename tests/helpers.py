@@ -26,6 +26,20 @@ def oracle_tapes(sims):
     bits, kinds, off, lat_to, lat_from = [], [], [0], [], []
     for s in sims:
         n = s.n_agents
+        if s.variant == 3:                            # rmsc03: oracle stream order symbol, exchange, agents 1..n-1, kernel; global stream separate
+            gk, gb = s.global_tape()                  # runtime draws; the oracle's __init__ megashock gap (drawn by the config) comes first
+            g0 = s.global_exp_tape()[:1]
+            glob = (np.concatenate([np.full(1, ord("e"), np.uint8), gk]), np.concatenate([g0.view(np.uint64), gb]))
+            streams = [s.tape(0), s.tape(n + 1), (np.zeros(0, np.uint8), np.zeros(0, np.uint64)), glob]
+            streams += [s.tape(a + 1) for a in range(1, n)]
+            for k, b in streams:
+                kinds.append(k)
+                bits.append(b)
+                off.append(off[-1] + len(b))
+            info = np.array([s.agent_info(a) for a in range(n)])
+            lat_to.append(info[:, 1].astype(np.float64))      # Noise/Value size (drawn by the config script)
+            lat_from.append(info[:, 2].astype(np.float64))    # NoiseAgent.wakeup_time
+            continue
         base = 4 if s.variant == 100 else 3           # oracle stream order: symbol, kernel, [latency], exchange, agents
         streams = [s.tape(0), s.tape(1)]
         streams.append(s.tape(2) if s.variant == 100 else (np.zeros(0, np.uint8), np.zeros(0, np.uint64)))

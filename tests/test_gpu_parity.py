@@ -100,3 +100,28 @@ def test_intermediate_state_matches_oracle():
     l1 = o2.book_l1()
     assert (int(st["best_bid"][0]), int(st["best_bid_qty"][0]), int(st["best_ask"][0]), int(st["best_ask_qty"][0]),
             int(st["last_trade"][0])) == tuple(int(x) for x in l1)
+
+
+@pytest.mark.parametrize("seed", [123456789, 1001])
+def test_rmsc03_tape_replay(seed):
+    """config/rmsc03.py (BASELINE.json configs[2]): value + noise + momentum + POV market-maker population; replayed draws incl.
+    the GLOBAL np.random stream; transacted-volume driven ladder sizes.  Bit-exact vs the oracle, which is pinned to
+    recordings of the live reference (tests/test_oracle_golden.py::test_rmsc03_digest_bit_exact)."""
+    from marl_optimal_execution_b200.sim import rmsc03_config
+    o = OracleSim(3, seed, TRACE_ALL)
+    n = o.run()
+    cfg = rmsc03_config(rng_mode=_lib.RNG_TAPE, trace_cap=400000, hash_pops=1)
+    sim = BatchedSim(cfg, 2)
+    sim.reset_tape(*oracle_tapes([o, o]))
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    assert (st["messages"] == n).all() and (st["flags"] == _lib.F_DONE).all(), (st["messages"], st["flags"])
+    assert (st["pop_hash"] == np.uint64(o.pop_hash())).all()
+    p, nt, sn = sim.split_trace(1)
+    for name, a, b in (("pops", p, o.trace("pops")), ("notes", nt, o.trace("notes")), ("snaps", sn, o.trace("snaps"))):
+        assert a.shape == b.shape, (name, a.shape, b.shape)
+        d = np.nonzero((a != b).any(axis=1))[0]
+        assert len(d) == 0, (name, int(d[0]), a[d[0]], b[d[0]])
+    assert np.array_equal(sim.holdings(0)[:, :4], o.holdings()[:, :4])
+    assert int(st["limit_orders"][0]) == o.counter("limit") and int(st["fills"][0]) == o.counter("fills")

@@ -79,3 +79,17 @@ def test_overflow_is_flagged_not_silent():
     sim.reset([1, 2])
     sim.run()
     assert (sim.stats()["flags"] & _lib.F_LEVEL_OVERFLOW).all()
+
+
+def test_rmsc03_batch_conservation():
+    from marl_optimal_execution_b200.sim import rmsc03_config
+    cfg = rmsc03_config()
+    n = 512
+    sim = BatchedSim(cfg, n)
+    sim.reset(np.arange(n, dtype=np.uint64) + 5)
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    assert (st["flags"] == _lib.F_DONE).all(), np.unique(st["flags"])
+    assert (st["sum_shares"] == 0).all() and (st["sum_cash"] == 63 * 10 ** 7).all()
+    assert 100000 < np.median(st["messages"]) < 250000        # envs whose market maker met a one-sided book stop quoting (reference behaviour)
