@@ -245,6 +245,48 @@ int32_t abx_env_step(abx_sim *h, const double *actions_dev, double *obs_dev, dou
 /* Same call with HOST buffers (pinned memory keeps the copies asynchronous); synchronises `stream`. */
 int32_t abx_env_step_host(abx_sim *h, const double *actions, double *obs, double *reward, uint8_t *done, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * DDQN execution shape: config/execution/marketreplay/execution_marketreplay_ddqn.py (-a rl) -- Exchange (id 0) +
+ * MarketReplayAgent (1) + n_momentum MomentumAgents (2..) + n_twap TWAPExecutionAgents + DDQLearningExecutionAgent (last id)
+ * under Kernel.runner, for n_envs environments at once.  The reference agent calls its Keras Q-network once per decision tick,
+ * batch 1, inside place_order (agent/execution/qlearning/ddqlearning_execution_agent.py:245,339-365); here one abx_dq_step runs
+ * every environment up to that call, the caller evaluates the Q-network for the whole batch (abx_qnet_forward below) and the
+ * next abx_dq_step resumes place_order with the chosen actions.  Handles are abx_sim* (stats / trace / snapshot / destroy work).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct abx_dq_config {
+  int32_t version;                 /* ABX_VERSION */
+  int32_t n_momentum;              /* MomentumAgents (config: 7), <= 8 */
+  int32_t n_twap;                  /* TWAPExecutionAgents (config -a rl: 1), 0..2 */
+  int32_t has_ddqn;                /* DDQLearningExecutionAgent present (the last agent id) */
+  int32_t is_buy;                  /* --direction BUY */
+  int32_t n_horizon;               /* len(execution_time_horizon): horizon_length / freq + 1 (config: 661) */
+  int64_t quantity;                /* --parent_qty */
+  int64_t start_ns, stop_ns;       /* Kernel.runner startTime (midnight) / stopTime (horizon end + 10 min, :317-318) */
+  int64_t mkt_open_ns, mkt_close_ns;
+  int64_t horizon_start_ns, horizon_step_ns;  /* --start_hour, --freq (the agent hard-codes 30 s intervals, :373) */
+  int64_t mom_wake_ns; int32_t mom_min_size, mom_max_size;   /* MomentumAgent wake_up_freq "20s", min_size 1, max_size 10 (:150-163) */
+  int32_t stream_history;
+  int32_t queue_cap, level_cap, order_cap;
+  int32_t trace_cap, hash_pops;
+} abx_dq_config;
+int32_t abx_dq_config_default(abx_dq_config *cfg);
+/* stream5 as abx_env_create. */
+int32_t abx_dq_create(const abx_dq_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out);
+/* Agent construction + Kernel.runner start-up (Kernel.py:154-175).  seeds: HOST uint64 [n_envs] keying the MomentumAgent size draws
+ * (random_state.randint(min_size, max_size), MomentumAgent.py:42); mom_sizes: optional HOST int32 [n_envs][n_momentum] that
+ * overrides the draws (replay of a recorded reference run); either may be NULL (seed 0). */
+int32_t abx_dq_reset(abx_sim *h, const uint64_t *seeds, const int32_t *mom_sizes, void *stream);
+/* One decision step for every environment.  DEVICE pointers: actions int32 [n_envs] in 0..23 (ACTIONS, :24-37; ignored by
+ * environments with no decision pending, i.e. on the first call), obs fp64 [n_envs][8] = the 6 observation features (:332) + the 2
+ * digitised state entries the network sees (:334, util.py:23-42), trans fp64 [n_envs][6] = the finalised experience entry of the
+ * previous tick (s0, s1, a, s'0, s'1, r; r NaN == None; all NaN before the first tick), reward fp64 [n_envs] = sum of the
+ * step_reward_hist entries since the previous decision (:535), done uint8 [n_envs] (the event loop ended). */
+int32_t abx_dq_step(abx_sim *h, const int32_t *actions_dev, double *obs_dev, double *trans_dev, double *reward_dev, uint8_t *done_dev, void *stream);
+int32_t abx_dq_step_host(abx_sim *h, const int32_t *actions, double *obs, double *trans, double *reward, uint8_t *done, void *stream);
+/* Final state of one environment.  out: HOST int64 [(n_agents-1) * 5] rows (agent id, shares, cash, last_trade, open orders or -1);
+ * exec_out: HOST double [n_exec * 5] rows (remaining quantity, arrival price, executed orders, remaining_time, t). */
+int32_t abx_dq_holdings(abx_sim *h, int32_t env, int64_t *out, double *exec_out, void *stream);
+
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t abx_sim_launch_count(const abx_sim *h);
 

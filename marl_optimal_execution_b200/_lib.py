@@ -70,6 +70,17 @@ class EnvConfig(C.Structure):
     ]
 
 
+class DqConfig(C.Structure):
+    """abx_dq_config (include/abides_b200.h)."""
+    _fields_ = [
+        ("version", C.c_int32), ("n_momentum", C.c_int32), ("n_twap", C.c_int32), ("has_ddqn", C.c_int32), ("is_buy", C.c_int32),
+        ("n_horizon", C.c_int32), ("quantity", C.c_int64), ("start_ns", C.c_int64), ("stop_ns", C.c_int64),
+        ("mkt_open_ns", C.c_int64), ("mkt_close_ns", C.c_int64), ("horizon_start_ns", C.c_int64), ("horizon_step_ns", C.c_int64),
+        ("mom_wake_ns", C.c_int64), ("mom_min_size", C.c_int32), ("mom_max_size", C.c_int32), ("stream_history", C.c_int32),
+        ("queue_cap", C.c_int32), ("level_cap", C.c_int32), ("order_cap", C.c_int32), ("trace_cap", C.c_int32), ("hash_pops", C.c_int32),
+    ]
+
+
 class EnvStats(C.Structure):
     """abx_env_stats (include/abides_b200.h)."""
     _fields_ = [
@@ -135,6 +146,12 @@ def _bind(L):
     sig("abx_env_reset", i32, vp, vp)
     sig("abx_env_step", i32, vp, vp, vp, vp, vp, vp)
     sig("abx_env_step_host", i32, vp, vp, vp, vp, vp, vp)
+    sig("abx_dq_config_default", i32, P(DqConfig))
+    sig("abx_dq_create", i32, P(DqConfig), P(i64), i64, i32, i32, P(vp))
+    sig("abx_dq_reset", i32, vp, vp, vp, vp)
+    sig("abx_dq_step", i32, vp, vp, vp, vp, vp, vp, vp)
+    sig("abx_dq_step_host", i32, vp, vp, vp, vp, vp, vp, vp)
+    sig("abx_dq_holdings", i32, vp, i32, vp, vp, vp)
     return L
 
 

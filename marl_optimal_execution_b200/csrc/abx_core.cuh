@@ -60,7 +60,7 @@ enum : uint32_t {
 };
 enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE = 1, ST_AWAITING_SPREAD = 2 }; // ZeroIntelligenceAgent.state
 enum : uint32_t { AF_TYPE_SHIFT = 16, AF_TYPE_MASK = 7u << 16 };
-enum { AT_ZI = 0, AT_NOISE = 1, AT_VALUE = 2, AT_MOMENTUM = 3, AT_POVMM = 4 };   // agent class (config/rmsc03.py population)
+enum { AT_ZI = 0, AT_NOISE = 1, AT_VALUE = 2, AT_MOMENTUM = 3, AT_POVMM = 4, AT_TWAP = 5, AT_DDQN = 6 };   // agent class (rmsc03 / DDQN execution populations)
 constexpr int AGENT_ORDER_CAP = 4;      // open orders tracked per trader (ZI holds <= 2)
 
 struct alignas(16) ZiAgent {            // 192 B per trader: TradingAgent + ZeroIntelligenceAgent state
@@ -80,6 +80,20 @@ static_assert(sizeof(ZiAgent) == 192, "ZiAgent layout");
 // rmsc03 agents overlay these 40 bytes on ZiAgent.theta (only ZI agents have private values)
 struct AgentAux { int32_t size, order_size, last_mid, tv; uint32_t mmflags; int32_t n_mids; double avg20, avg50; };
 static_assert(sizeof(AgentAux) == 40, "AgentAux overlays ZiAgent.theta");
+// Execution agents of the DDQN config (TWAPExecutionAgent / DDQLearningExecutionAgent) overlay these 88 bytes on ZiAgent.oid .. surplus
+// (their open orders live in a per-environment HBM table: a market order walks up to DQ_DEPTH levels).
+struct ExecAux {
+  int32_t rem_qty, executed_sum, n_executed, arr2;      // remaining_qty / rem_quantity, sum of fills, len(executed_orders), 2 * arrival_price (0 == None)
+  int32_t t, rem_time, n_pp, pp0_2;                     // DDQN: self.t, self.remaining_time, len(price_path), 2 * price_path[0]
+  int32_t pp_last2, child_qty, exflags, e_a;            // 2 * price_path[-1]; schedule quantity; EXF_*; experience[t-1] action
+  int16_t cur_s[2], sp[2];                              // self.s; s' of the pending decision
+  int16_t e_s[2], e_sp[2];                              // experience[t-1] = (s, a, s', r)
+  double e_r, step_reward;                              // r (valid with EXF_E_R); sum of step_reward_hist entries since the last decision
+};
+static_assert(sizeof(ExecAux) == 80 && sizeof(ExecAux) <= 112, "ExecAux overlays ZiAgent.oid .. surplus");
+enum : uint32_t { EXF_TRADE = 1u, EXF_E_VALID = 2u, EXF_E_R = 4u };
+constexpr int EXEC_ORDER_CAP = 512;     // self.orders of one execution agent
+constexpr int DQ_DEPTH = 500;           // getCurrentSpread(depth=500) execution_agent.py:77, ddqlearning_execution_agent.py:152
 enum : uint32_t { MMF_AW_SPREAD = 1u, MMF_AW_VOL = 2u, MMF_HAS_MID = 4u, MOF_HAS20 = 8u, MOF_HAS50 = 16u };
 constexpr int MM_ORDER_CAP = 128;       // POV market maker: 2 * (num_ticks + 1) = 42 orders placed per wake, cancelled at the next
 constexpr int TV_RING = 512;            // recent (time, qty) transaction tuples kept for get_transacted_volume
@@ -135,11 +149,15 @@ struct SimParams {
   struct EnvX *envx;                                // [n_envs]
   uint4 *idtab;                                     // [n_envs][n_ids] {agent-view qty, price<<1|is_buy, last registration epoch, epoch mask}
   int4 *lobs;                                       // [n_envs][LOB_CAP][3] stored QUERY_SPREAD replies (ABIDESEnvMetrics.data)
+  // ---- DDQN execution config (population 2): ids 0 exchange, 1 replay, 2.. momentum, then TWAP agents, then the DDQN agent ----
+  int32_t dq_n_mom, dq_n_twap, dq_has_ddqn, dq_order_base;   // dq_order_base: first idtab entry of the execution agents' order tables
+  int64_t dq_quantity;                              // parent order size
+  int64_t dq_id_limit;                              // smallest explicit ORDER_ID of the replayed stream: generated ids must stay below it
 };
 constexpr int LOB_CAP = 100;                        // ABIDESEnvMetrics(maxlen = 100) dummy_rl_execution_agent.py:125
 constexpr int RL_ORDER_CAP = 8;
 constexpr uint32_t REPLAY_ID_BASE = 0x40000000u;    // device order id of replayed order k = REPLAY_ID_BASE + dense id k
-enum : uint32_t { RLF_TRADE = 1u << 16, RLF_METRICS_INIT = 1u << 17 };
+enum : uint32_t { RLF_TRADE = 1u << 16, RLF_METRICS_INIT = 1u << 17, DQF_PENDING = 1u << 18 };   // DQF_PENDING: the DDQN agent waits inside place_order for its action
 
 struct alignas(16) EnvX {                           // per-environment state of the two ABIDESEnv traders (shared memory while stepping)
   int64_t ra_time, rl_time;                         // Kernel.agentCurrentTimes[1], [2]
@@ -275,6 +293,7 @@ typedef RngT<-1> Rng;
 // ---------------------------------------------------------------------------------------------------
 ABX_HD int agent_type_of(const abx_sim_config &c, int id) {
   if (c.population == 0) return AT_ZI;
+  if (c.population == 2) return id < 2 + c.n_momentum_agents ? AT_MOMENTUM : (id == c.n_agents - 1 && c.n_mm_agents ? AT_DDQN : AT_TWAP);   // n_mm_agents doubles as has_ddqn
   if (id <= c.n_noise_agents) return AT_NOISE;
   if (id <= c.n_noise_agents + c.n_value_agents) return AT_VALUE;
   if (id <= c.n_noise_agents + c.n_value_agents + c.n_mm_agents) return AT_POVMM;
@@ -328,6 +347,28 @@ ABX_HD void init_agent_record(const SimParams &P, int env, int id, uint64_t seed
   z->lat_to = lat_to; z->lat_from = lat_from; z->surplus = 0;
   if (rng.err) *err |= rng.err;
 }
+// DDQN execution config (population 2): MomentumAgent.__init__ (agent/examples/MomentumAgent.py:39-46), ExecutionAgent.__init__
+// (agent/execution/baselines/execution_agent.py:34-48), TWAP / DDQN generate_schedule (twap_agent.py:51-63, ddqlearning_execution_agent.py:496-505).
+// mom_size < 0: draw MomentumAgent.size = randint(min_size, max_size) from the agent's Philox stream.
+ABX_HD void init_agent_record_dq(const SimParams &P, int env, int id, uint64_t seed, int32_t mom_size, ZiAgent *z) {
+  int type = agent_type_of(P.c, id); uint32_t ctr = 0;
+  z->agent_time = P.c.start_ns; z->prev_wake = 0; z->r_t = 0.0; z->sigma_t = 0.0; z->cash = P.c.starting_cash; z->shares = 0; z->last_trade = 0;
+  z->daily_close = 0; z->bid = 0; z->bid_q = 0; z->ask = 0; z->ask_q = 0; z->n_orders = 0;
+  for (int i = 0; i < AGENT_ORDER_CAP; i++) { z->oid[i] = 0; z->oprice[i] = 0; z->oqty[i] = 0; }
+  for (int i = 0; i < 20; i++) z->theta[i] = 0;
+  z->lat_to = 0.0; z->lat_from = 0.0; z->surplus = 0;
+  if (type == AT_MOMENTUM) {
+    if (mom_size < 0) { RngT<ABX_RNG_PHILOX> rng; rng.P = &P; rng.env = env; rng.seed = seed; rng.err = 0; mom_size = P.c.mom_min_size + (int32_t)rng.randint(S_AGENT0 + id, ctr, (uint32_t)(P.c.mom_max_size - P.c.mom_min_size - 1)); }
+    AgentAux ax; ax.size = mom_size; ax.order_size = 0; ax.last_mid = 0; ax.tv = 0; ax.mmflags = 0; ax.n_mids = 0; ax.avg20 = 0.0; ax.avg50 = 0.0;
+    *reinterpret_cast<AgentAux *>(z->theta) = ax;
+  } else {
+    ExecAux ex; ex.rem_qty = (int32_t)P.dq_quantity; ex.executed_sum = 0; ex.n_executed = 0; ex.arr2 = 0; ex.t = 0; ex.rem_time = P.n_h - 1; ex.n_pp = 0; ex.pp0_2 = 0; ex.pp_last2 = 0;
+    ex.child_qty = type == AT_DDQN ? (int32_t)((double)P.dq_quantity / (double)(P.n_h - 1)) : (int32_t)((double)P.dq_quantity / (double)P.n_h);
+    ex.exflags = EXF_TRADE; ex.e_a = 0; for (int i = 0; i < 2; i++) { ex.cur_s[i] = 0; ex.sp[i] = 0; ex.e_s[i] = 0; ex.e_sp[i] = 0; } ex.e_r = 0.0; ex.step_reward = 0.0;
+    *reinterpret_cast<ExecAux *>(z->oid) = ex;
+  }
+  z->flags = ((uint32_t)type << AF_TYPE_SHIFT) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT); z->rng_ctr = ctr;
+}
 ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
   s.now = P.c.start_ns; s.ttl = 0; s.exch_time = P.c.start_ns; s.exch_comp_delay = P.c.default_computation_delay_ns;   // Kernel.py:97,105
   s.or_t = P.c.mkt_open_ns; s.ms_t = 0; s.ms_v = 0.0; s.pop_hash = 0xCBF29CE484222325ULL; s.seed = seed;
@@ -372,10 +413,10 @@ ABX_HD void regs_store(ZiAgent *z, const AgentRegs &a) {
 
 // RNG_MODE / LAT_MODEL: compile-time copies of cfg.rng_mode / cfg.latency_model (-1 = decide at run time);
 // INSTR: parity instrumentation (pop hash + trace records) compiled in or out.
-enum { SHAPE_ZI = 0, SHAPE_ENV = 1, SHAPE_R3 = 2 };   // sparse_zi population | ABIDESEnv / marketreplay | rmsc03 population
+enum { SHAPE_ZI = 0, SHAPE_ENV = 1, SHAPE_R3 = 2, SHAPE_DQ = 3 };   // sparse_zi population | ABIDESEnv / marketreplay | rmsc03 population | DDQN execution config
 template <class Ctx, int RNG_MODE = -1, int LAT_MODEL = -1, bool INSTR = true, int SHAPE = SHAPE_ZI>
 struct Sim {
-  static constexpr bool ENV = SHAPE == SHAPE_ENV, R3 = SHAPE == SHAPE_R3;
+  static constexpr bool DQ = SHAPE == SHAPE_DQ, ENV = SHAPE == SHAPE_ENV || DQ, R3 = SHAPE == SHAPE_R3;
   Ctx &c; const SimParams &P; EnvState s; RngT<RNG_MODE> rng; int64_t addl_delay; int n_out; int self_id;
   AgentRegs a; ZiAgent *z;                // the trader whose event is being handled (registers + staged record)
 
@@ -873,10 +914,11 @@ struct Sim {
       if (t_closed) f |= 4;
       f |= (nb > 2 ? 2 : nb) << 3; f |= (na > 2 ? 2 : na) << 5;
       p[4] = s.last_trade; p[5] = f;
+      if (DQ) b2 = (int32_t)s.ctr_kernel;                                               // DDQN config: the reply carries the book version instead (dq_exec_receive)
       exch_send(m.sender, ABX_QUERY_SPREAD, p, bits_dbl((uint64_t)(uint32_t)b2 | ((uint64_t)(uint32_t)a2 << 32)));
-    } else if (m.kind == ABX_LIMIT_ORDER) { s.c_limit++; book_handle_limit((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[2], 0.0); c.sync(); trace_snap(); }
-    else if (m.kind == ABX_CANCEL_ORDER) { s.c_cancel++; book_cancel((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], 0.0); c.sync(); trace_snap(); }
-    else if (m.kind == ABX_MODIFY_ORDER) { if (!(m.p[4] & 2)) book_modify((uint32_t)m.p[0], m.sender, m.p[4] & 1, m.p[1], m.p[3], m.p[5]); c.sync(); trace_snap(); }   // :326-340 (bit 1: ids differ, :343)
+    } else if (m.kind == ABX_LIMIT_ORDER) { s.c_limit++; s.ctr_kernel++; book_handle_limit((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[2], 0.0); c.sync(); trace_snap(); }
+    else if (m.kind == ABX_CANCEL_ORDER) { s.c_cancel++; s.ctr_kernel++; book_cancel((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], 0.0); c.sync(); trace_snap(); }
+    else if (m.kind == ABX_MODIFY_ORDER) { s.ctr_kernel++; if (!(m.p[4] & 2)) book_modify((uint32_t)m.p[0], m.sender, m.p[4] & 1, m.p[1], m.p[3], m.p[5]); c.sync(); trace_snap(); }   // :326-340 (bit 1: ids differ, :343)
   }
   // ---- MarketReplayAgent ----
   ABX_HD void replay_place(EnvX *x, int r) {                                            // placeOrder :69-96 for one row
@@ -1075,6 +1117,241 @@ struct Sim {
     return !more;
   }
 
+
+  // =================================================================================================
+  // DDQN execution config (config/execution/marketreplay/execution_marketreplay_ddqn.py, -a rl): Exchange (0) + MarketReplayAgent (1,
+  // EnvX) + MomentumAgents (2.., staged records, r3_* handlers) + TWAPExecutionAgent(s) + DDQLearningExecutionAgent (last id) under
+  // Kernel.runner; zero latency and computation delay.  agent/execution/baselines/execution_agent.py:66-130, twap_agent.py:51-63,
+  // agent/execution/qlearning/ddqlearning_execution_agent.py:20-37,141-185,228-447,507-611, agent/execution/util.py:6-42,
+  // agent/TradingAgent.py:351-397 (placeMarketOrder).  The Q-network is outside: one launch runs every environment up to the DDQN
+  // agent's next choose_action (:245) and the following launch resumes place_order with the action.
+  // Depth-500 QUERY_SPREAD replies: the execution agents read the lists only while handling the reply, and with zero delays no book
+  // operation can sort between the exchange's snapshot and that delivery, so the handlers read the live ladders; the reply carries the
+  // book-operation counter and a mismatch raises ABX_F_UNSUPPORTED instead of trading on different data.  L1 is cached in the record.
+  // =================================================================================================
+  ABX_HD ExecAux *exaux() { return reinterpret_cast<ExecAux *>(z->oid); }
+  ABX_HD int dq_order_base(int id) const { return P.dq_order_base + (id - (2 + P.dq_n_mom)) * EXEC_ORDER_CAP; }
+  ABX_HD int dq_horizon_index(int64_t t) const { if (t < P.h0_ns || (t - P.h0_ns) % P.h_step_ns) return -1; int64_t k = (t - P.h0_ns) / P.h_step_ns; return k < P.n_h ? (int)k : -1; }
+  ABX_HD void dq_place_limit(int id, int32_t size, bool buy, int32_t price) {           // TradingAgent.placeLimitOrder :309-349
+    uint32_t oid = s.next_order_id++;
+    if (size <= 0) return;
+    if (a.n_orders < EXEC_ORDER_CAP) { uint4 v; v.x = oid; v.y = (uint32_t)price; v.z = (uint32_t)(buy ? size : -size); v.w = 0; c.id_store(dq_order_base(id) + a.n_orders, v); a.n_orders++; }
+    else s.flags |= ABX_F_AGENT_ORDERS_OVERFLOW;
+    int32_t pl[6] = {(int32_t)oid, price, size, 0, buy, 0}; env_send(ABX_LIMIT_ORDER, pl, false);
+    if (n_out >= OUT_CAP - 3) flush();
+  }
+  ABX_HD void dq_cancel_all(int id) {                                                   // ExecutionAgent.cancelOrders :126-128 / DDQN cancel_orders :578-585
+    int base = dq_order_base(id);
+#pragma unroll 1
+    for (int i = 0; i < a.n_orders; i++) {
+      uint4 v = c.id_load(base + i); int32_t q = (int32_t)v.z;
+      int32_t p[6] = {(int32_t)v.x, (int32_t)v.y, q < 0 ? -q : q, 0, q > 0, 0}; env_send(ABX_CANCEL_ORDER, p, false);
+      if (n_out >= OUT_CAP - 3) flush();
+    }
+  }
+  ABX_HD void dq_order_update(int id, uint32_t oid, int32_t fill, bool cancel) {         // TradingAgent.orderExecuted :445-452, orderCancelled :480-483
+    int base = dq_order_base(id), f = -1;
+#pragma unroll 1
+    for (int i = 0; i < a.n_orders && f < 0; i++) { uint4 v = c.id_load(base + i); if (v.x == oid) f = i; }
+    if (f < 0) return;
+    uint4 v = c.id_load(base + f); int32_t q = (int32_t)v.z, aq = q < 0 ? -q : q;
+    if (!cancel && fill < aq) { v.z = (uint32_t)(q < 0 ? -(aq - fill) : (aq - fill)); c.id_store(base + f, v); return; }
+#pragma unroll 1
+    for (int i = f; i + 1 < a.n_orders; i++) c.id_store(base + i, c.id_load(base + i + 1));
+    a.n_orders--;
+  }
+  ABX_HD void dq_place_market(int id, int32_t quantity) {                               // TradingAgent.placeMarketOrder :351-397 over the cached opposite side
+    if (quantity <= 0) return;
+    int opp = P.rl_is_buy ? 1 : 0; int n = n_lv(opp); int depth = n < DQ_DEPTH ? n : DQ_DEPTH;
+    if (n == 0) { s.flags |= ABX_F_OBS_INVALID; return; }                               // the reference iterates None
+#pragma unroll 1
+    for (int i = 0; i < depth; i++) {
+      int32_t price = c.lv_price(opp, n - 1 - i), sz = c.lv_qty(opp, n - 1 - i);
+      bool last = quantity <= sz;
+      dq_place_limit(id, last ? quantity : sz, P.rl_is_buy != 0, price);
+      if (last) break;
+      quantity -= sz;
+    }
+  }
+  // np.digitize(x, np.linspace(0, 1, 201)[1:-1]): number of split points k * (1 / 200), k = 1 .. 199, that are <= x
+  ABX_HD int dq_digitize(double x) const {
+    int k = x > 0.0 ? (x < 1.0 ? (int)(x * 200.0) : 199) : 0; if (k > 199) k = 199;
+    while (k < 199 && dmul((double)(k + 1), 1.0 / 200) <= x) k++;
+    while (k > 0 && dmul((double)k, 1.0 / 200) > x) k--;
+    return k;
+  }
+  // DDQLearningExecutionAgent.get_observation :280-336 from the cached L1 (known_bids[0] / known_asks[0])
+  ABX_HD void dq_get_observation(ExecAux &ex, double obs[6], int disc[2]) {
+    int64_t curr = s.now - (s.now % P.h_step_ns); int hi = dq_horizon_index(curr);
+    ex.rem_time = hi >= 0 ? P.n_h - 1 - hi : P.n_h;
+    for (int i = 0; i < 6; i++) obs[i] = 0.0; disc[0] = disc[1] = 0;
+    if (!(a.flags & AF_HAS_BID) || !(a.flags & AF_HAS_ASK)) { s.flags |= ABX_F_OBS_INVALID; return; }
+    obs[0] = dsub(dmul(2.0, (double)ex.rem_time / (double)P.n_h), 1.0);
+    obs[1] = dsub(dmul(2.0, (double)ex.rem_qty / (double)P.dq_quantity), 1.0);
+    obs[2] = (double)(a.ask - a.bid);
+    obs[3] = (double)(a.ask_q - a.bid_q) / (double)(a.ask_q + a.bid_q);
+    int32_t mid2 = a.bid + a.ask, prev2 = ex.pp_last2; double mid = (double)mid2 / 2;
+    if (ex.n_pp == 0) ex.pp0_2 = mid2;
+    ex.pp_last2 = mid2; ex.n_pp++;                                                      // price_path.append(mid_p)
+    obs[4] = s.now == P.h0_ns ? 0.0 : log_ni(mid / ((double)prev2 / 2));
+    obs[5] = log_ni(mid / ((double)ex.pp0_2 / 2));
+    disc[0] = dq_digitize(obs[0]); disc[1] = dq_digitize(obs[1]);                       // the grid has two dimensions: zip() drops the other four features
+  }
+  ABX_HD void exaux_store(const ExecAux &ex) { c.sync(); if (c.onchip_writer()) *exaux() = ex; c.sync(); }
+  ABX_HD void dq_exec_wakeup(int id, int type) {
+    if (!ta_wakeup(a.flags)) return;
+    ExecAux ex = *exaux();
+    int64_t k = s.now < P.h0_ns ? 0 : (s.now - P.h0_ns) / P.h_step_ns + 1;              // first horizon time > now
+    bool query = false;
+    if (type == AT_DDQN) {                                                              // ddqlearning_execution_agent.py:141-153
+      if (ex.exflags & EXF_TRADE) { if (k < P.n_h) set_wakeup(id, P.h0_ns + k * P.h_step_ns); else ex.exflags &= ~EXF_TRADE; }
+      query = true;
+    } else if (ex.exflags & EXF_TRADE) {                                                // execution_agent.py:66-78
+      if (k < P.n_h) set_wakeup(id, P.h0_ns + k * P.h_step_ns);
+      query = true;
+    }
+    if (query) { int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); a.flags = (a.flags & ~AF_STATE_MASK) | (ST_AWAITING_SPREAD << AF_STATE_SHIFT); }
+    exaux_store(ex);
+  }
+  ABX_HD void dq_exec_receive(int id, int type, const Event &m, EnvX *x) {
+    bool had = (a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE);
+    ExecAux ex = *exaux();
+    if (m.kind == ABX_WHEN_MKT_OPEN) a.flags |= AF_HAS_OPEN;
+    else if (m.kind == ABX_WHEN_MKT_CLOSE) a.flags |= AF_HAS_CLOSE;
+    else if (m.kind == ABX_ORDER_EXECUTED) {                                            // TradingAgent.orderExecuted :422-462
+      int32_t q = m.p[2]; int32_t sq = m.p[4] ? q : -q; a.shares += sq; a.cash -= (int64_t)sq * m.p[3];
+      dq_order_update(id, (uint32_t)m.p[0], q, false);
+      ex.executed_sum += q; ex.n_executed++; ex.rem_qty = (int32_t)P.dq_quantity - ex.executed_sum;     // handleOrderExecution :88-92 / handle_order_execution :517-521
+    } else if (m.kind == ABX_ORDER_CANCELLED) dq_order_update(id, (uint32_t)m.p[0], 0, true);
+    else if (m.kind == ABX_MKT_CLOSED) a.flags |= AF_MKT_CLOSED;
+    else if (m.kind == ABX_QUERY_SPREAD) {                                              // querySpread :514-537
+      if (m.p[5] & 4) a.flags |= AF_MKT_CLOSED;
+      a.last_trade = m.p[4]; a.flags |= AF_HAS_LAST;
+      a.flags &= ~(AF_HAS_BID | AF_HAS_ASK);
+      if (m.p[5] & 1) { a.flags |= AF_HAS_BID; a.bid = m.p[0]; a.bid_q = m.p[1]; } else { a.bid = 0; a.bid_q = 0; }
+      if (m.p[5] & 2) { a.flags |= AF_HAS_ASK; a.ask = m.p[2]; a.ask_q = m.p[3]; } else { a.ask = 0; a.ask_q = 0; }
+      if ((uint32_t)m.x0 != s.ctr_kernel) s.flags |= ABX_F_UNSUPPORTED;                 // the book moved between snapshot and delivery
+    }
+    if ((a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE) && !had) set_wakeup(id, P.h0_ns);         // mkt_open + (start_time - mkt_open)
+    uint32_t st = (a.flags & AF_STATE_MASK) >> AF_STATE_SHIFT;
+    bool both = (a.flags & AF_HAS_BID) && (a.flags & AF_HAS_ASK);
+    if (type == AT_TWAP) {                                                              // ExecutionAgent.receiveMessage :80-86
+      if (ex.rem_qty > 0 && st == ST_AWAITING_SPREAD && m.kind == ABX_QUERY_SPREAD) {
+        dq_cancel_all(id);
+        int hi = dq_horizon_index(s.now);                                               // placeOrders :107-124
+        if (hi == P.n_h - 2) dq_place_market(id, ex.rem_qty);
+        else if (hi >= 0 && hi < P.n_h - 2) {
+          if (!both) s.flags |= ABX_F_OBS_INVALID;
+          else { if (hi == 0) ex.arr2 = a.bid + a.ask; dq_place_limit(id, ex.child_qty, P.rl_is_buy != 0, P.rl_is_buy ? a.ask : a.bid); }
+        }
+      }
+    } else if (m.kind == ABX_ORDER_ACCEPTED || m.kind == ABX_ORDER_EXECUTED) {         // handle_order_acceptance :550-576 / handle_order_execution :507-548
+      int64_t curr = s.now - (s.now % P.h_step_ns);
+      if (dq_horizon_index(curr) >= 0) {
+        double o6[6]; int sp[2]; dq_get_observation(ex, o6, sp);
+        ex.e_sp[0] = (int16_t)sp[0]; ex.e_sp[1] = (int16_t)sp[1]; ex.cur_s[0] = (int16_t)sp[0]; ex.cur_s[1] = (int16_t)sp[1];
+        if (m.kind == ABX_ORDER_EXECUTED) {                                             // compute_reward :411-447
+          double fp = (double)m.p[3], ar = (double)ex.arr2 / 2;
+          double slip = P.rl_is_buy ? dsub(fp, ar) : dsub(ar, fp);
+          double r = dmul(dmul(dsub(1.0, slip / ar), (double)m.p[2]) / (double)P.dq_quantity, 10000.0);
+          ex.e_r = r; ex.step_reward = dadd(ex.step_reward, r);
+        } else ex.e_r = 0.0;
+        ex.exflags |= EXF_E_R;
+      }
+    } else {
+      int hi = dq_horizon_index(s.now);
+      if (hi >= 0 && hi < P.n_h - 1 && ex.rem_qty > 0 && st == ST_AWAITING_SPREAD && m.kind == ABX_QUERY_SPREAD) {   // :164-172
+        dq_cancel_all(id);
+        if (!both) s.flags |= ABX_F_OBS_INVALID;
+        else {                                                                          // place_order :228-245 up to choose_action
+          double o6[6]; int sp[2];
+          if (hi == 0) { ex.arr2 = a.bid + a.ask; dq_get_observation(ex, o6, sp); ex.cur_s[0] = (int16_t)sp[0]; ex.cur_s[1] = (int16_t)sp[1]; }
+          dq_get_observation(ex, o6, sp); ex.sp[0] = (int16_t)sp[0]; ex.sp[1] = (int16_t)sp[1];
+          c.sync();
+          if (c.onchip_writer()) { for (int i = 0; i < 6; i++) x->obs[i] = o6[i]; x->obs[6] = sp[0]; x->obs[7] = sp[1]; x->obs_len = 8; x->rl_flags = x->rl_flags | DQF_PENDING; }
+          c.sync();
+        }
+      }
+    }
+    exaux_store(ex);
+  }
+  static ABX_HD double dq_alloc_frac(int alloc, int lv) {                               // SIZE_ALLOCATION :20
+    if (alloc == 1) return lv == 0 ? 1.0 : 0.0;
+    if (alloc == 2) return lv < 2 ? 0.5 : 0.0;
+    return lv == 0 ? 0.34 : (lv < 3 ? 0.33 : 0.0);
+  }
+  // place_order :245-278 from choose_action's return on, then receiveMessage :172 (self.t += 1); the DDQN agent's record is staged
+  ABX_HD void dq_resume(int id, int action) {
+    ExecAux ex = *exaux();
+    if (action < 0) action = 0; if (action > 23) action = 23;
+    int alloc = action / 6, j = action % 6; int32_t qty = ex.child_qty;                 // ACTIONS[a] = (allocation a / 6, SIZE_SCALE[a % 6]) :24-37
+    if (ex.rem_time == 1) { qty = ex.rem_qty; alloc = 0; }                              // take_action :380-384
+    else { double sc = j == 0 ? 0.1 : dmul(0.5, (double)j); qty = (int32_t)py_round_i64(dmul(sc, (double)qty)); if (qty < 0) qty = 0; }
+    ex.e_s[0] = ex.cur_s[0]; ex.e_s[1] = ex.cur_s[1]; ex.e_a = action; ex.e_sp[0] = ex.sp[0]; ex.e_sp[1] = ex.sp[1]; ex.e_r = 0.0;   // experience[t] = (self.s, a, s', None)
+    ex.exflags = (ex.exflags | EXF_E_VALID) & ~EXF_E_R; ex.cur_s[0] = ex.sp[0]; ex.cur_s[1] = ex.sp[1]; ex.t++; ex.step_reward = 0.0;
+    exaux_store(ex);
+    if (alloc == 0) dq_place_market(id, qty);
+    else {
+      int own = P.rl_is_buy ? 0 : 1, n = n_lv(own);
+#pragma unroll 1
+      for (int lv = 0; lv < 4; lv++) {                                                  // :395-409 (the price is read before the size test: IndexError below 4 levels)
+        int32_t size = (int32_t)py_round_i64(dmul(dq_alloc_frac(alloc, lv), (double)qty));
+        if (lv >= n) { s.flags |= ABX_F_UNSUPPORTED; break; }
+        int32_t price = c.lv_price(own, n - 1 - lv);
+        if (size != 0) dq_place_limit(id, size, P.rl_is_buy != 0, price);
+      }
+    }
+  }
+  // One decision step: finish the pending place_order with `action`, then Kernel.runner's loop (Kernel.py:190-292) until the DDQN agent
+  // reaches choose_action again (returns true) or the loop ends (ABX_F_DONE, returns false).
+  ABX_HD bool dq_step(int action) {
+    EnvX *x = c.envx(); int ddqn_id = P.dq_has_ddqn ? P.c.n_agents - 1 : -1;
+    if (x->rl_flags & DQF_PENDING) {
+      z = c.agent_stage(ddqn_id); regs_load(a, z); self_id = ddqn_id; addl_delay = 0;
+      dq_resume(ddqn_id, action);
+      c.sync(); if (c.onchip_writer()) { regs_store(z, a); x->rl_flags = x->rl_flags & ~DQF_PENDING; x->obs_len = 0; } c.sync();
+      c.agent_commit(ddqn_id); flush();
+    }
+    bool paused = false;
+#pragma unroll 1
+    while (!paused) {
+      uint64_t khi; uint32_t kuniq; int grp;
+      bool any = c.q_min(khi, kuniq, grp);
+      if (!any || !(s.now <= P.c.stop_ns)) { s.flags |= ABX_F_DONE; break; }
+      Event ev; c.q_fetch(grp, ev);
+      s.now = ev.t; s.ttl++;
+      if (INSTR && P.c.hash_pops) s.pop_hash = fnv_mix(fnv_mix(fnv_mix(fnv_mix(s.pop_hash, ev.t), ev.recipient), ev.type), ev.type == ABX_T_MESSAGE ? (int64_t)ev.uniq : -1);
+      if (INSTR && P.c.trace_cap > 0) {
+        abx_trace_rec r; r.tag = 0; r.a = ev.recipient; r.t = ev.t; for (int i = 0; i < 16; i++) r.v[i] = 0;
+        r.v[0] = ev.type; r.v[1] = ev.type == ABX_T_MESSAGE ? (int32_t)ev.uniq : -1; r.v[2] = ev.kind; trace_rec(r);
+      }
+      addl_delay = 0;
+      int id = ev.recipient;
+      if (id <= 1) {
+        int64_t at = id == 0 ? s.exch_time : x->ra_time;
+        if (at > s.now) { c.q_requeue(at); continue; }
+        c.q_remove(); s.q_count--; self_id = id;
+        if (id == 0) { if (ev.type == ABX_T_MESSAGE) env_exch_receive(ev); s.exch_time = s.now + s.exch_comp_delay + addl_delay; }
+        else { if (ev.type == ABX_T_WAKEUP) replay_wakeup(x); else replay_receive(x, ev); if (c.onchip_writer()) x->ra_time = s.now + P.c.default_computation_delay_ns + addl_delay; }
+      } else {
+        z = c.agent_stage(id); regs_load(a, z);
+        if (a.agent_time > s.now) { c.q_requeue(a.agent_time); continue; }
+        c.q_remove(); s.q_count--; self_id = id;
+        int type = (int)((a.flags & AF_TYPE_MASK) >> AF_TYPE_SHIFT);
+        if (type == AT_MOMENTUM) { if (ev.type == ABX_T_WAKEUP) r3_wakeup(id); else r3_receive(id, ev); }
+        else if (ev.type == ABX_T_WAKEUP) dq_exec_wakeup(id, type); else dq_exec_receive(id, type, ev, x);
+        a.agent_time = s.now + P.c.default_computation_delay_ns + addl_delay;
+        c.sync(); if (c.onchip_writer()) regs_store(z, a); c.sync();
+        c.agent_commit(id);
+        paused = (x->rl_flags & DQF_PENDING) != 0;
+      }
+      flush();
+    }
+    if ((int64_t)s.next_order_id >= P.dq_id_limit) s.flags |= ABX_F_UNSUPPORTED;        // generated ids reached the stream's explicit ids (util/order/Order.py:35-42 would skip them)
+    s.flags |= rng.err;
+    c.sync();
+    return paused;
+  }
 
   // =================================================================================================
   // rmsc03 population (config/rmsc03.py): NoiseAgent, ValueAgent, MomentumAgent, POVMarketMakerAgent + the exchange's

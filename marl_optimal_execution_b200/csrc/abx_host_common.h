@@ -125,7 +125,43 @@ static inline void env_fill_params(const abx_env_config &e, SimParams &P) {
   P.n_h = e.n_horizon; P.h0_ns = e.horizon_start_ns; P.h_step_ns = e.horizon_step_ns; P.rl_quantity = e.quantity; P.rl_steep = e.steep;
   P.order_level = e.order_level; P.rl_is_buy = e.is_buy;
 }
-struct EnvStreamHost { std::vector<int64_t> ts, id_orig; std::vector<int32_t> first; std::vector<int4> rows; };
+// ---- DDQN execution shape (config/execution/marketreplay/execution_marketreplay_ddqn.py) ----
+static inline int dq_config_default(abx_dq_config *c) {
+  if (!c) return ABX_ERR_ARG;
+  memset(c, 0, sizeof(*c));
+  c->version = ABX_VERSION; c->n_momentum = 7; c->n_twap = 1; c->has_ddqn = 1; c->is_buy = 1; c->n_horizon = 661; c->quantity = 500000;   // :140-258, scripts: BUY 5e5 from 10:00 over 330 min at 30 s
+  c->start_ns = 0; c->mkt_open_ns = (9 * 3600 + 1800) * NS; c->mkt_close_ns = 16 * 3600 * NS;                                     // :93-97
+  c->horizon_start_ns = 10 * 3600 * NS; c->horizon_step_ns = 30 * NS; c->stop_ns = c->horizon_start_ns + 660 * c->horizon_step_ns + 600 * NS;   // :317-318
+  c->mom_wake_ns = 20 * NS; c->mom_min_size = 1; c->mom_max_size = 10; c->stream_history = 10;
+  c->queue_cap = 1536;             // the closing market order walks up to DQ_DEPTH levels: <= 500 LIMIT_ORDERs in flight + 2 ORDER_EXECUTED each (recorded maximum 1 066)
+  c->level_cap = 256; c->order_cap = 16384; c->trace_cap = 0; c->hash_pops = 0;
+  return ABX_OK;
+}
+static inline int dq_config_validate(const abx_dq_config *c) {
+  if (!c || c->version != ABX_VERSION || c->n_momentum < 0 || c->n_momentum > 8 || c->n_twap < 0 || c->n_twap > 2 || c->n_horizon < 3) return ABX_ERR_ARG;
+  if (c->queue_cap < 32 || c->queue_cap % 32 || c->queue_cap > 4096 || c->level_cap < 8 || c->level_cap > 2048) return ABX_ERR_ARG;
+  if (c->order_cap < 8 || c->order_cap > 65535 || c->stop_ns >= KEY_T_MAX || c->start_ns < 0 || c->horizon_step_ns <= 0 || c->mom_wake_ns <= 0) return ABX_ERR_ARG;
+  if (c->stream_history < 0 || c->stream_history > 14 || c->quantity <= 0 || c->quantity > 0x3fffffffLL || c->trace_cap < 0 || c->mom_max_size <= c->mom_min_size) return ABX_ERR_ARG;
+  return ABX_OK;
+}
+static inline void dq_fill_params(const abx_dq_config &e, SimParams &P) {
+  abx_sim_config &c = P.c; memset(&c, 0, sizeof(c));
+  c.version = ABX_VERSION; c.population = 2; c.n_momentum_agents = e.n_momentum; c.n_mm_agents = e.has_ddqn ? 1 : 0;   // population 2: n_mm_agents == "has a DDQN agent" (agent_type_of)
+  c.n_agents = 2 + e.n_momentum + e.n_twap + (e.has_ddqn ? 1 : 0); c.n_groups = 0; c.q_max = 1;
+  c.start_ns = e.start_ns; c.stop_ns = e.stop_ns; c.mkt_open_ns = e.mkt_open_ns; c.mkt_close_ns = e.mkt_close_ns;
+  c.default_computation_delay_ns = 0; c.exchange_computation_delay_ns = 0; c.exchange_pipeline_delay_ns = 0; c.starting_cash = 0;           // :113-114,327 ; starting_cash=0 :141,163,...
+  c.stream_history = e.stream_history; c.latency_model = ABX_LAT_ZERO; c.n_noise = 1; c.mom_wake_ns = e.mom_wake_ns; c.mom_min_size = e.mom_min_size; c.mom_max_size = e.mom_max_size;
+  c.queue_cap = e.queue_cap; c.level_cap = e.level_cap; c.order_cap = e.order_cap; c.rng_mode = ABX_RNG_PHILOX; c.trace_cap = e.trace_cap; c.hash_pops = e.hash_pops;
+  P.n_qgroups = c.queue_cap / 32; P.n_streams = 0;
+  P.n_h = e.n_horizon; P.h0_ns = e.horizon_start_ns; P.h_step_ns = e.horizon_step_ns; P.rl_quantity = (double)e.quantity; P.rl_steep = 0.5; P.order_level = 0; P.rl_is_buy = e.is_buy;
+  P.dq_n_mom = e.n_momentum; P.dq_n_twap = e.n_twap; P.dq_has_ddqn = e.has_ddqn ? 1 : 0; P.dq_quantity = e.quantity;
+}
+// ids the generator can hand out in one run: momentum orders + execution-agent orders (market orders walk <= DQ_DEPTH levels)
+static inline int64_t dq_max_generated_ids(const abx_dq_config &e) {
+  int64_t wakes = (e.stop_ns - e.mkt_open_ns) / e.mom_wake_ns + 2;
+  return (int64_t)e.n_momentum * wakes + (int64_t)(e.n_twap + 1) * ((int64_t)e.n_horizon * 8 + 2 * DQ_DEPTH) + 16;
+}
+struct EnvStreamHost { std::vector<int64_t> ts, id_orig; std::vector<int32_t> first; std::vector<int4> rows; int64_t min_id; };
 // LOBSTER ORDER_IDs -> dense indices; rows grouped by identical timestamp (orders_dict of MarketReplayAgent.py:214)
 static inline int env_build_stream(const int64_t *s5, int64_t n, int64_t max_rl_ids, EnvStreamHost &o) {
   if (!s5 || n < 1 || n > 0x3fffffff) return ABX_ERR_ARG;
@@ -143,7 +179,7 @@ static inline int env_build_stream(const int64_t *s5, int64_t n, int64_t max_rl_
     if (i == 0 || r[0] != s5[5 * (i - 1)]) { o.ts.push_back(r[0]); o.first.push_back((int32_t)i); }
     int4 row; row.x = d; row.y = (int32_t)r[2]; row.z = (int32_t)r[3]; row.w = r[4] ? 1 : 0; o.rows[i] = row;
   }
-  o.first.push_back((int32_t)n);
+  o.first.push_back((int32_t)n); o.min_id = min_id;
   if (min_id <= max_rl_ids + 2 * n_zero) return ABX_ERR_ARG;          // explicit ids must stay clear of every id the generator can hand out (util/order/Order.py:35-42)
   if (o.id_orig.empty()) o.id_orig.push_back(0);
   return ABX_OK;
@@ -155,6 +191,17 @@ ABX_HD void init_envx(const SimParams &P, EnvX &x) {
   x.rem_time = P.n_h - 1; x.obs_len = 0; x.g0_qty = 0; x.steps = 0;
   for (int i = 0; i < RL_ORDER_CAP; i++) { x.rl_oid[i] = 0; x.rl_oprice[i] = 0; x.rl_oqty[i] = 0; }
   for (int i = 0; i < 9; i++) x.obs[i] = 0.0; x.g0_pq = 0; x.pad1 = 0;
+}
+
+// abx_dq_holdings rows from the trader records of one environment (agent/TradingAgent.py:124-126 final holdings)
+static inline void dq_holdings_rows(const SimParams &P, const ZiAgent *ag, const EnvX &x, int64_t *out, double *exec_out) {
+  int n = P.c.n_agents, ke = 0;
+  for (int id = 1; id < n; id++) { int64_t *r = out + 5 * (id - 1); r[0] = id;
+    if (id == 1) { r[1] = x.ra_shares; r[2] = x.ra_cash; r[3] = (x.ra_flags & AF_HAS_LAST) ? x.ra_last_trade : 0; r[4] = -1; continue; }
+    const ZiAgent &z = ag[id]; int type = (int)((z.flags & AF_TYPE_MASK) >> AF_TYPE_SHIFT);
+    r[1] = z.shares; r[2] = z.cash; r[3] = (z.flags & AF_HAS_LAST) ? z.last_trade : 0; r[4] = type == AT_MOMENTUM ? -1 : z.n_orders;
+    if (type != AT_MOMENTUM && exec_out) { const ExecAux *ex = reinterpret_cast<const ExecAux *>(z.oid); double *e = exec_out + 5 * ke++;
+      e[0] = ex->rem_qty; e[1] = (double)ex->arr2 / 2; e[2] = ex->n_executed; e[3] = ex->rem_time; e[4] = ex->t; } }
 }
 
 static inline const char *status_string(int32_t st) {

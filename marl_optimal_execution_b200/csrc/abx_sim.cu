@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <new>
+#include <vector>
 #include "abx_warp.cuh"
 #include "abx_host_common.h"
 
@@ -140,6 +141,63 @@ abx_env_step_kernel(SimParams P, const double *__restrict__ actions, double *__r
   if (ctx.lane == 0) { if (reward) reward[env] = 0.0; done[env] = (s.flags & ABX_F_DONE) ? 1 : 0; }
 }
 
+// ---- DDQN execution shape: reset and decision step ----
+typedef Sim<WarpCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_DQ> DqSimInstr;
+
+__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
+abx_dq_reset_kernel(SimParams P, const uint64_t *__restrict__ seeds, const int32_t *__restrict__ mom_sizes, size_t smem_per_warp) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
+  if (env >= P.n_envs) return;
+  WarpCtx ctx(P, env, smem + warp * smem_per_warp);
+  uint64_t seed = seeds ? seeds[env] : 0;
+  EnvState s; init_env_state(P, seed, s); s.last_trade = -1;            // no oracle: OrderBook.last_trade stays None until the first trade
+  init_envx(P, *ctx.envx()); ctx.sync();
+  ctx.q_clear();
+  for (int id = 2 + ctx.lane; id < P.c.n_agents; id += 32)             // one lane per trader record
+    init_agent_record_dq(P, env, id, seed, (mom_sizes && id < 2 + P.dq_n_mom) ? mom_sizes[(size_t)env * P.dq_n_mom + id - 2] : -1, P.agents + (size_t)env * P.c.n_agents + id);
+  __syncwarp();
+  DqSimInstr sim(ctx, P, s, env);
+  sim.env_reset();
+  ctx.store_onchip(sim.s); ctx.envx_store();
+  env_store(P.env + env, sim.s, ctx.lane);
+}
+
+template <bool INSTR>
+__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
+abx_dq_step_kernel(SimParams P, const int32_t *__restrict__ actions, double *__restrict__ obs, double *__restrict__ trans, double *__restrict__ reward,
+                   uint8_t *__restrict__ done, size_t smem_per_warp) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
+  if (env >= P.n_envs) return;
+  WarpCtx ctx(P, env, smem + warp * smem_per_warp);
+  EnvState s = env_load(P.env + env);
+  bool was_done = (s.flags & ABX_F_DONE) != 0, paused = false;
+  if (!was_done) {
+    ctx.envx_load(); ctx.load_onchip(s);
+    Sim<WarpCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, INSTR, SHAPE_DQ> sim(ctx, P, s, env);
+    paused = sim.dq_step(actions ? actions[env] : 0);
+    ctx.store_onchip(sim.s); ctx.envx_store();
+    env_store(P.env + env, sim.s, ctx.lane);
+    s.flags = sim.s.flags;
+  }
+  // outputs: 8 + 6 + 1 doubles and the done byte per environment
+  const EnvX *x = ctx.envx();
+  if (ctx.lane < 8) obs[8 * env + ctx.lane] = paused ? x->obs[ctx.lane] : 0.0;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  double tv = qnan, rw = 0.0;
+  if (!was_done && P.dq_has_ddqn) {
+    const ZiAgent *z = ctx.agent_stage(P.c.n_agents - 1); const ExecAux *ex = reinterpret_cast<const ExecAux *>(z->oid);
+    if (ex->exflags & EXF_E_VALID) {
+      int l = ctx.lane;
+      tv = l == 0 ? (double)ex->e_s[0] : l == 1 ? (double)ex->e_s[1] : l == 2 ? (double)ex->e_a : l == 3 ? (double)ex->e_sp[0] : l == 4 ? (double)ex->e_sp[1] : ((ex->exflags & EXF_E_R) ? ex->e_r : qnan);
+    }
+    rw = ex->step_reward;
+  }
+  if (ctx.lane < 6) trans[6 * env + ctx.lane] = tv;
+  if (ctx.lane == 0) { if (reward) reward[env] = rw; done[env] = (s.flags & ABX_F_DONE) ? 1 : 0; }
+}
+
 __global__ void abx_stats_kernel(SimParams P, abx_env_stats *__restrict__ out) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= P.n_envs) return;
@@ -162,7 +220,8 @@ struct abx_sim {
   SimParams P; int n_envs, device; bool reset_done; size_t smem_per_warp; int64_t bytes, launches;
   uint64_t *d_seeds; uint32_t *d_init_err; abx_env_stats *d_stats; int64_t *d_until;
   uint64_t *d_tbits; uint8_t *d_tkinds; int64_t *d_toff;
-  bool is_env; EnvStreamHost *st; int64_t *d_ts; int32_t *d_first; int4 *d_rows; double *d_act, *d_obs, *d_rew; uint8_t *d_done;
+  bool is_env, is_dq; EnvStreamHost *st; int64_t *d_ts; int32_t *d_first; int4 *d_rows; double *d_act, *d_obs, *d_rew; uint8_t *d_done;
+  int32_t *d_iact, *d_msizes; double *d_trans;
 };
 
 template <class T> static int dalloc(T **p, size_t n, int64_t *acc) {
@@ -184,7 +243,7 @@ int32_t abx_sim_destroy(abx_sim *h) {
   cudaSetDevice(h->device);
   void *ptrs[] = {h->P.qkey, h->P.qpay0, h->P.qpay1, h->P.qcache, h->P.agents, h->P.lv_price, h->P.lv_qty, h->P.lv_ht, h->P.nodes, h->P.env,
                   h->P.trace, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff,
-                  h->P.envx, h->P.idtab, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done};
+                  h->P.envx, h->P.idtab, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_iact, h->d_msizes, h->d_trans};
   for (void *p : ptrs) if (p) cudaFree(p);
   delete h->st; delete h; return ABX_OK;
 }
@@ -405,6 +464,96 @@ int32_t abx_env_step_host(abx_sim *h, const double *actions, double *obs, double
   if (reward) CU(cudaMemcpyAsync(reward, h->d_rew, sizeof(double) * E, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(done, h->d_done, E, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  return ABX_OK;
+}
+
+// ---------------- DDQN execution shape ----------------
+int32_t abx_dq_config_default(abx_dq_config *cfg) { return dq_config_default(cfg); }
+
+int32_t abx_dq_create(const abx_dq_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
+  if (!out || n_envs < 1 || dq_config_validate(cfg) != ABX_OK) return ABX_ERR_ARG;
+  EnvStreamHost *st = new (std::nothrow) EnvStreamHost(); if (!st) return ABX_ERR_ARG;
+  if (env_build_stream(stream5, n_rows, dq_max_generated_ids(*cfg), *st) != ABX_OK) { delete st; return ABX_ERR_ARG; }
+  int ndev = 0; cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || device < 0 || device >= ndev) { delete st; snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d not present (%d visible): %s", device, ndev, cudaGetErrorString(ce)); return ABX_ERR_CUDA; }
+  if (cudaSetDevice(device) != cudaSuccess) { delete st; return ABX_ERR_CUDA; }
+  abx_sim *h = new (std::nothrow) abx_sim(); if (!h) { delete st; return ABX_ERR_ARG; }
+  memset(h, 0, sizeof(*h)); h->is_env = true; h->is_dq = true; h->st = st; h->n_envs = n_envs; h->device = device;
+  dq_fill_params(*cfg, h->P); h->P.n_envs = n_envs;
+  h->P.n_ts = (int)st->ts.size(); h->P.n_rows = (int)n_rows; h->P.dq_order_base = (int)st->id_orig.size(); h->P.dq_id_limit = st->min_id;
+  int n_exec = cfg->n_twap + (cfg->has_ddqn ? 1 : 0);
+  h->P.n_ids = h->P.dq_order_base + n_exec * EXEC_ORDER_CAP;
+  h->smem_per_warp = (warp_smem_bytes(h->P.c, true) + 15) & ~(size_t)15;
+  size_t smem_cta = h->smem_per_warp * ABX_WARPS_PER_CTA;
+  if (smem_cta > 227 * 1024) { abx_sim_destroy(h); return ABX_ERR_ARG; }
+  const abx_sim_config &c = h->P.c; size_t E = (size_t)n_envs; int stt;
+#define DA(ptr, n) if ((stt = dalloc(&(ptr), (n), &h->bytes)) != ABX_OK) { abx_sim_destroy(h); return stt; }
+  DA(h->P.qkey, E * c.queue_cap) DA(h->P.qpay0, E * c.queue_cap) DA(h->P.qpay1, E * c.queue_cap) DA(h->P.qcache, E * h->P.n_qgroups)
+  DA(h->P.agents, E * c.n_agents) DA(h->P.lv_price, E * 2 * c.level_cap) DA(h->P.lv_qty, E * 2 * c.level_cap) DA(h->P.lv_ht, E * 2 * c.level_cap)
+  DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap) DA(h->d_stats, E) DA(h->d_seeds, E)
+  DA(h->P.envx, E) DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
+  DA(h->d_ts, st->ts.size()) DA(h->d_first, st->first.size()) DA(h->d_rows, st->rows.size())
+  DA(h->d_iact, E) DA(h->d_obs, E * 8) DA(h->d_trans, E * 6) DA(h->d_rew, E) DA(h->d_done, E) DA(h->d_msizes, E * (cfg->n_momentum > 0 ? cfg->n_momentum : 1))
+#undef DA
+  CU(cudaMemcpy(h->d_ts, st->ts.data(), sizeof(int64_t) * st->ts.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_first, st->first.data(), sizeof(int32_t) * st->first.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_rows, st->rows.data(), sizeof(int4) * st->rows.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemset(h->P.agents, 0, E * c.n_agents * sizeof(ZiAgent)));
+  h->P.st_ts = h->d_ts; h->P.st_first = h->d_first; h->P.st_rows = h->d_rows;
+  if (smem_cta > 48 * 1024) {
+    CU(cudaFuncSetAttribute(abx_dq_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CU(cudaFuncSetAttribute(abx_dq_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CU(cudaFuncSetAttribute(abx_dq_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+  }
+  *out = h; return ABX_OK;
+}
+
+int32_t abx_dq_reset(abx_sim *h, const uint64_t *seeds, const int32_t *mom_sizes, void *stream) {
+  if (!h || !h->is_dq) return ABX_ERR_ARG;
+  CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
+  if (seeds) CU(cudaMemcpyAsync(h->d_seeds, seeds, sizeof(uint64_t) * h->n_envs, cudaMemcpyHostToDevice, st));
+  if (mom_sizes && h->P.dq_n_mom > 0) CU(cudaMemcpyAsync(h->d_msizes, mom_sizes, sizeof(int32_t) * (size_t)h->n_envs * h->P.dq_n_mom, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(h->P.idtab, 0, sizeof(uint4) * (size_t)h->n_envs * h->P.n_ids, st));
+  CU(cudaMemsetAsync(h->P.lobs, 0, sizeof(int4) * (size_t)h->n_envs * LOB_CAP * 3, st));
+  abx_dq_reset_kernel<<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, st>>>(h->P, seeds ? h->d_seeds : nullptr, (mom_sizes && h->P.dq_n_mom > 0) ? h->d_msizes : nullptr, h->smem_per_warp);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  h->reset_done = true; return ABX_OK;
+}
+
+int32_t abx_dq_step(abx_sim *h, const int32_t *actions_dev, double *obs_dev, double *trans_dev, double *reward_dev, uint8_t *done_dev, void *stream) {
+  if (!h || !h->is_dq || !obs_dev || !trans_dev || !done_dev) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  CU(cudaSetDevice(h->device));
+  bool instr = h->P.c.trace_cap > 0 || h->P.c.hash_pops != 0;
+  if (instr) abx_dq_step_kernel<true><<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, (cudaStream_t)stream>>>(h->P, actions_dev, obs_dev, trans_dev, reward_dev, done_dev, h->smem_per_warp);
+  else abx_dq_step_kernel<false><<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, (cudaStream_t)stream>>>(h->P, actions_dev, obs_dev, trans_dev, reward_dev, done_dev, h->smem_per_warp);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return ABX_OK;
+}
+
+int32_t abx_dq_step_host(abx_sim *h, const int32_t *actions, double *obs, double *trans, double *reward, uint8_t *done, void *stream) {
+  if (!h || !h->is_dq || !obs || !trans || !done) return ABX_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream; size_t E = (size_t)h->n_envs;
+  CU(cudaSetDevice(h->device));
+  if (actions) CU(cudaMemcpyAsync(h->d_iact, actions, sizeof(int32_t) * E, cudaMemcpyHostToDevice, st));
+  int32_t rc = abx_dq_step(h, actions ? h->d_iact : nullptr, h->d_obs, h->d_trans, h->d_rew, h->d_done, stream); if (rc != ABX_OK) return rc;
+  CU(cudaMemcpyAsync(obs, h->d_obs, sizeof(double) * 8 * E, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(trans, h->d_trans, sizeof(double) * 6 * E, cudaMemcpyDeviceToHost, st));
+  if (reward) CU(cudaMemcpyAsync(reward, h->d_rew, sizeof(double) * E, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(done, h->d_done, E, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return ABX_OK;
+}
+
+int32_t abx_dq_holdings(abx_sim *h, int32_t env, int64_t *out, double *exec_out, void *stream) {
+  if (!h || !h->is_dq || !out || env < 0 || env >= h->n_envs) return ABX_ERR_ARG;
+  CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
+  int n = h->P.c.n_agents; std::vector<ZiAgent> tmp(n); EnvX x;
+  CU(cudaMemcpyAsync(tmp.data(), h->P.agents + (size_t)env * n, sizeof(ZiAgent) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&x, h->P.envx + env, sizeof(EnvX), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  dq_holdings_rows(h->P, tmp.data(), x, out, exec_out);
   return ABX_OK;
 }
 

@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import EnvConfig
+from ._lib import DqConfig, EnvConfig
 
 
 def env_config(lib=None, **overrides):
@@ -120,3 +120,84 @@ class ABIDESEnv:
     @property
     def launch_count(self):
         return int(self._L.abx_sim_launch_count(self._h))
+
+
+def dq_config(lib=None, **overrides):
+    """abx_dq_config with the defaults of config/execution/marketreplay/execution_marketreplay_ddqn.py (BUY 500 000 from 10:00
+    over 330 min at 30 s; 7 MomentumAgents, one TWAP agent, the DDQN agent)."""
+    L = lib or _lib.load()
+    cfg = DqConfig()
+    _lib.check(L, L.abx_dq_config_default(C.byref(cfg)), "abx_dq_config_default")
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError("abx_dq_config has no field %r" % k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+class DDQNExecutionEnv(ABIDESEnv):
+    """The reference's DDQN execution simulation (config/execution/marketreplay/execution_marketreplay_ddqn.py, -a rl) as a
+    batched decision process: Exchange + MarketReplayAgent + MomentumAgents + TWAPExecutionAgent + DDQLearningExecutionAgent.
+
+        env = DDQNExecutionEnv(stream, n_envs=8192); env.reset(seeds)
+        obs, trans, reward, done = env.step(None)            # runs to the first decision tick (10:00)
+        obs, trans, reward, done = env.step(actions)         # actions int32 [n_envs] in 0..23 (ACTIONS, ddqlearning_execution_agent.py:24-37)
+
+    obs [n_envs, 8]: the 6 features of get_observation (:332) followed by the 2 digitised entries the Q-network sees (:334);
+    trans [n_envs, 6]: the finalised experience entry of the previous tick (s0, s1, a, s'0, s'1, r) -- what the reference stores
+    in self.experience (:251,540-541,572-573), r NaN where it holds None; reward: sum of the per-fill rewards (:411-447) since
+    the previous decision; done: the event loop ended (the reference's kernel.runner returned)."""
+    OBS_SIZE = 8
+    N_ACTIONS = 24
+
+    def __init__(self, stream, n_envs=1, device=0, cfg=None, lib_path=None):
+        self._L = _lib.load(lib_path)
+        self.cfg = cfg or dq_config(self._L)
+        self.n_envs, self.device = int(n_envs), int(device)
+        self.n_agents = 2 + int(self.cfg.n_momentum) + int(self.cfg.n_twap) + (1 if self.cfg.has_ddqn else 0)
+        self.n_exec = int(self.cfg.n_twap) + (1 if self.cfg.has_ddqn else 0)
+        st = np.ascontiguousarray(stream, dtype=np.int64)
+        if st.ndim != 2 or st.shape[1] != 5:
+            raise ValueError("stream must be int64 [n, 5]: (t_ns, ORDER_ID, PRICE, SIZE, is_buy)")
+        self._h = C.c_void_p()
+        _lib.check(self._L, self._L.abx_dq_create(C.byref(self.cfg), st.ctypes.data_as(C.POINTER(C.c_int64)), len(st), self.n_envs,
+                                                  self.device, C.byref(self._h)), "abx_dq_create")
+        self._torch_out = None
+
+    def reset(self, seeds=None, mom_sizes=None, stream=None):
+        sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64).reshape(self.n_envs)
+        ms = None if mom_sizes is None else np.ascontiguousarray(mom_sizes, dtype=np.int32).reshape(self.n_envs, int(self.cfg.n_momentum))
+        _lib.check(self._L, self._L.abx_dq_reset(self._h, None if sd is None else sd.ctypes.data, None if ms is None else ms.ctypes.data, stream), "abx_dq_reset")
+        self._keep = (sd, ms)
+        return None
+
+    def step(self, actions, stream=None):
+        try:
+            import torch
+            is_torch = isinstance(actions, torch.Tensor)
+        except ImportError:      # pragma: no cover
+            is_torch = False
+        if is_torch and actions.is_cuda:
+            import torch
+            a = actions.to(torch.int32).contiguous().view(self.n_envs)
+            if self._torch_out is None:
+                self._torch_out = (torch.zeros(self.n_envs, 8, dtype=torch.float64, device=a.device), torch.zeros(self.n_envs, 6, dtype=torch.float64, device=a.device),
+                                   torch.zeros(self.n_envs, dtype=torch.float64, device=a.device), torch.zeros(self.n_envs, dtype=torch.uint8, device=a.device))
+            obs, trans, rew, done = self._torch_out
+            sp = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream) if stream is None else stream
+            _lib.check(self._L, self._L.abx_dq_step(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(obs.data_ptr()), C.c_void_p(trans.data_ptr()),
+                                                    C.c_void_p(rew.data_ptr()), C.c_void_p(done.data_ptr()), sp), "abx_dq_step")
+            return obs, trans, rew, done
+        a = None if actions is None else np.ascontiguousarray(np.asarray(actions, dtype=np.int32).reshape(self.n_envs))
+        obs, trans = np.zeros((self.n_envs, 8)), np.zeros((self.n_envs, 6))
+        rew, done = np.zeros(self.n_envs), np.zeros(self.n_envs, dtype=np.uint8)
+        _lib.check(self._L, self._L.abx_dq_step_host(self._h, None if a is None else a.ctypes.data, obs.ctypes.data, trans.ctypes.data, rew.ctypes.data,
+                                                     done.ctypes.data, stream), "abx_dq_step_host")
+        return obs, trans, rew, done
+
+    def holdings(self, env, stream=None):
+        """(rows (agent id, shares, cash, last_trade, open orders | -1), rows per execution agent (remaining qty, arrival, fills, remaining_time, t))"""
+        out = np.zeros((self.n_agents - 1, 5), dtype=np.int64)
+        ex = np.zeros((max(self.n_exec, 1), 5))
+        _lib.check(self._L, self._L.abx_dq_holdings(self._h, int(env), out.ctypes.data, ex.ctypes.data, stream), "abx_dq_holdings")
+        return out, ex[: self.n_exec]

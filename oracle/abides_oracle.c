@@ -955,8 +955,11 @@ typedef struct {
   int has_open, has_close, mkt_closed; int64_t mkt_open, mkt_close; int64_t shares, cash; int has_last_trade; int64_t last_trade;
 } tagent_t;
 
+typedef struct { int64_t p, q; } pq_t;                                                /* one (price, quantity) level of a QUERY_SPREAD reply */
+struct dq_state;
 struct abo_env {
-  heap_t q; int64_t now, stop_time; int64_t agent_time[3]; int64_t comp_delay[3]; int64_t ttl, uniq; int done;
+  heap_t q; int64_t now, stop_time; int64_t agent_time[16]; int64_t comp_delay[16]; int64_t ttl, uniq; int done;
+  struct dq_state *dq;                      /* DDQN execution config (execution_marketreplay_ddqn.py): momentum + TWAP + DDQN agents */
   int64_t next_order_id; omap_t used_ids;   /* util/order/Order.py:8-9,35-42 global id allocator (ids seen so far) */
   abo_book book; int64_t mkt_open, mkt_close;
   /* replay agent (id 1) */
@@ -1007,6 +1010,7 @@ static void env_trace_op(abo_env *s, int op, const order_t *o, int64_t np, int64
   if (!(s->trace & ABO_TRACE_OPS)) return;
   int64_t row[9] = { s->now, op, o->agent_id, o->order_id, o->is_buy, o->limit_price, o->quantity, np, nq }; ib_push(&s->ops, row, 9);
 }
+static void dq_snapshot(abo_env *s, int recipient);
 /* ExchangeAgent.receiveMessage :129-340 (oracle None, depth-k QUERY_SPREAD, MODIFY_ORDER) */
 static void env_exch_receive(abo_env *s, const event_t *m) {
   s->comp_delay[0] = 0;
@@ -1024,7 +1028,9 @@ static void env_exch_receive(abo_env *s, const event_t *m) {
       int64_t pq[4]; e.kind = ABO_QUERY_SPREAD;
       e.n_bids = book_inside(&s->book, 1, 2, pq); if (e.n_bids > 0) { e.has_bid = 1; e.bid = pq[0]; e.bid_q = pq[1]; } if (e.n_bids > 1) e.bid2 = pq[2];
       e.n_asks = book_inside(&s->book, 0, 2, pq); if (e.n_asks > 0) { e.has_ask = 1; e.ask = pq[0]; e.ask_q = pq[1]; } if (e.n_asks > 1) e.ask2 = pq[2];
-      e.data = s->book.has_last_trade ? s->book.last_trade : -1; e.mkt_closed = t_closed; env_exch_send(s, m->sender, &e); break; }
+      e.data = s->book.has_last_trade ? s->book.last_trade : -1; e.mkt_closed = t_closed;
+      if (s->dq) dq_snapshot(s, m->sender);                                                   /* depth-500 lists ride in the reply body */
+      env_exch_send(s, m->sender, &e); break; }
     case ABO_LIMIT_ORDER: env_trace_op(s, 0, &m->order, 0, 0); book_handle_limit(&s->book, m->order); env_trace_snap(s); break;
     case ABO_CANCEL_ORDER: env_trace_op(s, 1, &m->order, 0, 0); book_cancel(&s->book, &m->order); env_trace_snap(s); break;
     case ABO_MODIFY_ORDER: env_trace_op(s, 2, &m->order, m->new_order.limit_price, m->new_order.quantity); book_modify(&s->book, &m->order, &m->new_order); env_trace_snap(s); break; /* :326-340 */
@@ -1219,8 +1225,9 @@ abo_env *abo_env_new2(const int64_t *stream5, int64_t n_rows, double quantity, i
   return s;
 }
 abo_env *abo_env_new(const int64_t *stream5, int64_t n_rows, double quantity, int order_level, int trace) { return abo_env_new2(stream5, n_rows, quantity, order_level, trace, (16 * 3600 + 600) * NS_PER_S); }
+static void dq_free(abo_env *s);
 void abo_env_free(abo_env *s) {
-  if (!s) return; book_destroy(&s->book); free(s->rows); free(s->ts); free(s->ts_first); free(s->ra_orders.e); free(s->used_ids.e); free(s->rl_orders); free(s->rl_oqty);
+  if (!s) return; dq_free(s); book_destroy(&s->book); free(s->rows); free(s->ts); free(s->ts_first); free(s->ra_orders.e); free(s->used_ids.e); free(s->rl_orders); free(s->rl_oqty);
   free(s->horizon); free(s->q.e); free(s->pops.v); free(s->ops.v); free(s->notes.v); free(s->snaps.v); free(s->ckpt); free(s);
 }
 /* GymKernel.stepRunner :158-306.  Returns obs length (0 or 9); *done as ABIDESEnv.step computes it (ABIDESEnv.py:42-46). */
@@ -1256,3 +1263,253 @@ const uint64_t *abo_env_hash_ckpt(abo_env *s) { return s->ckpt; }
 int64_t abo_env_trace(abo_env *s, int which, const int64_t **rows) { i64buf *b = which == 0 ? &s->pops : which == 1 ? &s->ops : which == 2 ? &s->notes : &s->snaps; int w = which == 0 ? 5 : which == 1 ? 9 : which == 2 ? 13 : 16; *rows = b->v; return b->n / w; }
 void abo_env_final(abo_env *s, double *out8) { out8[0] = s->rem_quantity; out8[1] = (double)s->rl.shares; out8[2] = (double)s->rl.cash; out8[3] = (double)s->n_executed; out8[4] = (double)s->ra.shares; out8[5] = (double)s->ra.cash; out8[6] = (double)s->ra_orders.n; out8[7] = (double)s->now; }
 int64_t abo_env_counter(abo_env *s, int w) { switch (w) { case 0: return s->max_queue; case 1: return s->max_bid_lv; case 2: return s->max_ask_lv; case 3: return s->max_resting; case 4: return s->uniq; case 5: return s->next_order_id; default: return -1; } }
+
+/* ====================================================================================================
+ * DDQN execution config: config/execution/marketreplay/execution_marketreplay_ddqn.py (-a rl)
+ *   Exchange (0) + MarketReplayAgent (1) + n_mom MomentumAgents (2..) + TWAPExecutionAgent + DDQLearningExecutionAgent
+ *   under Kernel.runner, zero latency / computation delay, stop = horizon end + 10 min (:317-318).
+ *   agent/examples/MomentumAgent.py:53-99, agent/execution/baselines/execution_agent.py:66-130, twap_agent.py:51-63,
+ *   agent/execution/qlearning/ddqlearning_execution_agent.py:20-37,141-185,228-447,507-611, agent/execution/util.py:6-42,
+ *   agent/TradingAgent.py:351-397 (placeMarketOrder), :564-574 (getKnownBidAsk).
+ * The Q-network is NOT part of this restatement: the action of every decision tick is an input (the agent's
+ * choose_action is np.argmax of the network output, :362-364).  The event loop pauses where the reference calls
+ * choose_action (inside place_order :245) and resumes with the supplied action.
+ * ==================================================================================================== */
+typedef struct { tagent_t ta; int state; int64_t size; int has_bid, has_ask; int64_t bid, ask; double *mids; int n_mids, cap_mids; double avg20, avg50; int has20, has50; } mom_t;
+typedef struct {
+  tagent_t ta; int id, is_ddqn, state, trade; int64_t quantity, rem_qty, executed_sum, n_executed;
+  open_order_t *orders; int n_orders, cap_orders;                                             /* self.orders, insertion ordered */
+  pq_t *kb, *ka; int nkb, nka, cap_k;                                                        /* known_bids / known_asks */
+  pq_t *fb, *fa; int nfb, nfa;                                                               /* lists of the in-flight QUERY_SPREAD reply */
+  double arrival; int has_arrival; int64_t child_qty;
+  int t, rem_time, pending, cur_s[2], sp[2]; double obs6[6];                                  /* DDQN: self.t, remaining_time, decision pending, self.s */
+  double *pp; int n_pp, cap_pp; double *exp; int n_exp, cap_exp; double *rew; int n_rew, cap_rew; double *ahist; int n_ahist, cap_ahist;
+  double step_reward;                                                                         /* sum of step rewards since the last decision */
+} exec_t;
+struct dq_state { int n_mom, n_twap, has_ddqn, n_agents; mom_t mom[8]; exec_t ex[3]; int n_ex; int64_t h0, h_step; int n_h; int64_t mom_wake_ns; int is_buy; int error; };
+typedef struct dq_state dq_state;
+enum { DQ_DEPTH = 500, DQ_ERR_EMPTY_SIDE = 1, DQ_ERR_LEVELS = 2 };
+
+static exec_t *dq_exec(abo_env *s, int id) { dq_state *d = s->dq; int k = id - (2 + d->n_mom); return (k >= 0 && k < d->n_ex) ? &d->ex[k] : NULL; }
+static void dq_snapshot(abo_env *s, int recipient) {                                          /* ExchangeAgent.py:231-245 with depth = 500 */
+  exec_t *e = dq_exec(s, recipient); if (!e) return;
+  int64_t *tmp = (int64_t *)malloc(sizeof(int64_t) * 2 * DQ_DEPTH);
+  e->nfb = book_inside(&s->book, 1, DQ_DEPTH, tmp); for (int i = 0; i < e->nfb; i++) { e->fb[i].p = tmp[2 * i]; e->fb[i].q = tmp[2 * i + 1]; }
+  e->nfa = book_inside(&s->book, 0, DQ_DEPTH, tmp); for (int i = 0; i < e->nfa; i++) { e->fa[i].p = tmp[2 * i]; e->fa[i].q = tmp[2 * i + 1]; }
+  free(tmp);
+}
+static void dq_get_spread(abo_env *s, int id) { event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_QUERY_SPREAD; env_send(s, id, 0, &e, 0); s->uniq++; }   /* getCurrentSpread + msg_copy (TradingAgent.py:277-282) */
+/* TradingAgent.placeLimitOrder :309-349 */
+static void dq_place_limit(abo_env *s, int id, open_order_t **orders, int *n, int *cap, int64_t qty, int is_buy, int64_t price) {
+  int64_t oid = env_new_order_id(s, 0);
+  if (qty <= 0) return;
+  if (orders) { if (*n == *cap) { *cap = *cap ? 2 * *cap : 16; *orders = (open_order_t *)realloc(*orders, sizeof(open_order_t) * *cap); }
+    open_order_t *o = &(*orders)[(*n)++]; o->order_id = oid; o->quantity = qty; o->limit_price = price; o->is_buy = is_buy; }
+  event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_LIMIT_ORDER; e.order.agent_id = id; e.order.order_id = oid; e.order.quantity = qty; e.order.limit_price = price; e.order.is_buy = is_buy;
+  env_send(s, id, 0, &e, 0);
+}
+/* ---- MomentumAgent ---- */
+static void dq_mom_wakeup(abo_env *s, int id) { mom_t *a = &s->dq->mom[id - 2]; if (env_ta_wakeup(s, id, &a->ta)) { dq_get_spread(s, id); a->state = ST_AWAITING_SPREAD; } }
+static void dq_mom_receive(abo_env *s, int id, const event_t *m) {
+  mom_t *a = &s->dq->mom[id - 2];
+  int newly = env_ta_receive(s, &a->ta, m);
+  if (m->kind == ABO_QUERY_SPREAD) { a->has_bid = m->has_bid; a->has_ask = m->has_ask; a->bid = m->bid; a->ask = m->ask; }
+  if (newly) env_set_wakeup(s, id, a->ta.mkt_open + s->dq->mom_wake_ns);                      /* getWakeFrequency :89-90 */
+  if (a->state == ST_AWAITING_SPREAD && m->kind == ABO_QUERY_SPREAD) {                        /* :65-71 */
+    if (a->has_bid && a->bid != 0 && a->has_ask && a->ask != 0) {                             /* placeOrders :78-93 */
+      if (a->n_mids == a->cap_mids) { a->cap_mids = a->cap_mids ? 2 * a->cap_mids : 64; a->mids = (double *)realloc(a->mids, 8 * a->cap_mids); }
+      a->mids[a->n_mids++] = (double)(a->bid + a->ask) / 2;
+      int L = a->n_mids;
+      for (int w = 0; w < 2; w++) { int n = w ? 50 : 20;
+        if (L > n) { double c1 = 0, c0 = 0; for (int i = 0; i < L; i++) { c1 += a->mids[i]; if (i == L - 1 - n) c0 = c1; }
+          double v = np_round2((c1 - c0) / n); if (w) { a->avg50 = v; a->has50 = 1; } else { a->avg20 = v; a->has20 = 1; } } }
+      if (a->has20 && a->has50) { if (a->avg20 >= a->avg50) dq_place_limit(s, id, NULL, NULL, NULL, a->size, 1, a->ask); else dq_place_limit(s, id, NULL, NULL, NULL, a->size, 0, a->bid); }
+    }
+    env_set_wakeup(s, id, s->now + s->dq->mom_wake_ns); a->state = ST_AWAITING_WAKEUP;
+  }
+}
+/* ---- execution agents: shared parts ---- */
+static void dq_exec_orders_remove(exec_t *e, int i) { memmove(e->orders + i, e->orders + i + 1, sizeof(open_order_t) * (e->n_orders - i - 1)); e->n_orders--; }
+static void dq_exec_cancel_all(abo_env *s, exec_t *e) {                                       /* cancelOrders / cancel_orders */
+  for (int i = 0; i < e->n_orders; i++) { event_t ev; memset(&ev, 0, sizeof(ev)); ev.kind = ABO_CANCEL_ORDER; ev.order.agent_id = e->id; ev.order.order_id = e->orders[i].order_id;
+    ev.order.quantity = e->orders[i].quantity; ev.order.limit_price = e->orders[i].limit_price; ev.order.is_buy = e->orders[i].is_buy; env_send(s, e->id, 0, &ev, 0); }
+}
+static void dq_place_market(abo_env *s, exec_t *e, int64_t quantity) {                         /* TradingAgent.placeMarketOrder :351-397 */
+  if (quantity <= 0) return;
+  const pq_t *side = s->dq->is_buy ? e->ka : e->kb; int n = s->dq->is_buy ? e->nka : e->nkb;
+  if (n == 0) { s->dq->error |= DQ_ERR_EMPTY_SIDE; return; }                                  /* the reference iterates None: TypeError */
+  int nq = 0; int64_t *qp = (int64_t *)malloc(16 * (n + 1));
+  for (int i = 0; i < n; i++) { if (quantity <= side[i].q) { qp[2 * nq] = side[i].p; qp[2 * nq + 1] = quantity; nq++; break; } qp[2 * nq] = side[i].p; qp[2 * nq + 1] = side[i].q; nq++; quantity -= side[i].q; }
+  for (int i = 0; i < nq; i++) dq_place_limit(s, e->id, &e->orders, &e->n_orders, &e->cap_orders, qp[2 * i + 1], s->dq->is_buy, qp[2 * i]);
+  free(qp);
+}
+static int dq_horizon_index(const dq_state *d, int64_t t) { if (t < d->h0 || (t - d->h0) % d->h_step) return -1; int64_t k = (t - d->h0) / d->h_step; return k < d->n_h ? (int)k : -1; }
+static void dq_exec_wakeup(abo_env *s, exec_t *e) {
+  dq_state *d = s->dq;
+  if (!env_ta_wakeup(s, e->id, &e->ta)) return;
+  int64_t k = s->now < d->h0 ? 0 : (s->now - d->h0) / d->h_step + 1;                          /* first horizon time > now */
+  if (e->is_ddqn) {                                                                           /* ddqlearning_execution_agent.py:141-153 */
+    if (e->trade) { if (k < d->n_h) env_set_wakeup(s, e->id, d->h0 + k * d->h_step); else e->trade = 0; }
+    dq_get_spread(s, e->id); e->state = ST_AWAITING_SPREAD;
+  } else if (e->trade) {                                                                      /* execution_agent.py:66-78 */
+    if (k < d->n_h) env_set_wakeup(s, e->id, d->h0 + k * d->h_step);
+    dq_get_spread(s, e->id); e->state = ST_AWAITING_SPREAD;
+  }
+}
+/* np.digitize(x, np.linspace(0, 1, 201)[1:-1]): number of split points k * (1/200), k = 1..199, that are <= x (agent/execution/util.py:6-42) */
+static int dq_digitize(double x) { int k = 0; while (k < 199 && (double)(k + 1) * (1.0 / 200) <= x) k++; return k; }
+/* DDQLearningExecutionAgent.get_observation :280-336 */
+static void dq_get_observation(abo_env *s, exec_t *e, double *obs, int *disc) {
+  dq_state *d = s->dq;
+  int64_t curr = s->now - (s->now % d->h_step); int hi = dq_horizon_index(d, curr);
+  e->rem_time = hi >= 0 ? d->n_h - 1 - hi : d->n_h;
+  if (e->nkb == 0 || e->nka == 0) { d->error |= DQ_ERR_EMPTY_SIDE; for (int i = 0; i < 6; i++) obs[i] = 0; disc[0] = disc[1] = 0; return; }
+  obs[0] = 2 * ((double)e->rem_time / (double)d->n_h) - 1;
+  obs[1] = 2 * ((double)e->rem_qty / (double)e->quantity) - 1;
+  obs[2] = (double)(e->ka[0].p - e->kb[0].p);
+  obs[3] = (double)(e->ka[0].q - e->kb[0].q) / (double)(e->ka[0].q + e->kb[0].q);
+  double mid = (double)(e->kb[0].p + e->ka[0].p) / 2;
+  if (e->n_pp == e->cap_pp) { e->cap_pp = e->cap_pp ? 2 * e->cap_pp : 1024; e->pp = (double *)realloc(e->pp, 8 * e->cap_pp); }
+  e->pp[e->n_pp++] = mid;
+  obs[4] = s->now == d->h0 ? 0.0 : log(mid / e->pp[e->n_pp - 2]);
+  obs[5] = log(mid / e->pp[0]);
+  disc[0] = dq_digitize(obs[0]); disc[1] = dq_digitize(obs[1]);                               /* the grid has TWO dimensions: zip() drops the other four features */
+}
+static double *dq_exp_row(exec_t *e, int t) { return e->exp + 6 * t; }
+/* handle_order_execution :507-548 / handle_order_acceptance :550-576 (after TradingAgent.receiveMessage) */
+static void dq_ddqn_order_event(abo_env *s, exec_t *e, const event_t *m) {
+  dq_state *d = s->dq;
+  int64_t curr = s->now - (s->now % d->h_step);
+  if (dq_horizon_index(d, curr) < 0) return;
+  double o6[6]; int sp[2]; dq_get_observation(s, e, o6, sp);
+  double *row = dq_exp_row(e, e->t - 1); row[3] = sp[0]; row[4] = sp[1]; e->cur_s[0] = sp[0]; e->cur_s[1] = sp[1];
+  if (m->kind == ABO_ORDER_EXECUTED) {                                                        /* compute_reward :411-447 (BUY / SELL) */
+    double fp = (double)m->order.fill_price, ar = e->arrival;
+    double r = (1 - (d->is_buy ? (fp - ar) : (ar - fp)) / ar) * (double)m->order.quantity / (double)e->quantity * 10000;
+    if (e->n_rew == e->cap_rew) { e->cap_rew = e->cap_rew ? 2 * e->cap_rew : 1024; e->rew = (double *)realloc(e->rew, 8 * e->cap_rew); }
+    e->rew[e->n_rew++] = r; e->step_reward += r; row[5] = r;
+  } else row[5] = 0;
+}
+static void dq_exec_receive(abo_env *s, exec_t *e, const event_t *m) {
+  dq_state *d = s->dq;
+  int newly = env_ta_receive(s, &e->ta, m);
+  if (m->kind == ABO_ORDER_EXECUTED) {                                                        /* TradingAgent.orderExecuted :445-452 */
+    for (int i = 0; i < e->n_orders; i++) if (e->orders[i].order_id == m->order.order_id) { if (m->order.quantity >= e->orders[i].quantity) dq_exec_orders_remove(e, i); else e->orders[i].quantity -= m->order.quantity; break; }
+  } else if (m->kind == ABO_ORDER_CANCELLED) { for (int i = 0; i < e->n_orders; i++) if (e->orders[i].order_id == m->order.order_id) { dq_exec_orders_remove(e, i); break; } }
+  else if (m->kind == ABO_QUERY_SPREAD) { e->nkb = e->nfb; e->nka = e->nfa; memcpy(e->kb, e->fb, sizeof(pq_t) * e->nfb); memcpy(e->ka, e->fa, sizeof(pq_t) * e->nfa); }   /* querySpread :514-537 */
+  if (newly) env_set_wakeup(s, e->id, e->ta.mkt_open + (d->h0 - e->ta.mkt_open));             /* getWakeFrequency: start_time - mkt_open */
+  if (m->kind == ABO_ORDER_EXECUTED) { e->executed_sum += m->order.quantity; e->n_executed++; e->rem_qty = e->quantity - e->executed_sum; }
+  if (!e->is_ddqn) {                                                                          /* ExecutionAgent.receiveMessage :80-86 */
+    if (e->rem_qty > 0 && e->state == ST_AWAITING_SPREAD && m->kind == ABO_QUERY_SPREAD) {
+      dq_exec_cancel_all(s, e);
+      int hi = dq_horizon_index(d, s->now);                                                   /* placeOrders :107-124 */
+      if (hi == d->n_h - 2) dq_place_market(s, e, e->rem_qty);
+      else if (hi >= 0 && hi < d->n_h - 2) {
+        if (e->nkb == 0 || e->nka == 0) { d->error |= DQ_ERR_EMPTY_SIDE; return; }
+        if (hi == 0) { e->arrival = (double)(e->kb[0].p + e->ka[0].p) / 2; e->has_arrival = 1; }
+        dq_place_limit(s, e->id, &e->orders, &e->n_orders, &e->cap_orders, e->child_qty, d->is_buy, d->is_buy ? e->ka[0].p : e->kb[0].p);
+      }
+    }
+    return;
+  }
+  if (m->kind == ABO_ORDER_ACCEPTED || m->kind == ABO_ORDER_EXECUTED) dq_ddqn_order_event(s, e, m);   /* :158-163 */
+  else { int hi = dq_horizon_index(d, s->now);
+    if (hi >= 0 && hi < d->n_h - 1 && e->rem_qty > 0 && e->state == ST_AWAITING_SPREAD && m->kind == ABO_QUERY_SPREAD) {   /* :164-172 */
+      dq_exec_cancel_all(s, e);
+      /* place_order :228-245 up to choose_action */
+      if (e->nkb == 0 || e->nka == 0) { d->error |= DQ_ERR_EMPTY_SIDE; return; }
+      if (hi == 0) { e->arrival = (double)(e->kb[0].p + e->ka[0].p) / 2; e->has_arrival = 1; double o6[6]; dq_get_observation(s, e, o6, e->cur_s); }
+      dq_get_observation(s, e, e->obs6, e->sp);
+      e->pending = 1;
+    } }
+}
+/* place_order :245-278 from choose_action's return on, then receiveMessage :172 (self.t += 1) */
+static void dq_ddqn_resume(abo_env *s, exec_t *e, int a) {
+  dq_state *d = s->dq;
+  static const double SCALE[6] = { 0.1, 0.5, 1.0, 1.5, 2.0, 2.5 };
+  static const double ALLOC[4][4] = { { 0, 0, 0, 0 }, { 1, 0, 0, 0 }, { 0.5, 0.5, 0, 0 }, { 0.34, 0.33, 0.33, 0 } };
+  if (a < 0) a = 0; if (a > 23) a = 23;
+  int alloc = a / 6; int64_t qty = e->child_qty;                                              /* take_action :367-409 */
+  if (e->rem_time == 1) { qty = e->rem_qty; alloc = 0; } else { qty = py_round(SCALE[a % 6] * (double)qty); if (qty < 0) qty = 0; }
+  if (e->n_ahist == e->cap_ahist) { e->cap_ahist = e->cap_ahist ? 2 * e->cap_ahist : 1024; e->ahist = (double *)realloc(e->ahist, 8 * e->cap_ahist); }
+  e->ahist[e->n_ahist++] = (double)qty / (double)e->quantity;
+  if (alloc == 0) dq_place_market(s, e, qty);
+  else for (int lv = 0; lv < 4; lv++) {
+    int64_t size = py_round(ALLOC[alloc][lv] * (double)qty);
+    int n = d->is_buy ? e->nkb : e->nka; if (lv >= n) { d->error |= DQ_ERR_LEVELS; break; }   /* IndexError in the reference */
+    int64_t price = d->is_buy ? e->kb[lv].p : e->ka[lv].p;
+    if (size != 0) dq_place_limit(s, e->id, &e->orders, &e->n_orders, &e->cap_orders, size, d->is_buy, price);
+  }
+  if (e->t >= e->cap_exp) { e->cap_exp = e->cap_exp ? 2 * e->cap_exp : 1024; e->exp = (double *)realloc(e->exp, 8 * 6 * e->cap_exp); }
+  double *row = dq_exp_row(e, e->t); row[0] = e->cur_s[0]; row[1] = e->cur_s[1]; row[2] = a; row[3] = e->sp[0]; row[4] = e->sp[1]; row[5] = NAN; e->n_exp = e->t + 1;
+  e->cur_s[0] = e->sp[0]; e->cur_s[1] = e->sp[1]; e->t++; e->pending = 0;
+}
+
+/* stream5 as abo_env_new.  sizes: MomentumAgent.size per agent (config: random_state.randint(1, 10), MomentumAgent.py:42). */
+abo_env *abo_dq_new(const int64_t *stream5, int64_t n_rows, int n_mom, const int64_t *mom_sizes, int n_twap, int has_ddqn, int is_buy, int64_t quantity,
+                    int64_t h0_ns, int64_t h_step_ns, int n_h, int64_t mom_wake_ns, int trace) {
+  if (n_mom < 0 || n_mom > 8 || n_twap < 0 || n_twap > 2 || n_twap + (has_ddqn ? 1 : 0) > 3 || n_h < 3) return NULL;
+  abo_env *s = abo_env_new2(stream5, n_rows, (double)quantity, 0, trace, h0_ns + (int64_t)(n_h - 1) * h_step_ns + 600 * NS_PER_S);
+  s->q.n = 0;                                                                                 /* rebuild the start-up wakeups for the full agent list */
+  dq_state *d = (dq_state *)calloc(1, sizeof(dq_state)); s->dq = d;
+  d->n_mom = n_mom; d->n_twap = n_twap; d->has_ddqn = has_ddqn; d->n_ex = n_twap + (has_ddqn ? 1 : 0); d->n_agents = 2 + n_mom + d->n_ex;
+  d->h0 = h0_ns; d->h_step = h_step_ns; d->n_h = n_h; d->mom_wake_ns = mom_wake_ns; d->is_buy = is_buy;
+  for (int i = 0; i < n_mom; i++) d->mom[i].size = mom_sizes[i];
+  for (int k = 0; k < d->n_ex; k++) { exec_t *e = &d->ex[k]; e->id = 2 + n_mom + k; e->is_ddqn = has_ddqn && k == d->n_ex - 1; e->trade = 1; e->state = ST_AWAITING_WAKEUP;
+    e->quantity = e->rem_qty = quantity; e->child_qty = e->is_ddqn ? (int64_t)((double)quantity / (double)(n_h - 1)) : (int64_t)((double)quantity / (double)n_h);   /* generate_schedule :499 / twap_agent.py:55 */
+    e->kb = (pq_t *)malloc(sizeof(pq_t) * DQ_DEPTH); e->ka = (pq_t *)malloc(sizeof(pq_t) * DQ_DEPTH); e->fb = (pq_t *)malloc(sizeof(pq_t) * DQ_DEPTH); e->fa = (pq_t *)malloc(sizeof(pq_t) * DQ_DEPTH); }
+  for (int i = 0; i < d->n_agents; i++) env_set_wakeup(s, i, 0);
+  return s;
+}
+static void dq_free(abo_env *s) {
+  dq_state *d = s->dq; if (!d) return;
+  for (int i = 0; i < d->n_mom; i++) free(d->mom[i].mids);
+  for (int k = 0; k < d->n_ex; k++) { exec_t *e = &d->ex[k]; free(e->orders); free(e->kb); free(e->ka); free(e->fb); free(e->fa); free(e->pp); free(e->exp); free(e->rew); free(e->ahist); }
+  free(d); s->dq = NULL;
+}
+/* One decision step.  `action` completes the pending decision (ignored when none is pending: first call).  Runs Kernel.runner's loop
+ * (Kernel.py:190-292) until the DDQN agent reaches choose_action again or the loop ends.  out8: the 6 observation features + s' (2 digitised
+ * features); trans6: the finalised experience row of the previous tick (s0, s1, a, s'0, s'1, r; r NaN == None); returns 1 when a decision is
+ * pending, 0 when the simulation ended (*done = 1). */
+int abo_dq_step(abo_env *s, int action, double *out8, double *trans6, double *reward, int *done) {
+  dq_state *d = s->dq; exec_t *dd = d->has_ddqn ? &d->ex[d->n_ex - 1] : NULL;
+  if (dd && dd->pending) { dq_ddqn_resume(s, dd, action); s->agent_time[dd->id] += s->comp_delay[dd->id]; }
+  if (dd) dd->step_reward = 0;
+  int paused = 0;
+  while (!paused && s->q.n > 0 && s->now <= s->stop_time) {
+    event_t ev; heap_pop(&s->q, &ev); s->now = ev.t; s->ttl++;
+    s->pop_hash = fnv_mix(fnv_mix(fnv_mix(fnv_mix(s->pop_hash, ev.t), ev.recipient), ev.type), ev.uniq);
+    if (s->ttl % 1000 == 0) { if (s->n_ckpt == s->cap_ckpt) { s->cap_ckpt = s->cap_ckpt ? s->cap_ckpt * 2 : 256; s->ckpt = (uint64_t *)realloc(s->ckpt, 8 * s->cap_ckpt); } s->ckpt[s->n_ckpt++] = s->pop_hash; }
+    if (s->trace & ABO_TRACE_POPS) { int64_t row[5] = { ev.t, ev.recipient, ev.type, ev.uniq, ev.kind }; ib_push(&s->pops, row, 5); }
+    int a = ev.recipient;
+    if (s->agent_time[a] > s->now) { ev.t = s->agent_time[a]; env_put(s, &ev); continue; }
+    s->agent_time[a] = s->now;
+    exec_t *e = dq_exec(s, a);
+    if (ev.type == ABO_T_WAKEUP) { if (a == 1) replay_wakeup(s); else if (e) dq_exec_wakeup(s, e); else if (a >= 2) dq_mom_wakeup(s, a); }
+    else { if (a == 0) env_exch_receive(s, &ev); else if (a == 1) replay_receive(s, &ev); else if (e) dq_exec_receive(s, e, &ev); else dq_mom_receive(s, a, &ev); }
+    if (dd && dd->pending) { paused = 1; break; }                                             /* agent_time is advanced when the handler resumes */
+    s->agent_time[a] += s->comp_delay[a];
+  }
+  *done = !paused;
+  for (int i = 0; i < 8; i++) out8[i] = 0; for (int i = 0; i < 6; i++) trans6[i] = NAN; *reward = dd ? dd->step_reward : 0;
+  if (dd) {
+    if (paused) { for (int i = 0; i < 6; i++) out8[i] = dd->obs6[i]; out8[6] = dd->sp[0]; out8[7] = dd->sp[1]; }
+    int tprev = dd->t - 1; if (tprev >= 0) for (int i = 0; i < 6; i++) trans6[i] = dq_exp_row(dd, tprev)[i];
+  }
+  return paused;
+}
+int abo_dq_error(abo_env *s) { return s->dq ? s->dq->error : 0; }
+/* which: 0 price_path, 1 experience rows (x6), 2 step_reward_hist, 3 action_hist */
+int64_t abo_dq_series(abo_env *s, int which, const double **v) {
+  dq_state *d = s->dq; exec_t *e = &d->ex[d->n_ex - 1];
+  switch (which) { case 0: *v = e->pp; return e->n_pp; case 1: *v = e->exp; return e->n_exp; case 2: *v = e->rew; return e->n_rew; default: *v = e->ahist; return e->n_ahist; }
+}
+/* per trader (ids 1..n-1): rows (id, shares, cash, last_trade, open orders) */
+void abo_dq_holdings(abo_env *s, int64_t *out5) {
+  dq_state *d = s->dq;
+  for (int id = 1; id < d->n_agents; id++) { const tagent_t *a; int64_t no = 0; exec_t *e = dq_exec(s, id);
+    if (id == 1) { a = &s->ra; no = s->ra_orders.n; } else if (e) { a = &e->ta; no = e->n_orders; } else { a = &d->mom[id - 2].ta; no = -1; }
+    int64_t *r = out5 + 5 * (id - 1); r[0] = id; r[1] = a->shares; r[2] = a->cash; r[3] = a->has_last_trade ? a->last_trade : 0; r[4] = no; }
+}
+/* execution agent k (0 .. n_exec-1): rem_qty, arrival price, executed orders, remaining_time, t */
+void abo_dq_exec_final(abo_env *s, int k, double *out5) { exec_t *e = &s->dq->ex[k]; out5[0] = (double)e->rem_qty; out5[1] = e->arrival; out5[2] = (double)e->n_executed; out5[3] = e->rem_time; out5[4] = e->t; }

@@ -124,6 +124,17 @@ int64_t abo_env_trace(abo_env *, int which, const int64_t **rows);
 void abo_env_final(abo_env *, double *out8); /* rl rem_quantity, shares, cash, n_executed, replay shares, cash, open orders, now */
 int64_t abo_env_counter(abo_env *, int which); /* 0 max queue, 1 max bid levels, 2 max ask levels, 3 max resting, 4 uniq, 5 next order id */
 
+/* ---------------- DDQN execution config: config/execution/marketreplay/execution_marketreplay_ddqn.py (-a rl) ----------------
+ * Exchange + MarketReplayAgent + n_mom MomentumAgents + n_twap TWAPExecutionAgents + DDQLearningExecutionAgent under Kernel.runner.
+ * The Q-network is an input (the action of every decision tick); handles are abo_env (abo_env_free / n_pops / hashes / trace work). */
+abo_env *abo_dq_new(const int64_t *stream5, int64_t n_rows, int n_mom, const int64_t *mom_sizes, int n_twap, int has_ddqn, int is_buy,
+                    int64_t quantity, int64_t h0_ns, int64_t h_step_ns, int n_h, int64_t mom_wake_ns, int trace_flags);
+int abo_dq_step(abo_env *, int action, double *out8, double *trans6, double *reward, int *done);
+int abo_dq_error(abo_env *);
+int64_t abo_dq_series(abo_env *, int which /*0 price_path, 1 experience x6, 2 step_reward_hist, 3 action_hist*/, const double **v);
+void abo_dq_holdings(abo_env *, int64_t *out5);
+void abo_dq_exec_final(abo_env *, int k, double *out5);
+
 #ifdef __cplusplus
 }
 #endif

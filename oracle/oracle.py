@@ -106,6 +106,12 @@ def lib():
     sig("abo_env_trace", i64, vp, i32, P(P(i64)))
     sig("abo_env_final", None, vp, P(dbl))
     sig("abo_env_counter", i64, vp, i32)
+    sig("abo_dq_new", vp, P(i64), i64, i32, P(i64), i32, i32, i32, i64, i64, i64, i32, i64, i32)
+    sig("abo_dq_step", i32, vp, i32, P(dbl), P(dbl), P(dbl), P(i32))
+    sig("abo_dq_error", i32, vp)
+    sig("abo_dq_series", i64, vp, i32, P(P(dbl)))
+    sig("abo_dq_holdings", None, vp, P(i64))
+    sig("abo_dq_exec_final", None, vp, i32, P(dbl))
     _lib = L
     return L
 
@@ -379,3 +385,48 @@ class OracleEnv:
     def counter(self, which):
         names = ["max_queue", "max_bid_levels", "max_ask_levels", "max_resting", "uniq", "next_order_id"]
         return lib().abo_env_counter(self._h, names.index(which))
+
+
+class OracleDDQNEnv(OracleEnv):
+    """config/execution/marketreplay/execution_marketreplay_ddqn.py (-a rl) restated: Exchange + MarketReplayAgent + MomentumAgents +
+    TWAPExecutionAgent + DDQLearningExecutionAgent under Kernel.runner, paused at every choose_action of the DDQN agent."""
+
+    def __init__(self, stream, mom_sizes, n_twap=1, has_ddqn=True, is_buy=True, quantity=500000, h0_ns=10 * 3600 * 10 ** 9,
+                 h_step_ns=30 * 10 ** 9, n_h=661, mom_wake_ns=20 * 10 ** 9, trace=0):
+        self._stream = np.ascontiguousarray(stream, dtype=np.int64)
+        ms = np.ascontiguousarray(mom_sizes, dtype=np.int64)
+        self.n_agents = 2 + len(ms) + n_twap + (1 if has_ddqn else 0)
+        self.n_exec = n_twap + (1 if has_ddqn else 0)
+        self._h = lib().abo_dq_new(self._stream.ctypes.data_as(C.POINTER(C.c_int64)), len(self._stream), len(ms), ms.ctypes.data_as(C.POINTER(C.c_int64)),
+                                   int(n_twap), int(bool(has_ddqn)), int(bool(is_buy)), int(quantity), int(h0_ns), int(h_step_ns), int(n_h), int(mom_wake_ns), int(trace))
+        if not self._h:
+            raise ValueError("abo_dq_new rejected the configuration")
+
+    def step(self, action):
+        """-> (obs8 = 6 features + 2 digitised state entries, trans6 = finalised (s, a, s', r) of the previous tick, reward, done)"""
+        out8, tr = np.zeros(8), np.zeros(6)
+        rew, done = C.c_double(0), C.c_int(0)
+        lib().abo_dq_step(self._h, int(action), out8.ctypes.data_as(C.POINTER(C.c_double)), tr.ctypes.data_as(C.POINTER(C.c_double)), C.byref(rew), C.byref(done))
+        return out8, tr, float(rew.value), int(done.value)
+
+    def error(self):
+        return lib().abo_dq_error(self._h)
+
+    def series(self, which):
+        w = {"price_path": (0, 1), "experience": (1, 6), "step_reward_hist": (2, 1), "action_hist": (3, 1)}[which]
+        p = C.POINTER(C.c_double)()
+        n = lib().abo_dq_series(self._h, w[0], C.byref(p))
+        if n == 0:
+            return np.zeros((0, w[1])) if w[1] > 1 else np.zeros(0)
+        a = np.ctypeslib.as_array(p, shape=(n * w[1],)).copy()
+        return a.reshape(n, w[1]) if w[1] > 1 else a
+
+    def holdings(self):
+        out = np.zeros((self.n_agents - 1, 5), dtype=np.int64)
+        lib().abo_dq_holdings(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)))
+        return out
+
+    def exec_final(self, k):
+        out = np.zeros(5)
+        lib().abo_dq_exec_final(self._h, int(k), out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out

@@ -241,4 +241,59 @@ int32_t abx_env_step_host(abx_sim *h, const double *actions, double *obs, double
   return ABX_OK;
 }
 int32_t abx_env_step(abx_sim *h, const double *a, double *o, double *r, uint8_t *d, void *s) { return abx_env_step_host(h, a, o, r, d, s); }
+
+// ---- DDQN execution shape ----
+typedef Sim<HostCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_DQ> DqSimHost;
+int32_t abx_dq_config_default(abx_dq_config *cfg) { return dq_config_default(cfg); }
+int32_t abx_dq_create(const abx_dq_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
+  (void)device; if (!out || n_envs < 1 || dq_config_validate(cfg) != ABX_OK) return ABX_ERR_ARG;
+  abx_sim *h = new abx_sim(); memset(&h->P, 0, sizeof(h->P)); h->is_env = true; h->n_envs = n_envs; h->reset_done = false;
+  if (env_build_stream(stream5, n_rows, dq_max_generated_ids(*cfg), h->st) != ABX_OK) { delete h; return ABX_ERR_ARG; }
+  dq_fill_params(*cfg, h->P); h->P.n_envs = n_envs; const abx_sim_config &c = h->P.c; size_t E = n_envs;
+  h->P.n_ts = (int)h->st.ts.size(); h->P.n_rows = (int)n_rows; h->P.dq_order_base = (int)h->st.id_orig.size(); h->P.dq_id_limit = h->st.min_id;
+  h->P.n_ids = h->P.dq_order_base + (cfg->n_twap + (cfg->has_ddqn ? 1 : 0)) * EXEC_ORDER_CAP;
+  h->qkey.resize(E * c.queue_cap); h->qpay0.resize(E * c.queue_cap); h->qpay1.resize(E * c.queue_cap); h->qcache.resize(E * h->P.n_qgroups);
+  h->agents.resize(E * c.n_agents); h->lvp.resize(E * 2 * c.level_cap); h->lvq.resize(E * 2 * c.level_cap); h->lvht.resize(E * 2 * c.level_cap);
+  h->nodes.resize(E * c.order_cap); h->env.resize(E); h->trace.resize(E * (size_t)c.trace_cap);
+  h->envx.resize(E); h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3);
+  h->P.qkey = h->qkey.data(); h->P.qpay0 = h->qpay0.data(); h->P.qpay1 = h->qpay1.data(); h->P.qcache = h->qcache.data(); h->P.agents = h->agents.data();
+  h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
+  h->P.trace = c.trace_cap ? h->trace.data() : nullptr; h->P.envx = h->envx.data(); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data();
+  h->P.st_ts = h->st.ts.data(); h->P.st_first = h->st.first.data(); h->P.st_rows = h->st.rows.data();
+  *out = h; return ABX_OK;
+}
+int32_t abx_dq_reset(abx_sim *h, const uint64_t *seeds, const int32_t *mom_sizes, void *stream) {
+  (void)stream; if (!h || !h->is_env || h->P.c.population != 2) return ABX_ERR_ARG;
+  memset(h->idtab.data(), 0, h->idtab.size() * sizeof(uint4)); memset(h->lobs.data(), 0, h->lobs.size() * sizeof(int4));
+  for (int e = 0; e < h->n_envs; e++) {
+    uint64_t seed = seeds ? seeds[e] : 0;
+    EnvState s; init_env_state(h->P, seed, s); s.last_trade = -1; init_envx(h->P, h->envx[e]);
+    for (int id = 2; id < h->P.c.n_agents; id++)
+      init_agent_record_dq(h->P, e, id, seed, (mom_sizes && id < 2 + h->P.dq_n_mom) ? mom_sizes[(size_t)e * h->P.dq_n_mom + id - 2] : -1, &h->agents[(size_t)e * h->P.c.n_agents + id]);
+    HostCtx ctx(h->P, e); ctx.q_clear(); DqSimHost sim(ctx, h->P, s, e); sim.env_reset(); h->env[e] = sim.s;
+  }
+  h->reset_done = true; return ABX_OK;
+}
+int32_t abx_dq_step_host(abx_sim *h, const int32_t *actions, double *obs, double *trans, double *reward, uint8_t *done, void *stream) {
+  (void)stream; if (!h || !h->is_env || h->P.c.population != 2 || !obs || !trans || !done) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  for (int e = 0; e < h->n_envs; e++) {
+    EnvX &x = h->envx[e]; bool was_done = (h->env[e].flags & ABX_F_DONE) != 0, paused = false;
+    if (!was_done) { HostCtx ctx(h->P, e); DqSimHost sim(ctx, h->P, h->env[e], e); paused = sim.dq_step(actions ? actions[e] : 0); h->env[e] = sim.s; }
+    for (int i = 0; i < 8; i++) obs[8 * e + i] = paused ? x.obs[i] : 0.0;
+    for (int i = 0; i < 6; i++) trans[6 * e + i] = NAN;
+    double rw = 0.0;
+    if (!was_done && h->P.dq_has_ddqn) {
+      const ZiAgent &z = h->agents[(size_t)e * h->P.c.n_agents + h->P.c.n_agents - 1]; const ExecAux *ex = reinterpret_cast<const ExecAux *>(z.oid);
+      if (ex->exflags & EXF_E_VALID) { double *t = trans + 6 * e; t[0] = ex->e_s[0]; t[1] = ex->e_s[1]; t[2] = ex->e_a; t[3] = ex->e_sp[0]; t[4] = ex->e_sp[1]; t[5] = (ex->exflags & EXF_E_R) ? ex->e_r : NAN; }
+      rw = ex->step_reward;
+    }
+    if (reward) reward[e] = rw; done[e] = (h->env[e].flags & ABX_F_DONE) ? 1 : 0;
+  }
+  return ABX_OK;
+}
+int32_t abx_dq_step(abx_sim *h, const int32_t *a, double *o, double *t, double *r, uint8_t *d, void *s) { return abx_dq_step_host(h, a, o, t, r, d, s); }
+int32_t abx_dq_holdings(abx_sim *h, int32_t env, int64_t *out, double *exec_out, void *stream) {
+  (void)stream; if (!h || !h->is_env || h->P.c.population != 2 || !out || env < 0 || env >= h->n_envs) return ABX_ERR_ARG;
+  dq_holdings_rows(h->P, &h->agents[(size_t)env * h->P.c.n_agents], h->envx[env], out, exec_out); return ABX_OK;
+}
 }

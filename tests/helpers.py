@@ -16,7 +16,7 @@ def build_emu():
                     for f in ("abx_core.cuh", "abx_host_common.h")] + [os.path.join(ROOT, "include", "abides_b200.h")]
     if os.path.exists(EMU_LIB) and all(os.path.getmtime(EMU_LIB) >= os.path.getmtime(d) for d in deps):
         return EMU_LIB
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-Wno-unknown-pragmas",
                            "-o", EMU_LIB, src])
     return EMU_LIB
 

@@ -1,0 +1,89 @@
+"""CPU CI of the product's DDQN-execution-shape logic (abx_core.cuh compiled as plain C++ by tests/emu; a test tool, never a
+fallback): the recorded reference runs of config/execution/marketreplay/execution_marketreplay_ddqn.py must be reproduced tick by
+tick -- event order, exchange messages, book snapshots, observations, experience tuples, rewards, holdings."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import build_emu
+from marl_optimal_execution_b200 import _lib
+from marl_optimal_execution_b200.env import DDQNExecutionEnv, dq_config
+from oracle.oracle import OracleDDQNEnv, TRACE_ALL
+
+FIXTURES = ["ddqn_IBM_2003-01-14_s4242.npz", "ddqn_IBM_2003-01-16_s99_sell.npz"]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return build_emu()
+
+
+def run_episode(env, o, g, n_envs):
+    acts = g["actions"]
+    obs, trans, rew, done = env.step(None)
+    oo, otr, orw, od = o.step(0)
+    k, total = 0, 0.0
+    while not done[0]:
+        assert not od and np.allclose(obs[0], oo, rtol=1e-12, atol=0), k
+        assert np.allclose(obs[0, :6], g["observation"][k], rtol=1e-6, atol=1e-12), k        # vs the reference recording: 1e-6 relative, fp64
+        a = np.full(n_envs, int(acts[k]), dtype=np.int32)
+        if n_envs > 1:
+            a[1] = (int(acts[k]) + 7) % 24                                                     # env 1 follows another policy: must diverge
+        obs, trans, rew, done = env.step(a)
+        oo, otr, orw, od = o.step(int(acts[k]))
+        assert np.array_equal(np.nan_to_num(trans[0], nan=-7.0), np.nan_to_num(otr, nan=-7.0)), (k, trans[0], otr)
+        assert rew[0] == orw, k
+        total += rew[0]
+        k += 1
+    assert od and k == len(acts) == len(g["experience"])
+    return k, total
+
+
+@pytest.mark.parametrize("fixture", FIXTURES)
+def test_ddqn_episode_matches_oracle_and_reference(emu, golden_dir, fixture):
+    g = np.load(os.path.join(golden_dir, fixture))
+    L = _lib.load(emu)
+    is_buy = int(g["is_buy"]) if "is_buy" in g.files else 1
+    env = DDQNExecutionEnv(g["stream"], n_envs=2, cfg=dq_config(L, is_buy=is_buy, trace_cap=420000, hash_pops=1), lib_path=emu)
+    env.reset(mom_sizes=np.tile(g["mom_sizes"].astype(np.int32), (2, 1)))
+    o = OracleDDQNEnv(g["stream"], g["mom_sizes"], is_buy=bool(is_buy), trace=TRACE_ALL)
+    k, total = run_episode(env, o, g, 2)
+    st = env.stats()
+    assert int(st["messages"][0]) == o.n_pops == int(g["n_pops"]) and int(st["flags"][0]) == _lib.F_DONE and o.error() == 0
+    assert int(st["pop_hash"][0]) == o.pop_hash() == int(g["pop_hash_ckpt"][-1])
+    p, nt, sn = env.split_trace(0)
+    assert np.array_equal(p, o.trace("pops")) and np.array_equal(nt, o.trace("notes")) and np.array_equal(sn, o.trace("snaps"))
+    assert np.array_equal(p[: len(g["pops_head"])], g["pops_head"]) and np.array_equal(nt[: len(g["notes_head"])], g["notes_head"])
+    assert abs(total - float(g["step_reward_hist"].sum())) < 1e-6 * abs(total)
+    hold, ex = env.holdings(0)
+    assert np.array_equal(hold[:, :4], g["holdings"][:, :4]) and np.array_equal(hold[:, :4], o.holdings()[:, :4])
+    assert np.array_equal(hold[-2:, 4], g["holdings"][-2:, 4])                                # open orders of the two execution agents
+    assert ex[0, 0] == g["twap_final"][0] and ex[0, 1] == g["twap_final"][1] and ex[0, 2] == g["twap_final"][2]
+    assert ex[1, 0] == g["ddqn_final"][0] and ex[1, 1] == g["ddqn_final"][3] and ex[1, 2] == g["ddqn_final"][4] and ex[1, 4] == g["ddqn_final"][2]
+    assert int(st["flags"][1]) == _lib.F_DONE and int(st["pop_hash"][1]) != int(st["pop_hash"][0])
+
+
+def test_oracle_reproduces_reference_recording(golden_dir):
+    """The oracle alone against everything the recorder kept of the live reference run."""
+    for fixture in FIXTURES:
+        g = np.load(os.path.join(golden_dir, fixture))
+        is_buy = int(g["is_buy"]) if "is_buy" in g.files else 1
+        o = OracleDDQNEnv(g["stream"], g["mom_sizes"], is_buy=bool(is_buy), trace=TRACE_ALL)
+        out, tr, r, done = o.step(0)
+        k = 0
+        while not done:
+            assert np.allclose(out[:6], g["observation"][k], rtol=1e-12, atol=1e-15)
+            out, tr, r, done = o.step(int(g["actions"][k]))
+            k += 1
+        assert o.n_pops == int(g["n_pops"]) and o.pop_hash() == int(g["pop_hash_ckpt"][-1]) and o.error() == 0
+        assert o.note_hash() == int(g["note_hash"]) and o.snap_hash() == int(g["snap_hash"])
+        ck = o.hash_ckpt()
+        assert np.array_equal(ck[: len(g["pop_hash_ckpt"]) - 1], g["pop_hash_ckpt"][:-1])
+        ex, ge = o.series("experience"), g["experience"]
+        assert np.array_equal(np.nan_to_num(ex, nan=-7.0), np.nan_to_num(ge, nan=-7.0))
+        assert np.array_equal(o.series("price_path"), g["price_path"]) and np.array_equal(o.series("action_hist"), g["action_hist"])
+        assert np.array_equal(o.series("step_reward_hist"), g["step_reward_hist"])
+        assert np.array_equal(o.holdings()[:, :4], g["holdings"][:, :4])
+        ops = o.trace("ops")
+        assert np.array_equal(ops[ops[:, 2] >= 9], g["rl_ops"])

@@ -237,7 +237,7 @@ def install_hooks():
             row[3:8] = [o.order_id, int(o.is_buy_order), int(o.quantity), int(o.limit_price),
                         0 if o.fill_price is None else int(o.fill_price)]
         if b["msg"] == "QUERY_SPREAD":
-            row[7] = int(b["data"])
+            row[7] = -1 if b["data"] is None else int(b["data"])      # last_trade None before the first trade (no oracle)
             if b["bids"]:
                 row[8], row[9] = b["bids"][0]
             if b["asks"]:
