@@ -287,6 +287,29 @@ int32_t abx_dq_step_host(abx_sim *h, const int32_t *actions, double *obs, double
  * exec_out: HOST double [n_exec * 5] rows (remaining quantity, arrival price, executed orders, remaining_time, t). */
 int32_t abx_dq_holdings(abx_sim *h, int32_t env, int64_t *out, double *exec_out, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Batched Q-network forward of the DDQN agent on the tensor cores (tcgen05 / TMEM; csrc/abx_qnet.cu).
+ * Replaces: eval_model.predict(s_array_2d) + np.argmax / the epsilon branch of choose_action
+ * (agent/execution/qlearning/ddqlearning_execution_agent.py:339-365) and the network of util/model/QNets.py:7-27,55-60
+ * (Dense + ReLU hidden layers, linear output; Dropout is the identity at inference), for a whole batch of states per launch.
+ * dims: n_layers + 1 sizes (reference: 2, 32, 64, 128, 128, 64, 32, 24); dims[0] <= 16, every other size <= 128, n_layers <= 8.
+ * params: HOST fp32, per layer W[out][in] row major (the transpose of a Keras Dense kernel) followed by b[out].
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct abx_qnet abx_qnet; /* opaque */
+const char *abx_qnet_last_error(void);
+int32_t abx_qnet_param_count(const int32_t *dims, int32_t n_layers);
+int32_t abx_qnet_create(const int32_t *dims, int32_t n_layers, const float *params, int32_t device, abx_qnet **out);
+/* New weights (the learner's update / the target-network sync of train_neural_nets :486-490); synchronises `stream`. */
+int32_t abx_qnet_set_params(abx_qnet *q, const float *params, void *stream);
+int32_t abx_qnet_destroy(abx_qnet *q);
+int64_t abx_qnet_launch_count(const abx_qnet *q);
+/* x_dev: DEVICE fp64 [n][x_stride]; the state of row i is x_dev[i * x_stride + x_offset ...+ dims[0]) (abx_dq_step's obs with
+ * x_stride 8, x_offset 6).  q_out_dev: DEVICE fp32 [n][dims[n_layers]] or NULL; action_out_dev: DEVICE int32 [n] or NULL: the
+ * first maximum of the Q row (np.argmax) with probability greedy_prob, otherwise uniform over the actions (Philox keyed by
+ * (seed, counter, row); greedy_prob >= 1 draws nothing). */
+int32_t abx_qnet_forward(abx_qnet *q, const double *x_dev, int32_t x_stride, int32_t x_offset, int32_t n, float *q_out_dev,
+                         int32_t *action_out_dev, double greedy_prob, uint64_t seed, uint64_t counter, void *stream);
+
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t abx_sim_launch_count(const abx_sim *h);
 

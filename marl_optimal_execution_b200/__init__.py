@@ -6,3 +6,4 @@ Python host mirror of the reference's config / Kernel / ABIDESEnv surfaces.  No 
 from ._lib import AbxError, SimConfig, EnvStats  # noqa: F401
 from .sim import BatchedSim, sparse_zi_config  # noqa: F401
 from .env import ABIDESEnv, DDQNExecutionEnv, dq_config, env_config  # noqa: F401
+from .qnet import QNetwork  # noqa: F401

@@ -152,6 +152,14 @@ def _bind(L):
     sig("abx_dq_step", i32, vp, vp, vp, vp, vp, vp, vp)
     sig("abx_dq_step_host", i32, vp, vp, vp, vp, vp, vp, vp)
     sig("abx_dq_holdings", i32, vp, i32, vp, vp, vp)
+    if hasattr(L, "abx_qnet_create"):                 # the host emulation harness of the CPU test-suite has no tensor-core kernels
+        sig("abx_qnet_last_error", C.c_char_p)
+        sig("abx_qnet_param_count", i32, P(i32), i32)
+        sig("abx_qnet_create", i32, P(i32), i32, P(C.c_float), i32, P(vp))
+        sig("abx_qnet_set_params", i32, vp, P(C.c_float), vp)
+        sig("abx_qnet_destroy", i32, vp)
+        sig("abx_qnet_launch_count", i64, vp)
+        sig("abx_qnet_forward", i32, vp, vp, i32, i32, i32, vp, vp, C.c_double, C.c_uint64, C.c_uint64, vp)
     return L
 
 

@@ -1,0 +1,70 @@
+"""Numerics of the tcgen05 Q-network forward (csrc/abx_qnet.cu) against a plain PyTorch fp32 reference of the same network
+(util/model/QNets.py:7-27; TensorFlow is absent from the image, so the Keras arithmetic itself is unpinned -- SURVEY section 8c).
+Tolerance: the kernel multiplies bf16 hi/lo splits on the tensor cores (three MMAs per k step, fp32 accumulation), which keeps
+~16 mantissa bits per operand: |q - q_ref| <= 2e-4 * max|q_ref| + 1e-5; actions must equal np.argmax except at near-ties."""
+import numpy as np
+import pytest
+import torch
+
+from marl_optimal_execution_b200.qnet import DEFAULT_DIMS, QNetwork, init_params, torch_reference
+
+pytestmark = pytest.mark.gpu
+
+
+def states(n, seed, stride=8, offset=6, n_in=2):
+    rs = np.random.RandomState(seed)
+    x = rs.uniform(-5, 5, size=(n, stride))
+    x[:, offset:offset + n_in] = rs.randint(0, 200, size=(n, n_in))       # digitised features: integers 0..199
+    return torch.from_numpy(x).cuda()
+
+
+def check(net, x, offset, tol=2e-4):
+    q, act = net.forward(x, x_offset=offset)
+    ref = torch_reference(net.params, x[:, offset:offset + net.dims[0]], net.dims)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    err = float((q - ref).abs().max())
+    assert err <= tol * scale + 1e-5, (err, scale)
+    ra = ref.argmax(dim=1).to(torch.int32)
+    top2 = ref.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 4 * (tol * scale + 1e-5)
+    assert bool((act[clear] == ra[clear]).all()) and float(clear.float().mean()) > 0.5
+    assert bool((act == q.argmax(dim=1).to(torch.int32)).all())                # the kernel's own rule: first maximum of its Q row
+    return err / max(scale, 1e-30)
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 8192, 40000])
+def test_reference_network_matches_torch_fp32(n):
+    net = QNetwork(DEFAULT_DIMS, seed=11)
+    rel = check(net, states(n, n), 6)
+    assert rel < 2e-4
+
+
+def test_trained_like_weights_biases_and_other_shapes():
+    rs = np.random.RandomState(5)
+    for dims in [(2, 32, 64, 128, 128, 64, 32, 24), (6, 32, 64, 128, 128, 64, 32, 24), (3, 16, 24), (16, 128, 128, 7), (1, 48, 24)]:
+        p = init_params(dims, seed=3) * 3.0
+        p += rs.normal(0, 0.05, size=p.shape).astype(np.float32)            # non-zero biases too
+        net = QNetwork(dims, params=p)
+        x = states(1000, 9, stride=dims[0] + 3, offset=2, n_in=dims[0])
+        check(net, x, 2)
+
+
+def test_set_params_and_epsilon_rule():
+    net = QNetwork(DEFAULT_DIMS, seed=1)
+    x = states(20000, 4)
+    q0, a0 = net.forward(x, x_offset=6)
+    net.set_params(init_params(DEFAULT_DIMS, seed=2))
+    q1, a1 = net.forward(x, x_offset=6)
+    assert not torch.equal(q0, q1)
+    check(net, x, 6)
+    # greedy_prob 0.9 (the reference's epsilon_max): ~10 % uniform actions, deterministic in (seed, counter)
+    _, e1 = net.forward(x, x_offset=6, greedy_prob=0.9, seed=7, counter=3)
+    _, e2 = net.forward(x, x_offset=6, greedy_prob=0.9, seed=7, counter=3)
+    _, e3 = net.forward(x, x_offset=6, greedy_prob=0.9, seed=7, counter=4)
+    assert torch.equal(e1, e2) and not torch.equal(e1, e3)
+    frac = float((e1 != a1).float().mean())
+    assert 0.06 < frac < 0.13, frac                                         # 0.1 * (1 - 1/24) expected
+    _, r = net.forward(x, x_offset=6, greedy_prob=0.0, seed=1, counter=0)
+    counts = torch.bincount(r.to(torch.int64), minlength=24).float()
+    assert int(r.min()) >= 0 and int(r.max()) <= 23 and float(counts.min()) > 0.7 * 20000 / 24
