@@ -1,0 +1,98 @@
+"""Host logic of the DDQN learner (marl_optimal_execution_b200/ddqn.py) on the CPU: the update must equal a numpy restatement of
+train_neural_nets (agent/execution/qlearning/ddqlearning_execution_agent.py:449-505) with Keras' RMSprop rule, and the acting /
+storing / learning loop must run over the batched environment (host emulation harness of the simulator logic; a test tool)."""
+import os
+
+import numpy as np
+import torch
+
+from helpers import build_emu
+from marl_optimal_execution_b200 import _lib
+from marl_optimal_execution_b200.ddqn import DDQNTrainer, ReplayBuffer, TorchMLP
+from marl_optimal_execution_b200.env import DDQNExecutionEnv, dq_config
+from marl_optimal_execution_b200.qnet import DEFAULT_DIMS, init_params, unpack_params
+
+
+def np_forward(flat, x, dims=DEFAULT_DIMS):
+    h = x.astype(np.float32)
+    layers = unpack_params(flat, dims)
+    for i, (w, b) in enumerate(layers):
+        h = h @ w.T + b
+        if i + 1 < len(layers):
+            h = np.maximum(h, 0)
+    return h
+
+
+def test_learn_step_equals_reference_update_rule():
+    tr = DDQNTrainer(batch_size=16, seed=3, buffer_capacity=64)
+    rs = np.random.RandomState(0)
+    t = np.column_stack([rs.randint(0, 200, (40, 2)), rs.randint(0, 24, 40), rs.randint(0, 200, (40, 2)), rs.uniform(0, 20, 40)])
+    t[5, 5] = np.nan                                                      # r None: skipped
+    assert tr.buffer.push(torch.from_numpy(t)) == 39
+    # replicate the sampling, then the reference arithmetic in numpy
+    g = torch.Generator(); g.manual_seed(3)
+    idx = torch.randint(0, 39, (16,), generator=g).numpy()
+    ok = np.delete(t, 5, axis=0)[idx]
+    s, a, sp, r = ok[:, 0:2], ok[:, 2].astype(int), ok[:, 3:5], ok[:, 5].astype(np.float32)
+    ev0, tg0 = tr.eval_net.flat(), tr.target_net.flat()
+    q_next = np_forward(tg0, sp)
+    tgt_a = r + np.float32(0.98) * q_next[np.arange(16), q_next.argmax(1)]     # r + gamma * q_next[argmax q_eval4next], both from the TARGET net
+    ref = TorchMLP(DEFAULT_DIMS, flat=ev0)
+    s_t = torch.from_numpy(s.astype(np.float32))
+    q_target = ref(s_t).detach().clone()                                      # q_eval.copy(): RMSprop normalises gradients, so the untouched
+    assert np.allclose(q_target.numpy(), np_forward(ev0, s), rtol=1e-4, atol=1e-3)   # entries must cancel exactly, as in train_on_batch
+    new_a = torch.from_numpy(tgt_a)
+    assert np.allclose(tr.target_net(torch.from_numpy(sp.astype(np.float32))).detach().numpy(), q_next, rtol=1e-4, atol=1e-3)
+    cost = tr.learn()
+    # learn_step_counter 0 -> the target network was replaced by the eval network BEFORE the fit (:487-490)
+    assert np.array_equal(tr.target_net.flat(), ev0)
+    # MSE gradient + Keras RMSprop: v = 0.9 v + 0.1 g^2 ; w -= lr g / (sqrt(v) + 1e-7)
+    tn = TorchMLP(DEFAULT_DIMS, flat=tg0)
+    with torch.no_grad():
+        qn = tn(torch.from_numpy(sp.astype(np.float32)))
+        q_target[torch.arange(16), torch.from_numpy(a)] = torch.from_numpy(r) + 0.98 * qn.gather(1, qn.argmax(1)[:, None])[:, 0]
+    assert np.allclose(q_target[torch.arange(16), torch.from_numpy(a)].numpy(), new_a.numpy(), rtol=1e-4, atol=1e-3)
+    loss = ((ref(s_t) - q_target) ** 2).mean()
+    loss.backward()
+    assert abs(float(loss.detach()) - cost) <= 1e-5 * max(1.0, abs(cost))
+    for p, q in zip(ref.params, tr.eval_net.params):
+        gnp = p.grad.numpy()
+        want = p.detach().numpy() - 0.01 * gnp / (np.sqrt(0.1 * gnp * gnp) + 1e-7)
+        assert np.allclose(q.detach().numpy(), want, rtol=1e-4, atol=1e-6)
+    assert tr.learn_step_counter == 1 and tr.epsilon == 0.9
+
+
+def test_replay_buffer_wraps_and_epsilon_schedule():
+    b = ReplayBuffer(8, "cpu")
+    t = torch.arange(60, dtype=torch.float64).reshape(10, 6)
+    assert b.push(t) == 8 and b.size == 8
+    assert set(b.r.tolist()) == {float(6 * i + 5) for i in range(2, 10)}
+    tr = DDQNTrainer(batch_size=4, epsilon_increment=0.3, buffer_capacity=32)
+    assert tr.epsilon == 0.0 and tr.greedy_prob() == 0.0
+    tr.buffer.push(torch.rand(10, 6, dtype=torch.float64) * 20)
+    for _ in range(5):
+        tr.learn()
+    assert abs(tr.epsilon - 0.9) < 1e-9 or tr.epsilon >= 0.9              # 0 -> .3 -> .6 -> .9 -> 1.2? no: clamps to epsilon_max once >= max
+    assert tr.epsilon <= 1.2 + 1e-9
+
+
+def test_training_loop_over_the_batched_environment(golden_dir):
+    emu = build_emu()
+    L = _lib.load(emu)
+    g = np.load(os.path.join(golden_dir, "ddqn_IBM_2003-01-14_s4242.npz"))
+    env = DDQNExecutionEnv(g["stream"], n_envs=4, cfg=dq_config(L), lib_path=emu)
+    env.reset(seeds=np.arange(4, dtype=np.uint64))
+    tr = DDQNTrainer(batch_size=8, seed=1, buffer_capacity=4096)
+    pushed = []
+
+    def act(obs, greedy_prob, tick):
+        q = tr.eval_net(torch.as_tensor(obs[:, 6:8], dtype=torch.float32))
+        a = q.argmax(dim=1).numpy().astype(np.int32)
+        rnd = np.random.RandomState(tick).randint(0, 24, len(a)).astype(np.int32)
+        return np.where(np.random.RandomState(1000 + tick).uniform(size=len(a)) < greedy_prob, a, rnd)
+
+    total, ticks = tr.run_episode(env, act, sync_fn=lambda flat: pushed.append(flat), max_ticks=60)
+    assert ticks == 60 and tr.buffer.size > 150 and tr.learn_step_counter >= 8 and len(pushed) == tr.learn_step_counter
+    assert np.isfinite(tr.cost_hist).all() and float(total.min()) > 0.0           # every environment filled something: rewards are positive
+    st = env.stats()
+    assert (st["flags"] & _lib.F_ERROR_MASK == 0).all()

@@ -68,3 +68,34 @@ def test_set_params_and_epsilon_rule():
     _, r = net.forward(x, x_offset=6, greedy_prob=0.0, seed=1, counter=0)
     counts = torch.bincount(r.to(torch.int64), minlength=24).float()
     assert int(r.min()) >= 0 and int(r.max()) <= 23 and float(counts.min()) > 0.7 * 20000 / 24
+
+
+def test_acting_and_learning_loop_on_the_gpu(golden_dir):
+    """Closed loop: tcgen05 Q-network picks the actions from the environment's device-resident observation, the environment steps,
+    the learner (ddqn.py) trains on the experience tuples and pushes new weights into the acting network."""
+    import os
+    from marl_optimal_execution_b200 import _lib
+    from marl_optimal_execution_b200.ddqn import DDQNTrainer
+    from marl_optimal_execution_b200.env import DDQNExecutionEnv
+    g = np.load(os.path.join(golden_dir, "ddqn_IBM_2003-01-14_s4242.npz"))
+    n = 512
+    env = DDQNExecutionEnv(g["stream"], n_envs=n)
+    env.reset(seeds=np.arange(n, dtype=np.uint64))
+    tr = DDQNTrainer(device="cuda", batch_size=256, seed=2, buffer_capacity=1 << 16)
+    net = QNetwork(DEFAULT_DIMS, params=tr.eval_net.flat())
+    seen = []
+
+    def act(obs, greedy_prob, tick):
+        q, a = net.forward(obs, x_offset=6, greedy_prob=greedy_prob, seed=5, counter=tick)
+        if tick == 20:
+            ref = torch_reference(net.params, obs[:, 6:8])
+            assert float((q - ref).abs().max()) <= 2e-4 * float(ref.abs().max()) + 1e-5
+        seen.append(int(torch.unique(a).numel()))
+        return a
+
+    total, ticks = tr.run_episode(env, act, sync_fn=net.set_params, max_ticks=40)
+    assert ticks == 40 and tr.learn_step_counter >= 6 and tr.buffer.size >= 30 * n
+    assert max(seen) > 10 and float(total.min()) > 0.0 and np.isfinite(tr.cost_hist).all()
+    st = env.stats()
+    assert (st["flags"] & _lib.F_ERROR_MASK == 0).all()
+    assert np.array_equal(net.params, tr.eval_net.flat())
