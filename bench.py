@@ -26,6 +26,8 @@ sys.path.insert(0, ROOT)
 
 NS = 10 ** 9
 FIXTURE = os.path.join(ROOT, "tests", "golden", "env_IBM_2003-01-14_s789.npz")   # LOBSTER sample day as the reference parsed it
+DQ_FIXTURE = os.path.join(ROOT, "tests", "golden", "ddqn_IBM_2003-01-14_s4242.npz")   # same day, with the recorded MomentumAgent sizes
+QNET_FLOP_PER_ROW = 2 * (2 * 32 + 32 * 64 + 64 * 128 + 128 * 128 + 128 * 64 + 64 * 32 + 32 * 24)   # util/model/QNets.py:7-27 with the 2-entry state
 B_MSG = 320                 # algorithmic bytes per LOB message (DESIGN.md "Roofline")
 PUBLISHED_MSGS_PER_S = 3100.4   # reference's own sparse_zi_1000 run (tests/sparse_zi_1000.txt:22)
 
@@ -54,6 +56,18 @@ def measured_peak_hbm():
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_peak_tflops():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["bf16_tflops"]), "measured burst cuBLAS bf16 (MEASURED_PEAKS.json)"
+    except Exception:
+        return 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def sim_closed(sim):
+    return getattr(sim, "_h", None) is None or not sim._h
 
 
 def profiled_traffic():
@@ -153,6 +167,37 @@ def oracle_env_steps_per_s(n_episodes, steps, threads):
     return sum(r[0] for r in res), sum(r[1] for r in res), sum(r[2] for r in res) / threads if n_episodes >= threads else busy, wall
 
 
+def oracle_ddqn_ticks_per_s(n_episodes, ticks, threads):
+    """Reference CPU algorithm of the DDQN execution config (oracle port; the Q-network is replaced by random actions) on host threads."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.oracle import OracleDDQNEnv, lib
+    lib()
+    with np.load(DQ_FIXTURE) as g:                         # materialise before the threads start: NpzFile is not thread safe
+        dq_stream, dq_sizes = g["stream"].copy(), g["mom_sizes"].copy()
+
+    def one(i):
+        rng = np.random.RandomState(300 + i)
+        env = OracleDDQNEnv(dq_stream, dq_sizes)
+        env.step(0)                                        # 00:00 -> 10:00 start-up, untimed like the GPU arm
+        n0 = env.n_pops
+        t0 = time.perf_counter()
+        for _ in range(ticks):
+            env.step(int(rng.randint(0, 24)))
+        return ticks, env.n_pops - n0, time.perf_counter() - t0
+
+    with ThreadPoolExecutor(threads) as ex:
+        res = list(ex.map(one, range(n_episodes)))
+    busy = sum(r[2] for r in res) / threads if n_episodes >= threads else max(r[2] for r in res)
+    return sum(r[0] for r in res), sum(r[1] for r in res), busy
+
+
+def reference_ddqn_block(cores):
+    st, msgs, busy = oracle_ddqn_ticks_per_s(max(cores, 2), 100, cores)
+    return {"metric": "DDQN execution env ticks/sec", "value": st / busy, "unit": "steps/s", "msgs_per_s": msgs / busy, "cores": cores, "kind": "port",
+            "sample": "%d runs x 100 decision ticks after the 10:00 start-up (IBM 2003-01-14 LOBSTER fixture, random actions, no network), %d threads" % (max(cores, 2), cores)}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -175,7 +220,7 @@ def run_reference(args, rank, world):
                                "(oracle/abides_oracle.c port of the Python reference) on host cores" % (args.variant, args.variant)},
         "cpu_baseline": {"value": v, "unit": "msgs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "msgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "env": reference_env_block(cores),
+        "gpu_launches": 0, "env": reference_env_block(cores), "ddqn": reference_ddqn_block(cores),
     })
 
 
@@ -259,6 +304,12 @@ def run_ours(args, rank, local_rank, world):
         sim.close()
         env_local = bench_env(args, rank, local_rank, dev, stream, sp)
 
+    dq_local = None
+    if not args.no_ddqn:
+        if not sim_closed(sim):
+            sim.close()
+        dq_local = bench_ddqn(args, rank, local_rank, dev, stream, sp)
+
     # ---- aggregate over ranks: sums by all-gather of the summary vectors (NCCL), times by max
     g = D.gather_summaries(torch.tensor([msgs_local, e2e_msgs_local, err_envs], dtype=torch.int64), device=dev)
     elapsed_ms = D.max_over_ranks(elapsed_ms, device=dev)
@@ -275,6 +326,27 @@ def run_ours(args, rank, local_rank, world):
                              "d2h_bytes_per_step": 81 * args.env_envs_per_gpu},
                      "gpu_launches": env_local["launches"], "workload": "ABIDESEnv.py shape: exchange + MarketReplayAgent (IBM 2003-01-14 LOBSTER sample day fixture) + "
                      "DummyRLExecutionAgent (BUY 1e5, 30 s, order_level 2), random actions; one abx_env_step_kernel launch per step"}
+    dq_block = None
+    if dq_local is not None:
+        gd = D.gather_summaries(torch.tensor([dq_local["steps"], dq_local["msgs"], dq_local["e2e_steps"], dq_local["errs"]], dtype=torch.int64), device=dev)
+        t_dq = D.max_over_ranks(dq_local["ms"], device=dev) / 1e3
+        t_dq_e2e = D.max_over_ranks(dq_local["e2e_s"], device=dev)
+        nd, Kd = args.ddqn_envs_per_gpu, args.ddqn_steps
+        tf_peak = measured_peak_tflops()
+        q_ach = nd * QNET_FLOP_PER_ROW / (dq_local["qnet_ms"] / 1e3) / 1e12
+        dq_block = {"metric": "DDQN execution env ticks/sec (Q-network forward + environment step)", "value": int(gd[:, 0].sum()) / t_dq, "unit": "steps/s",
+                    "msgs_per_s": int(gd[:, 1].sum()) / t_dq, "envs_per_gpu": nd, "steps": Kd, "ms_per_step": 1e3 * t_dq / Kd,
+                    "messages_per_env_step": int(gd[:, 1].sum()) / max(int(gd[:, 0].sum()), 1), "error_envs": int(gd[:, 3].sum()),
+                    "e2e": {"value": int(gd[:, 2].sum()) / t_dq_e2e, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 121 * nd,
+                            "note": "actions are produced on the device by the Q-network; every tick obs, experience tuple, reward and done are read back to pinned host memory"},
+                    "gpu_launches": dq_local["launches"], "dtype": "int64+f64 (environment), bf16x3 -> fp32 accumulate (Q-network)",
+                    "qnet_roofline": {"bound": "tensor", "achieved": q_ach, "peak": tf_peak[0], "unit": "TFLOP/s", "frac": q_ach / tf_peak[0], "traffic": None,
+                                      "peak_source": tf_peak[1], "kernel": "abx_qnet_forward_kernel", "kernel_ms": dq_local["qnet_ms"],
+                                      "algorithmic_flop_per_row": QNET_FLOP_PER_ROW, "share_of_tick": dq_local["qnet_ms"] * Kd / dq_local["ms"],
+                                      "note": "7 dependent layers per 128-row tile, %d tiles on 148 SMs: latency bound by construction, not a throughput kernel" % ((nd + 127) // 128)},
+                    "workload": "config/execution/marketreplay/execution_marketreplay_ddqn.py shape: exchange + MarketReplayAgent (IBM 2003-01-14 LOBSTER fixture) + 7 MomentumAgents + "
+                    "TWAPExecutionAgent + DDQLearningExecutionAgent (BUY 5e5, 30 s ticks from 10:00), epsilon-greedy (0.9) actions from a random-init 2-32-64-128-128-64-32-24 network; "
+                    "per tick one abx_qnet_forward_kernel + one abx_dq_step_kernel launch"}
     if rank != 0:
         return
     msgs, e2e_msgs, errs = int(g[:, 0].sum()), int(g[:, 1].sum()), int(g[:, 2].sum())
@@ -308,6 +380,8 @@ def run_ours(args, rank, local_rank, world):
     }
     if not args.no_env:
         out["env"] = env_block
+    if dq_block is not None:
+        out["ddqn"] = dq_block
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_days = max(2 * cores, 16)
@@ -318,6 +392,8 @@ def run_ours(args, rank, local_rank, world):
                                "single_thread_value": m / cpu_s}
         if not args.no_env:
             out["cpu_baseline"]["env"] = reference_env_block(cores)
+        if not args.no_ddqn:
+            out["cpu_baseline"]["ddqn"] = reference_ddqn_block(cores)
     emit_json(out)
 
 
@@ -362,6 +438,59 @@ def bench_env(args, rank, local_rank, dev, stream, sp):
     return {"steps": n * K, "msgs": m1 - m0, "ms": e0.elapsed_time(e1), "e2e_steps": n * K, "e2e_s": e2e_s, "errs": errs, "launches": int(launches)}
 
 
+def bench_ddqn(args, rank, local_rank, dev, stream, sp):
+    """DDQN acting loop: per decision tick one tcgen05 Q-network forward over all environments + one environment step."""
+    import numpy as np
+    import torch
+    from marl_optimal_execution_b200 import _lib, distributed as D
+    from marl_optimal_execution_b200.env import DDQNExecutionEnv
+    from marl_optimal_execution_b200.qnet import QNetwork
+
+    n, K, W = args.ddqn_envs_per_gpu, args.ddqn_steps, max(args.warmup, 3)
+    g = np.load(DQ_FIXTURE)
+    env = DDQNExecutionEnv(g["stream"], n_envs=n, device=local_rank)
+    net = QNetwork(device=local_rank, seed=args.seed % 1000)
+    env.reset(seeds=np.arange(rank * n, (rank + 1) * n, dtype=np.uint64) + np.uint64(args.seed), stream=sp)
+    obs, trans, rew, done = env.step(torch.zeros(n, dtype=torch.int32, device=dev), stream=sp)      # 00:00 -> 10:00 start-up (~30 k messages/env), untimed
+    qbuf = (None, torch.empty(n, dtype=torch.int32, device=dev))
+    tick = 0
+    for _ in range(W):
+        _, a = net.forward(obs, x_offset=6, want_q=False, greedy_prob=0.9, seed=args.seed, counter=tick, out=qbuf, stream=sp)
+        obs, trans, rew, done = env.step(a, stream=sp); tick += 1
+    torch.cuda.synchronize(dev)
+    m0 = int(env.stats(stream=sp)["messages"].sum()); l0 = env.launch_count + net.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    qe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    D.barrier(); torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for k in range(K):
+        qe[k][0].record(stream)
+        _, a = net.forward(obs, x_offset=6, want_q=False, greedy_prob=0.9, seed=args.seed, counter=tick, out=qbuf, stream=sp)
+        qe[k][1].record(stream)
+        obs, trans, rew, done = env.step(a, stream=sp); tick += 1
+    e1.record(stream)
+    torch.cuda.synchronize(dev); D.barrier()
+    launches = env.launch_count + net.launch_count - l0
+    m1 = int(env.stats(stream=sp)["messages"].sum())
+    qnet_ms = statistics.mean(a_.elapsed_time(b_) for a_, b_ in qe)
+    # e2e: the same loop with every tick's results read back to pinned host memory (what a host-side learner consumes)
+    o_pin = torch.empty(n, 8, dtype=torch.float64).pin_memory(); t_pin = torch.empty(n, 6, dtype=torch.float64).pin_memory()
+    r_pin = torch.empty(n, dtype=torch.float64).pin_memory(); d_pin = torch.empty(n, dtype=torch.uint8).pin_memory()
+    D.barrier(); torch.cuda.synchronize(dev)
+    w0 = time.perf_counter()
+    for k in range(K):
+        _, a = net.forward(obs, x_offset=6, want_q=False, greedy_prob=0.9, seed=args.seed, counter=tick, out=qbuf, stream=sp)
+        obs, trans, rew, done = env.step(a, stream=sp); tick += 1
+        o_pin.copy_(obs, non_blocking=True); t_pin.copy_(trans, non_blocking=True); r_pin.copy_(rew, non_blocking=True); d_pin.copy_(done, non_blocking=True)
+        torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - w0
+    D.barrier()
+    st = env.stats(stream=sp)
+    errs = int(((st["flags"] & _lib.F_ERROR_MASK) != 0).sum()) + int(d_pin.sum())       # no environment may have ended inside the measured ticks
+    env.close(); net.close()
+    return {"steps": n * K, "msgs": m1 - m0, "ms": e0.elapsed_time(e1), "e2e_steps": n * K, "e2e_s": e2e_s, "errs": errs, "launches": int(launches), "qnet_ms": qnet_ms}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -376,6 +505,9 @@ def main():
     ap.add_argument("--no-env", action="store_true", help="skip the ABIDESEnv steps/s measurement")
     ap.add_argument("--env-envs-per-gpu", type=int, default=8192)
     ap.add_argument("--env-steps", type=int, default=40)
+    ap.add_argument("--no-ddqn", action="store_true", help="skip the DDQN execution shape (Q-network forward + environment step per tick)")
+    ap.add_argument("--ddqn-envs-per-gpu", type=int, default=8192)
+    ap.add_argument("--ddqn-steps", type=int, default=40)
     args = ap.parse_args()
     quiet_stdout()
     if args.warmup < 3 and args.impl == "ours":

@@ -142,7 +142,8 @@ class DDQNTrainer:
         act_fn(obs, greedy_prob, tick) -> int32 actions [n_envs]; sync_fn(flat_params) is called after each learn step (push the new
         weights to the acting network).  The caller has reset `env`.  Returns (total reward per environment, ticks)."""
         import torch
-        obs, trans, rew, done = env.step(None)
+        first = None if str(self.device) == "cpu" else torch.zeros(env.n_envs, dtype=torch.int32, device=self.device)   # ignored: no decision is pending yet
+        obs, trans, rew, done = env.step(first)
         total = torch.zeros(env.n_envs, dtype=torch.float64, device=self.device)
         tick = 0
         while True:
