@@ -168,7 +168,7 @@ _cache = {}
 
 def load(path=None):
     """Load the C-ABI library.  `path` is only overridden by the CPU test-suite's host emulation harness."""
-    path = path or LIB_PATH
+    path = path or os.environ.get("ABX_LIB_PATH") or LIB_PATH          # ABX_LIB_PATH: kernel A/B experiments (tools/), never set in production
     if path in _cache:
         return _cache[path]
     if not os.path.exists(path):
