@@ -113,6 +113,11 @@ typedef struct abx_sim_config {
   int64_t noise_wake_lo_ns, noise_wake_hi_ns;  /* util.get_wake_time(noise_mkt_open, noise_mkt_close) window (config/rmsc03.py:115-116) */
   int32_t mom_min_size, mom_max_size; int64_t mom_wake_ns;            /* MomentumAgent min_size, max_size, wake_up_freq */
   double mm_pov; int32_t mm_min_order_size, mm_window_size, mm_num_ticks, _pad1; int64_t mm_wake_ns;   /* POVMarketMakerAgent */
+  /* population 1, optional: one POVExecutionAgent (agent/execution/baselines/pov_agent.py; config/execution_iabs_plots.py:200-226) as the LAST
+   * agent id -- BASELINE.json configs[2] "rmsc03 ... with POV execution agent".  Every `freq` it cancels its orders, asks for the whole book
+   * (depth sys.maxsize) and the transacted volume of the last `lookback`, and sends round(pov * volume) as a client-side market order. */
+  int32_t n_pov_exec, pov_exec_is_buy;
+  double pov_exec_pov; int64_t pov_exec_quantity, pov_exec_start_ns, pov_exec_end_ns, pov_exec_freq_ns, pov_exec_lookback_ns;
 } abx_sim_config;
 
 /* Per-environment counters; replaces the "Event Queue elapsed ..., messages: N" line (Kernel.py:321-327). */
@@ -153,6 +158,10 @@ int32_t abx_device_count(void);
 int32_t abx_config_sparse_zi(int32_t variant, abx_sim_config *cfg);
 /* config/rmsc03.py:49-232: 1 exchange + 50 Noise + 10 Value + 1 POV market maker + 2 Momentum agents, 09:30 -> 09:45 (+1 min). */
 int32_t abx_config_rmsc03(abx_sim_config *cfg);
+/* The same population plus one POVExecutionAgent (id 64): BUY 120 000 at 50 % of the volume transacted in the last 30 s, every 30 s, 09:32 -> 09:43. */
+int32_t abx_config_rmsc03_pov(abx_sim_config *cfg);
+/* POVExecutionAgent of one environment: out HOST int64 [3] = remaining quantity, executed orders, open orders. */
+int32_t abx_sim_pov_exec(abx_sim *h, int32_t env, int64_t *out, void *stream);
 
 /* Replaces: Kernel(...) construction + agent list construction (config/sparse_zi_1000.py:146-251).
  * Allocates all per-environment state for n_envs independent simulations on CUDA device `device`. */

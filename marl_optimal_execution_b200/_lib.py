@@ -56,6 +56,8 @@ class SimConfig(C.Structure):
         ("mom_min_size", C.c_int32), ("mom_max_size", C.c_int32), ("mom_wake_ns", C.c_int64),
         ("mm_pov", C.c_double), ("mm_min_order_size", C.c_int32), ("mm_window_size", C.c_int32), ("mm_num_ticks", C.c_int32),
         ("_pad1", C.c_int32), ("mm_wake_ns", C.c_int64),
+        ("n_pov_exec", C.c_int32), ("pov_exec_is_buy", C.c_int32), ("pov_exec_pov", C.c_double), ("pov_exec_quantity", C.c_int64),
+        ("pov_exec_start_ns", C.c_int64), ("pov_exec_end_ns", C.c_int64), ("pov_exec_freq_ns", C.c_int64), ("pov_exec_lookback_ns", C.c_int64),
     ]
 
 
@@ -127,6 +129,8 @@ def _bind(L):
     sig("abx_device_count", i32)
     sig("abx_config_sparse_zi", i32, i32, P(SimConfig))
     sig("abx_config_rmsc03", i32, P(SimConfig))
+    sig("abx_config_rmsc03_pov", i32, P(SimConfig))
+    sig("abx_sim_pov_exec", i32, vp, i32, P(i64), vp)
     sig("abx_sim_create", i32, P(SimConfig), i32, i32, P(vp))
     sig("abx_sim_destroy", i32, vp)
     sig("abx_sim_device_bytes", i64, vp)

@@ -58,9 +58,9 @@ enum : uint32_t {
   AF_HAS_OPEN = 1u, AF_HAS_CLOSE = 2u, AF_MKT_CLOSED = 4u, AF_HAS_LAST = 8u, AF_HAS_DAILY = 16u, AF_HAS_PREV = 32u,
   AF_HAS_BID = 64u, AF_HAS_ASK = 128u, AF_STATE_SHIFT = 8, AF_STATE_MASK = 3u << 8, AF_GROUP_SHIFT = 12, AF_GROUP_MASK = 7u << 12
 };
-enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE = 1, ST_AWAITING_SPREAD = 2 }; // ZeroIntelligenceAgent.state
+enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE = 1, ST_AWAITING_SPREAD = 2, ST_AWAITING_TV = 3 }; // ZeroIntelligenceAgent.state; POVExecutionAgent AWAITING_TRANSACTED_VOLUME
 enum : uint32_t { AF_TYPE_SHIFT = 16, AF_TYPE_MASK = 7u << 16 };
-enum { AT_ZI = 0, AT_NOISE = 1, AT_VALUE = 2, AT_MOMENTUM = 3, AT_POVMM = 4, AT_TWAP = 5, AT_DDQN = 6 };   // agent class (rmsc03 / DDQN execution populations)
+enum { AT_ZI = 0, AT_NOISE = 1, AT_VALUE = 2, AT_MOMENTUM = 3, AT_POVMM = 4, AT_TWAP = 5, AT_DDQN = 6, AT_POVEXEC = 7 };   // agent class (rmsc03 / DDQN execution populations)
 constexpr int AGENT_ORDER_CAP = 4;      // open orders tracked per trader (ZI holds <= 2)
 
 struct alignas(16) ZiAgent {            // 192 B per trader: TradingAgent + ZeroIntelligenceAgent state
@@ -80,7 +80,7 @@ static_assert(sizeof(ZiAgent) == 192, "ZiAgent layout");
 // rmsc03 agents overlay these 40 bytes on ZiAgent.theta (only ZI agents have private values)
 struct AgentAux { int32_t size, order_size, last_mid, tv; uint32_t mmflags; int32_t n_mids; double avg20, avg50; };
 static_assert(sizeof(AgentAux) == 40, "AgentAux overlays ZiAgent.theta");
-// Execution agents of the DDQN config (TWAPExecutionAgent / DDQLearningExecutionAgent) overlay these 88 bytes on ZiAgent.oid .. surplus
+// Execution agents (TWAPExecutionAgent / DDQLearningExecutionAgent of the DDQN config, POVExecutionAgent of the rmsc03 population) overlay these 88 bytes on ZiAgent.oid .. surplus
 // (their open orders live in a per-environment HBM table: a market order walks up to DQ_DEPTH levels).
 struct ExecAux {
   int32_t rem_qty, executed_sum, n_executed, arr2;      // remaining_qty / rem_quantity, sum of fills, len(executed_orders), 2 * arrival_price (0 == None)
@@ -88,9 +88,10 @@ struct ExecAux {
   int32_t pp_last2, child_qty, exflags, e_a;            // 2 * price_path[-1]; schedule quantity; EXF_*; experience[t-1] action
   int16_t cur_s[2], sp[2];                              // self.s; s' of the pending decision
   int16_t e_s[2], e_sp[2];                              // experience[t-1] = (s, a, s', r)
+  int32_t tv, pad0;                                     // POVExecutionAgent: transacted_volume[symbol]
   double e_r, step_reward;                              // r (valid with EXF_E_R); sum of step_reward_hist entries since the last decision
 };
-static_assert(sizeof(ExecAux) == 80 && sizeof(ExecAux) <= 112, "ExecAux overlays ZiAgent.oid .. surplus");
+static_assert(sizeof(ExecAux) == 88 && sizeof(ExecAux) <= 112, "ExecAux overlays ZiAgent.oid .. surplus");
 enum : uint32_t { EXF_TRADE = 1u, EXF_E_VALID = 2u, EXF_E_R = 4u };
 constexpr int EXEC_ORDER_CAP = 512;     // self.orders of one execution agent
 constexpr int DQ_DEPTH = 500;           // getCurrentSpread(depth=500) execution_agent.py:77, ddqlearning_execution_agent.py:152
@@ -297,6 +298,7 @@ ABX_HD int agent_type_of(const abx_sim_config &c, int id) {
   if (id <= c.n_noise_agents) return AT_NOISE;
   if (id <= c.n_noise_agents + c.n_value_agents) return AT_VALUE;
   if (id <= c.n_noise_agents + c.n_value_agents + c.n_mm_agents) return AT_POVMM;
+  if (c.n_pov_exec && id == c.n_agents - 1) return AT_POVEXEC;
   return AT_MOMENTUM;
 }
 // util.get_wake_time (util/util.py:35-58): U-quadratic inverse CDF on [0, 1]
@@ -321,6 +323,11 @@ ABX_HD void init_agent_record_r3(const SimParams &P, int env, int id, uint64_t s
   AgentAux ax; ax.size = size; ax.order_size = P.c.mm_min_order_size; ax.last_mid = 0; ax.tv = 0; ax.mmflags = type == AT_POVMM ? (MMF_AW_SPREAD | MMF_AW_VOL) : 0u; ax.n_mids = 0; ax.avg20 = 0.0; ax.avg50 = 0.0;
   *reinterpret_cast<AgentAux *>(z->theta) = ax;
   z->lat_to = 0.0; z->lat_from = 0.0; z->surplus = 0;
+  if (type == AT_POVEXEC) {                                                           // POVExecutionAgent.__init__ (pov_agent.py:34-48)
+    ExecAux ex; ex.rem_qty = (int32_t)P.c.pov_exec_quantity; ex.executed_sum = 0; ex.n_executed = 0; ex.arr2 = 0; ex.t = 0; ex.rem_time = 0; ex.n_pp = 0; ex.pp0_2 = 0; ex.pp_last2 = 0; ex.child_qty = 0;
+    ex.exflags = EXF_TRADE; ex.e_a = 0; for (int i = 0; i < 2; i++) { ex.cur_s[i] = 0; ex.sp[i] = 0; ex.e_s[i] = 0; ex.e_sp[i] = 0; } ex.tv = 0; ex.pad0 = 0; ex.e_r = 0.0; ex.step_reward = 0.0;
+    *reinterpret_cast<ExecAux *>(z->oid) = ex;
+  }
   if (rng.err) *err |= rng.err;
 }
 ABX_HD void init_agent_record(const SimParams &P, int env, int id, uint64_t seed, ZiAgent *z, uint32_t *err) {
@@ -364,7 +371,7 @@ ABX_HD void init_agent_record_dq(const SimParams &P, int env, int id, uint64_t s
   } else {
     ExecAux ex; ex.rem_qty = (int32_t)P.dq_quantity; ex.executed_sum = 0; ex.n_executed = 0; ex.arr2 = 0; ex.t = 0; ex.rem_time = P.n_h - 1; ex.n_pp = 0; ex.pp0_2 = 0; ex.pp_last2 = 0;
     ex.child_qty = type == AT_DDQN ? (int32_t)((double)P.dq_quantity / (double)(P.n_h - 1)) : (int32_t)((double)P.dq_quantity / (double)P.n_h);
-    ex.exflags = EXF_TRADE; ex.e_a = 0; for (int i = 0; i < 2; i++) { ex.cur_s[i] = 0; ex.sp[i] = 0; ex.e_s[i] = 0; ex.e_sp[i] = 0; } ex.e_r = 0.0; ex.step_reward = 0.0;
+    ex.exflags = EXF_TRADE; ex.e_a = 0; for (int i = 0; i < 2; i++) { ex.cur_s[i] = 0; ex.sp[i] = 0; ex.e_s[i] = 0; ex.e_sp[i] = 0; } ex.tv = 0; ex.pad0 = 0; ex.e_r = 0.0; ex.step_reward = 0.0;
     *reinterpret_cast<ExecAux *>(z->oid) = ex;
   }
   z->flags = ((uint32_t)type << AF_TYPE_SHIFT) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT); z->rng_ctr = ctr;
@@ -1130,7 +1137,7 @@ struct Sim {
   // book-operation counter and a mismatch raises ABX_F_UNSUPPORTED instead of trading on different data.  L1 is cached in the record.
   // =================================================================================================
   ABX_HD ExecAux *exaux() { return reinterpret_cast<ExecAux *>(z->oid); }
-  ABX_HD int dq_order_base(int id) const { return P.dq_order_base + (id - (2 + P.dq_n_mom)) * EXEC_ORDER_CAP; }
+  ABX_HD int dq_order_base(int id) const { return R3 ? P.dq_order_base : P.dq_order_base + (id - (2 + P.dq_n_mom)) * EXEC_ORDER_CAP; }   // rmsc03 population: one POV execution agent
   ABX_HD int dq_horizon_index(int64_t t) const { if (t < P.h0_ns || (t - P.h0_ns) % P.h_step_ns) return -1; int64_t k = (t - P.h0_ns) / P.h_step_ns; return k < P.n_h ? (int)k : -1; }
   ABX_HD void dq_place_limit(int id, int32_t size, bool buy, int32_t price) {           // TradingAgent.placeLimitOrder :309-349
     uint32_t oid = s.next_order_id++;
@@ -1160,15 +1167,16 @@ struct Sim {
     for (int i = f; i + 1 < a.n_orders; i++) c.id_store(base + i, c.id_load(base + i + 1));
     a.n_orders--;
   }
-  ABX_HD void dq_place_market(int id, int32_t quantity) {                               // TradingAgent.placeMarketOrder :351-397 over the cached opposite side
+  ABX_HD void dq_place_market(int id, int32_t quantity) { dq_place_market(id, quantity, P.rl_is_buy != 0); }
+  ABX_HD void dq_place_market(int id, int32_t quantity, bool is_buy) {                  // TradingAgent.placeMarketOrder :351-397 over the cached opposite side
     if (quantity <= 0) return;
-    int opp = P.rl_is_buy ? 1 : 0; int n = n_lv(opp); int depth = n < DQ_DEPTH ? n : DQ_DEPTH;
+    int opp = is_buy ? 1 : 0; int n = n_lv(opp); int depth = n < DQ_DEPTH ? n : DQ_DEPTH;
     if (n == 0) { s.flags |= ABX_F_OBS_INVALID; return; }                               // the reference iterates None
 #pragma unroll 1
     for (int i = 0; i < depth; i++) {
       int32_t price = c.lv_price(opp, n - 1 - i), sz = c.lv_qty(opp, n - 1 - i);
       bool last = quantity <= sz;
-      dq_place_limit(id, last ? quantity : sz, P.rl_is_buy != 0, price);
+      dq_place_limit(id, last ? quantity : sz, is_buy, price);
       if (last) break;
       quantity -= sz;
     }
@@ -1402,9 +1410,9 @@ struct Sim {
       if (nb > 0) { p[0] = c.lv_price(0, nb - 1); p[1] = c.lv_qty(0, nb - 1); f |= 1; }
       if (na > 0) { p[2] = c.lv_price(1, na - 1); p[3] = c.lv_qty(1, na - 1); f |= 2; }
       if (t_closed) f |= 4;
-      p[4] = s.last_trade; p[5] = f; exch_send(m.sender, ABX_QUERY_SPREAD, p, 0.0);
-    } else if (m.kind == ABX_LIMIT_ORDER) { s.c_limit++; book_handle_limit((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[2], 0.0); c.sync(); trace_snap(); }
-    else if (m.kind == ABX_CANCEL_ORDER) { s.c_cancel++; book_cancel((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], 0.0); c.sync(); trace_snap(); }
+      p[4] = s.last_trade; p[5] = f; exch_send(m.sender, ABX_QUERY_SPREAD, p, bits_dbl((uint64_t)s.ctr_kernel));   // + book-operation counter (POV execution agent reads the live ladders)
+    } else if (m.kind == ABX_LIMIT_ORDER) { s.c_limit++; s.ctr_kernel++; book_handle_limit((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[2], 0.0); c.sync(); trace_snap(); }
+    else if (m.kind == ABX_CANCEL_ORDER) { s.c_cancel++; s.ctr_kernel++; book_cancel((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], 0.0); c.sync(); trace_snap(); }
   }
   ABX_HD AgentAux *aux() { return reinterpret_cast<AgentAux *>(z->theta); }
   // TradingAgent.placeLimitOrder :309-349 for the staged trader; `track`: the agent later iterates self.orders (Value, market maker)
@@ -1449,6 +1457,13 @@ struct Sim {
       }
     } else if (type == AT_MOMENTUM) {                                                   // agent/examples/MomentumAgent.py:53-63
       if (can_trade) { int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); st = ST_AWAITING_SPREAD; }
+    } else if (type == AT_POVEXEC) {                                                    // agent/execution/baselines/pov_agent.py:55-64
+      if (can_trade && exaux()->rem_qty > 0 && s.now < P.c.pov_exec_end_ns) {
+        set_wakeup(id, s.now + P.c.pov_exec_freq_ns); dq_cancel_all(id);
+        int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true);         // depth = sys.maxsize
+        int32_t q[6] = {(int32_t)(uint32_t)(uint64_t)P.c.pov_exec_lookback_ns, (int32_t)(uint32_t)((uint64_t)P.c.pov_exec_lookback_ns >> 32), 0, 0, 0, 0}; env_send(ABX_QUERY_TRANSACTED_VOLUME, q, false);
+        st = ST_AWAITING_TV;
+      }
     } else {                                                                            // POVMarketMakerAgent.py:83-100 (with the getTransactedVolume alias)
       if (can_trade) {
         int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true);
@@ -1505,13 +1520,16 @@ struct Sim {
       int32_t q = m.p[2]; int32_t sq = m.p[4] ? q : -q; a.shares += sq; a.cash -= (int64_t)sq * m.p[3];
       if (type == AT_VALUE) { int i = orders_find((uint32_t)m.p[0]); if (i >= 0) { int32_t oq0 = z->oqty[i]; int32_t oq = oq0 < 0 ? -oq0 : oq0; if (q >= oq) orders_remove(i); else { c.sync(); if (c.onchip_writer()) z->oqty[i] = oq0 < 0 ? -(oq - q) : (oq - q); c.sync(); } } }
       else if (type == AT_POVMM) r3_mm_order_update((uint32_t)m.p[0], q, false);
+      else if (type == AT_POVEXEC) { dq_order_update(id, (uint32_t)m.p[0], q, false); ExecAux ex = *exaux(); ex.executed_sum += q; ex.n_executed++; ex.rem_qty = (int32_t)P.c.pov_exec_quantity - ex.executed_sum; exaux_store(ex); }   // handleOrderExecution :103-107
     } else if (m.kind == ABX_ORDER_CANCELLED) {
       if (type == AT_VALUE) { int i = orders_find((uint32_t)m.p[0]); if (i >= 0) orders_remove(i); }
       else if (type == AT_POVMM) r3_mm_order_update((uint32_t)m.p[0], 0, true);
+      else if (type == AT_POVEXEC) dq_order_update(id, (uint32_t)m.p[0], 0, true);
     } else if (m.kind == ABX_MKT_CLOSED) a.flags |= AF_MKT_CLOSED;
     else if (m.kind == ABX_QUERY_TRANSACTED_VOLUME) {                                   // :248-251,556-558
       if (m.p[5] & 4) a.flags |= AF_MKT_CLOSED;
-      AgentAux ax = *aux(); ax.tv = m.p[0]; c.sync(); if (c.onchip_writer()) *aux() = ax; c.sync();
+      if (type == AT_POVEXEC) { ExecAux ex = *exaux(); ex.tv = m.p[0]; exaux_store(ex); }
+      else { AgentAux ax = *aux(); ax.tv = m.p[0]; c.sync(); if (c.onchip_writer()) *aux() = ax; c.sync(); }
     } else if (m.kind == ABX_QUERY_SPREAD) {
       if (m.p[5] & 4) a.flags |= AF_MKT_CLOSED;
       a.last_trade = m.p[4]; a.flags |= AF_HAS_LAST;
@@ -1521,10 +1539,21 @@ struct Sim {
       if (m.p[5] & 2) { a.flags |= AF_HAS_ASK; a.ask = m.p[2]; a.ask_q = m.p[3]; } else { a.ask = 0; a.ask_q = 0; }
     }
     if ((a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE) && !had) {                  // :258-268 getWakeFrequency per class
-      int64_t off = type == AT_MOMENTUM ? P.c.mom_wake_ns : (type == AT_POVMM ? P.c.mm_wake_ns : rng.randint(S_AGENT0 + id, a.rng_ctr, 99));
+      int64_t off = type == AT_MOMENTUM ? P.c.mom_wake_ns : (type == AT_POVMM ? P.c.mm_wake_ns : (type == AT_POVEXEC ? P.c.pov_exec_freq_ns : rng.randint(S_AGENT0 + id, a.rng_ctr, 99)));
       set_wakeup(id, P.c.mkt_open_ns + off);
     }
     uint32_t st = (a.flags & AF_STATE_MASK) >> AF_STATE_SHIFT;
+    if (type == AT_POVEXEC) {                                                           // POVExecutionAgent.receiveMessage :69-99
+      if (m.kind == ABX_QUERY_SPREAD && (uint32_t)m.x0 != s.ctr_kernel) s.flags |= ABX_F_UNSUPPORTED;   // the cached lists would differ from the live ladders
+      if (s.now > P.c.pov_exec_end_ns) return;
+      ExecAux ex = *exaux();
+      if (ex.rem_qty > 0 && st == ST_AWAITING_TV && m.kind == ABX_QUERY_TRANSACTED_VOLUME && s.now > P.c.pov_exec_start_ns) {
+        int32_t qty = (int32_t)py_round_i64(dmul(P.c.pov_exec_pov, (double)ex.tv));
+        dq_cancel_all(id);
+        dq_place_market(id, qty, P.c.pov_exec_is_buy != 0);
+      }
+      return;
+    }
     if (type == AT_POVMM) {                                                             // POVMarketMakerAgent.receiveMessage :102-150
       AgentAux ax = *aux();
       if (m.kind == ABX_QUERY_TRANSACTED_VOLUME && (ax.mmflags & MMF_AW_VOL)) {         // updateOrderSize :152-156

@@ -63,6 +63,13 @@ static inline int config_rmsc03(abx_sim_config *c) {
   c->queue_cap = 256; c->level_cap = 128; c->order_cap = 512; c->rng_mode = ABX_RNG_PHILOX; c->trace_cap = 0; c->hash_pops = 0;
   return ABX_OK;
 }
+// rmsc03 population + one POVExecutionAgent (BASELINE.json configs[2]; parameters in the style of config/execution_iabs_plots.py:200-226, scaled to the 15-minute session)
+static inline int config_rmsc03_pov(abx_sim_config *c) {
+  int st = config_rmsc03(c); if (st != ABX_OK) return st;
+  c->n_pov_exec = 1; c->n_agents += 1; c->pov_exec_is_buy = 1; c->pov_exec_pov = 0.5; c->pov_exec_quantity = 120000;
+  c->pov_exec_start_ns = (9 * 3600 + 32 * 60) * NS; c->pov_exec_end_ns = (9 * 3600 + 43 * 60) * NS; c->pov_exec_freq_ns = 30 * NS; c->pov_exec_lookback_ns = 30 * NS;
+  return ABX_OK;
+}
 static inline int config_validate(const abx_sim_config *c) {
   if (!c || c->version != ABX_VERSION) return ABX_ERR_ARG;
   if (c->n_agents < 2 || c->n_agents > 32767 || c->n_groups < 0 || c->n_groups > 8 || c->q_max < 1 || c->q_max > 10) return ABX_ERR_ARG;
@@ -71,7 +78,8 @@ static inline int config_validate(const abx_sim_config *c) {
   else if (c->population == 1) {
     if (c->n_noise_agents < 0 || c->n_value_agents < 0 || c->n_mm_agents < 0 || c->n_mm_agents > 1 || c->n_momentum_agents < 0 || c->n_momentum_agents > 4) return ABX_ERR_ARG;
     if (c->latency_model != ABX_LAT_ZERO || c->size_hi <= c->size_lo || c->mom_max_size <= c->mom_min_size || 2 * (c->mm_num_ticks + 1) > MM_ORDER_CAP / 2 || c->mm_wake_ns <= 0 || c->mom_wake_ns <= 0) return ABX_ERR_ARG;
-    n += c->n_noise_agents + c->n_value_agents + c->n_mm_agents + c->n_momentum_agents;
+    if (c->n_pov_exec < 0 || c->n_pov_exec > 1 || (c->n_pov_exec && (!(c->pov_exec_pov > 0) || c->pov_exec_quantity <= 0 || c->pov_exec_quantity > 0x3fffffffLL || c->pov_exec_freq_ns <= 0 || c->pov_exec_lookback_ns <= 0))) return ABX_ERR_ARG;
+    n += c->n_noise_agents + c->n_value_agents + c->n_mm_agents + c->n_momentum_agents + c->n_pov_exec;
   } else return ABX_ERR_ARG;
   if (n != c->n_agents) return ABX_ERR_ARG;
   if (c->queue_cap < 32 || c->queue_cap % 32 || c->queue_cap > 4096) return ABX_ERR_ARG;

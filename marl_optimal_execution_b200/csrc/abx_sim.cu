@@ -237,6 +237,7 @@ const char *abx_last_cuda_error(void) { return g_cuda_err; }
 int32_t abx_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 int32_t abx_config_sparse_zi(int32_t variant, abx_sim_config *cfg) { return config_sparse_zi(variant, cfg); }
 int32_t abx_config_rmsc03(abx_sim_config *cfg) { return config_rmsc03(cfg); }
+int32_t abx_config_rmsc03_pov(abx_sim_config *cfg) { return config_rmsc03_pov(cfg); }
 
 int32_t abx_sim_destroy(abx_sim *h) {
   if (!h) return ABX_OK;
@@ -264,7 +265,8 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   DA(h->P.agents, E * c.n_agents) DA(h->P.lv_price, E * 2 * c.level_cap) DA(h->P.lv_qty, E * 2 * c.level_cap) DA(h->P.lv_ht, E * 2 * c.level_cap)
   DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap)
   DA(h->d_seeds, E) DA(h->d_init_err, E) DA(h->d_stats, E) DA(h->d_until, E)
-  if (c.population == 1) { h->P.n_ids = MM_ORDER_CAP + TV_RING; DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3) }   // market maker orders + transaction ring; momentum mids
+  if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + TV_RING; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0);       // market maker orders + transaction ring [+ POV execution agent orders]; momentum mids
+    DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3) }
 #undef DA
   if (smem_cta > 48 * 1024) {
     CU(cudaFuncSetAttribute((const void *)run_kernel_for(*cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
@@ -368,6 +370,14 @@ int32_t abx_sim_holdings(abx_sim *h, int32_t env, int64_t *out, void *stream) {
   for (int id = 1; id < n; id++) { const ZiAgent &z = tmp[id]; int64_t *r = out + 5 * (id - 1);      // agent/TradingAgent.py:124-126, markToMarket :609-633
     r[0] = id; r[1] = z.shares; r[2] = z.cash; r[3] = z.cash + (int64_t)z.shares * ((z.flags & AF_HAS_LAST) ? z.last_trade : 0); r[4] = z.surplus; }
   free(tmp); return ABX_OK;
+}
+
+int32_t abx_sim_pov_exec(abx_sim *h, int32_t env, int64_t *out, void *stream) {
+  if (!h || h->is_env || !out || env < 0 || env >= h->n_envs || h->P.c.population != 1 || !h->P.c.n_pov_exec) return ABX_ERR_ARG;
+  CU(cudaSetDevice(h->device)); ZiAgent z;
+  CU(cudaMemcpyAsync(&z, h->P.agents + (size_t)env * h->P.c.n_agents + (h->P.c.n_agents - 1), sizeof(z), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  const ExecAux *ex = reinterpret_cast<const ExecAux *>(z.oid); out[0] = ex->rem_qty; out[1] = ex->n_executed; out[2] = z.n_orders; return ABX_OK;
 }
 
 int32_t abx_sim_book_snapshot(abx_sim *h, int32_t env, int32_t is_bid, int32_t depth, int32_t *out, int32_t *n_levels, void *stream) {

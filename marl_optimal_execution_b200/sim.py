@@ -24,11 +24,15 @@ def sparse_zi_config(variant, lib=None, **overrides):
     return cfg
 
 
-def rmsc03_config(lib=None, **overrides):
-    """abx_sim_config for config/rmsc03.py (50 Noise + 10 Value + 1 POV market maker + 2 Momentum agents, 09:30-09:45)."""
+def rmsc03_config(lib=None, pov_exec=False, **overrides):
+    """abx_sim_config for config/rmsc03.py (50 Noise + 10 Value + 1 POV market maker + 2 Momentum agents, 09:30-09:45);
+    pov_exec=True appends one POVExecutionAgent (agent/execution/baselines/pov_agent.py) as agent 64."""
     L = lib or _lib.load()
     cfg = SimConfig()
-    _lib.check(L, L.abx_config_rmsc03(C.byref(cfg)), "abx_config_rmsc03")
+    if pov_exec:
+        _lib.check(L, L.abx_config_rmsc03_pov(C.byref(cfg)), "abx_config_rmsc03_pov")
+    else:
+        _lib.check(L, L.abx_config_rmsc03(C.byref(cfg)), "abx_config_rmsc03")
     for k, v in overrides.items():
         if not hasattr(cfg, k):
             raise AttributeError("abx_sim_config has no field %r" % k)
@@ -112,6 +116,12 @@ class BatchedSim:
     def stats_into(self, device_ptr, stream=None):
         """Leave the abx_env_stats records on the device (device_ptr: e.g. torch tensor .data_ptr(), 112 B/env)."""
         _lib.check(self._L, self._L.abx_sim_stats_device(self._h, C.c_void_p(device_ptr), stream), "abx_sim_stats_device")
+
+    def pov_exec(self, env, stream=None):
+        """POVExecutionAgent of one environment: (remaining quantity, executed orders, open orders)."""
+        out = np.zeros(3, dtype=np.int64)
+        _lib.check(self._L, self._L.abx_sim_pov_exec(self._h, int(env), out.ctypes.data_as(C.POINTER(C.c_int64)), stream), "abx_sim_pov_exec")
+        return out
 
     def holdings(self, env, stream=None):
         out = np.zeros((self.n_agents - 1, 5), dtype=np.int64)

@@ -340,8 +340,9 @@ typedef struct {            /* TradingAgent (agent/TradingAgent.py:19-98) + Zero
   int64_t wakeup_time, size;                            /* NoiseAgent.wakeup_time[0]; NoiseAgent/ValueAgent/MomentumAgent.size */
   double *mids; int n_mids, cap_mids; double avg20, avg50; int has20, has50;   /* MomentumAgent.mid_list, avg_20_list[-1], avg_50_list[-1] */
   int64_t order_size, last_mid, transacted_volume; int has_last_mid, aw_spread, aw_vol;   /* POVMarketMakerAgent */
+  int64_t *kside[2], *fside[2]; int nk[2], nf[2], capk; int64_t px_rem, px_executed, px_n_executed;   /* POVExecutionAgent: known_bids/asks (price, qty pairs), lists in flight, rem_quantity */
 } zi_t;
-enum { AT_ZI = 0, AT_NOISE, AT_VALUE, AT_MOMENTUM, AT_POVMM };
+enum { AT_ZI = 0, AT_NOISE, AT_VALUE, AT_MOMENTUM, AT_POVMM, AT_POVEXEC };
 
 struct abo_sim {
   int variant; uint32_t seed; int trace; int n_agents;
@@ -358,6 +359,7 @@ struct abo_sim {
   /* agents */
   zi_t *zi; double sigma_n, agent_kappa, sigma_s, lambda_a;
   double mm_pov; int64_t mm_min_size, mm_window, mm_ticks, mm_wake_ns, mom_wake_ns;   /* config/rmsc03.py:41-45,176-200 */
+  int px_id, px_is_buy; double px_pov; int64_t px_quantity, px_start, px_end, px_freq, px_lookback;   /* POVExecutionAgent (agent/execution/baselines/pov_agent.py), 0 = none */
   /* traces */
   i64buf pops, ops, notes, snaps; uint64_t pop_hash, note_hash, snap_hash; uint64_t *ckpt; int64_t n_ckpt, cap_ckpt;
   int64_t c_limit, c_cancel, c_query, max_queue, max_bid_lv, max_ask_lv, max_resting;
@@ -481,6 +483,10 @@ static void exch_receive(abo_sim *s, const event_t *m) {
       e.kind = ABO_QUERY_SPREAD;
       if (book_inside(&s->book, 1, 1, pq)) { e.has_bid = 1; e.bid = pq[0]; e.bid_q = pq[1]; }
       if (book_inside(&s->book, 0, 1, pq)) { e.has_ask = 1; e.ask = pq[0]; e.ask_q = pq[1]; }
+      if (s->px_id && m->sender == s->px_id) {                                                /* depth = sys.maxsize: the whole book rides in the reply */
+        zi_t *a = &s->zi[s->px_id]; int need = s->book.bids.n > s->book.asks.n ? s->book.bids.n : s->book.asks.n;
+        if (need > a->capk) { a->capk = need * 2 + 64; for (int k = 0; k < 2; k++) { a->kside[k] = (int64_t *)realloc(a->kside[k], 16 * a->capk); a->fside[k] = (int64_t *)realloc(a->fside[k], 16 * a->capk); } }
+        a->nf[0] = book_inside(&s->book, 1, a->capk, a->fside[0]); a->nf[1] = book_inside(&s->book, 0, a->capk, a->fside[1]); }
       e.data = s->book.last_trade; e.mkt_closed = t_closed; exch_send(s, m->sender, &e); break; }
     case ABO_LIMIT_ORDER: s->c_limit++; trace_op(s, 0, &m->order, 0, 0); s->book.now = s->now; book_handle_limit(&s->book, m->order); trace_snap(s); break; /* :304-312 */
     case ABO_CANCEL_ORDER: s->c_cancel++; trace_op(s, 1, &m->order, 0, 0); s->book.now = s->now; book_cancel(&s->book, &m->order); trace_snap(s); break;   /* :313-325 */
@@ -570,7 +576,7 @@ static void zi_place_order(abo_sim *s, int id) {
   ta_place_limit(s, id, 100, buy, p);                                                       /* :308-309 */
 }
 static void orders_remove(zi_t *a, int i) { memmove(a->orders + i, a->orders + i + 1, sizeof(open_order_t) * (a->n_orders - i - 1)); a->n_orders--; }
-static void povmm_receive_tail(abo_sim *s, int id, const event_t *m); static void momentum_place_orders(abo_sim *s, int id);
+static void povmm_receive_tail(abo_sim *s, int id, const event_t *m); static void momentum_place_orders(abo_sim *s, int id); static void povexec_receive_tail(abo_sim *s, int id, const event_t *m);
 static void noise_place_order(abo_sim *s, int id); static void value_place_order(abo_sim *s, int id);
 /* TradingAgent.receiveMessage :181-268 + ZeroIntelligenceAgent.receiveMessage :311-334 */
 static void zi_receive(abo_sim *s, int id, const event_t *m) {
@@ -584,6 +590,7 @@ static void zi_receive(abo_sim *s, int id, const event_t *m) {
       a->shares += qty; a->cash -= qty * m->order.fill_price;
       for (int i = 0; i < a->n_orders; i++) if (a->orders[i].order_id == m->order.order_id) {
         if (m->order.quantity >= a->orders[i].quantity) orders_remove(a, i); else a->orders[i].quantity -= m->order.quantity; break; }
+      if (a->type == AT_POVEXEC) { a->px_executed += m->order.quantity; a->px_n_executed++; a->px_rem = s->px_quantity - a->px_executed; }   /* handleOrderExecution :103-107 */
       break; }
     case ABO_ORDER_ACCEPTED: break;
     case ABO_ORDER_CANCELLED:                                                               /* orderCancelled :476-489 */
@@ -596,15 +603,17 @@ static void zi_receive(abo_sim *s, int id, const event_t *m) {
       a->last_trade = m->data; a->has_last_trade = 1;
       if (a->mkt_closed) { a->daily_close = a->last_trade; a->has_daily_close = 1; }
       a->has_known = 1; a->has_bid = m->has_bid; a->bid = m->bid; a->bid_q = m->bid_q; a->has_ask = m->has_ask; a->ask = m->ask; a->ask_q = m->ask_q;
+      if (a->type == AT_POVEXEC) for (int k = 0; k < 2; k++) { a->nk[k] = a->nf[k]; memcpy(a->kside[k], a->fside[k], 16 * (size_t)a->nf[k]); }
       break;
     default: break;
   }
   if (a->has_open && a->has_close && !had) {                                                /* :258-268 */
-    int64_t off = a->type == AT_MOMENTUM ? s->mom_wake_ns : a->type == AT_POVMM ? s->mm_wake_ns
+    int64_t off = a->type == AT_MOMENTUM ? s->mom_wake_ns : a->type == AT_POVMM ? s->mm_wake_ns : a->type == AT_POVEXEC ? s->px_freq
                 : abo_rng_randint(a->rs, 0, 100);                                           /* ZI/Noise/Value.getWakeFrequency: randint(0, 100) ns */
     k_set_wakeup(s, id, a->mkt_open + off);
   }
   if (a->type == AT_POVMM) { povmm_receive_tail(s, id, m); return; }
+  if (a->type == AT_POVEXEC) { povexec_receive_tail(s, id, m); return; }
   if (a->type == AT_MOMENTUM) {                                                             /* MomentumAgent.receiveMessage :65-76 */
     if (a->state == ST_AWAITING_SPREAD && m->kind == ABO_QUERY_SPREAD) { momentum_place_orders(s, id); k_set_wakeup(s, id, s->now + s->mom_wake_ns); a->state = ST_AWAITING_WAKEUP; }
     return;
@@ -726,9 +735,35 @@ static void povmm_receive_tail(abo_sim *s, int id, const event_t *m) {          
     k_set_wakeup(s, id, s->now + s->mm_wake_ns);
   }
 }
+/* POVExecutionAgent (agent/execution/baselines/pov_agent.py): wakeup :55-64, receiveMessage :69-99, placeMarketOrder TradingAgent.py:351-397 */
+enum { ST_AWAITING_TV = 3 };
+static void povexec_wakeup(abo_sim *s, int id) {
+  zi_t *a = &s->zi[id];
+  if (!ta_wakeup_common(s, id)) return;
+  if (a->px_rem > 0 && s->now < s->px_end) {
+    k_set_wakeup(s, id, s->now + s->px_freq); ta_cancel_all(s, id); ta_get_spread(s, id);                 /* depth = sys.maxsize */
+    event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_QUERY_TRANSACTED_VOLUME; e.lookback = s->px_lookback; ta_send(s, id, &e);
+    a->state = ST_AWAITING_TV;
+  }
+}
+static void povexec_receive_tail(abo_sim *s, int id, const event_t *m) {
+  zi_t *a = &s->zi[id];
+  if (s->now > s->px_end) return;
+  if (a->px_rem > 0 && a->state == ST_AWAITING_TV && m->kind == ABO_QUERY_TRANSACTED_VOLUME && s->now > s->px_start) {
+    int64_t quantity = py_round(s->px_pov * (double)a->transacted_volume);
+    ta_cancel_all(s, id);
+    if (quantity > 0) {                                                                      /* walk the cached opposite side, one limit order per level */
+      int k = s->px_is_buy ? 1 : 0; const int64_t *side = a->kside[k]; int n = a->nk[k];
+      int nq = 0; int64_t *qp = (int64_t *)malloc(16 * (size_t)(n + 1));
+      for (int i = 0; i < n; i++) { if (quantity <= side[2 * i + 1]) { qp[2 * nq] = side[2 * i]; qp[2 * nq + 1] = quantity; nq++; break; } qp[2 * nq] = side[2 * i]; qp[2 * nq + 1] = side[2 * i + 1]; nq++; quantity -= side[2 * i + 1]; }
+      for (int i = 0; i < nq; i++) ta_place_limit(s, id, qp[2 * i + 1], s->px_is_buy, qp[2 * i]);
+      free(qp);
+    }
+  }
+}
 static void agent_wakeup(abo_sim *s, int id) {
   switch (s->zi[id].type) { case AT_NOISE: noise_wakeup(s, id); break; case AT_VALUE: value_wakeup(s, id); break; case AT_MOMENTUM: momentum_wakeup(s, id); break;
-    case AT_POVMM: povmm_wakeup(s, id); break; default: zi_wakeup(s, id); }
+    case AT_POVMM: povmm_wakeup(s, id); break; case AT_POVEXEC: povexec_wakeup(s, id); break; default: zi_wakeup(s, id); }
 }
 
 /* ---------------- config: config/sparse_zi_100.py / config/sparse_zi_1000.py ---------------- */
@@ -800,10 +835,12 @@ static double u_quadratic_inverse_cdf(double y) {                      /* util/u
   double c = n < 0 ? -pow(-n, 1.0 / 3.0) : pow(n, 1.0 / 3.0);
   return c + beta;
 }
-abo_sim *abo_sim_new_rmsc03(uint32_t seed, int trace) {
+/* pov > 0: one POVExecutionAgent (id 64) is appended to the population with a RandomState outside the config's seed cascade (it never draws) */
+abo_sim *abo_sim_new_rmsc03_pov(uint32_t seed, int trace, double pov, int64_t quantity, int is_buy, int64_t start_ns, int64_t end_ns, int64_t freq_ns, int64_t lookback_ns) {
   abo_sim *s = (abo_sim *)calloc(1, sizeof(abo_sim));
   s->variant = 3; s->seed = seed; s->trace = trace; s->pop_hash = s->note_hash = s->snap_hash = FNV_OFF;
-  int n = 1 + 50 + 10 + 1 + 2; s->n_agents = n;
+  int n0 = 1 + 50 + 10 + 1 + 2, n = n0 + (pov > 0 ? 1 : 0); s->n_agents = n;
+  if (pov > 0) { s->px_id = n0; s->px_pov = pov; s->px_quantity = quantity; s->px_is_buy = is_buy; s->px_start = start_ns; s->px_end = end_ns; s->px_freq = freq_ns; s->px_lookback = lookback_ns; }
   s->g = abo_rng_new(seed);                                              /* np.random.seed(seed) :58 */
   s->mkt_open = (9 * 3600 + 30 * 60) * NS_PER_S; s->mkt_close = (9 * 3600 + 45 * 60) * NS_PER_S;   /* :69-70 */
   s->start_time = s->mkt_open; s->stop_time = s->mkt_close + 60 * NS_PER_S;                           /* :205-207 */
@@ -826,6 +863,7 @@ abo_sim *abo_sim_new_rmsc03(uint32_t seed, int trace) {
       a->rs = new_stream(s); a->size = abo_rng_randint(s->g, 20, 50);
     } else if (id <= 60) { a->type = AT_VALUE; a->rs = new_stream(s); a->size = abo_rng_randint(s->g, 20, 50); a->r_t = s->r_bar; a->sigma_t = 0; }   /* :137-155 */
     else if (id == 61) { a->type = AT_POVMM; a->rs = new_stream(s); a->order_size = s->mm_min_size; a->aw_spread = a->aw_vol = 1; }                  /* :160-178 */
+    else if (id == n0) { a->type = AT_POVEXEC; a->rs = abo_rng_new(0); a->px_rem = quantity; }
     else { a->type = AT_MOMENTUM; a->rs = new_stream(s); a->size = abo_rng_randint(a->rs, 1, 10); }                                                   /* :183-200, MomentumAgent.py:42 */
   }
   s->kernel_rs = new_stream(s);                                          /* :201-204 */
@@ -834,9 +872,12 @@ abo_sim *abo_sim_new_rmsc03(uint32_t seed, int trace) {
   for (int i = 0; i < n; i++) { s->agent_time[i] = s->start_time; s->comp_delay[i] = 0; }           /* defaultComputationDelay 0 :208 */
   return s;
 }
+abo_sim *abo_sim_new_rmsc03(uint32_t seed, int trace) { return abo_sim_new_rmsc03_pov(seed, trace, 0.0, 0, 1, 0, 0, 0, 0); }
+/* POVExecutionAgent: rem_quantity, executed orders, open orders */
+void abo_sim_pov_exec(abo_sim *s, int64_t *out3) { out3[0] = out3[1] = out3[2] = 0; if (s->px_id) { zi_t *a = &s->zi[s->px_id]; out3[0] = a->px_rem; out3[1] = a->px_n_executed; out3[2] = a->n_orders; } }
 void abo_sim_free(abo_sim *s) {
   if (!s) return;
-  for (int i = 1; i < s->n_agents; i++) { abo_rng_free(s->zi[i].rs); free(s->zi[i].orders); free(s->zi[i].mids); }
+  for (int i = 1; i < s->n_agents; i++) { abo_rng_free(s->zi[i].rs); free(s->zi[i].orders); free(s->zi[i].mids); for (int k = 0; k < 2; k++) { free(s->zi[i].kside[k]); free(s->zi[i].fside[k]); } }
   free(s->zi); abo_rng_free(s->g); abo_rng_free(s->kernel_rs); abo_rng_free(s->lat_rs); abo_rng_free(s->sym_rs); abo_rng_free(s->exch_rs);
   book_destroy(&s->book); free(s->latency); free(s->agent_time); free(s->comp_delay); free(s->q.e); free(s->gexp);
   free(s->pops.v); free(s->ops.v); free(s->notes.v); free(s->snaps.v); free(s->ckpt); free(s);

@@ -68,6 +68,10 @@ typedef struct abo_sim abo_sim;
 abo_sim *abo_sim_new_sparse_zi(int variant, uint32_t seed, int trace_flags);
 /* config/rmsc03.py: 1 exchange + 50 NoiseAgents + 10 ValueAgents + 1 POVMarketMakerAgent + 2 MomentumAgents, 09:30-09:45 */
 abo_sim *abo_sim_new_rmsc03(uint32_t seed, int trace_flags);
+/* the same population plus one POVExecutionAgent (agent/execution/baselines/pov_agent.py) as the last agent; times ns since midnight */
+abo_sim *abo_sim_new_rmsc03_pov(uint32_t seed, int trace_flags, double pov, int64_t quantity, int is_buy, int64_t start_ns, int64_t end_ns,
+                                int64_t freq_ns, int64_t lookback_ns);
+void abo_sim_pov_exec(abo_sim *, int64_t *out3); /* rem_quantity, executed orders, open orders */
 void abo_sim_free(abo_sim *);
 /* runtime draws on the GLOBAL np.random stream (kinds 'e','u','i') */
 int64_t abo_sim_global_tape(abo_sim *, const uint8_t **kinds, const uint64_t **bits);

@@ -67,6 +67,8 @@ def lib():
     sig("abo_book_level_orders", i32, vp, i32, i32, P(i64), i32)
     sig("abo_sim_new_sparse_zi", vp, i32, u32, i32)
     sig("abo_sim_new_rmsc03", vp, u32, i32)
+    sig("abo_sim_new_rmsc03_pov", vp, u32, i32, dbl, i64, i32, i64, i64, i64, i64)
+    sig("abo_sim_pov_exec", None, vp, P(i64))
     sig("abo_sim_global_tape", i64, vp, P(P(C.c_uint8)), P(P(u64)))
     sig("abo_sim_agent_info", None, vp, i32, P(i64))
     sig("abo_sim_free", None, vp)
@@ -204,9 +206,15 @@ class OracleBook:
 class OracleSim:
     """config/sparse_zi_100.py / sparse_zi_1000.py + Kernel.runner restated (oracle/abides_oracle.c)."""
 
-    def __init__(self, variant, seed, trace=0):
-        """variant 100 / 1000: config/sparse_zi_*.py; variant 3: config/rmsc03.py."""
-        self._h = lib().abo_sim_new_rmsc03(seed, trace) if variant == 3 else lib().abo_sim_new_sparse_zi(variant, seed, trace)
+    def __init__(self, variant, seed, trace=0, pov_exec=None):
+        """variant 100 / 1000: config/sparse_zi_*.py; variant 3: config/rmsc03.py.  pov_exec (variant 3 only): dict(pov, quantity, is_buy,
+        start_ns, end_ns, freq_ns, lookback_ns) appends one POVExecutionAgent (agent/execution/baselines/pov_agent.py) as the last agent."""
+        if variant == 3 and pov_exec:
+            p = pov_exec
+            self._h = lib().abo_sim_new_rmsc03_pov(seed, trace, float(p["pov"]), int(p["quantity"]), int(bool(p["is_buy"])), int(p["start_ns"]), int(p["end_ns"]),
+                                                   int(p["freq_ns"]), int(p["lookback_ns"]))
+        else:
+            self._h = lib().abo_sim_new_rmsc03(seed, trace) if variant == 3 else lib().abo_sim_new_sparse_zi(variant, seed, trace)
         if not self._h:
             raise ValueError("unknown sparse_zi variant %r" % (variant,))
         self.variant, self.seed = variant, seed
@@ -218,6 +226,11 @@ class OracleSim:
 
     def run(self):
         return lib().abo_sim_run(self._h)
+
+    def pov_exec(self):
+        out = np.zeros(3, dtype=np.int64)
+        lib().abo_sim_pov_exec(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)))
+        return out
 
     def start(self):
         lib().abo_sim_start(self._h)

@@ -110,6 +110,12 @@ const char *abx_last_cuda_error(void) { return "host emulation harness: no CUDA"
 int32_t abx_device_count(void) { return 0; }
 int32_t abx_config_sparse_zi(int32_t variant, abx_sim_config *cfg) { return config_sparse_zi(variant, cfg); }
 int32_t abx_config_rmsc03(abx_sim_config *cfg) { return config_rmsc03(cfg); }
+int32_t abx_config_rmsc03_pov(abx_sim_config *cfg) { return config_rmsc03_pov(cfg); }
+int32_t abx_sim_pov_exec(abx_sim *h, int32_t env, int64_t *out, void *stream) {
+  (void)stream; if (!h || !out || env < 0 || env >= h->n_envs || h->P.c.population != 1 || !h->P.c.n_pov_exec) return ABX_ERR_ARG;
+  const ZiAgent &z = h->agents[(size_t)env * h->P.c.n_agents + h->P.c.n_agents - 1]; const ExecAux *ex = reinterpret_cast<const ExecAux *>(z.oid);
+  out[0] = ex->rem_qty; out[1] = ex->n_executed; out[2] = z.n_orders; return ABX_OK;
+}
 typedef Sim<HostCtx, -1, ABX_LAT_ZERO, true, SHAPE_R3> R3SimHost;
 
 int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device, abx_sim **out) {
@@ -123,7 +129,7 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   h->P.qkey = h->qkey.data(); h->P.qpay0 = h->qpay0.data(); h->P.qpay1 = h->qpay1.data(); h->P.qcache = h->qcache.data(); h->P.agents = h->agents.data();
   h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
   h->P.trace = c.trace_cap ? h->trace.data() : nullptr;
-  if (c.population == 1) { h->P.n_ids = MM_ORDER_CAP + TV_RING; h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); }
+  if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + TV_RING; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0); h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); }
   *out = h; return ABX_OK;
 }
 int32_t abx_sim_destroy(abx_sim *h) { delete h; return ABX_OK; }

@@ -105,3 +105,30 @@ def test_rmsc03_philox_conservation(emu):
     # an environment whose market maker meets a one-sided book stops quoting for good (POVMarketMakerAgent.py:121-126), so message
     # counts are bimodal across seeds; seed 1 keeps its ladder all session
     assert 100000 < st["messages"][0] < 250000 and st["limit_orders"][0] > 30000
+
+
+POV_EXEC = dict(pov=0.5, quantity=120000, is_buy=1, start_ns=(9 * 3600 + 32 * 60) * 10 ** 9, end_ns=(9 * 3600 + 43 * 60) * 10 ** 9,
+                freq_ns=30 * 10 ** 9, lookback_ns=30 * 10 ** 9)
+
+
+def test_rmsc03_with_pov_execution_agent_matches_oracle(emu):
+    """BASELINE.json configs[2]: the rmsc03 population plus one POVExecutionAgent (agent/execution/baselines/pov_agent.py): whole-book
+    QUERY_SPREAD, QUERY_TRANSACTED_VOLUME and the client-side market order walk, bit-exact vs the oracle (itself pinned to a recording of the
+    reference with that agent appended, tests/test_oracle_golden.py::test_rmsc03_with_pov_execution_agent)."""
+    from marl_optimal_execution_b200.sim import rmsc03_config
+    o = OracleSim(3, 123456789, TRACE_ALL, pov_exec=POV_EXEC)
+    n = o.run()
+    cfg = rmsc03_config(lib=_lib.load(emu), pov_exec=True, rng_mode=_lib.RNG_TAPE, trace_cap=400000, hash_pops=1)
+    assert cfg.n_agents == 65 and cfg.n_pov_exec == 1
+    sim = BatchedSim(cfg, 1, lib_path=emu)
+    sim.reset_tape(*oracle_tapes([o]))
+    sim.run()
+    sim.finalize()
+    st = sim.stats()[0]
+    assert int(st["messages"]) == n == 161747 and int(st["flags"]) == _lib.F_DONE
+    assert int(st["pop_hash"]) == o.pop_hash()
+    p, nt, sn = sim.split_trace(0)
+    assert np.array_equal(p, o.trace("pops")) and np.array_equal(nt, o.trace("notes")) and np.array_equal(sn, o.trace("snaps"))
+    assert np.array_equal(sim.holdings(0)[:, :4], o.holdings()[:, :4])
+    assert np.array_equal(sim.pov_exec(0), o.pov_exec()) and sim.pov_exec(0)[1] == 214
+    assert int(st["sum_shares"]) == 0 and int(st["sum_cash"]) == 64 * 10 ** 7

@@ -125,3 +125,26 @@ def test_rmsc03_tape_replay(seed):
         assert len(d) == 0, (name, int(d[0]), a[d[0]], b[d[0]])
     assert np.array_equal(sim.holdings(0)[:, :4], o.holdings()[:, :4])
     assert int(st["limit_orders"][0]) == o.counter("limit") and int(st["fills"][0]) == o.counter("fills")
+
+
+def test_rmsc03_with_pov_execution_agent_tape_replay():
+    """BASELINE.json configs[2] "rmsc03 ... with POV execution agent": bit-exact vs the oracle (pinned to a recording of the reference with
+    its POVExecutionAgent appended); one environment per seed plus a duplicate."""
+    from marl_optimal_execution_b200.sim import rmsc03_config
+    NS = 10 ** 9
+    pv = dict(pov=0.5, quantity=120000, is_buy=1, start_ns=(9 * 3600 + 32 * 60) * NS, end_ns=(9 * 3600 + 43 * 60) * NS, freq_ns=30 * NS, lookback_ns=30 * NS)
+    os_ = [OracleSim(3, seed, TRACE_ALL, pov_exec=pv) for seed in (123456789, 1001, 123456789)]
+    ns = [o.run() for o in os_]
+    cfg = rmsc03_config(pov_exec=True, rng_mode=_lib.RNG_TAPE, trace_cap=400000, hash_pops=1)
+    sim = BatchedSim(cfg, 3)
+    sim.reset_tape(*oracle_tapes(os_))
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    assert list(st["messages"]) == ns and ns[0] == 161747 and (st["flags"] == _lib.F_DONE).all(), (st["messages"], st["flags"])
+    for e, o in enumerate(os_):
+        assert int(st["pop_hash"][e]) == o.pop_hash()
+        p, nt, sn = sim.split_trace(e)
+        assert np.array_equal(p, o.trace("pops")) and np.array_equal(nt, o.trace("notes")) and np.array_equal(sn, o.trace("snaps"))
+        assert np.array_equal(sim.holdings(e)[:, :4], o.holdings()[:, :4]) and np.array_equal(sim.pov_exec(e), o.pov_exec())
+    assert (st["sum_shares"] == 0).all() and (st["sum_cash"] == 64 * 10 ** 7).all()

@@ -82,3 +82,22 @@ def test_rmsc03_digest_bit_exact(golden_dir, seed):
     gk, gb = s.global_tape()
     assert np.array_equal(gk, g["global_kind"].view(np.uint8)) and np.array_equal(gb, g["global_bits"])
     assert s.counter("max_bid_levels") == g["max_levels"][0] and s.counter("max_resting") == int(g["max_resting"])
+
+
+def test_rmsc03_with_pov_execution_agent(golden_dir):
+    """config/rmsc03.py with the reference's POVExecutionAgent appended by the recorder (tools/record_reference.py --pov-exec): the
+    "rmsc03 ... with POV execution agent" shape of BASELINE.json configs[2]."""
+    g = np.load(os.path.join(golden_dir, "rmsc03_pov_s123456789.npz"))
+    NS = 10 ** 9
+    pv = dict(pov=float(g["pov_exec"][0]), quantity=int(g["pov_exec"][1]), is_buy=int(g["pov_exec"][2]), start_ns=(9 * 3600 + 32 * 60) * NS,
+              end_ns=(9 * 3600 + 43 * 60) * NS, freq_ns=30 * NS, lookback_ns=30 * NS)
+    s = OracleSim(3, 123456789, 31, pov_exec=pv)
+    assert s.run() == int(g["n_pops"]) == 161747
+    assert np.array_equal(s.hash_ckpt(), g["pop_hash_ckpt"])
+    assert s.note_hash() == int(g["note_hash"]) and s.snap_hash() == int(g["snap_hash"])
+    assert np.array_equal(s.holdings()[:, :4], g["holdings"][:, :4])
+    ops = s.trace("ops")
+    assert np.array_equal(ops[ops[:, 2] == 64], g["pov_ops"]) and len(g["pov_ops"]) == 183
+    assert list(s.pov_exec()) == [int(g["pov_exec"][3]), int(g["pov_exec"][4]), int(g["pov_exec"][5])]
+    gk, gb = s.global_tape()
+    assert np.array_equal(gk, g["global_kind"].view(np.uint8)) and np.array_equal(gb, g["global_bits"])

@@ -284,6 +284,35 @@ def main():
         # simulation ended and is out of scope, so the recorder skips it.
         import agent.ExchangeAgent as EA
         EA.ExchangeAgent.logOrderBookSnapshots = lambda self, symbol: None
+    pov_args = None
+    if "--pov-exec" in rest:
+        # "rmsc03 with a POV execution agent" (BASELINE.json configs[2]): the shipped config/rmsc03.py has no execution agent, so the recorder
+        # appends the reference's own POVExecutionAgent (agent/execution/baselines/pov_agent.py, parameters in the style of
+        # config/execution_iabs_plots.py:200-226 scaled to the 15-minute session) to the agent list the UNMODIFIED config script hands to
+        # Kernel.runner.  The agent gets a fixed-seed RandomState (it never draws), so the config's own seed cascade is untouched.
+        import Kernel as K
+        from agent.execution.baselines.pov_agent import POVExecutionAgent
+        i = rest.index("--pov-exec")
+        pov, qty, direction = float(rest[i + 1]), int(rest[i + 2]), rest[i + 3]
+        pov_args = (pov, qty, direction)
+        r1 = K.Kernel.runner
+
+        def runner_with_pov(self, agents, *a, **k):
+            import warnings
+            import pandas as pd
+            day = pd.to_datetime(date)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ag = POVExecutionAgent(id=len(agents), name="POV_EXECUTION_AGENT", type="ExecutionAgent", symbol=agents[1].symbol, starting_cash=10000000,
+                                       direction=direction, quantity=qty, pov=pov, start_time=day + pd.to_timedelta("09:32:00"), freq="30s",
+                                       lookback_period="30s", end_time=day + pd.to_timedelta("09:43:00"), trade=True, log_orders=False,
+                                       random_state=np.random.mtrand.RandomState.__new__(np.random.mtrand.RandomState))
+            agents.append(ag)
+            n = len(agents)
+            k["agentLatency"] = np.zeros((n, n))
+            return r1(self, agents=agents, *a, **k)
+
+        K.Kernel.runner = runner_with_pov
     mod = run(config, seed, extra, date)
 
     pops = np.array(REC.pops, dtype=np.int64).reshape(-1, 5)
@@ -339,6 +368,10 @@ def main():
         data["stream"] = np.array([(REC.ns(ts), int(r["ORDER_ID"]), int(r["PRICE"]), int(r["SIZE"]), 1 if r["BUY_SELL_FLAG"] == "BUY" else 0)
                                    for ts in od for r in od[ts]], dtype=np.int64)
     data["pops_head"], data["notes_head"], data["snaps_head"] = pops[:20000], notes[:20000], snaps[:10000]
+    if pov_args is not None:
+        pa = agents[-1]
+        data["pov_exec"] = np.array([pov_args[0], pov_args[1], 1 if pov_args[2] == "BUY" else 0, pa.rem_quantity, len(pa.executed_orders), len(pa.orders)], dtype=np.float64)
+        data["pov_ops"] = ops[ops[:, 2] == pa.id]
     if full:
         kinds = np.frombuffer(b"".join(b"".join(s.tape_kind) for s in REC.streams), dtype="S1")
         vals = []
