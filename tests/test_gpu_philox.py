@@ -93,3 +93,46 @@ def test_rmsc03_batch_conservation():
     assert (st["flags"] == _lib.F_DONE).all(), np.unique(st["flags"])
     assert (st["sum_shares"] == 0).all() and (st["sum_cash"] == 63 * 10 ** 7).all()
     assert 100000 < np.median(st["messages"]) < 250000        # envs whose market maker met a one-sided book stop quoting (reference behaviour)
+
+
+def test_stylized_facts_agree_in_distribution_with_reference_rng_runs():
+    """north_star: "under GPU-native RNG, stylized facts (returns, spread and order-flow statistics from realism/) must agree in
+    distribution".  Minute bars of 256 Philox environments (realism.minute_bars: one launch per simulated minute) against minute bars of
+    12 reference-RNG oracle runs of the same config; per-run summaries of the reference's metrics (realism/metrics/*.py, restated in
+    realism.py and pinned by tests/test_realism_metrics.py) must agree within 6 standard errors (+ 10 % of the oracle spread)."""
+    from marl_optimal_execution_b200 import realism as R
+    n_min = 390
+
+    def summaries(close, volume):
+        r = R.minutely_returns(close)
+        with np.errstate(invalid="ignore"):
+            return np.stack([r.std(axis=1), np.abs(r).mean(axis=1), R.kurtosis(close)[:, 0], np.nanmean(R.autocorrelation(close), axis=1),
+                             R.volatility_clustering(close)[:, 0], R.returns_volatility_correlation(close), R.volume_volatility_correlation(close, volume),
+                             volume.sum(axis=1)], axis=1)
+
+    ref_c, ref_v = [], []
+    for s in range(2001, 2013):
+        o = OracleSim(100, s, 0)
+        o.start()
+        c, v, prev = np.zeros(n_min), np.zeros(n_min), 0
+        t0 = (9 * 3600 + 1800) * NS
+        for k in range(n_min):
+            o.run_until(t0 + (k + 1) * 60 * NS - 1)
+            c[k] = o.book_l1()[4]
+            f = o.counter("fills")
+            v[k] = 100 * (f - prev)
+            prev = f
+        ref_c.append(c); ref_v.append(v)
+    ref = summaries(np.array(ref_c), np.array(ref_v))
+    cfg = sparse_zi_config(100)
+    n = 256
+    sim = BatchedSim(cfg, n)
+    sim.reset(np.arange(n, dtype=np.uint64) + 4242)
+    close, volume = R.minute_bars(sim, n_min)
+    assert (sim.stats()["flags"] & _lib.F_ERROR_MASK == 0).all() and (close > 0).all()
+    got = summaries(close, volume)
+    names = ["std(r)", "mean|r|", "kurtosis", "autocorr", "vol-clustering lag 1", "corr(r,|r|)", "corr(volume,|r|)", "volume"]
+    for k, name in enumerate(names):
+        g, rf = got[:, k][np.isfinite(got[:, k])], ref[:, k][np.isfinite(ref[:, k])]
+        se = np.sqrt(rf.var(ddof=1) / len(rf) + g.var(ddof=1) / len(g))
+        assert abs(g.mean() - rf.mean()) < 6 * se + 0.1 * rf.std(ddof=1), (name, g.mean(), rf.mean(), se)
