@@ -193,16 +193,16 @@ def oracle_ddqn_ticks_per_s(n_episodes, ticks, threads):
 
 
 def reference_ddqn_block(cores):
-    st, msgs, busy = oracle_ddqn_ticks_per_s(max(cores, 2), 100, cores)
+    st, msgs, busy = oracle_ddqn_ticks_per_s(max(4 * cores, 8), 400, cores)
     return {"metric": "DDQN execution env ticks/sec", "value": st / busy, "unit": "steps/s", "msgs_per_s": msgs / busy, "cores": cores, "kind": "port",
-            "sample": "%d runs x 100 decision ticks after the 10:00 start-up (IBM 2003-01-14 LOBSTER fixture, random actions, no network), %d threads" % (max(cores, 2), cores)}
+            "sample": "%d runs x 400 decision ticks after the 10:00 start-up (IBM 2003-01-14 LOBSTER fixture, random actions, no network), %d threads" % (max(4 * cores, 8), cores)}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = max(2 * cores, 8)
+    per_step = max(4 * cores, 16)
     oracle_msgs_per_s(min(cores, 8), cores, args.variant)                       # warm-up (library load, page-in)
     for _ in range(max(args.warmup - 1, 0)):
         oracle_msgs_per_s(per_step, cores, args.variant)
@@ -225,9 +225,9 @@ def run_reference(args, rank, world):
 
 
 def reference_env_block(cores):
-    st, msgs, busy, wall = oracle_env_steps_per_s(max(cores, 2), 120, cores)
+    st, msgs, busy, wall = oracle_env_steps_per_s(max(2 * cores, 4), 400, cores)
     return {"metric": "ABIDESEnv steps/sec", "value": st / busy, "unit": "steps/s", "msgs_per_s": msgs / busy, "cores": cores, "kind": "port",
-            "sample": "%d episodes x 120 steps after the 09:40 start-up (IBM 2003-01-14 LOBSTER fixture), %d threads" % (max(cores, 2), cores)}
+            "sample": "%d episodes x 400 steps after the 09:40 start-up (IBM 2003-01-14 LOBSTER fixture), %d threads" % (max(2 * cores, 4), cores)}
 
 
 def run_ours(args, rank, local_rank, world):
@@ -331,6 +331,7 @@ def run_ours(args, rank, local_rank, world):
         gd = D.gather_summaries(torch.tensor([dq_local["steps"], dq_local["msgs"], dq_local["e2e_steps"], dq_local["errs"]], dtype=torch.int64), device=dev)
         t_dq = D.max_over_ranks(dq_local["ms"], device=dev) / 1e3
         t_dq_e2e = D.max_over_ranks(dq_local["e2e_s"], device=dev)
+        t_dq_train = D.max_over_ranks(dq_local["train_s"], device=dev)
         nd, Kd = args.ddqn_envs_per_gpu, args.ddqn_steps
         tf_peak = measured_peak_tflops()
         q_ach = nd * QNET_FLOP_PER_ROW / (dq_local["qnet_ms"] / 1e3) / 1e12
@@ -339,6 +340,10 @@ def run_ours(args, rank, local_rank, world):
                     "messages_per_env_step": int(gd[:, 1].sum()) / max(int(gd[:, 0].sum()), 1), "error_envs": int(gd[:, 3].sum()),
                     "e2e": {"value": int(gd[:, 2].sum()) / t_dq_e2e, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 121 * nd,
                             "note": "actions are produced on the device by the Q-network; every tick obs, experience tuple, reward and done are read back to pinned host memory"},
+                    "training": {"value": int(gd[:, 0].sum()) / t_dq_train, "unit": "steps/s", "learn_steps": dq_local["learn_steps"], "batch": args.ddqn_batch,
+                                 "replay_buffer_rows": dq_local["buffer"], "note": "same loop with the learner on: experience tuples into a device replay buffer, one "
+                                 "train_neural_nets-style update (PyTorch fp32 autograd, RMSprop) every 5 ticks, new weights pushed to the tcgen05 network; wall clock; "
+                                 "each rank trains its own copy (no gradient all-reduce in this round)"},
                     "gpu_launches": dq_local["launches"], "dtype": "int64+f64 (environment), bf16x3 -> fp32 accumulate (Q-network)",
                     "qnet_roofline": {"bound": "tensor", "achieved": q_ach, "peak": tf_peak[0], "unit": "TFLOP/s", "frac": q_ach / tf_peak[0], "traffic": None,
                                       "peak_source": tf_peak[1], "kernel": "abx_qnet_forward_kernel", "kernel_ms": dq_local["qnet_ms"],
@@ -384,7 +389,7 @@ def run_ours(args, rank, local_rank, world):
         out["ddqn"] = dq_block
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_days = max(2 * cores, 16)
+        n_days = max(12 * cores, 64)                          # ~0.07 CPU-s per env-day: 10-20 s of CPU work
         oracle_msgs_per_s(min(cores, 4), cores, args.variant)
         m, w, cpu_s = oracle_msgs_per_s(n_days, cores, args.variant)
         out["cpu_baseline"] = {"value": m / w, "unit": "msgs/s", "cores": cores, "kind": "port",
@@ -485,10 +490,32 @@ def bench_ddqn(args, rank, local_rank, dev, stream, sp):
         torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - w0
     D.barrier()
+    # training loop (marketreplay_ddqn_train shape): act, step, store the experience tuples, learn every 5 ticks on a batch from the shared
+    # replay buffer (the reference's update rule, ddqn.py) and push the new weights into the acting network
+    from marl_optimal_execution_b200.ddqn import DDQNTrainer
+    tr = DDQNTrainer(device=dev, batch_size=args.ddqn_batch, seed=args.seed % 1000, buffer_capacity=max(4 * n * 8, 1 << 16))
+    net.set_params(tr.eval_net.flat())
+    for _ in range(6):                                    # fill the buffer / warm the autograd kernels, untimed
+        _, a = net.forward(obs, x_offset=6, want_q=False, greedy_prob=tr.greedy_prob(), seed=args.seed, counter=tick, out=qbuf, stream=sp)
+        obs, trans, rew, done = env.step(a, stream=sp); tick += 1
+        tr.buffer.push(trans)
+    tr.learn()
+    D.barrier(); torch.cuda.synchronize(dev)
+    w0 = time.perf_counter(); l_before = tr.learn_step_counter
+    for k in range(K):
+        _, a = net.forward(obs, x_offset=6, want_q=False, greedy_prob=tr.greedy_prob(), seed=args.seed, counter=tick, out=qbuf, stream=sp)
+        obs, trans, rew, done = env.step(a, stream=sp); tick += 1
+        tr.buffer.push(trans)
+        if k % tr.train_every == 0 and tr.learn() is not None:
+            net.set_params(tr.eval_net.flat())
+    torch.cuda.synchronize(dev)
+    train_s = time.perf_counter() - w0
+    D.barrier()
     st = env.stats(stream=sp)
-    errs = int(((st["flags"] & _lib.F_ERROR_MASK) != 0).sum()) + int(d_pin.sum())       # no environment may have ended inside the measured ticks
+    errs = int(((st["flags"] & _lib.F_ERROR_MASK) != 0).sum()) + int(d_pin.sum()) + int(done.sum())       # no environment may have ended inside the measured ticks
     env.close(); net.close()
-    return {"steps": n * K, "msgs": m1 - m0, "ms": e0.elapsed_time(e1), "e2e_steps": n * K, "e2e_s": e2e_s, "errs": errs, "launches": int(launches), "qnet_ms": qnet_ms}
+    return {"steps": n * K, "msgs": m1 - m0, "ms": e0.elapsed_time(e1), "e2e_steps": n * K, "e2e_s": e2e_s, "errs": errs, "launches": int(launches), "qnet_ms": qnet_ms,
+            "train_s": train_s, "learn_steps": tr.learn_step_counter - l_before, "buffer": tr.buffer.size}
 
 
 def main():
@@ -508,6 +535,7 @@ def main():
     ap.add_argument("--no-ddqn", action="store_true", help="skip the DDQN execution shape (Q-network forward + environment step per tick)")
     ap.add_argument("--ddqn-envs-per-gpu", type=int, default=8192)
     ap.add_argument("--ddqn-steps", type=int, default=40)
+    ap.add_argument("--ddqn-batch", type=int, default=4096, help="learner batch size of the DDQN training sub-measurement")
     args = ap.parse_args()
     quiet_stdout()
     if args.warmup < 3 and args.impl == "ours":

@@ -319,6 +319,22 @@ int64_t abx_qnet_launch_count(const abx_qnet *q);
 int32_t abx_qnet_forward(abx_qnet *q, const double *x_dev, int32_t x_stride, int32_t x_offset, int32_t n, float *q_out_dev,
                          int32_t *action_out_dev, double greedy_prob, uint64_t seed, uint64_t counter, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Book surface: n_envs bare limit-order books driven by an operation tape recorded at the reference's
+ * exchange boundary (what agent/ExchangeAgent.py:311,324,339 passes to OrderBook.handleLimitOrder / cancelOrder / modifyOrder,
+ * util/OrderBook.py:38,284,341) -- "order streams recorded from the reference are replayed through the GPU books".
+ * Handles are abx_sim*: after a replay abx_sim_trace returns, per operation, every notification the book sent (tag 1: ORDER_EXECUTED
+ * pairs, ORDER_ACCEPTED, ORDER_CANCELLED, ORDER_MODIFIED; the reference's owner.sendMessage calls) followed by the book state (tag 2:
+ * level counts, resting orders, three best levels per side, last_trade); abx_sim_book_snapshot is getInsideBids/Asks(depth);
+ * abx_sim_stats has the counters.
+ * ------------------------------------------------------------------------------------------------------------ */
+int32_t abx_book_create(int32_t stream_history, int32_t level_cap, int32_t order_cap, int32_t trace_cap, int32_t n_envs, int32_t device, abx_sim **out);
+/* ops9: HOST int64 [n_ops][9] rows (t_ns, op: 0 handleLimitOrder / 1 cancelOrder / 2 modifyOrder, agent id, order_id, is_buy, limit
+ * price, quantity, new price, new quantity) -- the rows tools/record_reference.py records.  Every book of the handle replays the tape
+ * (from an empty book; a second call continues on the current books).  A modify row with order_id 0 is a no-op: in the reference its
+ * new_order carries a freshly generated id and isSameOrder fails (util/order/Order.py:27, util/OrderBook.py:343). */
+int32_t abx_book_replay(abx_sim *h, const int64_t *ops9, int64_t n_ops, void *stream);
+
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t abx_sim_launch_count(const abx_sim *h);
 

@@ -150,6 +150,8 @@ def _bind(L):
     sig("abx_env_reset", i32, vp, vp)
     sig("abx_env_step", i32, vp, vp, vp, vp, vp, vp)
     sig("abx_env_step_host", i32, vp, vp, vp, vp, vp, vp)
+    sig("abx_book_create", i32, i32, i32, i32, i32, i32, i32, P(vp))
+    sig("abx_book_replay", i32, vp, P(i64), i64, vp)
     sig("abx_dq_config_default", i32, P(DqConfig))
     sig("abx_dq_create", i32, P(DqConfig), P(i64), i64, i32, i32, P(vp))
     sig("abx_dq_reset", i32, vp, vp, vp, vp)

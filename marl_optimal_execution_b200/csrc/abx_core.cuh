@@ -420,10 +420,10 @@ ABX_HD void regs_store(ZiAgent *z, const AgentRegs &a) {
 
 // RNG_MODE / LAT_MODEL: compile-time copies of cfg.rng_mode / cfg.latency_model (-1 = decide at run time);
 // INSTR: parity instrumentation (pop hash + trace records) compiled in or out.
-enum { SHAPE_ZI = 0, SHAPE_ENV = 1, SHAPE_R3 = 2, SHAPE_DQ = 3 };   // sparse_zi population | ABIDESEnv / marketreplay | rmsc03 population | DDQN execution config
+enum { SHAPE_ZI = 0, SHAPE_ENV = 1, SHAPE_R3 = 2, SHAPE_DQ = 3, SHAPE_BOOK = 4 };   // sparse_zi population | ABIDESEnv / marketreplay | rmsc03 population | DDQN execution config | bare order books (op-tape replay)
 template <class Ctx, int RNG_MODE = -1, int LAT_MODEL = -1, bool INSTR = true, int SHAPE = SHAPE_ZI>
 struct Sim {
-  static constexpr bool DQ = SHAPE == SHAPE_DQ, ENV = SHAPE == SHAPE_ENV || DQ, R3 = SHAPE == SHAPE_R3;
+  static constexpr bool DQ = SHAPE == SHAPE_DQ, BOOK = SHAPE == SHAPE_BOOK, ENV = SHAPE == SHAPE_ENV || DQ || BOOK, R3 = SHAPE == SHAPE_R3;
   Ctx &c; const SimParams &P; EnvState s; RngT<RNG_MODE> rng; int64_t addl_delay; int n_out; int self_id;
   AgentRegs a; ZiAgent *z;                // the trader whose event is being handled (registers + staged record)
 
@@ -527,6 +527,7 @@ struct Sim {
         e.sender = from_exch ? 0 : self_id; e.lat_back = from_exch ? 0.0 : a.lat_from;
         e.x0 = (int32_t)o[7]; e.x1 = (int32_t)o[8];                                   // exchange replies: level-2 prices ride in the latency words
       }
+      if (BOOK) continue;                                                             // bare-book replay: the notification is the output (traced above), there is no kernel queue
       if (!c.q_push(e)) s.flags |= ABX_F_QUEUE_OVERFLOW;                              // Kernel.py:425 / :462
       else { s.q_count++; if (s.q_count > s.max_q) s.max_q = s.q_count; }
     }
@@ -1124,6 +1125,28 @@ struct Sim {
     return !more;
   }
 
+
+  // =================================================================================================
+  // Book surface: what ExchangeAgent calls on util/OrderBook.py -- handleLimitOrder :38-170, cancelOrder :284-339,
+  // modifyOrder :341-372 -- driven by an operation tape recorded at the exchange boundary instead of by agents.  ops: rows of 9 int64
+  // (t_ns, op 0 limit / 1 cancel / 2 modify, agent, device order id, is_buy, price, qty, new_price, new_qty).  Every notification the book
+  // sends (ORDER_EXECUTED pairs, ORDER_ACCEPTED, ORDER_CANCELLED, ORDER_MODIFIED) and the book state after every operation go to the trace.
+  // =================================================================================================
+  ABX_HD void book_replay(const int64_t *ops, int64_t n_ops) {
+    self_id = 0;
+#pragma unroll 1
+    for (int64_t i = 0; i < n_ops; i++) {
+      const int64_t *r = ops + 9 * i;
+      s.now = r[0]; s.ttl++; addl_delay = 0;
+      int op = (int)r[1], agent = (int)r[2], is_buy = (int)r[4]; uint32_t oid = (uint32_t)r[3]; int32_t price = (int32_t)r[5], qty = (int32_t)r[6];
+      if (op == 0) { s.c_limit++; book_handle_limit(oid, agent, is_buy, price, qty, 0.0); }
+      else if (op == 1) { s.c_cancel++; book_cancel(oid, agent, is_buy, price, 0.0); }
+      else if (op == 2 && oid != 0xffffffffu) book_modify(oid, agent, is_buy, price, (int32_t)r[7], (int32_t)r[8]);   // id 0xffffffff: isSameOrder fails (:343)
+      c.sync(); trace_snap();
+      flush();
+    }
+    s.flags |= ABX_F_DONE;
+  }
 
   // =================================================================================================
   // DDQN execution config (config/execution/marketreplay/execution_marketreplay_ddqn.py, -a rl): Exchange (0) + MarketReplayAgent (1,

@@ -192,6 +192,19 @@ static inline int env_build_stream(const int64_t *s5, int64_t n, int64_t max_rl_
   if (o.id_orig.empty()) o.id_orig.push_back(0);
   return ABX_OK;
 }
+// Book surface: recorded op rows -> device rows (order ids become dense device ids; a modify of order id 0 is a no-op, see abides_b200.h)
+static inline int book_ops_to_device(const int64_t *ops9, int64_t n, std::unordered_map<int64_t, int32_t> &dense, std::vector<int64_t> &id_orig, std::vector<int64_t> &out) {
+  out.assign(ops9, ops9 + 9 * n);
+  for (int64_t i = 0; i < n; i++) {
+    int64_t *r = out.data() + 9 * i;
+    if (r[1] < 0 || r[1] > 2 || r[2] < 0 || r[2] > 0xffff || r[0] < 0 || r[0] >= KEY_T_MAX || r[5] > 0x3fffffffLL || r[6] > 0x7fffffffLL || r[5] < -0x3fffffffLL) return ABX_ERR_ARG;
+    if (r[1] == 2 && r[3] == 0) { r[3] = 0xffffffffLL; continue; }
+    auto it = dense.find(r[3]); int32_t d;
+    if (it == dense.end()) { if (id_orig.size() >= 0x3fffffffu) return ABX_ERR_ARG; d = (int32_t)id_orig.size(); dense.emplace(r[3], d); id_orig.push_back(r[3]); } else d = it->second;
+    r[3] = (int64_t)REPLAY_ID_BASE + d;
+  }
+  return ABX_OK;
+}
 ABX_HD void init_envx(const SimParams &P, EnvX &x) {
   x.ra_time = x.rl_time = P.c.start_ns; x.ra_cash = x.rl_cash = 0; x.rem_quantity = P.rl_quantity; x.executed_sum = 0.0;   // starting_cash 0 (agent_config.py:73,133)
   x.ra_shares = x.rl_shares = 0; x.ra_last_trade = x.rl_last_trade = 0; x.ra_flags = 0;

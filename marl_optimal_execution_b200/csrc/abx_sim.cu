@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <new>
 #include <vector>
+#include <unordered_map>
 #include "abx_warp.cuh"
 #include "abx_host_common.h"
 
@@ -198,6 +199,22 @@ abx_dq_step_kernel(SimParams P, const int32_t *__restrict__ actions, double *__r
   if (ctx.lane == 0) { if (reward) reward[env] = rw; done[env] = (s.flags & ABX_F_DONE) ? 1 : 0; }
 }
 
+// ---- Book surface: op-tape replay through bare books ----
+__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
+abx_book_replay_kernel(SimParams P, const int64_t *__restrict__ ops, int64_t n_ops, int fresh, size_t smem_per_warp) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
+  if (env >= P.n_envs) return;
+  WarpCtx ctx(P, env, smem + warp * smem_per_warp);
+  EnvState s;
+  if (fresh) { init_env_state(P, 0, s); s.last_trade = -1; ctx.q_clear(); }      // OrderBook.__init__: last_trade None
+  else { s = env_load(P.env + env); s.flags &= ~ABX_F_DONE; ctx.load_onchip(s); }
+  Sim<WarpCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_BOOK> sim(ctx, P, s, env);
+  sim.book_replay(ops, n_ops);
+  ctx.store_onchip(sim.s);
+  env_store(P.env + env, sim.s, ctx.lane);
+}
+
 __global__ void abx_stats_kernel(SimParams P, abx_env_stats *__restrict__ out) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= P.n_envs) return;
@@ -222,6 +239,7 @@ struct abx_sim {
   uint64_t *d_tbits; uint8_t *d_tkinds; int64_t *d_toff;
   bool is_env, is_dq; EnvStreamHost *st; int64_t *d_ts; int32_t *d_first; int4 *d_rows; double *d_act, *d_obs, *d_rew; uint8_t *d_done;
   int32_t *d_iact, *d_msizes; double *d_trans;
+  bool is_book; int64_t *d_ops; int64_t ops_cap; std::unordered_map<int64_t, int32_t> *book_ids;
 };
 
 template <class T> static int dalloc(T **p, size_t n, int64_t *acc) {
@@ -244,9 +262,9 @@ int32_t abx_sim_destroy(abx_sim *h) {
   cudaSetDevice(h->device);
   void *ptrs[] = {h->P.qkey, h->P.qpay0, h->P.qpay1, h->P.qcache, h->P.agents, h->P.lv_price, h->P.lv_qty, h->P.lv_ht, h->P.nodes, h->P.env,
                   h->P.trace, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff,
-                  h->P.envx, h->P.idtab, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_iact, h->d_msizes, h->d_trans};
+                  h->P.envx, h->P.idtab, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_iact, h->d_msizes, h->d_trans, h->d_ops};
   for (void *p : ptrs) if (p) cudaFree(p);
-  delete h->st; delete h; return ABX_OK;
+  delete h->st; delete h->book_ids; delete h; return ABX_OK;
 }
 
 int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device, abx_sim **out) {
@@ -565,6 +583,54 @@ int32_t abx_dq_holdings(abx_sim *h, int32_t env, int64_t *out, double *exec_out,
   CU(cudaStreamSynchronize(st));
   dq_holdings_rows(h->P, tmp.data(), x, out, exec_out);
   return ABX_OK;
+}
+
+// ---------------- Book surface ----------------
+int32_t abx_book_create(int32_t stream_history, int32_t level_cap, int32_t order_cap, int32_t trace_cap, int32_t n_envs, int32_t device, abx_sim **out) {
+  abx_env_config ec; env_config_default(&ec);
+  ec.order_level = 0; ec.stream_history = stream_history; ec.queue_cap = 32; ec.level_cap = level_cap; ec.order_cap = order_cap; ec.trace_cap = trace_cap; ec.hash_pops = 0;
+  if (!out || n_envs < 1 || env_config_validate(&ec) != ABX_OK) return ABX_ERR_ARG;
+  int ndev = 0; cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || device < 0 || device >= ndev) { snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d not present (%d visible): %s", device, ndev, cudaGetErrorString(ce)); return ABX_ERR_CUDA; }
+  CU(cudaSetDevice(device));
+  abx_sim *h = new (std::nothrow) abx_sim(); if (!h) return ABX_ERR_ARG;
+  memset(h, 0, sizeof(*h)); h->is_env = true; h->is_book = true; h->n_envs = n_envs; h->device = device;
+  h->st = new (std::nothrow) EnvStreamHost(); h->book_ids = new (std::nothrow) std::unordered_map<int64_t, int32_t>();
+  if (!h->st || !h->book_ids) { abx_sim_destroy(h); return ABX_ERR_ARG; }
+  env_fill_params(ec, h->P); h->P.n_envs = n_envs; h->P.c.n_agents = 2;
+  h->smem_per_warp = (warp_smem_bytes(h->P.c, true) + 15) & ~(size_t)15;
+  size_t smem_cta = h->smem_per_warp * ABX_WARPS_PER_CTA;
+  if (smem_cta > 227 * 1024) { abx_sim_destroy(h); return ABX_ERR_ARG; }
+  const abx_sim_config &c = h->P.c; size_t E = (size_t)n_envs; int stt;
+#define DA(ptr, n) if ((stt = dalloc(&(ptr), (n), &h->bytes)) != ABX_OK) { abx_sim_destroy(h); return stt; }
+  DA(h->P.qkey, E * c.queue_cap) DA(h->P.qpay0, E * c.queue_cap) DA(h->P.qpay1, E * c.queue_cap) DA(h->P.qcache, E * h->P.n_qgroups)
+  DA(h->P.lv_price, E * 2 * c.level_cap) DA(h->P.lv_qty, E * 2 * c.level_cap) DA(h->P.lv_ht, E * 2 * c.level_cap)
+  DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap) DA(h->d_stats, E) DA(h->P.envx, E)
+#undef DA
+  if (smem_cta > 48 * 1024) CU(cudaFuncSetAttribute(abx_book_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+  *out = h; return ABX_OK;
+}
+
+int32_t abx_book_replay(abx_sim *h, const int64_t *ops9, int64_t n_ops, void *stream) {
+  if (!h || !h->is_book || !ops9 || n_ops < 1) return ABX_ERR_ARG;
+  CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
+  std::vector<int64_t> dev_ops; int st_rc = book_ops_to_device(ops9, n_ops, *h->book_ids, h->st->id_orig, dev_ops);
+  if (st_rc != ABX_OK) return st_rc;
+  int n_ids = (int)h->st->id_orig.size(); bool fresh = !h->reset_done;
+  if (n_ids > h->P.n_ids) {                                            // grow the per-order history table (one 16-byte record per distinct order id), keeping its contents
+    uint4 *old = h->P.idtab; int old_n = h->P.n_ids; int new_n = n_ids + n_ids / 2 + 64; uint4 *nw = nullptr;
+    CU(cudaMalloc((void **)&nw, sizeof(uint4) * (size_t)h->n_envs * new_n)); CU(cudaMemsetAsync(nw, 0, sizeof(uint4) * (size_t)h->n_envs * new_n, st));
+    if (old && !fresh) CU(cudaMemcpy2DAsync(nw, sizeof(uint4) * new_n, old, sizeof(uint4) * old_n, sizeof(uint4) * old_n, h->n_envs, cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st)); if (old) cudaFree(old);
+    h->P.idtab = nw; h->P.n_ids = new_n;
+  }
+  if (n_ops > h->ops_cap) { if (h->d_ops) { CU(cudaStreamSynchronize(st)); cudaFree(h->d_ops); h->d_ops = nullptr; } CU(cudaMalloc((void **)&h->d_ops, sizeof(int64_t) * 9 * (size_t)n_ops)); h->ops_cap = n_ops; }
+  CU(cudaMemcpyAsync(h->d_ops, dev_ops.data(), sizeof(int64_t) * 9 * (size_t)n_ops, cudaMemcpyHostToDevice, st));
+  abx_book_replay_kernel<<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, st>>>(h->P, h->d_ops, n_ops, fresh ? 1 : 0, h->smem_per_warp);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));                                       // dev_ops is a local staging buffer
+  h->reset_done = true; return ABX_OK;
 }
 
 }  // extern "C"

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <unordered_map>
 #include "../../marl_optimal_execution_b200/csrc/abx_host_common.h"
 
 using namespace abx;
@@ -301,5 +302,39 @@ int32_t abx_dq_step(abx_sim *h, const int32_t *a, double *o, double *t, double *
 int32_t abx_dq_holdings(abx_sim *h, int32_t env, int64_t *out, double *exec_out, void *stream) {
   (void)stream; if (!h || !h->is_env || h->P.c.population != 2 || !out || env < 0 || env >= h->n_envs) return ABX_ERR_ARG;
   dq_holdings_rows(h->P, &h->agents[(size_t)env * h->P.c.n_agents], h->envx[env], out, exec_out); return ABX_OK;
+}
+
+// ---- Book surface ----
+typedef Sim<HostCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_BOOK> BookSimHost;
+static std::unordered_map<abx_sim *, std::unordered_map<int64_t, int32_t>> g_book_ids;
+int32_t abx_book_create(int32_t stream_history, int32_t level_cap, int32_t order_cap, int32_t trace_cap, int32_t n_envs, int32_t device, abx_sim **out) {
+  (void)device; abx_env_config ec; env_config_default(&ec);
+  ec.order_level = 0; ec.stream_history = stream_history; ec.queue_cap = 32; ec.level_cap = level_cap; ec.order_cap = order_cap; ec.trace_cap = trace_cap; ec.hash_pops = 0;
+  if (!out || n_envs < 1 || env_config_validate(&ec) != ABX_OK) return ABX_ERR_ARG;
+  abx_sim *h = new abx_sim(); memset(&h->P, 0, sizeof(h->P)); h->is_env = true; h->n_envs = n_envs; h->reset_done = false;
+  env_fill_params(ec, h->P); h->P.n_envs = n_envs; h->P.c.n_agents = 2; const abx_sim_config &c = h->P.c; size_t E = n_envs;
+  h->qkey.resize(E * c.queue_cap); h->qpay0.resize(E * c.queue_cap); h->qpay1.resize(E * c.queue_cap); h->qcache.resize(E * h->P.n_qgroups);
+  h->agents.resize(4); h->lvp.resize(E * 2 * c.level_cap); h->lvq.resize(E * 2 * c.level_cap); h->lvht.resize(E * 2 * c.level_cap);
+  h->nodes.resize(E * c.order_cap); h->env.resize(E); h->trace.resize(E * (size_t)c.trace_cap); h->envx.resize(E);
+  h->P.qkey = h->qkey.data(); h->P.qpay0 = h->qpay0.data(); h->P.qpay1 = h->qpay1.data(); h->P.qcache = h->qcache.data(); h->P.agents = h->agents.data();
+  h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
+  h->P.trace = c.trace_cap ? h->trace.data() : nullptr; h->P.envx = h->envx.data();
+  *out = h; return ABX_OK;
+}
+int32_t abx_book_replay(abx_sim *h, const int64_t *ops9, int64_t n_ops, void *stream) {
+  (void)stream; if (!h || !h->is_env || !ops9 || n_ops < 1) return ABX_ERR_ARG;
+  std::vector<int64_t> dev_ops; int rc = book_ops_to_device(ops9, n_ops, g_book_ids[h], h->st.id_orig, dev_ops); if (rc != ABX_OK) return rc;
+  int n_ids = (int)h->st.id_orig.size(); bool fresh = !h->reset_done;
+  if (n_ids > h->P.n_ids) {
+    int new_n = n_ids + n_ids / 2 + 64; std::vector<uint4> nw((size_t)h->n_envs * new_n); memset(nw.data(), 0, nw.size() * sizeof(uint4));
+    if (!fresh) for (int e = 0; e < h->n_envs; e++) memcpy(&nw[(size_t)e * new_n], &h->idtab[(size_t)e * h->P.n_ids], sizeof(uint4) * h->P.n_ids);
+    h->idtab.swap(nw); h->P.idtab = h->idtab.data(); h->P.n_ids = new_n;
+  }
+  for (int e = 0; e < h->n_envs; e++) {
+    HostCtx ctx(h->P, e); EnvState s;
+    if (fresh) { init_env_state(h->P, 0, s); s.last_trade = -1; ctx.q_clear(); } else { s = h->env[e]; s.flags &= ~ABX_F_DONE; }
+    BookSimHost sim(ctx, h->P, s, e); sim.book_replay(dev_ops.data(), n_ops); h->env[e] = sim.s;
+  }
+  h->reset_done = true; return ABX_OK;
 }
 }

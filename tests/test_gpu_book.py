@@ -1,0 +1,18 @@
+"""GPU parity of the book surface through the C ABI (abx_book_create / abx_book_replay): the reference's known-answer vector and
+operation tapes recorded at the reference's exchange boundary replayed through the GPU books, bit-exact in fills, notifications
+and book snapshots."""
+import pytest
+
+import book_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def test_kat1():
+    book_cases.kat1()
+
+
+@pytest.mark.parametrize("fixture,n_ops", [("env_IBM_2003-01-14_s789.npz", 10000), ("ddqn_IBM_2003-01-14_s4242.npz", 30000)])
+def test_recorded_operation_tape(golden_dir, fixture, n_ops):
+    fills, modifies = book_cases.recorded_tape(golden_dir, fixture, n_ops, n_envs=64)
+    assert fills > 500 and modifies > 1000
