@@ -342,7 +342,7 @@ def run_ours(args, rank, local_rank, world):
                             "note": "actions are produced on the device by the Q-network; every tick obs, experience tuple, reward and done are read back to pinned host memory"},
                     "training": {"value": int(gd[:, 0].sum()) / t_dq_train, "unit": "steps/s", "learn_steps": dq_local["learn_steps"], "batch": args.ddqn_batch,
                                  "replay_buffer_rows": dq_local["buffer"], "note": "same loop with the learner on: experience tuples into a device replay buffer, one "
-                                 "train_neural_nets-style update (PyTorch fp32 autograd, RMSprop) every 5 ticks, new weights pushed to the tcgen05 network; wall clock; "
+                                 "train_neural_nets-style update (PyTorch fp32 autograd, RMSprop) every 5 ticks, new weights packed into the tcgen05 operand image on the device; no host synchronisation inside the loop; wall clock; "
                                  "each rank trains its own copy (no gradient all-reduce in this round)"},
                     "gpu_launches": dq_local["launches"], "dtype": "int64+f64 (environment), bf16x3 -> fp32 accumulate (Q-network)",
                     "qnet_roofline": {"bound": "tensor", "achieved": q_ach, "peak": tf_peak[0], "unit": "TFLOP/s", "frac": q_ach / tf_peak[0], "traffic": None,
@@ -494,7 +494,7 @@ def bench_ddqn(args, rank, local_rank, dev, stream, sp):
     # replay buffer (the reference's update rule, ddqn.py) and push the new weights into the acting network
     from marl_optimal_execution_b200.ddqn import DDQNTrainer
     tr = DDQNTrainer(device=dev, batch_size=args.ddqn_batch, seed=args.seed % 1000, buffer_capacity=max(4 * n * 8, 1 << 16))
-    net.set_params(tr.eval_net.flat())
+    net.set_params_device(tr.eval_net.flat_device())
     for _ in range(6):                                    # fill the buffer / warm the autograd kernels, untimed
         _, a = net.forward(obs, x_offset=6, want_q=False, greedy_prob=tr.greedy_prob(), seed=args.seed, counter=tick, out=qbuf, stream=sp)
         obs, trans, rew, done = env.step(a, stream=sp); tick += 1
@@ -507,7 +507,7 @@ def bench_ddqn(args, rank, local_rank, dev, stream, sp):
         obs, trans, rew, done = env.step(a, stream=sp); tick += 1
         tr.buffer.push(trans)
         if k % tr.train_every == 0 and tr.learn() is not None:
-            net.set_params(tr.eval_net.flat())
+            net.set_params_device(tr.eval_net.flat_device())
     torch.cuda.synchronize(dev)
     train_s = time.perf_counter() - w0
     D.barrier()

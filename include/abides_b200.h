@@ -310,6 +310,8 @@ int32_t abx_qnet_param_count(const int32_t *dims, int32_t n_layers);
 int32_t abx_qnet_create(const int32_t *dims, int32_t n_layers, const float *params, int32_t device, abx_qnet **out);
 /* New weights (the learner's update / the target-network sync of train_neural_nets :486-490); synchronises `stream`. */
 int32_t abx_qnet_set_params(abx_qnet *q, const float *params, void *stream);
+/* Same from a DEVICE fp32 vector (the learner's parameters), asynchronous on `stream`: the hi/lo operand image is rebuilt by a kernel. */
+int32_t abx_qnet_set_params_device(abx_qnet *q, const float *params_dev, void *stream);
 int32_t abx_qnet_destroy(abx_qnet *q);
 int64_t abx_qnet_launch_count(const abx_qnet *q);
 /* x_dev: DEVICE fp64 [n][x_stride]; the state of row i is x_dev[i * x_stride + x_offset ...+ dims[0]) (abx_dq_step's obs with

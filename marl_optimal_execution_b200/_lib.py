@@ -163,6 +163,7 @@ def _bind(L):
         sig("abx_qnet_param_count", i32, P(i32), i32)
         sig("abx_qnet_create", i32, P(i32), i32, P(C.c_float), i32, P(vp))
         sig("abx_qnet_set_params", i32, vp, P(C.c_float), vp)
+        sig("abx_qnet_set_params_device", i32, vp, vp, vp)
         sig("abx_qnet_destroy", i32, vp)
         sig("abx_qnet_launch_count", i64, vp)
         sig("abx_qnet_forward", i32, vp, vp, i32, i32, i32, vp, vp, C.c_double, C.c_uint64, C.c_uint64, vp)

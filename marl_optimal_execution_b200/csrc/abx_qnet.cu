@@ -209,6 +209,30 @@ abx_qnet_forward_kernel(QnetDev net, const uint8_t *__restrict__ wimg, const flo
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)QN_TMEM_COLS) : "memory");
 }
 
+// Device-side version of pack_params: fp32 parameters (per layer W[out][in] then b[out]) -> bf16 hi/lo image in the MMA operand layout + bias
+// array, so that the learner can push new weights without a host round trip.  One thread per padded weight / bias element.
+__global__ void abx_qnet_pack_kernel(QnetDev net, int d0, int d1, int d2, int d3, int d4, int d5, int d6, int d7, int d8, const float *__restrict__ params,
+                                     uint8_t *__restrict__ wimg, float *__restrict__ bias) {
+  const int dims[9] = {d0, d1, d2, d3, d4, d5, d6, d7, d8};
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t acc = 0, poff = 0;
+  for (int l = 0; l < net.n_layers; l++) {
+    uint32_t K = net.kpad[l], N = net.npad[l], nw = N * K, in = dims[l], out = dims[l + 1];
+    if (t < acc + nw) {                                                   // weight element (o, i) of the padded layer
+      uint32_t e = t - acc, o = e / K, i = e % K;
+      float w = (o < out && i < in) ? params[poff + o * in + i] : 0.0f;
+      __nv_bfloat16 hi, lo; split_bf16(w, hi, lo);
+      uint32_t dst = (i >> 3) * (N * 8) + o * 8 + (i & 7);
+      __nv_bfloat16 *base = reinterpret_cast<__nv_bfloat16 *>(wimg + net.w_off[l]);
+      base[dst] = hi; base[(size_t)N * K + dst] = lo;
+      return;
+    }
+    acc += nw;
+    if (t < acc + N) { uint32_t o = t - acc; bias[net.b_off[l] + o] = o < out ? params[poff + out * in + o] : 0.0f; return; }
+    acc += N; poff += out * in + out;
+  }
+}
+
 thread_local char g_err[512] = "";
 
 }  // namespace
@@ -294,6 +318,17 @@ int32_t abx_qnet_set_params(abx_qnet *q, const float *params, void *stream) {
   QCU(cudaMemcpyAsync(q->d_wimg, q->h_wimg.data(), q->net.w_bytes, cudaMemcpyHostToDevice, st));
   QCU(cudaMemcpyAsync(q->d_bias, q->h_bias.data(), sizeof(float) * q->net.n_bias, cudaMemcpyHostToDevice, st));
   QCU(cudaStreamSynchronize(st));
+  return ABX_OK;
+}
+
+int32_t abx_qnet_set_params_device(abx_qnet *q, const float *params_dev, void *stream) {
+  if (!q || !params_dev) return ABX_ERR_ARG;
+  QCU(cudaSetDevice(q->device));
+  int d[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; for (size_t i = 0; i < q->dims.size() && i < 9; i++) d[i] = q->dims[i];
+  uint32_t total = 0; for (int l = 0; l < q->net.n_layers; l++) total += (uint32_t)q->net.npad[l] * q->net.kpad[l] + q->net.npad[l];
+  abx_qnet_pack_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(q->net, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], params_dev, q->d_wimg, q->d_bias);
+  q->launches += 1;
+  QCU(cudaGetLastError());
   return ABX_OK;
 }
 

@@ -23,7 +23,8 @@ from .qnet import DEFAULT_DIMS, init_params, param_count, unpack_params
 
 
 class ReplayBuffer:
-    """Ring of finalised experience tuples (s[2], a, s'[2], r) on one device; the reference keeps an OrderedDict per agent (:119)."""
+    """Ring of finalised experience tuples (s[2], a, s'[2], r) on one device; the reference keeps an OrderedDict per agent (:119).
+    No operation here synchronises the device: every push writes a fixed number of rows with a validity flag, sampling draws among valid rows."""
 
     def __init__(self, capacity, device):
         import torch
@@ -32,29 +33,33 @@ class ReplayBuffer:
         self.sp = torch.zeros(self.capacity, 2, dtype=torch.float32, device=device)
         self.a = torch.zeros(self.capacity, dtype=torch.int64, device=device)
         self.r = torch.zeros(self.capacity, dtype=torch.float32, device=device)
+        self.valid = torch.zeros(self.capacity, dtype=torch.float32, device=device)
         self.size, self.head = 0, 0
 
     def push(self, trans):
-        """trans: [n, 6] (s0, s1, a, s'0, s'1, r) as DDQNExecutionEnv.step returns it; rows with r NaN (the reference's None:
-        neither accepted nor executed) or without a transition are skipped, as they would break np.array arithmetic in :485."""
+        """trans: [n, 6] (s0, s1, a, s'0, s'1, r) as DDQNExecutionEnv.step returns it.  Rows with r NaN (the reference's None: neither accepted
+        nor executed) or without a transition are stored as invalid and never sampled: they would break np.array arithmetic in :485."""
         import torch
         t = trans.to(self.device)
-        ok = ~torch.isnan(t).any(dim=1)
-        t = t[ok]
         n = int(t.shape[0])
         if n == 0:
             return 0
         if n > self.capacity:
             t, n = t[-self.capacity:], self.capacity
+        ok = ~torch.isnan(t).any(dim=1)
+        t = torch.nan_to_num(t, nan=0.0)
         idx = (self.head + torch.arange(n, device=self.device)) % self.capacity
-        self.s[idx] = t[:, 0:2].float(); self.a[idx] = t[:, 2].long(); self.sp[idx] = t[:, 3:5].float(); self.r[idx] = t[:, 5].float()
+        self.s[idx] = t[:, 0:2].float(); self.a[idx] = t[:, 2].long(); self.sp[idx] = t[:, 3:5].float(); self.r[idx] = t[:, 5].float(); self.valid[idx] = ok.float()
         self.head = (self.head + n) % self.capacity
         self.size = min(self.size + n, self.capacity)
         return n
 
+    def n_valid(self):
+        return int(self.valid[: self.size].sum()) if self.size else 0
+
     def sample(self, batch, generator=None):
         import torch
-        idx = torch.randint(0, self.size, (batch,), device=self.device, generator=generator)       # np.random.choice(current_size, batch) :463
+        idx = torch.multinomial(self.valid[: self.size], batch, replacement=True, generator=generator)   # np.random.choice(current_size, batch) :463 over the valid rows
         return self.s[idx], self.a[idx], self.sp[idx], self.r[idx]
 
 
@@ -80,9 +85,12 @@ class TorchMLP:
         return h
 
     def flat(self):
+        return self.flat_device().cpu().numpy().astype(np.float32)
+
+    def flat_device(self):
         import torch
         with torch.no_grad():
-            return torch.cat([p.reshape(-1) for p in self.params]).cpu().numpy().astype(np.float32)
+            return torch.cat([p.reshape(-1) for p in self.params]).contiguous()
 
     def load(self, other):
         import torch
@@ -126,7 +134,7 @@ class DDQNTrainer:
         loss = ((self.eval_net(s) - q_target) ** 2).mean()                                          # loss="mse" over all outputs
         loss.backward()
         self.opt.step()
-        cost = float(loss.detach())
+        cost = loss.detach()                                                                       # stays on the device: no synchronisation per update
         self.cost_hist.append(cost)
         if self.epsilon_increment is not None:
             self.epsilon = self.epsilon + self.epsilon_increment if self.epsilon < self.epsilon_max else self.epsilon_max

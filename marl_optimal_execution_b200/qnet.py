@@ -89,6 +89,24 @@ class QNetwork:
         if st != 0:
             raise _lib.AbxError("abx_qnet_set_params failed: %s" % self._L.abx_qnet_last_error().decode())
 
+    def set_params_device(self, flat_dev, stream=None):
+        """Same from a CUDA fp32 tensor, without leaving the device (asynchronous on the current stream); `self.params` (the host copy) is
+        NOT refreshed -- call `sync_host_params` when the host copy is needed."""
+        import torch
+        if not (isinstance(flat_dev, torch.Tensor) and flat_dev.is_cuda and flat_dev.dtype == torch.float32 and flat_dev.is_contiguous()
+                and flat_dev.numel() == param_count(self.dims)):
+            raise ValueError("flat_dev must be a contiguous CUDA fp32 tensor with %d elements" % param_count(self.dims))
+        sp = C.c_void_p(torch.cuda.current_stream(flat_dev.device).cuda_stream) if stream is None else stream
+        st = self._L.abx_qnet_set_params_device(self._h, C.c_void_p(flat_dev.data_ptr()), sp)
+        if st != 0:
+            raise _lib.AbxError("abx_qnet_set_params_device failed: %s" % self._L.abx_qnet_last_error().decode())
+        self._dev_params = flat_dev
+
+    def sync_host_params(self):
+        if getattr(self, "_dev_params", None) is not None:
+            self.params = self._dev_params.detach().cpu().numpy().astype(np.float32)
+        return self.params
+
     def forward(self, x, x_offset=0, want_q=True, want_actions=True, greedy_prob=1.0, seed=0, counter=0, out=None, stream=None):
         """x: CUDA fp64 tensor [n, stride]; the state is x[:, x_offset : x_offset + dims[0]].  Returns (q fp32 [n, n_out] | None,
         actions int32 [n] | None) as CUDA tensors."""

@@ -12,7 +12,7 @@ def test_kat1():
     book_cases.kat1()
 
 
-@pytest.mark.parametrize("fixture,n_ops", [("env_IBM_2003-01-14_s789.npz", 10000), ("ddqn_IBM_2003-01-14_s4242.npz", 30000)])
+@pytest.mark.parametrize("fixture,n_ops", [("env_IBM_2003-01-14_s789.npz", 10000), ("ddqn_IBM_2003-01-14_s4242.npz", 15000)])
 def test_recorded_operation_tape(golden_dir, fixture, n_ops):
     fills, modifies = book_cases.recorded_tape(golden_dir, fixture, n_ops, n_envs=64)
     assert fills > 500 and modifies > 1000

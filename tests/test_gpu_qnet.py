@@ -95,7 +95,14 @@ def test_acting_and_learning_loop_on_the_gpu(golden_dir):
 
     total, ticks = tr.run_episode(env, act, sync_fn=net.set_params, max_ticks=40)
     assert ticks == 40 and tr.learn_step_counter >= 6 and tr.buffer.size >= 30 * n
-    assert max(seen) > 10 and float(total.min()) > 0.0 and np.isfinite(tr.cost_hist).all()
+    assert max(seen) > 10 and float(total.min()) > 0.0 and np.isfinite([float(c) for c in tr.cost_hist]).all()
     st = env.stats()
     assert (st["flags"] & _lib.F_ERROR_MASK == 0).all()
     assert np.array_equal(net.params, tr.eval_net.flat())
+    # device-side weight push (no host round trip) builds the same operand image as the host path
+    x = states(3000, 1)
+    q_host, _ = net.forward(x, x_offset=6)
+    net.set_params(init_params(DEFAULT_DIMS, seed=77))
+    net.set_params_device(tr.eval_net.flat_device())
+    q_dev, _ = net.forward(x, x_offset=6)
+    assert torch.equal(q_host, q_dev) and np.array_equal(net.sync_host_params(), tr.eval_net.flat())
