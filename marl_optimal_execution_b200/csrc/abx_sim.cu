@@ -262,7 +262,7 @@ int32_t abx_sim_destroy(abx_sim *h) {
   cudaSetDevice(h->device);
   void *ptrs[] = {h->P.qkey, h->P.qpay0, h->P.qpay1, h->P.qcache, h->P.agents, h->P.lv_price, h->P.lv_qty, h->P.lv_ht, h->P.nodes, h->P.env,
                   h->P.trace, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff,
-                  h->P.envx, h->P.idtab, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_iact, h->d_msizes, h->d_trans, h->d_ops};
+                  h->P.envx, h->P.idtab, h->P.idbook, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_iact, h->d_msizes, h->d_trans, h->d_ops};
   for (void *p : ptrs) if (p) cudaFree(p);
   delete h->st; delete h->book_ids; delete h; return ABX_OK;
 }
@@ -445,7 +445,7 @@ int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_
   DA(h->P.qkey, E * c.queue_cap) DA(h->P.qpay0, E * c.queue_cap) DA(h->P.qpay1, E * c.queue_cap) DA(h->P.qcache, E * h->P.n_qgroups)
   DA(h->P.lv_price, E * 2 * c.level_cap) DA(h->P.lv_qty, E * 2 * c.level_cap) DA(h->P.lv_ht, E * 2 * c.level_cap)
   DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap) DA(h->d_stats, E)
-  DA(h->P.envx, E) DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
+  DA(h->P.envx, E) DA(h->P.idtab, E * h->P.n_ids) DA(h->P.idbook, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
   DA(h->d_ts, st->ts.size()) DA(h->d_first, st->first.size()) DA(h->d_rows, st->rows.size())
   DA(h->d_act, E * 3) DA(h->d_obs, E * 9) DA(h->d_rew, E) DA(h->d_done, E)
 #undef DA
@@ -465,6 +465,7 @@ int32_t abx_env_reset(abx_sim *h, void *stream) {
   if (!h || !h->is_env) return ABX_ERR_ARG;
   CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
   CU(cudaMemsetAsync(h->P.idtab, 0, sizeof(uint4) * (size_t)h->n_envs * h->P.n_ids, st));
+  CU(cudaMemsetAsync(h->P.idbook, 0, sizeof(uint2) * (size_t)h->n_envs * h->P.n_ids, st));
   abx_env_reset_kernel<<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, st>>>(h->P, h->smem_per_warp);
   h->launches += 1;
   CU(cudaGetLastError());
@@ -519,7 +520,7 @@ int32_t abx_dq_create(const abx_dq_config *cfg, const int64_t *stream5, int64_t 
   DA(h->P.qkey, E * c.queue_cap) DA(h->P.qpay0, E * c.queue_cap) DA(h->P.qpay1, E * c.queue_cap) DA(h->P.qcache, E * h->P.n_qgroups)
   DA(h->P.agents, E * c.n_agents) DA(h->P.lv_price, E * 2 * c.level_cap) DA(h->P.lv_qty, E * 2 * c.level_cap) DA(h->P.lv_ht, E * 2 * c.level_cap)
   DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap) DA(h->d_stats, E) DA(h->d_seeds, E)
-  DA(h->P.envx, E) DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
+  DA(h->P.envx, E) DA(h->P.idtab, E * h->P.n_ids) DA(h->P.idbook, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
   DA(h->d_ts, st->ts.size()) DA(h->d_first, st->first.size()) DA(h->d_rows, st->rows.size())
   DA(h->d_iact, E) DA(h->d_obs, E * 8) DA(h->d_trans, E * 6) DA(h->d_rew, E) DA(h->d_done, E) DA(h->d_msizes, E * (cfg->n_momentum > 0 ? cfg->n_momentum : 1))
 #undef DA
@@ -542,6 +543,7 @@ int32_t abx_dq_reset(abx_sim *h, const uint64_t *seeds, const int32_t *mom_sizes
   if (seeds) CU(cudaMemcpyAsync(h->d_seeds, seeds, sizeof(uint64_t) * h->n_envs, cudaMemcpyHostToDevice, st));
   if (mom_sizes && h->P.dq_n_mom > 0) CU(cudaMemcpyAsync(h->d_msizes, mom_sizes, sizeof(int32_t) * (size_t)h->n_envs * h->P.dq_n_mom, cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(h->P.idtab, 0, sizeof(uint4) * (size_t)h->n_envs * h->P.n_ids, st));
+  CU(cudaMemsetAsync(h->P.idbook, 0, sizeof(uint2) * (size_t)h->n_envs * h->P.n_ids, st));
   CU(cudaMemsetAsync(h->P.lobs, 0, sizeof(int4) * (size_t)h->n_envs * LOB_CAP * 3, st));
   abx_dq_reset_kernel<<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, st>>>(h->P, seeds ? h->d_seeds : nullptr, (mom_sizes && h->P.dq_n_mom > 0) ? h->d_msizes : nullptr, h->smem_per_warp);
   h->launches += 1;
@@ -618,11 +620,15 @@ int32_t abx_book_replay(abx_sim *h, const int64_t *ops9, int64_t n_ops, void *st
   if (st_rc != ABX_OK) return st_rc;
   int n_ids = (int)h->st->id_orig.size(); bool fresh = !h->reset_done;
   if (n_ids > h->P.n_ids) {                                            // grow the per-order history table (one 16-byte record per distinct order id), keeping its contents
-    uint4 *old = h->P.idtab; int old_n = h->P.n_ids; int new_n = n_ids + n_ids / 2 + 64; uint4 *nw = nullptr;
+    uint4 *old = h->P.idtab; uint2 *oldb = h->P.idbook; int old_n = h->P.n_ids; int new_n = n_ids + n_ids / 2 + 64; uint4 *nw = nullptr; uint2 *nb = nullptr;
     CU(cudaMalloc((void **)&nw, sizeof(uint4) * (size_t)h->n_envs * new_n)); CU(cudaMemsetAsync(nw, 0, sizeof(uint4) * (size_t)h->n_envs * new_n, st));
-    if (old && !fresh) CU(cudaMemcpy2DAsync(nw, sizeof(uint4) * new_n, old, sizeof(uint4) * old_n, sizeof(uint4) * old_n, h->n_envs, cudaMemcpyDeviceToDevice, st));
-    CU(cudaStreamSynchronize(st)); if (old) cudaFree(old);
-    h->P.idtab = nw; h->P.n_ids = new_n;
+    CU(cudaMalloc((void **)&nb, sizeof(uint2) * (size_t)h->n_envs * new_n)); CU(cudaMemsetAsync(nb, 0, sizeof(uint2) * (size_t)h->n_envs * new_n, st));
+    if (old && !fresh) {
+      CU(cudaMemcpy2DAsync(nw, sizeof(uint4) * new_n, old, sizeof(uint4) * old_n, sizeof(uint4) * old_n, h->n_envs, cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemcpy2DAsync(nb, sizeof(uint2) * new_n, oldb, sizeof(uint2) * old_n, sizeof(uint2) * old_n, h->n_envs, cudaMemcpyDeviceToDevice, st));
+    }
+    CU(cudaStreamSynchronize(st)); if (old) cudaFree(old); if (oldb) cudaFree(oldb);
+    h->P.idtab = nw; h->P.idbook = nb; h->P.n_ids = new_n;
   }
   if (n_ops > h->ops_cap) { if (h->d_ops) { CU(cudaStreamSynchronize(st)); cudaFree(h->d_ops); h->d_ops = nullptr; } CU(cudaMalloc((void **)&h->d_ops, sizeof(int64_t) * 9 * (size_t)n_ops)); h->ops_cap = n_ops; }
   CU(cudaMemcpyAsync(h->d_ops, dev_ops.data(), sizeof(int64_t) * 9 * (size_t)n_ops, cudaMemcpyHostToDevice, st));

@@ -61,7 +61,7 @@ struct WarpCtx {
   uint4 *qkey, *qpay0, *qpay1; ZiAgent *agents; uint4 *nodes; abx_trace_rec *tr;
   // shared memory of this warp
   ZiAgent *staged; uint32_t *obox; uint4 *qc; int32_t *lvp, *lvq; uint32_t *lvht; EnvX *ex;
-  uint4 *idt; int4 *lob;          // ABIDESEnv shape: replay agent's per-order table, stored LOBs (HBM)
+  uint4 *idt; int4 *lob; uint2 *idb;   // ABIDESEnv shape: replay agent's per-order table, stored LOBs, per-order book census (HBM)
   // registers describing the group fetched by q_fetch
   uint64_t my_hi; uint32_t my_uniq; uint32_t cur_mask; int cur_group, cur_lane;
 
@@ -76,6 +76,7 @@ struct WarpCtx {
     lvq = reinterpret_cast<int32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
     lvht = reinterpret_cast<uint32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
     ex = reinterpret_cast<EnvX *>(smem);
+    idb = P.idbook ? P.idbook + (size_t)env * P.n_ids : nullptr;
     idt = P.idtab ? P.idtab + (size_t)env * P.n_ids : nullptr; lob = P.lobs ? P.lobs + (size_t)env * LOB_CAP * 3 : nullptr;
     cur_group = cur_lane = -1; cur_mask = 0; my_hi = KEY_EMPTY; my_uniq = 0xffffffffu;
   }
@@ -232,6 +233,8 @@ struct WarpCtx {
   __device__ void envx_store() { sync(); uint4 *dst = reinterpret_cast<uint4 *>(P.envx + env); for (int i = lane; i < (int)(sizeof(EnvX) / 16); i += 32) __stcg(dst + i, reinterpret_cast<const uint4 *>(ex)[i]); }
   __device__ __forceinline__ uint4 id_load(int i) const { return ldcg4(idt + i); }
   __device__ __forceinline__ void id_store(int i, uint4 v) { if (lane == 0) __stcg(idt + i, v); __syncwarp(); }
+  __device__ __forceinline__ uint2 ib_load(int i) const { return __ldcg(idb + i); }
+  __device__ __forceinline__ void ib_store(int i, uint2 v) { if (lane == 0) __stcg(idb + i, v); __syncwarp(); }
   __device__ __forceinline__ int4 row_load(int r) const { return __ldg(P.st_rows + r); }
   __device__ __forceinline__ int64_t ts_load(int k) const { return __ldg(P.st_ts + k); }
   __device__ __forceinline__ int first_load(int k) const { return __ldg(P.st_first + k); }

@@ -62,3 +62,40 @@ def recorded_tape(golden_dir, fixture, n_ops, lib_path=None, n_envs=2):
     assert b.inside(0, True, 3) == o.inside(True, 3) and b.inside(0, False, 3) == o.inside(False, 3)
     b.close()
     return int((ref[:, 2] == EXEC).sum()) // 2, int((ops[:, 1] == 2).sum())
+
+
+def random_tape_vs_oracle(lib_path=None, seed=0, n_ops=6000, n_ids=40):
+    """Adversarial tape: few order ids re-used across prices and sides, so that head-slot copies (modifyOrder's slot-0 overwrite), ids resting
+    in several levels and modifies / cancels at stale prices all occur; every notification and the book after every operation must equal
+    the oracle book's (which is pinned to the reference)."""
+    rs = np.random.RandomState(seed)
+    ops, t = [], T0
+    for _ in range(n_ops):
+        t += int(rs.randint(0, 3))
+        kind = rs.choice(3, p=[0.5, 0.15, 0.35])
+        oid, is_buy = int(rs.randint(1, n_ids + 1)), int(rs.randint(0, 2))
+        price = 1000 + int(rs.randint(-6, 7)) + (0 if is_buy else 2)
+        qty = int(rs.randint(1, 60))
+        ops.append(op(t, int(kind), int(rs.randint(1, 9)), oid, is_buy, price, qty, price, int(rs.randint(1, 60))))
+    ops = np.array(ops, dtype=np.int64)
+    b = OrderBookBatch(n_envs=2, trace_cap=16 * n_ops, level_cap=64, order_cap=8192, lib_path=lib_path)
+    b.replay(ops)
+    notes, snaps = b.notifications(1)
+    o = OracleBook(stream_history=10)
+    ref_snaps = []
+    for r in ops:
+        o.set_time(int(r[0]))
+        if r[1] == 0:
+            o.limit(int(r[2]), int(r[3]), bool(r[4]), int(r[5]), int(r[6]))
+        elif r[1] == 1:
+            o.cancel(int(r[2]), int(r[3]), bool(r[4]), int(r[5]))
+        else:
+            o.modify(int(r[2]), int(r[3]), bool(r[4]), int(r[5]), int(r[7]), int(r[8]))
+        ref_snaps.append((o.n_levels(True), o.n_levels(False), o.n_resting()) + tuple(x for pq in (o.inside(True, 3) + [(0, 0)] * 3)[:3] for x in pq)
+                         + tuple(x for pq in (o.inside(False, 3) + [(0, 0)] * 3)[:3] for x in pq) + (o.last_trade if o.last_trade is not None else -1,))
+    ref = o.take_notes()
+    assert notes.shape == ref.shape and np.array_equal(notes[:, :8], ref[:, :8]), (notes.shape, ref.shape)
+    assert np.array_equal(snaps, np.array(ref_snaps, dtype=np.int64))
+    assert (b.stats()["flags"] == 1).all()
+    b.close()
+    return int((ref[:, 2] == MOD).sum()), int((ref[:, 2] == EXEC).sum())

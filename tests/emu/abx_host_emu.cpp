@@ -77,6 +77,8 @@ struct HostCtx {
   void node_store(uint32_t i, const NodeRec &r) { uint4 v; v.x = r.id; v.y = (uint32_t)r.qty; v.z = r.agent; v.w = r.next; nodes[i] = v; }
   // ---- ABIDESEnv shape ----
   EnvX *envx() { return P.envx + env; }
+  uint2 ib_load(int i) { return P.idbook[(size_t)env * P.n_ids + i]; }
+  void ib_store(int i, uint2 v) { P.idbook[(size_t)env * P.n_ids + i] = v; }
   uint4 id_load(int i) { return idt[i]; }
   void id_store(int i, uint4 v) { idt[i] = v; }
   int4 row_load(int r) { return P.st_rows[r]; }
@@ -102,7 +104,7 @@ struct abx_sim {
   SimParams P; int n_envs; bool reset_done;
   std::vector<uint4> qkey, qpay0, qpay1, qcache, nodes; std::vector<ZiAgent> agents; std::vector<int32_t> lvp, lvq; std::vector<uint32_t> lvht;
   std::vector<EnvState> env; std::vector<abx_trace_rec> trace; std::vector<uint64_t> tbits; std::vector<uint8_t> tkinds; std::vector<int64_t> toff;
-  bool is_env; EnvStreamHost st; std::vector<EnvX> envx; std::vector<uint4> idtab; std::vector<int4> lobs;
+  bool is_env; EnvStreamHost st; std::vector<EnvX> envx; std::vector<uint4> idtab; std::vector<int4> lobs; std::vector<uint2> idbook;
 };
 
 extern "C" {
@@ -220,16 +222,16 @@ int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_
   h->qkey.resize(E * c.queue_cap); h->qpay0.resize(E * c.queue_cap); h->qpay1.resize(E * c.queue_cap); h->qcache.resize(E * h->P.n_qgroups);
   h->agents.resize(4); h->lvp.resize(E * 2 * c.level_cap); h->lvq.resize(E * 2 * c.level_cap); h->lvht.resize(E * 2 * c.level_cap);
   h->nodes.resize(E * c.order_cap); h->env.resize(E); h->trace.resize(E * (size_t)c.trace_cap);
-  h->envx.resize(E); h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3);
+  h->envx.resize(E); h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3); h->idbook.resize(E * h->P.n_ids);
   h->P.qkey = h->qkey.data(); h->P.qpay0 = h->qpay0.data(); h->P.qpay1 = h->qpay1.data(); h->P.qcache = h->qcache.data(); h->P.agents = h->agents.data();
   h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
-  h->P.trace = c.trace_cap ? h->trace.data() : nullptr; h->P.envx = h->envx.data(); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data();
+  h->P.trace = c.trace_cap ? h->trace.data() : nullptr; h->P.envx = h->envx.data(); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); h->P.idbook = h->idbook.data();
   h->P.st_ts = h->st.ts.data(); h->P.st_first = h->st.first.data(); h->P.st_rows = h->st.rows.data();
   *out = h; return ABX_OK;
 }
 int32_t abx_env_reset(abx_sim *h, void *stream) {
   (void)stream; if (!h || !h->is_env) return ABX_ERR_ARG;
-  memset(h->idtab.data(), 0, h->idtab.size() * sizeof(uint4));
+  memset(h->idtab.data(), 0, h->idtab.size() * sizeof(uint4)); memset(h->idbook.data(), 0, h->idbook.size() * sizeof(uint2));
   for (int e = 0; e < h->n_envs; e++) {
     EnvState s; init_env_state(h->P, 0, s); s.last_trade = -1; init_envx(h->P, h->envx[e]);     // no oracle: last_trade None (ExchangeAgent.py:97-102)
     HostCtx ctx(h->P, e); ctx.q_clear(); EnvSimHost sim(ctx, h->P, s, e); sim.env_reset(); h->env[e] = sim.s;
@@ -262,16 +264,16 @@ int32_t abx_dq_create(const abx_dq_config *cfg, const int64_t *stream5, int64_t 
   h->qkey.resize(E * c.queue_cap); h->qpay0.resize(E * c.queue_cap); h->qpay1.resize(E * c.queue_cap); h->qcache.resize(E * h->P.n_qgroups);
   h->agents.resize(E * c.n_agents); h->lvp.resize(E * 2 * c.level_cap); h->lvq.resize(E * 2 * c.level_cap); h->lvht.resize(E * 2 * c.level_cap);
   h->nodes.resize(E * c.order_cap); h->env.resize(E); h->trace.resize(E * (size_t)c.trace_cap);
-  h->envx.resize(E); h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3);
+  h->envx.resize(E); h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3); h->idbook.resize(E * h->P.n_ids);
   h->P.qkey = h->qkey.data(); h->P.qpay0 = h->qpay0.data(); h->P.qpay1 = h->qpay1.data(); h->P.qcache = h->qcache.data(); h->P.agents = h->agents.data();
   h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
-  h->P.trace = c.trace_cap ? h->trace.data() : nullptr; h->P.envx = h->envx.data(); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data();
+  h->P.trace = c.trace_cap ? h->trace.data() : nullptr; h->P.envx = h->envx.data(); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); h->P.idbook = h->idbook.data();
   h->P.st_ts = h->st.ts.data(); h->P.st_first = h->st.first.data(); h->P.st_rows = h->st.rows.data();
   *out = h; return ABX_OK;
 }
 int32_t abx_dq_reset(abx_sim *h, const uint64_t *seeds, const int32_t *mom_sizes, void *stream) {
   (void)stream; if (!h || !h->is_env || h->P.c.population != 2) return ABX_ERR_ARG;
-  memset(h->idtab.data(), 0, h->idtab.size() * sizeof(uint4)); memset(h->lobs.data(), 0, h->lobs.size() * sizeof(int4));
+  memset(h->idtab.data(), 0, h->idtab.size() * sizeof(uint4)); memset(h->lobs.data(), 0, h->lobs.size() * sizeof(int4)); memset(h->idbook.data(), 0, h->idbook.size() * sizeof(uint2));
   for (int e = 0; e < h->n_envs; e++) {
     uint64_t seed = seeds ? seeds[e] : 0;
     EnvState s; init_env_state(h->P, seed, s); s.last_trade = -1; init_envx(h->P, h->envx[e]);
@@ -319,6 +321,7 @@ int32_t abx_book_create(int32_t stream_history, int32_t level_cap, int32_t order
   h->P.qkey = h->qkey.data(); h->P.qpay0 = h->qpay0.data(); h->P.qpay1 = h->qpay1.data(); h->P.qcache = h->qcache.data(); h->P.agents = h->agents.data();
   h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
   h->P.trace = c.trace_cap ? h->trace.data() : nullptr; h->P.envx = h->envx.data();
+  g_book_ids.erase(h);                                                 // a recycled handle address must not inherit another book's id map
   *out = h; return ABX_OK;
 }
 int32_t abx_book_replay(abx_sim *h, const int64_t *ops9, int64_t n_ops, void *stream) {
@@ -328,6 +331,9 @@ int32_t abx_book_replay(abx_sim *h, const int64_t *ops9, int64_t n_ops, void *st
   if (n_ids > h->P.n_ids) {
     int new_n = n_ids + n_ids / 2 + 64; std::vector<uint4> nw((size_t)h->n_envs * new_n); memset(nw.data(), 0, nw.size() * sizeof(uint4));
     if (!fresh) for (int e = 0; e < h->n_envs; e++) memcpy(&nw[(size_t)e * new_n], &h->idtab[(size_t)e * h->P.n_ids], sizeof(uint4) * h->P.n_ids);
+    std::vector<uint2> nb((size_t)h->n_envs * new_n); memset(nb.data(), 0, nb.size() * sizeof(uint2));
+    if (!fresh) for (int e = 0; e < h->n_envs; e++) memcpy(&nb[(size_t)e * new_n], &h->idbook[(size_t)e * h->P.n_ids], sizeof(uint2) * h->P.n_ids);
+    h->idbook.swap(nb); h->P.idbook = h->idbook.data();
     h->idtab.swap(nw); h->P.idtab = h->idtab.data(); h->P.n_ids = new_n;
   }
   for (int e = 0; e < h->n_envs; e++) {

@@ -18,3 +18,9 @@ def test_kat1(emu):
 def test_recorded_operation_tape(emu, golden_dir, fixture, n_ops):
     fills, modifies = book_cases.recorded_tape(golden_dir, fixture, n_ops, emu)
     assert fills > 500 and modifies > 1000
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_adversarial_tape(emu, seed):
+    mods, execs = book_cases.random_tape_vs_oracle(emu, seed=seed)
+    assert mods > 200 and execs > 500

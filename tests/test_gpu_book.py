@@ -16,3 +16,9 @@ def test_kat1():
 def test_recorded_operation_tape(golden_dir, fixture, n_ops):
     fills, modifies = book_cases.recorded_tape(golden_dir, fixture, n_ops, n_envs=64)
     assert fills > 500 and modifies > 1000
+
+
+@pytest.mark.parametrize("seed", [0, 5])
+def test_adversarial_tape(seed):
+    mods, execs = book_cases.random_tape_vs_oracle(seed=seed, n_ops=20000)
+    assert mods > 500 and execs > 1500
