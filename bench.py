@@ -325,7 +325,8 @@ def run_ours(args, rank, local_rank, world):
                      "e2e": {"value": int(ge[:, 2].sum()) / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": 24 * args.env_envs_per_gpu,
                              "d2h_bytes_per_step": 81 * args.env_envs_per_gpu},
                      "gpu_launches": env_local["launches"], "workload": "ABIDESEnv.py shape: exchange + MarketReplayAgent (IBM 2003-01-14 LOBSTER sample day fixture) + "
-                     "DummyRLExecutionAgent (BUY 1e5, 30 s, order_level 2), random actions; one abx_env_step_kernel launch per step"}
+                     "DummyRLExecutionAgent (BUY 1e5, 30 s, order_level 2), random actions; one abx_env_step_kernel launch per step; the timed window is the whole episode "
+                     "(761 ticks) minus the start-up and warm-up steps"}
     dq_block = None
     if dq_local is not None:
         gd = D.gather_summaries(torch.tensor([dq_local["steps"], dq_local["msgs"], dq_local["e2e_steps"], dq_local["errs"]], dtype=torch.int64), device=dev)
@@ -428,7 +429,11 @@ def bench_env(args, rank, local_rank, dev, stream, sp):
     launches = env.launch_count - l0
     st = env.stats(stream=sp)
     m1 = int(st["messages"].sum())
-    # e2e: host (pinned) buffers through abx_env_step_host: actions H2D, obs/reward/done D2H every step
+    # e2e: host (pinned) buffers through abx_env_step_host: actions H2D, obs/reward/done D2H every step; a fresh episode (the timed
+    # window above may have used most of the day), same untimed start-up
+    env.reset(stream=sp)
+    for k in range(W + 1):
+        env.step(acts[k], stream=sp)
     a_pin = torch.rand(n, 3, dtype=torch.float64).pin_memory(); a_pin[:, 0] *= 0.04
     o_pin = torch.empty(n, 9, dtype=torch.float64).pin_memory(); r_pin = torch.empty(n, dtype=torch.float64).pin_memory()
     d_pin = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -531,10 +536,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-env", action="store_true", help="skip the ABIDESEnv steps/s measurement")
     ap.add_argument("--env-envs-per-gpu", type=int, default=8192)
-    ap.add_argument("--env-steps", type=int, default=40)
+    ap.add_argument("--env-steps", type=int, default=750, help="timed ABIDESEnv steps: 750 = the whole 761-tick episode after the start-up and warm-up steps")
     ap.add_argument("--no-ddqn", action="store_true", help="skip the DDQN execution shape (Q-network forward + environment step per tick)")
     ap.add_argument("--ddqn-envs-per-gpu", type=int, default=8192)
-    ap.add_argument("--ddqn-steps", type=int, default=40)
+    ap.add_argument("--ddqn-steps", type=int, default=200, help="timed DDQN decision ticks per sub-measurement (acting, e2e, training share one 660-tick day)")
     ap.add_argument("--ddqn-batch", type=int, default=4096, help="learner batch size of the DDQN training sub-measurement")
     args = ap.parse_args()
     quiet_stdout()
