@@ -344,7 +344,7 @@ def run_ours(args, rank, local_rank, world):
                     "training": {"value": int(gd[:, 0].sum()) / t_dq_train, "unit": "steps/s", "learn_steps": dq_local["learn_steps"], "batch": args.ddqn_batch,
                                  "replay_buffer_rows": dq_local["buffer"], "note": "same loop with the learner on: experience tuples into a device replay buffer, one "
                                  "train_neural_nets-style update (PyTorch fp32 autograd, RMSprop) every 5 ticks, new weights packed into the tcgen05 operand image on the device; no host synchronisation inside the loop; wall clock; "
-                                 "each rank trains its own copy (no gradient all-reduce in this round)"},
+                                 "with N ranks one policy is trained: the 38 k gradients are averaged by an NCCL all-reduce before every update"},
                     "gpu_launches": dq_local["launches"], "dtype": "int64+f64 (environment), bf16x3 -> fp32 accumulate (Q-network)",
                     "qnet_roofline": {"bound": "tensor", "achieved": q_ach, "peak": tf_peak[0], "unit": "TFLOP/s", "frac": q_ach / tf_peak[0], "traffic": None,
                                       "peak_source": tf_peak[1], "kernel": "abx_qnet_forward_kernel", "kernel_ms": dq_local["qnet_ms"],

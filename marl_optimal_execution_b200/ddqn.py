@@ -101,7 +101,7 @@ class TorchMLP:
 
 class DDQNTrainer:
     def __init__(self, dims=DEFAULT_DIMS, device="cpu", batch_size=32, learning_rate=0.01, reward_decay=0.98, replace_target_iter=5,
-                 epsilon_max=0.9, epsilon_increment=None, train_every=5, buffer_capacity=1 << 20, seed=0):
+                 epsilon_max=0.9, epsilon_increment=None, train_every=5, buffer_capacity=1 << 20, seed=0, sync_gradients=True):
         """Defaults are the agent's constructor defaults (:40-66)."""
         import torch
         self.device, self.batch_size, self.gamma = device, int(batch_size), float(reward_decay)
@@ -114,6 +114,7 @@ class DDQNTrainer:
         self.buffer = ReplayBuffer(buffer_capacity, device)
         self.gen = torch.Generator(device=device); self.gen.manual_seed(seed)
         self.learn_step_counter, self.train_step_counter, self.cost_hist = 0, 0, []
+        self.sync_gradients = bool(sync_gradients)
 
     def learn(self):
         """One train_neural_nets call (:449-505) on a batch from the shared buffer."""
@@ -133,6 +134,7 @@ class DDQNTrainer:
         self.opt.zero_grad(set_to_none=True)
         loss = ((self.eval_net(s) - q_target) ** 2).mean()                                          # loss="mse" over all outputs
         loss.backward()
+        self.allreduce_gradients()
         self.opt.step()
         cost = loss.detach()                                                                       # stays on the device: no synchronisation per update
         self.cost_hist.append(cost)
@@ -140,6 +142,23 @@ class DDQNTrainer:
             self.epsilon = self.epsilon + self.epsilon_increment if self.epsilon < self.epsilon_max else self.epsilon_max
         self.learn_step_counter += 1
         return cost
+
+    def allreduce_gradients(self):
+        """One policy trained by all ranks: average the 38 k fp32 gradients over the process group (NCCL over NVLink on the
+        GPU box, gloo in the CPU tests) before the optimizer step; every rank then applies the same update to identical weights.  No-op for a
+        single process or with sync_gradients=False (independent learners)."""
+        import torch
+        import torch.distributed as dist
+        if not self.sync_gradients or not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in self.eval_net.params])
+        dist.all_reduce(flat)
+        flat /= dist.get_world_size()
+        off = 0
+        for p in self.eval_net.params:
+            n = p.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            off += n
 
     def greedy_prob(self):
         """Probability of the network's action in choose_action (:349-357): epsilon once the buffer can feed a batch, else 0 (all random)."""

@@ -50,3 +50,32 @@ def test_shard_range_properties():
             r = [shard_range(n, k, w) for k in range(w)]
             assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
             assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def _learner(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from marl_optimal_execution_b200 import distributed as D
+    from marl_optimal_execution_b200.ddqn import DDQNTrainer
+    D.init("gloo")
+    tr = DDQNTrainer(batch_size=8, seed=5, buffer_capacity=256)             # same seed: identical initial weights on every rank
+    rs = np.random.RandomState(100 + rank)                                  # different experience per rank
+    t = np.column_stack([rs.randint(0, 200, (64, 2)), rs.randint(0, 24, 64), rs.randint(0, 200, (64, 2)), rs.uniform(0, 20, 64)])
+    tr.buffer.push(torch.from_numpy(t))
+    for _ in range(3):
+        tr.learn()
+    q.put((rank, tr.eval_net.flat().tolist(), float(tr.cost_hist[0])))
+    torch.distributed.destroy_process_group()
+
+
+def test_one_policy_across_ranks_gradient_allreduce_world2():
+    """The only collective of the training path: ranks hold different experience, average their gradients, and end with identical weights."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    ps = [ctx.Process(target=_learner, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=180) for _ in ps)
+    [p.join(60) for p in ps]
+    (_, w0, c0), (_, w1, c1) = res
+    assert w0 == w1 and c0 != c1                                            # same policy, different local batches
