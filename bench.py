@@ -28,6 +28,19 @@ NS = 10 ** 9
 FIXTURE = os.path.join(ROOT, "tests", "golden", "env_IBM_2003-01-14_s789.npz")   # LOBSTER sample day as the reference parsed it
 DQ_FIXTURE = os.path.join(ROOT, "tests", "golden", "ddqn_IBM_2003-01-14_s4242.npz")   # same day, with the recorded MomentumAgent sizes
 QNET_FLOP_PER_ROW = 2 * (2 * 32 + 32 * 64 + 64 * 128 + 128 * 128 + 128 * 64 + 64 * 32 + 32 * 24)   # util/model/QNets.py:7-27 with the 2-entry state
+DAY_FIXTURES = ("env_IBM_2003-01-14_s789.npz", "env_IBM_2003-01-15_s4242.npz", "ddqn_IBM_2003-01-16_s99_sell.npz")   # three IBM LOBSTER sample days as the reference parsed them
+
+
+def replay_days():
+    """The replayed order streams, round robin over environments (IBM sample days; environment e replays day e % 3)."""
+    import numpy as np
+    out = []
+    for f in DAY_FIXTURES:
+        with np.load(os.path.join(ROOT, "tests", "golden", f)) as g:
+            out.append(g["stream"].copy())
+    return out
+
+
 B_MSG = 320                 # algorithmic bytes per LOB message (SURVEY.md section 8d, DESIGN.md "Roofline")
 PUBLISHED_MSGS_PER_S = 3100.4   # BASELINE.md section 1: reference's own sparse_zi_1000 run (tests/sparse_zi_1000.txt:22)
 
@@ -147,11 +160,11 @@ def oracle_env_steps_per_s(n_episodes, steps, threads):
     from concurrent.futures import ThreadPoolExecutor
     from oracle.oracle import OracleEnv, lib
     lib()
-    stream = np.load(FIXTURE)["stream"]
+    days = replay_days()
 
     def one(i):
         rng = np.random.RandomState(100 + i)
-        env = OracleEnv(stream)
+        env = OracleEnv(days[i % len(days)])
         env.step(np.array([0.02, 0.5, 0.5]))              # 00:00 -> 09:40 start-up, untimed like the GPU arm
         n0 = env.n_pops
         t0 = time.perf_counter()
@@ -174,11 +187,12 @@ def oracle_ddqn_ticks_per_s(n_episodes, ticks, threads):
     from oracle.oracle import OracleDDQNEnv, lib
     lib()
     with np.load(DQ_FIXTURE) as g:                         # materialise before the threads start: NpzFile is not thread safe
-        dq_stream, dq_sizes = g["stream"].copy(), g["mom_sizes"].copy()
+        dq_sizes = g["mom_sizes"].copy()
+    days = replay_days()
 
     def one(i):
         rng = np.random.RandomState(300 + i)
-        env = OracleDDQNEnv(dq_stream, dq_sizes)
+        env = OracleDDQNEnv(days[i % len(days)], dq_sizes)
         env.step(0)                                        # 00:00 -> 10:00 start-up, untimed like the GPU arm
         n0 = env.n_pops
         t0 = time.perf_counter()
@@ -195,7 +209,7 @@ def oracle_ddqn_ticks_per_s(n_episodes, ticks, threads):
 def reference_ddqn_block(cores):
     st, msgs, busy = oracle_ddqn_ticks_per_s(max(4 * cores, 8), 400, cores)
     return {"metric": "DDQN execution env ticks/sec", "value": st / busy, "unit": "steps/s", "msgs_per_s": msgs / busy, "cores": cores, "kind": "port",
-            "sample": "%d runs x 400 decision ticks after the 10:00 start-up (IBM 2003-01-14 LOBSTER fixture, random actions, no network), %d threads" % (max(4 * cores, 8), cores)}
+            "sample": "%d runs x 400 decision ticks after the 10:00 start-up (IBM 2003-01-14/15/16 round robin, random actions, no network), %d threads" % (max(4 * cores, 8), cores)}
 
 
 def run_reference(args, rank, world):
@@ -227,7 +241,7 @@ def run_reference(args, rank, world):
 def reference_env_block(cores):
     st, msgs, busy, wall = oracle_env_steps_per_s(max(2 * cores, 4), 400, cores)
     return {"metric": "ABIDESEnv steps/sec", "value": st / busy, "unit": "steps/s", "msgs_per_s": msgs / busy, "cores": cores, "kind": "port",
-            "sample": "%d episodes x 400 steps after the 09:40 start-up (IBM 2003-01-14 LOBSTER fixture), %d threads" % (max(2 * cores, 4), cores)}
+            "sample": "%d episodes x 400 steps after the 09:40 start-up (IBM 2003-01-14/15/16, round robin), %d threads" % (max(2 * cores, 4), cores)}
 
 
 def run_ours(args, rank, local_rank, world):
@@ -324,7 +338,7 @@ def run_ours(args, rank, local_rank, world):
                      "messages_per_env_step": int(ge[:, 1].sum()) / max(int(ge[:, 0].sum()), 1), "error_envs": int(ge[:, 3].sum()),
                      "e2e": {"value": int(ge[:, 2].sum()) / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": 24 * args.env_envs_per_gpu,
                              "d2h_bytes_per_step": 81 * args.env_envs_per_gpu},
-                     "gpu_launches": env_local["launches"], "workload": "ABIDESEnv.py shape: exchange + MarketReplayAgent (IBM 2003-01-14 LOBSTER sample day fixture) + "
+                     "gpu_launches": env_local["launches"], "workload": "ABIDESEnv.py shape: exchange + MarketReplayAgent (IBM 2003-01-14/15/16 LOBSTER sample days, round robin over environments) + "
                      "DummyRLExecutionAgent (BUY 1e5, 30 s, order_level 2), random actions; one abx_env_step_kernel launch per step; the timed window is the whole episode "
                      "(761 ticks) minus the start-up and warm-up steps"}
     dq_block = None
@@ -350,7 +364,7 @@ def run_ours(args, rank, local_rank, world):
                                       "peak_source": tf_peak[1], "kernel": "abx_qnet_forward_kernel", "kernel_ms": dq_local["qnet_ms"],
                                       "algorithmic_flop_per_row": QNET_FLOP_PER_ROW, "share_of_tick": dq_local["qnet_ms"] * Kd / dq_local["ms"],
                                       "note": "7 dependent layers per 128-row tile, %d tiles on 148 SMs: latency bound by construction, not a throughput kernel" % ((nd + 127) // 128)},
-                    "workload": "config/execution/marketreplay/execution_marketreplay_ddqn.py shape: exchange + MarketReplayAgent (IBM 2003-01-14 LOBSTER fixture) + 7 MomentumAgents + "
+                    "workload": "config/execution/marketreplay/execution_marketreplay_ddqn.py shape: exchange + MarketReplayAgent (IBM 2003-01-14/15/16 LOBSTER sample days, round robin) + 7 MomentumAgents + "
                     "TWAPExecutionAgent + DDQLearningExecutionAgent (BUY 5e5, 30 s ticks from 10:00), epsilon-greedy (0.9) actions from a random-init 2-32-64-128-128-64-32-24 network; "
                     "per tick one abx_qnet_forward_kernel + one abx_dq_step_kernel launch"}
     if rank != 0:
@@ -410,7 +424,7 @@ def bench_env(args, rank, local_rank, dev, stream, sp):
     from marl_optimal_execution_b200.env import ABIDESEnv
 
     n, K, W = args.env_envs_per_gpu, args.env_steps, max(args.warmup, 3)
-    env = ABIDESEnv(np.load(FIXTURE)["stream"], n_envs=n, device=local_rank)
+    env = ABIDESEnv(replay_days(), n_envs=n, device=local_rank)
     env.reset(stream=sp)
     gen = torch.Generator(device=dev); gen.manual_seed(args.seed + rank)
     acts = torch.rand(W + K + 1, n, 3, dtype=torch.float64, device=dev, generator=gen)
@@ -457,8 +471,7 @@ def bench_ddqn(args, rank, local_rank, dev, stream, sp):
     from marl_optimal_execution_b200.qnet import QNetwork
 
     n, K, W = args.ddqn_envs_per_gpu, args.ddqn_steps, max(args.warmup, 3)
-    g = np.load(DQ_FIXTURE)
-    env = DDQNExecutionEnv(g["stream"], n_envs=n, device=local_rank)
+    env = DDQNExecutionEnv(replay_days(), n_envs=n, device=local_rank)
     net = QNetwork(device=local_rank, seed=args.seed % 1000)
     env.reset(seeds=np.arange(rank * n, (rank + 1) * n, dtype=np.uint64) + np.uint64(args.seed), stream=sp)
     obs, trans, rew, done = env.step(torch.zeros(n, dtype=torch.int32, device=dev), stream=sp)      # 00:00 -> 10:00 start-up (~30 k messages/env), untimed

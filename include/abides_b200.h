@@ -245,6 +245,9 @@ int32_t abx_env_config_default(abx_env_config *cfg);
  * output: the parsed stream).  stream5: HOST int64 [n_rows][5] rows (t_ns since midnight, ORDER_ID, PRICE cents, SIZE,
  * is_buy) sorted by time; every environment replays this stream. */
 int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out);
+/* Several replayed days in one handle (the reference runs one process per date, e.g. config/execution/marketreplay/*_parallel.py): stream5 is the
+ * concatenation of the days' rows, row_offsets HOST int64 [n_days + 1]; environment e replays day e % n_days. */
+int32_t abx_env_create_days(const abx_env_config *cfg, const int64_t *stream5, const int64_t *row_offsets, int32_t n_days, int32_t n_envs, int32_t device, abx_sim **out);
 /* Replaces: ABIDESEnv.reset() (ABIDESEnv.py:51-57): initAgents + GymKernel.initRunner. */
 int32_t abx_env_reset(abx_sim *h, void *stream);
 /* Replaces: ABIDESEnv.step(action) (ABIDESEnv.py:30-49) -> GymKernel.stepRunner (GymKernel.py:158-306) for every environment.
@@ -281,6 +284,8 @@ typedef struct abx_dq_config {
 int32_t abx_dq_config_default(abx_dq_config *cfg);
 /* stream5 as abx_env_create. */
 int32_t abx_dq_create(const abx_dq_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out);
+/* Several days, as abx_env_create_days. */
+int32_t abx_dq_create_days(const abx_dq_config *cfg, const int64_t *stream5, const int64_t *row_offsets, int32_t n_days, int32_t n_envs, int32_t device, abx_sim **out);
 /* Agent construction + Kernel.runner start-up (Kernel.py:154-175).  seeds: HOST uint64 [n_envs] keying the MomentumAgent size draws
  * (random_state.randint(min_size, max_size), MomentumAgent.py:42); mom_sizes: optional HOST int32 [n_envs][n_momentum] that
  * overrides the draws (replay of a recorded reference run); either may be NULL (seed 0). */

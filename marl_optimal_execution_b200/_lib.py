@@ -147,6 +147,8 @@ def _bind(L):
     sig("abx_sim_launch_count", i64, vp)
     sig("abx_env_config_default", i32, P(EnvConfig))
     sig("abx_env_create", i32, P(EnvConfig), P(i64), i64, i32, i32, P(vp))
+    sig("abx_env_create_days", i32, P(EnvConfig), P(i64), P(i64), i32, i32, i32, P(vp))
+    sig("abx_dq_create_days", i32, P(DqConfig), P(i64), P(i64), i32, i32, i32, P(vp))
     sig("abx_env_reset", i32, vp, vp)
     sig("abx_env_step", i32, vp, vp, vp, vp, vp, vp)
     sig("abx_env_step_host", i32, vp, vp, vp, vp, vp, vp)

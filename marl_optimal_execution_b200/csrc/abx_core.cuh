@@ -148,6 +148,7 @@ struct SimParams {
   const int64_t *st_ts;                             // [n_ts]      distinct timestamps (ns), ascending
   const int32_t *st_first;                          // [n_ts + 1]  first row of each timestamp
   const int4 *st_rows;                              // [n_rows]    {dense id, PRICE cents, SIZE, is_buy}
+  const int4 *day_tab; int32_t n_days, pad_days;    // [n_days] {first entry of st_ts, timestamps, first entry of st_first, -}: environment e replays day e % n_days
   struct EnvX *envx;                                // [n_envs]
   uint4 *idtab;                                     // [n_envs][n_ids] {agent-view qty, price<<1|is_buy, last registration epoch, epoch mask}
   uint2 *idbook;                                    // [n_envs][n_ids] {nodes in the book carrying the id | several-levels flag << 31, price<<1|side of their level}
@@ -988,7 +989,7 @@ struct Sim {
     ta_wakeup(x->ra_flags);
     if (!(x->ra_flags & AF_HAS_OPEN) || !(x->ra_flags & AF_HAS_CLOSE)) return;
     int cur = x->wt_cursor;
-    if (cur >= P.n_ts) return;                                                          // wakeup_times[0] -> IndexError: nothing placed
+    if (cur >= c.n_ts()) return;                                                        // wakeup_times[0] -> IndexError: nothing placed
     set_wakeup(1, c.ts_load(cur)); if (c.onchip_writer()) x->wt_cursor = cur + 1;       // setWakeup(wakeup_times[0]); pop(0)
     int k = cur == 0 ? 0 : cur - 1;                                                     // orders_dict[currentTime]: the list's first entry is woken twice
     if (c.ts_load(k) != s.now) { s.flags |= ABX_F_UNSUPPORTED; return; }

@@ -205,6 +205,26 @@ static inline int book_ops_to_device(const int64_t *ops9, int64_t n, std::unorde
   }
   return ABX_OK;
 }
+// Several replayed days in one handle: environment e replays day e % n_days.  Each day has its own dense order-id space; the device arrays
+// are the concatenation of the days' arrays plus one {first timestamp, timestamps, first `first` entry, -} record per day.
+struct EnvDaysHost { std::vector<EnvStreamHost> days; std::vector<int64_t> ts; std::vector<int32_t> first; std::vector<int4> rows, day_tab; int max_ids; int64_t min_id; };
+static inline int env_build_days(const int64_t *s5, const int64_t *row_off, int n_days, int64_t max_gen_ids, EnvDaysHost &o) {
+  if (!s5 || !row_off || n_days < 1 || n_days > 4096) return ABX_ERR_ARG;
+  o.days.resize(n_days); o.max_ids = 1; o.min_id = 0x7fffffffffffLL;
+  for (int d = 0; d < n_days; d++) {
+    int64_t n = row_off[d + 1] - row_off[d]; EnvStreamHost &sd = o.days[d];
+    int st = env_build_stream(s5 + 5 * row_off[d], n, max_gen_ids, sd); if (st != ABX_OK) return st;
+    if (o.rows.size() + (size_t)n > 0x3fffffffu) return ABX_ERR_ARG;
+    int4 rec; rec.x = (int32_t)o.ts.size(); rec.y = (int32_t)sd.ts.size(); rec.z = (int32_t)o.first.size(); rec.w = 0; o.day_tab.push_back(rec);
+    int32_t row_base = (int32_t)o.rows.size();
+    o.ts.insert(o.ts.end(), sd.ts.begin(), sd.ts.end());
+    for (int32_t f : sd.first) o.first.push_back(f + row_base);
+    o.rows.insert(o.rows.end(), sd.rows.begin(), sd.rows.end());
+    if ((int)sd.id_orig.size() > o.max_ids) o.max_ids = (int)sd.id_orig.size();
+    if (sd.min_id < o.min_id) o.min_id = sd.min_id;
+  }
+  return ABX_OK;
+}
 ABX_HD void init_envx(const SimParams &P, EnvX &x) {
   x.ra_time = x.rl_time = P.c.start_ns; x.ra_cash = x.rl_cash = 0; x.rem_quantity = P.rl_quantity; x.executed_sum = 0.0;   // starting_cash 0 (agent_config.py:73,133)
   x.ra_shares = x.rl_shares = 0; x.ra_last_trade = x.rl_last_trade = 0; x.ra_flags = 0;

@@ -237,7 +237,7 @@ struct abx_sim {
   SimParams P; int n_envs, device; bool reset_done; size_t smem_per_warp; int64_t bytes, launches;
   uint64_t *d_seeds; uint32_t *d_init_err; abx_env_stats *d_stats; int64_t *d_until;
   uint64_t *d_tbits; uint8_t *d_tkinds; int64_t *d_toff;
-  bool is_env, is_dq; EnvStreamHost *st; int64_t *d_ts; int32_t *d_first; int4 *d_rows; double *d_act, *d_obs, *d_rew; uint8_t *d_done;
+  bool is_env, is_dq; EnvStreamHost *st; EnvDaysHost *dh; int4 *d_daytab; int64_t *d_ts; int32_t *d_first; int4 *d_rows; double *d_act, *d_obs, *d_rew; uint8_t *d_done;
   int32_t *d_iact, *d_msizes; double *d_trans;
   bool is_book; int64_t *d_ops; int64_t ops_cap; std::unordered_map<int64_t, int32_t> *book_ids;
 };
@@ -262,9 +262,9 @@ int32_t abx_sim_destroy(abx_sim *h) {
   cudaSetDevice(h->device);
   void *ptrs[] = {h->P.qkey, h->P.qpay0, h->P.qpay1, h->P.qcache, h->P.agents, h->P.lv_price, h->P.lv_qty, h->P.lv_ht, h->P.nodes, h->P.env,
                   h->P.trace, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff,
-                  h->P.envx, h->P.idtab, h->P.idbook, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_iact, h->d_msizes, h->d_trans, h->d_ops};
+                  h->P.envx, h->P.idtab, h->P.idbook, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_iact, h->d_msizes, h->d_trans, h->d_ops, h->d_daytab};
   for (void *p : ptrs) if (p) cudaFree(p);
-  delete h->st; delete h->book_ids; delete h; return ABX_OK;
+  delete h->st; delete h->dh; delete h->book_ids; delete h; return ABX_OK;
 }
 
 int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device, abx_sim **out) {
@@ -419,24 +419,25 @@ int32_t abx_sim_trace(abx_sim *h, int32_t env, abx_trace_rec *out, int32_t max_r
   EnvState s; CU(cudaMemcpyAsync(&s, h->P.env + env, sizeof(s), cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st));
   int n = (int)s.trace_n; if (n > max_recs) n = max_recs; if (n > h->P.c.trace_cap) n = h->P.c.trace_cap;
   if (n > 0) { CU(cudaMemcpyAsync(out, h->P.trace + (size_t)env * h->P.c.trace_cap, sizeof(abx_trace_rec) * n, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
-  if (h->is_env) for (int i = 0; i < n; i++) if (out[i].tag == 1 && (uint32_t)out[i].v[1] >= REPLAY_ID_BASE) out[i].v[1] = (int32_t)h->st->id_orig[(uint32_t)out[i].v[1] - REPLAY_ID_BASE];
+  if (h->is_env) { const std::vector<int64_t> &ido = h->dh ? h->dh->days[env % (int)h->dh->days.size()].id_orig : h->st->id_orig;
+    for (int i = 0; i < n; i++) if (out[i].tag == 1 && (uint32_t)out[i].v[1] >= REPLAY_ID_BASE) out[i].v[1] = (int32_t)ido[(uint32_t)out[i].v[1] - REPLAY_ID_BASE]; }
   *n_recs = n; return ABX_OK;
 }
 
 // ---------------- ABIDESEnv shape ----------------
 int32_t abx_env_config_default(abx_env_config *cfg) { return env_config_default(cfg); }
 
-int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
+int32_t abx_env_create_days(const abx_env_config *cfg, const int64_t *stream5, const int64_t *row_offsets, int32_t n_days, int32_t n_envs, int32_t device, abx_sim **out) {
   if (!out || n_envs < 1 || env_config_validate(cfg) != ABX_OK) return ABX_ERR_ARG;
-  EnvStreamHost *st = new (std::nothrow) EnvStreamHost(); if (!st) return ABX_ERR_ARG;
-  if (env_build_stream(stream5, n_rows, 4LL * cfg->n_horizon + 16, *st) != ABX_OK) { delete st; return ABX_ERR_ARG; }
+  EnvDaysHost *dh = new (std::nothrow) EnvDaysHost(); if (!dh) return ABX_ERR_ARG;
+  if (env_build_days(stream5, row_offsets, n_days, 4LL * cfg->n_horizon + 16, *dh) != ABX_OK) { delete dh; return ABX_ERR_ARG; }
   int ndev = 0; cudaError_t ce = cudaGetDeviceCount(&ndev);
-  if (ce != cudaSuccess || device < 0 || device >= ndev) { delete st; snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d not present (%d visible): %s", device, ndev, cudaGetErrorString(ce)); return ABX_ERR_CUDA; }
-  if (cudaSetDevice(device) != cudaSuccess) { delete st; return ABX_ERR_CUDA; }
-  abx_sim *h = new (std::nothrow) abx_sim(); if (!h) { delete st; return ABX_ERR_ARG; }
-  memset(h, 0, sizeof(*h)); h->is_env = true; h->st = st; h->n_envs = n_envs; h->device = device;
+  if (ce != cudaSuccess || device < 0 || device >= ndev) { delete dh; snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d not present (%d visible): %s", device, ndev, cudaGetErrorString(ce)); return ABX_ERR_CUDA; }
+  if (cudaSetDevice(device) != cudaSuccess) { delete dh; return ABX_ERR_CUDA; }
+  abx_sim *h = new (std::nothrow) abx_sim(); if (!h) { delete dh; return ABX_ERR_ARG; }
+  memset(h, 0, sizeof(*h)); h->is_env = true; h->dh = dh; h->n_envs = n_envs; h->device = device;
   env_fill_params(*cfg, h->P); h->P.n_envs = n_envs;
-  h->P.n_ts = (int)st->ts.size(); h->P.n_rows = (int)n_rows; h->P.n_ids = (int)st->id_orig.size();
+  h->P.n_ts = (int)dh->ts.size(); h->P.n_rows = (int)dh->rows.size(); h->P.n_ids = dh->max_ids; h->P.n_days = n_days;
   h->smem_per_warp = (warp_smem_bytes(h->P.c, true) + 15) & ~(size_t)15;
   size_t smem_cta = h->smem_per_warp * ABX_WARPS_PER_CTA;
   if (smem_cta > 227 * 1024) { abx_sim_destroy(h); return ABX_ERR_ARG; }
@@ -446,19 +447,23 @@ int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_
   DA(h->P.lv_price, E * 2 * c.level_cap) DA(h->P.lv_qty, E * 2 * c.level_cap) DA(h->P.lv_ht, E * 2 * c.level_cap)
   DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap) DA(h->d_stats, E)
   DA(h->P.envx, E) DA(h->P.idtab, E * h->P.n_ids) DA(h->P.idbook, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
-  DA(h->d_ts, st->ts.size()) DA(h->d_first, st->first.size()) DA(h->d_rows, st->rows.size())
+  DA(h->d_ts, dh->ts.size()) DA(h->d_first, dh->first.size()) DA(h->d_rows, dh->rows.size()) DA(h->d_daytab, dh->day_tab.size())
   DA(h->d_act, E * 3) DA(h->d_obs, E * 9) DA(h->d_rew, E) DA(h->d_done, E)
 #undef DA
-  CU(cudaMemcpy(h->d_ts, st->ts.data(), sizeof(int64_t) * st->ts.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->d_first, st->first.data(), sizeof(int32_t) * st->first.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->d_rows, st->rows.data(), sizeof(int4) * st->rows.size(), cudaMemcpyHostToDevice));
-  h->P.st_ts = h->d_ts; h->P.st_first = h->d_first; h->P.st_rows = h->d_rows;
+  CU(cudaMemcpy(h->d_ts, dh->ts.data(), sizeof(int64_t) * dh->ts.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_first, dh->first.data(), sizeof(int32_t) * dh->first.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_rows, dh->rows.data(), sizeof(int4) * dh->rows.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_daytab, dh->day_tab.data(), sizeof(int4) * dh->day_tab.size(), cudaMemcpyHostToDevice));
+  h->P.st_ts = h->d_ts; h->P.st_first = h->d_first; h->P.st_rows = h->d_rows; h->P.day_tab = h->d_daytab;
   if (smem_cta > 48 * 1024) {
     CU(cudaFuncSetAttribute(abx_env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
     CU(cudaFuncSetAttribute(abx_env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
     CU(cudaFuncSetAttribute(abx_env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
   }
   *out = h; return ABX_OK;
+}
+int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
+  int64_t off[2] = {0, n_rows}; return abx_env_create_days(cfg, stream5, off, 1, n_envs, device, out);
 }
 
 int32_t abx_env_reset(abx_sim *h, void *stream) {
@@ -499,17 +504,17 @@ int32_t abx_env_step_host(abx_sim *h, const double *actions, double *obs, double
 // ---------------- DDQN execution shape ----------------
 int32_t abx_dq_config_default(abx_dq_config *cfg) { return dq_config_default(cfg); }
 
-int32_t abx_dq_create(const abx_dq_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
+int32_t abx_dq_create_days(const abx_dq_config *cfg, const int64_t *stream5, const int64_t *row_offsets, int32_t n_days, int32_t n_envs, int32_t device, abx_sim **out) {
   if (!out || n_envs < 1 || dq_config_validate(cfg) != ABX_OK) return ABX_ERR_ARG;
-  EnvStreamHost *st = new (std::nothrow) EnvStreamHost(); if (!st) return ABX_ERR_ARG;
-  if (env_build_stream(stream5, n_rows, dq_max_generated_ids(*cfg), *st) != ABX_OK) { delete st; return ABX_ERR_ARG; }
+  EnvDaysHost *dh = new (std::nothrow) EnvDaysHost(); if (!dh) return ABX_ERR_ARG;
+  if (env_build_days(stream5, row_offsets, n_days, dq_max_generated_ids(*cfg), *dh) != ABX_OK) { delete dh; return ABX_ERR_ARG; }
   int ndev = 0; cudaError_t ce = cudaGetDeviceCount(&ndev);
-  if (ce != cudaSuccess || device < 0 || device >= ndev) { delete st; snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d not present (%d visible): %s", device, ndev, cudaGetErrorString(ce)); return ABX_ERR_CUDA; }
-  if (cudaSetDevice(device) != cudaSuccess) { delete st; return ABX_ERR_CUDA; }
-  abx_sim *h = new (std::nothrow) abx_sim(); if (!h) { delete st; return ABX_ERR_ARG; }
-  memset(h, 0, sizeof(*h)); h->is_env = true; h->is_dq = true; h->st = st; h->n_envs = n_envs; h->device = device;
+  if (ce != cudaSuccess || device < 0 || device >= ndev) { delete dh; snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d not present (%d visible): %s", device, ndev, cudaGetErrorString(ce)); return ABX_ERR_CUDA; }
+  if (cudaSetDevice(device) != cudaSuccess) { delete dh; return ABX_ERR_CUDA; }
+  abx_sim *h = new (std::nothrow) abx_sim(); if (!h) { delete dh; return ABX_ERR_ARG; }
+  memset(h, 0, sizeof(*h)); h->is_env = true; h->is_dq = true; h->dh = dh; h->n_envs = n_envs; h->device = device;
   dq_fill_params(*cfg, h->P); h->P.n_envs = n_envs;
-  h->P.n_ts = (int)st->ts.size(); h->P.n_rows = (int)n_rows; h->P.dq_order_base = (int)st->id_orig.size(); h->P.dq_id_limit = st->min_id;
+  h->P.n_ts = (int)dh->ts.size(); h->P.n_rows = (int)dh->rows.size(); h->P.dq_order_base = dh->max_ids; h->P.dq_id_limit = dh->min_id; h->P.n_days = n_days;
   int n_exec = cfg->n_twap + (cfg->has_ddqn ? 1 : 0);
   h->P.n_ids = h->P.dq_order_base + n_exec * EXEC_ORDER_CAP;
   h->smem_per_warp = (warp_smem_bytes(h->P.c, true) + 15) & ~(size_t)15;
@@ -521,20 +526,24 @@ int32_t abx_dq_create(const abx_dq_config *cfg, const int64_t *stream5, int64_t 
   DA(h->P.agents, E * c.n_agents) DA(h->P.lv_price, E * 2 * c.level_cap) DA(h->P.lv_qty, E * 2 * c.level_cap) DA(h->P.lv_ht, E * 2 * c.level_cap)
   DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap) DA(h->d_stats, E) DA(h->d_seeds, E)
   DA(h->P.envx, E) DA(h->P.idtab, E * h->P.n_ids) DA(h->P.idbook, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
-  DA(h->d_ts, st->ts.size()) DA(h->d_first, st->first.size()) DA(h->d_rows, st->rows.size())
+  DA(h->d_ts, dh->ts.size()) DA(h->d_first, dh->first.size()) DA(h->d_rows, dh->rows.size()) DA(h->d_daytab, dh->day_tab.size())
   DA(h->d_iact, E) DA(h->d_obs, E * 8) DA(h->d_trans, E * 6) DA(h->d_rew, E) DA(h->d_done, E) DA(h->d_msizes, E * (cfg->n_momentum > 0 ? cfg->n_momentum : 1))
 #undef DA
-  CU(cudaMemcpy(h->d_ts, st->ts.data(), sizeof(int64_t) * st->ts.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->d_first, st->first.data(), sizeof(int32_t) * st->first.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->d_rows, st->rows.data(), sizeof(int4) * st->rows.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_ts, dh->ts.data(), sizeof(int64_t) * dh->ts.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_first, dh->first.data(), sizeof(int32_t) * dh->first.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_rows, dh->rows.data(), sizeof(int4) * dh->rows.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_daytab, dh->day_tab.data(), sizeof(int4) * dh->day_tab.size(), cudaMemcpyHostToDevice));
   CU(cudaMemset(h->P.agents, 0, E * c.n_agents * sizeof(ZiAgent)));
-  h->P.st_ts = h->d_ts; h->P.st_first = h->d_first; h->P.st_rows = h->d_rows;
+  h->P.st_ts = h->d_ts; h->P.st_first = h->d_first; h->P.st_rows = h->d_rows; h->P.day_tab = h->d_daytab;
   if (smem_cta > 48 * 1024) {
     CU(cudaFuncSetAttribute(abx_dq_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
     CU(cudaFuncSetAttribute(abx_dq_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
     CU(cudaFuncSetAttribute(abx_dq_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
   }
   *out = h; return ABX_OK;
+}
+int32_t abx_dq_create(const abx_dq_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
+  int64_t off[2] = {0, n_rows}; return abx_dq_create_days(cfg, stream5, off, 1, n_envs, device, out);
 }
 
 int32_t abx_dq_reset(abx_sim *h, const uint64_t *seeds, const int32_t *mom_sizes, void *stream) {

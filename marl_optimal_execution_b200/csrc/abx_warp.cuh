@@ -236,8 +236,10 @@ struct WarpCtx {
   __device__ __forceinline__ uint2 ib_load(int i) const { return __ldcg(idb + i); }
   __device__ __forceinline__ void ib_store(int i, uint2 v) { if (lane == 0) __stcg(idb + i, v); __syncwarp(); }
   __device__ __forceinline__ int4 row_load(int r) const { return __ldg(P.st_rows + r); }
-  __device__ __forceinline__ int64_t ts_load(int k) const { return __ldg(P.st_ts + k); }
-  __device__ __forceinline__ int first_load(int k) const { return __ldg(P.st_first + k); }
+  __device__ __forceinline__ int4 day_rec() const { return __ldg(P.day_tab + (P.n_days > 1 ? env % P.n_days : 0)); }     // this environment's replayed day
+  __device__ __forceinline__ int n_ts() const { return day_rec().y; }
+  __device__ __forceinline__ int64_t ts_load(int k) const { return __ldg(P.st_ts + day_rec().x + k); }
+  __device__ __forceinline__ int first_load(int k) const { return __ldg(P.st_first + day_rec().z + k); }
   __device__ __forceinline__ void lob_store(int slot, const int32_t w[12]) {
     if (lane < 3) __stcg(lob + slot * 3 + lane, make_int4(w[lane * 4], w[lane * 4 + 1], w[lane * 4 + 2], w[lane * 4 + 3]));
     __syncwarp();

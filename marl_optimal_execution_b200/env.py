@@ -29,6 +29,18 @@ def env_config(lib=None, **overrides):
     return cfg
 
 
+def _pack_days(stream):
+    """One stream (int64 [n, 5]) or a list of them (one per replayed day; environment e replays day e % n_days) -> (rows, offsets)."""
+    days = [stream] if isinstance(stream, np.ndarray) else list(stream)
+    arrs = [np.ascontiguousarray(d, dtype=np.int64) for d in days]
+    for a in arrs:
+        if a.ndim != 2 or a.shape[1] != 5:
+            raise ValueError("stream must be int64 [n, 5]: (t_ns, ORDER_ID, PRICE, SIZE, is_buy)")
+    off = np.zeros(len(arrs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(a) for a in arrs])
+    return np.ascontiguousarray(np.concatenate(arrs, axis=0)), off
+
+
 def load_lobster_fixture(path):
     """tests/golden/*.npz written by tools/record_reference_env.py: the stream as the reference parsed it."""
     return np.ascontiguousarray(np.load(path)["stream"], dtype=np.int64)
@@ -43,12 +55,11 @@ class ABIDESEnv:
         self.n_envs = int(n_envs)
         self.device = int(device)
         self.action_size = int(self.cfg.order_level) + 1                  # get_action_space_size :128-134
-        st = np.ascontiguousarray(stream, dtype=np.int64)
-        if st.ndim != 2 or st.shape[1] != 5:
-            raise ValueError("stream must be int64 [n, 5]: (t_ns, ORDER_ID, PRICE, SIZE, is_buy)")
+        st, off = _pack_days(stream)
+        self.n_days = len(off) - 1
         self._h = C.c_void_p()
-        _lib.check(self._L, self._L.abx_env_create(C.byref(self.cfg), st.ctypes.data_as(C.POINTER(C.c_int64)), len(st), self.n_envs,
-                                                   self.device, C.byref(self._h)), "abx_env_create")
+        _lib.check(self._L, self._L.abx_env_create_days(C.byref(self.cfg), st.ctypes.data_as(C.POINTER(C.c_int64)), off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                        self.n_days, self.n_envs, self.device, C.byref(self._h)), "abx_env_create_days")
         self._torch_out = None
 
     def close(self):
@@ -156,12 +167,11 @@ class DDQNExecutionEnv(ABIDESEnv):
         self.n_envs, self.device = int(n_envs), int(device)
         self.n_agents = 2 + int(self.cfg.n_momentum) + int(self.cfg.n_twap) + (1 if self.cfg.has_ddqn else 0)
         self.n_exec = int(self.cfg.n_twap) + (1 if self.cfg.has_ddqn else 0)
-        st = np.ascontiguousarray(stream, dtype=np.int64)
-        if st.ndim != 2 or st.shape[1] != 5:
-            raise ValueError("stream must be int64 [n, 5]: (t_ns, ORDER_ID, PRICE, SIZE, is_buy)")
+        st, off = _pack_days(stream)
+        self.n_days = len(off) - 1
         self._h = C.c_void_p()
-        _lib.check(self._L, self._L.abx_dq_create(C.byref(self.cfg), st.ctypes.data_as(C.POINTER(C.c_int64)), len(st), self.n_envs,
-                                                  self.device, C.byref(self._h)), "abx_dq_create")
+        _lib.check(self._L, self._L.abx_dq_create_days(C.byref(self.cfg), st.ctypes.data_as(C.POINTER(C.c_int64)), off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                       self.n_days, self.n_envs, self.device, C.byref(self._h)), "abx_dq_create_days")
         self._torch_out = None
 
     def reset(self, seeds=None, mom_sizes=None, stream=None):

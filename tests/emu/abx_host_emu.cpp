@@ -82,8 +82,10 @@ struct HostCtx {
   uint4 id_load(int i) { return idt[i]; }
   void id_store(int i, uint4 v) { idt[i] = v; }
   int4 row_load(int r) { return P.st_rows[r]; }
-  int64_t ts_load(int k) { return P.st_ts[k]; }
-  int first_load(int k) { return P.st_first[k]; }
+  int4 day_rec() { return P.day_tab[P.n_days > 1 ? env % P.n_days : 0]; }
+  int n_ts() { return day_rec().y; }
+  int64_t ts_load(int k) { return P.st_ts[day_rec().x + k]; }
+  int first_load(int k) { return P.st_first[day_rec().z + k]; }
   void lob_store(int slot, const int32_t w[12]) { for (int k = 0; k < 3; k++) { int4 v; v.x = w[4 * k]; v.y = w[4 * k + 1]; v.z = w[4 * k + 2]; v.w = w[4 * k + 3]; lob[slot * 3 + k] = v; } }
   void lob_load(int slot, int32_t w[12]) { for (int k = 0; k < 3; k++) { int4 v = lob[slot * 3 + k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; } }
   int32_t mid_load(int k, int slot) { return reinterpret_cast<int32_t *>(lob)[k * MOM_MIDS + slot]; }
@@ -104,7 +106,7 @@ struct abx_sim {
   SimParams P; int n_envs; bool reset_done;
   std::vector<uint4> qkey, qpay0, qpay1, qcache, nodes; std::vector<ZiAgent> agents; std::vector<int32_t> lvp, lvq; std::vector<uint32_t> lvht;
   std::vector<EnvState> env; std::vector<abx_trace_rec> trace; std::vector<uint64_t> tbits; std::vector<uint8_t> tkinds; std::vector<int64_t> toff;
-  bool is_env; EnvStreamHost st; std::vector<EnvX> envx; std::vector<uint4> idtab; std::vector<int4> lobs; std::vector<uint2> idbook;
+  bool is_env; EnvStreamHost st; EnvDaysHost dh; bool has_days = false; std::vector<EnvX> envx; std::vector<uint4> idtab; std::vector<int4> lobs; std::vector<uint2> idbook;
 };
 
 extern "C" {
@@ -206,19 +208,20 @@ int32_t abx_sim_trace(abx_sim *h, int32_t env, abx_trace_rec *out, int32_t max_r
   (void)stream; if (!h || !out || !n_recs || env < 0 || env >= h->n_envs) return ABX_ERR_ARG;
   int n = (int)h->env[env].trace_n; if (n > max_recs) n = max_recs;
   if (n) memcpy(out, h->P.trace + (size_t)env * h->P.c.trace_cap, sizeof(abx_trace_rec) * n);
-  if (h->is_env) for (int i = 0; i < n; i++) if (out[i].tag == 1 && (uint32_t)out[i].v[1] >= REPLAY_ID_BASE) out[i].v[1] = (int32_t)h->st.id_orig[(uint32_t)out[i].v[1] - REPLAY_ID_BASE];
+  if (h->is_env) { const std::vector<int64_t> &ido = h->has_days ? h->dh.days[env % (int)h->dh.days.size()].id_orig : h->st.id_orig;
+    for (int i = 0; i < n; i++) if (out[i].tag == 1 && (uint32_t)out[i].v[1] >= REPLAY_ID_BASE) out[i].v[1] = (int32_t)ido[(uint32_t)out[i].v[1] - REPLAY_ID_BASE]; }
   *n_recs = n; return ABX_OK;
 }
 int64_t abx_sim_launch_count(const abx_sim *h) { (void)h; return 0; }
 
 typedef Sim<HostCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_ENV> EnvSimHost;
 int32_t abx_env_config_default(abx_env_config *cfg) { return env_config_default(cfg); }
-int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
+int32_t abx_env_create_days(const abx_env_config *cfg, const int64_t *stream5, const int64_t *row_offsets, int32_t n_days, int32_t n_envs, int32_t device, abx_sim **out) {
   (void)device; if (!out || n_envs < 1 || env_config_validate(cfg) != ABX_OK) return ABX_ERR_ARG;
-  abx_sim *h = new abx_sim(); memset(&h->P, 0, sizeof(h->P)); h->is_env = true; h->n_envs = n_envs; h->reset_done = false;
-  if (env_build_stream(stream5, n_rows, 4LL * cfg->n_horizon + 16, h->st) != ABX_OK) { delete h; return ABX_ERR_ARG; }
+  abx_sim *h = new abx_sim(); memset(&h->P, 0, sizeof(h->P)); h->is_env = true; h->has_days = true; h->n_envs = n_envs; h->reset_done = false;
+  if (env_build_days(stream5, row_offsets, n_days, 4LL * cfg->n_horizon + 16, h->dh) != ABX_OK) { delete h; return ABX_ERR_ARG; }
   env_fill_params(*cfg, h->P); h->P.n_envs = n_envs; const abx_sim_config &c = h->P.c; size_t E = n_envs;
-  h->P.n_ts = (int)h->st.ts.size(); h->P.n_rows = (int)n_rows; h->P.n_ids = (int)h->st.id_orig.size();
+  h->P.n_ts = (int)h->dh.ts.size(); h->P.n_rows = (int)h->dh.rows.size(); h->P.n_ids = h->dh.max_ids; h->P.n_days = n_days;
   h->qkey.resize(E * c.queue_cap); h->qpay0.resize(E * c.queue_cap); h->qpay1.resize(E * c.queue_cap); h->qcache.resize(E * h->P.n_qgroups);
   h->agents.resize(4); h->lvp.resize(E * 2 * c.level_cap); h->lvq.resize(E * 2 * c.level_cap); h->lvht.resize(E * 2 * c.level_cap);
   h->nodes.resize(E * c.order_cap); h->env.resize(E); h->trace.resize(E * (size_t)c.trace_cap);
@@ -226,8 +229,11 @@ int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_
   h->P.qkey = h->qkey.data(); h->P.qpay0 = h->qpay0.data(); h->P.qpay1 = h->qpay1.data(); h->P.qcache = h->qcache.data(); h->P.agents = h->agents.data();
   h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
   h->P.trace = c.trace_cap ? h->trace.data() : nullptr; h->P.envx = h->envx.data(); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); h->P.idbook = h->idbook.data();
-  h->P.st_ts = h->st.ts.data(); h->P.st_first = h->st.first.data(); h->P.st_rows = h->st.rows.data();
+  h->P.st_ts = h->dh.ts.data(); h->P.st_first = h->dh.first.data(); h->P.st_rows = h->dh.rows.data(); h->P.day_tab = h->dh.day_tab.data();
   *out = h; return ABX_OK;
+}
+int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
+  int64_t off[2] = {0, n_rows}; return abx_env_create_days(cfg, stream5, off, 1, n_envs, device, out);
 }
 int32_t abx_env_reset(abx_sim *h, void *stream) {
   (void)stream; if (!h || !h->is_env) return ABX_ERR_ARG;
@@ -254,12 +260,12 @@ int32_t abx_env_step(abx_sim *h, const double *a, double *o, double *r, uint8_t 
 // ---- DDQN execution shape ----
 typedef Sim<HostCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_DQ> DqSimHost;
 int32_t abx_dq_config_default(abx_dq_config *cfg) { return dq_config_default(cfg); }
-int32_t abx_dq_create(const abx_dq_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
+int32_t abx_dq_create_days(const abx_dq_config *cfg, const int64_t *stream5, const int64_t *row_offsets, int32_t n_days, int32_t n_envs, int32_t device, abx_sim **out) {
   (void)device; if (!out || n_envs < 1 || dq_config_validate(cfg) != ABX_OK) return ABX_ERR_ARG;
-  abx_sim *h = new abx_sim(); memset(&h->P, 0, sizeof(h->P)); h->is_env = true; h->n_envs = n_envs; h->reset_done = false;
-  if (env_build_stream(stream5, n_rows, dq_max_generated_ids(*cfg), h->st) != ABX_OK) { delete h; return ABX_ERR_ARG; }
+  abx_sim *h = new abx_sim(); memset(&h->P, 0, sizeof(h->P)); h->is_env = true; h->has_days = true; h->n_envs = n_envs; h->reset_done = false;
+  if (env_build_days(stream5, row_offsets, n_days, dq_max_generated_ids(*cfg), h->dh) != ABX_OK) { delete h; return ABX_ERR_ARG; }
   dq_fill_params(*cfg, h->P); h->P.n_envs = n_envs; const abx_sim_config &c = h->P.c; size_t E = n_envs;
-  h->P.n_ts = (int)h->st.ts.size(); h->P.n_rows = (int)n_rows; h->P.dq_order_base = (int)h->st.id_orig.size(); h->P.dq_id_limit = h->st.min_id;
+  h->P.n_ts = (int)h->dh.ts.size(); h->P.n_rows = (int)h->dh.rows.size(); h->P.dq_order_base = h->dh.max_ids; h->P.dq_id_limit = h->dh.min_id; h->P.n_days = n_days;
   h->P.n_ids = h->P.dq_order_base + (cfg->n_twap + (cfg->has_ddqn ? 1 : 0)) * EXEC_ORDER_CAP;
   h->qkey.resize(E * c.queue_cap); h->qpay0.resize(E * c.queue_cap); h->qpay1.resize(E * c.queue_cap); h->qcache.resize(E * h->P.n_qgroups);
   h->agents.resize(E * c.n_agents); h->lvp.resize(E * 2 * c.level_cap); h->lvq.resize(E * 2 * c.level_cap); h->lvht.resize(E * 2 * c.level_cap);
@@ -268,8 +274,11 @@ int32_t abx_dq_create(const abx_dq_config *cfg, const int64_t *stream5, int64_t 
   h->P.qkey = h->qkey.data(); h->P.qpay0 = h->qpay0.data(); h->P.qpay1 = h->qpay1.data(); h->P.qcache = h->qcache.data(); h->P.agents = h->agents.data();
   h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
   h->P.trace = c.trace_cap ? h->trace.data() : nullptr; h->P.envx = h->envx.data(); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); h->P.idbook = h->idbook.data();
-  h->P.st_ts = h->st.ts.data(); h->P.st_first = h->st.first.data(); h->P.st_rows = h->st.rows.data();
+  h->P.st_ts = h->dh.ts.data(); h->P.st_first = h->dh.first.data(); h->P.st_rows = h->dh.rows.data(); h->P.day_tab = h->dh.day_tab.data();
   *out = h; return ABX_OK;
+}
+int32_t abx_dq_create(const abx_dq_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
+  int64_t off[2] = {0, n_rows}; return abx_dq_create_days(cfg, stream5, off, 1, n_envs, device, out);
 }
 int32_t abx_dq_reset(abx_sim *h, const uint64_t *seeds, const int32_t *mom_sizes, void *stream) {
   (void)stream; if (!h || !h->is_env || h->P.c.population != 2) return ABX_ERR_ARG;

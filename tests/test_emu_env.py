@@ -63,3 +63,24 @@ def test_marketreplay_config_matches_oracle(emu, golden_dir):
     assert int(st["pop_hash"]) == o.pop_hash() == int(g["pop_hash_ckpt"][-1])
     p, nt, sn = env.split_trace(0)
     assert np.array_equal(p, o.trace("pops")) and np.array_equal(nt, o.trace("notes")) and np.array_equal(sn, o.trace("snaps"))
+
+
+def test_several_days_in_one_batch(emu, golden_dir):
+    """Environment e replays day e % n_days: two recorded reference episodes (IBM 2003-01-14 and 2003-01-15) side by side in one handle,
+    each bit-exact against its own oracle; a third and fourth environment repeat the days."""
+    ga = np.load(os.path.join(golden_dir, "env_IBM_2003-01-14_s789.npz"))
+    gb = np.load(os.path.join(golden_dir, "env_IBM_2003-01-15_s4242.npz"))
+    L = _lib.load(emu)
+    env = ABIDESEnv([ga["stream"], gb["stream"]], n_envs=4, cfg=env_config(L, hash_pops=1), lib_path=emu)
+    env.reset()
+    oa, ob = OracleEnv(ga["stream"]), OracleEnv(gb["stream"])
+    n = 120
+    for k in range(n):
+        acts = np.stack([ga["actions"][k], gb["actions"][k], ga["actions"][k], gb["actions"][k]])
+        obs, rew, done, _ = env.step(acts)
+        xa, _, _, _ = oa.step(ga["actions"][k]); xb, _, _, _ = ob.step(gb["actions"][k])
+        assert np.allclose(obs[0][: len(xa)], xa, rtol=1e-9, atol=1e-12) and np.allclose(obs[1][: len(xb)], xb, rtol=1e-9, atol=1e-12), k
+        assert np.allclose(obs[0, :9], np.nan_to_num(ga["obs"][k], nan=0.0), rtol=1e-6, atol=1e-12) and np.allclose(obs[1, :9], np.nan_to_num(gb["obs"][k], nan=0.0), rtol=1e-6, atol=1e-12)
+    st = env.stats()
+    assert int(st["pop_hash"][0]) == int(st["pop_hash"][2]) == oa.pop_hash() and int(st["pop_hash"][1]) == int(st["pop_hash"][3]) == ob.pop_hash()
+    assert int(st["messages"][0]) == oa.n_pops and int(st["messages"][1]) == ob.n_pops and (st["flags"] & _lib.F_ERROR_MASK == 0).all()

@@ -76,3 +76,39 @@ def test_marketreplay_config_on_gpu(golden_dir):
     assert np.array_equal(p, o.trace("pops")) and np.array_equal(nt, o.trace("notes")) and np.array_equal(sn, o.trace("snaps"))
     assert np.array_equal(nt[: len(g["notes_head"])], g["notes_head"]) and np.array_equal(sn[: len(g["snaps_head"])], g["snaps_head"])
     assert int(st["max_queue"][0]) == o.counter("max_queue")
+
+
+def test_several_days_in_one_batch(golden_dir):
+    """Environment e replays day e % n_days (abx_env_create_days / abx_dq_create_days): three IBM days side by side, each environment
+    bit-exact against the oracle of its own day; ABIDESEnv and the DDQN execution shape."""
+    from marl_optimal_execution_b200.env import DDQNExecutionEnv, dq_config
+    from oracle.oracle import OracleDDQNEnv
+    gs = [np.load(os.path.join(golden_dir, f)) for f in ("env_IBM_2003-01-14_s789.npz", "env_IBM_2003-01-15_s4242.npz", "ddqn_IBM_2003-01-16_s99_sell.npz")]
+    days = [g["stream"] for g in gs]
+    env = ABIDESEnv(days, n_envs=6, cfg=env_config(hash_pops=1))
+    env.reset()
+    orc = [OracleEnv(d) for d in days]
+    rs = np.random.RandomState(0)
+    for k in range(150):
+        a = np.array([rs.uniform(0, 0.04), rs.uniform(), rs.uniform()])
+        obs, rew, done, _ = env.step(np.tile(a, (6, 1)))
+        for d, o in enumerate(orc):
+            x, _, _, _ = o.step(a)
+            assert np.allclose(obs[d][: len(x)], x, rtol=1e-9, atol=1e-12) and np.array_equal(obs[d], obs[d + 3]), (k, d)
+    st = env.stats()
+    assert [int(h) for h in st["pop_hash"]] == [o.pop_hash() for o in orc] * 2 and (st["flags"] & _lib.F_ERROR_MASK == 0).all()
+    ms = gs[2]["mom_sizes"].astype(np.int32)
+    denv = DDQNExecutionEnv(days, n_envs=3, cfg=dq_config(hash_pops=1))
+    denv.reset(mom_sizes=np.tile(ms, (3, 1)))
+    dorc = [OracleDDQNEnv(d, ms) for d in days]
+    obs, trans, rew, done = denv.step(None)
+    for o in dorc:
+        o.step(0)
+    for k in range(60):
+        a = int(rs.randint(0, 24))
+        obs, trans, rew, done = denv.step(np.full(3, a, dtype=np.int32))
+        for d, o in enumerate(dorc):
+            oo, otr, orw, od = o.step(a)
+            assert np.allclose(obs[d], oo, rtol=1e-9, atol=1e-12) and np.isclose(rew[d], orw, rtol=1e-9, atol=1e-12), (k, d)
+    dst = denv.stats()
+    assert [int(h) for h in dst["pop_hash"]] == [o.pop_hash() for o in dorc] and (dst["flags"] & _lib.F_ERROR_MASK == 0).all()
