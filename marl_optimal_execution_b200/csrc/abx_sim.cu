@@ -233,6 +233,10 @@ static thread_local char g_cuda_err[512] = "";
 #define CU(call)                                                                                         \
   do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_cuda_err, sizeof(g_cuda_err), "%s at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); return ABX_ERR_CUDA; } } while (0)
 
+// inside the create functions, once the handle exists: a failing CUDA call must not leak it
+#define CUH(call)                                                                                        \
+  do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_cuda_err, sizeof(g_cuda_err), "%s at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); abx_sim_destroy(h); return ABX_ERR_CUDA; } } while (0)
+
 struct abx_sim {
   SimParams P; int n_envs, device; bool reset_done; size_t smem_per_warp; int64_t bytes, launches;
   uint64_t *d_seeds; uint32_t *d_init_err; abx_env_stats *d_stats; int64_t *d_until;
@@ -287,11 +291,11 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
     DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3) }
 #undef DA
   if (smem_cta > 48 * 1024) {
-    CU(cudaFuncSetAttribute((const void *)run_kernel_for(*cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
-    CU(cudaFuncSetAttribute(abx_reset_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
-    CU(cudaFuncSetAttribute(abx_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CUH(cudaFuncSetAttribute((const void *)run_kernel_for(*cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CUH(cudaFuncSetAttribute(abx_reset_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CUH(cudaFuncSetAttribute(abx_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
   }
-  CU(cudaMemset(h->P.agents, 0, E * c.n_agents * sizeof(ZiAgent)));
+  CUH(cudaMemset(h->P.agents, 0, E * c.n_agents * sizeof(ZiAgent)));
   *out = h; return ABX_OK;
 }
 int64_t abx_sim_device_bytes(const abx_sim *h) { return h ? h->bytes : 0; }
@@ -450,15 +454,15 @@ int32_t abx_env_create_days(const abx_env_config *cfg, const int64_t *stream5, c
   DA(h->d_ts, dh->ts.size()) DA(h->d_first, dh->first.size()) DA(h->d_rows, dh->rows.size()) DA(h->d_daytab, dh->day_tab.size())
   DA(h->d_act, E * 3) DA(h->d_obs, E * 9) DA(h->d_rew, E) DA(h->d_done, E)
 #undef DA
-  CU(cudaMemcpy(h->d_ts, dh->ts.data(), sizeof(int64_t) * dh->ts.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->d_first, dh->first.data(), sizeof(int32_t) * dh->first.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->d_rows, dh->rows.data(), sizeof(int4) * dh->rows.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->d_daytab, dh->day_tab.data(), sizeof(int4) * dh->day_tab.size(), cudaMemcpyHostToDevice));
+  CUH(cudaMemcpy(h->d_ts, dh->ts.data(), sizeof(int64_t) * dh->ts.size(), cudaMemcpyHostToDevice));
+  CUH(cudaMemcpy(h->d_first, dh->first.data(), sizeof(int32_t) * dh->first.size(), cudaMemcpyHostToDevice));
+  CUH(cudaMemcpy(h->d_rows, dh->rows.data(), sizeof(int4) * dh->rows.size(), cudaMemcpyHostToDevice));
+  CUH(cudaMemcpy(h->d_daytab, dh->day_tab.data(), sizeof(int4) * dh->day_tab.size(), cudaMemcpyHostToDevice));
   h->P.st_ts = h->d_ts; h->P.st_first = h->d_first; h->P.st_rows = h->d_rows; h->P.day_tab = h->d_daytab;
   if (smem_cta > 48 * 1024) {
-    CU(cudaFuncSetAttribute(abx_env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
-    CU(cudaFuncSetAttribute(abx_env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
-    CU(cudaFuncSetAttribute(abx_env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CUH(cudaFuncSetAttribute(abx_env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CUH(cudaFuncSetAttribute(abx_env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CUH(cudaFuncSetAttribute(abx_env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
   }
   *out = h; return ABX_OK;
 }
@@ -529,16 +533,16 @@ int32_t abx_dq_create_days(const abx_dq_config *cfg, const int64_t *stream5, con
   DA(h->d_ts, dh->ts.size()) DA(h->d_first, dh->first.size()) DA(h->d_rows, dh->rows.size()) DA(h->d_daytab, dh->day_tab.size())
   DA(h->d_iact, E) DA(h->d_obs, E * 8) DA(h->d_trans, E * 6) DA(h->d_rew, E) DA(h->d_done, E) DA(h->d_msizes, E * (cfg->n_momentum > 0 ? cfg->n_momentum : 1))
 #undef DA
-  CU(cudaMemcpy(h->d_ts, dh->ts.data(), sizeof(int64_t) * dh->ts.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->d_first, dh->first.data(), sizeof(int32_t) * dh->first.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->d_rows, dh->rows.data(), sizeof(int4) * dh->rows.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->d_daytab, dh->day_tab.data(), sizeof(int4) * dh->day_tab.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemset(h->P.agents, 0, E * c.n_agents * sizeof(ZiAgent)));
+  CUH(cudaMemcpy(h->d_ts, dh->ts.data(), sizeof(int64_t) * dh->ts.size(), cudaMemcpyHostToDevice));
+  CUH(cudaMemcpy(h->d_first, dh->first.data(), sizeof(int32_t) * dh->first.size(), cudaMemcpyHostToDevice));
+  CUH(cudaMemcpy(h->d_rows, dh->rows.data(), sizeof(int4) * dh->rows.size(), cudaMemcpyHostToDevice));
+  CUH(cudaMemcpy(h->d_daytab, dh->day_tab.data(), sizeof(int4) * dh->day_tab.size(), cudaMemcpyHostToDevice));
+  CUH(cudaMemset(h->P.agents, 0, E * c.n_agents * sizeof(ZiAgent)));
   h->P.st_ts = h->d_ts; h->P.st_first = h->d_first; h->P.st_rows = h->d_rows; h->P.day_tab = h->d_daytab;
   if (smem_cta > 48 * 1024) {
-    CU(cudaFuncSetAttribute(abx_dq_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
-    CU(cudaFuncSetAttribute(abx_dq_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
-    CU(cudaFuncSetAttribute(abx_dq_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CUH(cudaFuncSetAttribute(abx_dq_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CUH(cudaFuncSetAttribute(abx_dq_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CUH(cudaFuncSetAttribute(abx_dq_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
   }
   *out = h; return ABX_OK;
 }
@@ -618,7 +622,7 @@ int32_t abx_book_create(int32_t stream_history, int32_t level_cap, int32_t order
   DA(h->P.lv_price, E * 2 * c.level_cap) DA(h->P.lv_qty, E * 2 * c.level_cap) DA(h->P.lv_ht, E * 2 * c.level_cap)
   DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap) DA(h->d_stats, E) DA(h->P.envx, E)
 #undef DA
-  if (smem_cta > 48 * 1024) CU(cudaFuncSetAttribute(abx_book_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+  if (smem_cta > 48 * 1024) CUH(cudaFuncSetAttribute(abx_book_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
   *out = h; return ABX_OK;
 }
 

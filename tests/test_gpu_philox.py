@@ -136,3 +136,36 @@ def test_stylized_facts_agree_in_distribution_with_reference_rng_runs():
         g, rf = got[:, k][np.isfinite(got[:, k])], ref[:, k][np.isfinite(ref[:, k])]
         se = np.sqrt(rf.var(ddof=1) / len(rf) + g.var(ddof=1) / len(g))
         assert abs(g.mean() - rf.mean()) < 6 * se + 0.1 * rf.std(ddof=1), (name, g.mean(), rf.mean(), se)
+
+
+def test_full_size_batches_conserve_and_finish():
+    """BASELINE.json sizes: 16 384 sparse_zi_1000 environments and 4 096 rmsc03 environments per GPU, whole sessions.  Size-independent
+    properties: every environment ends (F_DONE only, no capacity flag), shares sum to zero and cash to the starting total in every
+    environment (a checksum of checksums over ~3e9 messages), books end uncrossed, and the batch mean of the day's order flow sits where
+    the reference-RNG golden day does (185 200 messages, 24 416 limit orders, 5 459 fills: SURVEY App. B.3)."""
+    from marl_optimal_execution_b200.sim import rmsc03_config
+    cfg = sparse_zi_config(1000)
+    n = 16384
+    sim = BatchedSim(cfg, n)
+    sim.reset(np.arange(n, dtype=np.uint64) + 123456789)
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    assert (st["flags"] == _lib.F_DONE).all(), np.unique(st["flags"])
+    assert (st["sum_shares"] == 0).all() and (st["sum_cash"] == 1000 * cfg.starting_cash).all()
+    assert (st["best_bid"] < st["best_ask"]).all()
+    assert abs(st["messages"].mean() - 185200) < 0.02 * 185200 and abs(st["limit_orders"].mean() - 24416) < 0.02 * 24416
+    assert abs(st["fills"].mean() - 5459) < 0.05 * 5459 and int(st["messages"].sum()) > 2.9e9
+    assert st["max_queue"].max() <= cfg.queue_cap and st["n_bid_levels"].max() <= cfg.level_cap
+    sim.close()
+    cfg = rmsc03_config(pov_exec=True)
+    n = 4096
+    sim = BatchedSim(cfg, n)
+    sim.reset(np.arange(n, dtype=np.uint64) + 77)
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    assert (st["flags"] == _lib.F_DONE).all(), np.unique(st["flags"])
+    assert (st["sum_shares"] == 0).all() and (st["sum_cash"] == 64 * 10 ** 7).all()
+    pe = np.array([sim.pov_exec(e) for e in range(0, n, 512)])
+    assert (pe[:, 0] <= 120000).all() and (pe[:, 2] >= 0).all()
