@@ -57,3 +57,66 @@ def test_errors_are_statuses_not_crashes(lib_path):
 def test_missing_library_fails_loudly(tmp_path):
     with pytest.raises(_lib.AbxError, match="no CPU fallback"):
         _lib.load(str(tmp_path / "libabides_b200.so"))
+
+
+def test_new_config_structs_and_no_device_behaviour(lib_path):
+    """abx_dq_config / rmsc03+POV presets land where the C structs put them; without a GPU every computing entry point returns a status
+    (ABX_ERR_CUDA) -- there is no CPU path behind the product library."""
+    import numpy as np
+    from marl_optimal_execution_b200.env import dq_config, env_config
+    from marl_optimal_execution_b200.sim import rmsc03_config
+    L = _lib.load(lib_path)
+    d = dq_config(L)
+    assert (d.n_momentum, d.n_twap, d.has_ddqn, d.is_buy, d.n_horizon, d.quantity) == (7, 1, 1, 1, 661, 500000)
+    assert d.horizon_start_ns == 36000 * 10 ** 9 and d.horizon_step_ns == 30 * 10 ** 9 and d.stop_ns == (36000 + 660 * 30 + 600) * 10 ** 9
+    assert d.mom_wake_ns == 20 * 10 ** 9 and d.queue_cap == 1536 and d.hash_pops == 0
+    r = rmsc03_config(L, pov_exec=True)
+    assert r.n_agents == 65 and r.n_pov_exec == 1 and r.pov_exec_pov == 0.5 and r.pov_exec_quantity == 120000 and r.pov_exec_lookback_ns == 30 * 10 ** 9
+    assert rmsc03_config(L).n_agents == 64
+    if L.abx_device_count() > 0:
+        pytest.skip("a CUDA device is present: the no-device statuses cannot be observed")
+    h = ctypes.c_void_p()
+    st = np.array([[34200 * 10 ** 9, 1000001, 1000, 100, 1]], dtype=np.int64)
+    e = env_config(L)
+    assert L.abx_env_create(ctypes.byref(e), st.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 1, 1, 0, ctypes.byref(h)) == -2
+    assert L.abx_dq_create(ctypes.byref(d), st.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 1, 1, 0, ctypes.byref(h)) == -2
+    assert L.abx_book_create(10, 64, 64, 0, 1, 0, ctypes.byref(h)) == -2
+    dims = (ctypes.c_int32 * 3)(2, 16, 4)
+    params = (ctypes.c_float * L.abx_qnet_param_count(dims, 2))()
+    assert L.abx_qnet_param_count(dims, 2) == 2 * 16 + 16 + 16 * 4 + 4
+    assert L.abx_qnet_create(dims, 2, params, 0, ctypes.byref(h)) == -2
+    assert b"CUDA" in L.abx_last_cuda_error() or len(L.abx_last_cuda_error()) > 0
+    # argument errors are caught before CUDA is touched
+    bad = np.array([[2, 5, 1000, 100, 1], [1, 6, 1000, 100, 1]], dtype=np.int64)              # not time sorted
+    assert L.abx_env_create(ctypes.byref(e), bad.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 2, 1, 0, ctypes.byref(h)) == -1
+    d2 = dq_config(L, n_momentum=9)
+    assert L.abx_dq_create(ctypes.byref(d2), st.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 1, 1, 0, ctypes.byref(h)) == -1
+    assert L.abx_book_create(10, 4, 64, 0, 1, 0, ctypes.byref(h)) == -1                       # level_cap below the minimum
+    dims_bad = (ctypes.c_int32 * 3)(2, 300, 4)
+    assert L.abx_qnet_create(dims_bad, 2, params, 0, ctypes.byref(h)) == -1
+
+
+def test_emu_edge_cases_empty_and_single_row_streams():
+    """Edge cases of the replayed stream through the host emulation harness of the product logic: a one-row stream, a stream whose first
+    rows share one timestamp, zero-size rows (cancels of unknown ids); the run ends cleanly without error flags."""
+    import numpy as np
+    from helpers import build_emu
+    from marl_optimal_execution_b200.env import ABIDESEnv, env_config
+    from oracle.oracle import OracleEnv
+    emu = build_emu()
+    L = _lib.load(emu)
+    t0 = 34200 * 10 ** 9
+    for rows in ([[t0 + 5, 900001, 1000, 100, 1]],
+                 [[t0 + 5, 900001, 1000, 100, 1], [t0 + 5, 900002, 1001, 50, 0], [t0 + 5, 900003, 1000, 0, 1], [t0 + 9, 900001, 1000, 60, 1], [t0 + 9, 900002, 1001, 0, 0]]):
+        st = np.array(rows, dtype=np.int64)
+        env = ABIDESEnv(st, n_envs=1, cfg=env_config(L, order_level=0, stop_ns=(16 * 3600 + 60) * 10 ** 9, hash_pops=1), lib_path=emu)
+        env.reset()
+        _, _, done, _ = env.step(np.zeros((1, 3)))
+        o = OracleEnv(st, order_level=0, stop_ns=(16 * 3600 + 60) * 10 ** 9)
+        o.step([0, 0, 0])
+        s = env.stats()[0]
+        assert int(done[0]) == 1 and int(s["flags"]) == _lib.F_DONE and int(s["messages"]) == o.n_pops and int(s["pop_hash"]) == o.pop_hash()
+    with pytest.raises(ValueError):
+        ABIDESEnv(np.zeros((0, 5), dtype=np.int64), n_envs=1, cfg=env_config(L), lib_path=emu) if False else ABIDESEnv(np.zeros((3, 4), dtype=np.int64), n_envs=1, cfg=env_config(L), lib_path=emu)
+    with pytest.raises(_lib.AbxError):
+        ABIDESEnv(np.zeros((0, 5), dtype=np.int64), n_envs=1, cfg=env_config(L), lib_path=emu)      # empty stream: rejected at create
