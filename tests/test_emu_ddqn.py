@@ -87,3 +87,34 @@ def test_oracle_reproduces_reference_recording(golden_dir):
         assert np.array_equal(o.holdings()[:, :4], g["holdings"][:, :4])
         ops = o.trace("ops")
         assert np.array_equal(ops[ops[:, 2] >= 9], g["rl_ops"])
+
+
+def test_closed_loop_with_a_real_network_oracle_side(golden_dir):
+    """A third recorded reference run (IBM 2003-01-15) in which the agent's Keras model was replaced by a real fp32 network (numpy stand-in
+    for util/model/QNets.py, weights in the fixture): the oracle environment driven by the same network arithmetic reproduces the reference's
+    actions, event order and rewards -- choose_action (np.argmax of predict, :362-364) closed over the environment."""
+    from marl_optimal_execution_b200.qnet import DEFAULT_DIMS, unpack_params
+    g = np.load(os.path.join(golden_dir, "ddqn_mlp_IBM_2003-01-15_s31.npz"))
+    stream = np.load(os.path.join(golden_dir, str(g["stream_fixture"])))["stream"]
+    layers = unpack_params(g["mlp_params"], DEFAULT_DIMS)
+
+    def policy(s):
+        h = np.asarray(s, dtype=np.float32)[None, :]
+        for i, (w, b) in enumerate(layers):
+            h = h @ w.T + b
+            if i + 1 < len(layers):
+                h = np.maximum(h, np.float32(0))
+        return h[0]
+
+    o = OracleDDQNEnv(stream, g["mom_sizes"])
+    out, tr, r, done = o.step(0)
+    k, total = 0, 0.0
+    while not done:
+        q = policy(out[6:8])
+        assert np.allclose(q, g["mlp_q"][k], rtol=1e-5, atol=1e-5) and int(np.argmax(q)) == int(g["actions"][k]), k
+        out, tr, r, done = o.step(int(np.argmax(q)))
+        total += r
+        k += 1
+    assert k == 660 and o.n_pops == int(g["n_pops"]) and o.pop_hash() == int(g["pop_hash_ckpt"][-1]) and o.error() == 0
+    assert o.note_hash() == int(g["note_hash"]) and o.snap_hash() == int(g["snap_hash"])
+    assert abs(total - float(g["step_reward_hist"].sum())) < 1e-9 * abs(total)

@@ -106,3 +106,30 @@ def test_acting_and_learning_loop_on_the_gpu(golden_dir):
     net.set_params_device(tr.eval_net.flat_device())
     q_dev, _ = net.forward(x, x_offset=6)
     assert torch.equal(q_host, q_dev) and np.array_equal(net.sync_host_params(), tr.eval_net.flat())
+
+
+def test_closed_loop_reproduces_a_reference_run_with_a_real_network(golden_dir):
+    """End to end on the GPU: the tcgen05 Q-network picks every action from the environment's device-resident observation, the environment
+    steps -- and the whole run equals a recorded reference run whose agent used the same weights (numpy fp32 stand-in for the Keras model,
+    tools/record_reference_ddqn.py --mlp): same 660 actions, same 205 k events in the same order, same rewards."""
+    import os
+    from marl_optimal_execution_b200.env import DDQNExecutionEnv, dq_config
+    g = np.load(os.path.join(golden_dir, "ddqn_mlp_IBM_2003-01-15_s31.npz"))
+    stream = np.load(os.path.join(golden_dir, str(g["stream_fixture"])))["stream"]
+    env = DDQNExecutionEnv(stream, n_envs=2, cfg=dq_config(hash_pops=1))
+    env.reset(mom_sizes=np.tile(g["mom_sizes"].astype(np.int32), (2, 1)))
+    net = QNetwork(DEFAULT_DIMS, params=g["mlp_params"])
+    obs, trans, rew, done = env.step(torch.zeros(2, dtype=torch.int32, device="cuda"))
+    acts, total, k = [], 0.0, 0
+    ref_q = torch.from_numpy(g["mlp_q"]).cuda()
+    while not bool(done[0]):
+        q, a = net.forward(obs, x_offset=6)
+        assert float((q[0] - ref_q[k]).abs().max()) <= 2e-4 * float(ref_q[k].abs().max()) + 1e-5, k
+        acts.append(int(a[0]))
+        obs, trans, rew, done = env.step(a)
+        total += float(rew[0])
+        k += 1
+    assert acts == [int(x) for x in g["actions"]]
+    st = env.stats()
+    assert (st["messages"] == int(g["n_pops"])).all() and (st["pop_hash"] == np.uint64(int(g["pop_hash_ckpt"][-1]))).all() and (st["flags"] == 1).all()
+    assert abs(total - float(g["step_reward_hist"].sum())) < 1e-9 * abs(total)

@@ -31,7 +31,21 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import record_reference as R  # noqa: E402
 
-POLICY = {"rs": None, "actions": []}
+POLICY = {"rs": None, "actions": [], "mlp": None, "q": []}
+
+
+def numpy_mlp_forward(flat, dims, x):
+    """fp32 forward of util/model/QNets.py NNModel_1 (Dense + ReLU hidden layers, linear output; Dropout is the identity in predict) from the
+    flat parameter layout of marl_optimal_execution_b200/qnet.py (per layer W[out][in] then b[out])."""
+    h, p = np.asarray(x, dtype=np.float32), 0
+    n_layers = len(dims) - 1
+    for l in range(n_layers):
+        w = flat[p:p + dims[l] * dims[l + 1]].reshape(dims[l + 1], dims[l]); p += dims[l] * dims[l + 1]
+        b = flat[p:p + dims[l + 1]]; p += dims[l + 1]
+        h = h @ w.T + b
+        if l + 1 < n_layers:
+            h = np.maximum(h, np.float32(0))
+    return h.astype(np.float32)
 
 
 def install_stubs():
@@ -61,8 +75,14 @@ def install_stubs():
         def save_weights(self, path):
             pass
 
-        def predict(self, x):                      # policy tape: one-hot on a seeded random column
+        def predict(self, x):                      # policy tape: one-hot on a seeded random column (or, with --mlp, a real fp32 network)
             x = np.asarray(x)
+            if POLICY["mlp"] is not None:
+                flat, dims = POLICY["mlp"]
+                q = numpy_mlp_forward(flat, dims, x)
+                for i in range(x.shape[0]):
+                    POLICY["actions"].append(int(np.argmax(q[i]))); POLICY["q"].append(q[i].copy())
+                return q
             q = np.zeros((x.shape[0], 24), dtype=np.float32)
             for i in range(x.shape[0]):
                 a = int(POLICY["rs"].randint(0, 24))
@@ -92,6 +112,12 @@ def main():
     ticker, date, seed, out = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
     pseed = int(sys.argv[5]) if len(sys.argv) > 5 else seed + 17
     direction = sys.argv[6] if len(sys.argv) > 6 else "BUY"
+    if len(sys.argv) > 7 and sys.argv[7] == "--mlp":      # actions = argmax of a seeded Glorot-initialised network instead of the random tape
+        sys.path.insert(0, os.path.dirname(HERE))
+        from marl_optimal_execution_b200.qnet import DEFAULT_DIMS, init_params
+        flat = init_params(DEFAULT_DIMS, seed=pseed)
+        flat = (flat + np.random.RandomState.__new__(np.random.RandomState).__class__(pseed + 1).normal(0, 0.15, size=flat.shape)).astype(np.float32)   # trained-like: non-zero biases, no ties
+        POLICY["mlp"] = (flat, DEFAULT_DIMS)
     install_stubs()
     POLICY["rs"] = np.random.RandomState.__new__(np.random.RandomState)
     np.random.RandomState.__init__(POLICY["rs"], pseed)          # created before the hooks: not one of the reference's streams
@@ -176,6 +202,13 @@ def main():
         ddqn_final=np.array([dq.remaining_qty, dq.remaining_time, dq.t, dq.arrival_price, len(dq.executed_orders)], dtype=np.float64),
         twap_final=np.array([twap.rem_quantity, twap.arrival_price, len(twap.executed_orders)], dtype=np.float64),
     )
+    if POLICY["mlp"] is not None:                       # the network that chose the actions, its Q rows, and a slimmer fixture (the traces are pinned by the other goldens)
+        data["mlp_params"], data["mlp_q"] = POLICY["mlp"][0], np.array(POLICY["q"], dtype=np.float32)
+        for k in ("pops_head", "ops_head", "notes_head", "snaps_head", "rl_ops"):
+            data[k] = data[k][:2000]
+        with np.load(os.path.join(os.path.dirname(HERE), "tests", "golden", "env_IBM_%s_s4242.npz" % date)) as ge:      # the same day is already a fixture
+            assert np.array_equal(ge["stream"], data["stream"])
+        data["stream_fixture"] = np.array("env_IBM_%s_s4242.npz" % date); del data["stream"]
     os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
     np.savez_compressed(out, **data)
     print("recorded ddqn", ticker, date, "pops", len(pops), "ops", len(ops), "notes", len(notes), "ticks", T, "->", out)
