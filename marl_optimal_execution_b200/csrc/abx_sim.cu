@@ -101,14 +101,14 @@ abx_finalize_kernel(SimParams P, size_t smem_per_warp) {
 }
 
 // ---- ABIDESEnv shape: reset and step (GymKernel.initRunner / stepRunner) ----
-typedef Sim<WarpCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_ENV> EnvSimInstr;
-
+template <bool SMALLQ>
 __global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
 abx_env_reset_kernel(SimParams P, size_t smem_per_warp) {
+  typedef Sim<WarpCtxT<SMALLQ>, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_ENV> EnvSimInstr;
   extern __shared__ __align__(16) unsigned char smem[];
   int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
   if (env >= P.n_envs) return;
-  WarpCtx ctx(P, env, smem + warp * smem_per_warp);
+  WarpCtxT<SMALLQ> ctx(P, env, smem + warp * smem_per_warp);
   EnvState s; init_env_state(P, 0, s); s.last_trade = -1;               // no oracle: OrderBook.last_trade stays None (ExchangeAgent.py:97-102)
   init_envx(P, *ctx.envx()); ctx.sync();
   ctx.q_clear();
@@ -118,19 +118,19 @@ abx_env_reset_kernel(SimParams P, size_t smem_per_warp) {
   env_store(P.env + env, sim.s, ctx.lane);
 }
 
-template <bool INSTR>
+template <bool INSTR, bool SMALLQ>
 __global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
 abx_env_step_kernel(SimParams P, const double *__restrict__ actions, double *__restrict__ obs, double *__restrict__ reward,
                     uint8_t *__restrict__ done, size_t smem_per_warp) {
   extern __shared__ __align__(16) unsigned char smem[];
   int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
   if (env >= P.n_envs) return;
-  WarpCtx ctx(P, env, smem + warp * smem_per_warp);
+  WarpCtxT<SMALLQ> ctx(P, env, smem + warp * smem_per_warp);
   EnvState s = env_load(P.env + env);
   bool was_done = (s.flags & ABX_F_DONE) != 0;
   if (!was_done) {
     ctx.envx_load(); ctx.load_onchip(s);
-    Sim<WarpCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, INSTR, SHAPE_ENV> sim(ctx, P, s, env);
+    Sim<WarpCtxT<SMALLQ>, ABX_RNG_PHILOX, ABX_LAT_ZERO, INSTR, SHAPE_ENV> sim(ctx, P, s, env);
     sim.env_step(actions[3 * env], actions[3 * env + 1], actions[3 * env + 2]);
     ctx.store_onchip(sim.s); ctx.envx_store();
     env_store(P.env + env, sim.s, ctx.lane);
@@ -442,7 +442,7 @@ int32_t abx_env_create_days(const abx_env_config *cfg, const int64_t *stream5, c
   memset(h, 0, sizeof(*h)); h->is_env = true; h->dh = dh; h->n_envs = n_envs; h->device = device;
   env_fill_params(*cfg, h->P); h->P.n_envs = n_envs;
   h->P.n_ts = (int)dh->ts.size(); h->P.n_rows = (int)dh->rows.size(); h->P.n_ids = dh->max_ids; h->P.n_days = n_days;
-  h->smem_per_warp = (warp_smem_bytes(h->P.c, true) + 15) & ~(size_t)15;
+  h->smem_per_warp = (warp_smem_bytes(h->P.c, true, warp_small_queue(h->P.c)) + 15) & ~(size_t)15;
   size_t smem_cta = h->smem_per_warp * ABX_WARPS_PER_CTA;
   if (smem_cta > 227 * 1024) { abx_sim_destroy(h); return ABX_ERR_ARG; }
   const abx_sim_config &c = h->P.c; size_t E = (size_t)n_envs; int stt;
@@ -460,9 +460,12 @@ int32_t abx_env_create_days(const abx_env_config *cfg, const int64_t *stream5, c
   CUH(cudaMemcpy(h->d_daytab, dh->day_tab.data(), sizeof(int4) * dh->day_tab.size(), cudaMemcpyHostToDevice));
   h->P.st_ts = h->d_ts; h->P.st_first = h->d_first; h->P.st_rows = h->d_rows; h->P.day_tab = h->d_daytab;
   if (smem_cta > 48 * 1024) {
-    CUH(cudaFuncSetAttribute(abx_env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
-    CUH(cudaFuncSetAttribute(abx_env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
-    CUH(cudaFuncSetAttribute(abx_env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CUH(cudaFuncSetAttribute(abx_env_reset_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CUH(cudaFuncSetAttribute(abx_env_reset_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CUH(cudaFuncSetAttribute((abx_env_step_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CUH(cudaFuncSetAttribute((abx_env_step_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CUH(cudaFuncSetAttribute((abx_env_step_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    CUH(cudaFuncSetAttribute((abx_env_step_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
   }
   *out = h; return ABX_OK;
 }
@@ -475,7 +478,8 @@ int32_t abx_env_reset(abx_sim *h, void *stream) {
   CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
   CU(cudaMemsetAsync(h->P.idtab, 0, sizeof(uint4) * (size_t)h->n_envs * h->P.n_ids, st));
   CU(cudaMemsetAsync(h->P.idbook, 0, sizeof(uint2) * (size_t)h->n_envs * h->P.n_ids, st));
-  abx_env_reset_kernel<<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, st>>>(h->P, h->smem_per_warp);
+  if (warp_small_queue(h->P.c)) abx_env_reset_kernel<true><<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, st>>>(h->P, h->smem_per_warp);
+  else abx_env_reset_kernel<false><<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, st>>>(h->P, h->smem_per_warp);
   h->launches += 1;
   CU(cudaGetLastError());
   h->reset_done = true; return ABX_OK;
@@ -485,8 +489,11 @@ int32_t abx_env_step(abx_sim *h, const double *actions_dev, double *obs_dev, dou
   if (!h || !h->is_env || !actions_dev || !obs_dev || !done_dev) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
   CU(cudaSetDevice(h->device));
   bool instr = h->P.c.trace_cap > 0 || h->P.c.hash_pops != 0;
-  if (instr) abx_env_step_kernel<true><<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, (cudaStream_t)stream>>>(h->P, actions_dev, obs_dev, reward_dev, done_dev, h->smem_per_warp);
-  else abx_env_step_kernel<false><<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, (cudaStream_t)stream>>>(h->P, actions_dev, obs_dev, reward_dev, done_dev, h->smem_per_warp);
+  bool smallq = warp_small_queue(h->P.c);
+#define ENV_STEP(I, Q) abx_env_step_kernel<I, Q><<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, (cudaStream_t)stream>>>(h->P, actions_dev, obs_dev, reward_dev, done_dev, h->smem_per_warp)
+  if (instr) { if (smallq) ENV_STEP(true, true); else ENV_STEP(true, false); }
+  else { if (smallq) ENV_STEP(false, true); else ENV_STEP(false, false); }
+#undef ENV_STEP
   h->launches += 1;
   CU(cudaGetLastError());
   return ABX_OK;

@@ -46,8 +46,11 @@ __device__ __forceinline__ uint4 shfl4(uint4 v, int src) {
 }
 
 // bytes of shared memory one environment needs
-__host__ __device__ inline size_t warp_smem_bytes(const abx_sim_config &c, bool env_shape = false) {
-  return sizeof(ZiAgent) + OUT_CAP * OUT_WORDS * 4 + (size_t)(c.queue_cap / 32) * 16 + (size_t)c.level_cap * 2 * 12 + (env_shape ? sizeof(EnvX) : 0);
+constexpr int SMALLQ_CAP = 64;          // queue capacities up to this keep every key on chip (WarpCtxT<true>)
+__host__ __device__ inline bool warp_small_queue(const abx_sim_config &c) { return c.queue_cap <= SMALLQ_CAP; }
+__host__ __device__ inline size_t warp_smem_bytes(const abx_sim_config &c, bool env_shape = false, bool small_queue = false) {
+  size_t q = small_queue ? (size_t)SMALLQ_CAP * 16 : (size_t)(c.queue_cap / 32) * 16;
+  return sizeof(ZiAgent) + OUT_CAP * OUT_WORDS * 4 + q + (size_t)c.level_cap * 2 * 12 + (env_shape ? sizeof(EnvX) : 0);
 }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -55,7 +58,11 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-struct WarpCtx {
+// SMALLQ: event queues of at most SMALLQ_CAP entries (ABIDESEnv shape: <= 40 pending events) keep all keys {key.lo, key.hi, uniq, kind|sender} in
+// shared memory: a pop is two conflict-free key reads per lane + one warp arg-min + one 32-byte payload fetch, a push one key store + the payload;
+// no group cache, no second arg-min over a fetched group, no recomputation after a removal.  Larger queues use the grouped layout (header comment).
+template <bool SMALLQ>
+struct WarpCtxT {
   const SimParams &P; int env, lane;
   // HBM bases of this environment
   uint4 *qkey, *qpay0, *qpay1; ZiAgent *agents; uint4 *nodes; abx_trace_rec *tr;
@@ -65,13 +72,13 @@ struct WarpCtx {
   // registers describing the group fetched by q_fetch
   uint64_t my_hi; uint32_t my_uniq; uint32_t cur_mask; int cur_group, cur_lane;
 
-  __device__ WarpCtx(const SimParams &P_, int env_, unsigned char *smem) : P(P_), env(env_), lane(threadIdx.x & 31) {
+  __device__ WarpCtxT(const SimParams &P_, int env_, unsigned char *smem) : P(P_), env(env_), lane(threadIdx.x & 31) {
     size_t q = (size_t)env * P.c.queue_cap; qkey = P.qkey + q; qpay0 = P.qpay0 + q; qpay1 = P.qpay1 + q;
     agents = P.agents + (size_t)env * P.c.n_agents; nodes = P.nodes + (size_t)env * P.c.order_cap;
     tr = P.trace ? P.trace + (size_t)env * P.c.trace_cap : nullptr;
     staged = reinterpret_cast<ZiAgent *>(smem); smem += sizeof(ZiAgent);
     obox = reinterpret_cast<uint32_t *>(smem); smem += OUT_CAP * OUT_WORDS * 4;
-    qc = reinterpret_cast<uint4 *>(smem); smem += (size_t)P.n_qgroups * 16;
+    qc = reinterpret_cast<uint4 *>(smem); smem += SMALLQ ? (size_t)SMALLQ_CAP * 16 : (size_t)P.n_qgroups * 16;
     lvp = reinterpret_cast<int32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
     lvq = reinterpret_cast<int32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
     lvht = reinterpret_cast<uint32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
@@ -96,9 +103,12 @@ struct WarpCtx {
 
   // ---- staging of the on-chip structures between launches ----
   __device__ void load_onchip(const EnvState &s) {
-    const uint4 *gc = P.qcache + (size_t)env * P.n_qgroups;
+    if (SMALLQ) { qc[lane] = ldcg4(qkey + lane); qc[lane + 32] = ldcg4(qkey + lane + 32); }
+    else {
+      const uint4 *gc = P.qcache + (size_t)env * P.n_qgroups;
 #pragma unroll 1
-    for (int g = lane; g < P.n_qgroups; g += 32) qc[g] = ldcg4(gc + g);
+      for (int g = lane; g < P.n_qgroups; g += 32) qc[g] = ldcg4(gc + g);
+    }
     size_t l = (size_t)env * 2 * P.c.level_cap;
 #pragma unroll 1
     for (int side = 0; side < 2; side++)
@@ -110,9 +120,12 @@ struct WarpCtx {
   }
   __device__ void store_onchip(const EnvState &s) {
     sync();
-    uint4 *gc = P.qcache + (size_t)env * P.n_qgroups;
+    if (SMALLQ) { __stcg(qkey + lane, qc[lane]); __stcg(qkey + lane + 32, qc[lane + 32]); }
+    else {
+      uint4 *gc = P.qcache + (size_t)env * P.n_qgroups;
 #pragma unroll 1
-    for (int g = lane; g < P.n_qgroups; g += 32) gc[g] = qc[g];
+      for (int g = lane; g < P.n_qgroups; g += 32) gc[g] = qc[g];
+    }
     size_t l = (size_t)env * 2 * P.c.level_cap;
 #pragma unroll 1
     for (int side = 0; side < 2; side++)
@@ -121,10 +134,22 @@ struct WarpCtx {
       int k = side * P.c.level_cap + i; P.lv_price[l + k] = lvp[k]; P.lv_qty[l + k] = lvq[k]; P.lv_ht[l + k] = lvht[k];
     }
   }
-  __device__ void q_clear() { for (int g = lane; g < P.n_qgroups; g += 32) qc[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); sync(); }
+  __device__ void q_clear() {
+    if (SMALLQ) { qc[lane] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); qc[lane + 32] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); sync(); return; }
+    for (int g = lane; g < P.n_qgroups; g += 32) qc[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); sync(); }
 
   // ---- event queue ----
   __device__ __forceinline__ bool q_min(uint64_t &hi, uint32_t &uniq, int &grp) {
+    if (SMALLQ) {                                                          // grp = slot of the smallest key (empty slots hold KEY_EMPTY)
+      uint4 k0 = qc[lane], k1 = qc[lane + 32];
+      uint64_t h0 = (uint64_t)k0.x | ((uint64_t)k0.y << 32), h1 = (uint64_t)k1.x | ((uint64_t)k1.y << 32);
+      bool second = key_less(h1, k1.z, h0, k0.z);
+      uint64_t h = second ? h1 : h0; uint32_t u = second ? k1.z : k0.z;
+      int wl = warp_argmin(h, u, h != KEY_EMPTY);
+      if (wl < 0) return false;
+      grp = __shfl_sync(FULL, second ? lane + 32 : lane, wl); hi = shfl64(h, wl); uniq = __shfl_sync(FULL, u, wl);
+      return true;
+    }
     uint64_t bh = KEY_EMPTY; uint32_t bu = 0xffffffffu; int bg = -1;
     for (int g = lane; g < P.n_qgroups; g += 32) {
       uint4 cc = qc[g];
@@ -136,6 +161,11 @@ struct WarpCtx {
     return true;
   }
   __device__ __forceinline__ void q_fetch(int g, Event &e) {
+    if (SMALLQ) {                                                          // g is the slot: key on chip, 32 bytes of payload from HBM (same address in every lane: one transaction)
+      cur_group = g;
+      event_unpack(qc[g], ldcg4(qpay0 + g), ldcg4(qpay1 + g), e);
+      return;
+    }
     int slot = g * 32 + lane;
     uint4 k = ldcg4(qkey + slot), a = ldcg4(qpay0 + slot), b = ldcg4(qpay1 + slot);     // 3 x 512 B coalesced
     cur_mask = qc[g].w; cur_group = g;
@@ -153,8 +183,15 @@ struct WarpCtx {
     qc[cur_group] = make_uint4((uint32_t)nh, (uint32_t)(nh >> 32), nu, cur_mask);
     sync();
   }
-  __device__ __forceinline__ void q_remove() { cur_mask &= ~(1u << cur_lane); group_writeback(); }
+  __device__ __forceinline__ void q_remove() {
+    if (SMALLQ) { sync(); qc[cur_group] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); sync(); return; }
+    cur_mask &= ~(1u << cur_lane); group_writeback(); }
   __device__ __forceinline__ void q_requeue(int64_t t) {   // Kernel.py:226,260: same entry, new time, same uniq
+    if (SMALLQ) {
+      uint4 k = qc[cur_group]; uint64_t h = (uint64_t)k.x | ((uint64_t)k.y << 32);
+      h = key_pack(t < KEY_T_MAX ? t : KEY_T_MAX, key_recipient(h), key_type(h)); k.x = (uint32_t)h; k.y = (uint32_t)(h >> 32);
+      sync(); qc[cur_group] = k; sync(); return;
+    }
     if (lane == cur_lane) {
       my_hi = key_pack(t < KEY_T_MAX ? t : KEY_T_MAX, key_recipient(my_hi), key_type(my_hi));
       uint2 *kp = reinterpret_cast<uint2 *>(qkey + cur_group * 32 + lane); *kp = make_uint2((uint32_t)my_hi, (uint32_t)(my_hi >> 32));
@@ -162,6 +199,17 @@ struct WarpCtx {
     group_writeback();
   }
   __device__ __forceinline__ bool q_push(const Event &e) {
+    if (SMALLQ) {
+      bool f0 = qc[lane].y == 0xffffffffu && qc[lane].x == 0xffffffffu, f1 = qc[lane + 32].y == 0xffffffffu && qc[lane + 32].x == 0xffffffffu;
+      uint32_t b0 = __ballot_sync(FULL, f0), b1 = __ballot_sync(FULL, f1);
+      if (!(b0 | b1)) return false;
+      int slot = b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1;
+      uint4 k, a, b; event_pack(e, k, a, b);
+      sync(); qc[slot] = k;
+      if (lane < 2) { uint4 *dst = lane == 0 ? qpay0 : qpay1; dst[slot] = lane == 0 ? a : b; }
+      __syncwarp();
+      return true;
+    }
     int fg = -1;
     for (int g = lane; g < P.n_qgroups; g += 32) if (qc[g].w != 0xffffffffu) { fg = g; break; }
     uint32_t bal = __ballot_sync(FULL, fg >= 0);
@@ -277,5 +325,7 @@ struct WarpCtx {
   }
   __device__ __forceinline__ double agent_lat_from(int id) const { return __ldcg(&agents[id].lat_from); }
 };
+typedef WarpCtxT<false> WarpCtx;
+typedef WarpCtxT<true> WarpCtxSmallQ;
 
 }  // namespace abx
