@@ -149,6 +149,7 @@ static inline int dq_config_validate(const abx_dq_config *c) {
   if (!c || c->version != ABX_VERSION || c->n_momentum < 0 || c->n_momentum > 8 || c->n_twap < 0 || c->n_twap > 2 || c->n_horizon < 3) return ABX_ERR_ARG;
   if (c->queue_cap < 32 || c->queue_cap % 32 || c->queue_cap > 4096 || c->level_cap < 8 || c->level_cap > 2048) return ABX_ERR_ARG;
   if (c->order_cap < 8 || c->order_cap > 65535 || c->stop_ns >= KEY_T_MAX || c->start_ns < 0 || c->horizon_step_ns <= 0 || c->mom_wake_ns <= 0) return ABX_ERR_ARG;
+  if (c->queue_cap < 128) return ABX_ERR_ARG;                            // two-tier queue: the first two groups' slots belong to the on-chip tier
   if (c->stream_history < 0 || c->stream_history > 14 || c->quantity <= 0 || c->quantity > 0x3fffffffLL || c->trace_cap < 0 || c->mom_max_size <= c->mom_min_size) return ABX_ERR_ARG;
   return ABX_OK;
 }

@@ -104,11 +104,11 @@ abx_finalize_kernel(SimParams P, size_t smem_per_warp) {
 template <bool SMALLQ>
 __global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
 abx_env_reset_kernel(SimParams P, size_t smem_per_warp) {
-  typedef Sim<WarpCtxT<SMALLQ>, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_ENV> EnvSimInstr;
+  typedef Sim<WarpCtxT<SMALLQ ? 1 : 0>, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_ENV> EnvSimInstr;
   extern __shared__ __align__(16) unsigned char smem[];
   int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
   if (env >= P.n_envs) return;
-  WarpCtxT<SMALLQ> ctx(P, env, smem + warp * smem_per_warp);
+  WarpCtxT<SMALLQ ? 1 : 0> ctx(P, env, smem + warp * smem_per_warp);
   EnvState s; init_env_state(P, 0, s); s.last_trade = -1;               // no oracle: OrderBook.last_trade stays None (ExchangeAgent.py:97-102)
   init_envx(P, *ctx.envx()); ctx.sync();
   ctx.q_clear();
@@ -125,12 +125,12 @@ abx_env_step_kernel(SimParams P, const double *__restrict__ actions, double *__r
   extern __shared__ __align__(16) unsigned char smem[];
   int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
   if (env >= P.n_envs) return;
-  WarpCtxT<SMALLQ> ctx(P, env, smem + warp * smem_per_warp);
+  WarpCtxT<SMALLQ ? 1 : 0> ctx(P, env, smem + warp * smem_per_warp);
   EnvState s = env_load(P.env + env);
   bool was_done = (s.flags & ABX_F_DONE) != 0;
   if (!was_done) {
     ctx.envx_load(); ctx.load_onchip(s);
-    Sim<WarpCtxT<SMALLQ>, ABX_RNG_PHILOX, ABX_LAT_ZERO, INSTR, SHAPE_ENV> sim(ctx, P, s, env);
+    Sim<WarpCtxT<SMALLQ ? 1 : 0>, ABX_RNG_PHILOX, ABX_LAT_ZERO, INSTR, SHAPE_ENV> sim(ctx, P, s, env);
     sim.env_step(actions[3 * env], actions[3 * env + 1], actions[3 * env + 2]);
     ctx.store_onchip(sim.s); ctx.envx_store();
     env_store(P.env + env, sim.s, ctx.lane);
@@ -143,14 +143,14 @@ abx_env_step_kernel(SimParams P, const double *__restrict__ actions, double *__r
 }
 
 // ---- DDQN execution shape: reset and decision step ----
-typedef Sim<WarpCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_DQ> DqSimInstr;
+typedef Sim<WarpCtxHybridQ, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_DQ> DqSimInstr;
 
 __global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
 abx_dq_reset_kernel(SimParams P, const uint64_t *__restrict__ seeds, const int32_t *__restrict__ mom_sizes, size_t smem_per_warp) {
   extern __shared__ __align__(16) unsigned char smem[];
   int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
   if (env >= P.n_envs) return;
-  WarpCtx ctx(P, env, smem + warp * smem_per_warp);
+  WarpCtxHybridQ ctx(P, env, smem + warp * smem_per_warp);
   uint64_t seed = seeds ? seeds[env] : 0;
   EnvState s; init_env_state(P, seed, s); s.last_trade = -1;            // no oracle: OrderBook.last_trade stays None until the first trade
   init_envx(P, *ctx.envx()); ctx.sync();
@@ -165,18 +165,18 @@ abx_dq_reset_kernel(SimParams P, const uint64_t *__restrict__ seeds, const int32
 }
 
 template <bool INSTR>
-__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
+__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA, 16)      // 16 one-warp CTAs per SM: 128 registers (unbounded ptxas takes 168 -> 12 per SM)
 abx_dq_step_kernel(SimParams P, const int32_t *__restrict__ actions, double *__restrict__ obs, double *__restrict__ trans, double *__restrict__ reward,
                    uint8_t *__restrict__ done, size_t smem_per_warp) {
   extern __shared__ __align__(16) unsigned char smem[];
   int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
   if (env >= P.n_envs) return;
-  WarpCtx ctx(P, env, smem + warp * smem_per_warp);
+  WarpCtxHybridQ ctx(P, env, smem + warp * smem_per_warp);
   EnvState s = env_load(P.env + env);
   bool was_done = (s.flags & ABX_F_DONE) != 0, paused = false;
   if (!was_done) {
     ctx.envx_load(); ctx.load_onchip(s);
-    Sim<WarpCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, INSTR, SHAPE_DQ> sim(ctx, P, s, env);
+    Sim<WarpCtxHybridQ, ABX_RNG_PHILOX, ABX_LAT_ZERO, INSTR, SHAPE_DQ> sim(ctx, P, s, env);
     paused = sim.dq_step(actions ? actions[env] : 0);
     ctx.store_onchip(sim.s); ctx.envx_store();
     env_store(P.env + env, sim.s, ctx.lane);
@@ -528,7 +528,7 @@ int32_t abx_dq_create_days(const abx_dq_config *cfg, const int64_t *stream5, con
   h->P.n_ts = (int)dh->ts.size(); h->P.n_rows = (int)dh->rows.size(); h->P.dq_order_base = dh->max_ids; h->P.dq_id_limit = dh->min_id; h->P.n_days = n_days;
   int n_exec = cfg->n_twap + (cfg->has_ddqn ? 1 : 0);
   h->P.n_ids = h->P.dq_order_base + n_exec * EXEC_ORDER_CAP;
-  h->smem_per_warp = (warp_smem_bytes(h->P.c, true) + 15) & ~(size_t)15;
+  h->smem_per_warp = (warp_smem_bytes(h->P.c, true, false, true) + 15) & ~(size_t)15;
   size_t smem_cta = h->smem_per_warp * ABX_WARPS_PER_CTA;
   if (smem_cta > 227 * 1024) { abx_sim_destroy(h); return ABX_ERR_ARG; }
   const abx_sim_config &c = h->P.c; size_t E = (size_t)n_envs; int stt;

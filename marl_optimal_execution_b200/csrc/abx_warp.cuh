@@ -48,8 +48,8 @@ __device__ __forceinline__ uint4 shfl4(uint4 v, int src) {
 // bytes of shared memory one environment needs
 constexpr int SMALLQ_CAP = 64;          // queue capacities up to this keep every key on chip (WarpCtxT<true>)
 __host__ __device__ inline bool warp_small_queue(const abx_sim_config &c) { return c.queue_cap <= SMALLQ_CAP; }
-__host__ __device__ inline size_t warp_smem_bytes(const abx_sim_config &c, bool env_shape = false, bool small_queue = false) {
-  size_t q = small_queue ? (size_t)SMALLQ_CAP * 16 : (size_t)(c.queue_cap / 32) * 16;
+__host__ __device__ inline size_t warp_smem_bytes(const abx_sim_config &c, bool env_shape = false, bool small_queue = false, bool hybrid_queue = false) {
+  size_t q = hybrid_queue ? (size_t)SMALLQ_CAP * 16 + (size_t)(c.queue_cap / 32) * 16 : (small_queue ? (size_t)SMALLQ_CAP * 16 : (size_t)(c.queue_cap / 32) * 16);
   return sizeof(ZiAgent) + OUT_CAP * OUT_WORDS * 4 + q + (size_t)c.level_cap * 2 * 12 + (env_shape ? sizeof(EnvX) : 0);
 }
 __device__ __forceinline__ double warp_sum(double v) {
@@ -61,16 +61,20 @@ __device__ __forceinline__ double warp_sum(double v) {
 // SMALLQ: event queues of at most SMALLQ_CAP entries (ABIDESEnv shape: <= 40 pending events) keep all keys {key.lo, key.hi, uniq, kind|sender} in
 // shared memory: a pop is two conflict-free key reads per lane + one warp arg-min + one 32-byte payload fetch, a push one key store + the payload;
 // no group cache, no second arg-min over a fetched group, no recomputation after a removal.  Larger queues use the grouped layout (header comment).
-template <bool SMALLQ>
+// QMODE 0: grouped queue (header comment).  QMODE 1 (SMALLQ): all keys on chip.  QMODE 2: both -- the first SMALLQ_CAP events live on chip and only an
+// overflow (the DDQN config's closing market order: up to 500 orders in flight at once, one tick in 660) goes to the grouped structure, whose groups
+// 0 and 1 are left unused because their HBM slots hold the on-chip tier's payloads; a pop takes the smaller of the two tiers' minima.
+template <int QMODE>
 struct WarpCtxT {
+  static constexpr bool SMALLQ = QMODE >= 1, HYBRID = QMODE == 2; static constexpr int G0 = HYBRID ? SMALLQ_CAP / 32 : 0;
   const SimParams &P; int env, lane;
   // HBM bases of this environment
   uint4 *qkey, *qpay0, *qpay1; ZiAgent *agents; uint4 *nodes; abx_trace_rec *tr;
   // shared memory of this warp
-  ZiAgent *staged; uint32_t *obox; uint4 *qc; int32_t *lvp, *lvq; uint32_t *lvht; EnvX *ex;
+  ZiAgent *staged; uint32_t *obox; uint4 *qc, *qs; int32_t *lvp, *lvq; uint32_t *lvht; EnvX *ex;   // qc: group cache, qs: on-chip keys
   uint4 *idt; int4 *lob; uint2 *idb;   // ABIDESEnv shape: replay agent's per-order table, stored LOBs, per-order book census (HBM)
   // registers describing the group fetched by q_fetch
-  uint64_t my_hi; uint32_t my_uniq; uint32_t cur_mask; int cur_group, cur_lane;
+  uint64_t my_hi; uint32_t my_uniq; uint32_t cur_mask; int cur_group, cur_lane; int n_ovf; bool cur_t2;   // n_ovf: events in the overflow tier
 
   __device__ WarpCtxT(const SimParams &P_, int env_, unsigned char *smem) : P(P_), env(env_), lane(threadIdx.x & 31) {
     size_t q = (size_t)env * P.c.queue_cap; qkey = P.qkey + q; qpay0 = P.qpay0 + q; qpay1 = P.qpay1 + q;
@@ -78,14 +82,15 @@ struct WarpCtxT {
     tr = P.trace ? P.trace + (size_t)env * P.c.trace_cap : nullptr;
     staged = reinterpret_cast<ZiAgent *>(smem); smem += sizeof(ZiAgent);
     obox = reinterpret_cast<uint32_t *>(smem); smem += OUT_CAP * OUT_WORDS * 4;
-    qc = reinterpret_cast<uint4 *>(smem); smem += SMALLQ ? (size_t)SMALLQ_CAP * 16 : (size_t)P.n_qgroups * 16;
+    qs = reinterpret_cast<uint4 *>(smem); smem += SMALLQ ? (size_t)SMALLQ_CAP * 16 : 0;
+    qc = reinterpret_cast<uint4 *>(smem); smem += (SMALLQ && !HYBRID) ? 0 : (size_t)P.n_qgroups * 16;
     lvp = reinterpret_cast<int32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
     lvq = reinterpret_cast<int32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
     lvht = reinterpret_cast<uint32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
     ex = reinterpret_cast<EnvX *>(smem);
     idb = P.idbook ? P.idbook + (size_t)env * P.n_ids : nullptr;
     idt = P.idtab ? P.idtab + (size_t)env * P.n_ids : nullptr; lob = P.lobs ? P.lobs + (size_t)env * LOB_CAP * 3 : nullptr;
-    cur_group = cur_lane = -1; cur_mask = 0; my_hi = KEY_EMPTY; my_uniq = 0xffffffffu;
+    cur_group = cur_lane = -1; cur_mask = 0; my_hi = KEY_EMPTY; my_uniq = 0xffffffffu; n_ovf = 0; cur_t2 = false;
   }
   // Uniform code stores on-chip state from every lane (same value, same address: one STS, no branch).
   __device__ __forceinline__ bool onchip_writer() const { return true; }
@@ -103,11 +108,12 @@ struct WarpCtxT {
 
   // ---- staging of the on-chip structures between launches ----
   __device__ void load_onchip(const EnvState &s) {
-    if (SMALLQ) { qc[lane] = ldcg4(qkey + lane); qc[lane + 32] = ldcg4(qkey + lane + 32); }
-    else {
-      const uint4 *gc = P.qcache + (size_t)env * P.n_qgroups;
+    if (SMALLQ) { qs[lane] = ldcg4(qkey + lane); qs[lane + 32] = ldcg4(qkey + lane + 32); }
+    if (!SMALLQ || HYBRID) {
+      const uint4 *gc = P.qcache + (size_t)env * P.n_qgroups; int cnt = 0;
 #pragma unroll 1
-      for (int g = lane; g < P.n_qgroups; g += 32) qc[g] = ldcg4(gc + g);
+      for (int g = lane; g < P.n_qgroups; g += 32) { uint4 v = ldcg4(gc + g); qc[g] = v; if (HYBRID && g >= G0) cnt += __popc(v.w); }
+      if (HYBRID) n_ovf = __reduce_add_sync(FULL, cnt);
     }
     size_t l = (size_t)env * 2 * P.c.level_cap;
 #pragma unroll 1
@@ -120,8 +126,8 @@ struct WarpCtxT {
   }
   __device__ void store_onchip(const EnvState &s) {
     sync();
-    if (SMALLQ) { __stcg(qkey + lane, qc[lane]); __stcg(qkey + lane + 32, qc[lane + 32]); }
-    else {
+    if (SMALLQ) { __stcg(qkey + lane, qs[lane]); __stcg(qkey + lane + 32, qs[lane + 32]); }
+    if (!SMALLQ || HYBRID) {
       uint4 *gc = P.qcache + (size_t)env * P.n_qgroups;
 #pragma unroll 1
       for (int g = lane; g < P.n_qgroups; g += 32) gc[g] = qc[g];
@@ -135,36 +141,42 @@ struct WarpCtxT {
     }
   }
   __device__ void q_clear() {
-    if (SMALLQ) { qc[lane] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); qc[lane + 32] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); sync(); return; }
-    for (int g = lane; g < P.n_qgroups; g += 32) qc[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); sync(); }
+    if (SMALLQ) { qs[lane] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); qs[lane + 32] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); n_ovf = 0; }
+    if (!SMALLQ || HYBRID) for (int g = lane; g < P.n_qgroups; g += 32) qc[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
+    sync(); }
 
   // ---- event queue ----
+  // grp identifies the winner for q_fetch: a slot of the on-chip tier (SMALLQ: 0 .. SMALLQ_CAP-1), otherwise SMALLQ_CAP + group index
   __device__ __forceinline__ bool q_min(uint64_t &hi, uint32_t &uniq, int &grp) {
-    if (SMALLQ) {                                                          // grp = slot of the smallest key (empty slots hold KEY_EMPTY)
-      uint4 k0 = qc[lane], k1 = qc[lane + 32];
+    bool have1 = false;
+    if (SMALLQ) {                                                          // empty slots hold KEY_EMPTY
+      uint4 k0 = qs[lane], k1 = qs[lane + 32];
       uint64_t h0 = (uint64_t)k0.x | ((uint64_t)k0.y << 32), h1 = (uint64_t)k1.x | ((uint64_t)k1.y << 32);
       bool second = key_less(h1, k1.z, h0, k0.z);
       uint64_t h = second ? h1 : h0; uint32_t u = second ? k1.z : k0.z;
       int wl = warp_argmin(h, u, h != KEY_EMPTY);
-      if (wl < 0) return false;
-      grp = __shfl_sync(FULL, second ? lane + 32 : lane, wl); hi = shfl64(h, wl); uniq = __shfl_sync(FULL, u, wl);
-      return true;
+      if (wl >= 0) { have1 = true; grp = __shfl_sync(FULL, second ? lane + 32 : lane, wl); hi = shfl64(h, wl); uniq = __shfl_sync(FULL, u, wl); }
+      if (!HYBRID || n_ovf == 0) return have1;
     }
     uint64_t bh = KEY_EMPTY; uint32_t bu = 0xffffffffu; int bg = -1;
-    for (int g = lane; g < P.n_qgroups; g += 32) {
+    for (int g = G0 + lane; g < P.n_qgroups; g += 32) {
       uint4 cc = qc[g];
       if (cc.w) { uint64_t h = (uint64_t)cc.x | ((uint64_t)cc.y << 32); if (bg < 0 || key_less(h, cc.z, bh, bu)) { bh = h; bu = cc.z; bg = g; } }
     }
     int wl = warp_argmin(bh, bu, bg >= 0);
-    if (wl < 0) return false;
-    grp = __shfl_sync(FULL, bg, wl); hi = shfl64(bh, wl); uniq = __shfl_sync(FULL, bu, wl);
+    if (wl < 0) return have1;
+    int g2 = __shfl_sync(FULL, bg, wl); uint64_t h2 = shfl64(bh, wl); uint32_t u2 = __shfl_sync(FULL, bu, wl);
+    if (!have1 || key_less(h2, u2, hi, uniq)) { grp = (SMALLQ ? SMALLQ_CAP : 0) + g2; hi = h2; uniq = u2; }
     return true;
   }
   __device__ __forceinline__ void q_fetch(int g, Event &e) {
-    if (SMALLQ) {                                                          // g is the slot: key on chip, 32 bytes of payload from HBM (same address in every lane: one transaction)
-      cur_group = g;
-      event_unpack(qc[g], ldcg4(qpay0 + g), ldcg4(qpay1 + g), e);
-      return;
+    if (SMALLQ) {
+      if (g < SMALLQ_CAP) {                                                // a slot of the on-chip tier: key on chip, 32 bytes of payload from HBM (same address in every lane: one transaction)
+        cur_group = g; cur_t2 = false;
+        event_unpack(qs[g], ldcg4(qpay0 + g), ldcg4(qpay1 + g), e);
+        return;
+      }
+      g -= SMALLQ_CAP; cur_t2 = true;
     }
     int slot = g * 32 + lane;
     uint4 k = ldcg4(qkey + slot), a = ldcg4(qpay0 + slot), b = ldcg4(qpay1 + slot);     // 3 x 512 B coalesced
@@ -184,13 +196,14 @@ struct WarpCtxT {
     sync();
   }
   __device__ __forceinline__ void q_remove() {
-    if (SMALLQ) { sync(); qc[cur_group] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); sync(); return; }
+    if (SMALLQ && !cur_t2) { sync(); qs[cur_group] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); sync(); return; }
+    if (HYBRID) n_ovf--;
     cur_mask &= ~(1u << cur_lane); group_writeback(); }
   __device__ __forceinline__ void q_requeue(int64_t t) {   // Kernel.py:226,260: same entry, new time, same uniq
-    if (SMALLQ) {
-      uint4 k = qc[cur_group]; uint64_t h = (uint64_t)k.x | ((uint64_t)k.y << 32);
+    if (SMALLQ && !cur_t2) {
+      uint4 k = qs[cur_group]; uint64_t h = (uint64_t)k.x | ((uint64_t)k.y << 32);
       h = key_pack(t < KEY_T_MAX ? t : KEY_T_MAX, key_recipient(h), key_type(h)); k.x = (uint32_t)h; k.y = (uint32_t)(h >> 32);
-      sync(); qc[cur_group] = k; sync(); return;
+      sync(); qs[cur_group] = k; sync(); return;
     }
     if (lane == cur_lane) {
       my_hi = key_pack(t < KEY_T_MAX ? t : KEY_T_MAX, key_recipient(my_hi), key_type(my_hi));
@@ -200,18 +213,20 @@ struct WarpCtxT {
   }
   __device__ __forceinline__ bool q_push(const Event &e) {
     if (SMALLQ) {
-      bool f0 = qc[lane].y == 0xffffffffu && qc[lane].x == 0xffffffffu, f1 = qc[lane + 32].y == 0xffffffffu && qc[lane + 32].x == 0xffffffffu;
+      bool f0 = qs[lane].y == 0xffffffffu && qs[lane].x == 0xffffffffu, f1 = qs[lane + 32].y == 0xffffffffu && qs[lane + 32].x == 0xffffffffu;
       uint32_t b0 = __ballot_sync(FULL, f0), b1 = __ballot_sync(FULL, f1);
-      if (!(b0 | b1)) return false;
-      int slot = b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1;
-      uint4 k, a, b; event_pack(e, k, a, b);
-      sync(); qc[slot] = k;
-      if (lane < 2) { uint4 *dst = lane == 0 ? qpay0 : qpay1; dst[slot] = lane == 0 ? a : b; }
-      __syncwarp();
-      return true;
+      if (b0 | b1) {
+        int slot = b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1;
+        uint4 k, a, b; event_pack(e, k, a, b);
+        sync(); qs[slot] = k;
+        if (lane < 2) { uint4 *dst = lane == 0 ? qpay0 : qpay1; dst[slot] = lane == 0 ? a : b; }
+        __syncwarp();
+        return true;
+      }
+      if (!HYBRID) return false;
     }
     int fg = -1;
-    for (int g = lane; g < P.n_qgroups; g += 32) if (qc[g].w != 0xffffffffu) { fg = g; break; }
+    for (int g = G0 + lane; g < P.n_qgroups; g += 32) if (qc[g].w != 0xffffffffu) { fg = g; break; }
     uint32_t bal = __ballot_sync(FULL, fg >= 0);
     if (!bal) return false;
     int g = __shfl_sync(FULL, fg, __ffs(bal) - 1);
@@ -224,6 +239,7 @@ struct WarpCtxT {
       if (cc.w == 0 || key_less(h, k.z, ch, cc.z)) { cc.x = k.x; cc.y = k.y; cc.z = k.z; }
       cc.w |= 1u << i; qc[g] = cc;
     }
+    if (HYBRID) n_ovf++;
     __syncwarp();
     return true;
   }
@@ -325,7 +341,8 @@ struct WarpCtxT {
   }
   __device__ __forceinline__ double agent_lat_from(int id) const { return __ldcg(&agents[id].lat_from); }
 };
-typedef WarpCtxT<false> WarpCtx;
-typedef WarpCtxT<true> WarpCtxSmallQ;
+typedef WarpCtxT<0> WarpCtx;
+typedef WarpCtxT<1> WarpCtxSmallQ;
+typedef WarpCtxT<2> WarpCtxHybridQ;
 
 }  // namespace abx
