@@ -74,7 +74,7 @@ struct WarpCtxT {
   ZiAgent *staged; uint32_t *obox; uint4 *qc, *qs; int32_t *lvp, *lvq; uint32_t *lvht; EnvX *ex;   // qc: group cache, qs: on-chip keys
   uint4 *idt; int4 *lob; uint2 *idb;   // ABIDESEnv shape: replay agent's per-order table, stored LOBs, per-order book census (HBM)
   // registers describing the group fetched by q_fetch
-  uint64_t my_hi; uint32_t my_uniq; uint32_t cur_mask; int cur_group, cur_lane; int n_ovf; bool cur_t2;   // n_ovf: events in the overflow tier
+  uint64_t my_hi; uint32_t my_uniq; uint32_t cur_mask; int cur_group, cur_lane; int n_ovf; bool cur_t2; int day;   // day: the replayed day of this environment   // n_ovf: events in the overflow tier
 
   __device__ WarpCtxT(const SimParams &P_, int env_, unsigned char *smem) : P(P_), env(env_), lane(threadIdx.x & 31) {
     size_t q = (size_t)env * P.c.queue_cap; qkey = P.qkey + q; qpay0 = P.qpay0 + q; qpay1 = P.qpay1 + q;
@@ -91,6 +91,7 @@ struct WarpCtxT {
     idb = P.idbook ? P.idbook + (size_t)env * P.n_ids : nullptr;
     idt = P.idtab ? P.idtab + (size_t)env * P.n_ids : nullptr; lob = P.lobs ? P.lobs + (size_t)env * LOB_CAP * 3 : nullptr;
     cur_group = cur_lane = -1; cur_mask = 0; my_hi = KEY_EMPTY; my_uniq = 0xffffffffu; n_ovf = 0; cur_t2 = false;
+    day = P.n_days > 1 ? env % P.n_days : 0;                               // once per launch: an integer modulo is ~170 instructions
   }
   // Uniform code stores on-chip state from every lane (same value, same address: one STS, no branch).
   __device__ __forceinline__ bool onchip_writer() const { return true; }
@@ -300,7 +301,7 @@ struct WarpCtxT {
   __device__ __forceinline__ uint2 ib_load(int i) const { return __ldcg(idb + i); }
   __device__ __forceinline__ void ib_store(int i, uint2 v) { if (lane == 0) __stcg(idb + i, v); __syncwarp(); }
   __device__ __forceinline__ int4 row_load(int r) const { return __ldg(P.st_rows + r); }
-  __device__ __forceinline__ int4 day_rec() const { return __ldg(P.day_tab + (P.n_days > 1 ? env % P.n_days : 0)); }     // this environment's replayed day
+  __device__ __forceinline__ int4 day_rec() const { return __ldg(P.day_tab + day); }
   __device__ __forceinline__ int n_ts() const { return day_rec().y; }
   __device__ __forceinline__ int64_t ts_load(int k) const { return __ldg(P.st_ts + day_rec().x + k); }
   __device__ __forceinline__ int first_load(int k) const { return __ldg(P.st_first + day_rec().z + k); }

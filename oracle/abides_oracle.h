@@ -6,8 +6,13 @@
  *
  * Parity status: PINNED.  From the seed alone this restatement reproduces the reference's recorded
  * golden run tests/sparse_zi_1000.txt (185 200 messages, 1000 final-holdings lines) and the traces
- * recorded from the live reference by tools/record_reference.py (tests/golden/ .npz files): event-queue pop
- * order, exchange-boundary ops, every outbound exchange message, book snapshots and every RNG draw.
+ * recorded from the live reference by tools/record_reference*.py (tests/golden/ .npz files): event-queue pop
+ * order, exchange-boundary ops, every outbound exchange message, book snapshots and every RNG draw -- for
+ * sparse_zi_100 / sparse_zi_1000 (two seeds each), rmsc03 (two seeds) and rmsc03 with the reference's
+ * POVExecutionAgent appended, two ABIDESEnv episodes, the GOOG market-replay day, and three runs of the DDQN
+ * execution config (BUY, SELL, and one whose agent was driven by a real fp32 network).  NOT pinned: the
+ * arithmetic of the Keras Q-network (TensorFlow is absent from the image; the oracle takes the action of
+ * every decision tick as an input).
  *
  * Every function cites the reference file:line it restates (paths relative to /root/reference).
  */
