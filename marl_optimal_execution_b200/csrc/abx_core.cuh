@@ -627,6 +627,7 @@ struct Sim {
         if (is_buy ? price >= bp : price <= bp) {                                       // isMatch :242-254, head of best level only
           uint32_t h = c.lv_head(opp, n - 1); NodeRec hr = c.node_load(h);
           int32_t fq;
+          if (ENV && hr.id >= REPLAY_ID_BASE) c.id_prefetch((int)(hr.id - REPLAY_ID_BASE));   // its owner updates the record when ORDER_EXECUTED arrives
           if (qty >= hr.qty) {                                                          // :204-210 whole resting order consumed
             fq = hr.qty;
             if (hr.next == NIL) set_n_lv(opp, n - 1);                                    // level emptied: it is the last element
@@ -975,6 +976,7 @@ struct Sim {
     }
     uint32_t oid = REPLAY_ID_BASE + (uint32_t)row.x;
     uint4 t = c.id_load(row.x); bool existing = t.x != 0;
+    c.ib_prefetch(row.x);                                                               // the exchange reads the order's census when the message arrives
     if (!existing && row.z > 0) {                                                       // placeLimitOrder(order_id=ORDER_ID)
       t.x = (uint32_t)row.z; t.y = ((uint32_t)row.y << 1) | (uint32_t)(row.w & 1); c.id_store(row.x, t);
       int32_t p[6] = {(int32_t)oid, row.y, row.z, 0, row.w, 0}; env_send(ABX_LIMIT_ORDER, p, false);
@@ -994,8 +996,10 @@ struct Sim {
     int k = cur == 0 ? 0 : cur - 1;                                                     // orders_dict[currentTime]: the list's first entry is woken twice
     if (c.ts_load(k) != s.now) { s.flags |= ABX_F_UNSUPPORTED; return; }
     int r0 = c.first_load(k), r1 = c.first_load(k + 1);
+    int4 nxt = c.row_load(k + 1 < c.n_ts() ? r1 : r0);                                  // first row of the next wakeup: its per-order records are cold
 #pragma unroll 1
     for (int r = r0; r < r1; r++) replay_place(x, r);
+    if (nxt.x >= 0) { c.id_prefetch(nxt.x); c.ib_prefetch(nxt.x); }
   }
   ABX_HD void replay_receive(EnvX *x, const Event &m) {
     uint32_t fl = x->ra_flags; int32_t sh = x->ra_shares, lt = x->ra_last_trade; int64_t cash = x->ra_cash;
@@ -1556,8 +1560,8 @@ struct Sim {
     c.mid_store(k, ax.n_mids % MOM_MIDS, a.bid + a.ask);                                // 2 * mid: exact integer
     ax.n_mids++;
     int L = ax.n_mids;
-    if (L > 20) { int64_t sum2 = 0; for (int i = 0; i < 20; i++) sum2 += c.mid_load(k, (L - 1 - i) % MOM_MIDS); ax.avg20 = rint(dmul(((double)sum2 / 2) / 20, 100.0)) / 100.0; ax.mmflags |= MOF_HAS20; }
-    if (L > 50) { int64_t sum2 = 0; for (int i = 0; i < 50; i++) sum2 += c.mid_load(k, (L - 1 - i) % MOM_MIDS); ax.avg50 = rint(dmul(((double)sum2 / 2) / 50, 100.0)) / 100.0; ax.mmflags |= MOF_HAS50; }
+    if (L > 20) { int64_t sum2 = c.mid_sum(k, L, 20); ax.avg20 = rint(dmul(((double)sum2 / 2) / 20, 100.0)) / 100.0; ax.mmflags |= MOF_HAS20; }
+    if (L > 50) { int64_t sum2 = c.mid_sum(k, L, 50); ax.avg50 = rint(dmul(((double)sum2 / 2) / 50, 100.0)) / 100.0; ax.mmflags |= MOF_HAS50; }
     c.sync(); if (c.onchip_writer()) *aux() = ax; c.sync();
     if ((ax.mmflags & MOF_HAS20) && (ax.mmflags & MOF_HAS50)) { if (ax.avg20 >= ax.avg50) r3_place_limit(id, ax.size, true, a.ask, false); else r3_place_limit(id, ax.size, false, a.bid, false); }
   }

@@ -118,8 +118,11 @@ abx_env_reset_kernel(SimParams P, size_t smem_per_warp) {
   env_store(P.env + env, sim.s, ctx.lane);
 }
 
+#ifndef ABX_STEP_MINB
+#define ABX_STEP_MINB 16      // one-warp CTAs per SM the step kernels are compiled for (register budget = 65536 / (32 * ABX_STEP_MINB))
+#endif
 template <bool INSTR, bool SMALLQ>
-__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
+__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA, ABX_STEP_MINB)
 abx_env_step_kernel(SimParams P, const double *__restrict__ actions, double *__restrict__ obs, double *__restrict__ reward,
                     uint8_t *__restrict__ done, size_t smem_per_warp) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -165,7 +168,7 @@ abx_dq_reset_kernel(SimParams P, const uint64_t *__restrict__ seeds, const int32
 }
 
 template <bool INSTR>
-__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA, 16)      // 16 one-warp CTAs per SM: 128 registers (unbounded ptxas takes 168 -> 12 per SM)
+__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA, ABX_STEP_MINB)      // 16 one-warp CTAs per SM: 128 registers (unbounded ptxas takes 168 -> 12 per SM)
 abx_dq_step_kernel(SimParams P, const int32_t *__restrict__ actions, double *__restrict__ obs, double *__restrict__ trans, double *__restrict__ reward,
                    uint8_t *__restrict__ done, size_t smem_per_warp) {
   extern __shared__ __align__(16) unsigned char smem[];

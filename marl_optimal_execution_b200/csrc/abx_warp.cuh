@@ -49,7 +49,7 @@ __device__ __forceinline__ uint4 shfl4(uint4 v, int src) {
 constexpr int SMALLQ_CAP = 64;          // queue capacities up to this keep every key on chip (WarpCtxT<true>)
 __host__ __device__ inline bool warp_small_queue(const abx_sim_config &c) { return c.queue_cap <= SMALLQ_CAP; }
 __host__ __device__ inline size_t warp_smem_bytes(const abx_sim_config &c, bool env_shape = false, bool small_queue = false, bool hybrid_queue = false) {
-  size_t q = hybrid_queue ? (size_t)SMALLQ_CAP * 16 + (size_t)(c.queue_cap / 32) * 16 : (small_queue ? (size_t)SMALLQ_CAP * 16 : (size_t)(c.queue_cap / 32) * 16);
+  size_t q = hybrid_queue ? (size_t)SMALLQ_CAP * 48 + (size_t)(c.queue_cap / 32) * 16 : (small_queue ? (size_t)SMALLQ_CAP * 48 : (size_t)(c.queue_cap / 32) * 16);   // on-chip tier: key + 32-byte payload per slot
   return sizeof(ZiAgent) + OUT_CAP * OUT_WORDS * 4 + q + (size_t)c.level_cap * 2 * 12 + (env_shape ? sizeof(EnvX) : 0);
 }
 __device__ __forceinline__ double warp_sum(double v) {
@@ -71,7 +71,7 @@ struct WarpCtxT {
   // HBM bases of this environment
   uint4 *qkey, *qpay0, *qpay1; ZiAgent *agents; uint4 *nodes; abx_trace_rec *tr;
   // shared memory of this warp
-  ZiAgent *staged; uint32_t *obox; uint4 *qc, *qs; int32_t *lvp, *lvq; uint32_t *lvht; EnvX *ex;   // qc: group cache, qs: on-chip keys
+  ZiAgent *staged; uint32_t *obox; uint4 *qc, *qs, *qp0, *qp1; int32_t *lvp, *lvq; uint32_t *lvht; EnvX *ex;   // qc: group cache, qs: on-chip keys
   uint4 *idt; int4 *lob; uint2 *idb;   // ABIDESEnv shape: replay agent's per-order table, stored LOBs, per-order book census (HBM)
   // registers describing the group fetched by q_fetch
   uint64_t my_hi; uint32_t my_uniq; uint32_t cur_mask; int cur_group, cur_lane; int n_ovf; bool cur_t2; int day;   // day: the replayed day of this environment   // n_ovf: events in the overflow tier
@@ -83,6 +83,8 @@ struct WarpCtxT {
     staged = reinterpret_cast<ZiAgent *>(smem); smem += sizeof(ZiAgent);
     obox = reinterpret_cast<uint32_t *>(smem); smem += OUT_CAP * OUT_WORDS * 4;
     qs = reinterpret_cast<uint4 *>(smem); smem += SMALLQ ? (size_t)SMALLQ_CAP * 16 : 0;
+    qp0 = reinterpret_cast<uint4 *>(smem); smem += SMALLQ ? (size_t)SMALLQ_CAP * 16 : 0;
+    qp1 = reinterpret_cast<uint4 *>(smem); smem += SMALLQ ? (size_t)SMALLQ_CAP * 16 : 0;
     qc = reinterpret_cast<uint4 *>(smem); smem += (SMALLQ && !HYBRID) ? 0 : (size_t)P.n_qgroups * 16;
     lvp = reinterpret_cast<int32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
     lvq = reinterpret_cast<int32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
@@ -109,7 +111,11 @@ struct WarpCtxT {
 
   // ---- staging of the on-chip structures between launches ----
   __device__ void load_onchip(const EnvState &s) {
-    if (SMALLQ) { qs[lane] = ldcg4(qkey + lane); qs[lane + 32] = ldcg4(qkey + lane + 32); }
+    if (SMALLQ) {                                                            // keys and payloads of the on-chip tier (HBM only between launches)
+#pragma unroll
+      for (int j = 0; j < 2; j++) { int i = lane + 32 * j; uint4 k = ldcg4(qkey + i); qs[i] = k;
+        if ((k.x & k.y) != 0xffffffffu) { qp0[i] = ldcg4(qpay0 + i); qp1[i] = ldcg4(qpay1 + i); } }
+    }
     if (!SMALLQ || HYBRID) {
       const uint4 *gc = P.qcache + (size_t)env * P.n_qgroups; int cnt = 0;
 #pragma unroll 1
@@ -127,7 +133,11 @@ struct WarpCtxT {
   }
   __device__ void store_onchip(const EnvState &s) {
     sync();
-    if (SMALLQ) { __stcg(qkey + lane, qs[lane]); __stcg(qkey + lane + 32, qs[lane + 32]); }
+    if (SMALLQ) {
+#pragma unroll
+      for (int j = 0; j < 2; j++) { int i = lane + 32 * j; uint4 k = qs[i]; __stcg(qkey + i, k);
+        if ((k.x & k.y) != 0xffffffffu) { __stcg(qpay0 + i, qp0[i]); __stcg(qpay1 + i, qp1[i]); } }
+    }
     if (!SMALLQ || HYBRID) {
       uint4 *gc = P.qcache + (size_t)env * P.n_qgroups;
 #pragma unroll 1
@@ -172,9 +182,9 @@ struct WarpCtxT {
   }
   __device__ __forceinline__ void q_fetch(int g, Event &e) {
     if (SMALLQ) {
-      if (g < SMALLQ_CAP) {                                                // a slot of the on-chip tier: key on chip, 32 bytes of payload from HBM (same address in every lane: one transaction)
+      if (g < SMALLQ_CAP) {                                                // a slot of the on-chip tier: key and payload in shared memory (no L2 round trip per pop)
         cur_group = g; cur_t2 = false;
-        event_unpack(qs[g], ldcg4(qpay0 + g), ldcg4(qpay1 + g), e);
+        event_unpack(qs[g], qp0[g], qp1[g], e);
         return;
       }
       g -= SMALLQ_CAP; cur_t2 = true;
@@ -219,9 +229,7 @@ struct WarpCtxT {
       if (b0 | b1) {
         int slot = b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1;
         uint4 k, a, b; event_pack(e, k, a, b);
-        sync(); qs[slot] = k;
-        if (lane < 2) { uint4 *dst = lane == 0 ? qpay0 : qpay1; dst[slot] = lane == 0 ? a : b; }
-        __syncwarp();
+        sync(); qs[slot] = k; qp0[slot] = a; qp1[slot] = b; sync();
         return true;
       }
       if (!HYBRID) return false;
@@ -299,6 +307,9 @@ struct WarpCtxT {
   __device__ __forceinline__ uint4 id_load(int i) const { return ldcg4(idt + i); }
   __device__ __forceinline__ void id_store(int i, uint4 v) { if (lane == 0) __stcg(idt + i, v); __syncwarp(); }
   __device__ __forceinline__ uint2 ib_load(int i) const { return __ldcg(idb + i); }
+  // the per-order records are cold HBM sectors (one per order, ~1 MB per environment): ask L2 for them an event or more before they are needed
+  __device__ __forceinline__ void id_prefetch(int i) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(idt + i)); }
+  __device__ __forceinline__ void ib_prefetch(int i) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(idb + i)); }
   __device__ __forceinline__ void ib_store(int i, uint2 v) { if (lane == 0) __stcg(idb + i, v); __syncwarp(); }
   __device__ __forceinline__ int4 row_load(int r) const { return __ldg(P.st_rows + r); }
   __device__ __forceinline__ int4 day_rec() const { return __ldg(P.day_tab + day); }
@@ -315,6 +326,15 @@ struct WarpCtxT {
   }
   // rmsc03: momentum agent k's ring of doubled mid prices lives in the per-environment int4 table
   __device__ __forceinline__ int32_t mid_load(int k, int slot) const { return __ldcg(reinterpret_cast<const int32_t *>(lob) + k * MOM_MIDS + slot); }
+  // sum of the n (<= 64) most recent of the L stored doubled mids: lanes take entries lane, lane+32; 16-bit halves keep the REDUX sums exact
+  __device__ __forceinline__ int64_t mid_sum(int k, int L, int n) const {
+    static_assert((MOM_MIDS & (MOM_MIDS - 1)) == 0, "ring size");
+    const int32_t *m = reinterpret_cast<const int32_t *>(lob) + k * MOM_MIDS; int32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int j = 0; j < 2; j++) { int i = lane + 32 * j; if (i < n) { int32_t v = __ldcg(m + ((L - 1 - i) & (MOM_MIDS - 1))); lo += v & 0xffff; hi += v >> 16; } }
+    lo = __reduce_add_sync(FULL, lo); hi = __reduce_add_sync(FULL, hi);
+    return ((int64_t)hi << 16) + lo;
+  }
   __device__ __forceinline__ void mid_store(int k, int slot, int32_t v) { if (lane == 0) __stcg(reinterpret_cast<int32_t *>(lob) + k * MOM_MIDS + slot, v); __syncwarp(); }
   // np.std (ddof 0) of log(mid_i / p0) over the n stored LOBs: lanes take LOBs lane, lane+32, ... (ABIDESEnvMetrics.py:183-192)
   __device__ double lob_midvol(int n, int head, double p0, bool &bad) const {
