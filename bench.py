@@ -548,10 +548,10 @@ def main():
     ap.add_argument("--seed", type=int, default=123456789)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-env", action="store_true", help="skip the ABIDESEnv steps/s measurement")
-    ap.add_argument("--env-envs-per-gpu", type=int, default=8192)
+    ap.add_argument("--env-envs-per-gpu", type=int, default=9472, help="4 x 148 SMs x 16 resident one-warp CTAs: whole waves (8192 leaves the 4th wave 46 %% full)")
     ap.add_argument("--env-steps", type=int, default=750, help="timed ABIDESEnv steps: 750 = the whole 761-tick episode after the start-up and warm-up steps")
     ap.add_argument("--no-ddqn", action="store_true", help="skip the DDQN execution shape (Q-network forward + environment step per tick)")
-    ap.add_argument("--ddqn-envs-per-gpu", type=int, default=8192)
+    ap.add_argument("--ddqn-envs-per-gpu", type=int, default=9472, help="whole waves of 148 x 16 resident environments, like --env-envs-per-gpu")
     ap.add_argument("--ddqn-steps", type=int, default=200, help="timed DDQN decision ticks per sub-measurement (acting, e2e, training share one 660-tick day)")
     ap.add_argument("--ddqn-batch", type=int, default=4096, help="learner batch size of the DDQN training sub-measurement")
     args = ap.parse_args()

@@ -612,8 +612,8 @@ struct Sim {
   ABX_HD void book_handle_limit(uint32_t oid, int agent, int is_buy, int32_t price, int32_t qty, double lat_in) {
     if (qty <= 0) return;                                                               // :47-49
     if (ENV && oid >= REPLAY_ID_BASE) {                                                 // :52-60 history[0][order_id] = {...}
-      uint4 t = c.id_load((int)(oid - REPLAY_ID_BASE)); uint32_t d = s.trade_epoch - t.z;
-      t.w = (t.w == 0 || d >= 16) ? 1u : (((t.w << d) | 1u) & 0xffffu); t.z = s.trade_epoch; c.id_store((int)(oid - REPLAY_ID_BASE), t);
+      uint4 t = c.ord_load((int)(oid - REPLAY_ID_BASE)); uint32_t d = s.trade_epoch - t.z;
+      t.w = (t.w == 0 || d >= 16) ? 1u : (((t.w << d) | 1u) & 0xffffu); t.z = s.trade_epoch; c.ord_store((int)(oid - REPLAY_ID_BASE), t);
     }
     int opp = is_buy ? 1 : 0;                                                           // a buy matches asks (side 1)
     uint32_t epoch0 = s.trade_epoch;                                                    // the incoming order's history bucket (:52-60)
@@ -929,7 +929,7 @@ struct Sim {
     hr.id = oid; hr.qty = new_qty; hr.agent = (uint32_t)agent; c.node_store(head, hr);  // :352 book[i][0] = new_order  (slot 0, App. A-13)
     if (new_price != price) s.flags |= ABX_F_UNSUPPORTED;                               // a re-priced head would unsort the ladder; never in LOBSTER replays
     int buckets = 0;                                                                    // :353-367 one ORDER_MODIFIED per history bucket holding the id
-    if (oid >= REPLAY_ID_BASE) { uint4 t = c.id_load((int)(oid - REPLAY_ID_BASE)); uint32_t d = s.trade_epoch - t.z; if (t.w != 0 && d <= (uint32_t)P.c.stream_history) buckets = __popc_compat(t.w & ((1u << (P.c.stream_history + 1 - d)) - 1u)); }
+    if (oid >= REPLAY_ID_BASE) { uint4 t = c.ord_load((int)(oid - REPLAY_ID_BASE)); uint32_t d = s.trade_epoch - t.z; if (t.w != 0 && d <= (uint32_t)P.c.stream_history) buckets = __popc_compat(t.w & ((1u << (P.c.stream_history + 1 - d)) - 1u)); }
 #pragma unroll 1
     for (int k = 0; k < matches * buckets; k++) {
       exch_send_order(agent, ABX_ORDER_MODIFIED, oid, new_price, new_qty, 0, is_buy, 0.0);
@@ -975,10 +975,10 @@ struct Sim {
       return;
     }
     uint32_t oid = REPLAY_ID_BASE + (uint32_t)row.x;
-    uint4 t = c.id_load(row.x); bool existing = t.x != 0;
+    uint4 t = c.ord_load(row.x); bool existing = t.x != 0;
     c.ib_prefetch(row.x);                                                               // the exchange reads the order's census when the message arrives
     if (!existing && row.z > 0) {                                                       // placeLimitOrder(order_id=ORDER_ID)
-      t.x = (uint32_t)row.z; t.y = ((uint32_t)row.y << 1) | (uint32_t)(row.w & 1); c.id_store(row.x, t);
+      t.x = (uint32_t)row.z; t.y = ((uint32_t)row.y << 1) | (uint32_t)(row.w & 1); c.ord_store(row.x, t);
       int32_t p[6] = {(int32_t)oid, row.y, row.z, 0, row.w, 0}; env_send(ABX_LIMIT_ORDER, p, false);
     } else if (existing && row.z == 0) {                                                // cancelOrder(existing_order)
       int32_t p[6] = {(int32_t)oid, (int32_t)(t.y >> 1), (int32_t)t.x, 0, (int32_t)(t.y & 1u), 0}; env_send(ABX_CANCEL_ORDER, p, false);
@@ -1006,8 +1006,8 @@ struct Sim {
     bool newly = ta_receive(m, fl, sh, cash, lt);
     if (m.kind == ABX_ORDER_EXECUTED || m.kind == ABX_ORDER_CANCELLED) {                // orderExecuted :422-462 / orderCancelled :476-489
       uint32_t oid = (uint32_t)m.p[0];
-      if (oid >= REPLAY_ID_BASE) { uint4 t = c.id_load((int)(oid - REPLAY_ID_BASE));
-        if (t.x != 0) { if (m.kind == ABX_ORDER_CANCELLED || (uint32_t)m.p[2] >= t.x) t.x = 0; else t.x -= (uint32_t)m.p[2]; c.id_store((int)(oid - REPLAY_ID_BASE), t); } }
+      if (oid >= REPLAY_ID_BASE) { uint4 t = c.ord_load((int)(oid - REPLAY_ID_BASE));
+        if (t.x != 0) { if (m.kind == ABX_ORDER_CANCELLED || (uint32_t)m.p[2] >= t.x) t.x = 0; else t.x -= (uint32_t)m.p[2]; c.ord_store((int)(oid - REPLAY_ID_BASE), t); } }
       else if (oid == 0 && x->g0_qty != 0) { int32_t gq = x->g0_qty; gq = (m.kind == ABX_ORDER_CANCELLED || m.p[2] >= gq) ? 0 : gq - m.p[2]; c.sync(); if (c.onchip_writer()) x->g0_qty = gq; c.sync(); }
       if (m.kind == ABX_ORDER_EXECUTED) { lt = m.p[3]; fl |= AF_HAS_LAST; }             // MarketReplayAgent.receiveMessage :62-67
     }

@@ -48,9 +48,10 @@ __device__ __forceinline__ uint4 shfl4(uint4 v, int src) {
 // bytes of shared memory one environment needs
 constexpr int SMALLQ_CAP = 64;          // queue capacities up to this keep every key on chip (WarpCtxT<true>)
 __host__ __device__ inline bool warp_small_queue(const abx_sim_config &c) { return c.queue_cap <= SMALLQ_CAP; }
+constexpr int OC_N = 16;                 // entries of the on-chip cache of replayed orders' records
 __host__ __device__ inline size_t warp_smem_bytes(const abx_sim_config &c, bool env_shape = false, bool small_queue = false, bool hybrid_queue = false) {
   size_t q = hybrid_queue ? (size_t)SMALLQ_CAP * 48 + (size_t)(c.queue_cap / 32) * 16 : (small_queue ? (size_t)SMALLQ_CAP * 48 : (size_t)(c.queue_cap / 32) * 16);   // on-chip tier: key + 32-byte payload per slot
-  return sizeof(ZiAgent) + OUT_CAP * OUT_WORDS * 4 + q + (size_t)c.level_cap * 2 * 12 + (env_shape ? sizeof(EnvX) : 0);
+  return sizeof(ZiAgent) + OUT_CAP * OUT_WORDS * 4 + q + (size_t)c.level_cap * 2 * 12 + (env_shape ? sizeof(EnvX) + OC_N * 32 : 0);
 }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -72,6 +73,7 @@ struct WarpCtxT {
   uint4 *qkey, *qpay0, *qpay1; ZiAgent *agents; uint4 *nodes; abx_trace_rec *tr;
   // shared memory of this warp
   ZiAgent *staged; uint32_t *obox; uint4 *qc, *qs, *qp0, *qp1; int32_t *lvp, *lvq; uint32_t *lvht; EnvX *ex;   // qc: group cache, qs: on-chip keys
+  uint4 *oc_t; uint2 *oc_b; int32_t *oc_tag;   // on-chip cache of replayed orders' records (direct mapped, write-through)
   uint4 *idt; int4 *lob; uint2 *idb;   // ABIDESEnv shape: replay agent's per-order table, stored LOBs, per-order book census (HBM)
   // registers describing the group fetched by q_fetch
   uint64_t my_hi; uint32_t my_uniq; uint32_t cur_mask; int cur_group, cur_lane; int n_ovf; bool cur_t2; int day;   // day: the replayed day of this environment   // n_ovf: events in the overflow tier
@@ -89,7 +91,9 @@ struct WarpCtxT {
     lvp = reinterpret_cast<int32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
     lvq = reinterpret_cast<int32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
     lvht = reinterpret_cast<uint32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
-    ex = reinterpret_cast<EnvX *>(smem);
+    ex = reinterpret_cast<EnvX *>(smem); smem += sizeof(EnvX);
+    oc_t = reinterpret_cast<uint4 *>(smem); oc_b = reinterpret_cast<uint2 *>(smem + OC_N * 16); oc_tag = reinterpret_cast<int32_t *>(smem + OC_N * 24);
+    if (P.idbook && lane < OC_N) oc_tag[lane] = -1;
     idb = P.idbook ? P.idbook + (size_t)env * P.n_ids : nullptr;
     idt = P.idtab ? P.idtab + (size_t)env * P.n_ids : nullptr; lob = P.lobs ? P.lobs + (size_t)env * LOB_CAP * 3 : nullptr;
     cur_group = cur_lane = -1; cur_mask = 0; my_hi = KEY_EMPTY; my_uniq = 0xffffffffu; n_ovf = 0; cur_t2 = false;
@@ -306,11 +310,21 @@ struct WarpCtxT {
   __device__ void envx_store() { sync(); uint4 *dst = reinterpret_cast<uint4 *>(P.envx + env); for (int i = lane; i < (int)(sizeof(EnvX) / 16); i += 32) __stcg(dst + i, reinterpret_cast<const uint4 *>(ex)[i]); }
   __device__ __forceinline__ uint4 id_load(int i) const { return ldcg4(idt + i); }
   __device__ __forceinline__ void id_store(int i, uint4 v) { if (lane == 0) __stcg(idt + i, v); __syncwarp(); }
-  __device__ __forceinline__ uint2 ib_load(int i) const { return __ldcg(idb + i); }
+  // Replayed orders' records {agent-side entry of idtab, census entry of idbook}: one replayed order is touched by three to five consecutive events
+  // (placement, the exchange's registration and census, the acknowledgement), each a dependent L2/HBM round trip.  A miss fetches both halves at once;
+  // stores write through, so HBM is always current and the cache needs no flush.  Same value, same address from every lane: one transaction.
+  __device__ __forceinline__ int oc_slot(int i) {
+    int sl = i & (OC_N - 1);
+    if (oc_tag[sl] != i) { uint4 t = ldcg4(idt + i); uint2 b = __ldcg(idb + i); sync(); oc_tag[sl] = i; oc_t[sl] = t; oc_b[sl] = b; sync(); }
+    return sl;
+  }
+  __device__ __forceinline__ uint4 ord_load(int i) { return oc_t[oc_slot(i)]; }
+  __device__ __forceinline__ void ord_store(int i, uint4 v) { __stcg(idt + i, v); int sl = i & (OC_N - 1); sync(); if (oc_tag[sl] == i) oc_t[sl] = v; sync(); }
+  __device__ __forceinline__ uint2 ib_load(int i) { return oc_b[oc_slot(i)]; }
   // the per-order records are cold HBM sectors (one per order, ~1 MB per environment): ask L2 for them an event or more before they are needed
   __device__ __forceinline__ void id_prefetch(int i) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(idt + i)); }
   __device__ __forceinline__ void ib_prefetch(int i) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(idb + i)); }
-  __device__ __forceinline__ void ib_store(int i, uint2 v) { if (lane == 0) __stcg(idb + i, v); __syncwarp(); }
+  __device__ __forceinline__ void ib_store(int i, uint2 v) { __stcg(idb + i, v); int sl = i & (OC_N - 1); sync(); if (oc_tag[sl] == i) oc_b[sl] = v; sync(); }
   __device__ __forceinline__ int4 row_load(int r) const { return __ldg(P.st_rows + r); }
   __device__ __forceinline__ int4 day_rec() const { return __ldg(P.day_tab + day); }
   __device__ __forceinline__ int n_ts() const { return day_rec().y; }

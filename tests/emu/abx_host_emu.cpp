@@ -89,6 +89,7 @@ struct HostCtx {
   void lob_store(int slot, const int32_t w[12]) { for (int k = 0; k < 3; k++) { int4 v; v.x = w[4 * k]; v.y = w[4 * k + 1]; v.z = w[4 * k + 2]; v.w = w[4 * k + 3]; lob[slot * 3 + k] = v; } }
   void lob_load(int slot, int32_t w[12]) { for (int k = 0; k < 3; k++) { int4 v = lob[slot * 3 + k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; } }
   void id_prefetch(int) {} void ib_prefetch(int) {}
+  uint4 ord_load(int i) { return id_load(i); } void ord_store(int i, uint4 v) { id_store(i, v); }
   int64_t mid_sum(int k, int L, int n) { int64_t t = 0; for (int i = 0; i < n; i++) t += mid_load(k, (L - 1 - i) % MOM_MIDS); return t; }
   int32_t mid_load(int k, int slot) { return reinterpret_cast<int32_t *>(lob)[k * MOM_MIDS + slot]; }
   void mid_store(int k, int slot, int32_t v) { reinterpret_cast<int32_t *>(lob)[k * MOM_MIDS + slot] = v; }
