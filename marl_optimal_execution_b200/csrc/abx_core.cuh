@@ -238,6 +238,21 @@ ABX_NI U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
 }
 ABX_NI double exp_ni(double x) { return exp(x); }
 ABX_NI double log_ni(double x) { return log(x); }
+// log(x), x in (0, 1], for the Philox-mode variate transforms only (no parity constraint; ~1e-13 relative): fp32 seed, one Newton step on
+// exp(y) = x through the exp body the belief update keeps resident anyway.  The libm log body is 237 instructions of instruction-cache footprint.
+ABX_HD double log_unit(double x) {
+#if defined(__CUDA_ARCH__)
+  double y0 = (double)(__log2f((float)x) * 0.69314718f);
+  return (y0 - 1.0) + x * exp_ni(-y0);
+#else
+  return log(x);
+#endif
+}
+ABX_NI double box_muller(uint32_t a, uint32_t b, uint32_t cw) {                        // one body for every normal draw (value in, value out: nothing address-taken)
+  double u1 = 1.0 - ((a >> 5) * 67108864.0 + (b >> 6)) / 9007199254740992.0;           // u1 in (0,1]
+  float ang = (float)(cw >> 8) * (2.0f / 16777216.0f);                                 // angle / pi in [0, 2): 24 random bits, fp32 cos
+  return sqrt(-2.0 * log_unit(u1)) * (double)cospif(ang);
+}
 ABX_NI double pow_ni(double x, double y) { return pow(x, y); }
 enum { S_SYMBOL = 0, S_KERNEL = 1, S_LATENCY = 2, S_GLOBAL = 3, S_AGENT0 = 3 };  // agent a uses stream S_AGENT0 + a
 
@@ -259,13 +274,11 @@ struct RngT {
   ABX_HD double std_normal(int stream, uint32_t &ctr) {
     if (tape()) return bits_dbl(tape_next(stream, ctr, 'n'));
     U4 o = philox(stream, ctr);
-    double u1 = 1.0 - u53(o.x, o.y);                                         // u1 in (0,1]
-    float ang = (float)(o.z >> 8) * (2.0f / 16777216.0f);                    // angle / pi in [0, 2): 24 random bits, fp32 cos
-    return sqrt(-2.0 * log_ni(u1)) * (double)cospif(ang);
+    return box_muller(o.x, o.y, o.z);
   }
   ABX_HD double std_exponential(int stream, uint32_t &ctr) {
     if (tape()) return bits_dbl(tape_next(stream, ctr, 'e'));
-    U4 o = philox(stream, ctr); return -log_ni(1.0 - u53(o.x, o.y));
+    U4 o = philox(stream, ctr); return -log_unit(1.0 - u53(o.x, o.y));
   }
   ABX_HD double u01(int stream, uint32_t &ctr) {
     if (tape()) return bits_dbl(tape_next(stream, ctr, 'u'));
@@ -392,7 +405,7 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
 // ---------------------------------------------------------------------------------------------------
 // The simulation, templated on the context type that supplies the cooperative primitives:
 //   queue:   bool q_min(uint64_t&hi, uint32_t&uniq, int&group); void q_fetch(group, Event&); void q_remove(); void q_requeue(int64_t t);
-//            bool q_push(const Event&)            (false == overflow)
+//            bool q_push(const Event&, now)       (false == overflow)
 //   ladders: void lv_find(side, price, int n, int&pos, bool&found); lv_insert/lv_remove; lv_price/lv_qty/lv_head/lv_tail get/set
 //   nodes:   NodeRec node_load(i); void node_store(i, rec)
 //   agents:  ZiAgent* agent_stage(id)  -- 128-bit cooperative copy HBM -> on-chip staging record, returned pointer is
@@ -473,12 +486,18 @@ struct Sim {
   // entry words: [0] recipient | kind<<16 | flags, [1..6] payload, [7,8] pair latency (fp64 bits), [9,10] int64:
   // send offset (computation delay + additional + pipeline delay) for messages, absolute time for wakeups.
   ABX_HD void emit(uint32_t w0, const int32_t p[6], double lat, int64_t off) {
-    if (n_out >= OUT_CAP) { s.flags |= ABX_F_QUEUE_OVERFLOW; return; }
+    if (n_out >= Ctx::OUTN) { s.flags |= ABX_F_QUEUE_OVERFLOW; return; }
     if (c.onchip_writer()) {
-      uint32_t *o = c.outbox() + n_out * OUT_WORDS;
+      uint32_t *o = c.outbox() + n_out * OUT_WORDS; uint64_t lb = dbl_bits(lat);
+#if defined(__CUDA_ARCH__)                                                             // three 128-bit stores instead of eleven words: emit is inlined at every send site
+      uint4 *o4 = reinterpret_cast<uint4 *>(o);
+      o4[0] = make_uint4(w0, (uint32_t)p[0], (uint32_t)p[1], (uint32_t)p[2]); o4[1] = make_uint4((uint32_t)p[3], (uint32_t)p[4], (uint32_t)p[5], (uint32_t)lb);
+      o4[2] = make_uint4((uint32_t)(lb >> 32), (uint32_t)(uint64_t)off, (uint32_t)((uint64_t)off >> 32), 0u);
+#else
       o[0] = w0; for (int i = 0; i < 6; i++) o[1 + i] = (uint32_t)p[i];
-      uint64_t lb = dbl_bits(lat); o[7] = (uint32_t)lb; o[8] = (uint32_t)(lb >> 32);
+      o[7] = (uint32_t)lb; o[8] = (uint32_t)(lb >> 32);
       o[9] = (uint32_t)(uint64_t)off; o[10] = (uint32_t)((uint64_t)off >> 32);
+#endif
     }
     n_out++;
   }
@@ -501,7 +520,13 @@ struct Sim {
     c.sync();
 #pragma unroll 1
     for (int i = 0; i < n_out; i++) {
-      const uint32_t *o = c.outbox() + i * OUT_WORDS;
+      const uint32_t *op = c.outbox() + i * OUT_WORDS; uint32_t o[OUT_WORDS];
+#if defined(__CUDA_ARCH__)
+      { const uint4 *o4 = reinterpret_cast<const uint4 *>(op); uint4 v0 = o4[0], v1 = o4[1], v2 = o4[2];
+        o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v0.w; o[4] = v1.x; o[5] = v1.y; o[6] = v1.z; o[7] = v1.w; o[8] = v2.x; o[9] = v2.y; o[10] = v2.z; o[11] = v2.w; }
+#else
+      for (int k = 0; k < OUT_WORDS; k++) o[k] = op[k];
+#endif
       uint32_t w0 = o[0]; Event e;
       for (int k = 0; k < 6; k++) e.p[k] = (int32_t)o[1 + k];
       double lat = bits_dbl((uint64_t)o[7] | ((uint64_t)o[8] << 32));
@@ -531,7 +556,7 @@ struct Sim {
         e.x0 = (int32_t)o[7]; e.x1 = (int32_t)o[8];                                   // exchange replies: level-2 prices ride in the latency words
       }
       if (BOOK) continue;                                                             // bare-book replay: the notification is the output (traced above), there is no kernel queue
-      if (!c.q_push(e)) s.flags |= ABX_F_QUEUE_OVERFLOW;                              // Kernel.py:425 / :462
+      if (!c.q_push(e, s.now)) s.flags |= ABX_F_QUEUE_OVERFLOW;                              // Kernel.py:425 / :462
       else { s.q_count++; if (s.q_count > s.max_q) s.max_q = s.q_count; }
     }
     n_out = 0;
@@ -645,7 +670,7 @@ struct Sim {
           exch_send_order((int)(hr.agent & 0xffffu), ABX_ORDER_EXECUTED, hr.id, bp, fq, bp, !is_buy, (ENV || R3) ? 0.0 : c.agent_lat_from((int)hr.agent)); // :89-91
           trade_qty += fq; trade_px += (int64_t)bp * fq; s.c_fills++; matched = true;
           if (qty <= 0) matching = false;
-          if (n_out >= OUT_CAP - 3) flush(); else c.sync();
+          if (n_out >= Ctx::OUTN - 3) flush(); else c.sync();
         }
       }
       if (!matched) {
@@ -835,7 +860,7 @@ struct Sim {
 #pragma unroll 1
     for (int id = 0; id < P.c.n_agents; id++) {                                         // Agent.kernelStarting :78
       set_wakeup(id, P.c.start_ns);
-      if (n_out >= OUT_CAP - 1) flush();
+      if (n_out >= Ctx::OUTN - 1) flush();
     }
     flush();
     s.flags |= rng.err;
@@ -933,7 +958,7 @@ struct Sim {
 #pragma unroll 1
     for (int k = 0; k < matches * buckets; k++) {
       exch_send_order(agent, ABX_ORDER_MODIFIED, oid, new_price, new_qty, 0, is_buy, 0.0);
-      if (n_out >= OUT_CAP - 3) flush();
+      if (n_out >= Ctx::OUTN - 3) flush();
     }
   }
   ABX_HD void env_exch_receive(const Event &m) {                                        // ExchangeAgent.receiveMessage :129-340
@@ -971,7 +996,7 @@ struct Sim {
         s.next_order_id++;
         int32_t p[6] = {0, gp >> 1, gq, row.y, (gp & 1) | 2, row.z}; env_send(ABX_MODIFY_ORDER, p, false);
       }
-      if (n_out >= OUT_CAP - 3) flush();
+      if (n_out >= Ctx::OUTN - 3) flush();
       return;
     }
     uint32_t oid = REPLAY_ID_BASE + (uint32_t)row.x;
@@ -985,7 +1010,7 @@ struct Sim {
     } else if (existing) {                                                              // modifyOrder(existing_order, LimitOrder(new SIZE, PRICE))
       int32_t p[6] = {(int32_t)oid, (int32_t)(t.y >> 1), (int32_t)t.x, row.y, (int32_t)(t.y & 1u), row.z}; env_send(ABX_MODIFY_ORDER, p, false);
     }
-    if (n_out >= OUT_CAP - 3) flush();
+    if (n_out >= Ctx::OUTN - 3) flush();
   }
   ABX_HD void replay_wakeup(EnvX *x) {                                                  // wakeup :50-60
     ta_wakeup(x->ra_flags);
@@ -1199,7 +1224,7 @@ struct Sim {
     if (a.n_orders < EXEC_ORDER_CAP) { uint4 v; v.x = oid; v.y = (uint32_t)price; v.z = (uint32_t)(buy ? size : -size); v.w = 0; c.id_store(dq_order_base(id) + a.n_orders, v); a.n_orders++; }
     else s.flags |= ABX_F_AGENT_ORDERS_OVERFLOW;
     int32_t pl[6] = {(int32_t)oid, price, size, 0, buy, 0}; env_send(ABX_LIMIT_ORDER, pl, false);
-    if (n_out >= OUT_CAP - 3) flush();
+    if (n_out >= Ctx::OUTN - 3) flush();
   }
   ABX_HD void dq_cancel_all(int id) {                                                   // ExecutionAgent.cancelOrders :126-128 / DDQN cancel_orders :578-585
     int base = dq_order_base(id);
@@ -1207,7 +1232,7 @@ struct Sim {
     for (int i = 0; i < a.n_orders; i++) {
       uint4 v = c.id_load(base + i); int32_t q = (int32_t)v.z;
       int32_t p[6] = {(int32_t)v.x, (int32_t)v.y, q < 0 ? -q : q, 0, q > 0, 0}; env_send(ABX_CANCEL_ORDER, p, false);
-      if (n_out >= OUT_CAP - 3) flush();
+      if (n_out >= Ctx::OUTN - 3) flush();
     }
   }
   ABX_HD void dq_order_update(int id, uint32_t oid, int32_t fill, bool cancel) {         // TradingAgent.orderExecuted :445-452, orderCancelled :480-483
@@ -1480,7 +1505,7 @@ struct Sim {
       else s.flags |= ABX_F_AGENT_ORDERS_OVERFLOW;
     }
     int32_t pl[6] = {(int32_t)oid, price, size, 0, buy, 0}; env_send(ABX_LIMIT_ORDER, pl, false);
-    if (n_out >= OUT_CAP - 3) flush();
+    if (n_out >= Ctx::OUTN - 3) flush();
     (void)id;
   }
   ABX_HD void r3_cancel_all(int type) {                                                 // cancelOrders / cancelAllOrders
@@ -1489,7 +1514,7 @@ struct Sim {
       uint32_t oid; int32_t price, q;
       if (type == AT_POVMM) { uint4 v = c.id_load(i); oid = v.x; price = (int32_t)v.y; q = (int32_t)v.z; } else { oid = z->oid[i]; price = z->oprice[i]; q = z->oqty[i]; }
       int32_t p[6] = {(int32_t)oid, price, q < 0 ? -q : q, 0, q > 0, 0}; env_send(ABX_CANCEL_ORDER, p, false);
-      if (n_out >= OUT_CAP - 3) flush();
+      if (n_out >= Ctx::OUTN - 3) flush();
     }
   }
   ABX_HD void r3_wakeup(int id) {

@@ -34,7 +34,7 @@ static inline int config_sparse_zi(int variant, abx_sim_config *c) {
   c->sigma_n = 1000000.0; c->agent_kappa = 1.67e-15; c->sigma_s = 1e-4; c->sigma_pv = 5e6; c->lambda_a = 1e-12; // :232-250
   if (variant == 1000) {                                                      // :264-286 old latency model
     c->latency_model = ABX_LAT_MATRIX_NOISE; c->n_noise = 6; c->latency_mirrored = 1; c->latency_lo = 21000; c->latency_hi = 13000000;
-    c->queue_cap = 2560; c->level_cap = 448; c->order_cap = 2048;   // measured maxima over 128 seeds: queue 2 005, levels 357 / 349 (mean 311, sd ~15), resting 716
+    c->queue_cap = 2240; c->level_cap = 428; c->order_cap = 2048;   // measured maxima over 128 seeds: queue 2 005, levels 357 / 349 (mean 311, sd ~15), resting 716
   } else {                                                                    // sparse_zi_100.py:305-318 cubic model
     c->latency_model = ABX_LAT_CUBIC; c->n_noise = 1; c->latency_mirrored = 0; c->latency_lo = 21000; c->latency_hi = 100000;
     c->jitter = 0.3; c->jitter_clip = 0.05; c->jitter_unit = 5.0;

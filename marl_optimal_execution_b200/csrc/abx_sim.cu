@@ -3,6 +3,7 @@
 // Launch geometry: one warp per environment, ABX_WARPS_PER_CTA warps per CTA, each warp owning a private slice of
 // dynamic shared memory (abx_warp.cuh).  A warp runs its environment's whole event loop (Kernel.py:190-292) up to
 // the requested simulated time in one launch; environments never communicate.
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <new>
@@ -43,33 +44,42 @@ __device__ __forceinline__ void env_store(EnvState *g, const EnvState &s, int la
     for (int i = 0; i < (int)(sizeof(EnvState) / 16); i++) __stcg(dst + i, src[i]); }
 }
 
+template <class Ctx>
+__device__ void reset_env_with(const SimParams &P, EnvState &s, int env, unsigned char *smem) {
+  Ctx ctx(P, env, smem);
+  ctx.q_clear();
+  Sim<Ctx> sim(ctx, P, s, env);
+  sim.reset_env();
+  ctx.store_onchip(sim.s);
+  env_store(P.env + env, sim.s, ctx.lane);
+}
 __global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
 abx_reset_env_kernel(SimParams P, const uint64_t *__restrict__ seeds, const uint32_t *__restrict__ init_err, size_t smem_per_warp) {
   extern __shared__ __align__(16) unsigned char smem[];
   int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
   if (env >= P.n_envs) return;
-  WarpCtx ctx(P, env, smem + warp * smem_per_warp);
   EnvState s; init_env_state(P, seeds ? seeds[env] : 0, s); s.flags |= init_err[env];
-  ctx.q_clear();
-  Sim<WarpCtx> sim(ctx, P, s, env);
-  sim.reset_env();
-  ctx.store_onchip(sim.s);
-  env_store(P.env + env, sim.s, ctx.lane);
+  if (P.c.population == 0) reset_env_with<WarpCtxNearQ>(P, s, env, smem + warp * smem_per_warp);     // sparse_zi: near/far event queue
+  else reset_env_with<WarpCtx>(P, s, env, smem + warp * smem_per_warp);
 }
 
 // One instantiation per (RNG mode, latency model, instrumentation): the production path (Philox, no instrumentation)
 // carries neither the tape-replay branches nor the parity hash/trace code.
+#ifndef ABX_RUN_MINB
+#define ABX_RUN_MINB 16       // one-warp CTAs per SM the run kernel is compiled for
+#endif
 template <int RNG, int LAT, bool INSTR, int SHAPE = SHAPE_ZI>
-__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
+__global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA, ABX_RUN_MINB)
 abx_run_kernel(SimParams P, int64_t until_ns, const int64_t *__restrict__ until_each, size_t smem_per_warp) {
   extern __shared__ __align__(16) unsigned char smem[];
   int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
   if (env >= P.n_envs) return;
-  WarpCtx ctx(P, env, smem + warp * smem_per_warp);
+  typedef typename std::conditional<SHAPE == SHAPE_ZI, WarpCtxNearQ, WarpCtx>::type Ctx;
+  Ctx ctx(P, env, smem + warp * smem_per_warp);
   EnvState s = env_load(P.env + env);
   if (s.flags & ABX_F_DONE) return;
   ctx.load_onchip(s);
-  Sim<WarpCtx, RNG, LAT, INSTR, SHAPE> sim(ctx, P, s, env);
+  Sim<Ctx, RNG, LAT, INSTR, SHAPE> sim(ctx, P, s, env);
   if (SHAPE == SHAPE_R3) sim.r3_run(until_each ? until_each[env] : until_ns); else sim.run(until_each ? until_each[env] : until_ns);
   ctx.store_onchip(sim.s);
   env_store(P.env + env, sim.s, ctx.lane);
@@ -281,7 +291,7 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   CU(cudaSetDevice(device));
   abx_sim *h = new (std::nothrow) abx_sim(); if (!h) return ABX_ERR_ARG;
   memset(h, 0, sizeof(*h)); h->P.c = *cfg; h->P.n_envs = n_envs; h->n_envs = n_envs; h->device = device; derive_params(h->P);
-  h->smem_per_warp = (warp_smem_bytes(*cfg) + 15) & ~(size_t)15;
+  h->smem_per_warp = (warp_smem_bytes(*cfg, false, false, false, cfg->population == 0) + 15) & ~(size_t)15;
   size_t smem_cta = h->smem_per_warp * ABX_WARPS_PER_CTA;
   if (smem_cta > 227 * 1024) { delete h; return ABX_ERR_ARG; }
   const abx_sim_config &c = *cfg; size_t E = (size_t)n_envs; int st;

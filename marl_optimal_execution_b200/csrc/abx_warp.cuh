@@ -47,11 +47,14 @@ __device__ __forceinline__ uint4 shfl4(uint4 v, int src) {
 
 // bytes of shared memory one environment needs
 constexpr int SMALLQ_CAP = 64;          // queue capacities up to this keep every key on chip (WarpCtxT<true>)
+constexpr int NEAR_OUT_CAP = 8;
+constexpr int NEARQ_CAP = 32;           // QMODE 3: on-chip tier of the events due soon
+constexpr int64_t NEAR_NS = 4000000000LL;   // QMODE 3: an event due within 4 simulated seconds is 'near' (messages travel 1 s + latency; wakeups are ~1000 s away)
 __host__ __device__ inline bool warp_small_queue(const abx_sim_config &c) { return c.queue_cap <= SMALLQ_CAP; }
 constexpr int OC_N = 16;                 // entries of the on-chip cache of replayed orders' records
-__host__ __device__ inline size_t warp_smem_bytes(const abx_sim_config &c, bool env_shape = false, bool small_queue = false, bool hybrid_queue = false) {
-  size_t q = hybrid_queue ? (size_t)SMALLQ_CAP * 48 + (size_t)(c.queue_cap / 32) * 16 : (small_queue ? (size_t)SMALLQ_CAP * 48 : (size_t)(c.queue_cap / 32) * 16);   // on-chip tier: key + 32-byte payload per slot
-  return sizeof(ZiAgent) + OUT_CAP * OUT_WORDS * 4 + q + (size_t)c.level_cap * 2 * 12 + (env_shape ? sizeof(EnvX) + OC_N * 32 : 0);
+__host__ __device__ inline size_t warp_smem_bytes(const abx_sim_config &c, bool env_shape = false, bool small_queue = false, bool hybrid_queue = false, bool near_queue = false) {
+  size_t q = near_queue ? (size_t)NEARQ_CAP * 48 + (size_t)(c.queue_cap / 32) * 16 + 16 : hybrid_queue ? (size_t)SMALLQ_CAP * 48 + (size_t)(c.queue_cap / 32) * 16 : (small_queue ? (size_t)SMALLQ_CAP * 48 : (size_t)(c.queue_cap / 32) * 16);   // on-chip tier: key + 32-byte payload per slot
+  return sizeof(ZiAgent) + (near_queue ? NEAR_OUT_CAP : OUT_CAP) * OUT_WORDS * 4 + q + (size_t)c.level_cap * 2 * 12 + (env_shape ? sizeof(EnvX) + OC_N * 32 : 0);
 }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -63,16 +66,19 @@ __device__ __forceinline__ double warp_sum(double v) {
 // shared memory: a pop is two conflict-free key reads per lane + one warp arg-min + one 32-byte payload fetch, a push one key store + the payload;
 // no group cache, no second arg-min over a fetched group, no recomputation after a removal.  Larger queues use the grouped layout (header comment).
 // QMODE 0: grouped queue (header comment).  QMODE 1 (SMALLQ): all keys on chip.  QMODE 2: both -- the first SMALLQ_CAP events live on chip and only an
+// QMODE 3 (sparse_zi): like 2 with NEARQ_CAP on-chip slots, but only events due within NEAR_NS go on chip (the messages in flight; the ~1000 pending
+// wakeups stay in the grouped tier) and the minimum of the grouped tier is cached, so a message pop or push touches no HBM and scans no group cache.
 // overflow (the DDQN config's closing market order: up to 500 orders in flight at once, one tick in 660) goes to the grouped structure, whose groups
 // 0 and 1 are left unused because their HBM slots hold the on-chip tier's payloads; a pop takes the smaller of the two tiers' minima.
 template <int QMODE>
 struct WarpCtxT {
-  static constexpr bool SMALLQ = QMODE >= 1, HYBRID = QMODE == 2; static constexpr int G0 = HYBRID ? SMALLQ_CAP / 32 : 0;
+  static constexpr bool SMALLQ = QMODE >= 1, HYBRID = QMODE >= 2, NEARQ = QMODE == 3; static constexpr int NQ = NEARQ ? NEARQ_CAP : SMALLQ_CAP, G0 = HYBRID ? NQ / 32 : 0;
+  static constexpr int OUTN = NEARQ ? NEAR_OUT_CAP : OUT_CAP;             // outbox entries (sparse_zi handlers emit at most three messages)
   const SimParams &P; int env, lane;
   // HBM bases of this environment
   uint4 *qkey, *qpay0, *qpay1; ZiAgent *agents; uint4 *nodes; abx_trace_rec *tr;
   // shared memory of this warp
-  ZiAgent *staged; uint32_t *obox; uint4 *qc, *qs, *qp0, *qp1; int32_t *lvp, *lvq; uint32_t *lvht; EnvX *ex;   // qc: group cache, qs: on-chip keys
+  ZiAgent *staged; uint32_t *obox; uint4 *qc, *qs, *qp0, *qp1, *ovm; int32_t *lvp, *lvq; uint32_t *lvht; EnvX *ex;   // qc: group cache, qs: on-chip keys
   uint4 *oc_t; uint2 *oc_b; int32_t *oc_tag;   // on-chip cache of replayed orders' records (direct mapped, write-through)
   uint4 *idt; int4 *lob; uint2 *idb;   // ABIDESEnv shape: replay agent's per-order table, stored LOBs, per-order book census (HBM)
   // registers describing the group fetched by q_fetch
@@ -83,10 +89,11 @@ struct WarpCtxT {
     agents = P.agents + (size_t)env * P.c.n_agents; nodes = P.nodes + (size_t)env * P.c.order_cap;
     tr = P.trace ? P.trace + (size_t)env * P.c.trace_cap : nullptr;
     staged = reinterpret_cast<ZiAgent *>(smem); smem += sizeof(ZiAgent);
-    obox = reinterpret_cast<uint32_t *>(smem); smem += OUT_CAP * OUT_WORDS * 4;
-    qs = reinterpret_cast<uint4 *>(smem); smem += SMALLQ ? (size_t)SMALLQ_CAP * 16 : 0;
-    qp0 = reinterpret_cast<uint4 *>(smem); smem += SMALLQ ? (size_t)SMALLQ_CAP * 16 : 0;
-    qp1 = reinterpret_cast<uint4 *>(smem); smem += SMALLQ ? (size_t)SMALLQ_CAP * 16 : 0;
+    obox = reinterpret_cast<uint32_t *>(smem); smem += OUTN * OUT_WORDS * 4;
+    qs = reinterpret_cast<uint4 *>(smem); smem += SMALLQ ? (size_t)NQ * 16 : 0;
+    qp0 = reinterpret_cast<uint4 *>(smem); smem += SMALLQ ? (size_t)NQ * 16 : 0;
+    qp1 = reinterpret_cast<uint4 *>(smem); smem += SMALLQ ? (size_t)NQ * 16 : 0;
+    ovm = reinterpret_cast<uint4 *>(smem); smem += NEARQ ? 16 : 0;                   // cached minimum of the grouped tier {key lo, hi, uniq, group | ~0 = unknown}
     qc = reinterpret_cast<uint4 *>(smem); smem += (SMALLQ && !HYBRID) ? 0 : (size_t)P.n_qgroups * 16;
     lvp = reinterpret_cast<int32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
     lvq = reinterpret_cast<int32_t *>(smem); smem += (size_t)P.c.level_cap * 2 * 4;
@@ -117,8 +124,9 @@ struct WarpCtxT {
   __device__ void load_onchip(const EnvState &s) {
     if (SMALLQ) {                                                            // keys and payloads of the on-chip tier (HBM only between launches)
 #pragma unroll
-      for (int j = 0; j < 2; j++) { int i = lane + 32 * j; uint4 k = ldcg4(qkey + i); qs[i] = k;
+      for (int j = 0; j < NQ / 32; j++) { int i = lane + 32 * j; uint4 k = ldcg4(qkey + i); qs[i] = k;
         if ((k.x & k.y) != 0xffffffffu) { qp0[i] = ldcg4(qpay0 + i); qp1[i] = ldcg4(qpay1 + i); } }
+      if (NEARQ) ovm[0] = make_uint4(0u, 0u, 0u, 0xffffffffu);
     }
     if (!SMALLQ || HYBRID) {
       const uint4 *gc = P.qcache + (size_t)env * P.n_qgroups; int cnt = 0;
@@ -139,7 +147,7 @@ struct WarpCtxT {
     sync();
     if (SMALLQ) {
 #pragma unroll
-      for (int j = 0; j < 2; j++) { int i = lane + 32 * j; uint4 k = qs[i]; __stcg(qkey + i, k);
+      for (int j = 0; j < NQ / 32; j++) { int i = lane + 32 * j; uint4 k = qs[i]; __stcg(qkey + i, k);
         if ((k.x & k.y) != 0xffffffffu) { __stcg(qpay0 + i, qp0[i]); __stcg(qpay1 + i, qp1[i]); } }
     }
     if (!SMALLQ || HYBRID) {
@@ -156,7 +164,8 @@ struct WarpCtxT {
     }
   }
   __device__ void q_clear() {
-    if (SMALLQ) { qs[lane] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); qs[lane + 32] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); n_ovf = 0; }
+    if (SMALLQ) { qs[lane] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); if (NQ > 32) qs[lane + 32] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); n_ovf = 0;
+      if (NEARQ) ovm[0] = make_uint4(0u, 0u, 0u, 0xffffffffu); }
     if (!SMALLQ || HYBRID) for (int g = lane; g < P.n_qgroups; g += 32) qc[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
     sync(); }
 
@@ -165,13 +174,19 @@ struct WarpCtxT {
   __device__ __forceinline__ bool q_min(uint64_t &hi, uint32_t &uniq, int &grp) {
     bool have1 = false;
     if (SMALLQ) {                                                          // empty slots hold KEY_EMPTY
-      uint4 k0 = qs[lane], k1 = qs[lane + 32];
-      uint64_t h0 = (uint64_t)k0.x | ((uint64_t)k0.y << 32), h1 = (uint64_t)k1.x | ((uint64_t)k1.y << 32);
-      bool second = key_less(h1, k1.z, h0, k0.z);
-      uint64_t h = second ? h1 : h0; uint32_t u = second ? k1.z : k0.z;
+      uint4 k0 = qs[lane]; uint64_t h = (uint64_t)k0.x | ((uint64_t)k0.y << 32); uint32_t u = k0.z; bool second = false;
+      if (NQ > 32) { uint4 k1 = qs[lane + 32]; uint64_t h1 = (uint64_t)k1.x | ((uint64_t)k1.y << 32); second = key_less(h1, k1.z, h, u); if (second) { h = h1; u = k1.z; } }
       int wl = warp_argmin(h, u, h != KEY_EMPTY);
       if (wl >= 0) { have1 = true; grp = __shfl_sync(FULL, second ? lane + 32 : lane, wl); hi = shfl64(h, wl); uniq = __shfl_sync(FULL, u, wl); }
       if (!HYBRID || n_ovf == 0) return have1;
+      if (NEARQ) {                                                         // the grouped tier's minimum is cached until that tier loses an event
+        uint4 m = ovm[0];
+        if (m.w != 0xffffffffu) {
+          uint64_t h2 = (uint64_t)m.x | ((uint64_t)m.y << 32);
+          if (!have1 || key_less(h2, m.z, hi, uniq)) { grp = NQ + (int)m.w; hi = h2; uniq = m.z; }
+          return true;
+        }
+      }
     }
     uint64_t bh = KEY_EMPTY; uint32_t bu = 0xffffffffu; int bg = -1;
     for (int g = G0 + lane; g < P.n_qgroups; g += 32) {
@@ -181,17 +196,18 @@ struct WarpCtxT {
     int wl = warp_argmin(bh, bu, bg >= 0);
     if (wl < 0) return have1;
     int g2 = __shfl_sync(FULL, bg, wl); uint64_t h2 = shfl64(bh, wl); uint32_t u2 = __shfl_sync(FULL, bu, wl);
-    if (!have1 || key_less(h2, u2, hi, uniq)) { grp = (SMALLQ ? SMALLQ_CAP : 0) + g2; hi = h2; uniq = u2; }
+    if (NEARQ) { sync(); ovm[0] = make_uint4((uint32_t)h2, (uint32_t)(h2 >> 32), u2, (uint32_t)g2); sync(); }
+    if (!have1 || key_less(h2, u2, hi, uniq)) { grp = (SMALLQ ? NQ : 0) + g2; hi = h2; uniq = u2; }
     return true;
   }
   __device__ __forceinline__ void q_fetch(int g, Event &e) {
     if (SMALLQ) {
-      if (g < SMALLQ_CAP) {                                                // a slot of the on-chip tier: key and payload in shared memory (no L2 round trip per pop)
+      if (g < NQ) {                                                // a slot of the on-chip tier: key and payload in shared memory (no L2 round trip per pop)
         cur_group = g; cur_t2 = false;
         event_unpack(qs[g], qp0[g], qp1[g], e);
         return;
       }
-      g -= SMALLQ_CAP; cur_t2 = true;
+      g -= NQ; cur_t2 = true;
     }
     int slot = g * 32 + lane;
     uint4 k = ldcg4(qkey + slot), a = ldcg4(qpay0 + slot), b = ldcg4(qpay1 + slot);     // 3 x 512 B coalesced
@@ -213,6 +229,7 @@ struct WarpCtxT {
   __device__ __forceinline__ void q_remove() {
     if (SMALLQ && !cur_t2) { sync(); qs[cur_group] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); sync(); return; }
     if (HYBRID) n_ovf--;
+    if (NEARQ) ovm[0] = make_uint4(0u, 0u, 0u, 0xffffffffu);
     cur_mask &= ~(1u << cur_lane); group_writeback(); }
   __device__ __forceinline__ void q_requeue(int64_t t) {   // Kernel.py:226,260: same entry, new time, same uniq
     if (SMALLQ && !cur_t2) {
@@ -224,12 +241,13 @@ struct WarpCtxT {
       my_hi = key_pack(t < KEY_T_MAX ? t : KEY_T_MAX, key_recipient(my_hi), key_type(my_hi));
       uint2 *kp = reinterpret_cast<uint2 *>(qkey + cur_group * 32 + lane); *kp = make_uint2((uint32_t)my_hi, (uint32_t)(my_hi >> 32));
     }
+    if (NEARQ) ovm[0] = make_uint4(0u, 0u, 0u, 0xffffffffu);
     group_writeback();
   }
-  __device__ __forceinline__ bool q_push(const Event &e) {
-    if (SMALLQ) {
-      bool f0 = qs[lane].y == 0xffffffffu && qs[lane].x == 0xffffffffu, f1 = qs[lane + 32].y == 0xffffffffu && qs[lane + 32].x == 0xffffffffu;
-      uint32_t b0 = __ballot_sync(FULL, f0), b1 = __ballot_sync(FULL, f1);
+  __device__ __forceinline__ bool q_push(const Event &e, int64_t now) {
+    if (SMALLQ && (!NEARQ || e.t - now < NEAR_NS)) {
+      bool f0 = qs[lane].y == 0xffffffffu && qs[lane].x == 0xffffffffu, f1 = NQ > 32 && qs[NQ > 32 ? lane + 32 : lane].y == 0xffffffffu && qs[NQ > 32 ? lane + 32 : lane].x == 0xffffffffu;
+      uint32_t b0 = __ballot_sync(FULL, f0), b1 = NQ > 32 ? __ballot_sync(FULL, f1) : 0u;
       if (b0 | b1) {
         int slot = b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1;
         uint4 k, a, b; event_pack(e, k, a, b);
@@ -251,6 +269,7 @@ struct WarpCtxT {
       uint64_t h = (uint64_t)k.x | ((uint64_t)k.y << 32), ch = (uint64_t)cc.x | ((uint64_t)cc.y << 32);
       if (cc.w == 0 || key_less(h, k.z, ch, cc.z)) { cc.x = k.x; cc.y = k.y; cc.z = k.z; }
       cc.w |= 1u << i; qc[g] = cc;
+      if (NEARQ) { uint4 m = ovm[0]; if (m.w != 0xffffffffu && (n_ovf == 0 || key_less(h, k.z, (uint64_t)m.x | ((uint64_t)m.y << 32), m.z))) ovm[0] = make_uint4(k.x, k.y, k.z, (uint32_t)g); }
     }
     if (HYBRID) n_ovf++;
     __syncwarp();
@@ -379,5 +398,6 @@ struct WarpCtxT {
 typedef WarpCtxT<0> WarpCtx;
 typedef WarpCtxT<1> WarpCtxSmallQ;
 typedef WarpCtxT<2> WarpCtxHybridQ;
+typedef WarpCtxT<3> WarpCtxNearQ;
 
 }  // namespace abx

@@ -18,6 +18,7 @@ using namespace abx;
 struct HostCtx {
   const SimParams &P; int env;
   uint4 *qkey, *qpay0, *qpay1, *qcache; ZiAgent *agents; int32_t *lvp, *lvq; uint32_t *lvht; uint4 *nodes; abx_trace_rec *tr;
+  static constexpr int OUTN = OUT_CAP;
   uint32_t outbox_[OUT_CAP * OUT_WORDS]; ZiAgent staged; int cur_group, cur_slot; uint4 *idt; int4 *lob;
   HostCtx(const SimParams &P_, int e) : P(P_), env(e) {
     size_t q = (size_t)e * P.c.queue_cap; qkey = P.qkey + q; qpay0 = P.qpay0 + q; qpay1 = P.qpay1 + q; qcache = P.qcache + (size_t)e * P.n_qgroups;
@@ -51,7 +52,7 @@ struct HostCtx {
     uint4 &k = qkey[cur_group * 32 + cur_slot]; uint64_t h = (uint64_t)k.x | ((uint64_t)k.y << 32);
     h = key_pack(t < KEY_T_MAX ? t : KEY_T_MAX, key_recipient(h), key_type(h)); k.x = (uint32_t)h; k.y = (uint32_t)(h >> 32); group_recompute(cur_group);
   }
-  bool q_push(const Event &e) {
+  bool q_push(const Event &e, int64_t) {
     for (int g = 0; g < P.n_qgroups; g++) if (qcache[g].w != 0xffffffffu) {
       int i = __builtin_ctz(~qcache[g].w); event_pack(e, qkey[g * 32 + i], qpay0[g * 32 + i], qpay1[g * 32 + i]); qcache[g].w |= 1u << i; group_recompute(g); return true; }
     return false;
