@@ -238,6 +238,7 @@ ABX_NI U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
 }
 ABX_NI double exp_ni(double x) { return exp(x); }
 ABX_NI double log_ni(double x) { return log(x); }
+ABX_NI int64_t i64_div(int64_t a, int64_t b) { return a / b; }     // a software 64-bit division is ~55 instructions: one body instead of one per use
 // log(x), x in (0, 1], for the Philox-mode variate transforms only (no parity constraint; ~1e-13 relative): fp32 seed, one Newton step on
 // exp(y) = x through the exp body the belief update keeps resident anyway.  The libm log body is 237 instructions of instruction-cache footprint.
 ABX_HD double log_unit(double x) {
@@ -1044,11 +1045,11 @@ struct Sim {
     uint32_t fl = x->rl_flags;
     if (!ta_wakeup(fl)) return;
     if (fl & RLF_TRADE) {                                                               // first horizon time > now -> CANCEL_ORDER event (Timedelta(0.5) == 0)
-      int64_t k = s.now < P.h0_ns ? 0 : (s.now - P.h0_ns) / P.h_step_ns + 1;
+      int64_t k = s.now < P.h0_ns ? 0 : i64_div(s.now - P.h0_ns, P.h_step_ns) + 1;
       if (k < P.n_h) env_set_cancel(2, P.h0_ns + k * P.h_step_ns); else fl &= ~RLF_TRADE;
     }
     if (fl & RLF_TRADE) {                                                               // effective horizon = horizon[:-1]
-      int64_t k = s.now < P.h0_ns ? 0 : (s.now - P.h0_ns) / P.h_step_ns + 1;
+      int64_t k = s.now < P.h0_ns ? 0 : i64_div(s.now - P.h0_ns, P.h_step_ns) + 1;
       if (k < P.n_h - 1) set_wakeup(2, P.h0_ns + k * P.h_step_ns); else fl &= ~RLF_TRADE;
     }
     { int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); }         // getCurrentSpread(depth=500)
@@ -1085,8 +1086,8 @@ struct Sim {
     c.sync();
   }
   ABX_HD void rl_observe(EnvX *x) {                                                     // get_observation :294-315
-    int64_t curr = s.now - (s.now % P.h_step_ns); int rem = P.n_h;                      // get_remaining_time :282-292 (Timestamp.floor(freq))
-    if (curr >= P.h0_ns && (curr - P.h0_ns) / P.h_step_ns < P.n_h) rem = P.n_h - 1 - (int)((curr - P.h0_ns) / P.h_step_ns);
+    int64_t curr = i64_div(s.now, P.h_step_ns) * P.h_step_ns; int rem = P.n_h;                      // get_remaining_time :282-292 (Timestamp.floor(freq))
+    if (curr >= P.h0_ns) { int64_t kh = i64_div(curr - P.h0_ns, P.h_step_ns); if (kh < P.n_h) rem = P.n_h - 1 - (int)kh; }
     int n = x->n_lobs, head = x->lob_head; int obs_len = 0; double o[9];
     for (int i = 0; i < 9; i++) o[i] = 0.0;
     if (n > 0) {
@@ -1217,7 +1218,7 @@ struct Sim {
   // =================================================================================================
   ABX_HD ExecAux *exaux() { return reinterpret_cast<ExecAux *>(z->oid); }
   ABX_HD int dq_order_base(int id) const { return R3 ? P.dq_order_base : P.dq_order_base + (id - (2 + P.dq_n_mom)) * EXEC_ORDER_CAP; }   // rmsc03 population: one POV execution agent
-  ABX_HD int dq_horizon_index(int64_t t) const { if (t < P.h0_ns || (t - P.h0_ns) % P.h_step_ns) return -1; int64_t k = (t - P.h0_ns) / P.h_step_ns; return k < P.n_h ? (int)k : -1; }
+  ABX_HD int dq_horizon_index(int64_t t) const { if (t < P.h0_ns) return -1; int64_t k = i64_div(t - P.h0_ns, P.h_step_ns); return (k * P.h_step_ns == t - P.h0_ns && k < P.n_h) ? (int)k : -1; }
   ABX_HD void dq_place_limit(int id, int32_t size, bool buy, int32_t price) {           // TradingAgent.placeLimitOrder :309-349
     uint32_t oid = s.next_order_id++;
     if (size <= 0) return;
@@ -1269,7 +1270,7 @@ struct Sim {
   }
   // DDQLearningExecutionAgent.get_observation :280-336 from the cached L1 (known_bids[0] / known_asks[0])
   ABX_HD void dq_get_observation(ExecAux &ex, double obs[6], int disc[2]) {
-    int64_t curr = s.now - (s.now % P.h_step_ns); int hi = dq_horizon_index(curr);
+    int64_t curr = i64_div(s.now, P.h_step_ns) * P.h_step_ns; int hi = dq_horizon_index(curr);
     ex.rem_time = hi >= 0 ? P.n_h - 1 - hi : P.n_h;
     for (int i = 0; i < 6; i++) obs[i] = 0.0; disc[0] = disc[1] = 0;
     if (!(a.flags & AF_HAS_BID) || !(a.flags & AF_HAS_ASK)) { s.flags |= ABX_F_OBS_INVALID; return; }
@@ -1288,7 +1289,7 @@ struct Sim {
   ABX_HD void dq_exec_wakeup(int id, int type) {
     if (!ta_wakeup(a.flags)) return;
     ExecAux ex = *exaux();
-    int64_t k = s.now < P.h0_ns ? 0 : (s.now - P.h0_ns) / P.h_step_ns + 1;              // first horizon time > now
+    int64_t k = s.now < P.h0_ns ? 0 : i64_div(s.now - P.h0_ns, P.h_step_ns) + 1;              // first horizon time > now
     bool query = false;
     if (type == AT_DDQN) {                                                              // ddqlearning_execution_agent.py:141-153
       if (ex.exflags & EXF_TRADE) { if (k < P.n_h) set_wakeup(id, P.h0_ns + k * P.h_step_ns); else ex.exflags &= ~EXF_TRADE; }
@@ -1333,7 +1334,7 @@ struct Sim {
         }
       }
     } else if (m.kind == ABX_ORDER_ACCEPTED || m.kind == ABX_ORDER_EXECUTED) {         // handle_order_acceptance :550-576 / handle_order_execution :507-548
-      int64_t curr = s.now - (s.now % P.h_step_ns);
+      int64_t curr = i64_div(s.now, P.h_step_ns) * P.h_step_ns;
       if (dq_horizon_index(curr) >= 0) {
         double o6[6]; int sp[2]; dq_get_observation(ex, o6, sp);
         ex.e_sp[0] = (int16_t)sp[0]; ex.e_sp[1] = (int16_t)sp[1]; ex.cur_s[0] = (int16_t)sp[0]; ex.cur_s[1] = (int16_t)sp[1];
