@@ -417,7 +417,7 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
 // divergent branch), and c.sync() -- a compiler fence on the GPU, where a converged warp issues its memory
 // instructions in program order -- separates a write from later reads.
 // ---------------------------------------------------------------------------------------------------
-constexpr int OUT_CAP = 24, OUT_WORDS = 12;     // 24 x 48 B: with 448 price levels per side the sparse_zi_1000 environment fits 16 to an SM (13.4 KB + 1 KB reserved each)
+constexpr int OUT_CAP = 24, OUT_WORDS = 12;     // 24 x 48 B in the replay shapes (the DDQN agent's closing market order flushes in batches); the sparse_zi shape, whose handlers emit at most three messages, keeps 8 (Ctx::OUTN)
 enum : uint32_t { OF_WAKEUP = 1u << 24, OF_BUMP_UNIQ = 1u << 25, OF_FROM_EXCH = 1u << 26, OF_CANCEL_EVT = 1u << 27 };
 
 struct AgentRegs {                      // scalar part of ZiAgent held in registers while an event is handled
