@@ -762,10 +762,15 @@ struct Sim {
   ABX_HD void zi_place_order(int id) {
     int stream = S_AGENT0 + id;
     int32_t r_now = oracle_advance(s.now >= P.c.mkt_close_ns ? P.c.mkt_close_ns - 1 : s.now);             // observePrice :210-227
-    int32_t obs_t = (int32_t)py_round_i64(rng.normal(stream, a.rng_ctr, (double)r_now, P.sqrt_sigma_n));
+    // Philox mode: the three draws of one order placement (noisy observation, side, surplus R) come from ONE Philox block of the agent's stream
+    // (words 0-2 the normal, bit 0 of word 2 the side, word 3 R) instead of three blocks; tape mode replays the reference's draws one by one.
+    bool one_block = !rng.tape(); U4 blk; blk.x = blk.y = blk.z = blk.w = 0;
+    if (one_block) blk = rng.philox(stream, a.rng_ctr);
+    double z_obs = one_block ? box_muller(blk.x, blk.y, blk.z) : rng.std_normal(stream, a.rng_ctr);
+    int32_t obs_t = (int32_t)py_round_i64(dadd((double)r_now, dmul(P.sqrt_sigma_n, z_obs)));
     int q = (int)((double)a.shares / 100.0);                                            // :203 int(x / 100)
     int q_max = P.c.q_max; bool buy;
-    if (q >= q_max) buy = false; else if (q <= -q_max) buy = true; else buy = rng.randint(stream, a.rng_ctr, 1) != 0; // :205-213
+    if (q >= q_max) buy = false; else if (q <= -q_max) buy = true; else buy = one_block ? (blk.z & 1u) != 0 : rng.randint(stream, a.rng_ctr, 1) != 0; // :205-213
     if (!(a.flags & AF_HAS_PREV)) { a.prev_wake = P.c.mkt_open_ns; a.flags |= AF_HAS_PREV; }         // :217-218
     double r_bar = P.c.r_bar, sigma_n = P.c.sigma_n;
     double delta = (double)(s.now - a.prev_wake);                                       // :221
@@ -794,7 +799,7 @@ struct Sim {
     // placeOrder
     int grp = (a.flags & AF_GROUP_MASK) >> AF_GROUP_SHIFT;
     int32_t r_min = P.c.groups[grp].r_min, r_max = P.c.groups[grp].r_max; double eta = P.c.groups[grp].eta;
-    int32_t R = r_min + (int32_t)rng.randint(stream, a.rng_ctr, (uint32_t)(r_max - r_min));          // :284
+    int32_t R = r_min + (one_block ? (int32_t)((uint64_t(blk.w) * (uint64_t)(uint32_t)(r_max - r_min + 1)) >> 32) : (int32_t)rng.randint(stream, a.rng_ctr, (uint32_t)(r_max - r_min)));   // :284
     int32_t p = buy ? v - R : v + R;                                                    // :287
     int32_t ask_vol = (a.flags & AF_HAS_ASK) ? a.ask_q : 0, bid_vol = (a.flags & AF_HAS_BID) ? a.bid_q : 0;
     if (buy && ask_vol > 0) { int32_t R_ask = v - a.ask; if ((double)R_ask >= dmul(eta, (double)R)) p = a.ask; }             // :291-297
