@@ -149,6 +149,10 @@ typedef struct abx_trace_rec {
 
 typedef struct abx_sim abx_sim; /* opaque */
 
+/* Self-test of the device-side logarithm used by the Philox-mode variate transforms (Box-Muller, exponential inter-arrival times; the reference draws them
+ * with numpy's RandomState.normal / .exponential, e.g. agent/ZeroIntelligenceAgent.py:349-350, util/oracle/SparseMeanRevertingOracle.py:105-107):
+ * y[i] = log(x[i]) for x in (0, 1], host buffers.  Tests compare it with libm (relative error < 1e-11). */
+int32_t abx_selftest_log_unit(const double *x_host, double *y_host, int32_t n, int32_t device);
 const char *abx_strerror(int32_t status);
 const char *abx_last_cuda_error(void);
 int32_t abx_device_count(void);

@@ -239,12 +239,22 @@ ABX_NI U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
 ABX_NI double exp_ni(double x) { return exp(x); }
 ABX_NI double log_ni(double x) { return log(x); }
 ABX_NI int64_t i64_div(int64_t a, int64_t b) { return a / b; }     // a software 64-bit division is ~55 instructions: one body instead of one per use
-// log(x), x in (0, 1], for the Philox-mode variate transforms only (no parity constraint; ~1e-13 relative): fp32 seed, one Newton step on
-// exp(y) = x through the exp body the belief update keeps resident anyway.  The libm log body is 237 instructions of instruction-cache footprint.
+// log(x), x in (0, 1] and normal, for the Philox-mode variate transforms only (no parity constraint): fp64 throughout, relative error
+// < 1e-11 (checked against libm by tests/test_gpu_philox.py through abx_selftest_log_unit).  x = 2^e * m with m in [sqrt(1/2), sqrt(2)],
+// log(m) = 2 atanh(s), s = (m - 1) / (m + 1), seven terms of the series (|s| <= 0.1716), the quotient through a refined MUFU reciprocal.
+// ~30 instructions inline; the libm log body is 237 instructions of instruction-cache footprint and 3 of them run per order.
 ABX_HD double log_unit(double x) {
 #if defined(__CUDA_ARCH__)
-  double y0 = (double)(__log2f((float)x) * 0.69314718f);
-  return (y0 - 1.0) + x * exp_ni(-y0);
+  uint64_t b = dbl_bits(x);
+  int e = (int)(b >> 52) - 1023;
+  double m = bits_dbl((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);            // [1, 2)
+  if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+  double d = m + 1.0, r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = fma(r, fma(-d, r, 1.0), r); r = fma(r, fma(-d, r, 1.0), r);                      // two Newton steps: 1 / d to ~1 ulp
+  double s = (m - 1.0) * r, s2 = s * s;
+  double p = fma(s2, 1.0 / 13.0, 1.0 / 11.0); p = fma(p, s2, 1.0 / 9.0); p = fma(p, s2, 1.0 / 7.0); p = fma(p, s2, 1.0 / 5.0); p = fma(p, s2, 1.0 / 3.0); p = fma(p, s2, 1.0);
+  return fma((double)e, 0.6931471805599453, 2.0 * s * p);
 #else
   return log(x);
 #endif
@@ -777,7 +787,9 @@ struct Sim {
     double d2 = (double)(P.c.mkt_close_ns - s.now); if (!(d2 > 0)) d2 = 0;              // :251
     // (1 - kappa) ** x evaluated as exp(x * log(1 - kappa)) with the logarithm precomputed on the host (log1p): both are
     // within an ulp of the true power; the result only feeds int(round(.)) of values ~1e5.
-    double pw0 = exp_ni(dmul(delta, P.log_base_a)), pw1 = exp_ni(dmul(dmul(2.0, delta), P.log_base_a)), pw2 = exp_ni(dmul(d2, P.log_base_a));
+    // (1 - kappa) ** (2 delta) as the square of (1 - kappa) ** delta: it only enters through 1 - pw1 ~ 2 delta kappa ~ 1e-3 (sigma_t stays 0, :242), so an
+    // ulp of pw1 moves r_t by ~1e-11 -- and saves one of the seven exp evaluations per order (12 % of all executed instructions were exp).
+    double pw0 = exp_ni(dmul(delta, P.log_base_a)), pw1 = dmul(pw0, pw0), pw2 = exp_ni(dmul(d2, P.log_base_a));
     double r_tprime = dmul(dsub(1.0, pw0), r_bar);                                    // :229
     r_tprime = dadd(r_tprime, dmul(pw0, a.r_t));                                      // :230
     double sigma_tprime = dmul(pw1, a.sigma_t);                                       // :233

@@ -172,3 +172,20 @@ def test_full_size_batches_conserve_and_finish():
     assert (st["sum_shares"] == 0).all() and (st["sum_cash"] == 64 * 10 ** 7).all()
     pe = np.array([sim.pov_exec(e) for e in range(0, n, 512)])
     assert (pe[:, 0] <= 120000).all() and (pe[:, 2] >= 0).all()
+
+
+def test_device_log_of_the_variate_transforms_matches_libm():
+    """The Philox-mode Box-Muller / exponential transforms use a short fp64 logarithm (abx_core.cuh log_unit) instead of the 237-instruction libm
+    body; through the C ABI self-test it must agree with libm to 1e-11 relative over (0, 1], including the ends of the uniform grid."""
+    import ctypes as C
+    L = _lib.load()
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.random(200000), 1.0 - rng.random(1000) * 1e-9, rng.random(1000) * 1e-12 + 2.0 ** -53,
+                        np.array([1.0, 2.0 ** -53, 0.5, 0.70710678118654757, 0.7071067811865476, 1.0 - 2.0 ** -53])])
+    x = np.ascontiguousarray(x[x > 0]); y = np.empty_like(x)
+    _lib.check(L, L.abx_selftest_log_unit(x.ctypes.data_as(C.POINTER(C.c_double)), y.ctypes.data_as(C.POINTER(C.c_double)), len(x), 0), "selftest")
+    ref = np.log(x)
+    err = np.abs(y - ref) / np.maximum(np.abs(ref), 1e-300)
+    assert y[x == 1.0].max() == 0.0
+    nz = ref != 0
+    assert err[nz].max() < 1e-11, (err[nz].max(), x[nz][err[nz].argmax()])
