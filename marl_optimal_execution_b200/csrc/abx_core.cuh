@@ -144,6 +144,7 @@ struct SimParams {
   // ---- ABIDESEnv shape (exchange + MarketReplayAgent + RL execution agent); zero for the sparse_zi shape ----
   int32_t n_ts, n_rows, n_ids, n_h;                 // replayed stream: timestamps, rows, distinct order ids; horizon length
   int64_t h0_ns, h_step_ns;                         // execution_time_horizon = h0 + k * step, k < n_h (agent_config.py:134-136)
+  double h_step_inv;                                // 1 / h_step_ns (0 when there is no horizon): Sim::hdiv
   double rl_quantity, rl_steep; int32_t order_level, rl_is_buy;
   const int64_t *st_ts;                             // [n_ts]      distinct timestamps (ns), ascending
   const int32_t *st_first;                          // [n_ts + 1]  first row of each timestamp
@@ -238,7 +239,6 @@ ABX_NI U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
 }
 ABX_NI double exp_ni(double x) { return exp(x); }
 ABX_NI double log_ni(double x) { return log(x); }
-ABX_NI int64_t i64_div(int64_t a, int64_t b) { return a / b; }     // a software 64-bit division is ~55 instructions: one body instead of one per use
 // log(x), x in (0, 1] and normal, for the Philox-mode variate transforms only (no parity constraint): fp64 throughout, relative error
 // < 1e-11 (checked against libm by tests/test_gpu_philox.py through abx_selftest_log_unit).  x = 2^e * m with m in [sqrt(1/2), sqrt(2)],
 // log(m) = 2 atanh(s), s = (m - 1) / (m + 1), seven terms of the series (|s| <= 0.1716), the quotient through a refined MUFU reciprocal.
@@ -1062,11 +1062,11 @@ struct Sim {
     uint32_t fl = x->rl_flags;
     if (!ta_wakeup(fl)) return;
     if (fl & RLF_TRADE) {                                                               // first horizon time > now -> CANCEL_ORDER event (Timedelta(0.5) == 0)
-      int64_t k = s.now < P.h0_ns ? 0 : i64_div(s.now - P.h0_ns, P.h_step_ns) + 1;
+      int64_t k = s.now < P.h0_ns ? 0 : hdiv(s.now - P.h0_ns) + 1;
       if (k < P.n_h) env_set_cancel(2, P.h0_ns + k * P.h_step_ns); else fl &= ~RLF_TRADE;
     }
     if (fl & RLF_TRADE) {                                                               // effective horizon = horizon[:-1]
-      int64_t k = s.now < P.h0_ns ? 0 : i64_div(s.now - P.h0_ns, P.h_step_ns) + 1;
+      int64_t k = s.now < P.h0_ns ? 0 : hdiv(s.now - P.h0_ns) + 1;
       if (k < P.n_h - 1) set_wakeup(2, P.h0_ns + k * P.h_step_ns); else fl &= ~RLF_TRADE;
     }
     { int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); }         // getCurrentSpread(depth=500)
@@ -1103,8 +1103,8 @@ struct Sim {
     c.sync();
   }
   ABX_HD void rl_observe(EnvX *x) {                                                     // get_observation :294-315
-    int64_t curr = i64_div(s.now, P.h_step_ns) * P.h_step_ns; int rem = P.n_h;                      // get_remaining_time :282-292 (Timestamp.floor(freq))
-    if (curr >= P.h0_ns) { int64_t kh = i64_div(curr - P.h0_ns, P.h_step_ns); if (kh < P.n_h) rem = P.n_h - 1 - (int)kh; }
+    int64_t curr = hdiv(s.now) * P.h_step_ns; int rem = P.n_h;                      // get_remaining_time :282-292 (Timestamp.floor(freq))
+    if (curr >= P.h0_ns) { int64_t kh = hdiv(curr - P.h0_ns); if (kh < P.n_h) rem = P.n_h - 1 - (int)kh; }
     int n = x->n_lobs, head = x->lob_head; int obs_len = 0; double o[9];
     for (int i = 0; i < 9; i++) o[i] = 0.0;
     if (n > 0) {
@@ -1235,7 +1235,14 @@ struct Sim {
   // =================================================================================================
   ABX_HD ExecAux *exaux() { return reinterpret_cast<ExecAux *>(z->oid); }
   ABX_HD int dq_order_base(int id) const { return R3 ? P.dq_order_base : P.dq_order_base + (id - (2 + P.dq_n_mom)) * EXEC_ORDER_CAP; }   // rmsc03 population: one POV execution agent
-  ABX_HD int dq_horizon_index(int64_t t) const { if (t < P.h0_ns) return -1; int64_t k = i64_div(t - P.h0_ns, P.h_step_ns); return (k * P.h_step_ns == t - P.h0_ns && k < P.n_h) ? (int)k : -1; }
+  // floor(a / h_step_ns) for 0 <= a < 2^53 (nanoseconds of one day): a software 64-bit division is ~55 instructions per use; the product with the
+  // host-computed reciprocal is off by at most one, which the remainder corrects exactly.
+  ABX_HD int64_t hdiv(int64_t a) const {
+    int64_t q = (int64_t)((double)a * P.h_step_inv), r = a - q * P.h_step_ns;
+    if (r < 0) q--; else if (r >= P.h_step_ns) q++;
+    return q;
+  }
+  ABX_HD int dq_horizon_index(int64_t t) const { if (t < P.h0_ns) return -1; int64_t k = hdiv(t - P.h0_ns); return (k * P.h_step_ns == t - P.h0_ns && k < P.n_h) ? (int)k : -1; }
   ABX_HD void dq_place_limit(int id, int32_t size, bool buy, int32_t price) {           // TradingAgent.placeLimitOrder :309-349
     uint32_t oid = s.next_order_id++;
     if (size <= 0) return;
@@ -1287,7 +1294,7 @@ struct Sim {
   }
   // DDQLearningExecutionAgent.get_observation :280-336 from the cached L1 (known_bids[0] / known_asks[0])
   ABX_HD void dq_get_observation(ExecAux &ex, double obs[6], int disc[2]) {
-    int64_t curr = i64_div(s.now, P.h_step_ns) * P.h_step_ns; int hi = dq_horizon_index(curr);
+    int64_t curr = hdiv(s.now) * P.h_step_ns; int hi = dq_horizon_index(curr);
     ex.rem_time = hi >= 0 ? P.n_h - 1 - hi : P.n_h;
     for (int i = 0; i < 6; i++) obs[i] = 0.0; disc[0] = disc[1] = 0;
     if (!(a.flags & AF_HAS_BID) || !(a.flags & AF_HAS_ASK)) { s.flags |= ABX_F_OBS_INVALID; return; }
@@ -1306,7 +1313,7 @@ struct Sim {
   ABX_HD void dq_exec_wakeup(int id, int type) {
     if (!ta_wakeup(a.flags)) return;
     ExecAux ex = *exaux();
-    int64_t k = s.now < P.h0_ns ? 0 : i64_div(s.now - P.h0_ns, P.h_step_ns) + 1;              // first horizon time > now
+    int64_t k = s.now < P.h0_ns ? 0 : hdiv(s.now - P.h0_ns) + 1;              // first horizon time > now
     bool query = false;
     if (type == AT_DDQN) {                                                              // ddqlearning_execution_agent.py:141-153
       if (ex.exflags & EXF_TRADE) { if (k < P.n_h) set_wakeup(id, P.h0_ns + k * P.h_step_ns); else ex.exflags &= ~EXF_TRADE; }
@@ -1351,7 +1358,7 @@ struct Sim {
         }
       }
     } else if (m.kind == ABX_ORDER_ACCEPTED || m.kind == ABX_ORDER_EXECUTED) {         // handle_order_acceptance :550-576 / handle_order_execution :507-548
-      int64_t curr = i64_div(s.now, P.h_step_ns) * P.h_step_ns;
+      int64_t curr = hdiv(s.now) * P.h_step_ns;
       if (dq_horizon_index(curr) >= 0) {
         double o6[6]; int sp[2]; dq_get_observation(ex, o6, sp);
         ex.e_sp[0] = (int16_t)sp[0]; ex.e_sp[1] = (int16_t)sp[1]; ex.cur_s[0] = (int16_t)sp[0]; ex.cur_s[1] = (int16_t)sp[1];

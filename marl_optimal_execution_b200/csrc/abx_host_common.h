@@ -130,7 +130,7 @@ static inline void env_fill_params(const abx_env_config &e, SimParams &P) {
   c.stream_history = e.stream_history; c.latency_model = ABX_LAT_ZERO; c.n_noise = 1;
   c.queue_cap = e.queue_cap; c.level_cap = e.level_cap; c.order_cap = e.order_cap; c.rng_mode = ABX_RNG_PHILOX; c.trace_cap = e.trace_cap; c.hash_pops = e.hash_pops;
   P.n_qgroups = c.queue_cap / 32; P.n_streams = 0;
-  P.n_h = e.n_horizon; P.h0_ns = e.horizon_start_ns; P.h_step_ns = e.horizon_step_ns; P.rl_quantity = e.quantity; P.rl_steep = e.steep;
+  P.n_h = e.n_horizon; P.h0_ns = e.horizon_start_ns; P.h_step_ns = e.horizon_step_ns; P.h_step_inv = e.horizon_step_ns > 0 ? 1.0 / (double)e.horizon_step_ns : 0.0; P.rl_quantity = e.quantity; P.rl_steep = e.steep;
   P.order_level = e.order_level; P.rl_is_buy = e.is_buy;
 }
 // ---- DDQN execution shape (config/execution/marketreplay/execution_marketreplay_ddqn.py) ----
@@ -162,7 +162,7 @@ static inline void dq_fill_params(const abx_dq_config &e, SimParams &P) {
   c.stream_history = e.stream_history; c.latency_model = ABX_LAT_ZERO; c.n_noise = 1; c.mom_wake_ns = e.mom_wake_ns; c.mom_min_size = e.mom_min_size; c.mom_max_size = e.mom_max_size;
   c.queue_cap = e.queue_cap; c.level_cap = e.level_cap; c.order_cap = e.order_cap; c.rng_mode = ABX_RNG_PHILOX; c.trace_cap = e.trace_cap; c.hash_pops = e.hash_pops;
   P.n_qgroups = c.queue_cap / 32; P.n_streams = 0;
-  P.n_h = e.n_horizon; P.h0_ns = e.horizon_start_ns; P.h_step_ns = e.horizon_step_ns; P.rl_quantity = (double)e.quantity; P.rl_steep = 0.5; P.order_level = 0; P.rl_is_buy = e.is_buy;
+  P.n_h = e.n_horizon; P.h0_ns = e.horizon_start_ns; P.h_step_ns = e.horizon_step_ns; P.h_step_inv = e.horizon_step_ns > 0 ? 1.0 / (double)e.horizon_step_ns : 0.0; P.rl_quantity = (double)e.quantity; P.rl_steep = 0.5; P.order_level = 0; P.rl_is_buy = e.is_buy;
   P.dq_n_mom = e.n_momentum; P.dq_n_twap = e.n_twap; P.dq_has_ddqn = e.has_ddqn ? 1 : 0; P.dq_quantity = e.quantity;
 }
 // ids the generator can hand out in one run: momentum orders + execution-agent orders (market orders walk <= DQ_DEPTH levels)

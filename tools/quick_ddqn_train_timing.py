@@ -4,7 +4,7 @@ from marl_optimal_execution_b200.env import DDQNExecutionEnv
 from marl_optimal_execution_b200.qnet import QNetwork
 from marl_optimal_execution_b200.ddqn import DDQNTrainer
 g = np.load('/root/repo/tests/golden/ddqn_IBM_2003-01-14_s4242.npz')
-n = 8192; dev = torch.device('cuda', 0)
+n = 9472; dev = torch.device('cuda', 0)
 env = DDQNExecutionEnv(g['stream'], n_envs=n); env.reset(seeds=np.arange(n, dtype=np.uint64))
 net = QNetwork(seed=1)
 tr = DDQNTrainer(device=dev, batch_size=4096, seed=1, buffer_capacity=1 << 18)
