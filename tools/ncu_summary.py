@@ -13,7 +13,10 @@ keys = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "sm__icc_request_hit_rate.pct", "sass__inst_executed_local_loads", "sass__inst_executed_local_stores",
         "smsp__average_warp_latency_per_inst_issued.ratio", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "sass__inst_executed_shared_loads", "sass__inst_executed_shared_stores", "sass__inst_executed_global_loads", "sass__inst_executed_global_stores",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__shared_mem_per_block_dynamic"]
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__shared_mem_per_block_dynamic",
+        "dram__bytes.sum.per_second", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 for k in keys:
     if k in d:
         print("%-70s %s %s" % (k, d[k][0], d[k][1]))
