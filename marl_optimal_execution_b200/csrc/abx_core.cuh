@@ -1261,14 +1261,11 @@ struct Sim {
     }
   }
   ABX_HD void dq_order_update(int id, uint32_t oid, int32_t fill, bool cancel) {         // TradingAgent.orderExecuted :445-452, orderCancelled :480-483
-    int base = dq_order_base(id), f = -1;
-#pragma unroll 1
-    for (int i = 0; i < a.n_orders && f < 0; i++) { uint4 v = c.id_load(base + i); if (v.x == oid) f = i; }
+    int base = dq_order_base(id), f = c.tab_find(base, a.n_orders, oid);
     if (f < 0) return;
     uint4 v = c.id_load(base + f); int32_t q = (int32_t)v.z, aq = q < 0 ? -q : q;
     if (!cancel && fill < aq) { v.z = (uint32_t)(q < 0 ? -(aq - fill) : (aq - fill)); c.id_store(base + f, v); return; }
-#pragma unroll 1
-    for (int i = f; i + 1 < a.n_orders; i++) c.id_store(base + i, c.id_load(base + i + 1));
+    c.tab_remove(base, a.n_orders, f);                                                  // dict deletion keeps the order of the others
     a.n_orders--;
   }
   ABX_HD void dq_place_market(int id, int32_t quantity) { dq_place_market(id, quantity, P.rl_is_buy != 0); }
@@ -1695,14 +1692,11 @@ struct Sim {
   }
   // the market maker's self.orders: fill / cancel bookkeeping (TradingAgent.orderExecuted :445-452, orderCancelled :480-483)
   ABX_HD void r3_mm_order_update(uint32_t oid, int32_t fill, bool cancel) {
-    int f = -1;
-#pragma unroll 1
-    for (int i = 0; i < a.n_orders && f < 0; i++) { uint4 v = c.id_load(i); if (v.x == oid) f = i; }
+    int f = c.tab_find(0, a.n_orders, oid);
     if (f < 0) return;
     uint4 v = c.id_load(f); int32_t q = (int32_t)v.z, aq = q < 0 ? -q : q;
     if (!cancel && fill < aq) { v.z = (uint32_t)(q < 0 ? -(aq - fill) : (aq - fill)); c.id_store(f, v); return; }
-#pragma unroll 1
-    for (int i = f; i + 1 < a.n_orders; i++) c.id_store(i, c.id_load(i + 1));           // dict deletion keeps the order of the others
+    c.tab_remove(0, a.n_orders, f);                                                     // dict deletion keeps the order of the others
     a.n_orders--;
   }
   // Kernel.runner hot loop for the rmsc03 population

@@ -329,6 +329,27 @@ struct WarpCtxT {
   __device__ void envx_store() { sync(); uint4 *dst = reinterpret_cast<uint4 *>(P.envx + env); for (int i = lane; i < (int)(sizeof(EnvX) / 16); i += 32) __stcg(dst + i, reinterpret_cast<const uint4 *>(ex)[i]); }
   __device__ __forceinline__ uint4 id_load(int i) const { return ldcg4(idt + i); }
   __device__ __forceinline__ void id_store(int i, uint4 v) { if (lane == 0) __stcg(idt + i, v); __syncwarp(); }
+  // An agent's self.orders as a dense table of n 16-byte entries {order id, price, signed qty, -} at idt[base..]: index of `oid` (insertion order kept, so the
+  // first match is the dict's entry) and deletion of entry f.  32 entries per pass, coalesced, instead of one dependent L2 round trip per entry.
+  __device__ int tab_find(int base, int n, uint32_t oid) const {
+#pragma unroll 1
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      int i = i0 + lane; uint32_t x = i < n ? ldcg4(idt + base + i).x : 0u;
+      uint32_t m = __ballot_sync(FULL, i < n && x == oid);
+      if (m) return i0 + __ffs(m) - 1;
+    }
+    return -1;
+  }
+  __device__ void tab_remove(int base, int n, int f) {
+#pragma unroll 1
+    for (int i0 = f; i0 + 1 < n; i0 += 32) {                               // entries i0+1 .. i0+32 move down by one: all reads of a pass precede its writes
+      int i = i0 + lane; bool on = i + 1 < n; uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (on) v = ldcg4(idt + base + i + 1);
+      __syncwarp();
+      if (on) __stcg(idt + base + i, v);
+      __syncwarp();
+    }
+  }
   // Replayed orders' records {agent-side entry of idtab, census entry of idbook}: one replayed order is touched by three to five consecutive events
   // (placement, the exchange's registration and census, the acknowledgement), each a dependent L2/HBM round trip.  A miss fetches both halves at once;
   // stores write through, so HBM is always current and the cache needs no flush.  Same value, same address from every lane: one transaction.

@@ -82,6 +82,8 @@ struct HostCtx {
   void ib_store(int i, uint2 v) { P.idbook[(size_t)env * P.n_ids + i] = v; }
   uint4 id_load(int i) { return idt[i]; }
   void id_store(int i, uint4 v) { idt[i] = v; }
+  int tab_find(int base, int n, uint32_t oid) { for (int i = 0; i < n; i++) if (idt[base + i].x == oid) return i; return -1; }
+  void tab_remove(int base, int n, int f) { for (int i = f; i + 1 < n; i++) idt[base + i] = idt[base + i + 1]; }
   int4 row_load(int r) { return P.st_rows[r]; }
   int4 day_rec() { return P.day_tab[P.n_days > 1 ? env % P.n_days : 0]; }
   int n_ts() { return day_rec().y; }
