@@ -1,6 +1,6 @@
 """ABIDESEnv: batched, GPU-resident mirror of the reference's gym surface (ABIDESEnv.py:7-57).
 
-    env = ABIDESEnv(stream, n_envs=8192)      # stream: int64 [n,5] rows (t_ns, ORDER_ID, PRICE cents, SIZE, is_buy)
+    env = ABIDESEnv(stream, n_envs=9472)      # whole waves: a multiple of 148 SMs x 16 resident environments; stream: int64 [n,5] rows (t_ns, ORDER_ID, PRICE cents, SIZE, is_buy)
     env.reset()
     obs, reward, done, info = env.step(actions)   # actions [n_envs, 3] in [0,1]: (x_hat, o_hat_1, o_hat_2)
 
@@ -150,7 +150,7 @@ class DDQNExecutionEnv(ABIDESEnv):
     """The reference's DDQN execution simulation (config/execution/marketreplay/execution_marketreplay_ddqn.py, -a rl) as a
     batched decision process: Exchange + MarketReplayAgent + MomentumAgents + TWAPExecutionAgent + DDQLearningExecutionAgent.
 
-        env = DDQNExecutionEnv(stream, n_envs=8192); env.reset(seeds)
+        env = DDQNExecutionEnv(stream, n_envs=9472); env.reset(seeds)      # whole waves of 148 x 16 resident environments
         obs, trans, reward, done = env.step(None)            # runs to the first decision tick (10:00)
         obs, trans, reward, done = env.step(actions)         # actions int32 [n_envs] in 0..23 (ACTIONS, ddqlearning_execution_agent.py:24-37)
 
