@@ -343,7 +343,7 @@ def run_ours(args, rank, local_rank, world):
                      "(761 ticks) minus the start-up and warm-up steps"}
     dq_block = None
     if dq_local is not None:
-        gd = D.gather_summaries(torch.tensor([dq_local["steps"], dq_local["msgs"], dq_local["e2e_steps"], dq_local["errs"]], dtype=torch.int64), device=dev)
+        gd = D.gather_summaries(torch.tensor([dq_local["steps"], dq_local["msgs"], dq_local["e2e_steps"], dq_local["errs"], dq_local["train_done"]], dtype=torch.int64), device=dev)
         t_dq = D.max_over_ranks(dq_local["ms"], device=dev) / 1e3
         t_dq_e2e = D.max_over_ranks(dq_local["e2e_s"], device=dev)
         t_dq_train = D.max_over_ranks(dq_local["train_s"], device=dev)
@@ -356,8 +356,8 @@ def run_ours(args, rank, local_rank, world):
                     "e2e": {"value": int(gd[:, 2].sum()) / t_dq_e2e, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 121 * nd,
                             "note": "actions are produced on the device by the Q-network; every tick obs, experience tuple, reward and done are read back to pinned host memory"},
                     "training": {"value": int(gd[:, 0].sum()) / t_dq_train, "unit": "steps/s", "learn_steps": dq_local["learn_steps"], "batch": args.ddqn_batch,
-                                 "replay_buffer_rows": dq_local["buffer"], "note": "same loop with the learner on: experience tuples into a device replay buffer, one "
-                                 "train_neural_nets-style update (PyTorch fp32 autograd, RMSprop) every 5 ticks, new weights packed into the tcgen05 operand image on the device; no host synchronisation inside the loop; wall clock; "
+                                 "replay_buffer_rows": dq_local["buffer"], "finished_envs": int(gd[:, 4].sum()), "note": "same loop with the learner on: experience tuples into a device replay buffer, one "
+                                 "train_neural_nets-style update (PyTorch fp32 autograd, RMSprop) every 5 ticks, new weights packed into the tcgen05 operand image on the device; no host synchronisation inside the loop; wall clock; finished_envs = episodes whose parent order the learned policy completed before the last training tick (they idle from then on); "
                                  "with N ranks one policy is trained: the 38 k gradients are averaged by an NCCL all-reduce before every update"},
                     "gpu_launches": dq_local["launches"], "dtype": "int64+f64 (environment), bf16x3 -> fp32 accumulate (Q-network)",
                     "qnet_roofline": {"bound": "tensor", "achieved": q_ach, "peak": tf_peak[0], "unit": "TFLOP/s", "frac": q_ach / tf_peak[0], "traffic": None,
@@ -530,10 +530,11 @@ def bench_ddqn(args, rank, local_rank, dev, stream, sp):
     train_s = time.perf_counter() - w0
     D.barrier()
     st = env.stats(stream=sp)
-    errs = int(((st["flags"] & _lib.F_ERROR_MASK) != 0).sum()) + int(d_pin.sum()) + int(done.sum())       # no environment may have ended inside the measured ticks
+    errs = int(((st["flags"] & _lib.F_ERROR_MASK) != 0).sum()) + int(d_pin.sum())       # no environment may have ended inside the device-timed / e2e ticks
+    train_done = int(done.sum())       # the learner's policy may buy the parent order out before 15:30 (large scales): finished episodes, not errors
     env.close(); net.close()
     return {"steps": n * K, "msgs": m1 - m0, "ms": e0.elapsed_time(e1), "e2e_steps": n * K, "e2e_s": e2e_s, "errs": errs, "launches": int(launches), "qnet_ms": qnet_ms,
-            "train_s": train_s, "learn_steps": tr.learn_step_counter - l_before, "buffer": tr.buffer.size}
+            "train_s": train_s, "learn_steps": tr.learn_step_counter - l_before, "buffer": tr.buffer.size, "train_done": train_done}
 
 
 def main():
