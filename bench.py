@@ -234,7 +234,7 @@ def run_reference(args, rank, world):
                                "(oracle/abides_oracle.c port of the Python reference) on host cores" % (args.variant, args.variant)},
         "cpu_baseline": {"value": v, "unit": "msgs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "msgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "env": reference_env_block(cores), "ddqn": reference_ddqn_block(cores),
+        "gpu_launches": 0, "rmsc03": reference_rmsc03_block(cores), "env": reference_env_block(cores), "ddqn": reference_ddqn_block(cores),
     })
 
 
@@ -314,8 +314,13 @@ def run_ours(args, rank, local_rank, world):
     # ---- second headline metric: ABIDESEnv steps/s (Exchange + MarketReplayAgent + RL execution agent under GymKernel)
     env_local = None
     state_bytes = sim.device_bytes
-    if not args.no_env:
+    r3_local = None
+    if not args.no_rmsc03:
         sim.close()
+        r3_local = bench_rmsc03(args, rank, local_rank, dev, stream, sp)
+    if not args.no_env:
+        if not sim_closed(sim):
+            sim.close()
         env_local = bench_env(args, rank, local_rank, dev, stream, sp)
 
     dq_local = None
@@ -328,6 +333,29 @@ def run_ours(args, rank, local_rank, world):
     g = D.gather_summaries(torch.tensor([msgs_local, e2e_msgs_local, err_envs], dtype=torch.int64), device=dev)
     elapsed_ms = D.max_over_ranks(elapsed_ms, device=dev)
     e2e_s = D.max_over_ranks(e2e_s_local, device=dev)
+    r3_block = None
+    if r3_local is not None:
+        r3_block = {"metric": "LOB msgs/sec (rmsc03)", "unit": "msgs/s", "envs_per_gpu": args.rmsc03_envs_per_gpu,
+                    "workload": "config/rmsc03.py shape: 50 NoiseAgents + 10 ValueAgents + 2 MomentumAgents + POVMarketMakerAgent + exchange, 09:30-09:46, "
+                                "zero latency, %d envs/GPU (Philox streams); the whole run of every environment in one abx_run_kernel launch; "
+                                "2 timed runs on fresh seeds after one warm-up run, resets untimed" % args.rmsc03_envs_per_gpu}
+        for key in ("plain", "pov"):
+            r = r3_local[key]
+            gr = D.gather_summaries(torch.tensor([r["msgs"], r["errs"], r["invalid"], r["runs"]], dtype=torch.int64), device=dev)
+            t_r = D.max_over_ranks(r["ms"], device=dev) / 1e3
+            blk = {"value": int(gr[:, 0].sum()) / t_r, "messages_per_env_run": int(gr[:, 0].sum()) / max(int(gr[:, 3].sum()), 1),
+                   "ms_per_run": 1e3 * t_r / 2, "error_envs": int(gr[:, 1].sum()), "gpu_launches": int(r["launches"])}
+            if key == "plain":
+                r3_block.update(blk)
+                ach = int(gr[:, 0].sum()) / world * B_MSG / t_r / 1e9
+                r3_block["roofline"] = {"bound": "hbm", "achieved": ach, "peak": measured_peak_hbm()[0], "unit": "GB/s", "frac": ach / measured_peak_hbm()[0],
+                                        "traffic": None, "kernel": "abx_run_kernel<0,2,0,2>", "algorithmic_bytes_per_msg": B_MSG,
+                                        "note": "profiles/r01_rmsc03_run_kernel_ncu_full_summary.txt: the state of 4 096 environments sits in the L2; latency bound"}
+            else:
+                blk["one_sided_book_envs"] = int(gr[:, 2].sum())
+                blk["note"] = ("same population + POVExecutionAgent (agent/execution/baselines/pov_agent.py; BUY 120 000 at 50 % of volume, 09:32-09:43); "
+                               "one_sided_book_envs = runs in which the agent saw an empty book side (the reference raises TypeError there; flagged F_OBS_INVALID, the run continues)")
+                r3_block["with_pov_execution_agent"] = blk
     env_block = None
     if env_local is not None:
         ge = D.gather_summaries(torch.tensor([env_local["steps"], env_local["msgs"], env_local["e2e_steps"], env_local["errs"]], dtype=torch.int64), device=dev)
@@ -398,6 +426,8 @@ def run_ours(args, rank, local_rank, world):
                 "d2h_bytes_per_step": ctypes.sizeof(_lib.EnvStats) * n_envs},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if r3_block is not None:
+        out["rmsc03"] = r3_block
     if not args.no_env:
         out["env"] = env_block
     if dq_block is not None:
@@ -410,11 +440,53 @@ def run_ours(args, rank, local_rank, world):
         out["cpu_baseline"] = {"value": m / w, "unit": "msgs/s", "cores": cores, "kind": "port",
                                "sample": "%d full env-days of sparse_zi_%d, event loop only, %d threads, %.1f CPU-s" % (n_days, args.variant, cores, cpu_s),
                                "single_thread_value": m / cpu_s}
+        if not args.no_rmsc03:
+            out["cpu_baseline"]["rmsc03"] = reference_rmsc03_block(cores)
         if not args.no_env:
             out["cpu_baseline"]["env"] = reference_env_block(cores)
         if not args.no_ddqn:
             out["cpu_baseline"]["ddqn"] = reference_ddqn_block(cores)
     emit_json(out)
+
+
+def bench_rmsc03(args, rank, local_rank, dev, stream, sp):
+    """BASELINE configs[2]: config/rmsc03.py population (50 noise + 10 value + 2 momentum agents + POV market maker), without and with the POV
+    execution agent; one abx_run_kernel launch runs the whole 09:30-09:46 simulation of every environment.  Reset (construction) is untimed,
+    like Kernel.py:184,301; one warm-up run, then `reps` timed runs on fresh seeds."""
+    import torch
+    from marl_optimal_execution_b200 import _lib, distributed as D
+    from marl_optimal_execution_b200.sim import BatchedSim, rmsc03_config
+    n, reps, out = args.rmsc03_envs_per_gpu, 2, {}
+    for pov in (False, True):
+        sim = BatchedSim(rmsc03_config(pov_exec=pov), n, device=local_rank)
+        ms, msgs, errs, invalid, l0 = 0.0, 0, 0, 0, 0
+        for rep in range(reps + 1):
+            sim.reset(D.env_seeds(args.seed + 100003 * rep, rank * n, (rank + 1) * n), stream=sp)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            D.barrier(); torch.cuda.synchronize(dev)
+            lc = sim.launch_count
+            e0.record(stream)
+            sim.run(stream=sp)
+            e1.record(stream)
+            torch.cuda.synchronize(dev); D.barrier()
+            if rep > 0:
+                l0 += sim.launch_count - lc               # launches inside the timed regions only
+                st = sim.stats(stream=sp)
+                ms += e0.elapsed_time(e1); msgs += int(st["messages"].sum())
+                errs += int(((st["flags"] & (_lib.F_ERROR_MASK & ~_lib.F_OBS_INVALID)) != 0).sum())
+                invalid += int(((st["flags"] & _lib.F_OBS_INVALID) != 0).sum())
+        out["pov" if pov else "plain"] = {"msgs": msgs, "ms": ms, "errs": errs, "invalid": invalid, "runs": reps * n,
+                                          "launches": l0}
+        sim.close()
+    return out
+
+
+def reference_rmsc03_block(cores):
+    n_runs = max(8 * cores, 32)
+    oracle_msgs_per_s(min(cores, 4), cores, 3)
+    m, w, cpu_s = oracle_msgs_per_s(n_runs, cores, 3)
+    return {"metric": "LOB msgs/sec (rmsc03)", "value": m / w, "unit": "msgs/s", "cores": cores, "kind": "port", "single_thread_value": m / cpu_s,
+            "sample": "%d whole rmsc03 runs (09:30-09:46, no execution agent), event loop only, %d threads, %.1f CPU-s" % (n_runs, cores, cpu_s)}
 
 
 def bench_env(args, rank, local_rank, dev, stream, sp):
@@ -551,6 +623,8 @@ def main():
     ap.add_argument("--no-env", action="store_true", help="skip the ABIDESEnv steps/s measurement")
     ap.add_argument("--env-envs-per-gpu", type=int, default=9472, help="4 x 148 SMs x 16 resident one-warp CTAs: whole waves (8192 leaves the 4th wave 46 %% full)")
     ap.add_argument("--env-steps", type=int, default=750, help="timed ABIDESEnv steps: 750 = the whole 761-tick episode after the start-up and warm-up steps")
+    ap.add_argument("--no-rmsc03", action="store_true", help="skip the rmsc03 population (BASELINE configs[2])")
+    ap.add_argument("--rmsc03-envs-per-gpu", type=int, default=4096, help="BASELINE configs[2]: 4096 envs/GPU")
     ap.add_argument("--no-ddqn", action="store_true", help="skip the DDQN execution shape (Q-network forward + environment step per tick)")
     ap.add_argument("--ddqn-envs-per-gpu", type=int, default=9472, help="whole waves of 148 x 16 resident environments, like --env-envs-per-gpu")
     ap.add_argument("--ddqn-steps", type=int, default=200, help="timed DDQN decision ticks per sub-measurement (acting, e2e, training share one 660-tick day)")
