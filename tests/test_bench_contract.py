@@ -1,0 +1,50 @@
+"""bench.py contract on a box without a GPU: the reference arm prints one JSON line with the agreed keys (rank 0 only), and our arm
+refuses to run without a CUDA device (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(argv, env_extra=None, timeout=300):
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    env.update(env_extra or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + argv, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+
+
+def test_reference_arm_line_has_the_contract_keys():
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, "exactly one JSON line on stdout"
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "LOB msgs/sec" and d["unit"] == "msgs/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1 and d["gpu_launches"] == 0
+    assert d["value"] > 1e5 and d["ms_per_step"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sparse_zi_1000" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "msgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+    # the other configurations of BASELINE.json ride in the same line
+    assert d["rmsc03"]["unit"] == "msgs/s" and d["rmsc03"]["value"] > 1e5 and "rmsc03" in d["rmsc03"]["sample"]
+    assert d["env"]["unit"] == "steps/s" and d["env"]["value"] > 100
+    assert d["ddqn"]["unit"] == "steps/s" and d["ddqn"]["value"] > 100
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    r = _run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"], {"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_our_arm_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a CUDA device is present")
+    r = _run(["--steps", "1", "--warmup", "3", "--envs-per-gpu", "32"], timeout=120)
+    assert r.returncode != 0
+    assert "no CPU fallback" in (r.stderr + r.stdout) or "CUDA" in (r.stderr + r.stdout)
