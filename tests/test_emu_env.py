@@ -65,6 +65,22 @@ def test_marketreplay_config_matches_oracle(emu, golden_dir):
     assert np.array_equal(p, o.trace("pops")) and np.array_equal(nt, o.trace("notes")) and np.array_equal(sn, o.trace("snaps"))
 
 
+def test_sample_orders_file_matches_reference_recording(emu, golden_dir):
+    """The reference's 10-row L3 sample stream (data/sample_orders_file.csv) under config/marketreplay.py: all 41 messages of the live
+    reference's run, its 17 exchange messages and 10 book snapshots."""
+    g = np.load(os.path.join(golden_dir, "mr_sample_orders_file.npz"))
+    L = _lib.load(emu)
+    cfg = env_config(L, order_level=0, stop_ns=(16 * 3600 + 60) * 10 ** 9, queue_cap=64, level_cap=64, trace_cap=4096, hash_pops=1)
+    env = ABIDESEnv(g["stream"], n_envs=1, cfg=cfg, lib_path=emu)
+    env.reset()
+    _, _, done, _ = env.step(np.zeros((1, 3)))
+    st = env.stats()[0]
+    assert int(done[0]) == 1 and int(st["messages"]) == int(g["n_pops"]) == 41 and int(st["flags"]) == _lib.F_DONE
+    assert int(st["pop_hash"]) == int(g["pop_hash_ckpt"][-1])
+    p, nt, sn = env.split_trace(0)
+    assert np.array_equal(p, g["pops"]) and np.array_equal(nt, g["notes"]) and np.array_equal(sn, g["snaps"])
+
+
 def test_several_days_in_one_batch(emu, golden_dir):
     """Environment e replays day e % n_days: two recorded reference episodes (IBM 2003-01-14 and 2003-01-15) side by side in one handle,
     each bit-exact against its own oracle; a third and fourth environment repeat the days."""

@@ -78,6 +78,22 @@ def test_marketreplay_config_on_gpu(golden_dir):
     assert int(st["max_queue"][0]) == o.counter("max_queue")
 
 
+def test_sample_orders_file_on_gpu(golden_dir):
+    """data/sample_orders_file.csv replayed through the GPU books (config/marketreplay.py shape): every pop, exchange message and book
+    snapshot of the live reference's own run (tools/record_reference.py --orders-csv), in three environments of one batch."""
+    g = np.load(os.path.join(golden_dir, "mr_sample_orders_file.npz"))
+    cfg = env_config(order_level=0, stop_ns=(16 * 3600 + 60) * 10 ** 9, queue_cap=64, level_cap=64, trace_cap=4096, hash_pops=1)
+    env = ABIDESEnv(g["stream"], n_envs=3, cfg=cfg)
+    env.reset()
+    _, _, done, _ = env.step(np.zeros((3, 3)))
+    st = env.stats()
+    assert done.tolist() == [1, 1, 1] and (st["messages"] == 41).all() and (st["flags"] == _lib.F_DONE).all()
+    assert (st["pop_hash"] == np.uint64(int(g["pop_hash_ckpt"][-1]))).all()
+    for e in (0, 2):
+        p, nt, sn = env.split_trace(e)
+        assert np.array_equal(p, g["pops"]) and np.array_equal(nt, g["notes"]) and np.array_equal(sn, g["snaps"])
+
+
 def test_several_days_in_one_batch(golden_dir):
     """Environment e replays day e % n_days (abx_env_create_days / abx_dq_create_days): three IBM days side by side, each environment
     bit-exact against the oracle of its own day; ABIDESEnv and the DDQN execution shape."""

@@ -56,3 +56,19 @@ def test_marketreplay_config_matches_reference(golden_dir):
         assert np.array_equal(env.trace(name)[: len(b)], b), name
     assert env.counter("max_bid_levels") == g["max_levels"][0] and env.counter("max_ask_levels") == g["max_levels"][1]
     assert env.counter("max_resting") == int(g["max_resting"])
+
+
+def test_sample_orders_file_matches_reference(golden_dir):
+    """data/sample_orders_file.csv (the 10-row L3 order stream) replayed by config/marketreplay.py in the live reference
+    (tools/record_reference.py --orders-csv): 41 kernel messages; the first timestamp's two orders are replayed twice (second pass =
+    MODIFY_ORDER), fills remove orders before their later CANCEL / MODIFY rows arrive, the last timestamp is never replayed.  Every pop,
+    exchange message and book snapshot of the recording."""
+    g = np.load(os.path.join(golden_dir, "mr_sample_orders_file.npz"))
+    env = OracleEnv(g["stream"], order_level=0, trace=TRACE_ALL, stop_ns=(16 * 3600 + 60) * 10 ** 9)
+    _, _, done, _ = env.step([0, 0, 0])
+    assert done == 1 and env.n_pops == int(g["n_pops"]) == 41
+    assert env.pop_hash() == int(g["pop_hash_ckpt"][-1]) and env.note_hash() == int(g["note_hash"]) and env.snap_hash() == int(g["snap_hash"])
+    for name in ("pops", "notes", "snaps"):
+        assert np.array_equal(env.trace(name), g[name]), name
+    f = env.final()
+    assert f[4] == g["holdings"][0, 1] == 0 and f[5] == g["holdings"][0, 2] == 0      # the replay agent trades with itself: flat, cash unchanged

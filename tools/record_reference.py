@@ -284,6 +284,24 @@ def main():
         # simulation ended and is out of scope, so the recorder skips it.
         import agent.ExchangeAgent as EA
         EA.ExchangeAgent.logOrderBookSnapshots = lambda self, symbol: None
+    if "--orders-csv" in rest:
+        # Replay a plain L3 order file (TIMESTAMP,ORDER_ID,PRICE,SIZE,BUY_SELL_FLAG; data/sample_orders_file.csv) instead of a LOBSTER day: the
+        # reference's own L3OrdersProcessor cannot read that file (it expects a '|'-separated 17-column export,
+        # agent/examples/MarketReplayAgent.py:140-147), so the recorder hands MarketReplayAgent the orders dict in the processor's output format
+        # ({Timestamp: [{ORDER_ID, PRICE (cents = PRICE * 100, :152-153), SIZE, BUY_SELL_FLAG}]}, :158) and leaves everything after it unmodified.
+        import pandas as pd
+        import agent.examples.MarketReplayAgent as MRA
+        csv_path = rest[rest.index("--orders-csv") + 1]
+
+        def process_orders(self):
+            df = pd.read_csv(csv_path, dtype=str)
+            od = {}
+            for r in df.itertuples(index=False):
+                ts = pd.Timestamp(pd.to_datetime(r.TIMESTAMP[:21], format="%Y%m%d%H%M%S.%f"))      # microseconds, like convertDate (:126-130)
+                od.setdefault(ts, []).append({"ORDER_ID": int(r.ORDER_ID), "PRICE": int(float(r.PRICE) * 100), "SIZE": int(r.SIZE), "BUY_SELL_FLAG": r.BUY_SELL_FLAG})
+            return od
+
+        MRA.LOBSTEROrdersProcessor.processOrders = process_orders
     pov_args = None
     if "--pov-exec" in rest:
         # "rmsc03 with a POV execution agent" (BASELINE.json configs[2]): the shipped config/rmsc03.py has no execution agent, so the recorder
