@@ -40,6 +40,62 @@ def rmsc03_config(lib=None, pov_exec=False, **overrides):
     return cfg
 
 
+def _num(x):
+    """'{}'.format of a config literal: 1 -> '1', 0.8 -> '0.8' (config/sparse_zi_1000.py:211-219 writes eta as 1 or 0.8)."""
+    return str(int(x)) if float(x) == int(x) else repr(float(x))
+
+
+def agent_directory(cfg):
+    """(names, types) of agents 1 .. n_agents-1 exactly as the config scripts name them: config/sparse_zi_1000.py:224-250
+    ("ZI Agent {j} Type {k} [{R_min} <= R <= {R_max}, eta={eta}]" / "ZeroIntelligenceAgent Type ..."), config/rmsc03.py:118-200
+    (NoiseAgent, Value Agent, POV_MARKET_MAKER_AGENT_, MOMENTUM_AGENT_), and the recorder's POV_EXECUTION_AGENT / ExecutionAgent."""
+    names, types = [], []
+    j = 1
+    if cfg.population == 0:
+        for k in range(cfg.n_groups):
+            g = cfg.groups[k]
+            strat = "Type {} [{} <= R <= {}, eta={}]".format(k + 1, g.r_min, g.r_max, _num(g.eta))
+            for _ in range(g.count):
+                names.append("ZI Agent {} {}".format(j, strat)); types.append("ZeroIntelligenceAgent {}".format(strat)); j += 1
+    else:
+        for count, name, typ in ((cfg.n_noise_agents, "NoiseAgent {}", "NoiseAgent"), (cfg.n_value_agents, "Value Agent {}", "ValueAgent"),
+                                 (cfg.n_mm_agents, "POV_MARKET_MAKER_AGENT_{}", "POVMarketMakerAgent"), (cfg.n_momentum_agents, "MOMENTUM_AGENT_{}", "MomentumAgent")):
+            for _ in range(count):
+                names.append(name.format(j)); types.append(typ); j += 1
+        for _ in range(cfg.n_pov_exec):
+            names.append("POV_EXECUTION_AGENT"); types.append("ExecutionAgent"); j += 1
+    return names, types
+
+
+def format_kernel_summary(names, types, holdings, messages, starting_cash, symbol="JPM", elapsed_s=None):
+    """The text Kernel.runner leaves on stdout for one simulation, from the per-agent rows
+    (id, shares, cash, marked to market, surplus) of abx_sim_holdings:
+      * per trading agent "Final holdings for {name}: { SYM: n, CASH: c }.  Marked to market: m" (agent/TradingAgent.py:115-126; fmtHoldings
+        :670-680 -- a flat position has no symbol entry, orderExecuted deletes it);
+      * "Event Queue elapsed: {Timedelta}, messages: {N}, messages per second: {R:0.1f}" (Kernel.py:321-327);
+      * "Mean ending value by agent type:" + "{type}: {int(round(mean gain))}" in first-seen order (Kernel.py:337-341, TradingAgent.py:130-138);
+      * "Simulation ending!" (Kernel.py:343)."""
+    lines, gain, count = [], {}, {}
+    for (aid, shares, cash, mtm, _), name, typ in zip(holdings, names, types):
+        h = ("{}: {}, ".format(symbol, int(shares)) if int(shares) != 0 else "") + "CASH: {}".format(int(cash))
+        lines.append("Final holdings for {}: {}.  Marked to market: {}".format(name, "{ " + h + " }", int(mtm)))
+        gain[typ] = gain.get(typ, 0) + int(mtm) - int(starting_cash)
+        count[typ] = count.get(typ, 0) + 1
+    if elapsed_s is not None:
+        us = int(round(elapsed_s * 1e6))
+        d, rem = divmod(us, 86400 * 10 ** 6)
+        hh, rem = divmod(rem, 3600 * 10 ** 6)
+        mm, rem = divmod(rem, 60 * 10 ** 6)
+        ss, frac = divmod(rem, 10 ** 6)
+        td = "{} days {:02d}:{:02d}:{:02d}".format(d, hh, mm, ss) + (".{:06d}".format(frac) if frac else "")      # str(pd.Timedelta)
+        lines.append("Event Queue elapsed: {}, messages: {}, messages per second: {:0.1f}".format(td, int(messages), int(messages) / max(elapsed_s, 1e-12)))
+    lines.append("Mean ending value by agent type:")
+    for typ in gain:
+        lines.append("{}: {:d}".format(typ, int(round(gain[typ] / count[typ]))))
+    lines.append("Simulation ending!")
+    return lines
+
+
 class BatchedSim:
     """n_envs independent simulations of one population config on one GPU.
 
@@ -128,6 +184,12 @@ class BatchedSim:
         _lib.check(self._L, self._L.abx_sim_holdings(self._h, int(env), out.ctypes.data_as(C.POINTER(C.c_int64)), stream),
                    "abx_sim_holdings")
         return out
+
+    def kernel_summary(self, env=0, symbol="JPM", elapsed_s=None, stream=None):
+        """Kernel.runner's stdout report of environment `env` (call after run() + finalize()): see format_kernel_summary."""
+        names, types = agent_directory(self.cfg)
+        st = self.stats(stream=stream)[int(env)]
+        return format_kernel_summary(names, types, self.holdings(env, stream=stream), int(st["messages"]), int(self.cfg.starting_cash), symbol, elapsed_s)
 
     def book_snapshot(self, env, is_bid, depth, stream=None):
         out = np.zeros(2 * max(depth, 1), dtype=np.int32)

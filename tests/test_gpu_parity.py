@@ -68,6 +68,12 @@ def test_z1000_tape_replay_reproduces_reference_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "z1000_s123456789.npz"))        # recorded from the live reference
     assert np.array_equal(sim.holdings(0), g["holdings"])
     assert int(st["pop_hash"][0]) == int(g["pop_hash_ckpt"][-1])
+    # Kernel.runner's stdout contract (Kernel.py:321-343, TradingAgent.py:115-138): first line and the seven per-type means of the
+    # reference's own capture tests/sparse_zi_1000.txt:22-32 (the CPU suite compares all 1 008 lines with that file)
+    text = sim.kernel_summary(0, "JPM", elapsed_s=59.733625)
+    assert text[0] == "Final holdings for ZI Agent 1 Type 1 [0 <= R <= 250, eta=1]: { JPM: 400, CASH: -30025600 }.  Marked to market: 9586000"
+    assert text[1000] == "Event Queue elapsed: 0 days 00:00:59.733625, messages: 185200, messages per second: 3100.4"
+    assert [int(ln.rsplit(": ", 1)[1]) for ln in text[1002:1009]] == [-19781, -19338, -18593, 30137, 641, 5634, 27887]
 
 
 def test_sliced_runs_equal_single_run():
