@@ -46,6 +46,51 @@ def load_lobster_fixture(path):
     return np.ascontiguousarray(np.load(path)["stream"], dtype=np.int64)
 
 
+def load_lobster_csv(path, start_s=34200, end_s=57600):
+    """A LOBSTER message file -> the replayed stream int64 [n, 5] = (t_ns since midnight, ORDER_ID, PRICE cents, SIZE, is_buy), row for row
+    what LOBSTEROrdersProcessor.processOrders builds (agent/examples/MarketReplayAgent.py:196-216):
+      columns TIMESTAMP(s), EVENT_TYPE, ORDER_ID, SIZE, PRICE(x1e4), BUY_SELL_FLAG(+1/-1), every event type kept (:198-202);
+      TIMESTAMP = start_time + pd.to_timedelta(seconds, "s") - 09:30 (:206-208) -- pandas splits the float into whole seconds and a
+        fraction rounded to 9 decimals, and truncates fraction * 1e9 to integer nanoseconds;
+      PRICE = int(float(price) / 100) (:210-211: truncation to cents); SIZE int; rows with mkt_open <= t < mkt_close (:212);
+      grouped per timestamp in ascending order, file order inside a group (:216)."""
+    raw = np.loadtxt(path, delimiter=",", dtype=np.float64, usecols=(0, 2, 3, 4, 5), ndmin=2)
+    t = raw[:, 0]
+    base = np.trunc(t)
+    t_ns = base.astype(np.int64) * 10 ** 9 + (np.round(t - base, 9) * 1e9).astype(np.int64)
+    rows = np.stack([t_ns, raw[:, 1].astype(np.int64), (raw[:, 3] / 100).astype(np.int64), raw[:, 2].astype(np.int64),
+                     (raw[:, 4].astype(np.int64) == 1).astype(np.int64)], axis=1)
+    rows = rows[(t_ns >= int(start_s) * 10 ** 9) & (t_ns < int(end_s) * 10 ** 9)]
+    return np.ascontiguousarray(rows[np.argsort(rows[:, 0], kind="stable")])
+
+
+def lobster_message_path(ticker, date, data_root="data/lobster", level=1, dated_folder=False):
+    """Where the reference looks for a day's message file: agent_config.py:63-64 (ABIDESEnv: LOBSTER_SampleFile_{ticker}_{level}/) or, with
+    dated_folder=True, config/marketreplay.py:91-92 (LOBSTER_SampleFile_{ticker}_{date}_{level}/)."""
+    import os
+    folder = "LOBSTER_SampleFile_{}_{}_{}".format(ticker, date, level) if dated_folder else "LOBSTER_SampleFile_{}_{}".format(ticker, level)
+    return os.path.join(data_root, folder, "{}_{}_34200000_57600000_message_{}.csv".format(ticker, date, level))
+
+
+class Box:
+    """The two attributes of gym.spaces.Box the reference's callers read (ABIDESEnv.py:22-25): low / high (+ shape, dtype, sample, contains)."""
+
+    def __init__(self, low, high):
+        self.low = np.asarray(low, dtype=np.float32)
+        self.high = np.asarray(high, dtype=np.float32)
+        self.shape, self.dtype = self.low.shape, self.low.dtype
+
+    def sample(self, rng=None):
+        return (rng or np.random).uniform(self.low, self.high).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+    def __repr__(self):
+        return "Box(%s, %s, %s, %s)" % (self.low.min(), self.high.max(), self.shape, self.dtype)
+
+
 class ABIDESEnv:
     OBS_SIZE = 9          # get_observation returns 9 values (get_observation_space_size says 10, SURVEY section 8 a19)
 
@@ -55,12 +100,26 @@ class ABIDESEnv:
         self.n_envs = int(n_envs)
         self.device = int(device)
         self.action_size = int(self.cfg.order_level) + 1                  # get_action_space_size :128-134
+        # ABIDESEnv.py:18-25: actions in [0, 1]^(k+1); the observation Box is built from get_observation_space_size() = 10 zeros for low AND
+        # high (dummy_rl_execution_agent.py:317-322) although get_observation returns 9 values -- mirrored as is
+        self.action_space = Box([0.0] * self.action_size, [1.0] * self.action_size)
+        self.observation_space = Box([0] * 10, [0] * 10)
         st, off = _pack_days(stream)
         self.n_days = len(off) - 1
         self._h = C.c_void_p()
         _lib.check(self._L, self._L.abx_env_create_days(C.byref(self.cfg), st.ctypes.data_as(C.POINTER(C.c_int64)), off.ctypes.data_as(C.POINTER(C.c_int64)),
                                                         self.n_days, self.n_envs, self.device, C.byref(self._h)), "abx_env_create_days")
         self._torch_out = None
+
+    @classmethod
+    def from_lobster(cls, ticker, date, n_envs=1, data_root="data/lobster", level=1, **kw):
+        """The reference's constructor arguments (ABIDESEnv(ticker, date), ABIDESEnv.py:8-17): replays the day's LOBSTER message file found
+        where agent_config.py:63-64 looks for it under `data_root`.  `date` may be a list of 'yyyy-mm-dd' strings (environment e replays
+        day e % n_days).  log_dir / seed of the reference have no effect on this path (no random draws, no logging)."""
+        dates = [date] if isinstance(date, str) else list(date)
+        env = cls([load_lobster_csv(lobster_message_path(ticker, d, data_root, level)) for d in dates], n_envs=n_envs, **kw)
+        env.ticker, env.date = ticker, date
+        return env
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -173,6 +232,15 @@ class DDQNExecutionEnv(ABIDESEnv):
         _lib.check(self._L, self._L.abx_dq_create_days(C.byref(self.cfg), st.ctypes.data_as(C.POINTER(C.c_int64)), off.ctypes.data_as(C.POINTER(C.c_int64)),
                                                        self.n_days, self.n_envs, self.device, C.byref(self._h)), "abx_dq_create_days")
         self._torch_out = None
+
+    @classmethod
+    def from_lobster(cls, ticker, date, n_envs=1, data_root="data/lobster", level=1, **kw):
+        """(ticker, date) as config/execution/marketreplay/execution_marketreplay_ddqn.py takes them (-t, -d): the day's LOBSTER message
+        file(s) under `data_root`, parsed like LOBSTEROrdersProcessor (load_lobster_csv)."""
+        dates = [date] if isinstance(date, str) else list(date)
+        env = cls([load_lobster_csv(lobster_message_path(ticker, d, data_root, level)) for d in dates], n_envs=n_envs, **kw)
+        env.ticker, env.date = ticker, date
+        return env
 
     def reset(self, seeds=None, mom_sizes=None, stream=None):
         sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64).reshape(self.n_envs)
