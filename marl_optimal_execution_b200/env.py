@@ -72,6 +72,17 @@ def lobster_message_path(ticker, date, data_root="data/lobster", level=1, dated_
     return os.path.join(data_root, folder, "{}_{}_34200000_57600000_message_{}.csv".format(ticker, date, level))
 
 
+def _load_days(ticker, dates, data_root, level):
+    days = []
+    for d in dates:
+        path = lobster_message_path(ticker, d, data_root, level)
+        rows = load_lobster_csv(path)
+        if len(rows) == 0:          # the reference's constructor fails the same way: wakeup_times[0] of an empty dict (MarketReplayAgent.py:177)
+            raise IndexError("no orders between 09:30 and 16:00 in %s" % path)
+        days.append(rows)
+    return days
+
+
 class Box:
     """The two attributes of gym.spaces.Box the reference's callers read (ABIDESEnv.py:22-25): low / high (+ shape, dtype, sample, contains)."""
 
@@ -117,7 +128,7 @@ class ABIDESEnv:
         where agent_config.py:63-64 looks for it under `data_root`.  `date` may be a list of 'yyyy-mm-dd' strings (environment e replays
         day e % n_days).  log_dir / seed of the reference have no effect on this path (no random draws, no logging)."""
         dates = [date] if isinstance(date, str) else list(date)
-        env = cls([load_lobster_csv(lobster_message_path(ticker, d, data_root, level)) for d in dates], n_envs=n_envs, **kw)
+        env = cls(_load_days(ticker, dates, data_root, level), n_envs=n_envs, **kw)
         env.ticker, env.date = ticker, date
         return env
 
@@ -238,7 +249,7 @@ class DDQNExecutionEnv(ABIDESEnv):
         """(ticker, date) as config/execution/marketreplay/execution_marketreplay_ddqn.py takes them (-t, -d): the day's LOBSTER message
         file(s) under `data_root`, parsed like LOBSTEROrdersProcessor (load_lobster_csv)."""
         dates = [date] if isinstance(date, str) else list(date)
-        env = cls([load_lobster_csv(lobster_message_path(ticker, d, data_root, level)) for d in dates], n_envs=n_envs, **kw)
+        env = cls(_load_days(ticker, dates, data_root, level), n_envs=n_envs, **kw)
         env.ticker, env.date = ticker, date
         return env
 

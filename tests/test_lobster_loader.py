@@ -1,6 +1,9 @@
 """Data format on the input side of the replay path: LOBSTER message files parsed like the reference's LOBSTEROrdersProcessor
 (agent/examples/MarketReplayAgent.py:162-220), and the (ticker, date) constructor + gym spaces of the ABIDESEnv surface (ABIDESEnv.py:8-25)."""
 import os
+import subprocess
+import sys
+import warnings
 
 import numpy as np
 import pytest
@@ -23,11 +26,35 @@ def test_loader_equals_the_streams_the_live_reference_parsed(golden_dir, fixture
     assert got.dtype == np.int64 and np.array_equal(got, want)
 
 
+@pytest.mark.skipif(not os.path.isdir(REF_LOBSTER), reason="reference tree not present")
+@pytest.mark.parametrize("rel,date", [("LOBSTER_SampleFile_AMZN_2012-06-21_1/AMZN_2012-06-21", "2012-06-21")])
+def test_loader_equals_the_live_reference_processor(tmp_path, rel, date):
+    """A day no fixture holds: the unmodified LOBSTEROrdersProcessor run here (tools/reference_lobster_parse.py) vs load_lobster_csv
+    (CSCO 2003-01-13, 88 315 rows, was checked the same way by hand; one day keeps the CPU suite short)."""
+    csv = os.path.join(REF_LOBSTER, rel + "_34200000_57600000_message_1.csv")
+    out = str(tmp_path / "ref.npy")
+    subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "reference_lobster_parse.py"), csv, date, out],
+                   check=True, capture_output=True, timeout=300)
+    want = np.load(out)
+    assert len(want) > 50000 and np.array_equal(load_lobster_csv(csv), want)
+
+
+def test_empty_day_fails_like_the_reference(tmp_path):
+    """An empty message file (the reference ships MSFT 2003-01-20, a market holiday): LOBSTEROrdersProcessor raises IndexError at
+    wakeup_times[0] (MarketReplayAgent.py:177); so does the (ticker, date) constructor."""
+    _write_day(tmp_path, "XYZ", "2020-01-01", [])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert load_lobster_csv(lobster_message_path("XYZ", "2020-01-01", str(tmp_path))).shape == (0, 5)
+        with pytest.raises(IndexError):
+            ABIDESEnv.from_lobster("XYZ", "2020-01-01", data_root=str(tmp_path), lib_path=build_emu())
+
+
 def _write_day(root, ticker, date, lines):
     path = lobster_message_path(ticker, date, str(root))
     os.makedirs(os.path.dirname(path))
     with open(path, "w") as f:
-        f.write("\n".join(lines) + "\n")
+        f.write("\n".join(lines) + ("\n" if lines else ""))
     return path
 
 
