@@ -13,6 +13,11 @@ GPU box).  Nothing from /root/reference is copied: this script imports it with t
 Usage:  python tools/record_reference.py sparse_zi_100 123456789 tests/golden/z100_s123456789.npz [--full]
         --full  also stores the pop / op / notification traces and RNG tapes (default stores
                 checkpointed hashes, counts and final holdings only).
+        python tools/record_reference.py marketreplay 1 tests/golden/mr_GOOG_2012-06-21.npz --date 2012-06-21 --extra -t GOOG -d 2012-06-21
+        python tools/record_reference.py marketreplay 1 tests/golden/mr_sample_orders_file.npz --full --date 2019-06-03 \
+               --orders-csv /root/reference/data/sample_orders_file.csv --extra -t SAMPLE -d 2019-06-03
+        --orders-csv  replay a plain L3 order file (TIMESTAMP,ORDER_ID,PRICE,SIZE,BUY_SELL_FLAG) instead of a LOBSTER day
+        --pov-exec POV QTY BUY|SELL  (rmsc03) append the reference's POVExecutionAgent to the config's agent list
 """
 import importlib
 import os
