@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ABX_VERSION 1
+#define ABX_VERSION 2
 
 enum abx_status {
   ABX_OK = 0,
@@ -118,6 +118,9 @@ typedef struct abx_sim_config {
    * (depth sys.maxsize) and the transacted volume of the last `lookback`, and sends round(pov * volume) as a client-side market order. */
   int32_t n_pov_exec, pov_exec_is_buy;
   double pov_exec_pov; int64_t pov_exec_quantity, pov_exec_start_ns, pov_exec_end_ns, pov_exec_freq_ns, pov_exec_lookback_ns;
+  /* parity instrumentation (like trace_cap / hash_pops): > 0 keeps, per environment, a log of every standard variate the Philox streams
+   * hand out (abx_sim_draw_log), so that the reference's algorithm can be re-run on exactly those draws (oracle external tapes) */
+  int32_t draw_log_cap, _pad2;
 } abx_sim_config;
 
 /* Per-environment counters; replaces the "Event Queue elapsed ..., messages: N" line (Kernel.py:321-327). */
@@ -191,6 +194,11 @@ int32_t abx_sim_reset_tape(abx_sim *h, const uint64_t *tape_bits, const uint8_t 
                            const int64_t *tape_offsets, const double *lat_to_exchange,
                            const double *lat_from_exchange, void *stream);
 
+/* Tape-mode reset with SHARED tapes: n_tapes recorded runs, environment e replays run e % n_tapes (parity at production occupancy: thousands of
+ * environments without thousands of copies of the tapes).  tape_offsets [n_tapes*(n_agents+3)+1], lat_* [n_tapes*n_agents]. */
+int32_t abx_sim_reset_tape_shared(abx_sim *h, int32_t n_tapes, const uint64_t *tape_bits, const uint8_t *tape_kinds, const int64_t *tape_offsets,
+                                  const double *lat_to_exchange, const double *lat_from_exchange, void *stream);
+
 /* Replaces: the hot loop of Kernel.runner (Kernel.py:190-292) for every environment at once.  Pops events
  * while the next event time <= until_ns (and the reference loop condition holds).  Asynchronous on `stream`. */
 int32_t abx_sim_run(abx_sim *h, int64_t until_ns, void *stream);
@@ -218,6 +226,17 @@ int32_t abx_sim_holdings(abx_sim *h, int32_t env, int64_t *out, void *stream);
  * out: host int32 [2*depth] (price, qty) pairs best first; returns the number of levels in *n_levels. */
 int32_t abx_sim_book_snapshot(abx_sim *h, int32_t env, int32_t is_bid, int32_t depth, int32_t *out,
                               int32_t *n_levels, void *stream);
+
+/* One entry of the draw log (draw_log_cap > 0, ABX_RNG_PHILOX): stream (0 symbol, 1 kernel, 2 latency model, 3 global, 3 + a agent a -- the
+ * stream numbering of abx_sim_reset_tape), kind ('n' 'e' 'u' 'i', as on a tape) and the standard variate's bits, in the order drawn. */
+typedef struct abx_draw_rec { uint32_t stream_kind; /* stream | kind << 24 */ uint32_t bits_lo, bits_hi, _pad; } abx_draw_rec;
+/* Copy the draw log of one environment to the host.  out: host [max_recs]; *n_recs = entries written. */
+int32_t abx_sim_draw_log(abx_sim *h, int32_t env, abx_draw_rec *out, int32_t max_recs, int32_t *n_recs, void *stream);
+/* Start-of-run state of one environment's traders as the reset left it (what the config script / agent constructors draw before the kernel
+ * starts): theta HOST int32 [n_agents][20] (ZeroIntelligenceAgent private values, sorted), lat_to / lat_from HOST fp64 [n_agents]
+ * (latency[a][0], latency[0][a]), sizes HOST int32 [n_agents] (Noise / Value / Momentum order size), wakes HOST int64 [n_agents] (NoiseAgent
+ * wake-up time, ns).  Row 0 (the exchange) is zero.  Any pointer may be NULL.  Call after reset, before the first run. */
+int32_t abx_sim_agent_init(abx_sim *h, int32_t env, int32_t *theta, double *lat_to, double *lat_from, int32_t *sizes, int64_t *wakes, void *stream);
 
 /* Copy the trace of one environment to the host.  out: host [max_recs]; *n_recs = records written. */
 int32_t abx_sim_trace(abx_sim *h, int32_t env, abx_trace_rec *out, int32_t max_recs, int32_t *n_recs, void *stream);
@@ -249,7 +268,7 @@ int32_t abx_env_config_default(abx_env_config *cfg);
  * output: the parsed stream).  stream5: HOST int64 [n_rows][5] rows (t_ns since midnight, ORDER_ID, PRICE cents, SIZE,
  * is_buy) sorted by time; every environment replays this stream. */
 int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out);
-/* Several replayed days in one handle (the reference runs one process per date, e.g. config/execution/marketreplay/*_parallel.py): stream5 is the
+/* Several replayed days in one handle (the reference runs one process per date, e.g. config/execution/marketreplay/..._parallel.py): stream5 is the
  * concatenation of the days' rows, row_offsets HOST int64 [n_days + 1]; environment e replays day e % n_days. */
 int32_t abx_env_create_days(const abx_env_config *cfg, const int64_t *stream5, const int64_t *row_offsets, int32_t n_days, int32_t n_envs, int32_t device, abx_sim **out);
 /* Replaces: ABIDESEnv.reset() (ABIDESEnv.py:51-57): initAgents + GymKernel.initRunner. */

@@ -9,7 +9,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libabides_b200.so")
 
-ABX_VERSION = 1
+ABX_VERSION = 2
 ABX_OK = 0
 RNG_PHILOX, RNG_TAPE = 0, 1
 LAT_MATRIX_NOISE, LAT_CUBIC = 0, 1
@@ -58,6 +58,7 @@ class SimConfig(C.Structure):
         ("_pad1", C.c_int32), ("mm_wake_ns", C.c_int64),
         ("n_pov_exec", C.c_int32), ("pov_exec_is_buy", C.c_int32), ("pov_exec_pov", C.c_double), ("pov_exec_quantity", C.c_int64),
         ("pov_exec_start_ns", C.c_int64), ("pov_exec_end_ns", C.c_int64), ("pov_exec_freq_ns", C.c_int64), ("pov_exec_lookback_ns", C.c_int64),
+        ("draw_log_cap", C.c_int32), ("_pad2", C.c_int32),
     ]
 
 
@@ -107,6 +108,7 @@ STATS_DTYPE = [
     ("uniq", "<u4"), ("orders_allocated", "<u4"), ("sum_shares", "<i8"), ("sum_cash", "<i8"),
 ]
 TRACE_DTYPE = [("tag", "<i4"), ("a", "<i4"), ("t", "<i8"), ("v", "<i4", (16,))]
+DRAW_DTYPE = [("stream_kind", "<u4"), ("bits", "<u8"), ("_pad", "<u4")]          # abx_draw_rec (bits_lo, bits_hi read as one little-endian u64 at offset 4)
 
 assert C.sizeof(EnvStats) == 112 and C.sizeof(TraceRec) == 80
 
@@ -138,6 +140,7 @@ def _bind(L):
     sig("abx_sim_device_bytes", i64, vp)
     sig("abx_sim_reset_philox", i32, vp, P(C.c_uint64), vp)
     sig("abx_sim_reset_tape", i32, vp, P(C.c_uint64), P(C.c_uint8), P(i64), P(C.c_double), P(C.c_double), vp)
+    sig("abx_sim_reset_tape_shared", i32, vp, i32, P(C.c_uint64), P(C.c_uint8), P(i64), P(C.c_double), P(C.c_double), vp)
     sig("abx_sim_run", i32, vp, i64, vp)
     sig("abx_sim_run_each", i32, vp, vp, vp)
     sig("abx_sim_finalize", i32, vp, vp)
@@ -146,6 +149,8 @@ def _bind(L):
     sig("abx_sim_holdings", i32, vp, i32, P(i64), vp)
     sig("abx_sim_book_snapshot", i32, vp, i32, i32, i32, P(i32), P(i32), vp)
     sig("abx_sim_trace", i32, vp, i32, vp, i32, P(i32), vp)
+    sig("abx_sim_draw_log", i32, vp, i32, vp, i32, P(i32), vp)
+    sig("abx_sim_agent_init", i32, vp, i32, vp, vp, vp, vp, vp, vp)
     sig("abx_sim_launch_count", i64, vp)
     sig("abx_env_config_default", i32, P(EnvConfig))
     sig("abx_env_create", i32, P(EnvConfig), P(i64), i64, i32, i32, P(vp))

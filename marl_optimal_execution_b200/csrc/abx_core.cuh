@@ -52,8 +52,9 @@ struct alignas(16) EnvState {           // 192 B per environment
   uint32_t ctr_kernel, ctr_latency, ctr_global, trade_epoch;   // trade_epoch: OrderBook.history rotations (util/OrderBook.py:146)
   int64_t sum_shares, sum_cash;
   uint32_t kblk[4];                     // cached Philox block of the kernel (latency-noise) stream
+  uint32_t draw_n, evt_n, pad_a, pad_b; // entries in the draw log (parity runs) / in the LAST_TRADE, BEST_BID, BEST_ASK event ring
 };
-static_assert(sizeof(EnvState) == 192, "EnvState layout");
+static_assert(sizeof(EnvState) == 208, "EnvState layout");
 
 enum : uint32_t {
   AF_HAS_OPEN = 1u, AF_HAS_CLOSE = 2u, AF_MKT_CLOSED = 4u, AF_HAS_LAST = 8u, AF_HAS_DAILY = 16u, AF_HAS_PREV = 32u,
@@ -125,7 +126,7 @@ constexpr uint32_t NIL = 0xffffffffu;
 // Device-side parameter block (config + derived constants + HBM base pointers).
 struct SimParams {
   abx_sim_config c;
-  int32_t n_envs, n_qgroups, n_streams, pad0;
+  int32_t n_envs, n_qgroups, n_streams, n_tapes;   // n_tapes > 0: tape mode with shared tapes, environment e replays tape e % n_tapes
   double one_minus_kappa_a;     // 1 - agent_kappa
   double log_base_a;            // log(1 - agent_kappa)
   double sigma_denom;           // 1 - (1 - agent_kappa) ** 2      (host libm pow, ZeroIntelligenceAgent.py:234)
@@ -140,6 +141,7 @@ struct SimParams {
   uint4 *nodes;                 // [n_envs][order_cap]
   EnvState *env;                // [n_envs]
   abx_trace_rec *trace;         // [n_envs][trace_cap]
+  uint4 *draw_log;              // [n_envs][draw_log_cap] {stream | kind << 24, bits lo, bits hi, -}  (parity runs under Philox)
   const uint64_t *tape_bits; const uint8_t *tape_kinds; const int64_t *tape_off; // tape mode
   // ---- ABIDESEnv shape (exchange + MarketReplayAgent + RL execution agent); zero for the sparse_zi shape ----
   int32_t n_ts, n_rows, n_ids, n_h;                 // replayed stream: timestamps, rows, distinct order ids; horizon length
@@ -268,10 +270,16 @@ ABX_NI double pow_ni(double x, double y) { return pow(x, y); }
 enum { S_SYMBOL = 0, S_KERNEL = 1, S_LATENCY = 2, S_GLOBAL = 3, S_AGENT0 = 3 };  // agent a uses stream S_AGENT0 + a
 
 // MODE: ABX_RNG_PHILOX / ABX_RNG_TAPE fixed at compile time (one kernel instantiation per mode), or -1 = read P->c.rng_mode
-template <int MODE>
+// REC: keep a log of every standard variate the Philox streams hand out (parity instrumentation, compiled out of the production kernels)
+template <int MODE, bool REC = false>
 struct RngT {
-  const SimParams *P; int env; uint64_t seed; uint32_t err;
+  const SimParams *P; int env; uint64_t seed; uint32_t err; uint4 *lg; uint32_t lg_n, lg_cap;
   ABX_HD bool tape() const { return MODE < 0 ? P->c.rng_mode == ABX_RNG_TAPE : MODE == ABX_RNG_TAPE; }
+  ABX_HD void rec(int stream, uint8_t kind, uint64_t bits) {                            // uniform code: every lane stores the same entry
+    if (!REC || !lg) return;
+    if (lg_n >= lg_cap) { err |= ABX_F_TRACE_OVERFLOW; return; }
+    uint4 v; v.x = (uint32_t)stream | ((uint32_t)kind << 24); v.y = (uint32_t)bits; v.z = (uint32_t)(bits >> 32); v.w = 0u; lg[lg_n++] = v;
+  }
   ABX_HD uint64_t tape_next(int stream, uint32_t &ctr, uint8_t kind) {
     const int64_t *off = P->tape_off + (int64_t)env * P->n_streams + stream;
     int64_t i = off[0] + ctr;
@@ -285,21 +293,21 @@ struct RngT {
   ABX_HD double std_normal(int stream, uint32_t &ctr) {
     if (tape()) return bits_dbl(tape_next(stream, ctr, 'n'));
     U4 o = philox(stream, ctr);
-    return box_muller(o.x, o.y, o.z);
+    double z = box_muller(o.x, o.y, o.z); rec(stream, 'n', dbl_bits(z)); return z;
   }
   ABX_HD double std_exponential(int stream, uint32_t &ctr) {
     if (tape()) return bits_dbl(tape_next(stream, ctr, 'e'));
-    U4 o = philox(stream, ctr); return -log_unit(1.0 - u53(o.x, o.y));
+    U4 o = philox(stream, ctr); double e = -log_unit(1.0 - u53(o.x, o.y)); rec(stream, 'e', dbl_bits(e)); return e;
   }
   ABX_HD double u01(int stream, uint32_t &ctr) {
     if (tape()) return bits_dbl(tape_next(stream, ctr, 'u'));
-    U4 o = philox(stream, ctr); return u53(o.x, o.y);
+    U4 o = philox(stream, ctr); double u = u53(o.x, o.y); rec(stream, 'u', dbl_bits(u)); return u;
   }
   // integer in [0, range] (numpy randint(low, high) with range = high - 1 - low; no draw when range == 0)
   ABX_HD int64_t randint(int stream, uint32_t &ctr, uint32_t range) {
-    if (range == 0) { if (tape()) return (int64_t)tape_next(stream, ctr, 'i'); return 0; }
+    if (range == 0) { if (tape()) return (int64_t)tape_next(stream, ctr, 'i'); rec(stream, 'i', 0); return 0; }
     if (tape()) return (int64_t)tape_next(stream, ctr, 'i');
-    U4 o = philox(stream, ctr); return (int64_t)((uint64_t(o.x) * (uint64_t(range) + 1)) >> 32);
+    U4 o = philox(stream, ctr); int64_t v = (int64_t)((uint64_t(o.x) * (uint64_t(range) + 1)) >> 32); rec(stream, 'i', (uint64_t)v); return v;
   }
   // Latency-noise draws (one per sendMessage, Kernel.py:411) take successive 32-bit words of the kernel stream's Philox
   // blocks; the current block is cached in EnvState so only every 4th send runs the 10 rounds.
@@ -308,7 +316,7 @@ struct RngT {
     uint32_t i = ctr++;
     if ((i & 3u) == 0u) { U4 o = philox4x32_10(i >> 2, (uint32_t)stream, 0x4b424958u, 0, (uint32_t)seed, (uint32_t)(seed >> 32)); blk[0] = o.x; blk[1] = o.y; blk[2] = o.z; blk[3] = o.w; }
     uint32_t w = (i & 3u) == 0u ? blk[0] : ((i & 3u) == 1u ? blk[1] : ((i & 3u) == 2u ? blk[2] : blk[3]));
-    return (int64_t)((uint64_t(w) * (uint64_t(range) + 1)) >> 32);
+    int64_t v = (int64_t)((uint64_t(w) * (uint64_t(range) + 1)) >> 32); rec(stream, 'i', (uint64_t)v); return v;
   }
   ABX_HD double normal(int stream, uint32_t &ctr, double loc, double scale) { return dadd(loc, dmul(scale, std_normal(stream, ctr))); }
 };
@@ -335,7 +343,7 @@ ABX_HD double u_quadratic_inverse_cdf(double y) {
   return dadd(c, 0.5);
 }
 ABX_HD void init_agent_record_r3(const SimParams &P, int env, int id, uint64_t seed, ZiAgent *z, uint32_t *err) {
-  RngT<-1> rng; rng.P = &P; rng.env = env; rng.seed = seed; rng.err = 0;
+  RngT<-1> rng; rng.P = &P; rng.env = P.n_tapes > 0 ? env % P.n_tapes : env; rng.seed = seed; rng.err = 0;
   int type = agent_type_of(P.c, id); uint32_t ctr = 0, c2 = 0; int cs = P.n_streams + id;
   int32_t size = (int32_t)z->lat_to; int64_t wake = (int64_t)z->lat_from;        // tape mode: preloaded by the host (drawn by the config script)
   if (P.c.rng_mode == ABX_RNG_PHILOX) {
@@ -359,7 +367,7 @@ ABX_HD void init_agent_record_r3(const SimParams &P, int env, int id, uint64_t s
 }
 ABX_HD void init_agent_record(const SimParams &P, int env, int id, uint64_t seed, ZiAgent *z, uint32_t *err) {
   if (P.c.population != 0) { init_agent_record_r3(P, env, id, seed, z, err); return; }
-  Rng rng; rng.P = &P; rng.env = env; rng.seed = seed; rng.err = 0;
+  Rng rng; rng.P = &P; rng.env = P.n_tapes > 0 ? env % P.n_tapes : env; rng.seed = seed; rng.err = 0;
   int grp = 0, acc = 1;
   for (int g = 0; g < P.c.n_groups; g++) { if (id >= acc && id < acc + P.c.groups[g].count) grp = g; acc += P.c.groups[g].count; }
   uint32_t ctr = 0; int stream = S_AGENT0 + id; int m = 2 * P.c.q_max;
@@ -410,7 +418,7 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
   s.uniq = 0; s.next_order_id = 0; s.q_count = 0; s.max_q = 0; s.n_bid_lv = s.n_ask_lv = 0; s.n_resting = 0; s.free_head = NIL;
   s.pool_top = 0; s.flags = 0; s.trace_n = 0; s.c_limit = s.c_cancel = s.c_fills = s.c_query = 0;
   s.ctr_symbol = s.ctr_kernel = s.ctr_latency = s.ctr_global = 0; s.trade_epoch = 16; s.sum_shares = 0; s.sum_cash = 0;
-  s.kblk[0] = s.kblk[1] = s.kblk[2] = s.kblk[3] = 0;
+  s.kblk[0] = s.kblk[1] = s.kblk[2] = s.kblk[3] = 0; s.draw_n = 0; s.evt_n = 0; s.pad_a = 0; s.pad_b = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -451,12 +459,15 @@ enum { SHAPE_ZI = 0, SHAPE_ENV = 1, SHAPE_R3 = 2, SHAPE_DQ = 3, SHAPE_BOOK = 4 }
 template <class Ctx, int RNG_MODE = -1, int LAT_MODEL = -1, bool INSTR = true, int SHAPE = SHAPE_ZI>
 struct Sim {
   static constexpr bool DQ = SHAPE == SHAPE_DQ, BOOK = SHAPE == SHAPE_BOOK, ENV = SHAPE == SHAPE_ENV || DQ || BOOK, R3 = SHAPE == SHAPE_R3;
-  Ctx &c; const SimParams &P; EnvState s; RngT<RNG_MODE> rng; int64_t addl_delay; int n_out; int self_id;
+  Ctx &c; const SimParams &P; EnvState s; RngT<RNG_MODE, INSTR> rng; int64_t addl_delay; int n_out; int self_id;
   AgentRegs a; ZiAgent *z;                // the trader whose event is being handled (registers + staged record)
 
   ABX_HD Sim(Ctx &c_, const SimParams &P_, const EnvState &s_, int env) : c(c_), P(P_), s(s_), addl_delay(0), n_out(0), self_id(0), z(nullptr) {
-    rng.P = &P; rng.env = env; rng.seed = s.seed; rng.err = 0; a.lat_from = 0.0; a.lat_to = 0.0;
+    rng.P = &P; rng.env = P.n_tapes > 0 ? env % P.n_tapes : env; rng.seed = s.seed; rng.err = 0; a.lat_from = 0.0; a.lat_to = 0.0;
+    rng.lg = (INSTR && P.draw_log) ? P.draw_log + (size_t)env * (size_t)P.c.draw_log_cap : nullptr; rng.lg_n = s.draw_n; rng.lg_cap = (uint32_t)P.c.draw_log_cap;
   }
+  // fold the generator's error bits and draw-log cursor back into the environment state (end of every entry point that may have drawn)
+  ABX_HD void rng_sync() { s.flags |= rng.err; if (INSTR) s.draw_n = rng.lg_n; }
 
   ABX_HD int n_lv(int side) const { return side ? s.n_ask_lv : s.n_bid_lv; }
   ABX_HD void set_n_lv(int side, int n) { if (side) s.n_ask_lv = n; else s.n_bid_lv = n; }
@@ -777,10 +788,11 @@ struct Sim {
     bool one_block = !rng.tape(); U4 blk; blk.x = blk.y = blk.z = blk.w = 0;
     if (one_block) blk = rng.philox(stream, a.rng_ctr);
     double z_obs = one_block ? box_muller(blk.x, blk.y, blk.z) : rng.std_normal(stream, a.rng_ctr);
+    if (one_block) rng.rec(stream, 'n', dbl_bits(z_obs));                               // draw log: the same three entries a tape would hold
     int32_t obs_t = (int32_t)py_round_i64(dadd((double)r_now, dmul(P.sqrt_sigma_n, z_obs)));
     int q = (int)((double)a.shares / 100.0);                                            // :203 int(x / 100)
     int q_max = P.c.q_max; bool buy;
-    if (q >= q_max) buy = false; else if (q <= -q_max) buy = true; else buy = one_block ? (blk.z & 1u) != 0 : rng.randint(stream, a.rng_ctr, 1) != 0; // :205-213
+    if (q >= q_max) buy = false; else if (q <= -q_max) buy = true; else { buy = one_block ? (blk.z & 1u) != 0 : rng.randint(stream, a.rng_ctr, 1) != 0; if (one_block) rng.rec(stream, 'i', buy ? 1u : 0u); } // :205-213
     if (!(a.flags & AF_HAS_PREV)) { a.prev_wake = P.c.mkt_open_ns; a.flags |= AF_HAS_PREV; }         // :217-218
     double r_bar = P.c.r_bar, sigma_n = P.c.sigma_n;
     double delta = (double)(s.now - a.prev_wake);                                       // :221
@@ -812,6 +824,7 @@ struct Sim {
     int grp = (a.flags & AF_GROUP_MASK) >> AF_GROUP_SHIFT;
     int32_t r_min = P.c.groups[grp].r_min, r_max = P.c.groups[grp].r_max; double eta = P.c.groups[grp].eta;
     int32_t R = r_min + (one_block ? (int32_t)((uint64_t(blk.w) * (uint64_t)(uint32_t)(r_max - r_min + 1)) >> 32) : (int32_t)rng.randint(stream, a.rng_ctr, (uint32_t)(r_max - r_min)));   // :284
+    if (one_block) rng.rec(stream, 'i', (uint64_t)(uint32_t)(R - r_min));
     int32_t p = buy ? v - R : v + R;                                                    // :287
     int32_t ask_vol = (a.flags & AF_HAS_ASK) ? a.ask_q : 0, bid_vol = (a.flags & AF_HAS_BID) ? a.bid_q : 0;
     if (buy && ask_vol > 0) { int32_t R_ask = v - a.ask; if ((double)R_ask >= dmul(eta, (double)R)) p = a.ask; }             // :291-297
@@ -881,7 +894,7 @@ struct Sim {
       if (n_out >= Ctx::OUTN - 1) flush();
     }
     flush();
-    s.flags |= rng.err;
+    rng_sync();
   }
 
   // ---- Kernel.runner hot loop :190-292 ----
@@ -922,7 +935,7 @@ struct Sim {
       }
       flush();                                                                          // deliver what this event sent
     }
-    s.flags |= rng.err;
+    rng_sync();
   }
 
 
@@ -1457,7 +1470,7 @@ struct Sim {
       flush();
     }
     if ((int64_t)s.next_order_id >= P.dq_id_limit) s.flags |= ABX_F_UNSUPPORTED;        // generated ids reached the stream's explicit ids (util/order/Order.py:35-42 would skip them)
-    s.flags |= rng.err;
+    rng_sync();
     c.sync();
     return paused;
   }
@@ -1732,7 +1745,7 @@ struct Sim {
       }
       flush();
     }
-    s.flags |= rng.err;
+    rng_sync();
   }
   // kernelStopping: ValueAgent.kernelStopping :49-61 observes the fundamental (advances the oracle); holdings are read by the host
   ABX_HD void r3_finalize() {
@@ -1743,7 +1756,7 @@ struct Sim {
       if (agent_type_of(P.c, id) == AT_VALUE) { int64_t cur = a.agent_time - P.c.default_computation_delay_ns; oracle_advance(cur >= P.c.mkt_close_ns ? P.c.mkt_close_ns - 1 : cur); }
       sum_sh += a.shares; sum_cash += a.cash;
     }
-    s.sum_shares = sum_sh; s.sum_cash = sum_cash; s.flags |= rng.err;
+    s.sum_shares = sum_sh; s.sum_cash = sum_cash; rng_sync();
   }
 
   // ---- Kernel.runner :310-311 kernelStopping for every trader, in id order (ZeroIntelligenceAgent.py:80-123) ----
@@ -1767,7 +1780,7 @@ struct Sim {
       c.agent_commit(id);
     }
     s.sum_shares = sum_sh; s.sum_cash = sum_cash;
-    s.flags |= rng.err;
+    rng_sync();
   }
 };
 

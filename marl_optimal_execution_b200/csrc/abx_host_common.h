@@ -121,6 +121,10 @@ static inline int env_config_validate(const abx_env_config *c) {
   if (c->stream_history < 0 || c->stream_history > 14 || !(c->quantity > 0) || c->trace_cap < 0) return ABX_ERR_ARG;
   return ABX_OK;
 }
+// ABIDESEnv shape proper (abx_env_create*): the on-chip event queue of that shape always spans ENV_QUEUE_MIN slots per environment, so a smaller
+// queue_cap would overrun the next environment's slots (the bare-book surface uses the grouped queue and may go down to 32)
+constexpr int ENV_QUEUE_MIN = 64;
+static inline int env_shape_validate(const abx_env_config *c) { int st = env_config_validate(c); if (st != ABX_OK) return st; return c->queue_cap < ENV_QUEUE_MIN ? ABX_ERR_ARG : ABX_OK; }
 // the generic (abx_sim_config) part of the parameter block for the ABIDESEnv shape: 3 agents, zero delays, no oracle
 static inline void env_fill_params(const abx_env_config &e, SimParams &P) {
   abx_sim_config &c = P.c; memset(&c, 0, sizeof(c));
@@ -244,6 +248,19 @@ static inline void dq_holdings_rows(const SimParams &P, const ZiAgent *ag, const
     r[1] = z.shares; r[2] = z.cash; r[3] = (z.flags & AF_HAS_LAST) ? z.last_trade : 0; r[4] = type == AT_MOMENTUM ? -1 : z.n_orders;
     if (type != AT_MOMENTUM && exec_out) { const ExecAux *ex = reinterpret_cast<const ExecAux *>(z.oid); double *e = exec_out + 5 * ke++;
       e[0] = ex->rem_qty; e[1] = (double)ex->arr2 / 2; e[2] = ex->n_executed; e[3] = ex->rem_time; e[4] = ex->t; } }
+}
+
+// abx_sim_agent_init rows from the trader records of one freshly reset environment
+static inline void agent_init_rows(const SimParams &P, const ZiAgent *ag, int32_t *theta, double *lat_to, double *lat_from, int32_t *sizes, int64_t *wakes) {
+  int n = P.c.n_agents;
+  for (int id = 0; id < n; id++) {
+    const ZiAgent &z = ag[id]; int type = id == 0 ? -1 : agent_type_of(P.c, id);
+    if (theta) for (int i = 0; i < 20; i++) theta[(size_t)id * 20 + i] = type == AT_ZI ? z.theta[i] : 0;
+    if (lat_to) lat_to[id] = id ? z.lat_to : 0.0;
+    if (lat_from) lat_from[id] = id ? z.lat_from : 0.0;
+    if (sizes) sizes[id] = (type == AT_NOISE || type == AT_VALUE || type == AT_MOMENTUM) ? reinterpret_cast<const AgentAux *>(z.theta)->size : 0;
+    if (wakes) wakes[id] = type == AT_NOISE ? z.prev_wake : 0;
+  }
 }
 
 static inline const char *status_string(int32_t st) {

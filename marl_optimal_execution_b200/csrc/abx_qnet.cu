@@ -303,10 +303,13 @@ int32_t abx_qnet_create(const int32_t *dims, int32_t n_layers, const float *para
   if (q->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { snprintf(g_err, sizeof(g_err), "network needs %zu B of shared memory (limit %zu)", q->smem_bytes, (size_t)prop.sharedMemPerBlockOptin); delete q; return ABX_ERR_ARG; }
   q->h_wimg.resize(woff); q->h_bias.resize(boff);
   if (cudaMalloc((void **)&q->d_wimg, woff) != cudaSuccess || cudaMalloc((void **)&q->d_bias, sizeof(float) * boff) != cudaSuccess) { cudaFree(q->d_wimg); delete q; snprintf(g_err, sizeof(g_err), "cudaMalloc failed"); return ABX_ERR_CUDA; }
-  QCU(cudaFuncSetAttribute(abx_qnet_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q->smem_bytes));
+  // from here on a failing CUDA call must not leak the handle or its device buffers
+#define QCUH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_err, sizeof(g_err), "%s: %s", #call, cudaGetErrorString(e_)); cudaFree(q->d_wimg); cudaFree(q->d_bias); delete q; return ABX_ERR_CUDA; } } while (0)
+  QCUH(cudaFuncSetAttribute(abx_qnet_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q->smem_bytes));
   pack_params(q, params);
-  QCU(cudaMemcpy(q->d_wimg, q->h_wimg.data(), woff, cudaMemcpyHostToDevice));
-  QCU(cudaMemcpy(q->d_bias, q->h_bias.data(), sizeof(float) * boff, cudaMemcpyHostToDevice));
+  QCUH(cudaMemcpy(q->d_wimg, q->h_wimg.data(), woff, cudaMemcpyHostToDevice));
+  QCUH(cudaMemcpy(q->d_bias, q->h_bias.data(), sizeof(float) * boff, cudaMemcpyHostToDevice));
+#undef QCUH
   *out = q; return ABX_OK;
 }
 

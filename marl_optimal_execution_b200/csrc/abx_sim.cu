@@ -86,7 +86,7 @@ abx_run_kernel(SimParams P, int64_t until_ns, const int64_t *__restrict__ until_
 }
 typedef void (*run_kernel_fn)(SimParams, int64_t, const int64_t *, size_t);
 static run_kernel_fn run_kernel_for(const abx_sim_config &c) {
-  bool instr = c.trace_cap > 0 || c.hash_pops != 0; int r = c.rng_mode, l = c.latency_model;
+  bool instr = c.trace_cap > 0 || c.hash_pops != 0 || c.draw_log_cap > 0; int r = c.rng_mode, l = c.latency_model;
   if (c.population == 1) {                       // config/rmsc03.py population: zero latency
     if (r == ABX_RNG_PHILOX) return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_R3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_ZERO, false, SHAPE_R3>;
     return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_ZERO, true, SHAPE_R3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_ZERO, false, SHAPE_R3>;
@@ -292,7 +292,7 @@ int32_t abx_sim_destroy(abx_sim *h) {
   if (!h) return ABX_OK;
   cudaSetDevice(h->device);
   void *ptrs[] = {h->P.qkey, h->P.qpay0, h->P.qpay1, h->P.qcache, h->P.agents, h->P.lv_price, h->P.lv_qty, h->P.lv_ht, h->P.nodes, h->P.env,
-                  h->P.trace, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff,
+                  h->P.trace, h->P.draw_log, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff,
                   h->P.envx, h->P.idtab, h->P.idbook, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_iact, h->d_msizes, h->d_trans, h->d_ops, h->d_daytab};
   for (void *p : ptrs) if (p) cudaFree(p);
   delete h->st; delete h->dh; delete h->book_ids; delete h; return ABX_OK;
@@ -312,7 +312,7 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
 #define DA(ptr, n) if ((st = dalloc(&(ptr), (n), &h->bytes)) != ABX_OK) { abx_sim_destroy(h); return st; }
   DA(h->P.qkey, E * c.queue_cap) DA(h->P.qpay0, E * c.queue_cap) DA(h->P.qpay1, E * c.queue_cap) DA(h->P.qcache, E * h->P.n_qgroups)
   DA(h->P.agents, E * c.n_agents) DA(h->P.lv_price, E * 2 * c.level_cap) DA(h->P.lv_qty, E * 2 * c.level_cap) DA(h->P.lv_ht, E * 2 * c.level_cap)
-  DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap)
+  DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap) DA(h->P.draw_log, E * (size_t)c.draw_log_cap)
   DA(h->d_seeds, E) DA(h->d_init_err, E) DA(h->d_stats, E) DA(h->d_until, E)
   if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + TV_RING; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0);       // market maker orders + transaction ring [+ POV execution agent orders]; momentum mids
     DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3) }
@@ -346,11 +346,26 @@ int32_t abx_sim_reset_philox(abx_sim *h, const uint64_t *seeds, void *stream) {
   return do_reset(h, true, st);
 }
 
+static int32_t reset_tape_impl(abx_sim *h, int32_t n_tapes, const uint64_t *bits, const uint8_t *kinds, const int64_t *off, const double *lat_to,
+                               const double *lat_from, void *stream);
 int32_t abx_sim_reset_tape(abx_sim *h, const uint64_t *bits, const uint8_t *kinds, const int64_t *off, const double *lat_to,
-                           const double *lat_from, void *stream) {
+                           const double *lat_from, void *stream) { return reset_tape_impl(h, 0, bits, kinds, off, lat_to, lat_from, stream); }
+int32_t abx_sim_reset_tape_shared(abx_sim *h, int32_t n_tapes, const uint64_t *bits, const uint8_t *kinds, const int64_t *off, const double *lat_to,
+                                  const double *lat_from, void *stream) {
+  if (!h || n_tapes < 1 || n_tapes > h->n_envs || !lat_to || !lat_from) return ABX_ERR_ARG;
+  size_t na = (size_t)h->P.c.n_agents, E = (size_t)h->n_envs;
+  std::vector<double> lt(E * na), lf(E * na);                                   // per-environment copies of the shared runs' latency vectors
+  for (size_t e = 0; e < E; e++) { memcpy(&lt[e * na], lat_to + (e % n_tapes) * na, sizeof(double) * na); memcpy(&lf[e * na], lat_from + (e % n_tapes) * na, sizeof(double) * na); }
+  int32_t rc = reset_tape_impl(h, n_tapes, bits, kinds, off, lt.data(), lf.data(), stream); if (rc != ABX_OK) return rc;
+  CU(cudaStreamSynchronize((cudaStream_t)stream));                              // lt / lf are local staging buffers
+  return ABX_OK;
+}
+static int32_t reset_tape_impl(abx_sim *h, int32_t n_tapes, const uint64_t *bits, const uint8_t *kinds, const int64_t *off, const double *lat_to,
+                               const double *lat_from, void *stream) {
   if (!h || !bits || !kinds || !off || !lat_to || !lat_from || h->P.c.rng_mode != ABX_RNG_TAPE) return ABX_ERR_ARG;
   CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
-  size_t nS = (size_t)h->n_envs * h->P.n_streams; int64_t total = off[nS]; if (total < 0) return ABX_ERR_ARG;
+  h->P.n_tapes = n_tapes;
+  size_t nS = (size_t)(n_tapes > 0 ? n_tapes : h->n_envs) * h->P.n_streams; int64_t total = off[nS]; if (total < 0) return ABX_ERR_ARG;
   if (h->d_tbits) { cudaFree(h->d_tbits); h->d_tbits = nullptr; } if (h->d_tkinds) { cudaFree(h->d_tkinds); h->d_tkinds = nullptr; } if (h->d_toff) { cudaFree(h->d_toff); h->d_toff = nullptr; }
   int64_t dummy = 0;
   if (dalloc(&h->d_tbits, (size_t)total + 1, &dummy) || dalloc(&h->d_tkinds, (size_t)total + 1, &dummy) || dalloc(&h->d_toff, nS + 1, &dummy)) return ABX_ERR_CUDA;
@@ -455,11 +470,31 @@ int32_t abx_sim_trace(abx_sim *h, int32_t env, abx_trace_rec *out, int32_t max_r
   *n_recs = n; return ABX_OK;
 }
 
+int32_t abx_sim_draw_log(abx_sim *h, int32_t env, abx_draw_rec *out, int32_t max_recs, int32_t *n_recs, void *stream) {
+  if (!h || !out || !n_recs || env < 0 || env >= h->n_envs || h->is_env) return ABX_ERR_ARG;
+  CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
+  EnvState s; CU(cudaMemcpyAsync(&s, h->P.env + env, sizeof(s), cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st));
+  int n = (int)s.draw_n; if (n > max_recs) n = max_recs; if (n > h->P.c.draw_log_cap) n = h->P.c.draw_log_cap;
+  static_assert(sizeof(abx_draw_rec) == sizeof(uint4), "draw log entry layout");
+  if (n > 0) { CU(cudaMemcpyAsync(out, h->P.draw_log + (size_t)env * h->P.c.draw_log_cap, sizeof(uint4) * n, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
+  *n_recs = n; return ABX_OK;
+}
+
+int32_t abx_sim_agent_init(abx_sim *h, int32_t env, int32_t *theta, double *lat_to, double *lat_from, int32_t *sizes, int64_t *wakes, void *stream) {
+  if (!h || h->is_env || env < 0 || env >= h->n_envs) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
+  int n = h->P.c.n_agents; std::vector<ZiAgent> tmp(n);
+  CU(cudaMemcpyAsync(tmp.data(), h->P.agents + (size_t)env * n, sizeof(ZiAgent) * n, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st));
+  agent_init_rows(h->P, tmp.data(), theta, lat_to, lat_from, sizes, wakes);
+  return ABX_OK;
+}
+
 // ---------------- ABIDESEnv shape ----------------
 int32_t abx_env_config_default(abx_env_config *cfg) { return env_config_default(cfg); }
 
 int32_t abx_env_create_days(const abx_env_config *cfg, const int64_t *stream5, const int64_t *row_offsets, int32_t n_days, int32_t n_envs, int32_t device, abx_sim **out) {
-  if (!out || n_envs < 1 || env_config_validate(cfg) != ABX_OK) return ABX_ERR_ARG;
+  static_assert(ENV_QUEUE_MIN == SMALLQ_CAP, "queue_cap floor of the ABIDESEnv shape == slots of its on-chip queue");
+  if (!out || n_envs < 1 || env_shape_validate(cfg) != ABX_OK) return ABX_ERR_ARG;
   EnvDaysHost *dh = new (std::nothrow) EnvDaysHost(); if (!dh) return ABX_ERR_ARG;
   if (env_build_days(stream5, row_offsets, n_days, 4LL * cfg->n_horizon + 16, *dh) != ABX_OK) { delete dh; return ABX_ERR_ARG; }
   int ndev = 0; cudaError_t ce = cudaGetDeviceCount(&ndev);

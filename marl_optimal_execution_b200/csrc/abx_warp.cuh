@@ -108,14 +108,24 @@ struct WarpCtxT {
   }
   // Uniform code stores on-chip state from every lane (same value, same address: one STS, no branch).
   __device__ __forceinline__ bool onchip_writer() const { return true; }
-  // A converged warp issues its memory instructions in program order and the LSU serves one warp's shared-memory
-  // accesses in order, so between uniform code and the cooperative primitives a COMPILER fence is enough.  Real
-  // __syncwarp() (7 SASS instructions each: BSSY/WARPSYNC/ENDCOLLECTIVE/...) is kept only where lanes hand data to
-  // each other through HBM (q_push, node_store, agent_commit).  -DABX_STRICT_SYNC restores __syncwarp() everywhere.
+  // sync(): between UNIFORM stores (every lane writes the same value to the same address) and later reads a COMPILER fence is
+  // enough -- each lane reads back what it stored itself.  Real barriers (xsync(), __syncwarp()) stand wherever lanes hand
+  // DIFFERENT data to each other: ladder shifts, the staging copies, and everything that goes through HBM (q_push, node_store,
+  // agent_commit).  -DABX_STRICT_SYNC turns every sync() into __syncwarp() as well (the A/B build of tools/ab_sync_variants.sh;
+  // the GPU parity suite runs on both).
 #ifdef ABX_STRICT_SYNC
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 #else
   __device__ __forceinline__ void sync() const { asm volatile("" ::: "memory"); }
+#endif
+  // xsync(): ALWAYS a real warp barrier.  Used wherever one lane's shared-memory store is read by a DIFFERENT lane that did not
+  // store the same value itself (ladder shifts, staging copies where lane i moves element i): a compiler fence is not enough there
+  // under independent thread scheduling.  Uniform code (every lane stores the same value to the same address, then reads it back)
+  // only needs sync(): a thread always observes its own store.
+#ifdef ABX_FENCE_ONLY                     // A/B build only (tools/): the round-1 behaviour, never the shipped library
+  __device__ __forceinline__ void xsync() const { asm volatile("" ::: "memory"); }
+#else
+  __device__ __forceinline__ void xsync() const { __syncwarp(); }
 #endif
   __device__ __forceinline__ uint32_t *outbox() const { return obox; }
   __device__ __forceinline__ void trace(const abx_trace_rec &r, uint32_t i) { if (lane == 0) tr[i] = r; }
@@ -141,10 +151,10 @@ struct WarpCtxT {
       for (int i = lane; i < (side ? s.n_ask_lv : s.n_bid_lv); i += 32) {
       int k = side * P.c.level_cap + i; lvp[k] = P.lv_price[l + k]; lvq[k] = P.lv_qty[l + k]; lvht[k] = P.lv_ht[l + k];
     }
-    sync();
+    xsync();                                                                 // lane i staged element i; every lane reads all of them from here on
   }
   __device__ void store_onchip(const EnvState &s) {
-    sync();
+    xsync();
     if (SMALLQ) {
 #pragma unroll
       for (int j = 0; j < NQ / 32; j++) { int i = lane + 32 * j; uint4 k = qs[i]; __stcg(qkey + i, k);
@@ -167,7 +177,7 @@ struct WarpCtxT {
     if (SMALLQ) { qs[lane] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); if (NQ > 32) qs[lane + 32] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); n_ovf = 0;
       if (NEARQ) ovm[0] = make_uint4(0u, 0u, 0u, 0xffffffffu); }
     if (!SMALLQ || HYBRID) for (int g = lane; g < P.n_qgroups; g += 32) qc[g] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
-    sync(); }
+    xsync(); }
 
   // ---- event queue ----
   // grp identifies the winner for q_fetch: a slot of the on-chip tier (SMALLQ: 0 .. SMALLQ_CAP-1), otherwise SMALLQ_CAP + group index
@@ -300,9 +310,9 @@ struct WarpCtxT {
     for (int hi = n; hi > pos; hi -= 32) {                  // shift [pos, n) up by one, top chunk first
       int i = hi - 1 - lane; bool act = i >= pos; int32_t x = 0, y = 0; uint32_t z = 0;
       if (act) { x = lvp[b + i]; y = lvq[b + i]; z = lvht[b + i]; }
-      sync();
+      xsync();                                                               // lane L overwrites the slot lane L-1 has just read
       if (act) { lvp[b + i + 1] = x; lvq[b + i + 1] = y; lvht[b + i + 1] = z; }
-      sync();
+      xsync();
     }
     lvp[b + pos] = price; lvq[b + pos] = qty; lvht[b + pos] = head | (tail << 16);
     sync();
@@ -313,9 +323,9 @@ struct WarpCtxT {
     for (int lo = pos + 1; lo < n; lo += 32) {              // shift (pos, n) down by one, bottom chunk first
       int i = lo + lane; bool act = i < n; int32_t x = 0, y = 0; uint32_t z = 0;
       if (act) { x = lvp[b + i]; y = lvq[b + i]; z = lvht[b + i]; }
-      sync();
+      xsync();
       if (act) { lvp[b + i - 1] = x; lvq[b + i - 1] = y; lvht[b + i - 1] = z; }
-      sync();
+      xsync();
     }
   }
 
@@ -325,8 +335,8 @@ struct WarpCtxT {
 
   // ---- ABIDESEnv shape ----
   __device__ __forceinline__ EnvX *envx() const { return ex; }
-  __device__ void envx_load() { const uint4 *src = reinterpret_cast<const uint4 *>(P.envx + env); for (int i = lane; i < (int)(sizeof(EnvX) / 16); i += 32) reinterpret_cast<uint4 *>(ex)[i] = ldcg4(src + i); sync(); }
-  __device__ void envx_store() { sync(); uint4 *dst = reinterpret_cast<uint4 *>(P.envx + env); for (int i = lane; i < (int)(sizeof(EnvX) / 16); i += 32) __stcg(dst + i, reinterpret_cast<const uint4 *>(ex)[i]); }
+  __device__ void envx_load() { const uint4 *src = reinterpret_cast<const uint4 *>(P.envx + env); for (int i = lane; i < (int)(sizeof(EnvX) / 16); i += 32) reinterpret_cast<uint4 *>(ex)[i] = ldcg4(src + i); xsync(); }
+  __device__ void envx_store() { xsync(); uint4 *dst = reinterpret_cast<uint4 *>(P.envx + env); for (int i = lane; i < (int)(sizeof(EnvX) / 16); i += 32) __stcg(dst + i, reinterpret_cast<const uint4 *>(ex)[i]); }
   __device__ __forceinline__ uint4 id_load(int i) const { return ldcg4(idt + i); }
   __device__ __forceinline__ void id_store(int i, uint4 v) { if (lane == 0) __stcg(idt + i, v); __syncwarp(); }
   // An agent's self.orders as a dense table of n 16-byte entries {order id, price, signed qty, -} at idt[base..]: index of `oid` (insertion order kept, so the
@@ -407,7 +417,7 @@ struct WarpCtxT {
   __device__ __forceinline__ ZiAgent *agent_stage(int id) {
     sync();
     if (lane < (int)(sizeof(ZiAgent) / 16)) reinterpret_cast<uint4 *>(staged)[lane] = ldcg4(reinterpret_cast<const uint4 *>(agents + id) + lane);
-    sync();
+    xsync();                                                                 // 12 lanes staged 16 bytes each; every lane reads the whole record
     return staged;
   }
   __device__ __forceinline__ void agent_commit(int id) {

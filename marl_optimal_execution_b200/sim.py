@@ -147,6 +147,22 @@ class BatchedSim:
             off.ctypes.data_as(C.POINTER(C.c_int64)), lt.ctypes.data_as(C.POINTER(C.c_double)),
             lf.ctypes.data_as(C.POINTER(C.c_double)), stream), "abx_sim_reset_tape")
 
+    def reset_tape_shared(self, n_tapes, tape_bits, tape_kinds, tape_offsets, lat_to_exchange, lat_from_exchange, stream=None):
+        """Tape mode with `n_tapes` recorded runs shared by all environments: environment e replays run e % n_tapes (arrays as reset_tape, for
+        n_tapes runs)."""
+        n_streams = self.n_agents + 3
+        bits = np.ascontiguousarray(tape_bits, dtype=np.uint64)
+        kinds = np.ascontiguousarray(tape_kinds, dtype=np.uint8)
+        off = np.ascontiguousarray(tape_offsets, dtype=np.int64)
+        lt = np.ascontiguousarray(lat_to_exchange, dtype=np.float64)
+        lf = np.ascontiguousarray(lat_from_exchange, dtype=np.float64)
+        if off.shape != (n_tapes * n_streams + 1,) or off[-1] != bits.size or kinds.size != bits.size or lt.size != n_tapes * self.n_agents or lf.size != lt.size:
+            raise ValueError("tape arrays have inconsistent shapes")
+        _lib.check(self._L, self._L.abx_sim_reset_tape_shared(
+            self._h, int(n_tapes), bits.ctypes.data_as(C.POINTER(C.c_uint64)), kinds.ctypes.data_as(C.POINTER(C.c_uint8)),
+            off.ctypes.data_as(C.POINTER(C.c_int64)), lt.ctypes.data_as(C.POINTER(C.c_double)), lf.ctypes.data_as(C.POINTER(C.c_double)), stream),
+            "abx_sim_reset_tape_shared")
+
     # ---- stepping ----
     def run(self, until_ns=None, stream=None):
         until = int(self.cfg.stop_ns) + 10 ** 15 if until_ns is None else int(until_ns)
@@ -206,6 +222,33 @@ class BatchedSim:
         _lib.check(self._L, self._L.abx_sim_trace(self._h, int(env), out.ctypes.data, cap, C.byref(n), stream),
                    "abx_sim_trace")
         return out[: n.value]
+
+    def draw_log(self, env, stream=None):
+        """Parity instrumentation (cfg.draw_log_cap > 0, Philox mode): every standard variate environment `env` has drawn so far, in draw
+        order, as (stream, kind, bits) arrays -- stream numbering of reset_tape (0 symbol, 1 kernel, 2 latency model, 3 global, 3 + a agent a)."""
+        cap = int(self.cfg.draw_log_cap)
+        raw = np.zeros(max(cap, 1) * 4, dtype=np.uint32)
+        n = C.c_int32(0)
+        _lib.check(self._L, self._L.abx_sim_draw_log(self._h, int(env), raw.ctypes.data, cap, C.byref(n), stream), "abx_sim_draw_log")
+        r = raw[: 4 * n.value].reshape(-1, 4)
+        return (r[:, 0] & 0xFFFFFF).astype(np.int64), (r[:, 0] >> 24).astype(np.uint8), r[:, 1].astype(np.uint64) | (r[:, 2].astype(np.uint64) << np.uint64(32))
+
+    def draw_tapes(self, env, stream=None):
+        """The draw log split per stream, in the layout reset_tape / the oracle's external tapes take: (bits, kinds, offsets[n_agents + 4])."""
+        st, kinds, bits = self.draw_log(env, stream)
+        order = np.argsort(st, kind="stable")
+        counts = np.bincount(st, minlength=self.n_agents + 3)[: self.n_agents + 3]
+        off = np.zeros(self.n_agents + 4, dtype=np.int64)
+        off[1:] = np.cumsum(counts)
+        return bits[order], kinds[order], off
+
+    def agent_init(self, env, stream=None):
+        """Start-of-run trader state as the reset drew it: dict(theta [n_agents, 20], lat_to, lat_from, sizes, wakes)."""
+        n = self.n_agents
+        out = dict(theta=np.zeros((n, 20), np.int32), lat_to=np.zeros(n), lat_from=np.zeros(n), sizes=np.zeros(n, np.int32), wakes=np.zeros(n, np.int64))
+        _lib.check(self._L, self._L.abx_sim_agent_init(self._h, int(env), out["theta"].ctypes.data, out["lat_to"].ctypes.data, out["lat_from"].ctypes.data,
+                                                       out["sizes"].ctypes.data, out["wakes"].ctypes.data, stream), "abx_sim_agent_init")
+        return out
 
     def split_trace(self, env):
         """Trace -> (pops[n,5], notes[n,13], snaps[n,16]) int64 arrays in tools/record_reference.py row layout."""

@@ -30,6 +30,9 @@ static inline uint64_t fnv_mix(uint64_t h, int64_t sv) { uint64_t v = (uint64_t)
 struct abo_rng {
   uint32_t mt[624]; int pos; int has_gauss; double gauss; uint32_t seed;
   int record; uint8_t *tk; uint64_t *tv; int64_t tn, tcap;
+  /* external tape (abo_sim_set_external): the STANDARD variates come from a supplied list instead of MT19937 -- this is how a run of
+   * the CUDA simulator under its own counter-based generator is re-run here draw for draw */
+  int replay; const uint8_t *rk; const uint64_t *rv; int64_t rn, rpos; int rerr;   /* rerr: 1 underrun, 2 kind mismatch */
 };
 static void rng_seed(abo_rng *r, uint32_t seed) { /* mt19937_seed */
   r->seed = seed;
@@ -69,11 +72,18 @@ static double rng_gauss_raw(abo_rng *r) { /* legacy_gauss */
   r->gauss = f * x1; r->has_gauss = 1;
   return f * x2;
 }
+static inline double bits_d(uint64_t u) { double d; memcpy(&d, &u, 8); return d; }
+static uint64_t rng_replay_next(abo_rng *r, uint8_t kind) {
+  if (r->rpos >= r->rn) { r->rerr |= 1; return 0; }
+  if (r->rk[r->rpos] != kind) r->rerr |= 2;
+  return r->rv[r->rpos++];
+}
 uint32_t abo_rng_u32(abo_rng *r) { return rng_u32_raw(r); }
-double abo_rng_double(abo_rng *r) { double u = rng_double_raw(r); rng_rec(r, 'u', dbits(u)); return u; }
-double abo_rng_gauss(abo_rng *r) { double z = rng_gauss_raw(r); rng_rec(r, 'n', dbits(z)); return z; }
-double abo_rng_std_exponential(abo_rng *r) { double e = -log(1.0 - rng_double_raw(r)); rng_rec(r, 'e', dbits(e)); return e; }
+double abo_rng_double(abo_rng *r) { if (r->replay) return bits_d(rng_replay_next(r, 'u')); double u = rng_double_raw(r); rng_rec(r, 'u', dbits(u)); return u; }
+double abo_rng_gauss(abo_rng *r) { if (r->replay) return bits_d(rng_replay_next(r, 'n')); double z = rng_gauss_raw(r); rng_rec(r, 'n', dbits(z)); return z; }
+double abo_rng_std_exponential(abo_rng *r) { if (r->replay) return bits_d(rng_replay_next(r, 'e')); double e = -log(1.0 - rng_double_raw(r)); rng_rec(r, 'e', dbits(e)); return e; }
 int64_t abo_rng_randint(abo_rng *r, int64_t low, int64_t high) { /* _rand_int64 + random_bounded_uint64_fill, use_masked */
+  if (r->replay) return low + (int64_t)rng_replay_next(r, 'i');
   uint64_t rng = (uint64_t)(high - 1 - low), v;
   if (rng == 0) v = 0;
   else if (rng <= 0xFFFFFFFFULL) {
@@ -357,7 +367,7 @@ struct abo_sim {
   double r_bar, kappa, fund_vol, megashock_lambda, megashock_mean, megashock_var;
   int64_t or_t, or_v; int64_t ms_t; double ms_v; double *gexp; int64_t n_gexp, cap_gexp;
   /* agents */
-  zi_t *zi; double sigma_n, agent_kappa, sigma_s, lambda_a;
+  zi_t *zi; double sigma_n, agent_kappa, sigma_s, lambda_a; int64_t order_size, starting_cash; double value_percent_aggr; int64_t value_depth_spread;
   double mm_pov; int64_t mm_min_size, mm_window, mm_ticks, mm_wake_ns, mom_wake_ns;   /* config/rmsc03.py:41-45,176-200 */
   int px_id, px_is_buy; double px_pov; int64_t px_quantity, px_start, px_end, px_freq, px_lookback;   /* POVExecutionAgent (agent/execution/baselines/pov_agent.py), 0 = none */
   /* traces */
@@ -396,7 +406,7 @@ static void k_send(abo_sim *s, int sender, int recipient, event_t *e, int64_t de
 /* ---------------- SparseMeanRevertingOracle ---------------- */
 static inline int64_t ns_from_float_string(double x) { return (int64_t)x; } /* pd.Timedelta("{}ns".format(float)) truncates */
 static double g_exponential(abo_sim *s, double scale) { /* np.random.exponential on the GLOBAL stream :69,168 */
-  double e = -log(1.0 - rng_double_raw(s->g)); rng_rec(s->g, 'e', dbits(e));
+  double e = abo_rng_std_exponential(s->g);
   if (s->n_gexp == s->cap_gexp) { s->cap_gexp = s->cap_gexp ? s->cap_gexp * 2 : 32; s->gexp = (double *)realloc(s->gexp, 8 * s->cap_gexp); }
   s->gexp[s->n_gexp++] = e;
   return e * scale;
@@ -573,7 +583,7 @@ static void zi_place_order(abo_sim *s, int id) {
   int64_t ask_vol = a->has_ask ? a->ask_q : 0, bid_vol = a->has_bid ? a->bid_q : 0;         /* getKnownBidAsk :564-574 */
   if (buy && ask_vol > 0) { int64_t R_ask = v - a->ask; if ((double)R_ask >= a->eta * (double)R) p = a->ask; }   /* :291-297 */
   else if (!buy && bid_vol > 0) { int64_t R_bid = a->bid - v; if ((double)R_bid >= a->eta * (double)R) p = a->bid; } /* :298-305 */
-  ta_place_limit(s, id, 100, buy, p);                                                       /* :308-309 */
+  ta_place_limit(s, id, s->order_size, buy, p);                                             /* :308-309 (size 100) */
 }
 static void orders_remove(zi_t *a, int i) { memmove(a->orders + i, a->orders + i + 1, sizeof(open_order_t) * (a->n_orders - i - 1)); a->n_orders--; }
 static void povmm_receive_tail(abo_sim *s, int id, const event_t *m); static void momentum_place_orders(abo_sim *s, int id); static void povexec_receive_tail(abo_sim *s, int id, const event_t *m);
@@ -690,8 +700,8 @@ static void value_place_order(abo_sim *s, int id) {
   int buy; int64_t p;
   if (a->has_bid && a->bid != 0 && a->has_ask && a->ask != 0) {                              /* if bid and ask */
     int64_t mid = (int64_t)((double)(a->ask + a->bid) / 2); int64_t spread = llabs(a->ask - a->bid); int64_t adjust;
-    if (abo_rng_double(s->g) < 0.1) adjust = 0;                                              /* np.random.rand() < percent_aggr */
-    else adjust = abo_rng_randint(s->g, 0, 2 * spread);                                      /* np.random.randint(0, depth_spread * spread) */
+    if (abo_rng_double(s->g) < s->value_percent_aggr) adjust = 0;                            /* np.random.rand() < percent_aggr */
+    else adjust = abo_rng_randint(s->g, 0, s->value_depth_spread * spread);                                      /* np.random.randint(0, depth_spread * spread) */
     if (r_Ti < mid) { buy = 0; p = a->bid + adjust; } else { buy = 1; p = a->ask - adjust; }
   } else { buy = (int)abo_rng_randint(s->g, 0, 2); p = r_Ti; }
   ta_place_limit(s, id, a->size, buy, p);
@@ -770,62 +780,102 @@ static void agent_wakeup(abo_sim *s, int id) {
 static abo_rng *new_stream(abo_sim *s) { /* RandomState(seed=np.random.randint(0, 2**32, dtype=uint64)) */
   abo_rng *r = abo_rng_new(rng_u32_raw(s->g)); r->record = (s->trace & ABO_TRACE_TAPES) != 0; return r;
 }
-static const int ZI_1000[7][3] = { {143, 0, 250}, {143, 0, 500}, {143, 0, 1000}, {143, 0, 1000}, {143, 0, 2000}, {143, 250, 500}, {142, 250, 500} };
-static const int ZI_100[7][3] = { {15, 0, 250}, {15, 0, 500}, {14, 0, 1000}, {14, 0, 1000}, {14, 0, 2000}, {14, 250, 500}, {14, 250, 500} };
-static const double ZI_ETA[7] = { 1, 1, 0.8, 1, 0.8, 0.8, 1 };
 #define NS_PER_S 1000000000LL
 
-abo_sim *abo_sim_new_sparse_zi(int variant, uint32_t seed, int trace) {
-  if (variant != 100 && variant != 1000) return NULL;
+/* The numbers of the reference's config scripts as an abx_sim_config (the parameter surface the CUDA product takes as well: the same struct
+ * drives both, so a parity test can change any field on both sides at once).  variant 100 / 1000: config/sparse_zi_100.py / sparse_zi_1000.py;
+ * 3: config/rmsc03.py; 4: rmsc03 + one POVExecutionAgent in the style of config/execution_iabs_plots.py:200-226.  Capacities / rng_mode are the
+ * product's business and stay 0 here. */
+int abo_default_config(int variant, abx_sim_config *c) {
+  if (!c) return -1;
+  memset(c, 0, sizeof(*c)); c->version = ABX_VERSION;
+  if (variant == 100 || variant == 1000) {
+    static const int n1000[7] = { 143, 143, 143, 143, 143, 143, 142 }, n100[7] = { 15, 15, 14, 14, 14, 14, 14 };
+    static const int rmin[7] = { 0, 0, 0, 0, 0, 250, 250 }, rmax[7] = { 250, 500, 1000, 1000, 2000, 500, 500 };     /* sparse_zi_1000.py:196-204 */
+    static const double eta[7] = { 1, 1, 0.8, 1, 0.8, 0.8, 1 };
+    c->n_groups = 7; c->q_max = 10; c->n_agents = 1;
+    for (int g = 0; g < 7; g++) { c->groups[g].count = variant == 1000 ? n1000[g] : n100[g]; c->groups[g].r_min = rmin[g]; c->groups[g].r_max = rmax[g]; c->groups[g].eta = eta[g]; c->n_agents += c->groups[g].count; }
+    c->start_ns = 0; c->stop_ns = 17 * 3600 * NS_PER_S;                               /* :86-88 midnight .. 17:00 */
+    c->mkt_open_ns = (9 * 3600 + 30 * 60) * NS_PER_S; c->mkt_close_ns = 16 * 3600 * NS_PER_S;
+    c->default_computation_delay_ns = NS_PER_S; c->starting_cash = 10000000; c->order_size = 100; c->stream_history = 10;
+    c->r_bar = 1e5; c->kappa = 1.67e-12; c->fund_vol = 1e-4; c->megashock_lambda_a = 2.77778e-13; c->megashock_mean = 1e3; c->megashock_var = 5e4;   /* :130-142 */
+    c->sigma_n = 1000000.0; c->agent_kappa = 1.67e-15; c->sigma_s = 1e-4; c->sigma_pv = 5e6; c->lambda_a = 1e-12;                                  /* :232-250 */
+    if (variant == 1000) { c->latency_model = ABX_LAT_MATRIX_NOISE; c->n_noise = 6; c->latency_mirrored = 1; c->latency_lo = 21000; c->latency_hi = 13000000; }   /* :264-286 */
+    else { c->latency_model = ABX_LAT_CUBIC; c->n_noise = 1; c->latency_lo = 21000; c->latency_hi = 100000; c->jitter = 0.3; c->jitter_clip = 0.05; c->jitter_unit = 5.0; }   /* sparse_zi_100.py:305-318 */
+    return 0;
+  }
+  if (variant == 3 || variant == 4) {
+    c->population = 1; c->n_noise_agents = 50; c->n_value_agents = 10; c->n_mm_agents = 1; c->n_momentum_agents = 2; c->n_agents = 64; c->q_max = 10;
+    c->mkt_open_ns = (9 * 3600 + 30 * 60) * NS_PER_S; c->mkt_close_ns = (9 * 3600 + 45 * 60) * NS_PER_S;   /* rmsc03.py:69-70 */
+    c->start_ns = c->mkt_open_ns; c->stop_ns = c->mkt_close_ns + 60 * NS_PER_S;                              /* :205-207 */
+    c->starting_cash = 10000000; c->stream_history = 10;
+    c->r_bar = 1e5; c->kappa = 1.67e-12; c->fund_vol = 1e-4; c->megashock_lambda_a = 2.77778e-13; c->megashock_mean = 1e3; c->megashock_var = 5e4;
+    c->sigma_n = 1e5 / 10; c->agent_kappa = 1.67e-15; c->sigma_s = 100000; c->lambda_a = 7e-11;            /* :77-80; sigma_s is ValueAgent's default */
+    c->latency_model = ABX_LAT_ZERO; c->n_noise = 1;
+    c->size_lo = 20; c->size_hi = 50; c->value_depth_spread = 2; c->value_percent_aggr = 0.1;              /* NoiseAgent.py:34, ValueAgent.py:53-56 */
+    c->noise_wake_lo_ns = 9 * 3600 * NS_PER_S; c->noise_wake_hi_ns = 16 * 3600 * NS_PER_S;                  /* :115-116 */
+    c->mom_min_size = 1; c->mom_max_size = 10; c->mom_wake_ns = 20 * NS_PER_S;                              /* :190-192 */
+    c->mm_pov = 0.05; c->mm_min_order_size = 20; c->mm_window_size = 5; c->mm_num_ticks = 20; c->mm_wake_ns = NS_PER_S;   /* :41-45 */
+    if (variant == 4) { c->n_pov_exec = 1; c->n_agents += 1; c->pov_exec_is_buy = 1; c->pov_exec_pov = 0.5; c->pov_exec_quantity = 120000;
+      c->pov_exec_start_ns = (9 * 3600 + 32 * 60) * NS_PER_S; c->pov_exec_end_ns = (9 * 3600 + 43 * 60) * NS_PER_S; c->pov_exec_freq_ns = 30 * NS_PER_S; c->pov_exec_lookback_ns = 30 * NS_PER_S; }
+    return 0;
+  }
+  return -1;
+}
+
+/* config/sparse_zi_100.py / config/sparse_zi_1000.py (population 0) and config/rmsc03.py (population 1) with the parameters of `c`: the same
+ * np.random.seed(seed) cascade in the scripts' source order, whatever the agent counts are. */
+static abo_sim *new_population0(const abx_sim_config *c, uint32_t seed, int trace) {
   abo_sim *s = (abo_sim *)calloc(1, sizeof(abo_sim));
-  s->variant = variant; s->seed = seed; s->trace = trace;
+  int cubic = c->latency_model == ABX_LAT_CUBIC;
+  s->variant = cubic ? 100 : 1000; s->seed = seed; s->trace = trace;
   s->pop_hash = s->note_hash = s->snap_hash = FNV_OFF;
-  const int (*zi)[3] = variant == 1000 ? ZI_1000 : ZI_100;
-  int n = 1; for (int i = 0; i < 7; i++) n += zi[i][0];
-  s->n_agents = n;
+  int n = c->n_agents; s->n_agents = n;
   s->g = abo_rng_new(seed);                                              /* np.random.seed(seed)  sparse_zi_1000.py:72 */
-  s->start_time = 0; s->stop_time = 17 * 3600 * NS_PER_S;                /* :86-88 midnight .. 17:00 */
+  s->start_time = c->start_ns; s->stop_time = c->stop_ns;                /* :86-88 */
   /* symbols["JPM"] :130-142 */
-  s->r_bar = 1e5; s->kappa = 1.67e-12; s->agent_kappa = 1.67e-15; s->sigma_s = 1e-4; s->fund_vol = 1e-4;
-  s->megashock_lambda = 2.77778e-13; s->megashock_mean = 1e3; s->megashock_var = 5e4;
+  s->r_bar = c->r_bar; s->kappa = c->kappa; s->agent_kappa = c->agent_kappa; s->sigma_s = c->sigma_s; s->fund_vol = c->fund_vol;
+  s->megashock_lambda = c->megashock_lambda_a; s->megashock_mean = c->megashock_mean; s->megashock_var = c->megashock_var;
+  s->order_size = c->order_size; s->starting_cash = c->starting_cash;
   s->sym_rs = new_stream(s);                                             /* :140 */
   s->kernel_rs = new_stream(s);                                          /* :146-148 */
-  if (variant == 100) s->lat_rs = new_stream(s);                         /* sparse_zi_100.py:152 */
-  s->mkt_open = (9 * 3600 + 30 * 60) * NS_PER_S; s->mkt_close = 16 * 3600 * NS_PER_S;
+  if (cubic) s->lat_rs = new_stream(s);                                  /* sparse_zi_100.py:152 */
+  s->mkt_open = c->mkt_open_ns; s->mkt_close = c->mkt_close_ns;
   /* SparseMeanRevertingOracle.__init__ :36-79 */
   s->or_t = s->mkt_open; s->or_v = (int64_t)s->r_bar;
   oracle_new_megashock(s, s->mkt_open);
   /* ExchangeAgent :174-194 */
-  s->exch_rs = new_stream(s); s->pipeline_delay = 0; s->exch_comp_delay = 0;
-  book_init(&s->book, 10, s, exch_book_send);
+  s->exch_rs = new_stream(s); s->pipeline_delay = c->exchange_pipeline_delay_ns; s->exch_comp_delay = c->exchange_computation_delay_ns;
+  book_init(&s->book, c->stream_history, s, exch_book_send);
   /* ZI agents :211-251 */
-  s->sigma_n = 1000000.0; s->lambda_a = 1e-12;
+  s->sigma_n = c->sigma_n; s->lambda_a = c->lambda_a;
   s->zi = (zi_t *)calloc(n, sizeof(zi_t));
   int id = 1;
-  for (int g = 0; g < 7; g++) for (int k = 0; k < zi[g][0]; k++, id++) {
-    zi_t *a = &s->zi[id]; a->rs = new_stream(s); a->group = g; a->R_min = zi[g][1]; a->R_max = zi[g][2]; a->eta = ZI_ETA[g];
-    a->starting_cash = a->cash = 10000000; a->first_wake = 1; a->state = ST_AWAITING_WAKEUP; a->r_t = s->r_bar; a->sigma_t = 0; a->q_max = 10;
+  for (int g = 0; g < c->n_groups; g++) for (int k = 0; k < c->groups[g].count; k++, id++) {
+    zi_t *a = &s->zi[id]; a->rs = new_stream(s); a->group = g; a->R_min = c->groups[g].r_min; a->R_max = c->groups[g].r_max; a->eta = c->groups[g].eta;
+    a->starting_cash = a->cash = c->starting_cash; a->first_wake = 1; a->state = ST_AWAITING_WAKEUP; a->r_t = s->r_bar; a->sigma_t = 0; a->q_max = c->q_max;
     /* theta: sorted(np.round(normal(0, sqrt(sigma_pv), size=2*q_max)), reverse=True) -> int   ZeroIntelligenceAgent.py:65-70 */
     double th[64]; int m = 2 * a->q_max;
-    for (int i = 0; i < m; i++) th[i] = nearbyint(rng_normal(a->rs, 0.0, sqrt(5e6)));
+    for (int i = 0; i < m; i++) th[i] = nearbyint(rng_normal(a->rs, 0.0, sqrt(c->sigma_pv)));
     for (int i = 1; i < m; i++) { double x = th[i]; int j = i - 1; while (j >= 0 && th[j] < x) { th[j + 1] = th[j]; j--; } th[j + 1] = x; }
     for (int i = 0; i < m; i++) a->theta[i] = (int32_t)th[i];
   }
   /* latency :264-286 / sparse_zi_100.py:305-318 : N x N uniform draws from the global stream, row-major */
   s->latency = (double *)malloc(sizeof(double) * (size_t)n * n);
-  if (variant == 1000) {
-    for (size_t i = 0; i < (size_t)n * n; i++) s->latency[i] = 21000.0 + (13000000.0 - 21000.0) * rng_double_raw(s->g);
+  for (size_t i = 0; i < (size_t)n * n; i++) s->latency[i] = c->latency_lo + (c->latency_hi - c->latency_lo) * rng_double_raw(s->g);
+  if (!cubic) {
     /* mirror the upper triangle, diagonal 20000; the ZI<->ZI 24h override never fires */
     for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) { if (i > j) s->latency[(size_t)i * n + j] = s->latency[(size_t)j * n + i]; else if (i == j) s->latency[(size_t)i * n + j] = 20000; }
-    s->n_noise = 6; s->use_latency_model = 0;
-  } else {
-    for (size_t i = 0; i < (size_t)n * n; i++) s->latency[i] = 21000.0 + (100000.0 - 21000.0) * rng_double_raw(s->g);
-    s->use_latency_model = 1; s->jitter = 0.3; s->jitter_clip = 0.05; s->jitter_unit = 5.0;
-  }
+    s->n_noise = c->n_noise; s->use_latency_model = 0;
+  } else { s->use_latency_model = 1; s->jitter = c->jitter; s->jitter_clip = c->jitter_clip; s->jitter_unit = c->jitter_unit; }
   /* Kernel.runner :97,105 */
   s->agent_time = (int64_t *)calloc(n, sizeof(int64_t)); s->comp_delay = (int64_t *)malloc(sizeof(int64_t) * n);
-  for (int i = 0; i < n; i++) { s->agent_time[i] = s->start_time; s->comp_delay[i] = NS_PER_S; }      /* defaultComputationDelay 1e9 */
+  for (int i = 0; i < n; i++) { s->agent_time[i] = s->start_time; s->comp_delay[i] = c->default_computation_delay_ns; }      /* defaultComputationDelay */
   return s;
+}
+abo_sim *abo_sim_new_sparse_zi(int variant, uint32_t seed, int trace) {
+  abx_sim_config c; if ((variant != 100 && variant != 1000) || abo_default_config(variant, &c)) return NULL;
+  return new_population0(&c, seed, trace);
 }
 
 /* config/rmsc03.py:49-232 (ticker/date only name things): 1 exchange, 50 noise, 10 value, 1 POV market maker, 2 momentum */
@@ -835,44 +885,97 @@ static double u_quadratic_inverse_cdf(double y) {                      /* util/u
   double c = n < 0 ? -pow(-n, 1.0 / 3.0) : pow(n, 1.0 / 3.0);
   return c + beta;
 }
-/* pov > 0: one POVExecutionAgent (id 64) is appended to the population with a RandomState outside the config's seed cascade (it never draws) */
-abo_sim *abo_sim_new_rmsc03_pov(uint32_t seed, int trace, double pov, int64_t quantity, int is_buy, int64_t start_ns, int64_t end_ns, int64_t freq_ns, int64_t lookback_ns) {
+/* n_pov_exec: one POVExecutionAgent is appended to the population with a RandomState outside the config's seed cascade (it never draws) */
+static abo_sim *new_population1(const abx_sim_config *c, uint32_t seed, int trace) {
   abo_sim *s = (abo_sim *)calloc(1, sizeof(abo_sim));
   s->variant = 3; s->seed = seed; s->trace = trace; s->pop_hash = s->note_hash = s->snap_hash = FNV_OFF;
-  int n0 = 1 + 50 + 10 + 1 + 2, n = n0 + (pov > 0 ? 1 : 0); s->n_agents = n;
-  if (pov > 0) { s->px_id = n0; s->px_pov = pov; s->px_quantity = quantity; s->px_is_buy = is_buy; s->px_start = start_ns; s->px_end = end_ns; s->px_freq = freq_ns; s->px_lookback = lookback_ns; }
+  int n_noise = c->n_noise_agents, n_value = c->n_value_agents, n_mm = c->n_mm_agents, n_mom = c->n_momentum_agents;
+  int n0 = 1 + n_noise + n_value + n_mm + n_mom, n = n0 + (c->n_pov_exec ? 1 : 0); s->n_agents = n;
+  if (c->n_pov_exec) { s->px_id = n0; s->px_pov = c->pov_exec_pov; s->px_quantity = c->pov_exec_quantity; s->px_is_buy = c->pov_exec_is_buy; s->px_start = c->pov_exec_start_ns; s->px_end = c->pov_exec_end_ns;
+    s->px_freq = c->pov_exec_freq_ns; s->px_lookback = c->pov_exec_lookback_ns; }
   s->g = abo_rng_new(seed);                                              /* np.random.seed(seed) :58 */
-  s->mkt_open = (9 * 3600 + 30 * 60) * NS_PER_S; s->mkt_close = (9 * 3600 + 45 * 60) * NS_PER_S;   /* :69-70 */
-  s->start_time = s->mkt_open; s->stop_time = s->mkt_close + 60 * NS_PER_S;                           /* :205-207 */
-  s->r_bar = 1e5; s->kappa = 1.67e-12; s->fund_vol = 1e-4; s->megashock_lambda = 2.77778e-13; s->megashock_mean = 1e3; s->megashock_var = 5e4;
-  s->sigma_n = 1e5 / 10; s->agent_kappa = 1.67e-15; s->sigma_s = 100000; s->lambda_a = 7e-11;       /* :77-80; sigma_s is ValueAgent's default */
-  s->mm_pov = 0.05; s->mm_min_size = 20; s->mm_window = 5; s->mm_ticks = 20; s->mm_wake_ns = NS_PER_S; s->mom_wake_ns = 20 * NS_PER_S;
+  s->mkt_open = c->mkt_open_ns; s->mkt_close = c->mkt_close_ns;          /* :69-70 */
+  s->start_time = c->start_ns; s->stop_time = c->stop_ns;                /* :205-207 */
+  s->r_bar = c->r_bar; s->kappa = c->kappa; s->fund_vol = c->fund_vol; s->megashock_lambda = c->megashock_lambda_a; s->megashock_mean = c->megashock_mean; s->megashock_var = c->megashock_var;
+  s->sigma_n = c->sigma_n; s->agent_kappa = c->agent_kappa; s->sigma_s = c->sigma_s; s->lambda_a = c->lambda_a;       /* :77-80 */
+  s->mm_pov = c->mm_pov; s->mm_min_size = c->mm_min_order_size; s->mm_window = c->mm_window_size; s->mm_ticks = c->mm_num_ticks; s->mm_wake_ns = c->mm_wake_ns; s->mom_wake_ns = c->mom_wake_ns;
+  s->value_percent_aggr = c->value_percent_aggr; s->value_depth_spread = c->value_depth_spread; s->starting_cash = c->starting_cash;
   s->sym_rs = new_stream(s);                                             /* :88 */
   s->or_t = s->mkt_open; s->or_v = (int64_t)s->r_bar; oracle_new_megashock(s, s->mkt_open);          /* :91 oracle __init__ */
-  s->exch_rs = new_stream(s); s->pipeline_delay = 0; s->exch_comp_delay = 0;                          /* :108 */
-  book_init(&s->book, 10, s, exch_book_send);
+  s->exch_rs = new_stream(s); s->pipeline_delay = c->exchange_pipeline_delay_ns; s->exch_comp_delay = c->exchange_computation_delay_ns;   /* :108 */
+  book_init(&s->book, c->stream_history, s, exch_book_send);
   s->zi = (zi_t *)calloc(n, sizeof(zi_t));
-  int64_t n_open = 9 * 3600 * NS_PER_S, n_close = 16 * 3600 * NS_PER_S;                               /* noise_mkt_open/close :115-116 */
+  int64_t n_open = c->noise_wake_lo_ns, n_close = c->noise_wake_hi_ns;                                /* noise_mkt_open/close :115-116 */
   for (int id = 1; id < n; id++) {
-    zi_t *a = &s->zi[id]; a->starting_cash = a->cash = 10000000; a->first_wake = 1; a->state = ST_AWAITING_WAKEUP; a->q_max = 10;
-    if (id <= 50) {                                                      /* NoiseAgent :117-131: wakeup_time (global rand), seed, then __init__ size (global randint) */
+    zi_t *a = &s->zi[id]; a->starting_cash = a->cash = c->starting_cash; a->first_wake = 1; a->state = ST_AWAITING_WAKEUP; a->q_max = c->q_max;
+    if (id <= n_noise) {                                                 /* NoiseAgent :117-131: wakeup_time (global rand), seed, then __init__ size (global randint) */
       a->type = AT_NOISE; double mult = u_quadratic_inverse_cdf(rng_double_raw(s->g));
       /* float * Timedelta truncates to the Timedelta's unit: microseconds for string-parsed times under pandas >= 3 (the
          recording environment); the reference's pinned pandas 0.24 would truncate to nanoseconds (differs by < 1 us) */
       a->wakeup_time = n_open + (int64_t)(mult * (double)((n_close - n_open) / 1000)) * 1000;
-      a->rs = new_stream(s); a->size = abo_rng_randint(s->g, 20, 50);
-    } else if (id <= 60) { a->type = AT_VALUE; a->rs = new_stream(s); a->size = abo_rng_randint(s->g, 20, 50); a->r_t = s->r_bar; a->sigma_t = 0; }   /* :137-155 */
-    else if (id == 61) { a->type = AT_POVMM; a->rs = new_stream(s); a->order_size = s->mm_min_size; a->aw_spread = a->aw_vol = 1; }                  /* :160-178 */
-    else if (id == n0) { a->type = AT_POVEXEC; a->rs = abo_rng_new(0); a->px_rem = quantity; }
-    else { a->type = AT_MOMENTUM; a->rs = new_stream(s); a->size = abo_rng_randint(a->rs, 1, 10); }                                                   /* :183-200, MomentumAgent.py:42 */
+      a->rs = new_stream(s); a->size = abo_rng_randint(s->g, c->size_lo, c->size_hi);
+    } else if (id <= n_noise + n_value) { a->type = AT_VALUE; a->rs = new_stream(s); a->size = abo_rng_randint(s->g, c->size_lo, c->size_hi); a->r_t = s->r_bar; a->sigma_t = 0; }   /* :137-155 */
+    else if (id <= n_noise + n_value + n_mm) { a->type = AT_POVMM; a->rs = new_stream(s); a->order_size = s->mm_min_size; a->aw_spread = a->aw_vol = 1; }                  /* :160-178 */
+    else if (c->n_pov_exec && id == n0) { a->type = AT_POVEXEC; a->rs = abo_rng_new(0); a->px_rem = c->pov_exec_quantity; }
+    else { a->type = AT_MOMENTUM; a->rs = new_stream(s); a->size = abo_rng_randint(a->rs, c->mom_min_size, c->mom_max_size); }                                            /* :183-200, MomentumAgent.py:42 */
   }
   s->kernel_rs = new_stream(s);                                          /* :201-204 */
   s->latency = (double *)calloc((size_t)n * n, sizeof(double)); s->n_noise = 1; s->use_latency_model = 0;   /* np.zeros, noise [0.0] :209-210 */
   s->agent_time = (int64_t *)calloc(n, sizeof(int64_t)); s->comp_delay = (int64_t *)calloc(n, sizeof(int64_t));
-  for (int i = 0; i < n; i++) { s->agent_time[i] = s->start_time; s->comp_delay[i] = 0; }           /* defaultComputationDelay 0 :208 */
+  for (int i = 0; i < n; i++) { s->agent_time[i] = s->start_time; s->comp_delay[i] = c->default_computation_delay_ns; }           /* defaultComputationDelay 0 :208 */
   return s;
 }
+abo_sim *abo_sim_new_rmsc03_pov(uint32_t seed, int trace, double pov, int64_t quantity, int is_buy, int64_t start_ns, int64_t end_ns, int64_t freq_ns, int64_t lookback_ns) {
+  abx_sim_config c; abo_default_config(pov > 0 ? 4 : 3, &c);
+  if (pov > 0) { c.pov_exec_pov = pov; c.pov_exec_quantity = quantity; c.pov_exec_is_buy = is_buy; c.pov_exec_start_ns = start_ns; c.pov_exec_end_ns = end_ns; c.pov_exec_freq_ns = freq_ns; c.pov_exec_lookback_ns = lookback_ns; }
+  return new_population1(&c, seed, trace);
+}
 abo_sim *abo_sim_new_rmsc03(uint32_t seed, int trace) { return abo_sim_new_rmsc03_pov(seed, trace, 0.0, 0, 1, 0, 0, 0, 0); }
+abo_sim *abo_sim_new_config(const abx_sim_config *c, uint32_t seed, int trace) {
+  if (!c || c->n_agents < 2 || c->q_max < 1 || c->q_max > 32) return NULL;
+  if (c->population == 0) { int n = 1; for (int g = 0; g < c->n_groups; g++) n += c->groups[g].count; if (n != c->n_agents) return NULL; return new_population0(c, seed, trace); }
+  if (c->population == 1) { if (1 + c->n_noise_agents + c->n_value_agents + c->n_mm_agents + c->n_momentum_agents + (c->n_pov_exec ? 1 : 0) != c->n_agents || c->n_mm_agents > 1) return NULL; return new_population1(c, seed, trace); }
+  return NULL;
+}
+
+/* External tapes: re-run a simulation whose random variates were drawn elsewhere (the CUDA simulator under its Philox streams).  Streams in the
+ * product's order (include/abides_b200.h, abx_sim_reset_tape): 0 symbol, 1 kernel, 2 latency model, 3 global, 3 + a agent a; off has n_agents + 4
+ * entries.  The start-of-run state those generators produced comes with them: theta [n_agents][20] (population 0), latency[a][0] / latency[0][a],
+ * Noise/Value/Momentum sizes and NoiseAgent wake-up times (population 1).  Call before abo_sim_start / run; the arrays must outlive the run. */
+int abo_sim_set_external(abo_sim *s, const uint64_t *bits, const uint8_t *kinds, const int64_t *off, const int32_t *theta, const double *lat_to,
+                         const double *lat_from, const int32_t *sizes, const int64_t *wakes) {
+  if (!s || s->started || !bits || !kinds || !off) return -1;
+  int n = s->n_agents;
+  for (int st = 0; st < n + 3; st++) {
+    abo_rng *r = st == 0 ? s->sym_rs : st == 1 ? s->kernel_rs : st == 2 ? s->lat_rs : st == 3 ? s->g : s->zi[st - 3].rs;
+    if (!r) continue;
+    if (st == 1 && !s->use_latency_model && s->n_noise == 1) continue;   /* noise [x]: randint(0, 1) is 0 whatever the stream (the product draws nothing) */
+    r->replay = 1; r->rk = kinds + off[st]; r->rv = bits + off[st]; r->rn = off[st + 1] - off[st]; r->rpos = 0; r->rerr = 0; r->has_gauss = 0;
+  }
+  for (int a = 1; a < n; a++) {
+    zi_t *z = &s->zi[a];
+    if (theta && z->type == AT_ZI) for (int i = 0; i < 2 * z->q_max && i < 20; i++) z->theta[i] = theta[(size_t)a * 20 + i];
+    if (lat_to && lat_from) { s->latency[(size_t)a * n] = lat_to[a]; s->latency[a] = lat_from[a]; }
+    if (sizes && (z->type == AT_NOISE || z->type == AT_VALUE || z->type == AT_MOMENTUM)) z->size = sizes[a];
+    if (wakes && z->type == AT_NOISE) z->wakeup_time = wakes[a];
+  }
+  s->or_t = s->mkt_open; s->or_v = (int64_t)s->r_bar; s->n_gexp = 0;
+  oracle_new_megashock(s, s->mkt_open);                                  /* the oracle's __init__ draw, now from the supplied streams */
+  return 0;
+}
+int abo_sim_rng_error(abo_sim *s) {
+  int e = 0; abo_rng *rs[5] = { s->sym_rs, s->kernel_rs, s->lat_rs, s->g, s->exch_rs };
+  for (int i = 0; i < 5; i++) if (rs[i]) e |= rs[i]->rerr;
+  for (int a = 1; a < s->n_agents; a++) if (s->zi[a].rs) e |= s->zi[a].rs->rerr;
+  return e;
+}
+/* draws left unread on the external tapes (0 when the run consumed exactly what the other side drew) */
+int64_t abo_sim_external_unread(abo_sim *s) {
+  int64_t u = 0; abo_rng *rs[4] = { s->sym_rs, s->kernel_rs, s->lat_rs, s->g };
+  for (int i = 0; i < 4; i++) if (rs[i] && rs[i]->replay) u += rs[i]->rn - rs[i]->rpos;
+  for (int a = 1; a < s->n_agents; a++) if (s->zi[a].rs && s->zi[a].rs->replay) u += s->zi[a].rs->rn - s->zi[a].rs->rpos;
+  return u;
+}
 /* POVExecutionAgent: rem_quantity, executed orders, open orders */
 void abo_sim_pov_exec(abo_sim *s, int64_t *out3) { out3[0] = out3[1] = out3[2] = 0; if (s->px_id) { zi_t *a = &s->zi[s->px_id]; out3[0] = a->px_rem; out3[1] = a->px_n_executed; out3[2] = a->n_orders; } }
 void abo_sim_free(abo_sim *s) {

@@ -19,6 +19,7 @@
 #ifndef ABIDES_ORACLE_H
 #define ABIDES_ORACLE_H
 #include <stdint.h>
+#include "../include/abides_b200.h"   /* abx_sim_config only: the parameter struct both sides take, so parity tests change a field once for both */
 
 #ifdef __cplusplus
 extern "C" {
@@ -77,6 +78,15 @@ abo_sim *abo_sim_new_rmsc03(uint32_t seed, int trace_flags);
 abo_sim *abo_sim_new_rmsc03_pov(uint32_t seed, int trace_flags, double pov, int64_t quantity, int is_buy, int64_t start_ns, int64_t end_ns,
                                 int64_t freq_ns, int64_t lookback_ns);
 void abo_sim_pov_exec(abo_sim *, int64_t *out3); /* rem_quantity, executed orders, open orders */
+/* The config scripts' numbers as an abx_sim_config (variant 100 / 1000 / 3 = rmsc03 / 4 = rmsc03 + POV execution agent), and a simulation built from
+ * any such struct: the same seed cascade with other agent counts / parameters (parametrised parity). */
+int abo_default_config(int variant, abx_sim_config *cfg);
+abo_sim *abo_sim_new_config(const abx_sim_config *cfg, uint32_t seed, int trace_flags);
+/* External tapes (see abides_oracle.c): standard variates per stream in the product's stream order + the start-of-run state drawn with them. */
+int abo_sim_set_external(abo_sim *, const uint64_t *bits, const uint8_t *kinds, const int64_t *off, const int32_t *theta, const double *lat_to,
+                         const double *lat_from, const int32_t *sizes, const int64_t *wakes);
+int abo_sim_rng_error(abo_sim *);            /* 1 underrun | 2 kind mismatch on an external tape */
+int64_t abo_sim_external_unread(abo_sim *);
 void abo_sim_free(abo_sim *);
 /* runtime draws on the GLOBAL np.random stream (kinds 'e','u','i') */
 int64_t abo_sim_global_tape(abo_sim *, const uint8_t **kinds, const uint64_t **bits);

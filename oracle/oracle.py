@@ -18,7 +18,7 @@ TRACE_ALL = 31
 
 def build(force=False):
     """Compile the C restatement (gcc, -ffp-contract=off)."""
-    src = [os.path.join(_HERE, f) for f in ("abides_oracle.c", "abides_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("abides_oracle.c", "abides_oracle.h", os.path.join("..", "include", "abides_b200.h"))]
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
         return _LIB_PATH
@@ -69,6 +69,11 @@ def lib():
     sig("abo_sim_new_rmsc03", vp, u32, i32)
     sig("abo_sim_new_rmsc03_pov", vp, u32, i32, dbl, i64, i32, i64, i64, i64, i64)
     sig("abo_sim_pov_exec", None, vp, P(i64))
+    sig("abo_default_config", i32, i32, vp)
+    sig("abo_sim_new_config", vp, vp, u32, i32)
+    sig("abo_sim_set_external", i32, vp, P(u64), P(C.c_uint8), P(i64), P(C.c_int32), P(dbl), P(dbl), P(C.c_int32), P(i64))
+    sig("abo_sim_rng_error", i32, vp)
+    sig("abo_sim_external_unread", i64, vp)
     sig("abo_sim_global_tape", i64, vp, P(P(C.c_uint8)), P(P(u64)))
     sig("abo_sim_agent_info", None, vp, i32, P(i64))
     sig("abo_sim_free", None, vp)
@@ -209,6 +214,9 @@ class OracleSim:
     def __init__(self, variant, seed, trace=0, pov_exec=None):
         """variant 100 / 1000: config/sparse_zi_*.py; variant 3: config/rmsc03.py.  pov_exec (variant 3 only): dict(pov, quantity, is_buy,
         start_ns, end_ns, freq_ns, lookback_ns) appends one POVExecutionAgent (agent/execution/baselines/pov_agent.py) as the last agent."""
+        self._keep = None
+        if variant == "config":                       # OracleSim.from_config
+            return
         if variant == 3 and pov_exec:
             p = pov_exec
             self._h = lib().abo_sim_new_rmsc03_pov(seed, trace, float(p["pov"]), int(p["quantity"]), int(bool(p["is_buy"])), int(p["start_ns"]), int(p["end_ns"]),
@@ -218,6 +226,41 @@ class OracleSim:
         if not self._h:
             raise ValueError("unknown sparse_zi variant %r" % (variant,))
         self.variant, self.seed = variant, seed
+
+    @classmethod
+    def from_config(cls, cfg, seed, trace=0):
+        """A simulation built from an abx_sim_config -- the ctypes struct the product takes (marl_optimal_execution_b200._lib.SimConfig, or any
+        ctypes structure of that layout): same seed cascade as the config scripts, parameters and agent counts from `cfg`."""
+        self = cls("config", seed)
+        self._h = lib().abo_sim_new_config(C.addressof(cfg), int(seed), int(trace))
+        if not self._h:
+            raise ValueError("abo_sim_new_config rejected the configuration")
+        self.variant = 3 if cfg.population == 1 else (100 if cfg.latency_model == 1 else 1000)
+        self.seed = seed
+        return self
+
+    def set_external(self, bits, kinds, off, theta=None, lat_to=None, lat_from=None, sizes=None, wakes=None):
+        """Replace every RandomState by a supplied list of standard variates (product stream order: symbol, kernel, latency model, global,
+        agents 1..n-1) and install the start-of-run state drawn with them.  Used to re-run a Philox-seeded GPU simulation draw for draw."""
+        keep = [np.ascontiguousarray(bits, np.uint64), np.ascontiguousarray(kinds, np.uint8), np.ascontiguousarray(off, np.int64)]
+        opt = []
+        for a, dt in ((theta, np.int32), (lat_to, np.float64), (lat_from, np.float64), (sizes, np.int32), (wakes, np.int64)):
+            opt.append(None if a is None else np.ascontiguousarray(a, dt))
+        keep += opt
+        self._keep = keep                              # the C side keeps pointers into these arrays
+
+        def ptr(a, ct):
+            return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+        rc = lib().abo_sim_set_external(self._h, ptr(keep[0], C.c_uint64), ptr(keep[1], C.c_uint8), ptr(keep[2], C.c_int64), ptr(opt[0], C.c_int32),
+                                        ptr(opt[1], C.c_double), ptr(opt[2], C.c_double), ptr(opt[3], C.c_int32), ptr(opt[4], C.c_int64))
+        if rc != 0:
+            raise ValueError("abo_sim_set_external failed")
+
+    def rng_error(self):
+        return lib().abo_sim_rng_error(self._h)
+
+    def external_unread(self):
+        return lib().abo_sim_external_unread(self._h)
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -111,7 +111,7 @@ struct HostCtx {
 struct abx_sim {
   SimParams P; int n_envs; bool reset_done;
   std::vector<uint4> qkey, qpay0, qpay1, qcache, nodes; std::vector<ZiAgent> agents; std::vector<int32_t> lvp, lvq; std::vector<uint32_t> lvht;
-  std::vector<EnvState> env; std::vector<abx_trace_rec> trace; std::vector<uint64_t> tbits; std::vector<uint8_t> tkinds; std::vector<int64_t> toff;
+  std::vector<EnvState> env; std::vector<abx_trace_rec> trace; std::vector<uint4> draw_log; std::vector<uint64_t> tbits; std::vector<uint8_t> tkinds; std::vector<int64_t> toff;
   bool is_env; EnvStreamHost st; EnvDaysHost dh; bool has_days = false; std::vector<EnvX> envx; std::vector<uint4> idtab; std::vector<int4> lobs; std::vector<uint2> idbook;
 };
 
@@ -140,6 +140,7 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   h->P.qkey = h->qkey.data(); h->P.qpay0 = h->qpay0.data(); h->P.qpay1 = h->qpay1.data(); h->P.qcache = h->qcache.data(); h->P.agents = h->agents.data();
   h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
   h->P.trace = c.trace_cap ? h->trace.data() : nullptr;
+  h->draw_log.resize(E * (size_t)c.draw_log_cap); h->P.draw_log = c.draw_log_cap ? h->draw_log.data() : nullptr;
   if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + TV_RING; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0); h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); }
   *out = h; return ABX_OK;
 }
@@ -160,9 +161,19 @@ static int32_t do_reset(abx_sim *h, const uint64_t *seeds) {
 int32_t abx_sim_reset_philox(abx_sim *h, const uint64_t *seeds, void *stream) {
   (void)stream; if (!h || !seeds || h->P.c.rng_mode != ABX_RNG_PHILOX) return ABX_ERR_ARG; return do_reset(h, seeds);
 }
+static int32_t reset_tape_impl(abx_sim *h, int32_t n_tapes, const uint64_t *bits, const uint8_t *kinds, const int64_t *off, const double *lat_to, const double *lat_from);
 int32_t abx_sim_reset_tape(abx_sim *h, const uint64_t *bits, const uint8_t *kinds, const int64_t *off, const double *lat_to, const double *lat_from, void *stream) {
-  (void)stream; if (!h || !bits || !kinds || !off || !lat_to || !lat_from || h->P.c.rng_mode != ABX_RNG_TAPE) return ABX_ERR_ARG;
-  size_t nS = (size_t)h->n_envs * h->P.n_streams; int64_t total = off[nS];
+  (void)stream; return reset_tape_impl(h, 0, bits, kinds, off, lat_to, lat_from); }
+int32_t abx_sim_reset_tape_shared(abx_sim *h, int32_t n_tapes, const uint64_t *bits, const uint8_t *kinds, const int64_t *off, const double *lat_to, const double *lat_from, void *stream) {
+  (void)stream; if (!h || n_tapes < 1 || n_tapes > h->n_envs || !lat_to || !lat_from) return ABX_ERR_ARG;
+  size_t na = (size_t)h->P.c.n_agents, E = (size_t)h->n_envs; std::vector<double> lt(E * na), lf(E * na);
+  for (size_t e = 0; e < E; e++) { memcpy(&lt[e * na], lat_to + (e % n_tapes) * na, sizeof(double) * na); memcpy(&lf[e * na], lat_from + (e % n_tapes) * na, sizeof(double) * na); }
+  return reset_tape_impl(h, n_tapes, bits, kinds, off, lt.data(), lf.data());
+}
+static int32_t reset_tape_impl(abx_sim *h, int32_t n_tapes, const uint64_t *bits, const uint8_t *kinds, const int64_t *off, const double *lat_to, const double *lat_from) {
+  if (!h || !bits || !kinds || !off || !lat_to || !lat_from || h->P.c.rng_mode != ABX_RNG_TAPE) return ABX_ERR_ARG;
+  h->P.n_tapes = n_tapes;
+  size_t nS = (size_t)(n_tapes > 0 ? n_tapes : h->n_envs) * h->P.n_streams; int64_t total = off[nS];
   h->tbits.assign(bits, bits + total); h->tkinds.assign(kinds, kinds + total); h->toff.assign(off, off + nS + 1);
   h->P.tape_bits = h->tbits.data(); h->P.tape_kinds = h->tkinds.data(); h->P.tape_off = h->toff.data();
   for (int e = 0; e < h->n_envs; e++) for (int id = 0; id < h->P.c.n_agents; id++) { ZiAgent &z = h->agents[(size_t)e * h->P.c.n_agents + id]; z.lat_to = lat_to[(size_t)e * h->P.c.n_agents + id]; z.lat_from = lat_from[(size_t)e * h->P.c.n_agents + id]; }
@@ -210,6 +221,16 @@ int32_t abx_sim_book_snapshot(abx_sim *h, int32_t env, int32_t is_bid, int32_t d
   for (int k = 0; k < m; k++) { out[2 * k] = ctx.lv_price(side, n - 1 - k); out[2 * k + 1] = ctx.lv_qty(side, n - 1 - k); }
   *n_levels = m; return ABX_OK;
 }
+int32_t abx_sim_draw_log(abx_sim *h, int32_t env, abx_draw_rec *out, int32_t max_recs, int32_t *n_recs, void *stream) {
+  (void)stream; if (!h || !out || !n_recs || env < 0 || env >= h->n_envs || h->is_env) return ABX_ERR_ARG;
+  int n = (int)h->env[env].draw_n; if (n > max_recs) n = max_recs;
+  if (n) memcpy(out, h->P.draw_log + (size_t)env * h->P.c.draw_log_cap, sizeof(uint4) * n);
+  *n_recs = n; return ABX_OK;
+}
+int32_t abx_sim_agent_init(abx_sim *h, int32_t env, int32_t *theta, double *lat_to, double *lat_from, int32_t *sizes, int64_t *wakes, void *stream) {
+  (void)stream; if (!h || h->is_env || env < 0 || env >= h->n_envs) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  agent_init_rows(h->P, &h->agents[(size_t)env * h->P.c.n_agents], theta, lat_to, lat_from, sizes, wakes); return ABX_OK;
+}
 int32_t abx_sim_trace(abx_sim *h, int32_t env, abx_trace_rec *out, int32_t max_recs, int32_t *n_recs, void *stream) {
   (void)stream; if (!h || !out || !n_recs || env < 0 || env >= h->n_envs) return ABX_ERR_ARG;
   int n = (int)h->env[env].trace_n; if (n > max_recs) n = max_recs;
@@ -223,7 +244,7 @@ int64_t abx_sim_launch_count(const abx_sim *h) { (void)h; return 0; }
 typedef Sim<HostCtx, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_ENV> EnvSimHost;
 int32_t abx_env_config_default(abx_env_config *cfg) { return env_config_default(cfg); }
 int32_t abx_env_create_days(const abx_env_config *cfg, const int64_t *stream5, const int64_t *row_offsets, int32_t n_days, int32_t n_envs, int32_t device, abx_sim **out) {
-  (void)device; if (!out || n_envs < 1 || env_config_validate(cfg) != ABX_OK) return ABX_ERR_ARG;
+  (void)device; if (!out || n_envs < 1 || env_shape_validate(cfg) != ABX_OK) return ABX_ERR_ARG;
   abx_sim *h = new abx_sim(); memset(&h->P, 0, sizeof(h->P)); h->is_env = true; h->has_days = true; h->n_envs = n_envs; h->reset_done = false;
   if (env_build_days(stream5, row_offsets, n_days, 4LL * cfg->n_horizon + 16, h->dh) != ABX_OK) { delete h; return ABX_ERR_ARG; }
   env_fill_params(*cfg, h->P); h->P.n_envs = n_envs; const abx_sim_config &c = h->P.c; size_t E = n_envs;

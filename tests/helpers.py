@@ -56,3 +56,39 @@ def oracle_tapes(sims):
         lat_from.append(b)
     return (np.concatenate(bits), np.concatenate(kinds), np.array(off, np.int64), np.concatenate(lat_to),
             np.concatenate(lat_from))
+
+
+def oracle_rerun_of_philox_env(sim, env, init, trace):
+    """Re-run environment `env` of a Philox-seeded BatchedSim (cfg.draw_log_cap > 0) through the oracle: the oracle is built from the SAME
+    abx_sim_config, every RandomState is replaced by the standard variates the environment drew (sim.draw_tapes) and the start-of-run state
+    (`init` = sim.agent_init(env), taken right after reset) is installed.  Returns the finished OracleSim and its message count."""
+    from oracle.oracle import OracleSim
+    bits, kinds, off = sim.draw_tapes(env)
+    o = OracleSim.from_config(sim.cfg, 0, trace)
+    o.set_external(bits, kinds, off, theta=init["theta"], lat_to=init["lat_to"], lat_from=init["lat_from"], sizes=init["sizes"], wakes=init["wakes"])
+    n = o.run()
+    assert o.rng_error() == 0, "external tape underrun / kind mismatch: %d" % o.rng_error()
+    assert o.external_unread() == 0, "the oracle left %d of the environment's draws unread" % o.external_unread()
+    return o, n
+
+
+def assert_env_equals_oracle(sim, e, o, n, st, traces=True, holdings_cols=5, hashed=True):
+    """Counters, L1, fundamental, conservation sums, holdings (and pop hash / full traces when the run was instrumented) of environment e == oracle."""
+    from marl_optimal_execution_b200 import _lib
+    assert int(st["messages"][e]) == n, (int(st["messages"][e]), n)
+    assert int(st["flags"][e]) == _lib.F_DONE, hex(int(st["flags"][e]))
+    if hashed:
+        assert int(st["pop_hash"][e]) == o.pop_hash()
+    if traces:
+        p, nt, sn = sim.split_trace(e)
+        for name, a, b in (("pops", p, o.trace("pops")), ("notes", nt, o.trace("notes")), ("snaps", sn, o.trace("snaps"))):
+            assert a.shape == b.shape, (name, a.shape, b.shape)
+            d = np.nonzero((a != b).any(axis=1))[0]
+            assert len(d) == 0, (name, int(d[0]), a[d[0]], b[d[0]])
+    assert np.array_equal(sim.holdings(e)[:, :holdings_cols], o.holdings()[:, :holdings_cols])
+    for f, c in (("limit_orders", "limit"), ("cancels", "cancel"), ("fills", "fills"), ("spread_queries", "spread_queries"), ("max_queue", "max_queue"),
+                 ("uniq", "uniq"), ("orders_allocated", "orders_allocated")):
+        assert int(st[f][e]) == o.counter(c), (f, int(st[f][e]), o.counter(c))
+    l1 = o.book_l1()
+    assert (int(st["best_bid"][e]), int(st["best_bid_qty"][e]), int(st["best_ask"][e]), int(st["best_ask_qty"][e]), int(st["last_trade"][e])) == tuple(int(x) for x in l1)
+    assert int(st["fundamental"][e]) == o.fundamental()

@@ -132,3 +132,19 @@ def test_rmsc03_with_pov_execution_agent_matches_oracle(emu):
     assert np.array_equal(sim.holdings(0)[:, :4], o.holdings()[:, :4])
     assert np.array_equal(sim.pov_exec(0), o.pov_exec()) and sim.pov_exec(0)[1] == 214
     assert int(st["sum_shares"]) == 0 and int(st["sum_cash"]) == 64 * 10 ** 7
+
+
+def test_shared_tapes_round_robin(emu):
+    """abx_sim_reset_tape_shared: environment e replays recorded run e % n_tapes (the production-occupancy parity tests of the GPU suite)."""
+    seeds = [123456789, 1001, 7]
+    oracles = [OracleSim(100, s, TRACE_ALL) for s in seeds]
+    counts = [o.run() for o in oracles]
+    cfg = sparse_zi_config(100, lib=_lib.load(emu), rng_mode=_lib.RNG_TAPE, hash_pops=1)
+    sim = BatchedSim(cfg, 8, lib_path=emu)
+    sim.reset_tape_shared(3, *oracle_tapes(oracles))
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    for e in range(8):
+        assert int(st["messages"][e]) == counts[e % 3] and int(st["pop_hash"][e]) == oracles[e % 3].pop_hash() and int(st["flags"][e]) == _lib.F_DONE
+        assert np.array_equal(sim.holdings(e), oracles[e % 3].holdings())
