@@ -52,7 +52,7 @@ struct alignas(16) EnvState {           // 192 B per environment
   uint32_t ctr_kernel, ctr_latency, ctr_global, trade_epoch;   // trade_epoch: OrderBook.history rotations (util/OrderBook.py:146)
   int64_t sum_shares, sum_cash;
   uint32_t kblk[4];                     // cached Philox block of the kernel (latency-noise) stream
-  uint32_t draw_n, evt_n, pad_a, pad_b; // entries in the draw log (parity runs) / in the LAST_TRADE, BEST_BID, BEST_ASK event ring
+  uint32_t draw_n, evt_n, book_flags, pad_b; // entries in the draw log (parity runs) / in the LAST_TRADE, BEST_BID, BEST_ASK event ring; BKF_*
 };
 static_assert(sizeof(EnvState) == 208, "EnvState layout");
 
@@ -120,8 +120,23 @@ ABX_HD int key_type(uint64_t k) { return int(k & 3); }
 constexpr uint64_t KEY_EMPTY = ~uint64_t(0);
 
 struct EnvX;
-struct NodeRec { uint32_t id; int32_t qty; uint32_t agent; uint32_t next; };   // one resting order (16 B)
+// One resting order (16 B in HBM).  Replay shapes (ENV / DQ / BOOK), whose books see MODIFY_ORDER, store the order's own limit price
+// {id, qty, price, next | agent << 16}: the reference reads a level's price from its slot 0 (util/OrderBook.py:381,393), so after a re-pricing
+// modify the level takes the price of whichever order becomes its head.  The background populations never modify and keep
+// {id, qty, agent | history epoch << 16, next}.
+struct NodeRec { uint32_t id; int32_t qty; uint32_t agent; uint32_t next; int32_t price; };
+template <bool PRICED> ABX_HD uint4 node_pack(const NodeRec &r) {
+  uint4 v; v.x = r.id; v.y = (uint32_t)r.qty;
+  if (PRICED) { v.z = (uint32_t)r.price; v.w = (r.next & 0xffffu) | (r.agent << 16); } else { v.z = r.agent; v.w = r.next; }
+  return v;
+}
+template <bool PRICED> ABX_HD NodeRec node_unpack(const uint4 &v) {
+  NodeRec r; r.id = v.x; r.qty = (int32_t)v.y;
+  if (PRICED) { r.price = (int32_t)v.z; r.next = (v.w & 0xffffu) == 0xffffu ? 0xffffffffu : (v.w & 0xffffu); r.agent = v.w >> 16; } else { r.agent = v.z; r.next = v.w; r.price = 0; }
+  return r;
+}
 constexpr uint32_t NIL = 0xffffffffu;
+enum : uint32_t { BKF_REPRICED = 1u };   // a MODIFY changed a head order's price: level prices follow their heads from now on, ladders may be unsorted, the per-id census no longer names levels
 
 // Device-side parameter block (config + derived constants + HBM base pointers).
 struct SimParams {
@@ -230,9 +245,12 @@ ABX_HD bool key_less(uint64_t ah, uint32_t au, uint64_t bh, uint32_t bu) { retur
 // RNG: Philox4x32-10 counter streams, or replay of recorded standard variates (tape)
 // ---------------------------------------------------------------------------------------------------
 struct U4 { uint32_t x, y, z, w; };
+#ifndef ABX_PHILOX_ROUNDS
+#define ABX_PHILOX_ROUNDS 10
+#endif
 ABX_NI U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; r++) {
+#pragma unroll 1                                                                       // rolled: the unrolled rounds are 2 KB of a hot loop body that lives on the edge of the 32 KB instruction cache (+6 % msgs/s, profiles/r02_optimisation_log.md)
+  for (int r = 0; r < ABX_PHILOX_ROUNDS; r++) {
     uint64_t p0 = uint64_t(0xD2511F53u) * c0, p1 = uint64_t(0xCD9E8D57u) * c2;
     uint32_t n0 = uint32_t(p1 >> 32) ^ c1 ^ k0, n1 = uint32_t(p1), n2 = uint32_t(p0 >> 32) ^ c3 ^ k1, n3 = uint32_t(p0);
     c0 = n0; c1 = n1; c2 = n2; c3 = n3; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
@@ -267,6 +285,11 @@ ABX_NI double box_muller(uint32_t a, uint32_t b, uint32_t cw) {                 
   return sqrt(-2.0 * log_unit(u1)) * (double)cospif(ang);
 }
 ABX_NI double pow_ni(double x, double y) { return pow(x, y); }
+#ifdef ABX_OPT_DDIV
+ABX_NI double ddiv(double a, double b) { return a / b; }                                 // one IEEE division body for the belief update's three quotients
+#else
+ABX_HD double ddiv(double a, double b) { return a / b; }
+#endif
 enum { S_SYMBOL = 0, S_KERNEL = 1, S_LATENCY = 2, S_GLOBAL = 3, S_AGENT0 = 3 };  // agent a uses stream S_AGENT0 + a
 
 // MODE: ABX_RNG_PHILOX / ABX_RNG_TAPE fixed at compile time (one kernel instantiation per mode), or -1 = read P->c.rng_mode
@@ -418,7 +441,7 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
   s.uniq = 0; s.next_order_id = 0; s.q_count = 0; s.max_q = 0; s.n_bid_lv = s.n_ask_lv = 0; s.n_resting = 0; s.free_head = NIL;
   s.pool_top = 0; s.flags = 0; s.trace_n = 0; s.c_limit = s.c_cancel = s.c_fills = s.c_query = 0;
   s.ctr_symbol = s.ctr_kernel = s.ctr_latency = s.ctr_global = 0; s.trade_epoch = 16; s.sum_shares = 0; s.sum_cash = 0;
-  s.kblk[0] = s.kblk[1] = s.kblk[2] = s.kblk[3] = 0; s.draw_n = 0; s.evt_n = 0; s.pad_a = 0; s.pad_b = 0;
+  s.kblk[0] = s.kblk[1] = s.kblk[2] = s.kblk[3] = 0; s.draw_n = 0; s.evt_n = 0; s.book_flags = 0; s.pad_b = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -438,6 +461,14 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
 constexpr int OUT_CAP = 24, OUT_WORDS = 12;     // 24 x 48 B in the replay shapes (the DDQN agent's closing market order flushes in batches); the sparse_zi shape, whose handlers emit at most three messages, keeps 8 (Ctx::OUTN)
 enum : uint32_t { OF_WAKEUP = 1u << 24, OF_BUMP_UNIQ = 1u << 25, OF_FROM_EXCH = 1u << 26, OF_CANCEL_EVT = 1u << 27 };
 
+#if defined(__CUDA_ARCH__)
+// one out-of-line body for the twenty inlined outbox writes (values in, nothing address-taken)
+ABX_NI void emit_store(uint32_t *o, uint32_t w0, int32_t p0, int32_t p1, int32_t p2, int32_t p3, int32_t p4, int32_t p5, double lat, int64_t off) {
+  uint64_t lb = dbl_bits(lat); uint4 *o4 = reinterpret_cast<uint4 *>(o);
+  o4[0] = make_uint4(w0, (uint32_t)p0, (uint32_t)p1, (uint32_t)p2); o4[1] = make_uint4((uint32_t)p3, (uint32_t)p4, (uint32_t)p5, (uint32_t)lb);
+  o4[2] = make_uint4((uint32_t)(lb >> 32), (uint32_t)(uint64_t)off, (uint32_t)((uint64_t)off >> 32), 0u);
+}
+#endif
 struct AgentRegs {                      // scalar part of ZiAgent held in registers while an event is handled
   int64_t agent_time, prev_wake, cash; double r_t, sigma_t, lat_to, lat_from;
   int32_t shares, last_trade, daily_close, bid, bid_q, ask, ask_q, n_orders; uint32_t flags, rng_ctr;
@@ -509,6 +540,9 @@ struct Sim {
   // send offset (computation delay + additional + pipeline delay) for messages, absolute time for wakeups.
   ABX_HD void emit(uint32_t w0, const int32_t p[6], double lat, int64_t off) {
     if (n_out >= Ctx::OUTN) { s.flags |= ABX_F_QUEUE_OVERFLOW; return; }
+#if defined(ABX_OPT_EMITNI) && defined(__CUDA_ARCH__)
+    emit_store(c.outbox() + n_out * OUT_WORDS, w0, p[0], p[1], p[2], p[3], p[4], p[5], lat, off); n_out++; return;
+#endif
     if (c.onchip_writer()) {
       uint32_t *o = c.outbox() + n_out * OUT_WORDS; uint64_t lb = dbl_bits(lat);
 #if defined(__CUDA_ARCH__)                                                             // three 128-bit stores instead of eleven words: emit is inlined at every send site
@@ -578,6 +612,7 @@ struct Sim {
         e.x0 = (int32_t)o[7]; e.x1 = (int32_t)o[8];                                   // exchange replies: level-2 prices ride in the latency words
       }
       if (BOOK) continue;                                                             // bare-book replay: the notification is the output (traced above), there is no kernel queue
+      if (SHAPE == SHAPE_ZI && e.recipient != 0 && e.type == ABX_T_MESSAGE) c.agent_prefetch(e.recipient);   // the reply is popped within microseconds of simulated time: have the record in L2 by then
       if (!c.q_push(e, s.now)) s.flags |= ABX_F_QUEUE_OVERFLOW;                              // Kernel.py:425 / :462
       else { s.q_count++; if (s.q_count > s.max_q) s.max_q = s.q_count; }
     }
@@ -615,14 +650,19 @@ struct Sim {
   }
 
   // ---- order book (util/OrderBook.py).  Ladders are sorted so that the BEST level is the LAST element. ----
+  ABX_HD NodeRec nload(uint32_t i) { return c.template node_load<ENV>(i); }
+  ABX_HD void nstore(uint32_t i, const NodeRec &r) { c.template node_store<ENV>(i, r); }
   ABX_HD uint32_t node_alloc() {
     uint32_t n;
-    if (s.free_head != NIL) { n = s.free_head; s.free_head = c.node_load(n).next; }
+    if (s.free_head != NIL) { n = s.free_head; s.free_head = nload(n).next; }
     else if (s.pool_top < (uint32_t)P.c.order_cap) { n = s.pool_top++; }
     else { s.flags |= ABX_F_ORDER_OVERFLOW; return NIL; }
     return n;
   }
-  ABX_HD void node_free(uint32_t n) { NodeRec r; r.id = 0; r.qty = 0; r.agent = 0; r.next = s.free_head; c.node_store(n, r); s.free_head = n; }
+  ABX_HD void node_free(uint32_t n) { NodeRec r; r.id = 0; r.qty = 0; r.agent = 0; r.next = s.free_head; r.price = 0; nstore(n, r); s.free_head = n; }
+  // A level's head changed to node `h`: the level now shows that order's price (util/OrderBook.py:381,393 read book[i][0].limit_price).  Only after a
+  // re-pricing MODIFY can that differ from the price the level had.
+  ABX_HD void level_follow_head(int side, int pos, uint32_t h) { if (ENV && (s.book_flags & BKF_REPRICED)) c.lv_setp(side, pos, nload(h).price); }
 
   // Per-order-id census of the book (replayed orders only): how many resting nodes carry the id and in which level.  modifyOrder's live scan
   // of a whole price level (:350-351; 220 orders on average, up to 1 380, on an IBM 2003 day -- 3.5 M dependent node loads per environment-day
@@ -639,15 +679,16 @@ struct Sim {
     uint2 v = c.ib_load((int)(oid - REPLAY_ID_BASE)); uint32_t cnt = v.x & 0x7fffffffu;
     v.x = cnt <= 1 ? 0u : ((cnt - 1) | (v.x & 0x80000000u)); c.ib_store((int)(oid - REPLAY_ID_BASE), v);
   }
-  // enterOrder :256-282
+  // enterOrder :256-282: first level from the best whose slot-0 price the order beats (new level before it) or equals (joins its FIFO); worse
+  // than every level -> new worst level.  lv_find returns exactly that position (for sorted ladders the ordinary sorted insert).
   ABX_HD void book_enter(int side, uint32_t oid, int agent, int32_t price, int32_t qty) {
     int n = n_lv(side); int pos; bool found;
     c.lv_find(side, price, n, pos, found);
     uint32_t node = node_alloc(); if (node == NIL) return;
-    NodeRec r; r.id = oid; r.qty = qty; r.agent = (uint32_t)agent | (R3 ? (s.trade_epoch << 16) : 0u); r.next = NIL; c.node_store(node, r);   // R3: + registration epoch
+    NodeRec r; r.id = oid; r.qty = qty; r.agent = (uint32_t)agent | (R3 ? (s.trade_epoch << 16) : 0u); r.next = NIL; r.price = price; nstore(node, r);   // R3: + registration epoch
     if (found) {
       uint32_t tail = c.lv_tail(side, pos);
-      NodeRec tr = c.node_load(tail); tr.next = node; c.node_store(tail, tr);
+      NodeRec tr = nload(tail); tr.next = node; nstore(tail, tr);
       c.lv_set(side, pos, c.lv_qty(side, pos) + qty, c.lv_head(side, pos), node);
     } else {
       if (n >= P.c.level_cap) { s.flags |= ABX_F_LEVEL_OVERFLOW; node_free(node); return; }
@@ -672,16 +713,16 @@ struct Sim {
       if (n > 0) {
         int32_t bp = c.lv_price(opp, n - 1);
         if (is_buy ? price >= bp : price <= bp) {                                       // isMatch :242-254, head of best level only
-          uint32_t h = c.lv_head(opp, n - 1); NodeRec hr = c.node_load(h);
+          uint32_t h = c.lv_head(opp, n - 1); NodeRec hr = nload(h);
           int32_t fq;
           if (ENV && hr.id >= REPLAY_ID_BASE) c.id_prefetch((int)(hr.id - REPLAY_ID_BASE));   // its owner updates the record when ORDER_EXECUTED arrives
           if (qty >= hr.qty) {                                                          // :204-210 whole resting order consumed
             fq = hr.qty;
             if (hr.next == NIL) set_n_lv(opp, n - 1);                                    // level emptied: it is the last element
-            else c.lv_set(opp, n - 1, c.lv_qty(opp, n - 1) - fq, hr.next, c.lv_tail(opp, n - 1));
+            else { c.lv_set(opp, n - 1, c.lv_qty(opp, n - 1) - fq, hr.next, c.lv_tail(opp, n - 1)); level_follow_head(opp, n - 1, hr.next); }
             node_free(h); s.n_resting--; ib_dec(hr.id);
           } else {                                                                      // :212-217 partial
-            fq = qty; hr.qty -= fq; c.node_store(h, hr); c.lv_set(opp, n - 1, c.lv_qty(opp, n - 1) - fq, h, c.lv_tail(opp, n - 1));
+            fq = qty; hr.qty -= fq; nstore(h, hr); c.lv_set(opp, n - 1, c.lv_qty(opp, n - 1) - fq, h, c.lv_tail(opp, n - 1));
           }
           if (R3) {                                                                     // :227,230-237 history "transactions" tuples read back by get_transacted_volume
             tv_record(qty, epoch0);                                                     //   incoming order: its PRE-fill remaining quantity
@@ -703,28 +744,34 @@ struct Sim {
     }
     if (trade_qty > 0) { s.last_trade = (int32_t)py_round_i64((double)trade_px / (double)trade_qty); s.trade_epoch++; } // :131-149 (history.insert(0, {}))
   }
-  // cancelOrder :284-339
+  // cancelOrder :284-339: levels from the best whose slot-0 price equals the request's, the first that holds the id
   ABX_HD void book_cancel(uint32_t oid, int agent, int is_buy, int32_t price, double lat_in) {
     int side = is_buy ? 0 : 1; int n = n_lv(side); if (n == 0) return;
-    int pos; bool found; c.lv_find(side, price, n, pos, found);
-    if (!found) return;
-    uint32_t prev = NIL, cur = c.lv_head(side, pos);
+    int limit = n;
 #pragma unroll 1
-    while (cur != NIL) {
-      NodeRec r = c.node_load(cur);
-      if (r.id == oid) {
-        if (prev == NIL) {
-          if (r.next == NIL) { c.lv_remove(side, pos, n); set_n_lv(side, n - 1); }
-          else c.lv_set(side, pos, c.lv_qty(side, pos) - r.qty, r.next, c.lv_tail(side, pos));
-        } else {
-          NodeRec pr = c.node_load(prev); pr.next = r.next; c.node_store(prev, pr);
-          c.lv_set(side, pos, c.lv_qty(side, pos) - r.qty, c.lv_head(side, pos), r.next == NIL ? prev : c.lv_tail(side, pos));
+    for (;;) {
+      int cnt; int pos = c.lv_find_eq(side, price, limit, cnt);
+      if (pos < 0) return;
+      uint32_t prev = NIL, cur = c.lv_head(side, pos);
+#pragma unroll 1
+      while (cur != NIL) {
+        NodeRec r = nload(cur);
+        if (r.id == oid) {
+          if (prev == NIL) {
+            if (r.next == NIL) { c.lv_remove(side, pos, n); set_n_lv(side, n - 1); }
+            else { c.lv_set(side, pos, c.lv_qty(side, pos) - r.qty, r.next, c.lv_tail(side, pos)); level_follow_head(side, pos, r.next); }
+          } else {
+            NodeRec pr = nload(prev); pr.next = r.next; nstore(prev, pr);
+            c.lv_set(side, pos, c.lv_qty(side, pos) - r.qty, c.lv_head(side, pos), r.next == NIL ? prev : c.lv_tail(side, pos));
+          }
+          node_free(cur); s.n_resting--; ib_dec(r.id);
+          exch_send_order(agent, ABX_ORDER_CANCELLED, r.id, ENV ? r.price : price, r.qty, 0, is_buy, lat_in);   // :334-336 the BOOK's copy of the order, to the REQUEST's agent
+          return;
         }
-        node_free(cur); s.n_resting--; ib_dec(r.id);
-        exch_send_order(agent, ABX_ORDER_CANCELLED, r.id, price, r.qty, 0, is_buy, lat_in);           // :334-336 to the REQUEST's agent
-        return;
+        prev = cur; cur = r.next;
       }
-      prev = cur; cur = r.next;
+      if (cnt <= 1) return;                                                             // no other level shows that price (always, while the ladder is sorted)
+      limit = pos;
     }
   }
 
@@ -790,7 +837,7 @@ struct Sim {
     double z_obs = one_block ? box_muller(blk.x, blk.y, blk.z) : rng.std_normal(stream, a.rng_ctr);
     if (one_block) rng.rec(stream, 'n', dbl_bits(z_obs));                               // draw log: the same three entries a tape would hold
     int32_t obs_t = (int32_t)py_round_i64(dadd((double)r_now, dmul(P.sqrt_sigma_n, z_obs)));
-    int q = (int)((double)a.shares / 100.0);                                            // :203 int(x / 100)
+    int q = a.shares / 100;                                                             // :203 int(x / 100): the correctly rounded fp64 quotient of two ints truncates to the C quotient (|x| < 2^31, remainder / 100 <= 0.99)
     int q_max = P.c.q_max; bool buy;
     if (q >= q_max) buy = false; else if (q <= -q_max) buy = true; else { buy = one_block ? (blk.z & 1u) != 0 : rng.randint(stream, a.rng_ctr, 1) != 0; if (one_block) rng.rec(stream, 'i', buy ? 1u : 0u); } // :205-213
     if (!(a.flags & AF_HAS_PREV)) { a.prev_wake = P.c.mkt_open_ns; a.flags |= AF_HAS_PREV; }         // :217-218
@@ -805,11 +852,12 @@ struct Sim {
     double r_tprime = dmul(dsub(1.0, pw0), r_bar);                                    // :229
     r_tprime = dadd(r_tprime, dmul(pw0, a.r_t));                                      // :230
     double sigma_tprime = dmul(pw1, a.sigma_t);                                       // :233
-    sigma_tprime = dadd(sigma_tprime, dmul(dsub(1.0, pw1) / P.sigma_denom, P.c.sigma_s)); // :234
+    sigma_tprime = dadd(sigma_tprime, dmul(ddiv(dsub(1.0, pw1), P.sigma_denom), P.c.sigma_s)); // :234
     double den = dadd(sigma_n, sigma_tprime);
-    double r_t = dmul(sigma_n / den, r_tprime);                                         // :239
-    r_t = dadd(r_t, dmul(sigma_tprime / den, (double)obs_t));                           // :240
+    double r_t = dmul(ddiv(sigma_n, den), r_tprime);                                    // :239
+    r_t = dadd(r_t, dmul(ddiv(sigma_tprime, den), (double)obs_t));                      // :240
     a.r_t = r_t;
+    if (a.sigma_t != 0.0)                                                               // sigma_t starts at 0 and 0 * sigma_n / (sigma_n + 0) is exactly 0: the division only runs if a caller seeds it otherwise
     a.sigma_t = dmul(sigma_n, a.sigma_t) / dadd(sigma_n, a.sigma_t);                    // :242
     double r_T = dmul(dsub(1.0, pw2), r_bar);                                         // :255
     r_T = dadd(r_T, dmul(pw2, a.r_t));                                                // :256
@@ -905,6 +953,7 @@ struct Sim {
       bool any = c.q_min(khi, kuniq, grp);
       if (!any || !(s.now <= P.c.stop_ns)) { s.flags |= ABX_F_DONE; break; }            // :190 tested BEFORE the pop
       if (key_time(khi) > until) break;
+      { int rid = key_recipient(khi); if (rid != 0) c.agent_load_issue(rid); }          // the recipient's record is on its way while the event is unpacked
       Event ev; c.q_fetch(grp, ev);                                                     // :192
       s.now = ev.t; s.ttl++;                                                            // :211
       if (INSTR && P.c.hash_pops) s.pop_hash = fnv_mix(fnv_mix(fnv_mix(fnv_mix(s.pop_hash, ev.t), ev.recipient), ev.type), ev.type == ABX_T_MESSAGE ? (int64_t)ev.uniq : -1);
@@ -922,7 +971,7 @@ struct Sim {
         if (ev.type == ABX_T_MESSAGE) exch_receive(ev);                                 // exchange WAKEUP: Agent.wakeup is a no-op
         s.exch_time += s.exch_comp_delay + addl_delay;                                  // :240-242 / :274-276
       } else {
-        z = c.agent_stage(id); regs_load(a, z);
+        z = c.agent_stage_issued(id); regs_load(a, z);
         if (a.agent_time > s.now) { c.q_requeue(a.agent_time); continue; }
         c.q_remove(); s.q_count--;
         a.agent_time = s.now; self_id = id;
@@ -965,31 +1014,38 @@ struct Sim {
   // ---- exchange additions: MODIFY_ORDER (util/OrderBook.py:341-372) ----
   ABX_HD void book_modify(uint32_t oid, int agent, int is_buy, int32_t price, int32_t new_price, int32_t new_qty) {
     int side = is_buy ? 0 : 1; int n = n_lv(side); if (n == 0) return;                  // :345-347
-    int pos; bool found; c.lv_find(side, price, n, pos, found);                         // :349 level whose head price equals the OLD order's price
-    if (!found) return;
-    uint32_t head = c.lv_head(side, pos); int matches = 0; bool scan = true;
-    if (oid >= REPLAY_ID_BASE) {                                                        // :350-351 "every node of the level carrying the id": from the census when it can tell
-      uint2 v = c.ib_load((int)(oid - REPLAY_ID_BASE)); uint32_t cnt = v.x & 0x7fffffffu;
-      if (cnt == 0) return;
-      if (!(v.x >> 31)) { if (v.y != (((uint32_t)price << 1) | (uint32_t)side)) return; matches = (int)cnt; scan = false; }
-    }
-    if (scan) {
-      uint32_t cur = head;
-#pragma unroll 1
-      while (cur != NIL) { NodeRec r = c.node_load(cur); if (r.id == oid) matches++; cur = r.next; }   // live scan of the level
-    }
-    if (matches == 0) return;
-    NodeRec hr = c.node_load(head);
-    c.lv_set(side, pos, c.lv_qty(side, pos) - hr.qty + new_qty, head, c.lv_tail(side, pos));
-    if (hr.id != oid) { ib_dec(hr.id); ib_inc(oid, side, price); }                      // the head slot changes identity
-    hr.id = oid; hr.qty = new_qty; hr.agent = (uint32_t)agent; c.node_store(head, hr);  // :352 book[i][0] = new_order  (slot 0, App. A-13)
-    if (new_price != price) s.flags |= ABX_F_UNSUPPORTED;                               // a re-priced head would unsort the ladder; never in LOBSTER replays
     int buckets = 0;                                                                    // :353-367 one ORDER_MODIFIED per history bucket holding the id
     if (oid >= REPLAY_ID_BASE) { uint4 t = c.ord_load((int)(oid - REPLAY_ID_BASE)); uint32_t d = s.trade_epoch - t.z; if (t.w != 0 && d <= (uint32_t)P.c.stream_history) buckets = __popc_compat(t.w & ((1u << (P.c.stream_history + 1 - d)) - 1u)); }
+    int limit = n;
 #pragma unroll 1
-    for (int k = 0; k < matches * buckets; k++) {
-      exch_send_order(agent, ABX_ORDER_MODIFIED, oid, new_price, new_qty, 0, is_buy, 0.0);
-      if (n_out >= Ctx::OUTN - 3) flush();
+    for (;;) {                                                                          // :348-349 every level, best first, whose slot-0 price equals the OLD order's price
+      int cnt; int pos = c.lv_find_eq(side, price, limit, cnt);
+      if (pos < 0) return;
+      uint32_t head = c.lv_head(side, pos); int matches = 0; bool scan = true;
+      if (oid >= REPLAY_ID_BASE && !(s.book_flags & BKF_REPRICED)) {                    // :350-351 "every node of the level carrying the id": from the census when it can tell
+        uint2 v = c.ib_load((int)(oid - REPLAY_ID_BASE)); uint32_t k = v.x & 0x7fffffffu;
+        if (k == 0) return;
+        if (!(v.x >> 31)) { if (v.y != (((uint32_t)price << 1) | (uint32_t)side)) return; matches = (int)k; scan = false; }
+      }
+      if (scan) {
+        uint32_t cur = head;
+#pragma unroll 1
+        while (cur != NIL) { NodeRec r = nload(cur); if (r.id == oid) matches++; cur = r.next; }   // live scan of the level
+      }
+      if (matches > 0) {
+        NodeRec hr = nload(head);
+        c.lv_set(side, pos, c.lv_qty(side, pos) - hr.qty + new_qty, head, c.lv_tail(side, pos));
+        if (hr.id != oid) { ib_dec(hr.id); ib_inc(oid, side, price); }                  // the head slot changes identity
+        hr.id = oid; hr.qty = new_qty; hr.agent = (uint32_t)agent; hr.price = new_price; nstore(head, hr);   // :352 book[i][0] = new_order  (slot 0, App. A-13)
+        if (new_price != price) { s.book_flags |= BKF_REPRICED; c.lv_setp(side, pos, new_price); }          // the level now shows the new price where it stands: no re-sorting (:381,393)
+#pragma unroll 1
+        for (int k = 0; k < matches * buckets; k++) {
+          exch_send_order(agent, ABX_ORDER_MODIFIED, oid, new_price, new_qty, 0, is_buy, 0.0);
+          if (n_out >= Ctx::OUTN - 3) flush();
+        }
+      }
+      if (cnt <= 1) return;
+      limit = pos;
     }
   }
   ABX_HD void env_exch_receive(const Event &m) {                                        // ExchangeAgent.receiveMessage :129-340
@@ -1440,6 +1496,9 @@ struct Sim {
       uint64_t khi; uint32_t kuniq; int grp;
       bool any = c.q_min(khi, kuniq, grp);
       if (!any || !(s.now <= P.c.stop_ns)) { s.flags |= ABX_F_DONE; break; }
+#ifdef ABX_OPT_EARLY2
+      { int rid = key_recipient(khi); if (rid > 1) c.agent_load_issue(rid); }
+#endif
       Event ev; c.q_fetch(grp, ev);
       s.now = ev.t; s.ttl++;
       if (INSTR && P.c.hash_pops) s.pop_hash = fnv_mix(fnv_mix(fnv_mix(fnv_mix(s.pop_hash, ev.t), ev.recipient), ev.type), ev.type == ABX_T_MESSAGE ? (int64_t)ev.uniq : -1);
@@ -1456,7 +1515,11 @@ struct Sim {
         if (id == 0) { if (ev.type == ABX_T_MESSAGE) env_exch_receive(ev); s.exch_time = s.now + s.exch_comp_delay + addl_delay; }
         else { if (ev.type == ABX_T_WAKEUP) replay_wakeup(x); else replay_receive(x, ev); if (c.onchip_writer()) x->ra_time = s.now + P.c.default_computation_delay_ns + addl_delay; }
       } else {
+#ifdef ABX_OPT_EARLY2
+        z = c.agent_stage_issued(id); regs_load(a, z);
+#else
         z = c.agent_stage(id); regs_load(a, z);
+#endif
         if (a.agent_time > s.now) { c.q_requeue(a.agent_time); continue; }
         c.q_remove(); s.q_count--; self_id = id;
         int type = (int)((a.flags & AF_TYPE_MASK) >> AF_TYPE_SHIFT);
@@ -1599,7 +1662,7 @@ struct Sim {
     double sigma_tprime = dmul(pw1, a.sigma_t); sigma_tprime = dadd(sigma_tprime, dmul(dsub(1.0, pw1) / P.sigma_denom, P.c.sigma_s));
     double den = dadd(sigma_n, sigma_tprime);
     double r_t = dmul(sigma_n / den, r_tprime); r_t = dadd(r_t, dmul(sigma_tprime / den, (double)obs_t)); a.r_t = r_t;
-    a.sigma_t = dmul(sigma_n, a.sigma_t) / dadd(sigma_n, a.sigma_t);
+    if (a.sigma_t != 0.0) a.sigma_t = dmul(sigma_n, a.sigma_t) / dadd(sigma_n, a.sigma_t);
     double r_T = dmul(dsub(1.0, pw2), r_bar); r_T = dadd(r_T, dmul(pw2, a.r_t));
     int32_t r_Ti = (int32_t)py_round_i64(r_T); a.prev_wake = s.now;
     bool buy; int32_t p;
@@ -1720,6 +1783,9 @@ struct Sim {
       bool any = c.q_min(khi, kuniq, grp);
       if (!any || !(s.now <= P.c.stop_ns)) { s.flags |= ABX_F_DONE; break; }
       if (key_time(khi) > until) break;
+#ifdef ABX_OPT_EARLY2
+      { int rid = key_recipient(khi); if (rid != 0) c.agent_load_issue(rid); }
+#endif
       Event ev; c.q_fetch(grp, ev);
       s.now = ev.t; s.ttl++;
       if (INSTR && P.c.hash_pops) s.pop_hash = fnv_mix(fnv_mix(fnv_mix(fnv_mix(s.pop_hash, ev.t), ev.recipient), ev.type), ev.type == ABX_T_MESSAGE ? (int64_t)ev.uniq : -1);
@@ -1735,7 +1801,11 @@ struct Sim {
         if (ev.type == ABX_T_MESSAGE) r3_exch_receive(ev);
         s.exch_time = s.now + s.exch_comp_delay + addl_delay;
       } else {
+#ifdef ABX_OPT_EARLY2
+        z = c.agent_stage_issued(id); regs_load(a, z);
+#else
         z = c.agent_stage(id); regs_load(a, z);
+#endif
         if (a.agent_time > s.now) { c.q_requeue(a.agent_time); continue; }
         c.q_remove(); s.q_count--; self_id = id;
         if (ev.type == ABX_T_WAKEUP) r3_wakeup(id); else r3_receive(id, ev);

@@ -83,7 +83,7 @@ static inline int config_validate(const abx_sim_config *c) {
   } else return ABX_ERR_ARG;
   if (n != c->n_agents) return ABX_ERR_ARG;
   if (c->queue_cap < 32 || c->queue_cap % 32 || c->queue_cap > 4096) return ABX_ERR_ARG;
-  if (c->level_cap < 8 || c->level_cap > 2048 || c->order_cap < 8 || c->order_cap > 65535) return ABX_ERR_ARG;
+  if (c->level_cap < 8 || c->level_cap > 2048 || c->level_cap % 4 || c->order_cap < 8 || c->order_cap > 65535) return ABX_ERR_ARG;   // level_cap % 4: the ladders are searched with 128-bit shared-memory loads
   if (c->stop_ns >= KEY_T_MAX || c->start_ns < 0 || c->mkt_close_ns >= KEY_T_MAX) return ABX_ERR_ARG;
   if (c->latency_model != ABX_LAT_MATRIX_NOISE && c->latency_model != ABX_LAT_CUBIC && c->latency_model != ABX_LAT_ZERO) return ABX_ERR_ARG;
   if (c->latency_model == ABX_LAT_MATRIX_NOISE && c->n_noise < 1) return ABX_ERR_ARG;
@@ -116,7 +116,7 @@ static inline int env_config_default(abx_env_config *c) {                       
 }
 static inline int env_config_validate(const abx_env_config *c) {
   if (!c || c->version != ABX_VERSION || c->order_level < 0 || c->order_level > 2 || c->n_horizon < 2) return ABX_ERR_ARG;
-  if (c->queue_cap < 32 || c->queue_cap % 32 || c->queue_cap > 4096 || c->level_cap < 8 || c->level_cap > 2048) return ABX_ERR_ARG;
+  if (c->queue_cap < 32 || c->queue_cap % 32 || c->queue_cap > 4096 || c->level_cap < 8 || c->level_cap > 2048 || c->level_cap % 4) return ABX_ERR_ARG;
   if (c->order_cap < 8 || c->order_cap > 65535 || c->stop_ns >= KEY_T_MAX || c->start_ns < 0 || c->horizon_step_ns <= 0) return ABX_ERR_ARG;
   if (c->stream_history < 0 || c->stream_history > 14 || !(c->quantity > 0) || c->trace_cap < 0) return ABX_ERR_ARG;
   return ABX_OK;
@@ -151,7 +151,7 @@ static inline int dq_config_default(abx_dq_config *c) {
 }
 static inline int dq_config_validate(const abx_dq_config *c) {
   if (!c || c->version != ABX_VERSION || c->n_momentum < 0 || c->n_momentum > 8 || c->n_twap < 0 || c->n_twap > 2 || c->n_horizon < 3) return ABX_ERR_ARG;
-  if (c->queue_cap < 32 || c->queue_cap % 32 || c->queue_cap > 4096 || c->level_cap < 8 || c->level_cap > 2048) return ABX_ERR_ARG;
+  if (c->queue_cap < 32 || c->queue_cap % 32 || c->queue_cap > 4096 || c->level_cap < 8 || c->level_cap > 2048 || c->level_cap % 4) return ABX_ERR_ARG;
   if (c->order_cap < 8 || c->order_cap > 65535 || c->stop_ns >= KEY_T_MAX || c->start_ns < 0 || c->horizon_step_ns <= 0 || c->mom_wake_ns <= 0) return ABX_ERR_ARG;
   if (c->queue_cap < 128) return ABX_ERR_ARG;                            // two-tier queue: the first two groups' slots belong to the on-chip tier
   if (c->stream_history < 0 || c->stream_history > 14 || c->quantity <= 0 || c->quantity > 0x3fffffffLL || c->trace_cap < 0 || c->mom_max_size <= c->mom_min_size) return ABX_ERR_ARG;

@@ -104,7 +104,7 @@ abx_finalize_kernel(SimParams P, size_t smem_per_warp) {
   if (env >= P.n_envs) return;
   WarpCtx ctx(P, env, smem + warp * smem_per_warp);
   EnvState s = env_load(P.env + env);
-  if (P.c.population == 1) { Sim<WarpCtx, -1, ABX_LAT_ZERO, false, SHAPE_R3> sim(ctx, P, s, env); sim.r3_finalize(); env_store(P.env + env, sim.s, ctx.lane); return; }
+  if (P.c.population == 1) { Sim<WarpCtx, -1, ABX_LAT_ZERO, true, SHAPE_R3> sim(ctx, P, s, env); sim.r3_finalize(); env_store(P.env + env, sim.s, ctx.lane); return; }   // INSTR: the ValueAgents' closing observations go to the draw log
   Sim<WarpCtx> sim(ctx, P, s, env);
   sim.finalize();
   env_store(P.env + env, sim.s, ctx.lane);

@@ -296,14 +296,48 @@ struct WarpCtxT {
     lvq[side * P.c.level_cap + i] = qty; lvht[side * P.c.level_cap + i] = head | (tail << 16);
     sync();
   }
+  // enterOrder's scan (util/OrderBook.py:271-282) on the best-last arrays: the level nearest the best whose price the order beats or equals.
+  // found: it equals (the order joins that level); otherwise pos is where the new level goes.  On a sorted ladder this is the sorted insert.
   __device__ __forceinline__ void lv_find(int side, int32_t price, int n, int &pos, bool &found) {
-    const int32_t *p = lvp + side * P.c.level_cap; int cnt = 0, fidx = -1;
+    const int32_t *p = lvp + side * P.c.level_cap; int best = -1;
+#ifdef ABX_OPT_VFIND
 #pragma unroll 1
-    for (int i = lane; i < n; i += 32) { int32_t v = p[i]; if (v == price) fidx = i; else if (side == 0 ? v < price : v > price) cnt++; }
-    cnt = __reduce_add_sync(FULL, cnt);
-    uint32_t fb = __ballot_sync(FULL, fidx >= 0);
-    if (fb) { found = true; pos = __shfl_sync(FULL, fidx, __ffs(fb) - 1); } else { found = false; pos = cnt; }
+    for (int i = lane * 4; i < n; i += 128) {                                  // four levels per lane and pass (128-bit shared loads; level_cap is a multiple of 4)
+      int4 v = *reinterpret_cast<const int4 *>(p + i);
+      if (side == 0 ? v.x <= price : v.x >= price) best = i;
+      if (i + 1 < n && (side == 0 ? v.y <= price : v.y >= price)) best = i + 1;
+      if (i + 2 < n && (side == 0 ? v.z <= price : v.z >= price)) best = i + 2;
+      if (i + 3 < n && (side == 0 ? v.w <= price : v.w >= price)) best = i + 3;
+    }
+#else
+#pragma unroll 1
+    for (int i = lane; i < n; i += 32) { int32_t v = p[i]; if (side == 0 ? v <= price : v >= price) best = i; }
+#endif
+    best = __reduce_max_sync(FULL, best);
+    if (n > 0 && (side == 0 ? p[0] > price : p[0] < price)) best = -1;        // :267-270 tested first: worse than the LAST level -> new last level, whatever stands before it
+    found = best >= 0 && p[best] == price; pos = found ? best : best + 1;
   }
+  // cancelOrder / modifyOrder (:306, :349): the level nearest the best, below index `limit`, whose price EQUALS `price` (-1: none);
+  // cnt = how many such levels there are (1 on a sorted ladder)
+  __device__ __forceinline__ int lv_find_eq(int side, int32_t price, int limit, int &cnt) {
+    const int32_t *p = lvp + side * P.c.level_cap; int best = -1, k = 0;
+#ifdef ABX_OPT_VFIND
+#pragma unroll 1
+    for (int i = lane * 4; i < limit; i += 128) {
+      int4 v = *reinterpret_cast<const int4 *>(p + i);
+      if (v.x == price) { best = i; k++; }
+      if (i + 1 < limit && v.y == price) { best = i + 1; k++; }
+      if (i + 2 < limit && v.z == price) { best = i + 2; k++; }
+      if (i + 3 < limit && v.w == price) { best = i + 3; k++; }
+    }
+#else
+#pragma unroll 1
+    for (int i = lane; i < limit; i += 32) if (p[i] == price) { best = i; k++; }
+#endif
+    cnt = __reduce_add_sync(FULL, k);
+    return __reduce_max_sync(FULL, best);
+  }
+  __device__ __forceinline__ void lv_setp(int side, int i, int32_t price) { sync(); lvp[side * P.c.level_cap + i] = price; sync(); }
   __device__ __forceinline__ void lv_insert(int side, int pos, int n, int32_t price, int32_t qty, uint32_t head, uint32_t tail) {
     int b = side * P.c.level_cap;
     sync();
@@ -330,8 +364,8 @@ struct WarpCtxT {
   }
 
   // ---- order nodes (HBM, 16 B each) ----
-  __device__ __forceinline__ NodeRec node_load(uint32_t i) const { uint4 v = ldcg4(nodes + i); NodeRec r; r.id = v.x; r.qty = (int32_t)v.y; r.agent = v.z; r.next = v.w; return r; }
-  __device__ __forceinline__ void node_store(uint32_t i, const NodeRec &r) { if (lane == 0) __stcg(nodes + i, make_uint4(r.id, (uint32_t)r.qty, r.agent, r.next)); __syncwarp(); }
+  template <bool PRICED> __device__ __forceinline__ NodeRec node_load(uint32_t i) const { return node_unpack<PRICED>(ldcg4(nodes + i)); }
+  template <bool PRICED> __device__ __forceinline__ void node_store(uint32_t i, const NodeRec &r) { if (lane == 0) __stcg(nodes + i, node_pack<PRICED>(r)); __syncwarp(); }
 
   // ---- ABIDESEnv shape ----
   __device__ __forceinline__ EnvX *envx() const { return ex; }
@@ -419,6 +453,19 @@ struct WarpCtxT {
     if (lane < (int)(sizeof(ZiAgent) / 16)) reinterpret_cast<uint4 *>(staged)[lane] = ldcg4(reinterpret_cast<const uint4 *>(agents + id) + lane);
     xsync();                                                                 // 12 lanes staged 16 bytes each; every lane reads the whole record
     return staged;
+  }
+  // the same copy in two halves: issue the 128-bit loads as soon as the recipient is known, park them in shared memory once the event is unpacked
+  uint4 pre_v;
+  __device__ __forceinline__ void agent_load_issue(int id) { if (lane < (int)(sizeof(ZiAgent) / 16)) pre_v = ldcg4(reinterpret_cast<const uint4 *>(agents + id) + lane); }
+  __device__ __forceinline__ ZiAgent *agent_stage_issued(int) {
+    sync();
+    if (lane < (int)(sizeof(ZiAgent) / 16)) reinterpret_cast<uint4 *>(staged)[lane] = pre_v;
+    xsync();
+    return staged;
+  }
+  __device__ __forceinline__ void agent_prefetch(int id) const {
+    const char *p = reinterpret_cast<const char *>(agents + id);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
   }
   __device__ __forceinline__ void agent_commit(int id) {
     __syncwarp();

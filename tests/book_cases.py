@@ -64,9 +64,10 @@ def recorded_tape(golden_dir, fixture, n_ops, lib_path=None, n_envs=2):
     return int((ref[:, 2] == EXEC).sum()) // 2, int((ops[:, 1] == 2).sum())
 
 
-def random_tape_vs_oracle(lib_path=None, seed=0, n_ops=6000, n_ids=40):
+def random_tape_vs_oracle(lib_path=None, seed=0, n_ops=6000, n_ids=40, reprice=0.0):
     """Adversarial tape: few order ids re-used across prices and sides, so that head-slot copies (modifyOrder's slot-0 overwrite), ids resting
-    in several levels and modifies / cancels at stale prices all occur; every notification and the book after every operation must equal
+    in several levels and modifies / cancels at stale prices all occur; with reprice > 0 a share of the modifies changes the price, which
+    leaves the reference's level lists unsorted and several levels showing one price (util/OrderBook.py:350-352,381,393); every notification and the book after every operation must equal
     the oracle book's (which is pinned to the reference)."""
     rs = np.random.RandomState(seed)
     ops, t = [], T0
@@ -76,9 +77,10 @@ def random_tape_vs_oracle(lib_path=None, seed=0, n_ops=6000, n_ids=40):
         oid, is_buy = int(rs.randint(1, n_ids + 1)), int(rs.randint(0, 2))
         price = 1000 + int(rs.randint(-6, 7)) + (0 if is_buy else 2)
         qty = int(rs.randint(1, 60))
-        ops.append(op(t, int(kind), int(rs.randint(1, 9)), oid, is_buy, price, qty, price, int(rs.randint(1, 60))))
+        new_price = price + int(rs.randint(-3, 4)) if rs.uniform() < reprice else price       # a re-pricing MODIFY: the head slot takes the new price where it stands
+        ops.append(op(t, int(kind), int(rs.randint(1, 9)), oid, is_buy, price, qty, new_price, int(rs.randint(1, 60))))
     ops = np.array(ops, dtype=np.int64)
-    b = OrderBookBatch(n_envs=2, trace_cap=16 * n_ops, level_cap=64, order_cap=8192, lib_path=lib_path)
+    b = OrderBookBatch(n_envs=2, trace_cap=16 * n_ops, level_cap=64 if reprice == 0 else 512, order_cap=8192, lib_path=lib_path)       # unsorted level lists keep many more levels alive
     b.replay(ops)
     notes, snaps = b.notifications(1)
     o = OracleBook(stream_history=10)
@@ -99,3 +101,54 @@ def random_tape_vs_oracle(lib_path=None, seed=0, n_ops=6000, n_ids=40):
     assert (b.stats()["flags"] == 1).all()
     b.close()
     return int((ref[:, 2] == MOD).sum()), int((ref[:, 2] == EXEC).sum())
+
+
+def make_tape(seed, n_ops, n_ids, reprice):
+    """The generator of random_tape_vs_oracle, as tools/record_reference_book_tape.py uses it."""
+    rs = np.random.RandomState(seed)
+    ops, t = [], T0
+    for _ in range(n_ops):
+        t += int(rs.randint(0, 3))
+        kind = rs.choice(3, p=[0.5, 0.15, 0.35])
+        oid, is_buy = int(rs.randint(1, n_ids + 1)), int(rs.randint(0, 2))
+        price = 1000 + int(rs.randint(-6, 7)) + (0 if is_buy else 2)
+        qty = int(rs.randint(1, 60))
+        new_price = price + int(rs.randint(-3, 4)) if rs.uniform() < reprice else price
+        ops.append(op(t, int(kind), int(rs.randint(1, 9)), oid, is_buy, price, qty, new_price, int(rs.randint(1, 60))))
+    return np.array(ops, dtype=np.int64)
+
+
+def reprice_golden(golden_dir, lib_path=None, use_oracle=False):
+    """tests/golden/book_reprice_tapes.npz: three adversarial tapes with re-pricing modifies run through the LIVE reference util/OrderBook.py
+    (tools/record_reference_book_tape.py).  Every notification and the book after every operation must equal the reference's -- for the oracle
+    book (use_oracle) or for the product's books (CUDA library / its CPU emulation)."""
+    g = np.load(os.path.join(golden_dir, "book_reprice_tapes.npz"))
+    total_mod = 0
+    for seed in (0, 2, 4):
+        _, n_ops, n_ids, rp = (int(x) for x in g["params_s%d" % seed])
+        ops = make_tape(seed, n_ops, n_ids, rp / 100.0)
+        ref_notes, ref_snaps = g["notes_s%d" % seed], g["snaps_s%d" % seed]
+        if use_oracle:
+            o = OracleBook(stream_history=10)
+            snaps = []
+            for r in ops:
+                o.set_time(int(r[0]))
+                if r[1] == 0:
+                    o.limit(int(r[2]), int(r[3]), bool(r[4]), int(r[5]), int(r[6]))
+                elif r[1] == 1:
+                    o.cancel(int(r[2]), int(r[3]), bool(r[4]), int(r[5]))
+                else:
+                    o.modify(int(r[2]), int(r[3]), bool(r[4]), int(r[5]), int(r[7]), int(r[8]))
+                snaps.append((o.n_levels(True), o.n_levels(False), o.n_resting()) + tuple(x for pq in (o.inside(True, 3) + [(0, 0)] * 3)[:3] for x in pq)
+                             + tuple(x for pq in (o.inside(False, 3) + [(0, 0)] * 3)[:3] for x in pq) + (o.last_trade if o.last_trade is not None else -1,))
+            notes, snaps = o.take_notes(), np.array(snaps, dtype=np.int64)
+        else:
+            b = OrderBookBatch(n_envs=2, trace_cap=16 * n_ops, level_cap=256, order_cap=8192, lib_path=lib_path)
+            b.replay(ops)
+            notes, snaps = b.notifications(1)
+            assert (b.stats()["flags"] == 1).all()
+            b.close()
+        assert notes.shape == ref_notes.shape and np.array_equal(notes[:, :8], ref_notes[:, :8]), (seed, notes.shape, ref_notes.shape)
+        assert np.array_equal(snaps, ref_snaps), seed
+        total_mod += int((ref_notes[:, 2] == MOD).sum())
+    return total_mod

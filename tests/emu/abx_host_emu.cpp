@@ -64,9 +64,13 @@ struct HostCtx {
   uint32_t lv_tail(int side, int i) { return lvht[side * P.c.level_cap + i] >> 16; }
   void lv_set(int side, int i, int32_t qty, uint32_t head, uint32_t tail) { lvq[side * P.c.level_cap + i] = qty; lvht[side * P.c.level_cap + i] = head | (tail << 16); }
   void lv_find(int side, int32_t price, int n, int &pos, bool &found) {
-    pos = 0; found = false;
-    for (int i = 0; i < n; i++) { int32_t p = lv_price(side, i); if (p == price) { found = true; pos = i; return; } if (side == 0 ? p < price : p > price) pos = i + 1; }
+    int best = -1;
+    for (int i = 0; i < n; i++) { int32_t p = lv_price(side, i); if (side == 0 ? p <= price : p >= price) best = i; }
+    if (n > 0 && (side == 0 ? lv_price(side, 0) > price : lv_price(side, 0) < price)) best = -1;
+    found = best >= 0 && lv_price(side, best) == price; pos = found ? best : best + 1;
   }
+  int lv_find_eq(int side, int32_t price, int limit, int &cnt) { int best = -1; cnt = 0; for (int i = 0; i < limit; i++) if (lv_price(side, i) == price) { best = i; cnt++; } return best; }
+  void lv_setp(int side, int i, int32_t price) { lvp[side * P.c.level_cap + i] = price; }
   void lv_insert(int side, int pos, int n, int32_t price, int32_t qty, uint32_t head, uint32_t tail) {
     int b = side * P.c.level_cap;
     for (int i = n; i > pos; i--) { lvp[b + i] = lvp[b + i - 1]; lvq[b + i] = lvq[b + i - 1]; lvht[b + i] = lvht[b + i - 1]; }
@@ -74,8 +78,8 @@ struct HostCtx {
   }
   void lv_remove(int side, int pos, int n) { int b = side * P.c.level_cap; for (int i = pos; i + 1 < n; i++) { lvp[b + i] = lvp[b + i + 1]; lvq[b + i] = lvq[b + i + 1]; lvht[b + i] = lvht[b + i + 1]; } }
   // ---- order nodes ----
-  NodeRec node_load(uint32_t i) { uint4 v = nodes[i]; NodeRec r; r.id = v.x; r.qty = (int32_t)v.y; r.agent = v.z; r.next = v.w; return r; }
-  void node_store(uint32_t i, const NodeRec &r) { uint4 v; v.x = r.id; v.y = (uint32_t)r.qty; v.z = r.agent; v.w = r.next; nodes[i] = v; }
+  template <bool PRICED> NodeRec node_load(uint32_t i) { return node_unpack<PRICED>(nodes[i]); }
+  template <bool PRICED> void node_store(uint32_t i, const NodeRec &r) { nodes[i] = node_pack<PRICED>(r); }
   // ---- ABIDESEnv shape ----
   EnvX *envx() { return P.envx + env; }
   uint2 ib_load(int i) { return P.idbook[(size_t)env * P.n_ids + i]; }
@@ -104,6 +108,7 @@ struct HostCtx {
   }
   // ---- agents ----
   ZiAgent *agent_stage(int id) { staged = agents[id]; return &staged; }
+  void agent_load_issue(int) {} ZiAgent *agent_stage_issued(int id) { return agent_stage(id); } void agent_prefetch(int) {}
   void agent_commit(int id) { agents[id] = staged; }
   double agent_lat_from(int id) { return agents[id].lat_from; }
 };

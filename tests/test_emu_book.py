@@ -26,6 +26,16 @@ def test_adversarial_tape(emu, seed):
     assert mods > 200 and execs > 500
 
 
+@pytest.mark.parametrize("seed,reprice", [(0, 0.3), (1, 0.6), (2, 1.0), (3, 0.1), (4, 0.5), (5, 0.8)])
+def test_adversarial_tape_with_repricing_modifies(emu, seed, reprice):
+    mods, execs = book_cases.random_tape_vs_oracle(emu, seed=seed, reprice=reprice)
+    assert mods > 100 and execs > 300
+
+
+def test_repricing_modifies_match_the_live_reference(emu, golden_dir):
+    assert book_cases.reprice_golden(golden_dir, emu) > 300
+
+
 def test_reference_method_names(emu):
     """KAT-1 spelled with the reference's own calls: OrderBook.handleLimitOrder / modifyOrder / cancelOrder / getInsideBids /
     getInsideAsks / last_trade (util/OrderBook.py:38,284,341,377-398)."""

@@ -22,3 +22,15 @@ def test_recorded_operation_tape(golden_dir, fixture, n_ops):
 def test_adversarial_tape(seed):
     mods, execs = book_cases.random_tape_vs_oracle(seed=seed, n_ops=20000)
     assert mods > 500 and execs > 1500
+
+
+@pytest.mark.parametrize("seed,reprice", [(0, 0.3), (2, 1.0), (7, 0.6)])
+def test_adversarial_tape_with_repricing_modifies(seed, reprice):
+    """MODIFY_ORDER with a new price: slot 0 of the level takes the new order where it stands, the level shows the new price, the level lists go
+    unsorted and several levels may show one price (util/OrderBook.py:350-352,381,393) -- every notification and book snapshot equal to the oracle's."""
+    mods, execs = book_cases.random_tape_vs_oracle(seed=seed, n_ops=12000, reprice=reprice)
+    assert mods > 300 and execs > 800
+
+
+def test_repricing_modifies_match_the_live_reference(golden_dir):
+    assert book_cases.reprice_golden(golden_dir) > 300

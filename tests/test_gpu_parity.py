@@ -154,3 +154,36 @@ def test_rmsc03_with_pov_execution_agent_tape_replay():
         assert np.array_equal(p, o.trace("pops")) and np.array_equal(nt, o.trace("notes")) and np.array_equal(sn, o.trace("snaps"))
         assert np.array_equal(sim.holdings(e)[:, :4], o.holdings()[:, :4]) and np.array_equal(sim.pov_exec(e), o.pov_exec())
     assert (st["sum_shares"] == 0).all() and (st["sum_cash"] == 64 * 10 ** 7).all()
+
+
+# ---- parametrised parity: the oracle and the CUDA simulator built from the SAME mutated abx_sim_config (tests/param_cases.py) ----
+from helpers import assert_env_equals_oracle       # noqa: E402
+from param_cases import RMSC03_CASES, SPARSE_ZI_CASES   # noqa: E402
+
+
+def _run_param_case(cfg, seed, holdings_cols):
+    o = OracleSim.from_config(cfg, seed, TRACE_ALL)
+    n = o.run()
+    sim = BatchedSim(cfg, 3)
+    sim.reset_tape(*oracle_tapes([o, o, o]))
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    for e in range(3):
+        assert_env_equals_oracle(sim, e, o, n, st, traces=(e == 2), holdings_cols=holdings_cols)
+    return n
+
+
+@pytest.mark.parametrize("variant,mutate,seed", SPARSE_ZI_CASES, ids=lambda v: getattr(v, "__name__", str(v)))
+def test_sparse_zi_non_default_parameters(variant, mutate, seed):
+    cfg = sparse_zi_config(variant, rng_mode=_lib.RNG_TAPE, trace_cap=1500000 if variant == 1000 else 200000, hash_pops=1)
+    mutate(cfg)
+    assert _run_param_case(cfg, seed, 5) > 3000
+
+
+@pytest.mark.parametrize("pov,mutate,seed", RMSC03_CASES, ids=lambda v: getattr(v, "__name__", str(v)))
+def test_rmsc03_non_default_parameters(pov, mutate, seed):
+    from marl_optimal_execution_b200.sim import rmsc03_config
+    cfg = rmsc03_config(pov_exec=pov, rng_mode=_lib.RNG_TAPE, trace_cap=700000, hash_pops=1)
+    mutate(cfg)
+    assert _run_param_case(cfg, seed, 4) > 5000

@@ -55,3 +55,10 @@ def test_transacted_volume_dedup():
     b.limit(2, 2, True, 100, 50)                     # one fill: incoming records its pre-fill qty 50, resting records 50
     # both sides log (1000, 50): duplicates collapse (util/OrderBook.py:428)
     assert b.transacted_volume(10 ** 9) == 50
+
+
+def test_repricing_modifies_match_the_live_reference(golden_dir):
+    """Re-pricing MODIFY_ORDER (util/OrderBook.py:350-352: slot 0 takes the new order where the level stands; level prices are read from slot 0,
+    :381,393; the lists go unsorted): the oracle book against three tapes recorded from the live reference OrderBook."""
+    import book_cases
+    assert book_cases.reprice_golden(golden_dir, use_oracle=True) > 300
