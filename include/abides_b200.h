@@ -61,8 +61,11 @@ enum abx_latency_model {
 #define ABX_F_TAPE_KIND       0x080u /* tape entry kind differs from the draw the simulator asked for */
 #define ABX_F_TRACE_OVERFLOW  0x100u
 #define ABX_F_TIME_RANGE      0x200u
-#define ABX_F_UNSUPPORTED     0x400u /* a reference behaviour this build does not model was hit (e.g. re-pricing MODIFY) */
+#define ABX_F_UNSUPPORTED     0x400u /* a reference behaviour this build does not model was hit (no code path sets it since round 2; kept for ABI stability) */
 #define ABX_F_OBS_INVALID     0x800u /* get_observation would have raised in the reference (empty side / no stored LOB) */
+#define ABX_F_HISTORY_OVERFLOW 0x1000u /* the ring of transaction tuples behind get_transacted_volume overwrote one that could still count */
+#define ABX_F_REF_EXCEPTION   0x2000u /* the reference would have raised: KeyError of MarketReplayAgent.wakeup off a stream timestamp, IndexError of take_action below 4 levels */
+#define ABX_F_ID_RANGE        0x4000u /* generated order ids reached the replayed stream's explicit ORDER_IDs (the range abx_*_create checked was exceeded) */
 
 /* One ZeroIntelligenceAgent strategy group: config/sparse_zi_1000.py:196-204 tuples (n, R_min, R_max, eta). */
 typedef struct abx_zi_group {
@@ -273,6 +276,14 @@ int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_
 int32_t abx_env_create_days(const abx_env_config *cfg, const int64_t *stream5, const int64_t *row_offsets, int32_t n_days, int32_t n_envs, int32_t device, abx_sim **out);
 /* Replaces: ABIDESEnv.reset() (ABIDESEnv.py:51-57): initAgents + GymKernel.initRunner. */
 int32_t abx_env_reset(abx_sim *h, void *stream);
+/* ABIDESEnv.reset() of SOME environments (the reference's reset is per environment object, ABIDESEnv.py:51-57): mask_dev is a DEVICE uint8 [n_envs],
+ * environments with a non-zero entry start a fresh episode; advance_day != 0 moves each of them on to its next replayed day (environment e replays
+ * day (e + resets so far) % n_days -- the date sweep of config/execution/marketreplay/..._parallel.py), 0 restarts the same day.  Works on
+ * abx_env_create* and abx_dq_create* handles (the DDQN shape re-draws its MomentumAgent sizes from seed + episode unless sizes were supplied). */
+int32_t abx_env_reset_mask(abx_sim *h, const uint8_t *mask_dev, int32_t advance_day, void *stream);
+/* Auto-reset: after every abx_env_step / abx_dq_step the environments whose event loop has ended (done == 1 in that step's output) are reset
+ * before the next step.  mode 0 off (default), 1 restart the same day, 2 move on to the next day. */
+int32_t abx_env_set_auto_reset(abx_sim *h, int32_t mode);
 /* Replaces: ABIDESEnv.step(action) (ABIDESEnv.py:30-49) -> GymKernel.stepRunner (GymKernel.py:158-306) for every environment.
  * DEVICE pointers: actions fp64 [n_envs][3] (x_hat, o_hat_1, o_hat_2), obs fp64 [n_envs][9] (zeros when the reference
  * would return []), reward fp64 [n_envs] (0: the reference's get_reward returns None), done uint8 [n_envs]. */

@@ -17,7 +17,8 @@ LAT_MATRIX_NOISE, LAT_CUBIC = 0, 1
 F_DONE, F_QUEUE_OVERFLOW, F_LEVEL_OVERFLOW, F_ORDER_OVERFLOW, F_AGENT_ORDERS_OVERFLOW = 0x1, 0x2, 0x4, 0x8, 0x10
 F_THETA_INDEX, F_TAPE_UNDERRUN, F_TAPE_KIND, F_TRACE_OVERFLOW, F_TIME_RANGE = 0x20, 0x40, 0x80, 0x100, 0x200
 F_UNSUPPORTED, F_OBS_INVALID = 0x400, 0x800
-F_ERROR_MASK = 0xFFE
+F_HISTORY_OVERFLOW, F_REF_EXCEPTION, F_ID_RANGE = 0x1000, 0x2000, 0x4000
+F_ERROR_MASK = 0x7FFE
 
 MSG_KINDS = [
     "NONE", "WHEN_MKT_OPEN", "WHEN_MKT_CLOSE", "QUERY_SPREAD", "LIMIT_ORDER", "CANCEL_ORDER", "MODIFY_ORDER",
@@ -157,6 +158,8 @@ def _bind(L):
     sig("abx_env_create_days", i32, P(EnvConfig), P(i64), P(i64), i32, i32, i32, P(vp))
     sig("abx_dq_create_days", i32, P(DqConfig), P(i64), P(i64), i32, i32, i32, P(vp))
     sig("abx_env_reset", i32, vp, vp)
+    sig("abx_env_reset_mask", i32, vp, vp, i32, vp)
+    sig("abx_env_set_auto_reset", i32, vp, i32)
     sig("abx_env_step", i32, vp, vp, vp, vp, vp, vp)
     sig("abx_env_step_host", i32, vp, vp, vp, vp, vp, vp)
     sig("abx_book_create", i32, i32, i32, i32, i32, i32, i32, P(vp))

@@ -29,6 +29,7 @@
 
 #if !defined(__CUDACC__)
 struct alignas(8) uint2 { uint32_t x, y; };
+struct alignas(8) int2 { int32_t x, y; };
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
 struct alignas(16) int4 { int32_t x, y, z, w; };
 inline float cospif(float x) { return (float)cos(3.14159265358979323846 * (double)x); }
@@ -52,7 +53,7 @@ struct alignas(16) EnvState {           // 192 B per environment
   uint32_t ctr_kernel, ctr_latency, ctr_global, trade_epoch;   // trade_epoch: OrderBook.history rotations (util/OrderBook.py:146)
   int64_t sum_shares, sum_cash;
   uint32_t kblk[4];                     // cached Philox block of the kernel (latency-noise) stream
-  uint32_t draw_n, evt_n, book_flags, pad_b; // entries in the draw log (parity runs) / in the LAST_TRADE, BEST_BID, BEST_ASK event ring; BKF_*
+  uint32_t draw_n, evt_n, book_flags, episode; // entries in the draw log (parity runs) / in the LAST_TRADE, BEST_BID, BEST_ASK event ring; BKF_*; resets of this environment that moved on to the next replayed day
 };
 static_assert(sizeof(EnvState) == 208, "EnvState layout");
 
@@ -90,7 +91,7 @@ struct ExecAux {
   int32_t pp_last2, child_qty, exflags, e_a;            // 2 * price_path[-1]; schedule quantity; EXF_*; experience[t-1] action
   int16_t cur_s[2], sp[2];                              // self.s; s' of the pending decision
   int16_t e_s[2], e_sp[2];                              // experience[t-1] = (s, a, s', r)
-  int32_t tv, pad0;                                     // POVExecutionAgent: transacted_volume[symbol]
+  int32_t tv, snap_n;                                   // POVExecutionAgent: transacted_volume[symbol]; levels in the agent's cached book: bids | asks << 16 (known_bids / known_asks of the last QUERY_SPREAD reply)
   double e_r, step_reward;                              // r (valid with EXF_E_R); sum of step_reward_hist entries since the last decision
 };
 static_assert(sizeof(ExecAux) == 88 && sizeof(ExecAux) <= 112, "ExecAux overlays ZiAgent.oid .. surplus");
@@ -99,7 +100,7 @@ constexpr int EXEC_ORDER_CAP = 512;     // self.orders of one execution agent
 constexpr int DQ_DEPTH = 500;           // getCurrentSpread(depth=500) execution_agent.py:77, ddqlearning_execution_agent.py:152
 enum : uint32_t { MMF_AW_SPREAD = 1u, MMF_AW_VOL = 2u, MMF_HAS_MID = 4u, MOF_HAS20 = 8u, MOF_HAS50 = 16u };
 constexpr int MM_ORDER_CAP = 128;       // POV market maker: 2 * (num_ticks + 1) = 42 orders placed per wake, cancelled at the next
-constexpr int TV_RING = 512;            // recent (time, qty) transaction tuples kept for get_transacted_volume
+constexpr int TV_RING_MIN = 512;        // recent (time, qty) transaction tuples kept for get_transacted_volume: SimParams.tv_ring >= this, 64 per surviving history bucket
 constexpr int MOM_MIDS = 64;            // MomentumAgent: last 50 mid prices are all ma(20)/ma(50) need
 
 struct Event {                          // one PriorityQueue entry, unpacked
@@ -175,6 +176,10 @@ struct SimParams {
   int32_t dq_n_mom, dq_n_twap, dq_has_ddqn, dq_order_base;   // dq_order_base: first idtab entry of the execution agents' order tables
   int64_t dq_quantity;                              // parent order size
   int64_t dq_id_limit;                              // smallest explicit ORDER_ID of the replayed stream: generated ids must stay below it
+  // ---- deep QUERY_SPREAD replies (depth 500 / sys.maxsize: the execution agents): the exchange copies the first snap_depth levels of both sides into the
+  // asking agent's area when it PROCESSES the query (agent/ExchangeAgent.py:231-245); the agent reads that copy, not the live ladders ----
+  int2 *snap;                                       // [n_envs][n_snap][2][snap_depth] {price, qty}, best level first
+  int32_t snap_depth, n_snap, tv_ring, pad_s;       // tv_ring: entries of the transaction-tuple ring (rmsc03 population), a power of two sized from stream_history
 };
 constexpr int LOB_CAP = 100;                        // ABIDESEnvMetrics(maxlen = 100) dummy_rl_execution_agent.py:125
 constexpr int RL_ORDER_CAP = 8;
@@ -259,6 +264,26 @@ ABX_NI U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
 }
 ABX_NI double exp_ni(double x) { return exp(x); }
 ABX_NI double log_ni(double x) { return log(x); }
+// exp(x) where the simulators' arguments live: the belief update's (1 - kappa) ** delta = exp(delta * log(1 - kappa)) has |x| <= 0.1 over a whole day and
+// the OU decay between two consecutive observations |x| ~ 1e-3, so a degree-12 series (truncation < 1.3e-16 at |x| = 0.25, below half an ulp of the result)
+// serves them with twelve FMAs and the 200-instruction libm body stays out of the hot loop (it is called beyond 0.25: the first observation of a day, gaps
+// of hours).  Like libm's, the result is within an ulp of the true value, which is all the int(round(.)) consumers need.
+#ifdef ABX_EXPS_INLINE
+ABX_HD
+#else
+ABX_NI                                                                                 // ONE body: inlined at its four call sites the series costs more instruction-cache than it saves (A/B: -15 % msgs/s)
+#endif
+double exp_fast(double x) {
+#if defined(__CUDA_ARCH__) && !defined(ABX_NO_EXPS)
+  if (fabs(x) <= 0.25) {
+    double p = 1.0 / 479001600.0;
+    p = fma(p, x, 1.0 / 39916800.0); p = fma(p, x, 1.0 / 3628800.0); p = fma(p, x, 1.0 / 362880.0); p = fma(p, x, 1.0 / 40320.0); p = fma(p, x, 1.0 / 5040.0);
+    p = fma(p, x, 1.0 / 720.0); p = fma(p, x, 1.0 / 120.0); p = fma(p, x, 1.0 / 24.0); p = fma(p, x, 1.0 / 6.0); p = fma(p, x, 0.5); p = fma(p, x, 1.0); p = fma(p, x, 1.0);
+    return p;
+  }
+#endif
+  return exp(x);
+}
 // log(x), x in (0, 1] and normal, for the Philox-mode variate transforms only (no parity constraint): fp64 throughout, relative error
 // < 1e-11 (checked against libm by tests/test_gpu_philox.py through abx_selftest_log_unit).  x = 2^e * m with m in [sqrt(1/2), sqrt(2)],
 // log(m) = 2 atanh(s), s = (m - 1) / (m + 1), seven terms of the series (|s| <= 0.1716), the quotient through a refined MUFU reciprocal.
@@ -285,11 +310,6 @@ ABX_NI double box_muller(uint32_t a, uint32_t b, uint32_t cw) {                 
   return sqrt(-2.0 * log_unit(u1)) * (double)cospif(ang);
 }
 ABX_NI double pow_ni(double x, double y) { return pow(x, y); }
-#ifdef ABX_OPT_DDIV
-ABX_NI double ddiv(double a, double b) { return a / b; }                                 // one IEEE division body for the belief update's three quotients
-#else
-ABX_HD double ddiv(double a, double b) { return a / b; }
-#endif
 enum { S_SYMBOL = 0, S_KERNEL = 1, S_LATENCY = 2, S_GLOBAL = 3, S_AGENT0 = 3 };  // agent a uses stream S_AGENT0 + a
 
 // MODE: ABX_RNG_PHILOX / ABX_RNG_TAPE fixed at compile time (one kernel instantiation per mode), or -1 = read P->c.rng_mode
@@ -383,7 +403,7 @@ ABX_HD void init_agent_record_r3(const SimParams &P, int env, int id, uint64_t s
   z->lat_to = 0.0; z->lat_from = 0.0; z->surplus = 0;
   if (type == AT_POVEXEC) {                                                           // POVExecutionAgent.__init__ (pov_agent.py:34-48)
     ExecAux ex; ex.rem_qty = (int32_t)P.c.pov_exec_quantity; ex.executed_sum = 0; ex.n_executed = 0; ex.arr2 = 0; ex.t = 0; ex.rem_time = 0; ex.n_pp = 0; ex.pp0_2 = 0; ex.pp_last2 = 0; ex.child_qty = 0;
-    ex.exflags = EXF_TRADE; ex.e_a = 0; for (int i = 0; i < 2; i++) { ex.cur_s[i] = 0; ex.sp[i] = 0; ex.e_s[i] = 0; ex.e_sp[i] = 0; } ex.tv = 0; ex.pad0 = 0; ex.e_r = 0.0; ex.step_reward = 0.0;
+    ex.exflags = EXF_TRADE; ex.e_a = 0; for (int i = 0; i < 2; i++) { ex.cur_s[i] = 0; ex.sp[i] = 0; ex.e_s[i] = 0; ex.e_sp[i] = 0; } ex.tv = 0; ex.snap_n = 0; ex.e_r = 0.0; ex.step_reward = 0.0;
     *reinterpret_cast<ExecAux *>(z->oid) = ex;
   }
   if (rng.err) *err |= rng.err;
@@ -429,7 +449,7 @@ ABX_HD void init_agent_record_dq(const SimParams &P, int env, int id, uint64_t s
   } else {
     ExecAux ex; ex.rem_qty = (int32_t)P.dq_quantity; ex.executed_sum = 0; ex.n_executed = 0; ex.arr2 = 0; ex.t = 0; ex.rem_time = P.n_h - 1; ex.n_pp = 0; ex.pp0_2 = 0; ex.pp_last2 = 0;
     ex.child_qty = type == AT_DDQN ? (int32_t)((double)P.dq_quantity / (double)(P.n_h - 1)) : (int32_t)((double)P.dq_quantity / (double)P.n_h);
-    ex.exflags = EXF_TRADE; ex.e_a = 0; for (int i = 0; i < 2; i++) { ex.cur_s[i] = 0; ex.sp[i] = 0; ex.e_s[i] = 0; ex.e_sp[i] = 0; } ex.tv = 0; ex.pad0 = 0; ex.e_r = 0.0; ex.step_reward = 0.0;
+    ex.exflags = EXF_TRADE; ex.e_a = 0; for (int i = 0; i < 2; i++) { ex.cur_s[i] = 0; ex.sp[i] = 0; ex.e_s[i] = 0; ex.e_sp[i] = 0; } ex.tv = 0; ex.snap_n = 0; ex.e_r = 0.0; ex.step_reward = 0.0;
     *reinterpret_cast<ExecAux *>(z->oid) = ex;
   }
   z->flags = ((uint32_t)type << AF_TYPE_SHIFT) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT); z->rng_ctr = ctr;
@@ -441,7 +461,7 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
   s.uniq = 0; s.next_order_id = 0; s.q_count = 0; s.max_q = 0; s.n_bid_lv = s.n_ask_lv = 0; s.n_resting = 0; s.free_head = NIL;
   s.pool_top = 0; s.flags = 0; s.trace_n = 0; s.c_limit = s.c_cancel = s.c_fills = s.c_query = 0;
   s.ctr_symbol = s.ctr_kernel = s.ctr_latency = s.ctr_global = 0; s.trade_epoch = 16; s.sum_shares = 0; s.sum_cash = 0;
-  s.kblk[0] = s.kblk[1] = s.kblk[2] = s.kblk[3] = 0; s.draw_n = 0; s.evt_n = 0; s.book_flags = 0; s.pad_b = 0;
+  s.kblk[0] = s.kblk[1] = s.kblk[2] = s.kblk[3] = 0; s.draw_n = 0; s.evt_n = 0; s.book_flags = 0; s.episode = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -461,14 +481,6 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
 constexpr int OUT_CAP = 24, OUT_WORDS = 12;     // 24 x 48 B in the replay shapes (the DDQN agent's closing market order flushes in batches); the sparse_zi shape, whose handlers emit at most three messages, keeps 8 (Ctx::OUTN)
 enum : uint32_t { OF_WAKEUP = 1u << 24, OF_BUMP_UNIQ = 1u << 25, OF_FROM_EXCH = 1u << 26, OF_CANCEL_EVT = 1u << 27 };
 
-#if defined(__CUDA_ARCH__)
-// one out-of-line body for the twenty inlined outbox writes (values in, nothing address-taken)
-ABX_NI void emit_store(uint32_t *o, uint32_t w0, int32_t p0, int32_t p1, int32_t p2, int32_t p3, int32_t p4, int32_t p5, double lat, int64_t off) {
-  uint64_t lb = dbl_bits(lat); uint4 *o4 = reinterpret_cast<uint4 *>(o);
-  o4[0] = make_uint4(w0, (uint32_t)p0, (uint32_t)p1, (uint32_t)p2); o4[1] = make_uint4((uint32_t)p3, (uint32_t)p4, (uint32_t)p5, (uint32_t)lb);
-  o4[2] = make_uint4((uint32_t)(lb >> 32), (uint32_t)(uint64_t)off, (uint32_t)((uint64_t)off >> 32), 0u);
-}
-#endif
 struct AgentRegs {                      // scalar part of ZiAgent held in registers while an event is handled
   int64_t agent_time, prev_wake, cash; double r_t, sigma_t, lat_to, lat_from;
   int32_t shares, last_trade, daily_close, bid, bid_q, ask, ask_q, n_orders; uint32_t flags, rng_ctr;
@@ -540,9 +552,6 @@ struct Sim {
   // send offset (computation delay + additional + pipeline delay) for messages, absolute time for wakeups.
   ABX_HD void emit(uint32_t w0, const int32_t p[6], double lat, int64_t off) {
     if (n_out >= Ctx::OUTN) { s.flags |= ABX_F_QUEUE_OVERFLOW; return; }
-#if defined(ABX_OPT_EMITNI) && defined(__CUDA_ARCH__)
-    emit_store(c.outbox() + n_out * OUT_WORDS, w0, p[0], p[1], p[2], p[3], p[4], p[5], lat, off); n_out++; return;
-#endif
     if (c.onchip_writer()) {
       uint32_t *o = c.outbox() + n_out * OUT_WORDS; uint64_t lb = dbl_bits(lat);
 #if defined(__CUDA_ARCH__)                                                             // three 128-bit stores instead of eleven words: emit is inlined at every send site
@@ -629,8 +638,8 @@ struct Sim {
   }
   ABX_HD int32_t oracle_compute(int64_t ts, double v_adj, int64_t pt, int32_t pv) {     // :88-125
     double d = (double)(ts - pt); double mu = P.c.r_bar;
-    double loc = dadd(mu, dmul(dsub((double)pv, mu), exp_ni(dmul(-P.c.kappa, d))));
-    double scale = dmul(P.ou_scale, dsub(1.0, exp_ni(dmul(dmul(-2.0, P.c.kappa), d))));    // variance formula passed as scale
+    double loc = dadd(mu, dmul(dsub((double)pv, mu), exp_fast(dmul(-P.c.kappa, d))));
+    double scale = dmul(P.ou_scale, dsub(1.0, exp_fast(dmul(dmul(-2.0, P.c.kappa), d))));    // variance formula passed as scale
     double v = rng.normal(S_SYMBOL, s.ctr_symbol, loc, scale);
     v = dadd(v, v_adj); if (!(v > 0)) v = 0;
     int32_t iv = (int32_t)py_round_i64(v); s.or_t = ts; s.or_v = iv; return iv;
@@ -848,14 +857,14 @@ struct Sim {
     // within an ulp of the true power; the result only feeds int(round(.)) of values ~1e5.
     // (1 - kappa) ** (2 delta) as the square of (1 - kappa) ** delta: it only enters through 1 - pw1 ~ 2 delta kappa ~ 1e-3 (sigma_t stays 0, :242), so an
     // ulp of pw1 moves r_t by ~1e-11 -- and saves one of the seven exp evaluations per order (12 % of all executed instructions were exp).
-    double pw0 = exp_ni(dmul(delta, P.log_base_a)), pw1 = dmul(pw0, pw0), pw2 = exp_ni(dmul(d2, P.log_base_a));
+    double pw0 = exp_fast(dmul(delta, P.log_base_a)), pw1 = dmul(pw0, pw0), pw2 = exp_fast(dmul(d2, P.log_base_a));
     double r_tprime = dmul(dsub(1.0, pw0), r_bar);                                    // :229
     r_tprime = dadd(r_tprime, dmul(pw0, a.r_t));                                      // :230
     double sigma_tprime = dmul(pw1, a.sigma_t);                                       // :233
-    sigma_tprime = dadd(sigma_tprime, dmul(ddiv(dsub(1.0, pw1), P.sigma_denom), P.c.sigma_s)); // :234
+    sigma_tprime = dadd(sigma_tprime, dmul(dsub(1.0, pw1) / P.sigma_denom, P.c.sigma_s)); // :234
     double den = dadd(sigma_n, sigma_tprime);
-    double r_t = dmul(ddiv(sigma_n, den), r_tprime);                                    // :239
-    r_t = dadd(r_t, dmul(ddiv(sigma_tprime, den), (double)obs_t));                      // :240
+    double r_t = dmul(sigma_n / den, r_tprime);                                         // :239
+    r_t = dadd(r_t, dmul(sigma_tprime / den, (double)obs_t));                           // :240
     a.r_t = r_t;
     if (a.sigma_t != 0.0)                                                               // sigma_t starts at 0 and 0 * sigma_n / (sigma_n + 0) is exactly 0: the division only runs if a caller seeds it otherwise
     a.sigma_t = dmul(sigma_n, a.sigma_t) / dadd(sigma_n, a.sigma_t);                    // :242
@@ -1062,7 +1071,7 @@ struct Sim {
       if (t_closed) f |= 4;
       f |= (nb > 2 ? 2 : nb) << 3; f |= (na > 2 ? 2 : na) << 5;
       p[4] = s.last_trade; p[5] = f;
-      if (DQ) b2 = (int32_t)s.ctr_kernel;                                               // DDQN config: the reply carries the book version instead (dq_exec_receive)
+      if (DQ && m.sender >= 2 + P.dq_n_mom) b2 = snap_take(m.sender - (2 + P.dq_n_mom));  // execution agents (depth 500): the levels are copied NOW; the reply carries their counts
       exch_send(m.sender, ABX_QUERY_SPREAD, p, bits_dbl((uint64_t)(uint32_t)b2 | ((uint64_t)(uint32_t)a2 << 32)));
     } else if (m.kind == ABX_LIMIT_ORDER) { s.c_limit++; s.ctr_kernel++; book_handle_limit((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[2], 0.0); c.sync(); trace_snap(); }
     else if (m.kind == ABX_CANCEL_ORDER) { s.c_cancel++; s.ctr_kernel++; book_cancel((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], 0.0); c.sync(); trace_snap(); }
@@ -1106,7 +1115,7 @@ struct Sim {
     if (cur >= c.n_ts()) return;                                                        // wakeup_times[0] -> IndexError: nothing placed
     set_wakeup(1, c.ts_load(cur)); if (c.onchip_writer()) x->wt_cursor = cur + 1;       // setWakeup(wakeup_times[0]); pop(0)
     int k = cur == 0 ? 0 : cur - 1;                                                     // orders_dict[currentTime]: the list's first entry is woken twice
-    if (c.ts_load(k) != s.now) { s.flags |= ABX_F_UNSUPPORTED; return; }
+    if (c.ts_load(k) != s.now) { s.flags |= ABX_F_REF_EXCEPTION; return; }              // orders_dict[currentTime] of a wakeup that is not on a stream timestamp: KeyError in the reference (:57)
     int r0 = c.first_load(k), r1 = c.first_load(k + 1);
     int4 nxt = c.row_load(k + 1 < c.n_ts() ? r1 : r0);                                  // first row of the next wakeup: its per-order records are cold
 #pragma unroll 1
@@ -1298,11 +1307,18 @@ struct Sim {
   // agent/execution/qlearning/ddqlearning_execution_agent.py:20-37,141-185,228-447,507-611, agent/execution/util.py:6-42,
   // agent/TradingAgent.py:351-397 (placeMarketOrder).  The Q-network is outside: one launch runs every environment up to the DDQN
   // agent's next choose_action (:245) and the following launch resumes place_order with the action.
-  // Depth-500 QUERY_SPREAD replies: the execution agents read the lists only while handling the reply, and with zero delays no book
-  // operation can sort between the exchange's snapshot and that delivery, so the handlers read the live ladders; the reply carries the
-  // book-operation counter and a mismatch raises ABX_F_UNSUPPORTED instead of trading on different data.  L1 is cached in the record.
+  // Depth-500 QUERY_SPREAD replies: the exchange copies the first 500 levels of both sides into the asking agent's snapshot area in HBM when it
+  // PROCESSES the query (ExchangeAgent.py:231-245) and the reply carries the level counts; the agent's handlers (market-order walk,
+  // level prices of take_action) read that copy -- known_bids / known_asks -- never the live ladders.  L1 is cached in the record.
   // =================================================================================================
   ABX_HD ExecAux *exaux() { return reinterpret_cast<ExecAux *>(z->oid); }
+  ABX_HD int exec_index(int id) const { return R3 ? 0 : id - (2 + P.dq_n_mom); }        // which snapshot area / order table an execution agent owns
+  // ExchangeAgent.py:231-245 for a deep query: getInsideBids(depth) / getInsideAsks(depth) copied at processing time.  Returns bids | asks << 16.
+  ABX_HD int32_t snap_take(int k) {
+    int nb = s.n_bid_lv < P.snap_depth ? s.n_bid_lv : P.snap_depth, na = s.n_ask_lv < P.snap_depth ? s.n_ask_lv : P.snap_depth;
+    c.snap_store(k, 0, s.n_bid_lv, nb); c.snap_store(k, 1, s.n_ask_lv, na);
+    return (int32_t)((uint32_t)nb | ((uint32_t)na << 16));
+  }
   ABX_HD int dq_order_base(int id) const { return R3 ? P.dq_order_base : P.dq_order_base + (id - (2 + P.dq_n_mom)) * EXEC_ORDER_CAP; }   // rmsc03 population: one POV execution agent
   // floor(a / h_step_ns) for 0 <= a < 2^53 (nanoseconds of one day): a software 64-bit division is ~55 instructions per use; the product with the
   // host-computed reciprocal is off by at most one, which the remainder corrects exactly.
@@ -1340,11 +1356,11 @@ struct Sim {
   ABX_HD void dq_place_market(int id, int32_t quantity) { dq_place_market(id, quantity, P.rl_is_buy != 0); }
   ABX_HD void dq_place_market(int id, int32_t quantity, bool is_buy) {                  // TradingAgent.placeMarketOrder :351-397 over the cached opposite side
     if (quantity <= 0) return;
-    int opp = is_buy ? 1 : 0; int n = n_lv(opp); int depth = n < DQ_DEPTH ? n : DQ_DEPTH;
-    if (n == 0) { s.flags |= ABX_F_OBS_INVALID; return; }                               // the reference iterates None
+    int opp = is_buy ? 1 : 0, k = exec_index(id); int32_t sn = exaux()->snap_n; int depth = opp ? (sn >> 16) & 0xffff : sn & 0xffff;
+    if (depth == 0) { s.flags |= ABX_F_OBS_INVALID; return; }                           // the reference iterates None
 #pragma unroll 1
     for (int i = 0; i < depth; i++) {
-      int32_t price = c.lv_price(opp, n - 1 - i), sz = c.lv_qty(opp, n - 1 - i);
+      int2 lv = c.snap_load(k, opp, i); int32_t price = lv.x, sz = lv.y;
       bool last = quantity <= sz;
       dq_place_limit(id, last ? quantity : sz, is_buy, price);
       if (last) break;
@@ -1408,7 +1424,7 @@ struct Sim {
       a.flags &= ~(AF_HAS_BID | AF_HAS_ASK);
       if (m.p[5] & 1) { a.flags |= AF_HAS_BID; a.bid = m.p[0]; a.bid_q = m.p[1]; } else { a.bid = 0; a.bid_q = 0; }
       if (m.p[5] & 2) { a.flags |= AF_HAS_ASK; a.ask = m.p[2]; a.ask_q = m.p[3]; } else { a.ask = 0; a.ask_q = 0; }
-      if ((uint32_t)m.x0 != s.ctr_kernel) s.flags |= ABX_F_UNSUPPORTED;                 // the book moved between snapshot and delivery
+      ex.snap_n = m.x0;                                                                 // known_bids / known_asks = the lists the exchange copied when it processed the query
     }
     if ((a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE) && !had) set_wakeup(id, P.h0_ns);         // mkt_open + (start_time - mkt_open)
     uint32_t st = (a.flags & AF_STATE_MASK) >> AF_STATE_SHIFT;
@@ -1470,12 +1486,12 @@ struct Sim {
     exaux_store(ex);
     if (alloc == 0) dq_place_market(id, qty);
     else {
-      int own = P.rl_is_buy ? 0 : 1, n = n_lv(own);
+      int own = P.rl_is_buy ? 0 : 1, n = own ? (ex.snap_n >> 16) & 0xffff : ex.snap_n & 0xffff, k = exec_index(id);
 #pragma unroll 1
       for (int lv = 0; lv < 4; lv++) {                                                  // :395-409 (the price is read before the size test: IndexError below 4 levels)
         int32_t size = (int32_t)py_round_i64(dmul(dq_alloc_frac(alloc, lv), (double)qty));
-        if (lv >= n) { s.flags |= ABX_F_UNSUPPORTED; break; }
-        int32_t price = c.lv_price(own, n - 1 - lv);
+        if (lv >= n) { s.flags |= ABX_F_REF_EXCEPTION; break; }                         // bids[3] / asks[3] of a thinner book: the reference raises IndexError
+        int32_t price = c.snap_load(k, own, lv).x;
         if (size != 0) dq_place_limit(id, size, P.rl_is_buy != 0, price);
       }
     }
@@ -1496,9 +1512,6 @@ struct Sim {
       uint64_t khi; uint32_t kuniq; int grp;
       bool any = c.q_min(khi, kuniq, grp);
       if (!any || !(s.now <= P.c.stop_ns)) { s.flags |= ABX_F_DONE; break; }
-#ifdef ABX_OPT_EARLY2
-      { int rid = key_recipient(khi); if (rid > 1) c.agent_load_issue(rid); }
-#endif
       Event ev; c.q_fetch(grp, ev);
       s.now = ev.t; s.ttl++;
       if (INSTR && P.c.hash_pops) s.pop_hash = fnv_mix(fnv_mix(fnv_mix(fnv_mix(s.pop_hash, ev.t), ev.recipient), ev.type), ev.type == ABX_T_MESSAGE ? (int64_t)ev.uniq : -1);
@@ -1515,11 +1528,7 @@ struct Sim {
         if (id == 0) { if (ev.type == ABX_T_MESSAGE) env_exch_receive(ev); s.exch_time = s.now + s.exch_comp_delay + addl_delay; }
         else { if (ev.type == ABX_T_WAKEUP) replay_wakeup(x); else replay_receive(x, ev); if (c.onchip_writer()) x->ra_time = s.now + P.c.default_computation_delay_ns + addl_delay; }
       } else {
-#ifdef ABX_OPT_EARLY2
-        z = c.agent_stage_issued(id); regs_load(a, z);
-#else
         z = c.agent_stage(id); regs_load(a, z);
-#endif
         if (a.agent_time > s.now) { c.q_requeue(a.agent_time); continue; }
         c.q_remove(); s.q_count--; self_id = id;
         int type = (int)((a.flags & AF_TYPE_MASK) >> AF_TYPE_SHIFT);
@@ -1532,7 +1541,7 @@ struct Sim {
       }
       flush();
     }
-    if ((int64_t)s.next_order_id >= P.dq_id_limit) s.flags |= ABX_F_UNSUPPORTED;        // generated ids reached the stream's explicit ids (util/order/Order.py:35-42 would skip them)
+    if ((int64_t)s.next_order_id >= P.dq_id_limit) s.flags |= ABX_F_ID_RANGE;           // generated ids reached the stream's explicit ids (util/order/Order.py:35-42 would skip them): outside the id range abx_dq_create checked
     rng_sync();
     c.sync();
     return paused;
@@ -1542,29 +1551,29 @@ struct Sim {
   // rmsc03 population (config/rmsc03.py): NoiseAgent, ValueAgent, MomentumAgent, POVMarketMakerAgent + the exchange's
   // QUERY_TRANSACTED_VOLUME (util/OrderBook.py:400-436).  Zero latency, computation delay 0.
   // Per-environment tables (HBM): idtab[0 .. MM_ORDER_CAP) = the market maker's open orders {id, price, signed qty, -},
-  // idtab[MM_ORDER_CAP .. +TV_RING) = ring of transaction tuples {time lo, time hi, qty, record epoch | add epoch << 16},
+  // idtab[MM_ORDER_CAP .. +tv_ring) = ring of transaction tuples {time lo, time hi, qty, record epoch | add epoch << 16},
   // lobs[k * MOM_MIDS/4 ...] = last MOM_MIDS doubled mid prices of momentum agent k.
   // =================================================================================================
   ABX_HD void tv_record(int32_t qty, uint32_t rec_epoch) {
     uint32_t i = s.ctr_latency++;                                                       // ring cursor (the latency stream is unused with zero latency)
     uint4 v; v.x = (uint32_t)(uint64_t)s.now; v.y = (uint32_t)((uint64_t)s.now >> 32); v.z = (uint32_t)qty; v.w = (rec_epoch & 0xffffu) | (s.trade_epoch << 16);
-    c.id_store(MM_ORDER_CAP + (int)(i % TV_RING), v);
+    c.id_store(MM_ORDER_CAP + (int)(i & (uint32_t)(P.tv_ring - 1)), v);
   }
   // get_transacted_volume :400-436: distinct (time, qty) tuples on surviving history records with time >= now - lookback
   ABX_HD int32_t transacted_volume(int64_t lookback) {
-    uint32_t n = s.ctr_latency < (uint32_t)TV_RING ? s.ctr_latency : (uint32_t)TV_RING; int64_t start = s.now - lookback; int64_t sum = 0;
+    uint32_t RING = (uint32_t)P.tv_ring, n = s.ctr_latency < RING ? s.ctr_latency : RING; int64_t start = s.now - lookback; int64_t sum = 0;
     uint32_t E = s.trade_epoch;
-    if (s.ctr_latency > (uint32_t)TV_RING) { uint4 o = c.id_load(MM_ORDER_CAP + (int)(s.ctr_latency % TV_RING)); if (((E - (o.w >> 16)) & 0xffffu) <= (uint32_t)P.c.stream_history) s.flags |= ABX_F_UNSUPPORTED; }  // ring too short
+    if (s.ctr_latency > RING) { uint4 o = c.id_load(MM_ORDER_CAP + (int)(s.ctr_latency & (RING - 1))); if (((E - (o.w >> 16)) & 0xffffu) <= (uint32_t)P.c.stream_history) s.flags |= ABX_F_HISTORY_OVERFLOW; }  // a tuple that could still count was overwritten: capacity, like the queue / ladder / order pools
 #pragma unroll 1
     for (uint32_t k = 0; k < n; k++) {                                                  // newest first
-      uint4 v = c.id_load(MM_ORDER_CAP + (int)((s.ctr_latency - 1 - k) % TV_RING));
+      uint4 v = c.id_load(MM_ORDER_CAP + (int)((s.ctr_latency - 1 - k) & (RING - 1)));
       int64_t t = (int64_t)((uint64_t)v.x | ((uint64_t)v.y << 32));
       if (((E - (v.w >> 16)) & 0xffffu) > (uint32_t)P.c.stream_history + 1) break;      // added more than stream_history + 1 rotations ago: nothing older can survive
       if (t < start || ((E - (v.w & 0xffffu)) & 0xffffu) > (uint32_t)P.c.stream_history) continue;
       bool dup = false;
 #pragma unroll 1
       for (uint32_t j = 0; j < k && !dup; j++) {
-        uint4 w = c.id_load(MM_ORDER_CAP + (int)((s.ctr_latency - 1 - j) % TV_RING));
+        uint4 w = c.id_load(MM_ORDER_CAP + (int)((s.ctr_latency - 1 - j) & (RING - 1)));
         if (w.x == v.x && w.y == v.y && w.z == v.z && ((E - (w.w & 0xffffu)) & 0xffffu) <= (uint32_t)P.c.stream_history) dup = true;
       }
       if (!dup) sum += (int32_t)v.z;
@@ -1587,7 +1596,8 @@ struct Sim {
       if (nb > 0) { p[0] = c.lv_price(0, nb - 1); p[1] = c.lv_qty(0, nb - 1); f |= 1; }
       if (na > 0) { p[2] = c.lv_price(1, na - 1); p[3] = c.lv_qty(1, na - 1); f |= 2; }
       if (t_closed) f |= 4;
-      p[4] = s.last_trade; p[5] = f; exch_send(m.sender, ABX_QUERY_SPREAD, p, bits_dbl((uint64_t)s.ctr_kernel));   // + book-operation counter (POV execution agent reads the live ladders)
+      int32_t sn = (P.c.n_pov_exec && m.sender == P.c.n_agents - 1) ? snap_take(0) : 0;   // POVExecutionAgent asks for depth sys.maxsize: the whole book is copied now
+      p[4] = s.last_trade; p[5] = f; exch_send(m.sender, ABX_QUERY_SPREAD, p, bits_dbl((uint64_t)(uint32_t)sn));
     } else if (m.kind == ABX_LIMIT_ORDER) { s.c_limit++; s.ctr_kernel++; book_handle_limit((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[2], 0.0); c.sync(); trace_snap(); }
     else if (m.kind == ABX_CANCEL_ORDER) { s.c_cancel++; s.ctr_kernel++; book_cancel((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], 0.0); c.sync(); trace_snap(); }
   }
@@ -1657,7 +1667,7 @@ struct Sim {
     double r_bar = P.c.r_bar, sigma_n = P.c.sigma_n;
     double delta = (double)(s.now - a.prev_wake);
     double d2 = (double)(P.c.mkt_close_ns - s.now); if (!(d2 > 0)) d2 = 0;
-    double pw0 = exp_ni(dmul(delta, P.log_base_a)), pw1 = exp_ni(dmul(dmul(2.0, delta), P.log_base_a)), pw2 = exp_ni(dmul(d2, P.log_base_a));
+    double pw0 = exp_fast(dmul(delta, P.log_base_a)), pw1 = exp_fast(dmul(dmul(2.0, delta), P.log_base_a)), pw2 = exp_fast(dmul(d2, P.log_base_a));
     double r_tprime = dmul(dsub(1.0, pw0), r_bar); r_tprime = dadd(r_tprime, dmul(pw0, a.r_t));
     double sigma_tprime = dmul(pw1, a.sigma_t); sigma_tprime = dadd(sigma_tprime, dmul(dsub(1.0, pw1) / P.sigma_denom, P.c.sigma_s));
     double den = dadd(sigma_n, sigma_tprime);
@@ -1721,7 +1731,7 @@ struct Sim {
     }
     uint32_t st = (a.flags & AF_STATE_MASK) >> AF_STATE_SHIFT;
     if (type == AT_POVEXEC) {                                                           // POVExecutionAgent.receiveMessage :69-99
-      if (m.kind == ABX_QUERY_SPREAD && (uint32_t)m.x0 != s.ctr_kernel) s.flags |= ABX_F_UNSUPPORTED;   // the cached lists would differ from the live ladders
+      if (m.kind == ABX_QUERY_SPREAD) { ExecAux e0 = *exaux(); e0.snap_n = m.x0; exaux_store(e0); }     // known_bids / known_asks
       if (s.now > P.c.pov_exec_end_ns) return;
       ExecAux ex = *exaux();
       if (ex.rem_qty > 0 && st == ST_AWAITING_TV && m.kind == ABX_QUERY_TRANSACTED_VOLUME && s.now > P.c.pov_exec_start_ns) {
@@ -1783,9 +1793,6 @@ struct Sim {
       bool any = c.q_min(khi, kuniq, grp);
       if (!any || !(s.now <= P.c.stop_ns)) { s.flags |= ABX_F_DONE; break; }
       if (key_time(khi) > until) break;
-#ifdef ABX_OPT_EARLY2
-      { int rid = key_recipient(khi); if (rid != 0) c.agent_load_issue(rid); }
-#endif
       Event ev; c.q_fetch(grp, ev);
       s.now = ev.t; s.ttl++;
       if (INSTR && P.c.hash_pops) s.pop_hash = fnv_mix(fnv_mix(fnv_mix(fnv_mix(s.pop_hash, ev.t), ev.recipient), ev.type), ev.type == ABX_T_MESSAGE ? (int64_t)ev.uniq : -1);
@@ -1801,11 +1808,7 @@ struct Sim {
         if (ev.type == ABX_T_MESSAGE) r3_exch_receive(ev);
         s.exch_time = s.now + s.exch_comp_delay + addl_delay;
       } else {
-#ifdef ABX_OPT_EARLY2
-        z = c.agent_stage_issued(id); regs_load(a, z);
-#else
         z = c.agent_stage(id); regs_load(a, z);
-#endif
         if (a.agent_time > s.now) { c.q_requeue(a.agent_time); continue; }
         c.q_remove(); s.q_count--; self_id = id;
         if (ev.type == ABX_T_WAKEUP) r3_wakeup(id); else r3_receive(id, ev);

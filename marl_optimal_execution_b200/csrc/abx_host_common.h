@@ -92,6 +92,9 @@ static inline int config_validate(const abx_sim_config *c) {
   return ABX_OK;
 }
 
+// Entries of the transaction-tuple ring behind get_transacted_volume (util/OrderBook.py:400-436): the tuples of stream_history + 1 surviving history
+// buckets; 64 per bucket (an order sweeping more than that many resting orders between two trades raises ABX_F_HISTORY_OVERFLOW), a power of two >= 512.
+static inline int tv_ring_for(int stream_history) { int need = 64 * (stream_history + 2), r = TV_RING_MIN; while (r < need) r <<= 1; return r; }
 // Constants the reference evaluates with CPython/libm on every call; evaluated once here with the same libm.
 static inline void derive_params(SimParams &P) {
   const abx_sim_config &c = P.c;
@@ -102,6 +105,7 @@ static inline void derive_params(SimParams &P) {
   P.sqrt_sigma_n = sqrt(c.sigma_n); P.sqrt_sigma_pv = sqrt(c.sigma_pv); P.sqrt_megashock_var = sqrt(c.megashock_var);
   P.inv_lambda_a = 1.0 / c.lambda_a; P.inv_megashock_lambda = 1.0 / c.megashock_lambda_a;
   P.ou_scale = pow(c.fund_vol, 2.0) / (2 * c.kappa);               // SparseMeanRevertingOracle.py:106
+  P.tv_ring = tv_ring_for(c.stream_history);
 }
 
 // ---- ABIDESEnv shape ----

@@ -111,15 +111,29 @@ abx_finalize_kernel(SimParams P, size_t smem_per_warp) {
 }
 
 // ---- ABIDESEnv shape: reset and step (GymKernel.initRunner / stepRunner) ----
+// Which environments a reset touches: all (mask NULL, mode RESET_ALL), those with mask[e] != 0, or those whose event loop has ended (RESET_DONE: the
+// auto-reset pass after a step).  advance_day: the environment moves on to its next replayed day (episode + 1), otherwise it restarts the same day.
+enum { RESET_ALL = 0, RESET_MASK = 1, RESET_DONE = 2 };
+__device__ __forceinline__ bool reset_selected(const SimParams &P, int env, const uint8_t *mask, int mode, int advance_day, uint32_t &episode) {
+  episode = 0;
+  if (mode == RESET_ALL) return true;
+  if (mode == RESET_MASK && !mask[env]) return false;
+  EnvState old = env_load(P.env + env);
+  if (mode == RESET_DONE && !(old.flags & ABX_F_DONE)) return false;
+  episode = old.episode + (advance_day ? 1u : 0u);
+  return true;
+}
 template <bool SMALLQ>
 __global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
-abx_env_reset_kernel(SimParams P, size_t smem_per_warp) {
+abx_env_reset_kernel(SimParams P, const uint8_t *__restrict__ mask, int mode, int advance_day, size_t smem_per_warp) {
   typedef Sim<WarpCtxT<SMALLQ ? 1 : 0>, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_ENV> EnvSimInstr;
   extern __shared__ __align__(16) unsigned char smem[];
   int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
   if (env >= P.n_envs) return;
+  uint32_t episode; if (!reset_selected(P, env, mask, mode, advance_day, episode)) return;
   WarpCtxT<SMALLQ ? 1 : 0> ctx(P, env, smem + warp * smem_per_warp);
-  EnvState s; init_env_state(P, 0, s); s.last_trade = -1;               // no oracle: OrderBook.last_trade stays None (ExchangeAgent.py:97-102)
+  ctx.set_episode(episode); if (mode != RESET_ALL) ctx.clear_tables();
+  EnvState s; init_env_state(P, 0, s); s.last_trade = -1; s.episode = episode;   // no oracle: OrderBook.last_trade stays None (ExchangeAgent.py:97-102)
   init_envx(P, *ctx.envx()); ctx.sync();
   ctx.q_clear();
   EnvSimInstr sim(ctx, P, s, env);
@@ -142,7 +156,7 @@ abx_env_step_kernel(SimParams P, const double *__restrict__ actions, double *__r
   EnvState s = env_load(P.env + env);
   bool was_done = (s.flags & ABX_F_DONE) != 0;
   if (!was_done) {
-    ctx.envx_load(); ctx.load_onchip(s);
+    ctx.set_episode(s.episode); ctx.envx_load(); ctx.load_onchip(s);
     Sim<WarpCtxT<SMALLQ ? 1 : 0>, ABX_RNG_PHILOX, ABX_LAT_ZERO, INSTR, SHAPE_ENV> sim(ctx, P, s, env);
     sim.env_step(actions[3 * env], actions[3 * env + 1], actions[3 * env + 2]);
     ctx.store_onchip(sim.s); ctx.envx_store();
@@ -159,13 +173,15 @@ abx_env_step_kernel(SimParams P, const double *__restrict__ actions, double *__r
 typedef Sim<WarpCtxHybridQ, ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_DQ> DqSimInstr;
 
 __global__ void __launch_bounds__(32 * ABX_WARPS_PER_CTA)
-abx_dq_reset_kernel(SimParams P, const uint64_t *__restrict__ seeds, const int32_t *__restrict__ mom_sizes, size_t smem_per_warp) {
+abx_dq_reset_kernel(SimParams P, const uint64_t *__restrict__ seeds, const int32_t *__restrict__ mom_sizes, const uint8_t *__restrict__ mask, int mode, int advance_day, size_t smem_per_warp) {
   extern __shared__ __align__(16) unsigned char smem[];
   int warp = threadIdx.x >> 5, env = blockIdx.x * ABX_WARPS_PER_CTA + warp;
   if (env >= P.n_envs) return;
+  uint32_t episode; if (!reset_selected(P, env, mask, mode, advance_day, episode)) return;
   WarpCtxHybridQ ctx(P, env, smem + warp * smem_per_warp);
-  uint64_t seed = seeds ? seeds[env] : 0;
-  EnvState s; init_env_state(P, seed, s); s.last_trade = -1;            // no oracle: OrderBook.last_trade stays None until the first trade
+  ctx.set_episode(episode); if (mode != RESET_ALL) ctx.clear_tables();
+  uint64_t seed = (seeds ? seeds[env] : 0) + episode;                   // a later episode of the environment draws its MomentumAgent sizes afresh
+  EnvState s; init_env_state(P, seed, s); s.last_trade = -1; s.episode = episode;   // no oracle: OrderBook.last_trade stays None until the first trade
   init_envx(P, *ctx.envx()); ctx.sync();
   ctx.q_clear();
   for (int id = 2 + ctx.lane; id < P.c.n_agents; id += 32)             // one lane per trader record
@@ -188,7 +204,7 @@ abx_dq_step_kernel(SimParams P, const int32_t *__restrict__ actions, double *__r
   EnvState s = env_load(P.env + env);
   bool was_done = (s.flags & ABX_F_DONE) != 0, paused = false;
   if (!was_done) {
-    ctx.envx_load(); ctx.load_onchip(s);
+    ctx.set_episode(s.episode); ctx.envx_load(); ctx.load_onchip(s);
     Sim<WarpCtxHybridQ, ABX_RNG_PHILOX, ABX_LAT_ZERO, INSTR, SHAPE_DQ> sim(ctx, P, s, env);
     paused = sim.dq_step(actions ? actions[env] : 0);
     ctx.store_onchip(sim.s); ctx.envx_store();
@@ -254,8 +270,9 @@ struct abx_sim {
   SimParams P; int n_envs, device; bool reset_done; size_t smem_per_warp; int64_t bytes, launches;
   uint64_t *d_seeds; uint32_t *d_init_err; abx_env_stats *d_stats; int64_t *d_until;
   uint64_t *d_tbits; uint8_t *d_tkinds; int64_t *d_toff;
-  bool is_env, is_dq; EnvStreamHost *st; EnvDaysHost *dh; int4 *d_daytab; int64_t *d_ts; int32_t *d_first; int4 *d_rows; double *d_act, *d_obs, *d_rew; uint8_t *d_done;
+  bool is_env, is_dq, have_seeds, have_msizes; EnvStreamHost *st; EnvDaysHost *dh; int4 *d_daytab; int64_t *d_ts; int32_t *d_first; int4 *d_rows; double *d_act, *d_obs, *d_rew; uint8_t *d_done;
   int32_t *d_iact, *d_msizes; double *d_trans;
+  int auto_reset;                       // 0 off, 1 restart the same day, 2 move on to the next day: applied to finished environments after every step
   bool is_book; int64_t *d_ops; int64_t ops_cap; std::unordered_map<int64_t, int32_t> *book_ids;
 };
 
@@ -292,7 +309,7 @@ int32_t abx_sim_destroy(abx_sim *h) {
   if (!h) return ABX_OK;
   cudaSetDevice(h->device);
   void *ptrs[] = {h->P.qkey, h->P.qpay0, h->P.qpay1, h->P.qcache, h->P.agents, h->P.lv_price, h->P.lv_qty, h->P.lv_ht, h->P.nodes, h->P.env,
-                  h->P.trace, h->P.draw_log, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff,
+                  h->P.trace, h->P.draw_log, h->P.snap, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff,
                   h->P.envx, h->P.idtab, h->P.idbook, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_iact, h->d_msizes, h->d_trans, h->d_ops, h->d_daytab};
   for (void *p : ptrs) if (p) cudaFree(p);
   delete h->st; delete h->dh; delete h->book_ids; delete h; return ABX_OK;
@@ -314,8 +331,9 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   DA(h->P.agents, E * c.n_agents) DA(h->P.lv_price, E * 2 * c.level_cap) DA(h->P.lv_qty, E * 2 * c.level_cap) DA(h->P.lv_ht, E * 2 * c.level_cap)
   DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap) DA(h->P.draw_log, E * (size_t)c.draw_log_cap)
   DA(h->d_seeds, E) DA(h->d_init_err, E) DA(h->d_stats, E) DA(h->d_until, E)
-  if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + TV_RING; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0);       // market maker orders + transaction ring [+ POV execution agent orders]; momentum mids
-    DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3) }
+  if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + h->P.tv_ring; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0);       // market maker orders + transaction ring [+ POV execution agent orders]; momentum mids
+    DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
+    if (c.n_pov_exec) { h->P.n_snap = 1; h->P.snap_depth = c.level_cap; DA(h->P.snap, E * 2 * (size_t)c.level_cap) } }      // POVExecutionAgent asks for depth sys.maxsize
 #undef DA
   if (smem_cta > 48 * 1024) {
     CUH(cudaFuncSetAttribute((const void *)run_kernel_for(*cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
@@ -465,7 +483,7 @@ int32_t abx_sim_trace(abx_sim *h, int32_t env, abx_trace_rec *out, int32_t max_r
   EnvState s; CU(cudaMemcpyAsync(&s, h->P.env + env, sizeof(s), cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st));
   int n = (int)s.trace_n; if (n > max_recs) n = max_recs; if (n > h->P.c.trace_cap) n = h->P.c.trace_cap;
   if (n > 0) { CU(cudaMemcpyAsync(out, h->P.trace + (size_t)env * h->P.c.trace_cap, sizeof(abx_trace_rec) * n, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
-  if (h->is_env) { const std::vector<int64_t> &ido = h->dh ? h->dh->days[env % (int)h->dh->days.size()].id_orig : h->st->id_orig;
+  if (h->is_env) { const std::vector<int64_t> &ido = h->dh ? h->dh->days[(int)(((uint32_t)env + s.episode) % (uint32_t)h->dh->days.size())].id_orig : h->st->id_orig;
     for (int i = 0; i < n; i++) if (out[i].tag == 1 && (uint32_t)out[i].v[1] >= REPLAY_ID_BASE) out[i].v[1] = (int32_t)ido[(uint32_t)out[i].v[1] - REPLAY_ID_BASE]; }
   *n_recs = n; return ABX_OK;
 }
@@ -486,6 +504,14 @@ int32_t abx_sim_agent_init(abx_sim *h, int32_t env, int32_t *theta, double *lat_
   int n = h->P.c.n_agents; std::vector<ZiAgent> tmp(n);
   CU(cudaMemcpyAsync(tmp.data(), h->P.agents + (size_t)env * n, sizeof(ZiAgent) * n, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st));
   agent_init_rows(h->P, tmp.data(), theta, lat_to, lat_from, sizes, wakes);
+  return ABX_OK;
+}
+
+static int32_t dq_reset_launch(abx_sim *h, const uint8_t *mask_dev, int mode, int advance_day, cudaStream_t st) {
+  abx_dq_reset_kernel<<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, st>>>(h->P, h->have_seeds ? h->d_seeds : nullptr, h->have_msizes ? h->d_msizes : nullptr,
+                                                                                                                  mask_dev, mode, advance_day, h->smem_per_warp);
+  h->launches += 1;
+  CU(cudaGetLastError());
   return ABX_OK;
 }
 
@@ -535,16 +561,29 @@ int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_
   int64_t off[2] = {0, n_rows}; return abx_env_create_days(cfg, stream5, off, 1, n_envs, device, out);
 }
 
+static int32_t env_reset_launch(abx_sim *h, const uint8_t *mask_dev, int mode, int advance_day, cudaStream_t st) {
+  if (warp_small_queue(h->P.c)) abx_env_reset_kernel<true><<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, st>>>(h->P, mask_dev, mode, advance_day, h->smem_per_warp);
+  else abx_env_reset_kernel<false><<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, st>>>(h->P, mask_dev, mode, advance_day, h->smem_per_warp);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return ABX_OK;
+}
 int32_t abx_env_reset(abx_sim *h, void *stream) {
-  if (!h || !h->is_env) return ABX_ERR_ARG;
+  if (!h || !h->is_env || h->is_dq || h->is_book) return ABX_ERR_ARG;
   CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
   CU(cudaMemsetAsync(h->P.idtab, 0, sizeof(uint4) * (size_t)h->n_envs * h->P.n_ids, st));
   CU(cudaMemsetAsync(h->P.idbook, 0, sizeof(uint2) * (size_t)h->n_envs * h->P.n_ids, st));
-  if (warp_small_queue(h->P.c)) abx_env_reset_kernel<true><<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, st>>>(h->P, h->smem_per_warp);
-  else abx_env_reset_kernel<false><<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, st>>>(h->P, h->smem_per_warp);
-  h->launches += 1;
-  CU(cudaGetLastError());
+  int32_t rc = env_reset_launch(h, nullptr, RESET_ALL, 0, st); if (rc != ABX_OK) return rc;
   h->reset_done = true; return ABX_OK;
+}
+int32_t abx_env_reset_mask(abx_sim *h, const uint8_t *mask_dev, int32_t advance_day, void *stream) {
+  if (!h || !h->is_env || h->is_book || !mask_dev) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  CU(cudaSetDevice(h->device));
+  return h->is_dq ? dq_reset_launch(h, mask_dev, RESET_MASK, advance_day ? 1 : 0, (cudaStream_t)stream) : env_reset_launch(h, mask_dev, RESET_MASK, advance_day ? 1 : 0, (cudaStream_t)stream);
+}
+int32_t abx_env_set_auto_reset(abx_sim *h, int32_t mode) {
+  if (!h || !h->is_env || h->is_book || mode < 0 || mode > 2) return ABX_ERR_ARG;
+  h->auto_reset = mode; return ABX_OK;
 }
 
 int32_t abx_env_step(abx_sim *h, const double *actions_dev, double *obs_dev, double *reward_dev, uint8_t *done_dev, void *stream) {
@@ -558,6 +597,7 @@ int32_t abx_env_step(abx_sim *h, const double *actions_dev, double *obs_dev, dou
 #undef ENV_STEP
   h->launches += 1;
   CU(cudaGetLastError());
+  if (h->auto_reset) return env_reset_launch(h, nullptr, RESET_DONE, h->auto_reset == 2, (cudaStream_t)stream);   // finished episodes start over before the next step
   return ABX_OK;
 }
 
@@ -601,6 +641,7 @@ int32_t abx_dq_create_days(const abx_dq_config *cfg, const int64_t *stream5, con
   DA(h->P.envx, E) DA(h->P.idtab, E * h->P.n_ids) DA(h->P.idbook, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
   DA(h->d_ts, dh->ts.size()) DA(h->d_first, dh->first.size()) DA(h->d_rows, dh->rows.size()) DA(h->d_daytab, dh->day_tab.size())
   DA(h->d_iact, E) DA(h->d_obs, E * 8) DA(h->d_trans, E * 6) DA(h->d_rew, E) DA(h->d_done, E) DA(h->d_msizes, E * (cfg->n_momentum > 0 ? cfg->n_momentum : 1))
+  h->P.n_snap = n_exec > 0 ? n_exec : 1; h->P.snap_depth = DQ_DEPTH; DA(h->P.snap, E * (size_t)h->P.n_snap * 2 * DQ_DEPTH)                      // getCurrentSpread(depth=500) copies
 #undef DA
   CUH(cudaMemcpy(h->d_ts, dh->ts.data(), sizeof(int64_t) * dh->ts.size(), cudaMemcpyHostToDevice));
   CUH(cudaMemcpy(h->d_first, dh->first.data(), sizeof(int32_t) * dh->first.size(), cudaMemcpyHostToDevice));
@@ -627,9 +668,8 @@ int32_t abx_dq_reset(abx_sim *h, const uint64_t *seeds, const int32_t *mom_sizes
   CU(cudaMemsetAsync(h->P.idtab, 0, sizeof(uint4) * (size_t)h->n_envs * h->P.n_ids, st));
   CU(cudaMemsetAsync(h->P.idbook, 0, sizeof(uint2) * (size_t)h->n_envs * h->P.n_ids, st));
   CU(cudaMemsetAsync(h->P.lobs, 0, sizeof(int4) * (size_t)h->n_envs * LOB_CAP * 3, st));
-  abx_dq_reset_kernel<<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, st>>>(h->P, seeds ? h->d_seeds : nullptr, (mom_sizes && h->P.dq_n_mom > 0) ? h->d_msizes : nullptr, h->smem_per_warp);
-  h->launches += 1;
-  CU(cudaGetLastError());
+  h->have_seeds = seeds != nullptr; h->have_msizes = mom_sizes && h->P.dq_n_mom > 0;
+  int32_t rc = dq_reset_launch(h, nullptr, RESET_ALL, 0, st); if (rc != ABX_OK) return rc;
   h->reset_done = true; return ABX_OK;
 }
 
@@ -641,6 +681,7 @@ int32_t abx_dq_step(abx_sim *h, const int32_t *actions_dev, double *obs_dev, dou
   else abx_dq_step_kernel<false><<<grid_for(h->n_envs), 32 * ABX_WARPS_PER_CTA, h->smem_per_warp * ABX_WARPS_PER_CTA, (cudaStream_t)stream>>>(h->P, actions_dev, obs_dev, trans_dev, reward_dev, done_dev, h->smem_per_warp);
   h->launches += 1;
   CU(cudaGetLastError());
+  if (h->auto_reset) return dq_reset_launch(h, nullptr, RESET_DONE, h->auto_reset == 2, (cudaStream_t)stream);    // finished episodes start over: the next step runs them to their first decision tick
   return ABX_OK;
 }
 

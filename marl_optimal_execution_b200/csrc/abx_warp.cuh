@@ -24,7 +24,12 @@ constexpr unsigned FULL = 0xffffffffu;
 __device__ __forceinline__ uint4 ldcg4(const uint4 *p) { return __ldcg(p); }
 
 // lane index of the smallest (hi, uniq) among lanes with valid == true, or -1
-__device__ __forceinline__ int warp_argmin(uint64_t hi, uint32_t uniq, bool valid) {
+#ifdef ABX_ARGMIN_NI
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+int warp_argmin(uint64_t hi, uint32_t uniq, bool valid) {
   uint32_t h = valid ? (uint32_t)(hi >> 32) : 0xffffffffu;
   uint32_t m = __reduce_min_sync(FULL, h);
   bool c = valid && h == m;
@@ -81,6 +86,7 @@ struct WarpCtxT {
   ZiAgent *staged; uint32_t *obox; uint4 *qc, *qs, *qp0, *qp1, *ovm; int32_t *lvp, *lvq; uint32_t *lvht; EnvX *ex;   // qc: group cache, qs: on-chip keys
   uint4 *oc_t; uint2 *oc_b; int32_t *oc_tag;   // on-chip cache of replayed orders' records (direct mapped, write-through)
   uint4 *idt; int4 *lob; uint2 *idb;   // ABIDESEnv shape: replay agent's per-order table, stored LOBs, per-order book census (HBM)
+  int2 *snp;                           // deep QUERY_SPREAD replies: the execution agents' book snapshots (HBM)
   // registers describing the group fetched by q_fetch
   uint64_t my_hi; uint32_t my_uniq; uint32_t cur_mask; int cur_group, cur_lane; int n_ovf; bool cur_t2; int day;   // day: the replayed day of this environment   // n_ovf: events in the overflow tier
 
@@ -102,9 +108,21 @@ struct WarpCtxT {
     oc_t = reinterpret_cast<uint4 *>(smem); oc_b = reinterpret_cast<uint2 *>(smem + OC_N * 16); oc_tag = reinterpret_cast<int32_t *>(smem + OC_N * 24);
     if (P.idbook && lane < OC_N) oc_tag[lane] = -1;
     idb = P.idbook ? P.idbook + (size_t)env * P.n_ids : nullptr;
+    snp = P.snap ? P.snap + (size_t)env * P.n_snap * 2 * P.snap_depth : nullptr;
     idt = P.idtab ? P.idtab + (size_t)env * P.n_ids : nullptr; lob = P.lobs ? P.lobs + (size_t)env * LOB_CAP * 3 : nullptr;
     cur_group = cur_lane = -1; cur_mask = 0; my_hi = KEY_EMPTY; my_uniq = 0xffffffffu; n_ovf = 0; cur_t2 = false;
     day = P.n_days > 1 ? env % P.n_days : 0;                               // once per launch: an integer modulo is ~170 instructions
+  }
+  // environment e replays day (e + episode) % n_days: every day-advancing reset moves it on to its next day
+  __device__ __forceinline__ void set_episode(uint32_t episode) { if (P.n_days > 1 && episode) day = (int)(((uint32_t)env + episode) % (uint32_t)P.n_days); }
+  // per-order tables of one environment back to zero (masked resets; a whole-batch reset uses cudaMemsetAsync instead)
+  __device__ void clear_tables() {
+    uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    if (idt) for (int i = lane; i < P.n_ids; i += 32) __stcg(idt + i, z4);
+    if (idb) for (int i = lane; i < P.n_ids; i += 32) __stcg(idb + i, make_uint2(0u, 0u));
+    if (lob) for (int i = lane; i < LOB_CAP * 3; i += 32) __stcg(lob + i, make_int4(0, 0, 0, 0));
+    if (P.idbook && lane < OC_N) oc_tag[lane] = -1;
+    __syncwarp();
   }
   // Uniform code stores on-chip state from every lane (same value, same address: one STS, no branch).
   __device__ __forceinline__ bool onchip_writer() const { return true; }
@@ -300,19 +318,8 @@ struct WarpCtxT {
   // found: it equals (the order joins that level); otherwise pos is where the new level goes.  On a sorted ladder this is the sorted insert.
   __device__ __forceinline__ void lv_find(int side, int32_t price, int n, int &pos, bool &found) {
     const int32_t *p = lvp + side * P.c.level_cap; int best = -1;
-#ifdef ABX_OPT_VFIND
-#pragma unroll 1
-    for (int i = lane * 4; i < n; i += 128) {                                  // four levels per lane and pass (128-bit shared loads; level_cap is a multiple of 4)
-      int4 v = *reinterpret_cast<const int4 *>(p + i);
-      if (side == 0 ? v.x <= price : v.x >= price) best = i;
-      if (i + 1 < n && (side == 0 ? v.y <= price : v.y >= price)) best = i + 1;
-      if (i + 2 < n && (side == 0 ? v.z <= price : v.z >= price)) best = i + 2;
-      if (i + 3 < n && (side == 0 ? v.w <= price : v.w >= price)) best = i + 3;
-    }
-#else
 #pragma unroll 1
     for (int i = lane; i < n; i += 32) { int32_t v = p[i]; if (side == 0 ? v <= price : v >= price) best = i; }
-#endif
     best = __reduce_max_sync(FULL, best);
     if (n > 0 && (side == 0 ? p[0] > price : p[0] < price)) best = -1;        // :267-270 tested first: worse than the LAST level -> new last level, whatever stands before it
     found = best >= 0 && p[best] == price; pos = found ? best : best + 1;
@@ -321,19 +328,8 @@ struct WarpCtxT {
   // cnt = how many such levels there are (1 on a sorted ladder)
   __device__ __forceinline__ int lv_find_eq(int side, int32_t price, int limit, int &cnt) {
     const int32_t *p = lvp + side * P.c.level_cap; int best = -1, k = 0;
-#ifdef ABX_OPT_VFIND
-#pragma unroll 1
-    for (int i = lane * 4; i < limit; i += 128) {
-      int4 v = *reinterpret_cast<const int4 *>(p + i);
-      if (v.x == price) { best = i; k++; }
-      if (i + 1 < limit && v.y == price) { best = i + 1; k++; }
-      if (i + 2 < limit && v.z == price) { best = i + 2; k++; }
-      if (i + 3 < limit && v.w == price) { best = i + 3; k++; }
-    }
-#else
 #pragma unroll 1
     for (int i = lane; i < limit; i += 32) if (p[i] == price) { best = i; k++; }
-#endif
     cnt = __reduce_add_sync(FULL, k);
     return __reduce_max_sync(FULL, best);
   }
@@ -363,6 +359,15 @@ struct WarpCtxT {
     }
   }
 
+  // getInsideBids(depth) / getInsideAsks(depth) of a deep query, copied when the exchange processes it: the first n_copy of the side's n_total levels,
+  // best first, into execution agent k's area (32 levels per pass; a real barrier before anyone reads them back)
+  __device__ __forceinline__ void snap_store(int k, int side, int n_total, int n_copy) {
+    int2 *dst = snp + (size_t)(k * 2 + side) * P.snap_depth; int b = side * P.c.level_cap;
+#pragma unroll 1
+    for (int i = lane; i < n_copy; i += 32) __stcg(dst + i, make_int2(lvp[b + n_total - 1 - i], lvq[b + n_total - 1 - i]));
+    __syncwarp();
+  }
+  __device__ __forceinline__ int2 snap_load(int k, int side, int i) const { return __ldcg(snp + (size_t)(k * 2 + side) * P.snap_depth + i); }
   // ---- order nodes (HBM, 16 B each) ----
   template <bool PRICED> __device__ __forceinline__ NodeRec node_load(uint32_t i) const { return node_unpack<PRICED>(ldcg4(nodes + i)); }
   template <bool PRICED> __device__ __forceinline__ void node_store(uint32_t i, const NodeRec &r) { if (lane == 0) __stcg(nodes + i, node_pack<PRICED>(r)); __syncwarp(); }

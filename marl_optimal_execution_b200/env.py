@@ -105,7 +105,18 @@ class Box:
 class ABIDESEnv:
     OBS_SIZE = 9          # get_observation returns 9 values (get_observation_space_size says 10)
 
-    def __init__(self, stream, n_envs=1, device=0, cfg=None, lib_path=None):
+    def __init__(self, ticker, date=None, log_dir=None, seed=None, n_envs=1, device=0, cfg=None, lib_path=None, data_root="data/lobster", level=1):
+        """Positionally the reference's constructor: ABIDESEnv(ticker, date, log_dir=None, seed=None) (ABIDESEnv.py:8) replays the day's LOBSTER message
+        file found under `data_root` where agent_config.py:63-64 looks for it (`date` may be a list of days).  log_dir and seed are accepted and unused
+        on this path (no logging, no random draws: zero latency, noise [1.0]).  Batched form: the first argument may instead be the parsed stream
+        itself -- an int64 [n, 5] array of (t_ns, ORDER_ID, PRICE cents, SIZE, is_buy) rows, or a list of such arrays, one per replayed day."""
+        if isinstance(ticker, str):
+            if date is None:
+                raise TypeError("ABIDESEnv(ticker, date, ...): date is required")
+            self.ticker, self.date, self.log_dir, self.seed = ticker, date, log_dir, seed
+            stream = _load_days(ticker, [date] if isinstance(date, str) else list(date), data_root, level)
+        else:
+            stream = ticker
         self._L = _lib.load(lib_path)
         self.cfg = cfg or env_config(self._L)
         self.n_envs = int(n_envs)
@@ -127,10 +138,7 @@ class ABIDESEnv:
         """The reference's constructor arguments (ABIDESEnv(ticker, date), ABIDESEnv.py:8-17): replays the day's LOBSTER message file found
         where agent_config.py:63-64 looks for it under `data_root`.  `date` may be a list of 'yyyy-mm-dd' strings (environment e replays
         day e % n_days).  log_dir / seed of the reference have no effect on this path (no random draws, no logging)."""
-        dates = [date] if isinstance(date, str) else list(date)
-        env = cls(_load_days(ticker, dates, data_root, level), n_envs=n_envs, **kw)
-        env.ticker, env.date = ticker, date
-        return env
+        return cls(ticker, date, n_envs=n_envs, data_root=data_root, level=level, **kw)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -143,14 +151,44 @@ class ABIDESEnv:
         except Exception:
             pass
 
-    def reset(self, stream=None):
-        """ABIDESEnv.reset() (ABIDESEnv.py:51-57).  Like the reference it returns None: the first observation comes
-        from the first step()."""
-        _lib.check(self._L, self._L.abx_env_reset(self._h, stream), "abx_env_reset")
+    def reset(self, mask=None, advance_day=False, stream=None):
+        """ABIDESEnv.reset() (ABIDESEnv.py:51-57).  Like the reference it returns None: the first observation comes from the first step().
+        mask (bool / uint8 [n_envs], numpy or CUDA tensor): only those environments start over -- the reference's reset is per environment object;
+        advance_day moves each of them on to its next replayed day (environment e replays day (e + resets) % n_days)."""
+        if mask is None:
+            _lib.check(self._L, self._L.abx_env_reset(self._h, stream), "abx_env_reset")
+            return None
+        _lib.check(self._L, self._L.abx_env_reset_mask(self._h, self._mask_ptr(mask), int(bool(advance_day)), stream), "abx_env_reset_mask")
         return None
 
-    def step(self, actions, stream=None):
-        """(obs [n_envs, 9], reward [n_envs], done [n_envs], None), as ABIDESEnv.step (ABIDESEnv.py:30-49)."""
+    def _mask_ptr(self, mask):
+        """Device pointer of a uint8 [n_envs] mask (a CUDA tensor is used in place; a host array is copied through torch; the CPU emulation of the test-suite takes the host pointer)."""
+        try:
+            import torch
+        except ImportError:      # pragma: no cover
+            torch = None
+        if torch is not None and isinstance(mask, torch.Tensor) and mask.is_cuda:
+            self._mask_keep = mask.to(torch.uint8).contiguous().view(self.n_envs)
+            return C.c_void_p(self._mask_keep.data_ptr())
+        m = np.ascontiguousarray(np.asarray(mask).astype(np.uint8).reshape(self.n_envs))
+        if torch is not None and torch.cuda.is_available() and self._L.abx_device_count() > 0:
+            self._mask_keep = torch.from_numpy(m).to("cuda:%d" % self.device)
+            return C.c_void_p(self._mask_keep.data_ptr())
+        self._mask_keep = m
+        return C.c_void_p(m.ctypes.data)
+
+    def set_auto_reset(self, mode):
+        """After every step, environments whose episode has ended (done == 1 in that step's output) are reset before the next step:
+        0 / False off, 1 / True restart the same day, 2 / "next_day" move on to the next replayed day."""
+        mode = 2 if mode == "next_day" else int(mode)
+        _lib.check(self._L, self._L.abx_env_set_auto_reset(self._h, mode), "abx_env_set_auto_reset")
+
+    reuse_outputs = False      # True: the CUDA path returns the same three tensors on every step (no allocation in a tight loop; bench.py sets it)
+
+    def step(self, actions, stream=None, out=None):
+        """(obs [n_envs, 9], reward [n_envs], done [n_envs], None), as ABIDESEnv.step (ABIDESEnv.py:30-49).  actions: [n_envs, order_level + 1]
+        (x_hat, o_hat_1 .. o_hat_k) in [0, 1].  CUDA tensors in -> fresh CUDA tensors out (or `out=(obs, reward, done)` to fill preallocated ones,
+        or set `reuse_outputs`)."""
         try:
             import torch
             is_torch = isinstance(actions, torch.Tensor)
@@ -158,17 +196,35 @@ class ABIDESEnv:
             is_torch = False
         if is_torch and actions.is_cuda:
             import torch
-            a = actions.to(torch.float64).contiguous().view(self.n_envs, 3)
-            if self._torch_out is None:
-                self._torch_out = (torch.zeros(self.n_envs, 9, dtype=torch.float64, device=a.device),
-                                   torch.zeros(self.n_envs, dtype=torch.float64, device=a.device),
-                                   torch.zeros(self.n_envs, dtype=torch.uint8, device=a.device))
-            obs, rew, done = self._torch_out
+            a = actions.to(torch.float64).reshape(self.n_envs, -1)
+            if a.shape[1] != self.action_size and a.shape[1] != 3:
+                raise ValueError("actions must be [n_envs, %d] (order_level + 1)" % self.action_size)
+            if a.shape[1] < 3:                                            # the device layout always has three columns (x_hat, o_hat_1, o_hat_2)
+                a = torch.cat([a, torch.zeros(self.n_envs, 3 - a.shape[1], dtype=torch.float64, device=a.device)], dim=1)
+            a = a.contiguous()
+            if out is not None:
+                obs, rew, done = out
+            elif self.reuse_outputs:
+                if self._torch_out is None:
+                    self._torch_out = (torch.zeros(self.n_envs, 9, dtype=torch.float64, device=a.device),
+                                       torch.zeros(self.n_envs, dtype=torch.float64, device=a.device),
+                                       torch.zeros(self.n_envs, dtype=torch.uint8, device=a.device))
+                obs, rew, done = self._torch_out
+            else:                                                         # fresh tensors per step, like the reference's fresh arrays
+                obs = torch.empty(self.n_envs, 9, dtype=torch.float64, device=a.device)
+                rew = torch.empty(self.n_envs, dtype=torch.float64, device=a.device)
+                done = torch.empty(self.n_envs, dtype=torch.uint8, device=a.device)
             sp = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream) if stream is None else stream
+            self._keep_actions = a                                        # `a` may be a temporary and `stream` need not be torch's current stream: it stays referenced until the next step replaces it
             _lib.check(self._L, self._L.abx_env_step(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(obs.data_ptr()),
                                                      C.c_void_p(rew.data_ptr()), C.c_void_p(done.data_ptr()), sp), "abx_env_step")
             return obs, rew, done, None
-        a = np.ascontiguousarray(np.asarray(actions, dtype=np.float64).reshape(self.n_envs, 3))
+        a = np.asarray(actions, dtype=np.float64).reshape(self.n_envs, -1)
+        if a.shape[1] != self.action_size and a.shape[1] != 3:
+            raise ValueError("actions must be [n_envs, %d] (order_level + 1)" % self.action_size)
+        if a.shape[1] < 3:
+            a = np.concatenate([a, np.zeros((self.n_envs, 3 - a.shape[1]))], axis=1)
+        a = np.ascontiguousarray(a)
         obs = np.zeros((self.n_envs, 9))
         rew = np.zeros(self.n_envs)
         done = np.zeros(self.n_envs, dtype=np.uint8)
@@ -231,7 +287,15 @@ class DDQNExecutionEnv(ABIDESEnv):
     OBS_SIZE = 8
     N_ACTIONS = 24
 
-    def __init__(self, stream, n_envs=1, device=0, cfg=None, lib_path=None):
+    def __init__(self, ticker, date=None, log_dir=None, seed=None, n_envs=1, device=0, cfg=None, lib_path=None, data_root="data/lobster", level=1):
+        """(ticker, date) as the reference's config takes them (-t, -d), or the parsed stream(s) as the first argument (see ABIDESEnv)."""
+        if isinstance(ticker, str):
+            if date is None:
+                raise TypeError("DDQNExecutionEnv(ticker, date, ...): date is required")
+            self.ticker, self.date, self.log_dir, self.seed = ticker, date, log_dir, seed
+            stream = _load_days(ticker, [date] if isinstance(date, str) else list(date), data_root, level)
+        else:
+            stream = ticker
         self._L = _lib.load(lib_path)
         self.cfg = cfg or dq_config(self._L)
         self.n_envs, self.device = int(n_envs), int(device)
@@ -248,19 +312,21 @@ class DDQNExecutionEnv(ABIDESEnv):
     def from_lobster(cls, ticker, date, n_envs=1, data_root="data/lobster", level=1, **kw):
         """(ticker, date) as config/execution/marketreplay/execution_marketreplay_ddqn.py takes them (-t, -d): the day's LOBSTER message
         file(s) under `data_root`, parsed like LOBSTEROrdersProcessor (load_lobster_csv)."""
-        dates = [date] if isinstance(date, str) else list(date)
-        env = cls(_load_days(ticker, dates, data_root, level), n_envs=n_envs, **kw)
-        env.ticker, env.date = ticker, date
-        return env
+        return cls(ticker, date, n_envs=n_envs, data_root=data_root, level=level, **kw)
 
-    def reset(self, seeds=None, mom_sizes=None, stream=None):
+    def reset(self, seeds=None, mom_sizes=None, stream=None, mask=None, advance_day=False):
+        """Whole-batch reset with per-environment seeds (or recorded MomentumAgent sizes); with `mask`, only those environments start over, keeping the
+        seeds / sizes of the last whole-batch reset (seed + episode number for the Philox-drawn sizes), optionally on their next replayed day."""
+        if mask is not None:
+            _lib.check(self._L, self._L.abx_env_reset_mask(self._h, self._mask_ptr(mask), int(bool(advance_day)), stream), "abx_env_reset_mask")
+            return None
         sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64).reshape(self.n_envs)
         ms = None if mom_sizes is None else np.ascontiguousarray(mom_sizes, dtype=np.int32).reshape(self.n_envs, int(self.cfg.n_momentum))
         _lib.check(self._L, self._L.abx_dq_reset(self._h, None if sd is None else sd.ctypes.data, None if ms is None else ms.ctypes.data, stream), "abx_dq_reset")
         self._keep = (sd, ms)
         return None
 
-    def step(self, actions, stream=None):
+    def step(self, actions, stream=None, out=None):
         try:
             import torch
             is_torch = isinstance(actions, torch.Tensor)
@@ -269,10 +335,16 @@ class DDQNExecutionEnv(ABIDESEnv):
         if is_torch and actions.is_cuda:
             import torch
             a = actions.to(torch.int32).contiguous().view(self.n_envs)
-            if self._torch_out is None:
-                self._torch_out = (torch.zeros(self.n_envs, 8, dtype=torch.float64, device=a.device), torch.zeros(self.n_envs, 6, dtype=torch.float64, device=a.device),
-                                   torch.zeros(self.n_envs, dtype=torch.float64, device=a.device), torch.zeros(self.n_envs, dtype=torch.uint8, device=a.device))
-            obs, trans, rew, done = self._torch_out
+            if out is not None:
+                obs, trans, rew, done = out
+            elif self.reuse_outputs:
+                if self._torch_out is None:
+                    self._torch_out = (torch.zeros(self.n_envs, 8, dtype=torch.float64, device=a.device), torch.zeros(self.n_envs, 6, dtype=torch.float64, device=a.device),
+                                       torch.zeros(self.n_envs, dtype=torch.float64, device=a.device), torch.zeros(self.n_envs, dtype=torch.uint8, device=a.device))
+                obs, trans, rew, done = self._torch_out
+            else:
+                obs, trans = torch.empty(self.n_envs, 8, dtype=torch.float64, device=a.device), torch.empty(self.n_envs, 6, dtype=torch.float64, device=a.device)
+                rew, done = torch.empty(self.n_envs, dtype=torch.float64, device=a.device), torch.empty(self.n_envs, dtype=torch.uint8, device=a.device)
             sp = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream) if stream is None else stream
             _lib.check(self._L, self._L.abx_dq_step(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(obs.data_ptr()), C.c_void_p(trans.data_ptr()),
                                                     C.c_void_p(rew.data_ptr()), C.c_void_p(done.data_ptr()), sp), "abx_dq_step")

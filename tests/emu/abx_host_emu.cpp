@@ -89,13 +89,22 @@ struct HostCtx {
   int tab_find(int base, int n, uint32_t oid) { for (int i = 0; i < n; i++) if (idt[base + i].x == oid) return i; return -1; }
   void tab_remove(int base, int n, int f) { for (int i = f; i + 1 < n; i++) idt[base + i] = idt[base + i + 1]; }
   int4 row_load(int r) { return P.st_rows[r]; }
-  int4 day_rec() { return P.day_tab[P.n_days > 1 ? env % P.n_days : 0]; }
+  uint32_t episode = 0; void set_episode(uint32_t ep) { episode = ep; }
+  int4 day_rec() { return P.day_tab[P.n_days > 1 ? (int)(((uint32_t)env + episode) % (uint32_t)P.n_days) : 0]; }
+  void clear_tables() {
+    if (idt) memset(idt, 0, sizeof(uint4) * P.n_ids);
+    if (P.idbook) memset(P.idbook + (size_t)env * P.n_ids, 0, sizeof(uint2) * P.n_ids);
+    if (lob) memset(lob, 0, sizeof(int4) * LOB_CAP * 3);
+  }
   int n_ts() { return day_rec().y; }
   int64_t ts_load(int k) { return P.st_ts[day_rec().x + k]; }
   int first_load(int k) { return P.st_first[day_rec().z + k]; }
   void lob_store(int slot, const int32_t w[12]) { for (int k = 0; k < 3; k++) { int4 v; v.x = w[4 * k]; v.y = w[4 * k + 1]; v.z = w[4 * k + 2]; v.w = w[4 * k + 3]; lob[slot * 3 + k] = v; } }
   void lob_load(int slot, int32_t w[12]) { for (int k = 0; k < 3; k++) { int4 v = lob[slot * 3 + k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; } }
   void id_prefetch(int) {} void ib_prefetch(int) {}
+  void snap_store(int k, int side, int n_total, int n_copy) { int2 *dst = P.snap + ((size_t)env * P.n_snap * 2 + (size_t)(k * 2 + side)) * P.snap_depth;
+    for (int i = 0; i < n_copy; i++) { dst[i].x = lv_price(side, n_total - 1 - i); dst[i].y = lv_qty(side, n_total - 1 - i); } }
+  int2 snap_load(int k, int side, int i) { return P.snap[((size_t)env * P.n_snap * 2 + (size_t)(k * 2 + side)) * P.snap_depth + i]; }
   uint4 ord_load(int i) { return id_load(i); } void ord_store(int i, uint4 v) { id_store(i, v); }
   int64_t mid_sum(int k, int L, int n) { int64_t t = 0; for (int i = 0; i < n; i++) t += mid_load(k, (L - 1 - i) % MOM_MIDS); return t; }
   int32_t mid_load(int k, int slot) { return reinterpret_cast<int32_t *>(lob)[k * MOM_MIDS + slot]; }
@@ -117,7 +126,7 @@ struct abx_sim {
   SimParams P; int n_envs; bool reset_done;
   std::vector<uint4> qkey, qpay0, qpay1, qcache, nodes; std::vector<ZiAgent> agents; std::vector<int32_t> lvp, lvq; std::vector<uint32_t> lvht;
   std::vector<EnvState> env; std::vector<abx_trace_rec> trace; std::vector<uint4> draw_log; std::vector<uint64_t> tbits; std::vector<uint8_t> tkinds; std::vector<int64_t> toff;
-  bool is_env; EnvStreamHost st; EnvDaysHost dh; bool has_days = false; std::vector<EnvX> envx; std::vector<uint4> idtab; std::vector<int4> lobs; std::vector<uint2> idbook;
+  bool is_env; EnvStreamHost st; EnvDaysHost dh; bool has_days = false; std::vector<EnvX> envx; std::vector<uint4> idtab; std::vector<int4> lobs; std::vector<uint2> idbook; std::vector<int2> snap; int auto_reset = 0; std::vector<uint64_t> dq_seeds; std::vector<int32_t> dq_msizes;
 };
 
 extern "C" {
@@ -146,7 +155,8 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
   h->P.trace = c.trace_cap ? h->trace.data() : nullptr;
   h->draw_log.resize(E * (size_t)c.draw_log_cap); h->P.draw_log = c.draw_log_cap ? h->draw_log.data() : nullptr;
-  if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + TV_RING; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0); h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); }
+  if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + h->P.tv_ring; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0); h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data();
+    if (c.n_pov_exec) { h->P.n_snap = 1; h->P.snap_depth = c.level_cap; h->snap.resize(E * 2 * (size_t)c.level_cap); h->P.snap = h->snap.data(); } }
   *out = h; return ABX_OK;
 }
 int32_t abx_sim_destroy(abx_sim *h) { delete h; return ABX_OK; }
@@ -240,7 +250,7 @@ int32_t abx_sim_trace(abx_sim *h, int32_t env, abx_trace_rec *out, int32_t max_r
   (void)stream; if (!h || !out || !n_recs || env < 0 || env >= h->n_envs) return ABX_ERR_ARG;
   int n = (int)h->env[env].trace_n; if (n > max_recs) n = max_recs;
   if (n) memcpy(out, h->P.trace + (size_t)env * h->P.c.trace_cap, sizeof(abx_trace_rec) * n);
-  if (h->is_env) { const std::vector<int64_t> &ido = h->has_days ? h->dh.days[env % (int)h->dh.days.size()].id_orig : h->st.id_orig;
+  if (h->is_env) { const std::vector<int64_t> &ido = h->has_days ? h->dh.days[(int)(((uint32_t)env + h->env[env].episode) % (uint32_t)h->dh.days.size())].id_orig : h->st.id_orig;
     for (int i = 0; i < n; i++) if (out[i].tag == 1 && (uint32_t)out[i].v[1] >= REPLAY_ID_BASE) out[i].v[1] = (int32_t)ido[(uint32_t)out[i].v[1] - REPLAY_ID_BASE]; }
   *n_recs = n; return ABX_OK;
 }
@@ -267,24 +277,43 @@ int32_t abx_env_create_days(const abx_env_config *cfg, const int64_t *stream5, c
 int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
   int64_t off[2] = {0, n_rows}; return abx_env_create_days(cfg, stream5, off, 1, n_envs, device, out);
 }
-int32_t abx_env_reset(abx_sim *h, void *stream) {
-  (void)stream; if (!h || !h->is_env) return ABX_ERR_ARG;
-  memset(h->idtab.data(), 0, h->idtab.size() * sizeof(uint4)); memset(h->idbook.data(), 0, h->idbook.size() * sizeof(uint2));
+enum { RESET_ALL = 0, RESET_MASK = 1, RESET_DONE = 2 };
+static bool reset_selected(abx_sim *h, int e, const uint8_t *mask, int mode, int advance_day, uint32_t &episode) {
+  episode = 0; if (mode == RESET_ALL) return true;
+  if (mode == RESET_MASK && !mask[e]) return false;
+  if (mode == RESET_DONE && !(h->env[e].flags & ABX_F_DONE)) return false;
+  episode = h->env[e].episode + (advance_day ? 1u : 0u); return true;
+}
+static void emu_env_reset(abx_sim *h, const uint8_t *mask, int mode, int advance_day) {
   for (int e = 0; e < h->n_envs; e++) {
-    EnvState s; init_env_state(h->P, 0, s); s.last_trade = -1; init_envx(h->P, h->envx[e]);     // no oracle: last_trade None (ExchangeAgent.py:97-102)
-    HostCtx ctx(h->P, e); ctx.q_clear(); EnvSimHost sim(ctx, h->P, s, e); sim.env_reset(); h->env[e] = sim.s;
+    uint32_t episode; if (!reset_selected(h, e, mask, mode, advance_day, episode)) continue;
+    HostCtx ctx(h->P, e); ctx.set_episode(episode); ctx.clear_tables();
+    EnvState s; init_env_state(h->P, 0, s); s.last_trade = -1; s.episode = episode; init_envx(h->P, h->envx[e]);     // no oracle: last_trade None (ExchangeAgent.py:97-102)
+    ctx.q_clear(); EnvSimHost sim(ctx, h->P, s, e); sim.env_reset(); h->env[e] = sim.s;
   }
+}
+static void emu_dq_reset(abx_sim *h, const uint8_t *mask, int mode, int advance_day);
+int32_t abx_env_reset(abx_sim *h, void *stream) {
+  (void)stream; if (!h || !h->is_env || h->P.c.population == 2) return ABX_ERR_ARG;
+  emu_env_reset(h, nullptr, RESET_ALL, 0);
   h->reset_done = true; return ABX_OK;
 }
+int32_t abx_env_reset_mask(abx_sim *h, const uint8_t *mask, int32_t advance_day, void *stream) {
+  (void)stream; if (!h || !h->is_env || !mask) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  if (h->P.c.population == 2) emu_dq_reset(h, mask, RESET_MASK, advance_day ? 1 : 0); else emu_env_reset(h, mask, RESET_MASK, advance_day ? 1 : 0);
+  return ABX_OK;
+}
+int32_t abx_env_set_auto_reset(abx_sim *h, int32_t mode) { if (!h || !h->is_env || mode < 0 || mode > 2) return ABX_ERR_ARG; h->auto_reset = mode; return ABX_OK; }
 int32_t abx_env_step_host(abx_sim *h, const double *actions, double *obs, double *reward, uint8_t *done, void *stream) {
   (void)stream; if (!h || !h->is_env || !actions || !obs || !done) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
   for (int e = 0; e < h->n_envs; e++) {
     EnvX &x = h->envx[e];
-    if (!(h->env[e].flags & ABX_F_DONE)) { HostCtx ctx(h->P, e); EnvSimHost sim(ctx, h->P, h->env[e], e); sim.env_step(actions[3 * e], actions[3 * e + 1], actions[3 * e + 2]); h->env[e] = sim.s; }
+    if (!(h->env[e].flags & ABX_F_DONE)) { HostCtx ctx(h->P, e); ctx.set_episode(h->env[e].episode); EnvSimHost sim(ctx, h->P, h->env[e], e); sim.env_step(actions[3 * e], actions[3 * e + 1], actions[3 * e + 2]); h->env[e] = sim.s; }
     else x.obs_len = 0;
     for (int i = 0; i < 9; i++) obs[9 * e + i] = x.obs_len ? x.obs[i] : 0.0;
     if (reward) reward[e] = 0.0; done[e] = (h->env[e].flags & ABX_F_DONE) ? 1 : 0;
   }
+  if (h->auto_reset) emu_env_reset(h, nullptr, RESET_DONE, h->auto_reset == 2);
   return ABX_OK;
 }
 int32_t abx_env_step(abx_sim *h, const double *a, double *o, double *r, uint8_t *d, void *s) { return abx_env_step_host(h, a, o, r, d, s); }
@@ -307,28 +336,36 @@ int32_t abx_dq_create_days(const abx_dq_config *cfg, const int64_t *stream5, con
   h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
   h->P.trace = c.trace_cap ? h->trace.data() : nullptr; h->P.envx = h->envx.data(); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); h->P.idbook = h->idbook.data();
   h->P.st_ts = h->dh.ts.data(); h->P.st_first = h->dh.first.data(); h->P.st_rows = h->dh.rows.data(); h->P.day_tab = h->dh.day_tab.data();
+  { int n_exec = cfg->n_twap + (cfg->has_ddqn ? 1 : 0); h->P.n_snap = n_exec > 0 ? n_exec : 1; h->P.snap_depth = DQ_DEPTH; h->snap.resize(E * (size_t)h->P.n_snap * 2 * DQ_DEPTH); h->P.snap = h->snap.data(); }
   *out = h; return ABX_OK;
 }
 int32_t abx_dq_create(const abx_dq_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
   int64_t off[2] = {0, n_rows}; return abx_dq_create_days(cfg, stream5, off, 1, n_envs, device, out);
 }
+static void emu_dq_reset(abx_sim *h, const uint8_t *mask, int mode, int advance_day) {
+  for (int e = 0; e < h->n_envs; e++) {
+    uint32_t episode; if (!reset_selected(h, e, mask, mode, advance_day, episode)) continue;
+    HostCtx ctx(h->P, e); ctx.set_episode(episode); ctx.clear_tables();
+    uint64_t seed = (h->dq_seeds.empty() ? 0 : h->dq_seeds[e]) + episode;
+    EnvState s; init_env_state(h->P, seed, s); s.last_trade = -1; s.episode = episode; init_envx(h->P, h->envx[e]);
+    for (int id = 2; id < h->P.c.n_agents; id++)
+      init_agent_record_dq(h->P, e, id, seed, (!h->dq_msizes.empty() && id < 2 + h->P.dq_n_mom) ? h->dq_msizes[(size_t)e * h->P.dq_n_mom + id - 2] : -1, &h->agents[(size_t)e * h->P.c.n_agents + id]);
+    ctx.q_clear(); DqSimHost sim(ctx, h->P, s, e); sim.env_reset(); h->env[e] = sim.s;
+  }
+}
 int32_t abx_dq_reset(abx_sim *h, const uint64_t *seeds, const int32_t *mom_sizes, void *stream) {
   (void)stream; if (!h || !h->is_env || h->P.c.population != 2) return ABX_ERR_ARG;
-  memset(h->idtab.data(), 0, h->idtab.size() * sizeof(uint4)); memset(h->lobs.data(), 0, h->lobs.size() * sizeof(int4)); memset(h->idbook.data(), 0, h->idbook.size() * sizeof(uint2));
-  for (int e = 0; e < h->n_envs; e++) {
-    uint64_t seed = seeds ? seeds[e] : 0;
-    EnvState s; init_env_state(h->P, seed, s); s.last_trade = -1; init_envx(h->P, h->envx[e]);
-    for (int id = 2; id < h->P.c.n_agents; id++)
-      init_agent_record_dq(h->P, e, id, seed, (mom_sizes && id < 2 + h->P.dq_n_mom) ? mom_sizes[(size_t)e * h->P.dq_n_mom + id - 2] : -1, &h->agents[(size_t)e * h->P.c.n_agents + id]);
-    HostCtx ctx(h->P, e); ctx.q_clear(); DqSimHost sim(ctx, h->P, s, e); sim.env_reset(); h->env[e] = sim.s;
-  }
+  h->dq_seeds.clear(); h->dq_msizes.clear();
+  if (seeds) h->dq_seeds.assign(seeds, seeds + h->n_envs);
+  if (mom_sizes && h->P.dq_n_mom > 0) h->dq_msizes.assign(mom_sizes, mom_sizes + (size_t)h->n_envs * h->P.dq_n_mom);
+  emu_dq_reset(h, nullptr, RESET_ALL, 0);
   h->reset_done = true; return ABX_OK;
 }
 int32_t abx_dq_step_host(abx_sim *h, const int32_t *actions, double *obs, double *trans, double *reward, uint8_t *done, void *stream) {
   (void)stream; if (!h || !h->is_env || h->P.c.population != 2 || !obs || !trans || !done) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
   for (int e = 0; e < h->n_envs; e++) {
     EnvX &x = h->envx[e]; bool was_done = (h->env[e].flags & ABX_F_DONE) != 0, paused = false;
-    if (!was_done) { HostCtx ctx(h->P, e); DqSimHost sim(ctx, h->P, h->env[e], e); paused = sim.dq_step(actions ? actions[e] : 0); h->env[e] = sim.s; }
+    if (!was_done) { HostCtx ctx(h->P, e); ctx.set_episode(h->env[e].episode); DqSimHost sim(ctx, h->P, h->env[e], e); paused = sim.dq_step(actions ? actions[e] : 0); h->env[e] = sim.s; }
     for (int i = 0; i < 8; i++) obs[8 * e + i] = paused ? x.obs[i] : 0.0;
     for (int i = 0; i < 6; i++) trans[6 * e + i] = NAN;
     double rw = 0.0;
@@ -339,6 +376,7 @@ int32_t abx_dq_step_host(abx_sim *h, const int32_t *actions, double *obs, double
     }
     if (reward) reward[e] = rw; done[e] = (h->env[e].flags & ABX_F_DONE) ? 1 : 0;
   }
+  if (h->auto_reset) emu_dq_reset(h, nullptr, RESET_DONE, h->auto_reset == 2);
   return ABX_OK;
 }
 int32_t abx_dq_step(abx_sim *h, const int32_t *a, double *o, double *t, double *r, uint8_t *d, void *s) { return abx_dq_step_host(h, a, o, t, r, d, s); }

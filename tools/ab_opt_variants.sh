@@ -5,15 +5,11 @@ cd "$(dirname "$0")/.."
 PKG=marl_optimal_execution_b200
 FL="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared"
 declare -A V
-V[base]=""
-V[vfind]="-DABX_OPT_VFIND"
-V[ddiv]="-DABX_OPT_DDIV"
-V[emitni]="-DABX_OPT_EMITNI"
-V[early2]="-DABX_OPT_EARLY2"
-V[vd]="-DABX_OPT_VFIND -DABX_OPT_DDIV"
-V[vde]="-DABX_OPT_VFIND -DABX_OPT_DDIV -DABX_OPT_EMITNI"
-V[p7]="-DABX_PHILOX_ROUNDS=7"
-ORDER="base vfind ddiv emitni vd vde p7 early2"
+V[noexps]="-DABX_NO_EXPS"
+V[expsni]=""
+V[argni]="-DABX_NO_EXPS -DABX_ARGMIN_NI"
+V[both]="-DABX_ARGMIN_NI"
+ORDER="noexps expsni argni both"
 if [ "$1" = build ]; then
   mkdir -p build/ab
   for v in $ORDER; do ( nvcc $FL ${V[$v]} -o build/ab/opt_$v.so $PKG/csrc/abx_sim.cu $PKG/csrc/abx_qnet.cu ) & done
@@ -21,7 +17,7 @@ if [ "$1" = build ]; then
 fi
 mkdir -p gpurun_out; : > gpurun_out/ab_opt.log
 for rep in 1 2; do for v in $ORDER; do
-  EXTRA="--no-rmsc03 --no-ddqn --no-env"; [ $v = early2 ] && EXTRA="--env-steps 300 --ddqn-steps 100"; [ $v = base ] && [ $rep = 2 ] && EXTRA="--env-steps 300 --ddqn-steps 100"
+  EXTRA="--no-ddqn --no-env"
   echo -n "$v: " | tee -a gpurun_out/ab_opt.log
   ABX_LIB_PATH=$PWD/build/ab/opt_$v.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline $EXTRA 2>/dev/null | python -c "
 import json,sys
