@@ -79,6 +79,26 @@ def measured_peak_tflops():
         return 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def shared_config(args):
+    """The workload both arms are measured on (BASELINE.json configs[1]); arm-specific facts go under the line's "detail" key, so that the two
+    arms' `config` objects are identical."""
+    return {"workload": "config/sparse_zi_%d.py: %d ZeroIntelligenceAgents + ExchangeAgent, sparse mean-reverting OU oracle with megashocks, 00:00-17:00 (market 09:30-16:00); "
+                        "independent environments, environment e seeded %d+e; one message = one pop of the kernel event queue, counted like ttl_messages (Kernel.py:211)"
+                        % (args.variant, args.variant, args.seed),
+            "envs_per_gpu": args.envs_per_gpu, "variant": args.variant, "seed": args.seed}
+
+
+def python_reference_record():
+    """The unmodified Python reference under the config/parallel.py pattern, measured in the BUILD CONTAINER by tools/measure_python_reference.py (the
+    reference tree cannot travel to the GPU box, and nothing here may read it at run time): reported with its provenance, not as a same-box number."""
+    try:
+        r = json.load(open(os.path.join(ROOT, "profiles", "r02_python_reference_cpu.json")))
+        return {"value": r["msgs_per_s_event_loop"], "unit": "msgs/s", "processes": r["processes"], "cores": r["cores"], "where": r["where"], "what": r["what"],
+                "msgs_per_s_wall": r["msgs_per_s_wall"], "source": "profiles/r02_python_reference_cpu.json (tools/measure_python_reference.py)"}
+    except Exception:
+        return None
+
+
 def sim_closed(sim):
     return getattr(sim, "_h", None) is None or not sim._h
 
@@ -230,9 +250,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "LOB msgs/sec", "value": v, "unit": "msgs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_w / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": v / PUBLISHED_MSGS_PER_S, "dtype": "int64+f64", "data": "synthetic",
-        "config": {"workload": "config/sparse_zi_%d.py: %d ZI agents + exchange, sparse OU oracle; reference CPU algorithm "
-                               "(oracle/abides_oracle.c port of the Python reference) on host cores" % (args.variant, args.variant)},
-        "cpu_baseline": {"value": v, "unit": "msgs/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": shared_config(args),
+        "detail": {"arm": "reference CPU algorithm: oracle/abides_oracle.c (C port of the Python reference, pinned to it bit for bit) on all host threads; whole environment-days from MT19937 "
+                          "seeds, event loop only (construction excluded like Kernel.py:184,301)", "sample": sample, "python_reference": python_reference_record()},
+        "cpu_baseline": {"value": v, "unit": "msgs/s", "cores": cores, "kind": "port", "sample": sample, "python_reference": python_reference_record()},
         "e2e": {"value": v, "unit": "msgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "rmsc03": reference_rmsc03_block(cores), "env": reference_env_block(cores), "ddqn": reference_ddqn_block(cores),
     })
@@ -295,10 +316,20 @@ def run_ours(args, rank, local_rank, world):
     err_envs = int(((st1["flags"] & _lib.F_ERROR_MASK) != 0).sum())
 
     # ---- e2e: same metric through the C ABI with HOST buffers (pinned): per step H2D of the per-env horizons,
-    #      launch, D2H of every environment's abx_env_stats record; wall clock around sync points.
+    #      launch, D2H of every environment's abx_env_stats record; wall clock around sync points.  SAME simulated interval as the
+    #      device-timed loop: the batch is reset with the same seeds and brought to the same point (untimed) first.
     until_pin = torch.empty(n_envs, dtype=torch.int64).pin_memory()
     stats_pin = torch.empty(n_envs * ctypes.sizeof(_lib.EnvStats), dtype=torch.uint8).pin_memory()
     stats_np = stats_pin.numpy().view(_lib.STATS_DTYPE)
+    sim.reset(seeds, stream=sp)
+    t = t_open + prefix
+    sim.run(t, stream=sp)
+    for _ in range(args.warmup):
+        t += slice_ns
+        sim.run(t, stream=sp)
+    torch.cuda.synchronize(dev)
+    st2 = sim.stats(stream=sp)
+    assert int(st2["messages"].sum()) == int(st0["messages"].sum()), "the e2e leg does not start where the device-timed leg started"
     D.barrier(); torch.cuda.synchronize(dev)
     w0 = time.perf_counter()
     for k in range(args.steps):
@@ -309,7 +340,20 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.synchronize(dev)
     e2e_s_local = time.perf_counter() - w0
     D.barrier()
-    e2e_msgs_local = int(stats_np["messages"].sum() - st1["messages"].sum())
+    e2e_msgs_local = int(stats_np["messages"].sum() - st2["messages"].sum())
+    assert e2e_msgs_local == msgs_local, "e2e and device-timed legs must cover the same messages"
+
+    # ---- whole environment-days (what the reference arm times): fresh seeds, 00:00 -> 17:00 in ONE launch per batch, start-up transient included
+    wd_local = None
+    if not args.no_whole_day:
+        sim.reset(D.env_seeds(args.seed + 7777777, lo, lo + n_envs), stream=sp)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        D.barrier(); torch.cuda.synchronize(dev)
+        l_wd = sim.launch_count
+        e0.record(stream); sim.run(stream=sp); e1.record(stream)
+        torch.cuda.synchronize(dev); D.barrier()
+        stw = sim.stats(stream=sp)
+        wd_local = {"msgs": int(stw["messages"].sum()), "ms": e0.elapsed_time(e1), "errs": int(((stw["flags"] & _lib.F_ERROR_MASK) != 0).sum()), "launches": sim.launch_count - l_wd}
 
     # ---- second headline metric: ABIDESEnv steps/s (Exchange + MarketReplayAgent + RL execution agent under GymKernel)
     env_local = None
@@ -318,6 +362,11 @@ def run_ours(args, rank, local_rank, world):
     if not args.no_rmsc03:
         sim.close()
         r3_local = bench_rmsc03(args, rank, local_rank, dev, stream, sp)
+    mr_local = None
+    if not args.no_marketreplay:
+        if not sim_closed(sim):
+            sim.close()
+        mr_local = bench_marketreplay(args, rank, local_rank, dev, stream, sp)
     if not args.no_env:
         if not sim_closed(sim):
             sim.close()
@@ -395,6 +444,21 @@ def run_ours(args, rank, local_rank, world):
                     "workload": "config/execution/marketreplay/execution_marketreplay_ddqn.py shape: exchange + MarketReplayAgent (IBM 2003-01-14/15/16 LOBSTER sample days, round robin) + 7 MomentumAgents + "
                     "TWAPExecutionAgent + DDQLearningExecutionAgent (BUY 5e5, 30 s ticks from 10:00), epsilon-greedy (0.9) actions from a random-init 2-32-64-128-128-64-32-24 network; "
                     "per tick one abx_qnet_forward_kernel + one abx_dq_step_kernel launch"}
+    wd_block = None
+    if wd_local is not None:
+        gw = D.gather_summaries(torch.tensor([wd_local["msgs"], wd_local["errs"]], dtype=torch.int64), device=dev)
+        t_wd = D.max_over_ranks(wd_local["ms"], device=dev) / 1e3
+        wd_block = {"metric": "LOB msgs/sec, whole environment-days", "value": int(gw[:, 0].sum()) / t_wd, "unit": "msgs/s", "ms": 1e3 * t_wd, "messages_per_env_day": int(gw[:, 0].sum()) / (n_envs * world),
+                    "error_envs": int(gw[:, 1].sum()), "gpu_launches": wd_local["launches"],
+                    "note": "the interval the reference arm times: %d environments per GPU from fresh seeds, 00:00 -> 17:00 (start-up wake-ups, open, close, after-hours) in one abx_run_kernel launch" % n_envs}
+    mr_block = None
+    if mr_local is not None:
+        gm = D.gather_summaries(torch.tensor([mr_local["msgs"], mr_local["errs"]], dtype=torch.int64), device=dev)
+        t_mr = D.max_over_ranks(mr_local["ms"], device=dev) / 1e3
+        mr_block = {"metric": "LOB msgs/sec (marketreplay)", "value": int(gm[:, 0].sum()) / t_mr, "unit": "msgs/s", "envs_per_gpu": args.mr_envs_per_gpu, "ms": 1e3 * t_mr,
+                    "messages_per_env_day": int(gm[:, 0].sum()) / (args.mr_envs_per_gpu * world), "error_envs": int(gm[:, 1].sum()), "gpu_launches": mr_local["launches"],
+                    "workload": "config/marketreplay.py shape (BASELINE configs[4]): ExchangeAgent + MarketReplayAgent replaying the GOOG 2012-06-21 LOBSTER sample day (49 482 rows, "
+                                "the committed fixture the reference parsed) through the GPU books, one whole day per environment in one abx_env_step_kernel launch"}
     if rank != 0:
         return
     msgs, e2e_msgs, errs = int(g[:, 0].sum()), int(g[:, 1].sum()), int(g[:, 2].sum())
@@ -409,23 +473,30 @@ def run_ours(args, rank, local_rank, world):
         "metric": "LOB msgs/sec", "value": value, "unit": "msgs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": value / PUBLISHED_MSGS_PER_S, "dtype": "int64+f64", "data": "synthetic",
-        "config": {
-            "workload": "config/sparse_zi_%d.py shape: %d ZI agents + exchange, sparse OU oracle, %d envs/GPU, env e seeded %d+e "
-                        "(Philox streams)" % (args.variant, args.variant, n_envs, args.seed),
-            "envs_per_gpu": n_envs, "step": "%.1f simulated seconds per environment per launch" % (slice_ns / NS),
-            "messages_per_step": msgs // args.steps, "state_bytes_per_gpu": state_bytes,
-            "l2_policy": "inputs larger than L2: %.1f GB of per-environment state streamed per step, no flush needed" % (state_bytes / 1e9),
-            "vs_baseline_ref": "BASELINE.md section 1: 3100.4 msgs/s, reference single process, i7 2.6 GHz", "error_envs": errs,
-        },
+        "config": shared_config(args),
+        "detail": {"arm": "hand-written sm_100a kernels through the C ABI, GPU-native Philox streams", "step": "%.1f simulated seconds per environment per launch (mid-day slices after a "
+                   "09:30+120 s start-up transient)" % (slice_ns / NS), "messages_per_step": msgs // args.steps, "state_bytes_per_gpu": state_bytes,
+                   "l2_policy": "inputs larger than L2: %.1f GB of per-environment state streamed per step, no flush needed" % (state_bytes / 1e9),
+                   "vs_baseline_ref": "BASELINE.md section 1: 3100.4 msgs/s, the reference's own published single-process figure (i7 2.6 GHz); not a same-box measurement",
+                   "error_envs": errs},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic["dram_bytes_per_message"] * (msgs_local / args.steps) if traffic else None,
                      "traffic_source": traffic["source"] if traffic else None, "peak_source": peak_src,
-                     "kernel": "abx_run_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_msg": B_MSG,
+                     "kernel": "abx_run_kernel<PHILOX, MATRIX_NOISE, no instrumentation>", "kernel_ms": kern_ms, "algorithmic_bytes_per_msg": B_MSG,
+                     "limiter": "instruction issue / instruction fetch of one dependent event chain per environment, not memory bandwidth (profiles/)",
+                     "warp_instructions_per_message": traffic.get("warp_instructions_per_message") if traffic else None,
+                     "issue_frac": ((msgs_local / args.steps) / (kern_ms / 1e3) * traffic["warp_instructions_per_message"] / (148 * 4 * (clocks["sm_mhz"] or 1965.0) * 1e6)
+                                    if traffic and traffic.get("warp_instructions_per_message") and clocks else None),
+                     "issue_frac_note": "warp-instructions issued per second / (148 SMs x 4 schedulers x SM clock); instructions per message from the committed ncu capture",
                      "note": "latency-bound by design (one dependent event chain per environment); see DESIGN.md"},
         "e2e": {"value": e2e_msgs / e2e_s, "unit": "msgs/s", "h2d_bytes_per_step": 8 * n_envs * 1,
                 "d2h_bytes_per_step": ctypes.sizeof(_lib.EnvStats) * n_envs},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if wd_block is not None:
+        out["whole_day"] = wd_block
+    if mr_block is not None:
+        out["marketreplay"] = mr_block
     if r3_block is not None:
         out["rmsc03"] = r3_block
     if not args.no_env:
@@ -439,7 +510,7 @@ def run_ours(args, rank, local_rank, world):
         m, w, cpu_s = oracle_msgs_per_s(n_days, cores, args.variant)
         out["cpu_baseline"] = {"value": m / w, "unit": "msgs/s", "cores": cores, "kind": "port",
                                "sample": "%d full env-days of sparse_zi_%d, event loop only, %d threads, %.1f CPU-s" % (n_days, args.variant, cores, cpu_s),
-                               "single_thread_value": m / cpu_s}
+                               "single_thread_value": m / cpu_s, "python_reference": python_reference_record()}
         if not args.no_rmsc03:
             out["cpu_baseline"]["rmsc03"] = reference_rmsc03_block(cores)
         if not args.no_env:
@@ -479,6 +550,35 @@ def bench_rmsc03(args, rank, local_rank, dev, stream, sp):
                                           "launches": l0}
         sim.close()
     return out
+
+
+def bench_marketreplay(args, rank, local_rank, dev, stream, sp):
+    """BASELINE configs[4]: config/marketreplay.py -- the LOBSTER order stream of one day replayed through the books (no RL agent: order_level 0); one
+    abx_env_step_kernel launch runs the whole day of every environment.  One untimed warm-up day, then a timed one."""
+    import numpy as np
+    import torch
+    from marl_optimal_execution_b200 import _lib, distributed as D
+    from marl_optimal_execution_b200.env import ABIDESEnv, env_config
+    with np.load(os.path.join(ROOT, "tests", "golden", "mr_GOOG_2012-06-21.npz")) as g:
+        stream5 = g["stream"].copy()
+    n = args.mr_envs_per_gpu
+    env = ABIDESEnv(stream5, n_envs=n, device=local_rank, cfg=env_config(order_level=0, stop_ns=(16 * 3600 + 60) * NS, queue_cap=256, level_cap=1024))
+    env.reuse_outputs = True
+    acts = torch.zeros(n, 3, dtype=torch.float64, device=dev)
+    ms, msgs, errs, launches = 0.0, 0, 0, 0
+    for rep in range(2):
+        env.reset(stream=sp)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        D.barrier(); torch.cuda.synchronize(dev)
+        l0 = env.launch_count
+        e0.record(stream); env.step(acts, stream=sp); e1.record(stream)
+        torch.cuda.synchronize(dev); D.barrier()
+        if rep == 1:
+            st = env.stats(stream=sp)
+            ms, msgs, launches = e0.elapsed_time(e1), int(st["messages"].sum()), env.launch_count - l0
+            errs = int(((st["flags"] & _lib.F_ERROR_MASK) != 0).sum())
+    env.close()
+    return {"msgs": msgs, "ms": ms, "errs": errs, "launches": int(launches)}
 
 
 def reference_rmsc03_block(cores):
@@ -547,14 +647,21 @@ def bench_ddqn(args, rank, local_rank, dev, stream, sp):
     env = DDQNExecutionEnv(replay_days(), n_envs=n, device=local_rank)
     env.reuse_outputs = True
     net = QNetwork(device=local_rank, seed=args.seed % 1000)
-    env.reset(seeds=np.arange(rank * n, (rank + 1) * n, dtype=np.uint64) + np.uint64(args.seed), stream=sp)
-    obs, trans, rew, done = env.step(torch.zeros(n, dtype=torch.int32, device=dev), stream=sp)      # 00:00 -> 10:00 start-up (~30 k messages/env), untimed
     qbuf = (None, torch.empty(n, dtype=torch.int32, device=dev))
-    tick = 0
-    for _ in range(W):
-        _, a = net.forward(obs, x_offset=6, want_q=False, greedy_prob=0.9, seed=args.seed, counter=tick, out=qbuf, stream=sp)
-        obs, trans, rew, done = env.step(a, stream=sp); tick += 1
-    torch.cuda.synchronize(dev)
+    dq_seeds = np.arange(rank * n, (rank + 1) * n, dtype=np.uint64) + np.uint64(args.seed)
+
+    def start():
+        """fresh episodes brought to the first timed tick (untimed): 00:00 -> 10:00 start-up (~30 k messages/env) + W warm-up ticks; the device-timed and the
+        e2e legs both start here, on the same seeds and the same action stream, so they cover the same simulated interval"""
+        env.reset(seeds=dq_seeds, stream=sp)
+        o, tr, rw, dn = env.step(torch.zeros(n, dtype=torch.int32, device=dev), stream=sp)
+        tk = 0
+        for _ in range(W):
+            _, a_ = net.forward(o, x_offset=6, want_q=False, greedy_prob=0.9, seed=args.seed, counter=tk, out=qbuf, stream=sp)
+            o, tr, rw, dn = env.step(a_, stream=sp); tk += 1
+        torch.cuda.synchronize(dev)
+        return o, tk
+    obs, tick = start()
     m0 = int(env.stats(stream=sp)["messages"].sum()); l0 = env.launch_count + net.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     qe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -573,6 +680,8 @@ def bench_ddqn(args, rank, local_rank, dev, stream, sp):
     # e2e: the same loop with every tick's results read back to pinned host memory (what a host-side learner consumes)
     o_pin = torch.empty(n, 8, dtype=torch.float64).pin_memory(); t_pin = torch.empty(n, 6, dtype=torch.float64).pin_memory()
     r_pin = torch.empty(n, dtype=torch.float64).pin_memory(); d_pin = torch.empty(n, dtype=torch.uint8).pin_memory()
+    obs, tick = start()
+    m2 = int(env.stats(stream=sp)["messages"].sum())
     D.barrier(); torch.cuda.synchronize(dev)
     w0 = time.perf_counter()
     for k in range(K):
@@ -582,6 +691,7 @@ def bench_ddqn(args, rank, local_rank, dev, stream, sp):
         torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - w0
     D.barrier()
+    assert int(env.stats(stream=sp)["messages"].sum()) - m2 == m1 - m0, "e2e and device-timed DDQN legs must cover the same messages"
     # training loop (marketreplay_ddqn_train shape): act, step, store the experience tuples, learn every 5 ticks on a batch from the shared
     # replay buffer (the reference's update rule, ddqn.py) and push the new weights into the acting network
     from marl_optimal_execution_b200.ddqn import DDQNTrainer
@@ -626,6 +736,9 @@ def main():
     ap.add_argument("--env-envs-per-gpu", type=int, default=9472, help="4 x 148 SMs x 16 resident one-warp CTAs: whole waves (8192 leaves the 4th wave 46 %% full)")
     ap.add_argument("--env-steps", type=int, default=750, help="timed ABIDESEnv steps: 750 = the whole 761-tick episode after the start-up and warm-up steps")
     ap.add_argument("--no-rmsc03", action="store_true", help="skip the rmsc03 population (BASELINE configs[2])")
+    ap.add_argument("--no-whole-day", action="store_true", help="skip the whole-environment-day measurement of the headline workload")
+    ap.add_argument("--no-marketreplay", action="store_true", help="skip the config/marketreplay.py shape (BASELINE configs[4])")
+    ap.add_argument("--mr-envs-per-gpu", type=int, default=4736, help="2 x 148 SMs x 16 resident one-warp CTAs")
     ap.add_argument("--rmsc03-envs-per-gpu", type=int, default=4096, help="BASELINE configs[2]: 4096 envs/GPU")
     ap.add_argument("--no-ddqn", action="store_true", help="skip the DDQN execution shape (Q-network forward + environment step per tick)")
     ap.add_argument("--ddqn-envs-per-gpu", type=int, default=9472, help="whole waves of 148 x 16 resident environments, like --env-envs-per-gpu")

@@ -264,26 +264,6 @@ ABX_NI U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
 }
 ABX_NI double exp_ni(double x) { return exp(x); }
 ABX_NI double log_ni(double x) { return log(x); }
-// exp(x) where the simulators' arguments live: the belief update's (1 - kappa) ** delta = exp(delta * log(1 - kappa)) has |x| <= 0.1 over a whole day and
-// the OU decay between two consecutive observations |x| ~ 1e-3, so a degree-12 series (truncation < 1.3e-16 at |x| = 0.25, below half an ulp of the result)
-// serves them with twelve FMAs and the 200-instruction libm body stays out of the hot loop (it is called beyond 0.25: the first observation of a day, gaps
-// of hours).  Like libm's, the result is within an ulp of the true value, which is all the int(round(.)) consumers need.
-#ifdef ABX_EXPS_INLINE
-ABX_HD
-#else
-ABX_NI                                                                                 // ONE body: inlined at its four call sites the series costs more instruction-cache than it saves (A/B: -15 % msgs/s)
-#endif
-double exp_fast(double x) {
-#if defined(__CUDA_ARCH__) && !defined(ABX_NO_EXPS)
-  if (fabs(x) <= 0.25) {
-    double p = 1.0 / 479001600.0;
-    p = fma(p, x, 1.0 / 39916800.0); p = fma(p, x, 1.0 / 3628800.0); p = fma(p, x, 1.0 / 362880.0); p = fma(p, x, 1.0 / 40320.0); p = fma(p, x, 1.0 / 5040.0);
-    p = fma(p, x, 1.0 / 720.0); p = fma(p, x, 1.0 / 120.0); p = fma(p, x, 1.0 / 24.0); p = fma(p, x, 1.0 / 6.0); p = fma(p, x, 0.5); p = fma(p, x, 1.0); p = fma(p, x, 1.0);
-    return p;
-  }
-#endif
-  return exp(x);
-}
 // log(x), x in (0, 1] and normal, for the Philox-mode variate transforms only (no parity constraint): fp64 throughout, relative error
 // < 1e-11 (checked against libm by tests/test_gpu_philox.py through abx_selftest_log_unit).  x = 2^e * m with m in [sqrt(1/2), sqrt(2)],
 // log(m) = 2 atanh(s), s = (m - 1) / (m + 1), seven terms of the series (|s| <= 0.1716), the quotient through a refined MUFU reciprocal.
@@ -638,8 +618,8 @@ struct Sim {
   }
   ABX_HD int32_t oracle_compute(int64_t ts, double v_adj, int64_t pt, int32_t pv) {     // :88-125
     double d = (double)(ts - pt); double mu = P.c.r_bar;
-    double loc = dadd(mu, dmul(dsub((double)pv, mu), exp_fast(dmul(-P.c.kappa, d))));
-    double scale = dmul(P.ou_scale, dsub(1.0, exp_fast(dmul(dmul(-2.0, P.c.kappa), d))));    // variance formula passed as scale
+    double loc = dadd(mu, dmul(dsub((double)pv, mu), exp_ni(dmul(-P.c.kappa, d))));
+    double scale = dmul(P.ou_scale, dsub(1.0, exp_ni(dmul(dmul(-2.0, P.c.kappa), d))));    // variance formula passed as scale
     double v = rng.normal(S_SYMBOL, s.ctr_symbol, loc, scale);
     v = dadd(v, v_adj); if (!(v > 0)) v = 0;
     int32_t iv = (int32_t)py_round_i64(v); s.or_t = ts; s.or_v = iv; return iv;
@@ -789,26 +769,24 @@ struct Sim {
     s.exch_comp_delay = P.c.exchange_computation_delay_ns;                              // :139
     bool t_closed = s.now > P.c.mkt_close_ns;
     double lat = m.lat_back;                                                            // latency[0][sender]
-    int32_t p[6] = {0, 0, 0, 0, 0, 0};
-    if (t_closed) {                                                                     // :142-160
-      bool is_order = m.kind == ABX_LIMIT_ORDER || m.kind == ABX_CANCEL_ORDER || m.kind == ABX_MODIFY_ORDER;
-      bool is_query = m.kind == ABX_QUERY_SPREAD || m.kind == ABX_QUERY_LAST_TRADE || m.kind == ABX_QUERY_TRANSACTED_VOLUME || m.kind == ABX_QUERY_ORDER_STREAM;
-      if (is_order || !is_query) { exch_send(m.sender, ABX_MKT_CLOSED, p, lat); return; }
-    }
-    if (m.kind == ABX_WHEN_MKT_OPEN) { s.exch_comp_delay = 0; exch_send(m.sender, ABX_WHEN_MKT_OPEN, p, lat); }           // :175-183
-    else if (m.kind == ABX_WHEN_MKT_CLOSE) { s.exch_comp_delay = 0; exch_send(m.sender, ABX_WHEN_MKT_CLOSE, p, lat); }    // :184-192
+    int32_t p[6] = {0, 0, 0, 0, 0, 0}; int reply = ABX_NONE;                            // the direct reply, sent from ONE site below (every inlined send is ~12 instructions of loop body)
+    bool is_order = m.kind == ABX_LIMIT_ORDER || m.kind == ABX_CANCEL_ORDER || m.kind == ABX_MODIFY_ORDER;
+    bool is_query = m.kind == ABX_QUERY_SPREAD || m.kind == ABX_QUERY_LAST_TRADE || m.kind == ABX_QUERY_TRANSACTED_VOLUME || m.kind == ABX_QUERY_ORDER_STREAM;
+    if (t_closed && (is_order || !is_query)) reply = ABX_MKT_CLOSED;                    // :142-160
+    else if (m.kind == ABX_WHEN_MKT_OPEN || m.kind == ABX_WHEN_MKT_CLOSE) { s.exch_comp_delay = 0; reply = m.kind; }   // :175-192
     else if (m.kind == ABX_QUERY_SPREAD) {                                              // :215-245 (depth 1)
       s.c_query++; int f = 0;
       int nb = s.n_bid_lv, na = s.n_ask_lv;
       if (nb > 0) { p[0] = c.lv_price(0, nb - 1); p[1] = c.lv_qty(0, nb - 1); f |= 1; }
       if (na > 0) { p[2] = c.lv_price(1, na - 1); p[3] = c.lv_qty(1, na - 1); f |= 2; }
       if (t_closed) f |= 4;
-      p[4] = s.last_trade; p[5] = f; exch_send(m.sender, ABX_QUERY_SPREAD, p, lat);
+      p[4] = s.last_trade; p[5] = f; reply = ABX_QUERY_SPREAD;
     } else if (m.kind == ABX_LIMIT_ORDER) {                                             // :304-312
       s.c_limit++; book_handle_limit((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[2], lat); c.sync(); trace_snap();
     } else if (m.kind == ABX_CANCEL_ORDER) {                                            // :313-325
       s.c_cancel++; book_cancel((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], lat); c.sync(); trace_snap();
     }
+    if (reply != ABX_NONE) exch_send(m.sender, reply, p, lat);
   }
 
   // ---- TradingAgent / ZeroIntelligenceAgent (the trader is in `a` / `z`) ----
@@ -857,7 +835,7 @@ struct Sim {
     // within an ulp of the true power; the result only feeds int(round(.)) of values ~1e5.
     // (1 - kappa) ** (2 delta) as the square of (1 - kappa) ** delta: it only enters through 1 - pw1 ~ 2 delta kappa ~ 1e-3 (sigma_t stays 0, :242), so an
     // ulp of pw1 moves r_t by ~1e-11 -- and saves one of the seven exp evaluations per order (12 % of all executed instructions were exp).
-    double pw0 = exp_fast(dmul(delta, P.log_base_a)), pw1 = dmul(pw0, pw0), pw2 = exp_fast(dmul(d2, P.log_base_a));
+    double pw0 = exp_ni(dmul(delta, P.log_base_a)), pw1 = dmul(pw0, pw0), pw2 = exp_ni(dmul(d2, P.log_base_a));
     double r_tprime = dmul(dsub(1.0, pw0), r_bar);                                    // :229
     r_tprime = dadd(r_tprime, dmul(pw0, a.r_t));                                      // :230
     double sigma_tprime = dmul(pw1, a.sigma_t);                                       // :233
@@ -1667,7 +1645,7 @@ struct Sim {
     double r_bar = P.c.r_bar, sigma_n = P.c.sigma_n;
     double delta = (double)(s.now - a.prev_wake);
     double d2 = (double)(P.c.mkt_close_ns - s.now); if (!(d2 > 0)) d2 = 0;
-    double pw0 = exp_fast(dmul(delta, P.log_base_a)), pw1 = exp_fast(dmul(dmul(2.0, delta), P.log_base_a)), pw2 = exp_fast(dmul(d2, P.log_base_a));
+    double pw0 = exp_ni(dmul(delta, P.log_base_a)), pw1 = exp_ni(dmul(dmul(2.0, delta), P.log_base_a)), pw2 = exp_ni(dmul(d2, P.log_base_a));
     double r_tprime = dmul(dsub(1.0, pw0), r_bar); r_tprime = dadd(r_tprime, dmul(pw0, a.r_t));
     double sigma_tprime = dmul(pw1, a.sigma_t); sigma_tprime = dadd(sigma_tprime, dmul(dsub(1.0, pw1) / P.sigma_denom, P.c.sigma_s));
     double den = dadd(sigma_n, sigma_tprime);
@@ -1801,16 +1779,16 @@ struct Sim {
         r.v[0] = ev.type; r.v[1] = ev.type == ABX_T_MESSAGE ? (int32_t)ev.uniq : -1; r.v[2] = ev.kind; trace_rec(r);
       }
       addl_delay = 0;
-      int id = ev.recipient;
+      int id = ev.recipient; int64_t at = s.exch_time;
+      if (id != 0) { z = c.agent_stage(id); regs_load(a, z); at = a.agent_time; }
+      bool in_future = at > s.now;
+      c.q_settle(in_future, at);
+      if (in_future) continue;
+      s.q_count--; self_id = id;
       if (id == 0) {
-        if (s.exch_time > s.now) { c.q_requeue(s.exch_time); continue; }
-        c.q_remove(); s.q_count--; self_id = 0;
         if (ev.type == ABX_T_MESSAGE) r3_exch_receive(ev);
         s.exch_time = s.now + s.exch_comp_delay + addl_delay;
       } else {
-        z = c.agent_stage(id); regs_load(a, z);
-        if (a.agent_time > s.now) { c.q_requeue(a.agent_time); continue; }
-        c.q_remove(); s.q_count--; self_id = id;
         if (ev.type == ABX_T_WAKEUP) r3_wakeup(id); else r3_receive(id, ev);
         a.agent_time = s.now + P.c.default_computation_delay_ns + addl_delay;
         c.sync(); if (c.onchip_writer()) regs_store(z, a); c.sync();

@@ -24,12 +24,7 @@ constexpr unsigned FULL = 0xffffffffu;
 __device__ __forceinline__ uint4 ldcg4(const uint4 *p) { return __ldcg(p); }
 
 // lane index of the smallest (hi, uniq) among lanes with valid == true, or -1
-#ifdef ABX_ARGMIN_NI
-__device__ __noinline__
-#else
-__device__ __forceinline__
-#endif
-int warp_argmin(uint64_t hi, uint32_t uniq, bool valid) {
+__device__ __forceinline__ int warp_argmin(uint64_t hi, uint32_t uniq, bool valid) {
   uint32_t h = valid ? (uint32_t)(hi >> 32) : 0xffffffffu;
   uint32_t m = __reduce_min_sync(FULL, h);
   bool c = valid && h == m;
@@ -229,22 +224,22 @@ struct WarpCtxT {
     return true;
   }
   __device__ __forceinline__ void q_fetch(int g, Event &e) {
-    if (SMALLQ) {
-      if (g < NQ) {                                                // a slot of the on-chip tier: key and payload in shared memory (no L2 round trip per pop)
-        cur_group = g; cur_t2 = false;
-        event_unpack(qs[g], qp0[g], qp1[g], e);
-        return;
-      }
-      g -= NQ; cur_t2 = true;
+    uint4 k, a, b;                                                 // one unpack for both tiers (code size: the loop body lives on the edge of the instruction cache)
+    if (SMALLQ && g < NQ) {                                        // a slot of the on-chip tier: key and payload in shared memory (no L2 round trip per pop)
+      cur_group = g; cur_t2 = false;
+      k = qs[g]; a = qp0[g]; b = qp1[g];
+    } else {
+      if (SMALLQ) { g -= NQ; cur_t2 = true; }
+      int slot = g * 32 + lane;
+      k = ldcg4(qkey + slot); a = ldcg4(qpay0 + slot); b = ldcg4(qpay1 + slot);       // 3 x 512 B coalesced
+      cur_mask = qc[g].w; cur_group = g;
+      bool occ = (cur_mask >> lane) & 1u;
+      my_hi = (uint64_t)k.x | ((uint64_t)k.y << 32); my_uniq = k.z;
+      int w = warp_argmin(my_hi, my_uniq, occ);
+      cur_lane = w;
+      k = shfl4(k, w); a = shfl4(a, w); b = shfl4(b, w);
     }
-    int slot = g * 32 + lane;
-    uint4 k = ldcg4(qkey + slot), a = ldcg4(qpay0 + slot), b = ldcg4(qpay1 + slot);     // 3 x 512 B coalesced
-    cur_mask = qc[g].w; cur_group = g;
-    bool occ = (cur_mask >> lane) & 1u;
-    my_hi = (uint64_t)k.x | ((uint64_t)k.y << 32); my_uniq = k.z;
-    int w = warp_argmin(my_hi, my_uniq, occ);
-    cur_lane = w;
-    event_unpack(shfl4(k, w), shfl4(a, w), shfl4(b, w), e);
+    event_unpack(k, a, b, e);
   }
   __device__ __forceinline__ void group_writeback() {     // recompute the cached minimum of cur_group from the keys in registers
     bool occ = (cur_mask >> lane) & 1u;
@@ -254,31 +249,33 @@ struct WarpCtxT {
     qc[cur_group] = make_uint4((uint32_t)nh, (uint32_t)(nh >> 32), nu, cur_mask);
     sync();
   }
-  __device__ __forceinline__ void q_remove() {
-    if (SMALLQ && !cur_t2) { sync(); qs[cur_group] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u); sync(); return; }
-    if (HYBRID) n_ovf--;
-    if (NEARQ) ovm[0] = make_uint4(0u, 0u, 0u, 0xffffffffu);
-    cur_mask &= ~(1u << cur_lane); group_writeback(); }
-  __device__ __forceinline__ void q_requeue(int64_t t) {   // Kernel.py:226,260: same entry, new time, same uniq
+  // The fetched event either leaves the queue or goes back in at time t (Kernel.py:226,260: same entry, new time, same uniq).  ONE body for both, so
+  // that the grouped tier's cache recomputation (an arg-min over the fetched group) exists once per loop.
+  __device__ __forceinline__ void q_settle(bool requeue, int64_t t) {
     if (SMALLQ && !cur_t2) {
-      uint4 k = qs[cur_group]; uint64_t h = (uint64_t)k.x | ((uint64_t)k.y << 32);
-      h = key_pack(t < KEY_T_MAX ? t : KEY_T_MAX, key_recipient(h), key_type(h)); k.x = (uint32_t)h; k.y = (uint32_t)(h >> 32);
+      uint4 k = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
+      if (requeue) { k = qs[cur_group]; uint64_t h = (uint64_t)k.x | ((uint64_t)k.y << 32);
+        h = key_pack(t < KEY_T_MAX ? t : KEY_T_MAX, key_recipient(h), key_type(h)); k.x = (uint32_t)h; k.y = (uint32_t)(h >> 32); }
       sync(); qs[cur_group] = k; sync(); return;
     }
-    if (lane == cur_lane) {
-      my_hi = key_pack(t < KEY_T_MAX ? t : KEY_T_MAX, key_recipient(my_hi), key_type(my_hi));
-      uint2 *kp = reinterpret_cast<uint2 *>(qkey + cur_group * 32 + lane); *kp = make_uint2((uint32_t)my_hi, (uint32_t)(my_hi >> 32));
-    }
+    if (requeue) {
+      if (lane == cur_lane) {
+        my_hi = key_pack(t < KEY_T_MAX ? t : KEY_T_MAX, key_recipient(my_hi), key_type(my_hi));
+        uint2 *kp = reinterpret_cast<uint2 *>(qkey + cur_group * 32 + lane); *kp = make_uint2((uint32_t)my_hi, (uint32_t)(my_hi >> 32));
+      }
+    } else { if (HYBRID) n_ovf--; cur_mask &= ~(1u << cur_lane); }
     if (NEARQ) ovm[0] = make_uint4(0u, 0u, 0u, 0xffffffffu);
     group_writeback();
   }
+  __device__ __forceinline__ void q_remove() { q_settle(false, 0); }
+  __device__ __forceinline__ void q_requeue(int64_t t) { q_settle(true, t); }
   __device__ __forceinline__ bool q_push(const Event &e, int64_t now) {
+    uint4 k, a, b; event_pack(e, k, a, b);                                 // packed once for both tiers
     if (SMALLQ && (!NEARQ || e.t - now < NEAR_NS)) {
       bool f0 = qs[lane].y == 0xffffffffu && qs[lane].x == 0xffffffffu, f1 = NQ > 32 && qs[NQ > 32 ? lane + 32 : lane].y == 0xffffffffu && qs[NQ > 32 ? lane + 32 : lane].x == 0xffffffffu;
       uint32_t b0 = __ballot_sync(FULL, f0), b1 = NQ > 32 ? __ballot_sync(FULL, f1) : 0u;
       if (b0 | b1) {
         int slot = b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1;
-        uint4 k, a, b; event_pack(e, k, a, b);
         sync(); qs[slot] = k; qp0[slot] = a; qp1[slot] = b; sync();
         return true;
       }
@@ -290,7 +287,6 @@ struct WarpCtxT {
     if (!bal) return false;
     int g = __shfl_sync(FULL, fg, __ffs(bal) - 1);
     uint4 cc = qc[g]; int i = __ffs(~cc.w) - 1;
-    uint4 k, a, b; event_pack(e, k, a, b);
     int slot = g * 32 + i;
     if (lane < 3) { uint4 *dst = lane == 0 ? qkey : (lane == 1 ? qpay0 : qpay1); dst[slot] = lane == 0 ? k : (lane == 1 ? a : b); }
     {

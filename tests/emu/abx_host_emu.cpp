@@ -52,6 +52,7 @@ struct HostCtx {
     uint4 &k = qkey[cur_group * 32 + cur_slot]; uint64_t h = (uint64_t)k.x | ((uint64_t)k.y << 32);
     h = key_pack(t < KEY_T_MAX ? t : KEY_T_MAX, key_recipient(h), key_type(h)); k.x = (uint32_t)h; k.y = (uint32_t)(h >> 32); group_recompute(cur_group);
   }
+  void q_settle(bool requeue, int64_t t) { if (requeue) q_requeue(t); else q_remove(); }
   bool q_push(const Event &e, int64_t) {
     for (int g = 0; g < P.n_qgroups; g++) if (qcache[g].w != 0xffffffffu) {
       int i = __builtin_ctz(~qcache[g].w); event_pack(e, qkey[g * 32 + i], qpay0[g * 32 + i], qpay1[g * 32 + i]); qcache[g].w |= 1u << i; group_recompute(g); return true; }

@@ -1,0 +1,46 @@
+"""Per-environment reset, day rotation, auto-reset and order_level 1 on the CUDA kernels (the cases of tests/reset_cases.py), plus the masked reset
+with a CUDA mask tensor at batch scale."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from marl_optimal_execution_b200 import _lib
+from marl_optimal_execution_b200.env import ABIDESEnv, env_config
+from reset_cases import DAYS, abidesenv_masked_reset_and_rotation, ddqn_auto_reset, order_level_one
+
+pytestmark = pytest.mark.gpu
+
+
+def test_abidesenv_masked_reset_and_day_rotation(golden_dir):
+    abidesenv_masked_reset_and_rotation(golden_dir, n_steps=120)
+
+
+def test_ddqn_shape_auto_reset_next_day(golden_dir):
+    ddqn_auto_reset(golden_dir, ticks_after=60)
+
+
+def test_order_level_one_actions(golden_dir):
+    order_level_one(golden_dir, n_steps=200)
+
+
+def test_auto_reset_keeps_a_batch_running_across_episodes(golden_dir):
+    """512 ABIDESEnv environments, auto-reset on: every environment finishes its 761-step episode, restarts, and the second episode reproduces the
+    first one's pop hash at the same step count (same day, same actions) -- nothing of the finished episode leaks into the next."""
+    g = np.load(os.path.join(golden_dir, DAYS[0]))
+    n = 512
+    env = ABIDESEnv(g["stream"], n_envs=n, cfg=env_config(hash_pops=1))
+    env.set_auto_reset(1)
+    env.reset()
+    acts = torch.from_numpy(np.tile(g["actions"][:, None, :], (1, n, 1))).cuda()
+    hashes = []
+    for ep in range(2):
+        for k in range(len(acts)):
+            obs, _, done, _ = env.step(acts[k])
+            if k == 300:
+                hashes.append(env.stats()["pop_hash"].copy())
+        assert int(done.sum()) == n                                # the last step of the episode reports done; the reset follows it
+    assert np.array_equal(hashes[0], hashes[1]) and len(set(hashes[0].tolist())) == 1
+    assert (env.stats()["flags"] & _lib.F_ERROR_MASK == 0).all()
+    env.close()
