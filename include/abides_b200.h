@@ -123,7 +123,10 @@ typedef struct abx_sim_config {
   double pov_exec_pov; int64_t pov_exec_quantity, pov_exec_start_ns, pov_exec_end_ns, pov_exec_freq_ns, pov_exec_lookback_ns;
   /* parity instrumentation (like trace_cap / hash_pops): > 0 keeps, per environment, a log of every standard variate the Philox streams
    * hand out (abx_sim_draw_log), so that the reference's algorithm can be re-run on exactly those draws (oracle external tapes) */
-  int32_t draw_log_cap, _pad2;
+  int32_t draw_log_cap;
+  /* > 0: keep, per environment, a ring of the last event_ring_cap exchange events the reference logs for its realism tooling (abx_sim_events):
+   * order arrivals and the BEST_BID / BEST_ASK / LAST_TRADE lines of util/OrderBook.py:114-141 */
+  int32_t event_ring_cap;
 } abx_sim_config;
 
 /* Per-environment counters; replaces the "Event Queue elapsed ..., messages: N" line (Kernel.py:321-327). */
@@ -240,6 +243,16 @@ int32_t abx_sim_draw_log(abx_sim *h, int32_t env, abx_draw_rec *out, int32_t max
  * (latency[a][0], latency[0][a]), sizes HOST int32 [n_agents] (Noise / Value / Momentum order size), wakes HOST int64 [n_agents] (NoiseAgent
  * wake-up time, ns).  Row 0 (the exchange) is zero.  Any pointer may be NULL.  Call after reset, before the first run. */
 int32_t abx_sim_agent_init(abx_sim *h, int32_t env, int32_t *theta, double *lat_to, double *lat_from, int32_t *sizes, int64_t *wakes, void *stream);
+
+/* One record of the exchange event ring (event_ring_cap > 0), 16 bytes.  kind: ABX_EV_ORDER = a LIMIT_ORDER reached the book (a = limit price, b = quantity,
+ * signed: > 0 buy) -- the order stream behind realism/order_flow_stylized_facts.py; ABX_EV_BEST_BID / ABX_EV_BEST_ASK (a = price, b = total quantity of the
+ * level) and ABX_EV_LAST_TRADE (a = int(round(average price)), b = traded quantity) -- the logEvent lines of util/OrderBook.py:114-141.
+ * t_kind = t_ns | kind << 60. */
+enum abx_event_kind { ABX_EV_ORDER = 0, ABX_EV_BEST_BID = 1, ABX_EV_BEST_ASK = 2, ABX_EV_LAST_TRADE = 3 };
+typedef struct abx_event_rec { uint64_t t_kind; int32_t a, b; } abx_event_rec;
+/* Copy every environment's ring and event count into DEVICE buffers (e.g. torch tensors): out_dev [n_envs][event_ring_cap] records (slot i holds event
+ * number i mod cap), counts_dev uint32 [n_envs] = events logged since the reset.  Asynchronous on `stream`. */
+int32_t abx_sim_events_device(abx_sim *h, abx_event_rec *out_dev, uint32_t *counts_dev, void *stream);
 
 /* Copy the trace of one environment to the host.  out: host [max_recs]; *n_recs = records written. */
 int32_t abx_sim_trace(abx_sim *h, int32_t env, abx_trace_rec *out, int32_t max_recs, int32_t *n_recs, void *stream);

@@ -59,7 +59,7 @@ class SimConfig(C.Structure):
         ("_pad1", C.c_int32), ("mm_wake_ns", C.c_int64),
         ("n_pov_exec", C.c_int32), ("pov_exec_is_buy", C.c_int32), ("pov_exec_pov", C.c_double), ("pov_exec_quantity", C.c_int64),
         ("pov_exec_start_ns", C.c_int64), ("pov_exec_end_ns", C.c_int64), ("pov_exec_freq_ns", C.c_int64), ("pov_exec_lookback_ns", C.c_int64),
-        ("draw_log_cap", C.c_int32), ("_pad2", C.c_int32),
+        ("draw_log_cap", C.c_int32), ("event_ring_cap", C.c_int32),
     ]
 
 
@@ -152,6 +152,7 @@ def _bind(L):
     sig("abx_sim_trace", i32, vp, i32, vp, i32, P(i32), vp)
     sig("abx_sim_draw_log", i32, vp, i32, vp, i32, P(i32), vp)
     sig("abx_sim_agent_init", i32, vp, i32, vp, vp, vp, vp, vp, vp)
+    sig("abx_sim_events_device", i32, vp, vp, vp, vp)
     sig("abx_sim_launch_count", i64, vp)
     sig("abx_env_config_default", i32, P(EnvConfig))
     sig("abx_env_create", i32, P(EnvConfig), P(i64), i64, i32, i32, P(vp))

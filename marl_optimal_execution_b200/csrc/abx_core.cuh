@@ -158,6 +158,7 @@ struct SimParams {
   EnvState *env;                // [n_envs]
   abx_trace_rec *trace;         // [n_envs][trace_cap]
   uint4 *draw_log;              // [n_envs][draw_log_cap] {stream | kind << 24, bits lo, bits hi, -}  (parity runs under Philox)
+  uint4 *evt;                   // [n_envs][event_ring_cap] {t lo, t hi | kind << 28, a, b}: order arrivals, BEST_BID / BEST_ASK / LAST_TRADE (realism tooling)
   const uint64_t *tape_bits; const uint8_t *tape_kinds; const int64_t *tape_off; // tape mode
   // ---- ABIDESEnv shape (exchange + MarketReplayAgent + RL execution agent); zero for the sparse_zi shape ----
   int32_t n_ts, n_rows, n_ids, n_h;                 // replayed stream: timestamps, rows, distinct order ids; horizon length
@@ -482,11 +483,11 @@ enum { SHAPE_ZI = 0, SHAPE_ENV = 1, SHAPE_R3 = 2, SHAPE_DQ = 3, SHAPE_BOOK = 4 }
 template <class Ctx, int RNG_MODE = -1, int LAT_MODEL = -1, bool INSTR = true, int SHAPE = SHAPE_ZI>
 struct Sim {
   static constexpr bool DQ = SHAPE == SHAPE_DQ, BOOK = SHAPE == SHAPE_BOOK, ENV = SHAPE == SHAPE_ENV || DQ || BOOK, R3 = SHAPE == SHAPE_R3;
-  Ctx &c; const SimParams &P; EnvState s; RngT<RNG_MODE, INSTR> rng; int64_t addl_delay; int n_out; int self_id;
+  Ctx &c; const SimParams &P; EnvState s; RngT<RNG_MODE, INSTR> rng; int64_t addl_delay; int n_out; int self_id; int env_id;
   AgentRegs a; ZiAgent *z;                // the trader whose event is being handled (registers + staged record)
 
   ABX_HD Sim(Ctx &c_, const SimParams &P_, const EnvState &s_, int env) : c(c_), P(P_), s(s_), addl_delay(0), n_out(0), self_id(0), z(nullptr) {
-    rng.P = &P; rng.env = P.n_tapes > 0 ? env % P.n_tapes : env; rng.seed = s.seed; rng.err = 0; a.lat_from = 0.0; a.lat_to = 0.0;
+    rng.P = &P; rng.env = P.n_tapes > 0 ? env % P.n_tapes : env; env_id = env; rng.seed = s.seed; rng.err = 0; a.lat_from = 0.0; a.lat_to = 0.0;
     rng.lg = (INSTR && P.draw_log) ? P.draw_log + (size_t)env * (size_t)P.c.draw_log_cap : nullptr; rng.lg_n = s.draw_n; rng.lg_cap = (uint32_t)P.c.draw_log_cap;
   }
   // fold the generator's error bits and draw-log cursor back into the environment state (end of every entry point that may have drawn)
@@ -639,6 +640,12 @@ struct Sim {
   }
 
   // ---- order book (util/OrderBook.py).  Ladders are sorted so that the BEST level is the LAST element. ----
+  // the exchange's event log for the realism tooling (instrumented kernels only): slot = event number mod capacity
+  ABX_HD void evt_log(int kind, int32_t a_, int32_t b_) {
+    if (!INSTR || !P.evt) return;
+    uint4 v; v.x = (uint32_t)(uint64_t)s.now; v.y = (uint32_t)((uint64_t)s.now >> 32) | ((uint32_t)kind << 28); v.z = (uint32_t)a_; v.w = (uint32_t)b_;
+    P.evt[(size_t)env_id * (size_t)P.c.event_ring_cap + (s.evt_n % (uint32_t)P.c.event_ring_cap)] = v; s.evt_n++;
+  }
   ABX_HD NodeRec nload(uint32_t i) { return c.template node_load<ENV>(i); }
   ABX_HD void nstore(uint32_t i, const NodeRec &r) { c.template node_store<ENV>(i, r); }
   ABX_HD uint32_t node_alloc() {
@@ -692,6 +699,7 @@ struct Sim {
       uint4 t = c.ord_load((int)(oid - REPLAY_ID_BASE)); uint32_t d = s.trade_epoch - t.z;
       t.w = (t.w == 0 || d >= 16) ? 1u : (((t.w << d) | 1u) & 0xffffu); t.z = s.trade_epoch; c.ord_store((int)(oid - REPLAY_ID_BASE), t);
     }
+    evt_log(ABX_EV_ORDER, price, is_buy ? qty : -qty);
     int opp = is_buy ? 1 : 0;                                                           // a buy matches asks (side 1)
     uint32_t epoch0 = s.trade_epoch;                                                    // the incoming order's history bucket (:52-60)
     int64_t trade_qty = 0, trade_px = 0;
@@ -731,7 +739,11 @@ struct Sim {
         matching = false;
       }
     }
-    if (trade_qty > 0) { s.last_trade = (int32_t)py_round_i64((double)trade_px / (double)trade_qty); s.trade_epoch++; } // :131-149 (history.insert(0, {}))
+    if (INSTR && P.evt) {                                                               // :114-128 BEST_BID / BEST_ASK of the book as the order left it
+      if (s.n_bid_lv > 0) evt_log(ABX_EV_BEST_BID, c.lv_price(0, s.n_bid_lv - 1), c.lv_qty(0, s.n_bid_lv - 1));
+      if (s.n_ask_lv > 0) evt_log(ABX_EV_BEST_ASK, c.lv_price(1, s.n_ask_lv - 1), c.lv_qty(1, s.n_ask_lv - 1));
+    }
+    if (trade_qty > 0) { s.last_trade = (int32_t)py_round_i64((double)trade_px / (double)trade_qty); s.trade_epoch++; evt_log(ABX_EV_LAST_TRADE, s.last_trade, (int32_t)trade_qty); } // :131-149 (history.insert(0, {}))
   }
   // cancelOrder :284-339: levels from the best whose slot-0 price equals the request's, the first that holds the id
   ABX_HD void book_cancel(uint32_t oid, int agent, int is_buy, int32_t price, double lat_in) {

@@ -86,7 +86,7 @@ abx_run_kernel(SimParams P, int64_t until_ns, const int64_t *__restrict__ until_
 }
 typedef void (*run_kernel_fn)(SimParams, int64_t, const int64_t *, size_t);
 static run_kernel_fn run_kernel_for(const abx_sim_config &c) {
-  bool instr = c.trace_cap > 0 || c.hash_pops != 0 || c.draw_log_cap > 0; int r = c.rng_mode, l = c.latency_model;
+  bool instr = c.trace_cap > 0 || c.hash_pops != 0 || c.draw_log_cap > 0 || c.event_ring_cap > 0; int r = c.rng_mode, l = c.latency_model;
   if (c.population == 1) {                       // config/rmsc03.py population: zero latency
     if (r == ABX_RNG_PHILOX) return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_R3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_ZERO, false, SHAPE_R3>;
     return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_ZERO, true, SHAPE_R3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_ZERO, false, SHAPE_R3>;
@@ -309,7 +309,7 @@ int32_t abx_sim_destroy(abx_sim *h) {
   if (!h) return ABX_OK;
   cudaSetDevice(h->device);
   void *ptrs[] = {h->P.qkey, h->P.qpay0, h->P.qpay1, h->P.qcache, h->P.agents, h->P.lv_price, h->P.lv_qty, h->P.lv_ht, h->P.nodes, h->P.env,
-                  h->P.trace, h->P.draw_log, h->P.snap, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff,
+                  h->P.trace, h->P.draw_log, h->P.evt, h->P.snap, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff,
                   h->P.envx, h->P.idtab, h->P.idbook, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_iact, h->d_msizes, h->d_trans, h->d_ops, h->d_daytab};
   for (void *p : ptrs) if (p) cudaFree(p);
   delete h->st; delete h->dh; delete h->book_ids; delete h; return ABX_OK;
@@ -329,7 +329,7 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
 #define DA(ptr, n) if ((st = dalloc(&(ptr), (n), &h->bytes)) != ABX_OK) { abx_sim_destroy(h); return st; }
   DA(h->P.qkey, E * c.queue_cap) DA(h->P.qpay0, E * c.queue_cap) DA(h->P.qpay1, E * c.queue_cap) DA(h->P.qcache, E * h->P.n_qgroups)
   DA(h->P.agents, E * c.n_agents) DA(h->P.lv_price, E * 2 * c.level_cap) DA(h->P.lv_qty, E * 2 * c.level_cap) DA(h->P.lv_ht, E * 2 * c.level_cap)
-  DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap) DA(h->P.draw_log, E * (size_t)c.draw_log_cap)
+  DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap) DA(h->P.draw_log, E * (size_t)c.draw_log_cap) DA(h->P.evt, E * (size_t)c.event_ring_cap)
   DA(h->d_seeds, E) DA(h->d_init_err, E) DA(h->d_stats, E) DA(h->d_until, E)
   if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + h->P.tv_ring; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0);       // market maker orders + transaction ring [+ POV execution agent orders]; momentum mids
     DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
@@ -498,6 +498,17 @@ int32_t abx_sim_draw_log(abx_sim *h, int32_t env, abx_draw_rec *out, int32_t max
   *n_recs = n; return ABX_OK;
 }
 
+__global__ void abx_event_counts_kernel(SimParams P, uint32_t *__restrict__ out) { int e = blockIdx.x * blockDim.x + threadIdx.x; if (e < P.n_envs) out[e] = P.env[e].evt_n; }
+int32_t abx_sim_events_device(abx_sim *h, abx_event_rec *out_dev, uint32_t *counts_dev, void *stream) {
+  if (!h || h->is_env || !out_dev || !counts_dev || h->P.c.event_ring_cap <= 0) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;
+  static_assert(sizeof(abx_event_rec) == sizeof(uint4), "event record layout");
+  CU(cudaMemcpyAsync(out_dev, h->P.evt, sizeof(uint4) * (size_t)h->n_envs * h->P.c.event_ring_cap, cudaMemcpyDeviceToDevice, st));
+  abx_event_counts_kernel<<<(h->n_envs + 127) / 128, 128, 0, st>>>(h->P, counts_dev);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return ABX_OK;
+}
 int32_t abx_sim_agent_init(abx_sim *h, int32_t env, int32_t *theta, double *lat_to, double *lat_from, int32_t *sizes, int64_t *wakes, void *stream) {
   if (!h || h->is_env || env < 0 || env >= h->n_envs) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
   CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;

@@ -106,3 +106,128 @@ def volume_volatility_correlation(close, volume):
 def all_metrics(close, volume):
     return {"returns": minutely_returns(close), "autocorr": autocorrelation(close), "kurtosis": kurtosis(close), "aggnorm": aggregation_normality(close),
             "volclust": volatility_clustering(close), "retvol": returns_volatility_correlation(close), "volvol": volume_volatility_correlation(close, volume)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# Device-side event ring (cfg.event_ring_cap > 0): the exchange's BEST_BID / BEST_ASK / LAST_TRADE log lines (util/OrderBook.py:114-141) and
+# the order arrivals, reduced ON THE GPU (torch) to minute bars, the seven return metrics and the order-flow stylized facts of
+# realism/order_flow_stylized_facts.py:84-103,176-221 -- one pass over the ring, no per-minute launches, exact volumes for every population.
+# ---------------------------------------------------------------------------------------------------------------------------------------
+EV_ORDER, EV_BEST_BID, EV_BEST_ASK, EV_LAST_TRADE = 0, 1, 2, 3
+
+
+def events(sim, device=None, stream=None):
+    """The rings of a BatchedSim as torch tensors on the simulator's GPU: (t_ns int64 [n_envs, cap], kind int64, a int64, b int64, valid bool), in
+    chronological order per environment (the ring is unrolled; entries older than the capacity are gone and `valid` is False for unused slots)."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    cap = int(sim.cfg.event_ring_cap)
+    if cap <= 0:
+        raise ValueError("the simulator was created with event_ring_cap == 0")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    raw = torch.empty(sim.n_envs, cap, 4, dtype=torch.int32, device=dev)
+    cnt = torch.empty(sim.n_envs, dtype=torch.int32, device=dev)
+    sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream) if stream is None else stream
+    _lib.check(sim._L, sim._L.abx_sim_events_device(sim._h, C.c_void_p(raw.data_ptr()), C.c_void_p(cnt.data_ptr()), sp), "abx_sim_events_device")
+    return unroll_events(raw, cnt)
+
+
+def unroll_events(raw, counts):
+    """raw int32 [n_envs, cap, 4] ring slots + counts [n_envs] -> chronological tensors (works on CPU tensors too: the CPU suite feeds it the emulation's ring)."""
+    import torch
+    n, cap, _ = raw.shape
+    cnt = counts.to(torch.int64) & 0xFFFFFFFF
+    start = torch.where(cnt > cap, cnt % cap, torch.zeros_like(cnt))                  # oldest surviving slot
+    idx = (start[:, None] + torch.arange(cap, device=raw.device)[None, :]) % cap
+    r = torch.gather(raw.to(torch.int64) & 0xFFFFFFFF, 1, idx[:, :, None].expand(n, cap, 4))
+    t = r[..., 0] | ((r[..., 1] & 0x0FFFFFFF) << 32)
+    kind = r[..., 1] >> 28
+    sgn = lambda v: torch.where(v >= 2 ** 31, v - 2 ** 32, v)                         # noqa: E731  int32 payloads
+    valid = torch.arange(cap, device=raw.device)[None, :] < torch.clamp(cnt, max=cap)[:, None]
+    return t, kind, sgn(r[..., 2]), sgn(r[..., 3]), valid
+
+
+def bars_from_events(t, kind, a, b, valid, mkt_open_ns, n_minutes=390, open_price=None):
+    """Minute bars like realism/realism_utils.py:22-44 from the LAST_TRADE events: close = last trade price of the minute, forward filled (the price
+    before the first trade: `open_price`, where the reference has NaN); volume = shares traded in the minute (exact: the LAST_TRADE quantities).
+    Returns (close, volume) float64 [n_envs, n_minutes] on the events' device."""
+    import torch
+    n, cap = t.shape
+    m = ((t - int(mkt_open_ns)) // (60 * NS)).clamp(min=-1, max=n_minutes)           # left-closed bins: a trade on a boundary opens the next bar
+    tr = valid & (kind == EV_LAST_TRADE) & (m >= 0) & (m < n_minutes)
+    mi = torch.where(tr, m, torch.zeros_like(m))
+    volume = torch.zeros(n, n_minutes, dtype=torch.float64, device=t.device).scatter_add_(1, mi, torch.where(tr, b, torch.zeros_like(b)).to(torch.float64))
+    pos = torch.arange(cap, device=t.device)[None, :].expand(n, cap)
+    last = torch.full((n, n_minutes), -1, dtype=torch.int64, device=t.device).scatter_reduce_(1, mi, torch.where(tr, pos, torch.full_like(pos, -1)), reduce="amax")
+    has = last >= 0
+    px = torch.gather(a, 1, last.clamp(min=0)).to(torch.float64)
+    # forward fill: index of the latest minute with a trade at or before each minute
+    mm = torch.arange(n_minutes, device=t.device)[None, :].expand(n, n_minutes)
+    src = torch.cummax(torch.where(has, mm, torch.full_like(mm, -1)), dim=1).values
+    close = torch.gather(px, 1, src.clamp(min=0))
+    if open_price is not None:
+        close = torch.where(src >= 0, close, torch.full_like(close, float(open_price)))
+    return close, volume
+
+
+def order_flow_facts(t, kind, valid, mkt_open_ns, mkt_close_ns, binwidth_s=1):
+    """realism/order_flow_stylized_facts.py: interarrival times of the order stream (:84-103, seconds between consecutive order arrivals) and the number
+    of arrivals per `binwidth_s`-second bin (:176-221), per environment.  Returns dict(interarrival_mean, interarrival_std, interarrival_log10_hist
+    [n_envs, 12] over 1e-9..1e3 s, n_orders, bin_counts int64 [n_envs, n_bins], bin_count_mean, bin_count_var)."""
+    import torch
+    n, cap = t.shape
+    od = valid & (kind == EV_ORDER)
+    tf = t.to(torch.float64) / 1e9
+    # consecutive arrivals: sort order rows to the front (stable: chronological order is kept)
+    key = torch.where(od, torch.zeros_like(t), torch.ones_like(t))
+    order = torch.argsort(key, dim=1, stable=True)
+    ts = torch.gather(tf, 1, order)
+    k = od.sum(dim=1)
+    pair = torch.arange(cap - 1, device=t.device)[None, :] < (k - 1).clamp(min=0)[:, None]
+    d = (ts[:, 1:] - ts[:, :-1]) * pair
+    cntp = pair.sum(dim=1).clamp(min=1).to(torch.float64)
+    mean = d.sum(dim=1) / cntp
+    var = (((d - mean[:, None]) * pair) ** 2).sum(dim=1) / cntp
+    lg = torch.log10(d.clamp(min=1e-9))
+    hb = ((lg + 9.0).floor().clamp(min=0, max=11)).to(torch.int64)
+    hist = torch.zeros(n, 12, dtype=torch.int64, device=t.device).scatter_add_(1, torch.where(pair, hb, torch.zeros_like(hb)), pair.to(torch.int64))
+    n_bins = int((int(mkt_close_ns) - int(mkt_open_ns)) // (binwidth_s * NS))
+    bi = ((t - int(mkt_open_ns)) // (binwidth_s * NS))
+    inb = od & (bi >= 0) & (bi < n_bins)
+    bins = torch.zeros(n, n_bins, dtype=torch.int64, device=t.device).scatter_add_(1, torch.where(inb, bi, torch.zeros_like(bi)), inb.to(torch.int64))
+    bf = bins.to(torch.float64)
+    return {"interarrival_mean": mean, "interarrival_std": var.sqrt(), "interarrival_log10_hist": hist, "n_orders": k, "bin_counts": bins,
+            "bin_count_mean": bf.mean(dim=1), "bin_count_var": bf.var(dim=1, unbiased=False)}
+
+
+def spread_facts(t, kind, a, valid):
+    """Quoted spread from the BEST_BID / BEST_ASK lines: per environment the mean and the last value of (best ask - best bid) over the events at which both
+    sides are known (each event updates one side; the other side keeps its last logged value)."""
+    import torch
+    n, cap = t.shape
+    pos = torch.arange(cap, device=t.device)[None, :].expand(n, cap)
+    def last_seen(k):
+        m = valid & (kind == k)
+        src = torch.cummax(torch.where(m, pos, torch.full_like(pos, -1)), dim=1).values
+        return torch.gather(a, 1, src.clamp(min=0)), src >= 0
+    bid, hb = last_seen(EV_BEST_BID)
+    ask, ha = last_seen(EV_BEST_ASK)
+    upd = valid & ((kind == EV_BEST_BID) | (kind == EV_BEST_ASK)) & hb & ha
+    sp = (ask - bid).to(torch.float64) * upd
+    cnt = upd.sum(dim=1).clamp(min=1).to(torch.float64)
+    lastpos = torch.where(upd, pos, torch.full_like(pos, -1)).amax(dim=1)
+    return {"spread_mean": sp.sum(dim=1) / cnt, "spread_last": torch.gather(ask - bid, 1, lastpos.clamp(min=0)[:, None])[:, 0], "n_quotes": upd.sum(dim=1)}
+
+
+def stylized_facts_gpu(sim, n_minutes=390, binwidth_s=1):
+    """One pass over the device event ring of a finished (or running) BatchedSim: minute bars, the reference's seven return metrics and the order-flow /
+    spread statistics, all reduced on the GPU.  The seven metrics are the numpy restatements above applied to the [n_envs, 390] bars (tiny)."""
+    t, kind, a, b, valid = events(sim)
+    cfg = sim.cfg
+    close, volume = bars_from_events(t, kind, a, b, valid, cfg.mkt_open_ns, n_minutes, open_price=cfg.r_bar)
+    out = {"close": close, "volume": volume}
+    out.update(order_flow_facts(t, kind, valid, cfg.mkt_open_ns, cfg.mkt_close_ns, binwidth_s))
+    out.update(spread_facts(t, kind, a, valid))
+    out["metrics"] = all_metrics(close.cpu().numpy(), volume.cpu().numpy())
+    return out

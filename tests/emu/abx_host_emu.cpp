@@ -126,7 +126,7 @@ struct HostCtx {
 struct abx_sim {
   SimParams P; int n_envs; bool reset_done;
   std::vector<uint4> qkey, qpay0, qpay1, qcache, nodes; std::vector<ZiAgent> agents; std::vector<int32_t> lvp, lvq; std::vector<uint32_t> lvht;
-  std::vector<EnvState> env; std::vector<abx_trace_rec> trace; std::vector<uint4> draw_log; std::vector<uint64_t> tbits; std::vector<uint8_t> tkinds; std::vector<int64_t> toff;
+  std::vector<EnvState> env; std::vector<abx_trace_rec> trace; std::vector<uint4> draw_log, evt; std::vector<uint64_t> tbits; std::vector<uint8_t> tkinds; std::vector<int64_t> toff;
   bool is_env; EnvStreamHost st; EnvDaysHost dh; bool has_days = false; std::vector<EnvX> envx; std::vector<uint4> idtab; std::vector<int4> lobs; std::vector<uint2> idbook; std::vector<int2> snap; int auto_reset = 0; std::vector<uint64_t> dq_seeds; std::vector<int32_t> dq_msizes;
 };
 
@@ -156,6 +156,7 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
   h->P.trace = c.trace_cap ? h->trace.data() : nullptr;
   h->draw_log.resize(E * (size_t)c.draw_log_cap); h->P.draw_log = c.draw_log_cap ? h->draw_log.data() : nullptr;
+  h->evt.resize(E * (size_t)c.event_ring_cap); h->P.evt = c.event_ring_cap ? h->evt.data() : nullptr;
   if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + h->P.tv_ring; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0); h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data();
     if (c.n_pov_exec) { h->P.n_snap = 1; h->P.snap_depth = c.level_cap; h->snap.resize(E * 2 * (size_t)c.level_cap); h->P.snap = h->snap.data(); } }
   *out = h; return ABX_OK;
@@ -242,6 +243,10 @@ int32_t abx_sim_draw_log(abx_sim *h, int32_t env, abx_draw_rec *out, int32_t max
   int n = (int)h->env[env].draw_n; if (n > max_recs) n = max_recs;
   if (n) memcpy(out, h->P.draw_log + (size_t)env * h->P.c.draw_log_cap, sizeof(uint4) * n);
   *n_recs = n; return ABX_OK;
+}
+int32_t abx_sim_events_device(abx_sim *h, abx_event_rec *out, uint32_t *counts, void *stream) {
+  (void)stream; if (!h || h->is_env || !out || !counts || h->P.c.event_ring_cap <= 0) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
+  memcpy(out, h->evt.data(), sizeof(uint4) * h->evt.size()); for (int e = 0; e < h->n_envs; e++) counts[e] = h->env[e].evt_n; return ABX_OK;
 }
 int32_t abx_sim_agent_init(abx_sim *h, int32_t env, int32_t *theta, double *lat_to, double *lat_from, int32_t *sizes, int64_t *wakes, void *stream) {
   (void)stream; if (!h || h->is_env || env < 0 || env >= h->n_envs) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;

@@ -92,3 +92,33 @@ def assert_env_equals_oracle(sim, e, o, n, st, traces=True, holdings_cols=5, has
     l1 = o.book_l1()
     assert (int(st["best_bid"][e]), int(st["best_bid_qty"][e]), int(st["best_ask"][e]), int(st["best_ask_qty"][e]), int(st["last_trade"][e])) == tuple(int(x) for x in l1)
     assert int(st["fundamental"][e]) == o.fundamental()
+
+
+def oracle_events(o):
+    """The exchange event log of a finished OracleSim run (trace flags OPS | NOTES | SNAPS) in the layout of the device event ring: chronological
+    torch tensors (t, kind, a, b, valid) with one row -- order arrival, BEST_BID / BEST_ASK (util/OrderBook.py:114-128) and LAST_TRADE (:131-141)
+    per handleLimitOrder call, exactly what marl_optimal_execution_b200.realism reduces."""
+    import torch
+    ops, notes, snaps = o.trace("ops"), o.trace("notes"), o.trace("snaps")
+    rows = []
+    ex = notes[notes[:, 2] == 8]                      # ORDER_EXECUTED rows come in pairs (incoming copy first)
+    inc = ex[0::2]
+    k = 0
+    for i in range(len(ops)):
+        if ops[i, 1] != 0:
+            continue
+        t, oid = int(ops[i, 0]), int(ops[i, 3])
+        rows.append((t, 0, int(ops[i, 5]), int(ops[i, 6]) if ops[i, 4] else -int(ops[i, 6])))
+        sn = snaps[i]
+        if sn[0] > 0:
+            rows.append((t, 1, int(sn[3]), int(sn[4])))
+        if sn[1] > 0:
+            rows.append((t, 2, int(sn[9]), int(sn[10])))
+        q = pq = 0
+        while k < len(inc) and inc[k, 0] == t and inc[k, 3] == oid:
+            q += int(inc[k, 5]); pq += int(inc[k, 5]) * int(inc[k, 7]); k += 1
+        if q:
+            rows.append((t, 3, int(round(pq / q)), q))
+    r = np.array(rows, dtype=np.int64)
+    tt = torch.from_numpy(r.T.copy())
+    return tt[0][None], tt[1][None], tt[2][None], tt[3][None], torch.ones(1, len(r), dtype=torch.bool)

@@ -189,3 +189,55 @@ def test_device_log_of_the_variate_transforms_matches_libm():
     assert y[x == 1.0].max() == 0.0
     nz = ref != 0
     assert err[nz].max() < 1e-11, (err[nz].max(), x[nz][err[nz].argmax()])
+
+
+def _facts_summary(R, t, kind, a, b, valid, cfg, n_min):
+    """per-environment summary of the return metrics and the order-flow / spread statistics, reduced from an exchange event log"""
+    close, volume = R.bars_from_events(t, kind, a, b, valid, cfg.mkt_open_ns, n_min, open_price=cfg.r_bar)
+    f = R.order_flow_facts(t, kind, valid, cfg.mkt_open_ns, cfg.mkt_close_ns, binwidth_s=60)
+    sp = R.spread_facts(t, kind, a, valid)
+    c, v = close.cpu().numpy(), volume.cpu().numpy()
+    r = R.minutely_returns(c)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.stack([r.std(axis=1), np.abs(r).mean(axis=1), v.sum(axis=1), f["n_orders"].cpu().numpy().astype(float), f["interarrival_mean"].cpu().numpy(),
+                         f["interarrival_std"].cpu().numpy(), f["bin_count_var"].cpu().numpy(), sp["spread_mean"].cpu().numpy()], axis=1)
+
+
+@pytest.mark.parametrize("shape", ["sparse_zi_100", "rmsc03"])
+def test_order_flow_and_spread_statistics_from_the_device_event_ring(shape):
+    """north_star: "stylized facts (returns, spread and order-flow statistics from realism/) must agree in distribution".  The device-side event ring
+    (order arrivals, BEST_BID / BEST_ASK / LAST_TRADE) of Philox-seeded environments, reduced on the GPU (realism.stylized_facts_gpu: one pass, exact
+    volumes also for rmsc03's variable order sizes), against the same reductions of reference-RNG oracle runs' event logs: every summary statistic within
+    6 standard errors (+ 10 % of the oracle spread)."""
+    from helpers import oracle_events
+    from marl_optimal_execution_b200 import realism as R
+    from marl_optimal_execution_b200.sim import rmsc03_config
+    from oracle.oracle import TRACE_ALL
+    if shape == "rmsc03":
+        mk, variant, n, n_min, seeds, cap = (lambda **kw: rmsc03_config(**kw)), 3, 192, 15, range(3001, 3013), 1 << 17
+    else:
+        mk, variant, n, n_min, seeds, cap = (lambda **kw: sparse_zi_config(100, **kw)), 100, 256, 390, range(2001, 2013), 1 << 14
+    cfg = mk(event_ring_cap=cap)
+    ref = []
+    for s_ in seeds:
+        o = OracleSim(variant, s_, TRACE_ALL)
+        o.run()
+        ref.append(_facts_summary(R, *oracle_events(o), cfg, n_min)[0])
+    ref = np.array(ref)
+    sim = BatchedSim(cfg, n)
+    sim.reset(np.arange(n, dtype=np.uint64) + 90909)
+    sim.run(); sim.finalize()
+    st = sim.stats()
+    ok = (st["flags"] & _lib.F_ERROR_MASK) == 0
+    assert ok.mean() > 0.9
+    t, kind, a, b, valid = R.events(sim)
+    assert int(valid.sum(dim=1).max()) < cap                      # nothing was overwritten: the whole day is in the ring
+    got = _facts_summary(R, t, kind, a, b, valid, cfg, n_min)[ok]
+    assert np.array_equal(got[:, 3], st["limit_orders"][ok].astype(float))          # order arrivals == the exchange's limit-order counter
+    out = R.stylized_facts_gpu(sim, n_minutes=n_min, binwidth_s=60)
+    assert out["close"].is_cuda and out["bin_counts"].shape == (n, (int(cfg.mkt_close_ns) - int(cfg.mkt_open_ns)) // (60 * NS))
+    names = ["std(r)", "mean|r|", "volume", "orders", "interarrival mean", "interarrival std", "var(orders per minute)", "mean spread"]
+    for k, name in enumerate(names):
+        g, rf = got[:, k][np.isfinite(got[:, k])], ref[:, k][np.isfinite(ref[:, k])]
+        se = np.sqrt(rf.var(ddof=1) / len(rf) + g.var(ddof=1) / len(g))
+        assert abs(g.mean() - rf.mean()) < 6 * se + 0.1 * rf.std(ddof=1), (shape, name, g.mean(), rf.mean(), se)
