@@ -696,18 +696,19 @@ def bench_ddqn(args, rank, local_rank, dev, stream, sp):
     # replay buffer (the reference's update rule, ddqn.py) and push the new weights into the acting network
     from marl_optimal_execution_b200.ddqn import DDQNTrainer
     tr = DDQNTrainer(device=dev, batch_size=args.ddqn_batch, seed=args.seed % 1000, buffer_capacity=max(4 * n * 8, 1 << 16))
+    tr.agree_on_shard(n)
     net.set_params_device(tr.eval_net.flat_device())
     for _ in range(6):                                    # fill the buffer / warm the autograd kernels, untimed
         _, a = net.forward(obs, x_offset=6, want_q=False, greedy_prob=tr.greedy_prob(), seed=args.seed, counter=tick, out=qbuf, stream=sp)
         obs, trans, rew, done = env.step(a, stream=sp); tick += 1
-        tr.buffer.push(trans)
+        tr.store(trans)
     tr.learn()
     D.barrier(); torch.cuda.synchronize(dev)
     w0 = time.perf_counter(); l_before = tr.learn_step_counter
     for k in range(K):
         _, a = net.forward(obs, x_offset=6, want_q=False, greedy_prob=tr.greedy_prob(), seed=args.seed, counter=tick, out=qbuf, stream=sp)
         obs, trans, rew, done = env.step(a, stream=sp); tick += 1
-        tr.buffer.push(trans)
+        tr.store(trans)
         if k % tr.train_every == 0 and tr.learn() is not None:
             net.set_params_device(tr.eval_net.flat_device())
     torch.cuda.synchronize(dev)

@@ -169,6 +169,8 @@ struct SimParams {
   const int32_t *st_first;                          // [n_ts + 1]  first row of each timestamp
   const int4 *st_rows;                              // [n_rows]    {dense id, PRICE cents, SIZE, is_buy}
   const int4 *day_tab; int32_t n_days, pad_days;    // [n_days] {first entry of st_ts, timestamps, first entry of st_first, -}: environment e replays day e % n_days
+  const int4 *day_tab2;                             // [n_days] {first entry of st_xid, explicit ids, smallest, largest explicit ORDER_ID}
+  const int32_t *st_xid, *st_xfirst;                // per day: the explicit ORDER_IDs sorted ascending, and the first row of each
   struct EnvX *envx;                                // [n_envs]
   uint4 *idtab;                                     // [n_envs][n_ids] {agent-view qty, price<<1|is_buy, last registration epoch, epoch mask}
   uint2 *idbook;                                    // [n_envs][n_ids] {nodes in the book carrying the id | several-levels flag << 31, price<<1|side of their level}
@@ -196,7 +198,7 @@ struct alignas(16) EnvX {                           // per-environment state of 
   int32_t rl_n_orders, n_lobs, lob_head, p0;
   int32_t rem_time, obs_len, g0_qty, steps;          // g0_*: the replay agent's order under GENERATED id 0 (rows with ORDER_ID 0)
   uint32_t rl_oid[RL_ORDER_CAP]; int32_t rl_oprice[RL_ORDER_CAP]; int32_t rl_oqty[RL_ORDER_CAP];
-  double obs[9]; int32_t g0_pq, pad1;
+  double obs[9]; int32_t g0_pq, rows_done;           // rows_done: rows of the stream the replay agent has processed (which explicit ORDER_IDs count as used, Order.py:35-42)
 };
 static_assert(sizeof(EnvX) % 16 == 0, "EnvX layout");
 
@@ -640,6 +642,21 @@ struct Sim {
   }
 
   // ---- order book (util/OrderBook.py).  Ladders are sorted so that the BEST level is the LAST element. ----
+  // Order.generateOrderId (util/order/Order.py:35-42): the smallest id >= the class counter that no Order has used yet.  Generated ids are dense; the
+  // replayed stream's explicit ORDER_IDs count as used from the row that first carries them.  An explicit id the generator reaches BEFORE its first row
+  // would be handed out now and collide later in the reference (two orders, one id): flagged ABX_F_ID_RANGE, the run continues with separate ids.
+  ABX_HD uint32_t gen_id() {
+    uint32_t id = s.next_order_id;
+    if (ENV && !BOOK) {
+      int4 d2 = c.day_rec2();
+      if ((int32_t)id >= d2.z && (int32_t)id <= d2.w) {
+        int rows_done = c.envx()->rows_done;
+#pragma unroll 1
+        for (;;) { int fr = c.xid_first_row(d2, (int32_t)id); if (fr < 0) break; if (fr >= rows_done) { s.flags |= ABX_F_ID_RANGE; break; } id++; }
+      }
+    }
+    s.next_order_id = id + 1; return id;
+  }
   // the exchange's event log for the realism tooling (instrumented kernels only): slot = event number mod capacity
   ABX_HD void evt_log(int kind, int32_t a_, int32_t b_) {
     if (!INSTR || !P.evt) return;
@@ -1070,16 +1087,17 @@ struct Sim {
   // ---- MarketReplayAgent ----
   ABX_HD void replay_place(EnvX *x, int r) {                                            // placeOrder :69-96 for one row
     int4 row = c.row_load(r);
+    { int r0 = r - c.day_row0(); c.sync(); if (c.onchip_writer()) x->rows_done = r0 + (row.x >= 0 ? 1 : 0); c.sync(); }   // rows before this one are used ids; an explicit id counts from its own row on
     if (row.x < 0) {                                                                    // ORDER_ID 0 == "unset" (util/order/Order.py:27): orders.get(0) finds
       int32_t gq = x->g0_qty, gp = x->g0_pq;                                            // only the order that received GENERATED id 0
       if (gq == 0 && row.z > 0) {
-        uint32_t oid = s.next_order_id++;
+        uint32_t oid = gen_id();
         if (oid == 0) { c.sync(); if (c.onchip_writer()) { x->g0_qty = row.z; x->g0_pq = (row.y << 1) | (row.w & 1); } c.sync(); }
         int32_t p[6] = {(int32_t)oid, row.y, row.z, 0, row.w, 0}; env_send(ABX_LIMIT_ORDER, p, false);
       } else if (gq != 0 && row.z == 0) {
         int32_t p[6] = {0, gp >> 1, gq, 0, gp & 1, 0}; env_send(ABX_CANCEL_ORDER, p, false);
       } else if (gq != 0) {                                                             // new_order gets a fresh id != 0: isSameOrder fails at the exchange
-        s.next_order_id++;
+        gen_id();
         int32_t p[6] = {0, gp >> 1, gq, row.y, (gp & 1) | 2, row.z}; env_send(ABX_MODIFY_ORDER, p, false);
       }
       if (n_out >= Ctx::OUTN - 3) flush();
@@ -1212,7 +1230,7 @@ struct Sim {
     for (int lv = 0; lv < 2; lv++) if (lv < n) {
       if (lv >= l[7] || lv >= l[8]) continue;                                           // IndexError swallowed
       int32_t price = P.rl_is_buy ? (lv == 0 ? l[0] : l[2]) : (lv == 0 ? l[3] : l[5]);
-      uint32_t oid = s.next_order_id++;                                                 // LimitOrder() built before the quantity test
+      uint32_t oid = gen_id();                                                          // LimitOrder() built before the quantity test
       if (!(o[lv] > 0)) continue;
       int k = x->rl_n_orders;
       if (k < RL_ORDER_CAP) { c.sync(); if (c.onchip_writer()) { x->rl_oid[k] = oid; x->rl_oprice[k] = price; x->rl_oqty[k] = (int32_t)o[lv]; x->rl_n_orders = k + 1; } c.sync(); }
@@ -1319,7 +1337,7 @@ struct Sim {
   }
   ABX_HD int dq_horizon_index(int64_t t) const { if (t < P.h0_ns) return -1; int64_t k = hdiv(t - P.h0_ns); return (k * P.h_step_ns == t - P.h0_ns && k < P.n_h) ? (int)k : -1; }
   ABX_HD void dq_place_limit(int id, int32_t size, bool buy, int32_t price) {           // TradingAgent.placeLimitOrder :309-349
-    uint32_t oid = s.next_order_id++;
+    uint32_t oid = gen_id();
     if (size <= 0) return;
     if (a.n_orders < EXEC_ORDER_CAP) { uint4 v; v.x = oid; v.y = (uint32_t)price; v.z = (uint32_t)(buy ? size : -size); v.w = 0; c.id_store(dq_order_base(id) + a.n_orders, v); a.n_orders++; }
     else s.flags |= ABX_F_AGENT_ORDERS_OVERFLOW;
@@ -1531,7 +1549,6 @@ struct Sim {
       }
       flush();
     }
-    if ((int64_t)s.next_order_id >= P.dq_id_limit) s.flags |= ABX_F_ID_RANGE;           // generated ids reached the stream's explicit ids (util/order/Order.py:35-42 would skip them): outside the id range abx_dq_create checked
     rng_sync();
     c.sync();
     return paused;
@@ -1594,7 +1611,7 @@ struct Sim {
   ABX_HD AgentAux *aux() { return reinterpret_cast<AgentAux *>(z->theta); }
   // TradingAgent.placeLimitOrder :309-349 for the staged trader; `track`: the agent later iterates self.orders (Value, market maker)
   ABX_HD void r3_place_limit(int id, int32_t size, bool buy, int32_t price, bool track) {
-    uint32_t oid = s.next_order_id++;
+    uint32_t oid = gen_id();
     if (size <= 0) return;
     if (track) {
       int type = (int)((a.flags & AF_TYPE_MASK) >> AF_TYPE_SHIFT);

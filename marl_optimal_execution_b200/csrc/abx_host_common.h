@@ -6,6 +6,8 @@
 #include <string.h>
 #include <vector>
 #include <unordered_map>
+#include <algorithm>
+#include <utility>
 #include "abx_core.cuh"
 
 namespace abx {
@@ -178,7 +180,7 @@ static inline int64_t dq_max_generated_ids(const abx_dq_config &e) {
   int64_t wakes = (e.stop_ns - e.mkt_open_ns) / e.mom_wake_ns + 2;
   return (int64_t)e.n_momentum * wakes + (int64_t)(e.n_twap + 1) * ((int64_t)e.n_horizon * 8 + 2 * DQ_DEPTH) + 16;
 }
-struct EnvStreamHost { std::vector<int64_t> ts, id_orig; std::vector<int32_t> first; std::vector<int4> rows; int64_t min_id; };
+struct EnvStreamHost { std::vector<int64_t> ts, id_orig; std::vector<int32_t> first, xid, xfirst; std::vector<int4> rows; int64_t min_id, max_id; };   // xid: the explicit ORDER_IDs sorted, xfirst: first row of each
 // LOBSTER ORDER_IDs -> dense indices; rows grouped by identical timestamp (orders_dict of MarketReplayAgent.py:214)
 static inline int env_build_stream(const int64_t *s5, int64_t n, int64_t max_rl_ids, EnvStreamHost &o) {
   if (!s5 || n < 1 || n > 0x3fffffff) return ABX_ERR_ARG;
@@ -187,7 +189,7 @@ static inline int env_build_stream(const int64_t *s5, int64_t n, int64_t max_rl_
   for (int64_t i = 0; i < n; i++) {
     const int64_t *r = s5 + 5 * i;
     if (i > 0 && r[0] < s5[5 * (i - 1)]) return ABX_ERR_ARG;                                     // must be time sorted
-    if (r[1] < 0 || r[1] > 0x3fffffffLL || r[2] <= 0 || r[2] > 0x3fffffffLL || r[3] < 0 || r[3] > 0x7fffffffLL) return ABX_ERR_ARG;
+    if (r[1] < 0 || r[1] > 0x3fffffffLL || r[2] < 0 || r[2] > 0x3fffffffLL || r[3] < 0 || r[3] > 0x7fffffffLL) return ABX_ERR_ARG;
     int32_t d;
     if (r[1] == 0) { d = -1; n_zero++; }                                                          // ORDER_ID 0: "unset", the agent gets generated ids
     else { if (r[1] < min_id) min_id = r[1];
@@ -196,9 +198,16 @@ static inline int env_build_stream(const int64_t *s5, int64_t n, int64_t max_rl_
     if (i == 0 || r[0] != s5[5 * (i - 1)]) { o.ts.push_back(r[0]); o.first.push_back((int32_t)i); }
     int4 row; row.x = d; row.y = (int32_t)r[2]; row.z = (int32_t)r[3]; row.w = r[4] ? 1 : 0; o.rows[i] = row;
   }
-  o.first.push_back((int32_t)n); o.min_id = min_id;
-  if (min_id <= max_rl_ids + 2 * n_zero) return ABX_ERR_ARG;          // explicit ids must stay clear of every id the generator can hand out (util/order/Order.py:35-42)
-  if (o.id_orig.empty()) o.id_orig.push_back(0);
+  o.first.push_back((int32_t)n); o.min_id = min_id; o.max_id = 0; (void)max_rl_ids; (void)n_zero;
+  // util/order/Order.py:35-42: generateOrderId skips every id already used, explicit ORDER_IDs of the stream included once their first row was replayed.
+  // The device keeps the explicit ids sorted with the first row of each, so the generator can ask "has this id been used yet" (Sim::gen_id).
+  { std::vector<std::pair<int64_t, int32_t>> v; v.reserve(dense.size());
+    std::vector<int32_t> first_row(o.id_orig.size(), -1);
+    for (int64_t i = 0; i < n; i++) { int32_t d = o.rows[i].x; if (d >= 0 && first_row[d] < 0) first_row[d] = (int32_t)i; }
+    for (size_t d = 0; d < o.id_orig.size(); d++) v.push_back(std::make_pair(o.id_orig[d], first_row[d]));
+    std::sort(v.begin(), v.end());
+    for (auto &pr : v) { o.xid.push_back((int32_t)pr.first); o.xfirst.push_back(pr.second); if (pr.first > o.max_id) o.max_id = pr.first; } }
+  if (o.id_orig.empty()) { o.id_orig.push_back(0); o.min_id = 0x7fffffffLL; }
   return ABX_OK;
 }
 // Book surface: recorded op rows -> device rows (order ids become dense device ids; a modify of order id 0 is a no-op, see abides_b200.h)
@@ -216,7 +225,7 @@ static inline int book_ops_to_device(const int64_t *ops9, int64_t n, std::unorde
 }
 // Several replayed days in one handle: environment e replays day e % n_days.  Each day has its own dense order-id space; the device arrays
 // are the concatenation of the days' arrays plus one {first timestamp, timestamps, first `first` entry, -} record per day.
-struct EnvDaysHost { std::vector<EnvStreamHost> days; std::vector<int64_t> ts; std::vector<int32_t> first; std::vector<int4> rows, day_tab; int max_ids; int64_t min_id; };
+struct EnvDaysHost { std::vector<EnvStreamHost> days; std::vector<int64_t> ts; std::vector<int32_t> first, xid, xfirst; std::vector<int4> rows, day_tab, day_tab2; int max_ids; int64_t min_id; };
 static inline int env_build_days(const int64_t *s5, const int64_t *row_off, int n_days, int64_t max_gen_ids, EnvDaysHost &o) {
   if (!s5 || !row_off || n_days < 1 || n_days > 4096) return ABX_ERR_ARG;
   o.days.resize(n_days); o.max_ids = 1; o.min_id = 0x7fffffffffffLL;
@@ -225,6 +234,8 @@ static inline int env_build_days(const int64_t *s5, const int64_t *row_off, int 
     int st = env_build_stream(s5 + 5 * row_off[d], n, max_gen_ids, sd); if (st != ABX_OK) return st;
     if (o.rows.size() + (size_t)n > 0x3fffffffu) return ABX_ERR_ARG;
     int4 rec; rec.x = (int32_t)o.ts.size(); rec.y = (int32_t)sd.ts.size(); rec.z = (int32_t)o.first.size(); rec.w = 0; o.day_tab.push_back(rec);
+    int4 r2; r2.x = (int32_t)o.xid.size(); r2.y = (int32_t)sd.xid.size(); r2.z = (int32_t)(sd.min_id > 0x7fffffffLL ? 0x7fffffffLL : sd.min_id); r2.w = (int32_t)sd.max_id; o.day_tab2.push_back(r2);
+    o.xid.insert(o.xid.end(), sd.xid.begin(), sd.xid.end()); o.xfirst.insert(o.xfirst.end(), sd.xfirst.begin(), sd.xfirst.end());
     int32_t row_base = (int32_t)o.rows.size();
     o.ts.insert(o.ts.end(), sd.ts.begin(), sd.ts.end());
     for (int32_t f : sd.first) o.first.push_back(f + row_base);
@@ -240,7 +251,7 @@ ABX_HD void init_envx(const SimParams &P, EnvX &x) {
   x.rl_flags = RLF_TRADE | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT); x.wt_cursor = 0; x.n_executed = 0; x.rl_n_orders = 0; x.n_lobs = 0; x.lob_head = 0; x.p0 = 0;
   x.rem_time = P.n_h - 1; x.obs_len = 0; x.g0_qty = 0; x.steps = 0;
   for (int i = 0; i < RL_ORDER_CAP; i++) { x.rl_oid[i] = 0; x.rl_oprice[i] = 0; x.rl_oqty[i] = 0; }
-  for (int i = 0; i < 9; i++) x.obs[i] = 0.0; x.g0_pq = 0; x.pad1 = 0;
+  for (int i = 0; i < 9; i++) x.obs[i] = 0.0; x.g0_pq = 0; x.rows_done = 0;
 }
 
 // abx_dq_holdings rows from the trader records of one environment (agent/TradingAgent.py:124-126 final holdings)

@@ -270,7 +270,7 @@ struct abx_sim {
   SimParams P; int n_envs, device; bool reset_done; size_t smem_per_warp; int64_t bytes, launches;
   uint64_t *d_seeds; uint32_t *d_init_err; abx_env_stats *d_stats; int64_t *d_until;
   uint64_t *d_tbits; uint8_t *d_tkinds; int64_t *d_toff;
-  bool is_env, is_dq, have_seeds, have_msizes; EnvStreamHost *st; EnvDaysHost *dh; int4 *d_daytab; int64_t *d_ts; int32_t *d_first; int4 *d_rows; double *d_act, *d_obs, *d_rew; uint8_t *d_done;
+  bool is_env, is_dq, have_seeds, have_msizes; EnvStreamHost *st; EnvDaysHost *dh; int4 *d_daytab, *d_daytab2; int32_t *d_xid, *d_xfirst; int64_t *d_ts; int32_t *d_first; int4 *d_rows; double *d_act, *d_obs, *d_rew; uint8_t *d_done;
   int32_t *d_iact, *d_msizes; double *d_trans;
   int auto_reset;                       // 0 off, 1 restart the same day, 2 move on to the next day: applied to finished environments after every step
   bool is_book; int64_t *d_ops; int64_t ops_cap; std::unordered_map<int64_t, int32_t> *book_ids;
@@ -310,7 +310,7 @@ int32_t abx_sim_destroy(abx_sim *h) {
   cudaSetDevice(h->device);
   void *ptrs[] = {h->P.qkey, h->P.qpay0, h->P.qpay1, h->P.qcache, h->P.agents, h->P.lv_price, h->P.lv_qty, h->P.lv_ht, h->P.nodes, h->P.env,
                   h->P.trace, h->P.draw_log, h->P.evt, h->P.snap, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff,
-                  h->P.envx, h->P.idtab, h->P.idbook, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_iact, h->d_msizes, h->d_trans, h->d_ops, h->d_daytab};
+                  h->P.envx, h->P.idtab, h->P.idbook, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_iact, h->d_msizes, h->d_trans, h->d_ops, h->d_daytab, h->d_daytab2, h->d_xid, h->d_xfirst};
   for (void *p : ptrs) if (p) cudaFree(p);
   delete h->st; delete h->dh; delete h->book_ids; delete h; return ABX_OK;
 }
@@ -551,13 +551,16 @@ int32_t abx_env_create_days(const abx_env_config *cfg, const int64_t *stream5, c
   DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap) DA(h->d_stats, E)
   DA(h->P.envx, E) DA(h->P.idtab, E * h->P.n_ids) DA(h->P.idbook, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
   DA(h->d_ts, dh->ts.size()) DA(h->d_first, dh->first.size()) DA(h->d_rows, dh->rows.size()) DA(h->d_daytab, dh->day_tab.size())
+  DA(h->d_daytab2, dh->day_tab2.size()) DA(h->d_xid, dh->xid.size() + 1) DA(h->d_xfirst, dh->xfirst.size() + 1)
   DA(h->d_act, E * 3) DA(h->d_obs, E * 9) DA(h->d_rew, E) DA(h->d_done, E)
 #undef DA
   CUH(cudaMemcpy(h->d_ts, dh->ts.data(), sizeof(int64_t) * dh->ts.size(), cudaMemcpyHostToDevice));
   CUH(cudaMemcpy(h->d_first, dh->first.data(), sizeof(int32_t) * dh->first.size(), cudaMemcpyHostToDevice));
   CUH(cudaMemcpy(h->d_rows, dh->rows.data(), sizeof(int4) * dh->rows.size(), cudaMemcpyHostToDevice));
   CUH(cudaMemcpy(h->d_daytab, dh->day_tab.data(), sizeof(int4) * dh->day_tab.size(), cudaMemcpyHostToDevice));
-  h->P.st_ts = h->d_ts; h->P.st_first = h->d_first; h->P.st_rows = h->d_rows; h->P.day_tab = h->d_daytab;
+  CUH(cudaMemcpy(h->d_daytab2, dh->day_tab2.data(), sizeof(int4) * dh->day_tab2.size(), cudaMemcpyHostToDevice));
+  if (!dh->xid.empty()) { CUH(cudaMemcpy(h->d_xid, dh->xid.data(), sizeof(int32_t) * dh->xid.size(), cudaMemcpyHostToDevice)); CUH(cudaMemcpy(h->d_xfirst, dh->xfirst.data(), sizeof(int32_t) * dh->xfirst.size(), cudaMemcpyHostToDevice)); }
+  h->P.st_ts = h->d_ts; h->P.st_first = h->d_first; h->P.st_rows = h->d_rows; h->P.day_tab = h->d_daytab; h->P.day_tab2 = h->d_daytab2; h->P.st_xid = h->d_xid; h->P.st_xfirst = h->d_xfirst;
   if (smem_cta > 48 * 1024) {
     CUH(cudaFuncSetAttribute(abx_env_reset_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
     CUH(cudaFuncSetAttribute(abx_env_reset_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
@@ -651,6 +654,7 @@ int32_t abx_dq_create_days(const abx_dq_config *cfg, const int64_t *stream5, con
   DA(h->P.nodes, E * c.order_cap) DA(h->P.env, E) DA(h->P.trace, E * (size_t)c.trace_cap) DA(h->d_stats, E) DA(h->d_seeds, E)
   DA(h->P.envx, E) DA(h->P.idtab, E * h->P.n_ids) DA(h->P.idbook, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
   DA(h->d_ts, dh->ts.size()) DA(h->d_first, dh->first.size()) DA(h->d_rows, dh->rows.size()) DA(h->d_daytab, dh->day_tab.size())
+  DA(h->d_daytab2, dh->day_tab2.size()) DA(h->d_xid, dh->xid.size() + 1) DA(h->d_xfirst, dh->xfirst.size() + 1)
   DA(h->d_iact, E) DA(h->d_obs, E * 8) DA(h->d_trans, E * 6) DA(h->d_rew, E) DA(h->d_done, E) DA(h->d_msizes, E * (cfg->n_momentum > 0 ? cfg->n_momentum : 1))
   h->P.n_snap = n_exec > 0 ? n_exec : 1; h->P.snap_depth = DQ_DEPTH; DA(h->P.snap, E * (size_t)h->P.n_snap * 2 * DQ_DEPTH)                      // getCurrentSpread(depth=500) copies
 #undef DA
@@ -658,8 +662,10 @@ int32_t abx_dq_create_days(const abx_dq_config *cfg, const int64_t *stream5, con
   CUH(cudaMemcpy(h->d_first, dh->first.data(), sizeof(int32_t) * dh->first.size(), cudaMemcpyHostToDevice));
   CUH(cudaMemcpy(h->d_rows, dh->rows.data(), sizeof(int4) * dh->rows.size(), cudaMemcpyHostToDevice));
   CUH(cudaMemcpy(h->d_daytab, dh->day_tab.data(), sizeof(int4) * dh->day_tab.size(), cudaMemcpyHostToDevice));
+  CUH(cudaMemcpy(h->d_daytab2, dh->day_tab2.data(), sizeof(int4) * dh->day_tab2.size(), cudaMemcpyHostToDevice));
+  if (!dh->xid.empty()) { CUH(cudaMemcpy(h->d_xid, dh->xid.data(), sizeof(int32_t) * dh->xid.size(), cudaMemcpyHostToDevice)); CUH(cudaMemcpy(h->d_xfirst, dh->xfirst.data(), sizeof(int32_t) * dh->xfirst.size(), cudaMemcpyHostToDevice)); }
   CUH(cudaMemset(h->P.agents, 0, E * c.n_agents * sizeof(ZiAgent)));
-  h->P.st_ts = h->d_ts; h->P.st_first = h->d_first; h->P.st_rows = h->d_rows; h->P.day_tab = h->d_daytab;
+  h->P.st_ts = h->d_ts; h->P.st_first = h->d_first; h->P.st_rows = h->d_rows; h->P.day_tab = h->d_daytab; h->P.day_tab2 = h->d_daytab2; h->P.st_xid = h->d_xid; h->P.st_xfirst = h->d_xfirst;
   if (smem_cta > 48 * 1024) {
     CUH(cudaFuncSetAttribute(abx_dq_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
     CUH(cudaFuncSetAttribute(abx_dq_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));

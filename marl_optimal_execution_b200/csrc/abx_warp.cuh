@@ -415,6 +415,15 @@ struct WarpCtxT {
   __device__ __forceinline__ int n_ts() const { return day_rec().y; }
   __device__ __forceinline__ int64_t ts_load(int k) const { return __ldg(P.st_ts + day_rec().x + k); }
   __device__ __forceinline__ int first_load(int k) const { return __ldg(P.st_first + day_rec().z + k); }
+  __device__ __forceinline__ int day_row0() const { return first_load(0); }               // rows of all days are stored back to back
+  __device__ __forceinline__ int4 day_rec2() const { return __ldg(P.day_tab2 + day); }
+  // first row (day-local) that carries explicit ORDER_ID `id`, or -1 when the day's stream never uses it: binary search over the sorted ids
+  __device__ int xid_first_row(int4 d2, int32_t id) const {
+    int lo = 0, hi = d2.y - 1;
+#pragma unroll 1
+    while (lo <= hi) { int mid = (lo + hi) >> 1; int32_t v = __ldg(P.st_xid + d2.x + mid); if (v == id) return __ldg(P.st_xfirst + d2.x + mid); if (v < id) lo = mid + 1; else hi = mid - 1; }
+    return -1;
+  }
   __device__ __forceinline__ void lob_store(int slot, const int32_t w[12]) {
     if (lane < 3) __stcg(lob + slot * 3 + lane, make_int4(w[lane * 4], w[lane * 4 + 1], w[lane * 4 + 2], w[lane * 4 + 3]));
     __syncwarp();

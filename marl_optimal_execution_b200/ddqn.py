@@ -58,9 +58,12 @@ class ReplayBuffer:
         return int(self.valid[: self.size].sum()) if self.size else 0
 
     def sample(self, batch, generator=None):
+        """-> (s, a, s', r, weight): np.random.choice(current_size, batch) (:463) over the valid rows.  Invalid rows carry a vanishing weight instead of zero
+        so that a buffer holding only invalid rows cannot raise inside multinomial (that would take a device synchronisation to rule out beforehand); the
+        returned weight is 1 for valid rows and 0 otherwise, and the caller's loss ignores the latter."""
         import torch
-        idx = torch.multinomial(self.valid[: self.size], batch, replacement=True, generator=generator)   # np.random.choice(current_size, batch) :463 over the valid rows
-        return self.s[idx], self.a[idx], self.sp[idx], self.r[idx]
+        idx = torch.multinomial(self.valid[: self.size] + 1e-30, batch, replacement=True, generator=generator)
+        return self.s[idx], self.a[idx], self.sp[idx], self.r[idx], self.valid[idx]
 
 
 class TorchMLP:
@@ -75,13 +78,18 @@ class TorchMLP:
         for w, b in unpack_params(flat, self.dims):
             self.params += [torch.tensor(w, device=device, requires_grad=True), torch.tensor(b, device=device, requires_grad=True)]
 
-    def __call__(self, x):
+    DROPOUT = 0.1      # util/model/QNets.py:16: Dropout(0.1) after every hidden layer but the first (:21-25); identity in predict(), active in train_on_batch()
+
+    def __call__(self, x, training=False, generator=None):
         import torch
         h = x
         for i in range(0, len(self.params), 2):
             h = h @ self.params[i].T + self.params[i + 1]
             if i + 2 < len(self.params):
                 h = torch.relu(h)
+                if training and i >= 2 and self.DROPOUT > 0:             # Keras inverted dropout: kept units scaled by 1 / (1 - rate)
+                    keep = (torch.rand(h.shape, device=h.device, generator=generator) >= self.DROPOUT).to(h.dtype)
+                    h = h * keep / (1.0 - self.DROPOUT)
         return h
 
     def flat(self):
@@ -115,13 +123,37 @@ class DDQNTrainer:
         self.gen = torch.Generator(device=device); self.gen.manual_seed(seed)
         self.learn_step_counter, self.train_step_counter, self.cost_hist = 0, 0, []
         self.sync_gradients = bool(sync_gradients)
+        self.rows_pushed, self.min_rows_per_push = 0, None              # the learn gate every rank evaluates identically (see agree_on_shard)
+
+    def agree_on_shard(self, n_envs):
+        """With several ranks training ONE policy every rank must take the learn / no-learn decision on the same ticks, or the gradient all-reduces pair up
+        wrongly (or hang).  Shards may differ by one environment (distributed.shard_range), so the gate counts min-over-ranks rows per push: one tiny
+        all-reduce here, none per step."""
+        import torch
+        import torch.distributed as dist
+        m = int(n_envs)
+        if self.sync_gradients and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            t = torch.tensor([m], dtype=torch.int64, device=self.device if str(self.device) != "cpu" else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            m = int(t.item())
+        self.min_rows_per_push = m
+        return m
+
+    def store(self, trans):
+        """buffer.push + the rank-agreed row count behind the learn gate"""
+        n = self.buffer.push(trans)
+        self.rows_pushed += n if self.min_rows_per_push is None else min(n, self.min_rows_per_push)
+        return n
+
+    def can_learn(self):
+        return min(self.rows_pushed, self.buffer.capacity) > self.batch_size                      # num_effective_experience > batch_size :262
 
     def learn(self):
         """One train_neural_nets call (:449-505) on a batch from the shared buffer."""
         import torch
-        if self.buffer.size <= self.batch_size:                                                     # num_effective_experience > batch_size :262
+        if not (self.can_learn() if self.rows_pushed else self.buffer.size > self.batch_size):       # num_effective_experience > batch_size :262
             return None
-        s, a, sp, r = self.buffer.sample(self.batch_size, self.gen)
+        s, a, sp, r, wt = self.buffer.sample(self.batch_size, self.gen)
         with torch.no_grad():
             q_next = self.target_net(sp)
             q_eval4next = self.target_net(sp)
@@ -132,7 +164,8 @@ class DDQNTrainer:
         if self.learn_step_counter % self.replace_target_iter == 0:
             self.target_net.load(self.eval_net)
         self.opt.zero_grad(set_to_none=True)
-        loss = ((self.eval_net(s) - q_target) ** 2).mean()                                          # loss="mse" over all outputs
+        err = (self.eval_net(s, training=True, generator=self.gen) - q_target) ** 2                 # train_on_batch: Dropout(0.1) active (util/model/QNets.py:16-25); loss="mse" over all outputs
+        loss = (err.mean(dim=1) * wt).sum() / wt.sum().clamp(min=1.0)                               # rows that hold no transition (weight 0) do not train
         loss.backward()
         self.allreduce_gradients()
         self.opt.step()
@@ -162,7 +195,7 @@ class DDQNTrainer:
 
     def greedy_prob(self):
         """Probability of the network's action in choose_action (:349-357): epsilon once the buffer can feed a batch, else 0 (all random)."""
-        return self.epsilon if self.buffer.size + 1 > self.batch_size else 0.0
+        return self.epsilon if (self.rows_pushed or self.buffer.size) + 1 > self.batch_size else 0.0
 
     def run_episode(self, env, act_fn, sync_fn=None, max_ticks=None):
         """One pass over the batched environment: act, step, store, learn every `train_every` ticks (:259-266).
@@ -179,10 +212,30 @@ class DDQNTrainer:
                 break
             actions = act_fn(obs, self.greedy_prob(), tick)
             obs, trans, rew, done = env.step(actions)
-            self.buffer.push(torch.as_tensor(trans))
+            self.store(torch.as_tensor(trans))
             total += torch.as_tensor(rew).to(self.device)
             if self.train_step_counter % self.train_every == 0 and self.learn() is not None and sync_fn is not None:
                 sync_fn(self.eval_net.flat())
             self.train_step_counter += 1
             tick += 1
         return total, tick
+
+    def run_episodes(self, env, act_fn, n_episodes, sync_fn=None, on_episode=None):
+        """The reference's training sweep (config/execution/marketreplay/execution_marketreplay_ddqn_parallel.py:40-75: one simulation per train date, the
+        network carried from one to the next) on the batched environment: `env` replays several days (environment e starts on day e % n_days), auto-reset
+        moves every finished environment on to its next day, and one policy learns from all of them.  Returns the list of per-episode dicts
+        (mean / std of the total step reward over environments, ticks, learn steps, mean loss)."""
+        import torch
+        env.set_auto_reset("next_day")
+        self.agree_on_shard(env.n_envs)
+        hist = []
+        for ep in range(n_episodes):
+            l0, c0 = self.learn_step_counter, len(self.cost_hist)
+            total, ticks = self.run_episode(env, act_fn, sync_fn)
+            costs = torch.stack(self.cost_hist[c0:]).float() if len(self.cost_hist) > c0 else torch.zeros(1)
+            rec = {"episode": ep, "ticks": ticks, "mean_total_reward": float(total.mean()), "std_total_reward": float(total.std()), "learn_steps": self.learn_step_counter - l0,
+                   "mean_loss": float(costs.mean()), "epsilon": float(self.epsilon)}
+            hist.append(rec)
+            if on_episode is not None:
+                on_episode(rec)
+        return hist

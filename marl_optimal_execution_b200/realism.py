@@ -52,6 +52,7 @@ def _corr(a, b):
 def autocorrelation(close, lag=1, window=30):
     """Autocorrelation.compute (autocorrelation.py:15-18): lag-`lag` autocorrelation of the returns over every full centred window."""
     r = minutely_returns(close)
+    window = min(int(window), r.shape[-1])                 # a run shorter than the window (rmsc03's 15 minutes) is one window
     w = np.lib.stride_tricks.sliding_window_view(r, window, axis=-1)
     return _corr(w[..., lag:], w[..., :-lag])
 

@@ -100,6 +100,9 @@ struct HostCtx {
   int n_ts() { return day_rec().y; }
   int64_t ts_load(int k) { return P.st_ts[day_rec().x + k]; }
   int first_load(int k) { return P.st_first[day_rec().z + k]; }
+  int day_row0() { return first_load(0); }
+  int4 day_rec2() { return P.day_tab2[P.n_days > 1 ? (int)(((uint32_t)env + episode) % (uint32_t)P.n_days) : 0]; }
+  int xid_first_row(int4 d2, int32_t id) { const int32_t *b = P.st_xid + d2.x; const int32_t *e = b + d2.y; const int32_t *it = std::lower_bound(b, e, id); return (it != e && *it == id) ? P.st_xfirst[d2.x + (it - b)] : -1; }
   void lob_store(int slot, const int32_t w[12]) { for (int k = 0; k < 3; k++) { int4 v; v.x = w[4 * k]; v.y = w[4 * k + 1]; v.z = w[4 * k + 2]; v.w = w[4 * k + 3]; lob[slot * 3 + k] = v; } }
   void lob_load(int slot, int32_t w[12]) { for (int k = 0; k < 3; k++) { int4 v = lob[slot * 3 + k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; } }
   void id_prefetch(int) {} void ib_prefetch(int) {}
@@ -277,7 +280,7 @@ int32_t abx_env_create_days(const abx_env_config *cfg, const int64_t *stream5, c
   h->P.qkey = h->qkey.data(); h->P.qpay0 = h->qpay0.data(); h->P.qpay1 = h->qpay1.data(); h->P.qcache = h->qcache.data(); h->P.agents = h->agents.data();
   h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
   h->P.trace = c.trace_cap ? h->trace.data() : nullptr; h->P.envx = h->envx.data(); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); h->P.idbook = h->idbook.data();
-  h->P.st_ts = h->dh.ts.data(); h->P.st_first = h->dh.first.data(); h->P.st_rows = h->dh.rows.data(); h->P.day_tab = h->dh.day_tab.data();
+  h->P.st_ts = h->dh.ts.data(); h->P.st_first = h->dh.first.data(); h->P.st_rows = h->dh.rows.data(); h->P.day_tab = h->dh.day_tab.data(); h->P.day_tab2 = h->dh.day_tab2.data(); h->P.st_xid = h->dh.xid.data(); h->P.st_xfirst = h->dh.xfirst.data();
   *out = h; return ABX_OK;
 }
 int32_t abx_env_create(const abx_env_config *cfg, const int64_t *stream5, int64_t n_rows, int32_t n_envs, int32_t device, abx_sim **out) {
@@ -341,7 +344,7 @@ int32_t abx_dq_create_days(const abx_dq_config *cfg, const int64_t *stream5, con
   h->P.qkey = h->qkey.data(); h->P.qpay0 = h->qpay0.data(); h->P.qpay1 = h->qpay1.data(); h->P.qcache = h->qcache.data(); h->P.agents = h->agents.data();
   h->P.lv_price = h->lvp.data(); h->P.lv_qty = h->lvq.data(); h->P.lv_ht = h->lvht.data(); h->P.nodes = h->nodes.data(); h->P.env = h->env.data();
   h->P.trace = c.trace_cap ? h->trace.data() : nullptr; h->P.envx = h->envx.data(); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); h->P.idbook = h->idbook.data();
-  h->P.st_ts = h->dh.ts.data(); h->P.st_first = h->dh.first.data(); h->P.st_rows = h->dh.rows.data(); h->P.day_tab = h->dh.day_tab.data();
+  h->P.st_ts = h->dh.ts.data(); h->P.st_first = h->dh.first.data(); h->P.st_rows = h->dh.rows.data(); h->P.day_tab = h->dh.day_tab.data(); h->P.day_tab2 = h->dh.day_tab2.data(); h->P.st_xid = h->dh.xid.data(); h->P.st_xfirst = h->dh.xfirst.data();
   { int n_exec = cfg->n_twap + (cfg->has_ddqn ? 1 : 0); h->P.n_snap = n_exec > 0 ? n_exec : 1; h->P.snap_depth = DQ_DEPTH; h->snap.resize(E * (size_t)h->P.n_snap * 2 * DQ_DEPTH); h->P.snap = h->snap.data(); }
   *out = h; return ABX_OK;
 }

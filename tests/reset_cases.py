@@ -95,3 +95,36 @@ def order_level_one(golden_dir, lib_path=None, n_steps=30):
     st = env.stats()
     assert (st["pop_hash"] == np.uint64(o.pop_hash())).all() and (st["flags"] & _lib.F_ERROR_MASK == 0).all()
     env.close()
+
+
+def generated_ids_skip_explicit_ids(lib_path=None):
+    """util/order/Order.py:35-42: generateOrderId hands out the smallest id no Order has used yet -- explicit ORDER_IDs of the replayed stream included,
+    from the row that first carries them.  A synthetic day whose explicit ids (3, 5, 6, 9) lie inside the range the RL agent's generated ids run through:
+    every exchange message (order ids included) must equal the oracle's, which keeps the reference's used-id list.  An explicit id that the generator
+    reaches BEFORE its first row (the reference would then run two orders under one id) raises ABX_F_ID_RANGE."""
+    NS, T = 10 ** 9, 34200 * 10 ** 9
+    rows = [(T + 1 * NS, 3, 9990, 500, 1), (T + 2 * NS, 5, 10010, 500, 0), (T + 3 * NS, 6, 9980, 300, 1), (T + 4 * NS, 9, 10020, 300, 0)]
+    rows += [(T + (700 + 40 * k) * NS, 3 if k % 2 else 5, 9990 if k % 2 else 10010, 500 - k, k % 2) for k in range(1, 30)]       # modifies of ids 3 / 5 through the day
+    stream = np.array(rows, dtype=np.int64)
+    L = _lib.load(lib_path)
+    env = ABIDESEnv(stream, n_envs=2, cfg=env_config(L, trace_cap=20000, hash_pops=1), lib_path=lib_path)
+    env.reset()
+    o = OracleEnv(stream, trace=31)
+    rs = np.random.RandomState(4)
+    for _ in range(12):
+        a = np.array([rs.uniform(0.001, 0.01), rs.uniform(), rs.uniform()])
+        env.step(np.tile(a, (2, 1)))
+        o.step(a)
+    st = env.stats()
+    p, nt, sn = env.split_trace(1)
+    assert np.array_equal(p, o.trace("pops")) and np.array_equal(nt, o.trace("notes")) and np.array_equal(sn, o.trace("snaps"))
+    ids = sorted(set(int(x) for x in nt[nt[:, 2] == 7][:, 3]))                  # ORDER_ACCEPTED ids: the stream's 3, 5, 6, 9 and generated ones around them
+    assert {3, 5, 6, 9} <= set(ids) and {0, 1, 2, 4, 7, 8, 10} <= set(ids) and (st["flags"] & _lib.F_ID_RANGE == 0).all()
+    env.close()
+    late = np.array(rows + [(T + 20000 * NS, 12, 9970, 100, 1)], dtype=np.int64)                                          # id 12 first appears at 15:03: the generator gets there first
+    env = ABIDESEnv(late, n_envs=1, cfg=env_config(L), lib_path=lib_path)
+    env.reset()
+    for _ in range(12):
+        env.step(np.array([[0.005, 0.5, 0.5]]))
+    assert (env.stats()["flags"] & _lib.F_ID_RANGE != 0).all()
+    env.close()

@@ -25,6 +25,7 @@ def np_forward(flat, x, dims=DEFAULT_DIMS):
 
 def test_learn_step_equals_reference_update_rule():
     tr = DDQNTrainer(batch_size=16, seed=3, buffer_capacity=64)
+    tr.eval_net.DROPOUT = 0.0                                             # the exact update rule first; the training-time Dropout(0.1) has its own test below
     rs = np.random.RandomState(0)
     t = np.column_stack([rs.randint(0, 200, (40, 2)), rs.randint(0, 24, 40), rs.randint(0, 200, (40, 2)), rs.uniform(0, 20, 40)])
     t[5, 5] = np.nan                                                      # r None: skipped
@@ -32,7 +33,7 @@ def test_learn_step_equals_reference_update_rule():
     # replicate the sampling, then the reference arithmetic in numpy
     g = torch.Generator(); g.manual_seed(3)
     valid = torch.ones(40); valid[5] = 0
-    idx = torch.multinomial(valid, 16, replacement=True, generator=g).numpy()
+    idx = torch.multinomial(valid + 1e-30, 16, replacement=True, generator=g).numpy()
     assert 5 not in idx
     ok = t[idx]
     s, a, sp, r = ok[:, 0:2], ok[:, 2].astype(int), ok[:, 3:5], ok[:, 5].astype(np.float32)
@@ -63,6 +64,37 @@ def test_learn_step_equals_reference_update_rule():
         want = p.detach().numpy() - 0.01 * gnp / (np.sqrt(0.1 * gnp * gnp) + 1e-7)
         assert np.allclose(q.detach().numpy(), want, rtol=1e-4, atol=1e-6)
     assert tr.learn_step_counter == 1 and tr.epsilon == 0.9
+
+
+def test_training_forward_applies_keras_dropout():
+    """util/model/QNets.py:16-25: Dropout(0.1) after hidden layers 2..6 in train_on_batch (inverted dropout: kept units / 0.9), identity in predict()."""
+    net = TorchMLP(DEFAULT_DIMS, seed=5)
+    x = torch.rand(4096, 2) * 200
+    g = torch.Generator(); g.manual_seed(1)
+    with torch.no_grad():
+        plain, again, train = net(x), net(x, training=False), net(x, training=True, generator=g)
+        assert torch.equal(plain, again) and not torch.equal(plain, train)
+        # first hidden layer untouched, second one: ~10 % of the positive units zeroed, the others scaled by 1 / 0.9
+        w1, b1, w2, b2 = (p.detach() for p in net.params[:4])
+        h1 = torch.relu(x @ w1.T + b1)
+        h2 = torch.relu(h1 @ w2.T + b2)
+        g2 = torch.Generator(); g2.manual_seed(1)
+        keep = (torch.rand(h2.shape, generator=g2) >= 0.1).float()
+        assert abs(float(keep.mean()) - 0.9) < 0.01
+        h2d = h2 * keep / 0.9
+        assert abs(float(h2d.mean()) / float(h2.mean()) - 1.0) < 0.02          # expectation preserved
+    # the learner's loss uses the training forward, its targets the inference forward
+    tr = DDQNTrainer(batch_size=32, seed=2, buffer_capacity=256)
+    tr.store(torch.rand(200, 6, dtype=torch.float64) * 20)
+    assert tr.can_learn() and tr.learn() is not None and np.isfinite(float(tr.cost_hist[-1]))
+
+
+def test_buffer_without_valid_rows_cannot_break_sampling():
+    tr = DDQNTrainer(batch_size=4, seed=2, buffer_capacity=64)
+    t = torch.rand(20, 6, dtype=torch.float64); t[:, 5] = float("nan")        # only r == None rows
+    tr.store(t)
+    before = tr.eval_net.flat()
+    assert tr.learn() is not None and np.array_equal(tr.eval_net.flat(), before)   # zero-weight batch: no update, no exception
 
 
 def test_replay_buffer_wraps_and_epsilon_schedule():

@@ -41,11 +41,9 @@ def test_episode_matches_oracle_and_reference(emu, golden_dir, fixture):
     assert int(st["flags"][1]) == _lib.F_DONE and int(st["pop_hash"][1]) != int(st["pop_hash"][0])
 
 
-def test_rejects_streams_whose_ids_collide_with_generated_ids(emu):
-    L = _lib.load(emu)
-    bad = np.array([[34200 * 10 ** 9, 5, 1000, 100, 1]], dtype=np.int64)      # ORDER_ID 5 could equal an RL-agent order id
-    with pytest.raises(_lib.AbxError):
-        ABIDESEnv(bad, n_envs=1, cfg=env_config(L), lib_path=emu)
+def test_generated_ids_skip_the_streams_explicit_ids(emu):
+    from reset_cases import generated_ids_skip_explicit_ids
+    generated_ids_skip_explicit_ids(emu)
 
 
 def test_marketreplay_config_matches_oracle(emu, golden_dir):

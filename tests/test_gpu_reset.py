@@ -8,7 +8,7 @@ import torch
 
 from marl_optimal_execution_b200 import _lib
 from marl_optimal_execution_b200.env import ABIDESEnv, env_config
-from reset_cases import DAYS, abidesenv_masked_reset_and_rotation, ddqn_auto_reset, order_level_one
+from reset_cases import DAYS, abidesenv_masked_reset_and_rotation, ddqn_auto_reset, generated_ids_skip_explicit_ids, order_level_one
 
 pytestmark = pytest.mark.gpu
 
@@ -23,6 +23,34 @@ def test_ddqn_shape_auto_reset_next_day(golden_dir):
 
 def test_order_level_one_actions(golden_dir):
     order_level_one(golden_dir, n_steps=200)
+
+
+def test_generated_ids_skip_the_streams_explicit_ids():
+    generated_ids_skip_explicit_ids()
+
+
+def test_train_date_whose_ids_reach_into_the_generated_range(golden_dir):
+    """IBM 2003-01-17 (one of the reference's nine train dates): its smallest LOBSTER ORDER_ID is 10 511, inside the range the day's generated ids run through
+    (momentum + execution agents); the whole DDQN-shape day must match the oracle, which keeps the reference's used-id list."""
+    from marl_optimal_execution_b200.env import DDQNExecutionEnv, dq_config
+    from oracle.oracle import OracleDDQNEnv
+    stream = np.load(os.path.join(golden_dir, "days", "IBM_2003-01-17.npz"))["stream"]
+    ms = np.array([5, 3, 9, 2, 7, 4, 6], dtype=np.int32)
+    env = DDQNExecutionEnv(stream, n_envs=2, cfg=dq_config(hash_pops=1))
+    env.reset(mom_sizes=np.tile(ms, (2, 1)))
+    o = OracleDDQNEnv(stream, ms)
+    rs = np.random.RandomState(2)
+    obs, trans, rew, done = env.step(None)
+    out = o.step(0)
+    while not done.all():
+        assert np.allclose(obs[0], out[0], rtol=1e-9, atol=1e-12)
+        a = int(rs.randint(0, 24))
+        obs, trans, rew, done = env.step(np.full(2, a, dtype=np.int32))
+        out = o.step(a)
+    st = env.stats()
+    assert (st["pop_hash"] == np.uint64(o.pop_hash())).all() and (st["messages"] == o.n_pops).all() and (st["flags"] & _lib.F_ERROR_MASK == 0).all()
+    assert int(st["orders_allocated"][0]) > 10511                              # the generator did run past the stream's smallest id
+    env.close()
 
 
 def test_auto_reset_keeps_a_batch_running_across_episodes(golden_dir):

@@ -18,6 +18,8 @@ Usage:  python tools/record_reference.py sparse_zi_100 123456789 tests/golden/z1
                --orders-csv /root/reference/data/sample_orders_file.csv --extra -t SAMPLE -d 2019-06-03
         --orders-csv  replay a plain L3 order file (TIMESTAMP,ORDER_ID,PRICE,SIZE,BUY_SELL_FLAG) instead of a LOBSTER day
         --pov-exec POV QTY BUY|SELL  (rmsc03) append the reference's POVExecutionAgent to the config's agent list
+        --stop HH:MM:SS  replace Kernel.runner's stopTime (shortened recordings of long configs, e.g. rmsc01)
+        python tools/record_reference.py rmsc01 123456789 tests/golden/rmsc01_s123456789_0945.npz --full --stop 09:45:00
 """
 import importlib
 import os
@@ -336,6 +338,19 @@ def main():
             return r1(self, agents=agents, *a, **k)
 
         K.Kernel.runner = runner_with_pov
+    if "--stop" in rest:
+        # shortened run: the UNMODIFIED config script is executed as is, only Kernel.runner's stopTime is replaced (rmsc01 under the current code makes
+        # ~2 M messages per day, dominated by the market maker's 20 quotes per second; a recorded prefix of the day pins the same logic)
+        import Kernel as K
+        import pandas as pd
+        hms = rest[rest.index("--stop") + 1]
+        r0 = K.Kernel.runner
+
+        def runner_with_stop(self, *a, **k):
+            k["stopTime"] = pd.to_datetime(date) + pd.to_timedelta(hms)
+            return r0(self, *a, **k)
+
+        K.Kernel.runner = runner_with_stop
     mod = run(config, seed, extra, date)
 
     pops = np.array(REC.pops, dtype=np.int64).reshape(-1, 5)
