@@ -286,6 +286,9 @@ def main():
         TA.TradingAgent.getTransactedVolume = TA.TradingAgent.get_transacted_volume
         import agent.ExchangeAgent as EA
         EA.ExchangeAgent.logOrderBookSnapshots = lambda self, symbol: None      # archival: pd.SparseDataFrame, out of scope
+    if config in ("rmsc01", "rmsc02"):
+        import agent.ExchangeAgent as EA
+        EA.ExchangeAgent.logOrderBookSnapshots = lambda self, symbol: None      # archival after the run (book_freq "M" is rejected by current pandas): out of scope
     if config == "marketreplay":
         # order-book archival (agent/ExchangeAgent.py:389-469) uses pd.SparseDataFrame, removed from pandas; it runs after the
         # simulation ended and is out of scope, so the recorder skips it.
