@@ -108,7 +108,7 @@ typedef struct abx_sim_config {
   int32_t hash_pops;               /* 1: maintain the FNV-1a hash of the pop sequence (parity runs) */
   /* population layout.  0: ZeroIntelligence groups (above).  1: config/rmsc03.py -- ids 1..n_noise_agents NoiseAgents, then n_value_agents
    * ValueAgents (they use sigma_n / agent_kappa / sigma_s / lambda_a above), n_mm_agents POVMarketMakerAgents (0 or 1), n_momentum_agents
-   * MomentumAgents; zero latency (latency_model ABX_LAT_ZERO). */
+   * MomentumAgents; zero latency (latency_model ABX_LAT_ZERO).  3: config/rmsc01.py (see hbl_L below). */
   int32_t population, n_noise_agents, n_value_agents, n_mm_agents, n_momentum_agents;
   int32_t size_lo, size_hi;        /* Noise/Value order size = np.random.randint(lo, hi) (agent/NoiseAgent.py:34, ValueAgent.py:55) */
   int32_t value_depth_spread;      /* ValueAgent.depth_spread (2) */
@@ -127,6 +127,12 @@ typedef struct abx_sim_config {
   /* > 0: keep, per environment, a ring of the last event_ring_cap exchange events the reference logs for its realism tooling (abx_sim_events):
    * order arrivals and the BEST_BID / BEST_ASK / LAST_TRADE lines of util/OrderBook.py:114-141 */
   int32_t event_ring_cap;
+  /* population 3, config/rmsc01.py: ids 1..n_mm_agents MarketMakerAgents (agent/market_makers/MarketMakerAgent.py, polling mode), then groups[0].count
+   * ZeroIntelligenceAgents, groups[1].count HeuristicBeliefLearningAgents (agent/HeuristicBeliefLearningAgent.py, history length hbl_L), then n_momentum_agents
+   * MomentumAgents; zero latency.  hist_log_cap: entries of the per-environment order-history log behind QUERY_ORDER_STREAM (util/OrderBook.py:52-60). */
+  int32_t hbl_L, mkm_min_size, mkm_max_size, mkm_num_levels;
+  int64_t mkm_wake_ns;
+  int32_t hist_log_cap, _pad3;
 } abx_sim_config;
 
 /* Per-environment counters; replaces the "Event Queue elapsed ..., messages: N" line (Kernel.py:321-327). */

@@ -54,16 +54,17 @@ struct alignas(16) EnvState {           // 192 B per environment
   int64_t sum_shares, sum_cash;
   uint32_t kblk[4];                     // cached Philox block of the kernel (latency-noise) stream
   uint32_t draw_n, evt_n, book_flags, episode; // entries in the draw log (parity runs) / in the LAST_TRADE, BEST_BID, BEST_ASK event ring; BKF_*; resets of this environment that moved on to the next replayed day
+  uint32_t hist_n, pad_h0, pad_h1, pad_h2;     // orders registered in the order-history log (population 3: what QUERY_ORDER_STREAM hands out)
 };
-static_assert(sizeof(EnvState) == 208, "EnvState layout");
+static_assert(sizeof(EnvState) == 224, "EnvState layout");
 
 enum : uint32_t {
   AF_HAS_OPEN = 1u, AF_HAS_CLOSE = 2u, AF_MKT_CLOSED = 4u, AF_HAS_LAST = 8u, AF_HAS_DAILY = 16u, AF_HAS_PREV = 32u,
   AF_HAS_BID = 64u, AF_HAS_ASK = 128u, AF_STATE_SHIFT = 8, AF_STATE_MASK = 3u << 8, AF_GROUP_SHIFT = 12, AF_GROUP_MASK = 7u << 12
 };
-enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE = 1, ST_AWAITING_SPREAD = 2, ST_AWAITING_TV = 3 }; // ZeroIntelligenceAgent.state; POVExecutionAgent AWAITING_TRANSACTED_VOLUME
-enum : uint32_t { AF_TYPE_SHIFT = 16, AF_TYPE_MASK = 7u << 16 };
-enum { AT_ZI = 0, AT_NOISE = 1, AT_VALUE = 2, AT_MOMENTUM = 3, AT_POVMM = 4, AT_TWAP = 5, AT_DDQN = 6, AT_POVEXEC = 7 };   // agent class (rmsc03 / DDQN execution populations)
+enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE = 1, ST_AWAITING_SPREAD = 2, ST_AWAITING_TV = 3, ST_AWAITING_STREAM = 3 };   // 3: AWAITING_TRANSACTED_VOLUME (POV execution agent) or AWAITING_STREAM (HBL agent): no class uses both // ZeroIntelligenceAgent.state; POVExecutionAgent AWAITING_TRANSACTED_VOLUME
+enum : uint32_t { AF_TYPE_SHIFT = 16, AF_TYPE_MASK = 15u << 16 };
+enum { AT_ZI = 0, AT_NOISE = 1, AT_VALUE = 2, AT_MOMENTUM = 3, AT_POVMM = 4, AT_TWAP = 5, AT_DDQN = 6, AT_POVEXEC = 7, AT_MKM = 8, AT_HBL = 9 };   // agent class (rmsc03 / DDQN execution populations)
 constexpr int AGENT_ORDER_CAP = 4;      // open orders tracked per trader (ZI holds <= 2)
 
 struct alignas(16) ZiAgent {            // 192 B per trader: TradingAgent + ZeroIntelligenceAgent state
@@ -158,6 +159,8 @@ struct SimParams {
   EnvState *env;                // [n_envs]
   abx_trace_rec *trace;         // [n_envs][trace_cap]
   uint4 *draw_log;              // [n_envs][draw_log_cap] {stream | kind << 24, bits lo, bits hi, -}  (parity runs under Philox)
+  uint4 *hlog;                  // [n_envs][hist_log_cap] {order id, limit price, history epoch at registration, is_buy | has transactions << 1}  (population 3)
+  int32_t lob_stride, pad_l0;   // int4 entries per environment in `lobs`
   uint4 *evt;                   // [n_envs][event_ring_cap] {t lo, t hi | kind << 28, a, b}: order arrivals, BEST_BID / BEST_ASK / LAST_TRADE (realism tooling)
   const uint64_t *tape_bits; const uint8_t *tape_kinds; const int64_t *tape_off; // tape mode
   // ---- ABIDESEnv shape (exchange + MarketReplayAgent + RL execution agent); zero for the sparse_zi shape ----
@@ -355,6 +358,12 @@ typedef RngT<-1> Rng;
 // ---------------------------------------------------------------------------------------------------
 ABX_HD int agent_type_of(const abx_sim_config &c, int id) {
   if (c.population == 0) return AT_ZI;
+  if (c.population == 3) {                                                              // config/rmsc01.py: market maker(s), ZI, HBL, momentum
+    if (id <= c.n_mm_agents) return AT_MKM;
+    if (id <= c.n_mm_agents + c.groups[0].count) return AT_ZI;
+    if (id <= c.n_mm_agents + c.groups[0].count + c.groups[1].count) return AT_HBL;
+    return AT_MOMENTUM;
+  }
   if (c.population == 2) return id < 2 + c.n_momentum_agents ? AT_MOMENTUM : (id == c.n_agents - 1 && c.n_mm_agents ? AT_DDQN : AT_TWAP);   // n_mm_agents doubles as has_ddqn
   if (id <= c.n_noise_agents) return AT_NOISE;
   if (id <= c.n_noise_agents + c.n_value_agents) return AT_VALUE;
@@ -391,10 +400,27 @@ ABX_HD void init_agent_record_r3(const SimParams &P, int env, int id, uint64_t s
   }
   if (rng.err) *err |= rng.err;
 }
+// round(x / 2) of MarketMakerAgent.size (agent/market_makers/MarketMakerAgent.py:55,99): Python's round half to even on the float quotient
+ABX_HD int32_t mkm_half(int64_t v) { return (int32_t)rint((double)v / 2); }
 ABX_HD void init_agent_record(const SimParams &P, int env, int id, uint64_t seed, ZiAgent *z, uint32_t *err) {
-  if (P.c.population != 0) { init_agent_record_r3(P, env, id, seed, z, err); return; }
+  if (P.c.population == 1) { init_agent_record_r3(P, env, id, seed, z, err); return; }
   Rng rng; rng.P = &P; rng.env = P.n_tapes > 0 ? env % P.n_tapes : env; rng.seed = seed; rng.err = 0;
-  int grp = 0, acc = 1;
+  int grp = 0, acc = 1, type3 = P.c.population == 3 ? agent_type_of(P.c, id) : AT_ZI;
+  if (P.c.population == 3) acc += P.c.n_mm_agents;
+  if (type3 == AT_MKM || type3 == AT_MOMENTUM) {                                        // population 3: MarketMakerAgent.__init__ :55 / MomentumAgent.__init__ :42 draw their size from the agent's stream
+    uint32_t ctr = 0; int32_t size;
+    if (type3 == AT_MKM) size = mkm_half(P.c.mkm_min_size + rng.randint(S_AGENT0 + id, ctr, (uint32_t)(P.c.mkm_max_size - P.c.mkm_min_size - 1)));
+    else size = P.c.mom_min_size + (int32_t)rng.randint(S_AGENT0 + id, ctr, (uint32_t)(P.c.mom_max_size - P.c.mom_min_size - 1));
+    z->agent_time = P.c.start_ns; z->prev_wake = 0; z->r_t = P.c.r_bar; z->sigma_t = 0.0; z->cash = P.c.starting_cash; z->shares = 0; z->last_trade = 0;
+    z->daily_close = 0; z->bid = 0; z->bid_q = 0; z->ask = 0; z->ask_q = 0;
+    z->flags = ((uint32_t)type3 << AF_TYPE_SHIFT) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT); z->rng_ctr = ctr; z->n_orders = 0;
+    for (int i = 0; i < AGENT_ORDER_CAP; i++) { z->oid[i] = 0; z->oprice[i] = 0; z->oqty[i] = 0; }
+    AgentAux ax; ax.size = size; ax.order_size = 0; ax.last_mid = 0; ax.tv = 0; ax.mmflags = 0; ax.n_mids = 0; ax.avg20 = 0.0; ax.avg50 = 0.0;
+    *reinterpret_cast<AgentAux *>(z->theta) = ax;
+    z->lat_to = 0.0; z->lat_from = 0.0; z->surplus = 0;
+    if (rng.err) *err |= rng.err;
+    return;
+  }
   for (int g = 0; g < P.c.n_groups; g++) { if (id >= acc && id < acc + P.c.groups[g].count) grp = g; acc += P.c.groups[g].count; }
   uint32_t ctr = 0; int stream = S_AGENT0 + id; int m = 2 * P.c.q_max;
   double th[20];
@@ -402,13 +428,14 @@ ABX_HD void init_agent_record(const SimParams &P, int env, int id, uint64_t seed
   for (int i = 0; i < m; i++) th[i] = rint(rng.normal(stream, ctr, 0.0, P.sqrt_sigma_pv));   // np.round(normal(0, sqrt(sigma_pv)))
   for (int i = 1; i < m; i++) { double x = th[i]; int j = i - 1; while (j >= 0 && th[j] < x) { th[j + 1] = th[j]; j--; } th[j + 1] = x; }  // sorted(reverse=True)
   double lat_to = z->lat_to, lat_from = z->lat_from;
-  if (P.c.rng_mode == ABX_RNG_PHILOX) {           // the config's pairwise latency matrix row/column 0, drawn per environment
+  if (P.c.population == 3) { lat_to = 0.0; lat_from = 0.0; }                            // np.zeros latency matrix (config/rmsc01.py:250)
+  else if (P.c.rng_mode == ABX_RNG_PHILOX) {      // the config's pairwise latency matrix row/column 0, drawn per environment
     uint32_t c2 = 0; int cs = P.n_streams + id;
     lat_to = dadd(P.c.latency_lo, dmul(dsub(P.c.latency_hi, P.c.latency_lo), rng.u01(cs, c2)));
     lat_from = P.c.latency_mirrored ? lat_to : dadd(P.c.latency_lo, dmul(dsub(P.c.latency_hi, P.c.latency_lo), rng.u01(cs, c2)));
   }
   z->agent_time = P.c.start_ns; z->prev_wake = 0; z->r_t = P.c.r_bar; z->sigma_t = 0.0; z->cash = P.c.starting_cash; z->shares = 0; z->last_trade = 0;
-  z->daily_close = 0; z->bid = 0; z->bid_q = 0; z->ask = 0; z->ask_q = 0; z->flags = ((uint32_t)grp << AF_GROUP_SHIFT) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT);
+  z->daily_close = 0; z->bid = 0; z->bid_q = 0; z->ask = 0; z->ask_q = 0; z->flags = ((uint32_t)grp << AF_GROUP_SHIFT) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT) | ((uint32_t)type3 << AF_TYPE_SHIFT);
   z->rng_ctr = ctr; z->n_orders = 0;
   for (int i = 0; i < AGENT_ORDER_CAP; i++) { z->oid[i] = 0; z->oprice[i] = 0; z->oqty[i] = 0; }
   for (int i = 0; i < 20; i++) { double v = th[i]; if (v > 32767.0) { v = 32767.0; rng.err |= ABX_F_THETA_INDEX; } if (v < -32768.0) { v = -32768.0; rng.err |= ABX_F_THETA_INDEX; } z->theta[i] = (int16_t)v; }
@@ -444,7 +471,7 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
   s.uniq = 0; s.next_order_id = 0; s.q_count = 0; s.max_q = 0; s.n_bid_lv = s.n_ask_lv = 0; s.n_resting = 0; s.free_head = NIL;
   s.pool_top = 0; s.flags = 0; s.trace_n = 0; s.c_limit = s.c_cancel = s.c_fills = s.c_query = 0;
   s.ctr_symbol = s.ctr_kernel = s.ctr_latency = s.ctr_global = 0; s.trade_epoch = 16; s.sum_shares = 0; s.sum_cash = 0;
-  s.kblk[0] = s.kblk[1] = s.kblk[2] = s.kblk[3] = 0; s.draw_n = 0; s.evt_n = 0; s.book_flags = 0; s.episode = 0;
+  s.kblk[0] = s.kblk[1] = s.kblk[2] = s.kblk[3] = 0; s.draw_n = 0; s.evt_n = 0; s.book_flags = 0; s.episode = 0; s.hist_n = 0; s.pad_h0 = s.pad_h1 = s.pad_h2 = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -481,10 +508,10 @@ ABX_HD void regs_store(ZiAgent *z, const AgentRegs &a) {
 
 // RNG_MODE / LAT_MODEL: compile-time copies of cfg.rng_mode / cfg.latency_model (-1 = decide at run time);
 // INSTR: parity instrumentation (pop hash + trace records) compiled in or out.
-enum { SHAPE_ZI = 0, SHAPE_ENV = 1, SHAPE_R3 = 2, SHAPE_DQ = 3, SHAPE_BOOK = 4 };   // sparse_zi population | ABIDESEnv / marketreplay | rmsc03 population | DDQN execution config | bare order books (op-tape replay)
+enum { SHAPE_ZI = 0, SHAPE_ENV = 1, SHAPE_R3 = 2, SHAPE_DQ = 3, SHAPE_BOOK = 4, SHAPE_P3 = 5 };   // sparse_zi population | ABIDESEnv / marketreplay | rmsc03 population | DDQN execution config | bare order books (op-tape replay)
 template <class Ctx, int RNG_MODE = -1, int LAT_MODEL = -1, bool INSTR = true, int SHAPE = SHAPE_ZI>
 struct Sim {
-  static constexpr bool DQ = SHAPE == SHAPE_DQ, BOOK = SHAPE == SHAPE_BOOK, ENV = SHAPE == SHAPE_ENV || DQ || BOOK, R3 = SHAPE == SHAPE_R3;
+  static constexpr bool DQ = SHAPE == SHAPE_DQ, BOOK = SHAPE == SHAPE_BOOK, ENV = SHAPE == SHAPE_ENV || DQ || BOOK, R3 = SHAPE == SHAPE_R3, P3 = SHAPE == SHAPE_P3;   // P3: config/rmsc01.py population (runs the rmsc03 loop with more agent classes)
   Ctx &c; const SimParams &P; EnvState s; RngT<RNG_MODE, INSTR> rng; int64_t addl_delay; int n_out; int self_id; int env_id;
   AgentRegs a; ZiAgent *z;                // the trader whose event is being handled (registers + staged record)
 

@@ -110,14 +110,15 @@ typedef struct { int64_t agent_id, order_id, quantity, limit_price, fill_price; 
 typedef struct { order_t *o; int n, cap; } level_t;          /* one price level: FIFO list, oldest at 0 */
 typedef struct { level_t *lv; int n, cap; } side_t;          /* OrderBook.bids / .asks, best at 0 (OrderBook.py:24-25) */
 typedef struct { int64_t t, q; } tx_t;
-typedef struct { int64_t order_id; tx_t *tx; int ntx, captx; } hrec_t; /* history record (OrderBook.py:52-60), only what is read back */
-typedef struct { hrec_t *r; int n, cap; } hbucket_t;
+typedef struct { int64_t order_id, limit_price; int is_buy; tx_t *tx; int ntx, captx; } hrec_t; /* history record (OrderBook.py:52-60), only what is read back */
+typedef struct { hrec_t *r; int n, cap; int64_t serial; } hbucket_t;   /* serial: which history.insert(0, {}) created it (the exchange hands out REFERENCES to these dicts, ExchangeAgent.py:276) */
 
 typedef void (*send_fn)(void *owner, int64_t recipient, int kind, const order_t *o);
 
 struct abo_book {
   side_t bids, asks; int64_t last_trade; int has_last_trade;
   hbucket_t *hist; int nhist; int stream_history;
+  hbucket_t *arch; int n_arch, cap_arch; int keep_dropped; int64_t next_serial;   /* buckets that fell off history[:stream_history+1] but may still be referenced by an agent's stream_history */
   int64_t now; void *owner; send_fn send;
   i64buf notes; /* standalone use */
   int64_t n_fills;
@@ -150,6 +151,8 @@ static void book_destroy(abo_book *b) {
   for (int i = 0; i < b->asks.n; i++) free(b->asks.lv[i].o);
   free(b->bids.lv); free(b->asks.lv);
   for (int i = 0; i < b->nhist; i++) hist_bucket_free(&b->hist[i]);
+  for (int i = 0; i < b->n_arch; i++) hist_bucket_free(&b->arch[i]);
+  free(b->arch);
   free(b->hist); free(b->notes.v);
 }
 /* isMatch :242-254 (same-side case cannot occur: caller picks the opposite side) */
@@ -190,9 +193,10 @@ static void book_enter(abo_book *b, const order_t *order) {
 static void book_handle_limit(abo_book *b, order_t order) {
   if (order.quantity <= 0) return;                                                   /* :47-49 */
   hbucket_t *h0 = &b->hist[0]; hrec_t *r = hist_find(h0, order.order_id);            /* :52-60 */
-  if (r) { r->ntx = 0; }
+  if (r) { r->ntx = 0; r->limit_price = order.limit_price; r->is_buy = order.is_buy; }
   else { if (h0->n == h0->cap) { h0->cap = h0->cap ? h0->cap * 2 : 16; h0->r = (hrec_t *)realloc(h0->r, sizeof(hrec_t) * h0->cap); }
-         h0->r[h0->n].order_id = order.order_id; h0->r[h0->n].tx = NULL; h0->r[h0->n].ntx = h0->r[h0->n].captx = 0; h0->n++; }
+         h0->r[h0->n].order_id = order.order_id; h0->r[h0->n].limit_price = order.limit_price; h0->r[h0->n].is_buy = order.is_buy;
+         h0->r[h0->n].tx = NULL; h0->r[h0->n].ntx = h0->r[h0->n].captx = 0; h0->n++; }
   int matching = 1; int64_t trade_qty = 0, trade_price = 0; int executed = 0;
   while (matching) {                                                                 /* :68-110 */
     order_t matched;
@@ -212,8 +216,11 @@ static void book_handle_limit(abo_book *b, order_t order) {
   if (executed) {                                                                    /* :131-149 */
     b->last_trade = py_round((double)trade_price / (double)trade_qty); b->has_last_trade = 1; /* int(round(a / b)): true division */
     /* history.insert(0, {}) then truncate to stream_history+1 */
-    if (b->nhist == b->stream_history + 1) { hist_bucket_free(&b->hist[b->nhist - 1]); b->nhist--; }
-    memmove(b->hist + 1, b->hist, sizeof(hbucket_t) * b->nhist); memset(&b->hist[0], 0, sizeof(hbucket_t)); b->nhist++;
+    if (b->nhist == b->stream_history + 1) {
+      if (b->keep_dropped) { if (b->n_arch == b->cap_arch) { b->cap_arch = b->cap_arch ? 2 * b->cap_arch : 64; b->arch = (hbucket_t *)realloc(b->arch, sizeof(hbucket_t) * b->cap_arch); } b->arch[b->n_arch++] = b->hist[b->nhist - 1]; }
+      else hist_bucket_free(&b->hist[b->nhist - 1]);
+      b->nhist--; }
+    memmove(b->hist + 1, b->hist, sizeof(hbucket_t) * b->nhist); memset(&b->hist[0], 0, sizeof(hbucket_t)); b->hist[0].serial = ++b->next_serial; b->nhist++;
   }
 }
 /* cancelOrder :284-339 */
@@ -252,6 +259,11 @@ static void book_modify(abo_book *b, const order_t *order, const order_t *new_or
       }
     }
   }
+}
+static const hbucket_t *book_bucket(const abo_book *b, int64_t serial) {
+  for (int i = 0; i < b->nhist; i++) if (b->hist[i].serial == serial) return &b->hist[i];
+  for (int i = b->n_arch - 1; i >= 0; i--) if (b->arch[i].serial == serial) return &b->arch[i];
+  return NULL;
 }
 /* getInsideBids / getInsideAsks :377-398 */
 static int book_inside(const abo_book *b, int is_bid, int depth, int64_t *out) {
@@ -309,7 +321,8 @@ typedef struct {            /* one PriorityQueue entry: (deliverAt, (recipient, 
   int has_bid, has_ask;
   int64_t bid2, ask2; int n_bids, n_asks;                    /* depth > 1 replies: second level price, level counts (capped at 2) */
   order_t new_order;                                         /* MODIFY_ORDER body["new_order"] */
-  int64_t tv, lookback;                                      /* QUERY_TRANSACTED_VOLUME: transacted_volume / lookback_period (ns) */
+  int64_t tv, lookback;                                      /* QUERY_TRANSACTED_VOLUME: transacted_volume / lookback_period (ns); QUERY_ORDER_STREAM: lookback = length */
+  int n_stream; int64_t stream_serial[16];                   /* QUERY_ORDER_STREAM reply: "orders" = history[1 : length + 1], as references to the book's dicts */
 } event_t;
 
 static inline int ev_less(const event_t *a, const event_t *b) { /* tuple order (t, recipient, type.value, msg.uniq) */
@@ -330,7 +343,7 @@ static void heap_pop(heap_t *h, event_t *out) { /* heapq.heappop */
 }
 
 typedef struct { int64_t order_id, quantity, limit_price; int is_buy; } open_order_t;
-enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE, ST_AWAITING_SPREAD };
+enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE, ST_AWAITING_SPREAD, ST_AWAITING_TV_, ST_AWAITING_STREAM };
 
 typedef struct {            /* TradingAgent (agent/TradingAgent.py:19-98) + ZeroIntelligenceAgent (:65-70) state */
   abo_rng *rs; int group;
@@ -351,8 +364,10 @@ typedef struct {            /* TradingAgent (agent/TradingAgent.py:19-98) + Zero
   double *mids; int n_mids, cap_mids; double avg20, avg50; int has20, has50;   /* MomentumAgent.mid_list, avg_20_list[-1], avg_50_list[-1] */
   int64_t order_size, last_mid, transacted_volume; int has_last_mid, aw_spread, aw_vol;   /* POVMarketMakerAgent */
   int64_t *kside[2], *fside[2]; int nk[2], nf[2], capk; int64_t px_rem, px_executed, px_n_executed;   /* POVExecutionAgent: known_bids/asks (price, qty pairs), lists in flight, rem_quantity */
+  int L, n_stream; int64_t stream_serial[16];           /* HeuristicBeliefLearningAgent: L, stream_history[symbol] (references to the exchange's history dicts) */
+  int64_t mkm_min, mkm_max, last_spread;                /* MarketMakerAgent (agent/market_makers/MarketMakerAgent.py): min_size, max_size, last_spread (10, never updated) */
 } zi_t;
-enum { AT_ZI = 0, AT_NOISE, AT_VALUE, AT_MOMENTUM, AT_POVMM, AT_POVEXEC };
+enum { AT_ZI = 0, AT_NOISE, AT_VALUE, AT_MOMENTUM, AT_POVMM, AT_POVEXEC, AT_MKM, AT_HBL };
 
 struct abo_sim {
   int variant; uint32_t seed; int trace; int n_agents;
@@ -369,6 +384,7 @@ struct abo_sim {
   /* agents */
   zi_t *zi; double sigma_n, agent_kappa, sigma_s, lambda_a; int64_t order_size, starting_cash; double value_percent_aggr; int64_t value_depth_spread;
   double mm_pov; int64_t mm_min_size, mm_window, mm_ticks, mm_wake_ns, mom_wake_ns;   /* config/rmsc03.py:41-45,176-200 */
+  int64_t mkm_levels, mkm_wake_ns;                                                     /* MarketMakerAgent subscribe_num_levels (5), wake_up_freq ("1s") */
   int px_id, px_is_buy; double px_pov; int64_t px_quantity, px_start, px_end, px_freq, px_lookback;   /* POVExecutionAgent (agent/execution/baselines/pov_agent.py), 0 = none */
   /* traces */
   i64buf pops, ops, notes, snaps; uint64_t pop_hash, note_hash, snap_hash; uint64_t *ckpt; int64_t n_ckpt, cap_ckpt;
@@ -486,6 +502,10 @@ static void exch_receive(abo_sim *s, const event_t *m) {
   event_t e; memset(&e, 0, sizeof(e));
   switch (m->kind) {
     case ABO_QUERY_TRANSACTED_VOLUME: s->book.now = s->now; e.kind = ABO_QUERY_TRANSACTED_VOLUME; e.tv = book_transacted_volume(&s->book, m->lookback); e.mkt_closed = t_closed; exch_send(s, m->sender, &e); break; /* :280-303 */
+    case ABO_QUERY_ORDER_STREAM: {                                                          /* :251-279: orders = history[1 : length + 1] */
+      e.kind = ABO_QUERY_ORDER_STREAM; e.mkt_closed = t_closed; e.lookback = m->lookback;
+      for (int k = 1; k <= (int)m->lookback && k < s->book.nhist && e.n_stream < 16; k++) e.stream_serial[e.n_stream++] = s->book.hist[k].serial;
+      exch_send(s, m->sender, &e); break; }
     case ABO_WHEN_MKT_OPEN: s->comp_delay[0] = 0; e.kind = ABO_WHEN_MKT_OPEN; e.data = s->mkt_open; exch_send(s, m->sender, &e); break;     /* :175-183 */
     case ABO_WHEN_MKT_CLOSE: s->comp_delay[0] = 0; e.kind = ABO_WHEN_MKT_CLOSE; e.data = s->mkt_close; exch_send(s, m->sender, &e); break;  /* :184-192 */
     case ABO_QUERY_SPREAD: {                                                                /* :215-245, depth 1 on this path */
@@ -529,6 +549,8 @@ static void zi_wakeup(abo_sim *s, int id) {
     e.order.agent_id = id; e.order.order_id = a->orders[i].order_id; e.order.quantity = a->orders[i].quantity; e.order.limit_price = a->orders[i].limit_price; e.order.is_buy = a->orders[i].is_buy;
     ta_send(s, id, &e);
   }
+  if (a->type == AT_HBL) {                                                                  /* :183-187 a subclass is left "ACTIVE"; HeuristicBeliefLearningAgent.wakeup :61-74 */
+    event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_QUERY_ORDER_STREAM; e.lookback = a->L; ta_send(s, id, &e); a->state = ST_AWAITING_STREAM; return; }
   ta_get_spread(s, id); a->state = ST_AWAITING_SPREAD;                                      /* :183-185 */
 }
 /* ZeroIntelligenceAgent.updateEstimates :189-275 */
@@ -585,6 +607,66 @@ static void zi_place_order(abo_sim *s, int id) {
   else if (!buy && bid_vol > 0) { int64_t R_bid = a->bid - v; if ((double)R_bid >= a->eta * (double)R) p = a->bid; } /* :298-305 */
   ta_place_limit(s, id, s->order_size, buy, p);                                             /* :308-309 (size 100) */
 }
+/* HeuristicBeliefLearningAgent.placeOrder (agent/HeuristicBeliefLearningAgent.py:76-174): belief of a successful transaction per limit price from the
+ * orders that led up to the last L trades, limit price = argmax of probability x surplus; falls back to the ZI order without enough history. */
+static void hbl_place_order(abo_sim *s, int id) {
+  zi_t *a = &s->zi[id];
+  if (a->n_stream < a->L) { zi_place_order(s, id); return; }                                /* :83-87 len(stream_history) < L */
+  int64_t v; int buy;
+  if (zi_update_estimates(s, id, &v, &buy)) return;                                         /* :94 */
+  int64_t low_p = INT64_MAX, high_p = 0;                                                    /* :98-108 (sys.maxsize, 0) */
+  for (int k = 0; k < a->n_stream; k++) { const hbucket_t *h = book_bucket(&s->book, a->stream_serial[k]); if (!h) { fprintf(stderr, "abides_oracle: history bucket gone\n"); continue; }
+    for (int i = 0; i < h->n; i++) { int64_t p = h->r[i].limit_price; if (p < low_p) low_p = p; if (p > high_p) high_p = p; } }
+  if (low_p > high_p) return;                                                               /* empty history dicts: np.zeros((negative, 8)) raises in the reference */
+  int64_t R = high_p - low_p + 1;
+  double *nd = (double *)calloc((size_t)R * 8, sizeof(double));                              /* :112 columns sa, sb, ua, ub, num, denom, Pr, Es */
+  for (int k = 0; k < a->n_stream; k++) { const hbucket_t *h = book_bucket(&s->book, a->stream_serial[k]); if (!h) continue;
+    for (int i = 0; i < h->n; i++) { const hrec_t *o = &h->r[i]; int64_t p = o->limit_price;           /* :115-139: "transactions" non-empty == successful */
+      if (o->is_buy) { if (o->ntx) nd[(p - low_p) * 8 + 1] += 1; else nd[(p - low_p) * 8 + 3] += 1; }
+      else { if (o->ntx) nd[(p - low_p) * 8 + 0] += 1; else nd[(p - low_p) * 8 + 2] += 1; } } }
+  if (buy) {                                                                                /* :143-150 */
+    for (int64_t r = 1; r < R; r++) for (int c = 0; c < 3; c++) nd[r * 8 + c] += nd[(r - 1) * 8 + c];
+    for (int64_t r = R - 2; r >= 0; r--) nd[r * 8 + 3] += nd[(r + 1) * 8 + 3];
+    for (int64_t r = 0; r < R; r++) nd[r * 8 + 4] = (nd[r * 8 + 0] + nd[r * 8 + 1]) + nd[r * 8 + 2];
+  } else {
+    for (int64_t r = R - 2; r >= 0; r--) { nd[r * 8 + 0] += nd[(r + 1) * 8 + 0]; nd[r * 8 + 1] += nd[(r + 1) * 8 + 1]; nd[r * 8 + 3] += nd[(r + 1) * 8 + 3]; }
+    for (int64_t r = 1; r < R; r++) nd[r * 8 + 2] += nd[(r - 1) * 8 + 2];
+    for (int64_t r = 0; r < R; r++) nd[r * 8 + 4] = (nd[r * 8 + 0] + nd[r * 8 + 1]) + nd[r * 8 + 3];
+  }
+  int64_t best = 0; double best_es = 0.0;
+  for (int64_t r = 0; r < R; r++) {
+    double den = ((nd[r * 8 + 0] + nd[r * 8 + 1]) + nd[r * 8 + 2]) + nd[r * 8 + 3];         /* :152 np.sum(nd[:, 0:4], axis=1) */
+    double pr = den == 0.0 ? 0.0 : nd[r * 8 + 4] / den;                                     /* :158-159 nan_to_num(0 / 0) */
+    double es = buy ? pr * (double)(v - (low_p + r)) : pr * (double)((low_p + r) - v);      /* :162-165 */
+    if (r == 0 || es > best_es) { best = r; best_es = es; }                                 /* :168 np.argmax: first maximum */
+  }
+  free(nd);
+  if (best_es > 0) ta_place_limit(s, id, s->order_size, buy, low_p + best);                 /* :173-185 int(round(best_p)) */
+}
+/* MarketMakerAgent (agent/market_makers/MarketMakerAgent.py), polling mode (subscribe False): wakeup :66-77, receiveMessage :79-108 */
+static int64_t mkm_draw_size(zi_t *a) { double h = (double)abo_rng_randint(a->rs, a->mkm_min, a->mkm_max) / 2; return (int64_t)nearbyint(h); }   /* round(randint(min, max) / 2): half to even */
+static void ta_cancel_all(abo_sim *s, int id);
+static int ta_wakeup_common(abo_sim *s, int id);
+static void mkm_wakeup(abo_sim *s, int id) {
+  zi_t *a = &s->zi[id];
+  if (!ta_wakeup_common(s, id)) return;
+  ta_cancel_all(s, id); ta_get_spread(s, id); a->state = ST_AWAITING_SPREAD;                 /* getCurrentSpread(depth=subscribe_num_levels): the agent reads level 0 only */
+}
+static void mkm_receive_tail(abo_sim *s, int id, const event_t *m) {
+  zi_t *a = &s->zi[id];
+  if (!(a->state == ST_AWAITING_SPREAD && m->kind == ABO_QUERY_SPREAD)) return;
+  ta_cancel_all(s, id);
+  int64_t mid = a->last_trade, spread;
+  if (a->has_bid && a->bid != 0 && a->has_ask && a->ask != 0) { mid = (int64_t)((double)(a->ask + a->bid) / 2); spread = (int64_t)((double)llabs(a->ask - a->bid) / 2); }
+  else spread = a->last_spread;
+  for (int i = 0; i < 2 * (int)s->mkm_levels; i++) {
+    a->size = mkm_draw_size(a);
+    ta_place_limit(s, id, a->size, 1, mid - spread - i);
+    ta_place_limit(s, id, a->size, 0, mid + spread + i);
+  }
+  k_set_wakeup(s, id, s->now + s->mkm_wake_ns);
+  a->state = ST_AWAITING_WAKEUP;
+}
 static void orders_remove(zi_t *a, int i) { memmove(a->orders + i, a->orders + i + 1, sizeof(open_order_t) * (a->n_orders - i - 1)); a->n_orders--; }
 static void povmm_receive_tail(abo_sim *s, int id, const event_t *m); static void momentum_place_orders(abo_sim *s, int id); static void povexec_receive_tail(abo_sim *s, int id, const event_t *m);
 static void noise_place_order(abo_sim *s, int id); static void value_place_order(abo_sim *s, int id);
@@ -608,6 +690,7 @@ static void zi_receive(abo_sim *s, int id, const event_t *m) {
       break;
     case ABO_MKT_CLOSED: a->mkt_closed = 1; break;                                          /* marketClosed :492-499 */
     case ABO_QUERY_TRANSACTED_VOLUME: if (m->mkt_closed) a->mkt_closed = 1; a->transacted_volume = m->tv; break;   /* :248-251,556-558 */
+    case ABO_QUERY_ORDER_STREAM: if (m->mkt_closed) a->mkt_closed = 1; a->n_stream = m->n_stream; memcpy(a->stream_serial, m->stream_serial, sizeof(a->stream_serial)); break;   /* :240-246,549-554 */
     case ABO_QUERY_SPREAD:                                                                  /* :232-238, querySpread :514-537, queryLastTrade :502-511 */
       if (m->mkt_closed) a->mkt_closed = 1;
       a->last_trade = m->data; a->has_last_trade = 1;
@@ -618,11 +701,12 @@ static void zi_receive(abo_sim *s, int id, const event_t *m) {
     default: break;
   }
   if (a->has_open && a->has_close && !had) {                                                /* :258-268 */
-    int64_t off = a->type == AT_MOMENTUM ? s->mom_wake_ns : a->type == AT_POVMM ? s->mm_wake_ns : a->type == AT_POVEXEC ? s->px_freq
+    int64_t off = a->type == AT_MOMENTUM ? s->mom_wake_ns : a->type == AT_POVMM ? s->mm_wake_ns : a->type == AT_MKM ? s->mkm_wake_ns : a->type == AT_POVEXEC ? s->px_freq
                 : abo_rng_randint(a->rs, 0, 100);                                           /* ZI/Noise/Value.getWakeFrequency: randint(0, 100) ns */
     k_set_wakeup(s, id, a->mkt_open + off);
   }
   if (a->type == AT_POVMM) { povmm_receive_tail(s, id, m); return; }
+  if (a->type == AT_MKM) { mkm_receive_tail(s, id, m); return; }
   if (a->type == AT_POVEXEC) { povexec_receive_tail(s, id, m); return; }
   if (a->type == AT_MOMENTUM) {                                                             /* MomentumAgent.receiveMessage :65-76 */
     if (a->state == ST_AWAITING_SPREAD && m->kind == ABO_QUERY_SPREAD) { momentum_place_orders(s, id); k_set_wakeup(s, id, s->now + s->mom_wake_ns); a->state = ST_AWAITING_WAKEUP; }
@@ -630,8 +714,12 @@ static void zi_receive(abo_sim *s, int id, const event_t *m) {
   }
   if (a->state == ST_AWAITING_SPREAD && m->kind == ABO_QUERY_SPREAD) {                      /* ZI :319-334, NoiseAgent :123-129, ValueAgent :245-251 */
     if (a->mkt_closed) return;
-    if (a->type == AT_NOISE) noise_place_order(s, id); else if (a->type == AT_VALUE) value_place_order(s, id); else zi_place_order(s, id);
+    if (a->type == AT_NOISE) noise_place_order(s, id); else if (a->type == AT_VALUE) value_place_order(s, id); else if (a->type == AT_HBL) hbl_place_order(s, id); else zi_place_order(s, id);
     a->state = ST_AWAITING_WAKEUP;
+  }
+  if (a->type == AT_HBL && a->state == ST_AWAITING_STREAM && m->kind == ABO_QUERY_ORDER_STREAM) {   /* HeuristicBeliefLearningAgent.receiveMessage :176-195 */
+    if (a->mkt_closed) return;
+    ta_get_spread(s, id); a->state = ST_AWAITING_SPREAD;
   }
 }
 
@@ -773,7 +861,7 @@ static void povexec_receive_tail(abo_sim *s, int id, const event_t *m) {
 }
 static void agent_wakeup(abo_sim *s, int id) {
   switch (s->zi[id].type) { case AT_NOISE: noise_wakeup(s, id); break; case AT_VALUE: value_wakeup(s, id); break; case AT_MOMENTUM: momentum_wakeup(s, id); break;
-    case AT_POVMM: povmm_wakeup(s, id); break; case AT_POVEXEC: povexec_wakeup(s, id); break; default: zi_wakeup(s, id); }
+    case AT_POVMM: povmm_wakeup(s, id); break; case AT_POVEXEC: povexec_wakeup(s, id); break; case AT_MKM: mkm_wakeup(s, id); break; default: zi_wakeup(s, id); }
 }
 
 /* ---------------- config: config/sparse_zi_100.py / config/sparse_zi_1000.py ---------------- */
@@ -818,6 +906,20 @@ int abo_default_config(int variant, abx_sim_config *c) {
     c->mm_pov = 0.05; c->mm_min_order_size = 20; c->mm_window_size = 5; c->mm_num_ticks = 20; c->mm_wake_ns = NS_PER_S;   /* :41-45 */
     if (variant == 4) { c->n_pov_exec = 1; c->n_agents += 1; c->pov_exec_is_buy = 1; c->pov_exec_pov = 0.5; c->pov_exec_quantity = 120000;
       c->pov_exec_start_ns = (9 * 3600 + 32 * 60) * NS_PER_S; c->pov_exec_end_ns = (9 * 3600 + 43 * 60) * NS_PER_S; c->pov_exec_freq_ns = 30 * NS_PER_S; c->pov_exec_lookback_ns = 30 * NS_PER_S; }
+    return 0;
+  }
+  if (variant == 1) {                                                                       /* config/rmsc01.py */
+    c->population = 3; c->n_mm_agents = 1; c->n_groups = 2; c->q_max = 10; c->n_momentum_agents = 24;
+    c->groups[0].count = 50; c->groups[0].r_min = 0; c->groups[0].r_max = 100; c->groups[0].eta = 1;          /* ZI :134-157 */
+    c->groups[1].count = 25; c->groups[1].r_min = 0; c->groups[1].r_max = 100; c->groups[1].eta = 1; c->hbl_L = 2;   /* HBL :163-187 */
+    c->n_agents = 1 + 1 + 50 + 25 + 24;
+    c->mkt_open_ns = (9 * 3600 + 30 * 60) * NS_PER_S; c->mkt_close_ns = 16 * 3600 * NS_PER_S; c->start_ns = c->mkt_open_ns; c->stop_ns = (16 * 3600 + 60) * NS_PER_S;   /* :72-73,246-247 */
+    c->starting_cash = 10000000; c->order_size = 100; c->stream_history = 10;
+    c->r_bar = 1e5; c->kappa = 1.67e-12; c->fund_vol = 1e-4; c->megashock_lambda_a = 2.77778e-13; c->megashock_mean = 1e3; c->megashock_var = 5e4;
+    c->sigma_n = 10000; c->agent_kappa = 1.67e-15; c->sigma_s = 1e-4; c->sigma_pv = 5e4; c->lambda_a = 1e-12;        /* :141-153 */
+    c->latency_model = ABX_LAT_ZERO; c->n_noise = 1;
+    c->mom_min_size = 1; c->mom_max_size = 10; c->mom_wake_ns = 60 * NS_PER_S;                                     /* MomentumAgent default wake_up_freq "60s" */
+    c->mkm_min_size = 500; c->mkm_max_size = 1000; c->mkm_num_levels = 5; c->mkm_wake_ns = NS_PER_S;             /* MarketMakerAgent :100-110 + defaults */
     return 0;
   }
   return -1;
@@ -931,9 +1033,43 @@ abo_sim *abo_sim_new_rmsc03_pov(uint32_t seed, int trace, double pov, int64_t qu
   return new_population1(&c, seed, trace);
 }
 abo_sim *abo_sim_new_rmsc03(uint32_t seed, int trace) { return abo_sim_new_rmsc03_pov(seed, trace, 0.0, 0, 1, 0, 0, 0, 0); }
+/* config/rmsc01.py (population 3): ExchangeAgent, MarketMakerAgent(s), ZeroIntelligenceAgents (groups[0]), HeuristicBeliefLearningAgents (groups[1]),
+ * MomentumAgents -- seeds in the script's source order: exchange :89, market makers :109, symbol :129 (+ oracle __init__), ZI :154, HBL :184, momentum :205, kernel :243 */
+static abo_sim *new_population3(const abx_sim_config *c, uint32_t seed, int trace) {
+  abo_sim *s = (abo_sim *)calloc(1, sizeof(abo_sim));
+  s->variant = 1; s->seed = seed; s->trace = trace; s->pop_hash = s->note_hash = s->snap_hash = FNV_OFF;
+  int n_mm = c->n_mm_agents, n_zi = c->groups[0].count, n_hbl = c->groups[1].count, n_mom = c->n_momentum_agents, n = 1 + n_mm + n_zi + n_hbl + n_mom; s->n_agents = n;
+  s->g = abo_rng_new(seed);
+  s->mkt_open = c->mkt_open_ns; s->mkt_close = c->mkt_close_ns; s->start_time = c->start_ns; s->stop_time = c->stop_ns;
+  s->r_bar = c->r_bar; s->kappa = c->kappa; s->fund_vol = c->fund_vol; s->megashock_lambda = c->megashock_lambda_a; s->megashock_mean = c->megashock_mean; s->megashock_var = c->megashock_var;
+  s->sigma_n = c->sigma_n; s->agent_kappa = c->agent_kappa; s->sigma_s = c->sigma_s; s->lambda_a = c->lambda_a; s->order_size = c->order_size; s->starting_cash = c->starting_cash;
+  s->mom_wake_ns = c->mom_wake_ns; s->mkm_levels = c->mkm_num_levels; s->mkm_wake_ns = c->mkm_wake_ns;
+  s->exch_rs = new_stream(s); s->pipeline_delay = c->exchange_pipeline_delay_ns; s->exch_comp_delay = c->exchange_computation_delay_ns;
+  book_init(&s->book, c->stream_history, s, exch_book_send); s->book.keep_dropped = 1;
+  s->zi = (zi_t *)calloc(n, sizeof(zi_t));
+  for (int id = 1; id <= n_mm; id++) { zi_t *a = &s->zi[id]; a->type = AT_MKM; a->rs = new_stream(s); a->mkm_min = c->mkm_min_size; a->mkm_max = c->mkm_max_size; a->last_spread = 10; a->size = mkm_draw_size(a); }   /* __init__ :55 */
+  s->sym_rs = new_stream(s);
+  s->or_t = s->mkt_open; s->or_v = (int64_t)s->r_bar; oracle_new_megashock(s, s->mkt_open);
+  for (int id = 1 + n_mm; id < 1 + n_mm + n_zi + n_hbl; id++) {
+    int g = id < 1 + n_mm + n_zi ? 0 : 1; zi_t *a = &s->zi[id]; a->type = g ? AT_HBL : AT_ZI; a->L = c->hbl_L; a->rs = new_stream(s); a->group = g;
+    a->R_min = c->groups[g].r_min; a->R_max = c->groups[g].r_max; a->eta = c->groups[g].eta; a->r_t = s->r_bar; a->sigma_t = 0; a->q_max = c->q_max;
+    double th[64]; int m = 2 * a->q_max;
+    for (int i = 0; i < m; i++) th[i] = nearbyint(rng_normal(a->rs, 0.0, sqrt(c->sigma_pv)));
+    for (int i = 1; i < m; i++) { double x = th[i]; int j = i - 1; while (j >= 0 && th[j] < x) { th[j + 1] = th[j]; j--; } th[j + 1] = x; }
+    for (int i = 0; i < m; i++) a->theta[i] = (int32_t)th[i];
+  }
+  for (int id = 1 + n_mm + n_zi + n_hbl; id < n; id++) { zi_t *a = &s->zi[id]; a->type = AT_MOMENTUM; a->rs = new_stream(s); a->size = abo_rng_randint(a->rs, c->mom_min_size, c->mom_max_size); }
+  for (int id = 1; id < n; id++) { zi_t *a = &s->zi[id]; a->starting_cash = a->cash = c->starting_cash; a->first_wake = 1; a->state = ST_AWAITING_WAKEUP; if (!a->q_max) a->q_max = c->q_max; }
+  s->kernel_rs = new_stream(s);
+  s->latency = (double *)calloc((size_t)n * n, sizeof(double)); s->n_noise = 1; s->use_latency_model = 0;
+  s->agent_time = (int64_t *)calloc(n, sizeof(int64_t)); s->comp_delay = (int64_t *)calloc(n, sizeof(int64_t));
+  for (int i = 0; i < n; i++) { s->agent_time[i] = s->start_time; s->comp_delay[i] = c->default_computation_delay_ns; }
+  return s;
+}
 abo_sim *abo_sim_new_config(const abx_sim_config *c, uint32_t seed, int trace) {
   if (!c || c->n_agents < 2 || c->q_max < 1 || c->q_max > 32) return NULL;
   if (c->population == 0) { int n = 1; for (int g = 0; g < c->n_groups; g++) n += c->groups[g].count; if (n != c->n_agents) return NULL; return new_population0(c, seed, trace); }
+  if (c->population == 3) { if (c->n_groups != 2 || 1 + c->n_mm_agents + c->groups[0].count + c->groups[1].count + c->n_momentum_agents != c->n_agents || c->hbl_L < 1 || c->hbl_L > 16) return NULL; return new_population3(c, seed, trace); }
   if (c->population == 1) { if (1 + c->n_noise_agents + c->n_value_agents + c->n_mm_agents + c->n_momentum_agents + (c->n_pov_exec ? 1 : 0) != c->n_agents || c->n_mm_agents > 1) return NULL; return new_population1(c, seed, trace); }
   return NULL;
 }
@@ -1023,7 +1159,7 @@ int64_t abo_sim_run_until(abo_sim *s, int64_t until, int *done) {
 void abo_sim_stop(abo_sim *s) {
   for (int id = 1; id < s->n_agents; id++) {
     zi_t *a = &s->zi[id];
-    if (a->type != AT_ZI) { if (a->type == AT_VALUE) oracle_observe(s, a->current_time, 0, a->rs); a->surplus = 0; continue; }   /* ValueAgent.kernelStopping :57-61 advances the fundamental */
+    if (a->type != AT_ZI && a->type != AT_HBL) { if (a->type == AT_VALUE) oracle_observe(s, a->current_time, 0, a->rs); a->surplus = 0; continue; }   /* ValueAgent.kernelStopping :57-61 advances the fundamental */
     double hr = nearbyint((double)a->shares / 100.0) * 100.0; /* round(int, -2): half-even on hundreds */
     int64_t H = (int64_t)(hr / 100);
     int64_t rT = oracle_observe(s, a->current_time, 0, a->rs);
@@ -1054,7 +1190,7 @@ int64_t abo_sim_trace(abo_sim *s, int which, const int64_t **rows) {
   *rows = b->v; return b->n / w;
 }
 static abo_rng *stream_at(abo_sim *s, int i) {
-  if (s->variant == 3) { if (i == 0) return s->sym_rs; if (i == 1) return s->exch_rs; if (i == s->n_agents + 1) return s->kernel_rs; return s->zi[i - 1].rs; }
+  if (s->variant == 3 || s->variant == 1) { if (i == 0) return s->sym_rs; if (i == 1) return s->exch_rs; if (i == s->n_agents + 1) return s->kernel_rs; return s->zi[i - 1].rs; }
   int base = s->variant == 100 ? 4 : 3;
   if (i == 0) return s->sym_rs; if (i == 1) return s->kernel_rs;
   if (s->variant == 100) { if (i == 2) return s->lat_rs; if (i == 3) return s->exch_rs; } else if (i == 2) return s->exch_rs;

@@ -101,3 +101,31 @@ def test_rmsc03_with_pov_execution_agent(golden_dir):
     assert list(s.pov_exec()) == [int(g["pov_exec"][3]), int(g["pov_exec"][4]), int(g["pov_exec"][5])]
     gk, gb = s.global_tape()
     assert np.array_equal(gk, g["global_kind"].view(np.uint8)) and np.array_equal(gb, g["global_bits"])
+
+
+def rmsc01_config(stop_ns=(9 * 3600 + 45 * 60) * 10 ** 9):
+    """config/rmsc01.py as the oracle's `abo_default_config(1)` states it (1 MarketMakerAgent + 50 ZI + 25 HBL + 24 Momentum, zero
+    latency, oracle megashock-free r_bar 1e5), cut at `stop_ns`: the full day is ~2 M messages under the current reference code
+    (tests/rmsc01.txt's 128 918 predates it), so the recording stops at 09:45:00."""
+    import ctypes as C
+    from marl_optimal_execution_b200 import _lib
+    from oracle.oracle import lib
+    cfg = _lib.SimConfig()
+    assert lib().abo_default_config(1, C.addressof(cfg)) == 0
+    cfg.stop_ns = stop_ns
+    return cfg
+
+
+def test_rmsc01_full_trace_bit_exact(golden_dir):
+    """config/rmsc01.py run live to 09:45:00 (tools/record_reference.py rmsc01 123456789 --full --stop 09:45:00): every kernel pop,
+    every order-book operation incl. the HBL agents' QUERY_ORDER_STREAM-driven limit prices and the MarketMakerAgent's ladder,
+    every agent notification, every book snapshot, every stream's draw count and the final holdings."""
+    g = np.load(os.path.join(golden_dir, "rmsc01_s123456789_0945.npz"))
+    s = OracleSim.from_config(rmsc01_config(), 123456789, TRACE_ALL)
+    assert s.run() == int(g["n_pops"]) == 77119
+    for name in ("pops", "ops", "notes", "snaps"):
+        assert np.array_equal(s.trace(name), g[name]), name
+    assert np.array_equal(s.hash_ckpt(), g["pop_hash_ckpt"])
+    assert np.array_equal(s.holdings()[:, :4], g["holdings"][:, :4])
+    mine, ref = [len(s.tape(i)[0]) for i in range(s.n_streams)], [int(x) for x in g["stream_draws"]]
+    assert mine[3:] == ref[3:] and sorted(mine[:3]) == sorted(ref[:3])     # config/rmsc01.py creates its first three streams in another order
