@@ -362,6 +362,11 @@ def run_ours(args, rank, local_rank, world):
     if not args.no_rmsc03:
         sim.close()
         r3_local = bench_rmsc03(args, rank, local_rank, dev, stream, sp)
+    r1_local = None
+    if not args.no_rmsc01:
+        if not sim_closed(sim):
+            sim.close()
+        r1_local = bench_rmsc01(args, rank, local_rank, dev, stream, sp)
     mr_local = None
     if not args.no_marketreplay:
         if not sim_closed(sim):
@@ -405,6 +410,16 @@ def run_ours(args, rank, local_rank, world):
                 blk["note"] = ("same population + POVExecutionAgent (agent/execution/baselines/pov_agent.py; BUY 120 000 at 50 % of volume, 09:32-09:43); "
                                "one_sided_book_envs = runs in which the agent saw an empty book side (the reference raises TypeError there; flagged F_OBS_INVALID, the run continues)")
                 r3_block["with_pov_execution_agent"] = blk
+    r1_block = None
+    if r1_local is not None:
+        g1 = D.gather_summaries(torch.tensor([r1_local["msgs"], r1_local["errs"], r1_local["hbl_orders"]], dtype=torch.int64), device=dev)
+        t1 = D.max_over_ranks(r1_local["ms"], device=dev) / 1e3
+        r1_block = {"metric": "LOB msgs/sec (rmsc01)", "unit": "msgs/s", "value": int(g1[:, 0].sum()) / t1, "envs_per_gpu": args.rmsc01_envs_per_gpu, "ms_per_run": 1e3 * t1,
+                    "messages_per_env_run": int(g1[:, 0].sum()) / (world * args.rmsc01_envs_per_gpu), "error_envs": int(g1[:, 1].sum()), "gpu_launches": int(r1_local["launches"]),
+                    "limit_orders_per_env_run": int(g1[:, 2].sum()) / (world * args.rmsc01_envs_per_gpu),
+                    "workload": "config/rmsc01.py shape: MarketMakerAgent + 50 ZI + 25 HeuristicBeliefLearningAgents (QUERY_ORDER_STREAM, L = 2) + 24 MomentumAgents + exchange, "
+                                "09:30-10:00 of the day, zero latency, %d envs/GPU (Philox streams), one abx_run_kernel<0,2,0,5> launch; one timed run on fresh seeds after a "
+                                "warm-up run, resets untimed" % args.rmsc01_envs_per_gpu}
     env_block = None
     if env_local is not None:
         ge = D.gather_summaries(torch.tensor([env_local["steps"], env_local["msgs"], env_local["e2e_steps"], env_local["errs"]], dtype=torch.int64), device=dev)
@@ -499,6 +514,8 @@ def run_ours(args, rank, local_rank, world):
         out["marketreplay"] = mr_block
     if r3_block is not None:
         out["rmsc03"] = r3_block
+    if r1_block is not None:
+        out["rmsc01"] = r1_block
     if not args.no_env:
         out["env"] = env_block
     if dq_block is not None:
@@ -550,6 +567,30 @@ def bench_rmsc03(args, rank, local_rank, dev, stream, sp):
                                           "launches": l0}
         sim.close()
     return out
+
+
+def bench_rmsc01(args, rank, local_rank, dev, stream, sp):
+    """config/rmsc01.py population (MarketMakerAgent, ZI, HBL over QUERY_ORDER_STREAM, Momentum); the first half hour of the day of every
+    environment in one abx_run_kernel launch.  Reset untimed; one warm-up run, one timed run on fresh seeds."""
+    import torch
+    from marl_optimal_execution_b200 import _lib, distributed as D
+    from marl_optimal_execution_b200.sim import BatchedSim, rmsc01_config
+    n = args.rmsc01_envs_per_gpu
+    sim = BatchedSim(rmsc01_config(stop_ns=10 * 3600 * NS), n, device=local_rank)
+    res = None
+    for rep in range(2):
+        sim.reset(D.env_seeds(args.seed + 700001 * rep, rank * n, (rank + 1) * n), stream=sp)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        D.barrier(); torch.cuda.synchronize(dev)
+        lc = sim.launch_count
+        e0.record(stream); sim.run(stream=sp); e1.record(stream)
+        torch.cuda.synchronize(dev); D.barrier()
+        if rep == 1:
+            st = sim.stats(stream=sp)
+            res = {"msgs": int(st["messages"].sum()), "ms": e0.elapsed_time(e1), "errs": int(((st["flags"] & _lib.F_ERROR_MASK) != 0).sum()),
+                   "hbl_orders": int(st["limit_orders"].sum()), "launches": sim.launch_count - lc}
+    sim.close()
+    return res
 
 
 def bench_marketreplay(args, rank, local_rank, dev, stream, sp):
@@ -737,6 +778,8 @@ def main():
     ap.add_argument("--env-envs-per-gpu", type=int, default=9472, help="4 x 148 SMs x 16 resident one-warp CTAs: whole waves (8192 leaves the 4th wave 46 %% full)")
     ap.add_argument("--env-steps", type=int, default=750, help="timed ABIDESEnv steps: 750 = the whole 761-tick episode after the start-up and warm-up steps")
     ap.add_argument("--no-rmsc03", action="store_true", help="skip the rmsc03 population (BASELINE configs[2])")
+    ap.add_argument("--no-rmsc01", action="store_true", help="skip the rmsc01 population (MarketMaker + ZI + HBL + Momentum)")
+    ap.add_argument("--rmsc01-envs-per-gpu", type=int, default=2368, help="148 SMs x 16 resident one-warp CTAs")
     ap.add_argument("--no-whole-day", action="store_true", help="skip the whole-environment-day measurement of the headline workload")
     ap.add_argument("--no-marketreplay", action="store_true", help="skip the config/marketreplay.py shape (BASELINE configs[4])")
     ap.add_argument("--mr-envs-per-gpu", type=int, default=4736, help="2 x 148 SMs x 16 resident one-warp CTAs")

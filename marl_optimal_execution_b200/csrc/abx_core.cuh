@@ -65,6 +65,7 @@ enum : uint32_t {
 enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE = 1, ST_AWAITING_SPREAD = 2, ST_AWAITING_TV = 3, ST_AWAITING_STREAM = 3 };   // 3: AWAITING_TRANSACTED_VOLUME (POV execution agent) or AWAITING_STREAM (HBL agent): no class uses both // ZeroIntelligenceAgent.state; POVExecutionAgent AWAITING_TRANSACTED_VOLUME
 enum : uint32_t { AF_TYPE_SHIFT = 16, AF_TYPE_MASK = 15u << 16 };
 enum { AT_ZI = 0, AT_NOISE = 1, AT_VALUE = 2, AT_MOMENTUM = 3, AT_POVMM = 4, AT_TWAP = 5, AT_DDQN = 6, AT_POVEXEC = 7, AT_MKM = 8, AT_HBL = 9 };   // agent class (rmsc03 / DDQN execution populations)
+constexpr uint32_t EPOCH_START = 16;    // EnvState.trade_epoch of a fresh book (so that epoch differences of up to 16 never wrap below zero)
 constexpr int AGENT_ORDER_CAP = 4;      // open orders tracked per trader (ZI holds <= 2)
 
 struct alignas(16) ZiAgent {            // 192 B per trader: TradingAgent + ZeroIntelligenceAgent state
@@ -160,7 +161,6 @@ struct SimParams {
   abx_trace_rec *trace;         // [n_envs][trace_cap]
   uint4 *draw_log;              // [n_envs][draw_log_cap] {stream | kind << 24, bits lo, bits hi, -}  (parity runs under Philox)
   uint4 *hlog;                  // [n_envs][hist_log_cap] {order id, limit price, history epoch at registration, is_buy | has transactions << 1}  (population 3)
-  int32_t lob_stride, pad_l0;   // int4 entries per environment in `lobs`
   uint4 *evt;                   // [n_envs][event_ring_cap] {t lo, t hi | kind << 28, a, b}: order arrivals, BEST_BID / BEST_ASK / LAST_TRADE (realism tooling)
   const uint64_t *tape_bits; const uint8_t *tape_kinds; const int64_t *tape_off; // tape mode
   // ---- ABIDESEnv shape (exchange + MarketReplayAgent + RL execution agent); zero for the sparse_zi shape ----
@@ -356,6 +356,8 @@ typedef RngT<-1> Rng;
 // reset: agent construction (config/sparse_zi_1000.py:211-251, ZeroIntelligenceAgent.__init__ :65-70) -- one
 // thread per (environment, trader) on the GPU.  In tape mode lat_to / lat_from were preloaded by the host.
 // ---------------------------------------------------------------------------------------------------
+// int4 entries per environment in SimParams.lobs: the ABIDESEnv LOB ring, or the momentum agents' mid-price rings (population 3 has 24 of them)
+ABX_HD int lob_stride_of(const abx_sim_config &c) { int need = c.population == 3 ? (c.n_momentum_agents * MOM_MIDS + 3) / 4 : 0; return need > LOB_CAP * 3 ? need : LOB_CAP * 3; }
 ABX_HD int agent_type_of(const abx_sim_config &c, int id) {
   if (c.population == 0) return AT_ZI;
   if (c.population == 3) {                                                              // config/rmsc01.py: market maker(s), ZI, HBL, momentum
@@ -470,7 +472,7 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
   s.or_v = (int32_t)P.c.r_bar; s.last_trade = (int32_t)P.c.r_bar;     // SparseMeanRevertingOracle.py:58; ExchangeAgent.kernelInitializing :91-102
   s.uniq = 0; s.next_order_id = 0; s.q_count = 0; s.max_q = 0; s.n_bid_lv = s.n_ask_lv = 0; s.n_resting = 0; s.free_head = NIL;
   s.pool_top = 0; s.flags = 0; s.trace_n = 0; s.c_limit = s.c_cancel = s.c_fills = s.c_query = 0;
-  s.ctr_symbol = s.ctr_kernel = s.ctr_latency = s.ctr_global = 0; s.trade_epoch = 16; s.sum_shares = 0; s.sum_cash = 0;
+  s.ctr_symbol = s.ctr_kernel = s.ctr_latency = s.ctr_global = 0; s.trade_epoch = EPOCH_START; s.sum_shares = 0; s.sum_cash = 0;
   s.kblk[0] = s.kblk[1] = s.kblk[2] = s.kblk[3] = 0; s.draw_n = 0; s.evt_n = 0; s.book_flags = 0; s.episode = 0; s.hist_n = 0; s.pad_h0 = s.pad_h1 = s.pad_h2 = 0;
 }
 
@@ -511,8 +513,8 @@ ABX_HD void regs_store(ZiAgent *z, const AgentRegs &a) {
 enum { SHAPE_ZI = 0, SHAPE_ENV = 1, SHAPE_R3 = 2, SHAPE_DQ = 3, SHAPE_BOOK = 4, SHAPE_P3 = 5 };   // sparse_zi population | ABIDESEnv / marketreplay | rmsc03 population | DDQN execution config | bare order books (op-tape replay)
 template <class Ctx, int RNG_MODE = -1, int LAT_MODEL = -1, bool INSTR = true, int SHAPE = SHAPE_ZI>
 struct Sim {
-  static constexpr bool DQ = SHAPE == SHAPE_DQ, BOOK = SHAPE == SHAPE_BOOK, ENV = SHAPE == SHAPE_ENV || DQ || BOOK, R3 = SHAPE == SHAPE_R3, P3 = SHAPE == SHAPE_P3;   // P3: config/rmsc01.py population (runs the rmsc03 loop with more agent classes)
-  Ctx &c; const SimParams &P; EnvState s; RngT<RNG_MODE, INSTR> rng; int64_t addl_delay; int n_out; int self_id; int env_id;
+  static constexpr bool DQ = SHAPE == SHAPE_DQ, BOOK = SHAPE == SHAPE_BOOK, ENV = SHAPE == SHAPE_ENV || DQ || BOOK, P3 = SHAPE == SHAPE_P3, R3 = SHAPE == SHAPE_R3 || P3;   // P3: config/rmsc01.py population (runs the rmsc03 loop with more agent classes)
+  Ctx &c; const SimParams &P; EnvState s; RngT<RNG_MODE, INSTR> rng; int64_t addl_delay; int n_out; int self_id; int env_id; uint32_t hidx = 0;   // hidx: order-history log index of the order handleLimitOrder is working on (population 3)
   AgentRegs a; ZiAgent *z;                // the trader whose event is being handled (registers + staged record)
 
   ABX_HD Sim(Ctx &c_, const SimParams &P_, const EnvState &s_, int env) : c(c_), P(P_), s(s_), addl_delay(0), n_out(0), self_id(0), z(nullptr) {
@@ -725,7 +727,7 @@ struct Sim {
     int n = n_lv(side); int pos; bool found;
     c.lv_find(side, price, n, pos, found);
     uint32_t node = node_alloc(); if (node == NIL) return;
-    NodeRec r; r.id = oid; r.qty = qty; r.agent = (uint32_t)agent | (R3 ? (s.trade_epoch << 16) : 0u); r.next = NIL; r.price = price; nstore(node, r);   // R3: + registration epoch
+    NodeRec r; r.id = oid; r.qty = qty; r.agent = (uint32_t)agent | (P3 ? (hidx << 16) : R3 ? (s.trade_epoch << 16) : 0u); r.next = NIL; r.price = price; nstore(node, r);   // rmsc03: + registration epoch; population 3: + index of its order-history log entry
     if (found) {
       uint32_t tail = c.lv_tail(side, pos);
       NodeRec tr = nload(tail); tr.next = node; nstore(tail, tr);
@@ -744,6 +746,7 @@ struct Sim {
       t.w = (t.w == 0 || d >= 16) ? 1u : (((t.w << d) | 1u) & 0xffffu); t.z = s.trade_epoch; c.ord_store((int)(oid - REPLAY_ID_BASE), t);
     }
     evt_log(ABX_EV_ORDER, price, is_buy ? qty : -qty);
+    if (P3) hidx = s.hist_n++ & 0xffffu;                                                // :52-60 history[0][order_id] = {...}: the entry is written below, once "transactions" is known
     int opp = is_buy ? 1 : 0;                                                           // a buy matches asks (side 1)
     uint32_t epoch0 = s.trade_epoch;                                                    // the incoming order's history bucket (:52-60)
     int64_t trade_qty = 0, trade_px = 0;
@@ -765,7 +768,10 @@ struct Sim {
           } else {                                                                      // :212-217 partial
             fq = qty; hr.qty -= fq; nstore(h, hr); c.lv_set(opp, n - 1, c.lv_qty(opp, n - 1) - fq, h, c.lv_tail(opp, n - 1));
           }
-          if (R3) {                                                                     // :227,230-237 history "transactions" tuples read back by get_transacted_volume
+          if (P3) {                                                                     // :230-237 the resting order's record gets a transaction if one of the retained buckets still holds it
+            uint32_t sl = (hr.agent >> 16) & (uint32_t)(P.c.hist_log_cap - 1); uint4 h4 = c.hist_load((int)sl);
+            if (h4.x == hr.id && epoch0 - h4.z <= (uint32_t)P.c.stream_history && !(h4.w & 2u)) { h4.w |= 2u; c.hist_store((int)sl, h4); }
+          } else if (R3) {                                                              // :227,230-237 history "transactions" tuples read back by get_transacted_volume
             tv_record(qty, epoch0);                                                     //   incoming order: its PRE-fill remaining quantity
             uint32_t re = hr.agent >> 16; if (((epoch0 - re) & 0xffffu) <= (uint32_t)P.c.stream_history) tv_record(fq, (epoch0 & 0xffff0000u) | re);   // resting order, if its bucket survives
           }
@@ -783,6 +789,7 @@ struct Sim {
         matching = false;
       }
     }
+    if (P3) { uint4 h4; h4.x = oid; h4.y = (uint32_t)price; h4.z = epoch0; h4.w = (is_buy ? 1u : 0u) | (trade_qty > 0 ? 2u : 0u); c.hist_store((int)(hidx & (uint32_t)(P.c.hist_log_cap - 1)), h4); }   // :52-60 + :227
     if (INSTR && P.evt) {                                                               // :114-128 BEST_BID / BEST_ASK of the book as the order left it
       if (s.n_bid_lv > 0) evt_log(ABX_EV_BEST_BID, c.lv_price(0, s.n_bid_lv - 1), c.lv_qty(0, s.n_bid_lv - 1));
       if (s.n_ask_lv > 0) evt_log(ABX_EV_BEST_ASK, c.lv_price(1, s.n_ask_lv - 1), c.lv_qty(1, s.n_ask_lv - 1));
@@ -865,12 +872,14 @@ struct Sim {
           ta_send(ABX_CANCEL_ORDER, p, false);
         }
       }
-      ta_get_spread(); st = ST_AWAITING_SPREAD;                                         // :164 / :183-185
+      if (P3 && ((a.flags & AF_TYPE_MASK) >> AF_TYPE_SHIFT) == AT_HBL && !((a.flags & AF_MKT_CLOSED) && !(a.flags & AF_HAS_DAILY))) {   // HeuristicBeliefLearningAgent.wakeup :61-74: the ZI wakeup left it "ACTIVE"
+        int32_t p[6] = {P.c.hbl_L, 0, 0, 0, 0, 0}; ta_send(ABX_QUERY_ORDER_STREAM, p, false); st = ST_AWAITING_STREAM;                    // getOrderStream(length = L)
+      } else { ta_get_spread(); st = ST_AWAITING_SPREAD; }                              // :164 / :183-185
     }
     a.flags = (a.flags & ~AF_STATE_MASK) | (st << AF_STATE_SHIFT);
   }
   // ZeroIntelligenceAgent.placeOrder :277-309 (+ updateEstimates :189-275, TradingAgent.placeLimitOrder :309-349)
-  ABX_HD void zi_place_order(int id) {
+  ABX_HD void zi_place_order(int id, bool hbl = false) {                                // hbl: HeuristicBeliefLearningAgent.placeOrder with a full order stream (population 3)
     int stream = S_AGENT0 + id;
     int32_t r_now = oracle_advance(s.now >= P.c.mkt_close_ns ? P.c.mkt_close_ns - 1 : s.now);             // observePrice :210-227
     // Philox mode: the three draws of one order placement (noisy observation, side, surplus R) come from ONE Philox block of the agent's stream
@@ -911,6 +920,7 @@ struct Sim {
     if (idx < 0) idx += n;
     if (idx < 0 || idx >= n) { s.flags |= ABX_F_THETA_INDEX; idx = idx < 0 ? 0 : n - 1; }
     int32_t v = r_Ti + (int32_t)z->theta[idx];                                          // :270
+    if (P3 && hbl) { hbl_place_order(v, buy); return; }
     // placeOrder
     int grp = (a.flags & AF_GROUP_MASK) >> AF_GROUP_SHIFT;
     int32_t r_min = P.c.groups[grp].r_min, r_max = P.c.groups[grp].r_max; double eta = P.c.groups[grp].eta;
@@ -920,7 +930,10 @@ struct Sim {
     int32_t ask_vol = (a.flags & AF_HAS_ASK) ? a.ask_q : 0, bid_vol = (a.flags & AF_HAS_BID) ? a.bid_q : 0;
     if (buy && ask_vol > 0) { int32_t R_ask = v - a.ask; if ((double)R_ask >= dmul(eta, (double)R)) p = a.ask; }             // :291-297
     else if (!buy && bid_vol > 0) { int32_t R_bid = a.bid - v; if ((double)R_bid >= dmul(eta, (double)R)) p = a.bid; }       // :298-305
-    // TradingAgent.placeLimitOrder :309-349
+    zi_submit(buy, p);
+  }
+  // TradingAgent.placeLimitOrder :309-349 for the staged ZI / HBL trader
+  ABX_HD void zi_submit(bool buy, int32_t p) {
     uint32_t oid = s.next_order_id++;                                                   // util/order/Order.py:27,35-42
     int32_t size = P.c.order_size;
     if (size > 0) {
@@ -931,6 +944,16 @@ struct Sim {
       int32_t pl[6] = {(int32_t)oid, p, size, 0, buy, 0};
       ta_send(ABX_LIMIT_ORDER, pl, false);                                              // :343
     }
+  }
+  // HeuristicBeliefLearningAgent.placeOrder :98-185 once v and the side are known: the belief Pr(an order at price p transacts) from the orders in the
+  // `n` history buckets the exchange handed out (epochs E_q - n .. E_q - 1 of the order-history log, read NOW: the reference holds references to the
+  // exchange's dicts), limit price = first argmax of Pr(p) * surplus(p) over every price between the lowest and the highest order in them.
+  ABX_HD void hbl_place_order(int32_t v, bool buy) {
+    uint32_t E_q = (uint32_t)(uint64_t)z->surplus, n = (uint32_t)((uint64_t)z->surplus >> 32);
+    int32_t best_p = 0; uint32_t err = 0;
+    bool place = c.hbl_best(s.hist_n, E_q - n, E_q - 1, buy, v, best_p, err);
+    s.flags |= err;
+    if (place) zi_submit(buy, best_p);
   }
   // index of order_id in self.orders, or -1
   ABX_HD int orders_find(uint32_t oid) { int f = -1; for (int i = 0; i < AGENT_ORDER_CAP; i++) if (i < a.n_orders && f < 0 && z->oid[i] == oid) f = i; return f; }
@@ -964,6 +987,9 @@ struct Sim {
       a.flags &= ~(AF_HAS_BID | AF_HAS_ASK);
       if (m.p[5] & 1) { a.flags |= AF_HAS_BID; a.bid = m.p[0]; a.bid_q = m.p[1]; } else { a.bid = 0; a.bid_q = 0; }
       if (m.p[5] & 2) { a.flags |= AF_HAS_ASK; a.ask = m.p[2]; a.ask_q = m.p[3]; } else { a.ask = 0; a.ask_q = 0; }
+    } else if (P3 && m.kind == ABX_QUERY_ORDER_STREAM) {                                // :240-246, queryOrderStream :549-554: self.stream_history[symbol] = the references
+      if (m.p[5] & 4) a.flags |= AF_MKT_CLOSED;
+      c.sync(); if (c.onchip_writer()) z->surplus = (int64_t)((uint64_t)(uint32_t)m.p[0] | ((uint64_t)(uint32_t)m.p[1] << 32)); c.sync();
     }
     if ((a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE) && !had) {                  // :258-268
       int64_t off = rng.randint(S_AGENT0 + id, a.rng_ctr, 99);                          // ZI.getWakeFrequency :349-350
@@ -971,8 +997,12 @@ struct Sim {
     }
     uint32_t st = (a.flags & AF_STATE_MASK) >> AF_STATE_SHIFT;
     if (st == ST_AWAITING_SPREAD && m.kind == ABX_QUERY_SPREAD && !(a.flags & AF_MKT_CLOSED)) {      // ZI :319-334
-      zi_place_order(id);
+      if (P3) zi_place_order(id, ((a.flags & AF_TYPE_MASK) >> AF_TYPE_SHIFT) == AT_HBL && (uint32_t)((uint64_t)z->surplus >> 32) >= (uint32_t)P.c.hbl_L);   // HBL :83-87: fewer than L buckets -> the ZI order
+      else zi_place_order(id);
       a.flags = (a.flags & ~AF_STATE_MASK) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT);
+    }
+    if (P3 && st == ST_AWAITING_STREAM && m.kind == ABX_QUERY_ORDER_STREAM && ((a.flags & AF_TYPE_MASK) >> AF_TYPE_SHIFT) == AT_HBL && !(a.flags & AF_MKT_CLOSED)) {   // HBL.receiveMessage :176-195
+      ta_get_spread(); a.flags = (a.flags & ~AF_STATE_MASK) | (ST_AWAITING_SPREAD << AF_STATE_SHIFT);
     }
   }
 
@@ -994,7 +1024,7 @@ struct Sim {
     while (!(s.flags & ABX_F_DONE)) {
       uint64_t khi; uint32_t kuniq; int grp;
       bool any = c.q_min(khi, kuniq, grp);
-      if (!any || !(s.now <= P.c.stop_ns)) { s.flags |= ABX_F_DONE; break; }            // :190 tested BEFORE the pop
+      if (!any || !(s.now <= P.c.stop_ns) || (rng.tape() && (rng.err & ABX_F_TAPE_UNDERRUN))) { s.flags |= ABX_F_DONE; break; }   // an exhausted tape hands out zeros: with zero delays an agent would re-wake itself at the same instant for ever            // :190 tested BEFORE the pop
       if (key_time(khi) > until) break;
       { int rid = key_recipient(khi); if (rid != 0) c.agent_load_issue(rid); }          // the recipient's record is on its way while the event is unpacked
       Event ev; c.q_fetch(grp, ev);                                                     // :192
@@ -1546,7 +1576,7 @@ struct Sim {
     while (!paused) {
       uint64_t khi; uint32_t kuniq; int grp;
       bool any = c.q_min(khi, kuniq, grp);
-      if (!any || !(s.now <= P.c.stop_ns)) { s.flags |= ABX_F_DONE; break; }
+      if (!any || !(s.now <= P.c.stop_ns) || (rng.tape() && (rng.err & ABX_F_TAPE_UNDERRUN))) { s.flags |= ABX_F_DONE; break; }   // an exhausted tape hands out zeros: with zero delays an agent would re-wake itself at the same instant for ever
       Event ev; c.q_fetch(grp, ev);
       s.now = ev.t; s.ttl++;
       if (INSTR && P.c.hash_pops) s.pop_hash = fnv_mix(fnv_mix(fnv_mix(fnv_mix(s.pop_hash, ev.t), ev.recipient), ev.type), ev.type == ABX_T_MESSAGE ? (int64_t)ev.uniq : -1);
@@ -1618,8 +1648,13 @@ struct Sim {
     s.exch_comp_delay = P.c.exchange_computation_delay_ns;
     bool t_closed = s.now > P.c.mkt_close_ns;
     int32_t p[6] = {0, 0, 0, 0, 0, 0};
-    bool is_query = m.kind == ABX_QUERY_SPREAD || m.kind == ABX_QUERY_TRANSACTED_VOLUME;
+    bool is_query = m.kind == ABX_QUERY_SPREAD || m.kind == ABX_QUERY_TRANSACTED_VOLUME || (P3 && m.kind == ABX_QUERY_ORDER_STREAM);
     if (t_closed && !is_query) { exch_send(m.sender, ABX_MKT_CLOSED, p, 0.0); return; }
+    if (P3 && m.kind == ABX_QUERY_ORDER_STREAM) {                                       // :251-279 history[1 : length + 1]: REFERENCES to the bucket dicts of the last `length` trades.  The reply names them
+      uint32_t E = s.trade_epoch, n = (uint32_t)m.p[0];                                 // by epoch {current epoch, how many}; the agent reads the log when it places its order, so it sees what the dicts hold THEN
+      if (n > E - EPOCH_START) n = E - EPOCH_START; if (n > (uint32_t)P.c.stream_history) n = (uint32_t)P.c.stream_history;   // len(history) - 1 buckets exist besides the open one
+      p[0] = (int32_t)E; p[1] = (int32_t)n; p[5] = t_closed ? 4 : 0; exch_send(m.sender, ABX_QUERY_ORDER_STREAM, p, 0.0); return;
+    }
     if (m.kind == ABX_WHEN_MKT_OPEN) { s.exch_comp_delay = 0; exch_send(m.sender, ABX_WHEN_MKT_OPEN, p, 0.0); }
     else if (m.kind == ABX_WHEN_MKT_CLOSE) { s.exch_comp_delay = 0; exch_send(m.sender, ABX_WHEN_MKT_CLOSE, p, 0.0); }
     else if (m.kind == ABX_QUERY_TRANSACTED_VOLUME) {                                   // :280-303
@@ -1642,7 +1677,7 @@ struct Sim {
     if (size <= 0) return;
     if (track) {
       int type = (int)((a.flags & AF_TYPE_MASK) >> AF_TYPE_SHIFT);
-      if (type == AT_POVMM) { if (a.n_orders < MM_ORDER_CAP) { uint4 v; v.x = oid; v.y = (uint32_t)price; v.z = (uint32_t)(buy ? size : -size); v.w = 0; c.id_store(a.n_orders, v); a.n_orders++; } else s.flags |= ABX_F_AGENT_ORDERS_OVERFLOW; }
+      if (type == AT_POVMM || (P3 && type == AT_MKM)) { if (a.n_orders < MM_ORDER_CAP) { uint4 v; v.x = oid; v.y = (uint32_t)price; v.z = (uint32_t)(buy ? size : -size); v.w = 0; c.id_store(a.n_orders, v); a.n_orders++; } else s.flags |= ABX_F_AGENT_ORDERS_OVERFLOW; }
       else if (a.n_orders < AGENT_ORDER_CAP) { c.sync(); if (c.onchip_writer()) { int k = a.n_orders; z->oid[k] = oid; z->oprice[k] = price; z->oqty[k] = buy ? size : -size; } c.sync(); a.n_orders++; }
       else s.flags |= ABX_F_AGENT_ORDERS_OVERFLOW;
     }
@@ -1654,13 +1689,14 @@ struct Sim {
 #pragma unroll 1
     for (int i = 0; i < a.n_orders; i++) {
       uint32_t oid; int32_t price, q;
-      if (type == AT_POVMM) { uint4 v = c.id_load(i); oid = v.x; price = (int32_t)v.y; q = (int32_t)v.z; } else { oid = z->oid[i]; price = z->oprice[i]; q = z->oqty[i]; }
+      if (type == AT_POVMM || (P3 && type == AT_MKM)) { uint4 v = c.id_load(i); oid = v.x; price = (int32_t)v.y; q = (int32_t)v.z; } else { oid = z->oid[i]; price = z->oprice[i]; q = z->oqty[i]; }
       int32_t p[6] = {(int32_t)oid, price, q < 0 ? -q : q, 0, q > 0, 0}; env_send(ABX_CANCEL_ORDER, p, false);
       if (n_out >= Ctx::OUTN - 3) flush();
     }
   }
   ABX_HD void r3_wakeup(int id) {
     int type = (int)((a.flags & AF_TYPE_MASK) >> AF_TYPE_SHIFT);
+    if (P3 && (type == AT_ZI || type == AT_HBL)) { zi_wakeup(id); return; }
     bool can_trade = ta_wakeup(a.flags);                                                // TradingAgent.wakeup :142-158
     uint32_t st = (a.flags & AF_STATE_MASK) >> AF_STATE_SHIFT;
     bool hours = (a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE);
@@ -1678,6 +1714,8 @@ struct Sim {
       }
     } else if (type == AT_MOMENTUM) {                                                   // agent/examples/MomentumAgent.py:53-63
       if (can_trade) { int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); st = ST_AWAITING_SPREAD; }
+    } else if (P3 && type == AT_MKM) {                                                  // agent/market_makers/MarketMakerAgent.py:66-77 (polling mode)
+      if (can_trade) { r3_cancel_all(type); int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); st = ST_AWAITING_SPREAD; }
     } else if (type == AT_POVEXEC) {                                                    // agent/execution/baselines/pov_agent.py:55-64
       if (can_trade && exaux()->rem_qty > 0 && s.now < P.c.pov_exec_end_ns) {
         set_wakeup(id, s.now + P.c.pov_exec_freq_ns); dq_cancel_all(id);
@@ -1723,7 +1761,7 @@ struct Sim {
     bool has_bid = (a.flags & AF_HAS_BID) && a.bid != 0, has_ask = (a.flags & AF_HAS_ASK) && a.ask != 0;
     if (!has_bid || !has_ask) return;
     AgentAux ax = *aux();
-    int k = id - (1 + P.c.n_noise_agents + P.c.n_value_agents + P.c.n_mm_agents);                            // momentum agent index
+    int k = id - (P3 ? 1 + P.c.n_mm_agents + P.c.groups[0].count + P.c.groups[1].count : 1 + P.c.n_noise_agents + P.c.n_value_agents + P.c.n_mm_agents);   // momentum agent index
     c.mid_store(k, ax.n_mids % MOM_MIDS, a.bid + a.ask);                                // 2 * mid: exact integer
     ax.n_mids++;
     int L = ax.n_mids;
@@ -1734,17 +1772,18 @@ struct Sim {
   }
   ABX_HD void r3_receive(int id, const Event &m) {
     int type = (int)((a.flags & AF_TYPE_MASK) >> AF_TYPE_SHIFT);
+    if (P3 && (type == AT_ZI || type == AT_HBL)) { zi_receive(id, m); return; }
     bool had = (a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE);
     if (m.kind == ABX_WHEN_MKT_OPEN) a.flags |= AF_HAS_OPEN;
     else if (m.kind == ABX_WHEN_MKT_CLOSE) a.flags |= AF_HAS_CLOSE;
     else if (m.kind == ABX_ORDER_EXECUTED) {                                            // orderExecuted :422-462
       int32_t q = m.p[2]; int32_t sq = m.p[4] ? q : -q; a.shares += sq; a.cash -= (int64_t)sq * m.p[3];
       if (type == AT_VALUE) { int i = orders_find((uint32_t)m.p[0]); if (i >= 0) { int32_t oq0 = z->oqty[i]; int32_t oq = oq0 < 0 ? -oq0 : oq0; if (q >= oq) orders_remove(i); else { c.sync(); if (c.onchip_writer()) z->oqty[i] = oq0 < 0 ? -(oq - q) : (oq - q); c.sync(); } } }
-      else if (type == AT_POVMM) r3_mm_order_update((uint32_t)m.p[0], q, false);
+      else if (type == AT_POVMM || (P3 && type == AT_MKM)) r3_mm_order_update((uint32_t)m.p[0], q, false);
       else if (type == AT_POVEXEC) { dq_order_update(id, (uint32_t)m.p[0], q, false); ExecAux ex = *exaux(); ex.executed_sum += q; ex.n_executed++; ex.rem_qty = (int32_t)P.c.pov_exec_quantity - ex.executed_sum; exaux_store(ex); }   // handleOrderExecution :103-107
     } else if (m.kind == ABX_ORDER_CANCELLED) {
       if (type == AT_VALUE) { int i = orders_find((uint32_t)m.p[0]); if (i >= 0) orders_remove(i); }
-      else if (type == AT_POVMM) r3_mm_order_update((uint32_t)m.p[0], 0, true);
+      else if (type == AT_POVMM || (P3 && type == AT_MKM)) r3_mm_order_update((uint32_t)m.p[0], 0, true);
       else if (type == AT_POVEXEC) dq_order_update(id, (uint32_t)m.p[0], 0, true);
     } else if (m.kind == ABX_MKT_CLOSED) a.flags |= AF_MKT_CLOSED;
     else if (m.kind == ABX_QUERY_TRANSACTED_VOLUME) {                                   // :248-251,556-558
@@ -1760,7 +1799,7 @@ struct Sim {
       if (m.p[5] & 2) { a.flags |= AF_HAS_ASK; a.ask = m.p[2]; a.ask_q = m.p[3]; } else { a.ask = 0; a.ask_q = 0; }
     }
     if ((a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE) && !had) {                  // :258-268 getWakeFrequency per class
-      int64_t off = type == AT_MOMENTUM ? P.c.mom_wake_ns : (type == AT_POVMM ? P.c.mm_wake_ns : (type == AT_POVEXEC ? P.c.pov_exec_freq_ns : rng.randint(S_AGENT0 + id, a.rng_ctr, 99)));
+      int64_t off = type == AT_MOMENTUM ? P.c.mom_wake_ns : (type == AT_POVMM ? P.c.mm_wake_ns : (type == AT_POVEXEC ? P.c.pov_exec_freq_ns : ((P3 && type == AT_MKM) ? P.c.mkm_wake_ns : rng.randint(S_AGENT0 + id, a.rng_ctr, 99))));
       set_wakeup(id, P.c.mkt_open_ns + off);
     }
     uint32_t st = (a.flags & AF_STATE_MASK) >> AF_STATE_SHIFT;
@@ -1772,6 +1811,21 @@ struct Sim {
         int32_t qty = (int32_t)py_round_i64(dmul(P.c.pov_exec_pov, (double)ex.tv));
         dq_cancel_all(id);
         dq_place_market(id, qty, P.c.pov_exec_is_buy != 0);
+      }
+      return;
+    }
+    if (P3 && type == AT_MKM) {                                                         // MarketMakerAgent.receiveMessage :79-108 (polling mode)
+      if (st == ST_AWAITING_SPREAD && m.kind == ABX_QUERY_SPREAD) {
+        r3_cancel_all(type);
+        int32_t mid = a.last_trade, spread = 10;                                        // self.last_spread = 10 is never updated
+        if ((a.flags & AF_HAS_BID) && a.bid != 0 && (a.flags & AF_HAS_ASK) && a.ask != 0) { mid = (int32_t)((double)(a.ask + a.bid) / 2); int32_t d = a.ask > a.bid ? a.ask - a.bid : a.bid - a.ask; spread = (int32_t)((double)d / 2); }
+#pragma unroll 1
+        for (int i = 0; i < 2 * P.c.mkm_num_levels; i++) {                              // :98-103 a fresh size per level
+          int32_t size = mkm_half(P.c.mkm_min_size + rng.randint(S_AGENT0 + id, a.rng_ctr, (uint32_t)(P.c.mkm_max_size - P.c.mkm_min_size - 1)));
+          r3_place_limit(id, size, true, mid - spread - i, true); r3_place_limit(id, size, false, mid + spread + i, true);
+        }
+        set_wakeup(id, s.now + P.c.mkm_wake_ns);
+        a.flags = (a.flags & ~AF_STATE_MASK) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT);
       }
       return;
     }
@@ -1825,7 +1879,7 @@ struct Sim {
     while (!(s.flags & ABX_F_DONE)) {
       uint64_t khi; uint32_t kuniq; int grp;
       bool any = c.q_min(khi, kuniq, grp);
-      if (!any || !(s.now <= P.c.stop_ns)) { s.flags |= ABX_F_DONE; break; }
+      if (!any || !(s.now <= P.c.stop_ns) || (rng.tape() && (rng.err & ABX_F_TAPE_UNDERRUN))) { s.flags |= ABX_F_DONE; break; }   // an exhausted tape hands out zeros: with zero delays an agent would re-wake itself at the same instant for ever
       if (key_time(khi) > until) break;
       Event ev; c.q_fetch(grp, ev);
       s.now = ev.t; s.ttl++;
@@ -1856,6 +1910,7 @@ struct Sim {
   }
   // kernelStopping: ValueAgent.kernelStopping :49-61 observes the fundamental (advances the oracle); holdings are read by the host
   ABX_HD void r3_finalize() {
+    if (P3) { finalize(); return; }
     int64_t sum_sh = 0, sum_cash = 0;
 #pragma unroll 1
     for (int id = 1; id < P.c.n_agents; id++) {
@@ -1872,6 +1927,7 @@ struct Sim {
 #pragma unroll 1
     for (int id = 1; id < P.c.n_agents; id++) {
       z = c.agent_stage(id); regs_load(a, z);
+      if (P3) { int t = (int)((a.flags & AF_TYPE_MASK) >> AF_TYPE_SHIFT); if (t != AT_ZI && t != AT_HBL) { sum_sh += a.shares; sum_cash += a.cash; continue; } }   // market maker / momentum agents have no closing valuation
       double hr = dmul(rint((double)a.shares / 100.0), 100.0);                          // round(int, -2): half-even on hundreds
       int H = (int)(hr / 100.0);
       int64_t cur = a.agent_time - P.c.default_computation_delay_ns;                    // Agent.currentTime of the trader's last event

@@ -72,6 +72,26 @@ static inline int config_rmsc03_pov(abx_sim_config *c) {
   c->pov_exec_start_ns = (9 * 3600 + 32 * 60) * NS; c->pov_exec_end_ns = (9 * 3600 + 43 * 60) * NS; c->pov_exec_freq_ns = 30 * NS; c->pov_exec_lookback_ns = 30 * NS;
   return ABX_OK;
 }
+// config/rmsc01.py:60-262: 1 MarketMakerAgent, 50 ZeroIntelligenceAgents, 25 HeuristicBeliefLearningAgents (L = 2), 24 MomentumAgents, 09:30-16:00
+static inline int config_rmsc01(abx_sim_config *c) {
+  if (!c) return ABX_ERR_ARG;
+  memset(c, 0, sizeof(*c));
+  c->version = ABX_VERSION; c->population = 3; c->n_mm_agents = 1; c->n_groups = 2; c->q_max = 10; c->n_momentum_agents = 24;
+  c->groups[0].count = 50; c->groups[0].r_min = 0; c->groups[0].r_max = 100; c->groups[0].eta = 1;                  // ZI :134-157
+  c->groups[1].count = 25; c->groups[1].r_min = 0; c->groups[1].r_max = 100; c->groups[1].eta = 1; c->hbl_L = 2;   // HBL :163-187
+  c->n_agents = 1 + 1 + 50 + 25 + 24;
+  c->mkt_open_ns = (9 * 3600 + 1800) * NS; c->mkt_close_ns = 16 * 3600 * NS; c->start_ns = c->mkt_open_ns; c->stop_ns = (16 * 3600 + 60) * NS;   // :72-73, :246-247
+  c->default_computation_delay_ns = 0; c->exchange_computation_delay_ns = 0; c->exchange_pipeline_delay_ns = 0;     // :85-86, :249
+  c->starting_cash = 10000000; c->order_size = 100; c->stream_history = 10;
+  c->r_bar = 1e5; c->kappa = 1.67e-12; c->fund_vol = 1e-4; c->megashock_lambda_a = 2.77778e-13; c->megashock_mean = 1e3; c->megashock_var = 5e4;
+  c->sigma_n = 10000; c->agent_kappa = 1.67e-15; c->sigma_s = 1e-4; c->sigma_pv = 5e4; c->lambda_a = 1e-12;          // :141-153
+  c->latency_model = ABX_LAT_ZERO; c->n_noise = 1;                                                                  // :250-251
+  c->mom_min_size = 1; c->mom_max_size = 10; c->mom_wake_ns = 60 * NS;                                              // MomentumAgent defaults, wake_up_freq "60s"
+  c->mkm_min_size = 500; c->mkm_max_size = 1000; c->mkm_num_levels = 5; c->mkm_wake_ns = NS;                        // MarketMakerAgent :100-110 + defaults
+  c->queue_cap = 512; c->level_cap = 256; c->order_cap = 2048; c->hist_log_cap = 32768;                             // 09:30-09:45 of seed 123456789 peaks at 31 levels a side, 67 resting orders
+  c->rng_mode = ABX_RNG_PHILOX; c->trace_cap = 0; c->hash_pops = 0;
+  return ABX_OK;
+}
 static inline int config_validate(const abx_sim_config *c) {
   if (!c || c->version != ABX_VERSION) return ABX_ERR_ARG;
   if (c->n_agents < 2 || c->n_agents > 32767 || c->n_groups < 0 || c->n_groups > 8 || c->q_max < 1 || c->q_max > 10) return ABX_ERR_ARG;
@@ -82,6 +102,13 @@ static inline int config_validate(const abx_sim_config *c) {
     if (c->latency_model != ABX_LAT_ZERO || c->size_hi <= c->size_lo || c->mom_max_size <= c->mom_min_size || 2 * (c->mm_num_ticks + 1) > MM_ORDER_CAP / 2 || c->mm_wake_ns <= 0 || c->mom_wake_ns <= 0) return ABX_ERR_ARG;
     if (c->n_pov_exec < 0 || c->n_pov_exec > 1 || (c->n_pov_exec && (!(c->pov_exec_pov > 0) || c->pov_exec_quantity <= 0 || c->pov_exec_quantity > 0x3fffffffLL || c->pov_exec_freq_ns <= 0 || c->pov_exec_lookback_ns <= 0))) return ABX_ERR_ARG;
     n += c->n_noise_agents + c->n_value_agents + c->n_mm_agents + c->n_momentum_agents + c->n_pov_exec;
+  } else if (c->population == 3) {
+    if (c->n_groups != 2 || c->n_mm_agents < 0 || c->n_mm_agents > 1 || c->n_momentum_agents < 0 || c->n_momentum_agents > 64 || c->latency_model != ABX_LAT_ZERO) return ABX_ERR_ARG;
+    for (int g = 0; g < 2; g++) { if (c->groups[g].count < 0 || c->groups[g].r_max < c->groups[g].r_min) return ABX_ERR_ARG; n += c->groups[g].count; }
+    if (c->hbl_L < 1 || c->hbl_L > 16 || c->stream_history < 1 || c->hist_log_cap < 64 || c->hist_log_cap > 65536 || (c->hist_log_cap & (c->hist_log_cap - 1))) return ABX_ERR_ARG;
+    if (c->mom_max_size <= c->mom_min_size || c->mom_wake_ns <= 0) return ABX_ERR_ARG;
+    if (c->n_mm_agents && (c->mkm_max_size <= c->mkm_min_size || c->mkm_num_levels < 1 || 4 * c->mkm_num_levels > MM_ORDER_CAP / 2 || c->mkm_wake_ns <= 0)) return ABX_ERR_ARG;
+    n += c->n_mm_agents + c->n_momentum_agents;
   } else return ABX_ERR_ARG;
   if (n != c->n_agents) return ABX_ERR_ARG;
   if (c->queue_cap < 32 || c->queue_cap % 32 || c->queue_cap > 4096) return ABX_ERR_ARG;
@@ -270,10 +297,10 @@ static inline void agent_init_rows(const SimParams &P, const ZiAgent *ag, int32_
   int n = P.c.n_agents;
   for (int id = 0; id < n; id++) {
     const ZiAgent &z = ag[id]; int type = id == 0 ? -1 : agent_type_of(P.c, id);
-    if (theta) for (int i = 0; i < 20; i++) theta[(size_t)id * 20 + i] = type == AT_ZI ? z.theta[i] : 0;
+    if (theta) for (int i = 0; i < 20; i++) theta[(size_t)id * 20 + i] = (type == AT_ZI || type == AT_HBL) ? z.theta[i] : 0;
     if (lat_to) lat_to[id] = id ? z.lat_to : 0.0;
     if (lat_from) lat_from[id] = id ? z.lat_from : 0.0;
-    if (sizes) sizes[id] = (type == AT_NOISE || type == AT_VALUE || type == AT_MOMENTUM) ? reinterpret_cast<const AgentAux *>(z.theta)->size : 0;
+    if (sizes) sizes[id] = (type == AT_NOISE || type == AT_VALUE || type == AT_MOMENTUM || type == AT_MKM) ? reinterpret_cast<const AgentAux *>(z.theta)->size : 0;
     if (wakes) wakes[id] = type == AT_NOISE ? z.prev_wake : 0;
   }
 }

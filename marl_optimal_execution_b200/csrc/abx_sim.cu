@@ -80,7 +80,7 @@ abx_run_kernel(SimParams P, int64_t until_ns, const int64_t *__restrict__ until_
   if (s.flags & ABX_F_DONE) return;
   ctx.load_onchip(s);
   Sim<Ctx, RNG, LAT, INSTR, SHAPE> sim(ctx, P, s, env);
-  if (SHAPE == SHAPE_R3) sim.r3_run(until_each ? until_each[env] : until_ns); else sim.run(until_each ? until_each[env] : until_ns);
+  if (SHAPE == SHAPE_R3 || SHAPE == SHAPE_P3) sim.r3_run(until_each ? until_each[env] : until_ns); else sim.run(until_each ? until_each[env] : until_ns);
   ctx.store_onchip(sim.s);
   env_store(P.env + env, sim.s, ctx.lane);
 }
@@ -90,6 +90,10 @@ static run_kernel_fn run_kernel_for(const abx_sim_config &c) {
   if (c.population == 1) {                       // config/rmsc03.py population: zero latency
     if (r == ABX_RNG_PHILOX) return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_R3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_ZERO, false, SHAPE_R3>;
     return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_ZERO, true, SHAPE_R3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_ZERO, false, SHAPE_R3>;
+  }
+  if (c.population == 3) {                       // config/rmsc01.py population: the rmsc03 loop over more agent classes
+    if (r == ABX_RNG_PHILOX) return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_P3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_ZERO, false, SHAPE_P3>;
+    return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_ZERO, true, SHAPE_P3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_ZERO, false, SHAPE_P3>;
   }
 #define PICK(R, L) (instr ? (run_kernel_fn)abx_run_kernel<R, L, true> : (run_kernel_fn)abx_run_kernel<R, L, false>)
   if (r == ABX_RNG_PHILOX) return l == ABX_LAT_CUBIC ? PICK(ABX_RNG_PHILOX, ABX_LAT_CUBIC) : PICK(ABX_RNG_PHILOX, ABX_LAT_MATRIX_NOISE);
@@ -105,6 +109,7 @@ abx_finalize_kernel(SimParams P, size_t smem_per_warp) {
   WarpCtx ctx(P, env, smem + warp * smem_per_warp);
   EnvState s = env_load(P.env + env);
   if (P.c.population == 1) { Sim<WarpCtx, -1, ABX_LAT_ZERO, true, SHAPE_R3> sim(ctx, P, s, env); sim.r3_finalize(); env_store(P.env + env, sim.s, ctx.lane); return; }   // INSTR: the ValueAgents' closing observations go to the draw log
+  if (P.c.population == 3) { Sim<WarpCtx, -1, ABX_LAT_ZERO, true, SHAPE_P3> sim(ctx, P, s, env); sim.r3_finalize(); env_store(P.env + env, sim.s, ctx.lane); return; }
   Sim<WarpCtx> sim(ctx, P, s, env);
   sim.finalize();
   env_store(P.env + env, sim.s, ctx.lane);
@@ -304,12 +309,13 @@ int32_t abx_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSu
 int32_t abx_config_sparse_zi(int32_t variant, abx_sim_config *cfg) { return config_sparse_zi(variant, cfg); }
 int32_t abx_config_rmsc03(abx_sim_config *cfg) { return config_rmsc03(cfg); }
 int32_t abx_config_rmsc03_pov(abx_sim_config *cfg) { return config_rmsc03_pov(cfg); }
+int32_t abx_config_rmsc01(abx_sim_config *cfg) { return config_rmsc01(cfg); }
 
 int32_t abx_sim_destroy(abx_sim *h) {
   if (!h) return ABX_OK;
   cudaSetDevice(h->device);
   void *ptrs[] = {h->P.qkey, h->P.qpay0, h->P.qpay1, h->P.qcache, h->P.agents, h->P.lv_price, h->P.lv_qty, h->P.lv_ht, h->P.nodes, h->P.env,
-                  h->P.trace, h->P.draw_log, h->P.evt, h->P.snap, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff,
+                  h->P.trace, h->P.draw_log, h->P.evt, h->P.hlog, h->P.snap, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff,
                   h->P.envx, h->P.idtab, h->P.idbook, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_iact, h->d_msizes, h->d_trans, h->d_ops, h->d_daytab, h->d_daytab2, h->d_xid, h->d_xfirst};
   for (void *p : ptrs) if (p) cudaFree(p);
   delete h->st; delete h->dh; delete h->book_ids; delete h; return ABX_OK;
@@ -334,6 +340,7 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + h->P.tv_ring; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0);       // market maker orders + transaction ring [+ POV execution agent orders]; momentum mids
     DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
     if (c.n_pov_exec) { h->P.n_snap = 1; h->P.snap_depth = c.level_cap; DA(h->P.snap, E * 2 * (size_t)c.level_cap) } }      // POVExecutionAgent asks for depth sys.maxsize
+  if (c.population == 3) { h->P.n_ids = MM_ORDER_CAP; DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * (size_t)lob_stride_of(c)) DA(h->P.hlog, E * (size_t)c.hist_log_cap) }   // market maker orders; momentum mids; order-history log
 #undef DA
   if (smem_cta > 48 * 1024) {
     CUH(cudaFuncSetAttribute((const void *)run_kernel_for(*cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));

@@ -82,6 +82,7 @@ struct WarpCtxT {
   uint4 *oc_t; uint2 *oc_b; int32_t *oc_tag;   // on-chip cache of replayed orders' records (direct mapped, write-through)
   uint4 *idt; int4 *lob; uint2 *idb;   // ABIDESEnv shape: replay agent's per-order table, stored LOBs, per-order book census (HBM)
   int2 *snp;                           // deep QUERY_SPREAD replies: the execution agents' book snapshots (HBM)
+  uint4 *hl;                           // population 3: the exchange's order-history log (HBM ring)
   // registers describing the group fetched by q_fetch
   uint64_t my_hi; uint32_t my_uniq; uint32_t cur_mask; int cur_group, cur_lane; int n_ovf; bool cur_t2; int day;   // day: the replayed day of this environment   // n_ovf: events in the overflow tier
 
@@ -104,7 +105,8 @@ struct WarpCtxT {
     if (P.idbook && lane < OC_N) oc_tag[lane] = -1;
     idb = P.idbook ? P.idbook + (size_t)env * P.n_ids : nullptr;
     snp = P.snap ? P.snap + (size_t)env * P.n_snap * 2 * P.snap_depth : nullptr;
-    idt = P.idtab ? P.idtab + (size_t)env * P.n_ids : nullptr; lob = P.lobs ? P.lobs + (size_t)env * LOB_CAP * 3 : nullptr;
+    idt = P.idtab ? P.idtab + (size_t)env * P.n_ids : nullptr; lob = P.lobs ? P.lobs + (size_t)env * lob_stride_of(P.c) : nullptr;
+    hl = P.hlog ? P.hlog + (size_t)env * P.c.hist_log_cap : nullptr;
     cur_group = cur_lane = -1; cur_mask = 0; my_hi = KEY_EMPTY; my_uniq = 0xffffffffu; n_ovf = 0; cur_t2 = false;
     day = P.n_days > 1 ? env % P.n_days : 0;                               // once per launch: an integer modulo is ~170 instructions
   }
@@ -431,6 +433,56 @@ struct WarpCtxT {
   __device__ __forceinline__ void lob_load(int slot, int32_t w[12]) const {
 #pragma unroll
     for (int k = 0; k < 3; k++) { int4 v = __ldcg(lob + slot * 3 + k); w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+  }
+  // ---- population 3 (config/rmsc01.py): the exchange's order history as a ring of {order id, limit price, history epoch, is_buy | transacted << 1} ----
+  __device__ __forceinline__ uint4 hist_load(int slot) const { return ldcg4(hl + slot); }
+  __device__ __forceinline__ void hist_store(int slot, uint4 v) { if (lane == 0) __stcg(hl + slot, v); __syncwarp(); }
+  // HeuristicBeliefLearningAgent.placeOrder :98-168 over the log entries of epochs e_lo .. e_hi (a contiguous run: epochs never decrease along the log).
+  // The reference fills one row per price between the lowest and the highest of those orders with cumulative counts of successful / unsuccessful asks and
+  // bids and takes the first argmax of Pr * surplus.  Pr is piecewise constant and only changes at p_i (counts "at or below") or p_i + 1 ("at or above"), and
+  // within a piece Pr * surplus is strictly monotonic, so the argmax over all rows is the argmax over {low, high, p_i - 1, p_i, p_i + 1}: lanes take
+  // candidates 32 at a time and count the run for each (integer counts, the reference's fp64 quotient and product), ties go to the lower price.
+  __device__ bool hbl_best(uint32_t hist_n, uint32_t e_lo, uint32_t e_hi, bool buy, int32_t v, int32_t &best_p, uint32_t &err) const {
+    uint32_t cap = (uint32_t)P.c.hist_log_cap, avail = hist_n < cap ? hist_n : cap, k_first = avail, k_end = avail; bool stop = false;
+#pragma unroll 1
+    for (uint32_t k0 = 0; k0 < avail && !stop; k0 += 32) {                  // k counts back from the newest entry
+      uint32_t k = k0 + lane; bool on = k < avail; uint32_t ep = on ? ldcg4(hl + ((hist_n - 1 - k) & (cap - 1))).z : 0u;
+      uint32_t inr = __ballot_sync(FULL, on && ep >= e_lo && ep <= e_hi), older = __ballot_sync(FULL, on && ep < e_lo);
+      if (inr && k_first == avail) k_first = k0 + __ffs(inr) - 1;
+      if (older) { k_end = k0 + __ffs(older) - 1; stop = true; }
+    }
+    if (!stop && hist_n > cap) err |= ABX_F_HISTORY_OVERFLOW;               // the ring no longer reaches back to bucket e_lo
+    if (k_first >= k_end) { err |= ABX_F_REF_EXCEPTION; return false; }     // empty buckets: np.zeros((negative, 8)) raises in the reference (cannot happen: every bucket holds the order whose trade closed it)
+    uint32_t N = k_end - k_first, top = hist_n - 1 - k_first;               // entries top, top - 1, .. top - N + 1
+    int32_t lo = 0x7fffffff, hi = -0x7fffffff - 1;
+#pragma unroll 1
+    for (uint32_t j = lane; j < N; j += 32) { int32_t pr = (int32_t)ldcg4(hl + ((top - j) & (cap - 1))).y; lo = pr < lo ? pr : lo; hi = pr > hi ? pr : hi; }
+    lo = __reduce_min_sync(FULL, lo); hi = __reduce_max_sync(FULL, hi);
+    double bes = -1.0e300; int32_t bp = 0x7fffffff; uint32_t ncand = 3 * N + 2;
+#pragma unroll 1
+    for (uint32_t ci = lane; ci < ncand; ci += 32) {
+      int32_t p;
+      if (ci < 3 * N) { uint32_t j = ci / 3; p = (int32_t)ldcg4(hl + ((top - j) & (cap - 1))).y + (int32_t)(ci - 3 * j) - 1; } else p = ci == 3 * N ? lo : hi;
+      if (p < lo || p > hi) continue;
+      uint32_t num = 0, den = 0;
+#pragma unroll 4
+      for (uint32_t j = 0; j < N; j++) {
+        uint4 r = ldcg4(hl + ((top - j) & (cap - 1))); int32_t q = (int32_t)r.y; bool isb = r.w & 1u, tx = (r.w & 2u) != 0, le = q <= p, ge = q >= p;
+        bool in_num = buy ? (le && (tx || !isb)) : (ge && (tx || isb)), extra = buy ? (!tx && isb && ge) : (!tx && !isb && le);   // :115-150 columns 0-2 (buy) / 0, 1, 3 (sell) over column 3 / 2
+        num += in_num; den += in_num || extra;
+      }
+      double pr = den == 0 ? 0.0 : (double)num / (double)den;               // :152-159 nan_to_num(0 / 0)
+      double es = pr * (double)(buy ? v - p : p - v);                       // :162-165
+      if (es > bes || (es == bes && p < bp)) { bes = es; bp = p; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      uint64_t b = dbl_bits(bes); uint32_t l = __shfl_xor_sync(FULL, (uint32_t)b, o), h = __shfl_xor_sync(FULL, (uint32_t)(b >> 32), o); int32_t op = __shfl_xor_sync(FULL, bp, o);
+      double oes = bits_dbl((uint64_t)l | ((uint64_t)h << 32));
+      if (oes > bes || (oes == bes && op < bp)) { bes = oes; bp = op; }
+    }
+    best_p = bp; return bes > 0.0;                                          // :173 only a positive expected surplus is worth an order
   }
   // rmsc03: momentum agent k's ring of doubled mid prices lives in the per-environment int4 table
   __device__ __forceinline__ int32_t mid_load(int k, int slot) const { return __ldcg(reinterpret_cast<const int32_t *>(lob) + k * MOM_MIDS + slot); }

@@ -40,6 +40,19 @@ def rmsc03_config(lib=None, pov_exec=False, **overrides):
     return cfg
 
 
+def rmsc01_config(lib=None, **overrides):
+    """abx_sim_config for config/rmsc01.py (1 MarketMakerAgent + 50 ZI + 25 HBL + 24 Momentum agents, 09:30-16:00; the HBL agents read the
+    exchange's order stream, agent/HeuristicBeliefLearningAgent.py:61-195)."""
+    L = lib or _lib.load()
+    cfg = SimConfig()
+    _lib.check(L, L.abx_config_rmsc01(C.byref(cfg)), "abx_config_rmsc01")
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError("abx_sim_config has no field %r" % k)
+        setattr(cfg, k, v)
+    return cfg
+
+
 def _num(x):
     """'{}'.format of a config literal: 1 -> '1', 0.8 -> '0.8' (config/sparse_zi_1000.py:211-219 writes eta as 1 or 0.8)."""
     return str(int(x)) if float(x) == int(x) else repr(float(x))
@@ -57,6 +70,11 @@ def agent_directory(cfg):
             strat = "Type {} [{} <= R <= {}, eta={}]".format(k + 1, g.r_min, g.r_max, _num(g.eta))
             for _ in range(g.count):
                 names.append("ZI Agent {} {}".format(j, strat)); types.append("ZeroIntelligenceAgent {}".format(strat)); j += 1
+    elif cfg.population == 3:                         # config/rmsc01.py:98-210
+        for count, name, typ in ((cfg.n_mm_agents, "MARKET_MAKER_AGENT_{}", "MarketMakerAgent"), (cfg.groups[0].count, "ZI_AGENT_{}", "ZeroIntelligenceAgent"),
+                                 (cfg.groups[1].count, "HBL_AGENT_{}", "HeuristicBeliefLearningAgent"), (cfg.n_momentum_agents, "MOMENTUM_AGENT_{}", "MomentumAgent")):
+            for _ in range(count):
+                names.append(name.format(j)); types.append(typ); j += 1
     else:
         for count, name, typ in ((cfg.n_noise_agents, "NoiseAgent {}", "NoiseAgent"), (cfg.n_value_agents, "Value Agent {}", "ValueAgent"),
                                  (cfg.n_mm_agents, "POV_MARKET_MAKER_AGENT_{}", "POVMarketMakerAgent"), (cfg.n_momentum_agents, "MOMENTUM_AGENT_{}", "MomentumAgent")):

@@ -1090,7 +1090,7 @@ int abo_sim_set_external(abo_sim *s, const uint64_t *bits, const uint8_t *kinds,
   }
   for (int a = 1; a < n; a++) {
     zi_t *z = &s->zi[a];
-    if (theta && z->type == AT_ZI) for (int i = 0; i < 2 * z->q_max && i < 20; i++) z->theta[i] = theta[(size_t)a * 20 + i];
+    if (theta && (z->type == AT_ZI || z->type == AT_HBL)) for (int i = 0; i < 2 * z->q_max && i < 20; i++) z->theta[i] = theta[(size_t)a * 20 + i];
     if (lat_to && lat_from) { s->latency[(size_t)a * n] = lat_to[a]; s->latency[a] = lat_from[a]; }
     if (sizes && (z->type == AT_NOISE || z->type == AT_VALUE || z->type == AT_MOMENTUM)) z->size = sizes[a];
     if (wakes && z->type == AT_NOISE) z->wakeup_time = wakes[a];

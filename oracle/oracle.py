@@ -235,7 +235,7 @@ class OracleSim:
         self._h = lib().abo_sim_new_config(C.addressof(cfg), int(seed), int(trace))
         if not self._h:
             raise ValueError("abo_sim_new_config rejected the configuration")
-        self.variant = 3 if cfg.population == 1 else (100 if cfg.latency_model == 1 else 1000)
+        self.variant = 3 if cfg.population == 1 else 1 if cfg.population == 3 else (100 if cfg.latency_model == 1 else 1000)
         self.seed = seed
         return self
 

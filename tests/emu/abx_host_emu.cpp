@@ -19,12 +19,13 @@ struct HostCtx {
   const SimParams &P; int env;
   uint4 *qkey, *qpay0, *qpay1, *qcache; ZiAgent *agents; int32_t *lvp, *lvq; uint32_t *lvht; uint4 *nodes; abx_trace_rec *tr;
   static constexpr int OUTN = OUT_CAP;
-  uint32_t outbox_[OUT_CAP * OUT_WORDS]; ZiAgent staged; int cur_group, cur_slot; uint4 *idt; int4 *lob;
+  uint32_t outbox_[OUT_CAP * OUT_WORDS]; ZiAgent staged; int cur_group, cur_slot; uint4 *idt; int4 *lob; uint4 *hl;
   HostCtx(const SimParams &P_, int e) : P(P_), env(e) {
     size_t q = (size_t)e * P.c.queue_cap; qkey = P.qkey + q; qpay0 = P.qpay0 + q; qpay1 = P.qpay1 + q; qcache = P.qcache + (size_t)e * P.n_qgroups;
     agents = P.agents + (size_t)e * P.c.n_agents; size_t l = (size_t)e * 2 * P.c.level_cap; lvp = P.lv_price + l; lvq = P.lv_qty + l; lvht = P.lv_ht + l;
     nodes = P.nodes + (size_t)e * P.c.order_cap; tr = P.trace ? P.trace + (size_t)e * P.c.trace_cap : nullptr; cur_group = cur_slot = -1;
-    idt = P.idtab ? P.idtab + (size_t)e * P.n_ids : nullptr; lob = P.lobs ? P.lobs + (size_t)e * LOB_CAP * 3 : nullptr;
+    idt = P.idtab ? P.idtab + (size_t)e * P.n_ids : nullptr; lob = P.lobs ? P.lobs + (size_t)e * lob_stride_of(P.c) : nullptr;
+    hl = P.hlog ? P.hlog + (size_t)e * P.c.hist_log_cap : nullptr;
   }
   bool onchip_writer() { return true; }
   void sync() {}
@@ -109,6 +110,36 @@ struct HostCtx {
   void snap_store(int k, int side, int n_total, int n_copy) { int2 *dst = P.snap + ((size_t)env * P.n_snap * 2 + (size_t)(k * 2 + side)) * P.snap_depth;
     for (int i = 0; i < n_copy; i++) { dst[i].x = lv_price(side, n_total - 1 - i); dst[i].y = lv_qty(side, n_total - 1 - i); } }
   int2 snap_load(int k, int side, int i) { return P.snap[((size_t)env * P.n_snap * 2 + (size_t)(k * 2 + side)) * P.snap_depth + i]; }
+  // population 3: order-history log and the HBL belief argmax, the candidate-price form of abx_warp.cuh hbl_best one candidate at a time
+  uint4 hist_load(int slot) { return hl[slot]; }
+  void hist_store(int slot, uint4 v) { hl[slot] = v; }
+  bool hbl_best(uint32_t hist_n, uint32_t e_lo, uint32_t e_hi, bool buy, int32_t v, int32_t &best_p, uint32_t &err) {
+    uint32_t cap = (uint32_t)P.c.hist_log_cap, avail = hist_n < cap ? hist_n : cap, k_first = avail, k_end = avail; bool stop = false;
+    for (uint32_t k = 0; k < avail && !stop; k++) {
+      uint32_t ep = hl[(hist_n - 1 - k) & (cap - 1)].z;
+      if (ep >= e_lo && ep <= e_hi && k_first == avail) k_first = k;
+      if (ep < e_lo) { k_end = k; stop = true; }
+    }
+    if (!stop && hist_n > cap) err |= ABX_F_HISTORY_OVERFLOW;
+    if (k_first >= k_end) { err |= ABX_F_REF_EXCEPTION; return false; }
+    uint32_t N = k_end - k_first, top = hist_n - 1 - k_first;
+    int32_t lo = INT32_MAX, hi = INT32_MIN;
+    for (uint32_t j = 0; j < N; j++) { int32_t q = (int32_t)hl[(top - j) & (cap - 1)].y; lo = std::min(lo, q); hi = std::max(hi, q); }
+    double bes = -1.0e300; int32_t bp = INT32_MAX;
+    for (uint32_t ci = 0; ci < 3 * N + 2; ci++) {
+      int32_t p = ci < 3 * N ? (int32_t)hl[(top - ci / 3) & (cap - 1)].y + (int32_t)(ci % 3) - 1 : (ci == 3 * N ? lo : hi);
+      if (p < lo || p > hi) continue;
+      uint32_t num = 0, den = 0;
+      for (uint32_t j = 0; j < N; j++) {
+        uint4 r = hl[(top - j) & (cap - 1)]; int32_t q = (int32_t)r.y; bool isb = r.w & 1u, tx = (r.w & 2u) != 0, le = q <= p, ge = q >= p;
+        bool in_num = buy ? (le && (tx || !isb)) : (ge && (tx || isb)), extra = buy ? (!tx && isb && ge) : (!tx && !isb && le);
+        num += in_num; den += in_num || extra;
+      }
+      double pr = den == 0 ? 0.0 : (double)num / (double)den, es = pr * (double)(buy ? v - p : p - v);
+      if (es > bes || (es == bes && p < bp)) { bes = es; bp = p; }
+    }
+    best_p = bp; return bes > 0.0;
+  }
   uint4 ord_load(int i) { return id_load(i); } void ord_store(int i, uint4 v) { id_store(i, v); }
   int64_t mid_sum(int k, int L, int n) { int64_t t = 0; for (int i = 0; i < n; i++) t += mid_load(k, (L - 1 - i) % MOM_MIDS); return t; }
   int32_t mid_load(int k, int slot) { return reinterpret_cast<int32_t *>(lob)[k * MOM_MIDS + slot]; }
@@ -129,7 +160,7 @@ struct HostCtx {
 struct abx_sim {
   SimParams P; int n_envs; bool reset_done;
   std::vector<uint4> qkey, qpay0, qpay1, qcache, nodes; std::vector<ZiAgent> agents; std::vector<int32_t> lvp, lvq; std::vector<uint32_t> lvht;
-  std::vector<EnvState> env; std::vector<abx_trace_rec> trace; std::vector<uint4> draw_log, evt; std::vector<uint64_t> tbits; std::vector<uint8_t> tkinds; std::vector<int64_t> toff;
+  std::vector<EnvState> env; std::vector<abx_trace_rec> trace; std::vector<uint4> draw_log, evt, hlog; std::vector<uint64_t> tbits; std::vector<uint8_t> tkinds; std::vector<int64_t> toff;
   bool is_env; EnvStreamHost st; EnvDaysHost dh; bool has_days = false; std::vector<EnvX> envx; std::vector<uint4> idtab; std::vector<int4> lobs; std::vector<uint2> idbook; std::vector<int2> snap; int auto_reset = 0; std::vector<uint64_t> dq_seeds; std::vector<int32_t> dq_msizes;
 };
 
@@ -140,12 +171,14 @@ int32_t abx_device_count(void) { return 0; }
 int32_t abx_config_sparse_zi(int32_t variant, abx_sim_config *cfg) { return config_sparse_zi(variant, cfg); }
 int32_t abx_config_rmsc03(abx_sim_config *cfg) { return config_rmsc03(cfg); }
 int32_t abx_config_rmsc03_pov(abx_sim_config *cfg) { return config_rmsc03_pov(cfg); }
+int32_t abx_config_rmsc01(abx_sim_config *cfg) { return config_rmsc01(cfg); }
 int32_t abx_sim_pov_exec(abx_sim *h, int32_t env, int64_t *out, void *stream) {
   (void)stream; if (!h || !out || env < 0 || env >= h->n_envs || h->P.c.population != 1 || !h->P.c.n_pov_exec) return ABX_ERR_ARG;
   const ZiAgent &z = h->agents[(size_t)env * h->P.c.n_agents + h->P.c.n_agents - 1]; const ExecAux *ex = reinterpret_cast<const ExecAux *>(z.oid);
   out[0] = ex->rem_qty; out[1] = ex->n_executed; out[2] = z.n_orders; return ABX_OK;
 }
 typedef Sim<HostCtx, -1, ABX_LAT_ZERO, true, SHAPE_R3> R3SimHost;
+typedef Sim<HostCtx, -1, ABX_LAT_ZERO, true, SHAPE_P3> P3SimHost;
 
 int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device, abx_sim **out) {
   (void)device;
@@ -162,6 +195,7 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   h->evt.resize(E * (size_t)c.event_ring_cap); h->P.evt = c.event_ring_cap ? h->evt.data() : nullptr;
   if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + h->P.tv_ring; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0); h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data();
     if (c.n_pov_exec) { h->P.n_snap = 1; h->P.snap_depth = c.level_cap; h->snap.resize(E * 2 * (size_t)c.level_cap); h->P.snap = h->snap.data(); } }
+  if (c.population == 3) { h->P.n_ids = MM_ORDER_CAP; h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * lob_stride_of(c)); h->hlog.resize(E * (size_t)c.hist_log_cap); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); h->P.hlog = h->hlog.data(); }
   *out = h; return ABX_OK;
 }
 int32_t abx_sim_destroy(abx_sim *h) { delete h; return ABX_OK; }
@@ -203,6 +237,7 @@ int32_t abx_sim_run(abx_sim *h, int64_t until_ns, void *stream) {
   (void)stream; if (!h) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
   for (int e = 0; e < h->n_envs; e++) { HostCtx ctx(h->P, e);
     if (h->P.c.population == 1) { R3SimHost sim(ctx, h->P, h->env[e], e); sim.r3_run(until_ns); h->env[e] = sim.s; }
+    else if (h->P.c.population == 3) { P3SimHost sim(ctx, h->P, h->env[e], e); sim.r3_run(until_ns); h->env[e] = sim.s; }
     else { Sim<HostCtx> sim(ctx, h->P, h->env[e], e); sim.run(until_ns); h->env[e] = sim.s; } }
   return ABX_OK;
 }
@@ -210,6 +245,7 @@ int32_t abx_sim_run_each(abx_sim *h, const int64_t *until, void *stream) {
   (void)stream; if (!h || !until) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
   for (int e = 0; e < h->n_envs; e++) { HostCtx ctx(h->P, e);
     if (h->P.c.population == 1) { R3SimHost sim(ctx, h->P, h->env[e], e); sim.r3_run(until[e]); h->env[e] = sim.s; }
+    else if (h->P.c.population == 3) { P3SimHost sim(ctx, h->P, h->env[e], e); sim.r3_run(until[e]); h->env[e] = sim.s; }
     else { Sim<HostCtx> sim(ctx, h->P, h->env[e], e); sim.run(until[e]); h->env[e] = sim.s; } }
   return ABX_OK;
 }
@@ -217,6 +253,7 @@ int32_t abx_sim_finalize(abx_sim *h, void *stream) {
   (void)stream; if (!h) return ABX_ERR_ARG; if (!h->reset_done) return ABX_ERR_STATE;
   for (int e = 0; e < h->n_envs; e++) { HostCtx ctx(h->P, e);
     if (h->P.c.population == 1) { R3SimHost sim(ctx, h->P, h->env[e], e); sim.r3_finalize(); h->env[e] = sim.s; }
+    else if (h->P.c.population == 3) { P3SimHost sim(ctx, h->P, h->env[e], e); sim.r3_finalize(); h->env[e] = sim.s; }
     else { Sim<HostCtx> sim(ctx, h->P, h->env[e], e); sim.finalize(); h->env[e] = sim.s; } }
   return ABX_OK;
 }

@@ -26,7 +26,7 @@ def oracle_tapes(sims):
     bits, kinds, off, lat_to, lat_from = [], [], [0], [], []
     for s in sims:
         n = s.n_agents
-        if s.variant == 3:                            # rmsc03: oracle stream order symbol, exchange, agents 1..n-1, kernel; global stream separate
+        if s.variant in (3, 1):                       # rmsc03 / rmsc01: oracle stream order symbol, exchange, agents 1..n-1, kernel; global stream separate
             gk, gb = s.global_tape()                  # runtime draws; the oracle's __init__ megashock gap (drawn by the config) comes first
             g0 = s.global_exp_tape()[:1]
             glob = (np.concatenate([np.full(1, ord("e"), np.uint8), gk]), np.concatenate([g0.view(np.uint64), gb]))
@@ -36,6 +36,10 @@ def oracle_tapes(sims):
                 kinds.append(k)
                 bits.append(b)
                 off.append(off[-1] + len(b))
+            if s.variant == 1:                        # rmsc01: every agent draws its own parameters from its own stream
+                lat_to.append(np.zeros(n))
+                lat_from.append(np.zeros(n))
+                continue
             info = np.array([s.agent_info(a) for a in range(n)])
             lat_to.append(info[:, 1].astype(np.float64))      # Noise/Value size (drawn by the config script)
             lat_from.append(info[:, 2].astype(np.float64))    # NoiseAgent.wakeup_time
@@ -56,6 +60,26 @@ def oracle_tapes(sims):
         lat_from.append(b)
     return (np.concatenate(bits), np.concatenate(kinds), np.array(off, np.int64), np.concatenate(lat_to),
             np.concatenate(lat_from))
+
+
+def oracle_rmsc01_config(stop_ns=(9 * 3600 + 45 * 60) * 10 ** 9):
+    """config/rmsc01.py as the oracle states it (abo_default_config(1): 1 MarketMakerAgent + 50 ZI + 25 HBL + 24 Momentum agents, zero latency), cut at
+    `stop_ns`: the full day is ~2 M messages under the current reference code (tests/rmsc01.txt's 128 918 predates it), so recordings and
+    parity runs stop early."""
+    import ctypes as C
+    from marl_optimal_execution_b200 import _lib
+    from oracle.oracle import lib
+    cfg = _lib.SimConfig()
+    assert lib().abo_default_config(1, C.addressof(cfg)) == 0
+    cfg.stop_ns = stop_ns
+    return cfg
+
+
+def oracle_rmsc01(seed, stop_ns, trace):
+    """A finished OracleSim of the rmsc01 population and its message count."""
+    from oracle.oracle import OracleSim
+    o = OracleSim.from_config(oracle_rmsc01_config(stop_ns), seed, trace)
+    return o, o.run()
 
 
 def oracle_rerun_of_philox_env(sim, env, init, trace):

@@ -134,6 +134,29 @@ def test_rmsc03_with_pov_execution_agent_matches_oracle(emu):
     assert int(st["sum_shares"]) == 0 and int(st["sum_cash"]) == 64 * 10 ** 7
 
 
+@pytest.mark.parametrize("seed,stop_s,pops", [(123456789, 15 * 60, 77119), (20231, 4 * 60, None)])
+def test_rmsc01_tape_replay_matches_oracle(emu, seed, stop_s, pops):
+    """config/rmsc01.py population through the product logic: MarketMakerAgent ladder, ZI agents, HeuristicBeliefLearningAgents fed by the exchange's
+    QUERY_ORDER_STREAM (order-history log + belief argmax), Momentum agents.  Seed 123456789 to 09:45:00 is the run the oracle is pinned to the live
+    reference on (tests/test_oracle_golden.py::test_rmsc01_full_trace_bit_exact)."""
+    from helpers import oracle_rmsc01
+    from marl_optimal_execution_b200.sim import rmsc01_config
+    stop = (9 * 3600 + 30 * 60 + stop_s) * 10 ** 9
+    o, n = oracle_rmsc01(seed, stop, TRACE_ALL)
+    assert pops is None or n == pops
+    cfg = rmsc01_config(lib=_lib.load(emu), rng_mode=_lib.RNG_TAPE, trace_cap=400000, hash_pops=1, stop_ns=stop)
+    sim = BatchedSim(cfg, 1, lib_path=emu)
+    sim.reset_tape(*oracle_tapes([o]))
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    from helpers import assert_env_equals_oracle
+    assert_env_equals_oracle(sim, 0, o, n, st)
+    ops = o.trace("ops")
+    hbl = ops[(ops[:, 1] == 0) & (ops[:, 2] >= 52) & (ops[:, 2] <= 76)]                 # limit orders of the 25 HBL agents
+    assert len(hbl) > 20 and int(st["sum_shares"][0]) == 0 and int(st["sum_cash"][0]) == 100 * 10 ** 7
+
+
 def test_shared_tapes_round_robin(emu):
     """abx_sim_reset_tape_shared: environment e replays recorded run e % n_tapes (the production-occupancy parity tests of the GPU suite)."""
     seeds = [123456789, 1001, 7]

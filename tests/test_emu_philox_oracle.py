@@ -7,7 +7,7 @@ import pytest
 
 from helpers import assert_env_equals_oracle, build_emu, oracle_rerun_of_philox_env
 from marl_optimal_execution_b200 import _lib
-from marl_optimal_execution_b200.sim import BatchedSim, rmsc03_config, sparse_zi_config
+from marl_optimal_execution_b200.sim import BatchedSim, rmsc01_config, rmsc03_config, sparse_zi_config
 from oracle.oracle import TRACE_ALL
 
 
@@ -46,3 +46,20 @@ def test_rmsc03_philox_run_equals_oracle_on_its_own_draws(emu, pov):
         if int(st["flags"][e]) & _lib.F_OBS_INVALID:      # the POV agent met an empty book side: the reference raises there, nothing to compare
             continue
         assert_env_equals_oracle(sim, e, o, n, st, holdings_cols=4)
+
+
+def test_rmsc01_philox_run_equals_oracle_on_its_own_draws(emu):
+    """config/rmsc01.py population seeded by Philox: the oracle, re-run on the environment's own draws, sees the same HBL limit prices, market-maker
+    ladders and trades (09:30 - 09:36)."""
+    stop = (9 * 3600 + 36 * 60) * 10 ** 9
+    cfg = rmsc01_config(lib=_lib.load(emu), trace_cap=300000, hash_pops=1, draw_log_cap=60000, stop_ns=stop)
+    sim = BatchedSim(cfg, 2, lib_path=emu)
+    sim.reset([31, 32])
+    init = [sim.agent_init(e) for e in range(2)]
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    for e in range(2):
+        o, n = oracle_rerun_of_philox_env(sim, e, init[e], TRACE_ALL)
+        assert_env_equals_oracle(sim, e, o, n, st)
+    assert st["pop_hash"][0] != st["pop_hash"][1] and st["fills"].min() > 5              # rmsc01 trades rarely: ~40 fills in the reference's first 15 minutes

@@ -133,6 +133,26 @@ def test_rmsc03_tape_replay(seed):
     assert int(st["limit_orders"][0]) == o.counter("limit") and int(st["fills"][0]) == o.counter("fills")
 
 
+@pytest.mark.parametrize("seed,stop_s", [(123456789, 15 * 60), (20231, 4 * 60)])
+def test_rmsc01_tape_replay(seed, stop_s):
+    """config/rmsc01.py population: MarketMakerAgent, ZI, HeuristicBeliefLearningAgents served by QUERY_ORDER_STREAM, Momentum agents.
+    Bit-exact pops, exchange messages, book snapshots and holdings vs the oracle, which is pinned to a live recording of the reference for seed
+    123456789 up to 09:45:00 (tests/test_oracle_golden.py::test_rmsc01_full_trace_bit_exact)."""
+    from helpers import assert_env_equals_oracle, oracle_rmsc01
+    from marl_optimal_execution_b200.sim import rmsc01_config
+    stop = (9 * 3600 + 30 * 60 + stop_s) * 10 ** 9
+    o, n = oracle_rmsc01(seed, stop, TRACE_ALL)
+    cfg = rmsc01_config(rng_mode=_lib.RNG_TAPE, trace_cap=400000, hash_pops=1, stop_ns=stop)
+    sim = BatchedSim(cfg, 2)
+    sim.reset_tape(*oracle_tapes([o, o]))
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    for e in range(2):
+        assert_env_equals_oracle(sim, e, o, n, st)
+    assert int(st["sum_shares"][0]) == 0 and int(st["sum_cash"][0]) == 100 * 10 ** 7
+
+
 def test_rmsc03_with_pov_execution_agent_tape_replay():
     """BASELINE.json configs[2] "rmsc03 ... with POV execution agent": bit-exact vs the oracle (pinned to a recording of the reference with
     its POVExecutionAgent appended); one environment per seed plus a duplicate."""

@@ -103,17 +103,7 @@ def test_rmsc03_with_pov_execution_agent(golden_dir):
     assert np.array_equal(gk, g["global_kind"].view(np.uint8)) and np.array_equal(gb, g["global_bits"])
 
 
-def rmsc01_config(stop_ns=(9 * 3600 + 45 * 60) * 10 ** 9):
-    """config/rmsc01.py as the oracle's `abo_default_config(1)` states it (1 MarketMakerAgent + 50 ZI + 25 HBL + 24 Momentum, zero
-    latency, oracle megashock-free r_bar 1e5), cut at `stop_ns`: the full day is ~2 M messages under the current reference code
-    (tests/rmsc01.txt's 128 918 predates it), so the recording stops at 09:45:00."""
-    import ctypes as C
-    from marl_optimal_execution_b200 import _lib
-    from oracle.oracle import lib
-    cfg = _lib.SimConfig()
-    assert lib().abo_default_config(1, C.addressof(cfg)) == 0
-    cfg.stop_ns = stop_ns
-    return cfg
+from helpers import oracle_rmsc01_config as rmsc01_config  # noqa: E402
 
 
 def test_rmsc01_full_trace_bit_exact(golden_dir):

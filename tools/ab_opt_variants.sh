@@ -13,7 +13,7 @@ if [ "$1" = build ]; then
 fi
 mkdir -p gpurun_out; : > gpurun_out/ab_opt.log
 for rep in 1 2; do for v in $ORDER; do
-  EXTRA="--no-ddqn --no-env --no-rmsc03 --no-whole-day --no-marketreplay"
+  EXTRA="--no-ddqn --no-env --no-rmsc03 --no-rmsc01 --no-whole-day --no-marketreplay"
   echo -n "$v: " | tee -a gpurun_out/ab_opt.log
   ABX_LIB_PATH=$PWD/build/ab/opt_$v.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline $EXTRA 2>/dev/null | python -c "
 import json,sys

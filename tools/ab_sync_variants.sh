@@ -17,7 +17,7 @@ mkdir -p gpurun_out
 for v in default strict fence_only default strict fence_only; do
   case $v in default) L=$PKG/libabides_b200.so;; strict) L=$PKG/libabides_b200_strict.so;; *) L=build/ab/fence_only.so;; esac
   echo "== $v" | tee -a gpurun_out/ab_sync.log
-  ABX_LIB_PATH=$PWD/$L python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-rmsc03 --no-ddqn --env-steps 300 2>/dev/null | python -c "
+  ABX_LIB_PATH=$PWD/$L python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-rmsc03 --no-rmsc01 --no-ddqn --env-steps 300 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.readline()); print('lob msgs/s %.4g  env steps/s %.4g' % (d['value'], d['env']['value']))" | tee -a gpurun_out/ab_sync.log
 done
