@@ -132,7 +132,7 @@ typedef struct abx_sim_config {
    * MomentumAgents; zero latency.  hist_log_cap: entries of the per-environment order-history log behind QUERY_ORDER_STREAM (util/OrderBook.py:52-60). */
   int32_t hbl_L, mkm_min_size, mkm_max_size, mkm_num_levels;
   int64_t mkm_wake_ns;
-  int32_t hist_log_cap, _pad3;
+  int32_t hist_log_cap, hbl_table_rows;   /* hbl_table_rows: price rows of the HBL belief table held per environment, 0 = hist_log_cap / 4 (the maximum); wider price spans take a slower exact form */
 } abx_sim_config;
 
 /* Per-environment counters; replaces the "Event Queue elapsed ..., messages: N" line (Kernel.py:321-327). */

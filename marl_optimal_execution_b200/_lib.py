@@ -61,7 +61,7 @@ class SimConfig(C.Structure):
         ("pov_exec_start_ns", C.c_int64), ("pov_exec_end_ns", C.c_int64), ("pov_exec_freq_ns", C.c_int64), ("pov_exec_lookback_ns", C.c_int64),
         ("draw_log_cap", C.c_int32), ("event_ring_cap", C.c_int32),
         ("hbl_L", C.c_int32), ("mkm_min_size", C.c_int32), ("mkm_max_size", C.c_int32), ("mkm_num_levels", C.c_int32), ("mkm_wake_ns", C.c_int64),
-        ("hist_log_cap", C.c_int32), ("_pad3", C.c_int32),
+        ("hist_log_cap", C.c_int32), ("hbl_table_rows", C.c_int32),
     ]
 
 

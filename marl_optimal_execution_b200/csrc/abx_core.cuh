@@ -160,7 +160,7 @@ struct SimParams {
   EnvState *env;                // [n_envs]
   abx_trace_rec *trace;         // [n_envs][trace_cap]
   uint4 *draw_log;              // [n_envs][draw_log_cap] {stream | kind << 24, bits lo, bits hi, -}  (parity runs under Philox)
-  uint4 *hlog;                  // [n_envs][hist_log_cap] {order id, limit price, history epoch at registration, is_buy | has transactions << 1}  (population 3)
+  uint4 *hlog;                  // [n_envs][hist_stride_of(c)] {order id, limit price, history epoch at registration, is_buy | has transactions << 1}  (population 3)
   uint4 *evt;                   // [n_envs][event_ring_cap] {t lo, t hi | kind << 28, a, b}: order arrivals, BEST_BID / BEST_ASK / LAST_TRADE (realism tooling)
   const uint64_t *tape_bits; const uint8_t *tape_kinds; const int64_t *tape_off; // tape mode
   // ---- ABIDESEnv shape (exchange + MarketReplayAgent + RL execution agent); zero for the sparse_zi shape ----
@@ -358,6 +358,8 @@ typedef RngT<-1> Rng;
 // ---------------------------------------------------------------------------------------------------
 // int4 entries per environment in SimParams.lobs: the ABIDESEnv LOB ring, or the momentum agents' mid-price rings (population 3 has 24 of them)
 ABX_HD int lob_stride_of(const abx_sim_config &c) { int need = c.population == 3 ? (c.n_momentum_agents * MOM_MIDS + 3) / 4 : 0; return need > LOB_CAP * 3 ? need : LOB_CAP * 3; }
+// uint4 entries per environment in SimParams.hlog: the ring of hist_log_cap order records + hist_log_cap / 4 scratch rows (8 B each) for the HBL belief table
+ABX_HD size_t hist_stride_of(const abx_sim_config &c) { return (size_t)c.hist_log_cap + (size_t)c.hist_log_cap / 8; }
 ABX_HD int agent_type_of(const abx_sim_config &c, int id) {
   if (c.population == 0) return AT_ZI;
   if (c.population == 3) {                                                              // config/rmsc01.py: market maker(s), ZI, HBL, momentum

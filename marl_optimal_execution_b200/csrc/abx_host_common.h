@@ -105,7 +105,7 @@ static inline int config_validate(const abx_sim_config *c) {
   } else if (c->population == 3) {
     if (c->n_groups != 2 || c->n_mm_agents < 0 || c->n_mm_agents > 1 || c->n_momentum_agents < 0 || c->n_momentum_agents > 64 || c->latency_model != ABX_LAT_ZERO) return ABX_ERR_ARG;
     for (int g = 0; g < 2; g++) { if (c->groups[g].count < 0 || c->groups[g].r_max < c->groups[g].r_min) return ABX_ERR_ARG; n += c->groups[g].count; }
-    if (c->hbl_L < 1 || c->hbl_L > 16 || c->stream_history < 1 || c->hist_log_cap < 64 || c->hist_log_cap > 65536 || (c->hist_log_cap & (c->hist_log_cap - 1))) return ABX_ERR_ARG;
+    if (c->hbl_L < 1 || c->hbl_L > 16 || c->stream_history < 1 || c->hist_log_cap < 64 || c->hist_log_cap > 65536 || (c->hist_log_cap & (c->hist_log_cap - 1)) || c->hbl_table_rows < 0 || c->hbl_table_rows > c->hist_log_cap / 4) return ABX_ERR_ARG;
     if (c->mom_max_size <= c->mom_min_size || c->mom_wake_ns <= 0) return ABX_ERR_ARG;
     if (c->n_mm_agents && (c->mkm_max_size <= c->mkm_min_size || c->mkm_num_levels < 1 || 4 * c->mkm_num_levels > MM_ORDER_CAP / 2 || c->mkm_wake_ns <= 0)) return ABX_ERR_ARG;
     n += c->n_mm_agents + c->n_momentum_agents;

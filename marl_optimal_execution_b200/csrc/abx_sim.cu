@@ -340,7 +340,7 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + h->P.tv_ring; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0);       // market maker orders + transaction ring [+ POV execution agent orders]; momentum mids
     DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
     if (c.n_pov_exec) { h->P.n_snap = 1; h->P.snap_depth = c.level_cap; DA(h->P.snap, E * 2 * (size_t)c.level_cap) } }      // POVExecutionAgent asks for depth sys.maxsize
-  if (c.population == 3) { h->P.n_ids = MM_ORDER_CAP; DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * (size_t)lob_stride_of(c)) DA(h->P.hlog, E * (size_t)c.hist_log_cap) }   // market maker orders; momentum mids; order-history log
+  if (c.population == 3) { h->P.n_ids = MM_ORDER_CAP; DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * (size_t)lob_stride_of(c)) DA(h->P.hlog, E * hist_stride_of(c)) }   // market maker orders; momentum mids; order-history log
 #undef DA
   if (smem_cta > 48 * 1024) {
     CUH(cudaFuncSetAttribute((const void *)run_kernel_for(*cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));

@@ -106,7 +106,7 @@ struct WarpCtxT {
     idb = P.idbook ? P.idbook + (size_t)env * P.n_ids : nullptr;
     snp = P.snap ? P.snap + (size_t)env * P.n_snap * 2 * P.snap_depth : nullptr;
     idt = P.idtab ? P.idtab + (size_t)env * P.n_ids : nullptr; lob = P.lobs ? P.lobs + (size_t)env * lob_stride_of(P.c) : nullptr;
-    hl = P.hlog ? P.hlog + (size_t)env * P.c.hist_log_cap : nullptr;
+    hl = P.hlog ? P.hlog + (size_t)env * hist_stride_of(P.c) : nullptr;
     cur_group = cur_lane = -1; cur_mask = 0; my_hi = KEY_EMPTY; my_uniq = 0xffffffffu; n_ovf = 0; cur_t2 = false;
     day = P.n_days > 1 ? env % P.n_days : 0;                               // once per launch: an integer modulo is ~170 instructions
   }
@@ -440,8 +440,10 @@ struct WarpCtxT {
   // HeuristicBeliefLearningAgent.placeOrder :98-168 over the log entries of epochs e_lo .. e_hi (a contiguous run: epochs never decrease along the log).
   // The reference fills one row per price between the lowest and the highest of those orders with cumulative counts of successful / unsuccessful asks and
   // bids and takes the first argmax of Pr * surplus.  Pr is piecewise constant and only changes at p_i (counts "at or below") or p_i + 1 ("at or above"), and
-  // within a piece Pr * surplus is strictly monotonic, so the argmax over all rows is the argmax over {low, high, p_i - 1, p_i, p_i + 1}: lanes take
-  // candidates 32 at a time and count the run for each (integer counts, the reference's fp64 quotient and product), ties go to the lower price.
+  // within a piece Pr * surplus is strictly monotonic, so the argmax over all rows is the argmax over {low, high, p_i - 1, p_i, p_i + 1}.  Two forms:
+  // while the price span fits the scratch rows (hist_log_cap / 4), the table is built as the reference builds it (histogram + prefix scan over the rows,
+  // 32 rows per pass); otherwise lanes take candidate prices 32 at a time and count the run for each.  Integer counts, the reference's fp64 quotient and
+  // product, ties to the lower price -- both forms are exact.
   __device__ bool hbl_best(uint32_t hist_n, uint32_t e_lo, uint32_t e_hi, bool buy, int32_t v, int32_t &best_p, uint32_t &err) const {
     uint32_t cap = (uint32_t)P.c.hist_log_cap, avail = hist_n < cap ? hist_n : cap, k_first = avail, k_end = avail; bool stop = false;
 #pragma unroll 1
@@ -458,7 +460,37 @@ struct WarpCtxT {
 #pragma unroll 1
     for (uint32_t j = lane; j < N; j += 32) { int32_t pr = (int32_t)ldcg4(hl + ((top - j) & (cap - 1))).y; lo = pr < lo ? pr : lo; hi = pr > hi ? pr : hi; }
     lo = __reduce_min_sync(FULL, lo); hi = __reduce_max_sync(FULL, hi);
-    double bes = -1.0e300; int32_t bp = 0x7fffffff; uint32_t ncand = 3 * N + 2;
+    double bes = -1.0e300; int32_t bp = 0x7fffffff;
+    uint32_t rows_cap = P.c.hbl_table_rows > 0 ? (uint32_t)P.c.hbl_table_rows : cap / 4; uint2 *scr = reinterpret_cast<uint2 *>(hl + cap);   // one {forward class, reverse class} counter pair per price row, behind the ring
+    if ((int64_t)hi - (int64_t)lo < (int64_t)rows_cap) {
+      // the reference's table itself (:112-165): histogram of the run over the price rows, one prefix scan, Pr * surplus per row -- O(N + rows)
+      uint32_t R = (uint32_t)(hi - lo) + 1u, atot = 0, btot = 0;
+#pragma unroll 1
+      for (uint32_t r = lane; r < R; r += 32) __stcg(scr + r, make_uint2(0u, 0u));
+      __syncwarp();
+#pragma unroll 1
+      for (uint32_t j0 = 0; j0 < N; j0 += 32) {
+        uint32_t j = j0 + lane; bool on = j < N; uint4 r = on ? ldcg4(hl + ((top - j) & (cap - 1))) : make_uint4(0u, 0u, 0u, 0u);
+        bool isb = r.w & 1u, tx = (r.w & 2u) != 0, fwd = on && (tx || (buy ? !isb : isb));   // counted towards num; every other order of the run only towards the denominator
+        if (on) atomicAdd(fwd ? &scr[(int32_t)r.y - lo].x : &scr[(int32_t)r.y - lo].y, 1u);
+        atot += __popc(__ballot_sync(FULL, fwd)); btot += __popc(__ballot_sync(FULL, on && !fwd));
+      }
+      __syncwarp();
+      uint32_t ca = 0, cb = 0;                                              // counts in the rows below the current 32
+#pragma unroll 1
+      for (uint32_t r0 = 0; r0 < R; r0 += 32) {
+        uint32_t r = r0 + lane; bool on = r < R; uint2 cnt = on ? __ldcg(scr + r) : make_uint2(0u, 0u); uint32_t ia = cnt.x, ib = cnt.y;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t ua = __shfl_up_sync(FULL, ia, o), ub = __shfl_up_sync(FULL, ib, o); if (lane >= o) { ia += ua; ib += ub; } }
+        // buy: num = orders of the forward class at or below the row, the rest of the denominator = reverse class at or above it; sell: the mirror image
+        uint32_t num = buy ? ca + ia : atot - (ca + ia - cnt.x), oth = buy ? btot - (cb + ib - cnt.y) : cb + ib, den = num + oth;
+        int32_t p = lo + (int32_t)r;
+        double pr = den == 0 ? 0.0 : (double)num / (double)den, es = pr * (double)(buy ? v - p : p - v);
+        if (on && (es > bes || (es == bes && p < bp))) { bes = es; bp = p; }
+        ca += __shfl_sync(FULL, ia, 31); cb += __shfl_sync(FULL, ib, 31);
+      }
+    } else {
+    uint32_t ncand = 3 * N + 2;                                             // price span wider than the scratch rows: the candidate form (exact, O(N^2 / 32))
 #pragma unroll 1
     for (uint32_t ci = lane; ci < ncand; ci += 32) {
       int32_t p;
@@ -474,6 +506,7 @@ struct WarpCtxT {
       double pr = den == 0 ? 0.0 : (double)num / (double)den;               // :152-159 nan_to_num(0 / 0)
       double es = pr * (double)(buy ? v - p : p - v);                       // :162-165
       if (es > bes || (es == bes && p < bp)) { bes = es; bp = p; }
+    }
     }
     __syncwarp();
 #pragma unroll

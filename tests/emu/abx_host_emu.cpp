@@ -25,7 +25,7 @@ struct HostCtx {
     agents = P.agents + (size_t)e * P.c.n_agents; size_t l = (size_t)e * 2 * P.c.level_cap; lvp = P.lv_price + l; lvq = P.lv_qty + l; lvht = P.lv_ht + l;
     nodes = P.nodes + (size_t)e * P.c.order_cap; tr = P.trace ? P.trace + (size_t)e * P.c.trace_cap : nullptr; cur_group = cur_slot = -1;
     idt = P.idtab ? P.idtab + (size_t)e * P.n_ids : nullptr; lob = P.lobs ? P.lobs + (size_t)e * lob_stride_of(P.c) : nullptr;
-    hl = P.hlog ? P.hlog + (size_t)e * P.c.hist_log_cap : nullptr;
+    hl = P.hlog ? P.hlog + (size_t)e * hist_stride_of(P.c) : nullptr;
   }
   bool onchip_writer() { return true; }
   void sync() {}
@@ -126,6 +126,20 @@ struct HostCtx {
     int32_t lo = INT32_MAX, hi = INT32_MIN;
     for (uint32_t j = 0; j < N; j++) { int32_t q = (int32_t)hl[(top - j) & (cap - 1)].y; lo = std::min(lo, q); hi = std::max(hi, q); }
     double bes = -1.0e300; int32_t bp = INT32_MAX;
+    uint32_t rows_cap = P.c.hbl_table_rows > 0 ? (uint32_t)P.c.hbl_table_rows : cap / 4; uint2 *scr = reinterpret_cast<uint2 *>(hl + cap);
+    if ((int64_t)hi - (int64_t)lo < (int64_t)rows_cap) {                                // histogram + prefix-scan form (the reference's own table), one row at a time
+      uint32_t R = (uint32_t)(hi - lo) + 1u, atot = 0, btot = 0, ca = 0, cb = 0;
+      for (uint32_t r = 0; r < R; r++) { scr[r].x = 0; scr[r].y = 0; }
+      for (uint32_t j = 0; j < N; j++) { uint4 r = hl[(top - j) & (cap - 1)]; bool isb = r.w & 1u, tx = (r.w & 2u) != 0, fwd = tx || (buy ? !isb : isb);
+        if (fwd) { scr[(int32_t)r.y - lo].x++; atot++; } else { scr[(int32_t)r.y - lo].y++; btot++; } }
+      for (uint32_t r = 0; r < R; r++) {
+        uint32_t ia = ca + scr[r].x, ib = cb + scr[r].y, num = buy ? ia : atot - ca, oth = buy ? btot - cb : ib, den = num + oth; int32_t p = lo + (int32_t)r;
+        double pr = den == 0 ? 0.0 : (double)num / (double)den, es = pr * (double)(buy ? v - p : p - v);
+        if (es > bes || (es == bes && p < bp)) { bes = es; bp = p; }
+        ca = ia; cb = ib;
+      }
+      best_p = bp; return bes > 0.0;
+    }
     for (uint32_t ci = 0; ci < 3 * N + 2; ci++) {
       int32_t p = ci < 3 * N ? (int32_t)hl[(top - ci / 3) & (cap - 1)].y + (int32_t)(ci % 3) - 1 : (ci == 3 * N ? lo : hi);
       if (p < lo || p > hi) continue;
@@ -195,7 +209,7 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   h->evt.resize(E * (size_t)c.event_ring_cap); h->P.evt = c.event_ring_cap ? h->evt.data() : nullptr;
   if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + h->P.tv_ring; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0); h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data();
     if (c.n_pov_exec) { h->P.n_snap = 1; h->P.snap_depth = c.level_cap; h->snap.resize(E * 2 * (size_t)c.level_cap); h->P.snap = h->snap.data(); } }
-  if (c.population == 3) { h->P.n_ids = MM_ORDER_CAP; h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * lob_stride_of(c)); h->hlog.resize(E * (size_t)c.hist_log_cap); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); h->P.hlog = h->hlog.data(); }
+  if (c.population == 3) { h->P.n_ids = MM_ORDER_CAP; h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * lob_stride_of(c)); h->hlog.resize(E * hist_stride_of(c)); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); h->P.hlog = h->hlog.data(); }
   *out = h; return ABX_OK;
 }
 int32_t abx_sim_destroy(abx_sim *h) { delete h; return ABX_OK; }

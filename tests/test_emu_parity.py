@@ -134,17 +134,20 @@ def test_rmsc03_with_pov_execution_agent_matches_oracle(emu):
     assert int(st["sum_shares"]) == 0 and int(st["sum_cash"]) == 64 * 10 ** 7
 
 
-@pytest.mark.parametrize("seed,stop_s,pops", [(123456789, 15 * 60, 77119), (20231, 4 * 60, None)])
-def test_rmsc01_tape_replay_matches_oracle(emu, seed, stop_s, pops):
+@pytest.mark.parametrize("seed,stop_s,pops,hist_cap", [(123456789, 15 * 60, 77119, 0), (20231, 4 * 60, None, 0), (123456789, 15 * 60, 77119, 256)])
+def test_rmsc01_tape_replay_matches_oracle(emu, seed, stop_s, pops, hist_cap):
     """config/rmsc01.py population through the product logic: MarketMakerAgent ladder, ZI agents, HeuristicBeliefLearningAgents fed by the exchange's
     QUERY_ORDER_STREAM (order-history log + belief argmax), Momentum agents.  Seed 123456789 to 09:45:00 is the run the oracle is pinned to the live
-    reference on (tests/test_oracle_golden.py::test_rmsc01_full_trace_bit_exact)."""
+    reference on (tests/test_oracle_golden.py::test_rmsc01_full_trace_bit_exact).  hbl_table_rows 256 leaves 256 scratch rows for the belief table: price spans
+    beyond that take the candidate-price form of the argmax instead of the histogram form (abx_warp.cuh hbl_best) -- both must give the reference's price."""
     from helpers import oracle_rmsc01
     from marl_optimal_execution_b200.sim import rmsc01_config
     stop = (9 * 3600 + 30 * 60 + stop_s) * 10 ** 9
     o, n = oracle_rmsc01(seed, stop, TRACE_ALL)
     assert pops is None or n == pops
     cfg = rmsc01_config(lib=_lib.load(emu), rng_mode=_lib.RNG_TAPE, trace_cap=400000, hash_pops=1, stop_ns=stop)
+    if hist_cap:
+        cfg.hbl_table_rows = hist_cap
     sim = BatchedSim(cfg, 1, lib_path=emu)
     sim.reset_tape(*oracle_tapes([o]))
     sim.run()

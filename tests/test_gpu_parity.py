@@ -133,8 +133,8 @@ def test_rmsc03_tape_replay(seed):
     assert int(st["limit_orders"][0]) == o.counter("limit") and int(st["fills"][0]) == o.counter("fills")
 
 
-@pytest.mark.parametrize("seed,stop_s", [(123456789, 15 * 60), (20231, 4 * 60)])
-def test_rmsc01_tape_replay(seed, stop_s):
+@pytest.mark.parametrize("seed,stop_s,hist_cap", [(123456789, 15 * 60, 0), (20231, 4 * 60, 0), (123456789, 15 * 60, 256)])
+def test_rmsc01_tape_replay(seed, stop_s, hist_cap):
     """config/rmsc01.py population: MarketMakerAgent, ZI, HeuristicBeliefLearningAgents served by QUERY_ORDER_STREAM, Momentum agents.
     Bit-exact pops, exchange messages, book snapshots and holdings vs the oracle, which is pinned to a live recording of the reference for seed
     123456789 up to 09:45:00 (tests/test_oracle_golden.py::test_rmsc01_full_trace_bit_exact)."""
@@ -143,6 +143,8 @@ def test_rmsc01_tape_replay(seed, stop_s):
     stop = (9 * 3600 + 30 * 60 + stop_s) * 10 ** 9
     o, n = oracle_rmsc01(seed, stop, TRACE_ALL)
     cfg = rmsc01_config(rng_mode=_lib.RNG_TAPE, trace_cap=400000, hash_pops=1, stop_ns=stop)
+    if hist_cap:                                          # 256 scratch rows: wider price spans take the candidate form of the HBL argmax
+        cfg.hbl_table_rows = hist_cap
     sim = BatchedSim(cfg, 2)
     sim.reset_tape(*oracle_tapes([o, o]))
     sim.run()
