@@ -35,7 +35,8 @@ enum abx_status {
 enum abx_msg_kind {
   ABX_NONE = 0, ABX_WHEN_MKT_OPEN, ABX_WHEN_MKT_CLOSE, ABX_QUERY_SPREAD, ABX_LIMIT_ORDER, ABX_CANCEL_ORDER,
   ABX_MODIFY_ORDER, ABX_ORDER_ACCEPTED, ABX_ORDER_EXECUTED, ABX_ORDER_CANCELLED, ABX_MKT_CLOSED,
-  ABX_QUERY_LAST_TRADE, ABX_QUERY_TRANSACTED_VOLUME, ABX_ORDER_MODIFIED, ABX_QUERY_ORDER_STREAM, ABX_MARKET_DATA
+  ABX_QUERY_LAST_TRADE, ABX_QUERY_TRANSACTED_VOLUME, ABX_ORDER_MODIFIED, ABX_QUERY_ORDER_STREAM, ABX_MARKET_DATA,
+  ABX_MARKET_DATA_SUBSCRIPTION_REQUEST, ABX_MARKET_DATA_SUBSCRIPTION_CANCELLATION
 };
 /* queue entry types, message/Message.py:5-10 (tie-break order MESSAGE < WAKEUP < CANCEL_ORDER) */
 enum abx_event_type { ABX_T_MESSAGE = 1, ABX_T_WAKEUP = 2, ABX_T_CANCEL_ORDER = 3 };
@@ -132,6 +133,11 @@ typedef struct abx_sim_config {
    * MomentumAgents; zero latency.  hist_log_cap: entries of the per-environment order-history log behind QUERY_ORDER_STREAM (util/OrderBook.py:52-60). */
   int32_t hbl_L, mkm_min_size, mkm_max_size, mkm_num_levels;
   int64_t mkm_wake_ns;
+  /* config/rmsc02.py: the same population with the market maker and / or the momentum agents in SUBSCRIPTION mode (MARKET_DATA_SUBSCRIPTION_REQUEST at their first
+   * wake-up, agent/TradingAgent.py:160-172; the exchange publishes MARKET_DATA after every book operation to subscribers whose `freq` ns have passed,
+   * agent/ExchangeAgent.py:342-387).  mkm_num_levels levels a side for the market maker (subscribe_num_levels), 1 for momentum agents. */
+  int32_t mkm_subscribe, mom_subscribe;
+  int64_t mkm_sub_freq_ns, mom_sub_freq_ns;   /* subscribe_freq (10e9) / MomentumAgent.py:58 (10e9) */
   int32_t hist_log_cap, hbl_table_rows;   /* hbl_table_rows: price rows of the HBL belief table held per environment, 0 = hist_log_cap / 4 (the maximum); wider price spans take a slower exact form */
 } abx_sim_config;
 

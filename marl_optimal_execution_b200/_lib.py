@@ -24,6 +24,7 @@ MSG_KINDS = [
     "NONE", "WHEN_MKT_OPEN", "WHEN_MKT_CLOSE", "QUERY_SPREAD", "LIMIT_ORDER", "CANCEL_ORDER", "MODIFY_ORDER",
     "ORDER_ACCEPTED", "ORDER_EXECUTED", "ORDER_CANCELLED", "MKT_CLOSED", "QUERY_LAST_TRADE",
     "QUERY_TRANSACTED_VOLUME", "ORDER_MODIFIED", "QUERY_ORDER_STREAM", "MARKET_DATA",
+    "MARKET_DATA_SUBSCRIPTION_REQUEST", "MARKET_DATA_SUBSCRIPTION_CANCELLATION",
 ]
 
 
@@ -61,6 +62,7 @@ class SimConfig(C.Structure):
         ("pov_exec_start_ns", C.c_int64), ("pov_exec_end_ns", C.c_int64), ("pov_exec_freq_ns", C.c_int64), ("pov_exec_lookback_ns", C.c_int64),
         ("draw_log_cap", C.c_int32), ("event_ring_cap", C.c_int32),
         ("hbl_L", C.c_int32), ("mkm_min_size", C.c_int32), ("mkm_max_size", C.c_int32), ("mkm_num_levels", C.c_int32), ("mkm_wake_ns", C.c_int64),
+        ("mkm_subscribe", C.c_int32), ("mom_subscribe", C.c_int32), ("mkm_sub_freq_ns", C.c_int64), ("mom_sub_freq_ns", C.c_int64),
         ("hist_log_cap", C.c_int32), ("hbl_table_rows", C.c_int32),
     ]
 

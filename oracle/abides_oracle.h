@@ -29,7 +29,8 @@ extern "C" {
 enum abo_kind {
   ABO_NONE = 0, ABO_WHEN_MKT_OPEN, ABO_WHEN_MKT_CLOSE, ABO_QUERY_SPREAD, ABO_LIMIT_ORDER, ABO_CANCEL_ORDER,
   ABO_MODIFY_ORDER, ABO_ORDER_ACCEPTED, ABO_ORDER_EXECUTED, ABO_ORDER_CANCELLED, ABO_MKT_CLOSED,
-  ABO_QUERY_LAST_TRADE, ABO_QUERY_TRANSACTED_VOLUME, ABO_ORDER_MODIFIED, ABO_QUERY_ORDER_STREAM, ABO_MARKET_DATA
+  ABO_QUERY_LAST_TRADE, ABO_QUERY_TRANSACTED_VOLUME, ABO_ORDER_MODIFIED, ABO_QUERY_ORDER_STREAM, ABO_MARKET_DATA,
+  ABO_MARKET_DATA_SUBSCRIPTION_REQUEST, ABO_MARKET_DATA_SUBSCRIPTION_CANCELLATION
 };
 /* queue entry types: message/Message.py:5-10 */
 enum abo_type { ABO_T_MESSAGE = 1, ABO_T_WAKEUP = 2, ABO_T_CANCEL_ORDER = 3 };

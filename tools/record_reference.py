@@ -38,6 +38,7 @@ MSG_KINDS = [
     "NONE", "WHEN_MKT_OPEN", "WHEN_MKT_CLOSE", "QUERY_SPREAD", "LIMIT_ORDER", "CANCEL_ORDER",
     "MODIFY_ORDER", "ORDER_ACCEPTED", "ORDER_EXECUTED", "ORDER_CANCELLED", "MKT_CLOSED",
     "QUERY_LAST_TRADE", "QUERY_TRANSACTED_VOLUME", "ORDER_MODIFIED", "QUERY_ORDER_STREAM", "MARKET_DATA",
+    "MARKET_DATA_SUBSCRIPTION_REQUEST", "MARKET_DATA_SUBSCRIPTION_CANCELLATION",
 ]
 KIND = {k: i for i, k in enumerate(MSG_KINDS)}
 
@@ -154,6 +155,8 @@ def install_hooks():
     if not hasattr(pandas.io.json, "json_normalize"):  # same alias tools/shims/sitecustomize.py installs
         pandas.io.json.json_normalize = pandas.json_normalize
 
+    if not hasattr(pandas.Timedelta, "delta"):       # pandas 2 dropped Timedelta.delta (total nanoseconds); agent/ExchangeAgent.py:373 and the subscription agents use it
+        pandas.Timedelta.delta = property(lambda self: self.value)
     queue.PriorityQueue = RecPQ
     np.random.RandomState = RecRS
 
@@ -250,6 +253,17 @@ def install_hooks():
             if b["asks"]:
                 row[10], row[11] = b["asks"][0]
             row[12] = int(bool(b["mkt_closed"]))
+        if b["msg"] == "MARKET_DATA":                                  # agent/ExchangeAgent.py:371-384: `levels` levels a side + last trade
+            bids, asks = b["bids"], b["asks"]
+            row[3], row[4] = len(bids), len(asks)
+            row[5] = sum((i + 1) * int(p) for i, (p, q) in enumerate(bids))     # position-weighted sums: every level's price and size is pinned
+            row[6] = sum((i + 1) * int(p) for i, (p, q) in enumerate(asks))
+            row[7] = -1 if b["last_transaction"] is None else int(b["last_transaction"])
+            if bids:
+                row[8], row[9] = bids[0]
+            if asks:
+                row[10], row[11] = asks[0]
+            row[12] = sum((i + 1) * (int(q) + 3 * int(q2)) for i, ((p, q), (p2, q2)) in enumerate(zip(bids, asks))) if bids and asks else 0
         REC.notes.append(tuple(int(x) for x in row))
         s0(self, recipientID, msg)
 
