@@ -120,6 +120,7 @@ struct abo_book {
   hbucket_t *hist; int nhist; int stream_history;
   hbucket_t *arch; int n_arch, cap_arch; int keep_dropped; int64_t next_serial;   /* buckets that fell off history[:stream_history+1] but may still be referenced by an agent's stream_history */
   int64_t now; void *owner; send_fn send;
+  int64_t last_update; int has_update;                     /* OrderBook.last_update_ts (:36,169,338,372): what publishOrderBookData compares with */
   i64buf notes; /* standalone use */
   int64_t n_fills;
 };
@@ -222,6 +223,7 @@ static void book_handle_limit(abo_book *b, order_t order) {
       b->nhist--; }
     memmove(b->hist + 1, b->hist, sizeof(hbucket_t) * b->nhist); memset(&b->hist[0], 0, sizeof(hbucket_t)); b->hist[0].serial = ++b->next_serial; b->nhist++;
   }
+  b->last_update = b->now; b->has_update = 1;                                        /* :169 */
 }
 /* cancelOrder :284-339 */
 static void book_cancel(abo_book *b, const order_t *order) {
@@ -235,6 +237,7 @@ static void book_cancel(abo_book *b, const order_t *order) {
           /* :314-321 history cancellations: never read back on this path */
           if (book->lv[i].n == 0) side_delete(book, i);                              /* :324-325 */
           b->send(b->owner, order->agent_id, ABO_ORDER_CANCELLED, &cancelled);       /* :334-336 recipient = REQUEST's agent_id */
+          b->last_update = b->now; b->has_update = 1;                                /* :338 only when the order was found */
           return;
         }
       }
@@ -259,6 +262,7 @@ static void book_modify(abo_book *b, const order_t *order, const order_t *new_or
       }
     }
   }
+  b->last_update = b->now; b->has_update = 1;                                        /* :372 */
 }
 static const hbucket_t *book_bucket(const abo_book *b, int64_t serial) {
   for (int i = 0; i < b->nhist; i++) if (b->hist[i].serial == serial) return &b->hist[i];
@@ -323,6 +327,8 @@ typedef struct {            /* one PriorityQueue entry: (deliverAt, (recipient, 
   order_t new_order;                                         /* MODIFY_ORDER body["new_order"] */
   int64_t tv, lookback;                                      /* QUERY_TRANSACTED_VOLUME: transacted_volume / lookback_period (ns); QUERY_ORDER_STREAM: lookback = length */
   int n_stream; int64_t stream_serial[16];                   /* QUERY_ORDER_STREAM reply: "orders" = history[1 : length + 1], as references to the book's dicts */
+  int md_nb, md_na; int64_t md_bids[10], md_asks[10]; int has_data;   /* MARKET_DATA: `levels` (price, quantity) pairs a side, last_transaction (None before the first trade) */
+  int sub_levels; double sub_freq;                           /* MARKET_DATA_SUBSCRIPTION_REQUEST body */
 } event_t;
 
 static inline int ev_less(const event_t *a, const event_t *b) { /* tuple order (t, recipient, type.value, msg.uniq) */
@@ -343,7 +349,7 @@ static void heap_pop(heap_t *h, event_t *out) { /* heapq.heappop */
 }
 
 typedef struct { int64_t order_id, quantity, limit_price; int is_buy; } open_order_t;
-enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE, ST_AWAITING_SPREAD, ST_AWAITING_TV_, ST_AWAITING_STREAM };
+enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE, ST_AWAITING_SPREAD, ST_AWAITING_TV_, ST_AWAITING_STREAM, ST_AWAITING_MARKET_DATA };
 
 typedef struct {            /* TradingAgent (agent/TradingAgent.py:19-98) + ZeroIntelligenceAgent (:65-70) state */
   abo_rng *rs; int group;
@@ -365,6 +371,7 @@ typedef struct {            /* TradingAgent (agent/TradingAgent.py:19-98) + Zero
   int64_t order_size, last_mid, transacted_volume; int has_last_mid, aw_spread, aw_vol;   /* POVMarketMakerAgent */
   int64_t *kside[2], *fside[2]; int nk[2], nf[2], capk; int64_t px_rem, px_executed, px_n_executed;   /* POVExecutionAgent: known_bids/asks (price, qty pairs), lists in flight, rem_quantity */
   int L, n_stream; int64_t stream_serial[16];           /* HeuristicBeliefLearningAgent: L, stream_history[symbol] (references to the exchange's history dicts) */
+  int subscribe, sub_requested; int kb_n, ka_n; int64_t kb[10], ka[10];   /* subscription mode: known_bids / known_asks as MARKET_DATA delivered them */
   int64_t mkm_min, mkm_max, last_spread;                /* MarketMakerAgent (agent/market_makers/MarketMakerAgent.py): min_size, max_size, last_spread (10, never updated) */
 } zi_t;
 enum { AT_ZI = 0, AT_NOISE, AT_VALUE, AT_MOMENTUM, AT_POVMM, AT_POVEXEC, AT_MKM, AT_HBL };
@@ -384,9 +391,12 @@ struct abo_sim {
   /* agents */
   zi_t *zi; double sigma_n, agent_kappa, sigma_s, lambda_a; int64_t order_size, starting_cash; double value_percent_aggr; int64_t value_depth_spread;
   double mm_pov; int64_t mm_min_size, mm_window, mm_ticks, mm_wake_ns, mom_wake_ns;   /* config/rmsc03.py:41-45,176-200 */
+  struct { int agent, levels; double freq; int64_t last; } subs[128]; int n_subs;      /* ExchangeAgent.subscription_dict in insertion order */
+  double mkm_sub_freq, mom_sub_freq;
   int64_t mkm_levels, mkm_wake_ns;                                                     /* MarketMakerAgent subscribe_num_levels (5), wake_up_freq ("1s") */
   int px_id, px_is_buy; double px_pov; int64_t px_quantity, px_start, px_end, px_freq, px_lookback;   /* POVExecutionAgent (agent/execution/baselines/pov_agent.py), 0 = none */
   /* traces */
+  i64buf live_qty;                                      /* by order id: quantity of the AGENT's order object (a CANCEL_ORDER message carries a reference to it, TradingAgent.py:399-406: partial fills the agent books while the message is in flight show in what the exchange receives) */
   i64buf pops, ops, notes, snaps; uint64_t pop_hash, note_hash, snap_hash; uint64_t *ckpt; int64_t n_ckpt, cap_ckpt;
   int64_t c_limit, c_cancel, c_query, max_queue, max_bid_lv, max_ask_lv, max_resting;
 };
@@ -461,6 +471,14 @@ static void trace_note(abo_sim *s, int recipient, const event_t *e) {
     row[3] = e->order.order_id; row[4] = e->order.is_buy; row[5] = e->order.quantity; row[6] = e->order.limit_price; row[7] = e->order.fill_price;
   }
   if (e->kind == ABO_QUERY_SPREAD) { row[7] = e->data; if (e->has_bid) { row[8] = e->bid; row[9] = e->bid_q; } if (e->has_ask) { row[10] = e->ask; row[11] = e->ask_q; } row[12] = e->mkt_closed; }
+  if (e->kind == ABO_MARKET_DATA) {                          /* the recorder's row: level counts, position-weighted price / size sums, top of book, last trade */
+    row[3] = e->md_nb; row[4] = e->md_na; row[7] = e->has_data ? e->data : -1;
+    for (int i = 0; i < e->md_nb; i++) row[5] += (i + 1) * e->md_bids[2 * i];
+    for (int i = 0; i < e->md_na; i++) row[6] += (i + 1) * e->md_asks[2 * i];
+    if (e->md_nb) { row[8] = e->md_bids[0]; row[9] = e->md_bids[1]; }
+    if (e->md_na) { row[10] = e->md_asks[0]; row[11] = e->md_asks[1]; }
+    for (int i = 0; i < e->md_nb && i < e->md_na; i++) row[12] += (i + 1) * (e->md_bids[2 * i + 1] + 3 * e->md_asks[2 * i + 1]);
+  }
   for (int i = 0; i < 13; i++) s->note_hash = fnv_mix(s->note_hash, row[i]);
   if (s->trace & ABO_TRACE_NOTES) ib_push(&s->notes, row, 13);
 }
@@ -490,6 +508,19 @@ static void trace_op(abo_sim *s, int op, const order_t *o, int64_t np, int64_t n
   if (!(s->trace & ABO_TRACE_OPS)) return;
   int64_t row[9] = { s->now, op, o->agent_id, o->order_id, o->is_buy, o->limit_price, o->quantity, np, nq }; ib_push(&s->ops, row, 9);
 }
+/* ExchangeAgent.publishOrderBookData :359-387 */
+static void exch_publish(abo_sim *s) {
+  for (int k = 0; k < s->n_subs; k++) {
+    int64_t lu = s->book.last_update, last = s->subs[k].last;
+    if (!(s->subs[k].freq == 0 || (lu > last && (double)(lu - last) >= s->subs[k].freq))) continue;
+    event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_MARKET_DATA;
+    int lv = s->subs[k].levels > 5 ? 5 : s->subs[k].levels;
+    e.md_nb = book_inside(&s->book, 1, lv, e.md_bids); e.md_na = book_inside(&s->book, 0, lv, e.md_asks);
+    e.data = s->book.last_trade; e.has_data = s->book.has_last_trade;
+    exch_send(s, s->subs[k].agent, &e);
+    s->subs[k].last = lu;
+  }
+}
 /* ExchangeAgent.receiveMessage :129-340 */
 static void exch_receive(abo_sim *s, const event_t *m) {
   s->comp_delay[0] = s->exch_comp_delay;                                                    /* :139 */
@@ -498,6 +529,12 @@ static void exch_receive(abo_sim *s, const event_t *m) {
     int is_order = m->kind == ABO_LIMIT_ORDER || m->kind == ABO_CANCEL_ORDER || m->kind == ABO_MODIFY_ORDER;
     int is_query = m->kind == ABO_QUERY_SPREAD || m->kind == ABO_QUERY_LAST_TRADE || m->kind == ABO_QUERY_TRANSACTED_VOLUME || m->kind == ABO_QUERY_ORDER_STREAM;
     if (is_order || !is_query) { event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_MKT_CLOSED; exch_send(s, m->sender, &e); return; }
+  }
+  if (m->kind == ABO_MARKET_DATA_SUBSCRIPTION_REQUEST) {                                   /* updateSubscriptionDict :342-357: dict[agent] = {symbol: [levels, freq, now]} (a repeat keeps its place) */
+    int k = 0; while (k < s->n_subs && s->subs[k].agent != m->sender) k++;
+    if (k == s->n_subs) { if (s->n_subs == 128) { fprintf(stderr, "abides_oracle: more than 128 subscribers\n"); return; } s->n_subs++; }
+    s->subs[k].agent = m->sender; s->subs[k].levels = m->sub_levels; s->subs[k].freq = m->sub_freq; s->subs[k].last = s->now;
+    return;
   }
   event_t e; memset(&e, 0, sizeof(e));
   switch (m->kind) {
@@ -518,8 +555,8 @@ static void exch_receive(abo_sim *s, const event_t *m) {
         if (need > a->capk) { a->capk = need * 2 + 64; for (int k = 0; k < 2; k++) { a->kside[k] = (int64_t *)realloc(a->kside[k], 16 * a->capk); a->fside[k] = (int64_t *)realloc(a->fside[k], 16 * a->capk); } }
         a->nf[0] = book_inside(&s->book, 1, a->capk, a->fside[0]); a->nf[1] = book_inside(&s->book, 0, a->capk, a->fside[1]); }
       e.data = s->book.last_trade; e.mkt_closed = t_closed; exch_send(s, m->sender, &e); break; }
-    case ABO_LIMIT_ORDER: s->c_limit++; trace_op(s, 0, &m->order, 0, 0); s->book.now = s->now; book_handle_limit(&s->book, m->order); trace_snap(s); break; /* :304-312 */
-    case ABO_CANCEL_ORDER: s->c_cancel++; trace_op(s, 1, &m->order, 0, 0); s->book.now = s->now; book_cancel(&s->book, &m->order); trace_snap(s); break;   /* :313-325 */
+    case ABO_LIMIT_ORDER: s->c_limit++; trace_op(s, 0, &m->order, 0, 0); s->book.now = s->now; book_handle_limit(&s->book, m->order); trace_snap(s); exch_publish(s); break; /* :304-312 */
+    case ABO_CANCEL_ORDER: s->c_cancel++; { order_t seen = m->order; if (seen.order_id < s->live_qty.n && s->live_qty.v[seen.order_id] > 0) seen.quantity = s->live_qty.v[seen.order_id]; trace_op(s, 1, &seen, 0, 0); } s->book.now = s->now; book_cancel(&s->book, &m->order); trace_snap(s); exch_publish(s); break;   /* :313-325 */
     default: break;
   }
 }
@@ -592,6 +629,7 @@ static void ta_place_limit(abo_sim *s, int id, int64_t qty, int is_buy, int64_t 
   if (qty <= 0) return;
   if (a->n_orders == a->cap_orders) { a->cap_orders = a->cap_orders ? a->cap_orders * 2 : 4; a->orders = (open_order_t *)realloc(a->orders, sizeof(open_order_t) * a->cap_orders); }
   open_order_t *oo = &a->orders[a->n_orders++]; oo->order_id = oid; oo->quantity = qty; oo->limit_price = price; oo->is_buy = is_buy; /* :342 */
+  if (s->trace & ABO_TRACE_OPS) { while (s->live_qty.n <= oid) { int64_t z = 0; ib_push(&s->live_qty, &z, 1); } s->live_qty.v[oid] = qty; }
   event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_LIMIT_ORDER;
   e.order.agent_id = id; e.order.order_id = oid; e.order.quantity = qty; e.order.limit_price = price; e.order.is_buy = is_buy;
   ta_send(s, id, &e);                                                                       /* :343 */
@@ -647,13 +685,42 @@ static void hbl_place_order(abo_sim *s, int id) {
 static int64_t mkm_draw_size(zi_t *a) { double h = (double)abo_rng_randint(a->rs, a->mkm_min, a->mkm_max) / 2; return (int64_t)nearbyint(h); }   /* round(randint(min, max) / 2): half to even */
 static void ta_cancel_all(abo_sim *s, int id);
 static int ta_wakeup_common(abo_sim *s, int id);
+/* TradingAgent.requestDataSubscription :160-172 */
+static void ta_request_subscription(abo_sim *s, int id, int levels, double freq) {
+  event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_MARKET_DATA_SUBSCRIPTION_REQUEST; e.sub_levels = levels; e.sub_freq = freq; ta_send(s, id, &e);
+}
 static void mkm_wakeup(abo_sim *s, int id) {
   zi_t *a = &s->zi[id];
-  if (!ta_wakeup_common(s, id)) return;
+  int can_trade = ta_wakeup_common(s, id);
+  if (a->subscribe) {                                                                        /* :69-72: the subscription is requested at the very first wake-up; nothing else ever happens on a wake-up */
+    if (!a->sub_requested) { ta_request_subscription(s, id, (int)s->mkm_levels, s->mkm_sub_freq); a->sub_requested = 1; a->state = ST_AWAITING_MARKET_DATA; }
+    return;
+  }
+  if (!can_trade) return;
   ta_cancel_all(s, id); ta_get_spread(s, id); a->state = ST_AWAITING_SPREAD;                 /* getCurrentSpread(depth=subscribe_num_levels): the agent reads level 0 only */
 }
+static void ta_place_limit(abo_sim *s, int id, int64_t qty, int is_buy, int64_t price);
 static void mkm_receive_tail(abo_sim *s, int id, const event_t *m) {
   zi_t *a = &s->zi[id];
+  if (a->subscribe) {                                                                        /* :108-139 subscription mode */
+    static const double split[5][5] = { { 1, 0, 0, 0, 0 }, { 0.5, 0.5, 0, 0, 0 }, { 0.34, 0.33, 0.33, 0, 0 }, { 0.25, 0.25, 0.25, 0.25, 0 }, { 0.20, 0.20, 0.20, 0.20, 0.20 } };   /* DEFAULT_LEVELS_QUOTE_DICT :6-12 */
+    if (!(a->state == ST_AWAITING_MARKET_DATA && m->kind == ABO_MARKET_DATA)) return;
+    ta_cancel_all(s, id);
+    int num_levels = (int)abo_rng_randint(a->rs, 1, 5);                                      /* randint(1, len(levels_quote_dict)) -> 1..4 */
+    if (a->kb_n && a->ka_n) {                                                                /* placeOrders :120-139 */
+      a->size = mkm_draw_size(a);
+      int64_t bp[5], bv[5], ap[5], av[5]; int nbq = 0, naq = 0;                              /* buy_quotes / sell_quotes: dicts keyed by price (a repeated key keeps its place, takes the new volume) */
+      for (int i = 0; i < num_levels; i++) {
+        int64_t vol = py_round(split[num_levels - 1][i] * (double)a->size);
+        int64_t pb = i < a->kb_n ? a->kb[2 * i] : a->kb[2 * (a->kb_n - 1)] - 1, pa = i < a->ka_n ? a->ka[2 * i] : a->ka[2 * (a->ka_n - 1)] + 1;
+        int k = 0; while (k < nbq && bp[k] != pb) k++; if (k == nbq) nbq++; bp[k] = pb; bv[k] = vol;
+        k = 0; while (k < naq && ap[k] != pa) k++; if (k == naq) naq++; ap[k] = pa; av[k] = vol;
+      }
+      for (int k = 0; k < nbq; k++) ta_place_limit(s, id, bv[k], 1, bp[k]);
+      for (int k = 0; k < naq; k++) ta_place_limit(s, id, av[k], 0, ap[k]);
+    }
+    return;
+  }
   if (!(a->state == ST_AWAITING_SPREAD && m->kind == ABO_QUERY_SPREAD)) return;
   ta_cancel_all(s, id);
   int64_t mid = a->last_trade, spread;
@@ -681,7 +748,7 @@ static void zi_receive(abo_sim *s, int id, const event_t *m) {
       int64_t qty = m->order.is_buy ? m->order.quantity : -m->order.quantity;
       a->shares += qty; a->cash -= qty * m->order.fill_price;
       for (int i = 0; i < a->n_orders; i++) if (a->orders[i].order_id == m->order.order_id) {
-        if (m->order.quantity >= a->orders[i].quantity) orders_remove(a, i); else a->orders[i].quantity -= m->order.quantity; break; }
+        if (m->order.quantity >= a->orders[i].quantity) orders_remove(a, i); else { a->orders[i].quantity -= m->order.quantity; if (m->order.order_id < s->live_qty.n) s->live_qty.v[m->order.order_id] = a->orders[i].quantity; } break; }
       if (a->type == AT_POVEXEC) { a->px_executed += m->order.quantity; a->px_n_executed++; a->px_rem = s->px_quantity - a->px_executed; }   /* handleOrderExecution :103-107 */
       break; }
     case ABO_ORDER_ACCEPTED: break;
@@ -689,6 +756,11 @@ static void zi_receive(abo_sim *s, int id, const event_t *m) {
       for (int i = 0; i < a->n_orders; i++) if (a->orders[i].order_id == m->order.order_id) { orders_remove(a, i); break; }
       break;
     case ABO_MKT_CLOSED: a->mkt_closed = 1; break;                                          /* marketClosed :492-499 */
+    case ABO_MARKET_DATA:                                                                   /* handleMarketData :539-546 */
+      a->kb_n = m->md_nb; a->ka_n = m->md_na; memcpy(a->kb, m->md_bids, sizeof(a->kb)); memcpy(a->ka, m->md_asks, sizeof(a->ka));
+      a->has_known = 1; a->has_bid = m->md_nb > 0; a->bid = m->md_bids[0]; a->bid_q = m->md_bids[1]; a->has_ask = m->md_na > 0; a->ask = m->md_asks[0]; a->ask_q = m->md_asks[1];
+      a->last_trade = m->data; a->has_last_trade = m->has_data;
+      break;
     case ABO_QUERY_TRANSACTED_VOLUME: if (m->mkt_closed) a->mkt_closed = 1; a->transacted_volume = m->tv; break;   /* :248-251,556-558 */
     case ABO_QUERY_ORDER_STREAM: if (m->mkt_closed) a->mkt_closed = 1; a->n_stream = m->n_stream; memcpy(a->stream_serial, m->stream_serial, sizeof(a->stream_serial)); break;   /* :240-246,549-554 */
     case ABO_QUERY_SPREAD:                                                                  /* :232-238, querySpread :514-537, queryLastTrade :502-511 */
@@ -709,6 +781,7 @@ static void zi_receive(abo_sim *s, int id, const event_t *m) {
   if (a->type == AT_MKM) { mkm_receive_tail(s, id, m); return; }
   if (a->type == AT_POVEXEC) { povexec_receive_tail(s, id, m); return; }
   if (a->type == AT_MOMENTUM) {                                                             /* MomentumAgent.receiveMessage :65-76 */
+    if (a->subscribe) { if (a->state == ST_AWAITING_MARKET_DATA && m->kind == ABO_MARKET_DATA && a->kb_n && a->ka_n) momentum_place_orders(s, id); return; }   /* :71-75 placeOrders(bids[0][0], asks[0][0]) */
     if (a->state == ST_AWAITING_SPREAD && m->kind == ABO_QUERY_SPREAD) { momentum_place_orders(s, id); k_set_wakeup(s, id, s->now + s->mom_wake_ns); a->state = ST_AWAITING_WAKEUP; }
     return;
   }
@@ -797,7 +870,9 @@ static void value_place_order(abo_sim *s, int id) {
 /* MomentumAgent.wakeup (agent/examples/MomentumAgent.py:53-63) */
 static void momentum_wakeup(abo_sim *s, int id) {
   zi_t *a = &s->zi[id];
-  if (ta_wakeup_common(s, id)) { ta_get_spread(s, id); a->state = ST_AWAITING_SPREAD; }
+  int can_trade = ta_wakeup_common(s, id);
+  if (a->subscribe) { if (!a->sub_requested) { ta_request_subscription(s, id, 1, s->mom_sub_freq); a->sub_requested = 1; a->state = ST_AWAITING_MARKET_DATA; } return; }   /* :56-59 levels=1, freq=10e9 */
+  if (can_trade) { ta_get_spread(s, id); a->state = ST_AWAITING_SPREAD; }
 }
 static double np_round2(double x) { return nearbyint(x * 100.0) / 100.0; }                   /* numpy float64.round(2) */
 static void momentum_place_orders(abo_sim *s, int id) {                                     /* placeOrders :78-93, ma :95-99 */
@@ -906,6 +981,13 @@ int abo_default_config(int variant, abx_sim_config *c) {
     c->mm_pov = 0.05; c->mm_min_order_size = 20; c->mm_window_size = 5; c->mm_num_ticks = 20; c->mm_wake_ns = NS_PER_S;   /* :41-45 */
     if (variant == 4) { c->n_pov_exec = 1; c->n_agents += 1; c->pov_exec_is_buy = 1; c->pov_exec_pov = 0.5; c->pov_exec_quantity = 120000;
       c->pov_exec_start_ns = (9 * 3600 + 32 * 60) * NS_PER_S; c->pov_exec_end_ns = (9 * 3600 + 43 * 60) * NS_PER_S; c->pov_exec_freq_ns = 30 * NS_PER_S; c->pov_exec_lookback_ns = 30 * NS_PER_S; }
+    return 0;
+  }
+  if (variant == 2) {                                                                       /* config/rmsc02.py: rmsc01 + subscription mode + the sparse_zi_1000 latency, midnight .. 17:00 */
+    if (abo_default_config(1, c)) return -1;
+    c->mkm_subscribe = 1; c->mom_subscribe = 1; c->mkm_sub_freq_ns = 10 * NS_PER_S; c->mom_sub_freq_ns = 10 * NS_PER_S;   /* :108,205; MarketMakerAgent subscribe_freq=10e9, MomentumAgent.py:58 */
+    c->start_ns = 0; c->stop_ns = 17 * 3600 * NS_PER_S;                                      /* :264-265 */
+    c->latency_model = ABX_LAT_MATRIX_NOISE; c->n_noise = 6; c->latency_mirrored = 0; c->latency_lo = 21000; c->latency_hi = 13000000;   /* :268-269 */
     return 0;
   }
   if (variant == 1) {                                                                       /* config/rmsc01.py */
@@ -1062,6 +1144,12 @@ static abo_sim *new_population3(const abx_sim_config *c, uint32_t seed, int trac
   for (int id = 1; id < n; id++) { zi_t *a = &s->zi[id]; a->starting_cash = a->cash = c->starting_cash; a->first_wake = 1; a->state = ST_AWAITING_WAKEUP; if (!a->q_max) a->q_max = c->q_max; }
   s->kernel_rs = new_stream(s);
   s->latency = (double *)calloc((size_t)n * n, sizeof(double)); s->n_noise = 1; s->use_latency_model = 0;
+  if (c->latency_model == ABX_LAT_MATRIX_NOISE) {                                      /* config/rmsc02.py:268-269: np.random.uniform(low, high, size=(n, n)) row major, noise list of n_noise entries */
+    for (size_t k = 0; k < (size_t)n * n; k++) s->latency[k] = rng_uniform(s->g, c->latency_lo, c->latency_hi);
+    s->n_noise = c->n_noise;
+  }
+  for (int id = 1; id < n; id++) { zi_t *a = &s->zi[id]; a->subscribe = a->type == AT_MKM ? c->mkm_subscribe : a->type == AT_MOMENTUM ? c->mom_subscribe : 0; }
+  s->mkm_sub_freq = (double)c->mkm_sub_freq_ns; s->mom_sub_freq = (double)c->mom_sub_freq_ns;
   s->agent_time = (int64_t *)calloc(n, sizeof(int64_t)); s->comp_delay = (int64_t *)calloc(n, sizeof(int64_t));
   for (int i = 0; i < n; i++) { s->agent_time[i] = s->start_time; s->comp_delay[i] = c->default_computation_delay_ns; }
   return s;
@@ -1118,7 +1206,7 @@ void abo_sim_free(abo_sim *s) {
   if (!s) return;
   for (int i = 1; i < s->n_agents; i++) { abo_rng_free(s->zi[i].rs); free(s->zi[i].orders); free(s->zi[i].mids); for (int k = 0; k < 2; k++) { free(s->zi[i].kside[k]); free(s->zi[i].fside[k]); } }
   free(s->zi); abo_rng_free(s->g); abo_rng_free(s->kernel_rs); abo_rng_free(s->lat_rs); abo_rng_free(s->sym_rs); abo_rng_free(s->exch_rs);
-  book_destroy(&s->book); free(s->latency); free(s->agent_time); free(s->comp_delay); free(s->q.e); free(s->gexp);
+  book_destroy(&s->book); free(s->latency); free(s->agent_time); free(s->comp_delay); free(s->q.e); free(s->gexp); free(s->live_qty.v);
   free(s->pops.v); free(s->ops.v); free(s->notes.v); free(s->snaps.v); free(s->ckpt); free(s);
 }
 

@@ -75,6 +75,24 @@ def oracle_rmsc01_config(stop_ns=(9 * 3600 + 45 * 60) * 10 ** 9):
     return cfg
 
 
+def oracle_rmsc02_config(stop_ns=17 * 3600 * 10 ** 9):
+    """config/rmsc02.py as the oracle states it (abo_default_config(2)): the rmsc01 population with the market maker and the momentum agents in subscription
+    mode, the sparse_zi_1000 latency model (uniform 21 us .. 13 ms matrix, 6-entry noise), midnight .. 17:00."""
+    import ctypes as C
+    from marl_optimal_execution_b200 import _lib
+    from oracle.oracle import lib
+    cfg = _lib.SimConfig()
+    assert lib().abo_default_config(2, C.addressof(cfg)) == 0
+    cfg.stop_ns = stop_ns
+    return cfg
+
+
+def oracle_rmsc02(seed, stop_ns, trace):
+    from oracle.oracle import OracleSim
+    o = OracleSim.from_config(oracle_rmsc02_config(stop_ns), seed, trace)
+    return o, o.run()
+
+
 def oracle_rmsc01(seed, stop_ns, trace):
     """A finished OracleSim of the rmsc01 population and its message count."""
     from oracle.oracle import OracleSim

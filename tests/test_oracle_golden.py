@@ -119,3 +119,21 @@ def test_rmsc01_full_trace_bit_exact(golden_dir):
     assert np.array_equal(s.holdings()[:, :4], g["holdings"][:, :4])
     mine, ref = [len(s.tape(i)[0]) for i in range(s.n_streams)], [int(x) for x in g["stream_draws"]]
     assert mine[3:] == ref[3:] and sorted(mine[:3]) == sorted(ref[:3])     # config/rmsc01.py creates its first three streams in another order
+
+
+def test_rmsc02_full_day_bit_exact(golden_dir):
+    """config/rmsc02.py, the WHOLE day run live (tools/record_reference.py rmsc02 123456789 --full): the rmsc01 population with MARKET_DATA subscriptions
+    (agent/ExchangeAgent.py:342-387: 25 subscribers served in subscription order after every book operation, at most every 10 s each), the market maker's
+    subscription-mode ladder (1-4 levels, levels_quote_dict split), pairwise latency + noise.  117 238 pops, 31 938 book operations -- incl. the quantity a
+    CANCEL_ORDER shows at the exchange when the agent booked a partial fill while the message was in flight (the message references the agent's order object)
+    -- 80 336 exchange messages with every level of every MARKET_DATA body, every book snapshot, the final holdings."""
+    from helpers import oracle_rmsc02_config
+    g = np.load(os.path.join(golden_dir, "rmsc02_s123456789.npz"))
+    s = OracleSim.from_config(oracle_rmsc02_config(), 123456789, TRACE_ALL)
+    assert s.run() == int(g["n_pops"]) == 117238
+    for name in ("pops", "ops", "notes", "snaps"):
+        assert np.array_equal(s.trace(name), g[name]), name
+    assert np.array_equal(s.hash_ckpt(), g["pop_hash_ckpt"])
+    assert np.array_equal(s.holdings()[:, :4], g["holdings"][:, :4])
+    notes = s.trace("notes")
+    assert (notes[:, 2] == 15).sum() > 20000            # MARKET_DATA
