@@ -362,11 +362,12 @@ def run_ours(args, rank, local_rank, world):
     if not args.no_rmsc03:
         sim.close()
         r3_local = bench_rmsc03(args, rank, local_rank, dev, stream, sp)
-    r1_local = None
+    r1_local = r2_local = None
     if not args.no_rmsc01:
         if not sim_closed(sim):
             sim.close()
         r1_local = bench_rmsc01(args, rank, local_rank, dev, stream, sp)
+        r2_local = bench_rmsc01(args, rank, local_rank, dev, stream, sp, subscriptions=True)
     mr_local = None
     if not args.no_marketreplay:
         if not sim_closed(sim):
@@ -420,6 +421,13 @@ def run_ours(args, rank, local_rank, world):
                     "workload": "config/rmsc01.py shape: MarketMakerAgent + 50 ZI + 25 HeuristicBeliefLearningAgents (QUERY_ORDER_STREAM, L = 2) + 24 MomentumAgents + exchange, "
                                 "09:30-10:00 of the day, zero latency, %d envs/GPU (Philox streams), one abx_run_kernel<0,2,0,5> launch; one timed run on fresh seeds after a "
                                 "warm-up run, resets untimed" % args.rmsc01_envs_per_gpu}
+    if r2_local is not None:
+        g2 = D.gather_summaries(torch.tensor([r2_local["msgs"], r2_local["errs"], r2_local["hbl_orders"]], dtype=torch.int64), device=dev)
+        t2 = D.max_over_ranks(r2_local["ms"], device=dev) / 1e3
+        r1_block["rmsc02"] = {"metric": "LOB msgs/sec (rmsc02)", "unit": "msgs/s", "value": int(g2[:, 0].sum()) / t2, "ms_per_run": 1e3 * t2,
+                              "messages_per_env_run": int(g2[:, 0].sum()) / (world * args.rmsc01_envs_per_gpu), "error_envs": int(g2[:, 1].sum()), "gpu_launches": int(r2_local["launches"]),
+                              "workload": "config/rmsc02.py shape: the rmsc01 population with MARKET_DATA subscriptions (market maker + 24 momentum agents), pairwise latency U(21 us, 13 ms) + "
+                                          "6-entry noise; the WHOLE day 00:00-17:00 of %d envs/GPU in one abx_run_kernel<0,0,0,5> launch" % args.rmsc01_envs_per_gpu}
     env_block = None
     if env_local is not None:
         ge = D.gather_summaries(torch.tensor([env_local["steps"], env_local["msgs"], env_local["e2e_steps"], env_local["errs"]], dtype=torch.int64), device=dev)
@@ -569,14 +577,14 @@ def bench_rmsc03(args, rank, local_rank, dev, stream, sp):
     return out
 
 
-def bench_rmsc01(args, rank, local_rank, dev, stream, sp):
+def bench_rmsc01(args, rank, local_rank, dev, stream, sp, subscriptions=False):
     """config/rmsc01.py population (MarketMakerAgent, ZI, HBL over QUERY_ORDER_STREAM, Momentum); the first half hour of the day of every
     environment in one abx_run_kernel launch.  Reset untimed; one warm-up run, one timed run on fresh seeds."""
     import torch
     from marl_optimal_execution_b200 import _lib, distributed as D
-    from marl_optimal_execution_b200.sim import BatchedSim, rmsc01_config
+    from marl_optimal_execution_b200.sim import BatchedSim, rmsc01_config, rmsc02_config
     n = args.rmsc01_envs_per_gpu
-    sim = BatchedSim(rmsc01_config(stop_ns=10 * 3600 * NS), n, device=local_rank)
+    sim = BatchedSim(rmsc02_config() if subscriptions else rmsc01_config(stop_ns=10 * 3600 * NS), n, device=local_rank)      # rmsc02: the whole day (~1.2e5 messages)
     res = None
     for rep in range(2):
         sim.reset(D.env_seeds(args.seed + 700001 * rep, rank * n, (rank + 1) * n), stream=sp)

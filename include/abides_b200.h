@@ -188,6 +188,9 @@ int32_t abx_config_rmsc03_pov(abx_sim_config *cfg);
 /* config/rmsc01.py:60-262: 1 exchange + 1 MarketMakerAgent + 50 ZeroIntelligenceAgents + 25 HeuristicBeliefLearningAgents (L = 2, served by the exchange's
  * QUERY_ORDER_STREAM, agent/ExchangeAgent.py:251-279) + 24 MomentumAgents, 09:30 -> 16:00 (+1 min); zero latency, zero computation delay. */
 int32_t abx_config_rmsc01(abx_sim_config *cfg);
+/* config/rmsc02.py: the rmsc01 population with the market maker and the momentum agents in subscription mode (MARKET_DATA), pairwise latency U(21 us, 13 ms) + 6-entry
+ * noise, midnight -> 17:00. */
+int32_t abx_config_rmsc02(abx_sim_config *cfg);
 /* POVExecutionAgent of one environment: out HOST int64 [3] = remaining quantity, executed orders, open orders. */
 int32_t abx_sim_pov_exec(abx_sim *h, int32_t env, int64_t *out, void *stream);
 

@@ -8,6 +8,7 @@ Flags mirrored (same spelling, same defaults):
   sparse_zi_100 / sparse_zi_1000   -s/--seed, -l/--log_dir, -b/--book_freq, -o/--log_orders, -v (config/sparse_zi_1000.py:17-34; logging flags accepted, no effect)
   rmsc03                           -t/--ticker, -d/--historical-date, -s, -l, -v, --mm-pov, --mm-min-order-size, --mm-window-size, --mm-num-ticks,
                                    --mm-wake-up-freq, --wide-book (config/rmsc03.py:30-46)
+  rmsc01 / rmsc02                  -s, -l, -v, -a/--agent_name (config/rmsc01.py:28-40; an --agent_name "agent under test" is a Python class and is rejected)
   marketreplay                     -t/--ticker, -d/--date, -l, -lvl/--level, -s, -v (config/marketreplay.py:19-28): ABIDESEnv with order_level 0
 """
 import argparse
@@ -16,7 +17,7 @@ import re
 import numpy as np
 
 from .env import ABIDESEnv, env_config, lobster_message_path, load_lobster_csv
-from .sim import BatchedSim, rmsc03_config, sparse_zi_config
+from .sim import BatchedSim, rmsc01_config, rmsc02_config, rmsc03_config, sparse_zi_config
 
 NS = 10 ** 9
 _UNITS = {"ns": 1, "us": 10 ** 3, "ms": 10 ** 6, "s": NS, "S": NS, "sec": NS, "min": 60 * NS, "T": 60 * NS, "h": 3600 * NS, "H": 3600 * NS}
@@ -65,6 +66,12 @@ def from_argv(argv, lib=None):
         a, _ = p.parse_known_args(argv)
         cfg = rmsc03_config(lib=lib, mm_pov=a.mm_pov, mm_min_order_size=a.mm_min_order_size, mm_window_size=a.mm_window_size, mm_num_ticks=a.mm_num_ticks,
                             mm_wake_ns=timedelta_ns(a.mm_wake_up_freq))
+    elif config in ("rmsc01", "rmsc02"):
+        p.add_argument("-a", "--agent_name", default=None)
+        a, _ = p.parse_known_args(argv)
+        if a.agent_name is not None:
+            raise SystemExit("abides.py -c %s -a %s: a user-defined agent under test is a Python class; outside the batched simulator's scope" % (config, a.agent_name))
+        cfg = (rmsc01_config if config == "rmsc01" else rmsc02_config)(lib=lib)
     elif config == "marketreplay":
         p.add_argument("-t", "--ticker", required=True)
         p.add_argument("-d", "--date", required=True)
@@ -72,7 +79,7 @@ def from_argv(argv, lib=None):
         a, _ = p.parse_known_args(argv)
         cfg = env_config(lib=lib, order_level=0, stop_ns=(16 * 3600 + 60) * NS, queue_cap=256, level_cap=1024)     # config/marketreplay.py:60-62 kernel stop 16:01
     else:
-        raise SystemExit("abides.py -c %s: this config is outside the batched simulator's scope (sparse_zi_100, sparse_zi_1000, rmsc03, marketreplay)" % config)
+        raise SystemExit("abides.py -c %s: this config is outside the batched simulator's scope (sparse_zi_100, sparse_zi_1000, rmsc01, rmsc02, rmsc03, marketreplay)" % config)
     seed = 0 if a.seed is None else int(a.seed)
 
     def run(n_envs=1, device=0, data_root="data/lobster", lib_path=None, **overrides):

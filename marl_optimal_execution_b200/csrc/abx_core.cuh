@@ -54,7 +54,7 @@ struct alignas(16) EnvState {           // 192 B per environment
   int64_t sum_shares, sum_cash;
   uint32_t kblk[4];                     // cached Philox block of the kernel (latency-noise) stream
   uint32_t draw_n, evt_n, book_flags, episode; // entries in the draw log (parity runs) / in the LAST_TRADE, BEST_BID, BEST_ASK event ring; BKF_*; resets of this environment that moved on to the next replayed day
-  uint32_t hist_n, pad_h0, pad_h1, pad_h2;     // orders registered in the order-history log (population 3: what QUERY_ORDER_STREAM hands out)
+  uint32_t hist_n, n_subs; int64_t book_update; // orders registered in the order-history log (population 3: what QUERY_ORDER_STREAM hands out); subscribers (ExchangeAgent.subscription_dict); OrderBook.last_update_ts
 };
 static_assert(sizeof(EnvState) == 224, "EnvState layout");
 
@@ -63,7 +63,7 @@ enum : uint32_t {
   AF_HAS_BID = 64u, AF_HAS_ASK = 128u, AF_STATE_SHIFT = 8, AF_STATE_MASK = 3u << 8, AF_GROUP_SHIFT = 12, AF_GROUP_MASK = 7u << 12
 };
 enum { ST_AWAITING_WAKEUP = 0, ST_INACTIVE = 1, ST_AWAITING_SPREAD = 2, ST_AWAITING_TV = 3, ST_AWAITING_STREAM = 3 };   // 3: AWAITING_TRANSACTED_VOLUME (POV execution agent) or AWAITING_STREAM (HBL agent): no class uses both // ZeroIntelligenceAgent.state; POVExecutionAgent AWAITING_TRANSACTED_VOLUME
-enum : uint32_t { AF_TYPE_SHIFT = 16, AF_TYPE_MASK = 15u << 16 };
+enum : uint32_t { AF_TYPE_SHIFT = 16, AF_TYPE_MASK = 15u << 16, AF_SUB_REQUESTED = 1u << 20 };   // AF_SUB_REQUESTED: subscription mode, request sent (the agent's state is AWAITING_MARKET_DATA from then on)
 enum { AT_ZI = 0, AT_NOISE = 1, AT_VALUE = 2, AT_MOMENTUM = 3, AT_POVMM = 4, AT_TWAP = 5, AT_DDQN = 6, AT_POVEXEC = 7, AT_MKM = 8, AT_HBL = 9 };   // agent class (rmsc03 / DDQN execution populations)
 constexpr uint32_t EPOCH_START = 16;    // EnvState.trade_epoch of a fresh book (so that epoch differences of up to 16 never wrap below zero)
 constexpr int AGENT_ORDER_CAP = 4;      // open orders tracked per trader (ZI holds <= 2)
@@ -101,6 +101,8 @@ enum : uint32_t { EXF_TRADE = 1u, EXF_E_VALID = 2u, EXF_E_R = 4u };
 constexpr int EXEC_ORDER_CAP = 512;     // self.orders of one execution agent
 constexpr int DQ_DEPTH = 500;           // getCurrentSpread(depth=500) execution_agent.py:77, ddqlearning_execution_agent.py:152
 enum : uint32_t { MMF_AW_SPREAD = 1u, MMF_AW_VOL = 2u, MMF_HAS_MID = 4u, MOF_HAS20 = 8u, MOF_HAS50 = 16u };
+constexpr int SUB_CAP = 64;             // market-data subscribers per exchange (config/rmsc02.py has 25); their table follows the market maker's orders in idtab
+constexpr int SUB_LEVELS = 8;           // levels a side a MARKET_DATA body can carry (MarketMakerAgent subscribes to 5)
 constexpr int MM_ORDER_CAP = 128;       // POV market maker: 2 * (num_ticks + 1) = 42 orders placed per wake, cancelled at the next
 constexpr int TV_RING_MIN = 512;        // recent (time, qty) transaction tuples kept for get_transacted_volume: SimParams.tv_ring >= this, 64 per surviving history bucket
 constexpr int MOM_MIDS = 64;            // MomentumAgent: last 50 mid prices are all ma(20)/ma(50) need
@@ -406,6 +408,17 @@ ABX_HD void init_agent_record_r3(const SimParams &P, int env, int id, uint64_t s
 }
 // round(x / 2) of MarketMakerAgent.size (agent/market_makers/MarketMakerAgent.py:55,99): Python's round half to even on the float quotient
 ABX_HD int32_t mkm_half(int64_t v) { return (int32_t)rint((double)v / 2); }
+// the trader's pair of entries of the config's latency matrix (to / from the exchange): zero (ABX_LAT_ZERO), what abx_sim_reset_tape handed in (tape mode), or
+// drawn per environment from the matrix' own Philox stream
+template <class R> ABX_HD void init_latency_pair(const SimParams &P, R &rng, int id, const ZiAgent *z, double &lat_to, double &lat_from) {
+  lat_to = z->lat_to; lat_from = z->lat_from;
+  if (P.c.latency_model == ABX_LAT_ZERO) { lat_to = 0.0; lat_from = 0.0; }              // np.zeros latency matrix (config/rmsc01.py:250)
+  else if (P.c.rng_mode == ABX_RNG_PHILOX) {
+    uint32_t c2 = 0; int cs = P.n_streams + id;
+    lat_to = dadd(P.c.latency_lo, dmul(dsub(P.c.latency_hi, P.c.latency_lo), rng.u01(cs, c2)));
+    lat_from = P.c.latency_mirrored ? lat_to : dadd(P.c.latency_lo, dmul(dsub(P.c.latency_hi, P.c.latency_lo), rng.u01(cs, c2)));
+  }
+}
 ABX_HD void init_agent_record(const SimParams &P, int env, int id, uint64_t seed, ZiAgent *z, uint32_t *err) {
   if (P.c.population == 1) { init_agent_record_r3(P, env, id, seed, z, err); return; }
   Rng rng; rng.P = &P; rng.env = P.n_tapes > 0 ? env % P.n_tapes : env; rng.seed = seed; rng.err = 0;
@@ -421,7 +434,8 @@ ABX_HD void init_agent_record(const SimParams &P, int env, int id, uint64_t seed
     for (int i = 0; i < AGENT_ORDER_CAP; i++) { z->oid[i] = 0; z->oprice[i] = 0; z->oqty[i] = 0; }
     AgentAux ax; ax.size = size; ax.order_size = 0; ax.last_mid = 0; ax.tv = 0; ax.mmflags = 0; ax.n_mids = 0; ax.avg20 = 0.0; ax.avg50 = 0.0;
     *reinterpret_cast<AgentAux *>(z->theta) = ax;
-    z->lat_to = 0.0; z->lat_from = 0.0; z->surplus = 0;
+    double lt, lf; init_latency_pair(P, rng, id, z, lt, lf);
+    z->lat_to = lt; z->lat_from = lf; z->surplus = 0;
     if (rng.err) *err |= rng.err;
     return;
   }
@@ -431,13 +445,7 @@ ABX_HD void init_agent_record(const SimParams &P, int env, int id, uint64_t seed
   for (int i = 0; i < 20; i++) th[i] = 0;
   for (int i = 0; i < m; i++) th[i] = rint(rng.normal(stream, ctr, 0.0, P.sqrt_sigma_pv));   // np.round(normal(0, sqrt(sigma_pv)))
   for (int i = 1; i < m; i++) { double x = th[i]; int j = i - 1; while (j >= 0 && th[j] < x) { th[j + 1] = th[j]; j--; } th[j + 1] = x; }  // sorted(reverse=True)
-  double lat_to = z->lat_to, lat_from = z->lat_from;
-  if (P.c.population == 3) { lat_to = 0.0; lat_from = 0.0; }                            // np.zeros latency matrix (config/rmsc01.py:250)
-  else if (P.c.rng_mode == ABX_RNG_PHILOX) {      // the config's pairwise latency matrix row/column 0, drawn per environment
-    uint32_t c2 = 0; int cs = P.n_streams + id;
-    lat_to = dadd(P.c.latency_lo, dmul(dsub(P.c.latency_hi, P.c.latency_lo), rng.u01(cs, c2)));
-    lat_from = P.c.latency_mirrored ? lat_to : dadd(P.c.latency_lo, dmul(dsub(P.c.latency_hi, P.c.latency_lo), rng.u01(cs, c2)));
-  }
+  double lat_to, lat_from; init_latency_pair(P, rng, id, z, lat_to, lat_from);
   z->agent_time = P.c.start_ns; z->prev_wake = 0; z->r_t = P.c.r_bar; z->sigma_t = 0.0; z->cash = P.c.starting_cash; z->shares = 0; z->last_trade = 0;
   z->daily_close = 0; z->bid = 0; z->bid_q = 0; z->ask = 0; z->ask_q = 0; z->flags = ((uint32_t)grp << AF_GROUP_SHIFT) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT) | ((uint32_t)type3 << AF_TYPE_SHIFT);
   z->rng_ctr = ctr; z->n_orders = 0;
@@ -475,7 +483,7 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
   s.uniq = 0; s.next_order_id = 0; s.q_count = 0; s.max_q = 0; s.n_bid_lv = s.n_ask_lv = 0; s.n_resting = 0; s.free_head = NIL;
   s.pool_top = 0; s.flags = 0; s.trace_n = 0; s.c_limit = s.c_cancel = s.c_fills = s.c_query = 0;
   s.ctr_symbol = s.ctr_kernel = s.ctr_latency = s.ctr_global = 0; s.trade_epoch = EPOCH_START; s.sum_shares = 0; s.sum_cash = 0;
-  s.kblk[0] = s.kblk[1] = s.kblk[2] = s.kblk[3] = 0; s.draw_n = 0; s.evt_n = 0; s.book_flags = 0; s.episode = 0; s.hist_n = 0; s.pad_h0 = s.pad_h1 = s.pad_h2 = 0;
+  s.kblk[0] = s.kblk[1] = s.kblk[2] = s.kblk[3] = 0; s.draw_n = 0; s.evt_n = 0; s.book_flags = 0; s.episode = 0; s.hist_n = 0; s.n_subs = 0; s.book_update = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -516,7 +524,7 @@ enum { SHAPE_ZI = 0, SHAPE_ENV = 1, SHAPE_R3 = 2, SHAPE_DQ = 3, SHAPE_BOOK = 4, 
 template <class Ctx, int RNG_MODE = -1, int LAT_MODEL = -1, bool INSTR = true, int SHAPE = SHAPE_ZI>
 struct Sim {
   static constexpr bool DQ = SHAPE == SHAPE_DQ, BOOK = SHAPE == SHAPE_BOOK, ENV = SHAPE == SHAPE_ENV || DQ || BOOK, P3 = SHAPE == SHAPE_P3, R3 = SHAPE == SHAPE_R3 || P3;   // P3: config/rmsc01.py population (runs the rmsc03 loop with more agent classes)
-  Ctx &c; const SimParams &P; EnvState s; RngT<RNG_MODE, INSTR> rng; int64_t addl_delay; int n_out; int self_id; int env_id; uint32_t hidx = 0;   // hidx: order-history log index of the order handleLimitOrder is working on (population 3)
+  Ctx &c; const SimParams &P; EnvState s; RngT<RNG_MODE, INSTR> rng; int64_t addl_delay; int n_out; int self_id; int env_id; bool cancel_found = false; uint32_t hidx = 0;   // cancel_found: the last book_cancel removed an order (it moves OrderBook.last_update_ts); hidx: order-history log index of the order handleLimitOrder is working on (population 3)
   AgentRegs a; ZiAgent *z;                // the trader whose event is being handled (registers + staged record)
 
   ABX_HD Sim(Ctx &c_, const SimParams &P_, const EnvState &s_, int env) : c(c_), P(P_), s(s_), addl_delay(0), n_out(0), self_id(0), z(nullptr) {
@@ -526,6 +534,7 @@ struct Sim {
   // fold the generator's error bits and draw-log cursor back into the environment state (end of every entry point that may have drawn)
   ABX_HD void rng_sync() { s.flags |= rng.err; if (INSTR) s.draw_n = rng.lg_n; }
 
+  ABX_HD bool lat_zero() const { return LAT_MODEL < 0 ? P.c.latency_model == ABX_LAT_ZERO : LAT_MODEL == ABX_LAT_ZERO; }
   ABX_HD int n_lv(int side) const { return side ? s.n_ask_lv : s.n_bid_lv; }
   ABX_HD void set_n_lv(int side, int n) { if (side) s.n_ask_lv = n; else s.n_bid_lv = n; }
 
@@ -546,6 +555,11 @@ struct Sim {
       if (p[5] & 1) { r.v[6] = p[0]; r.v[7] = p[1]; }
       if (p[5] & 2) { r.v[8] = p[2]; r.v[9] = p[3]; }
       r.v[10] = (p[5] >> 2) & 1;
+    } else if (P3 && kind == ABX_MARKET_DATA) {                                         // level counts, position-weighted price / size sums over the levels, top of book, last trade (what tools/record_reference.py stores)
+      int k = p[2]; r.v[1] = p[0]; r.v[2] = p[1]; r.v[5] = p[4];
+      for (int i = 0; i < p[0]; i++) { int2 lv = c.snap_load(k, 0, i); r.v[3] += (i + 1) * lv.x; if (i == 0) { r.v[6] = lv.x; r.v[7] = lv.y; } }
+      for (int i = 0; i < p[1]; i++) { int2 lv = c.snap_load(k, 1, i); r.v[4] += (i + 1) * lv.x; if (i == 0) { r.v[8] = lv.x; r.v[9] = lv.y; } }
+      for (int i = 0; i < p[0] && i < p[1]; i++) r.v[10] += (i + 1) * (c.snap_load(k, 0, i).y + 3 * c.snap_load(k, 1, i).y);
     }
     trace_rec(r);
   }
@@ -779,7 +793,7 @@ struct Sim {
           }
           qty -= fq;                                                                    // :77
           exch_send_order(agent, ABX_ORDER_EXECUTED, oid, price, fq, bp, is_buy, lat_in);             // :88 (incoming copy)
-          exch_send_order((int)(hr.agent & 0xffffu), ABX_ORDER_EXECUTED, hr.id, bp, fq, bp, !is_buy, (ENV || R3) ? 0.0 : c.agent_lat_from((int)hr.agent)); // :89-91
+          exch_send_order((int)(hr.agent & 0xffffu), ABX_ORDER_EXECUTED, hr.id, bp, fq, bp, !is_buy, (ENV || (R3 && (!P3 || lat_zero()))) ? 0.0 : c.agent_lat_from(P3 ? (int)(hr.agent & 0xffffu) : (int)hr.agent)); // :89-91
           trade_qty += fq; trade_px += (int64_t)bp * fq; s.c_fills++; matched = true;
           if (qty <= 0) matching = false;
           if (n_out >= Ctx::OUTN - 3) flush(); else c.sync();
@@ -800,6 +814,7 @@ struct Sim {
   }
   // cancelOrder :284-339: levels from the best whose slot-0 price equals the request's, the first that holds the id
   ABX_HD void book_cancel(uint32_t oid, int agent, int is_buy, int32_t price, double lat_in) {
+    cancel_found = false;
     int side = is_buy ? 0 : 1; int n = n_lv(side); if (n == 0) return;
     int limit = n;
 #pragma unroll 1
@@ -818,7 +833,7 @@ struct Sim {
             NodeRec pr = nload(prev); pr.next = r.next; nstore(prev, pr);
             c.lv_set(side, pos, c.lv_qty(side, pos) - r.qty, c.lv_head(side, pos), r.next == NIL ? prev : c.lv_tail(side, pos));
           }
-          node_free(cur); s.n_resting--; ib_dec(r.id);
+          node_free(cur); s.n_resting--; ib_dec(r.id); cancel_found = true;
           exch_send_order(agent, ABX_ORDER_CANCELLED, r.id, ENV ? r.price : price, r.qty, 0, is_buy, lat_in);   // :334-336 the BOOK's copy of the order, to the REQUEST's agent
           return;
         }
@@ -1069,7 +1084,7 @@ struct Sim {
   // agent/execution/baselines/execution_agent.py, ABIDESEnvMetrics.py).  Latency 0, computation delay 0, no oracle.
   // =================================================================================================
   ABX_HD void env_send(int kind, const int32_t p[6], bool bump) {                       // Agent.sendMessage from trader self_id to the exchange
-    emit(0u | ((uint32_t)kind << 16) | (bump ? OF_BUMP_UNIQ : 0u), p, 0.0, P.c.default_computation_delay_ns + addl_delay);
+    emit(0u | ((uint32_t)kind << 16) | (bump ? OF_BUMP_UNIQ : 0u), p, P3 ? a.lat_to : 0.0, P.c.default_computation_delay_ns + addl_delay);   // population 3 may run under a latency matrix (config/rmsc02.py)
   }
   ABX_HD void env_set_cancel(int sender, int64_t t) { int32_t p[6] = {0, 0, 0, 0, 0, 0}; emit((uint32_t)sender | OF_WAKEUP | OF_CANCEL_EVT, p, 0.0, t); }   // GymKernel.setCancelOrder :364-389
   ABX_HD bool ta_wakeup(uint32_t flags) {                                               // TradingAgent.wakeup :142-158 -> can_trade
@@ -1651,26 +1666,49 @@ struct Sim {
     bool t_closed = s.now > P.c.mkt_close_ns;
     int32_t p[6] = {0, 0, 0, 0, 0, 0};
     bool is_query = m.kind == ABX_QUERY_SPREAD || m.kind == ABX_QUERY_TRANSACTED_VOLUME || (P3 && m.kind == ABX_QUERY_ORDER_STREAM);
-    if (t_closed && !is_query) { exch_send(m.sender, ABX_MKT_CLOSED, p, 0.0); return; }
+    double lat = P3 ? m.lat_back : 0.0;                                                 // latency[0][sender] (zero in the zero-latency configs)
+    if (t_closed && !is_query) { exch_send(m.sender, ABX_MKT_CLOSED, p, lat); return; }
+    if (P3 && m.kind == ABX_MARKET_DATA_SUBSCRIPTION_REQUEST) {                         // updateSubscriptionDict :342-357: dict[agent] = [levels, freq, now]; a repeated request keeps its place
+      int k = c.tab_find(MM_ORDER_CAP, (int)s.n_subs, (uint32_t)m.sender);
+      if (k < 0) { if (s.n_subs >= (uint32_t)SUB_CAP) { s.flags |= ABX_F_AGENT_ORDERS_OVERFLOW; return; } k = (int)s.n_subs++; }
+      uint4 e4; e4.x = (uint32_t)m.sender; e4.y = (uint32_t)m.p[0]; e4.z = (uint32_t)(uint64_t)s.now; e4.w = (uint32_t)((uint64_t)s.now >> 32); c.id_store(MM_ORDER_CAP + k, e4);
+      return;
+    }
     if (P3 && m.kind == ABX_QUERY_ORDER_STREAM) {                                       // :251-279 history[1 : length + 1]: REFERENCES to the bucket dicts of the last `length` trades.  The reply names them
       uint32_t E = s.trade_epoch, n = (uint32_t)m.p[0];                                 // by epoch {current epoch, how many}; the agent reads the log when it places its order, so it sees what the dicts hold THEN
       if (n > E - EPOCH_START) n = E - EPOCH_START; if (n > (uint32_t)P.c.stream_history) n = (uint32_t)P.c.stream_history;   // len(history) - 1 buckets exist besides the open one
-      p[0] = (int32_t)E; p[1] = (int32_t)n; p[5] = t_closed ? 4 : 0; exch_send(m.sender, ABX_QUERY_ORDER_STREAM, p, 0.0); return;
+      p[0] = (int32_t)E; p[1] = (int32_t)n; p[5] = t_closed ? 4 : 0; exch_send(m.sender, ABX_QUERY_ORDER_STREAM, p, lat); return;
     }
-    if (m.kind == ABX_WHEN_MKT_OPEN) { s.exch_comp_delay = 0; exch_send(m.sender, ABX_WHEN_MKT_OPEN, p, 0.0); }
-    else if (m.kind == ABX_WHEN_MKT_CLOSE) { s.exch_comp_delay = 0; exch_send(m.sender, ABX_WHEN_MKT_CLOSE, p, 0.0); }
+    if (m.kind == ABX_WHEN_MKT_OPEN) { s.exch_comp_delay = 0; exch_send(m.sender, ABX_WHEN_MKT_OPEN, p, lat); }
+    else if (m.kind == ABX_WHEN_MKT_CLOSE) { s.exch_comp_delay = 0; exch_send(m.sender, ABX_WHEN_MKT_CLOSE, p, lat); }
     else if (m.kind == ABX_QUERY_TRANSACTED_VOLUME) {                                   // :280-303
       int64_t lookback = (int64_t)((uint64_t)(uint32_t)m.p[0] | ((uint64_t)(uint32_t)m.p[1] << 32));
-      p[0] = transacted_volume(lookback); p[5] = t_closed ? 4 : 0; exch_send(m.sender, ABX_QUERY_TRANSACTED_VOLUME, p, 0.0);
+      p[0] = transacted_volume(lookback); p[5] = t_closed ? 4 : 0; exch_send(m.sender, ABX_QUERY_TRANSACTED_VOLUME, p, lat);
     } else if (m.kind == ABX_QUERY_SPREAD) {
       s.c_query++; int f = 0; int nb = s.n_bid_lv, na = s.n_ask_lv;
       if (nb > 0) { p[0] = c.lv_price(0, nb - 1); p[1] = c.lv_qty(0, nb - 1); f |= 1; }
       if (na > 0) { p[2] = c.lv_price(1, na - 1); p[3] = c.lv_qty(1, na - 1); f |= 2; }
       if (t_closed) f |= 4;
       int32_t sn = (P.c.n_pov_exec && m.sender == P.c.n_agents - 1) ? snap_take(0) : 0;   // POVExecutionAgent asks for depth sys.maxsize: the whole book is copied now
-      p[4] = s.last_trade; p[5] = f; exch_send(m.sender, ABX_QUERY_SPREAD, p, bits_dbl((uint64_t)(uint32_t)sn));
-    } else if (m.kind == ABX_LIMIT_ORDER) { s.c_limit++; s.ctr_kernel++; book_handle_limit((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[2], 0.0); c.sync(); trace_snap(); }
-    else if (m.kind == ABX_CANCEL_ORDER) { s.c_cancel++; s.ctr_kernel++; book_cancel((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], 0.0); c.sync(); trace_snap(); }
+      p[4] = s.last_trade; p[5] = f; exch_send(m.sender, ABX_QUERY_SPREAD, p, P3 ? lat : bits_dbl((uint64_t)(uint32_t)sn));
+    } else if (m.kind == ABX_LIMIT_ORDER) { s.c_limit++; if (!P3) s.ctr_kernel++; book_handle_limit((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[2], lat); c.sync(); trace_snap(); if (P3 && m.p[2] > 0) { s.book_update = s.now; exch_publish(); } }   // ctr_kernel doubles as the book-operation counter where the kernel stream is unused
+    else if (m.kind == ABX_CANCEL_ORDER) { s.c_cancel++; if (!P3) s.ctr_kernel++; book_cancel((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], lat); c.sync(); trace_snap(); if (P3) { if (cancel_found) s.book_update = s.now; exch_publish(); } }
+  }
+  // ExchangeAgent.publishOrderBookData :359-387: after every book operation, MARKET_DATA to each subscriber (in subscription order) whose `freq` ns have passed since its
+  // last update.  The body's `levels` levels a side are copied into the subscriber's snapshot area NOW; the message carries the counts, the last trade and the slot.
+  ABX_HD void exch_publish() {
+#pragma unroll 1
+    for (int k = 0; k < (int)s.n_subs; k++) {
+      uint4 e4 = c.id_load(MM_ORDER_CAP + k); int agent = (int)e4.x, levels = (int)e4.y; int64_t last = (int64_t)((uint64_t)e4.z | ((uint64_t)e4.w << 32));
+      int64_t freq = agent_type_of(P.c, agent) == AT_MKM ? P.c.mkm_sub_freq_ns : P.c.mom_sub_freq_ns;
+      if (!(freq == 0 || (s.book_update > last && s.book_update - last >= freq))) continue;
+      int nb = s.n_bid_lv < levels ? s.n_bid_lv : levels, na = s.n_ask_lv < levels ? s.n_ask_lv : levels;
+      c.snap_store(k, 0, s.n_bid_lv, nb); c.snap_store(k, 1, s.n_ask_lv, na);
+      int32_t p[6] = {nb, na, k, 0, s.last_trade, 0};
+      exch_send(agent, ABX_MARKET_DATA, p, lat_zero() ? 0.0 : c.agent_lat_from(agent));
+      if (n_out >= Ctx::OUTN - 3) flush();
+      e4.z = (uint32_t)(uint64_t)s.book_update; e4.w = (uint32_t)((uint64_t)s.book_update >> 32); c.id_store(MM_ORDER_CAP + k, e4);
+    }
   }
   ABX_HD AgentAux *aux() { return reinterpret_cast<AgentAux *>(z->theta); }
   // TradingAgent.placeLimitOrder :309-349 for the staged trader; `track`: the agent later iterates self.orders (Value, market maker)
@@ -1715,9 +1753,11 @@ struct Sim {
         { int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); } st = ST_AWAITING_SPREAD;
       }
     } else if (type == AT_MOMENTUM) {                                                   // agent/examples/MomentumAgent.py:53-63
-      if (can_trade) { int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); st = ST_AWAITING_SPREAD; }
-    } else if (P3 && type == AT_MKM) {                                                  // agent/market_makers/MarketMakerAgent.py:66-77 (polling mode)
-      if (can_trade) { r3_cancel_all(type); int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); st = ST_AWAITING_SPREAD; }
+      if (P3 && P.c.mom_subscribe) { if (!(a.flags & AF_SUB_REQUESTED)) { int32_t p[6] = {1, 0, 0, 0, 0, 0}; env_send(ABX_MARKET_DATA_SUBSCRIPTION_REQUEST, p, false); a.flags |= AF_SUB_REQUESTED; } }   // :56-59 levels = 1, requested at the very first wake-up; wake-ups do nothing else
+      else if (can_trade) { int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); st = ST_AWAITING_SPREAD; }
+    } else if (P3 && type == AT_MKM) {                                                  // agent/market_makers/MarketMakerAgent.py:66-77
+      if (P.c.mkm_subscribe) { if (!(a.flags & AF_SUB_REQUESTED)) { int32_t p[6] = {P.c.mkm_num_levels, 0, 0, 0, 0, 0}; env_send(ABX_MARKET_DATA_SUBSCRIPTION_REQUEST, p, false); a.flags |= AF_SUB_REQUESTED; } }   // :69-72
+      else if (can_trade) { r3_cancel_all(type); int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); st = ST_AWAITING_SPREAD; }
     } else if (type == AT_POVEXEC) {                                                    // agent/execution/baselines/pov_agent.py:55-64
       if (can_trade && exaux()->rem_qty > 0 && s.now < P.c.pov_exec_end_ns) {
         set_wakeup(id, s.now + P.c.pov_exec_freq_ns); dq_cancel_all(id);
@@ -1799,6 +1839,10 @@ struct Sim {
       a.flags &= ~(AF_HAS_BID | AF_HAS_ASK);
       if (m.p[5] & 1) { a.flags |= AF_HAS_BID; a.bid = m.p[0]; a.bid_q = m.p[1]; } else { a.bid = 0; a.bid_q = 0; }
       if (m.p[5] & 2) { a.flags |= AF_HAS_ASK; a.ask = m.p[2]; a.ask_q = m.p[3]; } else { a.ask = 0; a.ask_q = 0; }
+    } else if (P3 && m.kind == ABX_MARKET_DATA) {                                       // handleMarketData :539-546: known_bids / known_asks = the body's lists (read from the snapshot slot), last_trade
+      a.last_trade = m.p[4]; a.flags |= AF_HAS_LAST; a.flags &= ~(AF_HAS_BID | AF_HAS_ASK);
+      if (m.p[0] > 0) { int2 lv = c.snap_load(m.p[2], 0, 0); a.flags |= AF_HAS_BID; a.bid = lv.x; a.bid_q = lv.y; } else { a.bid = 0; a.bid_q = 0; }
+      if (m.p[1] > 0) { int2 lv = c.snap_load(m.p[2], 1, 0); a.flags |= AF_HAS_ASK; a.ask = lv.x; a.ask_q = lv.y; } else { a.ask = 0; a.ask_q = 0; }
     }
     if ((a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE) && !had) {                  // :258-268 getWakeFrequency per class
       int64_t off = type == AT_MOMENTUM ? P.c.mom_wake_ns : (type == AT_POVMM ? P.c.mm_wake_ns : (type == AT_POVEXEC ? P.c.pov_exec_freq_ns : ((P3 && type == AT_MKM) ? P.c.mkm_wake_ns : rng.randint(S_AGENT0 + id, a.rng_ctr, 99))));
@@ -1813,6 +1857,29 @@ struct Sim {
         int32_t qty = (int32_t)py_round_i64(dmul(P.c.pov_exec_pov, (double)ex.tv));
         dq_cancel_all(id);
         dq_place_market(id, qty, P.c.pov_exec_is_buy != 0);
+      }
+      return;
+    }
+    if (P3 && type == AT_MKM && P.c.mkm_subscribe) {                                    // MarketMakerAgent.receiveMessage :108-118 + placeOrders :120-139 (subscription mode)
+      if ((a.flags & AF_SUB_REQUESTED) && m.kind == ABX_MARKET_DATA) {
+        r3_cancel_all(type);
+        int num_levels = 1 + (int)rng.randint(S_AGENT0 + id, a.rng_ctr, 3);             // randint(1, len(levels_quote_dict)): 1..4 levels
+        int nb = m.p[0], na = m.p[1], k = m.p[2];
+        if (nb > 0 && na > 0) {
+          int32_t size = mkm_half(P.c.mkm_min_size + rng.randint(S_AGENT0 + id, a.rng_ctr, (uint32_t)(P.c.mkm_max_size - P.c.mkm_min_size - 1)));
+          double w0 = num_levels == 1 ? 1.0 : num_levels == 2 ? 0.5 : num_levels == 3 ? 0.34 : 0.25, w1 = num_levels == 2 ? 0.5 : num_levels == 3 ? 0.33 : 0.25;   // DEFAULT_LEVELS_QUOTE_DICT :6-12
+          int32_t qp[2][4], qv[2][4]; int nq[2] = {0, 0};                                 // buy_quotes / sell_quotes: dicts keyed by price (a repeated key keeps its place and takes the new volume)
+          for (int i = 0; i < num_levels; i++) {
+            int32_t vol = (int32_t)py_round_i64(dmul(i == 0 ? w0 : w1, (double)size));
+            for (int side = 0; side < 2; side++) {
+              int n = side ? na : nb; int32_t px = i < n ? c.snap_load(k, side, i).x : c.snap_load(k, side, n - 1).x + (side ? 1 : -1);   // IndexError branch: one cent beyond the last level
+              int f = 0; while (f < nq[side] && qp[side][f] != px) f++;
+              if (f == nq[side]) nq[side]++;
+              qp[side][f] = px; qv[side][f] = vol;
+            }
+          }
+          for (int side = 0; side < 2; side++) for (int f = 0; f < nq[side]; f++) r3_place_limit(id, qv[side][f], side == 0, qp[side][f], true);
+        }
       }
       return;
     }
@@ -1854,6 +1921,7 @@ struct Sim {
       return;
     }
     if (type == AT_MOMENTUM) {                                                          // MomentumAgent.receiveMessage :65-76
+      if (P3 && P.c.mom_subscribe) { if ((a.flags & AF_SUB_REQUESTED) && m.kind == ABX_MARKET_DATA && m.p[0] > 0 && m.p[1] > 0) r3_momentum_place(id); return; }   // :71-75 placeOrders(bids[0][0], asks[0][0])
       if (st == ST_AWAITING_SPREAD && m.kind == ABX_QUERY_SPREAD) { r3_momentum_place(id); set_wakeup(id, s.now + P.c.mom_wake_ns); a.flags = (a.flags & ~AF_STATE_MASK) | (ST_AWAITING_WAKEUP << AF_STATE_SHIFT); }
       return;
     }

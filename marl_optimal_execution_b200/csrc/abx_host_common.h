@@ -92,6 +92,15 @@ static inline int config_rmsc01(abx_sim_config *c) {
   c->rng_mode = ABX_RNG_PHILOX; c->trace_cap = 0; c->hash_pops = 0;
   return ABX_OK;
 }
+// config/rmsc02.py: rmsc01 with the market maker and the momentum agents in subscription mode, the sparse_zi_1000 latency matrix + noise, midnight .. 17:00
+static inline int config_rmsc02(abx_sim_config *c) {
+  int st = config_rmsc01(c); if (st != ABX_OK) return st;
+  c->mkm_subscribe = 1; c->mom_subscribe = 1; c->mkm_sub_freq_ns = 10 * NS; c->mom_sub_freq_ns = 10 * NS;   // :108,205; subscribe_freq = 10e9, MomentumAgent.py:58
+  c->start_ns = 0; c->stop_ns = 17 * 3600 * NS;                                                              // :264-265
+  c->latency_model = ABX_LAT_MATRIX_NOISE; c->n_noise = 6; c->latency_mirrored = 0; c->latency_lo = 21000; c->latency_hi = 13000000;   // :268-269
+  c->hist_log_cap = 4096;                                                                                   // the whole day is ~32 000 book operations with ~4 000 fills: buckets are short
+  return ABX_OK;
+}
 static inline int config_validate(const abx_sim_config *c) {
   if (!c || c->version != ABX_VERSION) return ABX_ERR_ARG;
   if (c->n_agents < 2 || c->n_agents > 32767 || c->n_groups < 0 || c->n_groups > 8 || c->q_max < 1 || c->q_max > 10) return ABX_ERR_ARG;
@@ -103,7 +112,11 @@ static inline int config_validate(const abx_sim_config *c) {
     if (c->n_pov_exec < 0 || c->n_pov_exec > 1 || (c->n_pov_exec && (!(c->pov_exec_pov > 0) || c->pov_exec_quantity <= 0 || c->pov_exec_quantity > 0x3fffffffLL || c->pov_exec_freq_ns <= 0 || c->pov_exec_lookback_ns <= 0))) return ABX_ERR_ARG;
     n += c->n_noise_agents + c->n_value_agents + c->n_mm_agents + c->n_momentum_agents + c->n_pov_exec;
   } else if (c->population == 3) {
-    if (c->n_groups != 2 || c->n_mm_agents < 0 || c->n_mm_agents > 1 || c->n_momentum_agents < 0 || c->n_momentum_agents > 64 || c->latency_model != ABX_LAT_ZERO) return ABX_ERR_ARG;
+    if (c->n_groups != 2 || c->n_mm_agents < 0 || c->n_mm_agents > 1 || c->n_momentum_agents < 0 || c->n_momentum_agents > 60 || (c->latency_model != ABX_LAT_ZERO && c->latency_model != ABX_LAT_MATRIX_NOISE)) return ABX_ERR_ARG;
+    if ((c->mkm_subscribe && (c->mkm_sub_freq_ns < 0 || c->mkm_num_levels > SUB_LEVELS)) || (c->mom_subscribe && c->mom_sub_freq_ns < 0)) return ABX_ERR_ARG;
+    // one MARKET_DATA body per subscriber is in flight at a time (its levels wait in the subscriber's snapshot slot): the update period must exceed the longest delivery
+    if (c->latency_model != ABX_LAT_ZERO && ((c->mkm_subscribe && (double)c->mkm_sub_freq_ns <= c->latency_hi + c->n_noise) || (c->mom_subscribe && (double)c->mom_sub_freq_ns <= c->latency_hi + c->n_noise))) return ABX_ERR_ARG;
+    if (c->latency_model == ABX_LAT_ZERO && ((c->mkm_subscribe && c->mkm_sub_freq_ns == 0) || (c->mom_subscribe && c->mom_sub_freq_ns == 0))) return ABX_ERR_ARG;
     for (int g = 0; g < 2; g++) { if (c->groups[g].count < 0 || c->groups[g].r_max < c->groups[g].r_min) return ABX_ERR_ARG; n += c->groups[g].count; }
     if (c->hbl_L < 1 || c->hbl_L > 16 || c->stream_history < 1 || c->hist_log_cap < 64 || c->hist_log_cap > 65536 || (c->hist_log_cap & (c->hist_log_cap - 1)) || c->hbl_table_rows < 0 || c->hbl_table_rows > c->hist_log_cap / 4) return ABX_ERR_ARG;
     if (c->mom_max_size <= c->mom_min_size || c->mom_wake_ns <= 0) return ABX_ERR_ARG;

@@ -91,6 +91,10 @@ static run_kernel_fn run_kernel_for(const abx_sim_config &c) {
     if (r == ABX_RNG_PHILOX) return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_R3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_ZERO, false, SHAPE_R3>;
     return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_ZERO, true, SHAPE_R3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_ZERO, false, SHAPE_R3>;
   }
+  if (c.population == 3 && l == ABX_LAT_MATRIX_NOISE) {   // config/rmsc02.py: the same population under the pairwise latency matrix + noise
+    if (r == ABX_RNG_PHILOX) return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_MATRIX_NOISE, true, SHAPE_P3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_MATRIX_NOISE, false, SHAPE_P3>;
+    return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_MATRIX_NOISE, true, SHAPE_P3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_MATRIX_NOISE, false, SHAPE_P3>;
+  }
   if (c.population == 3) {                       // config/rmsc01.py population: the rmsc03 loop over more agent classes
     if (r == ABX_RNG_PHILOX) return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_ZERO, true, SHAPE_P3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_PHILOX, ABX_LAT_ZERO, false, SHAPE_P3>;
     return instr ? (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_ZERO, true, SHAPE_P3> : (run_kernel_fn)abx_run_kernel<ABX_RNG_TAPE, ABX_LAT_ZERO, false, SHAPE_P3>;
@@ -109,7 +113,7 @@ abx_finalize_kernel(SimParams P, size_t smem_per_warp) {
   WarpCtx ctx(P, env, smem + warp * smem_per_warp);
   EnvState s = env_load(P.env + env);
   if (P.c.population == 1) { Sim<WarpCtx, -1, ABX_LAT_ZERO, true, SHAPE_R3> sim(ctx, P, s, env); sim.r3_finalize(); env_store(P.env + env, sim.s, ctx.lane); return; }   // INSTR: the ValueAgents' closing observations go to the draw log
-  if (P.c.population == 3) { Sim<WarpCtx, -1, ABX_LAT_ZERO, true, SHAPE_P3> sim(ctx, P, s, env); sim.r3_finalize(); env_store(P.env + env, sim.s, ctx.lane); return; }
+  if (P.c.population == 3) { Sim<WarpCtx, -1, -1, true, SHAPE_P3> sim(ctx, P, s, env); sim.r3_finalize(); env_store(P.env + env, sim.s, ctx.lane); return; }
   Sim<WarpCtx> sim(ctx, P, s, env);
   sim.finalize();
   env_store(P.env + env, sim.s, ctx.lane);
@@ -310,6 +314,7 @@ int32_t abx_config_sparse_zi(int32_t variant, abx_sim_config *cfg) { return conf
 int32_t abx_config_rmsc03(abx_sim_config *cfg) { return config_rmsc03(cfg); }
 int32_t abx_config_rmsc03_pov(abx_sim_config *cfg) { return config_rmsc03_pov(cfg); }
 int32_t abx_config_rmsc01(abx_sim_config *cfg) { return config_rmsc01(cfg); }
+int32_t abx_config_rmsc02(abx_sim_config *cfg) { return config_rmsc02(cfg); }
 
 int32_t abx_sim_destroy(abx_sim *h) {
   if (!h) return ABX_OK;
@@ -340,7 +345,7 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + h->P.tv_ring; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0);       // market maker orders + transaction ring [+ POV execution agent orders]; momentum mids
     DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * LOB_CAP * 3)
     if (c.n_pov_exec) { h->P.n_snap = 1; h->P.snap_depth = c.level_cap; DA(h->P.snap, E * 2 * (size_t)c.level_cap) } }      // POVExecutionAgent asks for depth sys.maxsize
-  if (c.population == 3) { h->P.n_ids = MM_ORDER_CAP; DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * (size_t)lob_stride_of(c)) DA(h->P.hlog, E * hist_stride_of(c)) }   // market maker orders; momentum mids; order-history log
+  if (c.population == 3) { h->P.n_ids = MM_ORDER_CAP + SUB_CAP; h->P.n_snap = SUB_CAP; h->P.snap_depth = SUB_LEVELS; DA(h->P.snap, E * (size_t)SUB_CAP * 2 * SUB_LEVELS) DA(h->P.idtab, E * h->P.n_ids) DA(h->P.lobs, E * (size_t)lob_stride_of(c)) DA(h->P.hlog, E * hist_stride_of(c)) }   // market maker orders; momentum mids; order-history log
 #undef DA
   if (smem_cta > 48 * 1024) {
     CUH(cudaFuncSetAttribute((const void *)run_kernel_for(*cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));

@@ -53,6 +53,19 @@ def rmsc01_config(lib=None, **overrides):
     return cfg
 
 
+def rmsc02_config(lib=None, **overrides):
+    """abx_sim_config for config/rmsc02.py: the rmsc01 population with the market maker and the momentum agents subscribed to MARKET_DATA
+    (agent/ExchangeAgent.py:342-387), pairwise latency + noise, midnight-17:00."""
+    L = lib or _lib.load()
+    cfg = SimConfig()
+    _lib.check(L, L.abx_config_rmsc02(C.byref(cfg)), "abx_config_rmsc02")
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError("abx_sim_config has no field %r" % k)
+        setattr(cfg, k, v)
+    return cfg
+
+
 def _num(x):
     """'{}'.format of a config literal: 1 -> '1', 0.8 -> '0.8' (config/sparse_zi_1000.py:211-219 writes eta as 1 or 0.8)."""
     return str(int(x)) if float(x) == int(x) else repr(float(x))

@@ -186,13 +186,14 @@ int32_t abx_config_sparse_zi(int32_t variant, abx_sim_config *cfg) { return conf
 int32_t abx_config_rmsc03(abx_sim_config *cfg) { return config_rmsc03(cfg); }
 int32_t abx_config_rmsc03_pov(abx_sim_config *cfg) { return config_rmsc03_pov(cfg); }
 int32_t abx_config_rmsc01(abx_sim_config *cfg) { return config_rmsc01(cfg); }
+int32_t abx_config_rmsc02(abx_sim_config *cfg) { return config_rmsc02(cfg); }
 int32_t abx_sim_pov_exec(abx_sim *h, int32_t env, int64_t *out, void *stream) {
   (void)stream; if (!h || !out || env < 0 || env >= h->n_envs || h->P.c.population != 1 || !h->P.c.n_pov_exec) return ABX_ERR_ARG;
   const ZiAgent &z = h->agents[(size_t)env * h->P.c.n_agents + h->P.c.n_agents - 1]; const ExecAux *ex = reinterpret_cast<const ExecAux *>(z.oid);
   out[0] = ex->rem_qty; out[1] = ex->n_executed; out[2] = z.n_orders; return ABX_OK;
 }
 typedef Sim<HostCtx, -1, ABX_LAT_ZERO, true, SHAPE_R3> R3SimHost;
-typedef Sim<HostCtx, -1, ABX_LAT_ZERO, true, SHAPE_P3> P3SimHost;
+typedef Sim<HostCtx, -1, -1, true, SHAPE_P3> P3SimHost;   // latency model decided at run time: zero (rmsc01) or matrix + noise (rmsc02)
 
 int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device, abx_sim **out) {
   (void)device;
@@ -209,7 +210,7 @@ int32_t abx_sim_create(const abx_sim_config *cfg, int32_t n_envs, int32_t device
   h->evt.resize(E * (size_t)c.event_ring_cap); h->P.evt = c.event_ring_cap ? h->evt.data() : nullptr;
   if (c.population == 1) { h->P.dq_order_base = MM_ORDER_CAP + h->P.tv_ring; h->P.n_ids = h->P.dq_order_base + (c.n_pov_exec ? EXEC_ORDER_CAP : 0); h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * LOB_CAP * 3); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data();
     if (c.n_pov_exec) { h->P.n_snap = 1; h->P.snap_depth = c.level_cap; h->snap.resize(E * 2 * (size_t)c.level_cap); h->P.snap = h->snap.data(); } }
-  if (c.population == 3) { h->P.n_ids = MM_ORDER_CAP; h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * lob_stride_of(c)); h->hlog.resize(E * hist_stride_of(c)); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); h->P.hlog = h->hlog.data(); }
+  if (c.population == 3) { h->P.n_ids = MM_ORDER_CAP + SUB_CAP; h->P.n_snap = SUB_CAP; h->P.snap_depth = SUB_LEVELS; h->snap.resize(E * (size_t)SUB_CAP * 2 * SUB_LEVELS); h->P.snap = h->snap.data(); h->idtab.resize(E * h->P.n_ids); h->lobs.resize(E * lob_stride_of(c)); h->hlog.resize(E * hist_stride_of(c)); h->P.idtab = h->idtab.data(); h->P.lobs = h->lobs.data(); h->P.hlog = h->hlog.data(); }
   *out = h; return ABX_OK;
 }
 int32_t abx_sim_destroy(abx_sim *h) { delete h; return ABX_OK; }

@@ -36,9 +36,10 @@ def oracle_tapes(sims):
                 kinds.append(k)
                 bits.append(b)
                 off.append(off[-1] + len(b))
-            if s.variant == 1:                        # rmsc01: every agent draws its own parameters from its own stream
-                lat_to.append(np.zeros(n))
-                lat_from.append(np.zeros(n))
+            if s.variant == 1:                        # rmsc01 / rmsc02: every agent draws its own parameters from its own stream; latency matrix row / column 0
+                a, b = s.latency_vectors()
+                lat_to.append(a)
+                lat_from.append(b)
                 continue
             info = np.array([s.agent_info(a) for a in range(n)])
             lat_to.append(info[:, 1].astype(np.float64))      # Noise/Value size (drawn by the config script)

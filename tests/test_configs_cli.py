@@ -37,3 +37,17 @@ def test_sparse_zi_flags_and_seeding(emu):
     with pytest.raises(SystemExit):
         configs.from_argv(["-c", "twoSymbols"])
     assert configs.timedelta_ns("1S") == 10 ** 9 and configs.timedelta_ns("30s") == 30 * 10 ** 9 and configs.timedelta_ns("1min") == 60 * 10 ** 9
+
+
+def test_rmsc01_and_rmsc02_command_lines():
+    """`abides.py -c rmsc01 -s 7` / `-c rmsc02`: the presets of config/rmsc01.py / config/rmsc02.py; an --agent_name (a Python class under test) is rejected."""
+    import pytest
+    from marl_optimal_execution_b200 import _lib, configs
+    from helpers import build_emu
+    L = _lib.load(build_emu())
+    c1, run1 = configs.from_argv(["-c", "rmsc01", "-s", "7"], lib=L)
+    c2, run2 = configs.from_argv(["-c", "rmsc02", "-l", "x"], lib=L)
+    assert (c1.population, c1.n_agents, c1.hbl_L, c1.latency_model, c1.mkm_subscribe) == (3, 101, 2, _lib.LAT_ZERO if hasattr(_lib, "LAT_ZERO") else 2, 0) and run1.seed == 7
+    assert (c2.mkm_subscribe, c2.mom_subscribe, c2.n_noise, c2.start_ns, c2.stop_ns) == (1, 1, 6, 0, 17 * 3600 * 10 ** 9) and run2.seed == 0
+    with pytest.raises(SystemExit):
+        configs.from_argv(["-c", "rmsc01", "-a", "MyAgent"], lib=L)

@@ -160,6 +160,27 @@ def test_rmsc01_tape_replay_matches_oracle(emu, seed, stop_s, pops, hist_cap):
     assert len(hbl) > 20 and int(st["sum_shares"][0]) == 0 and int(st["sum_cash"][0]) == 100 * 10 ** 7
 
 
+@pytest.mark.parametrize("seed,stop_h,pops", [(123456789, 17.0, 117238), (777, 10.5, None)])
+def test_rmsc02_tape_replay_matches_oracle(emu, seed, stop_h, pops):
+    """config/rmsc02.py through the product logic: MARKET_DATA subscriptions (subscriber table, publish after every book operation, level snapshots), the
+    subscription-mode market maker and momentum agents, HBL / ZI agents under the pairwise latency matrix + noise.  Seed 123456789 is the WHOLE day the oracle
+    is pinned to the live reference on (tests/test_oracle_golden.py::test_rmsc02_full_day_bit_exact)."""
+    from helpers import assert_env_equals_oracle, oracle_rmsc02
+    from marl_optimal_execution_b200.sim import rmsc02_config
+    stop = int(stop_h * 3600) * 10 ** 9
+    o, n = oracle_rmsc02(seed, stop, TRACE_ALL)
+    assert pops is None or n == pops
+    cfg = rmsc02_config(lib=_lib.load(emu), rng_mode=_lib.RNG_TAPE, trace_cap=400000, hash_pops=1, stop_ns=stop)
+    sim = BatchedSim(cfg, 1, lib_path=emu)
+    sim.reset_tape(*oracle_tapes([o]))
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    assert_env_equals_oracle(sim, 0, o, n, st)
+    notes = o.trace("notes")
+    assert (notes[:, 2] == 15).sum() > 500 and int(st["sum_shares"][0]) == 0 and int(st["sum_cash"][0]) == 100 * 10 ** 7
+
+
 def test_shared_tapes_round_robin(emu):
     """abx_sim_reset_tape_shared: environment e replays recorded run e % n_tapes (the production-occupancy parity tests of the GPU suite)."""
     seeds = [123456789, 1001, 7]

@@ -7,7 +7,7 @@ import pytest
 
 from helpers import assert_env_equals_oracle, build_emu, oracle_rerun_of_philox_env
 from marl_optimal_execution_b200 import _lib
-from marl_optimal_execution_b200.sim import BatchedSim, rmsc01_config, rmsc03_config, sparse_zi_config
+from marl_optimal_execution_b200.sim import BatchedSim, rmsc01_config, rmsc02_config, rmsc03_config, sparse_zi_config
 from oracle.oracle import TRACE_ALL
 
 
@@ -63,3 +63,19 @@ def test_rmsc01_philox_run_equals_oracle_on_its_own_draws(emu):
         o, n = oracle_rerun_of_philox_env(sim, e, init[e], TRACE_ALL)
         assert_env_equals_oracle(sim, e, o, n, st)
     assert st["pop_hash"][0] != st["pop_hash"][1] and st["fills"].min() > 5              # rmsc01 trades rarely: ~40 fills in the reference's first 15 minutes
+
+
+def test_rmsc02_philox_run_equals_oracle_on_its_own_draws(emu):
+    """config/rmsc02.py seeded by Philox (latency matrix drawn on the device, kernel-noise stream, subscriptions): oracle re-run on the logged draws, midnight - 11:00."""
+    stop = 11 * 3600 * 10 ** 9
+    cfg = rmsc02_config(lib=_lib.load(emu), trace_cap=300000, hash_pops=1, draw_log_cap=100000, stop_ns=stop)
+    sim = BatchedSim(cfg, 2, lib_path=emu)
+    sim.reset([41, 42])
+    init = [sim.agent_init(e) for e in range(2)]
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    for e in range(2):
+        o, n = oracle_rerun_of_philox_env(sim, e, init[e], TRACE_ALL)
+        assert_env_equals_oracle(sim, e, o, n, st)
+    assert st["pop_hash"][0] != st["pop_hash"][1] and st["fills"].min() > 50

@@ -155,6 +155,24 @@ def test_rmsc01_tape_replay(seed, stop_s, hist_cap):
     assert int(st["sum_shares"][0]) == 0 and int(st["sum_cash"][0]) == 100 * 10 ** 7
 
 
+def test_rmsc02_whole_day_tape_replay():
+    """config/rmsc02.py, the whole day (117 238 messages): MARKET_DATA subscriptions, subscription-mode market maker / momentum agents, latency matrix + noise.
+    Full traces vs the oracle, which is pinned to a live recording of the reference for this seed (tests/test_oracle_golden.py::test_rmsc02_full_day_bit_exact)."""
+    from helpers import assert_env_equals_oracle, oracle_rmsc02
+    from marl_optimal_execution_b200.sim import rmsc02_config
+    stop = 17 * 3600 * 10 ** 9
+    o, n = oracle_rmsc02(123456789, stop, TRACE_ALL)
+    assert n == 117238
+    cfg = rmsc02_config(rng_mode=_lib.RNG_TAPE, trace_cap=400000, hash_pops=1)
+    sim = BatchedSim(cfg, 2)
+    sim.reset_tape(*oracle_tapes([o, o]))
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    for e in range(2):
+        assert_env_equals_oracle(sim, e, o, n, st)
+
+
 def test_rmsc03_with_pov_execution_agent_tape_replay():
     """BASELINE.json configs[2] "rmsc03 ... with POV execution agent": bit-exact vs the oracle (pinned to a recording of the reference with
     its POVExecutionAgent appended); one environment per seed plus a duplicate."""

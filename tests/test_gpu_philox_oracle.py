@@ -18,7 +18,7 @@ import torch
 from helpers import assert_env_equals_oracle, oracle_rerun_of_philox_env, oracle_tapes
 from marl_optimal_execution_b200 import _lib
 from marl_optimal_execution_b200.build import LIB_STRICT
-from marl_optimal_execution_b200.sim import BatchedSim, rmsc01_config, rmsc03_config, sparse_zi_config
+from marl_optimal_execution_b200.sim import BatchedSim, rmsc01_config, rmsc02_config, rmsc03_config, sparse_zi_config
 from oracle.oracle import OracleSim, TRACE_ALL
 
 pytestmark = pytest.mark.gpu
@@ -84,6 +84,12 @@ def test_rmsc01_philox_production_kernel_equals_oracle():
     _philox_vs_oracle(lambda **kw: rmsc01_config(stop_ns=stop, **{"draw_log_cap": 60000, **kw}), 48, 8800, 5)
 
 
+def test_rmsc02_philox_production_kernel_equals_oracle():
+    """config/rmsc02.py (subscriptions + latency matrix), midnight - 11:00, 48 Philox-seeded environments: production kernel == instrumented kernel == oracle on the logged draws."""
+    stop = 11 * 3600 * 10 ** 9
+    _philox_vs_oracle(lambda **kw: rmsc02_config(stop_ns=stop, **{"draw_log_cap": 100000, **kw}), 48, 9900, 5)
+
+
 def test_tape_mode_uninstrumented_kernel_equals_oracle():
     seeds = [123456789, 1001, 7, 424242]
     oracles = [OracleSim(100, s, TRACE_ALL) for s in seeds]
@@ -144,6 +150,14 @@ def test_full_wave_tape_parity_rmsc01(lib_path):
     stop = (9 * 3600 + 34 * 60) * 10 ** 9
     runs = [oracle_rmsc01(s, stop, TRACE_ALL) for s in (123456789, 1001, 5, 6, 7, 8, 9, 10)]
     _wave_tape_parity(rmsc01_config(rng_mode=_lib.RNG_TAPE, hash_pops=1, stop_ns=stop), [r[0] for r in runs], [r[1] for r in runs], lib_path, 5)
+
+
+@pytest.mark.parametrize("lib_path", LIBS)
+def test_full_wave_tape_parity_rmsc02(lib_path):
+    from helpers import oracle_rmsc02
+    stop = int(10.5 * 3600) * 10 ** 9
+    runs = [oracle_rmsc02(s, stop, TRACE_ALL) for s in (123456789, 1001, 5, 6, 7, 8, 9, 10)]
+    _wave_tape_parity(rmsc02_config(rng_mode=_lib.RNG_TAPE, hash_pops=1, stop_ns=stop), [r[0] for r in runs], [r[1] for r in runs], lib_path, 5)
 
 
 DAYS = ("env_IBM_2003-01-14_s789.npz", "env_IBM_2003-01-15_s4242.npz", "ddqn_IBM_2003-01-16_s99_sell.npz")
