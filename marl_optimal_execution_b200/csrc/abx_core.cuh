@@ -55,8 +55,9 @@ struct alignas(16) EnvState {           // 192 B per environment
   uint32_t kblk[4];                     // cached Philox block of the kernel (latency-noise) stream
   uint32_t draw_n, evt_n, book_flags, episode; // entries in the draw log (parity runs) / in the LAST_TRADE, BEST_BID, BEST_ASK event ring; BKF_*; resets of this environment that moved on to the next replayed day
   uint32_t hist_n, n_subs; int64_t book_update; // orders registered in the order-history log (population 3: what QUERY_ORDER_STREAM hands out); subscribers (ExchangeAgent.subscription_dict); OrderBook.last_update_ts
+  int64_t next_pub, pad_p;                      // earliest book-update time at which some subscriber is due a MARKET_DATA body (min over subscribers of last update + period)
 };
-static_assert(sizeof(EnvState) == 224, "EnvState layout");
+static_assert(sizeof(EnvState) == 240, "EnvState layout");
 
 enum : uint32_t {
   AF_HAS_OPEN = 1u, AF_HAS_CLOSE = 2u, AF_MKT_CLOSED = 4u, AF_HAS_LAST = 8u, AF_HAS_DAILY = 16u, AF_HAS_PREV = 32u,
@@ -261,8 +262,12 @@ struct U4 { uint32_t x, y, z, w; };
 #ifndef ABX_PHILOX_ROUNDS
 #define ABX_PHILOX_ROUNDS 10
 #endif
+#ifndef ABX_PHILOX_UNROLL
+#define ABX_PHILOX_UNROLL 1
+#endif
 ABX_NI U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-#pragma unroll 1                                                                       // rolled: the unrolled rounds are 2 KB of a hot loop body that lives on the edge of the 32 KB instruction cache (+6 % msgs/s, profiles/r02_optimisation_log.md)
+  constexpr int UNROLL = ABX_PHILOX_UNROLL;
+#pragma unroll UNROLL                                                       // rolled: the unrolled rounds are 2 KB of a hot loop body that lives on the edge of the 32 KB instruction cache (+6 % msgs/s, profiles/r02_optimisation_log.md)
   for (int r = 0; r < ABX_PHILOX_ROUNDS; r++) {
     uint64_t p0 = uint64_t(0xD2511F53u) * c0, p1 = uint64_t(0xCD9E8D57u) * c2;
     uint32_t n0 = uint32_t(p1 >> 32) ^ c1 ^ k0, n1 = uint32_t(p1), n2 = uint32_t(p0 >> 32) ^ c3 ^ k1, n3 = uint32_t(p0);
@@ -483,7 +488,7 @@ ABX_HD void init_env_state(const SimParams &P, uint64_t seed, EnvState &s) {
   s.uniq = 0; s.next_order_id = 0; s.q_count = 0; s.max_q = 0; s.n_bid_lv = s.n_ask_lv = 0; s.n_resting = 0; s.free_head = NIL;
   s.pool_top = 0; s.flags = 0; s.trace_n = 0; s.c_limit = s.c_cancel = s.c_fills = s.c_query = 0;
   s.ctr_symbol = s.ctr_kernel = s.ctr_latency = s.ctr_global = 0; s.trade_epoch = EPOCH_START; s.sum_shares = 0; s.sum_cash = 0;
-  s.kblk[0] = s.kblk[1] = s.kblk[2] = s.kblk[3] = 0; s.draw_n = 0; s.evt_n = 0; s.book_flags = 0; s.episode = 0; s.hist_n = 0; s.n_subs = 0; s.book_update = 0;
+  s.kblk[0] = s.kblk[1] = s.kblk[2] = s.kblk[3] = 0; s.draw_n = 0; s.evt_n = 0; s.book_flags = 0; s.episode = 0; s.hist_n = 0; s.n_subs = 0; s.book_update = 0; s.next_pub = KEY_T_MAX; s.pad_p = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -666,8 +671,10 @@ struct Sim {
   }
   ABX_HD int32_t oracle_compute(int64_t ts, double v_adj, int64_t pt, int32_t pv) {     // :88-125
     double d = (double)(ts - pt); double mu = P.c.r_bar;
-    double loc = dadd(mu, dmul(dsub((double)pv, mu), exp_ni(dmul(-P.c.kappa, d))));
-    double scale = dmul(P.ou_scale, dsub(1.0, exp_ni(dmul(dmul(-2.0, P.c.kappa), d))));    // variance formula passed as scale
+    // exp(-2 kappa d) as the square of exp(-kappa d): it only enters through 1 - e^{-2 kappa d} ~ 2 kappa d, where an ulp of the square moves the scale of the draw by < 1e-7
+    // relative -- far below what int(round(.)) of a value ~1e5 resolves -- and saves one of the two exp evaluations per oracle step (+3.7 % msgs/s, profiles/r02_optimisation_log.md)
+    double ek = exp_ni(dmul(-P.c.kappa, d)), scale = dmul(P.ou_scale, dsub(1.0, dmul(ek, ek)));   // variance formula passed as scale
+    double loc = dadd(mu, dmul(dsub((double)pv, mu), ek));
     double v = rng.normal(S_SYMBOL, s.ctr_symbol, loc, scale);
     v = dadd(v, v_adj); if (!(v > 0)) v = 0;
     int32_t iv = (int32_t)py_round_i64(v); s.or_t = ts; s.or_v = iv; return iv;
@@ -1672,6 +1679,7 @@ struct Sim {
       int k = c.tab_find(MM_ORDER_CAP, (int)s.n_subs, (uint32_t)m.sender);
       if (k < 0) { if (s.n_subs >= (uint32_t)SUB_CAP) { s.flags |= ABX_F_AGENT_ORDERS_OVERFLOW; return; } k = (int)s.n_subs++; }
       uint4 e4; e4.x = (uint32_t)m.sender; e4.y = (uint32_t)m.p[0]; e4.z = (uint32_t)(uint64_t)s.now; e4.w = (uint32_t)((uint64_t)s.now >> 32); c.id_store(MM_ORDER_CAP + k, e4);
+      int64_t due = s.now + (agent_type_of(P.c, m.sender) == AT_MKM ? P.c.mkm_sub_freq_ns : P.c.mom_sub_freq_ns); if (due < s.next_pub) s.next_pub = due;
       return;
     }
     if (P3 && m.kind == ABX_QUERY_ORDER_STREAM) {                                       // :251-279 history[1 : length + 1]: REFERENCES to the bucket dicts of the last `length` trades.  The reply names them
@@ -1697,18 +1705,22 @@ struct Sim {
   // ExchangeAgent.publishOrderBookData :359-387: after every book operation, MARKET_DATA to each subscriber (in subscription order) whose `freq` ns have passed since its
   // last update.  The body's `levels` levels a side are copied into the subscriber's snapshot area NOW; the message carries the counts, the last trade and the slot.
   ABX_HD void exch_publish() {
+    if (s.book_update < s.next_pub) return;                                             // nobody is due (a subscriber is served at most once per period; the book changes far more often)
+    int64_t next = KEY_T_MAX;
 #pragma unroll 1
     for (int k = 0; k < (int)s.n_subs; k++) {
       uint4 e4 = c.id_load(MM_ORDER_CAP + k); int agent = (int)e4.x, levels = (int)e4.y; int64_t last = (int64_t)((uint64_t)e4.z | ((uint64_t)e4.w << 32));
       int64_t freq = agent_type_of(P.c, agent) == AT_MKM ? P.c.mkm_sub_freq_ns : P.c.mom_sub_freq_ns;
-      if (!(freq == 0 || (s.book_update > last && s.book_update - last >= freq))) continue;
+      if (!(freq == 0 || (s.book_update > last && s.book_update - last >= freq))) { if (last + freq < next) next = last + freq; continue; }
       int nb = s.n_bid_lv < levels ? s.n_bid_lv : levels, na = s.n_ask_lv < levels ? s.n_ask_lv : levels;
       c.snap_store(k, 0, s.n_bid_lv, nb); c.snap_store(k, 1, s.n_ask_lv, na);
       int32_t p[6] = {nb, na, k, 0, s.last_trade, 0};
       exch_send(agent, ABX_MARKET_DATA, p, lat_zero() ? 0.0 : c.agent_lat_from(agent));
       if (n_out >= Ctx::OUTN - 3) flush();
       e4.z = (uint32_t)(uint64_t)s.book_update; e4.w = (uint32_t)((uint64_t)s.book_update >> 32); c.id_store(MM_ORDER_CAP + k, e4);
+      if (s.book_update + freq < next) next = s.book_update + freq;
     }
+    s.next_pub = next;
   }
   ABX_HD AgentAux *aux() { return reinterpret_cast<AgentAux *>(z->theta); }
   // TradingAgent.placeLimitOrder :309-349 for the staged trader; `track`: the agent later iterates self.orders (Value, market maker)

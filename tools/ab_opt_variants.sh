@@ -5,7 +5,8 @@ cd "$(dirname "$0")/.."
 PKG=marl_optimal_execution_b200
 FL="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared"
 declare -A V
-ORDER="cur ptxO2 expens minb12 minb20 p7"
+V[noise4]="-DABX_NOISE4"
+ORDER="noise4 cur"
 if [ "$1" = build ]; then
   mkdir -p build/ab
   for v in $ORDER; do ( nvcc $FL ${V[$v]} -o build/ab/opt_$v.so $PKG/csrc/abx_sim.cu $PKG/csrc/abx_qnet.cu ) & done
