@@ -355,6 +355,10 @@ int32_t abx_dq_create_days(const abx_dq_config *cfg, const int64_t *stream5, con
  * (random_state.randint(min_size, max_size), MomentumAgent.py:42); mom_sizes: optional HOST int32 [n_envs][n_momentum] that
  * overrides the draws (replay of a recorded reference run); either may be NULL (seed 0). */
 int32_t abx_dq_reset(abx_sim *h, const uint64_t *seeds, const int32_t *mom_sizes, void *stream);
+/* Baseline execution agent `k` (0 .. n_twap-1) becomes a VWAPExecutionAgent (agent/execution/baselines/vwap_agent.py:48-62): qty HOST int32 [n] are its schedule's
+ * per-bin child quantities, round(volume_profile[bin] * quantity) for the n_horizon - 1 bins of the horizon (what generate_schedule builds; the agent class differs from the
+ * TWAP agent in nothing else).  Entries < 0 and bins beyond n keep the TWAP quantity.  Takes effect from the next abx_dq_reset / step; same schedule in every environment. */
+int32_t abx_dq_set_schedule(abx_sim *h, int32_t k, const int32_t *qty, int32_t n);
 /* One decision step for every environment.  DEVICE pointers: actions int32 [n_envs] in 0..23 (ACTIONS, :24-37; ignored by
  * environments with no decision pending, i.e. on the first call), obs fp64 [n_envs][8] = the 6 observation features (:332) + the 2
  * digitised state entries the network sees (:334, util.py:23-42), trans fp64 [n_envs][6] = the finalised experience entry of the

@@ -141,6 +141,7 @@ def _bind(L):
     sig("abx_config_rmsc03_pov", i32, P(SimConfig))
     sig("abx_config_rmsc01", i32, P(SimConfig))
     sig("abx_config_rmsc02", i32, P(SimConfig))
+    sig("abx_dq_set_schedule", i32, vp, i32, P(i32), i32)
     sig("abx_sim_pov_exec", i32, vp, i32, P(i64), vp)
     sig("abx_sim_create", i32, P(SimConfig), i32, i32, P(vp))
     sig("abx_sim_destroy", i32, vp)

@@ -163,6 +163,7 @@ struct SimParams {
   EnvState *env;                // [n_envs]
   abx_trace_rec *trace;         // [n_envs][trace_cap]
   uint4 *draw_log;              // [n_envs][draw_log_cap] {stream | kind << 24, bits lo, bits hi, -}  (parity runs under Philox)
+  const int32_t *sched;         // [dq_n_twap][n_h] per-bin child quantities of the baseline execution agents (VWAP schedule), < 0 = the TWAP quantity; shared by all environments
   uint4 *hlog;                  // [n_envs][hist_stride_of(c)] {order id, limit price, history epoch at registration, is_buy | has transactions << 1}  (population 3)
   uint4 *evt;                   // [n_envs][event_ring_cap] {t lo, t hi | kind << 28, a, b}: order arrivals, BEST_BID / BEST_ASK / LAST_TRADE (realism tooling)
   const uint64_t *tape_bits; const uint8_t *tape_kinds; const int64_t *tape_off; // tape mode
@@ -1525,7 +1526,8 @@ struct Sim {
         if (hi == P.n_h - 2) dq_place_market(id, ex.rem_qty);
         else if (hi >= 0 && hi < P.n_h - 2) {
           if (!both) s.flags |= ABX_F_OBS_INVALID;
-          else { if (hi == 0) ex.arr2 = a.bid + a.ask; dq_place_limit(id, ex.child_qty, P.rl_is_buy != 0, P.rl_is_buy ? a.ask : a.bid); }
+          else { if (hi == 0) ex.arr2 = a.bid + a.ask; int32_t sq = P.sched ? P.sched[exec_index(id) * P.n_h + hi] : -1;      // self.schedule[pd.Interval(now, now + 30 s)] (execution_agent.py:121): TWAP's one quantity or the VWAP agent's per-bin one
+                 dq_place_limit(id, sq >= 0 ? sq : ex.child_qty, P.rl_is_buy != 0, P.rl_is_buy ? a.ask : a.bid); }
         }
       }
     } else if (m.kind == ABX_ORDER_ACCEPTED || m.kind == ABX_ORDER_EXECUTED) {         // handle_order_acceptance :550-576 / handle_order_execution :507-548

@@ -280,7 +280,7 @@ struct abx_sim {
   uint64_t *d_seeds; uint32_t *d_init_err; abx_env_stats *d_stats; int64_t *d_until;
   uint64_t *d_tbits; uint8_t *d_tkinds; int64_t *d_toff;
   bool is_env, is_dq, have_seeds, have_msizes; EnvStreamHost *st; EnvDaysHost *dh; int4 *d_daytab, *d_daytab2; int32_t *d_xid, *d_xfirst; int64_t *d_ts; int32_t *d_first; int4 *d_rows; double *d_act, *d_obs, *d_rew; uint8_t *d_done;
-  int32_t *d_iact, *d_msizes; double *d_trans;
+  int32_t *d_iact, *d_msizes, *d_sched; double *d_trans;
   int auto_reset;                       // 0 off, 1 restart the same day, 2 move on to the next day: applied to finished environments after every step
   bool is_book; int64_t *d_ops; int64_t ops_cap; std::unordered_map<int64_t, int32_t> *book_ids;
 };
@@ -321,7 +321,7 @@ int32_t abx_sim_destroy(abx_sim *h) {
   cudaSetDevice(h->device);
   void *ptrs[] = {h->P.qkey, h->P.qpay0, h->P.qpay1, h->P.qcache, h->P.agents, h->P.lv_price, h->P.lv_qty, h->P.lv_ht, h->P.nodes, h->P.env,
                   h->P.trace, h->P.draw_log, h->P.evt, h->P.hlog, h->P.snap, h->d_seeds, h->d_init_err, h->d_stats, h->d_until, h->d_tbits, h->d_tkinds, h->d_toff,
-                  h->P.envx, h->P.idtab, h->P.idbook, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_iact, h->d_msizes, h->d_trans, h->d_ops, h->d_daytab, h->d_daytab2, h->d_xid, h->d_xfirst};
+                  h->P.envx, h->P.idtab, h->P.idbook, h->P.lobs, h->d_ts, h->d_first, h->d_rows, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_iact, h->d_msizes, h->d_sched, h->d_trans, h->d_ops, h->d_daytab, h->d_daytab2, h->d_xid, h->d_xfirst};
   for (void *p : ptrs) if (p) cudaFree(p);
   delete h->st; delete h->dh; delete h->book_ids; delete h; return ABX_OK;
 }
@@ -668,8 +668,10 @@ int32_t abx_dq_create_days(const abx_dq_config *cfg, const int64_t *stream5, con
   DA(h->d_ts, dh->ts.size()) DA(h->d_first, dh->first.size()) DA(h->d_rows, dh->rows.size()) DA(h->d_daytab, dh->day_tab.size())
   DA(h->d_daytab2, dh->day_tab2.size()) DA(h->d_xid, dh->xid.size() + 1) DA(h->d_xfirst, dh->xfirst.size() + 1)
   DA(h->d_iact, E) DA(h->d_obs, E * 8) DA(h->d_trans, E * 6) DA(h->d_rew, E) DA(h->d_done, E) DA(h->d_msizes, E * (cfg->n_momentum > 0 ? cfg->n_momentum : 1))
+  if (cfg->n_twap > 0) { DA(h->d_sched, (size_t)cfg->n_twap * cfg->n_horizon) }
   h->P.n_snap = n_exec > 0 ? n_exec : 1; h->P.snap_depth = DQ_DEPTH; DA(h->P.snap, E * (size_t)h->P.n_snap * 2 * DQ_DEPTH)                      // getCurrentSpread(depth=500) copies
 #undef DA
+  if (h->d_sched) CUH(cudaMemset(h->d_sched, 0xFF, sizeof(int32_t) * (size_t)cfg->n_twap * cfg->n_horizon));     // -1: no per-bin schedule, the TWAP quantity
   CUH(cudaMemcpy(h->d_ts, dh->ts.data(), sizeof(int64_t) * dh->ts.size(), cudaMemcpyHostToDevice));
   CUH(cudaMemcpy(h->d_first, dh->first.data(), sizeof(int32_t) * dh->first.size(), cudaMemcpyHostToDevice));
   CUH(cudaMemcpy(h->d_rows, dh->rows.data(), sizeof(int4) * dh->rows.size(), cudaMemcpyHostToDevice));
@@ -689,6 +691,14 @@ int32_t abx_dq_create(const abx_dq_config *cfg, const int64_t *stream5, int64_t 
   int64_t off[2] = {0, n_rows}; return abx_dq_create_days(cfg, stream5, off, 1, n_envs, device, out);
 }
 
+int32_t abx_dq_set_schedule(abx_sim *h, int32_t k, const int32_t *qty, int32_t n) {
+  if (!h || !h->is_env || h->P.c.population != 2 || k < 0 || k >= h->P.dq_n_twap || !qty || n < 1 || !h->d_sched) return ABX_ERR_ARG;
+  CU(cudaSetDevice(h->device));
+  std::vector<int32_t> row((size_t)h->P.n_h, -1);
+  for (int i = 0; i < n && i < h->P.n_h; i++) row[i] = qty[i];
+  CU(cudaMemcpy(h->d_sched + (size_t)k * h->P.n_h, row.data(), sizeof(int32_t) * row.size(), cudaMemcpyHostToDevice));
+  h->P.sched = h->d_sched; return ABX_OK;
+}
 int32_t abx_dq_reset(abx_sim *h, const uint64_t *seeds, const int32_t *mom_sizes, void *stream) {
   if (!h || !h->is_dq) return ABX_ERR_ARG;
   CU(cudaSetDevice(h->device)); cudaStream_t st = (cudaStream_t)stream;

@@ -272,6 +272,18 @@ def dq_config(lib=None, **overrides):
     return cfg
 
 
+def vwap_schedule(volume_profile, quantity):
+    """VWAPExecutionAgent.generate_schedule (agent/execution/baselines/vwap_agent.py:48-62): per-bin child quantities round(profile[bin] * quantity) (Python's
+    round: half to even) for a volume profile given as one fraction per horizon bin."""
+    return np.array([int(round(float(f) * quantity)) for f in volume_profile], dtype=np.int32)
+
+
+def synthetic_volume_profile(n_bins):
+    """The U shape of VWAPExecutionAgent.synthetic_volume_profile (vwap_agent.py:64-78: x^2 + 2x + 2 over x = -n/2 .. n/2 - 1, normalised) over n_bins bins."""
+    w = np.array([x * x + 2 * x + 2 for x in range(int(-n_bins / 2), int(-n_bins / 2) + n_bins)], dtype=np.float64)
+    return w * (1.0 / w.sum())
+
+
 class DDQNExecutionEnv(ABIDESEnv):
     """The reference's DDQN execution simulation (config/execution/marketreplay/execution_marketreplay_ddqn.py, -a rl) as a
     batched decision process: Exchange + MarketReplayAgent + MomentumAgents + TWAPExecutionAgent + DDQLearningExecutionAgent.
@@ -313,6 +325,12 @@ class DDQNExecutionEnv(ABIDESEnv):
         """(ticker, date) as config/execution/marketreplay/execution_marketreplay_ddqn.py takes them (-t, -d): the day's LOBSTER message
         file(s) under `data_root`, parsed like LOBSTEROrdersProcessor (load_lobster_csv)."""
         return cls(ticker, date, n_envs=n_envs, data_root=data_root, level=level, **kw)
+
+    def set_schedule(self, k, qty):
+        """Baseline execution agent k (0 .. n_twap-1) trades a per-bin schedule instead of the TWAP quantity: the reference's VWAPExecutionAgent
+        (agent/execution/baselines/vwap_agent.py:48-62) -- `qty[b] = round(volume_profile[bin b] * quantity)`, see `vwap_schedule`.  Call before reset()."""
+        q = np.ascontiguousarray(qty, dtype=np.int32)
+        _lib.check(self._L, self._L.abx_dq_set_schedule(self._h, int(k), q.ctypes.data_as(C.POINTER(C.c_int32)), len(q)), "abx_dq_set_schedule")
 
     def reset(self, seeds=None, mom_sizes=None, stream=None, mask=None, advance_day=False):
         """Whole-batch reset with per-environment seeds (or recorded MomentumAgent sizes); with `mask`, only those environments start over, keeping the

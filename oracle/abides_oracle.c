@@ -1649,7 +1649,7 @@ typedef struct {
   open_order_t *orders; int n_orders, cap_orders;                                             /* self.orders, insertion ordered */
   pq_t *kb, *ka; int nkb, nka, cap_k;                                                        /* known_bids / known_asks */
   pq_t *fb, *fa; int nfb, nfa;                                                               /* lists of the in-flight QUERY_SPREAD reply */
-  double arrival; int has_arrival; int64_t child_qty;
+  double arrival; int has_arrival; int64_t child_qty; int64_t *sched; int n_sched;   /* sched: per-bin child quantities (VWAPExecutionAgent.generate_schedule, vwap_agent.py:48-62); NULL = one quantity (TWAP) */
   int t, rem_time, pending, cur_s[2], sp[2]; double obs6[6];                                  /* DDQN: self.t, remaining_time, decision pending, self.s */
   double *pp; int n_pp, cap_pp; double *exp; int n_exp, cap_exp; double *rew; int n_rew, cap_rew; double *ahist; int n_ahist, cap_ahist;
   double step_reward;                                                                         /* sum of step rewards since the last decision */
@@ -1775,7 +1775,7 @@ static void dq_exec_receive(abo_env *s, exec_t *e, const event_t *m) {
       else if (hi >= 0 && hi < d->n_h - 2) {
         if (e->nkb == 0 || e->nka == 0) { d->error |= DQ_ERR_EMPTY_SIDE; return; }
         if (hi == 0) { e->arrival = (double)(e->kb[0].p + e->ka[0].p) / 2; e->has_arrival = 1; }
-        dq_place_limit(s, e->id, &e->orders, &e->n_orders, &e->cap_orders, e->child_qty, d->is_buy, d->is_buy ? e->ka[0].p : e->kb[0].p);
+        dq_place_limit(s, e->id, &e->orders, &e->n_orders, &e->cap_orders, (e->sched && hi < e->n_sched) ? e->sched[hi] : e->child_qty, d->is_buy, d->is_buy ? e->ka[0].p : e->kb[0].p);   /* self.schedule[pd.Interval(now, now + 30 s)] */
       }
     }
     return;
@@ -1832,8 +1832,13 @@ abo_env *abo_dq_new(const int64_t *stream5, int64_t n_rows, int n_mom, const int
 static void dq_free(abo_env *s) {
   dq_state *d = s->dq; if (!d) return;
   for (int i = 0; i < d->n_mom; i++) free(d->mom[i].mids);
-  for (int k = 0; k < d->n_ex; k++) { exec_t *e = &d->ex[k]; free(e->orders); free(e->kb); free(e->ka); free(e->fb); free(e->fa); free(e->pp); free(e->exp); free(e->rew); free(e->ahist); }
+  for (int k = 0; k < d->n_ex; k++) { exec_t *e = &d->ex[k]; free(e->orders); free(e->kb); free(e->ka); free(e->fb); free(e->fa); free(e->pp); free(e->exp); free(e->rew); free(e->ahist); free(e->sched); }
   free(d); s->dq = NULL;
+}
+/* The baseline execution agent k gets a per-bin schedule: what VWAPExecutionAgent.generate_schedule builds from its volume profile (round(profile[bin] * quantity)). */
+int abo_dq_set_schedule(abo_env *s, int k, const int64_t *qty, int n) {
+  dq_state *d = s ? s->dq : NULL; if (!d || k < 0 || k >= d->n_twap || !qty || n < 1) return -1;
+  exec_t *e = &d->ex[k]; free(e->sched); e->sched = (int64_t *)malloc(sizeof(int64_t) * n); memcpy(e->sched, qty, sizeof(int64_t) * n); e->n_sched = n; return 0;
 }
 /* One decision step.  `action` completes the pending decision (ignored when none is pending: first call).  Runs Kernel.runner's loop
  * (Kernel.py:190-292) until the DDQN agent reaches choose_action again or the loop ends.  out8: the 6 observation features + s' (2 digitised

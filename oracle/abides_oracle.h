@@ -149,6 +149,7 @@ int64_t abo_env_counter(abo_env *, int which); /* 0 max queue, 1 max bid levels,
  * The Q-network is an input (the action of every decision tick); handles are abo_env (abo_env_free / n_pops / hashes / trace work). */
 abo_env *abo_dq_new(const int64_t *stream5, int64_t n_rows, int n_mom, const int64_t *mom_sizes, int n_twap, int has_ddqn, int is_buy,
                     int64_t quantity, int64_t h0_ns, int64_t h_step_ns, int n_h, int64_t mom_wake_ns, int trace_flags);
+int abo_dq_set_schedule(abo_env *, int k, const int64_t *qty, int n);   /* per-bin child quantities of baseline execution agent k (VWAP) */
 int abo_dq_step(abo_env *, int action, double *out8, double *trans6, double *reward, int *done);
 int abo_dq_error(abo_env *);
 int64_t abo_dq_series(abo_env *, int which /*0 price_path, 1 experience x6, 2 step_reward_hist, 3 action_hist*/, const double **v);

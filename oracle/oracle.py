@@ -113,6 +113,7 @@ def lib():
     sig("abo_env_trace", i64, vp, i32, P(P(i64)))
     sig("abo_env_final", None, vp, P(dbl))
     sig("abo_env_counter", i64, vp, i32)
+    sig("abo_dq_set_schedule", i32, vp, i32, P(i64), i32)
     sig("abo_dq_new", vp, P(i64), i64, i32, P(i64), i32, i32, i32, i64, i64, i64, i32, i64, i32)
     sig("abo_dq_step", i32, vp, i32, P(dbl), P(dbl), P(dbl), P(i32))
     sig("abo_dq_error", i32, vp)
@@ -457,6 +458,12 @@ class OracleDDQNEnv(OracleEnv):
                                    int(n_twap), int(bool(has_ddqn)), int(bool(is_buy)), int(quantity), int(h0_ns), int(h_step_ns), int(n_h), int(mom_wake_ns), int(trace))
         if not self._h:
             raise ValueError("abo_dq_new rejected the configuration")
+
+    def set_schedule(self, k, qty):
+        """Baseline execution agent k places qty[bin] instead of the TWAP child quantity (VWAPExecutionAgent.generate_schedule, vwap_agent.py:48-62)."""
+        q = np.ascontiguousarray(qty, dtype=np.int64)
+        if lib().abo_dq_set_schedule(self._h, int(k), q.ctypes.data_as(C.POINTER(C.c_int64)), len(q)) != 0:
+            raise ValueError("abo_dq_set_schedule rejected the schedule")
 
     def step(self, action):
         """-> (obs8 = 6 features + 2 digitised state entries, trans6 = finalised (s, a, s', r) of the previous tick, reward, done)"""

@@ -175,7 +175,7 @@ struct abx_sim {
   SimParams P; int n_envs; bool reset_done;
   std::vector<uint4> qkey, qpay0, qpay1, qcache, nodes; std::vector<ZiAgent> agents; std::vector<int32_t> lvp, lvq; std::vector<uint32_t> lvht;
   std::vector<EnvState> env; std::vector<abx_trace_rec> trace; std::vector<uint4> draw_log, evt, hlog; std::vector<uint64_t> tbits; std::vector<uint8_t> tkinds; std::vector<int64_t> toff;
-  bool is_env; EnvStreamHost st; EnvDaysHost dh; bool has_days = false; std::vector<EnvX> envx; std::vector<uint4> idtab; std::vector<int4> lobs; std::vector<uint2> idbook; std::vector<int2> snap; int auto_reset = 0; std::vector<uint64_t> dq_seeds; std::vector<int32_t> dq_msizes;
+  bool is_env; EnvStreamHost st; EnvDaysHost dh; bool has_days = false; std::vector<EnvX> envx; std::vector<uint4> idtab; std::vector<int4> lobs; std::vector<uint2> idbook; std::vector<int2> snap; int auto_reset = 0; std::vector<uint64_t> dq_seeds; std::vector<int32_t> dq_msizes, sched;
 };
 
 extern "C" {
@@ -413,6 +413,12 @@ static void emu_dq_reset(abx_sim *h, const uint8_t *mask, int mode, int advance_
       init_agent_record_dq(h->P, e, id, seed, (!h->dq_msizes.empty() && id < 2 + h->P.dq_n_mom) ? h->dq_msizes[(size_t)e * h->P.dq_n_mom + id - 2] : -1, &h->agents[(size_t)e * h->P.c.n_agents + id]);
     ctx.q_clear(); DqSimHost sim(ctx, h->P, s, e); sim.env_reset(); h->env[e] = sim.s;
   }
+}
+int32_t abx_dq_set_schedule(abx_sim *h, int32_t k, const int32_t *qty, int32_t n) {
+  if (!h || !h->is_env || h->P.c.population != 2 || k < 0 || k >= h->P.dq_n_twap || !qty || n < 1) return ABX_ERR_ARG;
+  if (h->sched.empty()) h->sched.assign((size_t)h->P.dq_n_twap * h->P.n_h, -1);
+  for (int i = 0; i < h->P.n_h; i++) h->sched[(size_t)k * h->P.n_h + i] = i < n ? qty[i] : -1;
+  h->P.sched = h->sched.data(); return ABX_OK;
 }
 int32_t abx_dq_reset(abx_sim *h, const uint64_t *seeds, const int32_t *mom_sizes, void *stream) {
   (void)stream; if (!h || !h->is_env || h->P.c.population != 2) return ABX_ERR_ARG;

@@ -118,3 +118,65 @@ def test_closed_loop_with_a_real_network_oracle_side(golden_dir):
     assert k == 660 and o.n_pops == int(g["n_pops"]) and o.pop_hash() == int(g["pop_hash_ckpt"][-1]) and o.error() == 0
     assert o.note_hash() == int(g["note_hash"]) and o.snap_hash() == int(g["snap_hash"])
     assert abs(total - float(g["step_reward_hist"].sum())) < 1e-9 * abs(total)
+
+
+VWAP_FIXTURE = "ddqn_vwap_IBM_2003-01-15_s77.npz"
+
+
+def load_vwap(golden_dir):
+    g = np.load(os.path.join(golden_dir, VWAP_FIXTURE))
+    stream = np.load(os.path.join(golden_dir, str(g["stream_fixture"])))["stream"]
+    return g, stream
+
+
+def test_vwap_schedule_helpers_equal_the_reference_agents(golden_dir):
+    """`vwap_schedule(synthetic_volume_profile(n), quantity)` == the schedule the reference's VWAPExecutionAgent built from the same profile
+    (tools/record_reference_ddqn.py --vwap stores both): 660 bins, 9 of them zero shares, total 500 003."""
+    from marl_optimal_execution_b200.env import synthetic_volume_profile, vwap_schedule
+    g, _ = load_vwap(golden_dir)
+    w = synthetic_volume_profile(660)
+    assert np.array_equal(w, g["vwap_profile"])
+    sch = vwap_schedule(w, 500000)
+    assert np.array_equal(sch, g["vwap_schedule"]) and int(sch.sum()) == 500003 and int((sch == 0).sum()) == 9
+
+
+def test_oracle_reproduces_the_vwap_recording(golden_dir):
+    """The config's baseline execution agent replaced by the reference's VWAPExecutionAgent (recorder --vwap): the oracle with the same per-bin schedule
+    reproduces 212 827 pops, every exchange message and book snapshot, every book operation of the two execution agents (zero-quantity bins consume an
+    order id and send nothing), the DDQN agent's observations, experience and rewards, and the holdings."""
+    g, stream = load_vwap(golden_dir)
+    o = OracleDDQNEnv(stream, g["mom_sizes"], is_buy=True, trace=TRACE_ALL)
+    o.set_schedule(0, g["vwap_schedule"])
+    out, tr, r, done = o.step(0)
+    k = 0
+    while not done:
+        assert np.allclose(out[:6], g["observation"][k], rtol=1e-12, atol=1e-15)
+        out, tr, r, done = o.step(int(g["actions"][k]))
+        k += 1
+    assert o.n_pops == int(g["n_pops"]) == 212827 and o.pop_hash() == int(g["pop_hash_ckpt"][-1]) and o.error() == 0
+    assert o.note_hash() == int(g["note_hash"]) and o.snap_hash() == int(g["snap_hash"])
+    ops = o.trace("ops")
+    assert np.array_equal(ops[ops[:, 2] >= 9], g["rl_ops"])
+    assert np.array_equal(o.series("step_reward_hist"), g["step_reward_hist"]) and np.array_equal(o.holdings()[:, :4], g["holdings"][:, :4])
+    fin = o.exec_final(0) if hasattr(o, "exec_final") else None
+    assert fin is None or (fin[0] == g["twap_final"][0] and fin[2] == g["twap_final"][2])
+
+
+def test_vwap_episode_matches_oracle_and_reference(emu, golden_dir):
+    """The product logic with `set_schedule` (abx_dq_set_schedule): the VWAP agent's episode tick by tick against the oracle and the recording."""
+    g, stream = load_vwap(golden_dir)
+    L = _lib.load(emu)
+    env = DDQNExecutionEnv(stream, n_envs=2, cfg=dq_config(L, is_buy=1, trace_cap=460000, hash_pops=1), lib_path=emu)
+    env.set_schedule(0, g["vwap_schedule"])
+    env.reset(mom_sizes=np.tile(g["mom_sizes"].astype(np.int32), (2, 1)))
+    o = OracleDDQNEnv(stream, g["mom_sizes"], is_buy=True, trace=TRACE_ALL)
+    o.set_schedule(0, g["vwap_schedule"])
+    k, total = run_episode(env, o, g, 2)
+    st = env.stats()
+    assert int(st["messages"][0]) == o.n_pops == int(g["n_pops"]) and int(st["flags"][0]) == _lib.F_DONE and o.error() == 0
+    assert int(st["pop_hash"][0]) == o.pop_hash() == int(g["pop_hash_ckpt"][-1])
+    p, nt, sn = env.split_trace(0)
+    assert np.array_equal(p, o.trace("pops")) and np.array_equal(nt, o.trace("notes")) and np.array_equal(sn, o.trace("snaps"))
+    hold, ex = env.holdings(0)
+    assert np.array_equal(hold[:, :4], g["holdings"][:, :4])
+    assert ex[0, 0] == g["twap_final"][0] and ex[0, 1] == g["twap_final"][1] and ex[0, 2] == g["twap_final"][2]

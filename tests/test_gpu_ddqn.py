@@ -55,6 +55,39 @@ def test_ddqn_run_matches_reference_recording_and_oracle(golden_dir, fixture):
     assert ex[1, 0] == g["ddqn_final"][0] and ex[1, 1] == g["ddqn_final"][3] and ex[1, 2] == g["ddqn_final"][4] and ex[1, 4] == g["ddqn_final"][2]
 
 
+def test_vwap_execution_agent_matches_reference_recording_and_oracle(golden_dir):
+    """the config's baseline execution agent as the reference's VWAPExecutionAgent (tools/record_reference_ddqn.py --vwap): per-bin schedule
+    through abx_dq_set_schedule; event order, exchange messages, snapshots, the agent's fills and the DDQN agent's rewards equal the oracle, which reproduces the
+    live recording (tests/test_emu_ddqn.py::test_oracle_reproduces_the_vwap_recording)."""
+    g = np.load(os.path.join(golden_dir, "ddqn_vwap_IBM_2003-01-15_s77.npz"))
+    stream = np.load(os.path.join(golden_dir, str(g["stream_fixture"])))["stream"]
+    env = DDQNExecutionEnv(stream, n_envs=2, cfg=dq_config(is_buy=1, trace_cap=460000, hash_pops=1))
+    env.set_schedule(0, g["vwap_schedule"])
+    env.reset(mom_sizes=np.tile(g["mom_sizes"].astype(np.int32), (2, 1)))
+    o = OracleDDQNEnv(stream, g["mom_sizes"], is_buy=True, trace=TRACE_ALL)
+    o.set_schedule(0, g["vwap_schedule"])
+    acts = g["actions"]
+    obs, trans, rew, done = env.step(None)
+    oo, otr, orw, od = o.step(0)
+    k = 0
+    while not done[0]:
+        assert not od and np.allclose(obs[0], oo, rtol=1e-9, atol=1e-12), k
+        assert np.allclose(obs[0, :6], g["observation"][k], rtol=1e-6, atol=1e-12), k
+        obs, trans, rew, done = env.step(np.full(2, int(acts[k]), dtype=np.int32))
+        oo, otr, orw, od = o.step(int(acts[k]))
+        assert np.isclose(rew[0], orw, rtol=1e-9, atol=1e-12), k
+        k += 1
+    assert od and k == 660
+    st = env.stats()
+    assert int(st["messages"][0]) == o.n_pops == int(g["n_pops"]) == 212827 and (st["flags"] == _lib.F_DONE).all(), st["flags"]
+    assert int(st["pop_hash"][0]) == int(st["pop_hash"][1]) == o.pop_hash() == int(g["pop_hash_ckpt"][-1])
+    p, nt, sn = env.split_trace(0)
+    assert np.array_equal(p, o.trace("pops")) and np.array_equal(nt, o.trace("notes")) and np.array_equal(sn, o.trace("snaps"))
+    hold, ex = env.holdings(0)
+    assert np.array_equal(hold[:, :4], g["holdings"][:, :4])
+    assert ex[0, 0] == g["twap_final"][0] and ex[0, 1] == g["twap_final"][1] and ex[0, 2] == g["twap_final"][2]
+
+
 def test_ddqn_batch_is_deterministic_and_seed_dependent(golden_dir):
     """Philox-drawn MomentumAgent sizes: same seed -> identical environments, different seeds -> different runs; no error flags."""
     g = np.load(os.path.join(golden_dir, "ddqn_IBM_2003-01-14_s4242.npz"))

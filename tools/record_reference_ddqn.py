@@ -2,6 +2,9 @@
 """Record a golden run of the DDQN execution config from the UNMODIFIED reference (build container only).
 
   python tools/record_reference_ddqn.py IBM 2003-01-14 4242 tests/golden/ddqn_IBM_2003-01-14_s4242.npz [policy_seed [BUY|SELL]]
+  python tools/record_reference_ddqn.py IBM 2003-01-15 77 tests/golden/ddqn_vwap_IBM_2003-01-15_s77.npz 94 BUY --vwap
+      --vwap: the config's baseline execution agent is the reference's VWAPExecutionAgent (agent/execution/baselines/vwap_agent.py) instead of its TWAP agent, with a
+      U-shaped volume profile pickled for volume_profile_path (the only way the class can be constructed as shipped); the profile and the schedule it yields are stored
 
 Runs config/execution/marketreplay/execution_marketreplay_ddqn.py (Exchange + MarketReplayAgent + 7 MomentumAgents +
 TWAPExecutionAgent + DDQLearningExecutionAgent, BUY 500 000 shares from 10:00 over 330 min at "30s") in `test` mode with
@@ -118,6 +121,7 @@ def main():
         flat = init_params(DEFAULT_DIMS, seed=pseed)
         flat = (flat + np.random.RandomState.__new__(np.random.RandomState).__class__(pseed + 1).normal(0, 0.15, size=flat.shape)).astype(np.float32)   # trained-like: non-zero biases, no ties
         POLICY["mlp"] = (flat, DEFAULT_DIMS)
+    vwap = "--vwap" in sys.argv
     install_stubs()
     POLICY["rs"] = np.random.RandomState.__new__(np.random.RandomState)
     np.random.RandomState.__init__(POLICY["rs"], pseed)          # created before the hooks: not one of the reference's streams
@@ -128,6 +132,31 @@ def main():
     import agent.Agent as AG
     AG.Agent.writeLog = lambda self, dfLog, filename=None: None             # bz2 log files, out of scope
     R.REC.midnight = pd.to_datetime(date)
+    if vwap:
+        # The config script names TWAPExecutionAgent; the recorder swaps the NAME it imports for a factory of the reference's own VWAPExecutionAgent, so that the
+        # unmodified config builds, registers and runs that class.  Profile: x^2 + 2x + 2 over the horizon's 30 s bins, normalised (the shape of the class's own
+        # synthetic_volume_profile, which cannot be used: its freq must be an int for f"{freq}s" while interval_range needs a string / Timedelta).
+        import pickle
+        import agent.execution.baselines.twap_agent as TW
+        from agent.execution.baselines.vwap_agent import VWAPExecutionAgent
+        prof_path = os.path.join(tempfile.mkdtemp(prefix="abides_vwap_"), "profile.pkl")
+
+        def make_vwap(**kw):
+            kw.pop("log_events", None)                       # VWAPExecutionAgent.__init__ has no such parameter
+            hz = kw["execution_time_horizon"]
+            lefts = pd.date_range(hz[0], hz[-1], freq=kw["freq"])[:-1]
+            n = len(lefts)
+            w = np.array([x * x + 2 * x + 2 for x in range(int(-n / 2), int(-n / 2) + n)], dtype=np.float64)
+            w = w * (1.0 / w.sum())
+            ser = pd.Series(w, index=lefts)
+            with open(prof_path, "wb") as f:
+                pickle.dump(ser, f)
+            POLICY["vwap_profile"] = w
+            ag = VWAPExecutionAgent(volume_profile_path=prof_path, **kw)
+            POLICY["vwap_schedule"] = np.array([ag.schedule[b] for b in ag.schedule], dtype=np.int64)
+            return ag
+
+        TW.TWAPExecutionAgent = make_vwap
     cfg = "execution.marketreplay.execution_marketreplay_ddqn"
     sys.argv = ["abides.py", "-c", cfg, "-s", str(seed), "-t", ticker, "-d", date, "--direction", direction, "--parent_qty", "500000",
                 "--start_hour", "10", "--horizon_length", "330", "--freq", "30s", "-m", "test", "-a", "rl", "-l", "rec_ddqn", "--code", "rec"]
@@ -172,7 +201,7 @@ def main():
     stream = np.array([(R.REC.ns(ts), int(r["ORDER_ID"]), int(r["PRICE"]), int(r["SIZE"]), 1 if r["BUY_SELL_FLAG"] == "BUY" else 0)
                        for ts in od for r in od[ts]], dtype=np.int64)
     mom = [a for a in agents if type(a).__name__ == "MomentumAgent"]
-    twap = [a for a in agents if type(a).__name__ == "TWAPExecutionAgent"][0]
+    twap = [a for a in agents if type(a).__name__ in ("TWAPExecutionAgent", "VWAPExecutionAgent")][0]
     dq = agents[-1]
     assert type(dq).__name__ == "DDQLearningExecutionAgent"
     T = len(dq.experience)
@@ -202,6 +231,8 @@ def main():
         ddqn_final=np.array([dq.remaining_qty, dq.remaining_time, dq.t, dq.arrival_price, len(dq.executed_orders)], dtype=np.float64),
         twap_final=np.array([twap.rem_quantity, twap.arrival_price, len(twap.executed_orders)], dtype=np.float64),
     )
+    if vwap:
+        data["vwap_profile"], data["vwap_schedule"] = POLICY["vwap_profile"], POLICY["vwap_schedule"]
     if POLICY["mlp"] is not None:                       # the network that chose the actions, its Q rows, and a slimmer fixture (the traces are pinned by the other goldens)
         data["mlp_params"], data["mlp_q"] = POLICY["mlp"][0], np.array(POLICY["q"], dtype=np.float32)
         for k in ("pops_head", "ops_head", "notes_head", "snaps_head", "rl_ops"):
