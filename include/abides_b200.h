@@ -138,6 +138,11 @@ typedef struct abx_sim_config {
    * agent/ExchangeAgent.py:342-387).  mkm_num_levels levels a side for the market maker (subscribe_num_levels), 1 for momentum agents. */
   int32_t mkm_subscribe, mom_subscribe;
   int64_t mkm_sub_freq_ns, mom_sub_freq_ns;   /* subscribe_freq (10e9) / MomentumAgent.py:58 (10e9) */
+  /* population 1, the optional execution agent (n_pov_exec = 1) as one of the other baselines instead of the POV agent: exec_kind 1 = PassiveAgent
+   * (agent/execution/baselines/passive_agent.py: one LIMIT order of pov_exec_quantity at pov_exec_start_ns, at exec_limit_price or, when that is 0, at the best bid (BUY) /
+   * ask (SELL) of a QUERY_SPREAD it sends then), 2 = AggressiveAgent (aggressive_agent.py: getCurrentSpread(depth=100) at pov_exec_start_ns, then a market order of
+   * pov_exec_quantity walked over the levels it was told, TradingAgent.py:351-397).  0 = POVExecutionAgent. */
+  int32_t exec_kind, exec_limit_price;
   int32_t hist_log_cap, hbl_table_rows;   /* hbl_table_rows: price rows of the HBL belief table held per environment, 0 = hist_log_cap / 4 (the maximum); wider price spans take a slower exact form */
 } abx_sim_config;
 

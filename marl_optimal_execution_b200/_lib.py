@@ -63,6 +63,7 @@ class SimConfig(C.Structure):
         ("draw_log_cap", C.c_int32), ("event_ring_cap", C.c_int32),
         ("hbl_L", C.c_int32), ("mkm_min_size", C.c_int32), ("mkm_max_size", C.c_int32), ("mkm_num_levels", C.c_int32), ("mkm_wake_ns", C.c_int64),
         ("mkm_subscribe", C.c_int32), ("mom_subscribe", C.c_int32), ("mkm_sub_freq_ns", C.c_int64), ("mom_sub_freq_ns", C.c_int64),
+        ("exec_kind", C.c_int32), ("exec_limit_price", C.c_int32),
         ("hist_log_cap", C.c_int32), ("hbl_table_rows", C.c_int32),
     ]
 

@@ -1404,8 +1404,9 @@ struct Sim {
   ABX_HD ExecAux *exaux() { return reinterpret_cast<ExecAux *>(z->oid); }
   ABX_HD int exec_index(int id) const { return R3 ? 0 : id - (2 + P.dq_n_mom); }        // which snapshot area / order table an execution agent owns
   // ExchangeAgent.py:231-245 for a deep query: getInsideBids(depth) / getInsideAsks(depth) copied at processing time.  Returns bids | asks << 16.
-  ABX_HD int32_t snap_take(int k) {
-    int nb = s.n_bid_lv < P.snap_depth ? s.n_bid_lv : P.snap_depth, na = s.n_ask_lv < P.snap_depth ? s.n_ask_lv : P.snap_depth;
+  ABX_HD int32_t snap_take(int k, int depth = 0x7fffffff) {
+    if (depth > P.snap_depth) depth = P.snap_depth;
+    int nb = s.n_bid_lv < depth ? s.n_bid_lv : depth, na = s.n_ask_lv < depth ? s.n_ask_lv : depth;
     c.snap_store(k, 0, s.n_bid_lv, nb); c.snap_store(k, 1, s.n_ask_lv, na);
     return (int32_t)((uint32_t)nb | ((uint32_t)na << 16));
   }
@@ -1699,7 +1700,7 @@ struct Sim {
       if (nb > 0) { p[0] = c.lv_price(0, nb - 1); p[1] = c.lv_qty(0, nb - 1); f |= 1; }
       if (na > 0) { p[2] = c.lv_price(1, na - 1); p[3] = c.lv_qty(1, na - 1); f |= 2; }
       if (t_closed) f |= 4;
-      int32_t sn = (P.c.n_pov_exec && m.sender == P.c.n_agents - 1) ? snap_take(0) : 0;   // POVExecutionAgent asks for depth sys.maxsize: the whole book is copied now
+      int32_t sn = (P.c.n_pov_exec && m.sender == P.c.n_agents - 1) ? snap_take(0, P.c.exec_kind == 2 ? 100 : 0x7fffffff) : 0;   // POVExecutionAgent asks for depth sys.maxsize (AggressiveAgent: 100): the levels are copied now
       p[4] = s.last_trade; p[5] = f; exch_send(m.sender, ABX_QUERY_SPREAD, p, P3 ? lat : bits_dbl((uint64_t)(uint32_t)sn));
     } else if (m.kind == ABX_LIMIT_ORDER) { s.c_limit++; if (!P3) s.ctr_kernel++; book_handle_limit((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], m.p[2], lat); c.sync(); trace_snap(); if (P3 && m.p[2] > 0) { s.book_update = s.now; exch_publish(); } }   // ctr_kernel doubles as the book-operation counter where the kernel stream is unused
     else if (m.kind == ABX_CANCEL_ORDER) { s.c_cancel++; if (!P3) s.ctr_kernel++; book_cancel((uint32_t)m.p[0], m.sender, m.p[4], m.p[1], lat); c.sync(); trace_snap(); if (P3) { if (cancel_found) s.book_update = s.now; exch_publish(); } }
@@ -1772,6 +1773,11 @@ struct Sim {
     } else if (P3 && type == AT_MKM) {                                                  // agent/market_makers/MarketMakerAgent.py:66-77
       if (P.c.mkm_subscribe) { if (!(a.flags & AF_SUB_REQUESTED)) { int32_t p[6] = {P.c.mkm_num_levels, 0, 0, 0, 0, 0}; env_send(ABX_MARKET_DATA_SUBSCRIPTION_REQUEST, p, false); a.flags |= AF_SUB_REQUESTED; } }   // :69-72
       else if (can_trade) { r3_cancel_all(type); int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); st = ST_AWAITING_SPREAD; }
+    } else if (type == AT_POVEXEC && P.c.exec_kind != 0) {                              // PassiveAgent.wakeup (passive_agent.py:40-58) / AggressiveAgent.wakeup (aggressive_agent.py:26-32): one action at the timestamp
+      if (can_trade && s.now == P.c.pov_exec_start_ns) {
+        if (P.c.exec_kind == 1 && P.c.exec_limit_price != 0) dq_place_limit(id, (int32_t)P.c.pov_exec_quantity, P.c.pov_exec_is_buy != 0, P.c.exec_limit_price);
+        else { int32_t p[6] = {0, 0, 0, 0, 0, 0}; env_send(ABX_QUERY_SPREAD, p, true); st = ST_AWAITING_SPREAD; }
+      }
     } else if (type == AT_POVEXEC) {                                                    // agent/execution/baselines/pov_agent.py:55-64
       if (can_trade && exaux()->rem_qty > 0 && s.now < P.c.pov_exec_end_ns) {
         set_wakeup(id, s.now + P.c.pov_exec_freq_ns); dq_cancel_all(id);
@@ -1859,12 +1865,20 @@ struct Sim {
       if (m.p[1] > 0) { int2 lv = c.snap_load(m.p[2], 1, 0); a.flags |= AF_HAS_ASK; a.ask = lv.x; a.ask_q = lv.y; } else { a.ask = 0; a.ask_q = 0; }
     }
     if ((a.flags & AF_HAS_OPEN) && (a.flags & AF_HAS_CLOSE) && !had) {                  // :258-268 getWakeFrequency per class
-      int64_t off = type == AT_MOMENTUM ? P.c.mom_wake_ns : (type == AT_POVMM ? P.c.mm_wake_ns : (type == AT_POVEXEC ? P.c.pov_exec_freq_ns : ((P3 && type == AT_MKM) ? P.c.mkm_wake_ns : rng.randint(S_AGENT0 + id, a.rng_ctr, 99))));
+      int64_t off = type == AT_MOMENTUM ? P.c.mom_wake_ns : (type == AT_POVMM ? P.c.mm_wake_ns : (type == AT_POVEXEC ? (P.c.exec_kind != 0 ? P.c.pov_exec_start_ns - P.c.mkt_open_ns : P.c.pov_exec_freq_ns) : ((P3 && type == AT_MKM) ? P.c.mkm_wake_ns : rng.randint(S_AGENT0 + id, a.rng_ctr, 99))));
       set_wakeup(id, P.c.mkt_open_ns + off);
     }
     uint32_t st = (a.flags & AF_STATE_MASK) >> AF_STATE_SHIFT;
     if (type == AT_POVEXEC) {                                                           // POVExecutionAgent.receiveMessage :69-99
       if (m.kind == ABX_QUERY_SPREAD) { ExecAux e0 = *exaux(); e0.snap_n = m.x0; exaux_store(e0); }     // known_bids / known_asks
+      if (P.c.exec_kind != 0) {                                                         // PassiveAgent.receiveMessage :60-70 / AggressiveAgent.receiveMessage :34-37 (the state is never left)
+        if (st == ST_AWAITING_SPREAD && m.kind == ABX_QUERY_SPREAD) {
+          bool buy = P.c.pov_exec_is_buy != 0;
+          if (P.c.exec_kind == 1) { if (!(a.flags & (buy ? AF_HAS_BID : AF_HAS_ASK))) s.flags |= ABX_F_OBS_INVALID; else dq_place_limit(id, (int32_t)P.c.pov_exec_quantity, buy, buy ? a.bid : a.ask); }   // an empty side: limit price None in the reference
+          else dq_place_market(id, (int32_t)P.c.pov_exec_quantity, buy);
+        }
+        return;
+      }
       if (s.now > P.c.pov_exec_end_ns) return;
       ExecAux ex = *exaux();
       if (ex.rem_qty > 0 && st == ST_AWAITING_TV && m.kind == ABX_QUERY_TRANSACTED_VOLUME && s.now > P.c.pov_exec_start_ns) {

@@ -110,6 +110,7 @@ static inline int config_validate(const abx_sim_config *c) {
     if (c->n_noise_agents < 0 || c->n_value_agents < 0 || c->n_mm_agents < 0 || c->n_mm_agents > 1 || c->n_momentum_agents < 0 || c->n_momentum_agents > 4) return ABX_ERR_ARG;
     if (c->latency_model != ABX_LAT_ZERO || c->size_hi <= c->size_lo || c->mom_max_size <= c->mom_min_size || 2 * (c->mm_num_ticks + 1) > MM_ORDER_CAP / 2 || c->mm_wake_ns <= 0 || c->mom_wake_ns <= 0) return ABX_ERR_ARG;
     if (c->n_pov_exec < 0 || c->n_pov_exec > 1 || (c->n_pov_exec && (!(c->pov_exec_pov > 0) || c->pov_exec_quantity <= 0 || c->pov_exec_quantity > 0x3fffffffLL || c->pov_exec_freq_ns <= 0 || c->pov_exec_lookback_ns <= 0))) return ABX_ERR_ARG;
+    if (c->exec_kind < 0 || c->exec_kind > 2 || c->exec_limit_price < 0 || (c->exec_kind && (!c->n_pov_exec || c->pov_exec_start_ns < c->mkt_open_ns))) return ABX_ERR_ARG;
     n += c->n_noise_agents + c->n_value_agents + c->n_mm_agents + c->n_momentum_agents + c->n_pov_exec;
   } else if (c->population == 3) {
     if (c->n_groups != 2 || c->n_mm_agents < 0 || c->n_mm_agents > 1 || c->n_momentum_agents < 0 || c->n_momentum_agents > 60 || (c->latency_model != ABX_LAT_ZERO && c->latency_model != ABX_LAT_MATRIX_NOISE)) return ABX_ERR_ARG;

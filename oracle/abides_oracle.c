@@ -394,6 +394,7 @@ struct abo_sim {
   struct { int agent, levels; double freq; int64_t last; } subs[128]; int n_subs;      /* ExchangeAgent.subscription_dict in insertion order */
   double mkm_sub_freq, mom_sub_freq;
   int64_t mkm_levels, mkm_wake_ns;                                                     /* MarketMakerAgent subscribe_num_levels (5), wake_up_freq ("1s") */
+  int px_kind; int64_t px_limit;                        /* 0 POVExecutionAgent, 1 PassiveAgent (px_limit: its limit_price, 0 = None), 2 AggressiveAgent */
   int px_id, px_is_buy; double px_pov; int64_t px_quantity, px_start, px_end, px_freq, px_lookback;   /* POVExecutionAgent (agent/execution/baselines/pov_agent.py), 0 = none */
   /* traces */
   i64buf live_qty;                                      /* by order id: quantity of the AGENT's order object (a CANCEL_ORDER message carries a reference to it, TradingAgent.py:399-406: partial fills the agent books while the message is in flight show in what the exchange receives) */
@@ -553,7 +554,8 @@ static void exch_receive(abo_sim *s, const event_t *m) {
       if (s->px_id && m->sender == s->px_id) {                                                /* depth = sys.maxsize: the whole book rides in the reply */
         zi_t *a = &s->zi[s->px_id]; int need = s->book.bids.n > s->book.asks.n ? s->book.bids.n : s->book.asks.n;
         if (need > a->capk) { a->capk = need * 2 + 64; for (int k = 0; k < 2; k++) { a->kside[k] = (int64_t *)realloc(a->kside[k], 16 * a->capk); a->fside[k] = (int64_t *)realloc(a->fside[k], 16 * a->capk); } }
-        a->nf[0] = book_inside(&s->book, 1, a->capk, a->fside[0]); a->nf[1] = book_inside(&s->book, 0, a->capk, a->fside[1]); }
+        int depth = s->px_kind == 2 ? 100 : a->capk;                                          /* AggressiveAgent: getCurrentSpread(depth=100) */
+        a->nf[0] = book_inside(&s->book, 1, depth, a->fside[0]); a->nf[1] = book_inside(&s->book, 0, depth, a->fside[1]); }
       e.data = s->book.last_trade; e.mkt_closed = t_closed; exch_send(s, m->sender, &e); break; }
     case ABO_LIMIT_ORDER: s->c_limit++; trace_op(s, 0, &m->order, 0, 0); s->book.now = s->now; book_handle_limit(&s->book, m->order); trace_snap(s); exch_publish(s); break; /* :304-312 */
     case ABO_CANCEL_ORDER: s->c_cancel++; { order_t seen = m->order; if (seen.order_id < s->live_qty.n && s->live_qty.v[seen.order_id] > 0) seen.quantity = s->live_qty.v[seen.order_id]; trace_op(s, 1, &seen, 0, 0); } s->book.now = s->now; book_cancel(&s->book, &m->order); trace_snap(s); exch_publish(s); break;   /* :313-325 */
@@ -773,7 +775,7 @@ static void zi_receive(abo_sim *s, int id, const event_t *m) {
     default: break;
   }
   if (a->has_open && a->has_close && !had) {                                                /* :258-268 */
-    int64_t off = a->type == AT_MOMENTUM ? s->mom_wake_ns : a->type == AT_POVMM ? s->mm_wake_ns : a->type == AT_MKM ? s->mkm_wake_ns : a->type == AT_POVEXEC ? s->px_freq
+    int64_t off = a->type == AT_MOMENTUM ? s->mom_wake_ns : a->type == AT_POVMM ? s->mm_wake_ns : a->type == AT_MKM ? s->mkm_wake_ns : a->type == AT_POVEXEC ? (s->px_kind ? s->px_start - a->mkt_open : s->px_freq)   /* Passive / AggressiveAgent.getWakeFrequency: timestamp - mkt_open */
                 : abo_rng_randint(a->rs, 0, 100);                                           /* ZI/Noise/Value.getWakeFrequency: randint(0, 100) ns */
     k_set_wakeup(s, id, a->mkt_open + off);
   }
@@ -910,9 +912,23 @@ static void povmm_receive_tail(abo_sim *s, int id, const event_t *m) {          
 }
 /* POVExecutionAgent (agent/execution/baselines/pov_agent.py): wakeup :55-64, receiveMessage :69-99, placeMarketOrder TradingAgent.py:351-397 */
 enum { ST_AWAITING_TV = 3 };
+static void px_market_order(abo_sim *s, int id, int64_t quantity) {                          /* TradingAgent.placeMarketOrder :351-397: one limit order per level of the cached opposite side */
+  zi_t *a = &s->zi[id];
+  if (quantity <= 0) return;
+  int k = s->px_is_buy ? 1 : 0; const int64_t *side = a->kside[k]; int n = a->nk[k];
+  int nq = 0; int64_t *qp = (int64_t *)malloc(16 * (size_t)(n + 1));
+  for (int i = 0; i < n; i++) { if (quantity <= side[2 * i + 1]) { qp[2 * nq] = side[2 * i]; qp[2 * nq + 1] = quantity; nq++; break; } qp[2 * nq] = side[2 * i]; qp[2 * nq + 1] = side[2 * i + 1]; nq++; quantity -= side[2 * i + 1]; }
+  for (int i = 0; i < nq; i++) ta_place_limit(s, id, qp[2 * i + 1], s->px_is_buy, qp[2 * i]);
+  free(qp);
+}
 static void povexec_wakeup(abo_sim *s, int id) {
   zi_t *a = &s->zi[id];
   if (!ta_wakeup_common(s, id)) return;
+  if (s->px_kind) {                                                                          /* PassiveAgent.wakeup :40-58 / AggressiveAgent.wakeup :26-32 */
+    if (s->now != s->px_start) return;
+    if (s->px_kind == 1 && s->px_limit) { ta_place_limit(s, id, s->px_quantity, s->px_is_buy, s->px_limit); return; }
+    ta_get_spread(s, id); a->state = ST_AWAITING_SPREAD; return;
+  }
   if (a->px_rem > 0 && s->now < s->px_end) {
     k_set_wakeup(s, id, s->now + s->px_freq); ta_cancel_all(s, id); ta_get_spread(s, id);                 /* depth = sys.maxsize */
     event_t e; memset(&e, 0, sizeof(e)); e.kind = ABO_QUERY_TRANSACTED_VOLUME; e.lookback = s->px_lookback; ta_send(s, id, &e);
@@ -921,6 +937,13 @@ static void povexec_wakeup(abo_sim *s, int id) {
 }
 static void povexec_receive_tail(abo_sim *s, int id, const event_t *m) {
   zi_t *a = &s->zi[id];
+  if (s->px_kind) {                                                                          /* PassiveAgent.receiveMessage :60-70 / AggressiveAgent.receiveMessage :34-37 (the state is never left) */
+    if (!(a->state == ST_AWAITING_SPREAD && m->kind == ABO_QUERY_SPREAD)) return;
+    if (s->px_kind == 1) { int has = s->px_is_buy ? a->has_bid : a->has_ask; if (!has) { fprintf(stderr, "abides_oracle: PassiveAgent met an empty book side (limit price None)\n"); return; }
+      ta_place_limit(s, id, s->px_quantity, s->px_is_buy, s->px_is_buy ? a->bid : a->ask); }
+    else px_market_order(s, id, s->px_quantity);
+    return;
+  }
   if (s->now > s->px_end) return;
   if (a->px_rem > 0 && a->state == ST_AWAITING_TV && m->kind == ABO_QUERY_TRANSACTED_VOLUME && s->now > s->px_start) {
     int64_t quantity = py_round(s->px_pov * (double)a->transacted_volume);
@@ -1075,7 +1098,7 @@ static abo_sim *new_population1(const abx_sim_config *c, uint32_t seed, int trac
   s->variant = 3; s->seed = seed; s->trace = trace; s->pop_hash = s->note_hash = s->snap_hash = FNV_OFF;
   int n_noise = c->n_noise_agents, n_value = c->n_value_agents, n_mm = c->n_mm_agents, n_mom = c->n_momentum_agents;
   int n0 = 1 + n_noise + n_value + n_mm + n_mom, n = n0 + (c->n_pov_exec ? 1 : 0); s->n_agents = n;
-  if (c->n_pov_exec) { s->px_id = n0; s->px_pov = c->pov_exec_pov; s->px_quantity = c->pov_exec_quantity; s->px_is_buy = c->pov_exec_is_buy; s->px_start = c->pov_exec_start_ns; s->px_end = c->pov_exec_end_ns;
+  if (c->n_pov_exec) { s->px_kind = c->exec_kind; s->px_limit = c->exec_limit_price; s->px_id = n0; s->px_pov = c->pov_exec_pov; s->px_quantity = c->pov_exec_quantity; s->px_is_buy = c->pov_exec_is_buy; s->px_start = c->pov_exec_start_ns; s->px_end = c->pov_exec_end_ns;
     s->px_freq = c->pov_exec_freq_ns; s->px_lookback = c->pov_exec_lookback_ns; }
   s->g = abo_rng_new(seed);                                              /* np.random.seed(seed) :58 */
   s->mkt_open = c->mkt_open_ns; s->mkt_close = c->mkt_close_ns;          /* :69-70 */

@@ -134,6 +134,29 @@ def test_rmsc03_with_pov_execution_agent_matches_oracle(emu):
     assert int(st["sum_shares"]) == 0 and int(st["sum_cash"]) == 64 * 10 ** 7
 
 
+@pytest.mark.parametrize("fixture,seed", [("rmsc03_aggressive_s123456789.npz", 123456789), ("rmsc03_passive_s123456789.npz", 123456789), ("rmsc03_passive_limit_s1001.npz", 1001)])
+def test_rmsc03_with_passive_or_aggressive_agent_matches_oracle(emu, golden_dir, fixture, seed):
+    """SURVEY section 8f-2, the last two execution baselines (agent/execution/baselines/passive_agent.py, aggressive_agent.py) as `exec_kind` 1 / 2 of the rmsc03
+    population's execution-agent slot: full traces vs the oracle, itself pinned to recordings of the reference with those agents appended."""
+    import os
+    from helpers import assert_env_equals_oracle
+    from test_oracle_golden import exec_agent_config
+    from marl_optimal_execution_b200.sim import rmsc03_config
+    g = np.load(os.path.join(golden_dir, fixture))
+    oc = exec_agent_config(g)
+    o = OracleSim.from_config(oc, seed, TRACE_ALL)
+    n = o.run()
+    assert n == int(g["n_pops"])
+    cfg = rmsc03_config(lib=_lib.load(emu), pov_exec=True, rng_mode=_lib.RNG_TAPE, trace_cap=400000, hash_pops=1, exec_kind=oc.exec_kind, pov_exec_start_ns=oc.pov_exec_start_ns,
+                        pov_exec_quantity=oc.pov_exec_quantity, pov_exec_is_buy=oc.pov_exec_is_buy, exec_limit_price=oc.exec_limit_price)
+    sim = BatchedSim(cfg, 1, lib_path=emu)
+    sim.reset_tape(*oracle_tapes([o]))
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    assert_env_equals_oracle(sim, 0, o, n, st, holdings_cols=4)
+
+
 @pytest.mark.parametrize("seed,stop_s,pops,hist_cap", [(123456789, 15 * 60, 77119, 0), (20231, 4 * 60, None, 0), (123456789, 15 * 60, 77119, 256)])
 def test_rmsc01_tape_replay_matches_oracle(emu, seed, stop_s, pops, hist_cap):
     """config/rmsc01.py population through the product logic: MarketMakerAgent ladder, ZI agents, HeuristicBeliefLearningAgents fed by the exchange's

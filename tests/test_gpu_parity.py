@@ -155,6 +155,30 @@ def test_rmsc01_tape_replay(seed, stop_s, hist_cap):
     assert int(st["sum_shares"][0]) == 0 and int(st["sum_cash"][0]) == 100 * 10 ** 7
 
 
+@pytest.mark.parametrize("fixture,seed", [("rmsc03_aggressive_s123456789.npz", 123456789), ("rmsc03_passive_s123456789.npz", 123456789), ("rmsc03_passive_limit_s1001.npz", 1001)])
+def test_rmsc03_with_passive_or_aggressive_agent_tape_replay(golden_dir, fixture, seed):
+    """PassiveAgent / AggressiveAgent (agent/execution/baselines/*.py) as exec_kind 1 / 2 of the rmsc03 population's execution-agent slot; full traces
+    vs the oracle, which reproduces recordings of the reference with those agents appended (tests/test_oracle_golden.py::test_rmsc03_with_passive_or_aggressive_agent)."""
+    import os
+    from helpers import assert_env_equals_oracle
+    from test_oracle_golden import exec_agent_config
+    from marl_optimal_execution_b200.sim import rmsc03_config
+    g = np.load(os.path.join(golden_dir, fixture))
+    oc = exec_agent_config(g)
+    o = OracleSim.from_config(oc, seed, TRACE_ALL)
+    n = o.run()
+    assert n == int(g["n_pops"])
+    cfg = rmsc03_config(pov_exec=True, rng_mode=_lib.RNG_TAPE, trace_cap=400000, hash_pops=1, exec_kind=oc.exec_kind, pov_exec_start_ns=oc.pov_exec_start_ns,
+                        pov_exec_quantity=oc.pov_exec_quantity, pov_exec_is_buy=oc.pov_exec_is_buy, exec_limit_price=oc.exec_limit_price)
+    sim = BatchedSim(cfg, 2)
+    sim.reset_tape(*oracle_tapes([o, o]))
+    sim.run()
+    sim.finalize()
+    st = sim.stats()
+    for e in range(2):
+        assert_env_equals_oracle(sim, e, o, n, st, holdings_cols=4)
+
+
 def test_rmsc02_whole_day_tape_replay():
     """config/rmsc02.py, the whole day (117 238 messages): MARKET_DATA subscriptions, subscription-mode market maker / momentum agents, latency matrix + noise.
     Full traces vs the oracle, which is pinned to a live recording of the reference for this seed (tests/test_oracle_golden.py::test_rmsc02_full_day_bit_exact)."""

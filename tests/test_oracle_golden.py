@@ -106,6 +106,35 @@ def test_rmsc03_with_pov_execution_agent(golden_dir):
 from helpers import oracle_rmsc01_config as rmsc01_config  # noqa: E402
 
 
+EXEC_AGENT_FIXTURES = [("rmsc03_aggressive_s123456789.npz", 123456789, 67901), ("rmsc03_passive_s123456789.npz", 123456789, 161383), ("rmsc03_passive_limit_s1001.npz", 1001, 161250)]
+
+
+def exec_agent_config(g):
+    """abx_sim_config of config/rmsc03.py + the appended PassiveAgent / AggressiveAgent of a recording (tools/record_reference.py --exec-agent)."""
+    import ctypes as C
+    from marl_optimal_execution_b200 import _lib
+    from oracle.oracle import lib
+    xa = g["exec_agent"]
+    cfg = _lib.SimConfig()
+    assert lib().abo_default_config(4, C.addressof(cfg)) == 0
+    cfg.exec_kind, cfg.pov_exec_start_ns, cfg.pov_exec_quantity, cfg.pov_exec_is_buy, cfg.exec_limit_price = int(xa[0]), int(xa[1]), int(xa[2]), int(xa[3]), int(xa[4])
+    return cfg
+
+
+@pytest.mark.parametrize("fixture,seed,pops", EXEC_AGENT_FIXTURES)
+def test_rmsc03_with_passive_or_aggressive_agent(golden_dir, fixture, seed, pops):
+    """config/rmsc03.py with the reference's AggressiveAgent (BUY 3 000 at 09:36: getCurrentSpread(depth=100) + a market order walked over 23 ask levels, after which
+    the POV market maker meets a one-sided book and stops quoting) or PassiveAgent (SELL 800 at the best ask of its own QUERY_SPREAD; BUY 600 at a fixed limit price)
+    appended by the recorder: pops, exchange messages, snapshots, the agent's own book operations and all holdings."""
+    g = np.load(os.path.join(golden_dir, fixture))
+    s = OracleSim.from_config(exec_agent_config(g), seed, TRACE_ALL)
+    assert s.run() == int(g["n_pops"]) == pops
+    assert np.array_equal(s.hash_ckpt(), g["pop_hash_ckpt"]) and s.note_hash() == int(g["note_hash"]) and s.snap_hash() == int(g["snap_hash"])
+    ops = s.trace("ops")
+    assert np.array_equal(ops[ops[:, 2] == 64], g["exec_ops"]) and len(g["exec_ops"]) == (23 if int(g["exec_agent"][0]) == 2 else 1)
+    assert np.array_equal(s.holdings()[:, :4], g["holdings"][:, :4])
+
+
 def test_rmsc01_full_trace_bit_exact(golden_dir):
     """config/rmsc01.py run live to 09:45:00 (tools/record_reference.py rmsc01 123456789 --full --stop 09:45:00): every kernel pop,
     every order-book operation incl. the HBL agents' QUERY_ORDER_STREAM-driven limit prices and the MarketMakerAgent's ladder,

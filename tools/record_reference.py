@@ -18,6 +18,8 @@ Usage:  python tools/record_reference.py sparse_zi_100 123456789 tests/golden/z1
                --orders-csv /root/reference/data/sample_orders_file.csv --extra -t SAMPLE -d 2019-06-03
         --orders-csv  replay a plain L3 order file (TIMESTAMP,ORDER_ID,PRICE,SIZE,BUY_SELL_FLAG) instead of a LOBSTER day
         --pov-exec POV QTY BUY|SELL  (rmsc03) append the reference's POVExecutionAgent to the config's agent list
+        --exec-agent passive|aggressive HH:MM:SS QTY BUY|SELL [LIMIT]  (rmsc03) append the reference's PassiveAgent / AggressiveAgent
+                (agent/execution/baselines/passive_agent.py, aggressive_agent.py: one limit / one market order at a timestamp; no shipped config instantiates them)
         --stop HH:MM:SS  replace Kernel.runner's stopTime (shortened recordings of long configs, e.g. rmsc01)
         python tools/record_reference.py rmsc01 123456789 tests/golden/rmsc01_s123456789_0945.npz --full --stop 09:45:00
 """
@@ -355,6 +357,33 @@ def main():
             return r1(self, agents=agents, *a, **k)
 
         K.Kernel.runner = runner_with_pov
+    ex_args = None
+    if "--exec-agent" in rest:
+        import Kernel as K
+        from agent.execution.baselines.passive_agent import PassiveAgent
+        from agent.execution.baselines.aggressive_agent import AggressiveAgent
+        i = rest.index("--exec-agent")
+        kind, hms, qty, direction = rest[i + 1], rest[i + 2], int(rest[i + 3]), rest[i + 4]
+        limit = int(rest[i + 5]) if len(rest) > i + 5 and rest[i + 5].lstrip("-").isdigit() else None
+        ex_args = (kind, hms, qty, direction, limit)
+        r2 = K.Kernel.runner
+
+        def runner_with_exec(self, agents, *a, **k):
+            import pandas as pd
+            ts = pd.to_datetime(date) + pd.to_timedelta(hms)
+            rs = np.random.mtrand.RandomState.__new__(np.random.mtrand.RandomState)
+            if kind == "passive":
+                ag = PassiveAgent(id=len(agents), name="PASSIVE_AGENT", type="PassiveAgent", symbol=agents[1].symbol, starting_cash=10000000, timestamp=ts,
+                                  direction=direction, quantity=qty, limit_price=limit, log_orders=False, random_state=rs)
+            else:
+                ag = AggressiveAgent(id=len(agents), name="AGGRESSIVE_AGENT", type="AggressiveAgent", symbol=agents[1].symbol, starting_cash=10000000, timestamp=ts,
+                                     direction=direction, quantity=qty, log_orders=False, random_state=rs)
+            agents.append(ag)
+            n = len(agents)
+            k["agentLatency"] = np.zeros((n, n))
+            return r2(self, agents=agents, *a, **k)
+
+        K.Kernel.runner = runner_with_exec
     if "--stop" in rest:
         # shortened run: the UNMODIFIED config script is executed as is, only Kernel.runner's stopTime is replaced (rmsc01 under the current code makes
         # ~2 M messages per day, dominated by the market maker's 20 quotes per second; a recorded prefix of the day pins the same logic)
@@ -427,6 +456,12 @@ def main():
         pa = agents[-1]
         data["pov_exec"] = np.array([pov_args[0], pov_args[1], 1 if pov_args[2] == "BUY" else 0, pa.rem_quantity, len(pa.executed_orders), len(pa.orders)], dtype=np.float64)
         data["pov_ops"] = ops[ops[:, 2] == pa.id]
+    if ex_args is not None:
+        xa = agents[-1]
+        import pandas as pd
+        data["exec_agent"] = np.array([1 if ex_args[0] == "passive" else 2, int(pd.to_timedelta(ex_args[1]).value), ex_args[2], 1 if ex_args[3] == "BUY" else 0,
+                                       0 if ex_args[4] is None else ex_args[4], len(xa.orders)], dtype=np.int64)
+        data["exec_ops"] = ops[ops[:, 2] == xa.id]
     if full:
         kinds = np.frombuffer(b"".join(b"".join(s.tape_kind) for s in REC.streams), dtype="S1")
         vals = []
