@@ -18,6 +18,10 @@
 // HBM traffic per row: 16 B of state in, 4 B of action out (+ 96 B when Q is requested); the weights (~150 KB) are read once per CTA
 // from L2.  The kernel is latency bound by construction (7 dependent layers per tile); it exists so that acting costs a few
 // microseconds per tick instead of 8 192 Keras calls.
+//
+// Networks that do not fit (util/model/QNets.py:30-52 NNModel_2: ... 128-256-128 ..., 347 KB of hi + lo weights) run through abx_qnet_forward_streamed_kernel: the same
+// tile loop, MMA sequence and epilogue, but every layer is cut into blocks of at most 128 x 128 weights (64 KB hi + lo) that are streamed from L2 into ONE shared-memory
+// buffer per tile -- N blocks land in their own 128 TMEM columns, K blocks accumulate -- while the A operand holds up to 256 features per row (2 x 64 KB).
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <math.h>
@@ -31,6 +35,7 @@
 namespace {
 
 constexpr int QN_MAX_LAYERS = 8, QN_TILE_M = 128, QN_MAX_DIM = 128, QN_THREADS = 128, QN_TMEM_COLS = 128;
+constexpr int QN_S_MAX_DIM = 256, QN_S_TMEM_COLS = 256, QN_BLK = 128;                     // streamed mode: layer widths up to 256, weight blocks of at most QN_BLK x QN_BLK
 
 struct QnetDev {
   int32_t n_layers, n_in, n_out, pad0;
@@ -38,6 +43,7 @@ struct QnetDev {
   uint32_t w_off[QN_MAX_LAYERS];       // byte offset of layer l's image (hi block then lo block) inside the weight image
   uint32_t b_off[QN_MAX_LAYERS];       // float offset of layer l's bias inside the bias array
   uint32_t w_bytes, n_bias;
+  int32_t kblk[QN_MAX_LAYERS], nblk[QN_MAX_LAYERS];   // weight block dims of layer l: the whole layer (resident mode) or min(dim, QN_BLK) (streamed mode); block (nb, kb) starts at w_off + (nb * (kpad / kblk) + kb) * 4 * nblk * kblk bytes: hi image then lo image, K-major core matrices
 };
 
 // Philox4x32-10 (same generator as the simulator's streams, abx_core.cuh), for the epsilon branch of choose_action
@@ -209,6 +215,130 @@ abx_qnet_forward_kernel(QnetDev net, const uint8_t *__restrict__ wimg, const flo
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)QN_TMEM_COLS) : "memory");
 }
 
+// Streamed mode (see the header comment).  Shared memory: [one weight block, 64 KB | A hi (128 x 256 bf16) | A lo | biases | 2 mbarriers | TMEM base]
+__global__ void __launch_bounds__(QN_THREADS, 1)
+abx_qnet_forward_streamed_kernel(QnetDev net, const uint8_t *__restrict__ wimg, const float *__restrict__ bias, const double *__restrict__ x, int x_stride, int x_offset, int n_rows,
+                                 float *__restrict__ q_out, int32_t *__restrict__ action_out, double greedy_prob, uint64_t seed, uint64_t counter) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint8_t *s_w = smem;
+  uint8_t *s_ahi = smem + 4 * QN_BLK * QN_BLK, *s_alo = s_ahi + QN_TILE_M * QN_S_MAX_DIM * 2;
+  float *s_bias = reinterpret_cast<float *>(s_alo + QN_TILE_M * QN_S_MAX_DIM * 2);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_bias + ((net.n_bias + 3) & ~3u));       // [0] a weight block landed, [1] the MMAs of a block retired
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2);
+  const uint32_t w_bar = smem_u32(s_bar), mma_bar = w_bar + 8u;
+  if (tid == 0) { mbar_init(w_bar, 1); mbar_init(mma_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)QN_S_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (uint32_t i = tid; i < net.n_bias; i += QN_THREADS) s_bias[i] = bias[i];
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *s_tmem;
+  uint32_t wphase = 0, mphase = 0;
+  const int n_tiles = (n_rows + QN_TILE_M - 1) / QN_TILE_M;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int row = tile * QN_TILE_M + tid;
+    {                                                                                       // layer-0 operand: the state, zero padded to kpad[0] (= 16)
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) v[k] = (row < n_rows && k < net.n_in) ? (float)x[(size_t)row * x_stride + x_offset + k] : 0.0f;
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        uint32_t h[4], lo4[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { __nv_bfloat16 h0, l0, h1, l1; split_bf16(v[8 * c + 2 * j], h0, l0); split_bf16(v[8 * c + 2 * j + 1], h1, l1); h[j] = pack2(h0, h1); lo4[j] = pack2(l0, l1); }
+        *reinterpret_cast<uint4 *>(s_ahi + c * (QN_TILE_M * 16) + tid * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(s_alo + c * (QN_TILE_M * 16) + tid * 16) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+      }
+    }
+#pragma unroll 1
+    for (int l = 0; l < net.n_layers; l++) {
+      const int K = net.kpad[l], N = net.npad[l], Kb = net.kblk[l], Nb = net.nblk[l], nkb = K / Kb, nnb = N / Nb;
+      const uint32_t blk_bytes = 4u * (uint32_t)Nb * (uint32_t)Kb;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                          // generic-proxy stores of A -> visible to the tensor core
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+#pragma unroll 1
+      for (int nb = 0; nb < nnb; nb++) {
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; kb++) {
+          if (tid == 0) {                                                                   // the previous block's MMAs have retired (mma_bar below): the buffer is free
+            mbar_expect_tx(w_bar, blk_bytes);
+            bulk_g2s(smem_u32(s_w), wimg + net.w_off[l] + (size_t)(nb * nkb + kb) * blk_bytes, blk_bytes, w_bar);
+            mbar_wait(w_bar, wphase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t idesc = umma_idesc_bf16(Nb);
+            const uint32_t a_lbo = QN_TILE_M * 16, b_lbo = (uint32_t)Nb * 16, sbo = 128;
+            const uint32_t a_hi = smem_u32(s_ahi) + (uint32_t)(kb * Kb / 8) * a_lbo, a_lo = smem_u32(s_alo) + (uint32_t)(kb * Kb / 8) * a_lbo;
+            const uint32_t b_hi = smem_u32(s_w), b_lo = b_hi + (uint32_t)Nb * (uint32_t)Kb * 2u, d = tmem + (uint32_t)(nb * Nb);
+#pragma unroll 1
+            for (int ks = 0; ks < Kb / 16; ks++) {
+              const uint64_t dah = umma_desc(a_hi + ks * 2 * a_lbo, a_lbo, sbo), dal = umma_desc(a_lo + ks * 2 * a_lbo, a_lbo, sbo);
+              const uint64_t dbh = umma_desc(b_hi + ks * 2 * b_lbo, b_lbo, sbo), dbl = umma_desc(b_lo + ks * 2 * b_lbo, b_lbo, sbo);
+              umma_bf16(d, dal, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);                   // small terms first
+              umma_bf16(d, dah, dbl, idesc, 1u);
+              umma_bf16(d, dah, dbh, idesc, 1u);
+            }
+            umma_commit(mma_bar);
+          }
+          wphase ^= 1u;
+          mbar_wait(mma_bar, mphase); mphase ^= 1u;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+      }
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+      const float *b = s_bias + net.b_off[l];
+      if (l + 1 < net.n_layers) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 16) {
+          uint32_t v[16]; tmem_ld16(taddr + (uint32_t)c0, v);
+          uint32_t h[8], lo8[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            float f0 = fmaxf(__uint_as_float(v[2 * j]) + b[c0 + 2 * j], 0.0f), f1 = fmaxf(__uint_as_float(v[2 * j + 1]) + b[c0 + 2 * j + 1], 0.0f);
+            __nv_bfloat16 h0, l0, h1, l1; split_bf16(f0, h0, l0); split_bf16(f1, h1, l1); h[j] = pack2(h0, h1); lo8[j] = pack2(l0, l1);
+          }
+          const int ch = c0 >> 3;
+          *reinterpret_cast<uint4 *>(s_ahi + ch * (QN_TILE_M * 16) + tid * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4 *>(s_ahi + (ch + 1) * (QN_TILE_M * 16) + tid * 16) = make_uint4(h[4], h[5], h[6], h[7]);
+          *reinterpret_cast<uint4 *>(s_alo + ch * (QN_TILE_M * 16) + tid * 16) = make_uint4(lo8[0], lo8[1], lo8[2], lo8[3]);
+          *reinterpret_cast<uint4 *>(s_alo + (ch + 1) * (QN_TILE_M * 16) + tid * 16) = make_uint4(lo8[4], lo8[5], lo8[6], lo8[7]);
+        }
+      } else {
+        float best = -INFINITY; int best_i = 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 16) {
+          uint32_t v[16]; tmem_ld16(taddr + (uint32_t)c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            int col = c0 + j;
+            if (col < net.n_out) {
+              float q = __uint_as_float(v[j]) + b[col];
+              if (q_out && row < n_rows) q_out[(size_t)row * net.n_out + col] = q;
+              if (q > best) { best = q; best_i = col; }
+            }
+          }
+        }
+        if (action_out && row < n_rows) {
+          int a = best_i;
+          if (greedy_prob < 1.0) {
+            uint4 r = qn_philox((uint32_t)row, (uint32_t)counter, (uint32_t)(counter >> 32), 0x514e4554u, (uint32_t)seed, (uint32_t)(seed >> 32));
+            double u = ((r.x >> 5) * 67108864.0 + (r.y >> 6)) / 9007199254740992.0;
+            if (!(u < greedy_prob)) a = (int)(((uint64_t)r.z * (uint64_t)net.n_out) >> 32);
+          }
+          action_out[row] = a;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)QN_S_TMEM_COLS) : "memory");
+}
+
 // Device-side version of pack_params: fp32 parameters (per layer W[out][in] then b[out]) -> bf16 hi/lo image in the MMA operand layout + bias
 // array, so that the learner can push new weights without a host round trip.  One thread per padded weight / bias element.
 __global__ void abx_qnet_pack_kernel(QnetDev net, int d0, int d1, int d2, int d3, int d4, int d5, int d6, int d7, int d8, const float *__restrict__ params,
@@ -222,9 +352,10 @@ __global__ void abx_qnet_pack_kernel(QnetDev net, int d0, int d1, int d2, int d3
       uint32_t e = t - acc, o = e / K, i = e % K;
       float w = (o < out && i < in) ? params[poff + o * in + i] : 0.0f;
       __nv_bfloat16 hi, lo; split_bf16(w, hi, lo);
-      uint32_t dst = (i >> 3) * (N * 8) + o * 8 + (i & 7);
-      __nv_bfloat16 *base = reinterpret_cast<__nv_bfloat16 *>(wimg + net.w_off[l]);
-      base[dst] = hi; base[(size_t)N * K + dst] = lo;
+      uint32_t Kb = net.kblk[l], Nb = net.nblk[l], nb = o / Nb, kb = i / Kb, oo = o % Nb, ii = i % Kb;   // block (nb, kb); resident mode: one block = the layer
+      uint32_t dst = (ii >> 3) * (Nb * 8) + oo * 8 + (ii & 7);
+      __nv_bfloat16 *base = reinterpret_cast<__nv_bfloat16 *>(wimg + net.w_off[l] + (size_t)(nb * (K / Kb) + kb) * 4u * Nb * Kb);
+      base[dst] = hi; base[(size_t)Nb * Kb + dst] = lo;
       return;
     }
     acc += nw;
@@ -238,7 +369,7 @@ thread_local char g_err[512] = "";
 }  // namespace
 
 struct abx_qnet {
-  QnetDev net; int device, n_sms; size_t smem_bytes; uint8_t *d_wimg; float *d_bias; std::vector<int32_t> dims; int64_t launches;
+  QnetDev net; bool streamed; int device, n_sms; size_t smem_bytes; uint8_t *d_wimg; float *d_bias; std::vector<int32_t> dims; int64_t launches;
   std::vector<uint8_t> h_wimg; std::vector<float> h_bias;
 };
 
@@ -259,10 +390,12 @@ static void pack_params(abx_qnet *q, const float *params) {
   std::fill(q->h_wimg.begin(), q->h_wimg.end(), 0); std::fill(q->h_bias.begin(), q->h_bias.end(), 0.0f);
   for (int l = 0; l < n.n_layers; l++) {
     int in = q->dims[l], out = q->dims[l + 1], K = n.kpad[l], N = n.npad[l];
-    uint16_t *hi = reinterpret_cast<uint16_t *>(q->h_wimg.data() + n.w_off[l]), *lo = hi + (size_t)N * K;
+    const int Kb = n.kblk[l], Nb = n.nblk[l]; (void)N;
     for (int o = 0; o < out; o++) for (int i = 0; i < in; i++) {
       float w = p[(size_t)o * in + i]; uint16_t h = f2bf(w), lw = f2bf(w - bf2f(h));
-      size_t e = (size_t)(i >> 3) * ((size_t)N * 8) + (size_t)o * 8 + (i & 7);                // K chunk (8 elements = 16 B per row), then row, then element
+      int nb = o / Nb, kb = i / Kb, oo = o % Nb, ii = i % Kb;                                 // block (nb, kb): the whole layer in resident mode
+      uint16_t *hi = reinterpret_cast<uint16_t *>(q->h_wimg.data() + n.w_off[l] + (size_t)(nb * (K / Kb) + kb) * 4u * Nb * Kb), *lo = hi + (size_t)Nb * Kb;
+      size_t e = (size_t)(ii >> 3) * ((size_t)Nb * 8) + (size_t)oo * 8 + (ii & 7);            // K chunk (8 elements = 16 B per row), then row, then element
       hi[e] = h; lo[e] = lw;
     }
     p += (size_t)out * in;
@@ -284,7 +417,8 @@ int32_t abx_qnet_param_count(const int32_t *dims, int32_t n_layers) {
 int32_t abx_qnet_create(const int32_t *dims, int32_t n_layers, const float *params, int32_t device, abx_qnet **out) {
   if (!out || !dims || !params || n_layers < 1 || n_layers > QN_MAX_LAYERS) return ABX_ERR_ARG;
   if (dims[0] < 1 || dims[0] > 16) return ABX_ERR_ARG;                                       // the state is staged as one 16-wide k step
-  for (int l = 1; l <= n_layers; l++) if (dims[l] < 1 || dims[l] > QN_MAX_DIM) return ABX_ERR_ARG;
+  bool wide = false;
+  for (int l = 1; l <= n_layers; l++) { if (dims[l] < 1 || dims[l] > QN_S_MAX_DIM) return ABX_ERR_ARG; if (dims[l] > QN_MAX_DIM) wide = true; }
   int ndev = 0; QCU(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) { snprintf(g_err, sizeof(g_err), "device %d not present (%d visible)", device, ndev); return ABX_ERR_CUDA; }
   QCU(cudaSetDevice(device));
@@ -294,18 +428,23 @@ int32_t abx_qnet_create(const int32_t *dims, int32_t n_layers, const float *para
   n.n_layers = n_layers; n.n_in = dims[0]; n.n_out = dims[n_layers];
   uint32_t woff = 0, boff = 0;
   for (int l = 0; l < n_layers; l++) {
-    n.kpad[l] = pad16(dims[l]); n.npad[l] = pad16(dims[l + 1]); if (l == n_layers - 1 && n.npad[l] < 32) n.npad[l] = 32;
+    n.kpad[l] = dims[l] > QN_MAX_DIM ? QN_S_MAX_DIM : pad16(dims[l]); n.npad[l] = dims[l + 1] > QN_MAX_DIM ? QN_S_MAX_DIM : pad16(dims[l + 1]); if (l == n_layers - 1 && n.npad[l] < 32) n.npad[l] = 32;
     n.w_off[l] = woff; n.b_off[l] = boff; woff += 2u * n.npad[l] * n.kpad[l] * 2u; boff += n.npad[l];
   }
   n.w_bytes = woff; n.n_bias = boff;
-  q->smem_bytes = (size_t)woff + 2 * QN_TILE_M * QN_MAX_DIM * 2 + (size_t)((boff + 3) & ~3u) * 4 + (QN_MAX_LAYERS + 1) * 8 + 16;
   cudaDeviceProp prop; QCU(cudaGetDeviceProperties(&prop, device)); q->n_sms = prop.multiProcessorCount;
+  q->smem_bytes = (size_t)woff + 2 * QN_TILE_M * QN_MAX_DIM * 2 + (size_t)((boff + 3) & ~3u) * 4 + (QN_MAX_LAYERS + 1) * 8 + 16;
+  { const char *f = getenv("ABX_QNET_FORCE_STREAMED"); if (f && f[0] == '1') wide = true; }   // test hook: run a network that would fit through the streamed kernel
+  q->streamed = wide || q->smem_bytes > (size_t)prop.sharedMemPerBlockOptin;                 // the resident kernel needs every layer <= 128 wide and the whole image on chip
+  for (int l = 0; l < n_layers; l++) { n.kblk[l] = (q->streamed && n.kpad[l] > QN_BLK) ? QN_BLK : n.kpad[l]; n.nblk[l] = (q->streamed && n.npad[l] > QN_BLK) ? QN_BLK : n.npad[l]; }
+  if (q->streamed) q->smem_bytes = (size_t)4 * QN_BLK * QN_BLK + 2 * QN_TILE_M * QN_S_MAX_DIM * 2 + (size_t)((boff + 3) & ~3u) * 4 + 2 * 8 + 16;
   if (q->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { snprintf(g_err, sizeof(g_err), "network needs %zu B of shared memory (limit %zu)", q->smem_bytes, (size_t)prop.sharedMemPerBlockOptin); delete q; return ABX_ERR_ARG; }
   q->h_wimg.resize(woff); q->h_bias.resize(boff);
   if (cudaMalloc((void **)&q->d_wimg, woff) != cudaSuccess || cudaMalloc((void **)&q->d_bias, sizeof(float) * boff) != cudaSuccess) { cudaFree(q->d_wimg); delete q; snprintf(g_err, sizeof(g_err), "cudaMalloc failed"); return ABX_ERR_CUDA; }
   // from here on a failing CUDA call must not leak the handle or its device buffers
 #define QCUH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(g_err, sizeof(g_err), "%s: %s", #call, cudaGetErrorString(e_)); cudaFree(q->d_wimg); cudaFree(q->d_bias); delete q; return ABX_ERR_CUDA; } } while (0)
-  QCUH(cudaFuncSetAttribute(abx_qnet_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q->smem_bytes));
+  if (q->streamed) QCUH(cudaFuncSetAttribute(abx_qnet_forward_streamed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q->smem_bytes));
+  else QCUH(cudaFuncSetAttribute(abx_qnet_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q->smem_bytes));
   pack_params(q, params);
   QCUH(cudaMemcpy(q->d_wimg, q->h_wimg.data(), woff, cudaMemcpyHostToDevice));
   QCUH(cudaMemcpy(q->d_bias, q->h_bias.data(), sizeof(float) * boff, cudaMemcpyHostToDevice));
@@ -343,7 +482,8 @@ int32_t abx_qnet_forward(abx_qnet *q, const double *x_dev, int32_t x_stride, int
   if (!q || !x_dev || n < 1 || x_stride < 1 || x_offset < 0 || x_offset + q->net.n_in > x_stride || (!q_out_dev && !action_out_dev)) return ABX_ERR_ARG;
   QCU(cudaSetDevice(q->device));
   int tiles = (n + QN_TILE_M - 1) / QN_TILE_M, grid = tiles < q->n_sms ? tiles : q->n_sms;
-  abx_qnet_forward_kernel<<<grid, QN_THREADS, q->smem_bytes, (cudaStream_t)stream>>>(q->net, q->d_wimg, q->d_bias, x_dev, x_stride, x_offset, n, q_out_dev, action_out_dev, greedy_prob, seed, counter);
+  if (q->streamed) abx_qnet_forward_streamed_kernel<<<grid, QN_THREADS, q->smem_bytes, (cudaStream_t)stream>>>(q->net, q->d_wimg, q->d_bias, x_dev, x_stride, x_offset, n, q_out_dev, action_out_dev, greedy_prob, seed, counter);
+  else abx_qnet_forward_kernel<<<grid, QN_THREADS, q->smem_bytes, (cudaStream_t)stream>>>(q->net, q->d_wimg, q->d_bias, x_dev, x_stride, x_offset, n, q_out_dev, action_out_dev, greedy_prob, seed, counter);
   q->launches += 1;
   QCU(cudaGetLastError());
   return ABX_OK;

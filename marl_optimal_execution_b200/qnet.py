@@ -15,6 +15,7 @@ import numpy as np
 from . import _lib
 
 DEFAULT_DIMS = (2, 32, 64, 128, 128, 64, 32, 24)      # the reference's state is 2-dimensional: discretize() zips 6 features with a 2-entry grid
+NNMODEL_2_DIMS = (2, 32, 64, 128, 256, 128, 64, 32, 24)  # util/model/QNets.py:30-52 NNModel_2: too large for shared memory, evaluated by the streamed kernel (layer widths up to 256)
 
 
 def param_count(dims):

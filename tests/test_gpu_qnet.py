@@ -50,6 +50,41 @@ def test_trained_like_weights_biases_and_other_shapes():
         check(net, x, 2)
 
 
+NNMODEL_2_DIMS = (2, 32, 64, 128, 256, 128, 64, 32, 24)      # util/model/QNets.py:30-52
+
+
+@pytest.mark.parametrize("n", [1, 129, 9472])
+def test_nnmodel_2_runs_through_the_streamed_kernel(n):
+    """The 256-wide NNModel_2 (347 KB of hi + lo weights: does not fit in shared memory) through abx_qnet_forward_streamed_kernel -- weight blocks of 128 x 128 streamed per
+    tile, two N blocks in separate TMEM column ranges for the 128 -> 256 layer, two accumulating K blocks for the 256 -> 128 layer -- against the PyTorch fp32 network."""
+    rs = np.random.RandomState(21)
+    p = init_params(NNMODEL_2_DIMS, seed=5) * 2.0
+    p += rs.normal(0, 0.05, size=p.shape).astype(np.float32)
+    net = QNetwork(NNMODEL_2_DIMS, params=p)
+    rel = check(net, states(n, n + 3), 6)
+    assert rel < 2e-4
+    p2 = init_params(NNMODEL_2_DIMS, seed=6)                                # the learner's device-side weight push packs the same block layout
+    net.set_params_device(torch.from_numpy(p2).cuda())
+    net.params = p2
+    check(net, states(n, n + 4), 6)
+
+
+def test_streamed_kernel_equals_resident_kernel_on_the_default_network(monkeypatch):
+    """ABX_QNET_FORCE_STREAMED=1 sends a network that fits through the streamed kernel: same Q rows as the resident kernel (same MMA sequence per layer)."""
+    x = states(5000, 77)
+    a = QNetwork(DEFAULT_DIMS, seed=4)
+    qa, acta = a.forward(x, x_offset=6)
+    monkeypatch.setenv("ABX_QNET_FORCE_STREAMED", "1")
+    b = QNetwork(DEFAULT_DIMS, seed=4)
+    qb, actb = b.forward(x, x_offset=6)
+    torch.cuda.synchronize()
+    assert torch.equal(qa, qb) and torch.equal(acta, actb)
+    for dims in [(3, 16, 24), (16, 128, 128, 7), (8, 256, 256, 24), (4, 200, 136, 9)]:
+        p = init_params(dims, seed=9) * 2.0
+        net = QNetwork(dims, params=p)
+        check(net, states(700, 3, stride=dims[0] + 3, offset=2, n_in=dims[0]), 2)
+
+
 def test_set_params_and_epsilon_rule():
     net = QNetwork(DEFAULT_DIMS, seed=1)
     x = states(20000, 4)
