@@ -89,6 +89,17 @@ def test_training_forward_applies_keras_dropout():
     assert tr.can_learn() and tr.learn() is not None and np.isfinite(float(tr.cost_hist[-1]))
 
 
+def test_learner_with_nnmodel_2():
+    """util/model/QNets.py:30-52 NNModel_2 (eight Dense layers, 256 wide in the middle, Dropout after hidden layers 2..7): the learner is generic over the layer list."""
+    from marl_optimal_execution_b200.qnet import NNMODEL_2_DIMS, param_count
+    assert param_count(NNMODEL_2_DIMS) == 87576
+    tr = DDQNTrainer(dims=NNMODEL_2_DIMS, batch_size=32, seed=3, buffer_capacity=256)
+    tr.store(torch.rand(200, 6, dtype=torch.float64) * 20)
+    before = tr.eval_net.flat().copy()
+    assert tr.can_learn() and tr.learn() is not None and np.isfinite(float(tr.cost_hist[-1]))
+    assert tr.eval_net.flat().size == 87576 and not np.array_equal(before, tr.eval_net.flat())
+
+
 def test_buffer_without_valid_rows_cannot_break_sampling():
     tr = DDQNTrainer(batch_size=4, seed=2, buffer_capacity=64)
     t = torch.rand(20, 6, dtype=torch.float64); t[:, 5] = float("nan")        # only r == None rows
