@@ -88,7 +88,8 @@ typedef struct abx_sim_config {
   int64_t exchange_computation_delay_ns, exchange_pipeline_delay_ns; /* ExchangeAgent.py:56-59 */
   int64_t starting_cash;           /* cents */
   int32_t order_size;              /* ZeroIntelligenceAgent.py:308 (100) */
-  int32_t stream_history;          /* ExchangeAgent stream_history (not read on this path) */
+  int32_t stream_history;          /* ExchangeAgent stream_history: OrderBook.history keeps this many trade-delimited buckets besides the open one (read by MODIFY_ORDER fan-out,
+                                    * get_transacted_volume and QUERY_ORDER_STREAM; the sparse_zi populations never read it) */
   /* util/oracle/SparseMeanRevertingOracle.py symbol parameters */
   double r_bar, kappa, fund_vol, megashock_lambda_a, megashock_mean, megashock_var;
   /* ZeroIntelligenceAgent parameters */
