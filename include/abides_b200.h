@@ -180,6 +180,9 @@ typedef struct abx_sim abx_sim; /* opaque */
  * with numpy's RandomState.normal / .exponential, e.g. agent/ZeroIntelligenceAgent.py:349-350, util/oracle/SparseMeanRevertingOracle.py:105-107):
  * y[i] = log(x[i]) for x in (0, 1], host buffers.  Tests compare it with libm (relative error < 1e-11). */
 int32_t abx_selftest_log_unit(const double *x_host, double *y_host, int32_t n, int32_t device);
+/* Device self-test of the exp the kernels use for exp(-kappa d) of the OU step (util/oracle/SparseMeanRevertingOracle.py:105-106) and the (1 - kappa) ** x
+ * powers of the ZI belief update (agent/ZeroIntelligenceAgent.py:229-256): y[i] = exp(x[i]), host buffers.  Tests compare it with libm (<= 1 ulp, equal on > 99.9 %). */
+int32_t abx_selftest_exp(const double *x_host, double *y_host, int32_t n, int32_t device);
 const char *abx_strerror(int32_t status);
 const char *abx_last_cuda_error(void);
 int32_t abx_device_count(void);

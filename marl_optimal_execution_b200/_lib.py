@@ -135,6 +135,8 @@ def _bind(L):
     sig("abx_strerror", C.c_char_p, i32)
     if hasattr(L, "abx_selftest_log_unit"):            # device self-test: not part of the host emulation used by the CPU tests
         sig("abx_selftest_log_unit", i32, P(C.c_double), P(C.c_double), i32, i32)
+    if hasattr(L, "abx_selftest_exp"):
+        sig("abx_selftest_exp", i32, P(C.c_double), P(C.c_double), i32, i32)
     sig("abx_last_cuda_error", C.c_char_p)
     sig("abx_device_count", i32)
     sig("abx_config_sparse_zi", i32, i32, P(SimConfig))

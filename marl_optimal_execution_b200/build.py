@@ -10,7 +10,7 @@ CSRC = os.path.join(_PKG, "csrc")
 LIB = os.path.join(_PKG, "libabides_b200.so")
 LIB_STRICT = os.path.join(_PKG, "libabides_b200_strict.so")
 SOURCES = ["abx_sim.cu", "abx_qnet.cu"]
-HEADERS = ["abx_core.cuh", "abx_warp.cuh", "abx_host_common.h", os.path.join("..", "..", "include", "abides_b200.h")]
+HEADERS = ["abx_core.cuh", "abx_warp.cuh", "abx_host_common.h", "abx_exp_table.h", os.path.join("..", "..", "include", "abides_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared", "-Xptxas", "-v"]
 

@@ -17,6 +17,7 @@
 #include <stdint.h>
 #include <math.h>
 #include "../../include/abides_b200.h"
+#include "abx_exp_table.h"
 
 #if defined(__CUDACC__)
 #define ABX_HD __host__ __device__ __forceinline__
@@ -276,7 +277,34 @@ ABX_NI U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
   }
   U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3; return o;
 }
+// exp(x) for the OU step of the fundamental and the (1 - kappa) ** x powers of the belief update (three per order placement).  The kernel is bound by dependent
+// fp64 chains (profiles/r02_optimisation_log.md: replacing this body by a two-instruction stand-in gained 10.7 %), and the libm body is a ~20-deep Horner chain.
+// Device: the table method of current libms (x = (128 k + j) ln2/128 + r, exp(x) = 2^k * H[j] * (1 + T[j] + r + r^2 (1/2 + r/6) + r^4 (1/24 + r/120))), nine
+// dependent operations, maximum error 0.51 ulp over 2e8 points against long-double expl and equal to glibc's exp on 99.94 % of them (tools/check_exp.c) -- closer to
+// the oracle's libm than the 1-ulp CUDA exp it replaces.  abx_selftest_exp exposes it to the tests.
+#if defined(__CUDACC__) && !defined(ABX_LIBM_EXP)
+__device__ __constant__ double2 abx_exp_tab[128] = { ABX_EXP_TABLE };
+#endif
+#if defined(__CUDA_ARCH__) && !defined(ABX_LIBM_EXP)
+ABX_NI double exp_ni(double x) {
+  const bool far = !(fabs(x) < 700.0);                                                   // results outside the normal range (or NaN): scaled in two exact steps below
+  if (far) { if (x != x) return x; x = x < -800.0 ? -800.0 : (x > 800.0 ? 800.0 : x); }
+  const double t = fma(x, ABX_EXP_INV_LN2N, 0x1.8p52);                                   // round(x * 128 / ln2) lands in the low mantissa bits
+  const int k = __double2loint(t);
+  const double kd = t - 0x1.8p52;
+  double r = fma(kd, -ABX_EXP_LN2N_HI, x); r = fma(kd, -ABX_EXP_LN2N_LO, r);
+  const double2 ht = abx_exp_tab[k & 127];
+  const double r2 = r * r;
+  const double p = fma(fma(1.0 / 120, r, 1.0 / 24), r2, fma(1.0 / 6, r, 0.5));
+  const double q = fma(p, r2, ht.y + r);
+  const double y = fma(ht.x, q, ht.x);
+  const int e = k >> 7;
+  if (far) { const int e1 = e / 2; return y * __hiloint2double((1023 + e1) << 20, 0) * __hiloint2double((1023 + e - e1) << 20, 0); }   // |e| <= 1155: both factors are normal powers of two, the last product rounds once (inf / subnormal / 0)
+  return __hiloint2double(__double2hiint(y) + (e << 20), __double2loint(y));
+}
+#else
 ABX_NI double exp_ni(double x) { return exp(x); }
+#endif
 ABX_NI double log_ni(double x) { return log(x); }
 // log(x), x in (0, 1] and normal, for the Philox-mode variate transforms only (no parity constraint): fp64 throughout, relative error
 // < 1e-11 (checked against libm by tests/test_gpu_philox.py through abx_selftest_log_unit).  x = 2^e * m with m in [sqrt(1/2), sqrt(2)],

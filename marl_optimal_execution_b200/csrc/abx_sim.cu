@@ -307,6 +307,20 @@ int32_t abx_selftest_log_unit(const double *x_host, double *y_host, int32_t n, i
   if (st != ABX_OK) snprintf(g_cuda_err, sizeof(g_cuda_err), "%s", cudaGetErrorString(cudaGetLastError()));
   cudaFree(dx); cudaFree(dy); return st;
 }
+__global__ void abx_selftest_exp_kernel(const double *__restrict__ x, double *__restrict__ y, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) y[i] = exp_ni(x[i]);
+}
+int32_t abx_selftest_exp(const double *x_host, double *y_host, int32_t n, int32_t device) {
+  if (!x_host || !y_host || n < 1) return ABX_ERR_ARG;
+  int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d not present", device); return ABX_ERR_CUDA; }
+  CU(cudaSetDevice(device));
+  double *dx = nullptr, *dy = nullptr; int32_t st = ABX_OK;
+  if (cudaMalloc(&dx, sizeof(double) * n) != cudaSuccess || cudaMalloc(&dy, sizeof(double) * n) != cudaSuccess) st = ABX_ERR_CUDA;
+  if (st == ABX_OK && cudaMemcpy(dx, x_host, sizeof(double) * n, cudaMemcpyHostToDevice) != cudaSuccess) st = ABX_ERR_CUDA;
+  if (st == ABX_OK) { abx_selftest_exp_kernel<<<(n + 127) / 128, 128>>>(dx, dy, n); if (cudaMemcpy(y_host, dy, sizeof(double) * n, cudaMemcpyDeviceToHost) != cudaSuccess) st = ABX_ERR_CUDA; }
+  if (st != ABX_OK) snprintf(g_cuda_err, sizeof(g_cuda_err), "%s", cudaGetErrorString(cudaGetLastError()));
+  cudaFree(dx); cudaFree(dy); return st;
+}
 const char *abx_strerror(int32_t st) { return status_string(st); }
 const char *abx_last_cuda_error(void) { return g_cuda_err; }
 int32_t abx_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
