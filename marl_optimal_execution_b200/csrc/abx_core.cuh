@@ -611,15 +611,16 @@ struct Sim {
 
   // ---- outbox: messages and wakeups produced while handling one event, delivered in order by flush() ----
   // entry words: [0] recipient | kind<<16 | flags, [1..6] payload, [7,8] pair latency (fp64 bits), [9,10] int64:
-  // send offset (computation delay + additional + pipeline delay) for messages, absolute time for wakeups.
+  // send offset (computation delay + additional + pipeline delay) for messages, absolute time for wakeups.  (The device keeps them as three quads in another
+  // order, see emit; the word numbers are those of the host layout and of flush's local copy.)
   ABX_HD void emit(uint32_t w0, const int32_t p[6], double lat, int64_t off) {
     if (n_out >= Ctx::OUTN) { s.flags |= ABX_F_QUEUE_OVERFLOW; return; }
     if (c.onchip_writer()) {
       uint32_t *o = c.outbox() + n_out * OUT_WORDS; uint64_t lb = dbl_bits(lat);
-#if defined(__CUDA_ARCH__)                                                             // three 128-bit stores instead of eleven words: emit is inlined at every send site
-      uint4 *o4 = reinterpret_cast<uint4 *>(o);
-      o4[0] = make_uint4(w0, (uint32_t)p[0], (uint32_t)p[1], (uint32_t)p[2]); o4[1] = make_uint4((uint32_t)p[3], (uint32_t)p[4], (uint32_t)p[5], (uint32_t)lb);
-      o4[2] = make_uint4((uint32_t)(lb >> 32), (uint32_t)(uint64_t)off, (uint32_t)((uint64_t)off >> 32), 0u);
+#if defined(__CUDA_ARCH__)                                                             // 128-bit stores instead of eleven words (emit is inlined at every send site); device layout {w0, off} {lat, p0, p1} {p2..p5}:
+      uint4 *o4 = reinterpret_cast<uint4 *>(o);                                         // a wakeup is its first quad alone (w0's flags are compile-time constants at every site, the test folds away)
+      o4[0] = make_uint4(w0, (uint32_t)(uint64_t)off, (uint32_t)((uint64_t)off >> 32), 0u);
+      if (!(w0 & OF_WAKEUP)) { o4[1] = make_uint4((uint32_t)lb, (uint32_t)(lb >> 32), (uint32_t)p[0], (uint32_t)p[1]); o4[2] = make_uint4((uint32_t)p[2], (uint32_t)p[3], (uint32_t)p[4], (uint32_t)p[5]); }
 #else
       o[0] = w0; for (int i = 0; i < 6; i++) o[1 + i] = (uint32_t)p[i];
       o[7] = (uint32_t)lb; o[8] = (uint32_t)(lb >> 32);
@@ -649,8 +650,9 @@ struct Sim {
     for (int i = 0; i < n_out; i++) {
       const uint32_t *op = c.outbox() + i * OUT_WORDS; uint32_t o[OUT_WORDS];
 #if defined(__CUDA_ARCH__)
-      { const uint4 *o4 = reinterpret_cast<const uint4 *>(op); uint4 v0 = o4[0], v1 = o4[1], v2 = o4[2];
-        o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v0.w; o[4] = v1.x; o[5] = v1.y; o[6] = v1.z; o[7] = v1.w; o[8] = v2.x; o[9] = v2.y; o[10] = v2.z; o[11] = v2.w; }
+      { const uint4 *o4 = reinterpret_cast<const uint4 *>(op); uint4 v0 = o4[0], v1 = make_uint4(0u, 0u, 0u, 0u), v2 = make_uint4(0u, 0u, 0u, 0u);
+        if (!(v0.x & OF_WAKEUP)) { v1 = o4[1]; v2 = o4[2]; }
+        o[0] = v0.x; o[9] = v0.y; o[10] = v0.z; o[11] = 0u; o[7] = v1.x; o[8] = v1.y; o[1] = v1.z; o[2] = v1.w; o[3] = v2.x; o[4] = v2.y; o[5] = v2.z; o[6] = v2.w; }
 #else
       for (int k = 0; k < OUT_WORDS; k++) o[k] = op[k];
 #endif

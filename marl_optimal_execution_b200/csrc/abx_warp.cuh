@@ -87,8 +87,9 @@ struct WarpCtxT {
   uint64_t my_hi; uint32_t my_uniq; uint32_t cur_mask; int cur_group, cur_lane; int n_ovf; bool cur_t2; int day;   // day: the replayed day of this environment   // n_ovf: events in the overflow tier
 
   __device__ WarpCtxT(const SimParams &P_, int env_, unsigned char *smem) : P(P_), env(env_), lane(threadIdx.x & 31) {
-    size_t q = (size_t)env * P.c.queue_cap; qkey = P.qkey + q; qpay0 = P.qpay0 + q; qpay1 = P.qpay1 + q;
-    agents = P.agents + (size_t)env * P.c.n_agents; nodes = P.nodes + (size_t)env * P.c.order_cap;
+    // unsigned 32 x 32 -> 64 products: the compiler recomputes these bases inside the loop body rather than hold them in registers, and the signed form is three instructions longer each time
+    size_t q = (size_t)((uint64_t)(uint32_t)env * (uint32_t)P.c.queue_cap); qkey = P.qkey + q; qpay0 = P.qpay0 + q; qpay1 = P.qpay1 + q;
+    agents = P.agents + (size_t)((uint64_t)(uint32_t)env * (uint32_t)P.c.n_agents); nodes = P.nodes + (size_t)((uint64_t)(uint32_t)env * (uint32_t)P.c.order_cap);
     tr = P.trace ? P.trace + (size_t)env * P.c.trace_cap : nullptr;
     staged = reinterpret_cast<ZiAgent *>(smem); smem += sizeof(ZiAgent);
     obox = reinterpret_cast<uint32_t *>(smem); smem += OUTN * OUT_WORDS * 4;
