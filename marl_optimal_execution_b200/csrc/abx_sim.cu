@@ -4,6 +4,7 @@
 // dynamic shared memory (abx_warp.cuh).  A warp runs its environment's whole event loop (Kernel.py:190-292) up to
 // the requested simulated time in one launch; environments never communicate.
 #include <type_traits>
+#include <cstddef>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <new>
@@ -38,11 +39,19 @@ __device__ __forceinline__ EnvState env_load(const EnvState *g) {
   for (int i = 0; i < (int)(sizeof(EnvState) / 16); i++) dst[i] = __ldcg(src + i);
   return s;
 }
+// SKIP: bit i set = the i-th 16-byte quad of the record cannot have changed in this kernel and is not written back -- its fields are then dead after the load and
+// free their registers for the whole event loop (the run kernels live at the 128-register limit of 16 one-warp CTAs per SM)
+template <uint32_t SKIP = 0u>
 __device__ __forceinline__ void env_store(EnvState *g, const EnvState &s, int lane) {
   if (lane == 0) { const uint4 *src = reinterpret_cast<const uint4 *>(&s); uint4 *dst = reinterpret_cast<uint4 *>(g);
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(EnvState) / 16); i++) __stcg(dst + i, src[i]); }
+    for (int i = 0; i < (int)(sizeof(EnvState) / 16); i++) if (!((SKIP >> i) & 1u)) __stcg(dst + i, src[i]); }
 }
+// quads of EnvState the sparse_zi event loop never writes without instrumentation: {sum_shares, sum_cash} (kernelStopping), {draw_n, evt_n, book_flags, episode},
+// {hist_n, n_subs, book_update}, {next_pub, pad}.  (Also skipping the lone cold words pop_hash and trace_n frees three more registers and measures 1.8 % SLOWER:
+// profiles/r02_optimisation_log.md.)
+constexpr uint32_t ENV_QUADS_COLD_ZI = (1u << 10) | (1u << 12) | (1u << 13) | (1u << 14);
+static_assert(offsetof(EnvState, sum_shares) == 160 && offsetof(EnvState, draw_n) == 192 && offsetof(EnvState, hist_n) == 208 && offsetof(EnvState, next_pub) == 224, "ENV_QUADS_COLD_ZI follows the EnvState layout");
 
 template <class Ctx>
 __device__ void reset_env_with(const SimParams &P, EnvState &s, int env, unsigned char *smem) {
@@ -82,7 +91,11 @@ abx_run_kernel(SimParams P, int64_t until_ns, const int64_t *__restrict__ until_
   Sim<Ctx, RNG, LAT, INSTR, SHAPE> sim(ctx, P, s, env);
   if (SHAPE == SHAPE_R3 || SHAPE == SHAPE_P3) sim.r3_run(until_each ? until_each[env] : until_ns); else sim.run(until_each ? until_each[env] : until_ns);
   ctx.store_onchip(sim.s);
+#ifndef ABX_NO_COLD_QUADS
+  env_store<(SHAPE == SHAPE_ZI && !INSTR) ? ENV_QUADS_COLD_ZI : 0u>(P.env + env, sim.s, ctx.lane);
+#else
   env_store(P.env + env, sim.s, ctx.lane);
+#endif
 }
 typedef void (*run_kernel_fn)(SimParams, int64_t, const int64_t *, size_t);
 static run_kernel_fn run_kernel_for(const abx_sim_config &c) {
