@@ -51,6 +51,17 @@ __device__ __forceinline__ void env_store(EnvState *g, const EnvState &s, int la
 // {hist_n, n_subs, book_update}, {next_pub, pad}.  (Also skipping the lone cold words pop_hash and trace_n frees three more registers and measures 1.8 % SLOWER:
 // profiles/r02_optimisation_log.md.)
 constexpr uint32_t ENV_QUADS_COLD_ZI = (1u << 10) | (1u << 12) | (1u << 13) | (1u << 14);
+#ifndef ABX_NO_COLD_QUADS_MORE
+// the other production kernels: the rmsc03 population runs at zero latency (no kernel-stream block, quad 11) and has neither order-stream history nor subscriptions
+// (quads 13, 14); the rmsc01 / rmsc02 population keeps those two; the replay shapes (ABIDESEnv, DDQN config) have no fundamental either ({or_t, ms_t}, {ms_v, pop_hash})
+// but follow re-priced levels (book_flags, quad 12)
+constexpr uint32_t ENV_QUADS_COLD_R3 = (1u << 10) | (1u << 11) | (1u << 12) | (1u << 13) | (1u << 14);
+constexpr uint32_t ENV_QUADS_COLD_P3 = (1u << 10) | (1u << 12), ENV_QUADS_COLD_P3_ZEROLAT = ENV_QUADS_COLD_P3 | (1u << 11);
+constexpr uint32_t ENV_QUADS_COLD_REPLAY = (1u << 2) | (1u << 3) | (1u << 10) | (1u << 11) | (1u << 13) | (1u << 14);
+#else
+constexpr uint32_t ENV_QUADS_COLD_R3 = 0, ENV_QUADS_COLD_P3 = 0, ENV_QUADS_COLD_P3_ZEROLAT = 0, ENV_QUADS_COLD_REPLAY = 0;
+#endif
+static_assert(offsetof(EnvState, or_t) == 32 && offsetof(EnvState, ms_v) == 48 && offsetof(EnvState, kblk) == 176, "ENV_QUADS_COLD_* follow the EnvState layout");
 static_assert(offsetof(EnvState, sum_shares) == 160 && offsetof(EnvState, draw_n) == 192 && offsetof(EnvState, hist_n) == 208 && offsetof(EnvState, next_pub) == 224, "ENV_QUADS_COLD_ZI follows the EnvState layout");
 
 template <class Ctx>
@@ -92,7 +103,7 @@ abx_run_kernel(SimParams P, int64_t until_ns, const int64_t *__restrict__ until_
   if (SHAPE == SHAPE_R3 || SHAPE == SHAPE_P3) sim.r3_run(until_each ? until_each[env] : until_ns); else sim.run(until_each ? until_each[env] : until_ns);
   ctx.store_onchip(sim.s);
 #ifndef ABX_NO_COLD_QUADS
-  env_store<(SHAPE == SHAPE_ZI && !INSTR) ? ENV_QUADS_COLD_ZI : 0u>(P.env + env, sim.s, ctx.lane);
+  env_store<INSTR ? 0u : SHAPE == SHAPE_ZI ? ENV_QUADS_COLD_ZI : SHAPE == SHAPE_R3 ? ENV_QUADS_COLD_R3 : SHAPE == SHAPE_P3 ? (LAT == ABX_LAT_ZERO ? ENV_QUADS_COLD_P3_ZEROLAT : ENV_QUADS_COLD_P3) : 0u>(P.env + env, sim.s, ctx.lane);
 #else
   env_store(P.env + env, sim.s, ctx.lane);
 #endif
@@ -182,7 +193,7 @@ abx_env_step_kernel(SimParams P, const double *__restrict__ actions, double *__r
     Sim<WarpCtxT<SMALLQ ? 1 : 0>, ABX_RNG_PHILOX, ABX_LAT_ZERO, INSTR, SHAPE_ENV> sim(ctx, P, s, env);
     sim.env_step(actions[3 * env], actions[3 * env + 1], actions[3 * env + 2]);
     ctx.store_onchip(sim.s); ctx.envx_store();
-    env_store(P.env + env, sim.s, ctx.lane);
+    env_store<INSTR ? 0u : ENV_QUADS_COLD_REPLAY>(P.env + env, sim.s, ctx.lane);
     s.flags = sim.s.flags;
   }
   // obs (9 x fp64), reward, done: lanes 0..8 write one observation value each (72 contiguous bytes per environment)
@@ -230,7 +241,7 @@ abx_dq_step_kernel(SimParams P, const int32_t *__restrict__ actions, double *__r
     Sim<WarpCtxHybridQ, ABX_RNG_PHILOX, ABX_LAT_ZERO, INSTR, SHAPE_DQ> sim(ctx, P, s, env);
     paused = sim.dq_step(actions ? actions[env] : 0);
     ctx.store_onchip(sim.s); ctx.envx_store();
-    env_store(P.env + env, sim.s, ctx.lane);
+    env_store<INSTR ? 0u : ENV_QUADS_COLD_REPLAY>(P.env + env, sim.s, ctx.lane);
     s.flags = sim.s.flags;
   }
   // outputs: 8 + 6 + 1 doubles and the done byte per environment
