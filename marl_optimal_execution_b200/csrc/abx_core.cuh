@@ -560,6 +560,7 @@ struct Sim {
   static constexpr bool DQ = SHAPE == SHAPE_DQ, BOOK = SHAPE == SHAPE_BOOK, ENV = SHAPE == SHAPE_ENV || DQ || BOOK, P3 = SHAPE == SHAPE_P3, R3 = SHAPE == SHAPE_R3 || P3;   // P3: config/rmsc01.py population (runs the rmsc03 loop with more agent classes)
   Ctx &c; const SimParams &P; EnvState s; RngT<RNG_MODE, INSTR> rng; int64_t addl_delay; int n_out; int self_id; int env_id; bool cancel_found = false; uint32_t hidx = 0;   // cancel_found: the last book_cancel removed an order (it moves OrderBook.last_update_ts); hidx: order-history log index of the order handleLimitOrder is working on (population 3)
   AgentRegs a; ZiAgent *z;                // the trader whose event is being handled (registers + staged record)
+  uint32_t kb_win = 0xffffffffu;          // device: which 32-block window of the kernel stream the lanes' s.kblk hold (kernel_noise)
 
   ABX_HD Sim(Ctx &c_, const SimParams &P_, const EnvState &s_, int env) : c(c_), P(P_), s(s_), addl_delay(0), n_out(0), self_id(0), z(nullptr) {
     rng.P = &P; rng.env = P.n_tapes > 0 ? env % P.n_tapes : env; env_id = env; rng.seed = s.seed; rng.err = 0; a.lat_from = 0.0; a.lat_to = 0.0;
@@ -643,6 +644,25 @@ struct Sim {
   ABX_HD void ta_send(int kind, const int32_t p[6], bool bump_uniq) {
     emit(0u | ((uint32_t)kind << 16) | (bump_uniq ? OF_BUMP_UNIQ : 0u), p, a.lat_to, P.c.default_computation_delay_ns + addl_delay);
   }
+  // Latency-noise draw of one sendMessage (Kernel.py:410-412): word (i & 3) of block (i >> 2) of the kernel stream, i = the draw's index.
+  ABX_HD int64_t kernel_noise() {
+#if defined(__CUDA_ARCH__) && !defined(ABX_SEQ_DRAWS)
+    // The 32 lanes hold 32 CONSECUTIVE blocks (lane L: block (i >> 7) * 32 + L), computed in one pass of the Philox rounds -- every lane runs the rounds anyway, each
+    // on its own counter -- so the ten rounds run once per 128 sends instead of once per 4 (same blocks, same words: the stream is unchanged).  The window lives in
+    // s.kblk of each lane and is recomputed after a launch boundary (kb_win).
+    if (!rng.tape()) {
+      uint32_t i = s.ctr_kernel++, win = i >> 7;
+      if (win != kb_win) {
+        U4 o = philox4x32_10((win << 5) + (threadIdx.x & 31u), (uint32_t)S_KERNEL, 0x4b424958u, 0, (uint32_t)rng.seed, (uint32_t)(rng.seed >> 32));
+        s.kblk[0] = o.x; s.kblk[1] = o.y; s.kblk[2] = o.z; s.kblk[3] = o.w; kb_win = win;
+      }
+      uint32_t w = (i & 3u) == 0u ? s.kblk[0] : ((i & 3u) == 1u ? s.kblk[1] : ((i & 3u) == 2u ? s.kblk[2] : s.kblk[3]));
+      w = __shfl_sync(0xffffffffu, w, (int)((i >> 2) & 31u));
+      int64_t v = (int64_t)((uint64_t(w) * (uint64_t)(uint32_t)P.c.n_noise) >> 32); rng.rec(S_KERNEL, 'i', (uint64_t)v); return v;
+    }
+#endif
+    return rng.randint_cached(S_KERNEL, s.ctr_kernel, (uint32_t)(P.c.n_noise - 1), s.kblk);
+  }
   // Kernel.sendMessage (Kernel.py:347-433) for every queued entry, in emission order
   ABX_HD void flush() {
     c.sync();
@@ -677,7 +697,7 @@ struct Sim {
           double latency = dadd(lat, dmul(P.c.jitter / pow_ni(x, 3.0), lat / P.c.jitter_unit));
           deliver = sent + (int64_t)latency;                                          // pd.Timedelta(float) truncates
         } else {                                                                      // Kernel.py:410-412
-          int64_t noise = rng.randint_cached(S_KERNEL, s.ctr_kernel, (uint32_t)(P.c.n_noise - 1), s.kblk);
+          int64_t noise = kernel_noise();
           deliver = sent + (int64_t)dadd(lat, (double)noise);
         }
         e.t = deliver < KEY_T_MAX ? deliver : KEY_T_MAX; e.type = ABX_T_MESSAGE;
@@ -701,12 +721,17 @@ struct Sim {
     s.ms_v = rng.randint(S_SYMBOL, s.ctr_symbol, 1) == 0 ? msv : -msv;
   }
   ABX_HD int32_t oracle_compute(int64_t ts, double v_adj, int64_t pt, int32_t pv) {     // :88-125
-    double d = (double)(ts - pt); double mu = P.c.r_bar;
+    double d = (double)(ts - pt);
     // exp(-2 kappa d) as the square of exp(-kappa d): it only enters through 1 - e^{-2 kappa d} ~ 2 kappa d, where an ulp of the square moves the scale of the draw by < 1e-7
     // relative -- far below what int(round(.)) of a value ~1e5 resolves -- and saves one of the two exp evaluations per oracle step (+3.7 % msgs/s, profiles/r02_optimisation_log.md)
-    double ek = exp_ni(dmul(-P.c.kappa, d)), scale = dmul(P.ou_scale, dsub(1.0, dmul(ek, ek)));   // variance formula passed as scale
+    double ek = exp_ni(dmul(-P.c.kappa, d));
+    return oracle_finish(ts, v_adj, pv, ek, rng.std_normal(S_SYMBOL, s.ctr_symbol));
+  }
+  // the rest of one OU step once exp(-kappa d) and the step's standard normal are known
+  ABX_HD int32_t oracle_finish(int64_t ts, double v_adj, int32_t pv, double ek, double z) {
+    double mu = P.c.r_bar, scale = dmul(P.ou_scale, dsub(1.0, dmul(ek, ek)));           // variance formula passed as scale
     double loc = dadd(mu, dmul(dsub((double)pv, mu), ek));
-    double v = rng.normal(S_SYMBOL, s.ctr_symbol, loc, scale);
+    double v = dadd(loc, dmul(scale, z));                                               // normal(loc, scale)
     v = dadd(v, v_adj); if (!(v > 0)) v = 0;
     int32_t iv = (int32_t)py_round_i64(v); s.or_t = ts; s.or_v = iv; return iv;
   }
@@ -936,12 +961,51 @@ struct Sim {
   // ZeroIntelligenceAgent.placeOrder :277-309 (+ updateEstimates :189-275, TradingAgent.placeLimitOrder :309-349)
   ABX_HD void zi_place_order(int id, bool hbl = false) {                                // hbl: HeuristicBeliefLearningAgent.placeOrder with a full order stream (population 3)
     int stream = S_AGENT0 + id;
-    int32_t r_now = oracle_advance(s.now >= P.c.mkt_close_ns ? P.c.mkt_close_ns - 1 : s.now);             // observePrice :210-227
+    const int64_t t_obs = s.now >= P.c.mkt_close_ns ? P.c.mkt_close_ns - 1 : s.now;     // observePrice :210-227
     // Philox mode: the three draws of one order placement (noisy observation, side, surplus R) come from ONE Philox block of the agent's stream
     // (words 0-2 the normal, bit 0 of word 2 the side, word 3 R) instead of three blocks; tape mode replays the reference's draws one by one.
     bool one_block = !rng.tape(); U4 blk; blk.x = blk.y = blk.z = blk.w = 0;
-    if (one_block) blk = rng.philox(stream, a.rng_ctr);
-    double z_obs = one_block ? box_muller(blk.x, blk.y, blk.z) : rng.std_normal(stream, a.rng_ctr);
+    int32_t r_now; double z_obs;
+#if defined(__CUDA_ARCH__) && !defined(ABX_SEQ_DRAWS)
+    double pw0_l = 0.0, pw2_l = 0.0;
+    if (one_block) {
+      // Lane-parallel evaluation: every lane of the warp runs the same scalar code anyway, so the independent chains of one order placement go to different lanes and
+      // run ONCE -- lane 0 the fundamental's OU step (Philox block of the symbol stream -> Box-Muller, exp(-kappa d)), lane 1 the agent's block (noisy observation,
+      // side, R) and (1 - kappa) ** delta, lane 2 (1 - kappa) ** d2: one pass of the Philox rounds, of Box-Muller and of exp instead of two, two and three.  Same
+      // functions on the same arguments as the sequential form.  A megashock due before the observation is one more trip through the same code (lane 0 steps to
+      // the shock; the other lanes' results are simply recomputed on the last trip).
+      const uint32_t ln = threadIdx.x & 31u; const bool need = t_obs > s.or_t;        // oracle_advance returns the stored value for t <= r[symbol][0]
+      const int64_t pwk = (a.flags & AF_HAS_PREV) ? a.prev_wake : P.c.mkt_open_ns;
+      const double dl = (double)(s.now - pwk); double dc = (double)(P.c.mkt_close_ns - s.now); if (!(dc > 0)) dc = 0;
+      r_now = s.or_v; uint32_t zlo, zhi, elo, ehi; U4 o;
+#pragma unroll 1
+      for (;;) {
+        const bool shock = need && s.ms_t < t_obs; const int64_t ts = shock ? s.ms_t : t_obs;
+        o = philox4x32_10(ln == 0u ? s.ctr_symbol : a.rng_ctr, ln == 0u ? (uint32_t)S_SYMBOL : (uint32_t)stream, 0x41424958u, 0, (uint32_t)rng.seed, (uint32_t)(rng.seed >> 32));
+        const uint64_t zb = dbl_bits(box_muller(o.x, o.y, o.z));
+        const uint64_t eb = dbl_bits(exp_ni(ln == 0u ? dmul(-P.c.kappa, (double)(ts - s.or_t)) : dmul(ln == 1u ? dl : dc, P.log_base_a)));
+        zlo = (uint32_t)zb; zhi = (uint32_t)(zb >> 32); elo = (uint32_t)eb; ehi = (uint32_t)(eb >> 32);
+        if (need) {
+          const double z_or = bits_dbl((uint64_t)__shfl_sync(0xffffffffu, zlo, 0) | ((uint64_t)__shfl_sync(0xffffffffu, zhi, 0) << 32));
+          const double ek = bits_dbl((uint64_t)__shfl_sync(0xffffffffu, elo, 0) | ((uint64_t)__shfl_sync(0xffffffffu, ehi, 0) << 32));
+          s.ctr_symbol++; rng.rec(S_SYMBOL, 'n', dbl_bits(z_or));
+          r_now = oracle_finish(ts, shock ? s.ms_v : 0.0, s.or_v, ek, z_or);
+        }
+        if (!shock) break;
+        oracle_new_megashock(ts);
+      }
+      a.rng_ctr++;
+      z_obs = bits_dbl((uint64_t)__shfl_sync(0xffffffffu, zlo, 1) | ((uint64_t)__shfl_sync(0xffffffffu, zhi, 1) << 32));
+      pw0_l = bits_dbl((uint64_t)__shfl_sync(0xffffffffu, elo, 1) | ((uint64_t)__shfl_sync(0xffffffffu, ehi, 1) << 32));
+      pw2_l = bits_dbl((uint64_t)__shfl_sync(0xffffffffu, elo, 2) | ((uint64_t)__shfl_sync(0xffffffffu, ehi, 2) << 32));
+      blk.z = __shfl_sync(0xffffffffu, o.z, 1); blk.w = __shfl_sync(0xffffffffu, o.w, 1);
+    } else
+#endif
+    {
+      r_now = oracle_advance(t_obs);
+      if (one_block) blk = rng.philox(stream, a.rng_ctr);
+      z_obs = one_block ? box_muller(blk.x, blk.y, blk.z) : rng.std_normal(stream, a.rng_ctr);
+    }
     if (one_block) rng.rec(stream, 'n', dbl_bits(z_obs));                               // draw log: the same three entries a tape would hold
     int32_t obs_t = (int32_t)py_round_i64(dadd((double)r_now, dmul(P.sqrt_sigma_n, z_obs)));
     int q = a.shares / 100;                                                             // :203 int(x / 100): the correctly rounded fp64 quotient of two ints truncates to the C quotient (|x| < 2^31, remainder / 100 <= 0.99)
@@ -955,7 +1019,11 @@ struct Sim {
     // within an ulp of the true power; the result only feeds int(round(.)) of values ~1e5.
     // (1 - kappa) ** (2 delta) as the square of (1 - kappa) ** delta: it only enters through 1 - pw1 ~ 2 delta kappa ~ 1e-3 (sigma_t stays 0, :242), so an
     // ulp of pw1 moves r_t by ~1e-11 -- and saves one of the seven exp evaluations per order (12 % of all executed instructions were exp).
+#if defined(__CUDA_ARCH__) && !defined(ABX_SEQ_DRAWS)
+    double pw0 = one_block ? pw0_l : exp_ni(dmul(delta, P.log_base_a)), pw1 = dmul(pw0, pw0), pw2 = one_block ? pw2_l : exp_ni(dmul(d2, P.log_base_a));
+#else
     double pw0 = exp_ni(dmul(delta, P.log_base_a)), pw1 = dmul(pw0, pw0), pw2 = exp_ni(dmul(d2, P.log_base_a));
+#endif
     double r_tprime = dmul(dsub(1.0, pw0), r_bar);                                    // :229
     r_tprime = dadd(r_tprime, dmul(pw0, a.r_t));                                      // :230
     double sigma_tprime = dmul(pw1, a.sigma_t);                                       // :233
